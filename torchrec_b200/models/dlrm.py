@@ -1,0 +1,242 @@
+"""DLRM model family: DLRM, DLRM_Projection, DLRM_DCN, DLRMTrain.
+
+Architecture parity with the reference (torchrec/models/dlrm.py:38-960): SparseArch (EBC ->
+[B, F, D]), DenseArch (bottom MLP), InteractionArch (pairwise dots) / InteractionDCNArch
+(low-rank cross net) / InteractionProjectionArch, OverArch (top MLP, last layer linear).
+Dense compute is routed through ``torchrec_b200.ops.dense`` so that on B200 the MLP layers and
+the dot interaction run as hand-written tcgen05 kernels.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from ..datasets.utils import Batch
+from ..modules.crossnet import LowRankCrossNet
+from ..modules.embedding_modules import EmbeddingBagCollection
+from ..modules.mlp import MLP
+from ..ops import dense as _dense
+from ..sparse.jagged_tensor import KeyedJaggedTensor, KeyedTensor
+
+
+def choose(n: int, k: int) -> int:
+    """n choose k (0 when k > n)."""
+    if 0 <= k <= n:
+        ntok = ktok = 1
+        for t in range(1, min(k, n - k) + 1):
+            ntok *= n
+            ktok *= t
+            n -= 1
+        return ntok // ktok
+    return 0
+
+
+class SparseArch(nn.Module):
+    """EBC lookup reshaped to ``[B, F, D]`` (all tables share D)."""
+
+    def __init__(self, embedding_bag_collection: EmbeddingBagCollection) -> None:
+        super().__init__()
+        self.embedding_bag_collection = embedding_bag_collection
+        cfgs = self.embedding_bag_collection.embedding_bag_configs()
+        assert cfgs, "Embedding bag collection cannot be empty!"
+        self.D: int = cfgs[0].embedding_dim
+        self._sparse_feature_names: List[str] = [name for c in cfgs for name in c.feature_names]
+        self.F: int = len(self._sparse_feature_names)
+
+    def forward(self, features: KeyedJaggedTensor) -> torch.Tensor:
+        sparse_features: KeyedTensor = self.embedding_bag_collection(features)
+        sparse_values = sparse_features.values()
+        return sparse_values.reshape(-1, self.F, self.D)
+
+    @property
+    def sparse_feature_names(self) -> List[str]:
+        return self._sparse_feature_names
+
+
+class DenseArch(nn.Module):
+    """Bottom MLP over the dense features."""
+
+    def __init__(self, in_features: int, layer_sizes: List[int], device: Optional[torch.device] = None) -> None:
+        super().__init__()
+        self.model: nn.Module = MLP(in_features, layer_sizes, bias=True, activation="relu", device=device)
+
+    def forward(self, features: torch.Tensor) -> torch.Tensor:
+        return self.model(features)
+
+
+class InteractionArch(nn.Module):
+    """cat(dense, pairwise dot products among [dense; sparse features])."""
+
+    def __init__(self, num_sparse_features: int) -> None:
+        super().__init__()
+        self.F: int = num_sparse_features
+
+    def forward(self, dense_features: torch.Tensor, sparse_features: torch.Tensor) -> torch.Tensor:
+        if self.F <= 0:
+            return dense_features
+        return _dense.dot_interaction(dense_features, sparse_features)
+
+
+class InteractionDCNArch(nn.Module):
+    """Cross-net (DCN-v2) interaction over cat(dense, flattened sparse)."""
+
+    def __init__(self, num_sparse_features: int, crossnet: nn.Module) -> None:
+        super().__init__()
+        self.F: int = num_sparse_features
+        self.crossnet = crossnet
+
+    def forward(self, dense_features: torch.Tensor, sparse_features: torch.Tensor) -> torch.Tensor:
+        if self.F <= 0:
+            return dense_features
+        B = dense_features.shape[0]
+        combined = torch.cat((dense_features.unsqueeze(1), sparse_features.to(dense_features.dtype)), dim=1)
+        return self.crossnet(combined.reshape(B, -1))
+
+
+class InteractionProjectionArch(nn.Module):
+    """Project the F+1 feature vectors with two MLPs and take dots between the projections."""
+
+    def __init__(self, num_sparse_features: int, interaction_branch1: nn.Module, interaction_branch2: nn.Module) -> None:
+        super().__init__()
+        self.F: int = num_sparse_features
+        self.interaction_branch1 = interaction_branch1
+        self.interaction_branch2 = interaction_branch2
+
+    def forward(self, dense_features: torch.Tensor, sparse_features: torch.Tensor) -> torch.Tensor:
+        if self.F <= 0:
+            return dense_features
+        B, D = dense_features.shape
+        combined = torch.cat((dense_features.unsqueeze(1), sparse_features.to(dense_features.dtype)), dim=1)
+        flat = torch.reshape(combined, (B, -1))
+        b1 = torch.reshape(self.interaction_branch1(flat), (B, -1, D))
+        b2 = torch.reshape(self.interaction_branch2(flat), (B, D, -1))
+        interactions = torch.bmm(b1, b2)
+        return torch.cat((dense_features, torch.reshape(interactions, (B, -1))), dim=1)
+
+
+class OverArch(nn.Module):
+    """Top MLP; the final layer has no activation."""
+
+    def __init__(self, in_features: int, layer_sizes: List[int], device: Optional[torch.device] = None) -> None:
+        super().__init__()
+        if len(layer_sizes) <= 1:
+            raise ValueError("OverArch must have multiple layers.")
+        self.model: nn.Module = nn.Sequential(
+            MLP(in_features, layer_sizes[:-1], bias=True, activation="relu", device=device),
+            nn.Linear(layer_sizes[-2], layer_sizes[-1], bias=True, device=device),
+        )
+
+    def forward(self, features: torch.Tensor) -> torch.Tensor:
+        return self.model(features)
+
+
+class DLRM(nn.Module):
+    """Deep Learning Recommendation Model (https://arxiv.org/abs/1906.00091)."""
+
+    def __init__(
+        self,
+        embedding_bag_collection: EmbeddingBagCollection,
+        dense_in_features: int,
+        dense_arch_layer_sizes: List[int],
+        over_arch_layer_sizes: List[int],
+        dense_device: Optional[torch.device] = None,
+    ) -> None:
+        super().__init__()
+        cfgs = embedding_bag_collection.embedding_bag_configs()
+        assert len(cfgs) > 0, "At least one embedding bag is required"
+        for i in range(len(cfgs)):
+            assert cfgs[i].embedding_dim == cfgs[0].embedding_dim, "Embedding dimensions of all embedding bags must be the same"
+        embedding_dim = cfgs[0].embedding_dim
+        if dense_arch_layer_sizes[-1] != embedding_dim:
+            raise ValueError(f"embedding_bag_collection dimension ({embedding_dim}) and final dense arch layer size ({dense_arch_layer_sizes[-1]}) must match.")
+        self.sparse_arch: SparseArch = SparseArch(embedding_bag_collection)
+        num_sparse_features = len(self.sparse_arch.sparse_feature_names)
+        self.dense_arch = DenseArch(in_features=dense_in_features, layer_sizes=dense_arch_layer_sizes, device=dense_device)
+        self.inter_arch = InteractionArch(num_sparse_features=num_sparse_features)
+        over_in_features = embedding_dim + choose(num_sparse_features, 2) + num_sparse_features
+        self.over_arch = OverArch(in_features=over_in_features, layer_sizes=over_arch_layer_sizes, device=dense_device)
+
+    def forward(self, dense_features: torch.Tensor, sparse_features: KeyedJaggedTensor) -> torch.Tensor:
+        embedded_dense = self.dense_arch(dense_features)
+        embedded_sparse = self.sparse_arch(sparse_features)
+        concatenated_dense = self.inter_arch(dense_features=embedded_dense, sparse_features=embedded_sparse)
+        return self.over_arch(concatenated_dense)
+
+
+class DLRM_Projection(DLRM):
+    """DLRM with projected interactions (DLRM_Projection in the reference)."""
+
+    def __init__(
+        self,
+        embedding_bag_collection: EmbeddingBagCollection,
+        dense_in_features: int,
+        dense_arch_layer_sizes: List[int],
+        over_arch_layer_sizes: List[int],
+        interaction_branch1_layer_sizes: List[int],
+        interaction_branch2_layer_sizes: List[int],
+        dense_device: Optional[torch.device] = None,
+    ) -> None:
+        super().__init__(embedding_bag_collection, dense_in_features, dense_arch_layer_sizes, over_arch_layer_sizes, dense_device)
+        embedding_dim = embedding_bag_collection.embedding_bag_configs()[0].embedding_dim
+        num_sparse_features = len(self.sparse_arch.sparse_feature_names)
+        if interaction_branch1_layer_sizes[-1] % embedding_dim != 0:
+            raise ValueError(f"Final interaction branch1 layer size ({interaction_branch1_layer_sizes[-1]}) is not a multiple of embedding size ({embedding_dim})")
+        projected_dim_1 = interaction_branch1_layer_sizes[-1] // embedding_dim
+        if interaction_branch2_layer_sizes[-1] % embedding_dim != 0:
+            raise ValueError(f"Final interaction branch2 layer size ({interaction_branch2_layer_sizes[-1]}) is not a multiple of embedding size ({embedding_dim})")
+        projected_dim_2 = interaction_branch2_layer_sizes[-1] // embedding_dim
+        self.inter_arch = InteractionProjectionArch(
+            num_sparse_features=num_sparse_features,
+            interaction_branch1=MLP(in_size=(num_sparse_features + 1) * embedding_dim, layer_sizes=interaction_branch1_layer_sizes, bias=True, device=dense_device),
+            interaction_branch2=MLP(in_size=(num_sparse_features + 1) * embedding_dim, layer_sizes=interaction_branch2_layer_sizes, bias=True, device=dense_device),
+        )
+        over_in_features = embedding_dim + projected_dim_1 * projected_dim_2
+        self.over_arch = OverArch(in_features=over_in_features, layer_sizes=over_arch_layer_sizes, device=dense_device)
+
+
+class DLRM_DCN(DLRM):
+    """DLRM with a DCN-v2 low-rank cross network interaction (MLPerf DLRM-DCNv2)."""
+
+    def __init__(
+        self,
+        embedding_bag_collection: EmbeddingBagCollection,
+        dense_in_features: int,
+        dense_arch_layer_sizes: List[int],
+        over_arch_layer_sizes: List[int],
+        dcn_num_layers: int,
+        dcn_low_rank_dim: int,
+        dense_device: Optional[torch.device] = None,
+    ) -> None:
+        super().__init__(embedding_bag_collection, dense_in_features, dense_arch_layer_sizes, over_arch_layer_sizes, dense_device)
+        embedding_dim = embedding_bag_collection.embedding_bag_configs()[0].embedding_dim
+        num_sparse_features = len(self.sparse_arch.sparse_feature_names)
+        over_in_features = embedding_dim * (num_sparse_features + 1)
+        crossnet = LowRankCrossNet(in_features=over_in_features, num_layers=dcn_num_layers, low_rank=dcn_low_rank_dim)
+        if dense_device is not None:
+            crossnet = crossnet.to(dense_device)
+        self.inter_arch = InteractionDCNArch(num_sparse_features=num_sparse_features, crossnet=crossnet)
+        self.over_arch = OverArch(in_features=over_in_features, layer_sizes=over_arch_layer_sizes, device=dense_device)
+
+
+class DLRMTrain(nn.Module):
+    """Training wrapper: BCE-with-logits loss; returns ``(loss, (loss.detach(), logits.detach(), labels.detach()))``."""
+
+    def __init__(self, dlrm_module: DLRM) -> None:
+        super().__init__()
+        self.model = dlrm_module
+        self.loss_fn: nn.Module = nn.BCEWithLogitsLoss()
+
+    def forward(self, batch: Batch) -> Tuple[torch.Tensor, Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
+        logits = self.model(batch.dense_features, batch.sparse_features)
+        logits = logits.squeeze(-1)
+        loss = self.loss_fn(logits.float(), batch.labels.float())
+        return loss, (loss.detach(), logits.detach(), batch.labels.detach())
+
+
+class DLRMWrapper(DLRM):
+    """DLRM taking a ``Batch``-like object as the single input (used by inference packaging)."""
+
+    def forward(self, model_input) -> torch.Tensor:  # type: ignore[override]
+        return super().forward(model_input.float_features, model_input.idlist_features)

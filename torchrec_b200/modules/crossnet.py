@@ -1,0 +1,122 @@
+"""Cross networks (DCN family). Reference torchrec/modules/crossnet.py:21-380."""
+from typing import Callable, Optional, Union
+
+import torch
+from torch import nn
+
+
+class CrossNet(nn.Module):
+    """Full-rank cross network: ``x_{l+1} = x_0 * (W_l x_l + b_l) + x_l``."""
+
+    def __init__(self, in_features: int, num_layers: int) -> None:
+        super().__init__()
+        self._num_layers = num_layers
+        self.kernels: nn.ParameterList = nn.ParameterList(
+            [nn.Parameter(nn.init.xavier_normal_(torch.empty(in_features, in_features))) for _ in range(num_layers)])
+        self.bias: nn.ParameterList = nn.ParameterList(
+            [nn.Parameter(nn.init.zeros_(torch.empty(in_features, 1))) for _ in range(num_layers)])
+
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
+        x_0 = input.unsqueeze(2)  # (B, N, 1)
+        x_l = x_0
+        for layer in range(self._num_layers):
+            xl_w = torch.matmul(self.kernels[layer], x_l)
+            x_l = x_0 * (xl_w + self.bias[layer]) + x_l
+        return torch.squeeze(x_l, dim=2)
+
+
+class LowRankCrossNet(nn.Module):
+    """Low-rank cross network: ``x_{l+1} = x_0 * (W_l (V_l x_l) + b_l) + x_l`` (DCN-v2)."""
+
+    def __init__(self, in_features: int, num_layers: int, low_rank: int = 1) -> None:
+        super().__init__()
+        assert low_rank >= 1, "Low rank must be larger or equal to 1"
+        self._num_layers = num_layers
+        self._low_rank = low_rank
+        W_kernels = nn.ParameterList()
+        for _ in range(num_layers):
+            Wp = nn.Parameter(torch.empty(in_features, low_rank))
+            nn.init.xavier_normal_(Wp)
+            W_kernels.append(Wp)
+        V_kernels = nn.ParameterList()
+        for _ in range(num_layers):
+            Vp = nn.Parameter(torch.empty(low_rank, in_features))
+            nn.init.xavier_normal_(Vp)
+            V_kernels.append(Vp)
+        self.W_kernels = W_kernels
+        self.V_kernels = V_kernels
+        self.bias: nn.ParameterList = nn.ParameterList(
+            [nn.Parameter(nn.init.zeros_(torch.empty(in_features))) for _ in range(num_layers)])
+
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
+        x_0 = input
+        x_l = x_0
+        for layer in range(self._num_layers):
+            x_l_v = torch.nn.functional.linear(x_l, self.V_kernels[layer])
+            x_l_w = torch.nn.functional.linear(x_l_v, self.W_kernels[layer])
+            x_l = x_0 * (x_l_w + self.bias[layer]) + x_l
+        return x_l
+
+
+class VectorCrossNet(nn.Module):
+    """Vector (DCN-v1) cross network: ``x_{l+1} = x_0 * (w_l^T x_l) + b_l + x_l``."""
+
+    def __init__(self, in_features: int, num_layers: int) -> None:
+        super().__init__()
+        self._num_layers = num_layers
+        self.kernels: nn.ParameterList = nn.ParameterList(
+            [nn.Parameter(nn.init.xavier_normal_(torch.empty(in_features, 1))) for _ in range(num_layers)])
+        self.bias: nn.ParameterList = nn.ParameterList(
+            [nn.Parameter(nn.init.zeros_(torch.empty(in_features, 1))) for _ in range(num_layers)])
+
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
+        x_0 = input.unsqueeze(2)
+        x_l = x_0
+        for layer in range(self._num_layers):
+            xl_w = torch.tensordot(x_l, self.kernels[layer], dims=([1], [0]))
+            x_l = torch.matmul(x_0, xl_w) + self.bias[layer] + x_l
+        return torch.squeeze(x_l, dim=2)
+
+
+class LowRankMixtureCrossNet(nn.Module):
+    """Mixture of low-rank experts cross network (DCN-Mix)."""
+
+    def __init__(self, in_features: int, num_layers: int, num_experts: int = 1, low_rank: int = 1,
+                 activation: Union[nn.Module, Callable[[torch.Tensor], torch.Tensor]] = torch.relu) -> None:
+        super().__init__()
+        assert num_experts >= 1 and low_rank >= 1
+        self._num_layers = num_layers
+        self._num_experts = num_experts
+        self._low_rank = low_rank
+        self._in_features = in_features
+        self.U_kernels = nn.ParameterList([
+            nn.Parameter(nn.init.xavier_normal_(torch.empty(num_experts, in_features, low_rank))) for _ in range(num_layers)])
+        self.V_kernels = nn.ParameterList([
+            nn.Parameter(nn.init.xavier_normal_(torch.empty(num_experts, low_rank, in_features))) for _ in range(num_layers)])
+        self.bias = nn.ParameterList([nn.Parameter(nn.init.zeros_(torch.empty(in_features, 1))) for _ in range(num_layers)])
+        self.gates: Optional[nn.Module] = nn.ModuleList([nn.Linear(in_features, 1, bias=False) for _ in range(num_experts)]) if num_experts > 1 else None
+        self._activation = activation
+        self.C_kernels = nn.ParameterList([
+            nn.Parameter(nn.init.xavier_normal_(torch.empty(num_experts, low_rank, low_rank))) for _ in range(num_layers)])
+
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
+        x_0 = input.unsqueeze(2)
+        x_l = x_0
+        for layer in range(self._num_layers):
+            if self._num_experts > 1:
+                gating = [self.gates[i](x_l.squeeze(2)) for i in range(self._num_experts)]
+                gating = torch.stack(gating, 1)  # (B, E, 1)
+            experts = []
+            for i in range(self._num_experts):
+                expert = torch.matmul(self.V_kernels[layer][i], x_l)
+                expert = torch.matmul(self.C_kernels[layer][i], self._activation(expert))
+                expert = torch.matmul(self.U_kernels[layer][i], self._activation(expert))
+                expert = x_0 * (expert + self.bias[layer])
+                experts.append(expert.squeeze(2))
+            experts = torch.stack(experts, 2)  # (B, N, E)
+            if self._num_experts > 1:
+                moe = torch.matmul(experts, torch.nn.functional.softmax(gating, 1))
+                x_l = moe + x_l
+            else:
+                x_l = experts + x_l
+        return torch.squeeze(x_l, dim=2)

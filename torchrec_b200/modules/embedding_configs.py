@@ -1,0 +1,130 @@
+"""Embedding table configuration types (reference torchrec/modules/embedding_configs.py:348-457)."""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from enum import Enum, unique
+from functools import partial
+from math import sqrt
+from typing import Callable, Dict, List, NamedTuple, Optional
+
+import torch
+
+from ..types import DataType
+
+
+@unique
+class PoolingType(Enum):
+    SUM = "SUM"
+    MEAN = "MEAN"
+    NONE = "NONE"
+
+
+# MEAN pooling under row-wise style shardings is computed as SUM + a divisor applied after the
+# reduce-scatter (reference embedding_configs.py:97-115)
+def pooling_type_to_pooling_mode(pooling_type: PoolingType, sharding_type: Optional[str] = None):
+    from ..ops.tbe import PoolingMode
+
+    if pooling_type == PoolingType.SUM:
+        return PoolingMode.SUM
+    if pooling_type == PoolingType.MEAN:
+        if sharding_type in ("row_wise", "table_row_wise", "grid_shard"):
+            return PoolingMode.SUM
+        return PoolingMode.MEAN
+    if pooling_type == PoolingType.NONE:
+        return PoolingMode.NONE
+    raise ValueError(f"unsupported pooling type {pooling_type}")
+
+
+def pooling_type_to_str(pooling_type: PoolingType) -> str:
+    return {PoolingType.SUM: "sum", PoolingType.MEAN: "mean"}[pooling_type]
+
+
+DATA_TYPE_NUM_BITS: Dict[DataType, int] = {
+    DataType.FP32: 32, DataType.FP16: 16, DataType.BF16: 16, DataType.INT8: 8, DataType.UINT8: 8,
+    DataType.INT4: 4, DataType.INT2: 2, DataType.FP8: 8, DataType.INT32: 32, DataType.INT64: 64,
+}
+
+
+def dtype_to_data_type(dtype: torch.dtype) -> DataType:
+    m = {
+        torch.float32: DataType.FP32, torch.float: DataType.FP32, torch.float16: DataType.FP16, torch.half: DataType.FP16,
+        torch.bfloat16: DataType.BF16, torch.int64: DataType.INT64, torch.long: DataType.INT64, torch.int32: DataType.INT32,
+        torch.int: DataType.INT32, torch.int8: DataType.INT8, torch.uint8: DataType.UINT8, torch.quint8: DataType.UINT8,
+        torch.qint8: DataType.INT8, torch.quint4x2: DataType.INT4, torch.quint2x4: DataType.INT2,
+    }
+    if dtype in m:
+        return m[dtype]
+    raise Exception(f"Invalid data type {dtype}")
+
+
+def data_type_to_dtype(data_type: DataType) -> torch.dtype:
+    m = {
+        DataType.FP32: torch.float32, DataType.FP16: torch.float16, DataType.BF16: torch.bfloat16, DataType.INT64: torch.int64,
+        DataType.INT32: torch.int32, DataType.INT8: torch.int8, DataType.UINT8: torch.uint8, DataType.INT4: torch.quint4x2,
+        DataType.INT2: torch.quint2x4, DataType.FP8: torch.float8_e4m3fn,
+    }
+    if data_type in m:
+        return m[data_type]
+    raise ValueError(f"DataType {data_type} cannot be converted to dtype")
+
+
+@dataclass
+class BaseEmbeddingConfig:
+    num_embeddings: int
+    embedding_dim: int
+    name: str = ""
+    data_type: DataType = DataType.FP32
+    feature_names: List[str] = field(default_factory=list)
+    weight_init_max: Optional[float] = None
+    weight_init_min: Optional[float] = None
+    num_embeddings_post_pruning: Optional[int] = None
+    init_fn: Optional[Callable[[torch.Tensor], Optional[torch.Tensor]]] = None
+    # when the position-weighted feature processor wraps the table
+    need_pos: bool = False
+    input_dim: Optional[int] = None
+    total_num_buckets: Optional[int] = None
+    use_virtual_table: bool = False
+    stash_weights: bool = False
+
+    def get_weight_init_max(self) -> float:
+        if self.weight_init_max is None:
+            return sqrt(1 / self.num_embeddings)
+        return self.weight_init_max
+
+    def get_weight_init_min(self) -> float:
+        if self.weight_init_min is None:
+            return -sqrt(1 / self.num_embeddings)
+        return self.weight_init_min
+
+    def num_features(self) -> int:
+        return len(self.feature_names)
+
+    def __post_init__(self) -> None:
+        if self.init_fn is None:
+            self.init_fn = partial(torch.nn.init.uniform_, a=self.get_weight_init_min(), b=self.get_weight_init_max())
+
+
+@dataclass
+class EmbeddingTableConfig(BaseEmbeddingConfig):
+    pooling: PoolingType = PoolingType.SUM
+    is_weighted: bool = False
+    has_feature_processor: bool = False
+    embedding_names: List[str] = field(default_factory=list)
+
+
+@dataclass
+class EmbeddingBagConfig(BaseEmbeddingConfig):
+    """Config of a pooled table (``nn.EmbeddingBag`` semantics)."""
+
+    pooling: PoolingType = PoolingType.SUM
+
+
+@dataclass
+class EmbeddingConfig(BaseEmbeddingConfig):
+    """Config of an unpooled (sequence) table (``nn.Embedding`` semantics)."""
+
+
+class QuantConfig(NamedTuple):
+    activation: object
+    weight: object
+    per_table_weight_dtype: Optional[Dict[str, torch.dtype]] = None

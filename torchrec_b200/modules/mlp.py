@@ -1,0 +1,81 @@
+"""Perceptron / MLP (reference torchrec/modules/mlp.py:18-190).
+
+On CUDA with bf16/fp16 compute enabled (``torchrec_b200.ops.dense.set_dense_backend``) a
+``Linear + bias + ReLU`` layer runs as ONE hand-written tcgen05/TMEM GEMM kernel with the bias
+and activation fused into the epilogue (``csrc/gemm_tcgen05.cu``); otherwise plain PyTorch.
+"""
+from typing import Callable, List, Optional, Union
+
+import torch
+from torch import nn
+
+from ..ops import dense as _dense
+from .activation import SwishLayerNorm
+from .utils import extract_module_or_tensor_callable
+
+
+class Perceptron(nn.Module):
+    """Linear layer followed by an activation."""
+
+    def __init__(
+        self,
+        in_size: int,
+        out_size: int,
+        bias: bool = True,
+        activation: Union[nn.Module, Callable[[torch.Tensor], torch.Tensor]] = torch.relu,
+        device: Optional[torch.device] = None,
+        dtype: torch.dtype = torch.float32,
+    ) -> None:
+        super().__init__()
+        self._out_size = out_size
+        self._in_size = in_size
+        self._linear: nn.Linear = nn.Linear(self._in_size, self._out_size, bias=bias, device=device, dtype=dtype)
+        self._activation_fn = activation
+
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
+        act = self._activation_fn
+        fused = _dense.fused_act_code(act)
+        if fused is not None and _dense.can_fuse(input, self._linear):
+            return _dense.linear_act(input, self._linear.weight, self._linear.bias, fused)
+        return act(self._linear(input))
+
+
+class MLP(nn.Module):
+    """Stack of Perceptrons. ``activation`` may be ``"relu"``, ``"sigmoid"``, ``"swish_layernorm"``,
+    a callable, or a module (factory)."""
+
+    def __init__(
+        self,
+        in_size: int,
+        layer_sizes: List[int],
+        bias: bool = True,
+        activation: Union[str, Callable[[], nn.Module], nn.Module, Callable[[torch.Tensor], torch.Tensor]] = torch.relu,
+        device: Optional[torch.device] = None,
+        dtype: torch.dtype = torch.float32,
+    ) -> None:
+        super().__init__()
+        if activation == "relu":
+            activation = torch.relu
+        elif activation == "sigmoid":
+            activation = torch.sigmoid
+        if not isinstance(activation, str):
+            self._mlp: nn.Module = nn.Sequential(*[
+                Perceptron(
+                    layer_sizes[i - 1] if i > 0 else in_size, layer_sizes[i], bias=bias,
+                    activation=extract_module_or_tensor_callable(activation), device=device, dtype=dtype,
+                )
+                for i in range(len(layer_sizes))
+            ])
+        elif activation == "swish_layernorm":
+            self._mlp = nn.Sequential(*[
+                Perceptron(
+                    layer_sizes[i - 1] if i > 0 else in_size, layer_sizes[i], bias=bias,
+                    activation=SwishLayerNorm(layer_sizes[i], device=device), device=device,
+                )
+                for i in range(len(layer_sizes))
+            ])
+        else:
+            raise ValueError(f"This MLP only supports str version activation function of relu, sigmoid, and swish_layernorm, got {activation}")
+
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
+        return self._mlp(input)

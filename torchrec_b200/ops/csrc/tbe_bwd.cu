@@ -1,0 +1,523 @@
+// Table-batched embedding backward fused with the sparse optimizer (sm_100a).
+//
+// Exact (deterministic, duplicate-safe) semantics like the reference's EXACT_* TBE optimizers
+// (torchrec/distributed/embedding_types.py:57-72; fused backward reached through autograd at
+// batched_embedding_kernel.py:3010-3058): the gradient of every *unique* row is summed over all
+// of its occurrences first, then the optimizer is applied once to that row. No dense gradient is
+// ever materialised.
+//
+// Pipeline (all stream-ordered, no host sync):
+//   K0  build keys     key[i] = row_base(feature) + indices[i]   (invalid / padding -> sentinel)
+//                      bag_of[i] = bag containing position i
+//   K1  cub radix sort (key, i)
+//   K2  chunk walk     one warp per 32 sorted positions: reduce each run of equal keys; runs that
+//                      live inside the chunk get the optimizer applied immediately, runs that
+//                      cross a chunk boundary leave a partial sum
+//   K3  span combine   one CTA per boundary-crossing run sums the partials and applies
+//
+// The gradient rows are read through TrbPeerPtrs: with W peer pointers the kernel *pulls*
+// grad[b_local, cols(f)] straight from the rank that owns sample b over NVLink — that is the
+// backward all-to-all of the reference (comm_ops.py:1581-1646) fused into the optimizer kernel.
+#include "common.cuh"
+#include <cub/device/device_radix_sort.cuh>
+
+enum TrbOpt : int {
+  OPT_SGD = 0,
+  OPT_ROWWISE_ADAGRAD = 1,
+  OPT_ADAGRAD = 2,
+  OPT_ADAM = 3,
+  OPT_PARTIAL_ROWWISE_ADAM = 4,
+  OPT_LAMB = 5,
+  OPT_PARTIAL_ROWWISE_LAMB = 6,
+  OPT_LARS_SGD = 7,
+  OPT_NONE = 8,  // accumulate summed gradient rows into a dense fp32 grad buffer (state1)
+};
+
+// hyper[] slots (device memory, refreshed by the host each step; graph-capture friendly)
+#define HP_LR 0
+#define HP_EPS 1
+#define HP_BETA1 2
+#define HP_BETA2 3
+#define HP_WD 4
+#define HP_STEP 5
+#define HP_MAXGRAD 6
+#define HP_MOMENTUM 7
+
+struct TbeBwdParams {
+  void* weights;
+  float* state1;  // rowwise: [total_rows]; elementwise: same layout as weights (fp32)
+  float* state2;
+  const float* hyper;
+  const int64_t* feat_woff;     // [F]
+  const int64_t* feat_rows;     // [F]
+  const int64_t* feat_rowbase;  // [F] first global row id of feature f's table
+  const int32_t* feat_dim;      // [F]
+  const int32_t* feat_col;      // [F]
+  const void* indices;
+  const void* offsets;
+  const float* psw;
+  TrbPeerPtrs grad;  // gradient sources
+  int64_t grad_stride;
+  int64_t n;  // capacity of indices
+  int64_t total_rows;
+  int32_t B, B_local, F;
+  int32_t idx64, off64, mean;
+  int32_t wd_mode;  // 0 none, 1 L2, 2 decoupled
+  // workspace
+  void* keys;
+  void* keys_sorted;
+  int32_t* vals;
+  int32_t* vals_sorted;
+  int32_t* bag_of;
+  float* partials;  // [chunks][2][max_dim]
+  uint8_t* span_flags;
+  int32_t max_dim;
+  int32_t key64;
+  int32_t opt;
+};
+
+__device__ __forceinline__ uint64_t ld_key(const void* p, int64_t i, int key64) {
+  return key64 ? reinterpret_cast<const uint64_t*>(p)[i] : (uint64_t) reinterpret_cast<const uint32_t*>(p)[i];
+}
+
+__global__ void __launch_bounds__(256) tbe_bwd_build_keys(const TbeBwdParams p) {
+  const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  const int64_t n_bags = (int64_t) p.F * p.B;
+  const int64_t total = trb_ld_idx(p.offsets, n_bags, p.off64);
+  uint64_t key = (uint64_t) p.total_rows;  // sentinel sorts last
+  int32_t bag = 0;
+  if (i < total) {
+    // largest bag with offsets[bag] <= i  (bags may be empty -> take the last such bag)
+    int64_t lo = 0, hi = n_bags - 1;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi + 1) >> 1;
+      if (trb_ld_idx(p.offsets, mid, p.off64) <= i) lo = mid; else hi = mid - 1;
+    }
+    bag = (int32_t) lo;
+    const int f = (int) (lo / p.B);
+    const int64_t idx = trb_ld_idx(p.indices, i, p.idx64);
+    if (idx >= 0 && idx < p.feat_rows[f]) key = (uint64_t) (p.feat_rowbase[f] + idx);
+  }
+  if (p.key64) reinterpret_cast<uint64_t*>(p.keys)[i] = key;
+  else reinterpret_cast<uint32_t*>(p.keys)[i] = (uint32_t) key;
+  p.vals[i] = (int32_t) i;
+  p.bag_of[i] = bag;
+}
+
+// ---- optimizer application on one unique row ------------------------------------------------
+// g[k] holds the summed gradient for elements (lane + 32k)*4 .. +3 of the row.
+template <typename W, int MAXV>
+__device__ __forceinline__ void apply_row(const TbeBwdParams& p, int64_t key, int f, float4 (&g)[MAXV], int lane) {
+  const int OPT = p.opt;
+  const int D = p.feat_dim[f];
+  const int nvec = D >> 2;
+  const int64_t row = key - p.feat_rowbase[f];
+  const int64_t eoff = p.feat_woff[f] + row * D;
+  W* w = reinterpret_cast<W*>(p.weights) + eoff;
+  const float lr = p.hyper[HP_LR], eps = p.hyper[HP_EPS], wd = p.hyper[HP_WD];
+  const float maxg = p.hyper[HP_MAXGRAD];
+
+  float4 wv[MAXV];
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int vi = lane + k * 32;
+    wv[k] = (vi < nvec && OPT != OPT_NONE) ? Vec4<W>::ld(w + vi * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (maxg > 0.f) {
+      g[k].x = fminf(fmaxf(g[k].x, -maxg), maxg);
+      g[k].y = fminf(fmaxf(g[k].y, -maxg), maxg);
+      g[k].z = fminf(fmaxf(g[k].z, -maxg), maxg);
+      g[k].w = fminf(fmaxf(g[k].w, -maxg), maxg);
+    }
+    if (p.wd_mode == 1 && OPT != OPT_NONE) g[k] = f4_fma(wv[k], wd, g[k]);
+    // decoupled decay for the non-Adam family (Adam/LAMB fold wd*w into their update below)
+    if (p.wd_mode == 2 && (OPT == OPT_SGD || OPT == OPT_ROWWISE_ADAGRAD || OPT == OPT_ADAGRAD || OPT == OPT_LARS_SGD))
+      wv[k] = f4_scale(wv[k], 1.f - lr * wd);
+  }
+
+  if (OPT == OPT_NONE) {
+    float* gw = p.state1 + eoff;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const int vi = lane + k * 32;
+      if (vi < nvec) {
+        float4 o = *reinterpret_cast<float4*>(gw + vi * 4);
+        *reinterpret_cast<float4*>(gw + vi * 4) = f4_add(o, g[k]);
+      }
+    }
+    return;
+  }
+
+  if (OPT == OPT_SGD) {
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) wv[k] = f4_fma(g[k], -lr, wv[k]);
+  } else if (OPT == OPT_ROWWISE_ADAGRAD) {
+    float sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) sq += f4_sq(g[k]);  // lanes beyond nvec hold zeros
+    sq = warp_sum(sq) / (float) D;
+    float st = (lane == 0) ? p.state1[key] : 0.f;
+    st = __shfl_sync(0xffffffffu, st, 0);
+    const float ns = st + sq;
+    if (lane == 0) p.state1[key] = ns;
+    const float mult = lr / (sqrtf(ns) + eps);
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) wv[k] = f4_fma(g[k], -mult, wv[k]);
+  } else if (OPT == OPT_ADAGRAD) {
+    float* s = p.state1 + eoff;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const int vi = lane + k * 32;
+      if (vi < nvec) {
+        float4 sv = *reinterpret_cast<float4*>(s + vi * 4);
+        sv.x += g[k].x * g[k].x; sv.y += g[k].y * g[k].y; sv.z += g[k].z * g[k].z; sv.w += g[k].w * g[k].w;
+        *reinterpret_cast<float4*>(s + vi * 4) = sv;
+        wv[k].x -= lr * g[k].x / (sqrtf(sv.x) + eps);
+        wv[k].y -= lr * g[k].y / (sqrtf(sv.y) + eps);
+        wv[k].z -= lr * g[k].z / (sqrtf(sv.z) + eps);
+        wv[k].w -= lr * g[k].w / (sqrtf(sv.w) + eps);
+      }
+    }
+  } else if (OPT == OPT_ADAM || OPT == OPT_PARTIAL_ROWWISE_ADAM || OPT == OPT_LAMB || OPT == OPT_PARTIAL_ROWWISE_LAMB) {
+    const float b1 = p.hyper[HP_BETA1], b2 = p.hyper[HP_BETA2], step = p.hyper[HP_STEP];
+    const float bc1 = 1.f - powf(b1, step), bc2 = 1.f - powf(b2, step);
+    const bool ROWV = (OPT == OPT_PARTIAL_ROWWISE_ADAM || OPT == OPT_PARTIAL_ROWWISE_LAMB);
+    const bool LAMB = (OPT == OPT_LAMB || OPT == OPT_PARTIAL_ROWWISE_LAMB);
+    float* m = p.state1 + eoff;
+    float vrow = 0.f;
+    if (ROWV) {
+      float sq = 0.f;
+#pragma unroll
+      for (int k = 0; k < MAXV; ++k) sq += f4_sq(g[k]);
+      sq = warp_sum(sq) / (float) D;
+      float st = (lane == 0) ? p.state2[key] : 0.f;
+      st = __shfl_sync(0xffffffffu, st, 0);
+      vrow = b2 * st + (1.f - b2) * sq;
+      if (lane == 0) p.state2[key] = vrow;
+    }
+    float4 upd[MAXV];
+    float un = 0.f, wn = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const int vi = lane + k * 32;
+      upd[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (vi < nvec) {
+        float4 mv = *reinterpret_cast<float4*>(m + vi * 4);
+        mv.x = b1 * mv.x + (1.f - b1) * g[k].x; mv.y = b1 * mv.y + (1.f - b1) * g[k].y;
+        mv.z = b1 * mv.z + (1.f - b1) * g[k].z; mv.w = b1 * mv.w + (1.f - b1) * g[k].w;
+        *reinterpret_cast<float4*>(m + vi * 4) = mv;
+        float4 vv;
+        if (ROWV) {
+          vv = make_float4(vrow, vrow, vrow, vrow);
+        } else {
+          float* v = p.state2 + eoff;
+          vv = *reinterpret_cast<float4*>(v + vi * 4);
+          vv.x = b2 * vv.x + (1.f - b2) * g[k].x * g[k].x; vv.y = b2 * vv.y + (1.f - b2) * g[k].y * g[k].y;
+          vv.z = b2 * vv.z + (1.f - b2) * g[k].z * g[k].z; vv.w = b2 * vv.w + (1.f - b2) * g[k].w * g[k].w;
+          *reinterpret_cast<float4*>(v + vi * 4) = vv;
+        }
+        upd[k].x = (mv.x / bc1) / (sqrtf(vv.x / bc2) + eps);
+        upd[k].y = (mv.y / bc1) / (sqrtf(vv.y / bc2) + eps);
+        upd[k].z = (mv.z / bc1) / (sqrtf(vv.z / bc2) + eps);
+        upd[k].w = (mv.w / bc1) / (sqrtf(vv.w / bc2) + eps);
+        if (LAMB || p.wd_mode == 2) upd[k] = f4_fma(wv[k], wd, upd[k]);
+        un += f4_sq(upd[k]);
+        wn += f4_sq(wv[k]);
+      }
+    }
+    float ratio = 1.f;
+    if (LAMB) {
+      un = sqrtf(warp_sum(un));
+      wn = sqrtf(warp_sum(wn));
+      ratio = (wn > 0.f && un > 0.f) ? wn / un : 1.f;
+    }
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) wv[k] = f4_fma(upd[k], -lr * ratio, wv[k]);
+  } else if (OPT == OPT_LARS_SGD) {
+    float gn = 0.f, wn = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) { gn += f4_sq(g[k]); wn += f4_sq(wv[k]); }
+    gn = sqrtf(warp_sum(gn));
+    wn = sqrtf(warp_sum(wn));
+    const float eta = p.hyper[HP_MOMENTUM] > 0.f ? p.hyper[HP_MOMENTUM] : 0.001f;
+    const float ratio = (wn > 0.f && gn > 0.f) ? eta * wn / (gn + wd * wn + eps) : 1.f;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) wv[k] = f4_fma(g[k], -lr * ratio, wv[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int vi = lane + k * 32;
+    if (vi < nvec) Vec4<W>::st(w + vi * 4, wv[k]);
+  }
+}
+
+template <typename G, int MAXV>
+__device__ __forceinline__ void load_grad_row(const TbeBwdParams& p, int bag, float scale, int lane, float4 (&acc)[MAXV]) {
+  const int f = bag / p.B;
+  const int b = bag - f * p.B;
+  const int s = b / p.B_local;
+  const int bl = b - s * p.B_local;
+  const int nvec = p.feat_dim[f] >> 2;
+  const G* src = reinterpret_cast<const G*>(p.grad.p[s]) + (int64_t) bl * p.grad_stride + p.feat_col[f];
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int vi = lane + k * 32;
+    if (vi < nvec) acc[k] = f4_fma(Vec4<G>::ld(src + vi * 4), scale, acc[k]);
+  }
+}
+
+template <typename W, typename G, int MAXV>
+__global__ void __launch_bounds__(256) tbe_bwd_chunk_kernel(const TbeBwdParams p) {
+  typedef uint64_t K;
+  const int lane = threadIdx.x & 31;
+  const int64_t chunk = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t base = chunk << 5;
+  if (base >= p.n) return;
+  const int cnt = (int) min((int64_t) 32, p.n - base);
+  const void* keys = p.keys_sorted;
+  const K sentinel = (K) p.total_rows;
+  const K key = lane < cnt ? ld_key(keys, base + lane, p.key64) : sentinel;
+  const int val = lane < cnt ? p.vals_sorted[base + lane] : 0;
+  int bag = 0;
+  float scale = 0.f;
+  if (lane < cnt && key != sentinel) {
+    bag = p.bag_of[val];
+    scale = p.psw ? p.psw[val] : 1.f;
+    if (p.mean) {
+      const int64_t L = trb_ld_idx(p.offsets, (int64_t) bag + 1, p.off64) - trb_ld_idx(p.offsets, bag, p.off64);
+      scale /= (float) (L > 0 ? L : 1);
+    }
+  }
+  const bool has_prev = base > 0, has_next = base + 32 < p.n;
+  const K prev_key = has_prev ? ld_key(keys, base - 1, p.key64) : sentinel;
+  const K next_key = has_next ? ld_key(keys, base + 32, p.key64) : sentinel;
+  const K up = __shfl_up_sync(0xffffffffu, key, 1);
+  const bool is_start = (lane == 0) || (key != up);
+  unsigned starts = __ballot_sync(0xffffffffu, lane < cnt && is_start);
+  bool wrote_slot1 = false;
+  while (starts) {
+    const int a = __ffs(starts) - 1;
+    starts &= starts - 1;
+    const int bnd = starts ? (__ffs(starts) - 1) : cnt;
+    const K rk = __shfl_sync(0xffffffffu, key, a);
+    if (rk == sentinel) break;  // padding / invalid ids sort last
+    float4 acc[MAXV];
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int e = a; e < bnd; ++e) {
+      const int ebag = __shfl_sync(0xffffffffu, bag, e);
+      const float esc = __shfl_sync(0xffffffffu, scale, e);
+      load_grad_row<G, MAXV>(p, ebag, esc, lane, acc);
+    }
+    const int f = __shfl_sync(0xffffffffu, bag, a) / p.B;
+    const bool head_open = (a == 0) && has_prev && (rk == prev_key);
+    const bool tail_open = (bnd == cnt) && has_next && (rk == next_key);
+    if (!head_open && !tail_open) {
+      apply_row<W, MAXV>(p, (int64_t) rk, f, acc, lane);
+    } else {
+      const int slot = head_open ? 0 : 1;
+      if (!head_open) wrote_slot1 = true;
+      float* dst = p.partials + ((chunk * 2 + slot) * (int64_t) p.max_dim);
+      const int nvec = p.feat_dim[f] >> 2;
+#pragma unroll
+      for (int k = 0; k < MAXV; ++k) {
+        const int vi = lane + k * 32;
+        if (vi < nvec) *reinterpret_cast<float4*>(dst + vi * 4) = acc[k];
+      }
+    }
+  }
+  if (lane == 0) p.span_flags[chunk] = wrote_slot1 ? 1 : 0;
+}
+
+// One CTA per run that crosses chunk boundaries. blockDim = 256 (8 warps).
+template <typename W, int MAXV>
+__global__ void __launch_bounds__(256) tbe_bwd_span_kernel(const TbeBwdParams p) {
+  typedef uint64_t K;
+  extern __shared__ float smem[];  // [8][max_dim]
+  const int64_t c = blockIdx.x;
+  if (!p.span_flags[c]) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const void* keys = p.keys_sorted;
+  const int64_t last = c * 32 + 31;
+  const K rk = ld_key(keys, last, p.key64);
+  // upper bound of rk in keys[last+1 .. n)
+  int64_t lo = last + 1, hi = p.n;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (ld_key(keys, mid, p.key64) <= rk) lo = mid + 1; else hi = mid;
+  }
+  const int64_t c_end = (lo - 1) >> 5;
+  const int f = p.bag_of[p.vals_sorted[last]] / p.B;
+  const int nvec = p.feat_dim[f] >> 2;
+  float4 acc[MAXV];
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // piece 0 is slot1 of chunk c, pieces j>=1 are slot0 of chunk c+j
+  for (int64_t j = warp; j <= c_end - c; j += 8) {
+    const float* src = p.partials + (((c + j) * 2 + (j == 0 ? 1 : 0)) * (int64_t) p.max_dim);
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const int vi = lane + k * 32;
+      if (vi < nvec) acc[k] = f4_add(acc[k], *reinterpret_cast<const float4*>(src + vi * 4));
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int vi = lane + k * 32;
+    if (vi < nvec) *reinterpret_cast<float4*>(smem + warp * p.max_dim + vi * 4) = acc[k];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const int vi = lane + k * 32;
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (vi < nvec)
+        for (int w8 = 0; w8 < 8; ++w8) s = f4_add(s, *reinterpret_cast<const float4*>(smem + w8 * p.max_dim + vi * 4));
+      acc[k] = s;
+    }
+    apply_row<W, MAXV>(p, (int64_t) rk, f, acc, lane);
+  }
+}
+
+static inline int bits_needed(int64_t v) {
+  int b = 1;
+  while (b < 64 && ((int64_t) 1 << b) <= v) ++b;
+  return b;
+}
+
+template <typename K>
+static size_t sort_temp_bytes(int64_t n) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const K*) nullptr, (K*) nullptr, (const int32_t*) nullptr,
+                                  (int32_t*) nullptr, n);
+  return bytes;
+}
+
+static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t) 255; }
+
+struct BwdLayout {
+  size_t keys, keys_sorted, vals, vals_sorted, bag_of, partials, flags, sort_tmp, total;
+};
+
+static BwdLayout bwd_layout(int64_t n, int max_dim, int key64) {
+  BwdLayout L;
+  const size_t ksz = key64 ? 8 : 4;
+  const int64_t chunks = (n + 31) / 32;
+  size_t o = 0;
+  L.keys = o; o += align_up(n * ksz);
+  L.keys_sorted = o; o += align_up(n * ksz);
+  L.vals = o; o += align_up(n * 4);
+  L.vals_sorted = o; o += align_up(n * 4);
+  L.bag_of = o; o += align_up(n * 4);
+  L.partials = o; o += align_up((size_t) chunks * 2 * max_dim * 4);
+  L.flags = o; o += align_up(chunks);
+  L.sort_tmp = o;
+  o += align_up(key64 ? sort_temp_bytes<uint64_t>(n) : sort_temp_bytes<uint32_t>(n));
+  L.total = o;
+  return L;
+}
+
+TRB_API int64_t trb_tbe_bwd_workspace_bytes(int64_t n, int max_dim, int64_t total_rows) {
+  const int key64 = total_rows >= ((int64_t) 1 << 32) - 1;
+  return (int64_t) bwd_layout(n > 0 ? n : 1, max_dim, key64).total;
+}
+
+template <typename W, typename G, int MAXV>
+static int run_bwd(TbeBwdParams& p, char* ws, cudaStream_t stream) {
+  const int key64 = p.key64;
+  BwdLayout L = bwd_layout(p.n, p.max_dim, key64);
+  p.keys = ws + L.keys;
+  p.keys_sorted = ws + L.keys_sorted;
+  p.vals = (int32_t*) (ws + L.vals);
+  p.vals_sorted = (int32_t*) (ws + L.vals_sorted);
+  p.bag_of = (int32_t*) (ws + L.bag_of);
+  p.partials = (float*) (ws + L.partials);
+  p.span_flags = (uint8_t*) (ws + L.flags);
+  const int threads = 256;
+  tbe_bwd_build_keys<<<(unsigned) ((p.n + threads - 1) / threads), threads, 0, stream>>>(p);
+  TRB_CHECK_LAUNCH();
+  size_t tmp_bytes = L.total - L.sort_tmp;
+  const int end_bit = bits_needed(p.total_rows);
+  if (key64) {
+    TRB_CUDA(cub::DeviceRadixSort::SortPairs(ws + L.sort_tmp, tmp_bytes, (const uint64_t*) p.keys,
+                                             (uint64_t*) p.keys_sorted, (const int32_t*) p.vals, p.vals_sorted, p.n, 0,
+                                             end_bit, stream));
+  } else {
+    TRB_CUDA(cub::DeviceRadixSort::SortPairs(ws + L.sort_tmp, tmp_bytes, (const uint32_t*) p.keys,
+                                             (uint32_t*) p.keys_sorted, (const int32_t*) p.vals, p.vals_sorted, p.n, 0,
+                                             end_bit, stream));
+  }
+  g_trb_launches += 4;  // radix sort passes (library kernels, counted approximately)
+  const int64_t chunks = (p.n + 31) / 32;
+  const int64_t blocks = (chunks + 7) / 8;
+  tbe_bwd_chunk_kernel<W, G, MAXV><<<(unsigned) blocks, threads, 0, stream>>>(p);
+  TRB_CHECK_LAUNCH();
+  const size_t smem = (size_t) 8 * p.max_dim * sizeof(float);
+  if (smem > 48 * 1024)
+    TRB_CUDA(cudaFuncSetAttribute(tbe_bwd_span_kernel<W, MAXV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  tbe_bwd_span_kernel<W, MAXV><<<(unsigned) chunks, threads, smem, stream>>>(p);
+  TRB_CHECK_LAUNCH();
+  return 0;
+}
+
+template <typename W, typename G>
+static int dispatch_dim(TbeBwdParams& p, char* ws, cudaStream_t stream) {
+  const int nvec = p.max_dim / 4;
+  if (nvec <= 32) return run_bwd<W, G, 1>(p, ws, stream);
+  if (nvec <= 128) return run_bwd<W, G, 4>(p, ws, stream);
+  if (nvec <= 512) return run_bwd<W, G, 16>(p, ws, stream);
+  return -2;
+}
+
+// Fused backward + optimizer. `workspace` must hold trb_tbe_bwd_workspace_bytes(n, max_dim, total_rows).
+TRB_API int trb_tbe_bwd_fused(void* weights, int w_dtype, float* state1, float* state2, const float* hyper, int opt,
+                              int wd_mode, const int64_t* feat_woff, const int64_t* feat_rows,
+                              const int64_t* feat_rowbase, const int32_t* feat_dim, const int32_t* feat_col,
+                              const void* indices, int idx64, const void* offsets, int off64, const float* psw,
+                              void* const* grad_ptrs, int n_grad, int grad_dtype, int64_t grad_stride, int64_t n,
+                              int64_t total_rows, int B, int B_local, int F, int max_dim, int mean, void* workspace,
+                              cudaStream_t stream) {
+  if (n <= 0) return 0;
+  if (n_grad < 1 || n_grad > TRB_MAX_PEERS) return -1;
+  if ((int64_t) B_local * n_grad != B) return -4;
+  TbeBwdParams p;
+  p.weights = weights;
+  p.state1 = state1;
+  p.state2 = state2;
+  p.hyper = hyper;
+  p.feat_woff = feat_woff;
+  p.feat_rows = feat_rows;
+  p.feat_rowbase = feat_rowbase;
+  p.feat_dim = feat_dim;
+  p.feat_col = feat_col;
+  p.indices = indices;
+  p.offsets = offsets;
+  p.psw = psw;
+  for (int i = 0; i < TRB_MAX_PEERS; ++i) p.grad.p[i] = i < n_grad ? grad_ptrs[i] : nullptr;
+  p.grad_stride = grad_stride;
+  p.n = n;
+  p.total_rows = total_rows;
+  p.B = B;
+  p.B_local = B_local;
+  p.F = F;
+  p.idx64 = idx64;
+  p.off64 = off64;
+  p.mean = mean;
+  p.wd_mode = wd_mode;
+  p.max_dim = max_dim;
+  p.key64 = total_rows >= ((int64_t) 1 << 32) - 1;
+  p.opt = opt;
+  if (opt < 0 || opt > OPT_NONE) return -5;
+  char* ws = reinterpret_cast<char*>(workspace);
+#define TRB_BWD_CASE(WC, WT, GC, GT) \
+  if (w_dtype == WC && grad_dtype == GC) return dispatch_dim<WT, GT>(p, ws, stream)
+  TRB_BWD_CASE(TRB_F32, float, TRB_F32, float);
+  TRB_BWD_CASE(TRB_F32, float, TRB_BF16, __nv_bfloat16);
+  TRB_BWD_CASE(TRB_BF16, __nv_bfloat16, TRB_F32, float);
+  TRB_BWD_CASE(TRB_BF16, __nv_bfloat16, TRB_BF16, __nv_bfloat16);
+  TRB_BWD_CASE(TRB_F16, __half, TRB_F32, float);
+#undef TRB_BWD_CASE
+  return -3;
+}

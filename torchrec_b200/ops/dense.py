@@ -1,0 +1,73 @@
+"""Dense-arch kernels front-end: fused Linear+bias+activation (tcgen05/TMEM GEMM), dot interaction.
+
+``set_dense_backend("tcgen05")`` routes ``Perceptron`` layers and ``InteractionArch`` through the
+hand-written sm_100a kernels in ``csrc/gemm_tcgen05.cu`` / ``csrc/interaction.cu`` (bf16 operands,
+fp32 accumulation in TMEM, bias+ReLU fused in the epilogue). ``"torch"`` keeps stock PyTorch ops
+(used on CPU and as the numerics oracle).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Callable, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+_BACKEND = "torch"
+
+ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
+
+
+def set_dense_backend(name: str) -> None:
+    global _BACKEND
+    if name not in ("torch", "tcgen05"):
+        raise ValueError(name)
+    if name == "tcgen05":
+        _lib.lib()
+    _BACKEND = name
+
+
+def get_dense_backend() -> str:
+    return _BACKEND
+
+
+def fused_act_code(act) -> Optional[int]:
+    if act is torch.relu or act is torch.nn.functional.relu or isinstance(act, nn.ReLU):
+        return ACT_RELU
+    if act is torch.sigmoid or isinstance(act, nn.Sigmoid):
+        return ACT_SIGMOID
+    if act is None or isinstance(act, nn.Identity):
+        return ACT_NONE
+    return None
+
+
+def can_fuse(x: torch.Tensor, linear: nn.Linear) -> bool:
+    if _BACKEND != "tcgen05" or not x.is_cuda or x.dim() != 2:
+        return False
+    # TMA needs 16-byte aligned row pitches: K and N multiples of 8 bf16 elements
+    return linear.in_features % 8 == 0 and linear.out_features % 8 == 0
+
+
+def linear_act(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], act: int) -> torch.Tensor:
+    from .gemm import LinearActFn
+
+    return LinearActFn.apply(x, weight, bias, act)
+
+
+def dot_interaction(dense: torch.Tensor, sparse: torch.Tensor) -> torch.Tensor:
+    """DLRM pairwise dot interaction. dense [B, D], sparse [B, F, D] ->
+    [B, D + (F+1)F/2] = cat(dense, strictly-lower-triangular(X X^T)) with X = [dense; sparse].
+    Parity: models/dlrm.py:210-222."""
+    if _BACKEND == "tcgen05" and dense.is_cuda:
+        from .interaction import DotInteractionFn
+
+        return DotInteractionFn.apply(dense, sparse)
+    B, D = dense.shape
+    F = sparse.shape[1]
+    combined = torch.cat((dense.unsqueeze(1), sparse.to(dense.dtype)), dim=1)
+    inter = torch.bmm(combined, combined.transpose(1, 2))
+    ti = torch.triu_indices(F + 1, F + 1, offset=1, device=dense.device)
+    flat = inter[:, ti[0], ti[1]]
+    return torch.cat((dense, flat), dim=1)

@@ -1,0 +1,359 @@
+"""Jagged / sparse utility ops (the ``torch.ops.fbgemm.*`` sparse-op surface the reference uses,
+SURVEY §2.4(b)), implemented for both CPU (PyTorch reference) and CUDA (sm_100a kernels in
+``csrc/jagged_ops.cu`` where a hot path needs one; composition of stream-ordered torch ops
+otherwise). No op here performs a hidden host sync unless its output size is data dependent and
+the caller did not pass it.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+
+def asynchronous_complete_cumsum(x: torch.Tensor) -> torch.Tensor:
+    """[n] -> [n+1] exclusive prefix sum with the total appended (works on 1-D or 2-D rows)."""
+    if x.dim() == 1:
+        out = x.new_zeros(x.numel() + 1)
+        torch.cumsum(x, 0, out=out[1:])
+        return out
+    out = x.new_zeros(x.shape[0], x.shape[1] + 1)
+    torch.cumsum(x, 1, out=out[:, 1:])
+    return out
+
+
+def asynchronous_inclusive_cumsum(x: torch.Tensor) -> torch.Tensor:
+    return torch.cumsum(x, 0)
+
+
+def asynchronous_exclusive_cumsum(x: torch.Tensor) -> torch.Tensor:
+    return torch.cumsum(x, 0) - x
+
+
+def offsets_range(offsets: torch.Tensor, range_size: int) -> torch.Tensor:
+    """arange restarting at every segment start: positions of each element inside its segment."""
+    if range_size == 0:
+        return offsets.new_zeros(0)
+    starts = offsets
+    ends = torch.cat([offsets[1:], offsets.new_tensor([range_size])])
+    seg_start = torch.repeat_interleave(starts, ends - starts, output_size=range_size)
+    return torch.arange(range_size, device=offsets.device, dtype=offsets.dtype) - seg_start
+
+
+def invert_permute(permute: torch.Tensor) -> torch.Tensor:
+    inv = torch.empty_like(permute)
+    inv[permute.long()] = torch.arange(permute.numel(), device=permute.device, dtype=permute.dtype)
+    return inv
+
+
+def segment_sum_csr(batch_size: int, csr_seg: torch.Tensor, values: torch.Tensor) -> torch.Tensor:
+    """Sum ``values`` over segments given by offsets ``csr_seg`` counted in units of ``batch_size`` rows."""
+    seg_off = csr_seg.long() * batch_size
+    lengths = seg_off[1:] - seg_off[:-1]
+    seg = torch.repeat_interleave(torch.arange(lengths.numel(), device=values.device), lengths, output_size=values.numel())
+    out = torch.zeros(lengths.numel(), dtype=values.dtype, device=values.device)
+    out.index_add_(0, seg, values)
+    return out
+
+
+def _segment_gather_index(in_starts: torch.Tensor, seg_lengths: torch.Tensor, total: int) -> torch.Tensor:
+    """Index tensor that concatenates ranges [in_starts[k], in_starts[k]+seg_lengths[k])."""
+    out_off = torch.cumsum(seg_lengths, 0) - seg_lengths
+    seg = torch.repeat_interleave(torch.arange(seg_lengths.numel(), device=seg_lengths.device), seg_lengths, output_size=total)
+    return in_starts[seg] + (torch.arange(total, device=seg_lengths.device) - out_off[seg])
+
+
+def permute_2D_sparse_data(
+    permute: torch.Tensor,
+    lengths: torch.Tensor,
+    values: torch.Tensor,
+    weights: Optional[torch.Tensor] = None,
+    permuted_lengths_sum: Optional[int] = None,
+) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+    """Permute the rows (features) of a [F, B] jagged layout. ``permute`` may repeat / drop rows."""
+    F, B = lengths.shape
+    if _lib.use_cuda_kernels(values) and values.numel() > 0 and permuted_lengths_sum is not None:
+        return _permute_2d_cuda(permute, lengths, values, weights, permuted_lengths_sum)
+    perm = permute.long()
+    out_lengths = lengths[perm]
+    len_per_key = lengths.sum(1)
+    in_key_off = torch.cumsum(len_per_key, 0) - len_per_key
+    out_len_per_key = len_per_key[perm]
+    total = int(out_len_per_key.sum()) if permuted_lengths_sum is None else permuted_lengths_sum
+    if total == 0:
+        return out_lengths, values.new_zeros(0), (None if weights is None else weights.new_zeros(0))
+    idx = _segment_gather_index(in_key_off[perm], out_len_per_key, total)
+    return out_lengths, values[idx], (None if weights is None else weights[idx])
+
+
+def _permute_2d_cuda(permute, lengths, values, weights, total):
+    F, B = lengths.shape
+    P = permute.numel()
+    L = _lib.lib()
+    lengths = lengths.contiguous()
+    permute = permute.to(torch.int32).contiguous()
+    out_lengths = torch.empty(P, B, dtype=lengths.dtype, device=lengths.device)
+    in_off = asynchronous_complete_cumsum(lengths.view(-1).to(torch.int64))
+    out_values = torch.empty(total, dtype=values.dtype, device=values.device)
+    out_weights = None if weights is None else torch.empty(total, dtype=weights.dtype, device=weights.device)
+    # out lengths + out offsets
+    out_lengths.copy_(lengths[permute.long()])
+    out_off = asynchronous_complete_cumsum(out_lengths.view(-1).to(torch.int64))
+    code = L.trb_permute_2d_data(
+        _lib.ptr(permute), P, B, _lib.ptr(in_off), _lib.ptr(out_off),
+        _lib.ptr(values), _lib.ptr(out_values), values.element_size(),
+        _lib.ptr(weights), _lib.ptr(out_weights), 0 if weights is None else weights.element_size(),
+        _lib.stream_ptr(values.device),
+    )
+    _lib.check(code, "trb_permute_2d_data")
+    return out_lengths, out_values, out_weights
+
+
+def permute_1D_sparse_data(
+    permute: torch.Tensor,
+    lengths: torch.Tensor,
+    values: torch.Tensor,
+    weights: Optional[torch.Tensor] = None,
+    permuted_lengths_sum: Optional[int] = None,
+) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+    """Permute variable-length segments of a 1-D jagged array."""
+    perm = permute.long()
+    out_lengths = lengths[perm]
+    in_off = torch.cumsum(lengths, 0) - lengths
+    total = int(out_lengths.sum()) if permuted_lengths_sum is None else permuted_lengths_sum
+    if total == 0:
+        return out_lengths, values.new_zeros(0), (None if weights is None else weights.new_zeros(0))
+    idx = _segment_gather_index(in_off[perm], out_lengths, total)
+    return out_lengths, values[idx], (None if weights is None else weights[idx])
+
+
+def expand_into_jagged_permute(permute: torch.Tensor, input_offsets: torch.Tensor, output_offsets: torch.Tensor, output_size: int) -> torch.Tensor:
+    in_len = input_offsets[1:] - input_offsets[:-1]
+    perm = permute.long()
+    seg_len = in_len[perm]
+    return _segment_gather_index(input_offsets[:-1][perm], seg_len, output_size)
+
+
+def block_bucketize_sparse_features(
+    lengths: torch.Tensor,
+    indices: torch.Tensor,
+    bucketize_pos: bool,
+    sequence: bool,
+    block_sizes: torch.Tensor,
+    my_size: int,
+    weights: Optional[torch.Tensor] = None,
+    batch_size_per_feature: Optional[torch.Tensor] = None,
+    max_B: int = -1,
+    block_bucketize_pos: Optional[List[torch.Tensor]] = None,
+    keep_orig_idx: bool = False,
+    total_num_blocks: Optional[torch.Tensor] = None,
+    keep_orig_idx_per_feature: Optional[torch.Tensor] = None,
+) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """Row-wise bucketization: id -> (bucket = id // block_size[f], local id = id % block_size[f]).
+
+    Input layout lengths [F*B] (feature major). Output lengths [my_size * F * B] ordered
+    (bucket, feature, sample); values re-sorted accordingly (stable within a bag). Returns
+    (new_lengths, new_indices, new_weights, new_pos, unbucketize_permute).
+    Parity: fbgemm.block_bucketize_sparse_features as called at embedding_sharding.py:312.
+    """
+    n = indices.numel()
+    FB = lengths.numel()
+    F = block_sizes.numel()
+    B = FB // max(F, 1)
+    dev = indices.device
+    lengths64 = lengths.to(torch.int64)
+    bag = torch.repeat_interleave(torch.arange(FB, device=dev), lengths64, output_size=n)
+    feat = bag // max(B, 1)
+    if block_bucketize_pos is not None:
+        bucket = torch.empty(n, dtype=torch.int64, device=dev)
+        local = torch.empty(n, dtype=indices.dtype, device=dev)
+        for f in range(F):
+            m = feat == f
+            pos = block_bucketize_pos[f].to(indices.dtype)
+            b_ = torch.bucketize(indices[m], pos[1:], right=True).clamp(max=my_size - 1)
+            bucket[m] = b_
+            local[m] = indices[m] - pos[b_]
+    else:
+        bs = block_sizes.to(indices.dtype)[feat]
+        blk = torch.div(indices, bs, rounding_mode="floor")
+        in_range = blk < my_size
+        # ids past the last block wrap round-robin (fbgemm semantics for un-hashed overflow ids)
+        bucket = torch.where(in_range, blk, indices % my_size).to(torch.int64)
+        local = torch.where(in_range, indices - blk * bs, torch.div(indices, my_size, rounding_mode="floor"))
+    if keep_orig_idx:
+        local = indices
+    new_bag = bucket * FB + bag
+    order = torch.argsort(new_bag, stable=True)
+    new_lengths = torch.zeros(my_size * FB, dtype=lengths.dtype, device=dev)
+    new_lengths.index_add_(0, new_bag, torch.ones(n, dtype=lengths.dtype, device=dev))
+    new_indices = local[order]
+    new_weights = None if weights is None else weights[order]
+    new_pos = None
+    if bucketize_pos:
+        off = torch.cumsum(lengths64, 0) - lengths64
+        pos_in_bag = torch.arange(n, device=dev) - off[bag]
+        new_pos = pos_in_bag[order].to(indices.dtype)
+    unbucketize = None
+    if sequence:
+        unbucketize = torch.empty(n, dtype=indices.dtype, device=dev)
+        unbucketize[order] = torch.arange(n, device=dev, dtype=indices.dtype)
+    return new_lengths, new_indices, new_weights, new_pos, unbucketize
+
+
+def jagged_to_padded_dense(values: torch.Tensor, offsets: Sequence[torch.Tensor], max_lengths: Sequence[int], padding_value: float = 0.0) -> torch.Tensor:
+    off = offsets[0].long()
+    N = off.numel() - 1
+    max_len = max_lengths[0]
+    lengths = off[1:] - off[:-1]
+    trail = values.shape[1:]
+    out = values.new_full((N, max_len) + tuple(trail), padding_value)
+    if values.numel() == 0 or N == 0:
+        return out
+    n = values.shape[0]
+    seg = torch.repeat_interleave(torch.arange(N, device=values.device), lengths, output_size=n)
+    pos = torch.arange(n, device=values.device) - off[:-1][seg]
+    keep = pos < max_len
+    out[seg[keep], pos[keep]] = values[keep]
+    return out
+
+
+def jagged_2d_to_dense(values: torch.Tensor, offsets: torch.Tensor, max_sequence_length: int) -> torch.Tensor:
+    return jagged_to_padded_dense(values, [offsets], [max_sequence_length], 0.0)
+
+
+def jagged_1d_to_dense(values: torch.Tensor, offsets: torch.Tensor, max_sequence_length: int, padding_value: float) -> torch.Tensor:
+    return jagged_to_padded_dense(values, [offsets], [max_sequence_length], padding_value)
+
+
+def dense_to_jagged(dense: torch.Tensor, offsets: Sequence[torch.Tensor], total_L: Optional[int] = None) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+    off = offsets[0].long()
+    lengths = off[1:] - off[:-1]
+    N, max_len = dense.shape[0], dense.shape[1]
+    mask = torch.arange(max_len, device=dense.device).unsqueeze(0) < lengths.unsqueeze(1)
+    return dense[mask], list(offsets)
+
+
+def jagged_index_select_2d(values: torch.Tensor, lengths: torch.Tensor, indices: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    off = torch.cumsum(lengths, 0) - lengths
+    out_len = lengths[indices.long()]
+    total = int(out_len.sum())
+    if total == 0:
+        return values[:0], out_len
+    idx = _segment_gather_index(off[indices.long()], out_len, total)
+    return values[idx], out_len
+
+
+def keyed_jagged_index_select_dim1(
+    values: torch.Tensor, lengths: torch.Tensor, offsets: torch.Tensor, indices: torch.Tensor, batch_size: int,
+    weights: Optional[torch.Tensor] = None, selected_lengths_sum: Optional[int] = None,
+) -> List[torch.Tensor]:
+    """Select the same batch positions from every key of a [F, B] jagged layout."""
+    F = lengths.numel() // batch_size
+    idx = indices.long()
+    sel = (torch.arange(F, device=lengths.device).unsqueeze(1) * batch_size + idx.unsqueeze(0)).reshape(-1)
+    out_len = lengths[sel]
+    total = int(out_len.sum()) if selected_lengths_sum is None else selected_lengths_sum
+    if total == 0:
+        res = [values[:0], out_len]
+    else:
+        g = _segment_gather_index(offsets[:-1][sel], out_len, total)
+        res = [values[g], out_len]
+        if weights is not None:
+            res.append(weights[g])
+            return res
+    if weights is not None:
+        res.append(weights[:0])
+    return res
+
+
+def batch_index_select_dim0(inputs: torch.Tensor, indices: torch.Tensor, input_num_indices: List[int], input_rows: List[int], input_columns: List[int], permute_output_dim_0_1: bool = False) -> torch.Tensor:
+    outs = []
+    io = ii = 0
+    for n_idx, rows, cols in zip(input_num_indices, input_rows, input_columns):
+        block = inputs[io : io + rows * cols].view(rows, cols)
+        outs.append(block[indices[ii : ii + n_idx].long()])
+        io += rows * cols
+        ii += n_idx
+    if permute_output_dim_0_1:
+        return torch.cat(outs, dim=1).reshape(-1)
+    return torch.cat([o.reshape(-1) for o in outs])
+
+
+def jagged_unique_indices(hash_size_cumsum: torch.Tensor, hash_size_offsets: torch.Tensor, offsets: torch.Tensor, indices: torch.Tensor):
+    """Per-table unique of a multi-feature id list. Returns (output_lengths, output_offsets,
+    unique_indices, reverse_index) like the fbgemm op (embedding.py:1404)."""
+    n = indices.numel()
+    FB = offsets.numel() - 1
+    num_feat = hash_size_offsets.numel() - 1
+    # feature of each bag: bags are feature-major with equal batch size
+    T = hash_size_cumsum.numel() - 1
+    B = FB // max(T, 1)
+    lengths = offsets[1:] - offsets[:-1]
+    bag = torch.repeat_interleave(torch.arange(FB, device=indices.device), lengths, output_size=n)
+    feat = bag // max(B, 1)
+    lin = indices.long() + hash_size_cumsum.long()[feat]
+    uniq, inv = torch.unique(lin, return_inverse=True)
+    # table of each unique id
+    table = torch.bucketize(uniq, hash_size_cumsum.long()[1:], right=True)
+    feat_of_table = hash_size_offsets.long()[:-1]
+    out_len_per_table = torch.bincount(table, minlength=num_feat)
+    out_lengths = torch.zeros(FB, dtype=offsets.dtype, device=indices.device)
+    # put all unique ids of a table into the first bag of its first feature (layout used by EC dedup)
+    first_bag = feat_of_table * B
+    out_lengths[first_bag] = out_len_per_table.to(offsets.dtype)[: first_bag.numel()]
+    out_offsets = asynchronous_complete_cumsum(out_lengths)
+    base = hash_size_cumsum.long()[torch.searchsorted(hash_size_cumsum.long()[1:], uniq, right=True)]
+    return out_lengths, out_offsets, (uniq - base).to(indices.dtype), inv
+
+
+def permute_pooled_embs(pooled: torch.Tensor, offset_dim_list: Sequence[int], permute_list: Sequence[int]) -> torch.Tensor:
+    """Column-block permutation of a [B, sum(D)] tensor (PermutePooledEmbeddings)."""
+    cols = []
+    for p in permute_list:
+        cols.append(torch.arange(offset_dim_list[p], offset_dim_list[p + 1], device=pooled.device))
+    if not cols:
+        return pooled[:, :0]
+    return pooled.index_select(1, torch.cat(cols))
+
+
+def fused_nbit_rowwise_quantize(weight: torch.Tensor, bit_rate: int) -> torch.Tensor:
+    """Row-wise N-bit quantization with fused fp16 (scale, bias) tail — the layout of fbgemm
+    ``FloatOrHalfToFusedNBitRowwiseQuantizedSBHalf`` (quant/embedding_modules.py:264).
+    Returns uint8 [rows, ceil(D*bits/8) + 4]."""
+    assert bit_rate in (2, 4, 8)
+    w = weight.float()
+    rows, D = w.shape
+    mn = w.min(dim=1, keepdim=True).values
+    mx = w.max(dim=1, keepdim=True).values
+    qmax = float((1 << bit_rate) - 1)
+    mn16 = mn.half().float()
+    scale = ((mx - mn16) / qmax).half().float()
+    scale = torch.where(scale == 0, torch.ones_like(scale), scale)
+    q = torch.clamp(torch.round((w - mn16) / scale), 0, qmax).to(torch.uint8)
+    per_byte = 8 // bit_rate
+    pad = (-D) % per_byte
+    if pad:
+        q = torch.cat([q, q.new_zeros(rows, pad)], 1)
+    q = q.view(rows, -1, per_byte)
+    packed = torch.zeros(rows, q.shape[1], dtype=torch.uint8, device=w.device)
+    for i in range(per_byte):
+        packed |= q[:, :, i] << (i * bit_rate)
+    tail = torch.cat([scale.half().view(torch.uint8).view(rows, 2), mn16.half().view(torch.uint8).view(rows, 2)], 1)
+    return torch.cat([packed, tail], 1)
+
+
+def fused_nbit_rowwise_dequantize(q: torch.Tensor, bit_rate: int, D: int) -> torch.Tensor:
+    rows = q.shape[0]
+    per_byte = 8 // bit_rate
+    nbytes = (D + per_byte - 1) // per_byte
+    packed = q[:, :nbytes]
+    tail = q[:, nbytes : nbytes + 4].contiguous()
+    scale = tail[:, 0:2].contiguous().view(torch.float16).float()
+    bias = tail[:, 2:4].contiguous().view(torch.float16).float()
+    mask = (1 << bit_rate) - 1
+    parts = [((packed >> (i * bit_rate)) & mask) for i in range(per_byte)]
+    vals = torch.stack(parts, dim=2).reshape(rows, -1)[:, :D].float()
+    return vals * scale + bias
