@@ -87,7 +87,8 @@ __global__ void __launch_bounds__(256) tbe_bwd_build_keys(const TbeBwdParams p) 
   const int64_t total = trb_ld_idx(p.offsets, n_bags, p.off64);
   uint64_t key = (uint64_t) p.total_rows;  // sentinel sorts last
   int32_t bag = 0;
-  if (i < total) {
+  const int64_t first = trb_ld_idx(p.offsets, 0, p.off64);  // offsets may be a window into a larger id array
+  if (i >= first && i < total) {
     // largest bag with offsets[bag] <= i  (bags may be empty -> take the last such bag)
     int64_t lo = 0, hi = n_bags - 1;
     while (lo < hi) {

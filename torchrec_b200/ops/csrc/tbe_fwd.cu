@@ -190,8 +190,9 @@ tbe_seq_fwd_kernel(const W* __restrict__ weights, const int64_t* __restrict__ fe
                    const void* __restrict__ offsets, int off64, int F, int B, int D, O* __restrict__ out,
                    const int64_t* __restrict__ total_ptr) {
   const int lig = threadIdx.x % LPB;
-  const int64_t i = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) / LPB;
+  const int64_t r = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) / LPB;  // output row
   const int64_t total = trb_ld_idx(offsets, (int64_t) F * B, off64);
+  const int64_t i = r + trb_ld_idx(offsets, 0, off64);  // offsets may be a window into a larger id array
   (void) total_ptr;
   if (i >= total) return;
   // binary search feature: largest f with offsets[f*B] <= i
@@ -204,7 +205,7 @@ tbe_seq_fwd_kernel(const W* __restrict__ weights, const int64_t* __restrict__ fe
   int64_t idx = trb_ld_idx(indices, i, idx64);
   const bool ok = idx >= 0 && idx < feat_rows[f];
   const W* row = weights + feat_woff[f] + (ok ? idx : 0) * D;
-  O* dst = out + i * D;
+  O* dst = out + r * D;
   const int nvec = D >> 2;
   for (int vi = lig; vi < nvec; vi += LPB) {
     float4 v = ok ? Vec4<W>::ld_nc(row + vi * 4) : make_float4(0.f, 0.f, 0.f, 0.f);

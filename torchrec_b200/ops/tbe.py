@@ -168,8 +168,9 @@ class TbeMeta:
 # ----------------------------------------------------------------------------------------------
 # reference (CPU / oracle) implementations
 # ----------------------------------------------------------------------------------------------
-def _ref_pooled_forward(meta: TbeMeta, weights, indices, offsets, psw, B: int, mean: bool, out_dtype) -> torch.Tensor:
-    out = torch.zeros(B, meta.total_cols, dtype=torch.float32, device=weights.device)
+def _ref_pooled_forward(meta: TbeMeta, weights, indices, offsets, psw, B: int, mean: bool, out_dtype, out=None) -> torch.Tensor:
+    if out is None:
+        out = torch.zeros(B, meta.total_cols, dtype=out_dtype, device=weights.device)
     offsets = offsets.to(torch.int64)
     indices = indices.to(torch.int64)
     for f in range(meta.num_features):
@@ -191,15 +192,16 @@ def _ref_pooled_forward(meta: TbeMeta, weights, indices, offsets, psw, B: int, m
         pooled.index_add_(0, seg, vals)
         if mean:
             pooled = pooled / lengths.clamp(min=1).unsqueeze(1).float()
-        out[:, meta.h_col[f] : meta.h_col[f] + D] = pooled
-    return out.to(out_dtype)
+        out[:, meta.h_col[f] : meta.h_col[f] + D] = pooled.to(out.dtype)
+    return out
 
 
 def _ref_seq_forward(meta: TbeMeta, weights, indices, offsets, B: int, out_dtype) -> torch.Tensor:
     D = meta.h_dim[0] if meta.num_features else 0
     offsets = offsets.to(torch.int64)
     indices = indices.to(torch.int64)
-    total = int(offsets[meta.num_features * B]) if meta.num_features else 0
+    first = int(offsets[0]) if meta.num_features else 0
+    total = (int(offsets[meta.num_features * B]) - first) if meta.num_features else 0
     out = torch.zeros(total, D, dtype=torch.float32, device=weights.device)
     for f in range(meta.num_features):
         rows = meta.h_rows[f]
@@ -208,7 +210,7 @@ def _ref_seq_forward(meta: TbeMeta, weights, indices, offsets, B: int, out_dtype
         idx = indices[lo:hi]
         valid = (idx >= 0) & (idx < rows)
         safe = torch.where(valid, idx, torch.zeros_like(idx))
-        out[lo:hi] = table[safe] * valid.unsqueeze(1).float()
+        out[lo - first : hi - first] = table[safe] * valid.unsqueeze(1).float()
     return out.to(out_dtype)
 
 
@@ -234,7 +236,8 @@ def _ref_row_grads(meta: TbeMeta, indices, offsets, psw, grad: torch.Tensor, B: 
                 scale = scale / lengths.clamp(min=1).float()[seg]
             g = g * scale.unsqueeze(1)
         else:
-            g = grad[lo:hi].float()
+            first = int(offsets[0])
+            g = grad[lo - first : hi - first].float()
         valid = (idx >= 0) & (idx < rows)
         idx, g = idx[valid], g[valid]
         key = meta.h_woff[f]
@@ -345,11 +348,7 @@ def pooled_forward(
     if not _lib.use_cuda_kernels(weights):
         if out_ptrs is not None:
             raise RuntimeError("peer-pointer outputs need CUDA")
-        res = _ref_pooled_forward(meta, weights, indices, offsets, per_sample_weights, B, mean, out_dtype)
-        if out is not None:
-            out.copy_(res)
-            return out
-        return res
+        return _ref_pooled_forward(meta, weights, indices, offsets, per_sample_weights, B, mean, out_dtype, out)
     if out_ptrs is None:
         if out is None:
             out = torch.empty(B, meta.total_cols, dtype=out_dtype, device=weights.device)
@@ -554,7 +553,11 @@ class TableBatchedEmbeddingBags(nn.Module):
         total = sum(r * d for r, d in self.embedding_specs)
         self.total_rows = sum(rows)
         dense = optimizer == OptimType.NONE
-        self.weights = nn.Parameter(torch.empty(total, dtype=weights_precision, device=device), requires_grad=dense)
+        if dense:
+            self.weights = nn.Parameter(torch.empty(total, dtype=weights_precision, device=device), requires_grad=True)
+        else:
+            # fused tables are updated in-kernel: a plain buffer, never seen by autograd / DDP / dense optimizers
+            self.register_buffer("weights", torch.empty(total, dtype=weights_precision, device=device), persistent=False)
         self._dummy = nn.Parameter(torch.zeros(1, device=device if not self._is_meta else "cpu"), requires_grad=True) if not dense else None
         if not self._is_meta:
             self.meta = TbeMeta.build(rows, dims, self.feature_table_map, device)

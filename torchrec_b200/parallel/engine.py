@@ -1,0 +1,454 @@
+"""Route-driven sharded lookup engine.
+
+Instead of one Python module zoo per sharding type (reference ``sharding/*.py``), every
+model-parallel sharding type is expressed with one notion, the *lookup unit*:
+
+    unit = (feature f, table shard = rows [row_lo,row_hi) x cols [col_lo,col_hi) on rank r)
+
+    TABLE_WISE        1 unit per feature                      (full rows, full cols)
+    COLUMN_WISE/TWCW  n_c units per feature                   (full rows, column slices)
+    ROW_WISE/TWRW     n_r units per feature                   (row ranges, full cols)
+    GRID_SHARD        n_c x n_r units per feature
+
+* input dist  : every id of feature f is routed to the unit(s) whose row range holds it (replicated
+                over column slices); one KJT all-to-all moves all units of all sharding types.
+* lookup      : each rank runs its table-batched kernel over its units for the global batch.
+* output dist : one pooled all-to-all returns ``[B_local, sum(unit dims)]``; units of the same
+                (feature, column slice) are *summed* at the destination (this is the row-wise
+                reduce-scatter, done as all-to-all + local add — the NVSwitch-friendly schedule), and
+                column slices are placed at their offset in the feature's output columns.
+
+The same unit tables drive the fused NVLink kernels in ``torchrec_b200.parallel.p2p`` (pooled rows
+written straight into the destination rank's output).
+"""
+from __future__ import annotations
+
+import itertools
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from ..modules.embedding_configs import BaseEmbeddingConfig, DataType, PoolingType, data_type_to_dtype
+from ..ops import jagged as J
+from ..ops.tbe import OptimType, PoolingMode, TableBatchedEmbeddingBags, WeightDecayMode
+from ..sparse.jagged_tensor import KeyedJaggedTensor
+from .dist_data import KJTAllToAll, PooledEmbeddingsAllToAll, SequenceEmbeddingsAllToAll
+from .sharding_plan import placement_rank
+from .types import Awaitable, NoWait, ParameterSharding, QuantizedCommCodecs, ShardingEnv, ShardingType
+
+
+@dataclass
+class TableShard:
+    table_idx: int
+    name: str
+    rank: int
+    row_off: int
+    col_off: int
+    rows: int
+    cols: int
+    group: int = 0
+    local_idx: int = -1  # index among the owner's tables of the group
+
+
+@dataclass
+class Unit:
+    feature: int  # flat feature index in the module's embedding-name order
+    shard: TableShard
+    gidx: int = -1  # global unit index (rank-major)
+
+
+@dataclass
+class OptimizerSpec:
+    """Sparse optimizer of one table (from ``apply_optimizer_in_backward`` tags or fused_params)."""
+
+    optim: OptimType = OptimType.EXACT_SGD
+    lr: float = 0.01
+    eps: float = 1.0e-8
+    beta1: float = 0.9
+    beta2: float = 0.999
+    weight_decay: float = 0.0
+    weight_decay_mode: WeightDecayMode = WeightDecayMode.NONE
+    max_gradient: float = 0.0
+    momentum: float = 0.0
+
+    def key(self) -> Tuple:
+        return (self.optim, self.lr, self.eps, self.beta1, self.beta2, self.weight_decay, int(self.weight_decay_mode), self.max_gradient, self.momentum)
+
+
+def shards_of(table_idx: int, cfg: BaseEmbeddingConfig, ps: ParameterSharding) -> List[TableShard]:
+    out: List[TableShard] = []
+    spec = ps.sharding_spec
+    assert spec is not None, f"table {cfg.name}: model-parallel sharding needs a sharding_spec"
+    for sm in spec.shards:  # type: ignore[attr-defined]
+        out.append(TableShard(table_idx, cfg.name, placement_rank(sm.placement), sm.shard_offsets[0], sm.shard_offsets[1],
+                              sm.shard_sizes[0], sm.shard_sizes[1]))
+    return out
+
+
+class _Group:
+    """Tables that can share one table-batched kernel on a rank (same dtype / pooling / optimizer)."""
+
+    def __init__(self, key: Tuple, pooling: PoolingMode, dtype: torch.dtype, opt: OptimizerSpec) -> None:
+        self.key = key
+        self.pooling = pooling
+        self.dtype = dtype
+        self.opt = opt
+        self.local_shards: List[TableShard] = []  # this rank's shards, unit order
+        self.unit_range: Tuple[int, int] = (0, 0)  # range in this rank's local unit list
+        self.col_range: Tuple[int, int] = (0, 0)  # columns in the local output buffer
+        self.tbe: Optional[TableBatchedEmbeddingBags] = None
+
+
+class ShardedLookupEngine(nn.Module):
+    """Input dist + lookup + output dist for the model-parallel tables of one embedding module."""
+
+    def __init__(
+        self,
+        tables: List[BaseEmbeddingConfig],
+        feature_names: List[str],  # flat (per table, per feature) input feature names
+        feature_table: List[int],  # table index of each flat feature
+        plan: Dict[str, ParameterSharding],
+        env: ShardingEnv,
+        device: torch.device,
+        pooled: bool,
+        is_weighted: bool,
+        opt_specs: Dict[str, OptimizerSpec],
+        output_dtype: torch.dtype = torch.float32,
+        qcomm_codecs: Optional[QuantizedCommCodecs] = None,
+    ) -> None:
+        super().__init__()
+        self._env = env
+        self._pg = env.process_group
+        self._W = env.world_size
+        self._rank = env.rank
+        self._device = device
+        self._pooled = pooled
+        self._is_weighted = is_weighted
+        self._tables = tables
+        self._feature_names = feature_names
+        self._feature_table = feature_table
+        self._output_dtype = output_dtype
+        self._codecs = qcomm_codecs
+        F = len(feature_names)
+
+        # ---- shards, groups ------------------------------------------------------------------
+        self._table_shards: Dict[int, List[TableShard]] = {}
+        self._mp_tables: List[int] = []
+        group_index: Dict[Tuple, int] = {}
+        self._groups: List[_Group] = []
+        self._post_mean_feature: List[bool] = [False] * F  # SUM in kernel, divide after the reduce
+        for ti, cfg in enumerate(tables):
+            ps = plan[cfg.name]
+            if ps.sharding_type == ShardingType.DATA_PARALLEL.value:
+                continue
+            self._mp_tables.append(ti)
+            shards = shards_of(ti, cfg, ps)
+            self._table_shards[ti] = shards
+            n_row_shards = len({(s.row_off, s.rows) for s in shards})
+            pooling = PoolingMode.NONE
+            if pooled:
+                pt = getattr(cfg, "pooling", PoolingType.SUM)
+                pooling = PoolingMode.MEAN if pt == PoolingType.MEAN else PoolingMode.SUM
+                if pooling == PoolingMode.MEAN and n_row_shards > 1:
+                    pooling = PoolingMode.SUM
+                    for fi in range(F):
+                        if feature_table[fi] == ti:
+                            self._post_mean_feature[fi] = True
+            dtype = torch.float32 if cfg.data_type == DataType.FP32 else data_type_to_dtype(cfg.data_type)
+            opt = opt_specs.get(cfg.name, OptimizerSpec())
+            key = (str(dtype), int(pooling), opt.key())
+            if key not in group_index:
+                group_index[key] = len(self._groups)
+                self._groups.append(_Group(key, pooling, dtype, opt))
+            for s in shards:
+                s.group = group_index[key]
+
+        # ---- unit order: rank-major, then group, then table (config order), shard, feature ----
+        feats_of_table: Dict[int, List[int]] = {}
+        for fi, ti in enumerate(feature_table):
+            feats_of_table.setdefault(ti, []).append(fi)
+        self._units: List[Unit] = []
+        self._units_per_rank: List[int] = []
+        self._dim_sum_per_rank: List[int] = []
+        for r in range(self._W):
+            n0 = len(self._units)
+            dsum = 0
+            for gi, g in enumerate(self._groups):
+                u0 = len(self._units) - n0
+                c0 = dsum
+                for ti in self._mp_tables:
+                    for s in self._table_shards[ti]:
+                        if s.rank != r or s.group != gi:
+                            continue
+                        if r == self._rank:
+                            s.local_idx = len(g.local_shards)
+                            g.local_shards.append(s)
+                        for fi in feats_of_table.get(ti, []):
+                            self._units.append(Unit(fi, s, len(self._units)))
+                            dsum += s.cols if pooled else 0
+                if r == self._rank:
+                    g.unit_range = (u0, len(self._units) - n0)
+                    g.col_range = (c0, dsum)
+            self._units_per_rank.append(len(self._units) - n0)
+            self._dim_sum_per_rank.append(dsum)
+        self._unit_start = list(itertools.accumulate([0] + self._units_per_rank))
+        self._local_units = self._units[self._unit_start[self._rank] : self._unit_start[self._rank + 1]]
+        self._mp_features: List[int] = sorted({u.feature for u in self._units})
+        self._has_mp = len(self._units) > 0
+
+        # ---- local kernels -------------------------------------------------------------------------
+        self._tbes = nn.ModuleList()
+        for gi, g in enumerate(self._groups):
+            if not g.local_shards:
+                self._tbes.append(nn.Identity())
+                continue
+            u0, u1 = g.unit_range
+            units = self._local_units[u0:u1]
+            tbe = TableBatchedEmbeddingBags(
+                embedding_specs=[(s.rows, s.cols) for s in g.local_shards],
+                feature_table_map=[u.shard.local_idx for u in units],
+                pooling_mode=g.pooling,
+                weights_precision=g.dtype,
+                output_dtype=output_dtype,
+                optimizer=g.opt.optim,
+                learning_rate=g.opt.lr, eps=g.opt.eps, beta1=g.opt.beta1, beta2=g.opt.beta2,
+                weight_decay=g.opt.weight_decay, weight_decay_mode=g.opt.weight_decay_mode,
+                max_gradient=g.opt.max_gradient, momentum=g.opt.momentum,
+                device=device, table_names=[s.name for s in g.local_shards],
+            )
+            g.tbe = tbe
+            self._tbes.append(tbe)
+
+        self._build_routes()
+        self._build_combine()
+
+        # ---- portable transport modules ---------------------------------------------------------------
+        self._kjt_a2a: Optional[KJTAllToAll] = None
+        self._pooled_a2a: Optional[PooledEmbeddingsAllToAll] = None
+        self._seq_a2a: Optional[SequenceEmbeddingsAllToAll] = None
+        if self._has_mp and self._pg is not None and self._W > 1:
+            self._kjt_a2a = KJTAllToAll(self._pg, self._units_per_rank)
+            if pooled:
+                self._pooled_a2a = PooledEmbeddingsAllToAll(self._pg, self._dim_sum_per_rank, device, codecs=qcomm_codecs)
+            else:
+                self._seq_a2a = SequenceEmbeddingsAllToAll(self._pg, self._units_per_rank, device, codecs=qcomm_codecs)
+
+    # ---------------------------------------------------------------------------------------------------
+    def _build_routes(self) -> None:
+        """Host tables used to turn the local KJT into the routed (unit-ordered) KJT."""
+        F = len(self._feature_names)
+        units_by_feature: Dict[int, List[Unit]] = {}
+        for u in self._units:
+            units_by_feature.setdefault(u.feature, []).append(u)
+        self._row_sharded = any(
+            len({(u.shard.row_off, u.shard.rows) for u in us}) > 1 for us in units_by_feature.values()
+        )
+        # fast path: routed KJT is a pure key permutation (with repeats for column shards)
+        self._perm_features = [self._mp_features.index(u.feature) for u in self._units]
+        self._routed_keys = [self._feature_names[u.feature] for u in self._units]
+        if not self._row_sharded:
+            return
+        # general path tables over the (feature, column-slice) pairs k and row shards j
+        mp_pos = {f: i for i, f in enumerate(self._mp_features)}
+        fc_count = [0] * len(self._mp_features)
+        fc_base = [0] * len(self._mp_features)
+        keyed_bounds: List[int] = []
+        row_lo_flat: List[int] = []
+        unit_flat: List[int] = []
+        k = 0
+        max_rows = max(self._tables[ti].num_embeddings for ti in self._mp_tables) + 1
+        self._BIG = max_rows
+        for f in self._mp_features:
+            us = units_by_feature[f]
+            cols = sorted({u.shard.col_off for u in us})
+            fc_base[mp_pos[f]] = k
+            fc_count[mp_pos[f]] = len(cols)
+            for c in cols:
+                rs = sorted([u for u in us if u.shard.col_off == c and u.shard.rows > 0], key=lambda u: u.shard.row_off)
+                if not rs:
+                    rs = [u for u in us if u.shard.col_off == c][:1]
+                for u in rs:
+                    keyed_bounds.append(k * self._BIG + u.shard.row_off)
+                    row_lo_flat.append(u.shard.row_off)
+                    unit_flat.append(u.gidx)
+                k += 1
+        dev = self._device
+        self.register_buffer("_fc_count", torch.tensor(fc_count, dtype=torch.int64, device=dev), persistent=False)
+        self.register_buffer("_fc_base", torch.tensor(fc_base, dtype=torch.int64, device=dev), persistent=False)
+        self.register_buffer("_keyed_bounds", torch.tensor(keyed_bounds, dtype=torch.int64, device=dev), persistent=False)
+        self.register_buffer("_row_lo_flat", torch.tensor(row_lo_flat, dtype=torch.int64, device=dev), persistent=False)
+        self.register_buffer("_unit_flat", torch.tensor(unit_flat, dtype=torch.int64, device=dev), persistent=False)
+        self._uniform_fc = len(set(fc_count)) == 1
+
+    def _build_combine(self) -> None:
+        """Map every received column (global unit order) to its output column."""
+        if not self._pooled:
+            return
+        dims = [self._tables[ti].embedding_dim for ti in self._feature_table]
+        self._out_base = list(itertools.accumulate([0] + dims))
+        mp_cols: List[int] = []
+        for u in self._units:
+            base = self._out_base[u.feature] + u.shard.col_off
+            mp_cols.extend(range(base, base + u.shard.cols))
+        self._mp_dest_cols = mp_cols
+        self._mp_is_perm = len(set(mp_cols)) == len(mp_cols)
+
+    # ---- input dist ---------------------------------------------------------------------------------------
+    def route(self, features: KeyedJaggedTensor) -> Tuple[KeyedJaggedTensor, Optional[torch.Tensor]]:
+        """Local KJT (keys = model-parallel features in flat order) -> routed KJT (global unit
+        order). Returns the unbucketize permutation for sequence outputs when ids were re-sorted."""
+        if not self._row_sharded:
+            if self._perm_features == list(range(len(features.keys()))):
+                return features, None
+            return features.permute(self._perm_features), None
+        B = features.stride()
+        Fm = len(self._mp_features)
+        lengths = features.lengths().to(torch.int64)
+        values = features.values()
+        n = values.numel()
+        dev = values.device
+        bag = torch.repeat_interleave(torch.arange(Fm * B, device=dev), lengths, output_size=n)
+        f = torch.div(bag, B, rounding_mode="floor")
+        b = bag - f * B
+        rep = self._fc_count[f]
+        if self._uniform_fc:
+            total = n * int(self._fc_count[0]) if Fm else 0
+        else:
+            total = int(rep.sum())
+        e = torch.repeat_interleave(torch.arange(n, device=dev), rep, output_size=total)
+        rep_start = torch.cumsum(rep, 0) - rep
+        c_local = torch.arange(total, device=dev) - rep_start[e]
+        k = self._fc_base[f[e]] + c_local
+        ids = values[e].to(torch.int64)
+        key = k * self._BIG + ids.clamp(min=0, max=self._BIG - 1)
+        pos = torch.searchsorted(self._keyed_bounds, key, right=True) - 1
+        unit = self._unit_flat[pos]
+        local_id = ids - self._row_lo_flat[pos]
+        U = len(self._units)
+        new_bag = unit * B + b[e]
+        order = torch.argsort(new_bag, stable=True)
+        new_lengths = torch.bincount(new_bag, minlength=U * B).to(features.lengths().dtype)
+        new_values = local_id[order].to(values.dtype)
+        w = features.weights_or_none()
+        new_weights = None if w is None else w[e][order]
+        unbucketize = torch.empty(total, dtype=torch.int64, device=dev)
+        unbucketize[order] = torch.arange(total, device=dev)
+        routed = KeyedJaggedTensor(keys=self._routed_keys, values=new_values, weights=new_weights, lengths=new_lengths, stride=B)
+        return routed, unbucketize
+
+    def input_dist(self, features: KeyedJaggedTensor) -> Tuple[Awaitable[Awaitable[KeyedJaggedTensor]], Optional[torch.Tensor]]:
+        routed, unbucketize = self.route(features)
+        if self._kjt_a2a is None:
+            return NoWait(NoWait(routed)), unbucketize
+        return self._kjt_a2a(routed), unbucketize
+
+    # ---- lookup -------------------------------------------------------------------------------------------
+    def lookup(self, dist_features: KeyedJaggedTensor) -> torch.Tensor:
+        """Run the table-batched kernels over this rank's units. Pooled: ``[B_global, D_local]``;
+        sequence: ``[n_values, D]`` (received order)."""
+        Bg = dist_features.stride()
+        values = dist_features.values()
+        offsets = dist_features.offsets()
+        weights = dist_features.weights_or_none() if self._is_weighted else None
+        outs: List[torch.Tensor] = []
+        for g in self._groups:
+            if g.tbe is None:
+                continue
+            u0, u1 = g.unit_range
+            window = offsets[u0 * Bg : u1 * Bg + 1]
+            if self._pooled:
+                outs.append(g.tbe(values, window, weights, batch_size=Bg))
+            else:
+                outs.append(g.tbe(values, window, None, batch_size=Bg))
+        if not outs:
+            D = 0 if self._pooled else self._tables[0].embedding_dim
+            return torch.zeros(Bg if self._pooled else 0, D, device=values.device, dtype=self._output_dtype)
+        if len(outs) == 1:
+            return outs[0]
+        if self._pooled:
+            return torch.cat(outs, dim=1)
+        # sequence groups own disjoint value windows: trim each to its window and concatenate
+        trimmed = []
+        for g, o in zip([g for g in self._groups if g.tbe is not None], outs):
+            u0, u1 = g.unit_range
+            lo, hi = int(offsets[u0 * Bg]), int(offsets[u1 * Bg])
+            trimmed.append(o[: hi - lo])
+        return torch.cat(trimmed, 0)
+
+    # ---- output dist (pooled) ---------------------------------------------------------------------------------
+    def output_dist(self, local_embs: torch.Tensor, batch_size_per_rank: Optional[List[int]] = None) -> Awaitable[torch.Tensor]:
+        if self._pooled_a2a is None:
+            return NoWait(local_embs)
+        return self._pooled_a2a(local_embs, batch_size_per_rank)
+
+    def combine(self, mp_embs: Optional[torch.Tensor], dp_embs: Optional[torch.Tensor], dp_cols: List[int], total_cols: int,
+                mean_divisor: Optional[torch.Tensor]) -> torch.Tensor:
+        """Place received unit columns (and data-parallel columns) into the module's output layout."""
+        parts, cols = [], []
+        if mp_embs is not None and mp_embs.shape[1] > 0:
+            parts.append(mp_embs)
+            cols.extend(self._mp_dest_cols)
+        if dp_embs is not None and dp_embs.shape[1] > 0:
+            parts.append(dp_embs.to(parts[0].dtype) if parts else dp_embs)
+            cols.extend(dp_cols)
+        x = parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
+        if cols == list(range(total_cols)):
+            out = x
+        else:
+            key = (tuple(cols), total_cols, x.device)
+            idx = self._combine_cache.get(key) if hasattr(self, "_combine_cache") else None
+            if idx is None:
+                if not hasattr(self, "_combine_cache"):
+                    self._combine_cache: Dict[Any, Tuple[bool, torch.Tensor]] = {}
+                is_perm = len(set(cols)) == len(cols) and len(cols) == total_cols
+                if is_perm:
+                    inv = [0] * total_cols
+                    for src, dst in enumerate(cols):
+                        inv[dst] = src
+                    idx = (True, torch.tensor(inv, dtype=torch.int64, device=x.device))
+                else:
+                    idx = (False, torch.tensor(cols, dtype=torch.int64, device=x.device))
+                self._combine_cache[key] = idx
+            if idx[0]:
+                out = x.index_select(1, idx[1])
+            else:
+                out = torch.zeros(x.shape[0], total_cols, dtype=x.dtype, device=x.device).index_add(1, idx[1], x)
+        if mean_divisor is not None:
+            out = out * mean_divisor
+        return out
+
+    # ---- misc -----------------------------------------------------------------------------------------------
+    @property
+    def units(self) -> List[Unit]:
+        return self._units
+
+    @property
+    def units_per_rank(self) -> List[int]:
+        return self._units_per_rank
+
+    @property
+    def dim_sum_per_rank(self) -> List[int]:
+        return self._dim_sum_per_rank
+
+    @property
+    def groups(self) -> List[_Group]:
+        return self._groups
+
+    @property
+    def mp_features(self) -> List[int]:
+        return self._mp_features
+
+    def local_shard_views(self) -> List[Tuple[TableShard, torch.Tensor, Dict[str, torch.Tensor], TableBatchedEmbeddingBags]]:
+        """(shard, weight view [rows, cols], optimizer state views, owning kernel) for every local shard."""
+        res = []
+        for g in self._groups:
+            if g.tbe is None:
+                continue
+            ws = g.tbe.split_embedding_weights()
+            sts = g.tbe.split_optimizer_states()
+            for s in g.local_shards:
+                res.append((s, ws[s.local_idx], sts[s.local_idx], g.tbe))
+        return res

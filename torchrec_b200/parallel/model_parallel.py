@@ -1,0 +1,433 @@
+"""DistributedModelParallel: entry point of model parallelism
+(reference torchrec/distributed/model_parallel.py:246-905).
+
+Walks the module tree, replaces every module that has a plan entry by its sharded twin,
+materialises remaining meta-device parameters, wraps the dense remainder in DDP (sharded parameters
+are ignored by DDP) and exposes the fused optimizers as one ``CombinedOptimizer`` whose state keys are
+parameter FQNs — the checkpoint layout of the unsharded model.
+"""
+from __future__ import annotations
+
+import abc
+import copy
+from collections import OrderedDict
+from typing import Any, Dict, Iterator, List, Mapping, Optional, Set, Tuple, Type, Union, cast
+
+import torch
+import torch.distributed as dist
+from torch import nn
+from torch.nn.modules.module import _IncompatibleKeys
+from torch.nn.parallel import DistributedDataParallel
+
+from ..optim.fused import FusedOptimizerModule
+from ..optim.keyed import CombinedOptimizer, KeyedOptimizer
+from .comm import get_local_size
+from .types import EmbeddingModuleShardingPlan, ModuleSharder, ShardedModule, ShardingEnv, ShardingEnv2D, ShardingPlan, DMPCollectionConfig, DMPCollectionContext, ShardingStrategy
+
+_DDP_STATE_DICT_PREFIX = "module."
+
+
+class DataParallelWrapper(abc.ABC):
+    """Wraps the non-sharded part of a DMP model for data parallelism."""
+
+    @abc.abstractmethod
+    def wrap(self, dmp: "DistributedModelParallel", env: ShardingEnv, device: torch.device) -> None:
+        ...
+
+
+class DefaultDataParallelWrapper(DataParallelWrapper):
+    """DDP over every parameter that was not sharded (reference model_parallel.py:133-213)."""
+
+    def __init__(self, bucket_cap_mb: int = 25, static_graph: bool = True, find_unused_parameters: bool = False,
+                 allreduce_comm_precision: Optional[str] = None, params_to_ignore: Optional[List[str]] = None,
+                 ddp_kwargs: Optional[Dict[str, Any]] = None) -> None:
+        self._bucket_cap_mb = bucket_cap_mb
+        self._static_graph = static_graph
+        self._find_unused_parameters = find_unused_parameters
+        self._allreduce_comm_precision = allreduce_comm_precision
+        self._additional_params_to_ignore: Set[str] = set(params_to_ignore or [])
+        self._ddp_kwargs: Dict[str, Any] = ddp_kwargs or {}
+
+    def wrap(self, dmp: "DistributedModelParallel", env: ShardingEnv, device: torch.device) -> None:
+        pg = env.process_group
+        if pg is None:
+            raise RuntimeError("Can only init process group with a process group")
+        all_names = {key for key, _ in dmp.named_parameters()}
+        sharded = set(DistributedModelParallel._sharded_parameter_names(dmp.module))
+        params_to_ignore = sharded.union(self._additional_params_to_ignore)
+        if params_to_ignore.issuperset(all_names) or not any(p.requires_grad for n, p in dmp.module.named_parameters() if n not in params_to_ignore):
+            return  # nothing left for data parallelism
+        DistributedDataParallel._set_params_and_buffers_to_ignore_for_model(module=dmp.module, params_and_buffers_to_ignore=params_to_ignore)
+        dmp._dmp_wrapped_module = cast(nn.Module, DistributedDataParallel(
+            module=dmp._dmp_wrapped_module.to(device),
+            device_ids=None if device.type == "cpu" else [device],
+            process_group=pg,
+            gradient_as_bucket_view=True,
+            broadcast_buffers=False,
+            static_graph=self._static_graph,
+            find_unused_parameters=self._find_unused_parameters,
+            bucket_cap_mb=self._bucket_cap_mb,
+            **self._ddp_kwargs,
+        ))
+        if self._allreduce_comm_precision == "fp16":
+            from torch.distributed.algorithms.ddp_comm_hooks import default_hooks as ddp_default_hooks
+
+            dmp._dmp_wrapped_module.register_comm_hook(None, ddp_default_hooks.fp16_compress_hook)
+        elif self._allreduce_comm_precision == "bf16":
+            from torch.distributed.algorithms.ddp_comm_hooks import default_hooks as ddp_default_hooks
+
+            dmp._dmp_wrapped_module.register_comm_hook(None, ddp_default_hooks.bf16_compress_hook)
+
+
+def get_unwrapped_module(module: nn.Module) -> nn.Module:
+    """Strip DMP / DDP / FSDP wrappers."""
+    while isinstance(module, (DistributedModelParallel, DistributedDataParallel)) or type(module).__name__ == "FullyShardedDataParallel":
+        if isinstance(module, DistributedModelParallel):
+            module = module._dmp_wrapped_module
+        else:
+            module = module.module
+    return module
+
+
+def get_module(module: nn.Module) -> nn.Module:
+    while isinstance(module, DistributedModelParallel):
+        module = module._dmp_wrapped_module
+    return module
+
+
+class DistributedModelParallel(nn.Module, FusedOptimizerModule):
+    """Entry point to model parallelism.
+
+    Args:
+        module: model to wrap (embedding collections may live on the ``meta`` device).
+        env: sharding environment (defaults to the world process group).
+        device: compute device.
+        plan: sharding plan; when ``None`` the planner builds one collectively.
+        sharders: module sharders (defaults to ``get_default_sharders()``).
+        init_data_parallel / init_parameters / data_parallel_wrapper: as in the reference.
+
+    Example::
+
+        model = DistributedModelParallel(DLRM(ebc, ...), device=torch.device("cuda"))
+        dense_opt = KeyedOptimizerWrapper(dict(in_backward_optimizer_filter(model.named_parameters())), lambda p: torch.optim.SGD(p, lr=0.1))
+        opt = CombinedOptimizer([model.fused_optimizer, dense_opt])
+    """
+
+    def __init__(
+        self,
+        module: nn.Module,
+        env: Optional[ShardingEnv] = None,
+        device: Optional[torch.device] = None,
+        plan: Optional[ShardingPlan] = None,
+        sharders: Optional[List[ModuleSharder[nn.Module]]] = None,
+        init_data_parallel: bool = True,
+        init_parameters: bool = True,
+        data_parallel_wrapper: Optional[DataParallelWrapper] = None,
+        model_tracker_config: Optional[Any] = None,
+    ) -> None:
+        super().__init__()
+        torch._C._log_api_usage_once(f"torchrec_b200.parallel.{self.__class__.__name__}")
+        self.init_parameters = init_parameters
+        self._ddp_wrapped: bool = False
+        if env is None:
+            pg = dist.GroupMember.WORLD if dist.is_initialized() else None
+            env = ShardingEnv.from_process_group(pg) if pg is not None else ShardingEnv.from_local(1, 0)
+        self._env: ShardingEnv = env
+        self.device: torch.device = torch.device(device) if device is not None else torch.device("cpu")
+        if sharders is None:
+            from .sharding_plan import get_default_sharders
+
+            sharders = get_default_sharders()
+        self._sharder_map: Dict[Type[nn.Module], ModuleSharder[nn.Module]] = {sharder.module_type: sharder for sharder in sharders}
+        if data_parallel_wrapper is None:
+            data_parallel_wrapper = DefaultDataParallelWrapper()
+        self._data_parallel_wrapper: DataParallelWrapper = data_parallel_wrapper
+        if plan is None:
+            from .planner import EmbeddingShardingPlanner, Topology
+
+            planner = EmbeddingShardingPlanner(topology=Topology(
+                local_world_size=get_local_size(self._env.world_size), world_size=self._env.world_size, compute_device=self.device.type))
+            pg = self._env.process_group
+            plan = planner.collective_plan(module, sharders, pg) if pg is not None else planner.plan(module, sharders)
+        self._plan: ShardingPlan = plan
+        self._dmp_wrapped_module: nn.Module = self._init_dmp(module)
+        self._optim: CombinedOptimizer = self._init_optim(self._dmp_wrapped_module)
+        if init_parameters:
+            self._init_parameters(self.module)
+        if init_data_parallel:
+            self.init_data_parallel()
+        self._model_tracker = None
+        if model_tracker_config is not None:
+            from .model_tracker import ModelDeltaTracker
+
+            self._model_tracker = ModelDeltaTracker(self._dmp_wrapped_module, **(model_tracker_config if isinstance(model_tracker_config, dict) else {}))
+
+    # ---- public surface -------------------------------------------------------------------------------------
+    @property
+    def module(self) -> nn.Module:
+        """The wrapped model without DDP."""
+        return get_unwrapped_module(self)
+
+    @module.setter
+    def module(self, value: nn.Module) -> None:
+        if isinstance(self.module, DistributedDataParallel):
+            raise RuntimeError("module can't be set after calling init_data_parallel(...)")
+        self._dmp_wrapped_module = value
+
+    def forward(self, *args, **kwargs) -> Any:
+        return self._dmp_wrapped_module(*args, **kwargs)
+
+    def init_data_parallel(self) -> None:
+        """Wrap the dense part in DDP (call after meta-device parameters were materialised)."""
+        if not self._ddp_wrapped:
+            if self._env.process_group is not None and self._env.world_size > 1:
+                self._data_parallel_wrapper.wrap(self, self._env, self.device)
+            else:
+                self._dmp_wrapped_module = self._dmp_wrapped_module.to(self.device) if self.device.type != "meta" else self._dmp_wrapped_module
+            self._ddp_wrapped = True
+
+    def copy(self, device: torch.device) -> "DistributedModelParallel":
+        assert isinstance(device, torch.device)
+        with torch.no_grad():
+            copy_dmp_wrapped_module = copy.deepcopy(self._dmp_wrapped_module).to(device)
+        new = copy.copy(self)
+        new.device = device
+        new._dmp_wrapped_module = copy_dmp_wrapped_module
+        return new
+
+    @property
+    def plan(self) -> ShardingPlan:
+        return self._plan
+
+    @property
+    def fused_optimizer(self) -> KeyedOptimizer:
+        return self._optim
+
+    # ---- init ------------------------------------------------------------------------------------------------
+    def _init_dmp(self, module: nn.Module) -> nn.Module:
+        return self._shard_modules_impl(module)
+
+    def _init_optim(self, module: nn.Module) -> CombinedOptimizer:
+        return CombinedOptimizer(self._fused_optim_impl(module, []))
+
+    def _fused_optim_impl(self, module: nn.Module, fused_optims: List[Tuple[str, KeyedOptimizer]], path: str = "") -> List[Tuple[str, KeyedOptimizer]]:
+        if isinstance(module, FusedOptimizerModule):
+            fused_optims.append((path, module.fused_optimizer))
+            return fused_optims
+        for name, child in module.named_children():
+            self._fused_optim_impl(child, fused_optims, path + "." + name if path else name)
+        return fused_optims
+
+    def _shard_modules_impl(self, module: nn.Module, path: str = "") -> nn.Module:
+        if isinstance(module, ShardedModule):
+            return module
+        module_sharding_plan = self._plan.get_plan_for_module(path)
+        if module_sharding_plan:
+            sharder_key = type(module)
+            if sharder_key not in self._sharder_map:
+                raise RuntimeError(f"no sharder registered for {sharder_key} (plan entry '{path}')")
+            module = self._sharder_map[sharder_key].shard(module, module_sharding_plan, self._env, self.device, path)
+            torch._C._log_api_usage_once(f"torchrec_b200.parallel.sharded.{type(module).__name__}")
+            return module
+        for name, child in module.named_children():
+            child = self._shard_modules_impl(child, path + "." + name if path else name)
+            setattr(module, name, child)
+        return module
+
+    def _init_parameters(self, module: nn.Module) -> None:
+        @torch.no_grad()
+        def init_parameters(m: nn.Module) -> None:
+            if isinstance(m, ShardedModule):
+                return
+            has_meta_param = False
+            for name, param in list(m._parameters.items()):
+                if isinstance(param, torch.Tensor) and param.device.type == "meta":
+                    m._parameters[name] = nn.Parameter(torch.empty_like(param, device=self.device), requires_grad=param.requires_grad)
+                    has_meta_param = True
+            for name, buffer in list(m._buffers.items()):
+                if isinstance(buffer, torch.Tensor) and buffer.device.type == "meta":
+                    m._buffers[name] = torch.zeros_like(buffer, device=self.device)
+            if has_meta_param and hasattr(m, "reset_parameters"):
+                m.reset_parameters()
+
+        def walk(m: nn.Module) -> None:
+            if isinstance(m, ShardedModule):
+                return
+            init_parameters(m)
+            for c in m.children():
+                walk(c)
+
+        walk(module)
+
+    # ---- state dict / parameters pass-through (keys of the unsharded model) -----------------------------------
+    def sparse_grad_parameter_names(self, destination: Optional[List[str]] = None, prefix: str = "") -> List[str]:
+        destination = [] if destination is None else destination
+        return self._sparse_grad_parameter_names(self.module, destination, prefix)
+
+    def _sparse_grad_parameter_names(self, module: nn.Module, destination: List[str], prefix: str = "") -> List[str]:
+        module = get_unwrapped_module(module)
+        if isinstance(module, ShardedModule):
+            pass
+        elif isinstance(module, nn.Embedding):
+            if module.sparse:
+                destination.append(append_prefix(prefix, "weight"))
+        elif isinstance(module, nn.EmbeddingBag):
+            if module.sparse:
+                destination.append(append_prefix(prefix, "weight"))
+        else:
+            for name, child in module.named_children():
+                self._sparse_grad_parameter_names(child, destination, append_prefix(prefix, name))
+        return destination
+
+    def state_dict(self, destination: Optional[Dict[str, Any]] = None, prefix: str = "", keep_vars: bool = False) -> Dict[str, Any]:
+        state_dict = get_module(self).state_dict(destination=destination, prefix=prefix, keep_vars=keep_vars)
+        torch.nn.modules.utils.consume_prefix_in_state_dict_if_present(state_dict, prefix + _DDP_STATE_DICT_PREFIX)
+        return state_dict
+
+    def load_state_dict(self, state_dict: "OrderedDict[str, torch.Tensor]", prefix: str = "", strict: bool = True, assign: bool = False) -> _IncompatibleKeys:
+        return self._load_state_dict(self, state_dict, prefix, strict)
+
+    def _load_state_dict(self, module: nn.Module, state_dict: "OrderedDict[str, torch.Tensor]", prefix: str = "", strict: bool = True) -> _IncompatibleKeys:
+        missing_keys: List[str] = []
+        unexpected_keys: List[str] = []
+        module = get_module(module)
+        if isinstance(module, DistributedDataParallel):
+            module = module.module
+        if isinstance(module, ShardedModule):
+            sub = OrderedDict((k[len(prefix):], v) for k, v in state_dict.items() if k.startswith(prefix))
+            res = module.load_state_dict(sub, strict=strict)
+            return _IncompatibleKeys([prefix + k for k in res.missing_keys], [prefix + k for k in res.unexpected_keys])
+        # direct params / buffers
+        own = OrderedDict()
+        for k, v in state_dict.items():
+            if k.startswith(prefix) and "." not in k[len(prefix):]:
+                own[k[len(prefix):]] = v
+        local_names = set(dict(module._parameters).keys()) | {k for k in module._buffers.keys() if k not in module._non_persistent_buffers_set}
+        with torch.no_grad():
+            for name in local_names:
+                t = module._parameters.get(name, None)
+                if t is None:
+                    t = module._buffers.get(name, None)
+                if t is None:
+                    continue
+                if name in own:
+                    t.copy_(own[name])
+                else:
+                    missing_keys.append(prefix + name)
+        for k in own:
+            if k not in local_names:
+                unexpected_keys.append(prefix + k)
+        for name, child in module.named_children():
+            res = self._load_state_dict(child, state_dict, prefix + name + ".", strict)
+            missing_keys.extend(res.missing_keys)
+            unexpected_keys.extend(res.unexpected_keys)
+        if prefix == "" and strict:
+            known = set()
+            for k in state_dict.keys():
+                known.add(k)
+            if missing_keys:
+                raise RuntimeError(f"Error(s) in loading state_dict: missing keys {missing_keys}")
+        return _IncompatibleKeys(missing_keys, unexpected_keys)
+
+    def _named_parameters(self, module: nn.Module, prefix: str = "", recurse: bool = True, strip_ddp: bool = True) -> Iterator[Tuple[str, torch.nn.Parameter]]:
+        if strip_ddp:
+            module = get_unwrapped_module(module)
+        if isinstance(module, ShardedModule):
+            yield from module.named_parameters(prefix, recurse)
+        else:
+            yield from module.named_parameters(prefix, recurse=False)
+            for name, child in module.named_children():
+                yield from self._named_parameters(child, append_prefix(prefix, name), recurse, strip_ddp)
+
+    def named_parameters(self, prefix: str = "", recurse: bool = True, remove_duplicate: bool = True) -> Iterator[Tuple[str, torch.nn.Parameter]]:
+        gen = self._named_parameters(self.module, prefix, recurse)
+        memo = set()
+        for key, param in gen:
+            if param in memo:
+                continue
+            if remove_duplicate:
+                memo.add(param)
+            yield key, param
+
+    def bare_named_parameters(self, prefix: str = "", recurse: bool = True) -> Iterator[Tuple[str, torch.nn.Parameter]]:
+        gen = self._named_parameters(self.module, prefix, recurse)
+        memo = set()
+        for key, param in gen:
+            if param in memo:
+                continue
+            memo.add(param)
+            yield key, param
+
+    @staticmethod
+    def _sharded_parameter_names(module: nn.Module, prefix: str = "") -> Iterator[str]:
+        module = get_unwrapped_module(module)
+        if isinstance(module, ShardedModule):
+            yield from module.sharded_parameter_names(prefix)
+        else:
+            for name, child in module.named_children():
+                yield from DistributedModelParallel._sharded_parameter_names(child, append_prefix(prefix, name))
+
+    def _named_buffers(self, module: nn.Module, prefix: str = "", recurse: bool = True) -> Iterator[Tuple[str, torch.Tensor]]:
+        module = get_unwrapped_module(module)
+        if isinstance(module, ShardedModule):
+            yield from module.named_buffers(prefix, recurse)
+        else:
+            yield from module.named_buffers(prefix, recurse=False)
+            for name, child in module.named_children():
+                yield from self._named_buffers(child, append_prefix(prefix, name), recurse)
+
+    def named_buffers(self, prefix: str = "", recurse: bool = True, remove_duplicate: bool = True) -> Iterator[Tuple[str, torch.Tensor]]:
+        gen = self._named_buffers(self.module, prefix, recurse)
+        memo = set()
+        for key, param in gen:
+            if param in memo:
+                continue
+            if remove_duplicate:
+                memo.add(param)
+            yield key, param
+
+    @property
+    def fused_optimizer_modules(self) -> List[nn.Module]:
+        return [m for m in self.module.modules() if isinstance(m, FusedOptimizerModule)]
+
+    def get_model_tracker(self):
+        assert self._model_tracker is not None, "Model tracker is not initialized. Add ModelTrackerConfig at DistributedModelParallel init."
+        return self._model_tracker
+
+    def get_delta(self, consumer: Optional[str] = None):
+        assert self._model_tracker is not None, "Model tracker is not initialized."
+        return self._model_tracker.get_delta(consumer)
+
+    def reshard(self, sharded_module_fqn: str, changed_shard_to_params: Dict[str, Any]) -> None:
+        """Move table shards to a new placement at runtime (dynamic re-sharding, reference model_parallel.py:793)."""
+        from .dynamic_sharding import reshard_module
+
+        steps = sharded_module_fqn.split(".")
+        parent = self.module
+        for s in steps[:-1]:
+            parent = getattr(parent, s)
+        old = getattr(parent, steps[-1])
+        new = reshard_module(old, changed_shard_to_params, self._env, self.device, self._sharder_map)
+        setattr(parent, steps[-1], new)
+        plan_for = self._plan.plan[sharded_module_fqn]
+        for k, v in changed_shard_to_params.items():
+            plan_for[k] = v  # type: ignore[index]
+        self._optim = self._init_optim(self._dmp_wrapped_module)
+
+
+def append_prefix(prefix: str, name: str) -> str:
+    if prefix != "" and name != "":
+        return prefix + "." + name
+    return prefix + name
+
+
+def add_prefix_to_state_dict(state_dict: Dict[str, Any], prefix: str) -> None:
+    keys = sorted(state_dict.keys())
+    for key in keys:
+        state_dict[prefix + key] = state_dict.pop(key)
+    if "_metadata" in state_dict:
+        metadata = state_dict["_metadata"]
+        for key in list(metadata.keys()):
+            if len(key) == 0:
+                continue
+            metadata[prefix + key] = metadata.pop(key)
