@@ -1,0 +1,124 @@
+"""Numerics of the sm_100a TBE kernels vs the fp32 PyTorch reference implementation."""
+import pytest
+import torch
+
+from torchrec_b200.ops import tbe as T
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(F, B, rows, maxL, device, seed=0, idx_dtype=torch.int64, hot=False):
+    g = torch.Generator().manual_seed(seed)
+    lengths = torch.randint(0, maxL + 1, (F * B,), generator=g)
+    offsets = torch.cat([torch.zeros(1, dtype=torch.int64), lengths.cumsum(0)])
+    idx = []
+    for f in range(F):
+        n = int(lengths[f * B : (f + 1) * B].sum())
+        hi = 3 if (hot and f == 0) else rows[f]
+        idx.append(torch.randint(0, hi, (n,), generator=g))
+    indices = torch.cat(idx).to(idx_dtype)
+    psw = torch.rand(indices.numel(), generator=g)
+    return indices.to(device), offsets.to(device), psw.to(device)
+
+
+@pytest.mark.parametrize("dim", [16, 64, 128, 256, 1024])
+@pytest.mark.parametrize("wdtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_pooled_forward(dim, wdtype, weighted):
+    dev = torch.device("cuda:0")
+    specs = [(100, dim), (57, dim), (1000, dim)]
+    fmap = [0, 1, 1, 2]
+    B = 33
+    meta_g = T.TbeMeta.build([r for r, _ in specs], [d for _, d in specs], fmap, dev)
+    meta_c = T.TbeMeta.build([r for r, _ in specs], [d for _, d in specs], fmap, torch.device("cpu"))
+    w = (torch.randn(sum(r * d for r, d in specs)) * 0.1).to(wdtype)
+    idx, off, psw = _inputs(4, B, [100, 57, 57, 1000], 5, dev, idx_dtype=torch.int32 if dim == 64 else torch.int64)
+    for mean in (False, True):
+        out = T.pooled_forward(meta_g, w.to(dev), idx, off, psw if weighted else None, B, mean, torch.float32)
+        ref = T._ref_pooled_forward(meta_c, w.float(), idx.cpu(), off.cpu(), psw.cpu() if weighted else None, B, mean, torch.float32)
+        torch.testing.assert_close(out.cpu(), ref, rtol=1e-4, atol=1e-4)
+    out_bf = T.pooled_forward(meta_g, w.to(dev), idx, off, None, B, False, torch.bfloat16)
+    ref = T._ref_pooled_forward(meta_c, w.float(), idx.cpu(), off.cpu(), None, B, False, torch.float32)
+    torch.testing.assert_close(out_bf.float().cpu(), ref, rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("opt", [T.OptimType.EXACT_SGD, T.OptimType.EXACT_ROWWISE_ADAGRAD, T.OptimType.EXACT_ADAGRAD, T.OptimType.ADAM,
+                                 T.OptimType.PARTIAL_ROWWISE_ADAM, T.OptimType.LAMB, T.OptimType.LARS_SGD, T.OptimType.NONE])
+@pytest.mark.parametrize("dim", [32, 128, 512])
+def test_fused_backward_matches_reference(opt, dim):
+    dev = torch.device("cuda:0")
+    specs = [(50, dim), (3, dim), (400, dim)]
+    fmap = [0, 1, 2, 2]
+    B = 300  # many duplicates on the 3-row table -> runs spanning several 32-wide chunks
+    torch.manual_seed(1)
+    cpu = T.TableBatchedEmbeddingBags(specs, fmap, optimizer=opt, learning_rate=0.05, weight_decay=0.01 if opt == T.OptimType.LAMB else 0.0)
+    gpu = T.TableBatchedEmbeddingBags(specs, fmap, optimizer=opt, learning_rate=0.05, weight_decay=0.01 if opt == T.OptimType.LAMB else 0.0, device=dev)
+    gpu.weights.data.copy_(cpu.weights.data)
+    for step in range(2):
+        idx, off, psw = _inputs(4, B, [50, 3, 400, 400], 4, dev, seed=step, hot=True)
+        proj = torch.randn(B, 4 * dim)
+        og = gpu(idx, off, psw)
+        oc = cpu(idx.cpu(), off.cpu(), psw.cpu())
+        torch.testing.assert_close(og.cpu(), oc, rtol=1e-4, atol=1e-4)
+        (og * proj.to(dev)).sum().backward()
+        (oc * proj).sum().backward()
+        if opt == T.OptimType.NONE:
+            torch.testing.assert_close(gpu.weights.grad.cpu(), cpu.weights.grad, rtol=2e-4, atol=2e-4)
+            gpu.weights.grad = None
+            cpu.weights.grad = None
+        else:
+            torch.testing.assert_close(gpu.weights.cpu(), cpu.weights, rtol=2e-4, atol=2e-4)
+            if gpu.state1 is not None:
+                torch.testing.assert_close(gpu.state1.cpu(), cpu.state1, rtol=2e-4, atol=1e-5)
+
+
+def test_bf16_tables_and_grads():
+    dev = torch.device("cuda:0")
+    specs = [(64, 128)]
+    cpu = T.TableBatchedEmbeddingBags(specs, [0], optimizer=T.OptimType.EXACT_SGD, learning_rate=0.1)
+    gpu = T.TableBatchedEmbeddingBags(specs, [0], optimizer=T.OptimType.EXACT_SGD, learning_rate=0.1, weights_precision=torch.bfloat16,
+                                      output_dtype=torch.bfloat16, device=dev)
+    cpu.weights.data.copy_(gpu.weights.data.float().cpu())
+    idx, off, _ = _inputs(1, 40, [64], 3, dev)
+    og = gpu(idx, off)
+    oc = cpu(idx.cpu(), off.cpu())
+    torch.testing.assert_close(og.float().cpu(), oc, rtol=2e-2, atol=2e-2)
+    og.sum().backward()
+    oc.sum().backward()
+    torch.testing.assert_close(gpu.weights.float().cpu(), cpu.weights, rtol=2e-2, atol=2e-2)
+
+
+def test_sequence_forward_backward():
+    dev = torch.device("cuda:0")
+    specs = [(30, 64), (40, 64)]
+    cpu = T.TableBatchedEmbeddingBags(specs, [0, 1, 1], pooling_mode=T.PoolingMode.NONE, optimizer=T.OptimType.EXACT_ROWWISE_ADAGRAD, learning_rate=0.1)
+    gpu = T.TableBatchedEmbeddingBags(specs, [0, 1, 1], pooling_mode=T.PoolingMode.NONE, optimizer=T.OptimType.EXACT_ROWWISE_ADAGRAD, learning_rate=0.1, device=dev)
+    gpu.weights.data.copy_(cpu.weights.data)
+    idx, off, _ = _inputs(3, 17, [30, 40, 40], 4, dev)
+    og = gpu(idx, off)
+    oc = cpu(idx.cpu(), off.cpu())
+    torch.testing.assert_close(og.cpu(), oc)
+    proj = torch.randn_like(oc)
+    (og * proj.to(dev)).sum().backward()
+    (oc * proj).sum().backward()
+    torch.testing.assert_close(gpu.weights.cpu(), cpu.weights, rtol=1e-4, atol=1e-5)
+
+
+def test_large_keys_64bit_path_and_launch_counter():
+    from torchrec_b200.ops import _lib
+
+    dev = torch.device("cuda:0")
+    n0 = _lib.launch_count()
+    specs = [(1 << 20, 32)]
+    gpu = T.TableBatchedEmbeddingBags(specs, [0], optimizer=T.OptimType.EXACT_SGD, learning_rate=1.0, device=dev)
+    w0 = gpu.weights.clone()
+    idx = torch.tensor([5, 5, 7, (1 << 20) - 1], device=dev)
+    off = torch.tensor([0, 2, 4], device=dev)
+    out = gpu(idx, off)
+    out.sum().backward()
+    torch.cuda.synchronize()
+    d = (gpu.weights - w0).view(-1, 32)
+    assert torch.allclose(d[5], torch.full((32,), -2.0, device=dev))
+    assert torch.allclose(d[7], torch.full((32,), -1.0, device=dev))
+    assert float(d.abs().sum()) == pytest.approx(32 * 4.0)
+    assert _lib.launch_count() > n0

@@ -1,0 +1,89 @@
+"""TrainPipelineSparseDist / Base vs a plain training loop on 2 CPU ranks: identical losses and
+weights step by step (methodology of the reference's train_pipeline/tests/test_train_pipelines.py)."""
+import copy
+
+import pytest
+import torch
+
+from torchrec_b200.utils.multiprocess import run_multi_process
+
+
+def _build(ctx, sharding, seed=0):
+    from torchrec_b200.models.dlrm import DLRM, DLRMTrain
+    from torchrec_b200.modules.embedding_configs import EmbeddingBagConfig
+    from torchrec_b200.modules.embedding_modules import EmbeddingBagCollection
+    from torchrec_b200.optim.apply_optimizer_in_backward import apply_optimizer_in_backward
+    from torchrec_b200.optim.keyed import CombinedOptimizer, KeyedOptimizerWrapper
+    from torchrec_b200.optim.optimizers import in_backward_optimizer_filter
+    from torchrec_b200.optim.rowwise_adagrad import RowWiseAdagrad
+    from torchrec_b200.parallel import sharding_plan as sp
+    from torchrec_b200.parallel.embeddingbag import EmbeddingBagCollectionSharder
+    from torchrec_b200.parallel.model_parallel import DistributedModelParallel
+    from torchrec_b200.parallel.types import ShardingPlan
+
+    torch.manual_seed(seed)
+    keys = [f"f{i}" for i in range(4)]
+    hashes = [50, 60, 70, 80]
+    tables = [EmbeddingBagConfig(name=f"t{i}", embedding_dim=8, num_embeddings=h, feature_names=[keys[i]]) for i, h in enumerate(hashes)]
+    ebc = EmbeddingBagCollection(tables)
+    apply_optimizer_in_backward(RowWiseAdagrad, ebc.parameters(), {"lr": 0.05})
+    model = DLRMTrain(DLRM(ebc, 5, [16, 8], [16, 1]))
+    W = ctx.world_size
+    gens = {f"t{i}": (sp.table_wise(rank=i % W) if sharding == "tw" else sp.row_wise()) for i in range(4)}
+    plan = sp.construct_module_sharding_plan(ebc, gens, sharder=EmbeddingBagCollectionSharder(), world_size=W, local_size=W, device_type="cpu")
+    dmp = DistributedModelParallel(model, device=torch.device("cpu"), plan=ShardingPlan({"model.sparse_arch.embedding_bag_collection": plan}),
+                                   sharders=[EmbeddingBagCollectionSharder()])
+    dense_opt = KeyedOptimizerWrapper(dict(in_backward_optimizer_filter(dmp.named_parameters())), lambda p: torch.optim.SGD(p, lr=0.1))
+    opt = CombinedOptimizer([dmp.fused_optimizer, dense_opt])
+    return dmp, opt, keys, hashes
+
+
+def _run(ctx, sharding: str, pipeline: str):
+    from torchrec_b200.datasets.random import RandomRecDataset
+    from torchrec_b200.parallel import train_pipeline as tp
+
+    dmp_a, opt_a, keys, hashes = _build(ctx, sharding)
+    dmp_b, opt_b, _, _ = _build(ctx, sharding)
+    dmp_b.load_state_dict(dmp_a.state_dict())
+    ds = RandomRecDataset(keys, 6, hash_sizes=hashes, ids_per_feature=3, min_ids_per_feature=0, num_dense=5, manual_seed=7 + ctx.rank,
+                          num_generated_batches=5, num_batches=5)
+    batches = list(iter(ds))
+    # plain loop
+    ref_losses = []
+    for b in batches:
+        opt_a.zero_grad()
+        loss, _ = dmp_a(b)
+        loss.backward()
+        opt_a.step()
+        ref_losses.append(loss.detach().clone())
+    cls = {"sparse": tp.TrainPipelineSparseDist, "base": tp.TrainPipelineBase, "lite": tp.TrainPipelineSparseDistLite,
+           "fused": tp.TrainPipelineFusedSparseDist, "prefetch": tp.PrefetchTrainPipelineSparseDist}[pipeline]
+    pipe = cls(dmp_b, opt_b, torch.device("cpu"))
+    it = iter(batches)
+    losses = []
+    while True:
+        try:
+            out = pipe.progress(it)
+        except StopIteration:
+            break
+        losses.append(out[0].clone())
+    assert len(losses) == len(ref_losses), (len(losses), len(ref_losses))
+    for a, b in zip(losses, ref_losses):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
+    sa, sb = dmp_a.state_dict(), dmp_b.state_dict()
+    for k in sa:
+        ta, tb = sa[k], sb[k]
+        if hasattr(ta, "local_shards"):
+            for x, y in zip(ta.local_shards(), tb.local_shards()):
+                torch.testing.assert_close(x.tensor, y.tensor, rtol=1e-5, atol=1e-6)
+        else:
+            torch.testing.assert_close(ta, tb, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("pipeline", ["sparse", "base", "lite", "fused", "prefetch"])
+def test_pipeline_matches_plain_loop_tw(pipeline):
+    run_multi_process(_run, world_size=2, backend="gloo", sharding="tw", pipeline=pipeline)
+
+
+def test_pipeline_matches_plain_loop_rw():
+    run_multi_process(_run, world_size=2, backend="gloo", sharding="rw", pipeline="sparse")

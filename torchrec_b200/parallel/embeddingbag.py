@@ -344,8 +344,11 @@ class ShardedEmbeddingBagCollection(
                 wview.copy_(src[shard.name][shard.row_off : shard.row_off + shard.rows, shard.col_off : shard.col_off + shard.cols])
             else:
                 if wview.numel() > 0:
-                    init = torch.empty(wview.shape, dtype=torch.float32, device=wview.device).uniform_(cfg.get_weight_init_min(), cfg.get_weight_init_max())
-                    wview.copy_(init)
+                    if wview.dtype == torch.float32:
+                        wview.uniform_(cfg.get_weight_init_min(), cfg.get_weight_init_max())
+                    else:
+                        init = torch.empty(wview.shape, dtype=torch.float32, device=wview.device).uniform_(cfg.get_weight_init_min(), cfg.get_weight_init_max())
+                        wview.copy_(init)
         if self._dp_tables:
             for ti, w in zip(self._dp_tables, self._dp_tbe.split_embedding_weights()):
                 cfg = self._embedding_bag_configs[ti]

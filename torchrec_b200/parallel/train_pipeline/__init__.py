@@ -1,0 +1,14 @@
+from .pipeline_context import EmbeddingTrainPipelineContext, PrefetchTrainPipelineContext, TrainPipelineContext  # noqa: F401
+from .train_pipelines import (  # noqa: F401
+    EvalPipelineSparseDist,
+    PipelinedForward,
+    PipelineStage,
+    PrefetchTrainPipelineSparseDist,
+    StagedTrainPipeline,
+    TrainPipeline,
+    TrainPipelineBase,
+    TrainPipelineFusedSparseDist,
+    TrainPipelineSemiSync,
+    TrainPipelineSparseDist,
+    TrainPipelineSparseDistLite,
+)
