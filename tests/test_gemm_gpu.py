@@ -1,0 +1,75 @@
+"""tcgen05 GEMM / fused Linear numerics vs fp32 PyTorch."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(a, b, bias, act):
+    y = a.float() @ b.float().t()
+    if bias is not None:
+        y = y + bias
+    if act == 1:
+        y = torch.relu(y)
+    elif act == 2:
+        y = torch.sigmoid(y)
+    return y
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 512), (1000, 512, 256), (4096, 1024, 480), (300, 64, 16), (128, 8, 1024), (4096, 128, 2048)])
+@pytest.mark.parametrize("act", [0, 1])
+def test_gemm_bf16_tn(M, N, K, act):
+    from torchrec_b200.ops.gemm import gemm_bf16_tn
+
+    torch.manual_seed(0)
+    dev = torch.device("cuda:0")
+    a = (torch.randn(M, K, device=dev) * 0.5).to(torch.bfloat16)
+    b = (torch.randn(N, K, device=dev) * 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device=dev)
+    out = gemm_bf16_tn(a, b, bias, act)
+    ref = _ref(a, b, bias, act)
+    torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=2e-1 if K > 512 else 6e-2)
+    out32 = gemm_bf16_tn(a, b, None, 0, out_dtype=torch.float32)
+    torch.testing.assert_close(out32, _ref(a, b, None, 0), rtol=1e-3, atol=1e-2)
+
+
+def test_gemm_split_k_and_mask():
+    from torchrec_b200.ops.gemm import ACT_RELU_GRAD, gemm_bf16_tn
+
+    dev = torch.device("cuda:0")
+    torch.manual_seed(1)
+    a = (torch.randn(256, 8192, device=dev) * 0.1).to(torch.bfloat16)
+    b = (torch.randn(128, 8192, device=dev) * 0.1).to(torch.bfloat16)
+    out = gemm_bf16_tn(a, b, out_dtype=torch.float32, split_k=16)
+    torch.testing.assert_close(out, a.float() @ b.float().t(), rtol=1e-3, atol=2e-2)
+    a2 = (torch.randn(512, 256, device=dev)).to(torch.bfloat16)
+    b2 = (torch.randn(128, 256, device=dev)).to(torch.bfloat16)
+    mask = torch.randn(512, 128, device=dev).to(torch.bfloat16)
+    o = gemm_bf16_tn(a2, b2, act=ACT_RELU_GRAD, mask=mask)
+    ref = (a2.float() @ b2.float().t()) * (mask.float() > 0)
+    torch.testing.assert_close(o.float(), ref, rtol=2e-2, atol=1e-1)
+
+
+def test_linear_act_autograd_matches_torch():
+    from torchrec_b200.ops import dense
+    from torchrec_b200.modules.mlp import MLP
+
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    ref = MLP(13, [64, 32, 16], device=dev)
+    mine = MLP(13, [64, 32, 16], device=dev)
+    mine.load_state_dict(ref.state_dict())
+    x = torch.randn(512, 13, device=dev)
+    yr = ref(x)
+    dense.set_dense_backend("tcgen05")
+    try:
+        ym = mine(x)
+    finally:
+        dense.set_dense_backend("torch")
+    torch.testing.assert_close(ym.float(), yr, rtol=5e-2, atol=5e-2)
+    g = torch.randn_like(yr)
+    yr.backward(g)
+    ym.backward(g.to(ym.dtype))
+    for (n, pr), (_, pm) in zip(ref.named_parameters(), mine.named_parameters()):
+        tol = 0.03 * float(pr.grad.abs().max()) + 1e-3
+        assert float((pm.grad - pr.grad).abs().max()) <= tol, (n, float((pm.grad - pr.grad).abs().max()), tol)

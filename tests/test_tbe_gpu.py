@@ -51,8 +51,8 @@ def test_fused_backward_matches_reference(opt, dim):
     fmap = [0, 1, 2, 2]
     B = 300  # many duplicates on the 3-row table -> runs spanning several 32-wide chunks
     torch.manual_seed(1)
-    cpu = T.TableBatchedEmbeddingBags(specs, fmap, optimizer=opt, learning_rate=0.05, weight_decay=0.01 if opt == T.OptimType.LAMB else 0.0)
-    gpu = T.TableBatchedEmbeddingBags(specs, fmap, optimizer=opt, learning_rate=0.05, weight_decay=0.01 if opt == T.OptimType.LAMB else 0.0, device=dev)
+    cpu = T.TableBatchedEmbeddingBags(specs, fmap, optimizer=opt, learning_rate=0.05, eps=1e-3, weight_decay=0.01 if opt == T.OptimType.LAMB else 0.0)
+    gpu = T.TableBatchedEmbeddingBags(specs, fmap, optimizer=opt, learning_rate=0.05, eps=1e-3, weight_decay=0.01 if opt == T.OptimType.LAMB else 0.0, device=dev)
     gpu.weights.data.copy_(cpu.weights.data)
     for step in range(2):
         idx, off, psw = _inputs(4, B, [50, 3, 400, 400], 4, dev, seed=step, hot=True)

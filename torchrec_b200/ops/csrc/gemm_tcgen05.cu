@@ -1,0 +1,483 @@
+// Hand-written sm_100a GEMM for the dense DLRM arch: C[M,N] = act(A[M,K] . B[N,K]^T + bias) with
+// bf16 operands staged by TMA (SWIZZLE_128B), tcgen05.mma (cta_group::1, M=128) accumulating in TMEM
+// and a fused epilogue (bias, ReLU / sigmoid, ReLU-gradient mask, bf16 or fp32 store).
+//
+// Structure (one persistent CTA per SM, 8 warps):
+//   warp 0      TMA producer      cp.async.bulk.tensor.2d -> smem ring (kStages x (A 128x64, B BNx64))
+//   warp 1      MMA issuer        one elected lane issues 4 x tcgen05.mma (UMMA_K=16) per k-block,
+//                                 tcgen05.commit frees the smem slot / publishes the accumulator
+//   warp 2      TMEM allocator    2 accumulator stages (2 x BLOCK_N fp32 columns)
+//   warps 4..7  epilogue          tcgen05.ld 32x32b (one TMEM lane == one output row per thread),
+//                                 bias + activation in registers, vectorised global stores
+// The accumulator is double buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Both operands are K-major (row-major [rows, K]), which is the natural layout of nn.Linear
+// (x [M,K], weight [N,K]); dgrad / wgrad are expressed with pre-transposed operands.
+// Replaces the reference's cuBLAS nn.Linear + separate bias/ReLU kernels (modules/mlp.py:18-190).
+#include "common.cuh"
+#include <cuda.h>
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int kNumThreads = 256;
+constexpr int kEpiWarp0 = 4;
+
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2, ACT_RELU_GRAD = 3 };
+
+struct GemmParams {
+  int M, N, K;
+  const float* bias;            // [N] or nullptr
+  const __nv_bfloat16* mask;    // ACT_RELU_GRAD: out *= (mask[m, n] > 0)
+  int64_t ld_mask;
+  void* out;
+  int64_t ldo;
+  int out_f32;                  // 1: fp32 output, 0: bf16
+  int act;
+  float alpha;                  // scale applied to the accumulator before bias
+  int split_k;                  // >1: K range split over CTAs, fp32 atomicAdd epilogue (out pre-zeroed)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  const uint32_t addr = smem_u32(bar);
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* smem, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// K-major, SWIZZLE_128B operand descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
+//   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major: 1) | [32,46) SBO>>4 = 1024 B (8 rows x 128 B)
+//   [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t) ((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t) 1 << 16;
+  d |= (uint64_t) (1024 >> 4) << 32;
+  d |= (uint64_t) 1 << 46;
+  d |= (uint64_t) 2 << 61;
+  return d;
+}
+
+// cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b_format BF16 (1) @7/@10, K-major both,
+// n_dim = N>>3 @17, m_dim = M>>4 @24
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t) (N >> 3) << 17) | ((uint32_t) (M >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BLOCK_N, int kStages>
+struct SmemLayout {
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
+  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kTotal = kBarOffset + (2 * kStages + 4) * 8 + 16;
+};
+
+template <int BLOCK_N, int kStages>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+  using L = SmemLayout<BLOCK_N, kStages>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // dynamic smem is only guaranteed 16 B aligned: round up to 1024 B for SWIZZLE_128B
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // power of two >= 32 for BLOCK_N in {64,128,256}
+
+  if (warp_idx == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int k_blocks_total = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int splits = p.split_k > 1 ? p.split_k : 1;
+  const int kb_per_split = (k_blocks_total + splits - 1) / splits;
+  const int mn_tiles = m_tiles * n_tiles;
+  const int num_tiles = mn_tiles * splits;
+
+  if (warp_idx == 0) {
+    // ================= TMA producer =================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mn = tile % mn_tiles, ks = tile / mn_tiles;
+        const int m_blk = mn / n_tiles, n_blk = mn % n_tiles;
+        const int kb0 = ks * kb_per_split, kb1 = min(k_blocks_total, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+          tma_load_2d(&tmap_a, &full_bar[stage], sa, kb * BLOCK_K, m_blk * BLOCK_M);
+          tma_load_2d(&tmap_b, &full_bar[stage], sb, kb * BLOCK_K, n_blk * BLOCK_N);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ================= MMA issuer =================
+    constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+    int stage = 0;
+    uint32_t phase = 0;
+    int accum_stage = 0;
+    uint32_t accum_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty_bar[accum_stage], accum_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + accum_stage * BLOCK_N;
+      const int ks = tile / mn_tiles;
+      const int kb0 = ks * kb_per_split, kb1 = min(k_blocks_total, kb0 + kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t b_addr = a_addr + L::kABytes;
+          const uint64_t adesc = make_kmajor_desc(a_addr);
+          const uint64_t bdesc = make_kmajor_desc(b_addr);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
+            umma_bf16(tmem_d, adesc + (uint64_t) (2 * k), bdesc + (uint64_t) (2 * k), idesc, ((kb - kb0) | k) != 0);
+          }
+        }
+        __syncwarp();
+        if (elect_one()) {
+          umma_commit(&empty_bar[stage]);                       // smem slot reusable once these MMAs retire
+          if (kb == kb1 - 1) umma_commit(&tmem_full_bar[accum_stage]);  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      if (++accum_stage == 2) { accum_stage = 0; accum_phase ^= 1; }
+    }
+  } else if (warp_idx >= kEpiWarp0) {
+    // ================= epilogue =================
+    const int ew = warp_idx - kEpiWarp0;  // == warp_idx % 4 -> TMEM lanes [32*ew, 32*ew+32)
+    int accum_stage = 0;
+    uint32_t accum_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mn = tile % mn_tiles;
+      const int m_blk = mn / n_tiles, n_blk = mn % n_tiles;
+      mbar_wait(&tmem_full_bar[accum_stage], accum_phase);
+      tc_fence_after();
+      const int row = m_blk * BLOCK_M + ew * 32 + lane;
+      const bool row_ok = row < p.M;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t) (ew * 32) << 16) + (uint32_t) (accum_stage * BLOCK_N + c * 32);
+        tmem_ld_32x32(taddr, r);
+        const int n0 = n_blk * BLOCK_N + c * 32;
+        if (n0 >= p.N) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (n0 + j < p.N) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          }
+        }
+        if (p.act == ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (p.act == ACT_SIGMOID) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
+        } else if (p.act == ACT_RELU_GRAD) {
+          if (row_ok) {
+            const __nv_bfloat16* mrow = p.mask + (int64_t) row * p.ld_mask + n0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (n0 + j < p.N) {
+                const uint4 m8 = *reinterpret_cast<const uint4*>(mrow + j);
+                const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&m8);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[j + q] = (__bfloat162float(mb[q]) > 0.f) ? v[j + q] : 0.f;
+              }
+            }
+          }
+        }
+        if (row_ok) {
+          if (splits > 1) {
+            float* orow = reinterpret_cast<float*>(p.out) + (int64_t) row * p.ldo + n0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) atomicAdd(orow + j, v[j]);
+          } else if (p.out_f32) {
+            float* orow = reinterpret_cast<float*>(p.out) + (int64_t) row * p.ldo + n0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (n0 + j < p.N) *reinterpret_cast<float4*>(orow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+            __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t) row * p.ldo + n0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (n0 + j < p.N) {
+                uint4 o;
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+                o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(orow + j) = o;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[accum_stage]);
+      if (++accum_stage == 2) { accum_stage = 0; accum_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// rows x K bf16 matrix, row pitch ld elements; box = [BLOCK_K, box_rows], SWIZZLE_128B
+int make_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return -10;
+  cuuint64_t dims[2] = {(cuuint64_t) K, (cuuint64_t) rows};
+  cuuint64_t strides[1] = {(cuuint64_t) ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t) BLOCK_K, (cuuint32_t) box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -11;
+}
+
+int g_num_sms = 0;
+
+template <int BLOCK_N, int kStages>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  using L = SmemLayout<BLOCK_N, kStages>;
+  constexpr int smem_bytes = L::kTotal + 1024;
+  static bool configured = false;
+  if (!configured) {
+    TRB_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BLOCK_N, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    configured = true;
+  }
+  if (g_num_sms == 0) {
+    int dev = 0;
+    TRB_CUDA(cudaGetDevice(&dev));
+    TRB_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N) * (p.split_k > 1 ? p.split_k : 1);
+  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  gemm_bf16_tcgen05_kernel<BLOCK_N, kStages><<<grid, kNumThreads, smem_bytes, stream>>>(ta, tb, p);
+  TRB_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace
+
+// C[M,N] = act(alpha * A[M,K] . B[N,K]^T + bias). A/B bf16 row-major with pitches lda/ldb (elements,
+// multiples of 8; K multiple of 8). out: bf16 or fp32 with pitch ldo.
+TRB_API int trb_gemm_bf16_tn(const void* A, int64_t lda, const void* B, int64_t ldb, void* out, int64_t ldo, int out_f32, int M, int N, int K,
+                             const float* bias, int act, const void* mask, int64_t ld_mask, float alpha, int split_k, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if ((K % 8) || (lda % 8) || (ldb % 8) || (N % 8)) return -12;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.bias = bias;
+  p.mask = reinterpret_cast<const __nv_bfloat16*>(mask);
+  p.ld_mask = ld_mask;
+  p.out = out;
+  p.ldo = ldo;
+  p.out_f32 = out_f32;
+  p.act = act;
+  p.alpha = alpha;
+  p.split_k = 1;
+  if (split_k > 1) {
+    if (!out_f32 || bias != nullptr || act != ACT_NONE) return -13;  // split-K only for plain fp32 accumulation
+    const int kb = (K + BLOCK_K - 1) / BLOCK_K;
+    int s = split_k < kb ? split_k : kb;
+    const int per = (kb + s - 1) / s;
+    s = (kb + per - 1) / per;  // no empty splits
+    p.split_k = s;
+    if (s > 1) TRB_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t) M * (size_t) ldo, stream));
+  }
+  CUtensorMap ta, tb;
+  int rc = make_tmap(&ta, A, M, K, lda, BLOCK_M);
+  if (rc) return rc;
+  if (N <= 64) {
+    rc = make_tmap(&tb, B, N, K, ldb, 64);
+    if (rc) return rc;
+    return launch_gemm<64, 6>(ta, tb, p, stream);
+  }
+  rc = make_tmap(&tb, B, N, K, ldb, 128);
+  if (rc) return rc;
+  return launch_gemm<128, 5>(ta, tb, p, stream);
+}
+
+// ---- helpers used around the GEMM ----------------------------------------------------------------------
+// bf16 transpose: out[c, r] = in[r, c]; 32x32 smem tiles, coalesced both ways.
+__global__ void __launch_bounds__(256) trb_transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int rows,
+                                                                   int cols, int64_t ld_in, int64_t ld_out) {
+  __shared__ __nv_bfloat16 tile[32][34];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int r = by + i, c = bx + tx;
+    tile[i][tx] = (r < rows && c < cols) ? in[(int64_t) r * ld_in + c] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = bx + i, r = by + tx;
+    if (c < cols && r < rows) out[(int64_t) c * ld_out + r] = tile[tx][i];
+  }
+}
+
+TRB_API int trb_transpose_bf16(const void* in, void* out, int rows, int cols, int64_t ld_in, int64_t ld_out, cudaStream_t stream) {
+  if (rows == 0 || cols == 0) return 0;
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+  trb_transpose_bf16_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*) in, (__nv_bfloat16*) out, rows, cols, ld_in, ld_out);
+  TRB_CHECK_LAUNCH();
+  return 0;
+}
+
+// column sums of a bf16 [rows, cols] matrix into fp32 (bias gradient)
+__global__ void __launch_bounds__(256) trb_colsum_bf16_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int rows, int cols,
+                                                                int64_t ld, int rows_per_block) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  float acc = 0.f;
+  if (c < cols)
+    for (int r = r0 + (threadIdx.x >> 5); r < r1; r += 8) acc += __bfloat162float(in[(int64_t) r * ld + c]);
+  __shared__ float red[8][33];
+  red[threadIdx.x >> 5][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32 && c < cols) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
+    atomicAdd(out + c, s);
+  }
+}
+
+TRB_API int trb_colsum_bf16(const void* in, float* out, int rows, int cols, int64_t ld, cudaStream_t stream) {
+  if (rows == 0 || cols == 0) return 0;
+  TRB_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, stream));
+  const int rows_per_block = 1024;
+  dim3 grid((cols + 31) / 32, (rows + rows_per_block - 1) / rows_per_block);
+  trb_colsum_bf16_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*) in, out, rows, cols, ld, rows_per_block);
+  TRB_CHECK_LAUNCH();
+  return 0;
+}

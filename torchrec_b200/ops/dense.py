@@ -60,7 +60,7 @@ def dot_interaction(dense: torch.Tensor, sparse: torch.Tensor) -> torch.Tensor:
     """DLRM pairwise dot interaction. dense [B, D], sparse [B, F, D] ->
     [B, D + (F+1)F/2] = cat(dense, strictly-lower-triangular(X X^T)) with X = [dense; sparse].
     Parity: models/dlrm.py:210-222."""
-    if _BACKEND == "tcgen05" and dense.is_cuda:
+    if _BACKEND == "tcgen05" and dense.is_cuda and _native_interaction():
         from .interaction import DotInteractionFn
 
         return DotInteractionFn.apply(dense, sparse)
@@ -68,6 +68,26 @@ def dot_interaction(dense: torch.Tensor, sparse: torch.Tensor) -> torch.Tensor:
     F = sparse.shape[1]
     combined = torch.cat((dense.unsqueeze(1), sparse.to(dense.dtype)), dim=1)
     inter = torch.bmm(combined, combined.transpose(1, 2))
-    ti = torch.triu_indices(F + 1, F + 1, offset=1, device=dense.device)
-    flat = inter[:, ti[0], ti[1]]
+    idx = _triu_flat_index(F + 1, dense.device)
+    flat = inter.reshape(B, (F + 1) * (F + 1)).index_select(1, idx)
     return torch.cat((dense, flat), dim=1)
+
+
+def _native_interaction() -> bool:
+    try:
+        from . import interaction  # noqa: F401
+
+        return True
+    except ImportError:
+        return False
+
+
+_TRIU_CACHE: dict = {}
+
+
+def _triu_flat_index(n: int, device: torch.device) -> torch.Tensor:
+    key = (n, str(device))
+    if key not in _TRIU_CACHE:
+        ti = torch.triu_indices(n, n, offset=1, device=device)
+        _TRIU_CACHE[key] = ti[0] * n + ti[1]
+    return _TRIU_CACHE[key]

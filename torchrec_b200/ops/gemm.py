@@ -1,0 +1,154 @@
+"""Python front-end of the hand-written tcgen05 GEMM (``csrc/gemm_tcgen05.cu``).
+
+``gemm_bf16_tn(a, b)`` computes ``act(alpha * a @ b.T + bias)`` with a ``[M, K]`` and b ``[N, K]``
+(both bf16, K-major). ``LinearActFn`` is the autograd op behind ``Perceptron``:
+
+    forward : y  = act(x W^T + b)                      one fused kernel (bias + ReLU in the epilogue)
+    dgrad   : dx = (dy ⊙ act') W   = gemm(dy', W^T)     ReLU mask fused in the *previous* layer's dgrad epilogue
+    wgrad   : dW = dy'^T x         = gemm(dy'^T, x^T)   operands transposed by a small tiled kernel, fp32 out
+    bgrad   : db = colsum(dy')
+
+Weights stay fp32 master copies (nn.Linear parameters); bf16 operand copies are made per call.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_RELU_GRAD = 0, 1, 2, 3
+
+
+def _check_bf16_2d(t: torch.Tensor, name: str) -> None:
+    assert t.is_cuda and t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1, f"{name}: need a row-major bf16 CUDA matrix"
+    assert t.stride(0) % 8 == 0 and t.shape[1] % 8 == 0, f"{name}: K and the row pitch must be multiples of 8 (16 B TMA alignment)"
+    assert t.data_ptr() % 16 == 0, f"{name}: base pointer must be 16 B aligned"
+
+
+def gemm_bf16_tn(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+                 out_dtype: torch.dtype = torch.bfloat16, mask: Optional[torch.Tensor] = None, alpha: float = 1.0,
+                 out: Optional[torch.Tensor] = None, split_k: int = 1) -> torch.Tensor:
+    """``act(alpha * a @ b.T + bias)``; ``mask`` (bf16 [M, N]) with ``ACT_RELU_GRAD`` zeroes outputs where mask <= 0."""
+    _check_bf16_2d(a, "a")
+    _check_bf16_2d(b, "b")
+    M, K = a.shape
+    N = b.shape[0]
+    assert b.shape[1] == K and N % 8 == 0
+    if out is None:
+        out = torch.empty(M, N, dtype=out_dtype, device=a.device)
+    assert out.stride(1) == 1 and out.dtype in (torch.bfloat16, torch.float32)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == N
+    if act == ACT_RELU_GRAD:
+        assert mask is not None and mask.dtype == torch.bfloat16 and mask.shape == (M, N) and mask.stride(1) == 1 and mask.stride(0) % 8 == 0
+    L = _lib.lib()
+    code = L.trb_gemm_bf16_tn(
+        _lib.ptr(a), ctypes.c_int64(a.stride(0)), _lib.ptr(b), ctypes.c_int64(b.stride(0)), _lib.ptr(out), ctypes.c_int64(out.stride(0)),
+        1 if out.dtype == torch.float32 else 0, M, N, K, _lib.ptr(bias), act, _lib.ptr(mask),
+        ctypes.c_int64(mask.stride(0) if mask is not None else 0), ctypes.c_float(alpha), int(split_k), _lib.stream_ptr(a.device),
+    )
+    _lib.check(code, "trb_gemm_bf16_tn")
+    return out
+
+
+def transpose_bf16(x: torch.Tensor, pad_cols_to: int = 8) -> torch.Tensor:
+    """``x [R, C]`` -> ``[C, R_pad]`` bf16 with the row pitch padded to a multiple of 8 (zero filled)."""
+    assert x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
+    R, C = x.shape
+    Rp = (R + pad_cols_to - 1) // pad_cols_to * pad_cols_to
+    out = torch.zeros(C, Rp, dtype=torch.bfloat16, device=x.device) if Rp != R else torch.empty(C, R, dtype=torch.bfloat16, device=x.device)
+    L = _lib.lib()
+    code = L.trb_transpose_bf16(_lib.ptr(x), _lib.ptr(out), R, C, ctypes.c_int64(x.stride(0)), ctypes.c_int64(out.stride(0)), _lib.stream_ptr(x.device))
+    _lib.check(code, "trb_transpose_bf16")
+    return out
+
+
+def colsum_bf16(x: torch.Tensor) -> torch.Tensor:
+    assert x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
+    out = torch.empty(x.shape[1], dtype=torch.float32, device=x.device)
+    L = _lib.lib()
+    code = L.trb_colsum_bf16(_lib.ptr(x), _lib.ptr(out), x.shape[0], x.shape[1], ctypes.c_int64(x.stride(0)), _lib.stream_ptr(x.device))
+    _lib.check(code, "trb_colsum_bf16")
+    return out
+
+
+_SMS = {}
+
+
+def _num_sms(device: torch.device) -> int:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _SMS:
+        _SMS[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    return _SMS[idx]
+
+
+def _pad_k(t: torch.Tensor, Kp: int) -> torch.Tensor:
+    if t.shape[1] == Kp:
+        return t
+    return torch.nn.functional.pad(t, (0, Kp - t.shape[1]))
+
+
+class LinearActFn(torch.autograd.Function):
+    """``act(x @ W^T + b)`` on the tcgen05 kernel; bf16 activations, fp32 master weights."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], act: int) -> torch.Tensor:
+        N, K = weight.shape
+        Kp = (K + 7) // 8 * 8
+        xb = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
+        xb = _pad_k(xb, Kp)
+        if xb.stride(1) != 1 or xb.stride(0) % 8 != 0:
+            xb = xb.contiguous()
+        wb = _pad_k(weight.detach().to(torch.bfloat16), Kp)
+        y = gemm_bf16_tn(xb, wb, bias.detach() if bias is not None else None, act)
+        # If this layer's input is the ReLU output of the previous fused layer, the ReLU gradient mask
+        # of that layer is applied in *this* layer's dgrad epilogue (mask = saved input > 0).
+        ctx.mask_input = bool(getattr(x, "_trb_relu_out", False)) and xb is x
+        if act == ACT_RELU:
+            y._trb_relu_out = True  # python attribute travels with the tensor object to the next layer
+        ctx.act = act
+        ctx.K = K
+        ctx.has_bias = bias is not None
+        ctx.x_dtype = x.dtype
+        ctx.save_for_backward(xb, wb, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy: torch.Tensor):
+        xb, wb, y = ctx.saved_tensors
+        act = ctx.act
+        already_masked = bool(getattr(gy, "_trb_masked", False))
+        gy = gy if gy.dtype == torch.bfloat16 else gy.to(torch.bfloat16)
+        if gy.stride(1) != 1 or gy.stride(0) % 8 != 0:
+            gy = gy.contiguous()
+        if act == ACT_RELU:
+            if not already_masked:
+                gy = torch.where(y > 0, gy, torch.zeros_like(gy))
+        elif act == ACT_SIGMOID:
+            yf = y.float()
+            gy = (gy.float() * yf * (1.0 - yf)).to(torch.bfloat16)
+        M = gy.shape[0]
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            wt = transpose_bf16(wb)  # [Kp, N]
+            if ctx.mask_input and xb.shape[1] == ctx.K:
+                gx = gemm_bf16_tn(gy, wt, act=ACT_RELU_GRAD, mask=xb)
+                gx._trb_masked = True
+            else:
+                gx = gemm_bf16_tn(gy, wt)[:, : ctx.K]
+            if ctx.x_dtype != torch.bfloat16:
+                gx = gx.to(ctx.x_dtype)
+        if ctx.needs_input_grad[1]:
+            gyt = transpose_bf16(gy)  # [N, M]
+            xt = transpose_bf16(xb)  # [Kp, M]
+            tiles = ((gyt.shape[0] + 127) // 128) * ((xt.shape[0] + 127) // 128)
+            split = max(1, min(32, (2 * _num_sms(gy.device) + tiles - 1) // tiles))
+            gw = gemm_bf16_tn(gyt, xt, out_dtype=torch.float32, split_k=split)[:, : ctx.K]
+            if gw.stride(1) != 1 or gw.shape[1] != gw.stride(0):
+                gw = gw.contiguous()
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = colsum_bf16(gy)
+        return gx, gw, gb, None
