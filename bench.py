@@ -159,7 +159,9 @@ def build_ours(args: argparse.Namespace, device, rank: int, world: int):
         backend = os.environ.get("TRB_DENSE_DEFAULT", "torch")
     _dense.set_dense_backend(backend)
 
-    sharder = EmbeddingBagCollectionSharder()
+    # bf16 pooled embeddings (half the NVLink / HBM bytes) when the dense arch computes in bf16
+    fused_params = {"output_dtype": torch.bfloat16} if backend == "tcgen05" else None
+    sharder = EmbeddingBagCollectionSharder(fused_params=fused_params)
     if args.sharding == "planner":
         plan = None
     else:

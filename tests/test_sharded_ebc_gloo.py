@@ -49,8 +49,9 @@ def _run(ctx, sharding: str, weighted: bool):
     set_gradient_division(False)
     torch.manual_seed(0)
     W, B = ctx.world_size, 6
-    gold = EmbeddingBagCollection(_tables(weighted), is_weighted=weighted)
-    local = EmbeddingBagCollection(_tables(weighted), is_weighted=weighted)
+    dev = ctx.device
+    gold = EmbeddingBagCollection(_tables(weighted), is_weighted=weighted, device=dev)
+    local = EmbeddingBagCollection(_tables(weighted), is_weighted=weighted, device=dev)
     local.load_state_dict(gold.state_dict())
     # row-wise adagrad over column shards normalises per shard (as in the reference), so the
     # column-sharded configurations are checked with SGD
@@ -66,7 +67,7 @@ def _run(ctx, sharding: str, weighted: bool):
         "mixed": {"t0": sp.row_wise(), "t1": sp.column_wise(ranks=[0, 1]), "t2": sp.row_wise(), "t3": sp.data_parallel()},
         "twrw": {"t0": sp.table_row_wise(host_index=0), "t1": sp.table_row_wise(host_index=0), "t2": sp.table_wise(rank=1), "t3": sp.grid_shard(host_indexes=[0])},
     }[sharding]
-    plan = sp.construct_module_sharding_plan(local, gens, sharder=EmbeddingBagCollectionSharder(), world_size=W, local_size=W, device_type="cpu")
+    plan = sp.construct_module_sharding_plan(local, gens, sharder=EmbeddingBagCollectionSharder(), world_size=W, local_size=W, device_type=dev.type)
 
     class Wrap(torch.nn.Module):
         def __init__(self, ebc):
@@ -76,18 +77,18 @@ def _run(ctx, sharding: str, weighted: bool):
         def forward(self, kjt):
             return self.ebc(kjt).values()
 
-    model = DistributedModelParallel(Wrap(local), device=torch.device("cpu"), plan=ShardingPlan({"ebc": plan}),
+    model = DistributedModelParallel(Wrap(local), device=dev, plan=ShardingPlan({"ebc": plan}),
                                      sharders=[EmbeddingBagCollectionSharder()])
     dense_params = [p for n, p in model.named_parameters() if p.requires_grad]
     dense_opt = torch.optim.SGD(dense_params, lr=0.1) if dense_params else None
     gold_opt = torch.optim.SGD(gold.parameters(), lr=0.1) if use_sgd else RowWiseAdagrad(gold.parameters(), lr=0.1, eps=1e-8)
     for step in range(2):
-        batches = [_make_batch(r + 10 * step, B, weighted) for r in range(W)]
+        batches = [_make_batch(r + 10 * step, B, weighted).to(dev) for r in range(W)]
         out = model(batches[ctx.rank])
         # golden on the global batch
         gouts = [gold(b).values() for b in batches]
-        torch.testing.assert_close(out, gouts[ctx.rank], rtol=1e-5, atol=1e-5)
-        proj = torch.linspace(0.5, 1.5, out.shape[1])
+        torch.testing.assert_close(out.float(), gouts[ctx.rank], rtol=1e-5, atol=1e-5)
+        proj = torch.linspace(0.5, 1.5, out.shape[1], device=dev)
         (out * proj).sum().backward()
         if dense_opt is not None:
             # DDP averages dense grads over ranks; the golden sums the per-rank losses -> scale

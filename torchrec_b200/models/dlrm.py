@@ -129,7 +129,11 @@ class OverArch(nn.Module):
         )
 
     def forward(self, features: torch.Tensor) -> torch.Tensor:
-        return self.model(features)
+        hidden = self.model[0](features)
+        last = self.model[1]
+        if hidden.dtype != last.weight.dtype:  # bf16 activations from the fused kernels -> fp32 logits
+            hidden = hidden.to(last.weight.dtype)
+        return last(hidden)
 
 
 class DLRM(nn.Module):

@@ -37,6 +37,10 @@ class Perceptron(nn.Module):
         fused = _dense.fused_act_code(act)
         if fused is not None and _dense.can_fuse(input, self._linear):
             return _dense.linear_act(input, self._linear.weight, self._linear.bias, fused)
+        if input.shape[-1] != self._in_size:  # producer emitted zero-padded columns (see ops.interaction)
+            input = input[..., : self._in_size]
+        if input.dtype != self._linear.weight.dtype and input.is_floating_point():
+            input = input.to(self._linear.weight.dtype)
         return act(self._linear(input))
 
 

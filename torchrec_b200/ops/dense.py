@@ -47,7 +47,8 @@ def can_fuse(x: torch.Tensor, linear: nn.Linear) -> bool:
     if _BACKEND != "tcgen05" or not x.is_cuda or x.dim() != 2:
         return False
     # TMA needs 16-byte aligned row pitches: K and N multiples of 8 bf16 elements
-    return linear.in_features % 8 == 0 and linear.out_features % 8 == 0
+    # N must be a multiple of 8 (16-byte TMA rows of the transposed operands); K is zero-padded to 8
+    return linear.out_features % 8 == 0
 
 
 def linear_act(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], act: int) -> torch.Tensor:
@@ -60,10 +61,11 @@ def dot_interaction(dense: torch.Tensor, sparse: torch.Tensor) -> torch.Tensor:
     """DLRM pairwise dot interaction. dense [B, D], sparse [B, F, D] ->
     [B, D + (F+1)F/2] = cat(dense, strictly-lower-triangular(X X^T)) with X = [dense; sparse].
     Parity: models/dlrm.py:210-222."""
-    if _BACKEND == "tcgen05" and dense.is_cuda and _native_interaction():
-        from .interaction import DotInteractionFn
+    if _BACKEND == "tcgen05" and dense.is_cuda:
+        from . import interaction as _inter
 
-        return DotInteractionFn.apply(dense, sparse)
+        if _inter.supported(dense, sparse):
+            return _inter.DotInteractionFn.apply(dense, sparse)
     B, D = dense.shape
     F = sparse.shape[1]
     combined = torch.cat((dense.unsqueeze(1), sparse.to(dense.dtype)), dim=1)
@@ -71,15 +73,6 @@ def dot_interaction(dense: torch.Tensor, sparse: torch.Tensor) -> torch.Tensor:
     idx = _triu_flat_index(F + 1, dense.device)
     flat = inter.reshape(B, (F + 1) * (F + 1)).index_select(1, idx)
     return torch.cat((dense, flat), dim=1)
-
-
-def _native_interaction() -> bool:
-    try:
-        from . import interaction  # noqa: F401
-
-        return True
-    except ImportError:
-        return False
 
 
 _TRIU_CACHE: dict = {}

@@ -99,6 +99,7 @@ class LinearActFn(torch.autograd.Function):
         N, K = weight.shape
         Kp = (K + 7) // 8 * 8
         xb = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
+        pre_padded = xb.shape[1] == Kp and Kp != K  # producer already emitted the zero K-padding
         xb = _pad_k(xb, Kp)
         if xb.stride(1) != 1 or xb.stride(0) % 8 != 0:
             xb = xb.contiguous()
@@ -113,6 +114,7 @@ class LinearActFn(torch.autograd.Function):
         ctx.K = K
         ctx.has_bias = bias is not None
         ctx.x_dtype = x.dtype
+        ctx.pre_padded = pre_padded
         ctx.save_for_backward(xb, wb, y)
         return y
 
@@ -138,7 +140,9 @@ class LinearActFn(torch.autograd.Function):
                 gx = gemm_bf16_tn(gy, wt, act=ACT_RELU_GRAD, mask=xb)
                 gx._trb_masked = True
             else:
-                gx = gemm_bf16_tn(gy, wt)[:, : ctx.K]
+                gx = gemm_bf16_tn(gy, wt)
+                if not ctx.pre_padded:
+                    gx = gx[:, : ctx.K]
             if ctx.x_dtype != torch.bfloat16:
                 gx = gx.to(ctx.x_dtype)
         if ctx.needs_input_grad[1]:

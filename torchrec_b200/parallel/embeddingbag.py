@@ -501,7 +501,34 @@ class ShardedEmbeddingBagCollection(
         return EmbeddingBagCollectionAwaitable(finish)
 
     def compute_and_output_dist(self, ctx: EmbeddingBagCollectionContext, input: KJTList) -> LazyAwaitable[KeyedTensor]:
+        eng = self._engine
+        if eng is not None and len(input) > 0:
+            kjt = input[0]
+            spr = kjt._stride_per_rank
+            if eng.fused_available(spr):
+                return self._fused_compute_and_output_dist(ctx, kjt)
         return self.output_dist(ctx, self.compute(ctx, input))
+
+    def _fused_compute_and_output_dist(self, ctx: EmbeddingBagCollectionContext, kjt: KeyedJaggedTensor) -> LazyAwaitable[KeyedTensor]:
+        """Single-NVLink-domain fast path: lookup fused with the pooled output dist (see engine.py)."""
+        from .comm_ops import get_gradient_division
+
+        eng = self._engine
+        W = self._env.world_size
+        B_local = kjt.stride() // W
+        scale = 1.0 / W if get_gradient_division() else 1.0
+        vals = eng.fused_lookup_dist(kjt, B_local, self._total_cols, scale)
+        if self._dp_lookup is not None:
+            f = ctx.dp_features
+            psw = f.weights_or_none() if self._is_weighted else None
+            dp_out = self._dp_lookup(f.values(), f.offsets(), psw, f.stride())
+            if not hasattr(self, "_dp_cols_t") or self._dp_cols_t.device != vals.device:
+                self._dp_cols_t = torch.tensor(self._dp_cols, dtype=torch.int64, device=vals.device)
+            vals = vals.index_copy(1, self._dp_cols_t, dp_out.to(vals.dtype))
+        if ctx.mean_divisor is not None:
+            vals = vals * ctx.mean_divisor.to(vals.dtype)
+        kt = KeyedTensor(keys=self._embedding_names, length_per_key=self._embedding_dims, values=vals, key_dim=1)
+        return EmbeddingBagCollectionAwaitable(lambda: kt)
 
     # ---- parameters / state ------------------------------------------------------------------------------------
     def named_parameters(self, prefix: str = "", recurse: bool = True, remove_duplicate: bool = True) -> Iterator[Tuple[str, nn.Parameter]]:

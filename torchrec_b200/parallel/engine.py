@@ -173,13 +173,19 @@ class ShardedLookupEngine(nn.Module):
         self._units: List[Unit] = []
         self._units_per_rank: List[int] = []
         self._dim_sum_per_rank: List[int] = []
+        self._table_row_sharded: Dict[int, bool] = {
+            ti: len({(s.row_off, s.rows) for s in self._table_shards[ti]}) > 1 for ti in self._mp_tables
+        }
+        # inside a group, tables that need no cross-rank reduction come first (lets the fused NVLink
+        # path cover them with one launch writing straight into the destination output)
+        ordered_tables = sorted(self._mp_tables, key=lambda ti: (self._table_row_sharded[ti], ti))
         for r in range(self._W):
             n0 = len(self._units)
             dsum = 0
             for gi, g in enumerate(self._groups):
                 u0 = len(self._units) - n0
                 c0 = dsum
-                for ti in self._mp_tables:
+                for ti in ordered_tables:
                     for s in self._table_shards[ti]:
                         if s.rank != r or s.group != gi:
                             continue
@@ -226,6 +232,8 @@ class ShardedLookupEngine(nn.Module):
         self._build_combine()
 
         # ---- portable transport modules ---------------------------------------------------------------
+        self._p2p: Optional["_P2PState"] = None
+        self._p2p_checked = False
         self._kjt_a2a: Optional[KJTAllToAll] = None
         self._pooled_a2a: Optional[PooledEmbeddingsAllToAll] = None
         self._seq_a2a: Optional[SequenceEmbeddingsAllToAll] = None
@@ -452,3 +460,171 @@ class ShardedLookupEngine(nn.Module):
             for s in g.local_shards:
                 res.append((s, ws[s.local_idx], sts[s.local_idx], g.tbe))
         return res
+
+
+    # ---- fused NVLink path (single NVLink domain) -----------------------------------------------------------------
+    def fused_available(self, batch_size_per_rank: Optional[List[int]]) -> bool:
+        """The fused lookup + output-dist kernels can serve this batch (CUDA, one host, even batch)."""
+        if not self._pooled or not self._has_mp or self._device.type != "cuda" or self._W < 2:
+            return False
+        if batch_size_per_rank is not None and len(set(batch_size_per_rank)) != 1:
+            return False
+        if not self._p2p_checked:
+            from .p2p import PeerGroup
+
+            self._p2p_ok = PeerGroup.supported(self._pg, self._device)
+            self._p2p_checked = True
+        return self._p2p_ok
+
+    def _ensure_p2p(self, B_local: int, total_cols: int) -> "_P2PState":
+        st = self._p2p
+        if st is not None and st.B_local == B_local and st.total_cols == total_cols:
+            return st
+        self._p2p = _P2PState(self, B_local, total_cols)
+        return self._p2p
+
+    def fused_lookup_dist(self, dist_features: KeyedJaggedTensor, B_local: int, total_cols: int, grad_scale: float) -> torch.Tensor:
+        """Lookup + pooled output dist in one pass: pooled rows are written straight into the owning
+        rank's ``[B_local, total_cols]`` output over NVLink (row-sharded tables via staging slabs
+        reduced at the destination). Returns the local output (final column layout)."""
+        st = self._ensure_p2p(B_local, total_cols)
+        anchor = None
+        for g in self._groups:
+            if g.tbe is not None:
+                anchor = g.tbe._dummy
+                break
+        if anchor is None:
+            anchor = st.dummy
+        weights = dist_features.weights_or_none() if self._is_weighted else None
+        return _FusedLookupDistFn.apply(anchor, self, st, dist_features.values(), dist_features.offsets(), weights, dist_features.stride(), grad_scale)
+
+
+class _P2PState:
+    """Symmetric buffers and per-group descriptor tables of the fused path."""
+
+    N_SLOTS = 2
+
+    def __init__(self, eng: ShardedLookupEngine, B_local: int, total_cols: int) -> None:
+        from ..ops.tbe import TbeMeta
+        from .p2p import PeerGroup
+
+        self.B_local = B_local
+        self.total_cols = total_cols
+        self.pg = PeerGroup.get(eng._pg, eng._device)
+        W = eng._W
+        self.wire_dtype = eng._output_dtype
+        esz = torch.empty(0, dtype=self.wire_dtype).element_size()
+        self.slab_bytes = B_local * total_cols * esz
+        self.has_staged = any(eng._table_row_sharded.values())
+        nbytes = self.slab_bytes * (self.N_SLOTS + 1 + (W if self.has_staged else 0))
+        self.buf = self.pg.alloc(nbytes)
+        self.out_off = [i * self.slab_bytes for i in range(self.N_SLOTS)]
+        self.grad_off = self.N_SLOTS * self.slab_bytes
+        self.staging_off = (self.N_SLOTS + 1) * self.slab_bytes
+        self.step = 0
+        self.dummy = torch.zeros(1, device=eng._device, requires_grad=True)
+        dims = [eng._tables[ti].embedding_dim for ti in eng._feature_table]
+        out_base = list(itertools.accumulate([0] + dims))
+        # per group: (direct window, staged window) of local units + metas
+        self.group_meta: List[Optional[Dict[str, Any]]] = []
+        col_mask = [0] * total_cols
+        for u in eng._units:
+            if eng._table_row_sharded[u.shard.table_idx]:
+                base = out_base[u.feature] + u.shard.col_off
+                for c in range(base, base + u.shard.cols):
+                    col_mask[c] |= 1 << u.shard.rank
+        self.col_mask = torch.tensor(col_mask, dtype=torch.int64, device=eng._device).to(torch.int32)
+        for g in eng._groups:
+            if g.tbe is None:
+                self.group_meta.append(None)
+                continue
+            u0, u1 = g.unit_range
+            units = eng._local_units[u0:u1]
+            cols = [out_base[u.feature] + u.shard.col_off for u in units]
+            staged = [eng._table_row_sharded[u.shard.table_idx] for u in units]
+            n_direct = staged.index(True) if True in staged else len(units)
+            assert all(staged[n_direct:]), "row-sharded units must follow direct units inside a group"
+            full = g.tbe.meta.with_cols(cols, total_cols)
+            self.group_meta.append({"full": full, "n_direct": n_direct, "n": len(units),
+                                    "direct": _slice_meta(full, 0, n_direct), "staged": _slice_meta(full, n_direct, len(units))})
+
+    def out_local(self, slot: int) -> torch.Tensor:
+        return self.buf.local(self.wire_dtype, (self.B_local, self.total_cols), self.out_off[slot])
+
+    def grad_local(self) -> torch.Tensor:
+        return self.buf.local(self.wire_dtype, (self.B_local, self.total_cols), self.grad_off)
+
+    def staging_local(self, W: int) -> torch.Tensor:
+        return self.buf.local(self.wire_dtype, (W, self.B_local, self.total_cols), self.staging_off)
+
+
+def _slice_meta(m, a: int, b: int):
+    from ..ops.tbe import TbeMeta
+
+    if b <= a:
+        return None
+    return TbeMeta(m.feat_woff[a:b].contiguous(), m.feat_rows[a:b].contiguous(), m.feat_rowbase[a:b].contiguous(), m.feat_dim[a:b].contiguous(),
+                   m.feat_col[a:b].contiguous(), m.h_woff[a:b], m.h_rows[a:b], m.h_rowbase[a:b], m.h_dim[a:b], m.h_col[a:b],
+                   max(m.h_dim[a:b]), m.total_rows, m.total_cols, b - a)
+
+
+class _FusedLookupDistFn(torch.autograd.Function):
+    """Forward: table-batched lookup writing pooled rows into the destination ranks' outputs over
+    NVLink + device barrier (+ staging reduce). Backward: stage the local gradient in the symmetric
+    buffer, barrier, fused backward+optimizer kernels pulling gradient rows from the peers."""
+
+    @staticmethod
+    def forward(ctx, anchor, eng: ShardedLookupEngine, st: _P2PState, values, offsets, weights, Bg: int, grad_scale: float):
+        from ..ops import tbe as T
+        from . import p2p
+
+        W = eng._W
+        slot = st.step % st.N_SLOTS
+        st.step += 1
+        out_ptrs = st.buf.peer_ptrs(st.out_off[slot])
+        esz = torch.empty(0, dtype=st.wire_dtype).element_size()
+        stage_ptrs = [p + st.staging_off + eng._rank * st.slab_bytes for p in st.buf.ptrs]
+        for g, gm in zip(eng._groups, st.group_meta):
+            if gm is None:
+                continue
+            u0, _ = g.unit_range
+            mean = g.pooling == T.PoolingMode.MEAN
+            if gm["direct"] is not None:
+                window = offsets[u0 * Bg : (u0 + gm["n_direct"]) * Bg + 1]
+                T.pooled_forward(gm["direct"], g.tbe.weights, values, window, weights, Bg, mean, st.wire_dtype,
+                                 out_ptrs=out_ptrs, out_stride=st.total_cols, B_local=st.B_local)
+            if gm["staged"] is not None:
+                window = offsets[(u0 + gm["n_direct"]) * Bg : (u0 + gm["n"]) * Bg + 1]
+                T.pooled_forward(gm["staged"], g.tbe.weights, values, window, weights, Bg, False, st.wire_dtype,
+                                 out_ptrs=stage_ptrs, out_stride=st.total_cols, B_local=st.B_local)
+        st.pg.barrier()
+        out = st.out_local(slot)
+        if st.has_staged:
+            p2p.staging_reduce(st.staging_local(W), out, st.col_mask, W)
+        ctx.eng, ctx.st, ctx.Bg, ctx.grad_scale = eng, st, Bg, grad_scale
+        ctx.save_for_backward(values, offsets, weights)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        from ..ops import tbe as T
+        from . import p2p
+
+        eng, st, Bg = ctx.eng, ctx.st, ctx.Bg
+        values, offsets, weights = ctx.saved_tensors
+        gbuf = st.grad_local()
+        if grad.stride(1) != 1:
+            grad = grad.contiguous()
+        p2p.cast_copy(grad, gbuf, ctx.grad_scale)
+        st.pg.barrier()
+        grad_ptrs = st.buf.peer_ptrs(st.grad_off)
+        for g, gm in zip(eng._groups, st.group_meta):
+            if gm is None:
+                continue
+            u0, u1 = g.unit_range
+            window = offsets[u0 * Bg : u1 * Bg + 1]
+            g.tbe._pre_update()
+            T.fused_backward(gm["full"], g.tbe.weights, g.tbe.state1, g.tbe.state2, g.tbe.hyper_dev, g.tbe.hyper_host, g.tbe.opt_code,
+                             int(g.tbe.weight_decay_mode), values, window, weights, Bg, g.pooling == T.PoolingMode.MEAN,
+                             grad_ptrs=grad_ptrs, grad_stride=st.total_cols, grad_dtype=st.wire_dtype, B_local=st.B_local)
+        return torch.zeros(1, dtype=torch.float32, device=grad.device), None, None, None, None, None, None, None
