@@ -50,7 +50,7 @@ struct SmemLayout {
   static constexpr int kTotal = kBarOffset + (2 * kStages + 4) * 8 + 16;
 };
 
-template <int BLOCK_N, int kStages>
+template <int BLOCK_N, int kStages, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
   using L = SmemLayout<BLOCK_N, kStages>;
@@ -113,15 +113,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           uint8_t* sa = smem + stage * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
           mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
-          tma_load_2d(&tmap_a, &full_bar[stage], sa, kb * BLOCK_K, m_blk * BLOCK_M);
-          tma_load_2d(&tmap_b, &full_bar[stage], sb, kb * BLOCK_K, n_blk * BLOCK_N);
+          if constexpr (A_MN) {
+            // MN-major operand: the matrix is [reduction rows, MN cols]; one 64-column atom ([64 rows x 128 B]) per load
+#pragma unroll
+            for (int h = 0; h < BLOCK_M / 64; ++h) tma_load_2d(&tmap_a, &full_bar[stage], sa + h * 8192, m_blk * BLOCK_M + 64 * h, kb * BLOCK_K);
+          } else {
+            tma_load_2d(&tmap_a, &full_bar[stage], sa, kb * BLOCK_K, m_blk * BLOCK_M);
+          }
+          if constexpr (B_MN) {
+#pragma unroll
+            for (int h = 0; h < BLOCK_N / 64; ++h) tma_load_2d(&tmap_b, &full_bar[stage], sb + h * 8192, n_blk * BLOCK_N + 64 * h, kb * BLOCK_K);
+          } else {
+            tma_load_2d(&tmap_b, &full_bar[stage], sb, kb * BLOCK_K, n_blk * BLOCK_N);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp_idx == 1) {
     // ================= MMA issuer =================
-    constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+    constexpr uint32_t idesc = make_idesc_major(BLOCK_M, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
     int stage = 0;
     uint32_t phase = 0;
     int accum_stage = 0;
@@ -143,7 +154,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
-            umma_bf16(tmem_d, adesc + (uint64_t) (2 * k), bdesc + (uint64_t) (2 * k), idesc, ((kb - kb0) | k) != 0);
+            // K-major: +32 B inside the 128 B swizzle row; MN-major: 16 reduction rows x 128 B = 2048 B
+            const uint64_t ad = A_MN ? make_mnmajor_desc(a_addr + k * 2048, 8192, 1024) : adesc + (uint64_t) (2 * k);
+            const uint64_t bd = B_MN ? make_mnmajor_desc(b_addr + k * 2048, 8192, 1024) : bdesc + (uint64_t) (2 * k);
+            umma_bf16(tmem_d, ad, bd, idesc, ((kb - kb0) | k) != 0);
           }
         }
         __syncwarp();
@@ -263,12 +277,12 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // rows x K bf16 matrix, row pitch ld elements; box = [BLOCK_K, box_rows], SWIZZLE_128B
-int make_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+int make_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int64_t ld, int box_rows, int box_cols = BLOCK_K) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return -10;
   cuuint64_t dims[2] = {(cuuint64_t) K, (cuuint64_t) rows};
   cuuint64_t strides[1] = {(cuuint64_t) ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t) BLOCK_K, (cuuint32_t) box_rows};
+  cuuint32_t box[2] = {(cuuint32_t) box_cols, (cuuint32_t) box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -277,13 +291,13 @@ int make_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int64_
 
 int g_num_sms = 0;
 
-template <int BLOCK_N, int kStages>
+template <int BLOCK_N, int kStages, bool A_MN, bool B_MN>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   using L = SmemLayout<BLOCK_N, kStages>;
   constexpr int smem_bytes = L::kTotal + 1024;
   static bool configured = false;
   if (!configured) {
-    TRB_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BLOCK_N, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    TRB_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BLOCK_N, kStages, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured = true;
   }
   if (g_num_sms == 0) {
@@ -293,19 +307,38 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& 
   }
   const int tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N) * (p.split_k > 1 ? p.split_k : 1);
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  gemm_bf16_tcgen05_kernel<BLOCK_N, kStages><<<grid, kNumThreads, smem_bytes, stream>>>(ta, tb, p);
+  gemm_bf16_tcgen05_kernel<BLOCK_N, kStages, A_MN, B_MN><<<grid, kNumThreads, smem_bytes, stream>>>(ta, tb, p);
   TRB_CHECK_LAUNCH();
   return 0;
 }
 
 }  // namespace
 
-// C[M,N] = act(alpha * A[M,K] . B[N,K]^T + bias). A/B bf16 row-major with pitches lda/ldb (elements,
-// multiples of 8; K multiple of 8). out: bf16 or fp32 with pitch ldo.
-TRB_API int trb_gemm_bf16_tn(const void* A, int64_t lda, const void* B, int64_t ldb, void* out, int64_t ldo, int out_f32, int M, int N, int K,
-                             const float* bias, int act, const void* mask, int64_t ld_mask, float alpha, int split_k, cudaStream_t stream) {
+// C[M,N] = act(alpha * op(A) . op(B)^T + bias), bf16 operands, fp32 accumulation.
+//   a_mn == 0: A is [M, K] row-major (K-major operand)      a_mn == 1: A is [K, M] row-major (MN-major operand)
+//   b_mn == 0: B is [N, K] row-major                        b_mn == 1: B is [K, N] row-major
+// Pitches lda/ldb in elements (multiples of 8). out: bf16 or fp32 with pitch ldo.
+template <bool A_MN, bool B_MN>
+static int gemm_dispatch(const void* A, int64_t lda, const void* B, int64_t ldb, GemmParams& p, cudaStream_t stream) {
+  CUtensorMap ta, tb;
+  int rc = A_MN ? make_tmap(&ta, A, p.K, p.M, lda, 64, 64) : make_tmap(&ta, A, p.M, p.K, lda, BLOCK_M);
+  if (rc) return rc;
+  if (p.N <= 64) {
+    rc = B_MN ? make_tmap(&tb, B, p.K, p.N, ldb, 64, 64) : make_tmap(&tb, B, p.N, p.K, ldb, 64);
+    if (rc) return rc;
+    return launch_gemm<64, 6, A_MN, B_MN>(ta, tb, p, stream);
+  }
+  rc = B_MN ? make_tmap(&tb, B, p.K, p.N, ldb, 64, 64) : make_tmap(&tb, B, p.N, p.K, ldb, 128);
+  if (rc) return rc;
+  return launch_gemm<128, 5, A_MN, B_MN>(ta, tb, p, stream);
+}
+
+TRB_API int trb_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* out, int64_t ldo, int out_f32, int M,
+                          int N, int K, const float* bias, int act, const void* mask, int64_t ld_mask, float alpha, int split_k,
+                          cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
-  if ((K % 8) || (lda % 8) || (ldb % 8) || (N % 8)) return -12;
+  if ((lda % 8) || (ldb % 8) || (N % 8)) return -12;
+  if ((!a_mn && (K % 8)) || (a_mn && (M % 8)) || (b_mn && (N % 8)) || (!b_mn && (K % 8))) return -12;
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
   p.bias = bias;
@@ -326,17 +359,15 @@ TRB_API int trb_gemm_bf16_tn(const void* A, int64_t lda, const void* B, int64_t 
     p.split_k = s;
     if (s > 1) TRB_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t) M * (size_t) ldo, stream));
   }
-  CUtensorMap ta, tb;
-  int rc = make_tmap(&ta, A, M, K, lda, BLOCK_M);
-  if (rc) return rc;
-  if (N <= 64) {
-    rc = make_tmap(&tb, B, N, K, ldb, 64);
-    if (rc) return rc;
-    return launch_gemm<64, 6>(ta, tb, p, stream);
-  }
-  rc = make_tmap(&tb, B, N, K, ldb, 128);
-  if (rc) return rc;
-  return launch_gemm<128, 5>(ta, tb, p, stream);
+  if (a_mn && b_mn) return gemm_dispatch<true, true>(A, lda, B, ldb, p, stream);
+  if (a_mn) return gemm_dispatch<true, false>(A, lda, B, ldb, p, stream);
+  if (b_mn) return gemm_dispatch<false, true>(A, lda, B, ldb, p, stream);
+  return gemm_dispatch<false, false>(A, lda, B, ldb, p, stream);
+}
+
+TRB_API int trb_gemm_bf16_tn(const void* A, int64_t lda, const void* B, int64_t ldb, void* out, int64_t ldo, int out_f32, int M, int N, int K,
+                             const float* bias, int act, const void* mask, int64_t ld_mask, float alpha, int split_k, cudaStream_t stream) {
+  return trb_gemm_bf16(A, lda, 0, B, ldb, 0, out, ldo, out_f32, M, N, K, bias, act, mask, ld_mask, alpha, split_k, stream);
 }
 
 // ---- helpers used around the GEMM ----------------------------------------------------------------------

@@ -111,6 +111,120 @@ __global__ void __launch_bounds__(256) tbe_pooled_fwd_kernel(const TbeFwdParams 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Wide-row variant (D >= 128): one warp walks 32 consecutive bags of a feature. The ids of those
+// bags are contiguous, so they are fetched with coalesced loads and the row gathers of up to U
+// ids are issued back to back (U independent 512 B requests in flight per warp) before any of
+// them is consumed — with one id per bag (Criteo) this is what hides the HBM latency.
+// ------------------------------------------------------------------------------------------------
+template <typename W, typename O, int MAXV, int U>
+__global__ void __launch_bounds__(256) tbe_pooled_fwd_chunk_kernel(const TbeFwdParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t chunk = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int cpf = (p.B + 31) >> 5;  // chunks per feature
+  if (chunk >= (int64_t) p.F * cpf) return;
+  const int f = (int) (chunk / cpf);
+  const int b0 = (int) (chunk - (int64_t) f * cpf) << 5;
+  const int nb = min(32, p.B - b0);
+  const int D = p.feat_dim[f];
+  const int nvec = D >> 2;
+  const int64_t rows = p.feat_rows[f];
+  const W* __restrict__ wbase = reinterpret_cast<const W*>(p.weights) + p.feat_woff[f];
+  const int col = p.feat_col[f];
+
+  const int64_t bag0 = (int64_t) f * p.B + b0;
+  const int64_t my_start = trb_ld_idx(p.offsets, bag0 + min(lane, nb), p.off64);
+  int64_t my_end = __shfl_down_sync(0xffffffffu, my_start, 1);
+  const int64_t last_end = trb_ld_idx(p.offsets, bag0 + nb, p.off64);
+  if (lane >= nb - 1) my_end = last_end;
+  const int64_t e_begin = __shfl_sync(0xffffffffu, my_start, 0);
+  const int64_t e_end = last_end;
+
+  float4 acc[MAXV];
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int cur = 0;
+  int64_t cur_start = e_begin;
+  int64_t cur_end = __shfl_sync(0xffffffffu, my_end, 0);
+
+  auto flush = [&](int bag_in_chunk, int64_t L) {
+    if (p.mean && L > 0) {
+      const float inv = 1.f / (float) L;
+#pragma unroll
+      for (int k = 0; k < MAXV; ++k) acc[k] = f4_scale(acc[k], inv);
+    }
+    const int b = b0 + bag_in_chunk;
+    const int s = b / p.B_local;
+    const int bl = b - s * p.B_local;
+    O* dst = reinterpret_cast<O*>(p.out.p[s]) + (int64_t) bl * p.out_stride + col;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const int vi = lane + k * 32;
+      if (vi < nvec) Vec4<O>::st(dst + vi * 4, acc[k]);
+      acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+
+  for (int64_t e0 = e_begin; e0 < e_end; e0 += 32) {
+    const int n = (int) min((int64_t) 32, e_end - e0);
+    int64_t my_idx = 0;
+    float my_w = 0.f;
+    if (lane < n) {
+      my_idx = trb_ld_idx(p.indices, e0 + lane, p.idx64);
+      my_w = p.psw ? p.psw[e0 + lane] : 1.f;
+      if (my_idx < 0 || my_idx >= rows) { my_idx = 0; my_w = 0.f; }
+    }
+    for (int j = 0; j < n; j += U) {
+      float4 v[U][MAXV];
+      float w[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int src = min(j + u, n - 1);
+        const int64_t idx = __shfl_sync(0xffffffffu, my_idx, src);
+        w[u] = __shfl_sync(0xffffffffu, my_w, src);
+        const W* row = wbase + idx * D;
+#pragma unroll
+        for (int k = 0; k < MAXV; ++k) {
+          const int vi = lane + k * 32;
+          v[u][k] = (vi < nvec && j + u < n) ? Vec4<W>::ld_nc(row + vi * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (j + u < n) {
+          const int64_t e = e0 + j + u;
+          while (e >= cur_end) {  // warp-uniform: close finished (possibly empty) bags
+            flush(cur, cur_end - cur_start);
+            ++cur;
+            cur_start = cur_end;
+            cur_end = __shfl_sync(0xffffffffu, my_end, min(cur, 31));
+          }
+#pragma unroll
+          for (int k = 0; k < MAXV; ++k) acc[k] = f4_fma(v[u][k], w[u], acc[k]);
+        }
+      }
+    }
+  }
+  // close the open bag and any trailing empty bags
+  while (cur < nb) {
+    flush(cur, cur_end - cur_start);
+    ++cur;
+    cur_start = cur_end;
+    cur_end = __shfl_sync(0xffffffffu, my_end, min(cur, 31));
+  }
+}
+
+template <typename W, typename O, int MAXV, int U>
+static int launch_pooled_chunk(const TbeFwdParams& p, cudaStream_t stream) {
+  const int64_t chunks = (int64_t) p.F * ((p.B + 31) / 32);
+  if (chunks == 0) return 0;
+  const int threads = 256;
+  const int64_t blocks = (chunks + 7) / 8;
+  tbe_pooled_fwd_chunk_kernel<W, O, MAXV, U><<<(unsigned) blocks, threads, 0, stream>>>(p);
+  TRB_CHECK_LAUNCH();
+  return 0;
+}
+
 template <typename W, typename O, int LPB, int MAXV>
 static int launch_pooled(const TbeFwdParams& p, cudaStream_t stream) {
   const int64_t n_bags = (int64_t) p.F * p.B;
@@ -128,9 +242,9 @@ static int dispatch_shape(const TbeFwdParams& p, int max_dim, cudaStream_t strea
   const int nvec = max_dim / 4;
   if (nvec <= 8) return launch_pooled<W, O, 8, 1>(p, stream);
   if (nvec <= 16) return launch_pooled<W, O, 16, 1>(p, stream);
-  if (nvec <= 32) return launch_pooled<W, O, 32, 1>(p, stream);
-  if (nvec <= 64) return launch_pooled<W, O, 32, 2>(p, stream);
-  if (nvec <= 128) return launch_pooled<W, O, 32, 4>(p, stream);
+  if (nvec <= 32) return launch_pooled_chunk<W, O, 1, 8>(p, stream);
+  if (nvec <= 64) return launch_pooled_chunk<W, O, 2, 4>(p, stream);
+  if (nvec <= 128) return launch_pooled_chunk<W, O, 4, 2>(p, stream);
   if (nvec <= 512) return launch_pooled<W, O, 32, 16>(p, stream);
   return -2;  // dim > 2048 unsupported
 }

@@ -28,15 +28,25 @@ def _check_bf16_2d(t: torch.Tensor, name: str) -> None:
     assert t.data_ptr() % 16 == 0, f"{name}: base pointer must be 16 B aligned"
 
 
-def gemm_bf16_tn(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
-                 out_dtype: torch.dtype = torch.bfloat16, mask: Optional[torch.Tensor] = None, alpha: float = 1.0,
-                 out: Optional[torch.Tensor] = None, split_k: int = 1) -> torch.Tensor:
-    """``act(alpha * a @ b.T + bias)``; ``mask`` (bf16 [M, N]) with ``ACT_RELU_GRAD`` zeroes outputs where mask <= 0."""
+def gemm_bf16(a: torch.Tensor, b: torch.Tensor, a_mn: bool = False, b_mn: bool = False, bias: Optional[torch.Tensor] = None,
+              act: int = ACT_NONE, out_dtype: torch.dtype = torch.bfloat16, mask: Optional[torch.Tensor] = None, alpha: float = 1.0,
+              out: Optional[torch.Tensor] = None, split_k: int = 1) -> torch.Tensor:
+    """``act(alpha * op(a) @ op(b)^T + bias)`` on the tcgen05 kernel.
+
+    ``a_mn=False``: a is ``[M, K]`` (K-major);  ``a_mn=True``: a is ``[K, M]`` (consumed MN-major, no transpose copy).
+    ``b_mn=False``: b is ``[N, K]``;            ``b_mn=True``: b is ``[K, N]``.
+    ``mask`` (bf16 [M, N]) with ``ACT_RELU_GRAD`` zeroes outputs where mask <= 0."""
     _check_bf16_2d(a, "a")
     _check_bf16_2d(b, "b")
-    M, K = a.shape
-    N = b.shape[0]
-    assert b.shape[1] == K and N % 8 == 0
+    if a_mn:
+        K, M = a.shape
+    else:
+        M, K = a.shape
+    if b_mn:
+        Kb, N = b.shape
+    else:
+        N, Kb = b.shape
+    assert Kb == K and N % 8 == 0, (a.shape, b.shape, a_mn, b_mn)
     if out is None:
         out = torch.empty(M, N, dtype=out_dtype, device=a.device)
     assert out.stride(1) == 1 and out.dtype in (torch.bfloat16, torch.float32)
@@ -45,13 +55,20 @@ def gemm_bf16_tn(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] 
     if act == ACT_RELU_GRAD:
         assert mask is not None and mask.dtype == torch.bfloat16 and mask.shape == (M, N) and mask.stride(1) == 1 and mask.stride(0) % 8 == 0
     L = _lib.lib()
-    code = L.trb_gemm_bf16_tn(
-        _lib.ptr(a), ctypes.c_int64(a.stride(0)), _lib.ptr(b), ctypes.c_int64(b.stride(0)), _lib.ptr(out), ctypes.c_int64(out.stride(0)),
-        1 if out.dtype == torch.float32 else 0, M, N, K, _lib.ptr(bias), act, _lib.ptr(mask),
+    code = L.trb_gemm_bf16(
+        _lib.ptr(a), ctypes.c_int64(a.stride(0)), int(a_mn), _lib.ptr(b), ctypes.c_int64(b.stride(0)), int(b_mn), _lib.ptr(out),
+        ctypes.c_int64(out.stride(0)), 1 if out.dtype == torch.float32 else 0, M, N, K, _lib.ptr(bias), act, _lib.ptr(mask),
         ctypes.c_int64(mask.stride(0) if mask is not None else 0), ctypes.c_float(alpha), int(split_k), _lib.stream_ptr(a.device),
     )
-    _lib.check(code, "trb_gemm_bf16_tn")
+    _lib.check(code, "trb_gemm_bf16")
     return out
+
+
+def gemm_bf16_tn(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+                 out_dtype: torch.dtype = torch.bfloat16, mask: Optional[torch.Tensor] = None, alpha: float = 1.0,
+                 out: Optional[torch.Tensor] = None, split_k: int = 1) -> torch.Tensor:
+    """``act(alpha * a @ b.T + bias)`` with a ``[M, K]`` and b ``[N, K]`` (both K-major)."""
+    return gemm_bf16(a, b, False, False, bias, act, out_dtype, mask, alpha, out, split_k)
 
 
 def transpose_bf16(x: torch.Tensor, pad_cols_to: int = 8) -> torch.Tensor:
@@ -135,22 +152,21 @@ class LinearActFn(torch.autograd.Function):
         M = gy.shape[0]
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            wt = transpose_bf16(wb)  # [Kp, N]
+            # dgrad: gx[M, Kp] = gy[M, N] . W[N, Kp]; W is consumed as an MN-major B operand (no transpose)
             if ctx.mask_input and xb.shape[1] == ctx.K:
-                gx = gemm_bf16_tn(gy, wt, act=ACT_RELU_GRAD, mask=xb)
+                gx = gemm_bf16(gy, wb, b_mn=True, act=ACT_RELU_GRAD, mask=xb)
                 gx._trb_masked = True
             else:
-                gx = gemm_bf16_tn(gy, wt)
+                gx = gemm_bf16(gy, wb, b_mn=True)
                 if not ctx.pre_padded:
                     gx = gx[:, : ctx.K]
             if ctx.x_dtype != torch.bfloat16:
                 gx = gx.to(ctx.x_dtype)
         if ctx.needs_input_grad[1]:
-            gyt = transpose_bf16(gy)  # [N, M]
-            xt = transpose_bf16(xb)  # [Kp, M]
-            tiles = ((gyt.shape[0] + 127) // 128) * ((xt.shape[0] + 127) // 128)
+            # wgrad: gw[N, Kp] = gy^T . x with BOTH operands consumed MN-major straight from their row-major storage
+            tiles = ((gy.shape[1] + 127) // 128) * ((xb.shape[1] + 127) // 128)
             split = max(1, min(32, (2 * _num_sms(gy.device) + tiles - 1) // tiles))
-            gw = gemm_bf16_tn(gyt, xt, out_dtype=torch.float32, split_k=split)[:, : ctx.K]
+            gw = gemm_bf16(gy, xb, a_mn=True, b_mn=True, out_dtype=torch.float32, split_k=split)[:, : ctx.K]
             if gw.stride(1) != 1 or gw.shape[1] != gw.stride(0):
                 gw = gw.contiguous()
         if ctx.has_bias and ctx.needs_input_grad[2]:
