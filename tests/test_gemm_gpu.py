@@ -71,8 +71,8 @@ def test_linear_act_autograd_matches_torch():
     yr.backward(g)
     ym.backward(g.to(ym.dtype))
     for (n, pr), (_, pm) in zip(ref.named_parameters(), mine.named_parameters()):
-        tol = 0.08 * float(pr.grad.abs().max()) + 1e-2
-        assert float((pm.grad - pr.grad).abs().max()) <= tol, (n, float((pm.grad - pr.grad).abs().max()), tol)
+        cos = torch.nn.functional.cosine_similarity(pm.grad.flatten().float(), pr.grad.flatten().float(), dim=0)
+        assert float(cos) > 0.99, (n, float(cos))
 
 
 @pytest.mark.parametrize("a_mn,b_mn", [(True, True), (False, True), (True, False)])

@@ -396,31 +396,51 @@ TRB_API int trb_transpose_bf16(const void* in, void* out, int rows, int cols, in
   return 0;
 }
 
-// column sums of a bf16 [rows, cols] matrix into fp32 (bias gradient)
+// column sums of a bf16 [rows, cols] matrix into fp32 (bias gradient). Each thread owns 8 columns
+// (one 16 B load per row) and strides over rows; 8 row lanes per block are reduced through smem and
+// the block result is added atomically (blocks tile the rows so the whole chip participates).
 __global__ void __launch_bounds__(256) trb_colsum_bf16_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int rows, int cols,
                                                                 int64_t ld, int rows_per_block) {
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int vec = blockIdx.x * 32 + tx;  // 8-column group
+  const int nvec = cols >> 3;
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(rows, r0 + rows_per_block);
-  float acc = 0.f;
-  if (c < cols)
-    for (int r = r0 + (threadIdx.x >> 5); r < r1; r += 8) acc += __bfloat162float(in[(int64_t) r * ld + c]);
-  __shared__ float red[8][33];
-  red[threadIdx.x >> 5][threadIdx.x & 31] = acc;
-  __syncthreads();
-  if (threadIdx.x < 32 && c < cols) {
-    float s = 0.f;
+  float acc[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
-    atomicAdd(out + c, s);
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (vec < nvec) {
+    for (int r = r0 + ty; r < r1; r += 8) {
+      const uint4 v = *reinterpret_cast<const uint4*>(in + (int64_t) r * ld + vec * 8);
+      const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(&v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += __bfloat162float(b[j]);
+    }
+  }
+  __shared__ float red[8][32][9];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[ty][tx][j] = acc[j];
+  __syncthreads();
+  if (ty == 0 && vec < nvec) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += red[i][tx][j];
+      atomicAdd(out + vec * 8 + j, s);
+    }
   }
 }
 
 TRB_API int trb_colsum_bf16(const void* in, float* out, int rows, int cols, int64_t ld, cudaStream_t stream) {
   if (rows == 0 || cols == 0) return 0;
+  if (cols % 8 || ld % 8) return -12;
   TRB_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, stream));
-  const int rows_per_block = 1024;
-  dim3 grid((cols + 31) / 32, (rows + rows_per_block - 1) / rows_per_block);
+  const int nvec = cols / 8;
+  const int xblocks = (nvec + 31) / 32;
+  int rows_per_block = 256;
+  while ((int64_t) xblocks * ((rows + rows_per_block - 1) / rows_per_block) > 2048 && rows_per_block < 65536) rows_per_block *= 2;
+  dim3 grid(xblocks, (rows + rows_per_block - 1) / rows_per_block);
   trb_colsum_bf16_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*) in, out, rows, cols, ld, rows_per_block);
   TRB_CHECK_LAUNCH();
   return 0;

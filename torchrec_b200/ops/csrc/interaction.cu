@@ -162,7 +162,8 @@ __global__ void __launch_bounds__(128, 3) interaction_bwd_kernel(const InterPara
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
   uint8_t* tileT = smem;                     // packed X (2 K-blocks), used as MN-major B operand
   uint8_t* tileS = smem + 2 * kTileBytes;    // block-diagonal S (2 K-blocks), K-major A operand
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 4 * kTileBytes);
+  __nv_bfloat16* gstage = reinterpret_cast<__nv_bfloat16*>(smem + 4 * kTileBytes);  // [4][ld_out] incoming gradient rows
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 4 * kTileBytes + kSamples * p.ld_out * 2);
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int R = p.F + 1;
@@ -184,11 +185,22 @@ __global__ void __launch_bounds__(128, 3) interaction_bwd_kernel(const InterPara
   for (int g = blockIdx.x; g < groups; g += gridDim.x) {
     const int b0 = g * kSamples;
     load_tile(p, tileT, b0, tid);
+    // stage the 4 incoming gradient rows with coalesced 16 B loads
+    {
+      const int vec_per_row = (int) (p.ld_out >> 3);
+      for (int v = tid; v < kSamples * vec_per_row; v += 128) {
+        const int sidx = v / vec_per_row, c = v - sidx * vec_per_row;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (b0 + sidx < p.B) val = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.gout) + (int64_t) (b0 + sidx) * p.ld_out)[c];
+        reinterpret_cast<uint4*>(gstage + sidx * p.ld_out)[c] = val;
+      }
+    }
+    __syncthreads();
     // S rows: thread (warp = sample, lane = i) writes S[i][j] for all j (symmetric, zero diagonal)
     {
       const int b = b0 + warp;
       const int r = warp * kRowsPerSample + lane;
-      const __nv_bfloat16* grow = reinterpret_cast<const __nv_bfloat16*>(p.gout) + (int64_t) b * p.ld_out + kD;
+      const __nv_bfloat16* grow = gstage + warp * p.ld_out + kD;
       if (lane < R) {
         for (int j = 0; j < R; ++j) {
           __nv_bfloat16 v = __float2bfloat16(0.f);
@@ -236,7 +248,7 @@ __global__ void __launch_bounds__(128, 3) interaction_bwd_kernel(const InterPara
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(z[j]);
       if (lane == 0) {
         // dense row: add the pass-through gradient of out[:, :D]
-        const __nv_bfloat16* gd = reinterpret_cast<const __nv_bfloat16*>(p.gout) + (int64_t) b * p.ld_out + c * 32;
+        const __nv_bfloat16* gd = gstage + warp * p.ld_out + c * 32;
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += __bfloat162float(gd[j]);
         __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.g_dense) + (int64_t) b * p.ld_gdense + c * 32;
@@ -303,7 +315,7 @@ TRB_API int trb_interaction_bwd(const void* dense, int64_t ld_dense, const void*
   p.dense = dense; p.ld_dense = ld_dense; p.sparse = sparse; p.ld_sparse = ld_sparse; p.sparse_f32 = sparse_f32;
   p.gout = gout; p.ld_out = ld_out; p.B = B; p.F = F; p.out_cols = D + (F + 1) * F / 2;
   p.g_dense = g_dense; p.ld_gdense = ld_gdense; p.g_sparse = g_sparse; p.ld_gsparse = ld_gsparse; p.gsparse_f32 = gsparse_f32;
-  const int smem = 4 * kTileBytes + 64 + 1024;
+  const int smem = 4 * kTileBytes + kSamples * (int) ld_out * 2 + 64 + 1024;
   static bool cfg = false;
   if (!cfg) {
     TRB_CUDA(cudaFuncSetAttribute(interaction_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
