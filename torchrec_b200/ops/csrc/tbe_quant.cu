@@ -1,0 +1,181 @@
+// Inference table-batched lookup over quantized rows (sm_100a).
+//
+// Row formats (per table, mixed freely inside one launch):
+//   FMT_FP32 / FMT_FP16 / FMT_BF16 : plain rows
+//   FMT_INT8 / FMT_INT4 / FMT_INT2 : row-wise quantized, fused tail [scale fp16][bias fp16] after the packed
+//                                    values (layout of fbgemm FloatOrHalfToFusedNBitRowwiseQuantizedSBHalf,
+//                                    reference quant/embedding_modules.py:206-283)
+//   FMT_FP8_BLOCK                  : B200-native format: e4m3 values + one fp16 scale per 32-element block
+//                                    ([D bytes][D/32 x fp16]) — the block-scaled layout tensor cores consume, so
+//                                    the same table bytes can feed fp8 GEMMs later without re-quantising
+// One warp per bag; lane l dequantises elements 4l..4l+3 (+128k), accumulates in fp32, writes fp32/bf16/fp16.
+// Parity: IntNBitTableBatchedEmbeddingBagsCodegen forward (reference quant_embedding_kernel.py:247-711).
+#include "common.cuh"
+#include <cuda_fp8.h>
+
+enum QFmt : int { FMT_FP32 = 0, FMT_FP16 = 1, FMT_BF16 = 2, FMT_INT8 = 3, FMT_INT4 = 4, FMT_INT2 = 5, FMT_FP8_BLOCK = 6 };
+
+struct QTbeParams {
+  const uint8_t* weights;
+  const int64_t* feat_woff;   // byte offset of the table
+  const int64_t* feat_rows;
+  const int32_t* feat_dim;
+  const int32_t* feat_col;
+  const int32_t* feat_fmt;
+  const int32_t* feat_row_bytes;
+  const void* indices;
+  const void* offsets;
+  const float* psw;
+  void* out;
+  int64_t out_stride;
+  int32_t B, F, idx64, off64, mean, pooled;
+};
+
+__device__ __forceinline__ float4 dequant4(const uint8_t* row, int fmt, int D, int e) {
+  // e = first element index (multiple of 4)
+  switch (fmt) {
+    case FMT_FP32: return *reinterpret_cast<const float4*>(row + e * 4);
+    case FMT_FP16: return Vec4<__half>::ld(reinterpret_cast<const __half*>(row) + e);
+    case FMT_BF16: return Vec4<__nv_bfloat16>::ld(reinterpret_cast<const __nv_bfloat16*>(row) + e);
+    case FMT_INT8: {
+      const uint32_t q = *reinterpret_cast<const uint32_t*>(row + e);
+      const __half2 sb = *reinterpret_cast<const __half2*>(row + D);
+      const float s = __low2float(sb), b = __high2float(sb);
+      return make_float4((q & 0xff) * s + b, ((q >> 8) & 0xff) * s + b, ((q >> 16) & 0xff) * s + b, (q >> 24) * s + b);
+    }
+    case FMT_INT4: {
+      const uint16_t q = *reinterpret_cast<const uint16_t*>(row + (e >> 1));
+      const __half2 sb = *reinterpret_cast<const __half2*>(row + ((D + 1) >> 1));
+      const float s = __low2float(sb), b = __high2float(sb);
+      return make_float4((q & 0xf) * s + b, ((q >> 4) & 0xf) * s + b, ((q >> 8) & 0xf) * s + b, ((q >> 12) & 0xf) * s + b);
+    }
+    case FMT_INT2: {
+      const uint8_t q = row[e >> 2];
+      const __half2 sb = *reinterpret_cast<const __half2*>(row + ((D + 3) >> 2));
+      const float s = __low2float(sb), b = __high2float(sb);
+      return make_float4((q & 3) * s + b, ((q >> 2) & 3) * s + b, ((q >> 4) & 3) * s + b, ((q >> 6) & 3) * s + b);
+    }
+    case FMT_FP8_BLOCK: {
+      const uint32_t q = *reinterpret_cast<const uint32_t*>(row + e);
+      const float s = __half2float(*reinterpret_cast<const __half*>(row + D + (e >> 5) * 2));
+      const __nv_fp8x4_e4m3 v = *reinterpret_cast<const __nv_fp8x4_e4m3*>(&q);
+      const float4 f = static_cast<float4>(v);
+      return make_float4(f.x * s, f.y * s, f.z * s, f.w * s);
+    }
+  }
+  return make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+template <typename O, int MAXV>
+__global__ void __launch_bounds__(256) qtbe_fwd_kernel(const QTbeParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t bag = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_bags = (int64_t) p.F * p.B;
+  if (bag >= n_bags) return;
+  const int f = (int) (bag / p.B);
+  const int b = (int) (bag - (int64_t) f * p.B);
+  const int D = p.feat_dim[f];
+  const int nvec = D >> 2;
+  const int fmt = p.feat_fmt[f];
+  const int64_t rows = p.feat_rows[f];
+  const int64_t rb = p.feat_row_bytes[f];
+  const uint8_t* wbase = p.weights + p.feat_woff[f];
+  const int64_t start = trb_ld_idx(p.offsets, bag, p.off64);
+  const int64_t end = trb_ld_idx(p.offsets, bag + 1, p.off64);
+  float4 acc[MAXV];
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t l0 = start; l0 < end; l0 += 32) {
+    const int n = (int) min((int64_t) 32, end - l0);
+    int64_t my_idx = 0;
+    float my_w = 0.f;
+    if (lane < n) {
+      my_idx = trb_ld_idx(p.indices, l0 + lane, p.idx64);
+      my_w = p.psw ? p.psw[l0 + lane] : 1.f;
+      if (my_idx < 0 || my_idx >= rows) { my_idx = 0; my_w = 0.f; }
+    }
+    for (int j = 0; j < n; ++j) {
+      const int64_t idx = __shfl_sync(0xffffffffu, my_idx, j);
+      const float w = __shfl_sync(0xffffffffu, my_w, j);
+      const uint8_t* row = wbase + idx * rb;
+#pragma unroll
+      for (int k = 0; k < MAXV; ++k) {
+        const int vi = lane + k * 32;
+        if (vi < nvec) acc[k] = f4_fma(dequant4(row, fmt, D, vi * 4), w, acc[k]);
+      }
+    }
+  }
+  if (p.mean && end > start) {
+    const float inv = 1.f / (float) (end - start);
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) acc[k] = f4_scale(acc[k], inv);
+  }
+  O* dst = reinterpret_cast<O*>(p.out) + (int64_t) b * p.out_stride + p.feat_col[f];
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int vi = lane + k * 32;
+    if (vi < nvec) Vec4<O>::st(dst + vi * 4, acc[k]);
+  }
+}
+
+// sequence (unpooled): one warp per id position
+template <typename O>
+__global__ void __launch_bounds__(256) qtbe_seq_kernel(const QTbeParams p, int64_t total) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= total) return;
+  int lo = 0, hi = p.F - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (trb_ld_idx(p.offsets, (int64_t) mid * p.B, p.off64) <= i) lo = mid; else hi = mid - 1;
+  }
+  const int f = lo;
+  const int D = p.feat_dim[f];
+  const int nvec = D >> 2;
+  int64_t idx = trb_ld_idx(p.indices, i, p.idx64);
+  const bool ok = idx >= 0 && idx < p.feat_rows[f];
+  const uint8_t* row = p.weights + p.feat_woff[f] + (ok ? idx : 0) * (int64_t) p.feat_row_bytes[f];
+  O* dst = reinterpret_cast<O*>(p.out) + i * p.out_stride;
+  for (int vi = lane; vi < nvec; vi += 32) {
+    float4 v = ok ? dequant4(row, p.feat_fmt[f], D, vi * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    Vec4<O>::st(dst + vi * 4, v);
+  }
+}
+
+template <typename O>
+static int launch_q(const QTbeParams& p, int max_dim, int64_t total, cudaStream_t stream) {
+  const int threads = 256;
+  if (!p.pooled) {
+    if (total == 0) return 0;
+    qtbe_seq_kernel<O><<<(unsigned) ((total * 32 + threads - 1) / threads), threads, 0, stream>>>(p, total);
+    TRB_CHECK_LAUNCH();
+    return 0;
+  }
+  const int64_t n_bags = (int64_t) p.F * p.B;
+  if (n_bags == 0) return 0;
+  const unsigned blocks = (unsigned) ((n_bags * 32 + threads - 1) / threads);
+  const int nvec = max_dim / 4;
+  if (nvec <= 32) qtbe_fwd_kernel<O, 1><<<blocks, threads, 0, stream>>>(p);
+  else if (nvec <= 128) qtbe_fwd_kernel<O, 4><<<blocks, threads, 0, stream>>>(p);
+  else if (nvec <= 512) qtbe_fwd_kernel<O, 16><<<blocks, threads, 0, stream>>>(p);
+  else return -2;
+  TRB_CHECK_LAUNCH();
+  return 0;
+}
+
+TRB_API int trb_qtbe_fwd(const void* weights, const int64_t* feat_woff, const int64_t* feat_rows, const int32_t* feat_dim, const int32_t* feat_col,
+                         const int32_t* feat_fmt, const int32_t* feat_row_bytes, const void* indices, int idx64, const void* offsets, int off64,
+                         const float* psw, void* out, int out_dtype, int64_t out_stride, int B, int F, int max_dim, int mean, int pooled,
+                         int64_t total, cudaStream_t stream) {
+  QTbeParams p;
+  p.weights = reinterpret_cast<const uint8_t*>(weights);
+  p.feat_woff = feat_woff; p.feat_rows = feat_rows; p.feat_dim = feat_dim; p.feat_col = feat_col; p.feat_fmt = feat_fmt;
+  p.feat_row_bytes = feat_row_bytes; p.indices = indices; p.offsets = offsets; p.psw = psw; p.out = out; p.out_stride = out_stride;
+  p.B = B; p.F = F; p.idx64 = idx64; p.off64 = off64; p.mean = mean; p.pooled = pooled;
+  switch (out_dtype) {
+    case TRB_F32: return launch_q<float>(p, max_dim, total, stream);
+    case TRB_F16: return launch_q<__half>(p, max_dim, total, stream);
+    case TRB_BF16: return launch_q<__nv_bfloat16>(p, max_dim, total, stream);
+  }
+  return -3;
+}
