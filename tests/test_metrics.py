@@ -1,0 +1,129 @@
+"""Each metric vs a straightforward reference formula (strategy of the reference's metrics/tests)."""
+import math
+
+import pytest
+import torch
+
+from torchrec_b200.metrics import (
+    DefaultMetricsConfig,
+    MetricsConfig,
+    RecComputeMode,
+    RecMetricDef,
+    RecMetricEnum,
+    RecMetricModule,
+    RecTaskInfo,
+    ThroughputDef,
+    generate_metric_module,
+)
+from torchrec_b200.metrics import metrics_impl as M
+from torchrec_b200.utils.multiprocess import run_multi_process
+
+
+def _data(n=200, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    p = torch.rand(n, generator=g)
+    l = (torch.rand(n, generator=g) < p).float()
+    w = torch.rand(n, generator=g) + 0.1
+    return p, l, w
+
+
+def _one(metric_cls, task="t", **kw):
+    return metric_cls(world_size=1, my_rank=0, batch_size=64, tasks=[RecTaskInfo(name=task)], window_size=1000, **kw)
+
+
+def test_ne_calibration_ctr_mse_mae_accuracy():
+    p, l, w = _data()
+    ne = _one(M.NEMetric, include_logloss=True)
+    cal, ctr, mse, mae, acc = _one(M.CalibrationMetric), _one(M.CTRMetric), _one(M.MSEMetric), _one(M.MAEMetric), _one(M.AccuracyMetric)
+    for m in (ne, cal, ctr, mse, mae, acc):
+        for i in range(0, 200, 50):
+            m.update(predictions={"t": p[i : i + 50]}, labels={"t": l[i : i + 50]}, weights={"t": w[i : i + 50]})
+    ce = -(w * (l * torch.log2(p.clamp(1e-12)) + (1 - l) * torch.log2((1 - p).clamp(1e-12)))).sum()
+    ml = (w * l).sum() / w.sum()
+    base = -((w * l).sum() * math.log2(ml) + (w * (1 - l)).sum() * math.log2(1 - ml))
+    r = ne.compute()
+    assert r["ne-t|lifetime_ne"].item() == pytest.approx((ce / base).item(), rel=1e-4)
+    assert r["ne-t|window_ne"].item() == pytest.approx((ce / base).item(), rel=1e-4)
+    assert "ne-t|lifetime_logloss" in r
+    assert cal.compute()["calibration-t|lifetime_calibration"].item() == pytest.approx(((w * p).sum() / (w * l).sum()).item(), rel=1e-5)
+    assert ctr.compute()["ctr-t|lifetime_ctr"].item() == pytest.approx(ml.item(), rel=1e-5)
+    assert mse.compute()["mse-t|lifetime_mse"].item() == pytest.approx(((w * (p - l) ** 2).sum() / w.sum()).item(), rel=1e-5)
+    assert mae.compute()["mae-t|lifetime_mae"].item() == pytest.approx(((w * (p - l).abs()).sum() / w.sum()).item(), rel=1e-5)
+    assert acc.compute()["accuracy-t|lifetime_accuracy"].item() == pytest.approx(((w * ((p >= 0.5).float() == l)).sum() / w.sum()).item(), rel=1e-5)
+
+
+def test_auc_matches_pairwise_definition():
+    p, l, w = _data(150, seed=3)
+    auc = _one(M.AUCMetric)
+    auc.update(predictions={"t": p}, labels={"t": l}, weights={"t": w})
+    pos, neg = l == 1, l == 0
+    num = ((p[pos].unsqueeze(1) > p[neg].unsqueeze(0)).float() + 0.5 * (p[pos].unsqueeze(1) == p[neg].unsqueeze(0)).float())
+    ref = (num * w[pos].unsqueeze(1) * w[neg].unsqueeze(0)).sum() / (w[pos].sum() * w[neg].sum())
+    assert auc.compute()["auc-t|window_auc"].item() == pytest.approx(ref.item(), rel=1e-5)
+
+
+def test_window_drops_old_batches():
+    m = M.CTRMetric(world_size=1, my_rank=0, batch_size=10, tasks=[RecTaskInfo(name="t")], window_size=20)
+    m.update(predictions={"t": torch.zeros(10)}, labels={"t": torch.ones(10)}, weights=None)
+    for _ in range(2):
+        m.update(predictions={"t": torch.zeros(10)}, labels={"t": torch.zeros(10)}, weights=None)
+    r = m.compute()
+    assert r["ctr-t|lifetime_ctr"].item() == pytest.approx(1 / 3, rel=1e-5)
+    assert r["ctr-t|window_ctr"].item() == pytest.approx(0.0, abs=1e-9)
+
+
+def test_fused_tasks_and_metric_module():
+    cfg = MetricsConfig(rec_tasks=[RecTaskInfo(name="a", label_name="la", prediction_name="pa", weight_name="wa"),
+                                   RecTaskInfo(name="b", label_name="lb", prediction_name="pb", weight_name="wb")],
+                        rec_metrics={RecMetricEnum.NE: RecMetricDef(rec_task_indices=[0, 1], window_size=1000),
+                                     RecMetricEnum.AUC: RecMetricDef(rec_task_indices=[0], window_size=1000)},
+                        throughput_metric=ThroughputDef(), rec_compute_mode=RecComputeMode.FUSED_TASKS_COMPUTATION, compute_interval_steps=1)
+    mod = generate_metric_module(RecMetricModule, cfg, batch_size=50, world_size=1, my_rank=0, state_metrics_mapping={}, device=torch.device("cpu"))
+    p, l, w = _data(50)
+    out = {"la": l, "pa": p, "wa": w, "lb": 1 - l, "pb": 1 - p, "wb": w}
+    mod.update(out)
+    r = mod.compute()
+    assert r["ne-a|lifetime_ne"].item() == pytest.approx(r["ne-b|lifetime_ne"].item(), rel=1e-6)
+    assert "auc-a|window_auc" in r and "throughput-throughput|total_examples" in r
+
+
+def _dist_metric(ctx):
+    p, l, w = _data(100, seed=ctx.rank)
+    m = M.NEMetric(world_size=ctx.world_size, my_rank=ctx.rank, batch_size=100, tasks=[RecTaskInfo(name="t")], window_size=1000, compute_on_all_ranks=True)
+    m.update(predictions={"t": p}, labels={"t": l}, weights={"t": w})
+    got = m.compute()["ne-t|lifetime_ne"].item()
+    ps, ls, ws = zip(*[_data(100, seed=r) for r in range(ctx.world_size)])
+    p, l, w = torch.cat(ps), torch.cat(ls), torch.cat(ws)
+    ce = -(w * (l * torch.log2(p.clamp(1e-12)) + (1 - l) * torch.log2((1 - p).clamp(1e-12)))).sum()
+    ml = (w * l).sum() / w.sum()
+    base = -((w * l).sum() * math.log2(ml) + (w * (1 - l)).sum() * math.log2(1 - ml))
+    assert got == pytest.approx((ce / base).item(), rel=1e-4)
+    auc = M.AUCMetric(world_size=ctx.world_size, my_rank=ctx.rank, batch_size=100, tasks=[RecTaskInfo(name="t")], window_size=1000, compute_on_all_ranks=True)
+    auc.update(predictions={"t": ps[ctx.rank]}, labels={"t": ls[ctx.rank]}, weights={"t": ws[ctx.rank]})
+    assert auc.compute()["auc-t|window_auc"].item() == pytest.approx(M._auc_from_samples(p.double(), l.double(), w.double()).item(), rel=1e-6)
+
+
+def test_metrics_sync_across_ranks():
+    run_multi_process(_dist_metric, world_size=2, backend="gloo")
+
+
+def test_ndcg_gauc_recall_session_and_others_run():
+    p, l, w = _data(60, seed=5)
+    sess = torch.arange(60) // 6
+    for cls, extra in ((M.NDCGMetric, {"session_ids": sess}), (M.GAUCMetric, {"grouping_keys": sess}), (M.RecallSessionMetric, {"session_ids": sess}),
+                       (M.PrecisionSessionMetric, {"session_ids": sess})):
+        m = _one(cls)
+        m.update(predictions={"t": p}, labels={"t": l}, weights={"t": w}, **extra)
+        v = list(m.compute().values())[0]
+        assert 0.0 <= float(v) <= 1.0
+    for cls in (M.PrecisionMetric, M.RecallMetric, M.WeightedAvgMetric, M.NMSEMetric, M.XAUCMetric, M.RAUCMetric, M.AUPRCMetric, M.CaliFreeNEMetric,
+                M.UnweightedNEMetric, M.ServingNEMetric, M.ServingCalibrationMetric, M.OutputMetric, M.AverageMetric, M.HindsightTargetPRMetric, M.ScalarMetric,
+                M.TowerQPSMetric, M.MultiLabelPrecisionMetric):
+        m = _one(cls)
+        for _ in range(3):
+            m.update(predictions={"t": p}, labels={"t": l}, weights={"t": w})
+        r = m.compute()
+        assert len(r) >= 1 and all(torch.isfinite(torch.as_tensor(v)).all() for v in r.values()), cls
+    mc = _one(M.MulticlassRecallMetric, number_of_classes=4)
+    mc.update(predictions={"t": torch.rand(60, 4)}, labels={"t": torch.randint(0, 4, (60,))}, weights={"t": w})
+    assert list(mc.compute().values())[0].shape[-1] == 4

@@ -1,0 +1,6 @@
+from .metric_module import CPUOffloadedRecMetricModule, RecMetricModule, StateMetric, generate_metric_module  # noqa: F401
+from .metrics_config import DefaultMetricsConfig, DefaultTaskInfo, MetricsConfig, RecMetricDef, RecMetricEnum, StateMetricEnum, ThroughputDef  # noqa: F401
+from .metrics_impl import *  # noqa: F401,F403
+from .metrics_namespace import MetricName, MetricNamespace, MetricPrefix, compose_metric_key  # noqa: F401
+from .rec_metric import RecComputeMode, RecMetric, RecMetricComputation, RecMetricList, RecTaskInfo  # noqa: F401
+from .throughput import ThroughputMetric  # noqa: F401
