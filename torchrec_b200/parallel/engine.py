@@ -233,6 +233,7 @@ class ShardedLookupEngine(nn.Module):
 
         # ---- portable transport modules ---------------------------------------------------------------
         self._p2p: Optional["_P2PState"] = None
+        self._p2p_in: Optional["_P2PInputState"] = None
         self._p2p_checked = False
         self._kjt_a2a: Optional[KJTAllToAll] = None
         self._pooled_a2a: Optional[PooledEmbeddingsAllToAll] = None
@@ -351,7 +352,18 @@ class ShardedLookupEngine(nn.Module):
         routed, unbucketize = self.route(features)
         if self._kjt_a2a is None:
             return NoWait(NoWait(routed)), unbucketize
+        if self._pooled and not routed.variable_stride_per_key() and self.fused_available(None) and self._uniform_batch(routed.stride()):
+            return NoWait(NoWait(self.p2p_input_dist(routed))), unbucketize
         return self._kjt_a2a(routed), unbucketize
+
+    def _uniform_batch(self, B: int) -> bool:
+        """All ranks feed the same local batch size (checked once per size; required by the fixed-slot NVLink buffers)."""
+        cache = self.__dict__.setdefault("_uniform_batch_cache", {})
+        if B not in cache:
+            t = torch.tensor([B, -B], device=self._device, dtype=torch.int64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self._pg)
+            cache[B] = int(t[0].item()) == B and int(-t[1].item()) == B
+        return cache[B]
 
     # ---- lookup -------------------------------------------------------------------------------------------
     def lookup(self, dist_features: KeyedJaggedTensor) -> torch.Tensor:
@@ -476,6 +488,62 @@ class ShardedLookupEngine(nn.Module):
             self._p2p_checked = True
         return self._p2p_ok
 
+    def p2p_input_dist(self, routed: KeyedJaggedTensor) -> KeyedJaggedTensor:
+        """NVLink input dist without host sync: publish the routed KJT, barrier, pull this rank's unit segments
+        from every peer. Returns the distributed KJT (values buffer sized to capacity, true sizes in ``offsets``)."""
+        import ctypes
+
+        from ..ops import _lib
+
+        B = routed.stride()
+        values = routed.values()
+        weights = routed.weights_or_none() if self._is_weighted else None
+        st = self._p2p_in
+        if st is None or st.B != B or st.idx_dtype != values.dtype or st.weighted != (weights is not None):
+            # one-time sizing: the largest id count any rank publishes, with head-room for later batches
+            n = torch.tensor([values.numel()], device=self._device, dtype=torch.int64)
+            dist.all_reduce(n, op=dist.ReduceOp.MAX, group=self._pg)
+            import os
+
+            slack = float(os.environ.get("TRB_ID_CAPACITY_SLACK", "1.5"))
+            cap = int(os.environ.get("TRB_MAX_IDS_PER_RANK", "0")) or int(int(n.item()) * slack) + 1024
+            st = self._p2p_in = _P2PInputState(self, B, cap, values.dtype, weights is not None)
+        if values.numel() > st.local_capacity:
+            raise RuntimeError(f"batch carries {values.numel()} ids but the NVLink input-dist buffers hold {st.local_capacity}; "
+                               "raise TRB_MAX_IDS_PER_RANK / TRB_ID_CAPACITY_SLACK")
+        slot = st.step % st.N_SLOTS
+        st.step += 1
+        base = slot * st.slot_bytes
+        U = len(self._units)
+        off_local = st.buf.local(torch.int64, (U * B + 1,), base)
+        off_local.copy_(routed.offsets())
+        val_local = st.buf.local(st.idx_dtype, (values.numel(),), base + st.off_bytes)
+        val_local.copy_(values)
+        if weights is not None:
+            st.buf.local(torch.float32, (values.numel(),), base + st.off_bytes + st.val_bytes).copy_(weights)
+        st.pg.barrier(st.CHANNEL)
+        W = self._W
+        n_seg = st.U_d * W
+        seg_base = torch.empty(n_seg + 1, dtype=torch.int64, device=self._device)
+        out_off = torch.empty(n_seg * B + 1, dtype=torch.int64, device=self._device)
+        out_val = torch.empty(st.out_capacity, dtype=st.idx_dtype, device=self._device)
+        out_wgt = torch.empty(st.out_capacity, dtype=torch.float32, device=self._device) if weights is not None else None
+        if st.U_d == 0:
+            out_off.zero_()
+        else:
+            L = _lib.lib()
+            code = L.trb_kjt_pull(
+                _lib.ptr_array(st.buf.peer_ptrs(base)), _lib.ptr_array(st.buf.peer_ptrs(base + st.off_bytes)),
+                _lib.ptr_array(st.buf.peer_ptrs(base + st.off_bytes + st.val_bytes)) if weights is not None else ctypes.c_void_p(0),
+                W, _lib.ptr(st.units), st.U_d, B, 8 if st.idx_dtype == torch.int64 else 4, _lib.ptr(seg_base), _lib.ptr(out_off), _lib.ptr(out_val),
+                _lib.ptr(out_wgt), ctypes.c_int64(st.out_capacity), _lib.ptr(st.overflow), ctypes.c_int64(max(1, values.numel() // max(U, 1))),
+                _lib.stream_ptr(self._device))
+            _lib.check(code, "trb_kjt_pull")
+        if st.step % 512 == 0:  # amortised check of the device-side overflow flag
+            if int(st.overflow.item()) != 0:
+                raise RuntimeError("NVLink input dist overflow: a rank received more ids than its buffer holds; raise TRB_ID_CAPACITY_SLACK")
+        return KeyedJaggedTensor(keys=st.keys, values=out_val, weights=out_wgt, offsets=out_off, stride=W * B, stride_per_rank=[B] * W)
+
     def _ensure_p2p(self, B_local: int, total_cols: int) -> "_P2PState":
         st = self._p2p
         if st is not None and st.B_local == B_local and st.total_cols == total_cols:
@@ -497,6 +565,38 @@ class ShardedLookupEngine(nn.Module):
             anchor = st.dummy
         weights = dist_features.weights_or_none() if self._is_weighted else None
         return _FusedLookupDistFn.apply(anchor, self, st, dist_features.values(), dist_features.offsets(), weights, dist_features.stride(), grad_scale)
+
+
+class _P2PInputState:
+    """Symmetric publish buffers + pull outputs of the NVLink input dist (see csrc/kjt_p2p.cu)."""
+
+    N_SLOTS = 2
+    CHANNEL = 1
+
+    def __init__(self, eng: ShardedLookupEngine, B: int, local_capacity: int, idx_dtype: torch.dtype, weighted: bool) -> None:
+        from .p2p import PeerGroup
+
+        self.pg = PeerGroup.get(eng._pg, eng._device)
+        self.B = B
+        self.W = eng._W
+        self.local_capacity = local_capacity  # ids a rank may publish per batch
+        self.idx_dtype = idx_dtype
+        self.weighted = weighted
+        U = len(eng._units)
+        esz = 8 if idx_dtype == torch.int64 else 4
+        self.off_bytes = (U * B + 1) * 8
+        self.off_bytes = (self.off_bytes + 255) // 256 * 256
+        self.val_bytes = (local_capacity * esz + 255) // 256 * 256
+        self.wgt_bytes = (local_capacity * 4 + 255) // 256 * 256 if weighted else 0
+        self.slot_bytes = self.off_bytes + self.val_bytes + self.wgt_bytes
+        self.buf = self.pg.alloc(self.slot_bytes * self.N_SLOTS)
+        self.step = 0
+        self.U_d = eng._units_per_rank[eng._rank]
+        self.units = torch.tensor([u.gidx for u in eng._local_units], dtype=torch.int32, device=eng._device)
+        self.out_capacity = local_capacity * self.W
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=eng._device)
+        self.keys = [eng._feature_names[u.feature] for u in eng._local_units]
+        self.checked_overflow_at = 0
 
 
 class _P2PState:

@@ -62,10 +62,14 @@ class PeerGroup:
         self._lib = _lib.lib()
         self._lib.trb_set_device(device.index if device.index is not None else torch.cuda.current_device())
         self._buffers: List[SymmetricBuffer] = []
-        self._pad = self.alloc(256)  # signal pad: uint32 flags[W]
-        self._epoch = torch.zeros(1, dtype=torch.int32, device=device)
-        self._pad_ptr_arr = _lib.ptr_array(self._pad.ptrs)
-        self.barrier()
+        # one signal pad (uint32 flags[W]) + epoch counter per barrier *channel*: collectives that may be in
+        # flight concurrently on different streams (input dist vs lookup/output dist) use different channels
+        self.N_CHANNELS = 4
+        self._pad = self.alloc(256 * self.N_CHANNELS)
+        self._epoch = torch.zeros(self.N_CHANNELS, dtype=torch.int32, device=device)
+        self._pad_ptr_arrs = [_lib.ptr_array([p + 256 * c for p in self._pad.ptrs]) for c in range(self.N_CHANNELS)]
+        for c in range(self.N_CHANNELS):
+            self.barrier(c)
         torch.cuda.synchronize(device)
 
     @staticmethod
@@ -128,9 +132,10 @@ class PeerGroup:
         dist.barrier(group=self.pg)
         return buf
 
-    def barrier(self) -> None:
+    def barrier(self, channel: int = 0) -> None:
         """Device-side barrier of all ranks on the current stream (graph capturable)."""
-        code = self._lib.trb_barrier(self._pad_ptr_arr, self.world, self.rank, _lib.ptr(self._epoch), _lib.stream_ptr(self.device))
+        code = self._lib.trb_barrier(self._pad_ptr_arrs[channel], self.world, self.rank, ctypes.c_void_p(self._epoch.data_ptr() + 4 * channel),
+                                     _lib.stream_ptr(self.device))
         _lib.check(code, "trb_barrier")
 
 
