@@ -1,0 +1,47 @@
+import torch
+
+from torchrec_b200.modules.embedding_configs import EmbeddingBagConfig
+from torchrec_b200.modules.embedding_modules import EmbeddingBagCollection
+from torchrec_b200.modules.mc_embedding_modules import ManagedCollisionEmbeddingBagCollection
+from torchrec_b200.modules.mc_modules import DistanceLFU_EvictionPolicy, LFU_EvictionPolicy, LRU_EvictionPolicy, ManagedCollisionCollection, MCHManagedCollisionModule
+from torchrec_b200.sparse import JaggedTensor, KeyedJaggedTensor
+
+
+def _jt(v):
+    return JaggedTensor(values=torch.tensor(v, dtype=torch.int64), lengths=torch.tensor([len(v)]))
+
+
+def test_sorted_zch_admits_frequent_ids_and_is_stable():
+    mc = MCHManagedCollisionModule(zch_size=4, device=torch.device("cpu"), eviction_policy=LFU_EvictionPolicy(), eviction_interval=1)
+    mc.train()
+    ids = [1000, 1000, 2000, 3000, 3000, 3000, 4000, 5000]
+    mc({"f": _jt(ids)})  # profile -> after the interval the 4 most frequent ids own the slots
+    out = mc({"f": _jt([1000, 3000, 2000])})["f"].values()
+    assert len(set(out.tolist())) == 3 and all(0 <= x < 4 for x in out.tolist())
+    again = mc({"f": _jt([1000, 3000, 2000])})["f"].values()
+    assert torch.equal(out, again)  # admitted ids keep their slot
+    assert int(mc.open_slots()) == 0
+    # a new very frequent id evicts the weakest resident
+    mc({"f": _jt([9000] * 20)})
+    ev = mc.evict()
+    assert ev is not None and ev.numel() == 1
+    nine = mc({"f": _jt([9000])})["f"].values()
+    assert int(nine) == int(ev[0])
+
+
+def test_lru_and_distance_lfu_policies_run():
+    for pol in (LRU_EvictionPolicy(), DistanceLFU_EvictionPolicy()):
+        mc = MCHManagedCollisionModule(zch_size=8, device=torch.device("cpu"), eviction_policy=pol, eviction_interval=2, mch_size=2)
+        mc.train()
+        for step in range(6):
+            out = mc({"f": _jt(list(range(step * 3, step * 3 + 5)))})["f"].values()
+            assert out.min() >= 0 and out.max() < 8
+
+
+def test_mc_ebc_end_to_end():
+    tables = [EmbeddingBagConfig(name="t", embedding_dim=8, num_embeddings=16, feature_names=["f"])]
+    mcc = ManagedCollisionCollection({"t": MCHManagedCollisionModule(zch_size=16, device=torch.device("cpu"), eviction_policy=LFU_EvictionPolicy(), eviction_interval=1)}, tables)
+    m = ManagedCollisionEmbeddingBagCollection(EmbeddingBagCollection(tables), mcc, return_remapped_features=True)
+    kjt = KeyedJaggedTensor(keys=["f"], values=torch.tensor([10**12, 5, 10**12 + 7, 5]), lengths=torch.tensor([2, 2]))
+    out, remapped = m(kjt)
+    assert out.values().shape == (2, 8) and remapped.values().max() < 16

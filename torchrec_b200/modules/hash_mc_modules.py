@@ -1,0 +1,223 @@
+"""Multi-probe zero-collision hash (MPZCH) managed collision module
+(reference torchrec/modules/hash_mc_modules.py:196, hash_mc_evictions.py, hash_mc_metrics.py).
+
+Open-addressing table of ``zch_size`` slots: an id hashes to a start slot inside its bucket and probes up to
+``max_probe`` consecutive slots for itself or for a free / evictable slot. Eviction scoring is pluggable (none, LRU by
+last-seen hour, TTL). Replaces ``fbgemm.zero_collision_hash`` / ``create_zch_buffer``; the probe loop runs vectorised in
+PyTorch on CPU and GPU (all ids probe one step per iteration)."""
+from __future__ import annotations
+
+import logging
+import time
+from enum import Enum, unique
+from typing import Any, Dict, List, Optional, Tuple
+
+import torch
+
+from ..sparse.jagged_tensor import JaggedTensor
+from .mc_modules import ManagedCollisionModule
+
+logger = logging.getLogger(__name__)
+
+
+@unique
+class HashZchEvictionPolicyName(Enum):
+    SINGLE_TTL_EVICTION = "SINGLE_TTL_EVICTION"
+    LRU_EVICTION = "LRU_EVICTION"
+    NONE = "NONE"
+
+
+class HashZchEvictionConfig:
+    def __init__(self, features: List[str], single_ttl: Optional[int] = None) -> None:
+        self.features = features
+        self.single_ttl = single_ttl
+
+
+class ScalarLogger(torch.nn.Module):
+    """Running hit / insert / collision statistics of one ZCH table (reference hash_mc_metrics.py)."""
+
+    def __init__(self, name: str, zch_size: int, frequency: int = 100, start_bucket: int = 0, log_file_path: str = "") -> None:
+        super().__init__()
+        self._name, self._zch_size, self._frequency = name, zch_size, frequency
+        self._steps = 0
+        self.stats: Dict[str, float] = {"hit": 0, "insert": 0, "collision": 0, "total": 0}
+
+    def update(self, hit: int, insert: int, collision: int, total: int) -> None:
+        self.stats["hit"] += hit
+        self.stats["insert"] += insert
+        self.stats["collision"] += collision
+        self.stats["total"] += total
+        self._steps += 1
+        if self._steps % self._frequency == 0:
+            t = max(self.stats["total"], 1)
+            logger.info(f"{self._name}: hit rate {self.stats['hit'] / t:.4f} insert rate {self.stats['insert'] / t:.4f} collision rate {self.stats['collision'] / t:.4f}")
+
+    def forward(self) -> Dict[str, float]:
+        return dict(self.stats)
+
+
+def _mix64(x: torch.Tensor) -> torch.Tensor:
+    """splitmix64-style finaliser on int64 tensors (wrap-around arithmetic)."""
+    x = x ^ (x >> 30)
+    x = x * -4658895280553007687  # 0xbf58476d1ce4e5b9
+    x = x ^ (x >> 27)
+    x = x * -7723592293110705685  # 0x94d049bb133111eb
+    return x ^ (x >> 31)
+
+
+class HashZchManagedCollisionModule(ManagedCollisionModule):
+    def __init__(self, zch_size: int, device: torch.device, total_num_buckets: int, max_probe: int = 128, input_hash_size: int = (2**63) - 1,
+                 output_segments: Optional[List[int]] = None, is_inference: bool = False, name: Optional[str] = None, tb_logging_frequency: int = 0,
+                 eviction_policy_name: Optional[HashZchEvictionPolicyName] = None, eviction_config: Optional[HashZchEvictionConfig] = None,
+                 inference_dispatch_div_train_world_size: bool = False, start_bucket: int = 0, end_bucket: Optional[int] = None,
+                 opt_in_prob: int = -1, percent_reserved_slots: float = 0, disable_fallback: bool = False) -> None:
+        if output_segments is None:
+            assert zch_size % total_num_buckets == 0, f"please pass output segments if not uniform buckets {zch_size=}, {total_num_buckets=}"
+            output_segments = [(zch_size // total_num_buckets) * bucket for bucket in range(total_num_buckets + 1)]
+        super().__init__(device=device, output_segments=output_segments, skip_state_validation=True)
+        self._zch_size_total = zch_size
+        self._total_num_buckets = total_num_buckets
+        self._start_bucket = start_bucket
+        self._end_bucket = end_bucket if end_bucket is not None else total_num_buckets
+        self._output_global_offset_tensor: Optional[torch.Tensor] = None
+        self._name = name
+        self._is_inference = is_inference
+        self._max_probe = max_probe
+        self._input_hash_size = input_hash_size
+        self._eviction_policy_name = eviction_policy_name or HashZchEvictionPolicyName.NONE
+        self._eviction_config = eviction_config
+        self._disable_fallback = disable_fallback
+        lo, hi = output_segments[self._start_bucket], output_segments[self._end_bucket]
+        self._zch_size = hi - lo
+        self._offset = lo
+        self._buckets_local = self._end_bucket - self._start_bucket
+        self._bucket_size = self._zch_size // max(self._buckets_local, 1)
+        self.register_buffer("_hash_zch_identities", torch.full((self._zch_size, 1), -1, dtype=torch.int64, device=device))
+        self.register_buffer("_hash_zch_metadata", torch.zeros((self._zch_size, 1), dtype=torch.int32, device=device))
+        self._scalar_logger = ScalarLogger(name or "zch", self._zch_size, tb_logging_frequency) if tb_logging_frequency > 0 else None
+        self._evicted_indices: List[torch.Tensor] = []
+
+    def preprocess(self, features: Dict[str, JaggedTensor]) -> Dict[str, JaggedTensor]:
+        return features
+
+    def _now(self) -> int:
+        return int(time.time() // 3600)
+
+    @torch.no_grad()
+    def _probe(self, ids: torch.Tensor, readonly: bool) -> torch.Tensor:
+        n = ids.numel()
+        if n == 0:
+            return ids
+        ident = self._hash_zch_identities.view(-1)
+        meta = self._hash_zch_metadata.view(-1)
+        h = _mix64(ids)
+        bucket = torch.remainder(h, max(self._buckets_local, 1))
+        start = torch.remainder(h >> 16, max(self._bucket_size, 1))
+        out = torch.full_like(ids, -1)
+        pending = torch.ones(n, dtype=torch.bool, device=ids.device)
+        now = self._now()
+        ttl = self._eviction_config.single_ttl if (self._eviction_config and self._eviction_config.single_ttl) else None
+        hits = inserts = 0
+        for p in range(min(self._max_probe, max(self._bucket_size, 1))):
+            if not bool(pending.any()):
+                break
+            idx = pending.nonzero(as_tuple=True)[0]
+            slot = bucket[idx] * self._bucket_size + torch.remainder(start[idx] + p, max(self._bucket_size, 1))
+            cur = ident[slot]
+            hit = cur == ids[idx]
+            out[idx[hit]] = slot[hit]
+            pending[idx[hit]] = False
+            hits += int(hit.sum())
+            if readonly:
+                continue
+            free = cur == -1
+            if self._eviction_policy_name == HashZchEvictionPolicyName.SINGLE_TTL_EVICTION and ttl is not None:
+                free = free | ((cur != -1) & ~hit & (meta[slot].long() + ttl < now))
+            cand = idx[free & ~hit]
+            if cand.numel():
+                cslot = slot[free & ~hit]
+                # several ids may want the same free slot in this round: the first one wins, the rest keep probing
+                uniq_slot, first = _first_occurrence(cslot)
+                # also de-duplicate identical ids (they will hit on the next probe round)
+                win_ids = ids[cand[first]]
+                old = ident[uniq_slot]
+                if bool((old != -1).any()):
+                    self._evicted_indices.append(uniq_slot[old != -1] + self._offset)
+                ident[uniq_slot] = win_ids
+                meta[uniq_slot] = now
+                out[cand[first]] = uniq_slot
+                pending[cand[first]] = False
+                inserts += int(uniq_slot.numel())
+                # duplicates of a winning id: resolve immediately
+                same = pending.clone()
+                same[:] = False
+                rest = cand[~_mask_of(first, cand.numel(), cand.device)]
+                if rest.numel():
+                    rs = cslot[~_mask_of(first, cand.numel(), cand.device)]
+                    again = ident[rs] == ids[rest]
+                    out[rest[again]] = rs[again]
+                    pending[rest[again]] = False
+        touched = out >= 0
+        if not readonly and bool(touched.any()):
+            meta[out[touched]] = now
+        if self._scalar_logger is not None:
+            self._scalar_logger.update(hits, inserts, int(pending.sum()), n)
+        # ids that found no slot fall back to their start slot (collision) unless disabled
+        fb = bucket * self._bucket_size + start
+        out = torch.where(out >= 0, out, fb if not self._disable_fallback else torch.full_like(out, -1))
+        return out
+
+    def remap(self, features: Dict[str, JaggedTensor]) -> Dict[str, JaggedTensor]:
+        res: Dict[str, JaggedTensor] = {}
+        readonly = self._is_inference or not self.training
+        for name, f in features.items():
+            slot = self._probe(f.values().to(torch.int64), readonly)
+            res[name] = JaggedTensor(values=slot + self._offset, lengths=f.lengths(), offsets=f.offsets(), weights=f.weights_or_none())
+        return res
+
+    def profile(self, features: Dict[str, JaggedTensor]) -> Dict[str, JaggedTensor]:
+        return features
+
+    def forward(self, features: Dict[str, JaggedTensor]) -> Dict[str, JaggedTensor]:
+        return self.remap(features)
+
+    def output_size(self) -> int:
+        return self._zch_size_total
+
+    def buckets(self) -> int:
+        return self._total_num_buckets
+
+    def input_size(self) -> int:
+        return self._input_hash_size
+
+    def open_slots(self) -> torch.Tensor:
+        return (self._hash_zch_identities.view(-1) == -1).sum().view(1)
+
+    def evict(self) -> Optional[torch.Tensor]:
+        if not self._evicted_indices:
+            return None
+        out = torch.cat(self._evicted_indices)
+        self._evicted_indices = []
+        return out
+
+    def rebuild_with_output_id_range(self, output_id_range: Tuple[int, int], output_segments: List[int], device: Optional[torch.device] = None):
+        start_bucket = output_segments.index(output_id_range[0])
+        end_bucket = output_segments.index(output_id_range[1])
+        return type(self)(zch_size=self._zch_size_total, device=device or self.device, total_num_buckets=self._total_num_buckets, max_probe=self._max_probe,
+                          input_hash_size=self._input_hash_size, output_segments=output_segments, is_inference=self._is_inference, name=self._name,
+                          eviction_policy_name=self._eviction_policy_name, eviction_config=self._eviction_config, start_bucket=start_bucket, end_bucket=end_bucket,
+                          disable_fallback=self._disable_fallback)
+
+
+def _first_occurrence(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Unique values of x and the index of their first occurrence."""
+    uniq, inv = torch.unique(x, return_inverse=True)
+    first = torch.full((uniq.numel(),), x.numel(), dtype=torch.long, device=x.device)
+    first.scatter_reduce_(0, inv, torch.arange(x.numel(), device=x.device), reduce="amin", include_self=True)
+    return uniq, first
+
+
+def _mask_of(idx: torch.Tensor, n: int, device) -> torch.Tensor:
+    m = torch.zeros(n, dtype=torch.bool, device=device)
+    m[idx] = True
+    return m
