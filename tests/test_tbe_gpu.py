@@ -122,3 +122,37 @@ def test_large_keys_64bit_path_and_launch_counter():
     assert torch.allclose(d[7], torch.full((32,), -1.0, device=dev))
     assert float(d.abs().sum()) == pytest.approx(32 * 4.0)
     assert _lib.launch_count() > n0
+
+
+@pytest.mark.gpu
+def test_psw_grad_matches_reference():
+    """Per-sample-weight gradient kernel vs autograd of F.embedding_bag."""
+    import torch.nn.functional as F
+
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    from torchrec_b200.ops.tbe import OptimType, PoolingMode, TableBatchedEmbeddingBags
+
+    B = 37
+    t = TableBatchedEmbeddingBags([(100, 16), (50, 128)], [0, 1, 1], pooling_mode=PoolingMode.SUM, optimizer=OptimType.EXACT_SGD, learning_rate=0.0, device=dev)
+    t.init_parameters([(-1, 1), (-1, 1)])
+    lengths = torch.randint(0, 5, (3 * B,), device=dev)
+    off = torch.cat([lengths.new_zeros(1), lengths.cumsum(0)])
+    n = int(off[-1])
+    rows = torch.tensor([100, 50, 50], device=dev).repeat_interleave(B).repeat_interleave(lengths)
+    idx = (torch.rand(n, device=dev) * rows).long()
+    psw = torch.rand(n, device=dev, requires_grad=True)
+    out = t(idx, off, psw, batch_size=B)
+    gout = torch.randn_like(out)
+    (out * gout).sum().backward()
+    ws = t.split_embedding_weights()
+    psw2 = psw.detach().clone().requires_grad_()
+    refs = []
+    for f, tb in enumerate([0, 1, 1]):
+        lo, hi = int(off[f * B]), int(off[(f + 1) * B])
+        o = off[f * B : (f + 1) * B] - lo
+        refs.append(F.embedding_bag(idx[lo:hi], ws[tb].float(), o, mode="sum", per_sample_weights=psw2[lo:hi]))
+    ref = torch.cat(refs, 1)
+    torch.testing.assert_close(out.float(), ref, atol=1e-4, rtol=1e-4)
+    (ref * gout).sum().backward()
+    torch.testing.assert_close(psw.grad, psw2.grad, atol=1e-4, rtol=1e-4)

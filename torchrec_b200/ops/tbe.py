@@ -451,6 +451,49 @@ def fused_backward(
     _lib.check(code, "trb_tbe_bwd_fused")
 
 
+def psw_grad(meta: TbeMeta, weights: torch.Tensor, indices: torch.Tensor, offsets: torch.Tensor, B: int, mean: bool, grad: Optional[torch.Tensor] = None,
+             grad_ptrs: Optional[Sequence[int]] = None, grad_stride: Optional[int] = None, grad_dtype: Optional[torch.dtype] = None,
+             B_local: Optional[int] = None) -> torch.Tensor:
+    """Gradient of the pooled lookup w.r.t. per-sample weights: ``d psw[i] = <grad[bag(i)], W[idx[i]]>`` (fp32 ``[n]``).
+    Call BEFORE ``fused_backward`` (which updates the rows in place). csrc/tbe_psw_grad.cu."""
+    n = indices.numel()
+    if not _lib.use_cuda_kernels(weights):
+        assert grad is not None
+        out = torch.zeros(n, dtype=torch.float32, device=weights.device)
+        off = offsets.to(torch.int64)
+        for f in range(meta.num_features):
+            o = off[f * B : (f + 1) * B + 1]
+            lo, hi = int(o[0]), int(o[-1])
+            if hi <= lo:
+                continue
+            D, col, rows = meta.h_dim[f], meta.h_col[f], meta.h_rows[f]
+            lengths = o[1:] - o[:-1]
+            b = torch.repeat_interleave(torch.arange(B, device=off.device), lengths, output_size=hi - lo)
+            idx = indices[lo:hi].long()
+            ok = (idx >= 0) & (idx < rows)
+            w = weights[meta.h_woff[f] : meta.h_woff[f] + rows * D].view(rows, D)[idx.clamp(0, rows - 1)].float()
+            v = (w * grad[b, col : col + D].float()).sum(1) * ok
+            if mean:
+                v = v / lengths[b].clamp(min=1).float()
+            out[lo:hi] = v
+        return out
+    out = torch.zeros(n, dtype=torch.float32, device=weights.device)
+    if n == 0:
+        return out
+    if grad_ptrs is None:
+        assert grad is not None
+        if grad.stride(1) != 1:
+            grad = grad.contiguous()
+        grad_ptrs, grad_stride, grad_dtype, B_local = [grad.data_ptr()], grad.stride(0), grad.dtype, B
+    L = _lib.lib()
+    code = L.trb_tbe_psw_grad(_lib.ptr(weights), _lib.dtype_code(weights.dtype), _lib.ptr(meta.feat_woff), _lib.ptr(meta.feat_rows), _lib.ptr(meta.feat_dim),
+                              _lib.ptr(meta.feat_col), _lib.ptr(indices), _is64(indices), _lib.ptr(offsets), _is64(offsets), _lib.ptr_array(grad_ptrs),
+                              len(grad_ptrs), _lib.dtype_code(grad_dtype), ctypes.c_int64(grad_stride), _lib.ptr(out), B, B_local, meta.num_features,
+                              meta.max_dim, int(mean), _lib.stream_ptr(weights.device))
+    _lib.check(code, "trb_tbe_psw_grad")
+    return out
+
+
 def sequence_backward(meta, weights, state1, state2, hyper_dev, hyper_host, opt, wd_mode, indices, offsets, B, grad):
     """Backward of the unpooled lookup: position i contributes grad[i] to row indices[i].
     Expressed as a pooled backward with one bag per position (column offset 0, stride D)."""
@@ -488,8 +531,12 @@ class _PooledLookupFn(torch.autograd.Function):
     def backward(ctx, grad):
         indices, offsets, psw = ctx.saved_tensors
         tbe = ctx.tbe
+        gpsw = None
+        if psw is not None and ctx.needs_input_grad[4]:
+            # windowed offsets (engine groups) index into the full values tensor: the gradient is positional
+            gpsw = psw_grad(tbe.meta, tbe.weights.detach(), indices, offsets, ctx.B, tbe.pooling_mode == PoolingMode.MEAN, grad=grad).to(psw.dtype)
         dense = tbe._backward(indices, offsets, psw, grad, ctx.B)
-        return dense, None, None, None, None, None
+        return dense, None, None, None, gpsw, None
 
 
 class _SeqLookupFn(torch.autograd.Function):

@@ -170,6 +170,10 @@ class ShardedEmbeddingCollection(ShardedModule[KJTList, List[torch.Tensor], Dict
             elif wview.numel() > 0:
                 wview.copy_(torch.empty(wview.shape, dtype=torch.float32, device=wview.device).uniform_(cfg.get_weight_init_min(), cfg.get_weight_init_max()))
 
+    def reset_rows(self, table: str, global_rows: torch.Tensor) -> int:
+        """Re-initialise rows of a sharded table (managed-collision eviction / ITEP); see engine.reset_rows."""
+        return self._engine.reset_rows(table, global_rows) if self._engine is not None else 0
+
     def _local_shards_by_table(self):
         res: Dict[str, List] = {}
         for item in self._engine.local_shard_views():
@@ -330,6 +334,10 @@ class ShardedEmbeddingCollection(ShardedModule[KJTList, List[torch.Tensor], Dict
     def sharded_parameter_names(self, prefix: str = "") -> Iterator[str]:
         for name in self._table_params:
             yield (prefix + "." if prefix else "") + f"embeddings.{name}.weight"
+        # the engine's storage (autograd anchor parameters) is rank-private: keep it out of DDP
+        for n, _ in nn.Module.named_parameters(self):
+            if n.startswith("_engine."):
+                yield (prefix + "." if prefix else "") + n
 
     def state_dict(self, destination: Optional[Dict[str, Any]] = None, prefix: str = "", keep_vars: bool = False) -> Dict[str, Any]:
         from .comm import get_local_size

@@ -359,6 +359,10 @@ class ShardedEmbeddingBagCollection(
             if self._pg is not None and self._env.world_size > 1:
                 dist.broadcast(self._dp_tbe.weights.data, src=dist.get_global_rank(self._pg, 0), group=self._pg)
 
+    def reset_rows(self, table: str, global_rows: torch.Tensor) -> int:
+        """Re-initialise rows of a sharded table (managed-collision eviction / ITEP); see engine.reset_rows."""
+        return self._engine.reset_rows(table, global_rows) if self._engine is not None else 0
+
     def _local_shards_by_table(self) -> Dict[str, List[Tuple[TableShard, torch.Tensor, Dict[str, torch.Tensor], TableBatchedEmbeddingBags]]]:
         res: Dict[str, List] = {}
         if self._engine is not None:
@@ -557,6 +561,10 @@ class ShardedEmbeddingBagCollection(
         if self._dp_lookup is not None:
             # replicated tables are all-reduced by their own DDP wrapper: hide them from the outer DDP
             yield (prefix + "." if prefix else "") + self._dp_param_name()
+        # the engine's storage (autograd anchor parameters) is rank-private: keep it out of DDP
+        for n, _ in nn.Module.named_parameters(self):
+            if n.startswith("_engine."):
+                yield (prefix + "." if prefix else "") + n
 
     def state_dict(self, destination: Optional[Dict[str, Any]] = None, prefix: str = "", keep_vars: bool = False) -> Dict[str, Any]:
         from .comm import get_local_size

@@ -474,6 +474,25 @@ class ShardedLookupEngine(nn.Module):
         return res
 
 
+    @torch.no_grad()
+    def reset_rows(self, table: str, global_rows: torch.Tensor) -> int:
+        """Re-initialise the given (global) rows of ``table`` wherever this rank holds them — weights back to the
+        table's init range, optimizer state to zero. Used by managed-collision eviction and ITEP pruning."""
+        n_reset = 0
+        for shard, w, st, _tbe in self.local_shard_views():
+            if shard.name != table or shard.rows == 0:
+                continue
+            cfg = self._tables[shard.table_idx]
+            ids = global_rows.to(w.device).long()
+            ids = ids[(ids >= shard.row_off) & (ids < shard.row_off + shard.rows)] - shard.row_off
+            if ids.numel() == 0:
+                continue
+            w[ids] = torch.empty(ids.numel(), w.shape[1], device=w.device, dtype=torch.float32).uniform_(cfg.get_weight_init_min(), cfg.get_weight_init_max()).to(w.dtype)
+            for v in st.values():
+                v[ids] = 0
+            n_reset += int(ids.numel())
+        return n_reset
+
     # ---- fused NVLink path (single NVLink domain) -----------------------------------------------------------------
     def fused_available(self, batch_size_per_rank: Optional[List[int]]) -> bool:
         """The fused lookup + output-dist kernels can serve this batch (CUDA, one host, even batch)."""
@@ -718,13 +737,21 @@ class _FusedLookupDistFn(torch.autograd.Function):
         p2p.cast_copy(grad, gbuf, ctx.grad_scale)
         st.pg.barrier()
         grad_ptrs = st.buf.peer_ptrs(st.grad_off)
+        gpsw = None
+        want_psw = weights is not None and ctx.needs_input_grad[5]
         for g, gm in zip(eng._groups, st.group_meta):
             if gm is None:
                 continue
             u0, u1 = g.unit_range
             window = offsets[u0 * Bg : u1 * Bg + 1]
+            if want_psw:  # per-sample-weight gradient (feature processors) from the pre-update rows
+                gp = T.psw_grad(gm["full"], g.tbe.weights, values, window, Bg, g.pooling == T.PoolingMode.MEAN, grad_ptrs=grad_ptrs,
+                                grad_stride=st.total_cols, grad_dtype=st.wire_dtype, B_local=st.B_local)
+                gpsw = gp if gpsw is None else gpsw + gp
             g.tbe._pre_update()
             T.fused_backward(gm["full"], g.tbe.weights, g.tbe.state1, g.tbe.state2, g.tbe.hyper_dev, g.tbe.hyper_host, g.tbe.opt_code,
                              int(g.tbe.weight_decay_mode), values, window, weights, Bg, g.pooling == T.PoolingMode.MEAN,
                              grad_ptrs=grad_ptrs, grad_stride=st.total_cols, grad_dtype=st.wire_dtype, B_local=st.B_local)
-        return torch.zeros(1, dtype=torch.float32, device=grad.device), None, None, None, None, None, None, None
+        if gpsw is not None:
+            gpsw = gpsw.to(weights.dtype)
+        return torch.zeros(1, dtype=torch.float32, device=grad.device), None, None, None, None, gpsw, None, None

@@ -12,6 +12,7 @@ def default_extra_sharders() -> List[ModuleSharder]:
         ("mc_embeddingbag", "ManagedCollisionEmbeddingBagCollectionSharder"),
         ("mc_embedding", "ManagedCollisionEmbeddingCollectionSharder"),
         ("itep_embeddingbag", "ITEPEmbeddingBagCollectionSharder"),
+        ("itep_embeddingbag", "ITEPEmbeddingCollectionSharder"),
         ("quant_embeddingbag", "QuantEmbeddingBagCollectionSharder"),
         ("quant_embedding", "QuantEmbeddingCollectionSharder"),
     ):

@@ -562,3 +562,12 @@ class ShardingBucketMetadata:
         self.num_buckets_per_shard = num_buckets_per_shard
         self.bucket_offsets_per_shard = bucket_offsets_per_shard
         self.bucket_size = bucket_size
+
+
+def delegating_named_parameters(module: nn.Module, prefix: str = "", recurse: bool = True) -> Iterator[Tuple[str, nn.Parameter]]:
+    """named_parameters for sharded *wrapper* modules (FP / MC / ITEP): own parameters + each child's own
+    ``named_parameters`` (so an inner sharded collection reports its table-keyed names, not its storage layout)."""
+    yield from nn.Module.named_parameters(module, prefix, recurse=False)
+    if recurse:
+        for name, child in module.named_children():
+            yield from child.named_parameters((prefix + "." if prefix else "") + name, recurse)
