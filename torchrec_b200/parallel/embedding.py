@@ -125,6 +125,9 @@ class ShardedEmbeddingCollection(ShardedModule[KJTList, List[torch.Tensor], Dict
         for t in tables:
             spec, _ = optimizer_spec_from(src_params.get(f"embeddings.{t.name}.weight"), fused_params)
             opt_specs[t.name] = spec
+        if getattr(module, "_trb_opt_specs", None):  # re-sharding keeps the optimizers of the module being replaced
+            opt_specs.update(module._trb_opt_specs)
+        self._opt_specs = opt_specs
         codecs = qcomm_codecs_registry.get(CommOp.SEQUENCE_EMBEDDINGS_ALL_TO_ALL.name) if qcomm_codecs_registry else None
         self._engine = ShardedLookupEngine(tables=tables, feature_names=self._feature_names, feature_table=self._feature_table, plan=self._plan,
                                            env=env, device=self._device, pooled=False, is_weighted=False, opt_specs=opt_specs, qcomm_codecs=codecs)
@@ -169,6 +172,10 @@ class ShardedEmbeddingCollection(ShardedModule[KJTList, List[torch.Tensor], Dict
                 wview.copy_(src[shard.name][shard.row_off : shard.row_off + shard.rows, shard.col_off : shard.col_off + shard.cols])
             elif wview.numel() > 0:
                 wview.copy_(torch.empty(wview.shape, dtype=torch.float32, device=wview.device).uniform_(cfg.get_weight_init_min(), cfg.get_weight_init_max()))
+
+    @property
+    def engine(self):
+        return self._engine
 
     def reset_rows(self, table: str, global_rows: torch.Tensor) -> int:
         """Re-initialise rows of a sharded table (managed-collision eviction / ITEP); see engine.reset_rows."""

@@ -273,6 +273,9 @@ class ShardedEmbeddingBagCollection(
             p = src_params.get(f"embedding_bags.{t.name}.weight")
             spec, tagged = optimizer_spec_from(p, fused_params)
             opt_specs[t.name] = spec
+        if getattr(module, "_trb_opt_specs", None):  # re-sharding keeps the optimizers of the module being replaced
+            opt_specs.update(module._trb_opt_specs)
+        self._opt_specs = opt_specs
         codecs = None
         if qcomm_codecs_registry is not None:
             codecs = qcomm_codecs_registry.get(CommOp.POOLED_EMBEDDINGS_ALL_TO_ALL.name, None)

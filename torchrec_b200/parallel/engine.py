@@ -369,6 +369,7 @@ class ShardedLookupEngine(nn.Module):
     def lookup(self, dist_features: KeyedJaggedTensor) -> torch.Tensor:
         """Run the table-batched kernels over this rank's units. Pooled: ``[B_global, D_local]``;
         sequence: ``[n_values, D]`` (received order)."""
+        self._run_lookup_hooks(dist_features)
         Bg = dist_features.stride()
         values = dist_features.values()
         offsets = dist_features.offsets()
@@ -441,6 +442,21 @@ class ShardedLookupEngine(nn.Module):
         return out
 
     # ---- misc -----------------------------------------------------------------------------------------------
+    def register_lookup_hook(self, fn):
+        """``fn(engine, dist_features)`` runs before every lookup over this rank's units (model delta tracker).
+        Returns a callable that removes the hook."""
+        hooks = self.__dict__.setdefault("_lookup_hooks", [])
+        hooks.append(fn)
+        return lambda: hooks.remove(fn) if fn in hooks else None
+
+    def _run_lookup_hooks(self, dist_features: KeyedJaggedTensor) -> None:
+        for fn in self.__dict__.get("_lookup_hooks", ()):
+            fn(self, dist_features)
+
+    @property
+    def local_units(self) -> List[Unit]:
+        return self._local_units
+
     @property
     def units(self) -> List[Unit]:
         return self._units
@@ -574,6 +590,7 @@ class ShardedLookupEngine(nn.Module):
         """Lookup + pooled output dist in one pass: pooled rows are written straight into the owning
         rank's ``[B_local, total_cols]`` output over NVLink (row-sharded tables via staging slabs
         reduced at the destination). Returns the local output (final column layout)."""
+        self._run_lookup_hooks(dist_features)
         st = self._ensure_p2p(B_local, total_cols)
         anchor = None
         for g in self._groups:

@@ -160,7 +160,13 @@ class DistributedModelParallel(nn.Module, FusedOptimizerModule):
         if model_tracker_config is not None:
             from .model_tracker import ModelDeltaTracker
 
-            self._model_tracker = ModelDeltaTracker(self._dmp_wrapped_module, **(model_tracker_config if isinstance(model_tracker_config, dict) else {}))
+            cfg = model_tracker_config
+            if isinstance(cfg, dict):
+                kw = dict(cfg)
+            else:  # DeltaTrackerConfig dataclass
+                kw = dict(consumers=getattr(cfg, "consumers", None), delete_on_read=getattr(cfg, "delete_on_read", True), auto_compact=getattr(cfg, "auto_compact", False),
+                          mode=getattr(cfg, "tracking_mode", None) or getattr(cfg, "mode"), fqns_to_skip=getattr(cfg, "fqns_to_skip", ()))
+            self._model_tracker = ModelDeltaTracker(self._dmp_wrapped_module, **kw)
 
     # ---- public surface -------------------------------------------------------------------------------------
     @property
