@@ -186,7 +186,7 @@ class DistributedModelParallel(nn.Module, FusedOptimizerModule):
     def init_data_parallel(self) -> None:
         """Wrap the dense part in DDP (call after meta-device parameters were materialised)."""
         if not self._ddp_wrapped:
-            if self._env.process_group is not None and self._env.world_size > 1:
+            if self._env.process_group is not None and getattr(self._env, "global_world_size", self._env.world_size) > 1:
                 self._data_parallel_wrapper.wrap(self, self._env, self.device)
             else:
                 self._dmp_wrapped_module = self._dmp_wrapped_module.to(self.device) if self.device.type != "meta" else self._dmp_wrapped_module
@@ -437,3 +437,145 @@ def add_prefix_to_state_dict(state_dict: Dict[str, Any], prefix: str) -> None:
             if len(key) == 0:
                 continue
             metadata[prefix + key] = metadata.pop(key)
+
+
+class DMPCollection(DistributedModelParallel):
+    """2D parallelism: model parallel inside *sharding groups* of ``sharding_group_size`` ranks, data parallel across the
+    ``world_size // sharding_group_size`` replicas of every shard (reference model_parallel.py:1008-1770).
+
+    The plan is written for ranks ``0..sharding_group_size-1``; every sharding group instantiates it over its own process
+    group (the lookup engine only ever sees group-local ranks, so no plan re-mapping is needed). Dense parameters are DDP'd
+    over the global group; embedding shards (+ fused optimizer state) are averaged across their replica group by ``sync()``,
+    which the training loop calls every N steps.
+
+    ``use_inter_host_allreduce=True`` makes sharding groups contiguous (all-to-all stays inside one NVLink domain, replicas
+    talk across hosts) — the natural layout for NVSwitch nodes; the default interleaves them like the reference."""
+
+    def __init__(self, module: nn.Module, device: torch.device, plan: ShardingPlan, world_size: int, sharding_group_size: int,
+                 global_pg: dist.ProcessGroup, sharding_strategy: ShardingStrategy = ShardingStrategy.DEFAULT, node_group_size: Optional[int] = None,
+                 sharders: Optional[List[ModuleSharder[nn.Module]]] = None, init_data_parallel: bool = True, init_parameters: bool = True,
+                 data_parallel_wrapper: Optional[DataParallelWrapper] = None, use_inter_host_allreduce: bool = False,
+                 custom_all_reduce: Optional[Any] = None, submodule_configs: Optional[List[DMPCollectionConfig]] = None,
+                 rs_awaitable_hook_module: Optional[str] = None) -> None:
+        assert world_size % sharding_group_size == 0, "world_size must be a multiple of sharding_group_size"
+        self._global_pg_ = global_pg
+        self._global_rank = dist.get_rank(global_pg)
+        self._custom_all_reduce = custom_all_reduce
+        self._world_size_2d = world_size
+        self._default_ctx = DMPCollectionContext(module=None, plan=plan, sharding_group_size=sharding_group_size, node_group_size=node_group_size,  # type: ignore[arg-type]
+                                                 use_inter_host_allreduce=use_inter_host_allreduce, sharding_strategy=sharding_strategy)
+        self._submodule_ctxs = [DMPCollectionContext(module=c.module, plan=c.plan, sharding_group_size=c.sharding_group_size, node_group_size=c.node_group_size,
+                                                     use_inter_host_allreduce=c.use_inter_host_allreduce, sharding_strategy=c.sharding_strategy)
+                                for c in (submodule_configs or [])]
+        self._ctxs: List[DMPCollectionContext] = [self._default_ctx] + self._submodule_ctxs
+        for ctx in self._ctxs:
+            ctx.device_mesh, ctx.sharding_pg, ctx.replica_pg = self._create_process_groups(self._global_rank, world_size, ctx.sharding_group_size, ctx.use_inter_host_allreduce)
+        env = ShardingEnv2D(sharding_pg=self._default_ctx.sharding_pg, global_pg=global_pg, device_mesh=self._default_ctx.device_mesh, node_group_size=node_group_size,
+                            use_inter_host_allreduce=use_inter_host_allreduce, replica_pg=self._default_ctx.replica_pg)
+        super().__init__(module, env, device, plan, sharders, init_data_parallel, init_parameters, data_parallel_wrapper)
+        self._sync_cache: Optional[List[torch.Tensor]] = None
+
+    # ---- process groups --------------------------------------------------------------------------------------
+    @staticmethod
+    def _create_process_groups(global_rank: int, world_size: int, local_size: int, use_inter_host_allreduce: bool = False):
+        """Returns (mesh as a [replicas, shards] rank matrix, my sharding pg, my replica pg). Collective: every rank
+        creates every group in the same order."""
+        R = world_size // local_size
+        if use_inter_host_allreduce:
+            matrix = [[g * local_size + i for i in range(local_size)] for g in range(R)]  # row g = sharding group g (contiguous)
+        else:
+            matrix = [[g + i * R for i in range(local_size)] for g in range(R)]  # interleaved (reference default)
+        sharding_pg = replica_pg = None
+        for row in matrix:
+            pg = dist.new_group(ranks=row)
+            if global_rank in row:
+                sharding_pg = pg
+        for col in range(local_size):
+            ranks = [matrix[g][col] for g in range(R)]
+            pg = dist.new_group(ranks=ranks)
+            if global_rank in ranks:
+                replica_pg = pg
+        return matrix, sharding_pg, replica_pg
+
+    # ---- sharding: each context's modules are sharded over that context's group -------------------------------------
+    def _ctx_for(self, module: nn.Module) -> DMPCollectionContext:
+        for ctx in self._submodule_ctxs:
+            if ctx.module is not None and isinstance(module, ctx.module):
+                return ctx
+        return self._default_ctx
+
+    def _shard_modules_impl(self, module: nn.Module, path: str = "", ctx: Optional[DMPCollectionContext] = None) -> nn.Module:
+        if isinstance(module, ShardedModule):
+            return module
+        if ctx is None or ctx is self._default_ctx:
+            ctx = self._ctx_for(module)
+        plan = ctx.plan if ctx.plan is not None else self._plan
+        module_sharding_plan = plan.get_plan_for_module(path)
+        if module_sharding_plan:
+            sharder_key = type(module)
+            env = ShardingEnv2D(sharding_pg=ctx.sharding_pg, global_pg=self._global_pg_, device_mesh=ctx.device_mesh, node_group_size=ctx.node_group_size,
+                                use_inter_host_allreduce=ctx.use_inter_host_allreduce, replica_pg=ctx.replica_pg)
+            # sharded modules address ranks inside the sharding group
+            env.process_group = ctx.sharding_pg
+            env.rank = dist.get_rank(ctx.sharding_pg)
+            sharded = self._sharder_map[sharder_key].shard(module, module_sharding_plan, env, self.device, path)
+            ctx.modules_to_sync.append((sharded, sharded))
+            return sharded
+        for name, child in module.named_children():
+            setattr(module, name, self._shard_modules_impl(child, path + "." + name if path else name, ctx))
+        return module
+
+    # ---- replica synchronisation ----------------------------------------------------------------------------------
+    def _sync_tensors(self, include_optimizer_state: bool) -> List[Tuple[torch.Tensor, Any]]:
+        out: List[Tuple[torch.Tensor, Any]] = []
+        for ctx in self._ctxs:
+            for sharded, _ in ctx.modules_to_sync:
+                inner = [m for m in sharded.modules() if hasattr(m, "engine")] or [sharded]
+                for m in inner:
+                    eng = getattr(m, "engine", None)
+                    if eng is None:
+                        continue
+                    for tbe in eng._tbes:
+                        out.append((tbe.weights.data, ctx.replica_pg))
+                        if include_optimizer_state:
+                            for st in (tbe.state1, tbe.state2):
+                                if st is not None and st.numel():
+                                    out.append((st, ctx.replica_pg))
+        return out
+
+    @torch.no_grad()
+    def sync(self, include_optimizer_state: bool = True) -> None:
+        """Average embedding shards (and optimizer state) over the replica groups (reference model_parallel.py:1314-1450)."""
+        by_pg: Dict[int, Tuple[Any, List[torch.Tensor]]] = {}
+        for t, pg in self._sync_tensors(include_optimizer_state):
+            by_pg.setdefault(id(pg), (pg, []))[1].append(t)
+        for pg, tensors in by_pg.values():
+            if pg is None or dist.get_world_size(pg) == 1:
+                continue
+            n = dist.get_world_size(pg)
+            if self._custom_all_reduce is not None:
+                self._custom_all_reduce(tensors)
+                continue
+            for t in tensors:
+                if t.dtype in (torch.float32, torch.float64):
+                    dist.all_reduce(t, group=pg)
+                    t.div_(n)
+                else:  # low-precision tables: reduce in fp32
+                    f = t.float()
+                    dist.all_reduce(f, group=pg)
+                    t.copy_((f / n).to(t.dtype))
+
+    def set_all_reduce_hook(self, reduce_hook: Any) -> None:
+        self._custom_all_reduce = reduce_hook
+
+    @property
+    def device_mesh(self):
+        return self._default_ctx.device_mesh
+
+    @property
+    def sharding_pg(self) -> dist.ProcessGroup:
+        return self._default_ctx.sharding_pg
+
+    @property
+    def replica_pg(self) -> dist.ProcessGroup:
+        return self._default_ctx.replica_pg
