@@ -1,0 +1,107 @@
+"""Datasets (Criteo TSV/binary, MovieLens), DeepFM model, KJT validator, TensorDict interop, packed tensor types."""
+import numpy as np
+import pytest
+import torch
+
+from torchrec_b200.sparse import JaggedTensor, KeyedJaggedTensor
+
+
+def _write_days(d, n_rows=50, days=2):
+    from torchrec_b200.datasets.criteo import BinaryCriteoUtils
+
+    rng = np.random.default_rng(0)
+    for day in range(days):
+        rows = []
+        for i in range(n_rows):
+            ints = [str(rng.integers(0, 100)) if rng.random() > 0.1 else "" for _ in range(13)]
+            cats = [format(rng.integers(0, 2**32), "x") if rng.random() > 0.1 else "" for _ in range(26)]
+            rows.append("\t".join([str(i % 2)] + ints + cats))
+        (d / f"day_{day}").write_text("\n".join(rows) + "\n")
+        BinaryCriteoUtils.tsv_to_npys(str(d / f"day_{day}"), str(d / f"day_{day}_dense.npy"), str(d / f"day_{day}_sparse.npy"), str(d / f"day_{day}_labels.npy"))
+
+
+def test_criteo_tsv_and_binary(tmp_path):
+    from torchrec_b200.datasets.criteo import DEFAULT_CAT_NAMES, BinaryCriteoUtils, InMemoryBinaryCriteoIterDataPipe, criteo_terabyte
+
+    _write_days(tmp_path)
+    rows = list(criteo_terabyte([str(tmp_path / "day_0")]))
+    assert len(rows) == 50 and set(rows[0]) >= {"label", "int_0", "cat_25"}
+    assert BinaryCriteoUtils.get_shape_from_npy(str(tmp_path / "day_0_sparse.npy")) == (50, 26)
+    ranges, rem = BinaryCriteoUtils.get_file_row_ranges_and_remainder([50, 50], rank=1, world_size=3)
+    assert ranges == {0: (34, 49), 1: (0, 16)} and rem == 1
+    paths = lambda kind: [str(tmp_path / f"day_{k}_{kind}.npy") for k in range(2)]
+    seen = 0
+    for r in range(2):
+        dp = InMemoryBinaryCriteoIterDataPipe("train", paths("dense"), paths("sparse"), paths("labels"), batch_size=16, rank=r, world_size=2, hashes=[1000] * 26)
+        bs = list(dp)
+        assert len(bs) == len(dp) == 4 and bs[0].sparse_features.keys() == DEFAULT_CAT_NAMES
+        assert bs[0].dense_features.shape == (16, 13) and int(bs[0].sparse_features.values().max()) < 1000
+        assert bs[0].sparse_features.lengths().sum() == 16 * 26
+        seen += sum(b.labels.numel() for b in bs)
+    assert seen == 100
+    val = InMemoryBinaryCriteoIterDataPipe("val", paths("dense"), paths("sparse"), paths("labels"), batch_size=8, rank=0, world_size=1)
+    test = InMemoryBinaryCriteoIterDataPipe("test", paths("dense"), paths("sparse"), paths("labels"), batch_size=8, rank=0, world_size=1)
+    assert sum(b.labels.numel() for b in val) == 25 and sum(b.labels.numel() for b in test) == 25
+    # first row of day_1 == first val row
+    torch.testing.assert_close(next(iter(val)).dense_features[0], torch.from_numpy(np.load(paths("dense")[1])[0]))
+    BinaryCriteoUtils.sparse_to_contiguous(paths("sparse"), str(tmp_path / "contig"), frequency_threshold=1)
+    c = np.load(str(tmp_path / "contig" / "day_0_sparse_contig_freq.npy"))
+    assert c.min() >= 0 and c.max() <= 100 + 2
+
+
+def test_movielens(tmp_path):
+    from torchrec_b200.datasets.movielens import movielens_20m
+
+    (tmp_path / "ratings.csv").write_text("userId,movieId,rating,timestamp\n1,10,4.5,100\n2,11,3.0,101\n")
+    (tmp_path / "movies.csv").write_text("movieId,title,genres\n10,Foo (1999),Drama\n11,Bar,Comedy|Action\n")
+    rows = list(movielens_20m(str(tmp_path), include_movies_data=True))
+    assert rows[0]["userId"] == 1 and rows[0]["rating"] == 4.5 and rows[1]["genres"] == "Comedy|Action"
+
+
+def test_deepfm_model():
+    from torchrec_b200.models.deepfm import SimpleDeepFMNN
+    from torchrec_b200.modules.embedding_configs import EmbeddingBagConfig
+    from torchrec_b200.modules.embedding_modules import EmbeddingBagCollection
+
+    ebc = EmbeddingBagCollection([EmbeddingBagConfig(name="t1", embedding_dim=8, num_embeddings=100, feature_names=["f1", "f3"]),
+                                  EmbeddingBagConfig(name="t2", embedding_dim=8, num_embeddings=100, feature_names=["f2"])])
+    m = SimpleDeepFMNN(num_dense_features=10, embedding_bag_collection=ebc, hidden_layer_size=20, deep_fm_dimension=5)
+    kjt = KeyedJaggedTensor.from_offsets_sync(keys=["f1", "f3", "f2"], values=torch.tensor([1, 2, 4, 5, 4, 3, 2, 9, 1, 2]), offsets=torch.tensor([0, 2, 4, 6, 8, 9, 10]))
+    out = m(torch.rand(2, 10), kjt)
+    assert out.shape == (2, 1) and bool(((out > 0) & (out < 1)).all())
+    out.sum().backward()
+    assert ebc.embedding_bags["t1"].weight.grad is not None
+
+
+def test_kjt_validator():
+    from torchrec_b200.modules.embedding_configs import EmbeddingBagConfig
+    from torchrec_b200.sparse.jagged_tensor_validator import validate_keyed_jagged_tensor
+
+    good = KeyedJaggedTensor(keys=["a", "b"], values=torch.tensor([1, 2, 3]), lengths=torch.tensor([1, 0, 2, 0]))
+    assert validate_keyed_jagged_tensor(good)
+    cfgs = [EmbeddingBagConfig(name="t", embedding_dim=4, num_embeddings=3, feature_names=["a", "b"])]
+    assert validate_keyed_jagged_tensor(good, cfgs) is False  # id 3 out of range
+    with pytest.raises(ValueError, match="Sum of lengths"):
+        validate_keyed_jagged_tensor(KeyedJaggedTensor(keys=["a"], values=torch.tensor([1, 2, 3]), lengths=torch.tensor([1, 1])))
+    with pytest.raises(ValueError, match="unique"):
+        validate_keyed_jagged_tensor(KeyedJaggedTensor(keys=["a", "a"], values=torch.tensor([1]), lengths=torch.tensor([1, 0])))
+    with pytest.raises(ValueError, match="weights size"):
+        validate_keyed_jagged_tensor(KeyedJaggedTensor(keys=["a"], values=torch.tensor([1, 2]), lengths=torch.tensor([2]), weights=torch.tensor([1.0])))
+    with pytest.raises(ValueError, match="first offset"):
+        validate_keyed_jagged_tensor(KeyedJaggedTensor(keys=["a"], values=torch.tensor([1, 2]), offsets=torch.tensor([1, 2])))
+
+
+def test_tensor_dict_interop_and_uintx():
+    from torchrec_b200.sparse.tensor_dict import maybe_td_to_kjt
+    from torchrec_b200.tensor_types import UInt2Tensor, UInt4Tensor
+
+    td = {"a": JaggedTensor(values=torch.tensor([1, 2, 3]), lengths=torch.tensor([2, 1])), "b": [torch.tensor([7]), torch.tensor([], dtype=torch.int64)]}
+    kjt = maybe_td_to_kjt(td)
+    assert kjt.keys() == ["a", "b"] and kjt.values().tolist() == [1, 2, 3, 7] and kjt.lengths().tolist() == [2, 1, 1, 0]
+    assert maybe_td_to_kjt(kjt) is kjt
+    v = torch.randint(0, 16, (3, 8))
+    p = UInt4Tensor.pack(v)
+    assert p.shape == (3, 8) and p.elem.shape == (3, 4) and torch.equal(p.unpack().long(), v)
+    v2 = torch.randint(0, 4, (2, 16))
+    p2 = UInt2Tensor.pack(v2)
+    assert p2.elem.shape == (2, 4) and torch.equal(p2.unpack().long(), v2) and p2[0].shape == (1, 16)

@@ -105,3 +105,64 @@ def idx_split_train_val(datapipe: Iterable, train_perc: float, decimal_places_co
                     yield x
 
     return _Split(True), _Split(False)
+
+
+class LoadFiles:
+    """(path, open file) pairs of the given paths."""
+
+    def __init__(self, datapipe: Iterable[str], mode: str = "b", length: int = -1, **open_kw: Any) -> None:
+        self.datapipe, self.mode, self.open_kw = datapipe, mode, open_kw
+
+    def __iter__(self) -> Iterator[Tuple[str, Any]]:
+        for path in self.datapipe:
+            mode = self.mode if "r" in self.mode else "r" + self.mode
+            with open(path, mode, **self.open_kw) as f:
+                yield path, f
+
+
+class ReadLinesFromCSV:
+    """Rows (list of str) of the CSV/TSV files yielded by ``LoadFiles``."""
+
+    def __init__(self, datapipe: Iterable[Tuple[str, Any]], skip_first_line: bool = False, **fmtparams: Any) -> None:
+        self.datapipe, self.skip_first_line, self.fmtparams = datapipe, skip_first_line, fmtparams
+
+    def __iter__(self) -> Iterator[List[str]]:
+        import csv
+
+        for _, f in self.datapipe:
+            rd = csv.reader(f, **self.fmtparams)
+            if self.skip_first_line:
+                next(rd, None)
+            yield from rd
+
+
+class ParallelReadConcat:
+    """Concatenate datapipes, giving every DataLoader worker (and rank) its own subset of them."""
+
+    def __init__(self, *datapipes: Iterable, dp_selector: Optional[Callable] = None) -> None:
+        self.datapipes = datapipes
+        self.dp_selector = dp_selector or _default_dp_selector
+
+    def __iter__(self) -> Iterator[Any]:
+        for dp in self.dp_selector(self.datapipes):
+            yield from dp
+
+
+def _default_dp_selector(datapipes):
+    from torch.utils.data import get_worker_info
+
+    info = get_worker_info()
+    if info is None or info.num_workers <= 1:
+        return datapipes
+    if info.num_workers > len(datapipes):
+        raise ValueError(f"Number of workers {info.num_workers} exceeds number of datapipes ({len(datapipes)})!")
+    return datapipes[info.id :: info.num_workers]
+
+
+def train_filter(key_fn: Callable[[int], int], train_perc: float, decimal_places_compared: int, idx: int) -> bool:
+    shift = 10**decimal_places_compared
+    return (key_fn(idx) % shift) < round(train_perc * shift)
+
+
+def val_filter(key_fn: Callable[[int], int], train_perc: float, decimal_places_compared: int, idx: int) -> bool:
+    return not train_filter(key_fn, train_perc, decimal_places_compared, idx)
