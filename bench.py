@@ -156,7 +156,7 @@ def build_ours(args: argparse.Namespace, device, rank: int, world: int):
 
     backend = args.dense_backend
     if backend == "auto":
-        backend = os.environ.get("TRB_DENSE_DEFAULT", "torch")
+        backend = os.environ.get("TRB_DENSE_DEFAULT", "tcgen05")  # bf16 tensor-core dense path is the product
     _dense.set_dense_backend(backend)
 
     # bf16 pooled embeddings (half the NVLink / HBM bytes) when the dense arch computes in bf16
