@@ -691,3 +691,115 @@ class EmbeddingBagCollectionSharder(BaseEmbeddingSharder[EmbeddingBagCollection]
     @property
     def module_type(self) -> Type[EmbeddingBagCollection]:
         return EmbeddingBagCollection
+
+
+# ---- nn.EmbeddingBag ------------------------------------------------------------------------------------------------
+class _BagAsCollection(nn.Module):
+    """Present one ``nn.EmbeddingBag`` as a single-table collection (table ``weight``-> feature ``dummy_feature``)."""
+
+    def __init__(self, bag: nn.EmbeddingBag, table_name: str) -> None:
+        super().__init__()
+        pooling = {"sum": PoolingType.SUM, "mean": PoolingType.MEAN}.get(bag.mode)
+        if pooling is None:
+            raise ValueError(f"nn.EmbeddingBag mode '{bag.mode}' cannot be sharded (sum / mean only)")
+        self._cfg = EmbeddingBagConfig(name=table_name, embedding_dim=bag.embedding_dim, num_embeddings=bag.num_embeddings, feature_names=["dummy_feature"], pooling=pooling)
+        self.embedding_bags = nn.ModuleDict({table_name: bag})
+
+    def embedding_bag_configs(self) -> List[EmbeddingBagConfig]:
+        return [self._cfg]
+
+    def is_weighted(self) -> bool:
+        return True
+
+
+class _BagAwaitable(LazyAwaitable[torch.Tensor]):
+    def __init__(self, inner: LazyAwaitable[KeyedTensor]) -> None:
+        super().__init__()
+        self._inner = inner
+
+    def _wait_impl(self) -> torch.Tensor:
+        return self._inner.wait().values()
+
+
+class ShardedEmbeddingBag(ShardedModule, FusedOptimizerModule):
+    """Sharded ``nn.EmbeddingBag``: ``forward(input, offsets=None, per_sample_weights=None) -> Tensor [B, D]``
+    (reference embeddingbag.py:2286-2507)."""
+
+    def __init__(self, module: nn.EmbeddingBag, table_name_to_parameter_sharding: Dict[str, ParameterSharding], env: ShardingEnv,
+                 fused_params: Optional[Dict[str, Any]] = None, device: Optional[torch.device] = None) -> None:
+        super().__init__()
+        assert len(table_name_to_parameter_sharding) == 1, "expect one and only one table (weight) in an nn.EmbeddingBag plan"
+        self._table_name = next(iter(table_name_to_parameter_sharding))  # "weight"
+        adapter = _BagAsCollection(module, self._table_name)
+        w = module.weight
+        # optimizer tags live on the bag's parameter; expose them under the collection's parameter name
+        self._ebc = ShardedEmbeddingBagCollection(adapter, table_name_to_parameter_sharding, env, fused_params, device)
+        self._device = self._ebc._device
+
+    def create_context(self) -> EmbeddingBagCollectionContext:
+        return self._ebc.create_context()
+
+    def _to_kjt(self, input: torch.Tensor, offsets: Optional[torch.Tensor], per_sample_weights: Optional[torch.Tensor]) -> KeyedJaggedTensor:
+        if input.dim() == 2:
+            B, L = input.shape
+            offsets = torch.arange(0, B * L + 1, L, device=input.device)
+            input = input.reshape(-1)
+            if per_sample_weights is not None:
+                per_sample_weights = per_sample_weights.reshape(-1)
+        else:
+            assert offsets is not None, "1-D input needs offsets"
+            if offsets.numel() == 0 or int(offsets[-1]) != input.numel():  # nn.EmbeddingBag default: no trailing offset
+                offsets = torch.cat([offsets, offsets.new_tensor([input.numel()])])
+        w = per_sample_weights if per_sample_weights is not None else torch.ones(input.numel(), device=input.device)
+        return KeyedJaggedTensor(keys=["dummy_feature"], values=input, offsets=offsets, weights=w)
+
+    def input_dist(self, ctx, input: torch.Tensor, offsets: Optional[torch.Tensor] = None, per_sample_weights: Optional[torch.Tensor] = None):
+        return self._ebc.input_dist(ctx, self._to_kjt(input, offsets, per_sample_weights))
+
+    def compute(self, ctx, dist_input):
+        return self._ebc.compute(ctx, dist_input)
+
+    def output_dist(self, ctx, output) -> LazyAwaitable[torch.Tensor]:
+        return _BagAwaitable(self._ebc.output_dist(ctx, output))
+
+    def compute_and_output_dist(self, ctx, input) -> LazyAwaitable[torch.Tensor]:
+        return _BagAwaitable(self._ebc.compute_and_output_dist(ctx, input))
+
+    def named_parameters(self, prefix: str = "", recurse: bool = True, remove_duplicate: bool = True):
+        for n, p in self._ebc.named_parameters("", recurse):
+            yield (prefix + "." if prefix else "") + "weight", p
+
+    def sharded_parameter_names(self, prefix: str = "") -> Iterator[str]:
+        yield from self._ebc.sharded_parameter_names((prefix + "." if prefix else "") + "_ebc")
+
+    def state_dict(self, destination=None, prefix: str = "", keep_vars: bool = False):
+        inner = self._ebc.state_dict(None, "", keep_vars)
+        destination = OrderedDict() if destination is None else destination
+        destination[prefix + "weight"] = inner[f"embedding_bags.{self._table_name}.weight"]
+        return destination
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        return self._ebc.load_state_dict({f"embedding_bags.{self._table_name}.weight": state_dict["weight"]}, strict)
+
+    @property
+    def fused_optimizer(self) -> KeyedOptimizer:
+        return self._ebc.fused_optimizer
+
+    @property
+    def engine(self):
+        return self._ebc.engine
+
+
+class EmbeddingBagSharder(BaseEmbeddingSharder[nn.EmbeddingBag]):
+    """Shards a bare ``nn.EmbeddingBag`` (reference embeddingbag.py:2510)."""
+
+    def shard(self, module: nn.EmbeddingBag, params: Dict[str, ParameterSharding], env: ShardingEnv, device: Optional[torch.device] = None,
+              module_fqn: Optional[str] = None) -> ShardedEmbeddingBag:
+        return ShardedEmbeddingBag(module, params, env, self.fused_params, device)
+
+    def shardable_parameters(self, module: nn.EmbeddingBag) -> Dict[str, nn.Parameter]:
+        return {name: param for name, param in module.named_parameters()}
+
+    @property
+    def module_type(self) -> Type[nn.EmbeddingBag]:
+        return nn.EmbeddingBag

@@ -13,6 +13,9 @@ def default_extra_sharders() -> List[ModuleSharder]:
         ("mc_embedding", "ManagedCollisionEmbeddingCollectionSharder"),
         ("itep_embeddingbag", "ITEPEmbeddingBagCollectionSharder"),
         ("itep_embeddingbag", "ITEPEmbeddingCollectionSharder"),
+        ("fused_embeddingbag", "FusedEmbeddingBagCollectionSharder"),
+        ("fused_embeddingbag", "FusedEmbeddingCollectionSharder"),
+        ("embeddingbag", "EmbeddingBagSharder"),
         ("quant_embeddingbag", "QuantEmbeddingBagCollectionSharder"),
         ("quant_embedding", "QuantEmbeddingCollectionSharder"),
     ):
