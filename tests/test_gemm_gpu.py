@@ -16,7 +16,7 @@ def _ref(a, b, bias, act):
     return y
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 512), (1000, 512, 256), (4096, 1024, 480), (300, 64, 16), (128, 8, 1024), (4096, 128, 2048)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 512), (1000, 512, 256), (4096, 1024, 480), (300, 64, 16), (128, 8, 1024), (4096, 128, 2048), (38000, 512, 192), (20000, 1024, 320)])
 @pytest.mark.parametrize("act", [0, 1])
 def test_gemm_bf16_tn(M, N, K, act):
     from torchrec_b200.ops.gemm import gemm_bf16_tn
@@ -76,7 +76,7 @@ def test_linear_act_autograd_matches_torch():
 
 
 @pytest.mark.parametrize("a_mn,b_mn", [(True, True), (False, True), (True, False)])
-@pytest.mark.parametrize("M,N,K", [(256, 128, 512), (1024, 512, 4096), (128, 16, 333), (480, 1024, 1000)])
+@pytest.mark.parametrize("M,N,K", [(256, 128, 512), (1024, 512, 4096), (128, 16, 333), (480, 1024, 1000), (38016, 256, 136), (1024, 1024, 40000)])
 def test_gemm_mn_major_operands(a_mn, b_mn, M, N, K):
     from torchrec_b200.ops.gemm import gemm_bf16
 

@@ -14,7 +14,7 @@ def _ref(dense, sparse):
     return torch.cat((dense, z[:, ti[0], ti[1]]), dim=1)
 
 
-@pytest.mark.parametrize("B,F", [(4, 26), (7, 26), (1000, 26), (513, 3), (64, 31)])
+@pytest.mark.parametrize("B,F", [(4, 26), (7, 26), (1000, 26), (513, 3), (64, 31), (5003, 26)])
 @pytest.mark.parametrize("sparse_dtype", [torch.float32, torch.bfloat16])
 def test_interaction_fwd_bwd(B, F, sparse_dtype):
     from torchrec_b200.ops.interaction import DotInteractionFn

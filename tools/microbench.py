@@ -1,0 +1,94 @@
+"""Per-op micro-benchmarks on one B200 (CUDA events, L2 flushed between iterations, median of N).
+Usage: python tools/microbench.py [gemm] [interaction] [tbe]   -> prints a markdown table (copied into profiles/)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from torchrec_b200.ops import gemm as G  # noqa: E402
+from torchrec_b200.ops import interaction as I  # noqa: E402
+from torchrec_b200.ops import tbe as T  # noqa: E402
+
+dev = torch.device("cuda:0")
+_flush = None
+
+
+def timeit(fn, iters=15, warm=3):
+    global _flush
+    if _flush is None:
+        _flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(iters):
+        _flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def bench_gemm():
+    print("| GEMM (M,N,K) | layout | us | TFLOP/s |\n|---|---|---|---|")
+    M = 32768
+    for (N, K) in [(1024, 480), (1024, 1024), (512, 1024), (256, 512), (512, 16), (256, 512), (128, 256)]:
+        a = torch.randn(M, max(K, 8), device=dev).bfloat16()
+        w = torch.randn(N, max(K, 8), device=dev).bfloat16()
+        bias = torch.zeros(N, device=dev)
+        us = timeit(lambda: G.gemm_bf16(a, w, bias=bias, act=G.ACT_RELU))
+        print(f"| {M},{N},{K} | fwd (K-major) | {us:.1f} | {2 * M * N * K / us / 1e6:.0f} |")
+        gy = torch.randn(M, N, device=dev).bfloat16()
+        wt = w  # dgrad: gy [M,N] @ w [N,K] -> [M,K]; b consumed MN-major
+        if K % 8 == 0 and K >= 64:
+            us = timeit(lambda: G.gemm_bf16(gy, wt, b_mn=True))
+            print(f"| {M},{K},{N} | dgrad (B MN-major) | {us:.1f} | {2 * M * N * K / us / 1e6:.0f} |")
+            us = timeit(lambda: G.gemm_bf16(gy, a, a_mn=True, b_mn=True, out_dtype=torch.float32, split_k=8))
+            print(f"| {N},{K},{M} | wgrad (A,B MN-major, split-K) | {us:.1f} | {2 * M * N * K / us / 1e6:.0f} |")
+
+
+def bench_interaction():
+    print("| interaction | us | GB moved | GB/s |\n|---|---|---|---|")
+    B, F, D = 32768, 26, 128
+    dense = torch.randn(B, D, device=dev).bfloat16().requires_grad_()
+    sparse = torch.randn(B, F, D, device=dev).bfloat16().requires_grad_()
+    out = I.DotInteractionFn.apply(dense, sparse)
+    g = torch.randn_like(out)
+    us = timeit(lambda: I.DotInteractionFn.apply(dense, sparse))
+    gb = (B * (F + 1) * D * 2 + out.numel() * 2) / 1e9
+    print(f"| fwd B={B} F={F} | {us:.1f} | {gb:.3f} | {gb / us * 1e6:.0f} |")
+    us = timeit(lambda: torch.autograd.grad(out, (dense, sparse), g, retain_graph=True))
+    gb = (2 * B * (F + 1) * D * 2 + out.numel() * 2) / 1e9
+    print(f"| bwd B={B} F={F} | {us:.1f} | {gb:.3f} | {gb / us * 1e6:.0f} |")
+
+
+def bench_tbe(rows_per_table=40_000_000, n_tables=8):
+    print("| TBE (fp32 rows, D=128, pooling 1) | us | GB moved | GB/s |\n|---|---|---|---|")
+    B, D = 32768, 128
+    for rows in (rows_per_table, 1_000_000):
+        tbe = T.TableBatchedEmbeddingBags([(rows, D)] * n_tables, list(range(n_tables)), pooling_mode=T.PoolingMode.SUM, optimizer=T.OptimType.EXACT_ROWWISE_ADAGRAD,
+                                          learning_rate=0.01, device=dev, output_dtype=torch.bfloat16)
+        idx = torch.randint(0, rows, (n_tables * B,), device=dev)
+        off = torch.arange(0, n_tables * B + 1, device=dev)
+        out = tbe(idx, off, None, batch_size=B)
+        g = torch.randn_like(out)
+        us = timeit(lambda: tbe(idx, off, None, batch_size=B))
+        gb = (n_tables * B * D * 4 + out.numel() * 2) / 1e9
+        print(f"| fwd {n_tables} x {rows} rows | {us:.1f} | {gb:.3f} | {gb / us * 1e6:.0f} |")
+        us = timeit(lambda: out.backward(g, retain_graph=True))
+        gb = (n_tables * B * D * 4 * 2 + out.numel() * 2) / 1e9
+        print(f"| bwd+adagrad {n_tables} x {rows} rows | {us:.1f} | {gb:.3f} | {gb / us * 1e6:.0f} |")
+        del tbe
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["gemm", "interaction", "tbe"]
+    print(f"env: TRB_GEMM_WIDE={os.environ.get('TRB_GEMM_WIDE')} TRB_INTERACTION_LEGACY={os.environ.get('TRB_INTERACTION_LEGACY')}\n")
+    for w in which:
+        {"gemm": bench_gemm, "interaction": bench_interaction, "tbe": bench_tbe}[w]()
+        print()

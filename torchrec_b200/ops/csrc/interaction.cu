@@ -15,6 +15,8 @@
 //
 // CTAs are small (128 threads, ~38 KB smem, 128 TMEM columns) so 4 fit per SM and hide the global
 // load latency of each other; each CTA loops over groups of 4 samples.
+#include <cstdlib>
+
 #include "tcgen05.cuh"
 
 using namespace trb;
@@ -272,6 +274,265 @@ __global__ void __launch_bounds__(128, 3) interaction_bwd_kernel(const InterPara
   if (warp == 0) tmem_dealloc(tmem_d, 128);
 }
 
+
+// ================================================================================================================
+// Pipelined bf16 kernels (the production path): operand tiles arrive through cp.async (16 B LDGSTS, every thread has
+// all of its loads in flight at once) into a DOUBLE-BUFFERED smem image, so the global->smem traffic of group g+1
+// overlaps the MMA + epilogue of group g; results leave through a swizzled smem staging area with fully coalesced
+// 16 B stores. The first-generation kernels above (synchronous loads, per-thread 4 B stores) ran at 17-27 % of the HBM
+// roofline (profiles/step_breakdown_1gpu_r1.md) and remain as the fp32-I/O fallback.
+// ================================================================================================================
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* g, bool valid) {
+  const int sz = valid ? 16 : 0;  // src-size 0 -> zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(g), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// issue (do not wait for) the loads of the packed tile of samples [b0, b0+4): bf16 dense + bf16 sparse
+__device__ __forceinline__ void issue_tile_loads(const InterParams& p, uint8_t* tile, int b0, int tid) {
+  const int R = p.F + 1;
+  const uint32_t tbase = smem_u32(tile);
+  const __nv_bfloat16* dense = reinterpret_cast<const __nv_bfloat16*>(p.dense);
+  const __nv_bfloat16* sparse = reinterpret_cast<const __nv_bfloat16*>(p.sparse);
+#pragma unroll
+  for (int s = 0; s < kSamples; ++s) {
+    const int b = b0 + s;
+    const bool ok = b < p.B;
+    const int bb = ok ? b : 0;
+    for (int idx = tid; idx < R * 16; idx += 128) {
+      const int i = idx >> 4, ch = idx & 15;
+      const __nv_bfloat16* src = (i == 0) ? dense + (int64_t) bb * p.ld_dense + ch * 8 : sparse + (int64_t) bb * p.ld_sparse + (i - 1) * kD + ch * 8;
+      const int r = s * kRowsPerSample + i;
+      cp_async16(tbase + (ch >> 3) * kTileBytes + sw128_offset(r, (ch & 7) * 8), src, ok);
+    }
+  }
+}
+
+// issue the loads of the 4 incoming-gradient rows (bwd)
+__device__ __forceinline__ void issue_gout_loads(const InterParams& p, __nv_bfloat16* gstage, int b0, int tid) {
+  const int vec_per_row = (int) (p.ld_out >> 3);
+  const uint32_t gbase = smem_u32(gstage);
+  for (int v = tid; v < kSamples * vec_per_row; v += 128) {
+    const int sidx = v / vec_per_row, c = v - sidx * vec_per_row;
+    const bool ok = b0 + sidx < p.B;
+    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(p.gout) + (int64_t) (ok ? b0 + sidx : 0) * p.ld_out + c * 8;
+    cp_async16(gbase + (uint32_t) (sidx * p.ld_out + c * 8) * 2, src, ok);
+  }
+}
+
+__global__ void __launch_bounds__(128, 3) interaction_fwd_pipe_kernel(const InterParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
+  uint8_t* tiles = smem;                                                               // 2 buffers x (2 x 16 KB)
+  __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(smem + 4 * kTileBytes);      // [4][ld_out]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 4 * kTileBytes + kSamples * p.ld_out * 2);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int R = p.F + 1;
+  for (int i = tid; i < 4 * kTileBytes / 16; i += 128) reinterpret_cast<uint4*>(tiles)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(tmem_ptr, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_ptr;
+  constexpr uint32_t idesc = make_idesc_major(128, 128, 0, 0);
+  uint32_t phase = 0;
+  const int groups = (p.B + kSamples - 1) / kSamples;
+  int cur = 0;
+  if ((int) blockIdx.x < groups) issue_tile_loads(p, tiles, blockIdx.x * kSamples, tid);
+  cp_async_commit();
+  for (int g = blockIdx.x; g < groups; g += gridDim.x, cur ^= 1) {
+    const int b0 = g * kSamples;
+    uint8_t* tile = tiles + cur * 2 * kTileBytes;
+    cp_async_wait_all();
+    fence_proxy_async();
+    __syncthreads();  // tile[cur] landed; everyone is done with tile[cur^1] and with `stage`
+    if (g + (int) gridDim.x < groups) issue_tile_loads(p, tiles + (cur ^ 1) * 2 * kTileBytes, (g + gridDim.x) * kSamples, tid);
+    cp_async_commit();
+    if (warp == 0) {
+      if (elect_one()) {
+        const uint32_t a0 = smem_u32(tile);
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          const uint64_t desc = make_kmajor_desc(a0 + kb * kTileBytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, desc + (uint64_t) (2 * k), desc + (uint64_t) (2 * k), idesc, (kb | k) != 0);
+        }
+        umma_commit(bar);
+      }
+      __syncwarp();
+    }
+    // dense passthrough + zero tail while the MMA runs
+    __nv_bfloat16* srow = stage + warp * p.ld_out;
+    for (int c = lane; c < kD / 8; c += 32) {
+      const int r = warp * kRowsPerSample;
+      reinterpret_cast<uint4*>(srow)[c] = *reinterpret_cast<const uint4*>(tile + (c >> 3) * kTileBytes + sw128_offset(r, (c & 7) * 8));
+    }
+    for (int c = p.out_cols + lane; c < p.ld_out; c += 32) srow[c] = __float2bfloat16(0.f);
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    uint32_t z[32];
+    tmem_ld_32x32(tmem_d + ((uint32_t) (warp * 32) << 16) + (uint32_t) (warp * 32), z);
+    if (lane < R) {
+      const int base = kD + tri_offset(lane, R);
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j > lane && j < R) srow[base + (j - lane - 1)] = __float2bfloat16(__uint_as_float(z[j]));
+    }
+    tc_fence_before();
+    __syncthreads();
+    const int vec_per_row = (int) (p.ld_out >> 3);
+    for (int v = tid; v < kSamples * vec_per_row; v += 128) {
+      const int s = v / vec_per_row, c = v - s * vec_per_row;
+      if (b0 + s < p.B)
+        reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t) (b0 + s) * p.ld_out)[c] = reinterpret_cast<const uint4*>(stage + s * p.ld_out)[c];
+    }
+  }
+  cp_async_wait_all();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, 128);
+}
+
+__global__ void __launch_bounds__(128, 2) interaction_bwd_pipe_kernel(const InterParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
+  uint8_t* tiles = smem;                       // T: 2 buffers x 32 KB (MN-major B operand)
+  uint8_t* tileS = smem + 4 * kTileBytes;      // S (K-major A operand, 32 KB); re-used as the output staging area after the MMA
+  __nv_bfloat16* gst = reinterpret_cast<__nv_bfloat16*>(smem + 6 * kTileBytes);  // 2 x [4][ld_out]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 6 * kTileBytes + 2 * kSamples * p.ld_out * 2);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int R = p.F + 1;
+  for (int i = tid; i < 4 * kTileBytes / 16; i += 128) reinterpret_cast<uint4*>(tiles)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(tmem_ptr, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_ptr;
+  constexpr uint32_t idesc = make_idesc_major(128, 128, 0, 1);
+  uint32_t phase = 0;
+  const int groups = (p.B + kSamples - 1) / kSamples;
+  const int gsz = kSamples * (int) p.ld_out;
+  int cur = 0;
+  if ((int) blockIdx.x < groups) {
+    issue_tile_loads(p, tiles, blockIdx.x * kSamples, tid);
+    issue_gout_loads(p, gst, blockIdx.x * kSamples, tid);
+  }
+  cp_async_commit();
+  const int r = warp * kRowsPerSample + lane;  // my row of the packed tile (sample = warp, row-in-sample = lane)
+  for (int g = blockIdx.x; g < groups; g += gridDim.x, cur ^= 1) {
+    const int b0 = g * kSamples;
+    uint8_t* tileT = tiles + cur * 2 * kTileBytes;
+    const __nv_bfloat16* gstage = gst + cur * gsz;
+    cp_async_wait_all();
+    fence_proxy_async();
+    __syncthreads();  // T[cur] / gout[cur] landed; copy-out of the previous group finished (staging == tileS is free)
+    if (g + (int) gridDim.x < groups) {
+      issue_tile_loads(p, tiles + (cur ^ 1) * 2 * kTileBytes, (g + gridDim.x) * kSamples, tid);
+      issue_gout_loads(p, gst + (cur ^ 1) * gsz, (g + gridDim.x) * kSamples, tid);
+    }
+    cp_async_commit();
+    // ---- S row of this thread: S[i][j] = g[triangle(min,max)] (0 on the diagonal / padding); the whole 256 B row of
+    //      blockdiag(S) is written (zeros outside the sample's own 32-column block) because the staging re-use clobbers it
+    {
+      const __nv_bfloat16* grow = gstage + warp * p.ld_out + kD;
+      const bool live = lane < R && (b0 + warp) < p.B;
+      uint32_t packed[16];
+#pragma unroll
+      for (int j2 = 0; j2 < 16; ++j2) {
+        __nv_bfloat16 v0 = __float2bfloat16(0.f), v1 = v0;
+        const int j0 = 2 * j2, j1 = 2 * j2 + 1;
+        if (live && j0 < R && j0 != lane) { const int lo = min(lane, j0), hi = max(lane, j0); v0 = grow[tri_offset(lo, R) + (hi - lo - 1)]; }
+        if (live && j1 < R && j1 != lane) { const int lo = min(lane, j1), hi = max(lane, j1); v1 = grow[tri_offset(lo, R) + (hi - lo - 1)]; }
+        __nv_bfloat162 h = __halves2bfloat162(v0, v1);
+        packed[j2] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      // row r: K-block kb holds k in [64 kb, 64 kb + 64) as 8 chunks of 16 B; own block = k in [32 warp, 32 warp + 32)
+      const int own_kb = warp >> 1, own_c0 = (warp & 1) * 4;
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint4 val = make_uint4(0, 0, 0, 0);
+          if (kb == own_kb && c >= own_c0 && c < own_c0 + 4) {
+            const int q = (c - own_c0) * 4;
+            val = make_uint4(packed[q], packed[q + 1], packed[q + 2], packed[q + 3]);
+          }
+          *reinterpret_cast<uint4*>(tileS + kb * kTileBytes + r * 128 + (((c ^ (r & 7)) & 7) << 4)) = val;
+        }
+      }
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (warp == 0) {
+      if (elect_one()) {
+        const uint32_t aS = smem_u32(tileS), aT = smem_u32(tileT);
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          const uint64_t adesc = make_kmajor_desc(aS + kb * kTileBytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t bdesc = make_mnmajor_desc(aT + (kb * 64 + k * 16) * 128, kTileBytes, 1024);
+            umma_bf16(tmem_d, adesc + (uint64_t) (2 * k), bdesc, idesc, (kb | k) != 0);
+          }
+        }
+        umma_commit(bar);
+      }
+      __syncwarp();
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue: TMEM -> bf16 -> swizzled staging ([128 rows][16 chunks of 16 B], chunk ^= row & 15) -----------------
+    uint8_t* ostage = tileS;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t z[32];
+      tmem_ld_32x32(tmem_d + ((uint32_t) (warp * 32) << 16) + (uint32_t) (c * 32), z);
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(z[j]);
+      if (lane == 0) {  // dense row: add the pass-through gradient of out[:, :D]
+        const __nv_bfloat16* gd = gstage + warp * p.ld_out + c * 32;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += __bfloat162float(gd[j]);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 o;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * q], v[8 * q + 1]), h1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]), h3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
+        o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+        o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+        const int chunk = c * 4 + q;
+        *reinterpret_cast<uint4*>(ostage + r * 256 + (((chunk ^ lane) & 15) << 4)) = o;
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    // ---- coalesced copy-out: 16 consecutive threads write one 256 B gradient row ----------------------------------------
+    for (int idx = tid; idx < kSamples * R * 16; idx += 128) {
+      const int row = idx >> 4, chunk = idx & 15;
+      const int s = row / R, i = row - s * R;
+      const int b = b0 + s;
+      if (b >= p.B) continue;
+      const uint4 val = *reinterpret_cast<const uint4*>(ostage + (s * kRowsPerSample + i) * 256 + (((chunk ^ i) & 15) << 4));
+      __nv_bfloat16* dst = (i == 0) ? reinterpret_cast<__nv_bfloat16*>(p.g_dense) + (int64_t) b * p.ld_gdense + chunk * 8
+                                    : reinterpret_cast<__nv_bfloat16*>(p.g_sparse) + (int64_t) b * p.ld_gsparse + (i - 1) * kD + chunk * 8;
+      *reinterpret_cast<uint4*>(dst) = val;
+    }
+  }
+  cp_async_wait_all();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, 128);
+}
+
 int g_sms = 0;
 int num_sms() {
   if (g_sms == 0) {
@@ -293,13 +554,25 @@ TRB_API int trb_interaction_fwd(const void* dense, int64_t ld_dense, const void*
   p.dense = dense; p.ld_dense = ld_dense; p.sparse = sparse; p.ld_sparse = ld_sparse; p.sparse_f32 = sparse_f32;
   p.out = out; p.ld_out = ld_out; p.B = B; p.F = F; p.out_cols = D + (F + 1) * F / 2;
   if (ld_out % 8 || ld_out < p.out_cols) return -21;
+  const int groups = (B + kSamples - 1) / kSamples;
+  if (!sparse_f32 && ld_dense % 8 == 0 && ld_sparse % 8 == 0 && !getenv("TRB_INTERACTION_LEGACY")) {
+    const int smem_p = 4 * kTileBytes + kSamples * (int) ld_out * 2 + 64 + 1024;
+    static bool cfg_p = false;
+    if (!cfg_p) {
+      TRB_CUDA(cudaFuncSetAttribute(interaction_fwd_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      cfg_p = true;
+    }
+    const int grid_p = groups < 3 * num_sms() ? groups : 3 * num_sms();
+    interaction_fwd_pipe_kernel<<<grid_p, 128, smem_p, stream>>>(p);
+    TRB_CHECK_LAUNCH();
+    return 0;
+  }
   const int smem = 2 * kTileBytes + kSamples * (int) ld_out * 2 + 64 + 1024;
   static bool cfg = false;
   if (!cfg) {
     TRB_CUDA(cudaFuncSetAttribute(interaction_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     cfg = true;
   }
-  const int groups = (B + kSamples - 1) / kSamples;
   const int grid = groups < 4 * num_sms() ? groups : 4 * num_sms();
   interaction_fwd_kernel<<<grid, 128, smem, stream>>>(p);
   TRB_CHECK_LAUNCH();
@@ -315,13 +588,26 @@ TRB_API int trb_interaction_bwd(const void* dense, int64_t ld_dense, const void*
   p.dense = dense; p.ld_dense = ld_dense; p.sparse = sparse; p.ld_sparse = ld_sparse; p.sparse_f32 = sparse_f32;
   p.gout = gout; p.ld_out = ld_out; p.B = B; p.F = F; p.out_cols = D + (F + 1) * F / 2;
   p.g_dense = g_dense; p.ld_gdense = ld_gdense; p.g_sparse = g_sparse; p.ld_gsparse = ld_gsparse; p.gsparse_f32 = gsparse_f32;
+  const int groups = (B + kSamples - 1) / kSamples;
+  if (!sparse_f32 && !gsparse_f32 && ld_dense % 8 == 0 && ld_sparse % 8 == 0 && ld_gdense % 8 == 0 && ld_gsparse % 8 == 0 && ld_out % 8 == 0 &&
+      !getenv("TRB_INTERACTION_LEGACY")) {
+    const int smem_p = 6 * kTileBytes + 2 * kSamples * (int) ld_out * 2 + 64 + 1024;
+    static bool cfg_p = false;
+    if (!cfg_p) {
+      TRB_CUDA(cudaFuncSetAttribute(interaction_bwd_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+      cfg_p = true;
+    }
+    const int grid_p = groups < 2 * num_sms() ? groups : 2 * num_sms();
+    interaction_bwd_pipe_kernel<<<grid_p, 128, smem_p, stream>>>(p);
+    TRB_CHECK_LAUNCH();
+    return 0;
+  }
   const int smem = 4 * kTileBytes + kSamples * (int) ld_out * 2 + 64 + 1024;
   static bool cfg = false;
   if (!cfg) {
     TRB_CUDA(cudaFuncSetAttribute(interaction_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     cfg = true;
   }
-  const int groups = (B + kSamples - 1) / kSamples;
   const int grid = groups < 3 * num_sms() ? groups : 3 * num_sms();
   interaction_bwd_kernel<<<grid, 128, smem, stream>>>(p);
   TRB_CHECK_LAUNCH();
