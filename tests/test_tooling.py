@@ -1,0 +1,133 @@
+"""Tooling: fx tracer, IR serializer, pt2 helpers, schema BC checker + frozen public signatures, linter, loggers."""
+import inspect
+import logging
+
+import torch
+from torch import nn
+
+from torchrec_b200.modules.embedding_configs import EmbeddingBagConfig
+from torchrec_b200.modules.embedding_modules import EmbeddingBagCollection
+from torchrec_b200.sparse import KeyedJaggedTensor
+
+
+def _ebc():
+    return EmbeddingBagCollection([EmbeddingBagConfig(name="t1", embedding_dim=4, num_embeddings=10, feature_names=["f1"]),
+                                   EmbeddingBagConfig(name="t2", embedding_dim=4, num_embeddings=10, feature_names=["f2"])])
+
+
+def test_fx_tracer_keeps_sparse_modules_as_leaves():
+    from torchrec_b200.fx import symbolic_trace
+
+    class M(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.ebc = _ebc()
+            self.lin = nn.Linear(8, 1)
+
+        def forward(self, kjt):
+            return self.lin(self.ebc(kjt).values())
+
+    m = M()
+    gm = symbolic_trace(m)
+    targets = [n.target for n in gm.graph.nodes if n.op == "call_module"]
+    assert "ebc" in targets and "lin" in targets
+    kjt = KeyedJaggedTensor(keys=["f1", "f2"], values=torch.tensor([1, 2, 3]), lengths=torch.tensor([1, 1, 1, 0]))
+    torch.testing.assert_close(gm(kjt), m(kjt))
+
+
+def test_ir_serializer_round_trip():
+    from torchrec_b200.ir.serializer import JsonSerializer, decapsulate_ir_modules, encapsulate_ir_modules
+    from torchrec_b200.modules.feature_processor_ import PositionWeightedModuleCollection
+    from torchrec_b200.modules.fp_embedding_modules import FeatureProcessedEmbeddingBagCollection
+
+    ebc = _ebc()
+    new = JsonSerializer.deserialize(JsonSerializer.serialize(ebc))
+    assert [c.name for c in new.embedding_bag_configs()] == ["t1", "t2"] and new.embedding_bag_configs()[0].feature_names == ["f1"]
+    fp = FeatureProcessedEmbeddingBagCollection(EmbeddingBagCollection(ebc.embedding_bag_configs(), is_weighted=True), PositionWeightedModuleCollection({"f1": 3, "f2": 4}))
+    fp2 = JsonSerializer.deserialize(JsonSerializer.serialize(fp))
+    assert isinstance(fp2, FeatureProcessedEmbeddingBagCollection) and fp2._feature_processors.max_feature_lengths == {"f1": 3, "f2": 4}
+
+    class M(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.sparse = ebc
+
+    m, fqns = encapsulate_ir_modules(M())
+    assert fqns == ["sparse"] and m.sparse.ir_metadata
+    w = m.sparse.embedding_bags["t1"].weight.detach().clone()
+    m2 = decapsulate_ir_modules(m)
+    assert m2.sparse is not ebc
+    torch.testing.assert_close(m2.sparse.embedding_bags["t1"].weight.detach(), w)
+
+
+def test_pt2_helpers():
+    from torchrec_b200.pt2.utils import is_pt2_compiling, kjt_for_pt2_tracing, pt2_checks_tensor_slice
+
+    assert not is_pt2_compiling()
+    pt2_checks_tensor_slice(torch.zeros(4), 0, 2)
+    kjt = KeyedJaggedTensor(keys=["a"], values=torch.tensor([1, 2]), lengths=torch.tensor([2, 0]))
+    k2 = kjt_for_pt2_tracing(kjt)
+    assert k2.keys() == ["a"] and k2.lengths().dtype == torch.int64
+
+
+def test_signature_compat_checker():
+    from torchrec_b200.schema.utils import is_signature_compatible as ok
+
+    def f0(a, b=1): ...
+    def f1(a, b=1, c=2): ...
+    def f2(a, c=2, b=1): ...
+    def f3(a, b): ...
+    def f4(a, b=1, *, d): ...
+    s = inspect.signature
+    assert ok(s(f0), s(f1)) and not ok(s(f0), s(f2)) and not ok(s(f0), s(f3)) and not ok(s(f0), s(f4)) and ok(s(f0), s(f0))
+
+
+def test_public_api_signatures_are_stable():
+    """Frozen signatures of the user-facing entry points (the reference's schema/api_tests)."""
+    from torchrec_b200.parallel.model_parallel import DistributedModelParallel
+    from torchrec_b200.parallel.planner import EmbeddingShardingPlanner
+    from torchrec_b200.parallel.train_pipeline import TrainPipelineSparseDist
+    from torchrec_b200.schema.utils import is_signature_compatible
+
+    def dmp(self, module, env=None, device=None, plan=None, sharders=None, init_data_parallel=True, init_parameters=True, data_parallel_wrapper=None): ...
+    def ebc(self, tables, is_weighted=False, device=None): ...
+    def kjt(self, keys, values, weights=None, lengths=None, offsets=None, stride=None, stride_per_key_per_rank=None): ...
+    def pipe(self, model, optimizer, device, execute_all_batches=True, apply_jit=False): ...
+    def plan(self, module, sharders): ...
+    for frozen, live in ((dmp, DistributedModelParallel.__init__), (ebc, EmbeddingBagCollection.__init__), (kjt, KeyedJaggedTensor.__init__), (pipe, TrainPipelineSparseDist.__init__),
+                         (plan, EmbeddingShardingPlanner.plan)):
+        assert is_signature_compatible(inspect.signature(frozen), inspect.signature(live)), (live.__qualname__, inspect.signature(live))
+
+
+def test_module_linter(tmp_path):
+    from torchrec_b200.linter.module_linter import linter_one_file
+
+    f = tmp_path / "m.py"
+    f.write_text("import torch.nn as nn\nclass Good(nn.Module):\n    '''Doc.\n\n    Args:\n        x: size\n\n    Example::\n        Good(1)\n    '''\n    def __init__(self, x):\n        super().__init__()\n"
+                 "    def forward(self, t):\n        return t\nclass Bad(nn.Module):\n    def __init__(self, a, b):\n        super().__init__()\nclass Half(nn.Module):\n    '''Doc only.'''\n    def __init__(self, a):\n        super().__init__()\n")
+    issues = linter_one_file(str(f))
+    names = sorted((i["name"], i["description"].split("`")[1]) for i in issues)
+    assert ("docstring-missing", "Bad") in names and ("args-section-missing", "Half") in names and not any(n[1] == "Good" for n in names)
+
+
+def test_loggers(caplog):
+    from torchrec_b200.parallel.logger import CappedLogger, EventLoggingHandler, LazyStr, _torchrec_method_logger, get_logger
+
+    calls = []
+    s = LazyStr(lambda: calls.append(1) or "expensive")
+    logging.getLogger("x").debug(s)
+    assert calls == [] and str(s) == "expensive"
+    with caplog.at_level(logging.WARNING):
+        c = CappedLogger(get_logger("t"), cap=2)
+        for _ in range(5):
+            c.warning("k", "hot path warning")
+    assert sum("hot path warning" in r.getMessage() for r in caplog.records) == 2
+    events = []
+    EventLoggingHandler.register("test", lambda e, f: events.append((e, f["success"])))
+
+    @EventLoggingHandler.event_logger("unit")
+    @_torchrec_method_logger()
+    def work(x):
+        return x + 1
+
+    assert work(1) == 2 and events == [("unit", True)]
