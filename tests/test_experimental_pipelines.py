@@ -1,0 +1,105 @@
+"""Experimental pipelines + HybridEvalDMP (CPU)."""
+import torch
+from torch import nn
+
+from torchrec_b200.datasets.random import RandomRecDataset
+
+
+def _model(device=torch.device("cpu"), cls=None, **kw):
+    from torchrec_b200.models.dlrm import DLRM, DLRMTrain
+    from torchrec_b200.modules.embedding_configs import EmbeddingBagConfig
+    from torchrec_b200.modules.embedding_modules import EmbeddingBagCollection
+    from torchrec_b200.optim.apply_optimizer_in_backward import apply_optimizer_in_backward
+    from torchrec_b200.optim.keyed import CombinedOptimizer, KeyedOptimizerWrapper
+    from torchrec_b200.optim.optimizers import in_backward_optimizer_filter
+    from torchrec_b200.optim.rowwise_adagrad import RowWiseAdagrad
+    from torchrec_b200.parallel import sharding_plan as sp
+    from torchrec_b200.parallel.embeddingbag import EmbeddingBagCollectionSharder
+    from torchrec_b200.parallel.model_parallel import DistributedModelParallel
+    from torchrec_b200.parallel.types import ShardingPlan
+
+    torch.manual_seed(0)
+    keys = ["a", "b", "c"]
+    tables = [EmbeddingBagConfig(name=f"t_{k}", embedding_dim=8, num_embeddings=50, feature_names=[k]) for k in keys]
+    ebc = EmbeddingBagCollection(tables, device=torch.device("meta"))
+    apply_optimizer_in_backward(RowWiseAdagrad, ebc.parameters(), {"lr": 0.05})
+    model = DLRMTrain(DLRM(ebc, 13, [16, 8], [16, 1], dense_device=device))
+    plan = sp.construct_module_sharding_plan(ebc, {t.name: sp.table_wise(rank=0) for t in tables}, sharder=EmbeddingBagCollectionSharder(), world_size=1, local_size=1, device_type="cpu")
+    dmp = (cls or DistributedModelParallel)(model, device=device, plan=ShardingPlan({"model.sparse_arch.embedding_bag_collection": plan}), sharders=[EmbeddingBagCollectionSharder()], **kw)
+    dense_opt = KeyedOptimizerWrapper(dict(in_backward_optimizer_filter(dmp.named_parameters())), lambda p: torch.optim.SGD(p, lr=0.05))
+    ds = RandomRecDataset(keys, 16, hash_sizes=[50] * 3, ids_per_features=[2] * 3, num_dense=13, manual_seed=1, num_generated_batches=6)
+    return dmp, CombinedOptimizer([dmp.fused_optimizer, dense_opt]), ds.batch_generator._generated_batches
+
+
+def _weights(dmp):
+    return torch.cat([t.weights.detach().flatten().clone() for t in dmp.module.model.sparse_arch.embedding_bag_collection.engine._tbes])
+
+
+def test_stash_and_bwd_injection_pipelines_match_plain():
+    from torchrec_b200.parallel.memory_stashing import MemoryStashingManager
+    from torchrec_b200.parallel.train_pipeline import TrainPipelineSparseDist
+    from torchrec_b200.parallel.train_pipeline.backward_injection import InjectionSite, InjectionTargetType
+    from torchrec_b200.parallel.train_pipeline.experimental_pipelines import (TrainPipelineSparseDistBwdOpt, TrainPipelineSparseDistEmbStash,
+                                                                                TrainPipelineSparseDistOptStash, TrainPipelineSparseDistT)
+
+    ref_dmp, ref_opt, batches = _model()
+    ref = TrainPipelineSparseDist(ref_dmp, ref_opt, torch.device("cpu"))
+    it = iter(batches)
+    ref_losses = [float(ref.progress(it)[0]) for _ in range(5)]
+    site = InjectionSite(fqn="model.over_arch", target_type=InjectionTargetType.PARAM_GRAD)
+    for cls, kw in ((TrainPipelineSparseDistOptStash, {"site": site}), (TrainPipelineSparseDistEmbStash, {}), (TrainPipelineSparseDistT, {}),
+                    (TrainPipelineSparseDistBwdOpt, {"site": site, "injected_work": lambda p: None})):
+        MemoryStashingManager.reset()
+        dmp, opt, _ = _model()
+        pipe = cls(dmp, opt, torch.device("cpu"), **kw)
+        it = iter(batches)
+        losses = [float(pipe.progress(it)[0]) for _ in range(5)]
+        torch.testing.assert_close(torch.tensor(losses), torch.tensor(ref_losses), rtol=1e-5, atol=1e-6)
+        if cls is TrainPipelineSparseDistOptStash:
+            assert MemoryStashingManager.stashed_bytes() > 0  # state parked on the host between steps
+        if cls is TrainPipelineSparseDistBwdOpt:
+            assert pipe.injected_calls == 5
+        MemoryStashingManager.reset()
+        torch.testing.assert_close(_weights(dmp), _weights(ref_dmp), rtol=1e-5, atol=1e-6)
+
+
+def test_train_eval_hybrid_pipeline():
+    from torchrec_b200.parallel.train_pipeline.experimental_pipelines import TrainEvalHybridPipelineBase
+
+    dmp, opt, batches = _model()
+    flags = [False, True, False, True, False]
+    for b, f in zip(batches, flags):
+        b.labels[0] = 7 if f else b.labels[0]  # the marker must survive Batch.to(device): carried in the data itself
+    pipe = TrainEvalHybridPipelineBase(dmp, opt, torch.device("cpu"), is_eval_batch=lambda b: int(b.labels[0]) == 7)
+    it = iter(batches[:5])
+    w_hist = []
+    for _ in range(5):
+        pipe.progress(it)
+        w_hist.append(_weights(dmp))
+    assert not torch.equal(w_hist[0], w_hist[2]) and torch.equal(w_hist[0], w_hist[1]) and torch.equal(w_hist[2], w_hist[3])
+    assert dmp.training
+
+
+def test_hybrid_eval_dmp_and_cpu_sparse_eval():
+    from torchrec_b200.parallel.model_parallel import HybridEvalDMP
+    from torchrec_b200.parallel.train_pipeline.experimental_pipelines import EvalPipelineCPUSparse
+
+    dmp, _, batches = _model(cls=HybridEvalDMP)
+    assert not dmp.training
+    dmp.to(torch.device("cpu"))
+    m = dmp.module.model
+
+    def sparse(batch):
+        return m.sparse_arch(batch.sparse_features)
+
+    def dense(batch, pooled):
+        d = m.dense_arch(batch.dense_features)
+        return m.over_arch(m.inter_arch(dense_features=d, sparse_features=pooled))
+
+    pipe = EvalPipelineCPUSparse(sparse, dense, torch.device("cpu"))
+    it = iter(batches[:3])
+    outs = [pipe.progress(it) for _ in range(3)]
+    with torch.no_grad():
+        ref = [m(b.dense_features, b.sparse_features) for b in batches[:3]]
+    for o, r in zip(outs, ref):
+        torch.testing.assert_close(o, r)

@@ -579,3 +579,50 @@ class DMPCollection(DistributedModelParallel):
     @property
     def replica_pg(self) -> dist.ProcessGroup:
         return self._default_ctx.replica_pg
+
+
+class HybridEvalDMP(DistributedModelParallel):
+    """Eval-only DMP with split placement: embedding shards stay where the plan put them (typically CPU / DDR for tables
+    that exceed HBM) while ``.to(device)`` moves only the dense part (reference model_parallel.py:908-1005).
+    ``share_embedding_memory(pg)`` de-duplicates CPU-resident table storage across the ranks of one host through POSIX
+    shared memory: rank 0 of ``pg`` owns the memory, the others map it."""
+
+    def __init__(self, module: nn.Module, *, init_data_parallel: bool = False, **kwargs: Any) -> None:
+        super().__init__(module, init_data_parallel=init_data_parallel, **kwargs)
+        self.eval()
+
+    def to(self, *args: Any, **kwargs: Any) -> "HybridEvalDMP":  # type: ignore[override]
+        def selective(mod: nn.Module) -> None:
+            for key, param in mod._parameters.items():
+                if param is not None:
+                    mod._parameters[key] = nn.Parameter(param.data.to(*args, **kwargs), requires_grad=param.requires_grad)
+            for key, buf in mod._buffers.items():
+                if buf is not None:
+                    mod._buffers[key] = buf.to(*args, **kwargs)
+            for child in mod.children():
+                if not isinstance(child, ShardedModule):
+                    selective(child)
+
+        selective(self.module)
+        return self
+
+    def share_embedding_memory(self, pg: dist.ProcessGroup) -> int:
+        """Returns the number of bytes now backed by shared memory."""
+        from .collective_utils import create_on_rank_and_share_result
+
+        shared_bytes = 0
+        for m in self.module.modules():
+            eng = getattr(m, "engine", None)
+            if eng is None or not hasattr(eng, "_tbes"):
+                continue
+            for tbe in eng._tbes:
+                w = tbe.weights
+                if w.device.type != "cpu" or w.numel() == 0:
+                    continue
+                src = w.data
+                shared = create_on_rank_and_share_result(pg, 0, lambda src=src: src.detach().clone())
+                w.data = shared  # parameter views are rebuilt lazily from tbe.weights
+                if hasattr(m, "_build_param_views"):
+                    m._build_param_views()
+                shared_bytes += shared.numel() * shared.element_size()
+        return shared_bytes
