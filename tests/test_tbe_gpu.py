@@ -43,7 +43,7 @@ def test_pooled_forward(dim, wdtype, weighted):
 
 
 @pytest.mark.parametrize("opt", [T.OptimType.EXACT_SGD, T.OptimType.EXACT_ROWWISE_ADAGRAD, T.OptimType.EXACT_ADAGRAD, T.OptimType.ADAM,
-                                 T.OptimType.PARTIAL_ROWWISE_ADAM, T.OptimType.LAMB, T.OptimType.LARS_SGD, T.OptimType.NONE])
+                                 T.OptimType.PARTIAL_ROWWISE_ADAM, T.OptimType.LAMB, T.OptimType.LARS_SGD, T.OptimType.NONE, T.OptimType.LION])
 @pytest.mark.parametrize("dim", [32, 128, 512])
 def test_fused_backward_matches_reference(opt, dim):
     dev = torch.device("cuda:0")

@@ -31,6 +31,7 @@ enum TrbOpt : int {
   OPT_PARTIAL_ROWWISE_LAMB = 6,
   OPT_LARS_SGD = 7,
   OPT_NONE = 8,  // accumulate summed gradient rows into a dense fp32 grad buffer (state1)
+  OPT_LION = 9,  // sign(beta1 m + (1-beta1) g) update, momentum refreshed with beta2
 };
 
 // hyper[] slots (device memory, refreshed by the host each step; graph-capture friendly)
@@ -234,6 +235,23 @@ __device__ __forceinline__ void apply_row(const TbeBwdParams& p, int64_t key, in
     }
 #pragma unroll
     for (int k = 0; k < MAXV; ++k) wv[k] = f4_fma(upd[k], -lr * ratio, wv[k]);
+  } else if (OPT == OPT_LION) {
+    const float b1 = p.hyper[HP_BETA1], b2 = p.hyper[HP_BETA2];
+    float* m = p.state1 + eoff;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const int vi = lane + k * 32;
+      if (vi < nvec) {
+        float4 mv = *reinterpret_cast<float4*>(m + vi * 4);
+        float4 c = make_float4(b1 * mv.x + (1.f - b1) * g[k].x, b1 * mv.y + (1.f - b1) * g[k].y, b1 * mv.z + (1.f - b1) * g[k].z, b1 * mv.w + (1.f - b1) * g[k].w);
+        float4 u = make_float4((c.x > 0.f) - (c.x < 0.f), (c.y > 0.f) - (c.y < 0.f), (c.z > 0.f) - (c.z < 0.f), (c.w > 0.f) - (c.w < 0.f));
+        if (p.wd_mode == 2) u = f4_fma(wv[k], wd, u);
+        wv[k] = f4_fma(u, -lr, wv[k]);
+        mv.x = b2 * mv.x + (1.f - b2) * g[k].x; mv.y = b2 * mv.y + (1.f - b2) * g[k].y;
+        mv.z = b2 * mv.z + (1.f - b2) * g[k].z; mv.w = b2 * mv.w + (1.f - b2) * g[k].w;
+        *reinterpret_cast<float4*>(m + vi * 4) = mv;
+      }
+    }
   } else if (OPT == OPT_LARS_SGD) {
     float gn = 0.f, wn = 0.f;
 #pragma unroll

@@ -36,6 +36,7 @@ class OptimType(enum.Enum):
     LAMB = "lamb"
     PARTIAL_ROWWISE_LAMB = "partial_row_wise_lamb"
     LARS_SGD = "lars_sgd"
+    LION = "lion"
     NONE = "none"  # dense gradient for an external optimizer / DDP
 
     def __str__(self) -> str:
@@ -54,6 +55,7 @@ _OPT_CODE = {
     OptimType.PARTIAL_ROWWISE_LAMB: 6,
     OptimType.LARS_SGD: 7,
     OptimType.NONE: 8,
+    OptimType.LION: 9,
 }
 
 # (state1 kind, state2 kind): "row" = one fp32 per row, "elem" = same shape as the weights
@@ -67,6 +69,7 @@ _OPT_STATE = {
     6: ("elem", "row"),
     7: (None, None),
     8: (None, None),
+    9: ("elem", None),
 }
 
 # names follow the reference's optimizer state keys (first state is always "momentum1",
@@ -78,6 +81,7 @@ _OPT_STATE_NAMES = {
     4: ("momentum1", "momentum2"),
     5: ("momentum1", "momentum2"),
     6: ("momentum1", "momentum2"),
+    9: ("momentum1", None),
 }
 
 HP_LR, HP_EPS, HP_BETA1, HP_BETA2, HP_WD, HP_STEP, HP_MAXGRAD, HP_MOMENTUM = range(8)
@@ -303,6 +307,14 @@ def _ref_apply(opt: int, wd_mode: int, hyper: List[float], weights, state1, stat
             un, wn = upd.norm(dim=1), w.norm(dim=1)
             ratio = torch.where((un > 0) & (wn > 0), wn / un, torch.ones_like(un)).unsqueeze(1)
         w = w - lr * ratio * upd
+    elif opt == 9:
+        m = state1[key : key + rows * D].view(rows, D)
+        c = b1 * m[uniq] + (1 - b1) * g
+        upd = torch.sign(c)
+        if wd_mode == 2:
+            upd = upd + wd * w
+        w = w - lr * upd
+        m[uniq] = b2 * m[uniq] + (1 - b2) * g
     elif opt == 7:
         eta = hyper[HP_MOMENTUM] if hyper[HP_MOMENTUM] > 0 else 0.001
         gn, wn = g.norm(dim=1), w.norm(dim=1)

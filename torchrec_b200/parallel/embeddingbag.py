@@ -455,9 +455,44 @@ class ShardedEmbeddingBagCollection(
         self._features_order = order
         self._has_features_permute = order != list(range(len(keys)))
 
+    @staticmethod
+    def _pad_vbe(features: KeyedJaggedTensor) -> KeyedJaggedTensor:
+        """Variable batch per feature -> uniform stride max_f(B_f) by appending empty bags (values untouched)."""
+        spk = features.stride_per_key()
+        Bm = max(spk) if spk else 0
+        lengths = features.lengths()
+        padded = lengths.new_zeros(len(spk), Bm)
+        pos = 0
+        for f, b in enumerate(spk):
+            padded[f, :b] = lengths[pos : pos + b]
+            pos += b
+        return KeyedJaggedTensor(keys=features.keys(), values=features.values(), weights=features.weights_or_none(), lengths=padded.reshape(-1), stride=Bm)
+
+    def _vbe_expand(self, ctx: EmbeddingBagCollectionContext, kt: KeyedTensor) -> KeyedTensor:
+        """Undo the de-duplication of a VBE batch: out[b, cols(f)] = pooled[inverse_indices[f, b], cols(f)]
+        (reference embeddingbag.py:405 / VariableBatchPooledEmbeddingsAllToAll semantics)."""
+        inv = ctx.inverse_indices
+        if inv is None:
+            return kt
+        keys, idx = inv
+        row = {k: i for i, k in enumerate(keys)}
+        vals = kt.values()
+        outs = []
+        c = 0
+        for name, d in zip(self._embedding_names, self._embedding_dims):
+            feat = name.split("@")[0]
+            outs.append(vals[:, c : c + d].index_select(0, idx[row[feat]].long()) if feat in row else vals[:, c : c + d])
+            c += d
+        return KeyedTensor(keys=kt.keys(), length_per_key=kt.length_per_key(), values=torch.cat(outs, dim=1), key_dim=1)
+
     def input_dist(self, ctx: EmbeddingBagCollectionContext, features: KeyedJaggedTensor) -> Awaitable[Awaitable[KJTList]]:
         if self._features_order is None:
             self._setup_feature_order(features)
+        if features.variable_stride_per_key():
+            # VBE: ship the de-duplicated bags (padded to one stride), expand with inverse_indices after the output dist
+            ctx.inverse_indices = features.inverse_indices_or_none()
+            ctx.variable_batch_per_feature = True
+            features = self._pad_vbe(features)
         with torch.no_grad():
             if self._has_features_permute:
                 features = features.permute(self._features_order)
@@ -503,7 +538,8 @@ class ShardedEmbeddingBagCollection(
             mp = mp_aw.wait() if mp_aw is not None else None
             eng = self._engine if self._engine is not None else _COMBINE_ONLY
             vals = eng.combine(mp, dp_out, self._dp_cols, self._total_cols, ctx.mean_divisor)
-            return KeyedTensor(keys=self._embedding_names, length_per_key=self._embedding_dims, values=vals, key_dim=1)
+            kt = KeyedTensor(keys=self._embedding_names, length_per_key=self._embedding_dims, values=vals, key_dim=1)
+            return self._vbe_expand(ctx, kt) if getattr(ctx, "variable_batch_per_feature", False) else kt
 
         return EmbeddingBagCollectionAwaitable(finish)
 
@@ -535,6 +571,8 @@ class ShardedEmbeddingBagCollection(
         if ctx.mean_divisor is not None:
             vals = vals * ctx.mean_divisor.to(vals.dtype)
         kt = KeyedTensor(keys=self._embedding_names, length_per_key=self._embedding_dims, values=vals, key_dim=1)
+        if getattr(ctx, "variable_batch_per_feature", False):
+            kt = self._vbe_expand(ctx, kt)
         return EmbeddingBagCollectionAwaitable(lambda: kt)
 
     # ---- parameters / state ------------------------------------------------------------------------------------
