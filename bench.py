@@ -75,14 +75,20 @@ class ClockSampler:
         def reader() -> None:
             assert self.proc is not None and self.proc.stdout is not None
             for line in self.proc.stdout:
-                self.lines.append(line.strip())
+                self.lines.append((time.time(), line.strip()))
 
         self._t = threading.Thread(target=reader, daemon=True)
         self._t.start()
 
+    def mark_start(self) -> None:
+        """The sampler is started before warm-up (nvidia-smi takes longer to start than a short timed region lasts);
+        only samples that arrive between mark_start() and stop() are reported."""
+        self.t0 = time.time()
+
     def stop(self) -> Dict[str, Any]:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t1 = time.time()
         time.sleep(0.12)
         self.proc.terminate()
         try:
@@ -91,7 +97,14 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        t0 = getattr(self, "t0", 0.0)
+        inside = [ln for ts, ln in self.lines if t0 <= ts <= t1 + 0.11]
+        window = "timed"
+        if not inside:  # region shorter than one sampling period: fall back to the closest samples taken under (warm-up) load
+            inside = [ln for ts, ln in self.lines][-3:]
+            window = "warmup+timed"
+        self.window = window
+        for ln in inside:
             parts = [x.strip() for x in ln.split(",")]
             if len(parts) < 9:
                 continue
@@ -103,7 +116,8 @@ class ClockSampler:
             for nm, v in zip(names, parts[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm),
+                "window": getattr(self, "window", "timed")}
 
 
 def reference_arm(args: argparse.Namespace) -> None:
@@ -233,11 +247,12 @@ def main() -> None:
         torch.cuda.synchronize()
 
     # ---------------- device-resident timing (kernel-side number) ----------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for i in range(max(args.warmup, 3)):
         step(dev_batches[i % len(dev_batches)])
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark_start()
     n0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -249,6 +264,14 @@ def main() -> None:
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count() - n0
     clocks = sampler.stop()
+    if world > 1:  # worst GPU of the job: lowest median SM clock, union of throttle reasons
+        allc: List[Any] = [None] * world
+        dist.all_gather_object(allc, clocks)
+        ok = [c for c in allc if c.get("sm_mhz") is not None]
+        if ok:
+            clocks = dict(min(ok, key=lambda c: c["sm_mhz"]))
+            clocks["reasons"] = sorted({r for c in allc for r in c.get("reasons", [])})
+            clocks["samples"] = sum(c.get("samples", 0) for c in ok)
     t = torch.tensor([ms], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
