@@ -168,3 +168,48 @@ TRB_API int trb_cast_copy(const void* src, int s_dtype, void* dst, int d_dtype, 
 #undef TRB_CC
   return -3;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Gradient push (backward "all-to-all" as posted NVLink stores): every rank scatters the column blocks of its local
+// gradient [B_local, total_cols] to the ranks that own the corresponding table shards, into THEIR gradient inbox
+// [W * B_local, pitch] at rows [src_rank * B_local, ...). Chunks of 4 elements are described by a small device table
+// (dst rank, src col, dst col). Posted remote writes pipeline far deeper than the remote row *reads* of a pull design
+// (peer load latency ~1.8k cycles, B300_MICROARCH.md), and the fused backward afterwards only touches local HBM.
+// Parity: the backward all_to_all_single of the pooled output dist (reference comm_ops.py:1581-1646).
+// ---------------------------------------------------------------------------------------------------------------
+template <typename S, typename D>
+__global__ void __launch_bounds__(256)
+trb_grad_push_kernel(const S* __restrict__ src, int64_t src_stride, const int32_t* __restrict__ chunks, int n_chunks, TrbPeerPtrs dst, int64_t dst_pitch,
+                     int64_t row_base, int B_local, float scale) {
+  const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t) B_local * n_chunks) return;
+  const int64_t b = i / n_chunks;
+  const int c = (int) (i - b * n_chunks);
+  const int rank = chunks[3 * c], sc = chunks[3 * c + 1], dc = chunks[3 * c + 2];
+  float4 v = Vec4<S>::ld(src + b * src_stride + sc);
+  if (scale != 1.f) v = f4_scale(v, scale);
+  Vec4<D>::st(reinterpret_cast<D*>(dst.p[rank]) + (row_base + b) * dst_pitch + dc, v);
+}
+
+TRB_API int trb_grad_push(const void* src, int s_dtype, int64_t src_stride, const int32_t* chunks, int n_chunks, void* const* dst_ptrs, int n_dst, int d_dtype,
+                          int64_t dst_pitch, int64_t row_base, int B_local, float scale, cudaStream_t stream) {
+  if (n_dst < 1 || n_dst > TRB_MAX_PEERS) return -1;
+  const int64_t n = (int64_t) B_local * n_chunks;
+  if (n == 0) return 0;
+  TrbPeerPtrs d;
+  for (int i = 0; i < n_dst; ++i) d.p[i] = dst_ptrs[i];
+  const int threads = 256;
+  const unsigned blocks = (unsigned) ((n + threads - 1) / threads);
+#define TRB_GP(SC, ST, DC, DT)                                                                                                              \
+  if (s_dtype == SC && d_dtype == DC) {                                                                                                     \
+    trb_grad_push_kernel<ST, DT><<<blocks, threads, 0, stream>>>((const ST*) src, src_stride, chunks, n_chunks, d, dst_pitch, row_base, B_local, scale); \
+    TRB_CHECK_LAUNCH();                                                                                                                      \
+    return 0;                                                                                                                                \
+  }
+  TRB_GP(TRB_F32, float, TRB_F32, float)
+  TRB_GP(TRB_F32, float, TRB_BF16, __nv_bfloat16)
+  TRB_GP(TRB_BF16, __nv_bfloat16, TRB_F32, float)
+  TRB_GP(TRB_BF16, __nv_bfloat16, TRB_BF16, __nv_bfloat16)
+#undef TRB_GP
+  return -3;
+}

@@ -24,6 +24,7 @@ written straight into the destination rank's output).
 from __future__ import annotations
 
 import itertools
+import os
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional, Tuple
 
@@ -652,11 +653,34 @@ class _P2PState:
         esz = torch.empty(0, dtype=self.wire_dtype).element_size()
         self.slab_bytes = B_local * total_cols * esz
         self.has_staged = any(eng._table_row_sharded.values())
-        nbytes = self.slab_bytes * (self.N_SLOTS + 1 + (W if self.has_staged else 0))
+        # gradient inbox: [W * B_local, pitch] per slot, pitch = widest per-rank sum of unit columns (same on every rank)
+        dims_f = [eng._tables[ti].embedding_dim for ti in eng._feature_table]
+        base_f = list(itertools.accumulate([0] + dims_f))
+        self.push = os.environ.get("TRB_GRAD_PUSH", "1") != "0"
+        chunks: List[List[int]] = []
+        local_cols_per_rank: List[List[int]] = []
+        for r in range(W):
+            c = 0
+            cols_r = []
+            for u in eng._units[eng._unit_start[r] : eng._unit_start[r + 1]]:
+                src0 = base_f[u.feature] + u.shard.col_off
+                cols_r.append(c)
+                for k in range(0, u.shard.cols, 4):
+                    chunks.append([r, src0 + k, c + k])
+                c += u.shard.cols
+            local_cols_per_rank.append(cols_r)
+        self.inbox_pitch = max(8, (max((sum(u.shard.cols for u in eng._units[eng._unit_start[r] : eng._unit_start[r + 1]]) for r in range(W)), default=8) + 7) // 8 * 8)
+        self.push = self.push and all(u.shard.cols % 4 == 0 for u in eng._units)
+        self.inbox_bytes = (W * B_local * self.inbox_pitch * esz + 255) // 256 * 256 if self.push else 0
+        self.chunks = torch.tensor(chunks, dtype=torch.int32, device=eng._device).contiguous() if self.push else None
+        self.local_cols = local_cols_per_rank[eng._rank]
+        nbytes = self.slab_bytes * (self.N_SLOTS + 1 + (W if self.has_staged else 0)) + 2 * self.inbox_bytes
         self.buf = self.pg.alloc(nbytes)
         self.out_off = [i * self.slab_bytes for i in range(self.N_SLOTS)]
         self.grad_off = self.N_SLOTS * self.slab_bytes
         self.staging_off = (self.N_SLOTS + 1) * self.slab_bytes
+        self.inbox_off = [self.slab_bytes * (self.N_SLOTS + 1 + (W if self.has_staged else 0)) + i * self.inbox_bytes for i in range(2)]
+        self.bwd_step = 0
         self.step = 0
         self.dummy = torch.zeros(1, device=eng._device, requires_grad=True)
         dims = [eng._tables[ti].embedding_dim for ti in eng._feature_table]
@@ -681,7 +705,8 @@ class _P2PState:
             n_direct = staged.index(True) if True in staged else len(units)
             assert all(staged[n_direct:]), "row-sharded units must follow direct units inside a group"
             full = g.tbe.meta.with_cols(cols, total_cols)
-            self.group_meta.append({"full": full, "n_direct": n_direct, "n": len(units),
+            local = g.tbe.meta.with_cols(self.local_cols[u0:u1], self.inbox_pitch) if self.push else None
+            self.group_meta.append({"full": full, "local": local, "n_direct": n_direct, "n": len(units),
                                     "direct": _slice_meta(full, 0, n_direct), "staged": _slice_meta(full, n_direct, len(units))})
 
     def out_local(self, slot: int) -> torch.Tensor:
@@ -748,12 +773,22 @@ class _FusedLookupDistFn(torch.autograd.Function):
 
         eng, st, Bg = ctx.eng, ctx.st, ctx.Bg
         values, offsets, weights = ctx.saved_tensors
-        gbuf = st.grad_local()
         if grad.stride(1) != 1:
             grad = grad.contiguous()
-        p2p.cast_copy(grad, gbuf, ctx.grad_scale)
-        st.pg.barrier()
-        grad_ptrs = st.buf.peer_ptrs(st.grad_off)
+        if st.push:
+            # push: scatter my gradient columns into the owners' inboxes (posted NVLink stores), barrier, local backward
+            slot = st.bwd_step % 2
+            st.bwd_step += 1
+            p2p.grad_push(grad, st.chunks, st.buf.peer_ptrs(st.inbox_off[slot]), st.wire_dtype, st.inbox_pitch, eng._rank * st.B_local, ctx.grad_scale)
+            st.pg.barrier()
+            grad_ptrs = [st.buf.local_ptr + st.inbox_off[slot]]
+            meta_key, g_stride, g_blocal = "local", st.inbox_pitch, Bg
+        else:
+            gbuf = st.grad_local()
+            p2p.cast_copy(grad, gbuf, ctx.grad_scale)
+            st.pg.barrier()
+            grad_ptrs = st.buf.peer_ptrs(st.grad_off)
+            meta_key, g_stride, g_blocal = "full", st.total_cols, st.B_local
         gpsw = None
         want_psw = weights is not None and ctx.needs_input_grad[5]
         for g, gm in zip(eng._groups, st.group_meta):
@@ -762,13 +797,13 @@ class _FusedLookupDistFn(torch.autograd.Function):
             u0, u1 = g.unit_range
             window = offsets[u0 * Bg : u1 * Bg + 1]
             if want_psw:  # per-sample-weight gradient (feature processors) from the pre-update rows
-                gp = T.psw_grad(gm["full"], g.tbe.weights, values, window, Bg, g.pooling == T.PoolingMode.MEAN, grad_ptrs=grad_ptrs,
-                                grad_stride=st.total_cols, grad_dtype=st.wire_dtype, B_local=st.B_local)
+                gp = T.psw_grad(gm[meta_key], g.tbe.weights, values, window, Bg, g.pooling == T.PoolingMode.MEAN, grad_ptrs=grad_ptrs,
+                                grad_stride=g_stride, grad_dtype=st.wire_dtype, B_local=g_blocal)
                 gpsw = gp if gpsw is None else gpsw + gp
             g.tbe._pre_update()
-            T.fused_backward(gm["full"], g.tbe.weights, g.tbe.state1, g.tbe.state2, g.tbe.hyper_dev, g.tbe.hyper_host, g.tbe.opt_code,
+            T.fused_backward(gm[meta_key], g.tbe.weights, g.tbe.state1, g.tbe.state2, g.tbe.hyper_dev, g.tbe.hyper_host, g.tbe.opt_code,
                              int(g.tbe.weight_decay_mode), values, window, weights, Bg, g.pooling == T.PoolingMode.MEAN,
-                             grad_ptrs=grad_ptrs, grad_stride=st.total_cols, grad_dtype=st.wire_dtype, B_local=st.B_local)
+                             grad_ptrs=grad_ptrs, grad_stride=g_stride, grad_dtype=st.wire_dtype, B_local=g_blocal)
         if gpsw is not None:
             gpsw = gpsw.to(weights.dtype)
         return torch.zeros(1, dtype=torch.float32, device=grad.device), None, None, None, None, gpsw, None, None
