@@ -59,3 +59,38 @@ TRB_API int trb_offsets_range(const int64_t* offsets, int64_t n_seg, int64_t tot
   TRB_CHECK_LAUNCH();
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Row mover for the software-managed embedding cache (UVM_CACHING): dst[dst_idx[i]] = src[src_idx[i]] for i < n, rows of
+// `row_bytes` (multiple of 4). Either side may be pinned HOST memory addressed zero-copy over PCIe / NVLink-C2C (the
+// backing store of tables larger than HBM) or device memory (the cache). A null index array means the identity.
+// Parity: the row movement inside fbgemm's lxu_cache_populate / lxu_cache_flush (reference call sites
+// distributed/embedding_lookup.py:714-767, batched_embedding_kernel.py `prefetch` / `flush`).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) trb_row_copy_kernel(uint8_t* __restrict__ dst, const int64_t* __restrict__ dst_idx, const uint8_t* __restrict__ src,
+                                                           const int64_t* __restrict__ src_idx, int64_t n, int row_words) {
+  // one warp per row for wide rows; consecutive lanes move consecutive 4-byte words (coalesced on both sides)
+  const int lane = threadIdx.x & 31;
+  const int64_t r = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= n) return;
+  const int64_t d = dst_idx ? dst_idx[r] : r;
+  const int64_t s = src_idx ? src_idx[r] : r;
+  if (d < 0 || s < 0) return;
+  const uint32_t* sp = reinterpret_cast<const uint32_t*>(src) + s * row_words;
+  uint32_t* dp = reinterpret_cast<uint32_t*>(dst) + d * row_words;
+  if ((row_words & 3) == 0 && ((reinterpret_cast<uintptr_t>(sp) | reinterpret_cast<uintptr_t>(dp)) & 15) == 0) {
+    for (int w = lane; w < (row_words >> 2); w += 32) reinterpret_cast<uint4*>(dp)[w] = reinterpret_cast<const uint4*>(sp)[w];
+  } else {
+    for (int w = lane; w < row_words; w += 32) dp[w] = sp[w];
+  }
+}
+
+TRB_API int trb_row_copy(void* dst, const int64_t* dst_idx, const void* src, const int64_t* src_idx, int64_t n, int64_t row_bytes, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  if (row_bytes % 4) return -2;
+  const int threads = 256;
+  const unsigned blocks = (unsigned) ((n * 32 + threads - 1) / threads);
+  trb_row_copy_kernel<<<blocks, threads, 0, stream>>>((uint8_t*) dst, dst_idx, (const uint8_t*) src, src_idx, n, (int) (row_bytes / 4));
+  TRB_CHECK_LAUNCH();
+  return 0;
+}

@@ -93,6 +93,16 @@ class WeightDecayMode(enum.IntEnum):
     DECOUPLE = 2
 
 
+class EmbeddingLocation(enum.IntEnum):
+    """Where a table-batched module keeps its rows (reference: fbgemm EmbeddingLocation / compute kernels
+    FUSED, FUSED_UVM, FUSED_UVM_CACHING)."""
+
+    DEVICE = 0            # HBM
+    MANAGED = 1           # pinned host memory read / written zero-copy by the kernels (tables larger than HBM)
+    MANAGED_CACHING = 2   # MANAGED backing store + software-managed HBM cache (ops/uvm.py)
+    HOST = 3              # plain CPU
+
+
 class PoolingMode(enum.IntEnum):
     SUM = 0
     MEAN = 1
@@ -357,13 +367,13 @@ def pooled_forward(
     """Pooled lookup. ``out_ptrs`` (peer-mapped raw pointers, one per destination rank) turns the
     call into the fused lookup + all-to-all; otherwise a local ``[B, total_cols]`` tensor is
     written/returned."""
-    if not _lib.use_cuda_kernels(weights):
+    if not _lib.use_cuda_kernels(weights, indices):
         if out_ptrs is not None:
             raise RuntimeError("peer-pointer outputs need CUDA")
         return _ref_pooled_forward(meta, weights, indices, offsets, per_sample_weights, B, mean, out_dtype, out)
     if out_ptrs is None:
         if out is None:
-            out = torch.empty(B, meta.total_cols, dtype=out_dtype, device=weights.device)
+            out = torch.empty(B, meta.total_cols, dtype=out_dtype, device=indices.device)
         assert out.stride(1) == 1
         out_ptrs = [out.data_ptr()]
         out_stride = out.stride(0)
@@ -376,25 +386,25 @@ def pooled_forward(
         _lib.ptr(indices), _is64(indices), _lib.ptr(offsets), _is64(offsets),
         _lib.ptr(per_sample_weights), _lib.ptr_array(out_ptrs), len(out_ptrs),
         _lib.dtype_code(out_dtype), ctypes.c_int64(out_stride), B, B_local, meta.num_features,
-        meta.max_dim, int(mean), _lib.stream_ptr(weights.device),
+        meta.max_dim, int(mean), _lib.stream_ptr(indices.device),
     )
     _lib.check(code, "trb_tbe_pooled_fwd")
     return out
 
 
 def sequence_forward(meta: TbeMeta, weights, indices, offsets, B: int, out_dtype: torch.dtype) -> torch.Tensor:
-    if not _lib.use_cuda_kernels(weights):
+    if not _lib.use_cuda_kernels(weights, indices):
         return _ref_seq_forward(meta, weights, indices, offsets, B, out_dtype)
     D = meta.h_dim[0] if meta.num_features else 0
     n = indices.numel()
-    out = torch.empty(n, D, dtype=out_dtype, device=weights.device)
+    out = torch.empty(n, D, dtype=out_dtype, device=indices.device)
     if n == 0:
         return out
     L = _lib.lib()
     code = L.trb_tbe_seq_fwd(
         _lib.ptr(weights), _lib.dtype_code(weights.dtype), _lib.ptr(meta.feat_woff), _lib.ptr(meta.feat_rows),
         _lib.ptr(indices), _is64(indices), _lib.ptr(offsets), _is64(offsets), meta.num_features, B, D,
-        _lib.ptr(out), _lib.dtype_code(out_dtype), ctypes.c_int64(n), _lib.stream_ptr(weights.device),
+        _lib.ptr(out), _lib.dtype_code(out_dtype), ctypes.c_int64(n), _lib.stream_ptr(indices.device),
     )
     _lib.check(code, "trb_tbe_seq_fwd")
     return out
@@ -433,7 +443,7 @@ def fused_backward(
     B_local: Optional[int] = None,
 ) -> None:
     """Exact fused backward + optimizer for a pooled lookup (gradient rows may live on peers)."""
-    if not _lib.use_cuda_kernels(weights):
+    if not _lib.use_cuda_kernels(weights, indices):
         assert grad is not None
         _ref_fused_backward(meta, weights, state1, state2, hyper_host, opt, wd_mode, indices, offsets, per_sample_weights, grad, B, mean)
         return
@@ -451,14 +461,14 @@ def fused_backward(
     L = _lib.lib()
     L.trb_tbe_bwd_workspace_bytes.restype = ctypes.c_int64
     nbytes = L.trb_tbe_bwd_workspace_bytes(ctypes.c_int64(n), meta.max_dim, ctypes.c_int64(meta.total_rows))
-    ws = _workspace(nbytes, weights.device)
+    ws = _workspace(nbytes, indices.device)
     code = L.trb_tbe_bwd_fused(
         _lib.ptr(weights), _lib.dtype_code(weights.dtype), _lib.ptr(state1), _lib.ptr(state2), _lib.ptr(hyper_dev),
         opt, wd_mode, _lib.ptr(meta.feat_woff), _lib.ptr(meta.feat_rows), _lib.ptr(meta.feat_rowbase),
         _lib.ptr(meta.feat_dim), _lib.ptr(meta.feat_col), _lib.ptr(indices), _is64(indices), _lib.ptr(offsets),
         _is64(offsets), _lib.ptr(per_sample_weights), _lib.ptr_array(grad_ptrs), len(grad_ptrs),
         _lib.dtype_code(grad_dtype), ctypes.c_int64(grad_stride), ctypes.c_int64(n), ctypes.c_int64(meta.total_rows),
-        B, B_local, meta.num_features, meta.max_dim, int(mean), _lib.ptr(ws), _lib.stream_ptr(weights.device),
+        B, B_local, meta.num_features, meta.max_dim, int(mean), _lib.ptr(ws), _lib.stream_ptr(indices.device),
     )
     _lib.check(code, "trb_tbe_bwd_fused")
 
@@ -469,7 +479,7 @@ def psw_grad(meta: TbeMeta, weights: torch.Tensor, indices: torch.Tensor, offset
     """Gradient of the pooled lookup w.r.t. per-sample weights: ``d psw[i] = <grad[bag(i)], W[idx[i]]>`` (fp32 ``[n]``).
     Call BEFORE ``fused_backward`` (which updates the rows in place). csrc/tbe_psw_grad.cu."""
     n = indices.numel()
-    if not _lib.use_cuda_kernels(weights):
+    if not _lib.use_cuda_kernels(weights, indices):
         assert grad is not None
         out = torch.zeros(n, dtype=torch.float32, device=weights.device)
         off = offsets.to(torch.int64)
@@ -489,7 +499,7 @@ def psw_grad(meta: TbeMeta, weights: torch.Tensor, indices: torch.Tensor, offset
                 v = v / lengths[b].clamp(min=1).float()
             out[lo:hi] = v
         return out
-    out = torch.zeros(n, dtype=torch.float32, device=weights.device)
+    out = torch.zeros(n, dtype=torch.float32, device=indices.device)
     if n == 0:
         return out
     if grad_ptrs is None:
@@ -501,7 +511,7 @@ def psw_grad(meta: TbeMeta, weights: torch.Tensor, indices: torch.Tensor, offset
     code = L.trb_tbe_psw_grad(_lib.ptr(weights), _lib.dtype_code(weights.dtype), _lib.ptr(meta.feat_woff), _lib.ptr(meta.feat_rows), _lib.ptr(meta.feat_dim),
                               _lib.ptr(meta.feat_col), _lib.ptr(indices), _is64(indices), _lib.ptr(offsets), _is64(offsets), _lib.ptr_array(grad_ptrs),
                               len(grad_ptrs), _lib.dtype_code(grad_dtype), ctypes.c_int64(grad_stride), _lib.ptr(out), B, B_local, meta.num_features,
-                              meta.max_dim, int(mean), _lib.stream_ptr(weights.device))
+                              meta.max_dim, int(mean), _lib.stream_ptr(indices.device))
     _lib.check(code, "trb_tbe_psw_grad")
     return out
 
@@ -509,7 +519,7 @@ def psw_grad(meta: TbeMeta, weights: torch.Tensor, indices: torch.Tensor, offset
 def sequence_backward(meta, weights, state1, state2, hyper_dev, hyper_host, opt, wd_mode, indices, offsets, B, grad):
     """Backward of the unpooled lookup: position i contributes grad[i] to row indices[i].
     Expressed as a pooled backward with one bag per position (column offset 0, stride D)."""
-    if not _lib.use_cuda_kernels(weights):
+    if not _lib.use_cuda_kernels(weights, indices):
         _ref_fused_backward(meta, weights, state1, state2, hyper_host, opt, wd_mode, indices, offsets, None, grad, B, False, pooled=False)
         return
     n = indices.numel()
@@ -593,6 +603,7 @@ class TableBatchedEmbeddingBags(nn.Module):
         momentum: float = 0.0,
         device: Optional[torch.device] = None,
         table_names: Optional[Sequence[str]] = None,
+        location: "EmbeddingLocation" = None,  # type: ignore[assignment]
     ) -> None:
         super().__init__()
         device = torch.device(device) if device is not None else torch.device("cpu")
@@ -605,6 +616,7 @@ class TableBatchedEmbeddingBags(nn.Module):
             weight_decay_mode = WeightDecayMode.DECOUPLE
         self.opt_code = _OPT_CODE[optimizer]
         self.weight_decay_mode = WeightDecayMode(weight_decay_mode)
+        self.location = EmbeddingLocation(location) if location is not None else (EmbeddingLocation.HOST if torch.device(device or "cpu").type == "cpu" else EmbeddingLocation.DEVICE)
         self.table_names = list(table_names) if table_names is not None else [f"t{i}" for i in range(len(self.embedding_specs))]
         rows = [r for r, _ in self.embedding_specs]
         dims = [d for _, d in self.embedding_specs]
@@ -616,12 +628,14 @@ class TableBatchedEmbeddingBags(nn.Module):
             self.weights = nn.Parameter(torch.empty(total, dtype=weights_precision, device=device), requires_grad=True)
         else:
             # fused tables are updated in-kernel: a plain buffer, never seen by autograd / DDP / dense optimizers
-            self.register_buffer("weights", torch.empty(total, dtype=weights_precision, device=device), persistent=False)
+            self.register_buffer("weights", self._alloc(total, weights_precision, device, big=True), persistent=False)
         self._dummy = nn.Parameter(torch.zeros(1, device=device if not self._is_meta else "cpu"), requires_grad=True) if not dense else None
         if not self._is_meta:
             self.meta = TbeMeta.build(rows, dims, self.feature_table_map, device)
         k1, k2 = _OPT_STATE[self.opt_code]
-        mk = lambda kind: None if kind is None else torch.zeros(self.total_rows if kind == "row" else total, dtype=torch.float32, device=device)
+        # element-wise optimizer state follows the weights' location; row-wise state (4 B / row) stays in HBM
+        mk = lambda kind: None if kind is None else (torch.zeros(self.total_rows, dtype=torch.float32, device=device) if kind == "row"
+                                                     else self._alloc(total, torch.float32, device, big=True).zero_())
         self.register_buffer("state1", mk(k1), persistent=False)
         self.register_buffer("state2", mk(k2), persistent=False)
         self._state_kinds = (k1, k2)
@@ -632,6 +646,23 @@ class TableBatchedEmbeddingBags(nn.Module):
         self._auto_step = True
         if not self._is_meta:
             self.init_parameters()
+
+    def _alloc(self, n: int, dtype: torch.dtype, device: torch.device, big: bool) -> torch.Tensor:
+        if big and self.location == EmbeddingLocation.MANAGED and device.type == "cuda":
+            return torch.empty(n, dtype=dtype, pin_memory=True)  # UVA: the same pointer is valid inside kernels
+        return torch.empty(n, dtype=dtype, device=device)
+
+    def _apply(self, fn, recurse: bool = True):
+        """``.to(device)`` / ``.cuda()`` must not drag zero-copy host tables into HBM."""
+        if self.location != EmbeddingLocation.MANAGED:
+            return super()._apply(fn, recurse)
+        keep = {k: self._buffers[k] for k in ("weights", "state1", "state2") if self._buffers.get(k) is not None and not self._buffers[k].is_cuda}
+        for k in keep:
+            self._buffers[k] = None
+        super()._apply(fn, recurse)
+        for k, v in keep.items():
+            self._buffers[k] = v
+        return self
 
     # ---- parameters -------------------------------------------------------------------------
     @torch.no_grad()
