@@ -289,22 +289,34 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* g, bo
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// issue (do not wait for) the loads of the packed tile of samples [b0, b0+4): bf16 dense + bf16 sparse
+// issue (do not wait for) the loads of the packed tile of samples [b0, b0+4): bf16 dense + bf16 sparse.
+// Thread t always moves column chunk (t & 15) of rows (t >> 4) + 8k, so the swizzle term and all strides are per-thread
+// constants (the first version recomputed them per chunk and was instruction-bound, profiles/ncu_interaction_bwd_pipe_kernel_r1.md).
+// EXTRA: also load gout[b][0:128] (the pass-through gradient of the dense row) as packed row R, so the backward MMA adds it
+// in fp32 through S[0][R] = 1 instead of a lane-0 epilogue special case.
+template <bool EXTRA>
 __device__ __forceinline__ void issue_tile_loads(const InterParams& p, uint8_t* tile, int b0, int tid) {
   const int R = p.F + 1;
-  const uint32_t tbase = smem_u32(tile);
-  const __nv_bfloat16* dense = reinterpret_cast<const __nv_bfloat16*>(p.dense);
-  const __nv_bfloat16* sparse = reinterpret_cast<const __nv_bfloat16*>(p.sparse);
+  const int ch = tid & 15, i0 = tid >> 4;
+  const uint32_t tbase = smem_u32(tile) + (ch >> 3) * kTileBytes + ((((ch & 7) ^ (i0 & 7)) & 7) << 4);
+  const __nv_bfloat16* dense = reinterpret_cast<const __nv_bfloat16*>(p.dense) + ch * 8;
+  const __nv_bfloat16* sparse = reinterpret_cast<const __nv_bfloat16*>(p.sparse) + ch * 8 - kD;  // row i (>= 1) lives at + i * kD
+  const __nv_bfloat16* gout = reinterpret_cast<const __nv_bfloat16*>(p.gout) + ch * 8;
 #pragma unroll
   for (int s = 0; s < kSamples; ++s) {
     const int b = b0 + s;
     const bool ok = b < p.B;
-    const int bb = ok ? b : 0;
-    for (int idx = tid; idx < R * 16; idx += 128) {
-      const int i = idx >> 4, ch = idx & 15;
-      const __nv_bfloat16* src = (i == 0) ? dense + (int64_t) bb * p.ld_dense + ch * 8 : sparse + (int64_t) bb * p.ld_sparse + (i - 1) * kD + ch * 8;
-      const int r = s * kRowsPerSample + i;
-      cp_async16(tbase + (ch >> 3) * kTileBytes + sw128_offset(r, (ch & 7) * 8), src, ok);
+    const int64_t bb = ok ? b : 0;
+    const __nv_bfloat16* srow = sparse + bb * p.ld_sparse;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = i0 + 8 * k;
+      const uint32_t dst = tbase + (uint32_t) ((s * kRowsPerSample + i) * 128);
+      if (i < R) {
+        cp_async16(dst, (i == 0) ? dense + bb * p.ld_dense : srow + (int64_t) i * kD, ok);
+      } else if (EXTRA && i == R) {
+        cp_async16(dst, gout + bb * p.ld_out, ok);
+      }
     }
   }
 }
@@ -313,11 +325,11 @@ __device__ __forceinline__ void issue_tile_loads(const InterParams& p, uint8_t* 
 __device__ __forceinline__ void issue_gout_loads(const InterParams& p, __nv_bfloat16* gstage, int b0, int tid) {
   const int vec_per_row = (int) (p.ld_out >> 3);
   const uint32_t gbase = smem_u32(gstage);
-  for (int v = tid; v < kSamples * vec_per_row; v += 128) {
-    const int sidx = v / vec_per_row, c = v - sidx * vec_per_row;
+#pragma unroll
+  for (int sidx = 0; sidx < kSamples; ++sidx) {
     const bool ok = b0 + sidx < p.B;
-    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(p.gout) + (int64_t) (ok ? b0 + sidx : 0) * p.ld_out + c * 8;
-    cp_async16(gbase + (uint32_t) (sidx * p.ld_out + c * 8) * 2, src, ok);
+    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(p.gout) + (int64_t) (ok ? b0 + sidx : 0) * p.ld_out;
+    for (int c = tid; c < vec_per_row; c += 128) cp_async16(gbase + (uint32_t) (sidx * p.ld_out + c * 8) * 2, src + c * 8, ok);
   }
 }
 
@@ -341,7 +353,7 @@ __global__ void __launch_bounds__(128, 3) interaction_fwd_pipe_kernel(const Inte
   uint32_t phase = 0;
   const int groups = (p.B + kSamples - 1) / kSamples;
   int cur = 0;
-  if ((int) blockIdx.x < groups) issue_tile_loads(p, tiles, blockIdx.x * kSamples, tid);
+  if ((int) blockIdx.x < groups) issue_tile_loads<false>(p, tiles, blockIdx.x * kSamples, tid);
   cp_async_commit();
   for (int g = blockIdx.x; g < groups; g += gridDim.x, cur ^= 1) {
     const int b0 = g * kSamples;
@@ -349,7 +361,7 @@ __global__ void __launch_bounds__(128, 3) interaction_fwd_pipe_kernel(const Inte
     cp_async_wait_all();
     fence_proxy_async();
     __syncthreads();  // tile[cur] landed; everyone is done with tile[cur^1] and with `stage`
-    if (g + (int) gridDim.x < groups) issue_tile_loads(p, tiles + (cur ^ 1) * 2 * kTileBytes, (g + gridDim.x) * kSamples, tid);
+    if (g + (int) gridDim.x < groups) issue_tile_loads<false>(p, tiles + (cur ^ 1) * 2 * kTileBytes, (g + gridDim.x) * kSamples, tid);
     cp_async_commit();
     if (warp == 0) {
       if (elect_one()) {
@@ -385,10 +397,12 @@ __global__ void __launch_bounds__(128, 3) interaction_fwd_pipe_kernel(const Inte
     tc_fence_before();
     __syncthreads();
     const int vec_per_row = (int) (p.ld_out >> 3);
-    for (int v = tid; v < kSamples * vec_per_row; v += 128) {
-      const int s = v / vec_per_row, c = v - s * vec_per_row;
-      if (b0 + s < p.B)
-        reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t) (b0 + s) * p.ld_out)[c] = reinterpret_cast<const uint4*>(stage + s * p.ld_out)[c];
+#pragma unroll
+    for (int s = 0; s < kSamples; ++s) {
+      if (b0 + s >= p.B) break;
+      uint4* orow = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t) (b0 + s) * p.ld_out);
+      const uint4* srow4 = reinterpret_cast<const uint4*>(stage + s * p.ld_out);
+      for (int c = tid; c < vec_per_row; c += 128) orow[c] = srow4[c];
     }
   }
   cp_async_wait_all();
@@ -397,6 +411,7 @@ __global__ void __launch_bounds__(128, 3) interaction_fwd_pipe_kernel(const Inte
   if (warp == 0) tmem_dealloc(tmem_d, 128);
 }
 
+template <bool EXTRA>
 __global__ void __launch_bounds__(128, 2) interaction_bwd_pipe_kernel(const InterParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
@@ -420,7 +435,7 @@ __global__ void __launch_bounds__(128, 2) interaction_bwd_pipe_kernel(const Inte
   const int gsz = kSamples * (int) p.ld_out;
   int cur = 0;
   if ((int) blockIdx.x < groups) {
-    issue_tile_loads(p, tiles, blockIdx.x * kSamples, tid);
+    issue_tile_loads<EXTRA>(p, tiles, blockIdx.x * kSamples, tid);
     issue_gout_loads(p, gst, blockIdx.x * kSamples, tid);
   }
   cp_async_commit();
@@ -433,7 +448,7 @@ __global__ void __launch_bounds__(128, 2) interaction_bwd_pipe_kernel(const Inte
     fence_proxy_async();
     __syncthreads();  // T[cur] / gout[cur] landed; copy-out of the previous group finished (staging == tileS is free)
     if (g + (int) gridDim.x < groups) {
-      issue_tile_loads(p, tiles + (cur ^ 1) * 2 * kTileBytes, (g + gridDim.x) * kSamples, tid);
+      issue_tile_loads<EXTRA>(p, tiles + (cur ^ 1) * 2 * kTileBytes, (g + gridDim.x) * kSamples, tid);
       issue_gout_loads(p, gst + (cur ^ 1) * gsz, (g + gridDim.x) * kSamples, tid);
     }
     cp_async_commit();
@@ -442,15 +457,24 @@ __global__ void __launch_bounds__(128, 2) interaction_bwd_pipe_kernel(const Inte
     {
       const __nv_bfloat16* grow = gstage + warp * p.ld_out + kD;
       const bool live = lane < R && (b0 + warp) < p.B;
+      // S[i][j] = g[tri(min) + (max - min - 1)]: for j < i the offset walks down the column (stride R - j - 2), for j > i it
+      // is contiguous in the row of i — no multiplications inside the loop
       uint32_t packed[16];
+      int off_lo = lane - 1;
+      const int off_hi = tri_offset(lane, R) - (lane + 1);
 #pragma unroll
       for (int j2 = 0; j2 < 16; ++j2) {
-        __nv_bfloat16 v0 = __float2bfloat16(0.f), v1 = v0;
-        const int j0 = 2 * j2, j1 = 2 * j2 + 1;
-        if (live && j0 < R && j0 != lane) { const int lo = min(lane, j0), hi = max(lane, j0); v0 = grow[tri_offset(lo, R) + (hi - lo - 1)]; }
-        if (live && j1 < R && j1 != lane) { const int lo = min(lane, j1), hi = max(lane, j1); v1 = grow[tri_offset(lo, R) + (hi - lo - 1)]; }
-        __nv_bfloat162 h = __halves2bfloat162(v0, v1);
-        packed[j2] = *reinterpret_cast<uint32_t*>(&h);
+        __nv_bfloat16 v[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int j = 2 * j2 + h;
+          v[h] = __float2bfloat16(0.f);
+          if (live && j < R && j != lane) v[h] = grow[(j < lane) ? off_lo : off_hi + j];
+          if (EXTRA && j == R && lane == 0) v[h] = __float2bfloat16(1.f);  // routes packed row R (pass-through gradient) into the dense row
+          off_lo += R - j - 2;
+        }
+        __nv_bfloat162 hh = __halves2bfloat162(v[0], v[1]);
+        packed[j2] = *reinterpret_cast<uint32_t*>(&hh);
       }
       // row r: K-block kb holds k in [64 kb, 64 kb + 64) as 8 chunks of 16 B; own block = k in [32 warp, 32 warp + 32)
       const int own_kb = warp >> 1, own_c0 = (warp & 1) * 4;
@@ -497,7 +521,7 @@ __global__ void __launch_bounds__(128, 2) interaction_bwd_pipe_kernel(const Inte
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(z[j]);
-      if (lane == 0) {  // dense row: add the pass-through gradient of out[:, :D]
+      if (!EXTRA && lane == 0) {  // R == 32: no spare packed row, add the pass-through gradient of out[:, :D] here
         const __nv_bfloat16* gd = gstage + warp * p.ld_out + c * 32;
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += __bfloat162float(gd[j]);
@@ -515,16 +539,24 @@ __global__ void __launch_bounds__(128, 2) interaction_bwd_pipe_kernel(const Inte
     }
     tc_fence_before();
     __syncthreads();
-    // ---- coalesced copy-out: 16 consecutive threads write one 256 B gradient row ----------------------------------------
-    for (int idx = tid; idx < kSamples * R * 16; idx += 128) {
-      const int row = idx >> 4, chunk = idx & 15;
-      const int s = row / R, i = row - s * R;
-      const int b = b0 + s;
-      if (b >= p.B) continue;
-      const uint4 val = *reinterpret_cast<const uint4*>(ostage + (s * kRowsPerSample + i) * 256 + (((chunk ^ i) & 15) << 4));
-      __nv_bfloat16* dst = (i == 0) ? reinterpret_cast<__nv_bfloat16*>(p.g_dense) + (int64_t) b * p.ld_gdense + chunk * 8
-                                    : reinterpret_cast<__nv_bfloat16*>(p.g_sparse) + (int64_t) b * p.ld_gsparse + (i - 1) * kD + chunk * 8;
-      *reinterpret_cast<uint4*>(dst) = val;
+    // ---- coalesced copy-out: 16 consecutive threads write one 256 B gradient row; thread t owns chunk (t & 15) of rows (t >> 4) + 8k
+    {
+      const int ch = tid & 15, i0 = tid >> 4;
+      __nv_bfloat16* gd_base = reinterpret_cast<__nv_bfloat16*>(p.g_dense) + ch * 8;
+      __nv_bfloat16* gs_base = reinterpret_cast<__nv_bfloat16*>(p.g_sparse) + ch * 8 - kD;
+#pragma unroll
+      for (int s4 = 0; s4 < kSamples; ++s4) {
+        const int b = b0 + s4;
+        if (b >= p.B) break;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = i0 + 8 * k;
+          if (i >= R) break;
+          const uint4 val = *reinterpret_cast<const uint4*>(ostage + (s4 * kRowsPerSample + i) * 256 + (((ch ^ i) & 15) << 4));
+          __nv_bfloat16* dst = (i == 0) ? gd_base + (int64_t) b * p.ld_gdense : gs_base + (int64_t) b * p.ld_gsparse + (int64_t) i * kD;
+          *reinterpret_cast<uint4*>(dst) = val;
+        }
+      }
     }
   }
   cp_async_wait_all();
@@ -594,11 +626,13 @@ TRB_API int trb_interaction_bwd(const void* dense, int64_t ld_dense, const void*
     const int smem_p = 6 * kTileBytes + 2 * kSamples * (int) ld_out * 2 + 64 + 1024;
     static bool cfg_p = false;
     if (!cfg_p) {
-      TRB_CUDA(cudaFuncSetAttribute(interaction_bwd_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+      TRB_CUDA(cudaFuncSetAttribute(interaction_bwd_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+      TRB_CUDA(cudaFuncSetAttribute(interaction_bwd_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
       cfg_p = true;
     }
     const int grid_p = groups < 2 * num_sms() ? groups : 2 * num_sms();
-    interaction_bwd_pipe_kernel<<<grid_p, 128, smem_p, stream>>>(p);
+    if (F + 1 < 32) interaction_bwd_pipe_kernel<true><<<grid_p, 128, smem_p, stream>>>(p);
+    else interaction_bwd_pipe_kernel<false><<<grid_p, 128, smem_p, stream>>>(p);
     TRB_CHECK_LAUNCH();
     return 0;
   }
