@@ -75,3 +75,54 @@ def test_managed_zero_copy_location_gpu():
     torch.testing.assert_close(b.weights, a.weights.cpu())
     b.to(dev)
     assert not b.weights.is_cuda  # .to() leaves zero-copy tables on the host
+
+
+def test_sharded_ebc_with_uvm_caching_kernel(monkeypatch):
+    """compute_kernel=fused_uvm_caching in the plan -> cached tables behind the sharded EBC (CPU emulation of the cache)."""
+    monkeypatch.setenv("TRB_UVM_ON_CPU", "1")
+    from torchrec_b200.modules.embedding_configs import EmbeddingBagConfig
+    from torchrec_b200.modules.embedding_modules import EmbeddingBagCollection
+    from torchrec_b200.ops.uvm import UvmCachedEmbeddingBags
+    from torchrec_b200.optim.apply_optimizer_in_backward import apply_optimizer_in_backward
+    from torchrec_b200.parallel import sharding_plan as sp
+    from torchrec_b200.parallel.embeddingbag import EmbeddingBagCollectionSharder
+    from torchrec_b200.parallel.model_parallel import DistributedModelParallel
+    from torchrec_b200.parallel.types import CacheParams, ShardingPlan
+    from torchrec_b200.sparse import KeyedJaggedTensor
+
+    torch.manual_seed(0)
+    tables = [EmbeddingBagConfig(name="big", embedding_dim=8, num_embeddings=5000, feature_names=["f0"]),
+              EmbeddingBagConfig(name="small", embedding_dim=8, num_embeddings=50, feature_names=["f1"])]
+    gold = EmbeddingBagCollection(tables)
+    local = EmbeddingBagCollection(tables)
+    local.load_state_dict(gold.state_dict())
+    apply_optimizer_in_backward(torch.optim.SGD, local.parameters(), {"lr": 0.5})
+    plan = sp.construct_module_sharding_plan(local, {"big": sp.table_wise(rank=0, compute_kernel="fused_uvm_caching"), "small": sp.table_wise(rank=0)},
+                                             sharder=EmbeddingBagCollectionSharder(), world_size=1, local_size=1, device_type="cpu")
+    plan["big"].cache_params = CacheParams(load_factor=0.05)
+
+    class W(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.ebc = local
+
+        def forward(self, k):
+            return self.ebc(k).values()
+
+    m = DistributedModelParallel(W(), device=torch.device("cpu"), plan=ShardingPlan({"ebc": plan}), sharders=[EmbeddingBagCollectionSharder()])
+    eng = m.module.ebc.engine
+    assert any(isinstance(t, UvmCachedEmbeddingBags) for t in eng._tbes)
+    opt = torch.optim.SGD(gold.parameters(), lr=0.5)
+    g = torch.Generator().manual_seed(3)
+    for _ in range(6):
+        kjt = KeyedJaggedTensor(keys=["f0", "f1"], values=torch.cat([torch.randint(0, 5000, (8,), generator=g), torch.randint(0, 50, (8,), generator=g)]), lengths=torch.full((8,), 2))
+        out, ref = m(kjt), gold(kjt).values()
+        torch.testing.assert_close(out, ref)
+        out.sum().backward()
+        opt.zero_grad()
+        ref.sum().backward()
+        opt.step()
+    sd = m.state_dict()
+    w = sd["ebc.embedding_bags.big.weight"]
+    w = w.local_shards()[0].tensor if hasattr(w, "local_shards") else w
+    torch.testing.assert_close(w, gold.embedding_bags["big"].weight.detach())

@@ -177,6 +177,11 @@ class ShardedEmbeddingCollection(ShardedModule[KJTList, List[torch.Tensor], Dict
     def engine(self):
         return self._engine
 
+    def prefetch(self, ctx, dist_input) -> None:
+        """Stage the rows of an already-distributed batch into the HBM caches of UVM_CACHING tables (prefetch pipeline)."""
+        if self._engine is not None and len(dist_input) > 0:
+            self._engine.prefetch(dist_input[0])
+
     def reset_rows(self, table: str, global_rows: torch.Tensor) -> int:
         """Re-initialise rows of a sharded table (managed-collision eviction / ITEP); see engine.reset_rows."""
         return self._engine.reset_rows(table, global_rows) if self._engine is not None else 0

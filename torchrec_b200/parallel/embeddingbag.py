@@ -362,6 +362,11 @@ class ShardedEmbeddingBagCollection(
             if self._pg is not None and self._env.world_size > 1:
                 dist.broadcast(self._dp_tbe.weights.data, src=dist.get_global_rank(self._pg, 0), group=self._pg)
 
+    def prefetch(self, ctx, dist_input) -> None:
+        """Stage the rows of an already-distributed batch into the HBM caches of UVM_CACHING tables (prefetch pipeline)."""
+        if self._engine is not None and len(dist_input) > 0:
+            self._engine.prefetch(dist_input[0])
+
     def reset_rows(self, table: str, global_rows: torch.Tensor) -> int:
         """Re-initialise rows of a sharded table (managed-collision eviction / ITEP); see engine.reset_rows."""
         return self._engine.reset_rows(table, global_rows) if self._engine is not None else 0

@@ -160,7 +160,14 @@ class ShardedLookupEngine(nn.Module):
                             self._post_mean_feature[fi] = True
             dtype = torch.float32 if cfg.data_type == DataType.FP32 else data_type_to_dtype(cfg.data_type)
             opt = opt_specs.get(cfg.name, OptimizerSpec())
-            key = (str(dtype), int(pooling), opt.key())
+            # storage location: compute kernel of the plan (HBM | zero-copy host | host + HBM cache), reference embedding_types.py:75-95
+            ck = getattr(ps, "compute_kernel", None) or "fused"
+            loc = {"fused_uvm": 1, "fused_uvm_caching": 2, "key_value": 2}.get(str(ck), 0) if device.type == "cuda" or os.environ.get("TRB_UVM_ON_CPU") else 0
+            clf = 0.2
+            cp = getattr(ps, "cache_params", None)
+            if cp is not None and getattr(cp, "load_factor", None):
+                clf = float(cp.load_factor)
+            key = (str(dtype), int(pooling), opt.key(), loc, clf if loc == 2 else 0)
             if key not in group_index:
                 group_index[key] = len(self._groups)
                 self._groups.append(_Group(key, pooling, dtype, opt))
@@ -214,7 +221,19 @@ class ShardedLookupEngine(nn.Module):
                 continue
             u0, u1 = g.unit_range
             units = self._local_units[u0:u1]
-            tbe = TableBatchedEmbeddingBags(
+            loc, clf = g.key[3], g.key[4]
+            extra: Dict[str, Any] = {}
+            cls = TableBatchedEmbeddingBags
+            if loc == 1:
+                from ..ops.tbe import EmbeddingLocation
+
+                extra["location"] = EmbeddingLocation.MANAGED
+            elif loc == 2:
+                from ..ops.uvm import UvmCachedEmbeddingBags
+
+                cls = UvmCachedEmbeddingBags
+                extra["cache_load_factor"] = clf
+            tbe = cls(
                 embedding_specs=[(s.rows, s.cols) for s in g.local_shards],
                 feature_table_map=[u.shard.local_idx for u in units],
                 pooling_mode=g.pooling,
@@ -224,7 +243,7 @@ class ShardedLookupEngine(nn.Module):
                 learning_rate=g.opt.lr, eps=g.opt.eps, beta1=g.opt.beta1, beta2=g.opt.beta2,
                 weight_decay=g.opt.weight_decay, weight_decay_mode=g.opt.weight_decay_mode,
                 max_gradient=g.opt.max_gradient, momentum=g.opt.momentum,
-                device=device, table_names=[s.name for s in g.local_shards],
+                device=device, table_names=[s.name for s in g.local_shards], **extra,
             )
             g.tbe = tbe
             self._tbes.append(tbe)
@@ -400,6 +419,18 @@ class ShardedLookupEngine(nn.Module):
             trimmed.append(o[: hi - lo])
         return torch.cat(trimmed, 0)
 
+    @torch.no_grad()
+    def prefetch(self, dist_features: KeyedJaggedTensor) -> None:
+        """Make the rows of the next batch resident in the HBM caches (UVM_CACHING groups); no-op otherwise.
+        Called by PrefetchTrainPipelineSparseDist on its prefetch stream (reference embedding_lookup.py:714-767)."""
+        Bg = dist_features.stride()
+        offsets = dist_features.offsets()
+        for g in self._groups:
+            if g.tbe is None or not getattr(g.tbe, "is_cached", False):
+                continue
+            u0, u1 = g.unit_range
+            g.tbe.prefetch(dist_features.values(), offsets[u0 * Bg : u1 * Bg + 1], Bg)
+
     # ---- output dist (pooled) ---------------------------------------------------------------------------------
     def output_dist(self, local_embs: torch.Tensor, batch_size_per_rank: Optional[List[int]] = None) -> Awaitable[torch.Tensor]:
         if self._pooled_a2a is None:
@@ -515,6 +546,8 @@ class ShardedLookupEngine(nn.Module):
         """The fused lookup + output-dist kernels can serve this batch (CUDA, one host, even batch)."""
         if not self._pooled or not self._has_mp or self._device.type != "cuda" or self._W < 2:
             return False
+        if any(getattr(g.tbe, "is_cached", False) for g in self._groups):
+            return False  # cached tables translate ids -> cache slots first: portable path
         if batch_size_per_rank is not None and len(set(batch_size_per_rank)) != 1:
             return False
         if not self._p2p_checked:
