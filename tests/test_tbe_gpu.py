@@ -156,3 +156,32 @@ def test_psw_grad_matches_reference():
     torch.testing.assert_close(out.float(), ref, atol=1e-4, rtol=1e-4)
     (ref * gout).sum().backward()
     torch.testing.assert_close(psw.grad, psw2.grad, atol=1e-4, rtol=1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("opt", [T.OptimType.EXACT_SGD, T.OptimType.EXACT_ROWWISE_ADAGRAD])
+@pytest.mark.parametrize("dim,gdtype", [(128, torch.bfloat16), (64, torch.float32), (256, torch.float32)])
+def test_fused_backward_unique_rows_fast_path(opt, dim, gdtype):
+    """Large tables -> (almost) all ids distinct: exercises the one-hot forward and the unique-rows backward fast paths,
+    mixed with a tiny table whose chunks take the generic walk."""
+    dev = torch.device("cuda:0")
+    specs = [(200_000, dim), (7, dim), (150_000, dim)]
+    fmap = [0, 1, 2]
+    B = 1000
+    torch.manual_seed(5)
+    cpu = T.TableBatchedEmbeddingBags(specs, fmap, optimizer=opt, learning_rate=0.05, eps=1e-3)
+    gpu = T.TableBatchedEmbeddingBags(specs, fmap, optimizer=opt, learning_rate=0.05, eps=1e-3, device=dev, output_dtype=gdtype)
+    gpu.weights.data.copy_(cpu.weights.data)
+    g = torch.Generator().manual_seed(0)
+    for step in range(2):
+        idx = torch.cat([torch.randint(0, r, (B,), generator=g) for r, _ in specs])
+        off = torch.arange(0, 3 * B + 1)
+        og = gpu(idx.to(dev), off.to(dev), None, batch_size=B)
+        oc = cpu(idx, off, None, batch_size=B)
+        torch.testing.assert_close(og.float().cpu(), oc, rtol=2e-2 if gdtype == torch.bfloat16 else 1e-5, atol=2e-2 if gdtype == torch.bfloat16 else 1e-5)
+        proj = torch.randn(B, 3 * dim, generator=g)
+        og.backward(proj.to(dev).to(gdtype))
+        oc.backward(proj.to(gdtype).float())
+        torch.testing.assert_close(gpu.weights.cpu(), cpu.weights, rtol=1e-4, atol=1e-5)
+        if gpu.state1 is not None:
+            torch.testing.assert_close(gpu.state1.cpu(), cpu.state1, rtol=1e-4, atol=1e-6)
