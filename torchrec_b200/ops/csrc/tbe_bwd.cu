@@ -450,7 +450,27 @@ __global__ void __launch_bounds__(256) tbe_bwd_span_kernel(const TbeBwdParams p)
 #pragma unroll
   for (int k = 0; k < MAXV; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   // piece 0 is slot1 of chunk c, pieces j>=1 are slot0 of chunk c+j
-  for (int64_t j = warp; j <= c_end - c; j += 8) {
+  // hot rows (tiny tables) span hundreds of chunks: keep 4 independent partial-row loads in flight per warp
+  const int64_t n_pieces = c_end - c + 1;
+  int64_t j = warp;
+  for (; j + 24 < n_pieces; j += 32) {
+    float4 t[4][MAXV];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t jj = j + 8 * q;
+      const float* src = p.partials + (((c + jj) * 2 + (jj == 0 ? 1 : 0)) * (int64_t) p.max_dim);
+#pragma unroll
+      for (int k = 0; k < MAXV; ++k) {
+        const int vi = lane + k * 32;
+        t[q][k] = (vi < nvec) ? *reinterpret_cast<const float4*>(src + vi * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int k = 0; k < MAXV; ++k) acc[k] = f4_add(acc[k], t[q][k]);
+  }
+  for (; j < n_pieces; j += 8) {
     const float* src = p.partials + (((c + j) * 2 + (j == 0 ? 1 : 0)) * (int64_t) p.max_dim);
 #pragma unroll
     for (int k = 0; k < MAXV; ++k) {
