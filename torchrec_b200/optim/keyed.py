@@ -170,7 +170,7 @@ class CombinedOptimizer(KeyedOptimizer):
     def __repr__(self) -> str:
         return f"{self.__class__.__name__}: {[opt for _, opt in self._optims]}"
 
-    def zero_grad(self, set_to_none: bool = False) -> None:
+    def zero_grad(self, set_to_none: bool = True) -> None:
         for _, opt in self._optims:
             opt.zero_grad(set_to_none=set_to_none)
 
@@ -230,7 +230,7 @@ class KeyedOptimizerWrapper(KeyedOptimizer):
         self._optimizer: optim.Optimizer = optim_factory(list(params.values()))
         super().__init__(params, self._optimizer.state, self._optimizer.param_groups)
 
-    def zero_grad(self, set_to_none: bool = False) -> None:
+    def zero_grad(self, set_to_none: bool = True) -> None:
         self._optimizer.zero_grad(set_to_none=set_to_none)
 
     def step(self, closure: Any = None) -> None:
@@ -252,7 +252,7 @@ class OptimizerWrapper(KeyedOptimizer):
     def __repr__(self) -> str:
         return self._optimizer.__repr__()
 
-    def zero_grad(self, set_to_none: bool = False) -> None:
+    def zero_grad(self, set_to_none: bool = True) -> None:
         self._optimizer.zero_grad(set_to_none=set_to_none)
 
     def step(self, closure: Any = None) -> None:
