@@ -131,6 +131,12 @@ class OverArch(nn.Module):
     def forward(self, features: torch.Tensor) -> torch.Tensor:
         hidden = self.model[0](features)
         last = self.model[1]
+        if hidden.dtype == torch.bfloat16 and last.out_features == 1:
+            from ..ops import dense as _dense
+            from ..ops import head as _head
+
+            if _dense.get_dense_backend() == "tcgen05" and _head.rowdot_supported(hidden, last.weight):
+                return _head.RowDotFn.apply(hidden, last.weight, last.bias)  # fused logit layer (+ ReLU mask of `hidden` in its dgrad)
         if hidden.dtype != last.weight.dtype:  # bf16 activations from the fused kernels -> fp32 logits
             hidden = hidden.to(last.weight.dtype)
         return last(hidden)
@@ -235,7 +241,12 @@ class DLRMTrain(nn.Module):
     def forward(self, batch: Batch) -> Tuple[torch.Tensor, Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
         logits = self.model(batch.dense_features, batch.sparse_features)
         logits = logits.squeeze(-1)
-        loss = self.loss_fn(logits.float(), batch.labels.float())
+        if type(self.loss_fn) is nn.BCEWithLogitsLoss and logits.is_cuda and logits.dtype == torch.float32:
+            from ..ops.head import bce_with_logits_mean
+
+            loss = bce_with_logits_mean(logits, batch.labels)  # loss + d(loss)/d(logits) in one kernel
+        else:
+            loss = self.loss_fn(logits.float(), batch.labels.float())
         return loss, (loss.detach(), logits.detach(), batch.labels.detach())
 
 
