@@ -333,7 +333,7 @@ static int gemm_dispatch(const void* A, int64_t lda, const void* B, int64_t ldb,
   // 128 x 256 tiles halve the A-operand smem / L2 traffic per FLOP; worth it once there are enough tiles to fill the SMs
   static const int wide = getenv("TRB_GEMM_WIDE") ? atoi(getenv("TRB_GEMM_WIDE")) : 1;
   const int64_t tiles256 = (int64_t) ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + 255) / 256) * (p.split_k > 1 ? p.split_k : 1);
-  if (wide && p.N % 256 == 0 && tiles256 >= 2 * 148) {
+  if (wide && p.split_k <= 1 && p.N % 256 == 0 && tiles256 >= 2 * 148) {  // split-K GEMMs pick their split for 128x128 wave quantisation (ops/gemm.py)
     rc = B_MN ? make_tmap(&tb, B, p.K, p.N, ldb, 64, 64) : make_tmap(&tb, B, p.N, p.K, ldb, 256);
     if (rc) return rc;
     return launch_gemm<256, 4, A_MN, B_MN>(ta, tb, p, stream);

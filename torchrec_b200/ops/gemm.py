@@ -102,6 +102,18 @@ def _num_sms(device: torch.device) -> int:
     return _SMS[idx]
 
 
+def _best_split(tiles: int, K: int, sms: int) -> int:
+    """Split-K factor that fills whole waves of the persistent grid: maximise tiles*s / (ceil(tiles*s / sms) * sms) over splits
+    that keep >= 512 reduction elements each (fewer, fuller waves beat many splits: every split adds a pass of fp32 atomics)."""
+    best, best_eff = 1, 0.0
+    for s in range(1, max(1, min(64, K // 512)) + 1):
+        items = tiles * s
+        eff = items / (((items + sms - 1) // sms) * sms)
+        if eff > best_eff + 0.02:
+            best, best_eff = s, eff
+    return best
+
+
 def _pad_k(t: torch.Tensor, Kp: int) -> torch.Tensor:
     if t.shape[1] == Kp:
         return t
@@ -165,7 +177,7 @@ class LinearActFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             # wgrad: gw[N, Kp] = gy^T . x with BOTH operands consumed MN-major straight from their row-major storage
             tiles = ((gy.shape[1] + 127) // 128) * ((xb.shape[1] + 127) // 128)
-            split = max(1, min(32, (2 * _num_sms(gy.device) + tiles - 1) // tiles))
+            split = _best_split(tiles, M, _num_sms(gy.device))
             gw = gemm_bf16(gy, xb, a_mn=True, b_mn=True, out_dtype=torch.float32, split_k=split)[:, : ctx.K]
             if gw.stride(1) != 1 or gw.shape[1] != gw.stride(0):
                 gw = gw.contiguous()
