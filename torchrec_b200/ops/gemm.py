@@ -105,12 +105,12 @@ def _num_sms(device: torch.device) -> int:
 def _best_split(tiles: int, K: int, sms: int) -> int:
     """Split-K factor that fills whole waves of the persistent grid: maximise tiles*s / (ceil(tiles*s / sms) * sms) over splits
     that keep >= 512 reduction elements each (fewer, fuller waves beat many splits: every split adds a pass of fp32 atomics)."""
-    best, best_eff = 1, 0.0
+    best, best_score = 1, -1.0
     for s in range(1, max(1, min(64, K // 512)) + 1):
         items = tiles * s
-        eff = items / (((items + sms - 1) // sms) * sms)
-        if eff > best_eff + 0.02:
-            best, best_eff = s, eff
+        score = items / (((items + sms - 1) // sms) * sms) - 0.004 * s
+        if score > best_score:
+            best, best_score = s, score
     return best
 
 
