@@ -4,6 +4,7 @@ mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > gpurun_out/g1_pytest.log; cat gpurun_out/g1_pytest.log
 timeout 300 python tools/microbench.py interaction tbe > gpurun_out/g1_micro.md 2>&1; cat gpurun_out/g1_micro.md
 timeout 600 python bench.py 2>&1 | tail -1 > gpurun_out/bench1c.json; cut -c1-330 gpurun_out/bench1c.json
+TRB_OVERLAP_SPARSE=1 timeout 600 python bench.py 2>&1 | tail -1 > gpurun_out/bench1c_overlap.json; cut -c1-330 gpurun_out/bench1c_overlap.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 300 -c 260 --csv --log-file gpurun_out/launches_r1b.csv python bench.py --steps 2 --warmup 3 --no-e2e > gpurun_out/ncu_launch_b.log 2>&1
 python - <<'PY'
 import csv, collections, re

@@ -168,9 +168,34 @@ class DLRM(nn.Module):
         over_in_features = embedding_dim + choose(num_sparse_features, 2) + num_sparse_features
         self.over_arch = OverArch(in_features=over_in_features, layer_sizes=over_arch_layer_sizes, device=dense_device)
 
+    # Run the (memory / latency-bound) embedding arch on a side CUDA stream concurrently with the (tensor-core bound) bottom
+    # MLP: their kernels co-reside on the SMs, in the forward AND in the backward (autograd replays every op on the stream of
+    # its forward). Opt in with ``model.overlap_sparse_dense = True`` or TRB_OVERLAP_SPARSE=1.
+    overlap_sparse_dense: bool = False
+
+    def _sparse_stream(self, device: torch.device):
+        st = self.__dict__.get("_trb_sparse_stream")
+        if st is None or st.device != device:
+            st = torch.cuda.Stream(device=device)
+            self.__dict__["_trb_sparse_stream"] = st
+        return st
+
     def forward(self, dense_features: torch.Tensor, sparse_features: KeyedJaggedTensor) -> torch.Tensor:
-        embedded_dense = self.dense_arch(dense_features)
-        embedded_sparse = self.sparse_arch(sparse_features)
+        import os
+
+        if dense_features.is_cuda and (self.overlap_sparse_dense or os.environ.get("TRB_OVERLAP_SPARSE") == "1"):
+            main = torch.cuda.current_stream(dense_features.device)
+            side = self._sparse_stream(dense_features.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                embedded_sparse = self.sparse_arch(sparse_features)
+                if isinstance(embedded_sparse, torch.Tensor):
+                    embedded_sparse.record_stream(main)  # allocated on the side stream's pool, consumed on the main stream
+            embedded_dense = self.dense_arch(dense_features)
+            main.wait_stream(side)
+        else:
+            embedded_dense = self.dense_arch(dense_features)
+            embedded_sparse = self.sparse_arch(sparse_features)
         concatenated_dense = self.inter_arch(dense_features=embedded_dense, sparse_features=embedded_sparse)
         return self.over_arch(concatenated_dense)
 
