@@ -66,6 +66,13 @@ def test_fused_backward_matches_reference(opt, dim):
             torch.testing.assert_close(gpu.weights.grad.cpu(), cpu.weights.grad, rtol=2e-4, atol=2e-4)
             gpu.weights.grad = None
             cpu.weights.grad = None
+        elif opt == T.OptimType.LION:
+            # sign() is discontinuous: a gradient sum that differs in the last ulp (different reduction order) may flip an
+            # element whose pre-sign value is ~0 -> allow a tiny fraction of 2*lr outliers
+            bad = ((gpu.weights.cpu() - cpu.weights).abs() > 2e-4).float().mean()
+            assert float(bad) < 5e-3, float(bad)
+            gpu.weights.data.copy_(cpu.weights.data)
+            gpu.state1.copy_(cpu.state1)
         else:
             torch.testing.assert_close(gpu.weights.cpu(), cpu.weights, rtol=2e-4, atol=2e-4)
             if gpu.state1 is not None:

@@ -18,6 +18,8 @@
 // The gradient rows are read through TrbPeerPtrs: with W peer pointers the kernel *pulls*
 // grad[b_local, cols(f)] straight from the rank that owns sample b over NVLink — that is the
 // backward all-to-all of the reference (comm_ops.py:1581-1646) fused into the optimizer kernel.
+#include <cstdlib>
+
 #include "common.cuh"
 #include <cub/device/device_radix_sort.cuh>
 
@@ -43,6 +45,8 @@ enum TrbOpt : int {
 #define HP_STEP 5
 #define HP_MAXGRAD 6
 #define HP_MOMENTUM 7
+
+constexpr int kSpanRange = 64;  // chunk flags scanned per block of the span kernel
 
 struct TbeBwdParams {
   void* weights;
@@ -72,6 +76,7 @@ struct TbeBwdParams {
   int32_t* bag_of;
   float* partials;  // [chunks][2][max_dim]
   uint8_t* span_flags;
+  uint8_t* chunk_done;  // [chunks] set by tbe_bwd_unique_kernel (nullptr: generic walk handles everything)
   int32_t max_dim;
   int32_t key64;
   int32_t opt;
@@ -285,6 +290,113 @@ __device__ __forceinline__ void load_grad_row(const TbeBwdParams& p, int bag, fl
   }
 }
 
+
+// ---- unique-rows kernel ------------------------------------------------------------------------------------------------
+// Handles the chunks whose 32 sorted keys are distinct valid rows that do not continue into the neighbouring chunks (the
+// common case for large tables) when the optimizer is SGD / row-wise Adagrad without clipping or decay; marks them in
+// chunk_done so the generic walk (tbe_bwd_chunk_kernel, lighter on registers, higher occupancy) skips them. Per-lane geometry
+// is computed ONCE in parallel (the generic walk re-derives it per row with integer divisions on every lane) and rows are
+// processed U at a time with all of their gradient / weight / state loads in flight together. The generic path alone was
+// instruction- and latency-bound: 182 warp instructions per id, one row in flight per warp
+// (profiles/ncu_tbe_bwd_chunk_kernel_r1.md).
+template <typename W, typename G, int MAXV>
+__global__ void __launch_bounds__(256) tbe_bwd_unique_kernel(const TbeBwdParams p) {
+  typedef uint64_t K;
+  const int lane = threadIdx.x & 31;
+  const int64_t chunk = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t base = chunk << 5;
+  if (base >= p.n) return;
+  const int cnt = (int) min((int64_t) 32, p.n - base);
+  const void* keys = p.keys_sorted;
+  const K sentinel = (K) p.total_rows;
+  const K key = lane < cnt ? ld_key(keys, base + lane, p.key64) : sentinel;
+  const bool has_prev = base > 0, has_next = base + 32 < p.n;
+  const K prev_key = has_prev ? ld_key(keys, base - 1, p.key64) : sentinel;
+  const K next_key = has_next ? ld_key(keys, base + 32, p.key64) : sentinel;
+  constexpr int U = MAXV == 1 ? 4 : 2;  // rows in flight per warp (register budget: U x MAXV x 2 float4)
+  const K down = __shfl_down_sync(0xffffffffu, key, 1);
+  const bool lane_ok = lane >= cnt || (key != sentinel && (lane == cnt - 1 || key != down));
+  const K key0 = __shfl_sync(0xffffffffu, key, 0), keyl = __shfl_sync(0xffffffffu, key, cnt - 1);
+  const int OPT = p.opt;
+  if (!__all_sync(0xffffffffu, lane_ok) || (has_prev && prev_key == key0) || (has_next && next_key == keyl) || p.hyper[HP_MAXGRAD] > 0.f) {
+    if (lane == 0) p.chunk_done[chunk] = 0;
+    return;
+  }
+  int bag = 0;
+  float scale = 0.f;
+  if (lane < cnt) {
+    const int val = p.vals_sorted[base + lane];
+    bag = p.bag_of[val];
+    scale = p.psw ? p.psw[val] : 1.f;
+    if (p.mean) {
+      const int64_t L = trb_ld_idx(p.offsets, (int64_t) bag + 1, p.off64) - trb_ld_idx(p.offsets, bag, p.off64);
+      scale /= (float) (L > 0 ? L : 1);
+    }
+  }
+  int64_t goff = 0, woff = 0;
+  int src_rank = 0, nvec_l = 0;
+  if (lane < cnt) {
+    const int f = bag / p.B;
+    const int b = bag - f * p.B;
+    src_rank = b / p.B_local;
+    const int D = p.feat_dim[f];
+    nvec_l = D >> 2;
+    goff = (int64_t) (b - src_rank * p.B_local) * p.grad_stride + p.feat_col[f];
+    woff = p.feat_woff[f] + ((int64_t) key - p.feat_rowbase[f]) * D;
+  }
+  const float lr = p.hyper[HP_LR], eps = p.hyper[HP_EPS];
+  W* const wbase = reinterpret_cast<W*>(p.weights);
+  for (int j = 0; j < cnt; j += U) {
+    float4 g[U][MAXV], wv[U][MAXV];
+    float st[U];
+    int64_t wo[U], ky[U];
+    int nv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int e = min(j + u, cnt - 1);
+      const int64_t go = __shfl_sync(0xffffffffu, goff, e);
+      wo[u] = __shfl_sync(0xffffffffu, woff, e);
+      ky[u] = (int64_t) __shfl_sync(0xffffffffu, key, e);
+      nv[u] = __shfl_sync(0xffffffffu, nvec_l, e);
+      const float sc = __shfl_sync(0xffffffffu, scale, e);
+      const int sr = __shfl_sync(0xffffffffu, src_rank, e);
+      const G* gp = reinterpret_cast<const G*>(p.grad.p[sr]) + go;
+      const W* wp = wbase + wo[u];
+#pragma unroll
+      for (int k = 0; k < MAXV; ++k) {
+        const int vi = lane + k * 32;
+        g[u][k] = (vi < nv[u]) ? f4_scale(Vec4<G>::ld(gp + vi * 4), sc) : make_float4(0.f, 0.f, 0.f, 0.f);
+        wv[u][k] = (vi < nv[u]) ? Vec4<W>::ld(wp + vi * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      st[u] = (OPT == OPT_ROWWISE_ADAGRAD) ? p.state1[ky[u]] : 0.f;  // same address on every lane: one broadcast transaction
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (j + u >= cnt) break;
+      float mult = lr;
+      if (OPT == OPT_ROWWISE_ADAGRAD) {
+        float sq = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXV; ++k) sq += f4_sq(g[u][k]);
+        sq = warp_sum(sq) / (float) (nv[u] << 2);
+        const float ns = st[u] + sq;
+        if (lane == 0) p.state1[ky[u]] = ns;
+        mult = lr / (sqrtf(ns) + eps);
+      }
+      W* wp = wbase + wo[u];
+#pragma unroll
+      for (int k = 0; k < MAXV; ++k) {
+        const int vi = lane + k * 32;
+        if (vi < nv[u]) Vec4<W>::st(wp + vi * 4, f4_fma(g[u][k], -mult, wv[u][k]));
+      }
+    }
+  }
+  if (lane == 0) {
+    p.chunk_done[chunk] = 1;
+    p.span_flags[chunk] = 0;
+  }
+}
+
 template <typename W, typename G, int MAXV>
 __global__ void __launch_bounds__(256) tbe_bwd_chunk_kernel(const TbeBwdParams p) {
   typedef uint64_t K;
@@ -310,83 +422,7 @@ __global__ void __launch_bounds__(256) tbe_bwd_chunk_kernel(const TbeBwdParams p
   const bool has_prev = base > 0, has_next = base + 32 < p.n;
   const K prev_key = has_prev ? ld_key(keys, base - 1, p.key64) : sentinel;
   const K next_key = has_next ? ld_key(keys, base + 32, p.key64) : sentinel;
-  // ---- fast path: all keys of the chunk are distinct valid rows that do not continue into the neighbouring chunks (the
-  // common case for large tables) and the optimizer is SGD / row-wise Adagrad without clipping or decay. Per-lane geometry is
-  // computed ONCE in parallel (the generic walk re-derived it per row with integer divisions on every lane), then rows are
-  // processed U at a time with all of their gradient / weight / state loads in flight together. The generic path was
-  // instruction- and latency-bound: 182 warp instructions per id, one row in flight per warp
-  // (profiles/ncu_tbe_bwd_chunk_kernel_r1.md).
-  if constexpr (MAXV <= 4) {
-    constexpr int U = MAXV == 1 ? 4 : 2;  // rows in flight per warp (register budget: U x MAXV x 2 float4)
-    const K down = __shfl_down_sync(0xffffffffu, key, 1);
-    const bool lane_ok = lane >= cnt || (key != sentinel && (lane == cnt - 1 || key != down));
-    const K key0 = __shfl_sync(0xffffffffu, key, 0), keyl = __shfl_sync(0xffffffffu, key, cnt - 1);
-    const int OPT = p.opt;
-    const bool simple = (OPT == OPT_SGD || OPT == OPT_ROWWISE_ADAGRAD) && p.wd_mode == 0 && p.hyper[HP_MAXGRAD] <= 0.f;
-    if (simple && __all_sync(0xffffffffu, lane_ok) && !(has_prev && prev_key == key0) && !(has_next && next_key == keyl)) {
-      int64_t goff = 0, woff = 0;
-      int src_rank = 0, nvec_l = 0;
-      if (lane < cnt) {
-        const int f = bag / p.B;
-        const int b = bag - f * p.B;
-        src_rank = b / p.B_local;
-        const int D = p.feat_dim[f];
-        nvec_l = D >> 2;
-        goff = (int64_t) (b - src_rank * p.B_local) * p.grad_stride + p.feat_col[f];
-        woff = p.feat_woff[f] + ((int64_t) key - p.feat_rowbase[f]) * D;
-      }
-      const float lr = p.hyper[HP_LR], eps = p.hyper[HP_EPS];
-      W* const wbase = reinterpret_cast<W*>(p.weights);
-      for (int j = 0; j < cnt; j += U) {
-        float4 g[U][MAXV], wv[U][MAXV];
-        float st[U];
-        int64_t wo[U], ky[U];
-        int nv[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int e = min(j + u, cnt - 1);
-          const int64_t go = __shfl_sync(0xffffffffu, goff, e);
-          wo[u] = __shfl_sync(0xffffffffu, woff, e);
-          ky[u] = (int64_t) __shfl_sync(0xffffffffu, key, e);
-          nv[u] = __shfl_sync(0xffffffffu, nvec_l, e);
-          const float sc = __shfl_sync(0xffffffffu, scale, e);
-          const int sr = __shfl_sync(0xffffffffu, src_rank, e);
-          const G* gp = reinterpret_cast<const G*>(p.grad.p[sr]) + go;
-          const W* wp = wbase + wo[u];
-#pragma unroll
-          for (int k = 0; k < MAXV; ++k) {
-            const int vi = lane + k * 32;
-            g[u][k] = (vi < nv[u]) ? f4_scale(Vec4<G>::ld(gp + vi * 4), sc) : make_float4(0.f, 0.f, 0.f, 0.f);
-            wv[u][k] = (vi < nv[u]) ? Vec4<W>::ld(wp + vi * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          st[u] = (OPT == OPT_ROWWISE_ADAGRAD) ? p.state1[ky[u]] : 0.f;  // same address on every lane: one broadcast transaction
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (j + u >= cnt) break;
-          float mult = lr;
-          if (OPT == OPT_ROWWISE_ADAGRAD) {
-            float sq = 0.f;
-#pragma unroll
-            for (int k = 0; k < MAXV; ++k) sq += f4_sq(g[u][k]);
-            sq = warp_sum(sq) / (float) (nv[u] << 2);
-            const float ns = st[u] + sq;
-            if (lane == 0) p.state1[ky[u]] = ns;
-            mult = lr / (sqrtf(ns) + eps);
-          }
-          W* wp = wbase + wo[u];
-#pragma unroll
-          for (int k = 0; k < MAXV; ++k) {
-            const int vi = lane + k * 32;
-            if (vi < nv[u]) Vec4<W>::st(wp + vi * 4, f4_fma(g[u][k], -mult, wv[u][k]));
-          }
-        }
-      }
-      if (lane == 0) p.span_flags[chunk] = 0;
-      return;
-    }
-  }
-
+  if (p.chunk_done != nullptr && p.chunk_done[chunk]) return;  // already handled by tbe_bwd_unique_kernel
   const K up = __shfl_up_sync(0xffffffffu, key, 1);
   const bool is_start = (lane == 0) || (key != up);
   unsigned starts = __ballot_sync(0xffffffffu, lane < cnt && is_start);
@@ -430,10 +466,20 @@ __global__ void __launch_bounds__(256) tbe_bwd_chunk_kernel(const TbeBwdParams p
 template <typename W, int MAXV>
 __global__ void __launch_bounds__(256) tbe_bwd_span_kernel(const TbeBwdParams p) {
   typedef uint64_t K;
-  extern __shared__ float smem[];  // [8][max_dim]
-  const int64_t c = blockIdx.x;
-  if (!p.span_flags[c]) return;
+  extern __shared__ float smem[];  // [8][max_dim] | count | list[kSpanRange]
+  int* s_count = reinterpret_cast<int*>(smem + 8 * p.max_dim);
+  int* s_list = s_count + 4;
+  const int64_t n_chunks = (p.n + 31) / 32;
+  const int64_t c_lo = (int64_t) blockIdx.x * kSpanRange;
+  if (threadIdx.x == 0) *s_count = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < kSpanRange; i += 256)
+    if (c_lo + i < n_chunks && p.span_flags[c_lo + i]) s_list[atomicAdd(s_count, 1)] = i;
+  __syncthreads();
+  const int n_work = *s_count;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int wi = 0; wi < n_work; ++wi) {
+  const int64_t c = c_lo + s_list[wi];
   const void* keys = p.keys_sorted;
   const int64_t last = c * 32 + 31;
   const K rk = ld_key(keys, last, p.key64);
@@ -495,6 +541,8 @@ __global__ void __launch_bounds__(256) tbe_bwd_span_kernel(const TbeBwdParams p)
     }
     apply_row<W, MAXV>(p, (int64_t) rk, f, acc, lane);
   }
+  __syncthreads();  // smem rows are reused by the next flagged chunk
+  }
 }
 
 static inline int bits_needed(int64_t v) {
@@ -514,7 +562,7 @@ static size_t sort_temp_bytes(int64_t n) {
 static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t) 255; }
 
 struct BwdLayout {
-  size_t keys, keys_sorted, vals, vals_sorted, bag_of, partials, flags, sort_tmp, total;
+  size_t keys, keys_sorted, vals, vals_sorted, bag_of, partials, flags, done, sort_tmp, total;
 };
 
 static BwdLayout bwd_layout(int64_t n, int max_dim, int key64) {
@@ -529,6 +577,7 @@ static BwdLayout bwd_layout(int64_t n, int max_dim, int key64) {
   L.bag_of = o; o += align_up(n * 4);
   L.partials = o; o += align_up((size_t) chunks * 2 * max_dim * 4);
   L.flags = o; o += align_up(chunks);
+  L.done = o; o += align_up(chunks);
   L.sort_tmp = o;
   o += align_up(key64 ? sort_temp_bytes<uint64_t>(n) : sort_temp_bytes<uint32_t>(n));
   L.total = o;
@@ -551,6 +600,7 @@ static int run_bwd(TbeBwdParams& p, char* ws, cudaStream_t stream) {
   p.bag_of = (int32_t*) (ws + L.bag_of);
   p.partials = (float*) (ws + L.partials);
   p.span_flags = (uint8_t*) (ws + L.flags);
+  p.chunk_done = nullptr;
   const int threads = 256;
   tbe_bwd_build_keys<<<(unsigned) ((p.n + threads - 1) / threads), threads, 0, stream>>>(p);
   TRB_CHECK_LAUNCH();
@@ -568,12 +618,25 @@ static int run_bwd(TbeBwdParams& p, char* ws, cudaStream_t stream) {
   g_trb_launches += 4;  // radix sort passes (library kernels, counted approximately)
   const int64_t chunks = (p.n + 31) / 32;
   const int64_t blocks = (chunks + 7) / 8;
+  // pass 1 (optional): chunks of distinct rows with a simple optimizer go through the high-MLP unique kernel
+  static const int fast_enabled = getenv("TRB_BWD_UNIQUE") ? atoi(getenv("TRB_BWD_UNIQUE")) : 1;
+  if constexpr (MAXV <= 4) {
+    if (fast_enabled && (p.opt == OPT_SGD || p.opt == OPT_ROWWISE_ADAGRAD) && p.wd_mode == 0) {
+      p.chunk_done = (uint8_t*) (ws + L.done);
+      tbe_bwd_unique_kernel<W, G, MAXV><<<(unsigned) blocks, threads, 0, stream>>>(p);
+      TRB_CHECK_LAUNCH();
+    }
+  }
+  // pass 2: generic run walk over the remaining chunks (duplicates, runs spanning chunks, other optimizers)
   tbe_bwd_chunk_kernel<W, G, MAXV><<<(unsigned) blocks, threads, 0, stream>>>(p);
   TRB_CHECK_LAUNCH();
-  const size_t smem = (size_t) 8 * p.max_dim * sizeof(float);
+  const size_t smem = (size_t) 8 * p.max_dim * sizeof(float) + 16 + sizeof(int32_t) * kSpanRange;
   if (smem > 48 * 1024)
     TRB_CUDA(cudaFuncSetAttribute(tbe_bwd_span_kernel<W, MAXV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  tbe_bwd_span_kernel<W, MAXV><<<(unsigned) chunks, threads, smem, stream>>>(p);
+  // pass 3: combine runs that span chunks; a compact grid (each block scans kSpanRange chunk flags) instead of one block per
+  // chunk — launching 26 k mostly-empty blocks cost more than the combining itself
+  const int64_t span_blocks = (chunks + kSpanRange - 1) / kSpanRange;
+  tbe_bwd_span_kernel<W, MAXV><<<(unsigned) span_blocks, threads, smem, stream>>>(p);
   TRB_CHECK_LAUNCH();
   return 0;
 }
