@@ -1,10 +1,12 @@
 #!/bin/bash
-# 1-GPU: numerics of every GPU test, micro-benchmarks, bench, launch list.
+# 1-GPU: numerics of every GPU test, micro-benchmarks, bench variants, launch list.
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > gpurun_out/g1_pytest.log; cat gpurun_out/g1_pytest.log
-timeout 300 python tools/microbench.py interaction tbe > gpurun_out/g1_micro.md 2>&1; cat gpurun_out/g1_micro.md
-timeout 600 python bench.py 2>&1 | tail -1 > gpurun_out/bench1c.json; cut -c1-330 gpurun_out/bench1c.json
-TRB_OVERLAP_SPARSE=1 timeout 600 python bench.py 2>&1 | tail -1 > gpurun_out/bench1c_overlap.json; cut -c1-330 gpurun_out/bench1c_overlap.json
+timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -6 > gpurun_out/g1_pytest.log; cat gpurun_out/g1_pytest.log
+timeout 300 python tools/microbench.py tbe > gpurun_out/g1_micro.md 2>&1; cat gpurun_out/g1_micro.md
+(echo "unique kernel off"; TRB_BWD_UNIQUE=0 timeout 300 python tools/microbench.py tbe) > gpurun_out/g1_micro_nouniq.md 2>&1; tail -7 gpurun_out/g1_micro_nouniq.md
+timeout 600 python bench.py 2>&1 | tail -1 > gpurun_out/bench1c.json; cut -c1-330 gpurun_out/bench1c.json; echo
+TRB_OVERLAP_SPARSE=1 timeout 600 python bench.py 2>&1 | tail -1 > gpurun_out/bench1c_overlap.json; cut -c1-330 gpurun_out/bench1c_overlap.json; echo
+TRB_BWD_UNIQUE=0 timeout 600 python bench.py --no-e2e 2>&1 | tail -1 > gpurun_out/bench1c_nouniq.json; cut -c1-330 gpurun_out/bench1c_nouniq.json; echo
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 300 -c 260 --csv --log-file gpurun_out/launches_r1b.csv python bench.py --steps 2 --warmup 3 --no-e2e > gpurun_out/ncu_launch_b.log 2>&1
 python - <<'PY'
 import csv, collections, re
@@ -17,5 +19,5 @@ for r in rows[a:b]:
     k=re.sub(r'\(.*','',re.sub(r'^void ','',r['Kernel Name']).replace('<unnamed>::',''))[:70]; d=float(r['Metric Value'])/1e3
     agg.setdefault(k,[0,0.0]); agg[k][0]+=1; agg[k][1]+=d; tot+=d
 print("kernel us per step", tot, "launches", b-a)
-for k,(c,d) in sorted(agg.items(), key=lambda kv:-kv[1][1])[:16]: print(f"{d:8.1f} {c:3d} {k}")
+for k,(c,d) in sorted(agg.items(), key=lambda kv:-kv[1][1])[:18]: print(f"{d:8.1f} {c:3d} {k}")
 PY
