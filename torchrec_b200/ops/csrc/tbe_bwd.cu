@@ -46,8 +46,6 @@ enum TrbOpt : int {
 #define HP_MAXGRAD 6
 #define HP_MOMENTUM 7
 
-constexpr int kSpanRange = 64;  // chunk flags scanned per block of the span kernel
-
 struct TbeBwdParams {
   void* weights;
   float* state1;  // rowwise: [total_rows]; elementwise: same layout as weights (fp32)
@@ -77,6 +75,8 @@ struct TbeBwdParams {
   float* partials;  // [chunks][2][max_dim]
   uint8_t* span_flags;
   uint8_t* chunk_done;  // [chunks] set by tbe_bwd_unique_kernel (nullptr: generic walk handles everything)
+  int32_t* long_list;   // [chunks] first chunks of spans longer than kLongSpan pieces
+  int32_t* long_count;  // zeroed by tbe_bwd_build_keys
   int32_t max_dim;
   int32_t key64;
   int32_t opt;
@@ -88,6 +88,7 @@ __device__ __forceinline__ uint64_t ld_key(const void* p, int64_t i, int key64) 
 
 __global__ void __launch_bounds__(256) tbe_bwd_build_keys(const TbeBwdParams p) {
   const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *p.long_count = 0;
   if (i >= p.n) return;
   const int64_t n_bags = (int64_t) p.F * p.B;
   const int64_t total = trb_ld_idx(p.offsets, n_bags, p.off64);
@@ -463,47 +464,22 @@ __global__ void __launch_bounds__(256) tbe_bwd_chunk_kernel(const TbeBwdParams p
 }
 
 // One CTA per run that crosses chunk boundaries. blockDim = 256 (8 warps).
-template <typename W, int MAXV>
-__global__ void __launch_bounds__(256) tbe_bwd_span_kernel(const TbeBwdParams p) {
-  typedef uint64_t K;
-  extern __shared__ float smem[];  // [8][max_dim] | count | list[kSpanRange]
-  int* s_count = reinterpret_cast<int*>(smem + 8 * p.max_dim);
-  int* s_list = s_count + 4;
-  const int64_t n_chunks = (p.n + 31) / 32;
-  const int64_t c_lo = (int64_t) blockIdx.x * kSpanRange;
-  if (threadIdx.x == 0) *s_count = 0;
-  __syncthreads();
-  for (int i = threadIdx.x; i < kSpanRange; i += 256)
-    if (c_lo + i < n_chunks && p.span_flags[c_lo + i]) s_list[atomicAdd(s_count, 1)] = i;
-  __syncthreads();
-  const int n_work = *s_count;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int wi = 0; wi < n_work; ++wi) {
-  const int64_t c = c_lo + s_list[wi];
-  const void* keys = p.keys_sorted;
-  const int64_t last = c * 32 + 31;
-  const K rk = ld_key(keys, last, p.key64);
-  // upper bound of rk in keys[last+1 .. n)
-  int64_t lo = last + 1, hi = p.n;
-  while (lo < hi) {
-    const int64_t mid = (lo + hi) >> 1;
-    if (ld_key(keys, mid, p.key64) <= rk) lo = mid + 1; else hi = mid;
-  }
-  const int64_t c_end = (lo - 1) >> 5;
-  const int f = p.bag_of[p.vals_sorted[last]] / p.B;
-  const int nvec = p.feat_dim[f] >> 2;
-  float4 acc[MAXV];
-#pragma unroll
-  for (int k = 0; k < MAXV; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-  // piece 0 is slot1 of chunk c, pieces j>=1 are slot0 of chunk c+j
-  // hot rows (tiny tables) span hundreds of chunks: keep 4 independent partial-row loads in flight per warp
-  const int64_t n_pieces = c_end - c + 1;
-  int64_t j = warp;
-  for (; j + 24 < n_pieces; j += 32) {
+// ---- span combine ------------------------------------------------------------------------------------------------------
+// A run of equal keys that crosses chunk boundaries left one partial row per chunk: slot 1 of its first chunk (flagged), slot 0
+// of every following chunk. One WARP per flagged chunk sums the pieces and applies the optimizer (short spans are the common
+// case: mid-size tables); spans longer than kLongSpan pieces (hot rows of tiny tables) are deferred to a worklist processed by
+// whole blocks in tbe_bwd_span_long_kernel. (The first version used one 256-thread block per chunk: 26 k mostly-empty blocks
+// cost 107 us; a later compact grid serialised neighbouring spans inside one block and cost 394 us.)
+constexpr int kLongSpan = 24;
+
+template <int MAXV>
+__device__ __forceinline__ void span_accumulate(const TbeBwdParams& p, int64_t c, int64_t j0, int64_t n_pieces, int64_t stride, int nvec, int lane, float4 (&acc)[MAXV]) {
+  int64_t j = j0;
+  for (; j + 3 * stride < n_pieces; j += 4 * stride) {
     float4 t[4][MAXV];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int64_t jj = j + 8 * q;
+      const int64_t jj = j + q * stride;
       const float* src = p.partials + (((c + jj) * 2 + (jj == 0 ? 1 : 0)) * (int64_t) p.max_dim);
 #pragma unroll
       for (int k = 0; k < MAXV; ++k) {
@@ -516,7 +492,7 @@ __global__ void __launch_bounds__(256) tbe_bwd_span_kernel(const TbeBwdParams p)
 #pragma unroll
       for (int k = 0; k < MAXV; ++k) acc[k] = f4_add(acc[k], t[q][k]);
   }
-  for (; j < n_pieces; j += 8) {
+  for (; j < n_pieces; j += stride) {
     const float* src = p.partials + (((c + j) * 2 + (j == 0 ? 1 : 0)) * (int64_t) p.max_dim);
 #pragma unroll
     for (int k = 0; k < MAXV; ++k) {
@@ -524,26 +500,77 @@ __global__ void __launch_bounds__(256) tbe_bwd_span_kernel(const TbeBwdParams p)
       if (vi < nvec) acc[k] = f4_add(acc[k], *reinterpret_cast<const float4*>(src + vi * 4));
     }
   }
-#pragma unroll
-  for (int k = 0; k < MAXV; ++k) {
-    const int vi = lane + k * 32;
-    if (vi < nvec) *reinterpret_cast<float4*>(smem + warp * p.max_dim + vi * 4) = acc[k];
+}
+
+__device__ __forceinline__ int64_t span_last_chunk(const TbeBwdParams& p, int64_t c, uint64_t* rk_out) {
+  const int64_t last = c * 32 + 31;
+  const uint64_t rk = ld_key(p.keys_sorted, last, p.key64);
+  int64_t lo = last + 1, hi = p.n;  // upper bound of rk in keys[last+1 .. n)
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (ld_key(p.keys_sorted, mid, p.key64) <= rk) lo = mid + 1; else hi = mid;
   }
-  __syncthreads();
-  if (warp == 0) {
+  *rk_out = rk;
+  return (lo - 1) >> 5;
+}
+
+template <typename W, int MAXV>
+__global__ void __launch_bounds__(256) tbe_bwd_span_kernel(const TbeBwdParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t c = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= (p.n + 31) / 32 || !p.span_flags[c]) return;
+  uint64_t rk;
+  const int64_t c_end = span_last_chunk(p, c, &rk);
+  const int64_t n_pieces = c_end - c + 1;
+  if (n_pieces > kLongSpan) {
+    if (lane == 0) p.long_list[atomicAdd(p.long_count, 1)] = (int32_t) c;
+    return;
+  }
+  const int f = p.bag_of[p.vals_sorted[c * 32 + 31]] / p.B;
+  const int nvec = p.feat_dim[f] >> 2;
+  float4 acc[MAXV];
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  span_accumulate<MAXV>(p, c, 0, n_pieces, 1, nvec, lane, acc);
+  apply_row<W, MAXV>(p, (int64_t) rk, f, acc, lane);
+}
+
+template <typename W, int MAXV>
+__global__ void __launch_bounds__(256) tbe_bwd_span_long_kernel(const TbeBwdParams p) {
+  extern __shared__ float smem[];  // [8][max_dim]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_long = *p.long_count;
+  for (int wi = blockIdx.x; wi < n_long; wi += gridDim.x) {
+    const int64_t c = p.long_list[wi];
+    uint64_t rk;
+    const int64_t c_end = span_last_chunk(p, c, &rk);
+    const int f = p.bag_of[p.vals_sorted[c * 32 + 31]] / p.B;
+    const int nvec = p.feat_dim[f] >> 2;
+    float4 acc[MAXV];
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    span_accumulate<MAXV>(p, c, warp, c_end - c + 1, 8, nvec, lane, acc);
 #pragma unroll
     for (int k = 0; k < MAXV; ++k) {
       const int vi = lane + k * 32;
-      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (vi < nvec)
-        for (int w8 = 0; w8 < 8; ++w8) s = f4_add(s, *reinterpret_cast<const float4*>(smem + w8 * p.max_dim + vi * 4));
-      acc[k] = s;
+      if (vi < nvec) *reinterpret_cast<float4*>(smem + warp * p.max_dim + vi * 4) = acc[k];
     }
-    apply_row<W, MAXV>(p, (int64_t) rk, f, acc, lane);
-  }
-  __syncthreads();  // smem rows are reused by the next flagged chunk
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+      for (int k = 0; k < MAXV; ++k) {
+        const int vi = lane + k * 32;
+        float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (vi < nvec)
+          for (int w8 = 0; w8 < 8; ++w8) s4 = f4_add(s4, *reinterpret_cast<const float4*>(smem + w8 * p.max_dim + vi * 4));
+        acc[k] = s4;
+      }
+      apply_row<W, MAXV>(p, (int64_t) rk, f, acc, lane);
+    }
+    __syncthreads();
   }
 }
+
 
 static inline int bits_needed(int64_t v) {
   int b = 1;
@@ -562,7 +589,7 @@ static size_t sort_temp_bytes(int64_t n) {
 static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t) 255; }
 
 struct BwdLayout {
-  size_t keys, keys_sorted, vals, vals_sorted, bag_of, partials, flags, done, sort_tmp, total;
+  size_t keys, keys_sorted, vals, vals_sorted, bag_of, partials, flags, done, long_list, long_count, sort_tmp, total;
 };
 
 static BwdLayout bwd_layout(int64_t n, int max_dim, int key64) {
@@ -578,6 +605,8 @@ static BwdLayout bwd_layout(int64_t n, int max_dim, int key64) {
   L.partials = o; o += align_up((size_t) chunks * 2 * max_dim * 4);
   L.flags = o; o += align_up(chunks);
   L.done = o; o += align_up(chunks);
+  L.long_list = o; o += align_up((size_t) chunks * 4);
+  L.long_count = o; o += align_up(16);
   L.sort_tmp = o;
   o += align_up(key64 ? sort_temp_bytes<uint64_t>(n) : sort_temp_bytes<uint32_t>(n));
   L.total = o;
@@ -601,6 +630,8 @@ static int run_bwd(TbeBwdParams& p, char* ws, cudaStream_t stream) {
   p.partials = (float*) (ws + L.partials);
   p.span_flags = (uint8_t*) (ws + L.flags);
   p.chunk_done = nullptr;
+  p.long_list = (int32_t*) (ws + L.long_list);
+  p.long_count = (int32_t*) (ws + L.long_count);
   const int threads = 256;
   tbe_bwd_build_keys<<<(unsigned) ((p.n + threads - 1) / threads), threads, 0, stream>>>(p);
   TRB_CHECK_LAUNCH();
@@ -619,7 +650,7 @@ static int run_bwd(TbeBwdParams& p, char* ws, cudaStream_t stream) {
   const int64_t chunks = (p.n + 31) / 32;
   const int64_t blocks = (chunks + 7) / 8;
   // pass 1 (optional): chunks of distinct rows with a simple optimizer go through the high-MLP unique kernel
-  static const int fast_enabled = getenv("TRB_BWD_UNIQUE") ? atoi(getenv("TRB_BWD_UNIQUE")) : 1;
+  static const int fast_enabled = getenv("TRB_BWD_UNIQUE") ? atoi(getenv("TRB_BWD_UNIQUE")) : 0;  // measured slower than the generic walk on B200 so far: opt-in
   if constexpr (MAXV <= 4) {
     if (fast_enabled && (p.opt == OPT_SGD || p.opt == OPT_ROWWISE_ADAGRAD) && p.wd_mode == 0) {
       p.chunk_done = (uint8_t*) (ws + L.done);
@@ -630,13 +661,13 @@ static int run_bwd(TbeBwdParams& p, char* ws, cudaStream_t stream) {
   // pass 2: generic run walk over the remaining chunks (duplicates, runs spanning chunks, other optimizers)
   tbe_bwd_chunk_kernel<W, G, MAXV><<<(unsigned) blocks, threads, 0, stream>>>(p);
   TRB_CHECK_LAUNCH();
-  const size_t smem = (size_t) 8 * p.max_dim * sizeof(float) + 16 + sizeof(int32_t) * kSpanRange;
+  // pass 3: combine runs that span chunks (warp per flagged chunk), then the few long spans with whole blocks
+  tbe_bwd_span_kernel<W, MAXV><<<(unsigned) blocks, threads, 0, stream>>>(p);
+  TRB_CHECK_LAUNCH();
+  const size_t smem = (size_t) 8 * p.max_dim * sizeof(float);
   if (smem > 48 * 1024)
-    TRB_CUDA(cudaFuncSetAttribute(tbe_bwd_span_kernel<W, MAXV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  // pass 3: combine runs that span chunks; a compact grid (each block scans kSpanRange chunk flags) instead of one block per
-  // chunk — launching 26 k mostly-empty blocks cost more than the combining itself
-  const int64_t span_blocks = (chunks + kSpanRange - 1) / kSpanRange;
-  tbe_bwd_span_kernel<W, MAXV><<<(unsigned) span_blocks, threads, smem, stream>>>(p);
+    TRB_CUDA(cudaFuncSetAttribute(tbe_bwd_span_long_kernel<W, MAXV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  tbe_bwd_span_long_kernel<W, MAXV><<<296, threads, smem, stream>>>(p);
   TRB_CHECK_LAUNCH();
   return 0;
 }
