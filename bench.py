@@ -47,6 +47,7 @@ def parse_args() -> argparse.Namespace:
     p.add_argument("--sharding", type=str, default="table_wise", choices=["table_wise", "row_wise", "column_wise", "planner"])
     p.add_argument("--dense-backend", type=str, default=os.environ.get("TRB_DENSE_BACKEND", "auto"))
     p.add_argument("--transport", type=str, default=os.environ.get("TRB_TRANSPORT", "auto"), help="auto | p2p | nccl")
+    p.add_argument("--dp-rows", type=int, default=int(os.environ.get("TRB_BENCH_DP_ROWS", 2000)), help="tables with at most this many rows are data-parallel when N > 1 (0 = all table-wise)")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--num-host-batches", type=int, default=8)
     return p.parse_args()
@@ -185,6 +186,15 @@ def build_ours(args: argparse.Namespace, device, rank: int, world: int):
             gens = {}
             order = sorted(range(26), key=lambda i: -hashes[i])
             tot = float(sum(hashes))
+            if world > 1 and args.dp_rows > 0:
+                # tiny tables are replicated (data parallel, dense gradient all-reduced) like the reference planner would place
+                # them: no all-to-all traffic for their features and the model-parallel tables divide evenly over the ranks
+                tiny = [i for i in order if hashes[i] <= args.dp_rows]
+                keep = (26 - len(tiny)) % world  # keep the MP table count a multiple of the world size when possible
+                tiny = tiny[keep:] if keep and len(tiny) > keep else tiny
+                for i in tiny:
+                    gens[tables[i].name] = sp.data_parallel()
+                order = [i for i in order if i not in tiny]
             for i in order:
                 r = min(range(world), key=lambda r: (load[r][0] / tot * world + load[r][1] / 26.0 * world, r))
                 load[r][0] += hashes[i]
@@ -330,7 +340,7 @@ def main() -> None:
                 "global_batch": B * world,
                 "per_gpu_batch": B,
                 "seq_len": args.pooling,
-                "parallelism": f"{args.sharding} embeddings over {world} GPU(s) + DDP dense",
+                "parallelism": f"{args.sharding} embeddings over {world} GPU(s) + DDP dense" + (f"; tables with <= {args.dp_rows} rows data-parallel (dense SGD)" if world > 1 and args.dp_rows > 0 and args.sharding == "table_wise" else ""),
                 "pipeline": "TrainPipelineSparseDist (e2e) / plain step (value)",
                 "l2_policy": "inputs > L2: %d distinct batches, random rows of multi-GB tables (L2 126 MB)" % len(dev_batches),
                 "dense_backend": dense_backend,

@@ -1,12 +1,10 @@
 #!/bin/bash
 # 1-GPU: numerics of every GPU test, micro-benchmarks, bench variants, launch list.
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -6 > gpurun_out/g1_pytest.log; cat gpurun_out/g1_pytest.log
-timeout 300 python tools/microbench.py tbe > gpurun_out/g1_micro.md 2>&1; cat gpurun_out/g1_micro.md
-(echo "unique kernel off"; TRB_BWD_UNIQUE=0 timeout 300 python tools/microbench.py tbe) > gpurun_out/g1_micro_nouniq.md 2>&1; tail -7 gpurun_out/g1_micro_nouniq.md
+timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -80 > gpurun_out/g1_pytest.log; tail -6 gpurun_out/g1_pytest.log
+timeout 300 python tools/microbench.py tbe > gpurun_out/g1_micro.md 2>&1; tail -7 gpurun_out/g1_micro.md
 timeout 600 python bench.py 2>&1 | tail -1 > gpurun_out/bench1c.json; cut -c1-330 gpurun_out/bench1c.json; echo
 TRB_OVERLAP_SPARSE=1 timeout 600 python bench.py 2>&1 | tail -1 > gpurun_out/bench1c_overlap.json; cut -c1-330 gpurun_out/bench1c_overlap.json; echo
-TRB_BWD_UNIQUE=0 timeout 600 python bench.py --no-e2e 2>&1 | tail -1 > gpurun_out/bench1c_nouniq.json; cut -c1-330 gpurun_out/bench1c_nouniq.json; echo
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 300 -c 260 --csv --log-file gpurun_out/launches_r1b.csv python bench.py --steps 2 --warmup 3 --no-e2e > gpurun_out/ncu_launch_b.log 2>&1
 python - <<'PY'
 import csv, collections, re
