@@ -44,7 +44,8 @@ def parse_args() -> argparse.Namespace:
     p.add_argument("--row-cap", type=int, default=int(os.environ.get("TRB_BENCH_ROW_CAP", 40_000_000)))
     p.add_argument("--pooling", type=int, default=1, help="ids per sparse feature (Criteo is one-hot)")
     p.add_argument("--lr", type=float, default=0.01)
-    p.add_argument("--sharding", type=str, default="table_wise", choices=["table_wise", "row_wise", "column_wise", "planner"])
+    p.add_argument("--sharding", type=str, default="auto", choices=["auto", "table_wise", "row_wise", "column_wise", "planner"],
+                   help="auto: greedy table-wise on 1 GPU, table-wise + data-parallel tiny tables (what EmbeddingShardingPlanner also picks) on N > 1")
     p.add_argument("--dense-backend", type=str, default=os.environ.get("TRB_DENSE_BACKEND", "auto"))
     p.add_argument("--transport", type=str, default=os.environ.get("TRB_TRANSPORT", "auto"), help="auto | p2p | nccl")
     p.add_argument("--dp-rows", type=int, default=int(os.environ.get("TRB_BENCH_DP_ROWS", 2000)), help="tables with at most this many rows are data-parallel when N > 1 (0 = all table-wise)")
@@ -177,6 +178,8 @@ def build_ours(args: argparse.Namespace, device, rank: int, world: int):
     # bf16 pooled embeddings (half the NVLink / HBM bytes) when the dense arch computes in bf16
     fused_params = {"output_dtype": torch.bfloat16} if backend == "tcgen05" else None
     sharder = EmbeddingBagCollectionSharder(fused_params=fused_params)
+    if args.sharding == "auto":
+        args.sharding = "table_wise"
     if args.sharding == "planner":
         plan = None
     else:
