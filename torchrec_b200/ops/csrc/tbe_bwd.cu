@@ -719,7 +719,7 @@ TRB_API int trb_tbe_bwd_fused(void* weights, int w_dtype, float* state1, float* 
   p.max_dim = max_dim;
   p.key64 = total_rows >= ((int64_t) 1 << 32) - 1;
   p.opt = opt;
-  if (opt < 0 || opt > OPT_NONE) return -5;
+  if (opt < 0 || opt > OPT_LION) return -5;
   char* ws = reinterpret_cast<char*>(workspace);
 #define TRB_BWD_CASE(WC, WT, GC, GT) \
   if (w_dtype == WC && grad_dtype == GC) return dispatch_dim<WT, GT>(p, ws, stream)
