@@ -209,39 +209,6 @@ class EmbeddingBagCollectionAwaitable(LazyAwaitable[KeyedTensor]):
         return self._finish()
 
 
-class _DPIntoBufferFn(torch.autograd.Function):
-    """Data-parallel tables inside the fused NVLink path: forward writes the locally pooled rows into the DP columns of the
-    (already distributed) output buffer in place; backward produces the dense weight gradient from the same strided gradient
-    tensor and averages it over the ranks (what DDP would do) — the model-parallel backward reads the other columns of the very
-    same tensor, so nothing is copied."""
-
-    @staticmethod
-    def forward(ctx, vals: torch.Tensor, weights: torch.Tensor, mod: "ShardedEmbeddingBagCollection", indices, offsets, psw, B: int):
-        from ..ops import tbe as T
-
-        tbe = mod._dp_tbe
-        T.pooled_forward(mod._dp_meta_cols, weights.detach(), indices, offsets, psw, B, tbe.pooling_mode == T.PoolingMode.MEAN, vals.dtype, out=vals)
-        ctx.mark_dirty(vals)
-        ctx.mod, ctx.B = mod, B
-        ctx.save_for_backward(indices, offsets, psw)
-        return vals
-
-    @staticmethod
-    def backward(ctx, grad: torch.Tensor):
-        from ..ops import tbe as T
-
-        mod = ctx.mod
-        tbe = mod._dp_tbe
-        indices, offsets, psw = ctx.saved_tensors
-        gw = torch.zeros(tbe.weights.numel(), dtype=torch.float32, device=tbe.weights.device)
-        T.fused_backward(mod._dp_meta_cols, tbe.weights.detach(), gw, None, tbe.hyper_dev, tbe.hyper_host, 8, 0, indices, offsets, psw, ctx.B,
-                         tbe.pooling_mode == T.PoolingMode.MEAN, grad=grad)
-        if mod._pg is not None and mod._env.world_size > 1:
-            dist.all_reduce(gw, group=mod._pg)
-            gw.div_(mod._env.world_size)
-        return grad, gw.to(tbe.weights.dtype), None, None, None, None, None
-
-
 class _TableParam(nn.Module):
     """Holder so that ``embedding_bags.<table>.weight`` exists in the module tree."""
 
@@ -598,15 +565,14 @@ class ShardedEmbeddingBagCollection(
         W = self._env.world_size
         B_local = kjt.stride() // W
         scale = 1.0 / W if get_gradient_division() else 1.0
-        vals = eng.fused_lookup_dist(kjt, B_local, self._total_cols, scale)
+        dp = None
         if self._dp_lookup is not None:
-            # replicated tables: looked up locally, pooled rows written straight into their columns of the output buffer;
-            # their dense gradient is all-reduced inside the backward (no copies of the [B, sum(D)] tensor either way)
-            f = ctx.dp_features
-            psw = f.weights_or_none() if self._is_weighted else None
-            if not hasattr(self, "_dp_meta_cols") or self._dp_meta_cols.feat_col.device != vals.device:
+            # replicated tables: looked up locally, pooled rows written straight into their columns of the output buffer inside
+            # the fused op; their dense gradient is all-reduced inside its backward (no copies of the [B, sum(D)] tensor)
+            if not hasattr(self, "_dp_meta_cols"):
                 self._dp_meta_cols = self._dp_tbe.meta.with_cols([self._out_base[fi] for fi in self._dp_features], self._total_cols)
-            vals = _DPIntoBufferFn.apply(vals, self._dp_tbe.weights, self, f.values(), f.offsets(), psw, f.stride())
+            dp = (self._dp_tbe, self._dp_meta_cols, ctx.dp_features, self._pg)
+        vals = eng.fused_lookup_dist(kjt, B_local, self._total_cols, scale, dp)
         if ctx.mean_divisor is not None:
             vals = vals * ctx.mean_divisor.to(vals.dtype)
         kt = KeyedTensor(keys=self._embedding_names, length_per_key=self._embedding_dims, values=vals, key_dim=1)

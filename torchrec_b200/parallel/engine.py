@@ -620,7 +620,7 @@ class ShardedLookupEngine(nn.Module):
         self._p2p = _P2PState(self, B_local, total_cols)
         return self._p2p
 
-    def fused_lookup_dist(self, dist_features: KeyedJaggedTensor, B_local: int, total_cols: int, grad_scale: float) -> torch.Tensor:
+    def fused_lookup_dist(self, dist_features: KeyedJaggedTensor, B_local: int, total_cols: int, grad_scale: float, dp: Optional[Tuple] = None) -> torch.Tensor:
         """Lookup + pooled output dist in one pass: pooled rows are written straight into the owning
         rank's ``[B_local, total_cols]`` output over NVLink (row-sharded tables via staging slabs
         reduced at the destination). Returns the local output (final column layout)."""
@@ -634,7 +634,10 @@ class ShardedLookupEngine(nn.Module):
         if anchor is None:
             anchor = st.dummy
         weights = dist_features.weights_or_none() if self._is_weighted else None
-        return _FusedLookupDistFn.apply(anchor, self, st, dist_features.values(), dist_features.offsets(), weights, dist_features.stride(), grad_scale)
+        # dp = (dense TBE of the replicated tables, its meta with output columns, local KJT of their features, process group):
+        # their rows are looked up locally and written into the same output buffer; the dense gradient is all-reduced in backward
+        dp_w = dp[0].weights if dp is not None else None
+        return _FusedLookupDistFn.apply(anchor, self, st, dist_features.values(), dist_features.offsets(), weights, dist_features.stride(), grad_scale, dp_w, dp)
 
 
 class _P2PInputState:
@@ -768,7 +771,7 @@ class _FusedLookupDistFn(torch.autograd.Function):
     buffer, barrier, fused backward+optimizer kernels pulling gradient rows from the peers."""
 
     @staticmethod
-    def forward(ctx, anchor, eng: ShardedLookupEngine, st: _P2PState, values, offsets, weights, Bg: int, grad_scale: float):
+    def forward(ctx, anchor, eng: ShardedLookupEngine, st: _P2PState, values, offsets, weights, Bg: int, grad_scale: float, dp_weights=None, dp=None):
         from ..ops import tbe as T
         from . import p2p
 
@@ -791,11 +794,17 @@ class _FusedLookupDistFn(torch.autograd.Function):
                 window = offsets[(u0 + gm["n_direct"]) * Bg : (u0 + gm["n"]) * Bg + 1]
                 T.pooled_forward(gm["staged"], g.tbe.weights, values, window, weights, Bg, False, st.wire_dtype,
                                  out_ptrs=stage_ptrs, out_stride=st.total_cols, B_local=st.B_local)
-        st.pg.barrier()
         out = st.out_local(slot)
+        if dp is not None:  # replicated tables: local lookup straight into their columns (nobody else writes them)
+            dp_tbe, dp_meta, dp_kjt, _pg = dp
+            dp_psw = dp_kjt.weights_or_none() if eng._is_weighted else None
+            T.pooled_forward(dp_meta, dp_weights.detach(), dp_kjt.values(), dp_kjt.offsets(), dp_psw, dp_kjt.stride(), dp_tbe.pooling_mode == T.PoolingMode.MEAN,
+                             st.wire_dtype, out=out)
+        st.pg.barrier()
         if st.has_staged:
             p2p.staging_reduce(st.staging_local(W), out, st.col_mask, W)
         ctx.eng, ctx.st, ctx.Bg, ctx.grad_scale = eng, st, Bg, grad_scale
+        ctx.dp = dp
         ctx.save_for_backward(values, offsets, weights)
         return out
 
@@ -839,4 +848,15 @@ class _FusedLookupDistFn(torch.autograd.Function):
                              grad_ptrs=grad_ptrs, grad_stride=g_stride, grad_dtype=st.wire_dtype, B_local=g_blocal)
         if gpsw is not None:
             gpsw = gpsw.to(weights.dtype)
-        return torch.zeros(1, dtype=torch.float32, device=grad.device), None, None, None, None, gpsw, None, None
+        g_dp = None
+        if ctx.dp is not None and ctx.needs_input_grad[8]:
+            dp_tbe, dp_meta, dp_kjt, pg = ctx.dp
+            dp_psw = dp_kjt.weights_or_none() if eng._is_weighted else None
+            gw = torch.zeros(dp_tbe.weights.numel(), dtype=torch.float32, device=grad.device)
+            T.fused_backward(dp_meta, dp_tbe.weights.detach(), gw, None, dp_tbe.hyper_dev, dp_tbe.hyper_host, 8, 0, dp_kjt.values(), dp_kjt.offsets(), dp_psw,
+                             dp_kjt.stride(), dp_tbe.pooling_mode == T.PoolingMode.MEAN, grad=grad)
+            if pg is not None and eng._W > 1:
+                dist.all_reduce(gw, group=pg)
+                gw.div_(eng._W)
+            g_dp = gw.to(dp_tbe.weights.dtype)
+        return torch.zeros(1, dtype=torch.float32, device=grad.device), None, None, None, None, gpsw, None, None, g_dp, None
