@@ -270,8 +270,10 @@ def main() -> None:
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    t_host0 = time.perf_counter()
     for i in range(args.steps):
         loss = step(dev_batches[i % len(dev_batches)])
+    host_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps  # CPU time to ENQUEUE a step: >= ms_per_step means launch-bound
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -350,6 +352,7 @@ def main() -> None:
             },
             "clocks": clocks,
             "gpu_launches": int(launches),
+            "host_enqueue_ms_per_step": host_ms,
             "loss": float(loss.item()),
         }
         if e2e is not None:

@@ -61,6 +61,9 @@ def _entry(rank: int, world_size: int, fn: Callable, port: int, backend: str, lo
     os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")
     os.environ.setdefault("NCCL_SOCKET_IFNAME", "lo")
     torch.set_num_threads(1)
+    import faulthandler
+
+    faulthandler.enable()  # a native crash (SIGSEGV in a kernel launcher, NCCL, IPC) prints the Python stack of the rank
     try:
         with MultiProcessContext(rank, world_size, backend, local_size) as ctx:
             fn(ctx, **kwargs)
