@@ -177,7 +177,9 @@ TRB_API int trb_cast_copy(const void* src, int s_dtype, void* dst, int d_dtype, 
 // (peer load latency ~1.8k cycles, B300_MICROARCH.md), and the fused backward afterwards only touches local HBM.
 // Parity: the backward all_to_all_single of the pooled output dist (reference comm_ops.py:1581-1646).
 // ---------------------------------------------------------------------------------------------------------------
-template <typename S, typename D>
+// VEC = elements per chunk (4 or 8). 8-element chunks move 16 B per thread for bf16 gradients (the 4-element version issued
+// 8 B accesses and reached only ~0.8 TB/s of combined local + NVLink traffic on 2 GPUs).
+template <typename S, typename D, int VEC>
 __global__ void __launch_bounds__(256)
 trb_grad_push_kernel(const S* __restrict__ src, int64_t src_stride, const int32_t* __restrict__ chunks, int n_chunks, TrbPeerPtrs dst, int64_t dst_pitch,
                      int64_t row_base, int B_local, float scale) {
@@ -186,25 +188,44 @@ trb_grad_push_kernel(const S* __restrict__ src, int64_t src_stride, const int32_
   const int64_t b = i / n_chunks;
   const int c = (int) (i - b * n_chunks);
   const int rank = chunks[3 * c], sc = chunks[3 * c + 1], dc = chunks[3 * c + 2];
-  float4 v = Vec4<S>::ld(src + b * src_stride + sc);
-  if (scale != 1.f) v = f4_scale(v, scale);
-  Vec4<D>::st(reinterpret_cast<D*>(dst.p[rank]) + (row_base + b) * dst_pitch + dc, v);
+  const S* sp = src + b * src_stride + sc;
+  D* dp = reinterpret_cast<D*>(dst.p[rank]) + (row_base + b) * dst_pitch + dc;
+  if constexpr (VEC == 8 && sizeof(S) == 2 && sizeof(D) == 2) {
+    uint4 v = *reinterpret_cast<const uint4*>(sp);
+    if (scale != 1.f) {
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float2 f = __bfloat1622float2(h[q]);
+        h[q] = __floats2bfloat162_rn(f.x * scale, f.y * scale);
+      }
+    }
+    *reinterpret_cast<uint4*>(dp) = v;
+  } else {
+#pragma unroll
+    for (int q = 0; q < VEC / 4; ++q) {
+      float4 v = Vec4<S>::ld(sp + 4 * q);
+      if (scale != 1.f) v = f4_scale(v, scale);
+      Vec4<D>::st(dp + 4 * q, v);
+    }
+  }
 }
 
-TRB_API int trb_grad_push(const void* src, int s_dtype, int64_t src_stride, const int32_t* chunks, int n_chunks, void* const* dst_ptrs, int n_dst, int d_dtype,
-                          int64_t dst_pitch, int64_t row_base, int B_local, float scale, cudaStream_t stream) {
-  if (n_dst < 1 || n_dst > TRB_MAX_PEERS) return -1;
+TRB_API int trb_grad_push(const void* src, int s_dtype, int64_t src_stride, const int32_t* chunks, int n_chunks, int vec, void* const* dst_ptrs, int n_dst,
+                          int d_dtype, int64_t dst_pitch, int64_t row_base, int B_local, float scale, cudaStream_t stream) {
+  if (n_dst < 1 || n_dst > TRB_MAX_PEERS || (vec != 4 && vec != 8)) return -1;
   const int64_t n = (int64_t) B_local * n_chunks;
   if (n == 0) return 0;
   TrbPeerPtrs d;
   for (int i = 0; i < n_dst; ++i) d.p[i] = dst_ptrs[i];
   const int threads = 256;
   const unsigned blocks = (unsigned) ((n + threads - 1) / threads);
-#define TRB_GP(SC, ST, DC, DT)                                                                                                              \
-  if (s_dtype == SC && d_dtype == DC) {                                                                                                     \
-    trb_grad_push_kernel<ST, DT><<<blocks, threads, 0, stream>>>((const ST*) src, src_stride, chunks, n_chunks, d, dst_pitch, row_base, B_local, scale); \
-    TRB_CHECK_LAUNCH();                                                                                                                      \
-    return 0;                                                                                                                                \
+#define TRB_GP(SC, ST, DC, DT)                                                                                                                           \
+  if (s_dtype == SC && d_dtype == DC) {                                                                                                                  \
+    if (vec == 8) trb_grad_push_kernel<ST, DT, 8><<<blocks, threads, 0, stream>>>((const ST*) src, src_stride, chunks, n_chunks, d, dst_pitch, row_base, B_local, scale); \
+    else trb_grad_push_kernel<ST, DT, 4><<<blocks, threads, 0, stream>>>((const ST*) src, src_stride, chunks, n_chunks, d, dst_pitch, row_base, B_local, scale);          \
+    TRB_CHECK_LAUNCH();                                                                                                                                   \
+    return 0;                                                                                                                                             \
   }
   TRB_GP(TRB_F32, float, TRB_F32, float)
   TRB_GP(TRB_F32, float, TRB_BF16, __nv_bfloat16)

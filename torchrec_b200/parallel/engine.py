@@ -695,13 +695,16 @@ class _P2PState:
         self.push = os.environ.get("TRB_GRAD_PUSH", "1") != "0"
         chunks: List[List[int]] = []
         local_cols_per_rank: List[List[int]] = []
+        # 8-element (16 B for bf16) chunks when every unit width and every source column offset allow it
+        vec = 8 if all(u.shard.cols % 8 == 0 and (base_f[u.feature] + u.shard.col_off) % 8 == 0 for u in eng._units) and total_cols % 8 == 0 else 4
+        self.push_vec = vec
         for r in range(W):
             c = 0
             cols_r = []
             for u in eng._units[eng._unit_start[r] : eng._unit_start[r + 1]]:
                 src0 = base_f[u.feature] + u.shard.col_off
                 cols_r.append(c)
-                for k in range(0, u.shard.cols, 4):
+                for k in range(0, u.shard.cols, vec):
                     chunks.append([r, src0 + k, c + k])
                 c += u.shard.cols
             local_cols_per_rank.append(cols_r)
@@ -821,7 +824,7 @@ class _FusedLookupDistFn(torch.autograd.Function):
             # push: scatter my gradient columns into the owners' inboxes (posted NVLink stores), barrier, local backward
             slot = st.bwd_step % 2
             st.bwd_step += 1
-            p2p.grad_push(grad, st.chunks, st.buf.peer_ptrs(st.inbox_off[slot]), st.wire_dtype, st.inbox_pitch, eng._rank * st.B_local, ctx.grad_scale)
+            p2p.grad_push(grad, st.chunks, st.buf.peer_ptrs(st.inbox_off[slot]), st.wire_dtype, st.inbox_pitch, eng._rank * st.B_local, ctx.grad_scale, st.push_vec)
             st.pg.barrier()
             grad_ptrs = [st.buf.local_ptr + st.inbox_off[slot]]
             meta_key, g_stride, g_blocal = "local", st.inbox_pitch, Bg

@@ -158,11 +158,11 @@ def staging_reduce(staging: torch.Tensor, out: torch.Tensor, col_mask: torch.Ten
     _lib.check(code, "trb_staging_reduce")
 
 
-def grad_push(src: torch.Tensor, chunks: torch.Tensor, dst_ptrs: List[int], dst_dtype: torch.dtype, dst_pitch: int, row_base: int, scale: float = 1.0) -> None:
+def grad_push(src: torch.Tensor, chunks: torch.Tensor, dst_ptrs: List[int], dst_dtype: torch.dtype, dst_pitch: int, row_base: int, scale: float = 1.0, vec: int = 4) -> None:
     """Scatter column chunks of ``src [B_local, cols]`` into the owners' gradient inboxes (native kernel ``trb_grad_push``).
-    ``chunks``: int32 ``[n, 3]`` rows of (destination rank, source column, destination column), 4 elements per chunk."""
+    ``chunks``: int32 ``[n, 3]`` rows of (destination rank, source column, destination column), ``vec`` (4 or 8) elements per chunk."""
     assert src.dim() == 2 and src.stride(1) == 1 and chunks.dtype == torch.int32 and chunks.is_contiguous()
     L = _lib.lib()
-    code = L.trb_grad_push(_lib.ptr(src), _lib.dtype_code(src.dtype), ctypes.c_int64(src.stride(0)), _lib.ptr(chunks), chunks.shape[0], _lib.ptr_array(dst_ptrs), len(dst_ptrs),
+    code = L.trb_grad_push(_lib.ptr(src), _lib.dtype_code(src.dtype), ctypes.c_int64(src.stride(0)), _lib.ptr(chunks), chunks.shape[0], int(vec), _lib.ptr_array(dst_ptrs), len(dst_ptrs),
                            _lib.dtype_code(dst_dtype), ctypes.c_int64(dst_pitch), ctypes.c_int64(row_base), src.shape[0], ctypes.c_float(scale), _lib.stream_ptr(src.device))
     _lib.check(code, "trb_grad_push")
