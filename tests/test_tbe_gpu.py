@@ -192,3 +192,35 @@ def test_fused_backward_unique_rows_fast_path(opt, dim, gdtype):
         torch.testing.assert_close(gpu.weights.cpu(), cpu.weights, rtol=1e-4, atol=1e-5)
         if gpu.state1 is not None:
             torch.testing.assert_close(gpu.state1.cpu(), cpu.state1, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("vec", [4, 8])
+@pytest.mark.parametrize("sdtype", [torch.bfloat16, torch.float32])
+def test_grad_push_kernel_single_gpu(vec, sdtype):
+    """The NVLink gradient scatter with both 'ranks' mapped to local buffers: checks the chunk addressing, scaling and casting."""
+    from torchrec_b200.parallel.p2p import grad_push
+
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    B, W = 37, 2
+    widths = [16, 8, 24, 8]          # unit widths; units 0,2 -> rank 0, units 1,3 -> rank 1
+    owner = [0, 1, 0, 1]
+    src_cols = [0, 16, 24, 48]
+    src = torch.randn(B, 56, device=dev).to(sdtype)
+    pitch = 40
+    inbox = [torch.zeros(W * B, pitch, dtype=torch.bfloat16, device=dev) for _ in range(W)]
+    chunks, dst_c = [], [0, 0]
+    for u, (w, r, sc) in enumerate(zip(widths, owner, src_cols)):
+        for k in range(0, w, vec):
+            chunks.append([r, sc + k, dst_c[r] + k])
+        dst_c[r] += w
+    ct = torch.tensor(chunks, dtype=torch.int32, device=dev)
+    my_rank = 1
+    grad_push(src, ct, [t.data_ptr() for t in inbox], torch.bfloat16, pitch, my_rank * B, 0.5, vec)
+    torch.cuda.synchronize()
+    exp0 = torch.cat([src[:, 0:16], src[:, 24:48]], 1).float() * 0.5
+    exp1 = torch.cat([src[:, 16:24], src[:, 48:56]], 1).float() * 0.5
+    torch.testing.assert_close(inbox[0][B : 2 * B, :40].float(), exp0.to(torch.bfloat16).float(), rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(inbox[1][B : 2 * B, :16].float(), exp1.to(torch.bfloat16).float(), rtol=1e-2, atol=1e-2)
+    assert float(inbox[0][:B].abs().sum()) == 0.0 and float(inbox[1][B:, 16:].abs().sum()) == 0.0
