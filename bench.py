@@ -49,6 +49,7 @@ def parse_args() -> argparse.Namespace:
     p.add_argument("--dense-backend", type=str, default=os.environ.get("TRB_DENSE_BACKEND", "auto"))
     p.add_argument("--transport", type=str, default=os.environ.get("TRB_TRANSPORT", "auto"), help="auto | p2p | nccl")
     p.add_argument("--dp-rows", type=int, default=int(os.environ.get("TRB_BENCH_DP_ROWS", 2000)), help="tables with at most this many rows are data-parallel when N > 1 (0 = all table-wise)")
+    p.add_argument("--cuda-graphs", type=int, default=int(os.environ.get("TRB_BENCH_GRAPHS", 1)), help="1: replay the dense sub-modules as CUDA graphs")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--num-host-batches", type=int, default=8)
     return p.parse_args()
@@ -247,6 +248,15 @@ def main() -> None:
     dev_batches = [b.to(device) for b in host_batches]
     torch.cuda.synchronize()
 
+    if args.cuda_graphs:
+        # the dense sub-modules (bottom MLP, interaction + top MLP + head) replay as CUDA graphs: their ~50 launches and ~100 ATen
+        # calls per step made the step launch-bound once DDP / NVLink dists were added (host enqueue 2.0 ms vs 2.1 ms of GPU time)
+        inner = dmp.module.model
+        with torch.no_grad():
+            sample_emb = inner.sparse_arch(dev_batches[0].sparse_features)
+        inner.capture_dense_graphs(dev_batches[0].dense_features, sample_emb)
+        torch.cuda.synchronize()
+
     def step(batch) -> "torch.Tensor":
         opt.zero_grad()
         loss, _ = dmp(batch)
@@ -349,6 +359,7 @@ def main() -> None:
                 "pipeline": "TrainPipelineSparseDist (e2e) / plain step (value)",
                 "l2_policy": "inputs > L2: %d distinct batches, random rows of multi-GB tables (L2 126 MB)" % len(dev_batches),
                 "dense_backend": dense_backend,
+                "cuda_graphs": "dense sub-modules (fwd+bwd)" if args.cuda_graphs else "off",
             },
             "clocks": clocks,
             "gpu_launches": int(launches),

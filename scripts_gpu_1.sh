@@ -1,11 +1,13 @@
 #!/bin/bash
-# 1-GPU: numerics of every GPU test, micro-benchmarks, bench variants, launch list.
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -80 > gpurun_out/g1_pytest.log; tail -6 gpurun_out/g1_pytest.log
-timeout 300 python tools/microbench.py tbe > gpurun_out/g1_micro.md 2>&1; tail -7 gpurun_out/g1_micro.md
-timeout 600 python bench.py 2>&1 | tail -1 > gpurun_out/bench1c.json; cut -c1-330 gpurun_out/bench1c.json; echo
-TRB_OVERLAP_SPARSE=1 timeout 600 python bench.py 2>&1 | tail -1 > gpurun_out/bench1c_overlap.json; cut -c1-330 gpurun_out/bench1c_overlap.json; echo
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 300 -c 260 --csv --log-file gpurun_out/launches_r1b.csv python bench.py --steps 2 --warmup 3 --no-e2e > gpurun_out/ncu_launch_b.log 2>&1
+health() { timeout 60 nvidia-smi --query-gpu=index,memory.used --format=csv,noheader || { echo "GPU UNHEALTHY after $1"; exit 7; }; }
+timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -60 > gpurun_out/g1_pytest.log; tail -5 gpurun_out/g1_pytest.log; health pytest
+timeout 600 python bench.py 2>&1 | tail -1 > gpurun_out/bench1d.json; health bench
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench1d.json')); print(round(d["value"]), d["ms_per_step"], "host_enqueue_ms", d.get("host_enqueue_ms_per_step"), "launches", d["gpu_launches"], "e2e", d["e2e"]["value"], d["clocks"])
+PY
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 300 -c 260 --csv --log-file gpurun_out/launches_r1b.csv python bench.py --steps 2 --warmup 3 --no-e2e > gpurun_out/ncu_launch_b.log 2>&1; health ncu
 python - <<'PY'
 import csv, collections, re
 rows=[r for r in csv.DictReader(l for l in open('gpurun_out/launches_r1b.csv') if l.startswith('"'))]

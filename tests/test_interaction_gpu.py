@@ -71,3 +71,48 @@ def test_dlrm_with_tcgen05_backend_matches_torch():
             continue
         tol = 0.06 * float(gref[n].abs().max()) + 1e-2
         assert float((p.grad - gref[n]).abs().max()) < tol, n
+
+
+@pytest.mark.gpu
+def test_dlrm_dense_cuda_graphs_match_eager():
+    """capture_dense_graphs: training with the dense sub-modules replayed as CUDA graphs equals eager training."""
+    from torchrec_b200.models.dlrm import DLRM, DLRMTrain
+    from torchrec_b200.datasets.random import RandomRecDataset
+    from torchrec_b200.modules.embedding_configs import EmbeddingBagConfig
+    from torchrec_b200.modules.embedding_modules import EmbeddingBagCollection
+    from torchrec_b200.ops import dense as _dense
+
+    dev = torch.device("cuda:0")
+    _dense.set_dense_backend("tcgen05")
+    try:
+        keys = [f"f{i}" for i in range(26)]
+
+        def make():
+            torch.manual_seed(0)
+            ebc = EmbeddingBagCollection([EmbeddingBagConfig(name=f"t{i}", embedding_dim=128, num_embeddings=500, feature_names=[k]) for i, k in enumerate(keys)], device=dev)
+            return DLRMTrain(DLRM(ebc, 13, [64, 128], [256, 64, 1], dense_device=dev))
+
+        a, b = make(), make()
+        b.load_state_dict(a.state_dict())
+        ds = RandomRecDataset(keys, 256, hash_sizes=[500] * 26, ids_per_features=[1] * 26, num_dense=13, manual_seed=3, num_generated_batches=4)
+        batches = [x.to(dev) for x in ds.batch_generator._generated_batches]
+        with torch.no_grad():
+            emb = b.model.sparse_arch(batches[0].sparse_features)
+        b.model.capture_dense_graphs(batches[0].dense_features, emb)
+        oa, ob = torch.optim.SGD(a.parameters(), lr=0.1), torch.optim.SGD(b.parameters(), lr=0.1)
+        for i in range(4):
+            la, _ = a(batches[i])
+            lb, _ = b(batches[i])
+            torch.testing.assert_close(lb, la, rtol=2e-2, atol=2e-3)
+            for m, o, l in ((a, oa, la), (b, ob, lb)):
+                o.zero_grad()
+                l.backward()
+                o.step()
+        for (n, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+            torch.testing.assert_close(pb, pa, rtol=5e-2, atol=5e-3, msg=n)
+        # a batch of another size falls back to the eager modules
+        small = RandomRecDataset(keys, 64, hash_sizes=[500] * 26, ids_per_features=[1] * 26, num_dense=13, manual_seed=4, num_generated_batches=1).batch_generator._generated_batches[0].to(dev)
+        lb, _ = b(small)
+        assert torch.isfinite(lb)
+    finally:
+        _dense.set_dense_backend("torch")

@@ -128,3 +128,9 @@ def launch_count_add(n: int) -> None:
     l = _load()
     if l is not None:
         l.trb_launch_count_add(ctypes.c_ulonglong(n))
+
+
+def add_launches(n: int) -> None:
+    """Account for native kernels replayed by a CUDA graph (the host-side launch counter only sees the capture)."""
+    if n > 0 and available():
+        lib().trb_launch_count_add(ctypes.c_ulonglong(int(n)))

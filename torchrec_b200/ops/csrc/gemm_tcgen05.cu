@@ -420,19 +420,7 @@ __global__ void __launch_bounds__(256) trb_colsum_bf16_kernel(const __nv_bfloat1
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   if (vec < nvec) {
-    int r = r0 + ty;
-    for (; r + 24 < r1; r += 32) {  // 4 independent 16 B loads in flight per thread
-      uint4 v[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) v[q] = *reinterpret_cast<const uint4*>(in + (int64_t) (r + 8 * q) * ld + vec * 8);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(&v[q]);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += __bfloat162float(b[j]);
-      }
-    }
-    for (; r < r1; r += 8) {
+    for (int r = r0 + ty; r < r1; r += 8) {
       const uint4 v = *reinterpret_cast<const uint4*>(in + (int64_t) r * ld + vec * 8);
       const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(&v);
 #pragma unroll
@@ -462,7 +450,6 @@ TRB_API int trb_colsum_bf16(const void* in, float* out, int rows, int cols, int6
   const int xblocks = (nvec + 31) / 32;
   int rows_per_block = 256;
   while ((int64_t) xblocks * ((rows + rows_per_block - 1) / rows_per_block) > 2048 && rows_per_block < 65536) rows_per_block *= 2;
-  while ((int64_t) xblocks * ((rows + rows_per_block - 1) / rows_per_block) < 4 * 148 && rows_per_block > 64) rows_per_block /= 2;  // narrow matrices: more row tiles
   dim3 grid(xblocks, (rows + rows_per_block - 1) / rows_per_block);
   trb_colsum_bf16_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*) in, out, rows, cols, ld, rows_per_block);
   TRB_CHECK_LAUNCH();
