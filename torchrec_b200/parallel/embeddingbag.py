@@ -499,6 +499,21 @@ class ShardedEmbeddingBagCollection(
             ctx.variable_batch_per_feature = True
             features = self._pad_vbe(features)
         with torch.no_grad():
+            eng = self._engine
+            if not self._post_mean and eng is not None and not eng._row_sharded:
+                # fast path: input order -> unit order in ONE key permutation (feature order, model-parallel subset and unit
+                # replication composed on the host once) instead of three KJT permutes per step
+                comp = self.__dict__.get("_composed_perm")
+                if comp is None:
+                    order = self._features_order
+                    mp_unit = [order[eng.mp_features[p]] for p in eng._perm_features]
+                    dp = [order[fi] for fi in self._dp_features]
+                    comp = self.__dict__["_composed_perm"] = (mp_unit, dp, mp_unit == list(range(len(features.keys()))))
+                mp_unit, dp, identity = comp
+                ctx.B_local = features.stride()
+                if self._dp_tables:
+                    ctx.dp_features = features.permute(dp)
+                return _InputDistAwaitable(eng.input_dist_routed(features if identity else features.permute(mp_unit)))
             if self._has_features_permute:
                 features = features.permute(self._features_order)
             B = features.stride()

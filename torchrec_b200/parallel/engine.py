@@ -368,6 +368,14 @@ class ShardedLookupEngine(nn.Module):
         routed = KeyedJaggedTensor(keys=self._routed_keys, values=new_values, weights=new_weights, lengths=new_lengths, stride=B)
         return routed, unbucketize
 
+    def input_dist_routed(self, routed: KeyedJaggedTensor) -> Awaitable[Awaitable[KeyedJaggedTensor]]:
+        """Input dist of a KJT that is already in global unit order (keys = unit features)."""
+        if self._kjt_a2a is None:
+            return NoWait(NoWait(routed))
+        if self._pooled and not routed.variable_stride_per_key() and self.fused_available(None) and self._uniform_batch(routed.stride()):
+            return NoWait(NoWait(self.p2p_input_dist(routed)))
+        return self._kjt_a2a(routed)
+
     def input_dist(self, features: KeyedJaggedTensor) -> Tuple[Awaitable[Awaitable[KeyedJaggedTensor]], Optional[torch.Tensor]]:
         routed, unbucketize = self.route(features)
         if self._kjt_a2a is None:
