@@ -49,7 +49,8 @@ def parse_args() -> argparse.Namespace:
     p.add_argument("--dense-backend", type=str, default=os.environ.get("TRB_DENSE_BACKEND", "auto"))
     p.add_argument("--transport", type=str, default=os.environ.get("TRB_TRANSPORT", "auto"), help="auto | p2p | nccl")
     p.add_argument("--dp-rows", type=int, default=int(os.environ.get("TRB_BENCH_DP_ROWS", 2000)), help="tables with at most this many rows are data-parallel when N > 1 (0 = all table-wise)")
-    p.add_argument("--cuda-graphs", type=int, default=int(os.environ.get("TRB_BENCH_GRAPHS", 1)), help="1: replay the dense sub-modules as CUDA graphs")
+    p.add_argument("--cuda-graphs", type=int, default=int(os.environ.get("TRB_BENCH_GRAPHS", -1)),
+                   help="1: replay the dense sub-modules as CUDA graphs; -1 (default): only when N > 1 (one GPU is not launch-bound, measured)")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--num-host-batches", type=int, default=8)
     return p.parse_args()
@@ -248,6 +249,8 @@ def main() -> None:
     dev_batches = [b.to(device) for b in host_batches]
     torch.cuda.synchronize()
 
+    if args.cuda_graphs < 0:
+        args.cuda_graphs = 1 if world > 1 else 0
     if args.cuda_graphs:
         # the dense sub-modules (bottom MLP, interaction + top MLP + head) replay as CUDA graphs: their ~50 launches and ~100 ATen
         # calls per step made the step launch-bound once DDP / NVLink dists were added (host enqueue 2.0 ms vs 2.1 ms of GPU time)
