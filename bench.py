@@ -51,6 +51,7 @@ def parse_args() -> argparse.Namespace:
     p.add_argument("--dp-rows", type=int, default=int(os.environ.get("TRB_BENCH_DP_ROWS", 2000)), help="tables with at most this many rows are data-parallel when N > 1 (0 = all table-wise)")
     p.add_argument("--cuda-graphs", type=int, default=int(os.environ.get("TRB_BENCH_GRAPHS", -1)),
                    help="1: replay the dense sub-modules as CUDA graphs; -1 (default): only when N > 1 (one GPU is not launch-bound, measured)")
+    p.add_argument("--profile-host", action="store_true", help="cProfile 10 extra steps on rank 0 (stderr)")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--num-host-batches", type=int, default=8)
     return p.parse_args()
@@ -336,6 +337,24 @@ def main() -> None:
                "h2d_bytes_per_step": host_batches[0].nbytes(), "d2h_bytes_per_step": 4, "ms_per_step": float(t2.item()) / args.steps,
                "loss": float(loss_host.item())}
 
+    if args.profile_host and rank == 0:
+        # where does the host time of a step go? (cProfile over a few un-timed steps; diagnostics only)
+        import cProfile
+        import io
+        import pstats
+
+        pr = cProfile.Profile()
+        pr.enable()
+        for i in range(10):
+            step(dev_batches[i % len(dev_batches)])
+        pr.disable()
+        torch.cuda.synchronize()
+        buf = io.StringIO()
+        pstats.Stats(pr, stream=buf).sort_stats("tottime").print_stats(45)
+        sys.stderr.write(buf.getvalue())
+    elif args.profile_host:
+        for i in range(10):
+            step(dev_batches[i % len(dev_batches)])
     if rank == 0:
         base = BASELINE_SAMPLES_PER_SEC.get(world)
         out = {
