@@ -212,7 +212,9 @@ def build_ours(args: argparse.Namespace, device, rank: int, world: int):
             gens = {t.name: (sp.column_wise(ranks=[(i + j) % world for j in range(min(world, 4))]) if world > 1 else sp.table_wise(rank=0)) for i, t in enumerate(tables)}
         mplan = sp.construct_module_sharding_plan(ebc, gens, sharder=sharder, world_size=world, local_size=world, device_type="cuda")
         plan = ShardingPlan({"model.sparse_arch.embedding_bag_collection": mplan})
-    dmp = DistributedModelParallel(model, device=device, plan=plan, sharders=[sharder])
+    # data-parallel wrapping is deferred (main() calls dmp.init_data_parallel()) so that CUDA graphs of the dense sub-modules can
+    # be captured first: DDP keeps the parameters' AccumulateGrad nodes alive on the default stream, which a capture may not touch
+    dmp = DistributedModelParallel(model, device=device, plan=plan, sharders=[sharder], init_data_parallel=False)
     dense_opt = KeyedOptimizerWrapper(dict(in_backward_optimizer_filter(dmp.named_parameters())), lambda params: torch.optim.SGD(params, lr=args.lr))
     opt = CombinedOptimizer([dmp.fused_optimizer, dense_opt])
     return dmp, opt, keys, hashes, backend
@@ -252,6 +254,8 @@ def main() -> None:
 
     if args.cuda_graphs < 0:
         args.cuda_graphs = 1 if world > 1 else 0
+    if not args.cuda_graphs:
+        dmp.init_data_parallel()
     if args.cuda_graphs:
         # the dense sub-modules (bottom MLP, interaction + top MLP + head) replay as CUDA graphs: their ~50 launches and ~100 ATen
         # calls per step made the step launch-bound once DDP / NVLink dists were added (host enqueue 2.0 ms vs 2.1 ms of GPU time)
@@ -260,6 +264,7 @@ def main() -> None:
             sample_emb = inner.sparse_arch(dev_batches[0].sparse_features)
         inner.capture_dense_graphs(dev_batches[0].dense_features, sample_emb)
         torch.cuda.synchronize()
+        dmp.init_data_parallel()
 
     def step(batch) -> "torch.Tensor":
         opt.zero_grad()

@@ -26,6 +26,7 @@ def main() -> None:
     from torchrec_b200.datasets.random import RandomRecDataset
 
     dmp, opt, keys, hashes, _ = bench.build_ours(args, device, rank, world)
+    dmp.init_data_parallel()
     ds = RandomRecDataset(keys, args.batch_size, hash_sizes=hashes, ids_per_features=[args.pooling] * 26, num_dense=13, manual_seed=1234 + rank, num_generated_batches=4)
     batches = [b.to(device) for b in ds.batch_generator._generated_batches]
 
