@@ -186,7 +186,11 @@ class DLRM(nn.Module):
         (``torch.cuda.make_graphed_callables``). The dense part of a DLRM step is ~50 small launches + ~100 ATen calls whose
         *enqueue* time (2.0 ms on the host) matched the GPU time of the whole step on B200 (2.1 ms): with more ranks (DDP, NVLink
         dists) the step became launch-bound. Replaying two graphs removes that host time; the sparse part stays eager, so jagged
-        inputs keep their dynamic shapes. Batches whose shapes differ from the samples fall back to the eager modules."""
+        inputs keep their dynamic shapes. Batches whose shapes differ from the samples fall back to the eager modules.
+
+        Call it BEFORE the dense part is wrapped in DDP (``DistributedModelParallel(..., init_data_parallel=False)``, capture, then
+        ``dmp.init_data_parallel()``): DDP keeps the parameters' AccumulateGrad nodes alive on the default stream and a capture that
+        has to synchronise with the legacy stream is rejected by CUDA (cudaErrorStreamCaptureImplicit)."""
         assert sample_dense_features.is_cuda, "CUDA graphs need CUDA tensors"
 
         class _InterOver(nn.Module):
