@@ -348,6 +348,10 @@ def main() -> None:
         import io
         import pstats
 
+        torch.cuda.set_sync_debug_mode("warn")  # every host<->stream synchronisation inside a step is reported on stderr
+        for i in range(2):
+            step(dev_batches[i % len(dev_batches)])
+        torch.cuda.set_sync_debug_mode("default")
         pr = cProfile.Profile()
         pr.enable()
         for i in range(10):

@@ -225,6 +225,21 @@ def _permute_tensor_by_segments(tensor: torch.Tensor, segment_sizes: torch.Tenso
     return values, w
 
 
+_PERM_INDEX_CACHE: Dict[Tuple[Tuple[int, ...], str], torch.Tensor] = {}
+
+
+def _perm_index_tensor(indices: List[int], device: torch.device) -> torch.Tensor:
+    """int32 device copy of a key permutation, cached per (permutation, device): ``torch.tensor(list, device="cuda")`` is a
+    pageable H2D copy followed by a stream synchronize, i.e. one full host/GPU sync per KJT permute in a train step."""
+    key = (tuple(indices), str(device))
+    t = _PERM_INDEX_CACHE.get(key)
+    if t is None:
+        if len(_PERM_INDEX_CACHE) > 4096:
+            _PERM_INDEX_CACHE.clear()
+        t = _PERM_INDEX_CACHE[key] = torch.tensor(indices, dtype=torch.int32, device=device)
+    return t
+
+
 class KeyedJaggedTensor(Pipelineable):
     """Multi-feature jagged batch (see module docstring). Layout: values are key-major; lengths are
     ``[F * B]`` (or a per-key variable batch when ``stride_per_key_per_rank`` is given)."""
@@ -512,7 +527,7 @@ class KeyedJaggedTensor(Pipelineable):
     def permute(self, indices: List[int], indices_tensor: Optional[torch.Tensor] = None) -> "KeyedJaggedTensor":
         """Reorder / select / repeat keys. Parity: jagged_tensor.py:2816-2925."""
         if indices_tensor is None:
-            indices_tensor = torch.tensor(indices, dtype=torch.int32, device=self.device())
+            indices_tensor = _perm_index_tensor(indices, self.device())
         length_per_key = self.length_per_key()
         permuted_keys = [self._keys[i] for i in indices]
         permuted_length_per_key = [length_per_key[i] for i in indices]
