@@ -127,3 +127,32 @@ def test_ndcg_gauc_recall_session_and_others_run():
     mc = _one(M.MulticlassRecallMetric, number_of_classes=4)
     mc.update(predictions={"t": torch.rand(60, 4)}, labels={"t": torch.randint(0, 4, (60,))}, weights={"t": w})
     assert list(mc.compute().values())[0].shape[-1] == 4
+
+
+def test_recalibrated_and_volume_metrics():
+    p, l, w = _data()
+    c = 0.25
+    rne, rcal = _one(M.RecalibratedNEMetric, recalibration_coefficient=c), _one(M.RecalibratedCalibrationMetric, recalibration_coefficient=c)
+    ae, npos, sw, nmiss, wsp = (_one(M.ServingAELossMetric), _one(M.NumPositiveSamplesMetric), _one(M.SumWeightsMetric),
+                                _one(M.NumMissingLabelsMetric), _one(M.WeightedSumPredictionsMetric))
+    l_nan = l.clone()
+    l_nan[::7] = float("nan")
+    for m in (rne, rcal, ae, npos, sw, wsp):
+        m.update(predictions={"t": p}, labels={"t": l}, weights={"t": w})
+    nmiss.update(predictions={"t": p}, labels={"t": l_nan}, weights={"t": w})
+    q = p.double() / (p.double() + (1 - p.double()) / c)
+    plain = _one(M.NEMetric)
+    plain.update(predictions={"t": q.float()}, labels={"t": l}, weights={"t": w})
+    assert rne.compute()["recalibrated_ne-t|lifetime_recalibrated_ne"].item() == pytest.approx(plain.compute()["ne-t|lifetime_ne"].item(), rel=1e-5)
+    assert rcal.compute()["recalibrated_calibration-t|lifetime_recalibrated_calibration"].item() == pytest.approx(
+        ((w * q).sum() / (w * l).sum()).item(), rel=1e-5)
+    assert ae.compute()["serving_ae_loss-t|lifetime_serving_ae_loss"].item() == pytest.approx(((w * (p - l).abs()).sum() / w.sum()).item(), rel=1e-5)
+    assert npos.compute()["num_positive_samples-t|lifetime_num_positive_samples"].item() == pytest.approx((w * l).sum().item(), rel=1e-5)
+    assert sw.compute()["sum_weights-t|window_sum_weights"].item() == pytest.approx(w.sum().item(), rel=1e-5)
+    assert nmiss.compute()["num_missing_labels-t|lifetime_num_missing_labels"].item() == pytest.approx(w[::7].sum().item(), rel=1e-5)
+    assert wsp.compute()["weighted_sum_predictions-t|lifetime_weighted_sum_predictions"].item() == pytest.approx((w * p).sum().item(), rel=1e-5)
+    mod = generate_metric_module(RecMetricModule, MetricsConfig(rec_tasks=[RecTaskInfo(name="t")], rec_metrics={
+        RecMetricEnum.RECALIBRATED_NE: RecMetricDef(rec_tasks=[RecTaskInfo(name="t")], window_size=1000, arguments={"recalibration_coefficient": c}),
+        RecMetricEnum.SUM_WEIGHTS: RecMetricDef(rec_tasks=[RecTaskInfo(name="t")], window_size=1000)}), batch_size=200, world_size=1, my_rank=0,
+        state_metrics_mapping={}, device=torch.device("cpu"))
+    assert len(mod.rec_metrics.rec_metrics) == 2

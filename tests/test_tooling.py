@@ -131,3 +131,51 @@ def test_loggers(caplog):
         return x + 1
 
     assert work(1) == 2 and events == [("unit", True)]
+
+
+def test_lazy_extension():
+    import torch
+
+    from torchrec_b200.modules.lazy_extension import LazyModuleExtensionMixin, lazy_apply
+
+    class LazyScale(LazyModuleExtensionMixin, torch.nn.Module):
+        cls_to_become = None
+
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.UninitializedParameter()
+
+        def initialize_parameters(self, x, *, bias=None):
+            if self.has_uninitialized_params():
+                self.w.materialize((x.shape[-1],))
+                with torch.no_grad():
+                    self.w.fill_(2.0)
+
+        def forward(self, x, *, bias=None):
+            y = x * self.w
+            return y if bias is None else y + bias
+
+    m = LazyScale()
+    import pytest
+
+    with pytest.raises(RuntimeError):
+        m.apply(lambda mod: None)
+    seen = []
+
+    @torch.no_grad()
+    def init(mod):
+        seen.append(type(mod).__name__)
+        if isinstance(mod, LazyScale):
+            mod.w.fill_(3.0)
+
+    lazy_apply(m, init)
+    x = torch.ones(2, 4)
+    out = m(x, bias=torch.ones(4))          # kwargs reach initialize_parameters; first forward still sees the 2.0 init
+    assert torch.equal(out, torch.full((2, 4), 3.0))
+    assert seen == ["LazyScale"] and torch.equal(m.w.detach(), torch.full((4,), 3.0))
+    m(x)
+    assert seen == ["LazyScale"]            # ran once
+    m.apply(lambda mod: None)               # initialized: plain apply is allowed again
+    seq = lazy_apply(torch.nn.Sequential(torch.nn.LazyLinear(2)), lambda mod: seen.append("s"))
+    seq(torch.randn(3, 5))
+    assert seen.count("s") == 2

@@ -33,6 +33,10 @@ REC_METRICS_MAPPING: Dict[RecMetricEnumBase, Type[RecMetric]] = {
     RecMetricEnum.TENSOR_WEIGHTED_AVG: M.TensorWeightedAvgMetric, RecMetricEnum.CALI_FREE_NE: M.CaliFreeNEMetric, RecMetricEnum.UNWEIGHTED_NE: M.UnweightedNEMetric,
     RecMetricEnum.HINDSIGHT_TARGET_PR: M.HindsightTargetPRMetric, RecMetricEnum.NMSE: M.NMSEMetric, RecMetricEnum.AVERAGE: M.AverageMetric,
     RecMetricEnum.GAUC: M.GAUCMetric, RecMetricEnum.MULTI_LABEL_PRECISION: M.MultiLabelPrecisionMetric,
+    RecMetricEnum.RECALIBRATED_NE: M.RecalibratedNEMetric, RecMetricEnum.RECALIBRATED_CALIBRATION: M.RecalibratedCalibrationMetric,
+    RecMetricEnum.SERVING_AE_LOSS: M.ServingAELossMetric, RecMetricEnum.NUM_POSITIVE_SAMPLES: M.NumPositiveSamplesMetric,
+    RecMetricEnum.SUM_WEIGHTS: M.SumWeightsMetric, RecMetricEnum.NUM_MISSING_LABELS: M.NumMissingLabelsMetric,
+    RecMetricEnum.WEIGHTED_SUM_PREDICTIONS: M.WeightedSumPredictionsMetric,
 }
 
 MODEL_METRIC_LABEL: str = "model_out"

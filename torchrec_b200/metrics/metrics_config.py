@@ -46,6 +46,13 @@ class RecMetricEnum(RecMetricEnumBase):
     AVERAGE = "average"
     GAUC = "gauc"
     MULTI_LABEL_PRECISION = "multi_label_precision"
+    RECALIBRATED_NE = "recalibrated_ne"
+    RECALIBRATED_CALIBRATION = "recalibrated_calibration"
+    SERVING_AE_LOSS = "serving_ae_loss"
+    NUM_POSITIVE_SAMPLES = "num_positive_samples"
+    SUM_WEIGHTS = "sum_weights"
+    NUM_MISSING_LABELS = "num_missing_labels"
+    WEIGHTED_SUM_PREDICTIONS = "weighted_sum_predictions"
 
 
 @dataclass(unsafe_hash=True, eq=True)

@@ -665,6 +665,114 @@ class MultiLabelPrecisionMetricComputation(PrecisionMetricComputation):
         return [MetricComputationReport(MetricName.MULTI_LABEL_PRECISION, prefix, r[0].value)]
 
 
+def _recalibrate(predictions: torch.Tensor, coef: float) -> torch.Tensor:
+    """Undo negative down-sampling: p -> p / (p + (1 - p) / c). Parity: ne_with_recalibration.py:76-85."""
+    p = predictions.double()
+    return p / (p + (1.0 - p) / coef)
+
+
+class RecalibratedNEMetricComputation(NEMetricComputation):
+    """NE on predictions re-calibrated for the training-time negative down-sampling rate. Parity: ne_with_recalibration.py:20-116."""
+
+    def __init__(self, *args: Any, recalibration_coefficient: float = 1.0, **kwargs: Any) -> None:
+        self._recalibration_coefficient = float(recalibration_coefficient)
+        super().__init__(*args, **kwargs)
+
+    def _batch_states(self, predictions, labels, weights, **kwargs):
+        return super()._batch_states(_recalibrate(predictions, self._recalibration_coefficient), labels, weights, **kwargs)
+
+    def _reports(self, get, prefix):
+        reps = super()._reports(get, prefix)
+        return [MetricComputationReport(MetricName.RECALIBRATED_NE, prefix, reps[0].value)] + reps[1:]
+
+
+class RecalibratedCalibrationMetricComputation(CalibrationMetricComputation):
+    """Calibration of re-calibrated predictions. Parity: calibration_with_recalibration.py:25-100."""
+
+    def __init__(self, *args: Any, recalibration_coefficient: float = 1.0, **kwargs: Any) -> None:
+        self._recalibration_coefficient = float(recalibration_coefficient)
+        super().__init__(*args, **kwargs)
+
+    def _batch_states(self, predictions, labels, weights, **kwargs):
+        return super()._batch_states(_recalibrate(predictions, self._recalibration_coefficient), labels, weights, **kwargs)
+
+    def _reports(self, get, prefix):
+        return [MetricComputationReport(MetricName.RECALIBRATED_CALIBRATION, prefix, get("calibration_num") / (get("calibration_denom") + EPS))]
+
+
+class ServingAELossMetricComputation(_SumStatesComputation):
+    """Weighted mean absolute error of the served prediction (the reference only reserves the name: metrics_config.py:48)."""
+
+    STATES = ["error_sum", "weighted_num_samples"]
+
+    def _batch_states(self, predictions, labels, weights, **kwargs):
+        return {"error_sum": (weights.double() * (labels.double() - predictions.double()).abs()).sum(-1), "weighted_num_samples": weights.double().sum(-1)}
+
+    def _reports(self, get, prefix):
+        return [MetricComputationReport(MetricName.SERVING_AE_LOSS, prefix, get("error_sum") / (get("weighted_num_samples") + EPS))]
+
+
+class _SingleSumComputation(_SumStatesComputation):
+    """One weighted sum reported as-is (data-volume monitors)."""
+
+    NAME: MetricName
+
+    def _needs(self):
+        return []
+
+    def _sum(self, predictions, labels, weights) -> torch.Tensor:
+        raise NotImplementedError
+
+    def _batch_states(self, predictions, labels, weights, **kwargs):
+        return {self.STATES[0]: self._sum(predictions, labels, weights)}
+
+    def _reports(self, get, prefix):
+        return [MetricComputationReport(self.NAME, prefix, get(self.STATES[0]))]
+
+
+class NumPositiveSamplesMetricComputation(_SingleSumComputation):
+    """sum w * label (NaN labels count 0). Parity: num_positive_samples.py:21-95."""
+
+    STATES = ["weighted_pos_sum"]
+    NAME = MetricName.NUM_POSITIVE_SAMPLES
+
+    def _sum(self, predictions, labels, weights):
+        return (weights.double() * torch.nan_to_num(labels.double(), 0.0)).sum(-1)
+
+
+class SumWeightsMetricComputation(_SingleSumComputation):
+    """sum w. Parity: sum_weights.py:21-95."""
+
+    STATES = ["weighted_sum"]
+    NAME = MetricName.SUM_WEIGHTS
+
+    def _sum(self, predictions, labels, weights):
+        return weights.double().sum(-1)
+
+
+class NumMissingLabelsMetricComputation(_SingleSumComputation):
+    """sum of weights of samples whose label is NaN. Parity: num_missing_labels.py:21-95."""
+
+    STATES = ["missing_label_sum"]
+    NAME = MetricName.NUM_MISSING_LABELS
+
+    def _sum(self, predictions, labels, weights):
+        return torch.where(torch.isnan(labels), weights.double(), torch.zeros_like(weights, dtype=torch.double)).sum(-1)
+
+
+class WeightedSumPredictionsMetricComputation(_SingleSumComputation):
+    """sum w * prediction (NaN predictions count 0). Parity: weighted_sum_predictions.py:21-99."""
+
+    STATES = ["weighted_predictions_sum"]
+    NAME = MetricName.WEIGHTED_SUM_PREDICTIONS
+
+    def _needs(self):
+        return ["predictions"]
+
+    def _sum(self, predictions, labels, weights):
+        return (weights.double() * torch.nan_to_num(predictions.double(), 0.0)).sum(-1)
+
+
 def _make(name: str, comp: Type[RecMetricComputation], ns: MetricNamespace) -> Type[RecMetric]:
     return type(name, (RecMetric,), {"_namespace": ns, "_computation_class": comp, "__doc__": comp.__doc__})
 
@@ -700,3 +808,10 @@ ServingCalibrationMetric = _make("ServingCalibrationMetric", ServingCalibrationM
 OutputMetric = _make("OutputMetric", OutputMetricComputation, MetricNamespace.OUTPUT)
 HindsightTargetPRMetric = _make("HindsightTargetPRMetric", HindsightTargetPRMetricComputation, MetricNamespace.HINDSIGHT_TARGET_PR)
 MultiLabelPrecisionMetric = _make("MultiLabelPrecisionMetric", MultiLabelPrecisionMetricComputation, MetricNamespace.MULTI_LABEL_PRECISION)
+RecalibratedNEMetric = _make("RecalibratedNEMetric", RecalibratedNEMetricComputation, MetricNamespace.RECALIBRATED_NE)
+RecalibratedCalibrationMetric = _make("RecalibratedCalibrationMetric", RecalibratedCalibrationMetricComputation, MetricNamespace.RECALIBRATED_CALIBRATION)
+ServingAELossMetric = _make("ServingAELossMetric", ServingAELossMetricComputation, MetricNamespace.SERVING_AE_LOSS)
+NumPositiveSamplesMetric = _make("NumPositiveSamplesMetric", NumPositiveSamplesMetricComputation, MetricNamespace.NUM_POSITIVE_SAMPLES)
+SumWeightsMetric = _make("SumWeightsMetric", SumWeightsMetricComputation, MetricNamespace.SUM_WEIGHTS)
+NumMissingLabelsMetric = _make("NumMissingLabelsMetric", NumMissingLabelsMetricComputation, MetricNamespace.NUM_MISSING_LABELS)
+WeightedSumPredictionsMetric = _make("WeightedSumPredictionsMetric", WeightedSumPredictionsMetricComputation, MetricNamespace.WEIGHTED_SUM_PREDICTIONS)

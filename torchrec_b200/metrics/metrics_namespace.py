@@ -50,6 +50,13 @@ class MetricName(StrValueMixin, Enum):
     AVERAGE = "average"
     SEGMENTED_NE = "segmented_ne"
     MULTI_LABEL_PRECISION = "multi_label_precision"
+    RECALIBRATED_NE = "recalibrated_ne"
+    RECALIBRATED_CALIBRATION = "recalibrated_calibration"
+    SERVING_AE_LOSS = "serving_ae_loss"
+    NUM_POSITIVE_SAMPLES = "num_positive_samples"
+    SUM_WEIGHTS = "sum_weights"
+    NUM_MISSING_LABELS = "num_missing_labels"
+    WEIGHTED_SUM_PREDICTIONS = "weighted_sum_predictions"
 
 
 class MetricNamespaceBase(StrValueMixin, Enum):
@@ -92,6 +99,13 @@ class MetricNamespace(MetricNamespaceBase):
     SEGMENTED_NE = "segmented_ne"
     GROUPED_AUC = "grouped_auc"
     MULTI_LABEL_PRECISION = "multi_label_precision"
+    RECALIBRATED_NE = "recalibrated_ne"
+    RECALIBRATED_CALIBRATION = "recalibrated_calibration"
+    SERVING_AE_LOSS = "serving_ae_loss"
+    NUM_POSITIVE_SAMPLES = "num_positive_samples"
+    SUM_WEIGHTS = "sum_weights"
+    NUM_MISSING_LABELS = "num_missing_labels"
+    WEIGHTED_SUM_PREDICTIONS = "weighted_sum_predictions"
 
 
 class MetricPrefix(StrValueMixin, Enum):
