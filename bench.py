@@ -362,7 +362,7 @@ def main() -> None:
         pstats.Stats(pr, stream=buf).sort_stats("tottime").print_stats(45)
         sys.stderr.write(buf.getvalue())
     elif args.profile_host:
-        for i in range(10):
+        for i in range(12):  # same number of steps as rank 0 (2 sync-debug + 10 profiled): the NVLink barriers are collective
             step(dev_batches[i % len(dev_batches)])
     if rank == 0:
         base = BASELINE_SAMPLES_PER_SEC.get(world)
