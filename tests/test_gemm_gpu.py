@@ -93,3 +93,26 @@ def test_gemm_mn_major_operands(a_mn, b_mn, M, N, K):
     torch.testing.assert_close(out, ref, rtol=1e-3, atol=2e-2)
     out2 = gemm_bf16(a, b, a_mn=a_mn, b_mn=b_mn, out_dtype=torch.float32, split_k=4)
     torch.testing.assert_close(out2, ref, rtol=1e-3, atol=2e-2)
+    if N % 256 == 0:  # split-K on 128 x 256 tiles (the wgrad plan of wide layers)
+        out3 = gemm_bf16(a, b, a_mn=a_mn, b_mn=b_mn, out_dtype=torch.float32, split_k=5, tile_n=256)
+        torch.testing.assert_close(out3, ref, rtol=1e-3, atol=2e-2)
+
+
+def test_wgrad_plan_fills_the_grid():
+    from torchrec_b200.ops.gemm import _wgrad_plan
+
+    for n_out, n_in in [(1024, 1024), (512, 1024), (256, 512), (1024, 480), (512, 16), (128, 256)]:
+        s, tn = _wgrad_plan(n_out, n_in, 32768, 148)
+        tiles = ((n_out + 127) // 128) * ((n_in + tn - 1) // tn) * s
+        assert tn in (128, 256) and (tn == 128 or n_in % 256 == 0)
+        assert tiles >= 0.85 * 148, (n_out, n_in, s, tn)
+
+
+@pytest.mark.parametrize("N", [128, 256, 480, 1024])
+def test_colsum_variants(N, monkeypatch):
+    from torchrec_b200.ops.gemm import colsum_bf16
+
+    x = (torch.randn(5003, N, device="cuda:0") * 0.5).to(torch.bfloat16)
+    torch.testing.assert_close(colsum_bf16(x), x.float().sum(0), rtol=1e-3, atol=5e-2)
+    xs = x[:, : N // 2] if (N // 2) % 8 == 0 else x  # strided view
+    torch.testing.assert_close(colsum_bf16(xs), xs.float().sum(0), rtol=1e-3, atol=5e-2)

@@ -48,8 +48,22 @@ def bench_gemm():
         if K % 8 == 0 and K >= 64:
             us = timeit(lambda: G.gemm_bf16(gy, wt, b_mn=True))
             print(f"| {M},{K},{N} | dgrad (B MN-major) | {us:.1f} | {2 * M * N * K / us / 1e6:.0f} |")
-            us = timeit(lambda: G.gemm_bf16(gy, a, a_mn=True, b_mn=True, out_dtype=torch.float32, split_k=8))
-            print(f"| {N},{K},{M} | wgrad (A,B MN-major, split-K) | {us:.1f} | {2 * M * N * K / us / 1e6:.0f} |")
+            sp, tn = G._wgrad_plan(N, a.shape[1], M, 148)
+            us = timeit(lambda: G.gemm_bf16(gy, a, a_mn=True, b_mn=True, out_dtype=torch.float32, split_k=sp, tile_n=tn))
+            print(f"| {N},{K},{M} | wgrad (A,B MN-major, split-K {sp}, tile_n {tn}) | {us:.1f} | {2 * M * N * K / us / 1e6:.0f} |")
+
+
+def bench_colsum():
+    print("| colsum bf16 [32768, N] | us | GB/s |\n|---|---|---|")
+    tot = 0.0
+    for N in (1024, 1024, 512, 256, 512, 256, 128):
+        x = torch.randn(32768, N, device=dev).bfloat16()
+        us = timeit(lambda: G.colsum_bf16(x))
+        tot += us
+        ref = x.float().sum(0)
+        err = (G.colsum_bf16(x) - ref).abs().max().item()
+        print(f"| {N} | {us:.1f} | {x.numel() * 2 / us / 1e3:.0f} | err {err:.3f}")
+    print(f"| total (the 7 bias gradients of one DLRM step) | {tot:.1f} | |")
 
 
 def bench_interaction():
@@ -90,5 +104,5 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "interaction", "tbe"]
     print(f"env: TRB_GEMM_WIDE={os.environ.get('TRB_GEMM_WIDE')} TRB_INTERACTION_LEGACY={os.environ.get('TRB_INTERACTION_LEGACY')}\n")
     for w in which:
-        {"gemm": bench_gemm, "interaction": bench_interaction, "tbe": bench_tbe}[w]()
+        {"gemm": bench_gemm, "interaction": bench_interaction, "tbe": bench_tbe, "colsum": bench_colsum}[w]()
         print()

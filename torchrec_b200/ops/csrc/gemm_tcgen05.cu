@@ -227,8 +227,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           if (splits > 1) {
             float* orow = reinterpret_cast<float*>(p.out) + (int64_t) row * p.ldo + n0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.N) atomicAdd(orow + j, v[j]);
+            for (int j = 0; j < 32; j += 4)  // N % 8 == 0 and 16 B aligned rows: one vector reduction per 4 columns
+              if (n0 + j < p.N)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3])
+                             : "memory");
           } else if (p.out_f32) {
             float* orow = reinterpret_cast<float*>(p.out) + (int64_t) row * p.ldo + n0;
 #pragma unroll
@@ -321,7 +323,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& 
 //   b_mn == 0: B is [N, K] row-major                        b_mn == 1: B is [K, N] row-major
 // Pitches lda/ldb in elements (multiples of 8). out: bf16 or fp32 with pitch ldo.
 template <bool A_MN, bool B_MN>
-static int gemm_dispatch(const void* A, int64_t lda, const void* B, int64_t ldb, GemmParams& p, cudaStream_t stream) {
+static int gemm_dispatch(const void* A, int64_t lda, const void* B, int64_t ldb, GemmParams& p, int tile_n, cudaStream_t stream) {
   CUtensorMap ta, tb;
   int rc = A_MN ? make_tmap(&ta, A, p.K, p.M, lda, 64, 64) : make_tmap(&ta, A, p.M, p.K, lda, BLOCK_M);
   if (rc) return rc;
@@ -333,7 +335,9 @@ static int gemm_dispatch(const void* A, int64_t lda, const void* B, int64_t ldb,
   // 128 x 256 tiles halve the A-operand smem / L2 traffic per FLOP; worth it once there are enough tiles to fill the SMs
   static const int wide = getenv("TRB_GEMM_WIDE") ? atoi(getenv("TRB_GEMM_WIDE")) : 1;
   const int64_t tiles256 = (int64_t) ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + 255) / 256) * (p.split_k > 1 ? p.split_k : 1);
-  if (wide && p.split_k <= 1 && p.N % 256 == 0 && tiles256 >= 2 * 148) {  // split-K GEMMs pick their split for 128x128 wave quantisation (ops/gemm.py)
+  // tile_n == 256: the caller sized its split-K for 128 x 256 tiles (ops/gemm.py: _wgrad_plan); 0: decide here
+  const bool use_wide = tile_n == 256 ? true : (tile_n == 0 && p.split_k <= 1 && tiles256 >= 2 * 148);
+  if (wide && use_wide && p.N % 256 == 0) {
     rc = B_MN ? make_tmap(&tb, B, p.K, p.N, ldb, 64, 64) : make_tmap(&tb, B, p.N, p.K, ldb, 256);
     if (rc) return rc;
     return launch_gemm<256, 4, A_MN, B_MN>(ta, tb, p, stream);
@@ -343,9 +347,9 @@ static int gemm_dispatch(const void* A, int64_t lda, const void* B, int64_t ldb,
   return launch_gemm<128, 5, A_MN, B_MN>(ta, tb, p, stream);
 }
 
-TRB_API int trb_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* out, int64_t ldo, int out_f32, int M,
-                          int N, int K, const float* bias, int act, const void* mask, int64_t ld_mask, float alpha, int split_k,
-                          cudaStream_t stream) {
+TRB_API int trb_gemm_bf16_ex(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* out, int64_t ldo, int out_f32, int M,
+                             int N, int K, const float* bias, int act, const void* mask, int64_t ld_mask, float alpha, int split_k, int tile_n,
+                             cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if ((lda % 8) || (ldb % 8) || (N % 8)) return -12;
   if ((!a_mn && (K % 8)) || (a_mn && (M % 8)) || (b_mn && (N % 8)) || (!b_mn && (K % 8))) return -12;
@@ -369,10 +373,16 @@ TRB_API int trb_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, i
     p.split_k = s;
     if (s > 1) TRB_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t) M * (size_t) ldo, stream));
   }
-  if (a_mn && b_mn) return gemm_dispatch<true, true>(A, lda, B, ldb, p, stream);
-  if (a_mn) return gemm_dispatch<true, false>(A, lda, B, ldb, p, stream);
-  if (b_mn) return gemm_dispatch<false, true>(A, lda, B, ldb, p, stream);
-  return gemm_dispatch<false, false>(A, lda, B, ldb, p, stream);
+  if (a_mn && b_mn) return gemm_dispatch<true, true>(A, lda, B, ldb, p, tile_n, stream);
+  if (a_mn) return gemm_dispatch<true, false>(A, lda, B, ldb, p, tile_n, stream);
+  if (b_mn) return gemm_dispatch<false, true>(A, lda, B, ldb, p, tile_n, stream);
+  return gemm_dispatch<false, false>(A, lda, B, ldb, p, tile_n, stream);
+}
+
+TRB_API int trb_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* out, int64_t ldo, int out_f32, int M,
+                          int N, int K, const float* bias, int act, const void* mask, int64_t ld_mask, float alpha, int split_k,
+                          cudaStream_t stream) {
+  return trb_gemm_bf16_ex(A, lda, a_mn, B, ldb, b_mn, out, ldo, out_f32, M, N, K, bias, act, mask, ld_mask, alpha, split_k, 0, stream);
 }
 
 TRB_API int trb_gemm_bf16_tn(const void* A, int64_t lda, const void* B, int64_t ldb, void* out, int64_t ldo, int out_f32, int M, int N, int K,
@@ -442,12 +452,92 @@ __global__ void __launch_bounds__(256) trb_colsum_bf16_kernel(const __nv_bfloat1
   }
 }
 
+// v2: (a) 4 independent 16 B loads in flight per thread (the v1 loop exposes one HBM round trip per iteration),
+// (b) narrow matrices fold several rows into one warp (vpr = lanes per row) so every lane loads.
+__global__ void __launch_bounds__(256) trb_colsum_bf16_v2_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int rows, int cols,
+                                                                   int64_t ld, int rows_per_block, int vpr_log2) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int vpr = 1 << vpr_log2, rpw = 32 >> vpr_log2;  // lanes per row, rows per warp
+  const int sub = lane >> vpr_log2;
+  const int vec = blockIdx.x * 32 + (lane & (vpr - 1));
+  const int nvec = cols >> 3;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  const int step = 8 * rpw;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (vec < nvec) {
+    const __nv_bfloat16* base = in + vec * 8;
+    int r = r0 + warp * rpw + sub;
+    for (; r + 3 * step < r1; r += 4 * step) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t) (r + u * step) * ld));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&v[u]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(b[j]);
+          acc[2 * j] += f.x;
+          acc[2 * j + 1] += f.y;
+        }
+      }
+    }
+    for (; r < r1; r += step) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + (int64_t) r * ld));
+      const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(b[j]);
+        acc[2 * j] += f.x;
+        acc[2 * j + 1] += f.y;
+      }
+    }
+  }
+  // fold the row lanes of a warp, then the 8 warps through smem
+  for (int o = vpr; o < 32; o <<= 1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+  }
+  __shared__ float red[8][32][9];
+  if (sub == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[warp][lane][j] = acc[j];
+  }
+  __syncthreads();
+  // 256 threads: thread t finishes (lane = t & 31, j = t >> 5)
+  {
+    const int l = threadIdx.x & 31, j = threadIdx.x >> 5;
+    const int v = blockIdx.x * 32 + l;
+    if (l < vpr && v < nvec) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += red[i][l][j];
+      atomicAdd(out + v * 8 + j, s);
+    }
+  }
+}
+
 TRB_API int trb_colsum_bf16(const void* in, float* out, int rows, int cols, int64_t ld, cudaStream_t stream) {
   if (rows == 0 || cols == 0) return 0;
   if (cols % 8 || ld % 8) return -12;
   TRB_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, stream));
   const int nvec = cols / 8;
   const int xblocks = (nvec + 31) / 32;
+  static const int variant = [] { const char* e = getenv("TRB_COLSUM"); return e ? atoi(e) : 2; }();
+  if (variant == 2) {
+    int vpr_log2 = 5;
+    while (vpr_log2 > 0 && (1 << (vpr_log2 - 1)) >= nvec) --vpr_log2;
+    // ~4 resident blocks per SM; every thread walks rows_per_block / (8 * rows-per-warp) rows
+    int rows_per_block = 128 * (32 >> vpr_log2);
+    while ((int64_t) xblocks * ((rows + rows_per_block - 1) / rows_per_block) > 1184 && rows_per_block < 65536) rows_per_block *= 2;
+    dim3 grid(xblocks, (rows + rows_per_block - 1) / rows_per_block);
+    trb_colsum_bf16_v2_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*) in, out, rows, cols, ld, rows_per_block, vpr_log2);
+    TRB_CHECK_LAUNCH();
+    return 0;
+  }
   int rows_per_block = 256;
   while ((int64_t) xblocks * ((rows + rows_per_block - 1) / rows_per_block) > 2048 && rows_per_block < 65536) rows_per_block *= 2;
   dim3 grid(xblocks, (rows + rows_per_block - 1) / rows_per_block);

@@ -13,6 +13,7 @@ Weights stay fp32 master copies (nn.Linear parameters); bf16 operand copies are 
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -30,8 +31,9 @@ def _check_bf16_2d(t: torch.Tensor, name: str) -> None:
 
 def gemm_bf16(a: torch.Tensor, b: torch.Tensor, a_mn: bool = False, b_mn: bool = False, bias: Optional[torch.Tensor] = None,
               act: int = ACT_NONE, out_dtype: torch.dtype = torch.bfloat16, mask: Optional[torch.Tensor] = None, alpha: float = 1.0,
-              out: Optional[torch.Tensor] = None, split_k: int = 1) -> torch.Tensor:
-    """``act(alpha * op(a) @ op(b)^T + bias)`` on the tcgen05 kernel.
+              out: Optional[torch.Tensor] = None, split_k: int = 1, tile_n: int = 0) -> torch.Tensor:
+    """``act(alpha * op(a) @ op(b)^T + bias)`` on the tcgen05 kernel. ``tile_n``: 0 = kernel picks 128 x {64,128,256} tiles,
+    128 / 256 = the caller sized ``split_k`` for that tile width.
 
     ``a_mn=False``: a is ``[M, K]`` (K-major);  ``a_mn=True``: a is ``[K, M]`` (consumed MN-major, no transpose copy).
     ``b_mn=False``: b is ``[N, K]``;            ``b_mn=True``: b is ``[K, N]``.
@@ -55,12 +57,12 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, a_mn: bool = False, b_mn: bool =
     if act == ACT_RELU_GRAD:
         assert mask is not None and mask.dtype == torch.bfloat16 and mask.shape == (M, N) and mask.stride(1) == 1 and mask.stride(0) % 8 == 0
     L = _lib.lib()
-    code = L.trb_gemm_bf16(
+    code = L.trb_gemm_bf16_ex(
         _lib.ptr(a), ctypes.c_int64(a.stride(0)), int(a_mn), _lib.ptr(b), ctypes.c_int64(b.stride(0)), int(b_mn), _lib.ptr(out),
         ctypes.c_int64(out.stride(0)), 1 if out.dtype == torch.float32 else 0, M, N, K, _lib.ptr(bias), act, _lib.ptr(mask),
-        ctypes.c_int64(mask.stride(0) if mask is not None else 0), ctypes.c_float(alpha), int(split_k), _lib.stream_ptr(a.device),
+        ctypes.c_int64(mask.stride(0) if mask is not None else 0), ctypes.c_float(alpha), int(split_k), int(tile_n), _lib.stream_ptr(a.device),
     )
-    _lib.check(code, "trb_gemm_bf16")
+    _lib.check(code, "trb_gemm_bf16_ex")
     return out
 
 
@@ -112,6 +114,18 @@ def _best_split(tiles: int, K: int, sms: int) -> int:
         if score > best_score:
             best, best_score = s, score
     return best
+
+
+def _wgrad_plan(n_out: int, n_in: int, batch: int, sms: int) -> "tuple[int, int]":
+    """(split_k, tile_n) of the weight-gradient GEMM ``[n_out, n_in] = gy^T[n_out, batch] . x[batch, n_in]``. 128 x 256 tiles move
+    48 KB of operands per 4.2 MFLOP instead of 32 KB per 2.1 MFLOP: the 1-CTA kernel is bound by L2 -> smem operand traffic, so
+    the wide tile wins whenever the split can still fill the grid. ``TRB_GEMM_SPLIT_WIDE=0`` keeps 128 x 128."""
+    m_tiles = (n_out + 127) // 128
+    if n_in % 256 == 0 and os.environ.get("TRB_GEMM_SPLIT_WIDE", "1") != "0":
+        s = _best_split(m_tiles * (n_in // 256), batch, sms)
+        if m_tiles * (n_in // 256) * s >= sms * 9 // 10:
+            return s, 256
+    return _best_split(m_tiles * ((n_in + 127) // 128), batch, sms), 128
 
 
 def _pad_k(t: torch.Tensor, Kp: int) -> torch.Tensor:
@@ -176,9 +190,8 @@ class LinearActFn(torch.autograd.Function):
                 gx = gx.to(ctx.x_dtype)
         if ctx.needs_input_grad[1]:
             # wgrad: gw[N, Kp] = gy^T . x with BOTH operands consumed MN-major straight from their row-major storage
-            tiles = ((gy.shape[1] + 127) // 128) * ((xb.shape[1] + 127) // 128)
-            split = _best_split(tiles, M, _num_sms(gy.device))
-            gw = gemm_bf16(gy, xb, a_mn=True, b_mn=True, out_dtype=torch.float32, split_k=split)[:, : ctx.K]
+            split, tile_n = _wgrad_plan(gy.shape[1], xb.shape[1], M, _num_sms(gy.device))
+            gw = gemm_bf16(gy, xb, a_mn=True, b_mn=True, out_dtype=torch.float32, split_k=split, tile_n=tile_n)[:, : ctx.K]
             if gw.stride(1) != 1 or gw.shape[1] != gw.stride(0):
                 gw = gw.contiguous()
         if ctx.has_bias and ctx.needs_input_grad[2]:
