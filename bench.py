@@ -342,28 +342,36 @@ def main() -> None:
                "h2d_bytes_per_step": host_batches[0].nbytes(), "d2h_bytes_per_step": 4, "ms_per_step": float(t2.item()) / args.steps,
                "loss": float(loss_host.item())}
 
-    if args.profile_host and rank == 0:
-        # where does the host time of a step go? (cProfile over a few un-timed steps; diagnostics only)
+    if args.profile_host:
+        # where does the host time of a step go? (diagnostics only; every rank runs the same steps: the NVLink barriers are collective)
         import cProfile
         import io
         import pstats
 
-        torch.cuda.set_sync_debug_mode("warn")  # every host<->stream synchronisation inside a step is reported on stderr
+        def profiled(label, fn, n=10):
+            pr = cProfile.Profile() if rank == 0 else None
+            if pr is not None:
+                pr.enable()
+            for i in range(n):
+                fn(i)
+            if pr is not None:
+                pr.disable()
+                torch.cuda.synchronize()
+                for key in ("tottime", "cumulative"):
+                    buf = io.StringIO()
+                    pstats.Stats(pr, stream=buf).sort_stats(key).print_stats(40)
+                    sys.stderr.write(f"==== host profile: {label} ({n} steps), sorted by {key}\n" + buf.getvalue())
+            torch.cuda.synchronize()
+
+        if rank == 0:
+            torch.cuda.set_sync_debug_mode("warn")  # every host<->stream synchronisation inside a step is reported on stderr
         for i in range(2):
             step(dev_batches[i % len(dev_batches)])
         torch.cuda.set_sync_debug_mode("default")
-        pr = cProfile.Profile()
-        pr.enable()
-        for i in range(10):
-            step(dev_batches[i % len(dev_batches)])
-        pr.disable()
-        torch.cuda.synchronize()
-        buf = io.StringIO()
-        pstats.Stats(pr, stream=buf).sort_stats("tottime").print_stats(45)
-        sys.stderr.write(buf.getvalue())
-    elif args.profile_host:
-        for i in range(12):  # same number of steps as rank 0 (2 sync-debug + 10 profiled): the NVLink barriers are collective
-            step(dev_batches[i % len(dev_batches)])
+        profiled("plain step", lambda i: step(dev_batches[i % len(dev_batches)]))
+        if not args.no_e2e:
+            it2 = host_iter(10 + 4)
+            profiled("TrainPipelineSparseDist.progress", lambda i: pipe.progress(it2))
     if rank == 0:
         base = BASELINE_SAMPLES_PER_SEC.get(world)
         out = {

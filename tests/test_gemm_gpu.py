@@ -104,6 +104,9 @@ def test_wgrad_plan_fills_the_grid():
     for n_out, n_in in [(1024, 1024), (512, 1024), (256, 512), (1024, 480), (512, 16), (128, 256)]:
         s, tn = _wgrad_plan(n_out, n_in, 32768, 148)
         tiles = ((n_out + 127) // 128) * ((n_in + tn - 1) // tn) * s
+        if tn == 512:  # CTA-pair kernel: 256 x 256 tiles over 74 clusters
+            assert ((n_out + 255) // 256) * ((n_in + 255) // 256) * s >= 0.85 * 74
+            continue
         assert tn in (128, 256) and (tn == 128 or n_in % 256 == 0)
         assert tiles >= 0.85 * 148, (n_out, n_in, s, tn)
 
@@ -116,3 +119,28 @@ def test_colsum_variants(N, monkeypatch):
     torch.testing.assert_close(colsum_bf16(x), x.float().sum(0), rtol=1e-3, atol=5e-2)
     xs = x[:, : N // 2] if (N // 2) % 8 == 0 else x  # strided view
     torch.testing.assert_close(colsum_bf16(xs), xs.float().sum(0), rtol=1e-3, atol=5e-2)
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K,split", [(256, 256, 64, 1), (512, 256, 512, 1), (4096, 1024, 480, 1), (5000, 480, 1024, 1), (1024, 1024, 40000, 9),
+                                         (40000, 512, 200, 1), (256, 512, 32768, 37), (300, 264, 136, 1)])
+def test_gemm_cta_pair_kernel(a_mn, b_mn, M, N, K, split):
+    """cta_group::2 kernel (256 x 256 tiles, one MMA per TPC) vs fp32 matmul, all operand majors, tails in M / N / K, split-K."""
+    from torchrec_b200.ops.gemm import ACT_RELU, gemm_bf16
+
+    dev = torch.device("cuda:0")
+    torch.manual_seed(5)
+    K = (K + 7) // 8 * 8
+    if a_mn:
+        M = (M + 7) // 8 * 8
+    A = (torch.randn(M, K, device=dev) * 0.3).to(torch.bfloat16)
+    Bm = (torch.randn(N, K, device=dev) * 0.3).to(torch.bfloat16)
+    a = A.t().contiguous() if a_mn else A
+    b = Bm.t().contiguous() if b_mn else Bm
+    ref = A.float() @ Bm.float().t()
+    out = gemm_bf16(a, b, a_mn=a_mn, b_mn=b_mn, out_dtype=torch.float32, split_k=split, tile_n=512)
+    torch.testing.assert_close(out, ref, rtol=2e-3, atol=3e-2 if K < 10000 else 0.2)
+    if split == 1:
+        bias = torch.randn(N, device=dev)
+        out_b = gemm_bf16(a, b, a_mn=a_mn, b_mn=b_mn, bias=bias, act=ACT_RELU, tile_n=512)
+        torch.testing.assert_close(out_b.float(), torch.relu(ref + bias), rtol=2e-2, atol=6e-2)

@@ -266,6 +266,244 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// CTA-pair kernel: one (2,1,1) cluster = the two SMs of a TPC computes a 256 x 256 output tile with
+// tcgen05.mma.cta_group::2 (UMMA 256 x 256 x 16). Per k-block every CTA stages only its own 128 rows of A and its
+// own 128 rows of B (32 KB for 4.2 MFLOP of its half of the tile; the 1-CTA 128 x 256 tile needs 48 KB), which is
+// what lifts the L2 -> smem operand-traffic bound of the kernels above. Roles per CTA are the same (warp 0 TMA,
+// warp 1 MMA (leader CTA only), warp 2 TMEM alloc, warps 4..7 epilogue over the CTA's own 128 TMEM lanes).
+//   full[s]      (leader)  1 arrival (leader producer, expect_tx = both CTAs' bytes); both producers' TMA complete_tx on it
+//   empty[s]     (each)    1 arrival: the leader's commit, multicast to both CTAs
+//   tmem_full[a] (each)    1 arrival: the leader's commit after the last k-block, multicast
+//   tmem_empty[a](leader)  256 arrivals: the epilogue threads of BOTH CTAs (remote arrive from the peer)
+constexpr int kPairN = 256;       // UMMA N of the pair
+constexpr int kPairStages = 6;    // 6 x 32 KB
+
+struct PairSmem {
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;       // this CTA's 128 rows of A
+  static constexpr int kBBytes = (kPairN / 2) * BLOCK_K * 2;  // this CTA's half of B
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = kPairStages * kStageBytes;
+  static constexpr int kTotal = kBarOffset + (2 * kPairStages + 4) * 8 + 16;
+};
+
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+  using L = PairSmem;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + kPairStages;
+  uint64_t* tmem_full_bar = empty_bar + kPairStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  constexpr uint32_t kTmemCols = 2 * kPairN;  // 2 accumulator stages x 256 fp32 columns = all 512 columns
+
+  if (warp_idx == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int i = 0; i < kPairStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 256);
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 2) tmem_alloc_2sm(tmem_ptr_smem, kTmemCols);
+  tc_fence_before();
+  cluster_sync_all();  // barrier inits + TMEM allocation of both CTAs visible before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int m_tiles = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int n_tiles = (p.N + kPairN - 1) / kPairN;
+  const int k_blocks_total = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int splits = p.split_k > 1 ? p.split_k : 1;
+  const int kb_per_split = (k_blocks_total + splits - 1) / splits;
+  const int mn_tiles = m_tiles * n_tiles;
+  const int num_tiles = mn_tiles * splits;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp_idx == 0) {
+    // ================= TMA producer (both CTAs; bytes are accounted on the LEADER's full barrier) =================
+    if (elect_one()) {
+      const uint32_t leader_full0 = mapa_shared(smem_u32(&full_bar[0]), 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int mn = tile % mn_tiles, ks = tile / mn_tiles;
+        const int m_blk = mn / n_tiles, n_blk = mn % n_tiles;
+        const int m0 = m_blk * 2 * BLOCK_M + (int) cta_rank * BLOCK_M;       // this CTA's A rows
+        const int n0 = n_blk * kPairN + (int) cta_rank * (kPairN / 2);       // this CTA's B rows
+        const int kb0 = ks * kb_per_split, kb1 = min(k_blocks_total, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          const uint32_t bar = leader_full0 + (uint32_t) stage * 8;
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+          if constexpr (A_MN) {
+#pragma unroll
+            for (int h = 0; h < BLOCK_M / 64; ++h) tma_load_2d_2sm(&tmap_a, bar, sa + h * 8192, m0 + 64 * h, kb * BLOCK_K);
+          } else {
+            tma_load_2d_2sm(&tmap_a, bar, sa, kb * BLOCK_K, m0);
+          }
+          if constexpr (B_MN) {
+#pragma unroll
+            for (int h = 0; h < (kPairN / 2) / 64; ++h) tma_load_2d_2sm(&tmap_b, bar, sb + h * 8192, n0 + 64 * h, kb * BLOCK_K);
+          } else {
+            tma_load_2d_2sm(&tmap_b, bar, sb, kb * BLOCK_K, n0);
+          }
+          if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ================= MMA issuer (leader CTA only) =================
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc_major(2 * BLOCK_M, kPairN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int accum_stage = 0;
+      uint32_t accum_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(&tmem_empty_bar[accum_stage], accum_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + accum_stage * kPairN;
+        const int ks = tile / mn_tiles;
+        const int kb0 = ks * kb_per_split, kb1 = min(k_blocks_total, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
+            const uint32_t b_addr = a_addr + L::kABytes;
+            const uint64_t adesc = make_kmajor_desc(a_addr);
+            const uint64_t bdesc = make_kmajor_desc(b_addr);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint64_t ad = A_MN ? make_mnmajor_desc(a_addr + k * 2048, 8192, 1024) : adesc + (uint64_t) (2 * k);
+              const uint64_t bd = B_MN ? make_mnmajor_desc(b_addr + k * 2048, 8192, 1024) : bdesc + (uint64_t) (2 * k);
+              umma_bf16_2sm(tmem_d, ad, bd, idesc, ((kb - kb0) | k) != 0);
+            }
+          }
+          __syncwarp();
+          if (elect_one()) {
+            umma_commit_2sm(&empty_bar[stage]);                              // both CTAs' smem slots reusable
+            if (kb == kb1 - 1) umma_commit_2sm(&tmem_full_bar[accum_stage]);  // both CTAs' halves of the accumulator complete
+          }
+          __syncwarp();
+          if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+        }
+        if (++accum_stage == 2) { accum_stage = 0; accum_phase ^= 1; }
+      }
+    }
+  } else if (warp_idx >= kEpiWarp0) {
+    // ================= epilogue (each CTA drains its own 128 accumulator rows) =================
+    const int ew = warp_idx - kEpiWarp0;
+    const uint32_t leader_tmem_empty0 = mapa_shared(smem_u32(&tmem_empty_bar[0]), 0);
+    int accum_stage = 0;
+    uint32_t accum_phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int mn = tile % mn_tiles;
+      const int m_blk = mn / n_tiles, n_blk = mn % n_tiles;
+      mbar_wait(&tmem_full_bar[accum_stage], accum_phase);
+      tc_fence_after();
+      const int row = m_blk * 2 * BLOCK_M + (int) cta_rank * BLOCK_M + ew * 32 + lane;
+      const bool row_ok = row < p.M;
+#pragma unroll 1
+      for (int c = 0; c < kPairN / 32; ++c) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t) (ew * 32) << 16) + (uint32_t) (accum_stage * kPairN + c * 32);
+        tmem_ld_32x32(taddr, r);
+        const int n0 = n_blk * kPairN + c * 32;
+        if (n0 >= p.N) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (n0 + j < p.N) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          }
+        }
+        if (p.act == ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (p.act == ACT_SIGMOID) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
+        } else if (p.act == ACT_RELU_GRAD) {
+          if (row_ok) {
+            const __nv_bfloat16* mrow = p.mask + (int64_t) row * p.ld_mask + n0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (n0 + j < p.N) {
+                const uint4 m8 = *reinterpret_cast<const uint4*>(mrow + j);
+                const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&m8);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[j + q] = (__bfloat162float(mb[q]) > 0.f) ? v[j + q] : 0.f;
+              }
+            }
+          }
+        }
+        if (row_ok) {
+          if (splits > 1) {
+            float* orow = reinterpret_cast<float*>(p.out) + (int64_t) row * p.ldo + n0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (n0 + j < p.N)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3])
+                             : "memory");
+          } else if (p.out_f32) {
+            float* orow = reinterpret_cast<float*>(p.out) + (int64_t) row * p.ldo + n0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (n0 + j < p.N) *reinterpret_cast<float4*>(orow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+            __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t) row * p.ldo + n0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (n0 + j < p.N) {
+                uint4 o;
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+                o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(orow + j) = o;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_cluster(leader_tmem_empty0 + (uint32_t) accum_stage * 8);  // leader's MMA warp waits for both CTAs' 128 threads
+      if (++accum_stage == 2) { accum_stage = 0; accum_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // neither CTA may free TMEM / exit while the peer can still multicast into its barriers
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, kTmemCols);
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
@@ -316,6 +554,26 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& 
   return 0;
 }
 
+template <bool A_MN, bool B_MN>
+int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  constexpr int smem_bytes = PairSmem::kTotal + 1024;
+  static bool configured = false;
+  if (!configured) {
+    TRB_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_pair_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    configured = true;
+  }
+  if (g_num_sms == 0) {
+    int dev = 0;
+    TRB_CUDA(cudaGetDevice(&dev));
+    TRB_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int tiles = ((p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((p.N + kPairN - 1) / kPairN) * (p.split_k > 1 ? p.split_k : 1);
+  const int clusters = tiles < g_num_sms / 2 ? tiles : g_num_sms / 2;
+  gemm_bf16_tcgen05_pair_kernel<A_MN, B_MN><<<2 * clusters, kNumThreads, smem_bytes, stream>>>(ta, tb, p);
+  TRB_CHECK_LAUNCH();
+  return 0;
+}
+
 }  // namespace
 
 // C[M,N] = act(alpha * op(A) . op(B)^T + bias), bf16 operands, fp32 accumulation.
@@ -331,6 +589,18 @@ static int gemm_dispatch(const void* A, int64_t lda, const void* B, int64_t ldb,
     rc = B_MN ? make_tmap(&tb, B, p.K, p.N, ldb, 64, 64) : make_tmap(&tb, B, p.N, p.K, ldb, 64);
     if (rc) return rc;
     return launch_gemm<64, 6, A_MN, B_MN>(ta, tb, p, stream);
+  }
+  // CTA-pair 256 x 256 tiles (cta_group::2): least operand traffic per FLOP. tile_n == 512: caller asked for it (split-K sized
+  // for 74 clusters); tile_n == 0: taken when the tile count fills the 74 clusters for >= 2 waves. TRB_GEMM_PAIR=0 disables.
+  static const int pair = getenv("TRB_GEMM_PAIR") ? atoi(getenv("TRB_GEMM_PAIR")) : 0;
+  {
+    const int64_t tiles_pair = (int64_t) ((p.M + 255) / 256) * ((p.N + 255) / 256) * (p.split_k > 1 ? p.split_k : 1);
+    const bool use_pair = tile_n == 512 || (pair && tile_n == 0 && p.split_k <= 1 && tiles_pair >= 2 * 74 && p.N >= 256);
+    if (use_pair) {
+      rc = B_MN ? make_tmap(&tb, B, p.K, p.N, ldb, 64, 64) : make_tmap(&tb, B, p.N, p.K, ldb, 128);
+      if (rc) return rc;
+      return launch_gemm_pair<A_MN, B_MN>(ta, tb, p, stream);
+    }
   }
   // 128 x 256 tiles halve the A-operand smem / L2 traffic per FLOP; worth it once there are enough tiles to fill the SMs
   static const int wide = getenv("TRB_GEMM_WIDE") ? atoi(getenv("TRB_GEMM_WIDE")) : 1;
@@ -452,10 +722,14 @@ __global__ void __launch_bounds__(256) trb_colsum_bf16_kernel(const __nv_bfloat1
   }
 }
 
-// v2: (a) 4 independent 16 B loads in flight per thread (the v1 loop exposes one HBM round trip per iteration),
-// (b) narrow matrices fold several rows into one warp (vpr = lanes per row) so every lane loads.
-__global__ void __launch_bounds__(256) trb_colsum_bf16_v2_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int rows, int cols,
-                                                                   int64_t ld, int rows_per_block, int vpr_log2) {
+// v3: contended fp32 atomics were the bottleneck of v1 (every 128 B line of `out` took rows/256 x 32 serialized L2 atomics:
+// 33 us for 67 MB). Now: (a) ~2 blocks per SM, each walking a tall row slab with 4 independent 16 B loads in flight per
+// thread, (b) narrow matrices fold several rows into one warp (vpr = lanes per row) so every lane loads, (c) block partials
+// go to a workspace and the LAST block of a column group (ticket counter) sums them in a fixed order: no float atomics,
+// deterministic result, one launch.
+__global__ void __launch_bounds__(256) trb_colsum_bf16_v3_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int rows, int cols,
+                                                                   int64_t ld, int rows_per_block, int vpr_log2, float* __restrict__ partial,
+                                                                   unsigned int* __restrict__ tickets) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int vpr = 1 << vpr_log2, rpw = 32 >> vpr_log2;  // lanes per row, rows per warp
   const int sub = lane >> vpr_log2;
@@ -502,42 +776,81 @@ __global__ void __launch_bounds__(256) trb_colsum_bf16_v2_kernel(const __nv_bflo
     for (int j = 0; j < 8; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
   }
   __shared__ float red[8][32][9];
+  __shared__ unsigned int s_ticket;
   if (sub == 0) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) red[warp][lane][j] = acc[j];
   }
   __syncthreads();
-  // 256 threads: thread t finishes (lane = t & 31, j = t >> 5)
-  {
-    const int l = threadIdx.x & 31, j = threadIdx.x >> 5;
-    const int v = blockIdx.x * 32 + l;
-    if (l < vpr && v < nvec) {
-      float s = 0.f;
+  // thread t owns column (blockIdx.x * 256 + t) of this block's 256-column group: vec lane t >> 3, element t & 7
+  const int l = threadIdx.x >> 3, j = threadIdx.x & 7;
+  const int col = blockIdx.x * 256 + threadIdx.x;
+  const bool col_ok = l < vpr && col < cols;
+  if (col_ok) {
+    float s = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s += red[i][l][j];
-      atomicAdd(out + v * 8 + j, s);
+    for (int i = 0; i < 8; ++i) s += red[i][l][j];
+    if (gridDim.y == 1) {
+      out[col] = s;
+      return;
     }
+    partial[(int64_t) blockIdx.y * cols + col] = s;
   }
+  if (gridDim.y == 1) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&tickets[blockIdx.x], 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.y - 1) return;
+  __threadfence();
+  if (col_ok) {
+    float s = 0.f;
+    for (int y = 0; y < (int) gridDim.y; ++y) s += __ldcg(partial + (int64_t) y * cols + col);
+    out[col] = s;
+  }
+  if (threadIdx.x == 0) tickets[blockIdx.x] = 0;  // ready for the next launch on this stream
 }
+
+// per-device workspace of the column-sum kernel (tickets + block partials); kernels that use it are stream ordered
+size_t g_colsum_ws_bytes_dev[64] = {};
+void* g_colsum_ws_dev[64] = {};
 
 TRB_API int trb_colsum_bf16(const void* in, float* out, int rows, int cols, int64_t ld, cudaStream_t stream) {
   if (rows == 0 || cols == 0) return 0;
   if (cols % 8 || ld % 8) return -12;
-  TRB_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, stream));
   const int nvec = cols / 8;
   const int xblocks = (nvec + 31) / 32;
-  static const int variant = [] { const char* e = getenv("TRB_COLSUM"); return e ? atoi(e) : 2; }();
-  if (variant == 2) {
+  static const int variant = [] { const char* e = getenv("TRB_COLSUM"); return e ? atoi(e) : 3; }();
+  if (variant == 3) {
     int vpr_log2 = 5;
     while (vpr_log2 > 0 && (1 << (vpr_log2 - 1)) >= nvec) --vpr_log2;
-    // ~4 resident blocks per SM; every thread walks rows_per_block / (8 * rows-per-warp) rows
-    int rows_per_block = 128 * (32 >> vpr_log2);
-    while ((int64_t) xblocks * ((rows + rows_per_block - 1) / rows_per_block) > 1184 && rows_per_block < 65536) rows_per_block *= 2;
-    dim3 grid(xblocks, (rows + rows_per_block - 1) / rows_per_block);
-    trb_colsum_bf16_v2_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*) in, out, rows, cols, ld, rows_per_block, vpr_log2);
+    const int rpw = 32 >> vpr_log2;
+    int yblocks = (2 * 148 + xblocks - 1) / xblocks;
+    int rows_per_block = (rows + yblocks - 1) / yblocks;
+    rows_per_block = (rows_per_block + 8 * rpw - 1) / (8 * rpw) * (8 * rpw);
+    yblocks = (rows + rows_per_block - 1) / rows_per_block;
+    // workspace (per process, stream-ordered use: the dense backward runs on one stream): tickets then partial sums
+    const size_t need = 4096 + sizeof(float) * (size_t) yblocks * (size_t) cols;
+    int dev = 0;
+    TRB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return -12;
+    size_t& g_colsum_ws_bytes = g_colsum_ws_bytes_dev[dev];
+    void*& g_colsum_ws = g_colsum_ws_dev[dev];
+    if (need > g_colsum_ws_bytes) {
+      if (g_colsum_ws) TRB_CUDA(cudaFree(g_colsum_ws));
+      g_colsum_ws_bytes = need < (8u << 20) ? (8u << 20) : need;
+      TRB_CUDA(cudaMalloc(&g_colsum_ws, g_colsum_ws_bytes));
+      TRB_CUDA(cudaMemset(g_colsum_ws, 0, 4096));
+    }
+    if (xblocks > 1024) return -12;
+    dim3 grid(xblocks, yblocks);
+    trb_colsum_bf16_v3_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*) in, out, rows, cols, ld, rows_per_block, vpr_log2,
+                                                        reinterpret_cast<float*>(static_cast<char*>(g_colsum_ws) + 4096),
+                                                        reinterpret_cast<unsigned int*>(g_colsum_ws));
     TRB_CHECK_LAUNCH();
     return 0;
   }
+  TRB_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, stream));
   int rows_per_block = 256;
   while ((int64_t) xblocks * ((rows + rows_per_block - 1) / rows_per_block) > 2048 && rows_per_block < 65536) rows_per_block *= 2;
   dim3 grid(xblocks, (rows + rows_per_block - 1) / rows_per_block);

@@ -104,6 +104,10 @@ def _num_sms(device: torch.device) -> int:
     return _SMS[idx]
 
 
+# cta_group::2 GEMM (csrc/gemm_tcgen05.cu: gemm_bf16_tcgen05_pair_kernel); the C++ dispatcher reads the same variable
+PAIR_DEFAULT = os.environ.get("TRB_GEMM_PAIR", "0") != "0"
+
+
 def _best_split(tiles: int, K: int, sms: int) -> int:
     """Split-K factor that fills whole waves of the persistent grid: maximise tiles*s / (ceil(tiles*s / sms) * sms) over splits
     that keep >= 512 reduction elements each (fewer, fuller waves beat many splits: every split adds a pass of fp32 atomics)."""
@@ -120,6 +124,12 @@ def _wgrad_plan(n_out: int, n_in: int, batch: int, sms: int) -> "tuple[int, int]
     """(split_k, tile_n) of the weight-gradient GEMM ``[n_out, n_in] = gy^T[n_out, batch] . x[batch, n_in]``. 128 x 256 tiles move
     48 KB of operands per 4.2 MFLOP instead of 32 KB per 2.1 MFLOP: the 1-CTA kernel is bound by L2 -> smem operand traffic, so
     the wide tile wins whenever the split can still fill the grid. ``TRB_GEMM_SPLIT_WIDE=0`` keeps 128 x 128."""
+    if PAIR_DEFAULT and n_out >= 256 and n_in >= 256:
+        # CTA-pair kernel: 256 x 256 tiles over sms / 2 clusters
+        tiles = ((n_out + 255) // 256) * ((n_in + 255) // 256)
+        s = _best_split(tiles, batch, sms // 2)
+        if tiles * s >= (sms // 2) * 9 // 10:
+            return s, 512
     m_tiles = (n_out + 127) // 128
     if n_in % 256 == 0 and os.environ.get("TRB_GEMM_SPLIT_WIDE", "1") != "0":
         s = _best_split(m_tiles * (n_in // 256), batch, sms)
