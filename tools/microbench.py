@@ -53,9 +53,33 @@ def bench_gemm():
             print(f"| {N},{K},{M} | wgrad (A,B MN-major, split-K {sp}, tile_n {tn}) | {us:.1f} | {2 * M * N * K / us / 1e6:.0f} |")
 
 
+def bench_gemmx():
+    """Mainloop vs epilogue: sweep K at fixed M, N for the 128 x 256 (tile_n=256) and CTA-pair (tile_n=512) kernels."""
+    print("| M,N,K | variant | tile 128x256 us (TF/s) | pair 256x256 us (TF/s) |\n|---|---|---|---|")
+    M, N = 32768, 1024
+    for K in (512, 1024, 2048, 4096, 8192):
+        a = torch.randn(M, K, device=dev).bfloat16()
+        w = torch.randn(N, K, device=dev).bfloat16()
+        wt = w.t().contiguous()
+        bias = torch.zeros(N, device=dev)
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        for name, fn in [
+            ("K-major B, bias+relu", lambda tn: G.gemm_bf16(a, w, bias=bias, act=G.ACT_RELU, out=out, tile_n=tn)),
+            ("K-major B, plain", lambda tn: G.gemm_bf16(a, w, out=out, tile_n=tn)),
+            ("MN-major B, plain", lambda tn: G.gemm_bf16(a, wt, b_mn=True, out=out, tile_n=tn)),
+        ]:
+            r = []
+            for tn in (256, 512):
+                us = timeit(lambda: fn(tn))
+                r.append(f"{us:.1f} ({2 * M * N * K / us / 1e6:.0f})")
+            print(f"| {M},{N},{K} | {name} | {r[0]} | {r[1]} |")
+
+
 def bench_colsum():
     print("| colsum bf16 [32768, N] | us | GB/s |\n|---|---|---|")
     tot = 0.0
+    tiny = torch.zeros(8, device=dev)
+    print(f"| (timing floor: one tiny kernel) | {timeit(lambda: tiny.add_(1.0)):.1f} | |")
     for N in (1024, 1024, 512, 256, 512, 256, 128):
         x = torch.randn(32768, N, device=dev).bfloat16()
         us = timeit(lambda: G.colsum_bf16(x))
@@ -104,5 +128,5 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "interaction", "tbe"]
     print(f"env: TRB_GEMM_WIDE={os.environ.get('TRB_GEMM_WIDE')} TRB_INTERACTION_LEGACY={os.environ.get('TRB_INTERACTION_LEGACY')}\n")
     for w in which:
-        {"gemm": bench_gemm, "interaction": bench_interaction, "tbe": bench_tbe, "colsum": bench_colsum}[w]()
+        {"gemm": bench_gemm, "interaction": bench_interaction, "tbe": bench_tbe, "colsum": bench_colsum, "gemmx": bench_gemmx}[w]()
         print()

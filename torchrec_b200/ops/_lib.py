@@ -98,7 +98,15 @@ def ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
     return ctypes.c_void_p(t.data_ptr())
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr(device: Optional[torch.device] = None) -> ctypes.c_void_p:
+    """cudaStream_t of the current stream of ``device``. ~30 calls per train step: use the raw C accessor (no Stream object,
+    no device-index normalisation in Python) when this torch build has it."""
+    if _raw_stream is not None:
+        idx = device.index if device is not None and device.index is not None else torch.cuda.current_device()
+        return ctypes.c_void_p(_raw_stream(idx))
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 

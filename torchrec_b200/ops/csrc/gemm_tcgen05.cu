@@ -26,6 +26,8 @@ constexpr int UMMA_K = 16;
 constexpr int kNumThreads = 256;
 constexpr int kEpiWarp0 = 4;
 
+using namespace trb;
+
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2, ACT_RELU_GRAD = 3 };
 
 struct GemmParams {
@@ -39,22 +41,116 @@ struct GemmParams {
   int act;
   float alpha;                  // scale applied to the accumulator before bias
   int split_k;                  // >1: K range split over CTAs, fp32 atomicAdd epilogue (out pre-zeroed)
+  int tma_store;                // 1: bf16 output leaves through smem + TMA stores (tmap_o valid)
 };
 
-using namespace trb;
+// ---- bf16 epilogue through shared memory + TMA stores ---------------------------------------------------------------
+// The direct epilogue (one thread = one output row, 16 B stores 2 KB apart) costs ~6.4 us per 128 x 256 tile, more than the
+// MMAs of a K <= 1024 tile: every fwd / dgrad GEMM of the DLRM MLPs was epilogue bound (tools/microbench.py gemmx). Here each
+// epilogue warp owns a [32 rows x 64 cols] SWIZZLE_128B slab (double buffered): TMEM -> registers (two tcgen05.ld in flight)
+// -> bias / activation / mask -> 16 B swizzled st.shared (conflict free) -> one TMA store per slab, which also clips the
+// M / N tails. Bias lives in a per-warp smem copy; the ReLU-gradient mask tile is fetched with coalesced 16 B loads.
+constexpr int kEpiSlabBytes = 32 * 128;                                   // [32 rows x 64 bf16]
+constexpr int kEpiBytesPerWarp = 3 * kEpiSlabBytes + 256 * 4;             // 2 store slabs + mask slab + bias[256]
+constexpr int kEpiBytes = 4 * kEpiBytesPerWarp;                           // 53248 B
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int BN>
+__device__ __forceinline__ void epilogue_bf16_tma(const CUtensorMap* tmap_o, const GemmParams& p, uint32_t tmem_acc, int row0, int n_base, int lane,
+                                                  uint8_t* epi_warp, uint32_t& store_count) {
+  uint8_t* store_slab = epi_warp;
+  uint8_t* mask_slab = epi_warp + 2 * kEpiSlabBytes;
+  float* bias_s = reinterpret_cast<float*>(epi_warp + 3 * kEpiSlabBytes);
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int i = lane * 4; i < BN; i += 128) {
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n_base + i < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n_base + i));
+      *reinterpret_cast<float4*>(bias_s + i) = b4;
+    }
+    __syncwarp();
+  }
+  const uint32_t sw = (uint32_t) (lane & 7);
+#pragma unroll 1
+  for (int g = 0; g < BN / 64; ++g) {
+    const int n0 = n_base + 64 * g;
+    if (n0 >= p.N) break;
+    uint32_t r0[32], r1[32];
+    tmem_ld_32x32_nowait(tmem_acc + (uint32_t) (64 * g), r0);
+    tmem_ld_32x32_nowait(tmem_acc + (uint32_t) (64 * g + 32), r1);
+    if (p.act == ACT_RELU_GRAD) {
+      // mask tile [32 rows x 64 cols] -> smem, 8 lanes per row (full 128 B lines)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + (lane >> 3), piece = lane & 7;
+        const int grow = row0 + rr, col = n0 + piece * 8;
+        uint4 m = make_uint4(0u, 0u, 0u, 0u);
+        if (grow < p.M && col < p.N) m = __ldg(reinterpret_cast<const uint4*>(p.mask + (int64_t) grow * p.ld_mask + col));
+        *reinterpret_cast<uint4*>(mask_slab + rr * 128 + ((piece ^ (rr & 7)) << 4)) = m;
+      }
+    }
+    // the TMA store that read this slab two groups ago must be done with it
+    if (lane == 0) bulk_wait_group_read<1>();
+    __syncwarp();
+    tmem_ld_wait();
+    uint8_t* slab = store_slab + (store_count & 1u) * kEpiSlabBytes;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {  // 8 columns per 16 B piece
+      float v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(j < 4 ? r0[j * 8 + q] : r1[(j - 4) * 8 + q]) * p.alpha;
+      if (p.bias != nullptr) {
+        const float4 b0 = *reinterpret_cast<const float4*>(bias_s + 64 * g + j * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias_s + 64 * g + j * 8 + 4);
+        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+      }
+      if (p.act == ACT_RELU) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
+      } else if (p.act == ACT_SIGMOID) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = 1.f / (1.f + __expf(-v[q]));
+      } else if (p.act == ACT_RELU_GRAD) {
+        const uint4 m8 = *reinterpret_cast<const uint4*>(mask_slab + lane * 128 + (((uint32_t) j ^ sw) << 4));
+        const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&m8);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = (__bfloat162float(mb[q]) > 0.f) ? v[q] : 0.f;
+      }
+      uint4 o;
+      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(slab + lane * 128 + (((uint32_t) j ^ sw) << 4)) = o;
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0 && row0 < p.M) {
+      tma_store_2d(tmap_o, slab, n0, row0);
+      bulk_commit_group();
+    }
+    ++store_count;
+  }
+}
+
 
 template <int BLOCK_N, int kStages>
 struct SmemLayout {
+  static constexpr bool kEpiTma = BLOCK_N <= 128;  // the 128 x 256 variant has no smem left for the epilogue slabs
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kEpiOffset = kStages * kStageBytes;
+  static constexpr int kBarOffset = kEpiOffset + (kEpiTma ? kEpiBytes : 0);
   static constexpr int kTotal = kBarOffset + (2 * kStages + 4) * 8 + 16;
 };
 
 template <int BLOCK_N, int kStages, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kNumThreads, 1)
-gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const __grid_constant__ CUtensorMap tmap_o, const GemmParams p) {
   using L = SmemLayout<BLOCK_N, kStages>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem is only guaranteed 16 B aligned: round up to 1024 B for SWIZZLE_128B
@@ -177,6 +273,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int ew = warp_idx - kEpiWarp0;  // == warp_idx % 4 -> TMEM lanes [32*ew, 32*ew+32)
     int accum_stage = 0;
     uint32_t accum_phase = 0;
+    uint32_t store_count = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mn = tile % mn_tiles;
       const int m_blk = mn / n_tiles, n_blk = mn % n_tiles;
@@ -184,6 +281,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       tc_fence_after();
       const int row = m_blk * BLOCK_M + ew * 32 + lane;
       const bool row_ok = row < p.M;
+      if constexpr (L::kEpiTma) {
+        if (p.tma_store) {
+          epilogue_bf16_tma<BLOCK_N>(&tmap_o, p, tmem_base + ((uint32_t) (ew * 32) << 16) + (uint32_t) (accum_stage * BLOCK_N),
+                                     m_blk * BLOCK_M + ew * 32, n_blk * BLOCK_N, lane, smem + L::kEpiOffset + ew * kEpiBytesPerWarp, store_count);
+          tc_fence_before();
+          mbar_arrive(&tmem_empty_bar[accum_stage]);
+          if (++accum_stage == 2) { accum_stage = 0; accum_phase ^= 1; }
+          continue;
+        }
+      }
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N / 32; ++c) {
         uint32_t r[32];
@@ -256,6 +363,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       mbar_arrive(&tmem_empty_bar[accum_stage]);
       if (++accum_stage == 2) { accum_stage = 0; accum_phase ^= 1; }
     }
+    if (lane == 0) bulk_wait_group<0>();  // smem slabs must outlive the last TMA stores
   }
 
   tc_fence_before();
@@ -277,19 +385,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 //   tmem_full[a] (each)    1 arrival: the leader's commit after the last k-block, multicast
 //   tmem_empty[a](leader)  256 arrivals: the epilogue threads of BOTH CTAs (remote arrive from the peer)
 constexpr int kPairN = 256;       // UMMA N of the pair
-constexpr int kPairStages = 6;    // 6 x 32 KB
+constexpr int kPairStages = 5;    // 5 x 32 KB (+ 52 KB of epilogue slabs)
 
 struct PairSmem {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;       // this CTA's 128 rows of A
   static constexpr int kBBytes = (kPairN / 2) * BLOCK_K * 2;  // this CTA's half of B
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOffset = kPairStages * kStageBytes;
+  static constexpr int kEpiOffset = kPairStages * kStageBytes;
+  static constexpr int kBarOffset = kEpiOffset + kEpiBytes;
   static constexpr int kTotal = kBarOffset + (2 * kPairStages + 4) * 8 + 16;
 };
 
 template <bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
-gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                              const __grid_constant__ CUtensorMap tmap_o, const GemmParams p) {
   using L = PairSmem;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
@@ -415,6 +525,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
     const uint32_t leader_tmem_empty0 = mapa_shared(smem_u32(&tmem_empty_bar[0]), 0);
     int accum_stage = 0;
     uint32_t accum_phase = 0;
+    uint32_t store_count = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int mn = tile % mn_tiles;
       const int m_blk = mn / n_tiles, n_blk = mn % n_tiles;
@@ -422,6 +533,15 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
       tc_fence_after();
       const int row = m_blk * 2 * BLOCK_M + (int) cta_rank * BLOCK_M + ew * 32 + lane;
       const bool row_ok = row < p.M;
+      if (p.tma_store) {
+        epilogue_bf16_tma<kPairN>(&tmap_o, p, tmem_base + ((uint32_t) (ew * 32) << 16) + (uint32_t) (accum_stage * kPairN),
+                                  m_blk * 2 * BLOCK_M + (int) cta_rank * BLOCK_M + ew * 32, n_blk * kPairN, lane,
+                                  smem + L::kEpiOffset + ew * kEpiBytesPerWarp, store_count);
+        tc_fence_before();
+        mbar_arrive_cluster(leader_tmem_empty0 + (uint32_t) accum_stage * 8);
+        if (++accum_stage == 2) { accum_stage = 0; accum_phase ^= 1; }
+        continue;
+      }
 #pragma unroll 1
       for (int c = 0; c < kPairN / 32; ++c) {
         uint32_t r[32];
@@ -494,6 +614,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
       mbar_arrive_cluster(leader_tmem_empty0 + (uint32_t) accum_stage * 8);  // leader's MMA warp waits for both CTAs' 128 threads
       if (++accum_stage == 2) { accum_stage = 0; accum_phase ^= 1; }
     }
+    if (lane == 0) bulk_wait_group<0>();
   }
 
   tc_fence_before();
@@ -531,10 +652,14 @@ int make_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int64_
   return r == CUDA_SUCCESS ? 0 : -11;
 }
 
+// bf16 output [M, N] with row pitch ldo: box = one epilogue slab [64 cols x 32 rows], SWIZZLE_128B
+int make_tmap_out(CUtensorMap* map, const void* ptr, int64_t M, int64_t N, int64_t ldo) { return make_tmap(map, ptr, M, N, ldo, 32, 64); }
+
 int g_num_sms = 0;
 
 template <int BLOCK_N, int kStages, bool A_MN, bool B_MN>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, GemmParams p, cudaStream_t stream) {
+  if (!SmemLayout<BLOCK_N, kStages>::kEpiTma) p.tma_store = 0;
   using L = SmemLayout<BLOCK_N, kStages>;
   constexpr int smem_bytes = L::kTotal + 1024;
   static bool configured = false;
@@ -549,13 +674,13 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& 
   }
   const int tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N) * (p.split_k > 1 ? p.split_k : 1);
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  gemm_bf16_tcgen05_kernel<BLOCK_N, kStages, A_MN, B_MN><<<grid, kNumThreads, smem_bytes, stream>>>(ta, tb, p);
+  gemm_bf16_tcgen05_kernel<BLOCK_N, kStages, A_MN, B_MN><<<grid, kNumThreads, smem_bytes, stream>>>(ta, tb, to, p);
   TRB_CHECK_LAUNCH();
   return 0;
 }
 
 template <bool A_MN, bool B_MN>
-int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmParams& p, cudaStream_t stream) {
   constexpr int smem_bytes = PairSmem::kTotal + 1024;
   static bool configured = false;
   if (!configured) {
@@ -569,7 +694,7 @@ int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
   }
   const int tiles = ((p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((p.N + kPairN - 1) / kPairN) * (p.split_k > 1 ? p.split_k : 1);
   const int clusters = tiles < g_num_sms / 2 ? tiles : g_num_sms / 2;
-  gemm_bf16_tcgen05_pair_kernel<A_MN, B_MN><<<2 * clusters, kNumThreads, smem_bytes, stream>>>(ta, tb, p);
+  gemm_bf16_tcgen05_pair_kernel<A_MN, B_MN><<<2 * clusters, kNumThreads, smem_bytes, stream>>>(ta, tb, to, p);
   TRB_CHECK_LAUNCH();
   return 0;
 }
@@ -582,13 +707,17 @@ int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
 // Pitches lda/ldb in elements (multiples of 8). out: bf16 or fp32 with pitch ldo.
 template <bool A_MN, bool B_MN>
 static int gemm_dispatch(const void* A, int64_t lda, const void* B, int64_t ldb, GemmParams& p, int tile_n, cudaStream_t stream) {
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, to;
   int rc = A_MN ? make_tmap(&ta, A, p.K, p.M, lda, 64, 64) : make_tmap(&ta, A, p.M, p.K, lda, BLOCK_M);
   if (rc) return rc;
+  static const int epi_tma = getenv("TRB_GEMM_EPI_TMA") ? atoi(getenv("TRB_GEMM_EPI_TMA")) : 1;
+  p.tma_store = (epi_tma && !p.out_f32 && p.split_k <= 1 && (p.ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(p.out) % 16) == 0) ? 1 : 0;
+  if (p.tma_store && make_tmap_out(&to, p.out, p.M, p.N, p.ldo) != 0) p.tma_store = 0;  // fall back to the direct epilogue
+  if (!p.tma_store) to = ta;                                                                // unused
   if (p.N <= 64) {
     rc = B_MN ? make_tmap(&tb, B, p.K, p.N, ldb, 64, 64) : make_tmap(&tb, B, p.N, p.K, ldb, 64);
     if (rc) return rc;
-    return launch_gemm<64, 6, A_MN, B_MN>(ta, tb, p, stream);
+    return launch_gemm<64, 6, A_MN, B_MN>(ta, tb, to, p, stream);
   }
   // CTA-pair 256 x 256 tiles (cta_group::2): least operand traffic per FLOP. tile_n == 512: caller asked for it (split-K sized
   // for 74 clusters); tile_n == 0: taken when the tile count fills the 74 clusters for >= 2 waves. TRB_GEMM_PAIR=0 disables.
@@ -599,7 +728,7 @@ static int gemm_dispatch(const void* A, int64_t lda, const void* B, int64_t ldb,
     if (use_pair) {
       rc = B_MN ? make_tmap(&tb, B, p.K, p.N, ldb, 64, 64) : make_tmap(&tb, B, p.N, p.K, ldb, 128);
       if (rc) return rc;
-      return launch_gemm_pair<A_MN, B_MN>(ta, tb, p, stream);
+      return launch_gemm_pair<A_MN, B_MN>(ta, tb, to, p, stream);
     }
   }
   // 128 x 256 tiles halve the A-operand smem / L2 traffic per FLOP; worth it once there are enough tiles to fill the SMs
@@ -610,11 +739,11 @@ static int gemm_dispatch(const void* A, int64_t lda, const void* B, int64_t ldb,
   if (wide && use_wide && p.N % 256 == 0) {
     rc = B_MN ? make_tmap(&tb, B, p.K, p.N, ldb, 64, 64) : make_tmap(&tb, B, p.N, p.K, ldb, 256);
     if (rc) return rc;
-    return launch_gemm<256, 4, A_MN, B_MN>(ta, tb, p, stream);
+    return launch_gemm<256, 4, A_MN, B_MN>(ta, tb, to, p, stream);
   }
   rc = B_MN ? make_tmap(&tb, B, p.K, p.N, ldb, 64, 64) : make_tmap(&tb, B, p.N, p.K, ldb, 128);
   if (rc) return rc;
-  return launch_gemm<128, 5, A_MN, B_MN>(ta, tb, p, stream);
+  return launch_gemm<128, 5, A_MN, B_MN>(ta, tb, to, p, stream);
 }
 
 TRB_API int trb_gemm_bf16_ex(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* out, int64_t ldo, int out_f32, int M,
@@ -723,7 +852,7 @@ __global__ void __launch_bounds__(256) trb_colsum_bf16_kernel(const __nv_bfloat1
 }
 
 // v3: contended fp32 atomics were the bottleneck of v1 (every 128 B line of `out` took rows/256 x 32 serialized L2 atomics:
-// 33 us for 67 MB). Now: (a) ~2 blocks per SM, each walking a tall row slab with 4 independent 16 B loads in flight per
+// 33 us for 67 MB). Now: (a) ~4 blocks per SM, each walking a tall row slab with 8 independent 16 B loads in flight per
 // thread, (b) narrow matrices fold several rows into one warp (vpr = lanes per row) so every lane loads, (c) block partials
 // go to a workspace and the LAST block of a column group (ticket counter) sums them in a fixed order: no float atomics,
 // deterministic result, one launch.
@@ -744,12 +873,13 @@ __global__ void __launch_bounds__(256) trb_colsum_bf16_v3_kernel(const __nv_bflo
   if (vec < nvec) {
     const __nv_bfloat16* base = in + vec * 8;
     int r = r0 + warp * rpw + sub;
-    for (; r + 3 * step < r1; r += 4 * step) {
-      uint4 v[4];
+    constexpr int U = 8;  // independent 16 B loads in flight per thread
+    for (; r + (U - 1) * step < r1; r += U * step) {
+      uint4 v[U];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t) (r + u * step) * ld));
+      for (int u = 0; u < U; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t) (r + u * step) * ld));
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&v[u]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -803,10 +933,33 @@ __global__ void __launch_bounds__(256) trb_colsum_bf16_v3_kernel(const __nv_bflo
   __syncthreads();
   if (s_ticket != gridDim.y - 1) return;
   __threadfence();
-  if (col_ok) {
+  // last block of this column group: fixed-order sum of the partials. C = vpr * 8 columns; 256 / C thread groups split the
+  // partial rows, 8 loads in flight each, then one smem pass over the groups
+  {
+    const int C = vpr * 8, G = 256 / C;
+    const int c = threadIdx.x & (C - 1), g = threadIdx.x / C;
+    const int gcol = blockIdx.x * 256 + c;
     float s = 0.f;
-    for (int y = 0; y < (int) gridDim.y; ++y) s += __ldcg(partial + (int64_t) y * cols + col);
-    out[col] = s;
+    if (gcol < cols) {
+      const float* pc = partial + gcol;
+      int y = g;
+      for (; y + 7 * G < (int) gridDim.y; y += 8 * G) {
+        float t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t[u] = __ldcg(pc + (int64_t) (y + u * G) * cols);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += t[u];
+      }
+      for (; y < (int) gridDim.y; y += G) s += __ldcg(pc + (int64_t) y * cols);
+    }
+    float* fin = &red[0][0][0];  // 256 floats needed, 2304 available; all earlier reads of red are done (barriers above)
+    fin[threadIdx.x] = s;
+    __syncthreads();
+    if (g == 0 && gcol < cols) {
+      float tot = 0.f;
+      for (int i = 0; i < G; ++i) tot += fin[i * C + c];
+      out[gcol] = tot;
+    }
   }
   if (threadIdx.x == 0) tickets[blockIdx.x] = 0;  // ready for the next launch on this stream
 }
@@ -825,7 +978,7 @@ TRB_API int trb_colsum_bf16(const void* in, float* out, int rows, int cols, int6
     int vpr_log2 = 5;
     while (vpr_log2 > 0 && (1 << (vpr_log2 - 1)) >= nvec) --vpr_log2;
     const int rpw = 32 >> vpr_log2;
-    int yblocks = (2 * 148 + xblocks - 1) / xblocks;
+    int yblocks = (4 * 148 + xblocks - 1) / xblocks;
     int rows_per_block = (rows + yblocks - 1) / yblocks;
     rows_per_block = (rows_per_block + 8 * rpw - 1) / (8 * rpw) * (8 * rpw);
     yblocks = (rows + rows_per_block - 1) / rows_per_block;
