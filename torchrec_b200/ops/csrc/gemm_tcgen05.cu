@@ -721,7 +721,7 @@ static int gemm_dispatch(const void* A, int64_t lda, const void* B, int64_t ldb,
   }
   // CTA-pair 256 x 256 tiles (cta_group::2): least operand traffic per FLOP. tile_n == 512: caller asked for it (split-K sized
   // for 74 clusters); tile_n == 0: taken when the tile count fills the 74 clusters for >= 2 waves. TRB_GEMM_PAIR=0 disables.
-  static const int pair = getenv("TRB_GEMM_PAIR") ? atoi(getenv("TRB_GEMM_PAIR")) : 0;
+  static const int pair = getenv("TRB_GEMM_PAIR") ? atoi(getenv("TRB_GEMM_PAIR")) : 1;
   {
     const int64_t tiles_pair = (int64_t) ((p.M + 255) / 256) * ((p.N + 255) / 256) * (p.split_k > 1 ? p.split_k : 1);
     const bool use_pair = tile_n == 512 || (pair && tile_n == 0 && p.split_k <= 1 && tiles_pair >= 2 * 74 && p.N >= 256);
@@ -979,6 +979,7 @@ TRB_API int trb_colsum_bf16(const void* in, float* out, int rows, int cols, int6
     while (vpr_log2 > 0 && (1 << (vpr_log2 - 1)) >= nvec) --vpr_log2;
     const int rpw = 32 >> vpr_log2;
     int yblocks = (4 * 148 + xblocks - 1) / xblocks;
+    if (yblocks > 64) yblocks = 64;  // the last block of a column group sums yblocks partials: keep that tail short
     int rows_per_block = (rows + yblocks - 1) / yblocks;
     rows_per_block = (rows_per_block + 8 * rpw - 1) / (8 * rpw) * (8 * rpw);
     yblocks = (rows + rows_per_block - 1) / rows_per_block;

@@ -77,6 +77,7 @@ struct TbeBwdParams {
   uint8_t* chunk_done;  // [chunks] set by tbe_bwd_unique_kernel (nullptr: generic walk handles everything)
   int32_t* long_list;   // [chunks] first chunks of spans longer than kLongSpan pieces
   int32_t* long_count;  // zeroed by tbe_bwd_build_keys
+  int prefetch;         // 1: lanes prefetch their key's rows into L2 ahead of the walk (bit 1: also the gradient rows = local memory)
   int32_t max_dim;
   int32_t key64;
   int32_t opt;
@@ -427,11 +428,43 @@ __global__ void __launch_bounds__(256) tbe_bwd_chunk_kernel(const TbeBwdParams p
   const K up = __shfl_up_sync(0xffffffffu, key, 1);
   const bool is_start = (lane == 0) || (key != up);
   unsigned starts = __ballot_sync(0xffffffffu, lane < cnt && is_start);
+  // The walk below is one dependent chain per run (gradient rows -> weight row -> optimizer state -> store): ~3 DRAM round
+  // trips per row with a single row in flight per warp made this kernel latency bound at 2 TB/s. Every lane therefore
+  // software-prefetches the lines of ITS key (weight row, gradient row, row state) into L2 a few runs before the walk reaches
+  // it, so the chain hits L2 (~250 cycles) instead of HBM. kPrefetchAhead keys in flight per warp keeps the footprint small.
+  constexpr int kPrefetchAhead = 6;
+  const char* pf_w = nullptr;
+  const char* pf_g = nullptr;
+  const char* pf_s = nullptr;
+  int pf_wbytes = 0, pf_gbytes = 0;
+  if (p.prefetch && lane < cnt && key != sentinel) {
+    const int pf = bag / p.B;
+    const int pb = bag - pf * p.B;
+    const int ps = pb / p.B_local;
+    const int pD = p.feat_dim[pf];
+    pf_w = reinterpret_cast<const char*>(reinterpret_cast<const W*>(p.weights) + p.feat_woff[pf] + ((int64_t) key - p.feat_rowbase[pf]) * pD);
+    pf_wbytes = p.opt == OPT_NONE ? 0 : pD * (int) sizeof(W);
+    pf_g = reinterpret_cast<const char*>(reinterpret_cast<const G*>(p.grad.p[ps]) + (int64_t) (pb - ps * p.B_local) * p.grad_stride + p.feat_col[pf]);
+    pf_gbytes = (p.prefetch & 2) ? pD * (int) sizeof(G) : 0;
+    if (p.opt == OPT_ROWWISE_ADAGRAD) pf_s = reinterpret_cast<const char*>(p.state1 + key);
+  }
+  auto prefetch_mine = [&]() {
+    for (int o = 0; o < pf_wbytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_w + o));
+    for (int o = 0; o < pf_gbytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_g + o));
+    if (pf_s != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_s));
+  };
+  int pf_upto = kPrefetchAhead < cnt ? kPrefetchAhead : cnt;
+  if (lane < pf_upto && pf_w != nullptr) prefetch_mine();
   bool wrote_slot1 = false;
   while (starts) {
     const int a = __ffs(starts) - 1;
     starts &= starts - 1;
     const int bnd = starts ? (__ffs(starts) - 1) : cnt;
+    {
+      const int upto = (bnd + kPrefetchAhead) < cnt ? (bnd + kPrefetchAhead) : cnt;
+      if (lane >= pf_upto && lane < upto && pf_w != nullptr) prefetch_mine();
+      pf_upto = upto > pf_upto ? upto : pf_upto;
+    }
     const K rk = __shfl_sync(0xffffffffu, key, a);
     if (rk == sentinel) break;  // padding / invalid ids sort last
     float4 acc[MAXV];
@@ -719,6 +752,10 @@ TRB_API int trb_tbe_bwd_fused(void* weights, int w_dtype, float* state1, float* 
   p.max_dim = max_dim;
   p.key64 = total_rows >= ((int64_t) 1 << 32) - 1;
   p.opt = opt;
+  {
+    static const int pf = getenv("TRB_BWD_PREFETCH") ? atoi(getenv("TRB_BWD_PREFETCH")) : 1;
+    p.prefetch = pf ? (1 | (n_grad <= 1 ? 2 : 0)) : 0;  // peer-resident gradient rows bypass the local L2: do not prefetch them
+  }
   if (opt < 0 || opt > OPT_LION) return -5;
   char* ws = reinterpret_cast<char*>(workspace);
 #define TRB_BWD_CASE(WC, WT, GC, GT) \

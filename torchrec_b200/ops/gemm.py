@@ -105,7 +105,7 @@ def _num_sms(device: torch.device) -> int:
 
 
 # cta_group::2 GEMM (csrc/gemm_tcgen05.cu: gemm_bf16_tcgen05_pair_kernel); the C++ dispatcher reads the same variable
-PAIR_DEFAULT = os.environ.get("TRB_GEMM_PAIR", "0") != "0"
+PAIR_DEFAULT = os.environ.get("TRB_GEMM_PAIR", "1") != "0"
 
 
 def _best_split(tiles: int, K: int, sms: int) -> int:
