@@ -59,30 +59,38 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int BN>
-__device__ __forceinline__ void epilogue_bf16_tma(const CUtensorMap* tmap_o, const GemmParams& p, uint32_t tmem_acc, int row0, int n_base, int lane,
-                                                  uint8_t* epi_warp, uint32_t& store_count) {
-  uint8_t* store_slab = epi_warp;
-  uint8_t* mask_slab = epi_warp + 2 * kEpiSlabBytes;
-  float* bias_s = reinterpret_cast<float*>(epi_warp + 3 * kEpiSlabBytes);
-  if (p.bias != nullptr) {
+// ACT / BIAS are compile-time: with runtime checks inside the unrolled 8-piece loop the epilogue warps (one per scheduler, no
+// other warp to hide latency) spent their time in branch resolution and instruction-cache misses (ncu source view).
+template <int BN, int ACT, bool BIAS>
+__device__ __forceinline__ void epilogue_bf16_tma_impl(const CUtensorMap* tmap_o, const GemmParams& p, uint32_t tmem_acc, int row0, int n_base, int lane,
+                                                       uint8_t* epi_warp, uint32_t& store_count) {
+  const uint32_t store_slab = smem_u32(epi_warp);
+  const uint32_t mask_slab = store_slab + 2 * kEpiSlabBytes;
+  const uint32_t bias_s = store_slab + 3 * kEpiSlabBytes;
+  if constexpr (BIAS) {
 #pragma unroll
     for (int i = lane * 4; i < BN; i += 128) {
       float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (n_base + i < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n_base + i));
-      *reinterpret_cast<float4*>(bias_s + i) = b4;
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(bias_s + (uint32_t) i * 4), "f"(b4.x), "f"(b4.y), "f"(b4.z), "f"(b4.w) : "memory");
     }
     __syncwarp();
   }
   const uint32_t sw = (uint32_t) (lane & 7);
+  const uint32_t my_row = (uint32_t) lane * 128;
+  const bool scale = p.alpha != 1.f;
 #pragma unroll 1
   for (int g = 0; g < BN / 64; ++g) {
     const int n0 = n_base + 64 * g;
     if (n0 >= p.N) break;
-    uint32_t r0[32], r1[32];
-    tmem_ld_32x32_nowait(tmem_acc + (uint32_t) (64 * g), r0);
-    tmem_ld_32x32_nowait(tmem_acc + (uint32_t) (64 * g + 32), r1);
-    if (p.act == ACT_RELU_GRAD) {
+    uint32_t r[64];
+    {
+      uint32_t(&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
+      uint32_t(&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
+      tmem_ld_32x32_nowait(tmem_acc + (uint32_t) (64 * g), r0);
+      tmem_ld_32x32_nowait(tmem_acc + (uint32_t) (64 * g + 32), r1);
+    }
+    if constexpr (ACT == ACT_RELU_GRAD) {
       // mask tile [32 rows x 64 cols] -> smem, 8 lanes per row (full 128 B lines)
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -90,51 +98,74 @@ __device__ __forceinline__ void epilogue_bf16_tma(const CUtensorMap* tmap_o, con
         const int grow = row0 + rr, col = n0 + piece * 8;
         uint4 m = make_uint4(0u, 0u, 0u, 0u);
         if (grow < p.M && col < p.N) m = __ldg(reinterpret_cast<const uint4*>(p.mask + (int64_t) grow * p.ld_mask + col));
-        *reinterpret_cast<uint4*>(mask_slab + rr * 128 + ((piece ^ (rr & 7)) << 4)) = m;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(mask_slab + (uint32_t) (rr * 128 + ((piece ^ (rr & 7)) << 4))), "r"(m.x),
+                     "r"(m.y), "r"(m.z), "r"(m.w)
+                     : "memory");
       }
     }
     // the TMA store that read this slab two groups ago must be done with it
     if (lane == 0) bulk_wait_group_read<1>();
     __syncwarp();
     tmem_ld_wait();
-    uint8_t* slab = store_slab + (store_count & 1u) * kEpiSlabBytes;
+    if (scale) {
+#pragma unroll
+      for (int q = 0; q < 64; ++q) r[q] = __float_as_uint(__uint_as_float(r[q]) * p.alpha);
+    }
+    const uint32_t slab = store_slab + (store_count & 1u) * kEpiSlabBytes;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {  // 8 columns per 16 B piece
       float v[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(j < 4 ? r0[j * 8 + q] : r1[(j - 4) * 8 + q]) * p.alpha;
-      if (p.bias != nullptr) {
-        const float4 b0 = *reinterpret_cast<const float4*>(bias_s + 64 * g + j * 8);
-        const float4 b1 = *reinterpret_cast<const float4*>(bias_s + 64 * g + j * 8 + 4);
+      for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(r[j * 8 + q]);
+      if constexpr (BIAS) {
+        float4 b0, b1;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b0.x), "=f"(b0.y), "=f"(b0.z), "=f"(b0.w) : "r"(bias_s + (uint32_t) (64 * g + j * 8) * 4));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b1.x), "=f"(b1.y), "=f"(b1.z), "=f"(b1.w) : "r"(bias_s + (uint32_t) (64 * g + j * 8 + 4) * 4));
         v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
         v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
       }
-      if (p.act == ACT_RELU) {
+      if constexpr (ACT == ACT_RELU) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
-      } else if (p.act == ACT_SIGMOID) {
+      } else if constexpr (ACT == ACT_SIGMOID) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) v[q] = 1.f / (1.f + __expf(-v[q]));
-      } else if (p.act == ACT_RELU_GRAD) {
-        const uint4 m8 = *reinterpret_cast<const uint4*>(mask_slab + lane * 128 + (((uint32_t) j ^ sw) << 4));
+      } else if constexpr (ACT == ACT_RELU_GRAD) {
+        uint4 m8;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(m8.x), "=r"(m8.y), "=r"(m8.z), "=r"(m8.w) : "r"(mask_slab + my_row + (((uint32_t) j ^ sw) << 4)));
         const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&m8);
 #pragma unroll
         for (int q = 0; q < 8; ++q) v[q] = (__bfloat162float(mb[q]) > 0.f) ? v[q] : 0.f;
       }
-      uint4 o;
-      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-      *reinterpret_cast<uint4*>(slab + lane * 128 + (((uint32_t) j ^ sw) << 4)) = o;
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slab + my_row + (((uint32_t) j ^ sw) << 4)), "r"(pack_bf16x2(v[0], v[1])),
+                   "r"(pack_bf16x2(v[2], v[3])), "r"(pack_bf16x2(v[4], v[5])), "r"(pack_bf16x2(v[6], v[7]))
+                   : "memory");
     }
     fence_proxy_async();
     __syncwarp();
     if (lane == 0 && row0 < p.M) {
-      tma_store_2d(tmap_o, slab, n0, row0);
+      asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tmap_o)), "r"(slab),
+                   "r"(n0), "r"(row0)
+                   : "memory");
       bulk_commit_group();
     }
     ++store_count;
   }
 }
 
+template <int BN>
+__device__ __noinline__ void epilogue_bf16_tma(const CUtensorMap* tmap_o, const GemmParams& p, uint32_t tmem_acc, int row0, int n_base, int lane,
+                                               uint8_t* epi_warp, uint32_t& store_count) {
+#define TRB_EPI(A, B) epilogue_bf16_tma_impl<BN, A, B>(tmap_o, p, tmem_acc, row0, n_base, lane, epi_warp, store_count)
+  const bool bias = p.bias != nullptr;
+  switch (p.act) {
+    case ACT_RELU: if (bias) TRB_EPI(ACT_RELU, true); else TRB_EPI(ACT_RELU, false); break;
+    case ACT_SIGMOID: if (bias) TRB_EPI(ACT_SIGMOID, true); else TRB_EPI(ACT_SIGMOID, false); break;
+    case ACT_RELU_GRAD: if (bias) TRB_EPI(ACT_RELU_GRAD, true); else TRB_EPI(ACT_RELU_GRAD, false); break;
+    default: if (bias) TRB_EPI(ACT_NONE, true); else TRB_EPI(ACT_NONE, false); break;
+  }
+#undef TRB_EPI
+}
 
 template <int BLOCK_N, int kStages>
 struct SmemLayout {

@@ -171,7 +171,7 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_smem_addr, uint32
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");  // default .release.cta, as cutlass ClusterBarrier::arrive(cta_id)
 }
 // TMA load into THIS CTA's smem whose bytes are accounted on an mbarrier of the pair's leader CTA (cluster address)
 __device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint32_t leader_bar_cluster_addr, void* smem, int c0, int c1) {
