@@ -64,63 +64,61 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 template <int BN, int ACT, bool BIAS>
 __device__ __forceinline__ void epilogue_bf16_tma_impl(const CUtensorMap* tmap_o, const GemmParams& p, uint32_t tmem_acc, int row0, int n_base, int lane,
                                                        uint8_t* epi_warp, uint32_t& store_count) {
-  const uint32_t store_slab = smem_u32(epi_warp);
-  const uint32_t mask_slab = store_slab + 2 * kEpiSlabBytes;
-  const uint32_t bias_s = store_slab + 3 * kEpiSlabBytes;
+  // plain C++ shared accesses on purpose: `asm volatile` ld/st.shared are kept in program order by the compiler, which
+  // serialised the 8 global loads of the mask tile (one HBM round trip each) and cost 0.36 ms per train step
+  uint8_t* store_slab = epi_warp;
+  uint8_t* mask_slab = epi_warp + 2 * kEpiSlabBytes;
+  float* bias_s = reinterpret_cast<float*>(epi_warp + 3 * kEpiSlabBytes);
   if constexpr (BIAS) {
 #pragma unroll
     for (int i = lane * 4; i < BN; i += 128) {
       float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (n_base + i < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n_base + i));
-      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(bias_s + (uint32_t) i * 4), "f"(b4.x), "f"(b4.y), "f"(b4.z), "f"(b4.w) : "memory");
+      *reinterpret_cast<float4*>(bias_s + i) = b4;
     }
     __syncwarp();
   }
   const uint32_t sw = (uint32_t) (lane & 7);
-  const uint32_t my_row = (uint32_t) lane * 128;
   const bool scale = p.alpha != 1.f;
 #pragma unroll 1
   for (int g = 0; g < BN / 64; ++g) {
     const int n0 = n_base + 64 * g;
     if (n0 >= p.N) break;
-    uint32_t r[64];
-    {
-      uint32_t(&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
-      uint32_t(&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
-      tmem_ld_32x32_nowait(tmem_acc + (uint32_t) (64 * g), r0);
-      tmem_ld_32x32_nowait(tmem_acc + (uint32_t) (64 * g + 32), r1);
-    }
+    uint32_t r0[32], r1[32];
+    tmem_ld_32x32_nowait(tmem_acc + (uint32_t) (64 * g), r0);
+    tmem_ld_32x32_nowait(tmem_acc + (uint32_t) (64 * g + 32), r1);
     if constexpr (ACT == ACT_RELU_GRAD) {
-      // mask tile [32 rows x 64 cols] -> smem, 8 lanes per row (full 128 B lines)
+      // mask tile [32 rows x 64 cols] -> smem, 8 lanes per row (full 128 B lines); all 8 loads in flight before the first store
+      uint4 m[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int grow = row0 + i * 4 + (lane >> 3), col = n0 + (lane & 7) * 8;
+        m[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (grow < p.M && col < p.N) m[i] = __ldg(reinterpret_cast<const uint4*>(p.mask + (int64_t) grow * p.ld_mask + col));
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int rr = i * 4 + (lane >> 3), piece = lane & 7;
-        const int grow = row0 + rr, col = n0 + piece * 8;
-        uint4 m = make_uint4(0u, 0u, 0u, 0u);
-        if (grow < p.M && col < p.N) m = __ldg(reinterpret_cast<const uint4*>(p.mask + (int64_t) grow * p.ld_mask + col));
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(mask_slab + (uint32_t) (rr * 128 + ((piece ^ (rr & 7)) << 4))), "r"(m.x),
-                     "r"(m.y), "r"(m.z), "r"(m.w)
-                     : "memory");
+        *reinterpret_cast<uint4*>(mask_slab + rr * 128 + ((piece ^ (rr & 7)) << 4)) = m[i];
       }
     }
     // the TMA store that read this slab two groups ago must be done with it
     if (lane == 0) bulk_wait_group_read<1>();
     __syncwarp();
     tmem_ld_wait();
-    if (scale) {
-#pragma unroll
-      for (int q = 0; q < 64; ++q) r[q] = __float_as_uint(__uint_as_float(r[q]) * p.alpha);
-    }
-    const uint32_t slab = store_slab + (store_count & 1u) * kEpiSlabBytes;
+    uint8_t* slab = store_slab + (store_count & 1u) * kEpiSlabBytes;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {  // 8 columns per 16 B piece
       float v[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(r[j * 8 + q]);
+      for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(j < 4 ? r0[j * 8 + q] : r1[(j - 4) * 8 + q]);
+      if (scale) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] *= p.alpha;
+      }
       if constexpr (BIAS) {
-        float4 b0, b1;
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b0.x), "=f"(b0.y), "=f"(b0.z), "=f"(b0.w) : "r"(bias_s + (uint32_t) (64 * g + j * 8) * 4));
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b1.x), "=f"(b1.y), "=f"(b1.z), "=f"(b1.w) : "r"(bias_s + (uint32_t) (64 * g + j * 8 + 4) * 4));
+        const float4 b0 = *reinterpret_cast<const float4*>(bias_s + 64 * g + j * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias_s + 64 * g + j * 8 + 4);
         v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
         v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
       }
@@ -131,22 +129,19 @@ __device__ __forceinline__ void epilogue_bf16_tma_impl(const CUtensorMap* tmap_o
 #pragma unroll
         for (int q = 0; q < 8; ++q) v[q] = 1.f / (1.f + __expf(-v[q]));
       } else if constexpr (ACT == ACT_RELU_GRAD) {
-        uint4 m8;
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(m8.x), "=r"(m8.y), "=r"(m8.z), "=r"(m8.w) : "r"(mask_slab + my_row + (((uint32_t) j ^ sw) << 4)));
+        const uint4 m8 = *reinterpret_cast<const uint4*>(mask_slab + lane * 128 + (((uint32_t) j ^ sw) << 4));
         const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&m8);
 #pragma unroll
         for (int q = 0; q < 8; ++q) v[q] = (__bfloat162float(mb[q]) > 0.f) ? v[q] : 0.f;
       }
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slab + my_row + (((uint32_t) j ^ sw) << 4)), "r"(pack_bf16x2(v[0], v[1])),
-                   "r"(pack_bf16x2(v[2], v[3])), "r"(pack_bf16x2(v[4], v[5])), "r"(pack_bf16x2(v[6], v[7]))
-                   : "memory");
+      uint4 o;
+      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(slab + lane * 128 + (((uint32_t) j ^ sw) << 4)) = o;
     }
     fence_proxy_async();
     __syncwarp();
     if (lane == 0 && row0 < p.M) {
-      asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tmap_o)), "r"(slab),
-                   "r"(n0), "r"(row0)
-                   : "memory");
+      tma_store_2d(tmap_o, slab, n0, row0);
       bulk_commit_group();
     }
     ++store_count;
