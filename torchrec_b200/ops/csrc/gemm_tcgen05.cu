@@ -80,6 +80,18 @@ __device__ __forceinline__ void epilogue_bf16_tma_impl(const CUtensorMap* tmap_o
   }
   const uint32_t sw = (uint32_t) (lane & 7);
   const bool scale = p.alpha != 1.f;
+  // ReLU-gradient mask: the [32 rows x 64 cols] tile of group g+1 is fetched (8 lanes per row, full 128 B lines, 8 loads in
+  // flight) while group g is processed; exposed HBM latency per group made the masked dgrad 2x slower than the plain one
+  uint4 m[8];
+  auto load_mask = [&](int n0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int grow = row0 + i * 4 + (lane >> 3), col = n0 + (lane & 7) * 8;
+      m[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (grow < p.M && col < p.N) m[i] = __ldg(reinterpret_cast<const uint4*>(p.mask + (int64_t) grow * p.ld_mask + col));
+    }
+  };
+  if constexpr (ACT == ACT_RELU_GRAD) load_mask(n_base);
 #pragma unroll 1
   for (int g = 0; g < BN / 64; ++g) {
     const int n0 = n_base + 64 * g;
@@ -88,19 +100,13 @@ __device__ __forceinline__ void epilogue_bf16_tma_impl(const CUtensorMap* tmap_o
     tmem_ld_32x32_nowait(tmem_acc + (uint32_t) (64 * g), r0);
     tmem_ld_32x32_nowait(tmem_acc + (uint32_t) (64 * g + 32), r1);
     if constexpr (ACT == ACT_RELU_GRAD) {
-      // mask tile [32 rows x 64 cols] -> smem, 8 lanes per row (full 128 B lines); all 8 loads in flight before the first store
-      uint4 m[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int grow = row0 + i * 4 + (lane >> 3), col = n0 + (lane & 7) * 8;
-        m[i] = make_uint4(0u, 0u, 0u, 0u);
-        if (grow < p.M && col < p.N) m[i] = __ldg(reinterpret_cast<const uint4*>(p.mask + (int64_t) grow * p.ld_mask + col));
-      }
+      // (all lanes finished reading the previous group's mask at the __syncwarp that ended the previous iteration)
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int rr = i * 4 + (lane >> 3), piece = lane & 7;
         *reinterpret_cast<uint4*>(mask_slab + rr * 128 + ((piece ^ (rr & 7)) << 4)) = m[i];
       }
+      if (g + 1 < BN / 64 && n0 + 64 < p.N) load_mask(n0 + 64);
     }
     // the TMA store that read this slab two groups ago must be done with it
     if (lane == 0) bulk_wait_group_read<1>();
