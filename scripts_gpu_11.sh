@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+health() { timeout 60 nvidia-smi --query-gpu=index,memory.used --format=csv,noheader || { echo "GPU UNHEALTHY after $1"; exit 7; }; }
+timeout 600 python -m pytest tests/test_gemm_gpu.py tests/test_tbe_gpu.py -x -q 2>&1 | tail -3; health tests
+echo "== gemmx"; timeout 300 python tools/microbench.py gemmx 2>&1 | grep "mask\|MN-major B, plain" ; health gemmx
+echo "== tbe"; timeout 200 python tools/microbench.py tbe 2>&1 | grep bwd; health tbe
+timeout 300 python bench.py --steps 30 --warmup 5 > gpurun_out/bench1_c39.log 2>&1; health bench
+grep "^{" gpurun_out/bench1_c39.log | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('bench1', round(d['value']), d['ms_per_step'], 'host', round(d['host_enqueue_ms_per_step'],3), 'e2e', round(d['e2e']['value']), d['e2e']['ms_per_step'])"

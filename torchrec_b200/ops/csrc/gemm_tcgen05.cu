@@ -322,7 +322,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const int mn = tile % mn_tiles;
       const int m_blk = mn / n_tiles, n_blk = mn % n_tiles;
       if constexpr (L::kEpiTma) {
-        if (p.tma_store && p.act == ACT_RELU_GRAD) prefetch_mask_tile<BLOCK_N>(p, m_blk * BLOCK_M + ew * 32, n_blk * BLOCK_N, lane);
+        if (p.tma_store && p.act == ACT_RELU_GRAD) {
+          // this tile's mask on the first iteration, then always the NEXT tile's: a whole epilogue ahead of its use
+          if (tile == (int) blockIdx.x) prefetch_mask_tile<BLOCK_N>(p, m_blk * BLOCK_M + ew * 32, n_blk * BLOCK_N, lane);
+          const int nt = tile + (int) gridDim.x;
+          if (nt < num_tiles) {
+            const int mn2 = nt % mn_tiles;
+            prefetch_mask_tile<BLOCK_N>(p, (mn2 / n_tiles) * BLOCK_M + ew * 32, (mn2 % n_tiles) * BLOCK_N, lane);
+          }
+        }
       }
       mbar_wait(&tmem_full_bar[accum_stage], accum_phase);
       tc_fence_after();
@@ -576,8 +584,15 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int mn = tile % mn_tiles;
       const int m_blk = mn / n_tiles, n_blk = mn % n_tiles;
-      if (p.tma_store && p.act == ACT_RELU_GRAD)
-        prefetch_mask_tile<kPairN>(p, m_blk * 2 * BLOCK_M + (int) cta_rank * BLOCK_M + ew * 32, n_blk * kPairN, lane);
+      if (p.tma_store && p.act == ACT_RELU_GRAD) {
+        // this tile's mask on the first iteration, then always the NEXT tile's: a whole epilogue ahead of its use
+        if (tile == cluster_id) prefetch_mask_tile<kPairN>(p, m_blk * 2 * BLOCK_M + (int) cta_rank * BLOCK_M + ew * 32, n_blk * kPairN, lane);
+        const int nt = tile + num_clusters;
+        if (nt < num_tiles) {
+          const int mn2 = nt % mn_tiles;
+          prefetch_mask_tile<kPairN>(p, (mn2 / n_tiles) * 2 * BLOCK_M + (int) cta_rank * BLOCK_M + ew * 32, (mn2 % n_tiles) * kPairN, lane);
+        }
+      }
       mbar_wait(&tmem_full_bar[accum_stage], accum_phase);
       tc_fence_after();
       const int row = m_blk * 2 * BLOCK_M + (int) cta_rank * BLOCK_M + ew * 32 + lane;

@@ -116,8 +116,12 @@ __global__ void __launch_bounds__(256) tbe_bwd_build_keys(const TbeBwdParams p) 
 
 // ---- optimizer application on one unique row ------------------------------------------------
 // g[k] holds the summed gradient for elements (lane + 32k)*4 .. +3 of the row.
-template <typename W, int MAXV>
-__device__ __forceinline__ void apply_row(const TbeBwdParams& p, int64_t key, int f, float4 (&g)[MAXV], int lane) {
+// PRE: the caller already issued the loads of the weight row (`wpre`) and, for row-wise Adagrad, of the row state (`spre`, lane 0)
+// BEFORE it accumulated the gradient: the three round trips of a run (gradient rows, weight row, state) overlap instead of
+// following each other.
+template <typename W, int MAXV, bool PRE = false>
+__device__ __forceinline__ void apply_row(const TbeBwdParams& p, int64_t key, int f, float4 (&g)[MAXV], int lane, const float4* wpre = nullptr,
+                                          float spre = 0.f) {
   const int OPT = p.opt;
   const int D = p.feat_dim[f];
   const int nvec = D >> 2;
@@ -131,7 +135,8 @@ __device__ __forceinline__ void apply_row(const TbeBwdParams& p, int64_t key, in
 #pragma unroll
   for (int k = 0; k < MAXV; ++k) {
     const int vi = lane + k * 32;
-    wv[k] = (vi < nvec && OPT != OPT_NONE) ? Vec4<W>::ld(w + vi * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (PRE) wv[k] = wpre[k];
+    else wv[k] = (vi < nvec && OPT != OPT_NONE) ? Vec4<W>::ld(w + vi * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     if (maxg > 0.f) {
       g[k].x = fminf(fmaxf(g[k].x, -maxg), maxg);
       g[k].y = fminf(fmaxf(g[k].y, -maxg), maxg);
@@ -165,7 +170,7 @@ __device__ __forceinline__ void apply_row(const TbeBwdParams& p, int64_t key, in
 #pragma unroll
     for (int k = 0; k < MAXV; ++k) sq += f4_sq(g[k]);  // lanes beyond nvec hold zeros
     sq = warp_sum(sq) / (float) D;
-    float st = (lane == 0) ? p.state1[key] : 0.f;
+    float st = PRE ? spre : ((lane == 0) ? p.state1[key] : 0.f);
     st = __shfl_sync(0xffffffffu, st, 0);
     const float ns = st + sq;
     if (lane == 0) p.state1[key] = ns;
@@ -467,6 +472,23 @@ __global__ void __launch_bounds__(256) tbe_bwd_chunk_kernel(const TbeBwdParams p
     }
     const K rk = __shfl_sync(0xffffffffu, key, a);
     if (rk == sentinel) break;  // padding / invalid ids sort last
+    const int f = __shfl_sync(0xffffffffu, bag, a) / p.B;
+    const bool head_open = (a == 0) && has_prev && (rk == prev_key);
+    const bool tail_open = (bnd == cnt) && has_next && (rk == next_key);
+    // weight row and row state first: their latency overlaps the gradient gather below
+    constexpr bool kPre = MAXV <= 4;  // wide rows (MAXV = 16) would spill: they keep the in-order loads
+    float4 wpre[kPre ? MAXV : 1];
+    float spre = 0.f;
+    if (kPre && !head_open && !tail_open) {
+      const int nvec_w = p.feat_dim[f] >> 2;
+      const W* wrow = reinterpret_cast<const W*>(p.weights) + p.feat_woff[f] + ((int64_t) rk - p.feat_rowbase[f]) * p.feat_dim[f];
+#pragma unroll
+      for (int k = 0; k < (kPre ? MAXV : 1); ++k) {
+        const int vi = lane + k * 32;
+        wpre[k] = (vi < nvec_w && p.opt != OPT_NONE) ? Vec4<W>::ld(wrow + vi * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (p.opt == OPT_ROWWISE_ADAGRAD && lane == 0) spre = p.state1[rk];
+    }
     float4 acc[MAXV];
 #pragma unroll
     for (int k = 0; k < MAXV; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -476,11 +498,9 @@ __global__ void __launch_bounds__(256) tbe_bwd_chunk_kernel(const TbeBwdParams p
       const float esc = __shfl_sync(0xffffffffu, scale, e);
       load_grad_row<G, MAXV>(p, ebag, esc, lane, acc);
     }
-    const int f = __shfl_sync(0xffffffffu, bag, a) / p.B;
-    const bool head_open = (a == 0) && has_prev && (rk == prev_key);
-    const bool tail_open = (bnd == cnt) && has_next && (rk == next_key);
     if (!head_open && !tail_open) {
-      apply_row<W, MAXV>(p, (int64_t) rk, f, acc, lane);
+      if constexpr (kPre) apply_row<W, MAXV, true>(p, (int64_t) rk, f, acc, lane, wpre, spre);
+      else apply_row<W, MAXV>(p, (int64_t) rk, f, acc, lane);
     } else {
       const int slot = head_open ? 0 : 1;
       if (!head_open) wrote_slot1 = true;
