@@ -330,9 +330,11 @@ def main() -> None:
             out = pipe.progress(it)
         barrier()
         e0.record()
+        t_e2e0 = time.perf_counter()
         for _ in range(args.steps):
             out = pipe.progress(it)
             loss_host.copy_(out[0].detach().reshape(1), non_blocking=True)  # D2H read of the step's loss
+        e2e_host_ms = (time.perf_counter() - t_e2e0) * 1e3 / args.steps
         e1.record()
         barrier()
         ms2 = e0.elapsed_time(e1)
@@ -340,7 +342,7 @@ def main() -> None:
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
         e2e = {"value": B * world * args.steps / (float(t2.item()) / 1e3), "unit": "samples/s",
-               "h2d_bytes_per_step": host_batches[0].nbytes(), "d2h_bytes_per_step": 4, "ms_per_step": float(t2.item()) / args.steps,
+               "h2d_bytes_per_step": host_batches[0].nbytes(), "d2h_bytes_per_step": 4, "ms_per_step": float(t2.item()) / args.steps, "host_enqueue_ms_per_step": e2e_host_ms,
                "loss": float(loss_host.item())}
 
     if args.profile_host:

@@ -920,9 +920,9 @@ __global__ void __launch_bounds__(256) trb_colsum_bf16_kernel(const __nv_bfloat1
 // thread, (b) narrow matrices fold several rows into one warp (vpr = lanes per row) so every lane loads, (c) block partials
 // go to a workspace and the LAST block of a column group (ticket counter) sums them in a fixed order: no float atomics,
 // deterministic result, one launch.
-__global__ void __launch_bounds__(256) trb_colsum_bf16_v3_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int rows, int cols,
-                                                                   int64_t ld, int rows_per_block, int vpr_log2, float* __restrict__ partial,
-                                                                   unsigned int* __restrict__ tickets) {
+template <bool CLUSTER>
+__device__ __forceinline__ void colsum_v3_body(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int rows, int cols, int64_t ld,
+                                               int rows_per_block, int vpr_log2, float* __restrict__ partial, unsigned int* __restrict__ tickets) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int vpr = 1 << vpr_log2, rpw = 32 >> vpr_log2;  // lanes per row, rows per warp
   const int sub = lane >> vpr_log2;
@@ -980,22 +980,37 @@ __global__ void __launch_bounds__(256) trb_colsum_bf16_v3_kernel(const __nv_bflo
   const int l = threadIdx.x >> 3, j = threadIdx.x & 7;
   const int col = blockIdx.x * 256 + threadIdx.x;
   const bool col_ok = l < vpr && col < cols;
+  float s = 0.f;
   if (col_ok) {
-    float s = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) s += red[i][l][j];
-    if (gridDim.y == 1) {
-      out[col] = s;
-      return;
-    }
-    partial[(int64_t) blockIdx.y * cols + col] = s;
   }
-  if (gridDim.y == 1) return;
+  // CLUSTER: the 8 CTAs of a (1,8,1) cluster first fold their column sums through the leader's shared memory (DSMEM), so a
+  // launch produces gridDim.y / 8 partials: short row slabs per thread (4 batches of 8 loads) AND a short last-block tail.
+  int n_part = (int) gridDim.y, my_part = (int) blockIdx.y;
+  if constexpr (CLUSTER) {
+    __shared__ float cl[8][256];
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t dst = mapa_shared(smem_u32(&cl[rank][threadIdx.x]), 0);
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(dst), "f"(s) : "memory");
+    cluster_sync_all();
+    if (rank != 0) return;
+    s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += cl[i][threadIdx.x];
+    n_part = (int) gridDim.y >> 3;
+    my_part = (int) blockIdx.y >> 3;
+  }
+  if (n_part == 1) {
+    if (col_ok) out[col] = s;
+    return;
+  }
+  if (col_ok) partial[(int64_t) my_part * cols + col] = s;
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_ticket = atomicAdd(&tickets[blockIdx.x], 1u);
   __syncthreads();
-  if (s_ticket != gridDim.y - 1) return;
+  if (s_ticket != (unsigned) n_part - 1) return;
   __threadfence();
   // last block of this column group: fixed-order sum of the partials. C = vpr * 8 columns; 256 / C thread groups split the
   // partial rows, 8 loads in flight each, then one smem pass over the groups
@@ -1007,14 +1022,14 @@ __global__ void __launch_bounds__(256) trb_colsum_bf16_v3_kernel(const __nv_bflo
     if (gcol < cols) {
       const float* pc = partial + gcol;
       int y = g;
-      for (; y + 7 * G < (int) gridDim.y; y += 8 * G) {
+      for (; y + 7 * G < n_part; y += 8 * G) {
         float t[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) t[u] = __ldcg(pc + (int64_t) (y + u * G) * cols);
 #pragma unroll
         for (int u = 0; u < 8; ++u) s += t[u];
       }
-      for (; y < (int) gridDim.y; y += G) s += __ldcg(pc + (int64_t) y * cols);
+      for (; y < n_part; y += G) s += __ldcg(pc + (int64_t) y * cols);
     }
     float* fin = &red[0][0][0];  // 256 floats needed, 2304 available; all earlier reads of red are done (barriers above)
     fin[threadIdx.x] = s;
@@ -1028,6 +1043,18 @@ __global__ void __launch_bounds__(256) trb_colsum_bf16_v3_kernel(const __nv_bflo
   if (threadIdx.x == 0) tickets[blockIdx.x] = 0;  // ready for the next launch on this stream
 }
 
+__global__ void __launch_bounds__(256) trb_colsum_bf16_v3_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int rows, int cols,
+                                                                   int64_t ld, int rows_per_block, int vpr_log2, float* __restrict__ partial,
+                                                                   unsigned int* __restrict__ tickets) {
+  colsum_v3_body<false>(in, out, rows, cols, ld, rows_per_block, vpr_log2, partial, tickets);
+}
+
+__global__ void __cluster_dims__(1, 8, 1) __launch_bounds__(256)
+trb_colsum_bf16_v4_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int rows, int cols, int64_t ld, int rows_per_block,
+                          int vpr_log2, float* __restrict__ partial, unsigned int* __restrict__ tickets) {
+  colsum_v3_body<true>(in, out, rows, cols, ld, rows_per_block, vpr_log2, partial, tickets);
+}
+
 // per-device workspace of the column-sum kernel (tickets + block partials); kernels that use it are stream ordered
 size_t g_colsum_ws_bytes_dev[64] = {};
 void* g_colsum_ws_dev[64] = {};
@@ -1038,15 +1065,21 @@ TRB_API int trb_colsum_bf16(const void* in, float* out, int rows, int cols, int6
   const int nvec = cols / 8;
   const int xblocks = (nvec + 31) / 32;
   static const int variant = [] { const char* e = getenv("TRB_COLSUM"); return e ? atoi(e) : 3; }();
-  if (variant == 3) {
+  if (variant == 3 || variant == 4) {
     int vpr_log2 = 5;
     while (vpr_log2 > 0 && (1 << (vpr_log2 - 1)) >= nvec) --vpr_log2;
     const int rpw = 32 >> vpr_log2;
     int yblocks = (4 * 148 + xblocks - 1) / xblocks;
-    if (yblocks > 64) yblocks = 64;  // the last block of a column group sums yblocks partials: keep that tail short
+    const bool clustered = variant == 4 && rows >= 2048;
+    if (clustered) {
+      if (yblocks > 256) yblocks = 256;  // 8-CTA clusters fold through DSMEM: 32 partials at most reach the last-block tail
+    } else if (yblocks > 64) {
+      yblocks = 64;  // the last block of a column group sums yblocks partials: keep that tail short
+    }
     int rows_per_block = (rows + yblocks - 1) / yblocks;
     rows_per_block = (rows_per_block + 8 * rpw - 1) / (8 * rpw) * (8 * rpw);
     yblocks = (rows + rows_per_block - 1) / rows_per_block;
+    if (clustered) yblocks = (yblocks + 7) / 8 * 8;  // trailing blocks past `rows` contribute zeros
     // workspace (per process, stream-ordered use: the dense backward runs on one stream): tickets then partial sums
     const size_t need = 4096 + sizeof(float) * (size_t) yblocks * (size_t) cols;
     int dev = 0;
@@ -1062,9 +1095,14 @@ TRB_API int trb_colsum_bf16(const void* in, float* out, int rows, int cols, int6
     }
     if (xblocks > 1024) return -12;
     dim3 grid(xblocks, yblocks);
-    trb_colsum_bf16_v3_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*) in, out, rows, cols, ld, rows_per_block, vpr_log2,
-                                                        reinterpret_cast<float*>(static_cast<char*>(g_colsum_ws) + 4096),
-                                                        reinterpret_cast<unsigned int*>(g_colsum_ws));
+    if (clustered)
+      trb_colsum_bf16_v4_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*) in, out, rows, cols, ld, rows_per_block, vpr_log2,
+                                                          reinterpret_cast<float*>(static_cast<char*>(g_colsum_ws) + 4096),
+                                                          reinterpret_cast<unsigned int*>(g_colsum_ws));
+    else
+      trb_colsum_bf16_v3_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*) in, out, rows, cols, ld, rows_per_block, vpr_log2,
+                                                          reinterpret_cast<float*>(static_cast<char*>(g_colsum_ws) + 4096),
+                                                          reinterpret_cast<unsigned int*>(g_colsum_ws));
     TRB_CHECK_LAUNCH();
     return 0;
   }
