@@ -240,6 +240,10 @@ def main() -> None:
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     device = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(device)
+    if os.environ.get("TRB_BENCH_BIND_NUMA", "1") != "0":
+        from torchrec_b200.utils.affinity import bind_to_gpu_numa
+
+        bind_to_gpu_numa(local_rank)  # pinned staging buffers + launch threads on the GPU's socket (H2D does not cross sockets)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group(backend="nccl", device_id=device)

@@ -179,3 +179,18 @@ def test_lazy_extension():
     seq = lazy_apply(torch.nn.Sequential(torch.nn.LazyLinear(2)), lambda mod: seen.append("s"))
     seq(torch.randn(3, 5))
     assert seen.count("s") == 2
+
+
+def test_affinity_helper_is_safe_without_gpu():
+    import os
+
+    from torchrec_b200.utils.affinity import bind_to_gpu_numa, gpu_local_cpus
+
+    before = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    cpus = gpu_local_cpus(0)
+    assert cpus is None or (isinstance(cpus, set) and all(isinstance(c, int) for c in cpus))
+    new = bind_to_gpu_numa(0)
+    if new is None and before is not None:
+        assert os.sched_getaffinity(0) == before  # no NVML / no GPU: nothing changes
+    if before is not None:
+        os.sched_setaffinity(0, before)

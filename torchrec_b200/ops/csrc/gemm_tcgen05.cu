@@ -1064,7 +1064,7 @@ TRB_API int trb_colsum_bf16(const void* in, float* out, int rows, int cols, int6
   if (cols % 8 || ld % 8) return -12;
   const int nvec = cols / 8;
   const int xblocks = (nvec + 31) / 32;
-  static const int variant = [] { const char* e = getenv("TRB_COLSUM"); return e ? atoi(e) : 3; }();
+  static const int variant = [] { const char* e = getenv("TRB_COLSUM"); return e ? atoi(e) : 4; }();
   if (variant == 3 || variant == 4) {
     int vpr_log2 = 5;
     while (vpr_log2 > 0 && (1 << (vpr_log2 - 1)) >= nvec) --vpr_log2;
