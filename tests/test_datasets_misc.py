@@ -105,3 +105,31 @@ def test_tensor_dict_interop_and_uintx():
     v2 = torch.randint(0, 4, (2, 16))
     p2 = UInt2Tensor.pack(v2)
     assert p2.elem.shape == (2, 4) and torch.equal(p2.unpack().long(), v2) and p2[0].shape == (1, 16)
+
+
+def test_group_index_select_and_inference_gathers():
+    import torch
+
+    from torchrec_b200.ops import jagged as J
+    from torchrec_b200.ops.uvm import is_uvm_tensor, new_unified_tensor
+    from torchrec_b200.parallel.dist_data import all_to_one_device, merge_pooled_embeddings, sum_reduce_to_one
+
+    g = torch.Generator().manual_seed(0)
+    xs = [torch.randn(5, 4, generator=g, requires_grad=True), torch.randn(7, 4, generator=g, requires_grad=True), torch.randn(3, 2, generator=g, requires_grad=True)]
+    idx = [torch.tensor([4, 0, 0, 2]), torch.tensor([6, 1]), torch.tensor([2, 2, 1])]
+    outs = J.group_index_select_dim0(xs, idx)
+    for x, i, o in zip(xs, idx, outs):
+        assert torch.equal(o, x.index_select(0, i))
+    sum(o.sum() for o in outs).backward()
+    assert torch.equal(xs[0].grad[:, 0], torch.tensor([2.0, 0.0, 1.0, 0.0, 1.0]))
+    lengths = torch.tensor([1, 2, 0, 1, 3, 1])  # F=3, stride=2
+    values = torch.arange(8)
+    pl, pv, _ = J.permute_2D_sparse_data_input1D(torch.tensor([2, 0], dtype=torch.int32), lengths, values, 2)
+    assert pl.tolist() == [3, 1, 1, 2] and pv.tolist() == [4, 5, 6, 7, 0, 1, 2]
+    cpu = torch.device("cpu")
+    a, b = torch.ones(2, 3), torch.full((2, 2), 2.0)
+    assert merge_pooled_embeddings([a, b], 2, cpu, 1).shape == (2, 5)
+    assert torch.equal(sum_reduce_to_one([a, a * 2], cpu), a * 3)
+    assert all_to_one_device([a, b], cpu)[1] is b
+    u = new_unified_tensor(a, (4, 8))
+    assert u.shape == (4, 8) and is_uvm_tensor(u) and not is_uvm_tensor(a)

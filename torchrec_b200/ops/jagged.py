@@ -7,7 +7,7 @@ the caller did not pass it.
 from __future__ import annotations
 
 import ctypes
-from typing import List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 
@@ -307,6 +307,42 @@ def jagged_unique_indices(hash_size_cumsum: torch.Tensor, hash_size_offsets: tor
     out_offsets = asynchronous_complete_cumsum(out_lengths)
     base = hash_size_cumsum.long()[torch.searchsorted(hash_size_cumsum.long()[1:], uniq, right=True)]
     return out_lengths, out_offsets, (uniq - base).to(indices.dtype), inv
+
+
+def group_index_select_dim0(inputs: Sequence[torch.Tensor], indices: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    """``[x.index_select(0, i) for x, i in zip(inputs, indices)]`` as one op (fbgemm ``group_index_select_dim0``: a single
+    launch over a group of tensors with different row counts / widths; used by the reference's pooled-embedding arch and VBE
+    re-expansion). Same-width members are gathered by one kernel over their concatenation; autograd flows through."""
+    assert len(inputs) == len(indices)
+    out: List[Optional[torch.Tensor]] = [None] * len(inputs)
+    by_shape: Dict[Tuple, List[int]] = {}
+    for k, x in enumerate(inputs):
+        by_shape.setdefault((tuple(x.shape[1:]), x.dtype, x.device), []).append(k)
+    for ks in by_shape.values():
+        if len(ks) == 1:
+            k = ks[0]
+            out[k] = inputs[k].index_select(0, indices[k].long())
+            continue
+        base, cat_idx = 0, []
+        for k in ks:
+            cat_idx.append(indices[k].long() + base)
+            base += inputs[k].shape[0]
+        gathered = torch.cat([inputs[k] for k in ks], dim=0).index_select(0, torch.cat(cat_idx))
+        pos = 0
+        for k in ks:
+            n = indices[k].numel()
+            out[k] = gathered[pos : pos + n]
+            pos += n
+    return out  # type: ignore[return-value]
+
+
+def permute_2D_sparse_data_input1D(permute: torch.Tensor, lengths: torch.Tensor, values: torch.Tensor, stride: int,
+                                   weights: Optional[torch.Tensor] = None, permuted_lengths_sum: Optional[int] = None):
+    """``permute_2D_sparse_data`` for lengths given flat (``[F * stride]``); returns flat permuted lengths (fbgemm op of the same
+    name, used by the KJT all-to-all recat)."""
+    F = lengths.numel() // max(stride, 1)
+    pl, pv, pw = permute_2D_sparse_data(permute, lengths.view(F, stride), values, weights, permuted_lengths_sum)
+    return pl.reshape(-1), pv, pw
 
 
 def permute_pooled_embs(pooled: torch.Tensor, offset_dim_list: Sequence[int], permute_list: Sequence[int]) -> torch.Tensor:

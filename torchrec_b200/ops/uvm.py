@@ -272,3 +272,25 @@ class UvmCachedEmbeddingBags(nn.Module):
             self.slot_of_row[t].fill_(-1)
             self.row_of_slot[t].fill_(-1)
             self.score[t].zero_()
+
+
+# ---- unified-memory tensor helpers (fbgemm ``new_unified_tensor`` / ``is_uvm_tensor``) ----------------------------
+_UVM_TENSORS: "weakref.WeakValueDictionary[int, torch.Tensor]" = None  # type: ignore[assignment]
+
+
+def new_unified_tensor(like: torch.Tensor, sizes: Sequence[int], is_host_mapped: bool = True) -> torch.Tensor:
+    """A tensor of ``like``'s dtype that both the host and the GPU of ``like`` can address: pinned host memory mapped into the
+    device address space (zero-copy, what ``EmbeddingLocation.MANAGED`` tables use). On a CPU-only box it is plain host memory."""
+    global _UVM_TENSORS
+    import weakref
+
+    if _UVM_TENSORS is None:
+        _UVM_TENSORS = weakref.WeakValueDictionary()
+    t = torch.empty(tuple(sizes), dtype=like.dtype, device="cpu", pin_memory=torch.cuda.is_available())
+    _UVM_TENSORS[t.data_ptr()] = t
+    return t
+
+
+def is_uvm_tensor(t: torch.Tensor) -> bool:
+    """True for tensors made by :func:`new_unified_tensor` (or views sharing their base pointer)."""
+    return _UVM_TENSORS is not None and t.device.type == "cpu" and t.data_ptr() in _UVM_TENSORS

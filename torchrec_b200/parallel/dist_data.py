@@ -461,6 +461,51 @@ class MergePooledEmbeddingsModule(nn.Module):
         return torch.cat([t.to(self._device, non_blocking=True) for t in tensors], dim=1)
 
 
+# ---- single-process multi-GPU gathers (fbgemm merge_pooled_embeddings / sum_reduce_to_one / all_to_one_device) ----
+def all_to_one_device(inputs: List[torch.Tensor], target_device: torch.device) -> List[torch.Tensor]:
+    """Copy every tensor to ``target_device`` (NVLink P2P, no NCCL). Each source device's copy is issued on that device's
+    current stream and the target stream waits for all of them, so the copies of different sources overlap."""
+    target_device = torch.device(target_device)
+    if target_device.type != "cuda":
+        return [t.to(target_device) for t in inputs]
+    out: List[torch.Tensor] = []
+    events = []
+    for t in inputs:
+        if t.device == target_device:
+            out.append(t)
+            continue
+        if t.is_cuda:
+            with torch.cuda.device(t.device):
+                moved = t.to(target_device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(t.device))
+            events.append(ev)
+        else:
+            moved = t.to(target_device, non_blocking=True)
+        out.append(moved)
+    cur = torch.cuda.current_stream(target_device)
+    for ev in events:
+        cur.wait_event(ev)
+    return out
+
+
+def merge_pooled_embeddings(pooled_embeddings: List[torch.Tensor], uncat_dim_size: int, target_device: torch.device, cat_dim: int = 1) -> torch.Tensor:
+    """Gather per-device pooled embeddings onto ``target_device`` and concatenate along ``cat_dim`` (the other dim has
+    ``uncat_dim_size`` entries)."""
+    moved = all_to_one_device(pooled_embeddings, target_device)
+    for t in moved:
+        assert t.shape[1 - cat_dim] == uncat_dim_size, (t.shape, uncat_dim_size, cat_dim)
+    return torch.cat(moved, dim=cat_dim) if len(moved) > 1 else moved[0]
+
+
+def sum_reduce_to_one(inputs: List[torch.Tensor], target_device: torch.device) -> torch.Tensor:
+    """Sum same-shaped per-device tensors on ``target_device`` (row-wise sharded inference output)."""
+    moved = all_to_one_device(inputs, target_device)
+    if len(moved) == 1:
+        return moved[0]
+    return torch.stack(moved, dim=0).sum(dim=0)
+
+
 class EmbeddingsAllToOne(nn.Module):
     def __init__(self, device: torch.device, world_size: int, cat_dim: int) -> None:
         super().__init__()
@@ -470,9 +515,7 @@ class EmbeddingsAllToOne(nn.Module):
 
     def forward(self, tensors: List[torch.Tensor]) -> torch.Tensor:
         assert len(tensors) <= self._world_size
-        non_cat = 1 - self._cat_dim
-        moved = [t.to(self._device, non_blocking=True) for t in tensors]
-        return torch.cat(moved, dim=self._cat_dim) if len(moved) > 1 else moved[0]
+        return merge_pooled_embeddings(tensors, tensors[0].shape[1 - self._cat_dim], self._device, self._cat_dim)
 
 
 class EmbeddingsAllToOneReduce(nn.Module):
@@ -482,11 +525,7 @@ class EmbeddingsAllToOneReduce(nn.Module):
         self._world_size = world_size
 
     def forward(self, tensors: List[torch.Tensor]) -> torch.Tensor:
-        moved = [t.to(self._device, non_blocking=True) for t in tensors]
-        out = moved[0]
-        for t in moved[1:]:
-            out = out + t
-        return out
+        return sum_reduce_to_one(tensors, self._device)
 
 
 class SeqEmbeddingsAllToOne(nn.Module):
@@ -496,4 +535,4 @@ class SeqEmbeddingsAllToOne(nn.Module):
         self._world_size = world_size
 
     def forward(self, tensors: List[torch.Tensor]) -> List[torch.Tensor]:
-        return [t.to(self._device, non_blocking=True) for t in tensors]
+        return all_to_one_device(tensors, self._device)
