@@ -54,6 +54,7 @@ def parse_args() -> argparse.Namespace:
                         "end to end 15.4 M -> 17.7 M samples/s on one GPU); 0: eager")
     p.add_argument("--profile-host", action="store_true", help="cProfile 10 extra steps on rank 0 (stderr)")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--trace-e2e", type=str, default="", help="diagnostics: torch.profiler trace (chrome json + op table) of 6 extra pipeline steps")
     p.add_argument("--num-host-batches", type=int, default=8)
     return p.parse_args()
 
@@ -349,6 +350,24 @@ def main() -> None:
                "h2d_bytes_per_step": host_batches[0].nbytes(), "d2h_bytes_per_step": 4, "ms_per_step": float(t2.item()) / args.steps, "host_enqueue_ms_per_step": e2e_host_ms,
                "loss": float(loss_host.item())}
 
+    if args.trace_e2e and not args.no_e2e:
+        from torch.profiler import ProfilerActivity, profile
+
+        it3 = host_iter(6 + 4)
+        for _ in range(2):
+            pipe.progress(it3)
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            for _ in range(4):
+                out = pipe.progress(it3)
+                loss_host.copy_(out[0].detach().reshape(1), non_blocking=True)
+            torch.cuda.synchronize()
+        if rank == 0:
+            prof.export_chrome_trace(args.trace_e2e)
+            with open(args.trace_e2e + ".txt", "w") as f:
+                f.write(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=45, max_name_column_width=70))
+                f.write("\n\n")
+                f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=30, max_name_column_width=70))
     if args.profile_host:
         # where does the host time of a step go? (diagnostics only; every rank runs the same steps: the NVLink barriers are collective)
         import cProfile

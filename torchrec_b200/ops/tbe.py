@@ -553,6 +553,8 @@ class _PooledLookupFn(torch.autograd.Function):
     def backward(ctx, grad):
         indices, offsets, psw = ctx.saved_tensors
         tbe = ctx.tbe
+        if tbe.__dict__.get("_fs") is not None:
+            tbe._fs.before_backward()
         gpsw = None
         if psw is not None and ctx.needs_input_grad[4]:
             # windowed offsets (engine groups) index into the full values tensor: the gradient is positional
@@ -572,6 +574,8 @@ class _SeqLookupFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad):
         indices, offsets = ctx.saved_tensors
+        if ctx.tbe.__dict__.get("_fs") is not None:
+            ctx.tbe._fs.before_backward()
         dense = ctx.tbe._backward_seq(indices, offsets, grad, ctx.B)
         return dense, None, None, None, None
 
@@ -728,9 +732,16 @@ class TableBatchedEmbeddingBags(nn.Module):
         F = len(self.feature_table_map)
         B = batch_size if batch_size is not None else (offsets.numel() - 1) // max(F, 1)
         anchor = self.weights if self._dummy is None else self._dummy
+        fs = self.__dict__.get("_fs")  # FULLY_SHARDED 2D strategy (parallel/fully_sharded.py): full weights only around the kernels
+        if fs is not None:
+            fs.before_forward()
         if self.pooling_mode == PoolingMode.NONE:
-            return _SeqLookupFn.apply(anchor, self, indices, offsets, B)
-        return _PooledLookupFn.apply(anchor, self, indices, offsets, per_sample_weights, B)
+            out = _SeqLookupFn.apply(anchor, self, indices, offsets, B)
+        else:
+            out = _PooledLookupFn.apply(anchor, self, indices, offsets, per_sample_weights, B)
+        if fs is not None and torch.is_grad_enabled():
+            fs.after_forward()
+        return out
 
     def _pre_update(self) -> None:
         if self._needs_step() and self._auto_step:

@@ -112,7 +112,19 @@ def _sharded_tensor_from_local(local: List[Tuple[torch.Tensor, List[int], List[i
     """Build a ShardedTensor from local shard tensors + the global shard layout (no communication)."""
     if pg is None or not dist.is_initialized():
         return local[0][0] if len(local) == 1 else torch.cat([t for t, _, _ in local], dim=len(size) - 1)
-    dev_of = lambda r: placement(device_type, r, local_size)
+    # shard layouts are written in ranks of the SHARDING group (2D parallel: a sub-group of the job); ShardedTensor wants global ranks
+    try:
+        to_global = (lambda r: r) if pg is dist.group.WORLD else (lambda r: dist.get_global_rank(pg, r))
+        to_global(0)
+    except Exception:
+        to_global = lambda r: r
+
+    def dev_of(r: int) -> str:
+        if r == rank and local:
+            d = local[0][0].device
+            return f"rank:{to_global(r)}/{d.type}" + (f":{d.index}" if d.index is not None else "")
+        return placement(device_type, to_global(r), local_size)
+
     metas = [ShardMetadata(shard_offsets=list(o), shard_sizes=list(s), placement=dev_of(r)) for o, s, r in global_shards]
     local_shards = [Shard(tensor=t, metadata=ShardMetadata(shard_offsets=list(o), shard_sizes=list(s), placement=dev_of(rank))) for t, o, s in local]
     md = ShardedTensorMetadata(

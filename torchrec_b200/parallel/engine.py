@@ -787,6 +787,9 @@ class _FusedLookupDistFn(torch.autograd.Function):
         from . import p2p
 
         W = eng._W
+        for tbe in eng._tbes:  # FULLY_SHARDED 2D strategy: full weights only around the kernels
+            if tbe.__dict__.get("_fs") is not None:
+                tbe._fs.before_forward()
         slot = st.step % st.N_SLOTS
         st.step += 1
         out_ptrs = st.buf.peer_ptrs(st.out_off[slot])
@@ -817,6 +820,10 @@ class _FusedLookupDistFn(torch.autograd.Function):
         ctx.eng, ctx.st, ctx.Bg, ctx.grad_scale = eng, st, Bg, grad_scale
         ctx.dp = dp
         ctx.save_for_backward(values, offsets, weights)
+        if any(t.requires_grad for t in (anchor,)):
+            for tbe in eng._tbes:
+                if tbe.__dict__.get("_fs") is not None:
+                    tbe._fs.after_forward()
         return out
 
     @staticmethod
@@ -826,6 +833,9 @@ class _FusedLookupDistFn(torch.autograd.Function):
 
         eng, st, Bg = ctx.eng, ctx.st, ctx.Bg
         values, offsets, weights = ctx.saved_tensors
+        for tbe in eng._tbes:
+            if tbe.__dict__.get("_fs") is not None:
+                tbe._fs.before_backward()
         if grad.stride(1) != 1:
             grad = grad.contiguous()
         if st.push:

@@ -474,6 +474,41 @@ class DMPCollection(DistributedModelParallel):
                             use_inter_host_allreduce=use_inter_host_allreduce, replica_pg=self._default_ctx.replica_pg)
         super().__init__(module, env, device, plan, sharders, init_data_parallel, init_parameters, data_parallel_wrapper)
         self._sync_cache: Optional[List[torch.Tensor]] = None
+        self._fully_sharded: List[Any] = []
+        self._attach_fully_sharded()
+
+    # ---- FULLY_SHARDED strategy (reference batched_embedding_kernel.py:4425-4640, model_parallel.py:1470-1530) --------------
+    def _engines(self, ctx: DMPCollectionContext):
+        for sharded, _ in ctx.modules_to_sync:
+            inner = [m for m in sharded.modules() if hasattr(m, "engine")] or [sharded]
+            for m in inner:
+                eng = getattr(m, "engine", None)
+                if eng is not None:
+                    yield eng
+
+    def _attach_fully_sharded(self) -> None:
+        """Embedding shards of FULLY_SHARDED contexts are replica-averaged after every forward lookup and held as 1/R slices
+        until their backward (``parallel/fully_sharded.py``)."""
+        from .fully_sharded import attach
+
+        for ctx in self._ctxs:
+            if ctx.sharding_strategy != ShardingStrategy.FULLY_SHARDED or ctx.replica_pg is None or dist.get_world_size(ctx.replica_pg) == 1:
+                continue
+            for eng in self._engines(ctx):
+                for tbe in eng._tbes:
+                    fs = attach(tbe, ctx.replica_pg)
+                    if fs is not None:
+                        self._fully_sharded.append(fs)
+
+    def await_rs_awaitables(self) -> None:
+        """Make every FULLY_SHARDED weight buffer whole again (before a checkpoint, an eval pass that bypasses the lookup
+        functions, or a plan change). Collective over the replica groups. Reference: model_parallel.py:1472-1503."""
+        for fs in self._fully_sharded:
+            fs.gather()
+
+    def state_dict(self, *args: Any, **kwargs: Any):  # type: ignore[override]
+        self.await_rs_awaitables()
+        return super().state_dict(*args, **kwargs)
 
     # ---- process groups --------------------------------------------------------------------------------------
     @staticmethod
@@ -536,7 +571,8 @@ class DMPCollection(DistributedModelParallel):
                     if eng is None:
                         continue
                     for tbe in eng._tbes:
-                        out.append((tbe.weights.data, ctx.replica_pg))
+                        if ctx.sharding_strategy != ShardingStrategy.FULLY_SHARDED:  # those are averaged by every forward
+                            out.append((tbe.weights.data, ctx.replica_pg))
                         if include_optimizer_state:
                             for st in (tbe.state1, tbe.state2):
                                 if st is not None and st.numel():
