@@ -244,7 +244,8 @@ def main() -> None:
     if os.environ.get("TRB_BENCH_BIND_NUMA", "1") != "0":
         from torchrec_b200.utils.affinity import bind_to_gpu_numa
 
-        bind_to_gpu_numa(local_rank)  # pinned staging buffers + launch threads on the GPU's socket (H2D does not cross sockets)
+        _bound = bind_to_gpu_numa(local_rank)  # pinned staging buffers + launch threads on the GPU's socket (H2D does not cross sockets)
+        globals()["_CPU_BINDING"] = f"{len(_bound)} NUMA-local cpus" if _bound else "unchanged"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group(backend="nccl", device_id=device)
@@ -425,6 +426,7 @@ def main() -> None:
                 "l2_policy": "inputs > L2: %d distinct batches, random rows of multi-GB tables (L2 126 MB)" % len(dev_batches),
                 "dense_backend": dense_backend,
                 "cuda_graphs": "dense sub-modules (fwd+bwd)" if args.cuda_graphs else "off",
+                "cpu_binding": globals().get("_CPU_BINDING", "off"),
             },
             "clocks": clocks,
             "gpu_launches": int(launches),

@@ -53,6 +53,12 @@ def _wait_for_batch(batch: In, stream: Optional[torch.Stream]) -> None:
     batch.record_stream(cur_stream)
 
 
+def _reduce_losses(losses: torch.Tensor) -> torch.Tensor:
+    """Scalar to differentiate: the sum over the leading dim for per-task / per-sample losses, the loss itself when the model
+    already returns a scalar (saves a reduction kernel + its autograd node on every step)."""
+    return losses if losses.dim() == 0 else torch.sum(losses, dim=0)
+
+
 def _wait_for_events(batch: In, context: TrainPipelineContext, stream: Optional[torch.Stream]) -> None:
     for event in context.events:
         event.wait()
@@ -115,7 +121,7 @@ class TrainPipelineBase(TrainPipeline[In, Out]):
 
     def _backward(self, losses: torch.Tensor) -> None:
         with record_function("## backward ##"):
-            torch.sum(losses, dim=0).backward()
+            _reduce_losses(losses).backward()
 
     def _copy_batch_to_gpu(self, cur_batch: In) -> None:
         with record_function("## copy_batch_to_gpu ##"):
@@ -458,7 +464,7 @@ class TrainPipelineSparseDist(TrainPipeline[In, Out]):
             self.wait_sparse_data_dist(self.contexts[1])
         if self._model.training:
             with record_function(f"## backward {self.contexts[0].index} ##"):
-                torch.sum(losses, dim=0).backward()
+                _reduce_losses(losses).backward()
             self.sync_embeddings()
             with record_function(f"## optimizer {self.contexts[0].index} ##"):
                 self._optimizer.step()
@@ -508,7 +514,7 @@ class TrainPipelineSparseDistLite(TrainPipelineSparseDist[In, Out]):
         if has_next:
             self.start_sparse_data_dist(self.batches[1], self.contexts[1])
         if self._model.training:
-            torch.sum(losses, dim=0).backward()
+            _reduce_losses(losses).backward()
         if has_next:
             self.wait_sparse_data_dist(self.contexts[1])
         if self._model.training:
@@ -608,7 +614,7 @@ class TrainPipelineSemiSync(TrainPipelineSparseDist[In, Out]):
             if self.contexts[1].index is not None and self.contexts[1].index >= self._start_batch:
                 self._start_embedding_lookup(self.batches[1], self.contexts[1])
         if self._model.training:
-            torch.sum(losses, dim=0).backward()
+            _reduce_losses(losses).backward()
             self._optimizer.step()
         self.dequeue_batch()
         return output
@@ -671,7 +677,7 @@ class TrainPipelineFusedSparseDist(TrainPipelineSparseDist[In, Out]):
         if len(self.batches) >= 2:
             self.wait_sparse_data_dist(self.contexts[1])
         if self._model.training:
-            torch.sum(losses, dim=0).backward()
+            _reduce_losses(losses).backward()
             if len(self.batches) >= 2 and not self._embedding_lookup_after_opt:
                 if self._emb_stream is not None:
                     self._emb_stream.wait_stream(torch.cuda.current_stream())
@@ -725,7 +731,7 @@ class PrefetchTrainPipelineSparseDist(TrainPipelineSparseDist[In, Out]):
             self.wait_sparse_data_dist(self.contexts[1])
             self._prefetch(self.contexts[1])
         if self._model.training:
-            torch.sum(losses, dim=0).backward()
+            _reduce_losses(losses).backward()
             self._optimizer.step()
         self.dequeue_batch()
         return output

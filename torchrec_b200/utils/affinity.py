@@ -28,6 +28,29 @@ def gpu_local_cpus(device_index: int) -> Optional[Set[int]]:
         finally:
             pynvml.nvmlShutdown()
         cpus = {w * 64 + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        if cpus:
+            return cpus
+    except Exception:
+        pass
+    return _sysfs_local_cpus(device_index)
+
+
+def _sysfs_local_cpus(device_index: int) -> Optional[Set[int]]:
+    """Fallback without NVML: the PCI device's ``local_cpulist`` in sysfs."""
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(device_index)
+        path = f"/sys/bus/pci/devices/{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0/local_cpulist"
+        with open(path) as f:
+            text = f.read().strip()
+        cpus: Set[int] = set()
+        for part in text.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
         return cpus or None
     except Exception:
         return None
