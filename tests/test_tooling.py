@@ -194,3 +194,59 @@ def test_affinity_helper_is_safe_without_gpu():
         assert os.sched_getaffinity(0) == before  # no NVML / no GPU: nothing changes
     if before is not None:
         os.sched_setaffinity(0, before)
+
+
+def test_benchmark_harness_cmd_conf_and_loggers(tmp_path):
+    from dataclasses import dataclass
+    from typing import List, Optional
+
+    import torch
+
+    from torchrec_b200.benchmarks.base import benchmark_func, cmd_conf
+    from torchrec_b200.parallel.global_settings import get_propogate_device, set_propogate_device
+    from torchrec_b200.parallel.logger import ForkedPdb, PercentileLogger, log_table_assignment
+
+    @dataclass
+    class RunCfg:
+        batch_size: int = 8
+        name: str = "x"
+        flags: Optional[List[int]] = None
+        fast: bool = False
+
+    @dataclass
+    class ModelCfg:
+        dim: int = 4
+        lr: float = 0.1
+
+    @cmd_conf
+    def main(run: RunCfg, model: ModelCfg, tag: str = "t"):
+        return run, model, tag
+
+    cfg = tmp_path / "c.yml"
+    cfg.write_text("batch_size: 32\nModelCfg:\n  dim: 16\n  lr: 0.5\ntag: from_file\n")
+    run, model, tag = main(["--yaml_config", str(cfg), "--dim", "64", "--flags", "1", "2", "--fast", "true"])
+    assert (run.batch_size, run.name, run.flags, run.fast) == (32, "x", [1, 2], True)
+    assert (model.dim, model.lr, tag) == (64, 0.5, "from_file")   # CLI > file > default
+
+    x = torch.randn(64, 64)
+    res = benchmark_func("matmul", lambda: x @ x, num_benchmarks=4, num_warmup=1, profile_dir=str(tmp_path / "prof"))
+    assert res.gpu_elapsed_time.numel() == 4 and res.runtime_percentile(50) >= 0 and "matmul" in str(res)
+    assert any(p.name.startswith("trace-matmul") for p in (tmp_path / "prof").iterdir())
+
+    pl = PercentileLogger("lat", log_every=10)
+    for i in range(100):
+        pl.add(i)
+    p = pl.percentiles()
+    assert p[50] in (49.0, 50.0) and p[99] >= 97.0 and "p90" in pl.summary()
+    set_propogate_device(True)
+    assert get_propogate_device()
+    set_propogate_device(False)
+    assert hasattr(ForkedPdb(), "set_trace")
+
+    class _PS:
+        sharding_type, compute_kernel, ranks = "table_wise", "fused", [1]
+
+    class _Plan:
+        plan = {"ebc": {"t0": _PS()}}
+
+    assert log_table_assignment(_Plan())[0]["table"] == "t0"

@@ -117,3 +117,88 @@ class EventLoggingHandler:
             return wrapper  # type: ignore[return-value]
 
         return decorator
+
+
+# ---- percentile logger, planner decision logs, multiprocess debugger (reference logging_handlers.py:207-441, utils.py:578-597) ----
+class PercentileLogger:
+    """Collects samples (e.g. per-step latencies, wait counters) and logs p50/p90/p99 every ``log_every`` additions."""
+
+    def __init__(self, name: str, log_every: int = 1000, max_samples: int = 100000, logger: "Optional[logging.Logger]" = None) -> None:
+        import logging as _logging
+
+        self.name, self.log_every, self.max_samples = name, log_every, max_samples
+        self._samples: "List[float]" = []
+        self._n = 0
+        self._logger = logger or _logging.getLogger(__name__)
+
+    def add(self, value: float) -> None:
+        self._n += 1
+        if len(self._samples) < self.max_samples:
+            self._samples.append(float(value))
+        else:
+            self._samples[self._n % self.max_samples] = float(value)
+        if self._n % self.log_every == 0:
+            self._logger.info("%s", self.summary())
+
+    def percentiles(self, qs=(50, 90, 99)) -> "Dict[int, float]":
+        if not self._samples:
+            return {q: float("nan") for q in qs}
+        s = sorted(self._samples)
+        return {q: s[min(len(s) - 1, int(round(q / 100.0 * (len(s) - 1))))] for q in qs}
+
+    def summary(self) -> str:
+        p = self.percentiles()
+        return f"[{self.name}] n={self._n} " + " ".join(f"p{q}={v:.4g}" for q, v in p.items())
+
+
+def log_planner_config(planner: object, logger: "Optional[logging.Logger]" = None) -> "Dict[str, object]":
+    """Structured record of how a planner was configured (topology, proposers, partitioner, constraints)."""
+    import logging as _logging
+
+    topo = getattr(planner, "_topology", None)
+    rec = {
+        "planner": type(planner).__name__,
+        "world_size": getattr(topo, "world_size", None), "local_world_size": getattr(topo, "local_world_size", None),
+        "compute_device": getattr(topo, "compute_device", None),
+        "hbm_cap": getattr(getattr(topo, "devices", [None])[0], "storage", None) and topo.devices[0].storage.hbm,
+        "proposers": [type(p).__name__ for p in getattr(planner, "_proposers", [])],
+        "partitioner": type(getattr(planner, "_partitioner", None)).__name__,
+        "constraints": sorted((getattr(planner, "_constraints", None) or {}).keys()),
+    }
+    (logger or _logging.getLogger(__name__)).info("planner config: %s", rec)
+    return rec
+
+
+def log_table_assignment(plan: object, logger: "Optional[logging.Logger]" = None) -> "List[Dict[str, object]]":
+    """One record per table of a ShardingPlan: sharding type, compute kernel, ranks."""
+    import logging as _logging
+
+    out = []
+    for path, mod_plan in getattr(plan, "plan", {}).items():
+        for table, ps in mod_plan.items():
+            out.append({"module": path, "table": table, "sharding_type": getattr(ps, "sharding_type", None),
+                        "compute_kernel": getattr(ps, "compute_kernel", None), "ranks": list(getattr(ps, "ranks", None) or [])})
+    lg = logger or _logging.getLogger(__name__)
+    for r in out:
+        lg.info("table assignment: %s", r)
+    return out
+
+
+class ForkedPdb:
+    """``pdb`` usable inside a forked / spawned rank: re-opens /dev/stdin for the session (reference distributed/utils.py:578-597).
+    ``ForkedPdb().set_trace()`` in a rank, attach from the launching terminal."""
+
+    def __new__(cls, *args, **kwargs):
+        import pdb
+        import sys
+
+        class _Forked(pdb.Pdb):
+            def interaction(self, *a, **k):
+                stdin = sys.stdin
+                try:
+                    sys.stdin = open("/dev/stdin")
+                    pdb.Pdb.interaction(self, *a, **k)
+                finally:
+                    sys.stdin = stdin
+
+        return _Forked(*args, **kwargs)
