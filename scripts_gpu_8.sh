@@ -2,8 +2,8 @@
 # 8-GPU box: bench at N=8 and N=4 (device-timed + e2e), health checks in between
 mkdir -p gpurun_out
 health() { timeout 60 nvidia-smi --query-gpu=index,memory.used --format=csv,noheader | tr '\n' ' '; echo; }
-for n in 8 4; do
-timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29550+n)) bench.py --gpus $n --steps 20 --warmup 5 > gpurun_out/bench${n}_full.log 2>&1; echo "rc=$?"; health
+for n in 8; do
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29550+n)) bench.py --gpus $n --steps 20 --warmup 5 > gpurun_out/bench${n}_full.log 2>&1; echo "rc=$?"; health
 grep "^{" gpurun_out/bench${n}_full.log | tail -1 > gpurun_out/bench${n}.json
 python - gpurun_out/bench${n}.json <<'PY'
 import json,sys
