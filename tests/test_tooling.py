@@ -250,3 +250,29 @@ def test_benchmark_harness_cmd_conf_and_loggers(tmp_path):
         plan = {"ebc": {"t0": _PS()}}
 
     assert log_table_assignment(_Plan())[0]["table"] == "t0"
+
+
+def test_benchmark_scripts_run_tiny():
+    from torchrec_b200.benchmarks import benchmark_ebc, benchmark_inference, benchmark_zch
+
+    res = benchmark_ebc.run(benchmark_ebc.EbcBenchConfig(num_tables=2, num_embeddings=100, embedding_dim=8, batch_size=16, pooling_factor=2, num_benchmarks=2, num_warmup=1,
+                                                        device="cpu"))
+    assert [r.short_name for r in res] == ["ebc_fwd_bwd_sgd", "fused_ebc_fwd_bwd_sgd", "quant_ebc_int8_fwd"]
+    z = benchmark_zch.run(benchmark_zch.ZchBenchConfig(zch_size=64, id_space=1000, batch_size=128, num_benchmarks=4, num_warmup=2, device="cpu"))
+    assert z["ids_per_s"] > 0 and 0.0 < z["in_zch_range"] <= 1.0
+    inf = benchmark_inference.run(benchmark_inference.InferenceBenchConfig(num_tables=2, num_embeddings=100, embedding_dim=8, batch_size=8, num_benchmarks=2, num_warmup=1))
+    assert inf[0].gpu_elapsed_time.numel() == 2
+
+
+def _lifecycle(ctx):
+    from torchrec_b200.benchmarks import benchmark_model_lifecycle as L
+
+    t = L.run(L.LifecycleConfig(num_tables=3, num_embeddings=200, embedding_dim=8, batch_size=8, device="cpu"))
+    assert set(t) == {"build_meta_ms", "plan_ms", "shard_materialise_ms", "state_dict_ms", "load_state_dict_ms", "first_step_ms"}
+    assert all(v >= 0 for v in t.values())
+
+
+def test_benchmark_model_lifecycle_gloo():
+    from torchrec_b200.utils.multiprocess import run_multi_process
+
+    run_multi_process(_lifecycle, world_size=2, backend="gloo")
