@@ -224,3 +224,28 @@ def test_grad_push_kernel_single_gpu(vec, sdtype):
     torch.testing.assert_close(inbox[0][B : 2 * B, :40].float(), exp0.to(torch.bfloat16).float(), rtol=1e-2, atol=1e-2)
     torch.testing.assert_close(inbox[1][B : 2 * B, :16].float(), exp1.to(torch.bfloat16).float(), rtol=1e-2, atol=1e-2)
     assert float(inbox[0][:B].abs().sum()) == 0.0 and float(inbox[1][B:, 16:].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("wdtype,ulp", [(torch.bfloat16, 2.0**-7), (torch.float16, 2.0**-10)])
+def test_stochastic_rounding_kernel_is_unbiased(wdtype, ulp):
+    """Low-precision tables: an update of ulp/16 per step is lost by round-to-nearest and kept in expectation by the kernel's
+    stochastic rounding (reproducible for a given sr_seed)."""
+    dev = torch.device("cuda:0")
+
+    def run(sr: bool, seed: int = 7):
+        tbe = T.TableBatchedEmbeddingBags([(256, 128)], optimizer=T.OptimType.EXACT_SGD, learning_rate=1.0, weights_precision=wdtype, output_dtype=torch.float32,
+                                          stochastic_rounding=sr, sr_seed=seed, device=dev)
+        with torch.no_grad():
+            tbe.weights.fill_(1.0)
+        idx, off = torch.arange(256, device=dev), torch.arange(257, device=dev)
+        g = torch.full((256, 128), -ulp / 16, device=dev)
+        for _ in range(32):
+            tbe(idx, off).backward(g)
+        return tbe.weights.float().cpu()
+
+    assert torch.equal(run(False), torch.ones(256 * 128))
+    w = run(True)
+    assert abs(w.mean().item() - (1.0 + 2 * ulp)) < 0.05 * ulp          # 32 steps x ulp/16 = 2 ulp on average
+    assert set(w.unique().tolist()) <= {1.0 + k * ulp for k in range(0, 9)} and w.unique().numel() >= 3
+    assert torch.equal(w, run(True))                                      # same seed, same noise
+    assert not torch.equal(w, run(True, seed=8))

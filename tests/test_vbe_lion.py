@@ -79,3 +79,32 @@ def _run_vbe(ctx, sharding: str):
 @pytest.mark.parametrize("sharding", ["tw", "rw"])
 def test_sharded_vbe(sharding):
     run_multi_process(_run_vbe, world_size=2, backend="gloo", sharding=sharding)
+
+
+def test_stochastic_rounding_is_unbiased_cpu_reference():
+    """bf16 / fp16 tables: an update far below half an ulp vanishes with round-to-nearest and survives in expectation with SR."""
+    import torch
+
+    from torchrec_b200.ops.tbe import OptimType, TableBatchedEmbeddingBags, stochastic_round
+
+    x = torch.full((200000,), 1.0 + 2.0**-10)       # bf16 ulp at 1.0 is 2^-7: x sits 1/8 of the way to the next value
+    r = stochastic_round(x, torch.bfloat16, torch.Generator().manual_seed(0)).float()
+    assert set(r.unique().tolist()) == {1.0, 1.0 + 2.0**-7}
+    assert abs(r.mean().item() - x[0].item()) < 2e-5
+    xh = torch.full((200000,), 1.0 + 2.0**-12)       # fp16 ulp at 1.0 is 2^-10: 1/4 of the way
+    rh = stochastic_round(xh, torch.float16, torch.Generator().manual_seed(1)).float()
+    assert abs(rh.mean().item() - xh[0].item()) < 1e-5 and rh.unique().numel() == 2
+
+    def run(sr: bool) -> float:
+        torch.manual_seed(0)
+        tbe = TableBatchedEmbeddingBags([(4, 64)], optimizer=OptimType.EXACT_SGD, learning_rate=1.0, weights_precision=torch.bfloat16, output_dtype=torch.float32,
+                                        stochastic_rounding=sr, sr_seed=7)
+        with torch.no_grad():
+            tbe.weights.fill_(1.0)
+        idx, off = torch.arange(4), torch.arange(5)
+        for _ in range(64):
+            tbe(idx, off).backward(torch.full((4, 64), -2.0**-11))   # each step wants +2^-11, 1/16 of a bf16 ulp
+        return tbe.weights.float().mean().item()
+
+    assert run(False) == 1.0                                  # round-to-nearest: every update is lost
+    assert abs(run(True) - (1.0 + 64 * 2.0**-11)) < 6e-3      # SR: the mean moves by the requested 2^-5 (noise ~ 1e-3)

@@ -77,6 +77,8 @@ struct TbeBwdParams {
   uint8_t* chunk_done;  // [chunks] set by tbe_bwd_unique_kernel (nullptr: generic walk handles everything)
   int32_t* long_list;   // [chunks] first chunks of spans longer than kLongSpan pieces
   int32_t* long_count;  // zeroed by tbe_bwd_build_keys
+  int sr;               // 1: stochastic rounding of the updated row when the table is bf16 / fp16 (unbiased low-precision training)
+  unsigned long long sr_seed;
   int prefetch;         // 1: lanes prefetch their key's rows into L2 ahead of the walk (bit 1: also the gradient rows = local memory)
   int32_t max_dim;
   int32_t key64;
@@ -112,6 +114,48 @@ __global__ void __launch_bounds__(256) tbe_bwd_build_keys(const TbeBwdParams p) 
   else reinterpret_cast<uint32_t*>(p.keys)[i] = (uint32_t) key;
   p.vals[i] = (int32_t) i;
   p.bag_of[i] = bag;
+}
+
+// ---- stochastic rounding (FBGEMM `stochastic_rounding=True` for FP16/BF16 tables) -------------------------------------------------
+// Round-to-nearest loses every update smaller than half an ulp of the stored weight; rounding up with probability
+// (x - lo) / (hi - lo) keeps the expected value exact. Random bits: splitmix64 of (seed, row key, vector index): one 64-bit hash =
+// 4 x 16 bits for the 4 elements a lane stores; deterministic for a given (seed, step).
+__device__ __forceinline__ unsigned long long trb_splitmix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+__device__ __forceinline__ __nv_bfloat16 trb_sr_bf16(float x, unsigned r16) {
+  unsigned b = __float_as_uint(x);
+  if ((b & 0x7F800000u) != 0x7F800000u) b += r16;  // finite: add 16 random low bits, then truncate
+  return __ushort_as_bfloat16((unsigned short) (b >> 16));
+}
+
+__device__ __forceinline__ __half trb_sr_half(float x, unsigned r16) {
+  const __half lo = __float2half_rd(x), hi = __float2half_ru(x);
+  const float flo = __half2float(lo), fhi = __half2float(hi);
+  if (!(fhi > flo)) return lo;  // exactly representable, inf or nan
+  const float pr = (x - flo) / (fhi - flo);
+  return ((float) r16 * (1.f / 65536.f) < pr) ? hi : lo;
+}
+
+template <typename W>
+__device__ __forceinline__ void trb_store_row4_sr(W* dst, float4 v, unsigned long long rnd) {
+  Vec4<W>::st(dst, v);
+}
+template <>
+__device__ __forceinline__ void trb_store_row4_sr<__nv_bfloat16>(__nv_bfloat16* dst, float4 v, unsigned long long rnd) {
+  __nv_bfloat16 o[4] = {trb_sr_bf16(v.x, (unsigned) (rnd & 0xFFFF)), trb_sr_bf16(v.y, (unsigned) ((rnd >> 16) & 0xFFFF)),
+                        trb_sr_bf16(v.z, (unsigned) ((rnd >> 32) & 0xFFFF)), trb_sr_bf16(v.w, (unsigned) ((rnd >> 48) & 0xFFFF))};
+  *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(o);
+}
+template <>
+__device__ __forceinline__ void trb_store_row4_sr<__half>(__half* dst, float4 v, unsigned long long rnd) {
+  __half o[4] = {trb_sr_half(v.x, (unsigned) (rnd & 0xFFFF)), trb_sr_half(v.y, (unsigned) ((rnd >> 16) & 0xFFFF)),
+                 trb_sr_half(v.z, (unsigned) ((rnd >> 32) & 0xFFFF)), trb_sr_half(v.w, (unsigned) ((rnd >> 48) & 0xFFFF))};
+  *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(o);
 }
 
 // ---- optimizer application on one unique row ------------------------------------------------
@@ -278,7 +322,10 @@ __device__ __forceinline__ void apply_row(const TbeBwdParams& p, int64_t key, in
 #pragma unroll
   for (int k = 0; k < MAXV; ++k) {
     const int vi = lane + k * 32;
-    if (vi < nvec) Vec4<W>::st(w + vi * 4, wv[k]);
+    if (vi < nvec) {
+      if (sizeof(W) == 2 && p.sr) trb_store_row4_sr<W>(w + vi * 4, wv[k], trb_splitmix64(p.sr_seed ^ ((unsigned long long) key * 0xD1B54A32D192ED03ull) ^ (unsigned long long) vi));
+      else Vec4<W>::st(w + vi * 4, wv[k]);
+    }
   }
 }
 
@@ -722,6 +769,14 @@ static int dispatch_dim(TbeBwdParams& p, char* ws, cudaStream_t stream) {
 }
 
 // Fused backward + optimizer. `workspace` must hold trb_tbe_bwd_workspace_bytes(n, max_dim, total_rows).
+TRB_API int trb_tbe_bwd_fused_ex(void* weights, int w_dtype, float* state1, float* state2, const float* hyper, int opt,
+                                 int wd_mode, const int64_t* feat_woff, const int64_t* feat_rows,
+                                 const int64_t* feat_rowbase, const int32_t* feat_dim, const int32_t* feat_col,
+                                 const void* indices, int idx64, const void* offsets, int off64, const float* psw,
+                                 void* const* grad_ptrs, int n_grad, int grad_dtype, int64_t grad_stride, int64_t n,
+                                 int64_t total_rows, int B, int B_local, int F, int max_dim, int mean, void* workspace,
+                                 int stochastic_rounding, unsigned long long sr_seed, cudaStream_t stream);
+
 TRB_API int trb_tbe_bwd_fused(void* weights, int w_dtype, float* state1, float* state2, const float* hyper, int opt,
                               int wd_mode, const int64_t* feat_woff, const int64_t* feat_rows,
                               const int64_t* feat_rowbase, const int32_t* feat_dim, const int32_t* feat_col,
@@ -729,6 +784,18 @@ TRB_API int trb_tbe_bwd_fused(void* weights, int w_dtype, float* state1, float* 
                               void* const* grad_ptrs, int n_grad, int grad_dtype, int64_t grad_stride, int64_t n,
                               int64_t total_rows, int B, int B_local, int F, int max_dim, int mean, void* workspace,
                               cudaStream_t stream) {
+  return trb_tbe_bwd_fused_ex(weights, w_dtype, state1, state2, hyper, opt, wd_mode, feat_woff, feat_rows, feat_rowbase, feat_dim, feat_col, indices,
+                              idx64, offsets, off64, psw, grad_ptrs, n_grad, grad_dtype, grad_stride, n, total_rows, B, B_local, F, max_dim, mean,
+                              workspace, 0, 0ull, stream);
+}
+
+TRB_API int trb_tbe_bwd_fused_ex(void* weights, int w_dtype, float* state1, float* state2, const float* hyper, int opt,
+                                 int wd_mode, const int64_t* feat_woff, const int64_t* feat_rows,
+                                 const int64_t* feat_rowbase, const int32_t* feat_dim, const int32_t* feat_col,
+                                 const void* indices, int idx64, const void* offsets, int off64, const float* psw,
+                                 void* const* grad_ptrs, int n_grad, int grad_dtype, int64_t grad_stride, int64_t n,
+                                 int64_t total_rows, int B, int B_local, int F, int max_dim, int mean, void* workspace,
+                                 int stochastic_rounding, unsigned long long sr_seed, cudaStream_t stream) {
   if (n <= 0) return 0;
   if (n_grad < 1 || n_grad > TRB_MAX_PEERS) return -1;
   if ((int64_t) B_local * n_grad != B) return -4;
@@ -759,6 +826,8 @@ TRB_API int trb_tbe_bwd_fused(void* weights, int w_dtype, float* state1, float* 
   p.max_dim = max_dim;
   p.key64 = total_rows >= ((int64_t) 1 << 32) - 1;
   p.opt = opt;
+  p.sr = stochastic_rounding ? 1 : 0;
+  p.sr_seed = sr_seed;
   {
     static const int pf = getenv("TRB_BWD_PREFETCH") ? atoi(getenv("TRB_BWD_PREFETCH")) : 1;
     p.prefetch = pf ? (1 | (n_grad <= 1 ? 2 : 0)) : 0;  // peer-resident gradient rows bypass the local L2: do not prefetch them

@@ -330,7 +330,32 @@ def _ref_apply(opt: int, wd_mode: int, hyper: List[float], weights, state1, stat
         gn, wn = g.norm(dim=1), w.norm(dim=1)
         ratio = torch.where((gn > 0) & (wn > 0), eta * wn / (gn + wd * wn + eps), torch.ones_like(gn)).unsqueeze(1)
         w = w - lr * ratio * g
-    table[uniq] = w.to(table.dtype)
+    if _SR_REF["on"] and table.dtype in (torch.bfloat16, torch.float16):
+        table[uniq] = stochastic_round(w, table.dtype, _SR_REF["gen"])
+    else:
+        table[uniq] = w.to(table.dtype)
+
+
+_SR_REF = {"on": False, "gen": None}  # set around the reference backward by fused_backward(stochastic_rounding=...)
+
+
+def stochastic_round(x: torch.Tensor, dtype: torch.dtype, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+    """Unbiased rounding of fp32 ``x`` to bf16 / fp16: up with probability (x - lo) / (hi - lo) (torch mirror of the kernel's
+    ``trb_sr_bf16`` / ``trb_sr_half``; FBGEMM ``stochastic_rounding=True``)."""
+    x = x.float()
+    if dtype == torch.bfloat16:
+        bits = x.contiguous().view(torch.int32)
+        noise = torch.randint(0, 1 << 16, x.shape, generator=generator, device=x.device, dtype=torch.int32)
+        finite = torch.isfinite(x)
+        out = torch.where(finite, (bits + noise) & ~0xFFFF, bits & ~0xFFFF)
+        return out.view(torch.float32).to(torch.bfloat16)
+    near = x.to(dtype)
+    nf = near.float()
+    other = torch.nextafter(near, torch.where(x > nf, torch.full_like(near, float("inf")), torch.full_like(near, float("-inf"))))
+    span = (other.float() - nf).abs()
+    pr = torch.where(span > 0, (x - nf).abs() / span, torch.zeros_like(x))
+    u = torch.rand(x.shape, generator=generator, device=x.device)
+    return torch.where((u < pr) & torch.isfinite(other.float()), other, near)
 
 
 def _ref_fused_backward(meta, weights, state1, state2, hyper, opt, wd_mode, indices, offsets, psw, grad, B, mean, pooled=True):
@@ -441,11 +466,19 @@ def fused_backward(
     grad_stride: Optional[int] = None,
     grad_dtype: Optional[torch.dtype] = None,
     B_local: Optional[int] = None,
+    stochastic_rounding: bool = False,
+    sr_seed: int = 0,
 ) -> None:
-    """Exact fused backward + optimizer for a pooled lookup (gradient rows may live on peers)."""
+    """Exact fused backward + optimizer for a pooled lookup (gradient rows may live on peers). ``stochastic_rounding`` applies to
+    bf16 / fp16 tables only: the updated row is rounded up or down with probability proportional to the distance."""
     if not _lib.use_cuda_kernels(weights, indices):
         assert grad is not None
-        _ref_fused_backward(meta, weights, state1, state2, hyper_host, opt, wd_mode, indices, offsets, per_sample_weights, grad, B, mean)
+        _SR_REF["on"] = bool(stochastic_rounding)
+        _SR_REF["gen"] = torch.Generator().manual_seed(int(sr_seed) & 0x7FFFFFFF) if stochastic_rounding else None
+        try:
+            _ref_fused_backward(meta, weights, state1, state2, hyper_host, opt, wd_mode, indices, offsets, per_sample_weights, grad, B, mean)
+        finally:
+            _SR_REF["on"] = False
         return
     n = indices.numel()
     if n == 0:
@@ -462,15 +495,16 @@ def fused_backward(
     L.trb_tbe_bwd_workspace_bytes.restype = ctypes.c_int64
     nbytes = L.trb_tbe_bwd_workspace_bytes(ctypes.c_int64(n), meta.max_dim, ctypes.c_int64(meta.total_rows))
     ws = _workspace(nbytes, indices.device)
-    code = L.trb_tbe_bwd_fused(
+    code = L.trb_tbe_bwd_fused_ex(
         _lib.ptr(weights), _lib.dtype_code(weights.dtype), _lib.ptr(state1), _lib.ptr(state2), _lib.ptr(hyper_dev),
         opt, wd_mode, _lib.ptr(meta.feat_woff), _lib.ptr(meta.feat_rows), _lib.ptr(meta.feat_rowbase),
         _lib.ptr(meta.feat_dim), _lib.ptr(meta.feat_col), _lib.ptr(indices), _is64(indices), _lib.ptr(offsets),
         _is64(offsets), _lib.ptr(per_sample_weights), _lib.ptr_array(grad_ptrs), len(grad_ptrs),
         _lib.dtype_code(grad_dtype), ctypes.c_int64(grad_stride), ctypes.c_int64(n), ctypes.c_int64(meta.total_rows),
-        B, B_local, meta.num_features, meta.max_dim, int(mean), _lib.ptr(ws), _lib.stream_ptr(indices.device),
+        B, B_local, meta.num_features, meta.max_dim, int(mean), _lib.ptr(ws), int(bool(stochastic_rounding)), ctypes.c_uint64(int(sr_seed) & 0xFFFFFFFFFFFFFFFF),
+        _lib.stream_ptr(indices.device),
     )
-    _lib.check(code, "trb_tbe_bwd_fused")
+    _lib.check(code, "trb_tbe_bwd_fused_ex")
 
 
 def psw_grad(meta: TbeMeta, weights: torch.Tensor, indices: torch.Tensor, offsets: torch.Tensor, B: int, mean: bool, grad: Optional[torch.Tensor] = None,
@@ -516,11 +550,16 @@ def psw_grad(meta: TbeMeta, weights: torch.Tensor, indices: torch.Tensor, offset
     return out
 
 
-def sequence_backward(meta, weights, state1, state2, hyper_dev, hyper_host, opt, wd_mode, indices, offsets, B, grad):
+def sequence_backward(meta, weights, state1, state2, hyper_dev, hyper_host, opt, wd_mode, indices, offsets, B, grad, stochastic_rounding: bool = False, sr_seed: int = 0):
     """Backward of the unpooled lookup: position i contributes grad[i] to row indices[i].
     Expressed as a pooled backward with one bag per position (column offset 0, stride D)."""
     if not _lib.use_cuda_kernels(weights, indices):
-        _ref_fused_backward(meta, weights, state1, state2, hyper_host, opt, wd_mode, indices, offsets, None, grad, B, False, pooled=False)
+        _SR_REF["on"] = bool(stochastic_rounding)
+        _SR_REF["gen"] = torch.Generator().manual_seed(int(sr_seed) & 0x7FFFFFFF) if stochastic_rounding else None
+        try:
+            _ref_fused_backward(meta, weights, state1, state2, hyper_host, opt, wd_mode, indices, offsets, None, grad, B, False, pooled=False)
+        finally:
+            _SR_REF["on"] = False
         return
     n = indices.numel()
     if n == 0:
@@ -535,7 +574,8 @@ def sequence_backward(meta, weights, state1, state2, hyper_dev, hyper_host, opt,
     # rows: f, cols: position boundary -> flatten as F bags-of-n with shared final sentinel
     flat = torch.cat([bag_off[:, :-1].reshape(-1), fstart[-1:].reshape(1)]).contiguous()
     seq_meta = meta.with_cols([0] * F, meta.h_dim[0])
-    fused_backward(seq_meta, weights, state1, state2, hyper_dev, hyper_host, opt, wd_mode, indices, flat, None, n, False, grad=grad.contiguous())
+    fused_backward(seq_meta, weights, state1, state2, hyper_dev, hyper_host, opt, wd_mode, indices, flat, None, n, False, grad=grad.contiguous(),
+                   stochastic_rounding=stochastic_rounding, sr_seed=sr_seed)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -608,8 +648,13 @@ class TableBatchedEmbeddingBags(nn.Module):
         device: Optional[torch.device] = None,
         table_names: Optional[Sequence[str]] = None,
         location: "EmbeddingLocation" = None,  # type: ignore[assignment]
+        stochastic_rounding: bool = True,
+        sr_seed: int = 0,
     ) -> None:
         super().__init__()
+        # FBGEMM default: low-precision (fp16 / bf16) tables are updated with stochastic rounding; no effect on fp32 tables
+        self.stochastic_rounding = bool(stochastic_rounding) and weights_precision in (torch.float16, torch.bfloat16)
+        self._sr_seed, self._sr_calls = int(sr_seed), 0
         device = torch.device(device) if device is not None else torch.device("cpu")
         self.embedding_specs = [(int(r), int(d)) for r, d in embedding_specs]
         self.feature_table_map = list(feature_table_map) if feature_table_map is not None else list(range(len(self.embedding_specs)))
@@ -743,6 +788,11 @@ class TableBatchedEmbeddingBags(nn.Module):
             fs.after_forward()
         return out
 
+    def next_sr_seed(self) -> int:
+        """Seed of the next backward's rounding noise (changes every call, reproducible for a given ``sr_seed``)."""
+        self._sr_calls += 1
+        return (self._sr_seed * 0x9E3779B1 + self._sr_calls * 0x85EBCA77) & 0xFFFFFFFFFFFF
+
     def _pre_update(self) -> None:
         if self._needs_step() and self._auto_step:
             self.hyper_host[HP_STEP] += 1.0
@@ -755,7 +805,8 @@ class TableBatchedEmbeddingBags(nn.Module):
             fused_backward(self.meta, self.weights.detach(), gw, None, self.hyper_dev, self.hyper_host, 8, 0, indices, offsets, psw, B, mean, grad=grad)
             return gw.to(self.weights.dtype)
         self._pre_update()
-        fused_backward(self.meta, self.weights.detach(), self.state1, self.state2, self.hyper_dev, self.hyper_host, self.opt_code, int(self.weight_decay_mode), indices, offsets, psw, B, mean, grad=grad)
+        fused_backward(self.meta, self.weights.detach(), self.state1, self.state2, self.hyper_dev, self.hyper_host, self.opt_code, int(self.weight_decay_mode), indices, offsets, psw, B, mean, grad=grad,
+                       stochastic_rounding=self.stochastic_rounding, sr_seed=self.next_sr_seed())
         return torch.zeros_like(self._dummy)
 
     def _backward_seq(self, indices, offsets, grad, B) -> Optional[torch.Tensor]:
@@ -764,5 +815,6 @@ class TableBatchedEmbeddingBags(nn.Module):
             sequence_backward(self.meta, self.weights.detach(), gw, None, self.hyper_dev, self.hyper_host, 8, 0, indices, offsets, B, grad)
             return gw.to(self.weights.dtype)
         self._pre_update()
-        sequence_backward(self.meta, self.weights.detach(), self.state1, self.state2, self.hyper_dev, self.hyper_host, self.opt_code, int(self.weight_decay_mode), indices, offsets, B, grad)
+        sequence_backward(self.meta, self.weights.detach(), self.state1, self.state2, self.hyper_dev, self.hyper_host, self.opt_code, int(self.weight_decay_mode), indices, offsets, B, grad,
+                          stochastic_rounding=self.stochastic_rounding, sr_seed=self.next_sr_seed())
         return torch.zeros_like(self._dummy)

@@ -103,6 +103,8 @@ def optimizer_spec_from(param: Optional[torch.Tensor], fused_params: Optional[Di
             setattr(spec, dst, float(fp[src]))
     if "weight_decay_mode" in fp:
         spec.weight_decay_mode = WeightDecayMode(int(getattr(fp["weight_decay_mode"], "value", fp["weight_decay_mode"])))
+    if fp.get("stochastic_rounding") is not None:
+        spec.stochastic_rounding = bool(fp["stochastic_rounding"])
     return spec, tagged
 
 

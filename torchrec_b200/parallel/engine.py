@@ -74,9 +74,11 @@ class OptimizerSpec:
     weight_decay_mode: WeightDecayMode = WeightDecayMode.NONE
     max_gradient: float = 0.0
     momentum: float = 0.0
+    stochastic_rounding: bool = True  # fp16 / bf16 tables only (fused_params["stochastic_rounding"], FBGEMM default True)
 
     def key(self) -> Tuple:
-        return (self.optim, self.lr, self.eps, self.beta1, self.beta2, self.weight_decay, int(self.weight_decay_mode), self.max_gradient, self.momentum)
+        return (self.optim, self.lr, self.eps, self.beta1, self.beta2, self.weight_decay, int(self.weight_decay_mode), self.max_gradient, self.momentum,
+                bool(self.stochastic_rounding))
 
 
 def shards_of(table_idx: int, cfg: BaseEmbeddingConfig, ps: ParameterSharding) -> List[TableShard]:
@@ -245,6 +247,8 @@ class ShardedLookupEngine(nn.Module):
                 max_gradient=g.opt.max_gradient, momentum=g.opt.momentum,
                 device=device, table_names=[s.name for s in g.local_shards], **extra,
             )
+            if cls is TableBatchedEmbeddingBags:
+                tbe.stochastic_rounding = bool(g.opt.stochastic_rounding) and g.dtype in (torch.float16, torch.bfloat16)
             g.tbe = tbe
             self._tbes.append(tbe)
 
@@ -866,7 +870,8 @@ class _FusedLookupDistFn(torch.autograd.Function):
             g.tbe._pre_update()
             T.fused_backward(gm[meta_key], g.tbe.weights, g.tbe.state1, g.tbe.state2, g.tbe.hyper_dev, g.tbe.hyper_host, g.tbe.opt_code,
                              int(g.tbe.weight_decay_mode), values, window, weights, Bg, g.pooling == T.PoolingMode.MEAN,
-                             grad_ptrs=grad_ptrs, grad_stride=g_stride, grad_dtype=st.wire_dtype, B_local=g_blocal)
+                             grad_ptrs=grad_ptrs, grad_stride=g_stride, grad_dtype=st.wire_dtype, B_local=g_blocal,
+                             stochastic_rounding=g.tbe.stochastic_rounding, sr_seed=g.tbe.next_sr_seed() if g.tbe.stochastic_rounding else 0)
         if gpsw is not None:
             gpsw = gpsw.to(weights.dtype)
         g_dp = None
