@@ -144,3 +144,32 @@ def test_gemm_cta_pair_kernel(a_mn, b_mn, M, N, K, split):
         bias = torch.randn(N, device=dev)
         out_b = gemm_bf16(a, b, a_mn=a_mn, b_mn=b_mn, bias=bias, act=ACT_RELU, tile_n=512)
         torch.testing.assert_close(out_b.float(), torch.relu(ref + bias), rtol=2e-2, atol=6e-2)
+
+
+def test_low_rank_crossnet_on_tcgen05_matches_torch():
+    from torchrec_b200.modules.crossnet import LowRankCrossNet
+    from torchrec_b200.ops import dense as D
+
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    net = LowRankCrossNet(in_features=256, num_layers=2, low_rank=64).to(dev)
+    with torch.no_grad():
+        for b in net.bias:
+            b.normal_(0, 0.1)
+    x = (torch.randn(1000, 256, device=dev) * 0.5).requires_grad_()
+    prev = D.get_dense_backend()
+    try:
+        D.set_dense_backend("torch")
+        ref = net(x)
+        ref.sum().backward()
+        gref, gw_ref = x.grad.clone(), net.W_kernels[0].grad.clone()
+        x.grad = None
+        net.zero_grad()
+        D.set_dense_backend("tcgen05")
+        out = net(x)
+        out.sum().backward()
+    finally:
+        D.set_dense_backend(prev)
+    torch.testing.assert_close(out, ref, rtol=3e-2, atol=6e-2)
+    torch.testing.assert_close(x.grad, gref, rtol=5e-2, atol=1e-1)
+    torch.testing.assert_close(net.W_kernels[0].grad, gw_ref, rtol=5e-2, atol=2.0)

@@ -1,0 +1,98 @@
+"""Unsharded model families and cross networks vs their defining formulas (reference models/tests/test_dlrm.py, test_deepfm.py,
+modules/tests/test_crossnet.py)."""
+import torch
+
+from torchrec_b200.datasets.utils import Batch
+from torchrec_b200.models.deepfm import SimpleDeepFMNN
+from torchrec_b200.models.dlrm import DLRM, DLRM_DCN, DLRM_Projection, DLRMTrain, InteractionArch
+from torchrec_b200.modules.crossnet import CrossNet, LowRankCrossNet, LowRankMixtureCrossNet, VectorCrossNet
+from torchrec_b200.modules.embedding_configs import EmbeddingBagConfig
+from torchrec_b200.modules.embedding_modules import EmbeddingBagCollection
+from torchrec_b200.sparse import KeyedJaggedTensor
+
+
+def _ebc(F=3, D=8, rows=50):
+    return EmbeddingBagCollection([EmbeddingBagConfig(name=f"t{i}", embedding_dim=D, num_embeddings=rows, feature_names=[f"f{i}"]) for i in range(F)])
+
+
+def _batch(B=6, F=3, rows=50, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    lengths = torch.randint(0, 4, (F * B,), generator=g)
+    kjt = KeyedJaggedTensor(keys=[f"f{i}" for i in range(F)], values=torch.randint(0, rows, (int(lengths.sum()),), generator=g), lengths=lengths)
+    return Batch(dense_features=torch.randn(B, 5, generator=g), sparse_features=kjt, labels=torch.randint(0, 2, (B,), generator=g).float())
+
+
+def test_interaction_arch_is_pairwise_dots():
+    B, F, D = 4, 3, 8
+    dense, sparse = torch.randn(B, D), torch.randn(B, F, D)
+    out = InteractionArch(F)(dense, sparse)
+    x = torch.cat([dense.unsqueeze(1), sparse], 1)
+    gram = torch.bmm(x, x.transpose(1, 2))
+    pairs = torch.stack([gram[:, i, j] for i in range(F + 1) for j in range(i)], 1)
+    assert out.shape == (B, D + (F + 1) * F // 2)
+    torch.testing.assert_close(out[:, :D], dense)
+    torch.testing.assert_close(out[:, D:].sort(1).values, pairs.sort(1).values)
+
+
+def test_dlrm_family_forward_backward():
+    b = _batch()
+    models = [
+        DLRM(_ebc(), dense_in_features=5, dense_arch_layer_sizes=[16, 8], over_arch_layer_sizes=[16, 1]),
+        DLRM_Projection(_ebc(), dense_in_features=5, dense_arch_layer_sizes=[16, 8], over_arch_layer_sizes=[16, 1], interaction_branch1_layer_sizes=[16, 16],
+                        interaction_branch2_layer_sizes=[16, 8]),
+        DLRM_DCN(_ebc(), dense_in_features=5, dense_arch_layer_sizes=[16, 8], over_arch_layer_sizes=[16, 1], dcn_num_layers=2, dcn_low_rank_dim=4),
+    ]
+    for m in models:
+        logits = m(b.dense_features, b.sparse_features)
+        assert logits.shape == (6, 1)
+        loss, (dl, dlogits, dlabels) = DLRMTrain(m)(b)
+        assert loss.dim() == 0 and dlogits.shape == (6,) and torch.equal(dlabels, b.labels)
+        loss.backward()
+        grads = [p.grad for p in m.parameters()]
+        assert all(g is not None for g in grads) and any(float(g.abs().sum()) > 0 for g in grads)
+    ref = torch.nn.functional.binary_cross_entropy_with_logits(models[0](b.dense_features, b.sparse_features).squeeze(-1), b.labels)
+    torch.testing.assert_close(DLRMTrain(models[0])(b)[0], ref)
+
+
+def test_deepfm_forward_backward():
+    b = _batch()
+    m = SimpleDeepFMNN(num_dense_features=5, embedding_bag_collection=_ebc(), hidden_layer_size=16, deep_fm_dimension=4)
+    out = m(b.dense_features, b.sparse_features)
+    assert out.shape == (6, 1) and bool(((out >= 0) & (out <= 1)).all())
+    out.sum().backward()
+    assert all(p.grad is not None for p in m.parameters())
+
+
+def test_crossnets_match_their_formulas():
+    torch.manual_seed(0)
+    B, N = 5, 12
+    x0 = torch.randn(B, N)
+    full = CrossNet(N, 2)
+    x = x0
+    for W, b in zip(full.kernels, full.bias):
+        x = x0 * (x @ W.t() + b.squeeze(1)) + x
+    torch.testing.assert_close(full(x0), x)
+
+    low = LowRankCrossNet(N, 3, low_rank=4)
+    with torch.no_grad():
+        for b in low.bias:
+            b.normal_()
+    x = x0
+    for W, V, b in zip(low.W_kernels, low.V_kernels, low.bias):
+        x = x0 * ((x @ V.t()) @ W.t() + b) + x
+    torch.testing.assert_close(low(x0), x)
+
+    vec = VectorCrossNet(N, 2)
+    x = x0
+    for w, b in zip(vec.kernels, vec.bias):
+        x = x0 * (x @ w) + b.squeeze(1) + x
+    torch.testing.assert_close(vec(x0), x)
+
+    mix = LowRankMixtureCrossNet(N, 2, num_experts=3, low_rank=4)
+    out = mix(x0)
+    assert out.shape == (B, N)
+    out.sum().backward()
+    assert all(p.grad is not None for p in mix.parameters())
+    one = LowRankMixtureCrossNet(N, 1, num_experts=1, low_rank=4, activation=torch.nn.Identity())
+    U, V, C, b = one.U_kernels[0][0], one.V_kernels[0][0], one.C_kernels[0][0], one.bias[0].squeeze(1)
+    torch.testing.assert_close(one(x0), x0 * (((x0 @ V.t()) @ C.t()) @ U.t() + b) + x0)

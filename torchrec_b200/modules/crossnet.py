@@ -48,9 +48,26 @@ class LowRankCrossNet(nn.Module):
         self.bias: nn.ParameterList = nn.ParameterList(
             [nn.Parameter(nn.init.zeros_(torch.empty(in_features))) for _ in range(num_layers)])
 
+    def _tcgen05_ok(self, x: torch.Tensor) -> bool:
+        from ..ops import dense as _dense
+
+        return (_dense.get_dense_backend() == "tcgen05" and x.is_cuda and x.dim() == 2 and x.shape[1] % 8 == 0 and self._low_rank % 8 == 0)
+
     def forward(self, input: torch.Tensor) -> torch.Tensor:
         x_0 = input
         x_l = x_0
+        if self._tcgen05_ok(input):
+            # both projections on the hand-written sm_100a GEMM (bf16 operands, fp32 accumulation in TMEM, bias fused in the
+            # epilogue of the second one); the Hadamard + residual stay element-wise in the activation dtype
+            from ..ops import dense as _dense
+
+            x_0 = x_0.to(torch.bfloat16)
+            x_l = x_0
+            for layer in range(self._num_layers):
+                x_l_v = _dense.linear_act(x_l, self.V_kernels[layer], None, _dense.ACT_NONE)
+                x_l_w = _dense.linear_act(x_l_v, self.W_kernels[layer], self.bias[layer], _dense.ACT_NONE)
+                x_l = x_0 * x_l_w + x_l
+            return x_l.to(input.dtype) if input.dtype != torch.bfloat16 else x_l
         for layer in range(self._num_layers):
             x_l_v = torch.nn.functional.linear(x_l, self.V_kernels[layer])
             x_l_w = torch.nn.functional.linear(x_l_v, self.W_kernels[layer])
