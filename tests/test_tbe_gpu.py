@@ -246,6 +246,6 @@ def test_stochastic_rounding_kernel_is_unbiased(wdtype, ulp):
     assert torch.equal(run(False), torch.ones(256 * 128))
     w = run(True)
     assert abs(w.mean().item() - (1.0 + 2 * ulp)) < 0.05 * ulp          # 32 steps x ulp/16 = 2 ulp on average
-    assert set(w.unique().tolist()) <= {1.0 + k * ulp for k in range(0, 9)} and w.unique().numel() >= 3
+    assert set(w.unique().tolist()) <= {1.0 + k * ulp for k in range(0, 20)} and w.unique().numel() >= 3  # Binomial(32, 1/16) steps up
     assert torch.equal(w, run(True))                                      # same seed, same noise
     assert not torch.equal(w, run(True, seed=8))
