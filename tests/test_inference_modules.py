@@ -31,3 +31,64 @@ def test_quantize_and_shard_dlrm_for_inference_cpu():
     sharded, _ = shard_quant_model(q2, world_size=2, compute_device="cpu")
     got = sharded.sparse_arch.embedding_bag_collection(kjt).values()
     assert float((got - unsharded).abs().max()) < 0.05
+
+
+def test_dlrm_predict_factory_packager_and_request(tmp_path):
+    import numpy as np
+    import torch
+
+    from torchrec_b200.inference.client import create_request
+    from torchrec_b200.inference.dlrm_predict import DLRMModelConfig, DLRMPredictFactory, create_training_batch
+    from torchrec_b200.inference.model_packager import PredictFactoryPackager, load_config_text, load_pickle_config, load_predict_factory
+
+    keys = ["cat_0", "cat_1", "cat_2"]
+    cfg = DLRMModelConfig(dense_arch_layer_sizes=[16, 8], dense_in_features=4, embedding_dim=8, id_list_features_keys=keys, num_embeddings_per_feature=[50, 60, 70],
+                          num_embeddings=100, over_arch_layer_sizes=[16, 1])
+    factory = DLRMPredictFactory(cfg)
+    assert set(factory.batching_metadata()) == {"float_features", "id_list_features"} and "sparse" in factory.batching_metadata_json()
+    module = factory.create_predict_module(world_size=1, device="cpu")
+    batch = create_training_batch(4, keys, 50, batch_size=6, ids_per_feature=2)
+    out = module({"float_features": batch.dense_features, "id_list_features.lengths": batch.sparse_features.lengths(),
+                  "id_list_features.values": batch.sparse_features.values()})
+    assert out["default"].shape == (6,) and bool(((out["default"] >= 0) & (out["default"] <= 1)).all())
+
+    archive = tmp_path / "dlrm.zip"
+    PredictFactoryPackager.save_predict_factory(DLRMPredictFactory, {"model_config": cfg}, archive, extra_files={"readme.txt": "dlrm int8"},
+                                                state_dict={"w": torch.ones(2)})
+    again = load_predict_factory(archive)
+    assert isinstance(again, DLRMPredictFactory) and again.model_config.id_list_features_keys == keys
+    assert load_config_text(archive, "readme.txt") == "dlrm int8" and load_pickle_config(archive, "model_config").embedding_dim == 8
+
+    req = create_request(batch, num_dense=4, num_id_list_features=3)
+    assert req.batch_size == 6 and req.float_features.num_features == 4
+    assert np.frombuffer(req.id_list_features.lengths, dtype=np.int32).tolist() == batch.sparse_features.lengths().tolist()
+    assert np.frombuffer(req.float_features.values, dtype=np.float32).size == 24
+
+
+def _sd_transform(ctx):
+    import torch
+    import torch.distributed as dist
+    from torch.distributed._shard.sharded_tensor import Shard, ShardedTensor
+
+    from torchrec_b200.inference.state_dict_transform import state_dict_all_gather_keys, state_dict_gather, state_dict_to_device
+
+    r, W = ctx.rank, ctx.world_size
+    local = torch.full((2, 4), float(r + 1))
+    st = ShardedTensor._init_from_local_shards([Shard.from_tensor_and_offsets(local, [2 * r, 0], r)], (2 * W, 4), process_group=dist.group.WORLD)
+    sd = {"emb.weight": st, "dense.bias": torch.arange(3.0)}
+    if r == 0:
+        sd["only_rank0"] = torch.zeros(1)
+    assert state_dict_all_gather_keys(sd, dist.group.WORLD) == ["dense.bias", "emb.weight", "only_rank0"]
+    moved = state_dict_to_device(sd, dist.group.WORLD, torch.device("cpu"))
+    assert isinstance(moved["emb.weight"], ShardedTensor) and torch.equal(moved["emb.weight"].local_shards()[0].tensor, local)
+    dst = {"emb.weight": torch.zeros(2 * W, 4), "dense.bias": torch.zeros(3)}
+    state_dict_gather(sd, dst)
+    assert torch.equal(dst["dense.bias"], torch.arange(3.0))
+    if r == 0:
+        assert torch.equal(dst["emb.weight"][:, 0], torch.tensor([1.0, 1.0, 2.0, 2.0]))
+
+
+def test_state_dict_transform_gloo():
+    from torchrec_b200.utils.multiprocess import run_multi_process
+
+    run_multi_process(_sd_transform, world_size=2, backend="gloo")
