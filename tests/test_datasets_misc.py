@@ -133,3 +133,39 @@ def test_group_index_select_and_inference_gathers():
     assert all_to_one_device([a, b], cpu)[1] is b
     u = new_unified_tensor(a, (4, 8))
     assert u.shape == (4, 8) and is_uvm_tensor(u) and not is_uvm_tensor(a)
+
+
+def test_examples_transfer_learning_and_prediction():
+    import importlib.util
+    import os
+
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples")
+
+    def load(name):
+        spec = importlib.util.spec_from_file_location(f"ex_{name}", os.path.join(root, f"{name}.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+
+    assert load("transfer_learning").main() < 0.25
+    assert load("prediction").main(steps=120) > 0.7
+
+
+def _sharding_types(ctx):
+    import importlib.util
+    import os
+
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples")
+    spec = importlib.util.spec_from_file_location("ex_sharding_types", os.path.join(root, "sharding_types.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    res = mod.run(ctx.world_size, ctx.rank, ctx.device)
+    assert set(res) == {"table_wise", "row_wise", "column_wise", "data_parallel", "mixed"}
+    for shape, _where in res.values():
+        assert shape == (8, 2 * 16 * ctx.world_size)
+
+
+def test_example_sharding_types_gloo():
+    from torchrec_b200.utils.multiprocess import run_multi_process
+
+    run_multi_process(_sharding_types, world_size=2, backend="gloo")
