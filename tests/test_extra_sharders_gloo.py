@@ -189,3 +189,80 @@ def _run_itep(ctx):
 
 def test_sharded_itep():
     run_multi_process(_run_itep, world_size=2, backend="gloo")
+
+
+def _towers(ctx):
+    import torch.distributed as dist
+
+    from torchrec_b200.modules.embedding_configs import EmbeddingBagConfig
+    from torchrec_b200.modules.embedding_modules import EmbeddingBagCollection
+    from torchrec_b200.modules.embedding_tower import EmbeddingTower, EmbeddingTowerCollection
+    from torchrec_b200.optim.apply_optimizer_in_backward import apply_optimizer_in_backward
+    from torchrec_b200.parallel import sharding_plan as sp
+    from torchrec_b200.parallel.embedding_tower_sharding import EmbeddingTowerCollectionSharder, EmbeddingTowerSharder, ShardedEmbeddingTower
+    from torchrec_b200.parallel.model_parallel import DistributedModelParallel
+    from torchrec_b200.parallel.sharding_plan import get_default_sharders
+    from torchrec_b200.parallel.types import ShardingEnv, ShardingPlan
+    from torchrec_b200.sparse import KeyedJaggedTensor
+
+    W, dev = ctx.world_size, ctx.device
+
+    class Inter(torch.nn.Module):
+        def __init__(self, in_dim, out_dim):
+            super().__init__()
+            self.lin = torch.nn.Linear(in_dim, out_dim)
+
+        def forward(self, kt):
+            return torch.relu(self.lin(kt.values()))
+
+    def build():
+        torch.manual_seed(0)
+        ebc_a = EmbeddingBagCollection([EmbeddingBagConfig(name="a0", embedding_dim=8, num_embeddings=30, feature_names=["fa0"]),
+                                        EmbeddingBagConfig(name="a1", embedding_dim=8, num_embeddings=40, feature_names=["fa1"])])
+        ebc_b = EmbeddingBagCollection([EmbeddingBagConfig(name="b0", embedding_dim=16, num_embeddings=50, feature_names=["fb0"])])
+        return EmbeddingTowerCollection([EmbeddingTower(ebc_a, Inter(16, 6)), EmbeddingTower(ebc_b, Inter(16, 4))])
+
+    class Model(torch.nn.Module):
+        def __init__(self, towers, single):
+            super().__init__()
+            self.towers, self.single = towers, single
+
+        def forward(self, kjt):
+            return torch.cat([self.towers(kjt), self.single(kjt)], dim=1)
+
+    def single_tower():
+        torch.manual_seed(1)
+        return EmbeddingTower(EmbeddingBagCollection([EmbeddingBagConfig(name="s0", embedding_dim=8, num_embeddings=20, feature_names=["fs0"])]), Inter(8, 3))
+
+    golden = Model(build(), single_tower())
+    model = Model(build(), single_tower())
+    for m in (model.towers.towers[0].embedding, model.towers.towers[1].embedding, model.single.embedding):
+        apply_optimizer_in_backward(torch.optim.SGD, m.parameters(), {"lr": 0.1})
+    tower_plan = sp.construct_module_sharding_plan(model.towers, {"a0": sp.table_wise(rank=0), "a1": sp.row_wise(), "b0": sp.column_wise(ranks=list(range(W)))},
+                                                   sharder=EmbeddingTowerCollectionSharder(), world_size=W, local_size=W, device_type=dev.type)
+    single_plan = sp.construct_module_sharding_plan(model.single, {"s0": sp.table_wise(rank=W - 1)}, sharder=EmbeddingTowerSharder(), world_size=W, local_size=W,
+                                                    device_type=dev.type)
+    dmp = DistributedModelParallel(model, env=ShardingEnv.from_process_group(dist.group.WORLD), device=dev,
+                                   plan=ShardingPlan({"towers": tower_plan, "single": single_plan}), sharders=get_default_sharders())
+    assert isinstance(dmp.module.single, ShardedEmbeddingTower)
+    dmp.load_state_dict(golden.state_dict())                       # unsharded keys: towers.towers.0.embedding.embedding_bags.a0.weight, ...interaction.lin.weight
+    assert set(dmp.state_dict().keys()) == set(golden.state_dict().keys())
+    g = torch.Generator().manual_seed(10 + ctx.rank)
+    keys = ["fa0", "fa1", "fb0", "fs0"]
+    lengths = torch.randint(0, 3, (len(keys) * 5,), generator=g)
+    kjt = KeyedJaggedTensor(keys=keys, values=torch.randint(0, 20, (int(lengths.sum()),), generator=g), lengths=lengths)
+    out, ref = dmp(kjt), golden(kjt)
+    assert out.shape == (5, 6 + 4 + 3)
+    torch.testing.assert_close(out, ref)
+    out.sum().backward()
+    gw = dmp.module.module.towers.towers[0].interaction.lin.weight.grad if hasattr(dmp.module, "module") else None
+    lin = [p for n, p in dmp.named_parameters() if n.endswith("towers.0.interaction.lin.weight")][0]
+    mine = lin.grad.clone()
+    allg = [torch.empty_like(mine) for _ in range(W)]
+    dist.all_gather(allg, mine)
+    for a in allg[1:]:
+        torch.testing.assert_close(a, allg[0])                      # interaction gradients are DDP-averaged
+
+
+def test_embedding_tower_sharders():
+    run_multi_process(_towers, world_size=2, backend="gloo")

@@ -130,3 +130,52 @@ def _run(ctx, sharding: str, weighted: bool):
 @pytest.mark.parametrize("weighted", [False, True])
 def test_sharded_ebc_matches_unsharded(sharding, weighted):
     run_multi_process(_run, world_size=2, backend="gloo", sharding=sharding, weighted=weighted)
+
+
+def _rank_without_shards(ctx):
+    """A module whose only table lives on ONE rank: the other rank holds no shard but must still join the backward collectives."""
+    import torch.distributed as dist
+
+    from torchrec_b200.modules.embedding_configs import EmbeddingBagConfig, EmbeddingConfig
+    from torchrec_b200.modules.embedding_modules import EmbeddingBagCollection, EmbeddingCollection
+    from torchrec_b200.optim.apply_optimizer_in_backward import apply_optimizer_in_backward
+    from torchrec_b200.parallel import sharding_plan as sp
+    from torchrec_b200.parallel.embedding import EmbeddingCollectionSharder
+    from torchrec_b200.parallel.embeddingbag import EmbeddingBagCollectionSharder
+    from torchrec_b200.parallel.model_parallel import DistributedModelParallel
+    from torchrec_b200.parallel.types import ShardingEnv, ShardingPlan
+    from torchrec_b200.sparse import KeyedJaggedTensor
+
+    W, dev = ctx.world_size, ctx.device
+    torch.manual_seed(0)
+    ebc = EmbeddingBagCollection([EmbeddingBagConfig(name="t", embedding_dim=8, num_embeddings=30, feature_names=["f"])])
+    ec = EmbeddingCollection([EmbeddingConfig(name="s", embedding_dim=8, num_embeddings=30, feature_names=["g"])])
+    for m in (ebc, ec):
+        apply_optimizer_in_backward(torch.optim.SGD, m.parameters(), {"lr": 0.1})
+
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.ebc, self.ec = ebc, ec
+            self.lin = torch.nn.Linear(8, 1)
+
+        def forward(self, kjt):
+            pooled = self.ebc(kjt).values()
+            seq = self.ec(kjt)["g"].values()
+            return self.lin(pooled).sum() + seq.sum()
+
+    plan = ShardingPlan({
+        "ebc": sp.construct_module_sharding_plan(ebc, {"t": sp.table_wise(rank=W - 1)}, sharder=EmbeddingBagCollectionSharder(), world_size=W, local_size=W, device_type=dev.type),
+        "ec": sp.construct_module_sharding_plan(ec, {"s": sp.table_wise(rank=0)}, sharder=EmbeddingCollectionSharder(), world_size=W, local_size=W, device_type=dev.type),
+    })
+    dmp = DistributedModelParallel(M(), env=ShardingEnv.from_process_group(dist.group.WORLD), device=dev, plan=plan,
+                                   sharders=[EmbeddingBagCollectionSharder(), EmbeddingCollectionSharder()])
+    g = torch.Generator().manual_seed(ctx.rank)
+    for _ in range(2):
+        lengths = torch.randint(1, 3, (2 * 4,), generator=g)
+        kjt = KeyedJaggedTensor(keys=["f", "g"], values=torch.randint(0, 30, (int(lengths.sum()),), generator=g), lengths=lengths)
+        dmp(kjt).backward()      # hung before: the shard-less rank skipped the output dist's backward all-to-all
+
+
+def test_rank_without_shards_joins_backward_collectives():
+    run_multi_process(_rank_without_shards, world_size=2, backend="gloo")

@@ -269,8 +269,8 @@ class _A2ASeqReq(Function):
         W = dist.get_world_size(pg)
         ctx.pg, ctx.h, ctx.info, ctx.W = pg, h, info, W
         ctx.in_dtype = x.dtype
-        if info.forward_recat_tensor is not None and info.lengths_after_sparse_data_all2all is not None:
-            # rows arrive unit-major; regroup them source-rank-major before sending them back
+        if info.forward_recat_tensor is not None and info.lengths_after_sparse_data_all2all is not None and info.forward_recat_tensor.numel() > 0:
+            # rows arrive unit-major; regroup them source-rank-major before sending them back (a rank without units has nothing to regroup)
             lengths = info.lengths_after_sparse_data_all2all
             nseg = info.forward_recat_tensor.numel()
             seg = lengths.view(nseg, -1).sum(1)

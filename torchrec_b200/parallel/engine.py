@@ -418,7 +418,9 @@ class ShardedLookupEngine(nn.Module):
                 outs.append(g.tbe(values, window, None, batch_size=Bg))
         if not outs:
             D = 0 if self._pooled else self._tables[0].embedding_dim
-            return torch.zeros(Bg if self._pooled else 0, D, device=values.device, dtype=self._output_dtype)
+            # a rank without shards of this module still has to run the BACKWARD collectives of the output dist with its peers:
+            # the empty result must be part of the autograd graph (found by the tower test: TW table on one rank only -> hang)
+            return torch.zeros(Bg if self._pooled else 0, D, device=values.device, dtype=self._output_dtype, requires_grad=torch.is_grad_enabled())
         if len(outs) == 1:
             return outs[0]
         if self._pooled:

@@ -71,6 +71,16 @@ class _ShardedITEPBase(ShardedModule):
 
         yield from delegating_named_parameters(self, prefix, recurse)
 
+    def state_dict(self, destination=None, prefix: str = "", keep_vars: bool = False):  # type: ignore[override]
+        from .types import delegating_state_dict
+
+        return delegating_state_dict(self, destination, prefix, keep_vars)
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):  # type: ignore[override]
+        from .types import delegating_load_state_dict
+
+        return delegating_load_state_dict(self, state_dict, strict)
+
     @property
     def fused_optimizer(self):
         return self._inner.fused_optimizer

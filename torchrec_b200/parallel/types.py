@@ -571,3 +571,52 @@ def delegating_named_parameters(module: nn.Module, prefix: str = "", recurse: bo
     if recurse:
         for name, child in module.named_children():
             yield from child.named_parameters((prefix + "." if prefix else "") + name, recurse)
+
+
+def delegating_state_dict(module: nn.Module, destination: Optional[Dict[str, Any]] = None, prefix: str = "", keep_vars: bool = False) -> Dict[str, Any]:
+    """state_dict for sharded *wrapper* modules: own tensors + every child's OWN ``state_dict`` (an inner sharded collection emits
+    its table-keyed ShardedTensors instead of its storage layout), so the keys equal the unsharded module's."""
+    from collections import OrderedDict
+
+    if destination is None:
+        destination = OrderedDict()
+    for name, p in module._parameters.items():
+        if p is not None:
+            destination[prefix + name] = p if keep_vars else p.detach()
+    for name, b in module._buffers.items():
+        if b is not None and name not in module._non_persistent_buffers_set:
+            destination[prefix + name] = b if keep_vars else b.detach()
+    for name, child in module.named_children():
+        child.state_dict(destination=destination, prefix=prefix + name + ".", keep_vars=keep_vars)
+    return destination
+
+
+def delegating_load_state_dict(module: nn.Module, state_dict: Dict[str, Any], strict: bool = True):
+    """Counterpart of :func:`delegating_state_dict`: routes every key prefix to the child's own ``load_state_dict``."""
+    from torch.nn.modules.module import _IncompatibleKeys
+
+    missing: List[str] = []
+    unexpected: List[str] = []
+    own = set()
+    with torch.no_grad():
+        for name, t in list(module._parameters.items()) + [(n, b) for n, b in module._buffers.items() if n not in module._non_persistent_buffers_set]:
+            if t is None:
+                continue
+            own.add(name)
+            if name in state_dict:
+                t.copy_(state_dict[name])
+            else:
+                missing.append(name)
+    children = dict(module.named_children())
+    for name, child in children.items():
+        pre = name + "."
+        sub = {k[len(pre):]: v for k, v in state_dict.items() if k.startswith(pre)}
+        res = child.load_state_dict(sub, strict=False)
+        missing.extend(pre + k for k in res.missing_keys)
+        unexpected.extend(pre + k for k in res.unexpected_keys)
+    for k in state_dict:
+        if k not in own and k.split(".", 1)[0] not in children:
+            unexpected.append(k)
+    if strict and (missing or unexpected):
+        raise RuntimeError(f"Error(s) in loading state_dict for {type(module).__name__}: missing {missing}, unexpected {unexpected}")
+    return _IncompatibleKeys(missing, unexpected)
