@@ -103,3 +103,67 @@ def test_hybrid_eval_dmp_and_cpu_sparse_eval():
         ref = [m(b.dense_features, b.sparse_features) for b in batches[:3]]
     for o, r in zip(outs, ref):
         torch.testing.assert_close(o, r)
+
+
+def test_data_loading_thread_postproc_and_pt2_pipeline():
+    import torch
+    from torch import nn
+
+    from torchrec_b200.datasets.random import RandomRecDataset
+    from torchrec_b200.models.dlrm import DLRM, DLRMTrain
+    from torchrec_b200.modules.embedding_configs import EmbeddingBagConfig
+    from torchrec_b200.modules.embedding_modules import EmbeddingBagCollection
+    from torchrec_b200.parallel.train_pipeline import DataLoadingThread, PipelinedPostproc, TrainPipelineContext, TrainPipelinePT2
+
+    dev = torch.device("cpu")
+    keys = ["f0", "f1"]
+    ds = RandomRecDataset(keys=keys, batch_size=8, hash_size=50, ids_per_feature=2, num_dense=4, manual_seed=0, num_batches=5)
+    t = DataLoadingThread(dev, iter(ds), queue_size=2)
+    t.start()
+    got = []
+    while True:
+        b = t.get(timeout=10)
+        if b is None:
+            break
+        got.append(b)
+    assert len(got) == 5 and got[0].dense_features.shape == (8, 4) and t.get(timeout=1) is None
+    t.join(timeout=5)
+
+    calls = []
+
+    class Remap(nn.Module):
+        def forward(self, x):
+            calls.append(1)
+            return x * 2
+
+    ctx = TrainPipelineContext(version=1)
+    pp = PipelinedPostproc(Remap(), "model.remap", ctx)
+    x = torch.ones(3)
+    assert torch.equal(pp(x), x * 2) and torch.equal(pp(x), x * 2) and len(calls) == 1      # second call: cached for this batch context
+    pp.set_context(TrainPipelineContext(version=1))
+    pp(x)
+    assert len(calls) == 2
+
+    tables = [EmbeddingBagConfig(name=f"t{i}", embedding_dim=8, num_embeddings=50, feature_names=[k]) for i, k in enumerate(keys)]
+    model = DLRMTrain(DLRM(EmbeddingBagCollection(tables), dense_in_features=4, dense_arch_layer_sizes=[8, 8], over_arch_layer_sizes=[8, 1]))
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    seen = {"pre": 0, "compiled": 0, "transformed": 0}
+
+    def compile_fn(m):
+        seen["compiled"] += 1
+        return m
+
+    def transform(b):
+        seen["transformed"] += 1
+        return b
+
+    pipe = TrainPipelinePT2(model, opt, dev, compile_fn=compile_fn, pre_compile_fn=lambda m: seen.__setitem__("pre", seen["pre"] + 1), input_transformer=transform,
+                            num_pre_compile_steps=2)
+    it = iter(RandomRecDataset(keys=keys, batch_size=8, hash_size=50, ids_per_feature=2, num_dense=4, manual_seed=1, num_batches=6))
+    losses = []
+    try:
+        while True:
+            losses.append(float(pipe.progress(it)[0]))
+    except StopIteration:
+        pass
+    assert len(losses) == 6 and seen["compiled"] == 1 and seen["pre"] == 1 and seen["transformed"] == 6

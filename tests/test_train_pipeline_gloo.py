@@ -87,3 +87,48 @@ def test_pipeline_matches_plain_loop_tw(pipeline):
 
 def test_pipeline_matches_plain_loop_rw():
     run_multi_process(_run, world_size=2, backend="gloo", sharding="rw", pipeline="sparse")
+
+
+def _staged(ctx):
+    """StagedTrainPipeline + SparseDataDistUtil (input dist of batch i+1 runs as its own stage) == plain loop."""
+    from torchrec_b200.datasets.random import RandomRecDataset
+    from torchrec_b200.parallel import train_pipeline as tp
+
+    dmp_a, opt_a, keys, hashes = _build(ctx, "tw")
+    dmp_b, opt_b, _, _ = _build(ctx, "tw")
+    dmp_b.load_state_dict(dmp_a.state_dict())
+    ds = RandomRecDataset(keys, 6, hash_sizes=hashes, ids_per_feature=3, min_ids_per_feature=0, num_dense=5, manual_seed=3 + ctx.rank, num_generated_batches=5, num_batches=5)
+    batches = list(iter(ds))
+    ref = []
+    for b in batches:
+        opt_a.zero_grad()
+        loss, _ = dmp_a(b)
+        loss.backward()
+        opt_a.step()
+        ref.append(loss.detach().clone())
+    util = tp.SparseDataDistUtil(dmp_b, data_dist_stream=None)
+    stages = [tp.PipelineStage("copy", lambda b: b.to(torch.device("cpu")), None),
+              tp.PipelineStage("sparse_dist", util.start_sparse_data_dist, None, fill_callback=util.wait_sparse_data_dist)]
+    pipe = tp.StagedTrainPipeline(stages)
+    it = iter(batches)
+    got = []
+    while True:
+        b = pipe.progress(it)
+        if b is None:
+            break
+        util.wait_sparse_data_dist()
+        opt_b.zero_grad()
+        loss, _ = dmp_b(b)
+        loss.backward()
+        opt_b.step()
+        got.append(loss.detach().clone())
+    assert len(got) == len(ref)
+    for a, b in zip(got, ref):
+        torch.testing.assert_close(a, b)
+    util.detach()
+    loss, _ = dmp_b(batches[0])      # original forwards restored
+    assert torch.isfinite(loss)
+
+
+def test_staged_pipeline_with_sparse_data_dist_util():
+    run_multi_process(_staged, world_size=2, backend="gloo")

@@ -11,4 +11,7 @@ from .train_pipelines import (  # noqa: F401
     TrainPipelineSemiSync,
     TrainPipelineSparseDist,
     TrainPipelineSparseDistLite,
+    TrainPipelinePT2,
+    TrainPipelineSparseDistCompAutograd,
 )
+from .utils import DataLoadingThread, PipelinedPostproc, SparseDataDistUtil  # noqa: F401

@@ -844,3 +844,76 @@ class StagedTrainPipeline(TrainPipeline[In, Optional[In]]):
 
     def flush_end(self) -> None:
         self._flushing = False
+
+
+class TrainPipelinePT2(TrainPipelineBase[In, Out]):
+    """``TrainPipelineBase`` whose model is handed to a graph compiler after ``pre_compile_fn`` has seen a batch (reference
+    train_pipelines.py:432-537, which calls ``torch.compile``). This framework's hot path is hand-written kernels + CUDA graphs, not a
+    tracing compiler, so the default ``compile_fn`` captures the dense sub-modules into CUDA graphs when the model offers
+    ``capture_dense_graphs`` and otherwise leaves the model untouched; pass ``compile_fn=torch.compile`` to get the reference
+    behaviour."""
+
+    def __init__(self, model: nn.Module, optimizer: torch.optim.Optimizer, device: torch.device, compile_fn: Optional[Callable[[nn.Module], nn.Module]] = None,
+                 pre_compile_fn: Optional[Callable[[nn.Module], None]] = None, post_compile_fn: Optional[Callable[[nn.Module], None]] = None,
+                 input_transformer: Optional[Callable[[In], In]] = None, num_pre_compile_steps: int = 1) -> None:
+        super().__init__(model, optimizer, device)
+        self._compile_fn = compile_fn
+        self._pre_compile_fn = pre_compile_fn
+        self._post_compile_fn = post_compile_fn
+        self._input_transformer = input_transformer
+        self._num_pre_compile_steps = max(0, num_pre_compile_steps)
+        self._steps = 0
+        self._compiled = False
+
+    def _maybe_compile(self) -> None:
+        if self._compiled or self._steps < self._num_pre_compile_steps:
+            return
+        if self._pre_compile_fn is not None:
+            self._pre_compile_fn(self._model)
+        if self._compile_fn is not None:
+            self._model = self._compile_fn(self._model)
+        if self._post_compile_fn is not None:
+            self._post_compile_fn(self._model)
+        self._compiled = True
+
+    def _next_batch(self, dataloader_iter: Iterator[In]) -> Optional[In]:
+        batch = super()._next_batch(dataloader_iter)
+        if batch is not None and self._input_transformer is not None:
+            batch = self._input_transformer(batch)
+        return batch
+
+    def _connect(self, dataloader_iter: Iterator[In]) -> None:
+        super()._connect(dataloader_iter)
+        if self._cur_batch is not None and self._input_transformer is not None:
+            self._cur_batch = self._input_transformer(self._cur_batch)
+
+    def progress(self, dataloader_iter: Iterator[In]) -> Out:
+        self._maybe_compile()
+        out = super().progress(dataloader_iter)
+        self._steps += 1
+        return out
+
+
+class TrainPipelineSparseDistCompAutograd(TrainPipelineSparseDist[In, Out]):
+    """``TrainPipelineSparseDist`` whose backward runs under compiled autograd when the installed torch provides it and
+    ``enable`` is set (reference train_pipelines.py:2269-2330). Off by default: the fused backward + optimizer kernels already are
+    the backward graph, and compiled autograd cannot trace through the ctypes launches."""
+
+    def __init__(self, *args: Any, enable: bool = False, compiler_fn: Optional[Callable[..., Any]] = None, **kwargs: Any) -> None:
+        super().__init__(*args, **kwargs)
+        self._ca_enable = enable
+        self._ca_compiler_fn = compiler_fn
+
+    def _backward_ctx(self):
+        if not self._ca_enable:
+            return contextlib.nullcontext()
+        try:
+            from torch._dynamo import compiled_autograd
+
+            return compiled_autograd._enable(self._ca_compiler_fn or (lambda gm: gm))
+        except Exception:
+            return contextlib.nullcontext()
+
+    def progress(self, dataloader_iter: Iterator[In]) -> Out:
+        with self._backward_ctx():
+            return super().progress(dataloader_iter)

@@ -1,0 +1,216 @@
+"""Pipeline building blocks that live outside the pipeline classes: background data loading, pipelined batch post-processing and the
+sparse-data-dist helper for ``StagedTrainPipeline``.
+
+Parity: reference ``train_pipeline/utils.py`` (``DataLoadingThread`` :780-900), ``postproc.py`` (``PipelinedPostproc`` :37-300),
+``pipeline_stage.py`` (``SparseDataDistUtil`` :100-330)."""
+from __future__ import annotations
+
+import queue
+import threading
+from typing import Any, Callable, Dict, Generic, Iterator, List, Optional, TypeVar
+
+import torch
+from torch import nn
+from torch.autograd.profiler import record_function
+
+from ..types import ShardedModule
+from .pipeline_context import TrainPipelineContext
+
+In = TypeVar("In")
+
+
+def _to_device(batch: Any, device: torch.device, non_blocking: bool = True) -> Any:
+    return batch.to(device=device, non_blocking=non_blocking) if hasattr(batch, "to") else batch
+
+
+class DataLoadingThread(threading.Thread, Generic[In]):
+    """Pulls batches from the dataloader iterator on a background thread, starts their H2D copy on ``memcpy_stream`` and hands
+    ``(batch, copy_done_event)`` to the trainer through a bounded queue. The host work of ``next(dataloader)`` (collation,
+    pin-memory) then overlaps the trainer's kernel launches instead of sitting in front of them."""
+
+    def __init__(self, device: torch.device, dataloader_iter: Iterator[In], to_device_non_blocking: bool = True, memcpy_stream_priority: int = 0,
+                 memcpy_stream: Optional[torch.Stream] = None, queue_size: int = 2) -> None:
+        super().__init__(daemon=True)
+        self._device = torch.device(device)
+        self._iter = dataloader_iter
+        self._non_blocking = to_device_non_blocking
+        self._queue: "queue.Queue[Any]" = queue.Queue(maxsize=max(1, queue_size))
+        self._stop_event = threading.Event()
+        self._exc: Optional[BaseException] = None
+        if memcpy_stream is None and self._device.type == "cuda":
+            memcpy_stream = torch.cuda.Stream(device=self._device, priority=memcpy_stream_priority)
+        self._memcpy_stream = memcpy_stream
+
+    def run(self) -> None:
+        if self._device.type == "cuda":
+            torch.cuda.set_device(self._device)
+        try:
+            while not self._stop_event.is_set():
+                with record_function("## load_batch ##"):
+                    batch = next(self._iter, None)
+                if batch is None:
+                    break
+                ev = None
+                if self._memcpy_stream is not None:
+                    with torch.cuda.stream(self._memcpy_stream):
+                        batch = _to_device(batch, self._device, self._non_blocking)
+                        ev = torch.cuda.Event()
+                        ev.record(self._memcpy_stream)
+                else:
+                    batch = _to_device(batch, self._device, self._non_blocking)
+                while not self._stop_event.is_set():
+                    try:
+                        self._queue.put((batch, ev), timeout=0.05)
+                        break
+                    except queue.Full:
+                        continue
+        except BaseException as e:  # surfaced to the trainer by get()
+            self._exc = e
+        finally:
+            while True:
+                try:
+                    self._queue.put(None, timeout=0.05)
+                    break
+                except queue.Full:
+                    if self._stop_event.is_set():
+                        break
+
+    def stop(self) -> None:
+        self._stop_event.set()
+
+    def get(self, timeout: Optional[float] = None) -> Optional[In]:
+        """Next device batch (the current stream is made to wait for its copy), or None at the end of the data."""
+        item = self._queue.get(timeout=timeout)
+        if item is None:
+            self._queue.put(None)  # keep signalling the end to later calls
+            if self._exc is not None:
+                raise self._exc
+            return None
+        batch, ev = item
+        if ev is not None:
+            torch.cuda.current_stream(self._device).wait_event(ev)
+            if hasattr(batch, "record_stream"):
+                batch.record_stream(torch.cuda.current_stream(self._device))
+        return batch
+
+
+class PipelinedPostproc(nn.Module):
+    """A batch post-processing module (id remapping, feature crossing, ...) hoisted out of the model's forward into the pipeline's
+    data-dist stage: the pipeline calls it once per batch on the data-dist stream, the model's own call returns the cached result
+    for that batch context (so it runs a step early and only once even if several sharded modules consume its output)."""
+
+    def __init__(self, postproc_module: nn.Module, fqn: str, context: Optional[TrainPipelineContext] = None, default_stream: Optional[torch.Stream] = None,
+                 dist_stream: Optional[torch.Stream] = None) -> None:
+        super().__init__()
+        self._postproc_module = postproc_module
+        self._fqn = fqn
+        self._context = context
+        self._default_stream = default_stream
+        self._dist_stream = dist_stream
+
+    @property
+    def postproc_module(self) -> nn.Module:
+        return self._postproc_module
+
+    @property
+    def fqn(self) -> str:
+        return self._fqn
+
+    def set_context(self, context: TrainPipelineContext) -> None:
+        self._context = context
+
+    def forward(self, *input: Any, **kwargs: Any) -> Any:
+        ctx = self._context
+        cache: Optional[Dict[str, Any]] = getattr(ctx, "postproc_fwd_results", None) if ctx is not None else None
+        if cache is not None and self._fqn in cache:
+            res = cache[self._fqn]
+            if self._dist_stream is not None and self._default_stream is not None:
+                self._default_stream.wait_stream(self._dist_stream)  # result was produced on the data-dist stream
+            return res
+        with record_function(f"## pipelined_postproc {self._fqn} ##"):
+            res = self._postproc_module(*input, **kwargs)
+        if ctx is not None:
+            if cache is None:
+                cache = {}
+                ctx.postproc_fwd_results = cache  # type: ignore[attr-defined]
+            cache[self._fqn] = res
+        return res
+
+
+class SparseDataDistUtil(Generic[In]):
+    """The two sparse-dist stage callables for a ``StagedTrainPipeline``:
+
+        util = SparseDataDistUtil(model, data_dist_stream)
+        stages = [PipelineStage("copy", copy_fn, memcpy_stream), PipelineStage("dist", util.start_sparse_data_dist, data_dist_stream,
+                                                                             fill_callback=util.wait_sparse_data_dist)]
+
+    ``start_sparse_data_dist(batch)`` launches every sharded module's input dist for ``batch``; ``wait_sparse_data_dist()`` finishes
+    them; the model's sharded modules then find their distributed inputs in the context of the batch they are called with."""
+
+    def __init__(self, model: nn.Module, data_dist_stream: Optional[torch.Stream], apply_jit: bool = False, prefetch_stream: Optional[torch.Stream] = None) -> None:
+        self.model = model
+        self.data_dist_stream = data_dist_stream
+        self.prefetch_stream = prefetch_stream
+        self.context = TrainPipelineContext(version=1)
+        self._modules: Dict[str, ShardedModule] = {n: m for n, m in model.named_modules() if isinstance(m, ShardedModule)}
+        self._getters: Dict[str, Callable[[Any], Any]] = {}
+        self._original: Dict[str, Callable[..., Any]] = {}
+        self._pending: Dict[int, TrainPipelineContext] = {}
+        for name, m in self._modules.items():
+            self._original[name] = m.forward
+            m.forward = self._make_forward(name, m)  # type: ignore[method-assign]
+
+    def _find_kjt(self, batch: Any, module: ShardedModule) -> Any:
+        from ...sparse.jagged_tensor import KeyedJaggedTensor
+
+        for attr in ("sparse_features", "id_list_features", "features"):
+            v = getattr(batch, attr, None)
+            if isinstance(v, KeyedJaggedTensor):
+                return v
+        if isinstance(batch, KeyedJaggedTensor):
+            return batch
+        raise RuntimeError(f"SparseDataDistUtil: cannot find the KeyedJaggedTensor input in a {type(batch).__name__}")
+
+    def _make_forward(self, name: str, module: ShardedModule) -> Callable[..., Any]:
+        def fwd(*input: Any, **kwargs: Any) -> Any:
+            ctx = self._pending.pop(id(input[0]), None) if input else None
+            if ctx is None or name not in ctx.input_dist_tensors_requests:
+                if ctx is not None:
+                    self._pending[id(input[0])] = ctx
+                return self._original[name](*input, **kwargs)
+            request = ctx.input_dist_tensors_requests.pop(name)
+            mctx = ctx.module_contexts.pop(name)
+            if ctx.input_dist_tensors_requests:
+                self._pending[id(input[0])] = ctx
+            if self.data_dist_stream is not None:
+                with torch.cuda.stream(self.data_dist_stream):
+                    data = request.wait()
+                torch.cuda.current_stream().wait_stream(self.data_dist_stream)
+            else:
+                data = request.wait()
+            return module.compute_and_output_dist(mctx, data)
+
+        return fwd
+
+    def start_sparse_data_dist(self, batch: In) -> In:
+        ctx = TrainPipelineContext(version=1)
+        for name, m in self._modules.items():
+            kjt = self._find_kjt(batch, m)
+            mctx = m.create_context()
+            ctx.module_contexts[name] = mctx
+            ctx.input_dist_splits_requests[name] = m.input_dist(mctx, kjt)
+            self._pending[id(kjt)] = ctx
+        self.context = ctx
+        return batch
+
+    def wait_sparse_data_dist(self) -> None:
+        ctx = self.context
+        for name, aw in list(ctx.input_dist_splits_requests.items()):
+            ctx.input_dist_tensors_requests[name] = aw.wait()
+        ctx.input_dist_splits_requests.clear()
+
+    def detach(self) -> nn.Module:
+        for name, m in self._modules.items():
+            m.forward = self._original[name]  # type: ignore[method-assign]
+        self._pending.clear()
+        return self.model
