@@ -167,3 +167,60 @@ def test_data_loading_thread_postproc_and_pt2_pipeline():
     except StopIteration:
         pass
     assert len(losses) == 6 and seen["compiled"] == 1 and seen["pre"] == 1 and seen["transformed"] == 6
+
+
+def test_runtime_forwards_and_arg_info():
+    import torch
+
+    from torchrec_b200.parallel.train_pipeline.pipeline_context import EmbeddingTrainPipelineContext, PrefetchTrainPipelineContext
+    from torchrec_b200.parallel.train_pipeline.runtime_forwards import (CPUEmbeddingPipelinedForward, EmbeddingPipelinedForward, InSyncEmbeddingPipelinedForward,
+                                                                       PrefetchEmbeddingPipelinedForward, PrefetchPipelinedForward)
+    from torchrec_b200.parallel.train_pipeline.types import ArgInfo, CallArgs, PipelinePhase, PipelineState
+    from torchrec_b200.parallel.types import NoWait
+
+    class FakeSharded:
+        def __init__(self):
+            self.calls = []
+
+        def compute_and_output_dist(self, ctx, data):
+            self.calls.append((ctx, data))
+            return data * 10
+
+    m = FakeSharded()
+    ctx = EmbeddingTrainPipelineContext(version=1, index=3)
+    ctx.embedding_a2a_requests["ebc"] = NoWait(torch.ones(2))
+    ctx.module_contexts["ebc"] = "mctx"
+    fwd = EmbeddingPipelinedForward("ebc", None, m, ctx)
+    assert torch.equal(fwd("ignored"), torch.ones(2)) and not ctx.embedding_a2a_requests and m.calls == []
+
+    ctx2 = EmbeddingTrainPipelineContext(version=1, index=3)
+    ctx2.embedding_a2a_requests["ebc"] = NoWait(torch.ones(2))          # computed before the update at step 5 -> stale
+    ctx2.input_dist_tensors_requests["ebc"] = NoWait(torch.full((2,), 2.0))
+    ctx2.module_contexts["ebc"] = "mctx"
+    insync = InSyncEmbeddingPipelinedForward("ebc", None, m, ctx2, fresh_since=lambda: 5)
+    assert torch.equal(insync(), torch.full((2,), 20.0)) and len(m.calls) == 1
+    ctx2.index = 7
+    ctx2.embedding_a2a_requests["ebc"] = NoWait(torch.ones(2))
+    assert torch.equal(insync(), torch.ones(2))                           # fresh enough: precomputed result is used
+
+    ctx3 = EmbeddingTrainPipelineContext(version=1)
+    ctx3.embedding_a2a_requests["ebc"] = NoWait({"f": torch.ones(1)})
+    cpu = CPUEmbeddingPipelinedForward("ebc", None, m, ctx3, device=torch.device("cpu"))
+    assert cpu()["f"].device.type == "cpu"
+
+    pctx = PrefetchTrainPipelineContext(version=1)
+    pctx.module_input_post_prefetch["ebc"] = torch.full((2,), 3.0)
+    pctx.module_contexts_post_prefetch["ebc"] = "pm"
+    assert torch.equal(PrefetchPipelinedForward("ebc", None, m, pctx)(), torch.full((2,), 30.0)) and m.calls[-1][0] == "pm"
+    pctx.module_input_post_prefetch["ebc"] = torch.full((2,), 3.0)
+    pctx.module_contexts_post_prefetch["ebc"] = "pm"
+    assert torch.equal(PrefetchEmbeddingPipelinedForward("ebc", None, m, pctx)(), torch.full((2,), 30.0))
+
+    class B:
+        sparse_features = {"k": [10, 20, 30]}
+
+    info = ArgInfo.from_path([("attr", "sparse_features"), ("item", "k"), ("item", 1)])
+    assert info.process(B()) == 20
+    args, kwargs = CallArgs([info], {"x": ArgInfo.from_path([("attr", "sparse_features")])}).build_args_kwargs(B())
+    assert args == [20] and kwargs["x"] is B.sparse_features
+    assert str(PipelineState.CALL_FWD) == "CALL_FWD" and PipelinePhase.FORWARD.value == "forward"
