@@ -266,3 +266,76 @@ def _towers(ctx):
 
 def test_embedding_tower_sharders():
     run_multi_process(_towers, world_size=2, backend="gloo")
+
+
+def _pec(ctx):
+    """Sharded PEC == plain sharded EC (weights after training), overlap masks are right, early non-overlapped lookup is exact."""
+    import torch.distributed as dist
+
+    from torchrec_b200.modules.embedding_configs import EmbeddingConfig
+    from torchrec_b200.modules.embedding_modules import EmbeddingCollection
+    from torchrec_b200.modules.pec_embedding_modules import PECEmbeddingCollection
+    from torchrec_b200.optim.apply_optimizer_in_backward import apply_optimizer_in_backward
+    from torchrec_b200.parallel import sharding_plan as sp
+    from torchrec_b200.parallel.embedding import EmbeddingCollectionSharder
+    from torchrec_b200.parallel.model_parallel import DistributedModelParallel
+    from torchrec_b200.parallel.pec_embedding import PECEmbeddingCollectionSharder, ShardedPECEmbeddingCollection
+    from torchrec_b200.parallel.types import ShardingEnv, ShardingPlan
+    from torchrec_b200.sparse import KeyedJaggedTensor
+
+    W, dev = ctx.world_size, ctx.device
+
+    def tables():
+        return [EmbeddingConfig(name="t0", embedding_dim=8, num_embeddings=40, feature_names=["f0", "f0b"]),
+                EmbeddingConfig(name="t1", embedding_dim=8, num_embeddings=30, feature_names=["f1"])]
+
+    def build(pec: bool):
+        torch.manual_seed(0)
+        ec = EmbeddingCollection(tables())
+        apply_optimizer_in_backward(torch.optim.SGD, ec.parameters(), {"lr": 0.5})
+        mod = PECEmbeddingCollection(ec) if pec else ec
+        sharder = PECEmbeddingCollectionSharder() if pec else EmbeddingCollectionSharder()
+        plan = sp.construct_module_sharding_plan(mod, {"t0": sp.row_wise(), "t1": sp.table_wise(rank=W - 1)}, sharder=sharder, world_size=W, local_size=W, device_type=dev.type)
+        return DistributedModelParallel(mod, env=ShardingEnv.from_process_group(dist.group.WORLD), device=dev, plan=ShardingPlan({"": plan}), sharders=[sharder])
+
+    a, b = build(True), build(False)
+    assert isinstance(a.module, ShardedPECEmbeddingCollection)
+    g = torch.Generator().manual_seed(5 + ctx.rank)
+    keys = ["f0", "f0b", "f1"]
+    batches = []
+    for _ in range(4):
+        lengths = torch.randint(0, 4, (len(keys) * 6,), generator=g)
+        batches.append(KeyedJaggedTensor(keys=keys, values=torch.randint(0, 12, (int(lengths.sum()),), generator=g), lengths=lengths))   # small id range: plenty of overlap
+    for kjt in batches:
+        oa, ob = a(kjt), b(kjt)
+        for k in keys:
+            torch.testing.assert_close(oa[k].values(), ob[k].values())
+        sum(v.values().sum() for v in oa.values()).backward()
+        sum(v.values().sum() for v in ob.values()).backward()
+    for ta, tb in zip(a.module._embedding_collection._engine._tbes, b.module._engine._tbes):
+        if hasattr(ta, "weights"):
+            torch.testing.assert_close(ta.weights.detach(), tb.weights.detach())
+    st = a.module.stats
+    tot = torch.tensor([st["values"], st["overlapped"]])
+    dist.all_reduce(tot)
+    assert 0 < int(tot[1]) < int(tot[0])                                      # some ids repeated between consecutive batches, not all
+
+    # explicit early stage: partition + gather the non-overlapped rows of the next batch BEFORE this batch's backward
+    m = a.module
+    out_cur = a(batches[0])
+    ctx_next = m.create_context()
+    dist_next = m.input_dist(ctx_next, batches[1]).wait().wait()
+    m.prefetch_nonoverlapped(ctx_next, dist_next)
+    sum(v.values().sum() for v in out_cur.values()).backward()               # updates rows of batches[0]
+    early = m.compute_and_output_dist(ctx_next, dist_next)
+    early = {k: v.values().detach().clone() for k, v in early.items()}
+    b(batches[0])["f0"].values().sum().backward() if False else None
+    ob = b(batches[0])
+    sum(v.values().sum() for v in ob.values()).backward()
+    ref = b(batches[1])
+    for k in keys:
+        torch.testing.assert_close(early[k], ref[k].values())
+
+
+def test_pec_embedding_collection():
+    run_multi_process(_pec, world_size=2, backend="gloo")

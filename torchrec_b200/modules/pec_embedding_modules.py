@@ -1,39 +1,47 @@
-"""Permissioned / position-encoded embedding collection ("PEC", reference torchrec/modules/pec_embedding_modules.py:26):
-an EmbeddingCollection whose lookup is preceded by a per-feature id transformation hook and that returns embeddings
-together with the remapped ids. Used where the id space is re-encoded per request (e.g. positional buckets)."""
-from typing import Callable, Dict, Optional
+"""Prioritized Embedding Communication (PEC) wrapper of an ``EmbeddingCollection`` (reference torchrec/modules/pec_embedding_modules.py:26-116).
 
-import torch
+PEC splits every batch's distributed ids into those that also occurred in the previous batch ("overlapped": their rows are being
+updated by the previous step's backward and must be looked up after it) and the rest ("non-overlapped": their lookup can start while
+the previous step is still running). The unsharded module only carries the configuration and delegates to the wrapped collection;
+the logic lives in ``parallel/pec_embedding.py: ShardedPECEmbeddingCollection``."""
+from enum import Enum
+from typing import Dict, List
+
 from torch import nn
 
 from ..sparse.jagged_tensor import JaggedTensor, KeyedJaggedTensor
+from .embedding_configs import EmbeddingConfig
 from .embedding_modules import EmbeddingCollection
 
 
+class OverlappingCheckerType(Enum):
+    """How overlap with the previous batch is detected. BOOLEAN: a boolean mask over the local rows of every shard."""
+
+    BOOLEAN = "boolean"
+
+
 class PECEmbeddingCollection(nn.Module):
-    def __init__(self, embedding_collection: EmbeddingCollection, encoders: Optional[Dict[str, Callable[[torch.Tensor, torch.Tensor], torch.Tensor]]] = None,
-                 return_encoded_features: bool = False) -> None:
-        """encoders: feature -> fn(values, position_in_bag) -> new ids (must stay inside the table)."""
+    def __init__(self, embedding_collection: EmbeddingCollection, checker_type: OverlappingCheckerType = OverlappingCheckerType.BOOLEAN) -> None:
         super().__init__()
         self._embedding_collection = embedding_collection
-        self._encoders = encoders or {}
-        self._return_encoded = return_encoded_features
+        self._checker_type = OverlappingCheckerType(checker_type)
 
-    def encode(self, features: KeyedJaggedTensor) -> KeyedJaggedTensor:
-        if not self._encoders:
-            return features
-        from ..ops import jagged as J
+    @property
+    def embedding_collection(self) -> EmbeddingCollection:
+        return self._embedding_collection
 
-        pos = J.offsets_range(features.offsets()[:-1].long(), features.values().numel())
-        lpk = features.length_per_key()
-        vals, poss = list(torch.split(features.values(), lpk)), torch.split(pos, lpk)
-        for i, k in enumerate(features.keys()):
-            if k in self._encoders:
-                vals[i] = self._encoders[k](vals[i], poss[i]).to(vals[i].dtype)
-        return KeyedJaggedTensor(keys=features.keys(), values=torch.cat(vals), lengths=features.lengths(), offsets=features.offsets(), weights=features.weights_or_none(),
-                                 stride=features.stride(), length_per_key=lpk)
+    @property
+    def checker_type(self) -> OverlappingCheckerType:
+        return self._checker_type
 
-    def forward(self, features: KeyedJaggedTensor):
-        enc = self.encode(features)
-        out: Dict[str, JaggedTensor] = self._embedding_collection(enc)
-        return (out, enc) if self._return_encoded else out
+    def forward(self, features: KeyedJaggedTensor) -> Dict[str, JaggedTensor]:
+        return self._embedding_collection(features)
+
+    def embedding_configs(self) -> List[EmbeddingConfig]:
+        return self._embedding_collection.embedding_configs()
+
+    def embedding_dim(self) -> int:
+        return self._embedding_collection.embedding_dim()
+
+    def need_indices(self) -> bool:
+        return self._embedding_collection.need_indices()

@@ -16,6 +16,7 @@ def default_extra_sharders() -> List[ModuleSharder]:
         ("fused_embeddingbag", "FusedEmbeddingBagCollectionSharder"),
         ("fused_embeddingbag", "FusedEmbeddingCollectionSharder"),
         ("embeddingbag", "EmbeddingBagSharder"),
+        ("pec_embedding", "PECEmbeddingCollectionSharder"),
         ("embedding_tower_sharding", "EmbeddingTowerSharder"),
         ("embedding_tower_sharding", "EmbeddingTowerCollectionSharder"),
         ("quant_embeddingbag", "QuantEmbeddingBagCollectionSharder"),
