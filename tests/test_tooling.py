@@ -276,3 +276,99 @@ def test_benchmark_model_lifecycle_gloo():
     from torchrec_b200.utils.multiprocess import run_multi_process
 
     run_multi_process(_lifecycle, world_size=2, backend="gloo")
+
+
+def test_distributed_helper_modules(tmp_path):
+    import copy
+
+    import torch
+    from torch import nn
+
+    from torchrec_b200.modules.embedding_configs import DataType, EmbeddingBagConfig
+    from torchrec_b200.modules.fused_embedding_modules import FusedEmbeddingBagCollection
+    from torchrec_b200.ops.tbe import OptimType
+    from torchrec_b200.parallel import fused_params as FP
+    from torchrec_b200.parallel import infer_utils as IU
+    from torchrec_b200.parallel import utils as U
+    from torchrec_b200.parallel.composable import TableBatchedEmbeddingSlice
+    from torchrec_b200.parallel.embedding_dim_bucketer import EmbDimBucketer, EmbDimBucketerPolicy
+    from torchrec_b200.parallel.shards_wrapper import LocalShardsWrapper
+    from torchrec_b200.parallel.types import ParameterSharding
+
+    # utils
+    assert U.append_prefix("a", "b") == "a.b" and U.append_prefix("", "b") == "b" and U.none_throws(3) == 3
+    sd = {"m.w": torch.ones(1), "m.sub.b": torch.zeros(1), "n.w": torch.ones(1)}
+    assert list(U.filter_state_dict(sd, "m")) == ["w", "sub.b"]
+    U.add_prefix_to_state_dict(sd, "x.")
+    assert set(sd) == {"x.m.w", "x.m.sub.b", "x.n.w"}
+    assert U.optimizer_type_to_emb_opt_type(torch.optim.Adagrad) == OptimType.EXACT_ADAGRAD and U.emb_opt_type_to_optimizer_class(OptimType.ADAM).__name__ == "Adam"
+    assert U.merge_fused_params({"learning_rate": 0.1, "eps": 1.0}, {"learning_rate": 0.5}) == {"learning_rate": 0.5, "eps": 1.0}
+    ps = ParameterSharding(sharding_type="table_wise", compute_kernel="fused", ranks=[0])
+    ps.stochastic_rounding = False
+    assert U.add_params_from_parameter_sharding({"eps": 1.0}, ps)["stochastic_rounding"] is False
+    lin = nn.Linear(3, 2, device="meta")
+    U.init_parameters(lin, torch.device("cpu"))
+    assert lin.weight.device.type == "cpu" and not lin.weight.is_meta
+    net = nn.Sequential(nn.Linear(2, 2), nn.ReLU())
+    assert U.get_unsharded_module_names(net) == [""]
+    with U.sharded_model_copy("cpu"):
+        net2 = copy.deepcopy(net)
+    assert torch.equal(net2[0].weight, net[0].weight) and net2[0].weight is not net[0].weight
+
+    class C(U.CopyableMixin):
+        def __init__(self):
+            super().__init__()
+            self.w = nn.Parameter(torch.ones(2))
+
+    assert torch.equal(C().copy(torch.device("cpu")).w, torch.ones(2))
+
+    # fused params
+    fp = {"learning_rate": 0.1, FP.FUSED_PARAM_REGISTER_TBE_BOOL: True, FP.FUSED_PARAM_TBE_ROW_ALIGNMENT: 16}
+    assert FP.is_fused_param_register_tbe(fp) and FP.get_fused_param_tbe_row_alignment(fp) == 16 and FP.tbe_fused_params(fp) == {"learning_rate": 0.1}
+    assert FP.get_embedding_table_index_type(None) == torch.int64 and not FP.is_fused_param_quant_state_dict_split_scale_bias(None)
+
+    # bucketer
+    class T:
+        def __init__(self, cols, dt):
+            self.local_cols, self.data_type = cols, dt
+
+    tabs = [T(16, DataType.FP32), T(32, DataType.FP32), T(64, DataType.FP16), T(200, DataType.FP32)]   # 64 B, 128 B, 128 B, 800 B
+    assert EmbDimBucketer(tabs, EmbDimBucketerPolicy.SINGLE_BUCKET).bucket_count() == 1
+    allb = EmbDimBucketer(tabs, EmbDimBucketerPolicy.ALL_BUCKETS)
+    assert allb.bucket_count() == 3 and allb.get_bucket(32, DataType.FP32) == allb.get_bucket(64, DataType.FP16)
+    cl = EmbDimBucketer(tabs, EmbDimBucketerPolicy.CACHELINE_BUCKETS)
+    assert cl.bucket_count() == 2 and cl.get_bucket(16, DataType.FP32) == cl.get_bucket(32, DataType.FP32) != cl.get_bucket(200, DataType.FP32)
+
+    # infer utils on a fused EBC
+    febc = FusedEmbeddingBagCollection([EmbeddingBagConfig(name="a", embedding_dim=8, num_embeddings=10, feature_names=["fa"]),
+                                        EmbeddingBagConfig(name="b", embedding_dim=8, num_embeddings=20, feature_names=["fb"])], torch.optim.SGD, {"lr": 0.1})
+    assert len(IU.get_tbes_from_sharded_module(febc)) == 1
+    specs = IU.get_tbe_specs_from_sharded_module(febc)
+    assert [(r, c) for _, r, c, _, _ in specs] == [(10, 8), (20, 8)] and U.weights_bytes_in_emb_kernel(febc) == 30 * 8 * 4
+    assert all(d == "cpu" for _, d in IU.get_path_device_tuples(febc)) and "" in IU.get_all_torchrec_modules(febc)
+
+    # parameter slice over a flat buffer
+    flat = torch.arange(24.0, requires_grad=True)
+    sl = TableBatchedEmbeddingSlice(flat, 4, 16, 3, 4)
+    assert sl.shape == (3, 4) and isinstance(sl, nn.Parameter) and float(sl[0, 0]) == 4.0
+    with torch.no_grad():
+        flat[4] = -1.0
+    assert float(sl[0, 0]) == -1.0                               # shares storage with the buffer
+    flat.grad = torch.ones(24)
+    assert sl.grad.shape == (3, 4) and float(sl.grad.sum()) == 12.0
+    assert copy.deepcopy(sl).shape == (3, 4)
+
+    # local shards wrapper
+    a, b = torch.ones(4, 2), torch.full((4, 3), 2.0)
+    w = LocalShardsWrapper([a, b], [(0, 0), (0, 2)])
+    assert tuple(w.shape) == (4, 5) and len(w.local_shards()) == 2 and w.local_offsets() == [(0, 0), (0, 2)]
+    assert torch.equal(w.full_tensor(), torch.cat([a, b], 1))
+    c = w.detach().clone()
+    assert isinstance(c, LocalShardsWrapper) and torch.equal(c.local_shards()[1], b) and c.local_shards()[1] is not b
+    full = torch.arange(20.0).view(4, 5)
+    c.copy_(full)
+    assert torch.equal(c.local_shards()[1], full[:, 2:5])
+    path = tmp_path / "w.pt"
+    torch.save({"t": w}, path)
+    back = torch.load(path, weights_only=False)["t"]
+    assert isinstance(back, LocalShardsWrapper) and torch.equal(back.local_shards()[0], a)
