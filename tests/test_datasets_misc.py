@@ -169,3 +169,26 @@ def test_example_sharding_types_gloo():
     from torchrec_b200.utils.multiprocess import run_multi_process
 
     run_multi_process(_sharding_types, world_size=2, backend="gloo")
+
+
+def test_virtual_table_eviction_policies_and_feature_scores():
+    import torch
+
+    from torchrec_b200.modules.embedding_configs import (CountBasedEvictionPolicy, DataType, EmbeddingBagConfig, FeatureScoreBasedEvictionPolicy, NoEvictionPolicy,
+                                                           TimestampBasedEvictionPolicy, eviction_policy_to_cache_algorithm)
+    from torchrec_b200.parallel.feature_score_utils import create_sharding_type_to_feature_score_mapping, may_collect_feature_scores
+    from torchrec_b200.sparse import KeyedJaggedTensor
+
+    pol = FeatureScoreBasedEvictionPolicy(feature_score_mapping={"fa": 2.0}, feature_score_default_value=0.5)
+    a = EmbeddingBagConfig(name="a", embedding_dim=8, num_embeddings=1 << 40, feature_names=["fa", "fa2"], use_virtual_table=True, virtual_table_eviction_policy=pol,
+                           data_type=DataType.FP16)
+    assert pol.initialized and pol.get_meta_header_len() == 8 and pol.get_embedding_dim() == 8       # 16 B header / 2 B elements
+    b = EmbeddingBagConfig(name="b", embedding_dim=8, num_embeddings=100, feature_names=["fb"])
+    acc, auto, mapping = create_sharding_type_to_feature_score_mapping([a, b], {"row_wise": ["a", "b"]})
+    assert acc and not auto and mapping == {"row_wise": {"fa": 2.0, "fa2": 0.5}}
+    assert CountBasedEvictionPolicy(eviction_threshold=3).inference_eviction_threshold == 3 and TimestampBasedEvictionPolicy().inference_eviction_ttl_mins == 1440
+    assert eviction_policy_to_cache_algorithm(pol) == "lfu" and eviction_policy_to_cache_algorithm(NoEvictionPolicy()) == "lru"
+    kjt = KeyedJaggedTensor(keys=["fa", "fa2"], values=torch.tensor([1, 2, 3]), lengths=torch.tensor([2, 0, 1, 0]))
+    scored = may_collect_feature_scores(kjt, True, mapping["row_wise"])
+    assert scored.weights().tolist() == [2.0, 2.0, 0.5]
+    assert create_sharding_type_to_feature_score_mapping([b], {"table_wise": ["b"]}) == (False, False, {})

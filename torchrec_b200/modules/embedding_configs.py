@@ -68,6 +68,106 @@ def data_type_to_dtype(data_type: DataType) -> torch.dtype:
     raise ValueError(f"DataType {data_type} cannot be converted to dtype")
 
 
+# ---- virtual (key-value backed) tables: eviction policies (reference embedding_configs.py:170-345) -----------------------------------
+@dataclass
+class VirtualTableEvictionPolicy:
+    """Base of the eviction policies of a virtual table: a table whose id space is larger than its resident rows and whose rows live
+    in a key-value store with an HBM cache in front (compute kernel ``key_value``). ``meta_header_len`` = elements of the per-row
+    header (8 B key, 4 B timestamp, 1 bit used + 31 bit count) in units of the table's element size."""
+
+    meta_header_len: int = 0
+    embedding_dim: int = 0
+    initialized: bool = False
+
+    def init_metaheader_config(self, data_type: DataType, embedding_dim: int) -> None:
+        if self.initialized:
+            return
+        self.meta_header_len = 16 // data_type_to_dtype(data_type).itemsize
+        self.embedding_dim = embedding_dim
+        self.initialized = True
+
+    def get_meta_header_len(self) -> int:
+        return self.meta_header_len
+
+    def get_embedding_dim(self) -> int:
+        return self.embedding_dim
+
+
+@dataclass
+class CountBasedEvictionPolicy(VirtualTableEvictionPolicy):
+    training_id_eviction_trigger_count: int = 0  # ids per rank that trigger an eviction pass
+    eviction_threshold: int = 15                 # rows seen fewer times than this are evicted (0: never)
+    decay_rate: float = 0.99
+    inference_eviction_threshold: Optional[int] = None
+
+    def __post_init__(self) -> None:
+        if self.inference_eviction_threshold is None:
+            self.inference_eviction_threshold = self.eviction_threshold
+
+
+@dataclass
+class FeatureScoreBasedEvictionPolicy(VirtualTableEvictionPolicy):
+    decay_rate: float = 0.99
+    training_id_eviction_trigger_count: int = 0
+    training_id_keep_count: int = 0
+    eviction_ttl_mins: int = 0
+    max_inference_id_num_per_rank: int = 0
+    inference_eviction_feature_score_threshold: Optional[float] = None
+    feature_score_mapping: Optional[Dict[str, float]] = None  # feature -> score weight
+    feature_score_default_value: Optional[float] = None
+    enable_auto_feature_score_collection: bool = False
+
+
+@dataclass
+class TimestampBasedEvictionPolicy(VirtualTableEvictionPolicy):
+    training_id_eviction_trigger_count: int = 0
+    eviction_ttl_mins: int = 24 * 60
+    inference_eviction_ttl_mins: Optional[int] = None
+
+    def __post_init__(self) -> None:
+        if self.inference_eviction_ttl_mins is None:
+            self.inference_eviction_ttl_mins = self.eviction_ttl_mins
+
+
+@dataclass
+class CountTimestampMixedEvictionPolicy(VirtualTableEvictionPolicy):
+    training_id_eviction_trigger_count: int = 0
+    eviction_threshold: int = 15
+    decay_rate: float = 0.99
+    eviction_ttl_mins: int = 24 * 60
+    inference_eviction_threshold: Optional[int] = None
+    inference_eviction_ttl_mins: Optional[int] = None
+
+    def __post_init__(self) -> None:
+        if self.inference_eviction_threshold is None:
+            self.inference_eviction_threshold = self.eviction_threshold
+        if self.inference_eviction_ttl_mins is None:
+            self.inference_eviction_ttl_mins = self.eviction_ttl_mins
+
+
+@dataclass
+class FeatureL2NormBasedEvictionPolicy(VirtualTableEvictionPolicy):
+    training_id_eviction_trigger_count: int = 0
+    eviction_threshold: float = 0.0
+    inference_eviction_threshold: Optional[float] = None
+
+    def __post_init__(self) -> None:
+        if self.inference_eviction_threshold is None:
+            self.inference_eviction_threshold = self.eviction_threshold
+
+
+@dataclass
+class NoEvictionPolicy(VirtualTableEvictionPolicy):
+    pass
+
+
+def eviction_policy_to_cache_algorithm(policy: Optional[VirtualTableEvictionPolicy]) -> str:
+    """Which victim selection of the HBM row cache (``ops/uvm.py``) realises a policy: count / score based -> LFU, time based -> LRU."""
+    if isinstance(policy, (CountBasedEvictionPolicy, FeatureScoreBasedEvictionPolicy, FeatureL2NormBasedEvictionPolicy)):
+        return "lfu"
+    return "lru"
+
+
 @dataclass
 class BaseEmbeddingConfig:
     num_embeddings: int
@@ -84,6 +184,8 @@ class BaseEmbeddingConfig:
     input_dim: Optional[int] = None
     total_num_buckets: Optional[int] = None
     use_virtual_table: bool = False
+    virtual_table_eviction_policy: Optional[VirtualTableEvictionPolicy] = None
+    enable_embedding_update: bool = False
     stash_weights: bool = False
 
     def get_weight_init_max(self) -> float:
@@ -102,6 +204,8 @@ class BaseEmbeddingConfig:
     def __post_init__(self) -> None:
         if self.init_fn is None:
             self.init_fn = partial(torch.nn.init.uniform_, a=self.get_weight_init_min(), b=self.get_weight_init_max())
+        if self.use_virtual_table and self.virtual_table_eviction_policy is not None:
+            self.virtual_table_eviction_policy.init_metaheader_config(self.data_type, self.embedding_dim)
 
 
 @dataclass
