@@ -92,3 +92,37 @@ def test_state_dict_transform_gloo():
     from torchrec_b200.utils.multiprocess import run_multi_process
 
     run_multi_process(_sd_transform, world_size=2, backend="gloo")
+
+
+def test_quant_state_specs():
+    import torch
+
+    from torchrec_b200.inference.modules import quantize_inference_model, shard_quant_model
+    from torchrec_b200.modules.embedding_configs import EmbeddingBagConfig
+    from torchrec_b200.modules.embedding_modules import EmbeddingBagCollection
+    from torchrec_b200.parallel.planner.types import ParameterConstraints
+    from torchrec_b200.parallel.quant_state import ShardedQuantEmbeddingModuleState, sharded_tbes_weights_spec
+    from torchrec_b200.parallel.shards_wrapper import LocalShardsWrapper
+
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.ebc = EmbeddingBagCollection([EmbeddingBagConfig(name="a", embedding_dim=16, num_embeddings=40, feature_names=["fa"]),
+                                               EmbeddingBagConfig(name="b", embedding_dim=16, num_embeddings=64, feature_names=["fb"])])
+
+        def forward(self, kjt):
+            return self.ebc(kjt).values()
+
+    q = quantize_inference_model(M())
+    sharded, _ = shard_quant_model(q, world_size=2, compute_device="cpu", sharding_device="cpu",
+                                   constraints={"a": ParameterConstraints(sharding_types=["table_wise"]), "b": ParameterConstraints(sharding_types=["row_wise"])})
+    specs = sharded_tbes_weights_spec(sharded)
+    by_table = {}
+    for k, s in specs.items():
+        assert k.startswith("ebc.tbes.") and s.fqn.startswith("ebc.embedding_bags.")
+        by_table.setdefault(s.fqn.split(".")[2], []).append(s)
+    assert len(by_table["a"]) == 1 and by_table["a"][0].sharding_type == "table_wise" and by_table["a"][0].shard_sizes == [40, 16]
+    assert len(by_table["b"]) == 2 and {s.sharding_type for s in by_table["b"]} == {"row_wise"} and sorted(s.shard_offsets[0] for s in by_table["b"]) == [0, 32]
+    sd = ShardedQuantEmbeddingModuleState.sharded_state_dict(sharded.ebc, prefix="ebc.")
+    assert sd["ebc.embedding_bags.a.weight"].dtype == torch.uint8 and sd["ebc.embedding_bags.a.weight"].shape[0] == 40
+    assert isinstance(sd["ebc.embedding_bags.b.weight"], LocalShardsWrapper) and sd["ebc.embedding_bags.b.weight"].local_offsets() == [(0, 0), (32, 0)]
