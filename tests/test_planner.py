@@ -84,3 +84,19 @@ def test_partitioners_and_dp_proposer():
     for part in (GreedyPerfPartitioner(), MemoryBalancedPartitioner()):
         plan = EmbeddingShardingPlanner(topology=topo, batch_size=512, partitioner=part, proposer=DynamicProgrammingProposer()).plan(m, [EmbeddingBagCollectionSharder()])
         assert set(plan.plan["sparse"].keys()) == {f"t{i}" for i in range(6)}
+
+
+def test_sharding_route_facade():
+    from torchrec_b200.modules.embedding_configs import EmbeddingBagConfig
+    from torchrec_b200.modules.embedding_modules import EmbeddingBagCollection
+    from torchrec_b200.parallel import sharding_plan as sp
+    from torchrec_b200.parallel.embeddingbag import EmbeddingBagCollectionSharder
+    from torchrec_b200.parallel.sharding import all_routes, describe, units_for
+
+    assert {r.sharding_type for r in all_routes()} == {"data_parallel", "table_wise", "column_wise", "table_column_wise", "row_wise", "table_row_wise", "grid_shard"}
+    assert "sum" in describe("row_wise").combine and describe("column_wise").reference_module.endswith("cw_sharding.py")
+    cfg = EmbeddingBagConfig(name="t", embedding_dim=16, num_embeddings=100, feature_names=["f"])
+    ebc = EmbeddingBagCollection([cfg], device="meta")
+    plan = sp.construct_module_sharding_plan(ebc, {"t": sp.row_wise()}, sharder=EmbeddingBagCollectionSharder(), world_size=4, local_size=4, device_type="cpu")
+    shards = units_for(0, cfg, plan["t"])
+    assert [s.rank for s in shards] == [0, 1, 2, 3] and sum(s.rows for s in shards) == 100 and all(s.cols == 16 for s in shards)
