@@ -116,3 +116,16 @@ def test_dynamic_embedding_training_matches_full_table():
     chk = PS("ebc.t", [out], url)
     chk.fetch(torch.stack([torch.arange(N), torch.arange(N)], 1))
     torch.testing.assert_close(out, full.embedding_bags["t"].weight.data)
+
+
+def test_native_cpp_tests_and_benchmark():
+    """The C++ test executable of the id transformer (reference test/cpp + benchmarks/cpp dynamic_embedding)."""
+    import subprocess
+
+    from torchrec_b200.csrc.build import build_native_test
+
+    exe = build_native_test("dynemb")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "all passed" in r.stdout, r.stderr
+    b = subprocess.run([exe, "--bench"], capture_output=True, text=True, timeout=300)
+    assert b.returncode == 0 and "M ids/s" in b.stdout

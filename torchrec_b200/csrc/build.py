@@ -34,6 +34,26 @@ def build_one(name: str, force: bool = False, verbose: bool = False) -> str:
     return lib
 
 
+def build_native_test(name: str = "dynemb", verbose: bool = False) -> str:
+    """Compile ``csrc/tests/<name>_test.cpp`` together with the library's sources into ``csrc/_lib/<name>_test`` (a plain executable:
+    the image has neither gtest nor google-benchmark). ``<exe>`` runs the checks, ``<exe> --bench`` the micro-benchmark."""
+    src_dir = os.path.join(HERE, name)
+    test_src = os.path.join(HERE, "tests", f"{name}_test.cpp")
+    srcs = sorted(os.path.join(src_dir, f) for f in os.listdir(src_dir) if f.endswith(".cpp") and f != "c_api.cpp")
+    exe = os.path.join(OUT, f"{name}_test")
+    os.makedirs(OUT, exist_ok=True)
+    deps = srcs + [test_src] + [os.path.join(src_dir, f) for f in os.listdir(src_dir) if f.endswith(".h")]
+    if os.path.exists(exe) and os.path.getmtime(exe) >= max(os.path.getmtime(d) for d in deps):
+        return exe
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-o", exe, test_src, *srcs, *LIBS.get(name, [])]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"g++ failed for {name}_test:\n{r.stdout}\n{r.stderr}")
+    if verbose:
+        print(f"[trb200 build] {os.path.basename(exe)} ok")
+    return exe
+
+
 def build(force: bool = False, verbose: bool = False) -> List[str]:
     return [build_one(n, force, verbose) for n in LIBS if os.path.isdir(os.path.join(HERE, n))]
 
