@@ -173,3 +173,30 @@ def test_low_rank_crossnet_on_tcgen05_matches_torch():
     torch.testing.assert_close(out, ref, rtol=3e-2, atol=6e-2)
     torch.testing.assert_close(x.grad, gref, rtol=5e-2, atol=1e-1)
     torch.testing.assert_close(net.W_kernels[0].grad, gw_ref, rtol=5e-2, atol=2.0)
+
+
+@pytest.mark.parametrize("tile_n", [0, 128, 256, 512])
+@pytest.mark.parametrize("M,N,K", [(512, 256, 128), (1000, 480, 256), (4100, 1024, 512), (300, 64, 64)])
+def test_relu_bit_mask_roundtrip(M, N, K, tile_n):
+    """Forward ReLU epilogue writes 1 bit per output; the masked dgrad consumes the bits instead of the bf16 activation."""
+    from torchrec_b200.ops.gemm import ACT_RELU, ACT_RELU_GRAD, gemm_bf16
+
+    if tile_n in (256, 512) and N % 256 != 0 and tile_n == 256:
+        pytest.skip("wide tiles need N % 256 == 0")
+    dev = torch.device("cuda:0")
+    torch.manual_seed(11)
+    a = (torch.randn(M, K, device=dev) * 0.3).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=dev) * 0.3).to(torch.bfloat16)
+    bias = torch.randn(N, device=dev) * 0.1
+    words = (N + 31) // 32
+    bits = torch.full((M, words), -1, dtype=torch.int32, device=dev)
+    y = gemm_bf16(a, w, bias=bias, act=ACT_RELU, relu_bits_out=bits, tile_n=tile_n)
+    cols = torch.arange(N, device=dev)
+    got = ((bits[:, cols // 32] >> (cols % 32)) & 1).bool()
+    assert torch.equal(got, y > 0)
+    gy = (torch.randn(M, N, device=dev) * 0.5).to(torch.bfloat16)
+    wt = (torch.randn(N, N, device=dev) * 0.1).to(torch.bfloat16)          # dgrad of a following N -> N layer: [M, N] = gy [M, N] . W [N, N]
+    ref = gemm_bf16(gy, wt, b_mn=True, act=ACT_RELU_GRAD, mask=y, tile_n=tile_n)
+    out = gemm_bf16(gy, wt, b_mn=True, act=ACT_RELU_GRAD, mask=y, mask_bits=bits, tile_n=tile_n)
+    assert torch.equal(out, ref)
+    assert torch.equal(out == 0, (ref == 0)) and bool(((out != 0) <= (y > 0)).all())

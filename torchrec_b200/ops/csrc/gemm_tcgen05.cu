@@ -42,6 +42,10 @@ struct GemmParams {
   float alpha;                  // scale applied to the accumulator before bias
   int split_k;                  // >1: K range split over CTAs, fp32 atomicAdd epilogue (out pre-zeroed)
   int tma_store;                // 1: bf16 output leaves through smem + TMA stores (tmap_o valid)
+  // 1 bit per element instead of re-reading the bf16 activation as the ReLU-gradient mask (67 MB -> 4 MB for 32768 x 1024):
+  uint32_t* relu_bits_out;      // ACT_RELU: bit (n % 32) of word [m, n / 32] = (out[m, n] > 0); nullptr: not wanted
+  const uint32_t* mask_bits;    // ACT_RELU_GRAD: the same words of the layer whose gradient this is; nullptr: use `mask`
+  int64_t ld_bits;              // words per row of either bit matrix
 };
 
 // ---- bf16 epilogue through shared memory + TMA stores ---------------------------------------------------------------
@@ -80,8 +84,11 @@ __device__ __forceinline__ void epilogue_bf16_tma_impl(const CUtensorMap* tmap_o
   }
   const uint32_t sw = (uint32_t) (lane & 7);
   const bool scale = p.alpha != 1.f;
-  // ReLU-gradient mask: the [32 rows x 64 cols] tile of group g+1 is fetched (8 lanes per row, full 128 B lines, 8 loads in
-  // flight) while group g is processed; exposed HBM latency per group made the masked dgrad 2x slower than the plain one
+  // ReLU-gradient mask: either one bit per element written by the forward epilogue of that layer (2 words per row and group,
+  // no smem staging) or, as fallback, the bf16 activation itself: its [32 rows x 64 cols] tile of group g+1 is fetched (8 lanes
+  // per row, full 128 B lines, 8 loads in flight) while group g is processed.
+  const bool use_bits = (ACT == ACT_RELU_GRAD) && p.mask_bits != nullptr;
+  const int my_row = row0 + lane;
   uint4 m[8];
   auto load_mask = [&](int n0) {
 #pragma unroll
@@ -91,7 +98,9 @@ __device__ __forceinline__ void epilogue_bf16_tma_impl(const CUtensorMap* tmap_o
       if (grow < p.M && col < p.N) m[i] = __ldg(reinterpret_cast<const uint4*>(p.mask + (int64_t) grow * p.ld_mask + col));
     }
   };
-  if constexpr (ACT == ACT_RELU_GRAD) load_mask(n_base);
+  if constexpr (ACT == ACT_RELU_GRAD) {
+    if (!use_bits) load_mask(n_base);
+  }
 #pragma unroll 1
   for (int g = 0; g < BN / 64; ++g) {
     const int n0 = n_base + 64 * g;
@@ -99,15 +108,25 @@ __device__ __forceinline__ void epilogue_bf16_tma_impl(const CUtensorMap* tmap_o
     uint32_t r0[32], r1[32];
     tmem_ld_32x32_nowait(tmem_acc + (uint32_t) (64 * g), r0);
     tmem_ld_32x32_nowait(tmem_acc + (uint32_t) (64 * g + 32), r1);
+    uint32_t mbits0 = 0u, mbits1 = 0u;
     if constexpr (ACT == ACT_RELU_GRAD) {
-      // (all lanes finished reading the previous group's mask at the __syncwarp that ended the previous iteration)
+      if (use_bits) {
+        if (my_row < p.M) {
+          const uint32_t* bw = p.mask_bits + (int64_t) my_row * p.ld_bits + (n0 >> 5);
+          mbits0 = __ldg(bw);
+          if (n0 + 32 < p.N) mbits1 = __ldg(bw + 1);
+        }
+      } else {
+        // (all lanes finished reading the previous group's mask at the __syncwarp that ended the previous iteration)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int rr = i * 4 + (lane >> 3), piece = lane & 7;
-        *reinterpret_cast<uint4*>(mask_slab + rr * 128 + ((piece ^ (rr & 7)) << 4)) = m[i];
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + (lane >> 3), piece = lane & 7;
+          *reinterpret_cast<uint4*>(mask_slab + rr * 128 + ((piece ^ (rr & 7)) << 4)) = m[i];
+        }
+        if (g + 1 < BN / 64 && n0 + 64 < p.N) load_mask(n0 + 64);
       }
-      if (g + 1 < BN / 64 && n0 + 64 < p.N) load_mask(n0 + 64);
     }
+    uint32_t obits0 = 0u, obits1 = 0u;
     // the TMA store that read this slab two groups ago must be done with it
     if (lane == 0) bulk_wait_group_read<1>();
     __syncwarp();
@@ -131,18 +150,37 @@ __device__ __forceinline__ void epilogue_bf16_tma_impl(const CUtensorMap* tmap_o
       if constexpr (ACT == ACT_RELU) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
+        if (p.relu_bits_out != nullptr) {
+          uint32_t b8 = 0u;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) b8 |= (v[q] > 0.f ? 1u : 0u) << q;
+          if (j < 4) obits0 |= b8 << (8 * j); else obits1 |= b8 << (8 * (j - 4));
+        }
       } else if constexpr (ACT == ACT_SIGMOID) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) v[q] = 1.f / (1.f + __expf(-v[q]));
       } else if constexpr (ACT == ACT_RELU_GRAD) {
-        const uint4 m8 = *reinterpret_cast<const uint4*>(mask_slab + lane * 128 + (((uint32_t) j ^ sw) << 4));
-        const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&m8);
+        if (use_bits) {
+          const uint32_t b8 = (j < 4 ? (mbits0 >> (8 * j)) : (mbits1 >> (8 * (j - 4)))) & 0xFFu;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = (__bfloat162float(mb[q]) > 0.f) ? v[q] : 0.f;
+          for (int q = 0; q < 8; ++q) v[q] = ((b8 >> q) & 1u) ? v[q] : 0.f;
+        } else {
+          const uint4 m8 = *reinterpret_cast<const uint4*>(mask_slab + lane * 128 + (((uint32_t) j ^ sw) << 4));
+          const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&m8);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[q] = (__bfloat162float(mb[q]) > 0.f) ? v[q] : 0.f;
+        }
       }
       uint4 o;
       o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
       *reinterpret_cast<uint4*>(slab + lane * 128 + (((uint32_t) j ^ sw) << 4)) = o;
+    }
+    if constexpr (ACT == ACT_RELU) {
+      if (p.relu_bits_out != nullptr && my_row < p.M) {
+        uint32_t* bw = p.relu_bits_out + (int64_t) my_row * p.ld_bits + (n0 >> 5);
+        bw[0] = obits0;
+        if (n0 + 32 < p.N) bw[1] = obits1;
+      }
     }
     fence_proxy_async();
     __syncwarp();
@@ -322,7 +360,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const int mn = tile % mn_tiles;
       const int m_blk = mn / n_tiles, n_blk = mn % n_tiles;
       if constexpr (L::kEpiTma) {
-        if (p.tma_store && p.act == ACT_RELU_GRAD) {
+        if (p.tma_store && p.act == ACT_RELU_GRAD && p.mask_bits == nullptr) {
           // this tile's mask on the first iteration, then always the NEXT tile's: a whole epilogue ahead of its use
           if (tile == (int) blockIdx.x) prefetch_mask_tile<BLOCK_N>(p, m_blk * BLOCK_M + ew * 32, n_blk * BLOCK_N, lane);
           const int nt = tile + (int) gridDim.x;
@@ -368,9 +406,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         if (p.act == ACT_RELU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          if (p.relu_bits_out != nullptr && row_ok) {
+            uint32_t w = 0u;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) w |= (v[j] > 0.f ? 1u : 0u) << j;
+            p.relu_bits_out[(int64_t) row * p.ld_bits + (n0 >> 5)] = w;
+          }
         } else if (p.act == ACT_SIGMOID) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
+        } else if (p.act == ACT_RELU_GRAD && p.mask_bits != nullptr) {
+          if (row_ok) {
+            const uint32_t w = __ldg(p.mask_bits + (int64_t) row * p.ld_bits + (n0 >> 5));
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = ((w >> j) & 1u) ? v[j] : 0.f;
+          }
         } else if (p.act == ACT_RELU_GRAD) {
           if (row_ok) {
             const __nv_bfloat16* mrow = p.mask + (int64_t) row * p.ld_mask + n0;
@@ -584,7 +634,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int mn = tile % mn_tiles;
       const int m_blk = mn / n_tiles, n_blk = mn % n_tiles;
-      if (p.tma_store && p.act == ACT_RELU_GRAD) {
+      if (p.tma_store && p.act == ACT_RELU_GRAD && p.mask_bits == nullptr) {
         // this tile's mask on the first iteration, then always the NEXT tile's: a whole epilogue ahead of its use
         if (tile == cluster_id) prefetch_mask_tile<kPairN>(p, m_blk * 2 * BLOCK_M + (int) cta_rank * BLOCK_M + ew * 32, n_blk * kPairN, lane);
         const int nt = tile + num_clusters;
@@ -628,9 +678,21 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
         if (p.act == ACT_RELU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          if (p.relu_bits_out != nullptr && row_ok) {
+            uint32_t w = 0u;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) w |= (v[j] > 0.f ? 1u : 0u) << j;
+            p.relu_bits_out[(int64_t) row * p.ld_bits + (n0 >> 5)] = w;
+          }
         } else if (p.act == ACT_SIGMOID) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
+        } else if (p.act == ACT_RELU_GRAD && p.mask_bits != nullptr) {
+          if (row_ok) {
+            const uint32_t w = __ldg(p.mask_bits + (int64_t) row * p.ld_bits + (n0 >> 5));
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = ((w >> j) & 1u) ? v[j] : 0.f;
+          }
         } else if (p.act == ACT_RELU_GRAD) {
           if (row_ok) {
             const __nv_bfloat16* mrow = p.mask + (int64_t) row * p.ld_mask + n0;
@@ -810,9 +872,21 @@ static int gemm_dispatch(const void* A, int64_t lda, const void* B, int64_t ldb,
   return launch_gemm<128, 5, A_MN, B_MN>(ta, tb, to, p, stream);
 }
 
+TRB_API int trb_gemm_bf16_ex2(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* out, int64_t ldo, int out_f32, int M,
+                              int N, int K, const float* bias, int act, const void* mask, int64_t ld_mask, float alpha, int split_k, int tile_n,
+                              const void* mask_bits, void* relu_bits_out, int64_t ld_bits, cudaStream_t stream);
+
 TRB_API int trb_gemm_bf16_ex(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* out, int64_t ldo, int out_f32, int M,
                              int N, int K, const float* bias, int act, const void* mask, int64_t ld_mask, float alpha, int split_k, int tile_n,
                              cudaStream_t stream) {
+  return trb_gemm_bf16_ex2(A, lda, a_mn, B, ldb, b_mn, out, ldo, out_f32, M, N, K, bias, act, mask, ld_mask, alpha, split_k, tile_n, nullptr, nullptr, 0,
+                           stream);
+}
+
+// mask_bits / relu_bits_out: int32 [M, ld_bits] bit matrices (bit n % 32 of word n / 32), see GemmParams
+TRB_API int trb_gemm_bf16_ex2(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* out, int64_t ldo, int out_f32, int M,
+                              int N, int K, const float* bias, int act, const void* mask, int64_t ld_mask, float alpha, int split_k, int tile_n,
+                              const void* mask_bits, void* relu_bits_out, int64_t ld_bits, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if ((lda % 8) || (ldb % 8) || (N % 8)) return -12;
   if ((!a_mn && (K % 8)) || (a_mn && (M % 8)) || (b_mn && (N % 8)) || (!b_mn && (K % 8))) return -12;
@@ -827,6 +901,10 @@ TRB_API int trb_gemm_bf16_ex(const void* A, int64_t lda, int a_mn, const void* B
   p.act = act;
   p.alpha = alpha;
   p.split_k = 1;
+  p.mask_bits = reinterpret_cast<const uint32_t*>(mask_bits);
+  p.relu_bits_out = reinterpret_cast<uint32_t*>(relu_bits_out);
+  p.ld_bits = ld_bits;
+  if ((mask_bits != nullptr || relu_bits_out != nullptr) && ld_bits * 32 < N) return -12;
   if (split_k > 1) {
     if (!out_f32 || bias != nullptr || act != ACT_NONE) return -13;  // split-K only for plain fp32 accumulation
     const int kb = (K + BLOCK_K - 1) / BLOCK_K;

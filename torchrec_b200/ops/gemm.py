@@ -31,9 +31,11 @@ def _check_bf16_2d(t: torch.Tensor, name: str) -> None:
 
 def gemm_bf16(a: torch.Tensor, b: torch.Tensor, a_mn: bool = False, b_mn: bool = False, bias: Optional[torch.Tensor] = None,
               act: int = ACT_NONE, out_dtype: torch.dtype = torch.bfloat16, mask: Optional[torch.Tensor] = None, alpha: float = 1.0,
-              out: Optional[torch.Tensor] = None, split_k: int = 1, tile_n: int = 0) -> torch.Tensor:
+              out: Optional[torch.Tensor] = None, split_k: int = 1, tile_n: int = 0, mask_bits: Optional[torch.Tensor] = None,
+              relu_bits_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``act(alpha * op(a) @ op(b)^T + bias)`` on the tcgen05 kernel. ``tile_n``: 0 = kernel picks 128 x {64,128,256} tiles,
-    128 / 256 = the caller sized ``split_k`` for that tile width.
+    128 / 256 = the caller sized ``split_k`` for that tile width. ``relu_bits_out`` (int32 ``[M, ceil(N / 32)]``, with ``ACT_RELU``):
+    receives one bit per output (> 0); ``mask_bits`` (same layout, with ``ACT_RELU_GRAD``): used instead of re-reading ``mask``.
 
     ``a_mn=False``: a is ``[M, K]`` (K-major);  ``a_mn=True``: a is ``[K, M]`` (consumed MN-major, no transpose copy).
     ``b_mn=False``: b is ``[N, K]``;            ``b_mn=True``: b is ``[K, N]``.
@@ -56,21 +58,27 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, a_mn: bool = False, b_mn: bool =
         assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == N
     if act == ACT_RELU_GRAD:
         assert mask is not None and mask.dtype == torch.bfloat16 and mask.shape == (M, N) and mask.stride(1) == 1 and mask.stride(0) % 8 == 0
+    bits = mask_bits if act == ACT_RELU_GRAD else (relu_bits_out if act == ACT_RELU else None)
+    ld_bits = 0
+    if bits is not None:
+        assert bits.dtype == torch.int32 and bits.dim() == 2 and bits.shape[0] == M and bits.stride(1) == 1 and bits.stride(0) * 32 >= N and bits.device == a.device
+        ld_bits = bits.stride(0)
     L = _lib.lib()
-    code = L.trb_gemm_bf16_ex(
+    code = L.trb_gemm_bf16_ex2(
         _lib.ptr(a), ctypes.c_int64(a.stride(0)), int(a_mn), _lib.ptr(b), ctypes.c_int64(b.stride(0)), int(b_mn), _lib.ptr(out),
         ctypes.c_int64(out.stride(0)), 1 if out.dtype == torch.float32 else 0, M, N, K, _lib.ptr(bias), act, _lib.ptr(mask),
-        ctypes.c_int64(mask.stride(0) if mask is not None else 0), ctypes.c_float(alpha), int(split_k), int(tile_n), _lib.stream_ptr(a.device),
+        ctypes.c_int64(mask.stride(0) if mask is not None else 0), ctypes.c_float(alpha), int(split_k), int(tile_n),
+        _lib.ptr(mask_bits if act == ACT_RELU_GRAD else None), _lib.ptr(relu_bits_out if act == ACT_RELU else None), ctypes.c_int64(ld_bits), _lib.stream_ptr(a.device),
     )
-    _lib.check(code, "trb_gemm_bf16_ex")
+    _lib.check(code, "trb_gemm_bf16_ex2")
     return out
 
 
 def gemm_bf16_tn(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
                  out_dtype: torch.dtype = torch.bfloat16, mask: Optional[torch.Tensor] = None, alpha: float = 1.0,
-                 out: Optional[torch.Tensor] = None, split_k: int = 1) -> torch.Tensor:
+                 out: Optional[torch.Tensor] = None, split_k: int = 1, relu_bits_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``act(alpha * a @ b.T + bias)`` with a ``[M, K]`` and b ``[N, K]`` (both K-major)."""
-    return gemm_bf16(a, b, False, False, bias, act, out_dtype, mask, alpha, out, split_k)
+    return gemm_bf16(a, b, False, False, bias, act, out_dtype, mask, alpha, out, split_k, relu_bits_out=relu_bits_out)
 
 
 def transpose_bf16(x: torch.Tensor, pad_cols_to: int = 8) -> torch.Tensor:
@@ -103,6 +111,9 @@ def _num_sms(device: torch.device) -> int:
         _SMS[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
     return _SMS[idx]
 
+
+# ReLU layers emit a bit mask of their output for the following layer's masked dgrad (TRB_GEMM_RELU_BITS=0: re-read the activation)
+RELU_BITS = os.environ.get("TRB_GEMM_RELU_BITS", "1") != "0"
 
 # cta_group::2 GEMM (csrc/gemm_tcgen05.cu: gemm_bf16_tcgen05_pair_kernel); the C++ dispatcher reads the same variable
 PAIR_DEFAULT = os.environ.get("TRB_GEMM_PAIR", "1") != "0"
@@ -157,12 +168,18 @@ class LinearActFn(torch.autograd.Function):
         if xb.stride(1) != 1 or xb.stride(0) % 8 != 0:
             xb = xb.contiguous()
         wb = _pad_k(weight.detach().to(torch.bfloat16), Kp)
-        y = gemm_bf16_tn(xb, wb, bias.detach() if bias is not None else None, act)
+        relu_bits = None
+        if act == ACT_RELU and RELU_BITS:
+            # one bit per output for the next layer's masked dgrad (it would otherwise re-read this whole activation)
+            relu_bits = torch.empty(xb.shape[0], (N + 31) // 32, dtype=torch.int32, device=xb.device)
+        y = gemm_bf16_tn(xb, wb, bias.detach() if bias is not None else None, act, relu_bits_out=relu_bits)
         # If this layer's input is the ReLU output of the previous fused layer, the ReLU gradient mask
         # of that layer is applied in *this* layer's dgrad epilogue (mask = saved input > 0).
         ctx.mask_input = bool(getattr(x, "_trb_relu_out", False)) and xb is x
+        ctx.mask_bits = getattr(x, "_trb_relu_bits", None) if ctx.mask_input else None
         if act == ACT_RELU:
             y._trb_relu_out = True  # python attribute travels with the tensor object to the next layer
+            y._trb_relu_bits = relu_bits
         ctx.act = act
         ctx.K = K
         ctx.has_bias = bias is not None
@@ -190,7 +207,7 @@ class LinearActFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             # dgrad: gx[M, Kp] = gy[M, N] . W[N, Kp]; W is consumed as an MN-major B operand (no transpose)
             if ctx.mask_input and xb.shape[1] == ctx.K:
-                gx = gemm_bf16(gy, wb, b_mn=True, act=ACT_RELU_GRAD, mask=xb)
+                gx = gemm_bf16(gy, wb, b_mn=True, act=ACT_RELU_GRAD, mask=xb, mask_bits=ctx.mask_bits)
                 gx._trb_masked = True
             else:
                 gx = gemm_bf16(gy, wb, b_mn=True)
