@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 health() { timeout 60 nvidia-smi --query-gpu=index,memory.used --format=csv,noheader | tr '\n' ' '; echo; }
 timeout 600 python -m pytest tests/test_sharded_ebc_nccl_gpu.py -x -q 2>&1 | tail -4; health
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29562 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/bench2_final.log 2>&1; echo "rc=$?"; health
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29562 bench.py --gpus 2 --steps 50 --warmup 10 > gpurun_out/bench2_final.log 2>&1; echo "rc=$?"; health
 grep "^{" gpurun_out/bench2_final.log | tail -1 > gpurun_out/bench2_final.json
 python - <<'PY'
 import json

@@ -156,3 +156,53 @@ def test_recalibrated_and_volume_metrics():
         RecMetricEnum.SUM_WEIGHTS: RecMetricDef(rec_tasks=[RecTaskInfo(name="t")], window_size=1000)}), batch_size=200, world_size=1, my_rank=0,
         state_metrics_mapping={}, device=torch.device("cpu"))
     assert len(mod.rec_metrics.rec_metrics) == 2
+
+
+def test_metric_extras_deferrable_snapshot_noop_cpu_comms():
+    from concurrent.futures import Future
+
+    from torchrec_b200.metrics import (CPUCommsRecMetricModule, DeferrableMetrics, MetricComputeJob, MetricStateSnapshot, MetricUpdateJob, NoOpMetricModule,
+                                       SynchronizationMarker)
+    from torchrec_b200.metrics.model_utils import is_empty_signals, parse_model_outputs, session_ids_to_tensor
+
+    # deferrable metrics
+    fut = Future()
+    dm = DeferrableMetrics(fut)
+    dm["local"] = 1.0
+    seen = []
+    dm.subscribe(seen.append)
+    assert not dm.is_resolved() and seen == []
+    fut.set_result({"ne": 0.5})
+    assert seen == [{"ne": 0.5, "local": 1.0}] and dm["ne"] == 0.5 and len(dm) == 2 and dm.resolve() == {"ne": 0.5, "local": 1.0}
+    plain = DeferrableMetrics({"a": 1})
+    plain.update({"b": 2})
+    assert dict(plain) == {"a": 1, "b": 2} and bool(plain) and not bool(DeferrableMetrics())
+
+    # no-op module
+    noop = NoOpMetricModule()
+    noop.update({"x": torch.ones(1)})
+    assert not noop.should_compute() and dict(noop.compute()) == {} and noop.async_compute().result() == {}
+
+    # snapshot -> cpu-comms clone computes the same numbers as the live module
+    p, l, w = _data()
+    cfg = MetricsConfig(rec_tasks=[RecTaskInfo(name="t")], rec_metrics={RecMetricEnum.NE: RecMetricDef(rec_tasks=[RecTaskInfo(name="t")], window_size=1000),
+                                                                         RecMetricEnum.AUC: RecMetricDef(rec_tasks=[RecTaskInfo(name="t")], window_size=1000)})
+    live = generate_metric_module(RecMetricModule, cfg, batch_size=200, world_size=1, my_rank=0, state_metrics_mapping={}, device=torch.device("cpu"))
+    live.update({"prediction": p, "label": l, "weight": w})
+    snap = MetricStateSnapshot.from_metrics(live.rec_metrics)
+    assert any(k.startswith("ne_") for k in snap.metric_states)
+    shadow = generate_metric_module(CPUCommsRecMetricModule, cfg, batch_size=200, world_size=1, my_rank=0, state_metrics_mapping={}, device=torch.device("cpu"))
+    got = shadow.compute_from_snapshot(snap)
+    want = live.compute()
+    for k in want:
+        if "ne" in k or "auc" in k:
+            assert float(got[k]) == pytest.approx(float(want[k]), rel=1e-6)
+    job = MetricUpdateJob({"x": torch.ones(1)}, {}, merged_count=3)
+    f2 = Future()
+    assert job.merged_count == 3 and MetricComputeJob(f2, snap).metric_state_snapshot is snap and SynchronizationMarker(f2).future is f2
+
+    # model utils
+    assert session_ids_to_tensor(["a", "a", "b", "a"]).tolist() == [0, 0, 1, 2]
+    lab, pred, wt = parse_model_outputs("l", "p", "w", {"l": torch.ones(4, 1), "p": torch.rand(4, 1), "w": torch.ones(4, 1)})
+    assert lab.shape == pred.shape == wt.shape == (4,)
+    assert is_empty_signals(torch.zeros(0), torch.zeros(0), torch.zeros(0))
