@@ -45,3 +45,37 @@ def test_mc_ebc_end_to_end():
     kjt = KeyedJaggedTensor(keys=["f"], values=torch.tensor([10**12, 5, 10**12 + 7, 5]), lengths=torch.tensor([2, 2]))
     out, remapped = m(kjt)
     assert out.values().shape == (2, 8) and remapped.values().max() < 16
+
+
+def test_mc_adapters_and_pruning_logger():
+    import torch
+
+    from torchrec_b200.modules.embedding_configs import EmbeddingBagConfig, EmbeddingConfig
+    from torchrec_b200.modules.mc_adapter import McEmbeddingBagCollectionAdapter, McEmbeddingCollectionAdapter
+    from torchrec_b200.modules.pruning_logger import PruningLoggerDefault
+    from torchrec_b200.sparse import KeyedJaggedTensor
+
+    dev = torch.device("cpu")
+    kjt = KeyedJaggedTensor(keys=["f0", "f1"], values=torch.tensor([10**12 + 5, 7, 10**12 + 5, 99, 123456789]), lengths=torch.tensor([2, 1, 1, 1]))
+    for method in ("mpzch", "sort_zch"):
+        ec = McEmbeddingCollectionAdapter([EmbeddingConfig(name="t0", embedding_dim=8, num_embeddings=64, feature_names=["f0"]),
+                                           EmbeddingConfig(name="t1", embedding_dim=8, num_embeddings=64, feature_names=["f1"])], input_hash_size=2**50, device=dev, world_size=1,
+                                          zch_method=method, mpzch_num_buckets=4, embedding_device=dev)
+        ec.train()
+        out = ec(kjt)
+        assert out["f0"].values().shape == (3, 8) and ec.remapped_ids is not None
+        rem = ec.remapped_ids["f0"].values()
+        assert int(rem.max()) < 64 and int(rem[0]) == int(rem[2])                 # huge raw ids land inside the table, same id -> same slot
+        assert len(list(ec.parameters())) == 2 and [c.name for c in ec.embedding_bag_configs()] == ["t0", "t1"]
+    ebc = McEmbeddingBagCollectionAdapter([EmbeddingBagConfig(name="b0", embedding_dim=8, num_embeddings=32, feature_names=["f0", "f1"])], input_hash_size=2**50, device=dev,
+                                          world_size=1, zch_method="mpzch", mpzch_num_buckets=2, embedding_device=dev)
+    ebc.train()
+    pooled = ebc(kjt)
+    assert pooled.values().shape == (2, 16)
+    import pytest
+
+    with pytest.raises(NotImplementedError):
+        McEmbeddingCollectionAdapter([EmbeddingConfig(name="t", embedding_dim=8, num_embeddings=8, feature_names=["f"])], 100, dev, 1, zch_method="")
+    with PruningLoggerDefault.pruning_logger(event="prune", trainer="t0") as log:
+        log.rows_pruned = 5
+    assert log.rows_pruned == 5
