@@ -192,3 +192,37 @@ def test_virtual_table_eviction_policies_and_feature_scores():
     scored = may_collect_feature_scores(kjt, True, mapping["row_wise"])
     assert scored.weights().tolist() == [2.0, 2.0, 0.5]
     assert create_sharding_type_to_feature_score_mapping([b], {"table_wise": ["b"]}) == (False, False, {})
+
+
+def test_criteo_scripts_and_test_utils(tmp_path):
+    import numpy as np
+
+    from torchrec_b200.datasets.criteo import CriteoIterDataPipe
+    from torchrec_b200.datasets.scripts import contiguous_preproc_criteo, shuffle_preproc_criteo
+    from torchrec_b200.datasets.test_utils.criteo_test_utils import CriteoTest
+
+    helper = CriteoTest()
+    with CriteoTest._create_dataset_tsv(num_rows=20) as tsv:
+        rows = list(CriteoIterDataPipe([tsv]))
+        assert len(rows) == 20
+        helper._validate_sample(rows[0])
+    days = 3
+    src = tmp_path / "npy"
+    src.mkdir()
+    rng = np.random.default_rng(0)
+    for d in range(days):
+        n = 30 + d
+        np.save(src / f"day_{d}_dense.npy", rng.random((n, 13), dtype=np.float32))
+        np.save(src / f"day_{d}_sparse.npy", rng.integers(0, 50, size=(n, 26), dtype=np.int32) * 1000003)
+        np.save(src / f"day_{d}_labels.npy", np.full((n, 1), d, dtype=np.int32))
+    out_c = tmp_path / "contig"
+    contiguous_preproc_criteo.main(["--input_dir", str(src), "--output_dir", str(out_c), "--days", str(days), "--frequency_threshold", "2"])
+    c0 = np.load(out_c / "day_0_sparse_contig_freq.npy")
+    assert c0.shape == (30, 26) and c0.min() >= 1 and c0.max() < 60                       # contiguous: 0 missing, 1 rare, 2.. kept ids
+    out_s = tmp_path / "shuf"
+    shuffle_preproc_criteo.main(["--input_dir_labels_and_dense", str(src), "--input_dir_sparse", str(src), "--output_dir_shuffled", str(out_s), "--days", str(days)])
+    l0, l1 = np.load(out_s / "day_0_labels.npy"), np.load(out_s / "day_1_labels.npy")
+    assert l0.shape[0] == 30 and l1.shape[0] == 31 and set(np.unique(np.concatenate([l0, l1])).tolist()) == {0, 1}   # train days mixed, last day untouched
+    assert not (out_s / "day_2_labels.npy").exists()
+    with CriteoTest._create_dataset_npys(num_rows=12, filenames=["a", "b"]) as paths:
+        assert len(paths) == 6 and np.load(paths[1]).shape == (12, 26)
