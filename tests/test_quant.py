@@ -49,3 +49,27 @@ def test_quant_ec_from_float_matches():
     for k in ref:
         torch.testing.assert_close(out[k].values(), ref[k].values(), rtol=0.1, atol=0.03)
         assert torch.equal(out[k].lengths(), ref[k].lengths())
+
+
+def test_quant_utils_fx_names_and_meta_to_cpu():
+    import torch
+
+    from torchrec_b200.modules.embedding_configs import DataType, EmbeddingBagConfig
+    from torchrec_b200.quant.embedding_modules import EmbeddingBagCollection as QEBC
+    from torchrec_b200.quant.utils import meta_to_cpu_placement, recursive_populate_fx_names
+
+    tables = [EmbeddingBagConfig(name="a", embedding_dim=8, num_embeddings=10, feature_names=["fa"], data_type=DataType.INT8),
+              EmbeddingBagConfig(name="b", embedding_dim=8, num_embeddings=12, feature_names=["fb"], data_type=DataType.INT8)]
+
+    class M(torch.nn.Module):
+        def __init__(self, dev):
+            super().__init__()
+            self.q = QEBC(tables, is_weighted=False, device=torch.device(dev))
+
+    m = M("cpu")
+    recursive_populate_fx_names(m)
+    assert m.q._tbes[0]._fx_path == "emb_module.a,b"
+    meta = M("meta")
+    assert meta.q.device.type == "meta"
+    meta_to_cpu_placement(meta)
+    assert meta.q.device.type == "cpu" and [c.name for c in meta.q.embedding_bag_configs()] == ["a", "b"]
