@@ -96,3 +96,34 @@ def test_crossnets_match_their_formulas():
     one = LowRankMixtureCrossNet(N, 1, num_experts=1, low_rank=4, activation=torch.nn.Identity())
     U, V, C, b = one.U_kernels[0][0], one.V_kernels[0][0], one.C_kernels[0][0], one.bias[0].squeeze(1)
     torch.testing.assert_close(one(x0), x0 * (((x0 @ V.t()) @ C.t()) @ U.t() + b) + x0)
+
+
+def test_transformer_dlrm_and_experimental_marker():
+    import warnings
+
+    from torchrec_b200.models.experimental.transformerdlrm import DLRM_Transformer, InteractionTransformerArch
+    from torchrec_b200.utils.experimental import experimental
+
+    b = _batch()
+    m = DLRM_Transformer(_ebc(D=8), dense_in_features=5, dense_arch_layer_sizes=[16, 8], over_arch_layer_sizes=[16, 1], nhead=2, ntransformer_layers=1)
+    m.eval()
+    out = m(b.dense_features, b.sparse_features)
+    assert out.shape == (6, 1)
+    m.train()
+    m(b.dense_features, b.sparse_features).sum().backward()
+    assert all(p.grad is not None for p in m.parameters())
+    assert InteractionTransformerArch(0, 8, nhead=2, ntransformer_layers=1)(torch.ones(2, 8), torch.ones(2, 0, 8)).shape == (2, 8)
+
+    @experimental
+    def f(x):
+        return x + 1
+
+    @experimental(feature="Thing", since="0.1")
+    class Thing:
+        def __init__(self, v):
+            self.v = v
+
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert f(1) == 2 and f(2) == 3 and Thing(3).v == 3 and Thing(4).v == 4
+    assert len([x for x in w if "experimental" in str(x.message)]) == 2      # once per object
