@@ -55,3 +55,14 @@ class EmbDimBucketer:
 
     def dim_in_bytes(self, dim: int, dtype: DataType) -> int:
         return (dim * DATA_TYPE_NUM_BITS[DataType(dtype)] + 7) // 8
+
+
+def should_do_dim_bucketing(embedding_tables: List[Any]) -> bool:
+    """Bucket only when it can matter: cached tables taking part in the prefetch pipeline, with more than one row width
+    (reference embedding_dim_bucketer.py:157-195)."""
+    widths = set()
+    for t in embedding_tables:
+        kernel = getattr(getattr(t, "compute_kernel", None), "value", str(getattr(t, "compute_kernel", "")))
+        if kernel in ("fused_uvm_caching", "quant_uvm_caching", "key_value") and bool((getattr(t, "fused_params", None) or {}).get("prefetch_pipeline", False)):
+            widths.add(int(getattr(t, "local_cols", None) or t.embedding_dim))
+    return len(widths) > 1
