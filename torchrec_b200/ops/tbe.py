@@ -236,6 +236,8 @@ def _ref_row_grads(meta: TbeMeta, indices, offsets, psw, grad: torch.Tensor, B: 
     tinfo: Dict[int, Tuple[int, int, int]] = {}
     for f in range(meta.num_features):
         D, rows = meta.h_dim[f], meta.h_rows[f]
+        if rows == 0:  # an empty shard shares its weight offset with the next table: nothing to update, and it must not alias that table's key
+            continue
         lo, hi = int(offsets[f * B]), int(offsets[(f + 1) * B])
         idx = indices[lo:hi]
         if pooled:
@@ -718,7 +720,7 @@ class TableBatchedEmbeddingBags(nn.Module):
     def init_parameters(self, init_ranges: Optional[Sequence[Tuple[float, float]]] = None) -> None:
         for t, w in enumerate(self.split_embedding_weights()):
             rows = self.embedding_specs[t][0]
-            lo, hi = init_ranges[t] if init_ranges is not None else (-math.sqrt(1.0 / rows), math.sqrt(1.0 / rows))
+            lo, hi = init_ranges[t] if init_ranges is not None else (-math.sqrt(1.0 / max(rows, 1)), math.sqrt(1.0 / max(rows, 1)))
             if w.dtype == torch.float32:
                 w.uniform_(lo, hi)
             else:

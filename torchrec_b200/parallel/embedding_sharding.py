@@ -233,20 +233,24 @@ def _set_sharding_context_post_a2a(kjts: List[KeyedJaggedTensor], ctx: C) -> Non
         if hasattr(sctx, "batch_size_per_rank_per_feature") and kjt.variable_stride_per_key() and kjt.stride_per_key_per_rank():
             spkpr = kjt.stride_per_key_per_rank()
             sctx.batch_size_per_rank_per_feature = [[spkpr[f][r] for f in range(len(spkpr))] for r in range(len(spkpr[0]))]
+        if hasattr(sctx, "lengths_after_input_dist"):
+            sctx.lengths_after_input_dist = kjt.lengths()
 
 
 def _set_sharding_context_intra_a2a(tensors_awaitables: List[Awaitable[KeyedJaggedTensor]], ctx: C) -> None:
     """Between the stages: per-rank strides and split sizes learnt from the size exchange."""
     for aw, sctx in zip(tensors_awaitables, getattr(ctx, "sharding_contexts", [])):
         if isinstance(aw, KJTAllToAllTensorsAwaitable):
+            vi = aw._input.dist_labels().index("values")
+            # the sequence output all-to-all runs the input dist backwards: it SENDS what was received and RECEIVES what was sent
             if hasattr(sctx, "input_splits"):
-                sctx.input_splits = aw._input_splits[1] if len(aw._input_splits) > 1 else aw._input_splits[0]
+                sctx.input_splits = list(aw._output_splits[vi])
             if hasattr(sctx, "output_splits"):
-                sctx.output_splits = aw._output_splits[1] if len(aw._output_splits) > 1 else aw._output_splits[0]
+                sctx.output_splits = list(aw._input_splits[vi])
             if hasattr(sctx, "sparse_features_recat"):
                 sctx.sparse_features_recat = aw._recat
             if hasattr(sctx, "batch_size_per_rank") and aw._stride_per_rank is not None:
-                sctx.batch_size_per_rank = aw._stride_per_rank
+                sctx.batch_size_per_rank = list(aw._stride_per_rank)
 
 
 def _split(flat_list: List[T], splits: List[int]) -> List[List[T]]:
