@@ -206,3 +206,48 @@ def test_metric_extras_deferrable_snapshot_noop_cpu_comms():
     lab, pred, wt = parse_model_outputs("l", "p", "w", {"l": torch.ones(4, 1), "p": torch.rand(4, 1), "w": torch.ones(4, 1)})
     assert lab.shape == pred.shape == wt.shape == (4,)
     assert is_empty_signals(torch.zeros(0), torch.zeros(0), torch.zeros(0))
+
+
+def test_per_metric_modules_and_functional_helpers():
+    """Every reference ``torchrec/metrics/<name>.py`` import path resolves; the stateless helpers agree with the stateful metrics."""
+    import importlib
+
+    import torch
+
+    from torchrec_b200.metrics.metrics_config import RecMetricEnum
+    from torchrec_b200.metrics.metric_module import REC_METRICS_MAPPING
+    from torchrec_b200.metrics.rec_metric import RecTaskInfo
+
+    for mod in ("accuracy", "auc", "auprc", "average", "cali_free_ne", "calibration", "calibration_with_recalibration", "cpu_offloaded_metric_module", "ctr", "gauc",
+                "hindsight_target_pr", "mae", "mse", "multi_label_precision", "multiclass_recall", "ndcg", "ne", "ne_positive", "ne_with_recalibration", "nmse",
+                "num_missing_labels", "num_positive_samples", "output", "precision", "precision_session", "rauc", "recall", "recall_session", "scalar", "segmented_ne",
+                "serving_calibration", "serving_ne", "sum_weights", "tensor_weighted_avg", "tower_qps", "unweighted_ne", "weighted_avg", "weighted_sum_predictions", "xauc"):
+        importlib.import_module(f"torchrec_b200.metrics.{mod}")
+    assert RecMetricEnum.NE_POSITIVE in REC_METRICS_MAPPING
+
+    from torchrec_b200.metrics.ne import compute_ne, get_ne_states
+    from torchrec_b200.metrics.ne_positive import NEPositiveMetric, compute_ne_positive, get_ne_positive_states
+    from torchrec_b200.metrics.mse import compute_mse, compute_r_squared, compute_rmse, get_mse_states
+    from torchrec_b200.metrics.rauc import compute_rauc, count_reverse_pairs_divide_and_conquer
+    from torchrec_b200.metrics.xauc import compute_xauc, get_xauc_states
+
+    g = torch.Generator().manual_seed(3)
+    p = torch.rand(1, 64, generator=g)
+    y = (torch.rand(1, 64, generator=g) > 0.6).float()
+    w = torch.rand(1, 64, generator=g)
+    task = RecTaskInfo(name="t", label_name="l", prediction_name="p", weight_name="w")
+    m = NEPositiveMetric(world_size=1, my_rank=0, batch_size=64, tasks=[task])
+    m.update(predictions={"t": p[0]}, labels={"t": y[0]}, weights={"t": w[0]})
+    got = m.compute()["ne_positive-t|lifetime_ne_positive"]
+    st = get_ne_positive_states(y, p, w, 1e-12)
+    want = compute_ne_positive(st["cross_entropy_positive_sum"], st["weighted_num_samples"], st["pos_labels"], st["neg_labels"], 1e-12)
+    torch.testing.assert_close(got.double().reshape(-1), want.reshape(-1))
+    ne = get_ne_states(y, p, w, 1e-12)
+    assert float(compute_ne(ne["cross_entropy_sum"], ne["weighted_num_samples"], ne["pos_labels"], ne["neg_labels"])) > 0
+    ms = get_mse_states(y, p, w)
+    torch.testing.assert_close(compute_rmse(ms["error_sum"], ms["weighted_num_samples"]) ** 2, compute_mse(ms["error_sum"], ms["weighted_num_samples"]))
+    assert float(compute_r_squared(ms["error_sum"], ms["weighted_num_samples"], ms["label_sum"], ms["label_squared_sum"])) <= 1.0
+    assert count_reverse_pairs_divide_and_conquer([4, 3, 2, 1]) == 6.0
+    torch.testing.assert_close(compute_rauc(1, torch.tensor([[0.1, 0.2, 0.3]]), torch.tensor([[1.0, 2.0, 3.0]]), torch.ones(1, 3)), torch.ones(1, dtype=torch.double))
+    xs = get_xauc_states(torch.tensor([[1.0, 2.0, 3.0]]), torch.tensor([[0.1, 0.3, 0.2]]), torch.ones(1, 3))
+    torch.testing.assert_close(compute_xauc(xs["error_sum"], xs["weighted_num_pairs"]), torch.tensor([2.0 / 3.0], dtype=torch.double))

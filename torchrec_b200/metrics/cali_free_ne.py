@@ -1,0 +1,11 @@
+"""NE after removing the calibration error.
+
+Reference module: ``torchrec/metrics/cali_free_ne.py``. The metric classes live in ``metrics_impl.py`` (one sum-state / sample-buffer base for all 40+ metrics);
+this module gives them their reference import path and holds the stateless ``compute_*`` / ``get_*_states`` helpers."""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from .metrics_impl import CaliFreeNEMetric, CaliFreeNEMetricComputation  # noqa: F401

@@ -36,7 +36,7 @@ REC_METRICS_MAPPING: Dict[RecMetricEnumBase, Type[RecMetric]] = {
     RecMetricEnum.RECALIBRATED_NE: M.RecalibratedNEMetric, RecMetricEnum.RECALIBRATED_CALIBRATION: M.RecalibratedCalibrationMetric,
     RecMetricEnum.SERVING_AE_LOSS: M.ServingAELossMetric, RecMetricEnum.NUM_POSITIVE_SAMPLES: M.NumPositiveSamplesMetric,
     RecMetricEnum.SUM_WEIGHTS: M.SumWeightsMetric, RecMetricEnum.NUM_MISSING_LABELS: M.NumMissingLabelsMetric,
-    RecMetricEnum.WEIGHTED_SUM_PREDICTIONS: M.WeightedSumPredictionsMetric,
+    RecMetricEnum.WEIGHTED_SUM_PREDICTIONS: M.WeightedSumPredictionsMetric, RecMetricEnum.NE_POSITIVE: M.NEPositiveMetric,
 }
 
 MODEL_METRIC_LABEL: str = "model_out"

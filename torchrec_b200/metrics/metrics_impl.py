@@ -773,11 +773,34 @@ class WeightedSumPredictionsMetricComputation(_SingleSumComputation):
         return (weights.double() * torch.nan_to_num(predictions.double(), 0.0)).sum(-1)
 
 
+class NEPositiveMetricComputation(_SumStatesComputation):
+    """Normalized entropy of the POSITIVE samples only: ``-sum w*y*log2(p)`` over the base-rate entropy of the positives
+    (reference metrics/ne_positive.py:25-70)."""
+
+    STATES = ["cross_entropy_positive_sum", "weighted_num_samples", "pos_labels", "neg_labels"]
+
+    def __init__(self, *args: Any, allow_missing_label_with_zero_weight: bool = False, **kwargs: Any) -> None:
+        super().__init__(*args, **kwargs)
+        self.eta = 1e-12
+
+    def _batch_states(self, predictions, labels, weights, **kwargs):
+        p = torch.clamp(predictions.double(), self.eta, 1 - self.eta)
+        w, y = weights.double(), labels.double()
+        return {"cross_entropy_positive_sum": (-w * y * torch.log2(p)).sum(-1), "weighted_num_samples": w.sum(-1),
+                "pos_labels": (w * y).sum(-1), "neg_labels": (w * (1 - y)).sum(-1)}
+
+    def _reports(self, get, prefix):
+        mean_label = get("pos_labels") / (get("weighted_num_samples") + EPS)
+        norm = -get("pos_labels") * torch.log2(mean_label + self.eta)
+        return [MetricComputationReport(MetricName.NE_POSITIVE, prefix, get("cross_entropy_positive_sum") / (norm + EPS))]
+
+
 def _make(name: str, comp: Type[RecMetricComputation], ns: MetricNamespace) -> Type[RecMetric]:
     return type(name, (RecMetric,), {"_namespace": ns, "_computation_class": comp, "__doc__": comp.__doc__})
 
 
 NEMetric = _make("NEMetric", NEMetricComputation, MetricNamespace.NE)
+NEPositiveMetric = _make("NEPositiveMetric", NEPositiveMetricComputation, MetricNamespace.NE_POSITIVE)
 CalibrationMetric = _make("CalibrationMetric", CalibrationMetricComputation, MetricNamespace.CALIBRATION)
 CTRMetric = _make("CTRMetric", CTRMetricComputation, MetricNamespace.CTR)
 MSEMetric = _make("MSEMetric", MSEMetricComputation, MetricNamespace.MSE)

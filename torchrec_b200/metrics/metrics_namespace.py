@@ -66,6 +66,7 @@ class MetricNamespaceBase(StrValueMixin, Enum):
 class MetricNamespace(MetricNamespaceBase):
     DEFAULT = ""
     NE = "ne"
+    NE_POSITIVE = "ne_positive"
     THROUGHPUT = "throughput"
     CTR = "ctr"
     CALIBRATION = "calibration"

@@ -1,0 +1,11 @@
+"""Session-level recall of the top-ranked items.
+
+Reference module: ``torchrec/metrics/recall_session.py``. The metric classes live in ``metrics_impl.py`` (one sum-state / sample-buffer base for all 40+ metrics);
+this module gives them their reference import path and holds the stateless ``compute_*`` / ``get_*_states`` helpers."""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from .metrics_impl import RecallSessionMetric, RecallSessionMetricComputation  # noqa: F401

@@ -16,6 +16,7 @@ from typing import Any, Callable, Dict, Generic, Iterator, List, Optional, Tuple
 import torch
 import torch.distributed as dist
 from torch import nn
+from torch.distributed._shard.sharded_tensor import Shard, ShardedTensor, ShardedTensorMetadata  # noqa: F401
 from torch.distributed._shard.sharding_spec import EnumerableShardingSpec, ShardingSpec, ShardMetadata  # noqa: F401
 
 from ..streamable import Multistreamable
