@@ -100,3 +100,67 @@ def test_sharding_route_facade():
     plan = sp.construct_module_sharding_plan(ebc, {"t": sp.row_wise()}, sharder=EmbeddingBagCollectionSharder(), world_size=4, local_size=4, device_type="cpu")
     shards = units_for(0, cfg, plan["t"])
     assert [s.rank for s in shards] == [0, 1, 2, 3] and sum(s.rows for s in shards) == 100 and all(s.cols == 16 for s in shards)
+
+
+def test_annotation_estimator_and_shard_estimators():
+    """The annotation-driven estimator package: evaluators per sharding type, config overrides through decorators, factory; functional storage helpers."""
+    import torch
+
+    from torchrec_b200.parallel.planner import constants as K
+    from torchrec_b200.parallel.planner.estimator import (
+        EmbeddingPerfEstimatorFactory, HardwarePerfConfig, ShardPerfContext, compute_block_usage_penalty, forward_compute, get_embedding_perf_sharding_evaluator,
+        get_forward_compute, hbm_mem_bw, intra_host_bw, supported_sharding_types)
+    from torchrec_b200.parallel.planner.shard_estimators import EmbeddingOffloadStats, calculate_pipeline_io_cost, calculate_shard_storages
+    from torchrec_b200.parallel.planner.types import PlannerError
+    from torchrec_b200.parallel.types import PipelineType
+
+    def ctx(st, W=8, L=8, cols=128, rows=1_000_000, n_row=1):
+        return ShardPerfContext(sharding_type=st, compute_kernel="fused", compute_device="cuda", world_size=W, local_world_size=L, batch_sizes=[2048], input_lengths=[20.0],
+                                num_poolings=[1.0], hash_size=rows, emb_dim=cols, shard_rows=rows // n_row, shard_cols=cols, num_row_shards=n_row, table_data_type_size=4.0,
+                                output_data_type_size=4.0, fwd_a2a_comm_data_type_size=4.0, bwd_a2a_comm_data_type_size=4.0, fwd_sr_comm_data_type_size=4.0,
+                                bwd_sr_comm_data_type_size=4.0, is_pooled=True, device_bw=K.HBM_MEM_BW, comms_bw=K.INTRA_NODE_BANDWIDTH)
+
+    tw = get_embedding_perf_sharding_evaluator("table_wise").evaluate(ctx("table_wise"))
+    rw = get_embedding_perf_sharding_evaluator("row_wise").evaluate(ctx("row_wise", n_row=8))
+    dp = get_embedding_perf_sharding_evaluator("data_parallel").evaluate(ctx("data_parallel"))
+    assert rw.fwd_compute < tw.fwd_compute            # 1/8 of the ids per shard
+    assert dp.input_dist_comms == 0 and dp.fwd_comms == 0 and dp.bwd_comms > tw.bwd_comms   # whole-table all-reduce
+    inf = get_embedding_perf_sharding_evaluator("table_wise", is_inference=True).evaluate(ctx("table_wise"))
+    assert inf.bwd_compute == 0 and inf.bwd_comms == 0 and inf.fwd_compute == tw.fwd_compute
+    two_hosts = get_embedding_perf_sharding_evaluator("table_row_wise").evaluate(ctx("table_row_wise", W=16, L=8, n_row=8))
+    one_host = get_embedding_perf_sharding_evaluator("table_row_wise").evaluate(ctx("table_row_wise", W=8, L=8, n_row=8))
+    assert two_hosts.fwd_comms > one_host.fwd_comms
+    assert compute_block_usage_penalty(128) == 1.0 and compute_block_usage_penalty(64) == K.HALF_BLOCK_PENALTY and compute_block_usage_penalty(16) == K.QUARTER_BLOCK_PENALTY
+
+    @hbm_mem_bw(1.0e6)
+    @intra_host_bw(2.0e5)
+    @supported_sharding_types("table_wise", "row_wise")
+    class Slow(HardwarePerfConfig):
+        name = "slow"
+
+        @forward_compute(sharding_type="row_wise")
+        def rw_fwd(self, c):
+            return 123.0
+
+    cfg = Slow()
+    assert cfg.hbm_mem_bw == 1.0e6 and HardwarePerfConfig.hbm_mem_bw == K.HBM_MEM_BW
+    assert get_forward_compute(cfg, "row_wise") is not None and get_forward_compute(cfg, "table_wise") is None
+    assert get_embedding_perf_sharding_evaluator("row_wise", cfg).evaluate(ctx("row_wise", n_row=8)).fwd_compute == 123.0
+    with pytest.raises(PlannerError):
+        get_embedding_perf_sharding_evaluator("grid_shard", cfg)
+    assert EmbeddingPerfEstimatorFactory.available() == ["b200", "gb200"]
+    assert EmbeddingPerfEstimatorFactory.get_config("gb200").hbm_to_ddr_mem_bw > K.HBM_TO_DDR_MEM_BW
+
+    # functional storage helpers
+    assert calculate_pipeline_io_cost(100, 50, 0, PipelineType.TRAIN_SPARSE_DIST, None) == 200
+    assert calculate_pipeline_io_cost(100, 50, 10, PipelineType.TRAIN_PREFETCH_SPARSE_DIST, 6, count_ephemeral_storage_cost=True) == 300 + 20 + 50
+    assert calculate_pipeline_io_cost(100, 50, 0, PipelineType.NONE, None) == 150 and calculate_pipeline_io_cost(1, 1, 1, PipelineType.NONE, None, is_inference=True) == 0
+    t = torch.empty(1000, 64)
+    st = calculate_shard_storages(None, "row_wise", t, "cuda", "fused", [[250, 64]] * 4, [32], 4, 4, [10.0], [1.0], 0.2, True)
+    assert len(st) == 4 and st[0].hbm >= 250 * 64 * 4 + 250 * 4 and st[0].ddr == 0
+    st_uvm = calculate_shard_storages(None, "table_wise", t, "cuda", "fused_uvm_caching", [[1000, 64]], [32], 4, 4, [10.0], [1.0], 0.25, True)
+    assert st_uvm[0].ddr >= 1000 * 64 * 4 and st_uvm[0].hbm < st_uvm[0].ddr
+
+    stats = EmbeddingOffloadStats(cacheability=0.3, expected_lookups=1000, mrc_hist_counts=torch.tensor([50.0, 30.0, 15.0, 5.0]), height=300)
+    assert stats.expected_miss_rate(0.0) == 1.0 and abs(stats.expected_miss_rate(1.0) - 0.05) < 1e-6
+    assert stats.expected_miss_rate(0.2) > stats.expected_miss_rate(0.6)
