@@ -224,3 +224,65 @@ def test_runtime_forwards_and_arg_info():
     args, kwargs = CallArgs([info], {"x": ArgInfo.from_path([("attr", "sparse_features")])}).build_args_kwargs(B())
     assert args == [20] and kwargs["x"] is B.sparse_features
     assert str(PipelineState.CALL_FWD) == "CALL_FWD" and PipelinePhase.FORWARD.value == "forward"
+
+
+def test_fx_tracing_discovers_pipelineable_modules_and_recipes():
+    """``train_pipeline/tracing.py``: shallow fx trace with sharded modules as leaves; inputs walked back to the batch as ArgInfo steps."""
+    import dataclasses
+
+    import torch
+    from torch import nn
+
+    from torchrec_b200.parallel.train_pipeline.pipeline_stage import PipelineStage, SparseDataDistUtil  # noqa: F401
+    from torchrec_b200.parallel.train_pipeline.postproc import NoOpStream, PipelinedPostproc  # noqa: F401
+    from torchrec_b200.parallel.train_pipeline.tracing import ArgInfoStepFactory, Tracer, _get_leaf_module_names, rewrite_model
+    from torchrec_b200.parallel.types import ShardedModule
+
+    class FakeSharded(ShardedModule):
+        def __init__(self):
+            nn.Module.__init__(self)
+
+        def create_context(self):
+            return None
+
+        def input_dist(self, ctx, *a, **k):
+            pass
+
+        def compute(self, ctx, x):
+            pass
+
+        def output_dist(self, ctx, x):
+            pass
+
+        def forward(self, x):
+            return x * 2
+
+    class Clamp(nn.Module):
+        def forward(self, x):
+            return x.clamp(max=3)
+
+    class M(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a, self.b, self.c, self.pp, self.lin = FakeSharded(), FakeSharded(), FakeSharded(), Clamp(), nn.Linear(2, 2)
+
+        def forward(self, batch):
+            return self.a(batch.sparse["u"]) + self.b(self.pp(batch.sparse["v"])) + self.c(self.lin(batch.dense)).sum()
+
+    @dataclasses.dataclass
+    class B:
+        sparse: dict
+        dense: torch.Tensor
+
+    m = M()
+    assert sorted(_get_leaf_module_names(m)) == ["a", "b", "c", "lin", "pp"]
+    ok, bad, postprocs = rewrite_model(m, pipeline_postproc=True)
+    assert [i.fqn for i in ok] == ["a", "b"] and bad == ["c"] and [type(p).__name__ for p in postprocs] == ["Clamp"]
+    b = B({"u": torch.tensor([1.0, 5.0]), "v": torch.tensor([2.0, 9.0])}, torch.ones(2))
+    assert ok[0].call_args.build_args_kwargs(b)[0][0].tolist() == [1.0, 5.0]
+    assert ok[1].call_args.build_args_kwargs(b)[0][0].tolist() == [2.0, 3.0]          # the postproc runs inside the recipe
+    ok2, bad2, _ = rewrite_model(m, pipeline_postproc=False)
+    assert [i.fqn for i in ok2] == ["a"] and bad2 == ["b", "c"]
+    assert ArgInfoStepFactory.from_scalar(7).process(None) == 7 and ArgInfoStepFactory.get_item("k").process({"k": 1}) == 1
+    with NoOpStream() as s:
+        s.wait_stream(None)

@@ -79,3 +79,35 @@ def test_mc_adapters_and_pruning_logger():
     with PruningLoggerDefault.pruning_logger(event="prune", trainer="t0") as log:
         log.rows_pruned = 5
     assert log.rows_pruned == 5
+
+
+def test_raw_id_tracker_streams_latest_raw_id_per_row():
+    import torch
+
+    from torchrec_b200.modules.embedding_configs import EmbeddingConfig
+    from torchrec_b200.modules.mc_modules import LFU_EvictionPolicy, ManagedCollisionCollection, MCHManagedCollisionModule
+    from torchrec_b200.parallel.model_tracker.trackers import RawIdTracker
+    from torchrec_b200.sparse import KeyedJaggedTensor
+
+    dev = torch.device("cpu")
+    mcc = ManagedCollisionCollection({"t": MCHManagedCollisionModule(zch_size=16, device=dev, eviction_policy=LFU_EvictionPolicy(), eviction_interval=1, input_hash_size=1 << 40)},
+                                     [EmbeddingConfig(name="t", num_embeddings=16, embedding_dim=4, feature_names=["f"])])
+    tracker = RawIdTracker(mcc, consumers=["a", "b"])
+    assert list(tracker.get_tracked_modules()) == ["_managed_collision_modules.t"]
+    raw1 = torch.tensor([1001, 2002, 1001, 3003])
+    out1 = mcc(KeyedJaggedTensor.from_lengths_sync(["f"], raw1, torch.tensor([2, 2])))
+    tracker.step()
+    raw2 = torch.tensor([2002, 4004])
+    out2 = mcc(KeyedJaggedTensor.from_lengths_sync(["f"], raw2, torch.tensor([1, 1])))
+    m = tracker.get_raw_id_map("a")["_managed_collision_modules.t"]
+    rows = torch.cat([out1.values(), out2.values()])
+    raws = torch.cat([raw1, raw2])
+    assert set(m["ids"].tolist()) == set(rows.tolist())
+    for row, raw in zip(m["ids"].tolist(), m["raw_ids"].tolist()):
+        last = [int(r) for r, x in zip(raws.tolist(), rows.tolist()) if x == row][-1]
+        assert raw == last
+    assert tracker.get_raw_id_map("a") == {}                       # consumer a is up to date
+    assert "_managed_collision_modules.t" in tracker.get_unique("b")  # consumer b still sees everything
+    mcc.eval()
+    mcc(KeyedJaggedTensor.from_lengths_sync(["f"], raw2, torch.tensor([1, 1])))
+    assert tracker.get_raw_id_map("a") == {}                       # eval lookups are not tracked
