@@ -39,3 +39,53 @@ def _run(ctx, replicated: bool):
 @pytest.mark.parametrize("replicated", [False, True])
 def test_sharded_pools(replicated):
     run_multi_process(_run, world_size=2, backend="gloo", replicated=replicated)
+
+
+def _composable_pool_shardings(ctx):
+    """The decomposed pool shardings (ids dist + values dists + local lookups) reproduce a replicated reference pool."""
+    import torch
+    import torch.distributed as dist
+
+    from torchrec_b200.modules.object_pool_lookups import TensorJaggedIndexSelectLookup, TensorLookup
+    from torchrec_b200.parallel.sharding.rw_kjt_pool_sharding import KeyedJaggedTensorPoolRwSharding
+    from torchrec_b200.parallel.sharding.rw_tensor_pool_sharding import TensorPoolRwSharding
+    from torchrec_b200.parallel.types import ShardingEnv
+    from torchrec_b200.sparse import KeyedJaggedTensor
+
+    W, rank, dev = ctx.world_size, ctx.rank, ctx.device
+    env = ShardingEnv.from_process_group(dist.group.WORLD)
+    pool_size, dim = 11, 4
+    sh = TensorPoolRwSharding(pool_size, dim, env, dev)
+    lookup = TensorLookup(sh.local_pool_size, dim, torch.float32, dev)
+    # update: rank r writes ids {r, 5 + r, 10 - r}
+    ids = torch.tensor([rank, 5 + rank, 10 - rank])
+    vals = torch.stack([torch.full((dim,), float(100 * rank + i)) for i in ids.tolist()])
+    c = sh.create_context()
+    local_ids = sh.create_update_ids_dist()(c, ids).wait().wait()
+    lookup.update(local_ids, sh.create_update_values_dist()(c, vals).wait())
+    dist.barrier()
+    q = torch.tensor([10 - rank, rank, 5 + rank, rank])
+    c2 = sh.create_context()
+    got = sh.create_lookup_values_dist()(c2, lookup.lookup(sh.create_lookup_ids_dist()(c2, q).wait().wait())).wait()
+    want = torch.stack([torch.full((dim,), float(100 * rank + i)) for i in q.tolist()])
+    torch.testing.assert_close(got, want)
+
+    fml = {"a": 3, "b": 2}
+    ks = KeyedJaggedTensorPoolRwSharding(env, dev, pool_size, 2, fml)
+    klookup = TensorJaggedIndexSelectLookup(ks.local_pool_size, torch.int64, fml, False, dev)
+    kids = torch.tensor([rank, 6 + rank])
+    kjt = KeyedJaggedTensor.from_lengths_sync(["a", "b"], torch.tensor([10 + rank, 11 + rank, 20 + rank, 30 + rank, 40 + rank, 41 + rank]), torch.tensor([2, 1, 1, 2]))
+    kc = ks.create_context()
+    lids = ks.create_update_ids_dist()(kc, kids).wait().wait()
+    klookup.update(lids, ks.create_update_values_dist()(kc, kjt).wait())
+    dist.barrier()
+    other = (rank + 1) % W
+    kq = torch.tensor([6 + other, rank])
+    kc2 = ks.create_context()
+    out = ks.create_lookup_values_dist()(kc2, klookup.lookup(ks.create_lookup_ids_dist()(kc2, kq).wait().wait())).wait()
+    assert out.keys() == ["a", "b"] and out.lengths().tolist() == [1, 2, 2, 1]
+    assert out.values().tolist() == [20 + other, 10 + rank, 11 + rank, 40 + other, 41 + other, 30 + rank]
+
+
+def test_composable_pool_shardings():
+    run_multi_process(_composable_pool_shardings, world_size=2)
