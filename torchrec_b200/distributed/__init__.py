@@ -20,10 +20,14 @@ class _AliasLoader(importlib.abc.Loader):
         self._target = target
 
     def create_module(self, spec):  # noqa: ANN001
-        return importlib.import_module(self._target)
+        mod = importlib.import_module(self._target)
+        self._real_spec = mod.__spec__
+        return mod
 
     def exec_module(self, module) -> None:  # noqa: ANN001
-        pass  # already executed under its real name
+        # already executed under its real name; the import machinery just stamped the ALIAS spec on it - put the real one back so the module keeps
+        # one identity (``__spec__.parent == __package__``, relative imports and pickling by qualified name keep working)
+        module.__spec__ = self._real_spec
 
 
 class _AliasFinder(importlib.abc.MetaPathFinder):

@@ -95,7 +95,14 @@ def optimizer_spec_from(param: Optional[torch.Tensor], fused_params: Optional[Di
             spec.momentum = float(kwargs["eta"])
     if "optimizer" in fp:
         o = fp["optimizer"]
-        spec.optim = o if isinstance(o, OptimType) else OptimType(str(getattr(o, "value", o)))
+        if isinstance(o, OptimType):
+            spec.optim = o
+        else:
+            key = str(getattr(o, "value", o))
+            try:
+                spec.optim = OptimType(key)
+            except ValueError:  # enum NAME spelling ("EXACT_ROWWISE_ADAGRAD"), as FBGEMM's ``EmbOptimType.X`` prints
+                spec.optim = OptimType[key.split(".")[-1].upper()]
         tagged = True
     for src, dst in (("learning_rate", "lr"), ("eps", "eps"), ("beta1", "beta1"), ("beta2", "beta2"), ("weight_decay", "weight_decay"),
                      ("max_gradient", "max_gradient"), ("momentum", "momentum")):
