@@ -129,3 +129,45 @@ def test_native_cpp_tests_and_benchmark():
     assert r.returncode == 0 and "all passed" in r.stdout, r.stderr
     b = subprocess.run([exe, "--bench"], capture_output=True, text=True, timeout=300)
     assert b.returncode == 0 and "M ids/s" in b.stdout
+
+
+def test_id_transformer_group_and_tensor_list(tmp_path):
+    """Two collections of one model translated concurrently; rows survive eviction through the PS; TensorList exposes raw pointers."""
+    import torch
+
+    from torchrec_b200.dynamic_embedding import IDTransformerGroup, TensorList
+    from torchrec_b200.modules.embedding_configs import EmbeddingBagConfig
+    from torchrec_b200.modules.embedding_modules import EmbeddingBagCollection
+    from torchrec_b200.sparse import KeyedJaggedTensor
+
+    class Two(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.user = EmbeddingBagCollection([EmbeddingBagConfig(name="u", embedding_dim=4, num_embeddings=8, feature_names=["uf"])])
+            self.item = EmbeddingBagCollection([EmbeddingBagConfig(name="i", embedding_dim=4, num_embeddings=8, feature_names=["if"])])
+
+    m = Two()
+    cfgs = {"user": m.user.embedding_bag_configs(), "item": m.item.embedding_bag_configs()}
+    group = IDTransformerGroup(f"file://{tmp_path}", m, cfgs)
+    assert "user" in group and "nope" not in group
+
+    def kjt(key, ids):
+        return KeyedJaggedTensor(keys=[key], values=torch.tensor(ids), lengths=torch.ones(len(ids), dtype=torch.int64))
+
+    out, handles = group.transform({"user": kjt("uf", [10**12 + 1, 10**12 + 2, 10**12 + 1]), "item": kjt("if", [7_000_000_007])})
+    u = out["user"].values().tolist()
+    assert u[0] == u[2] != u[1] and all(0 <= x < 8 for x in u) and 0 <= int(out["item"].values()[0]) < 8 and set(handles) == {"user", "item"}
+    # mark the row of id 10^12+1, then push it out of the 8-row cache with 20 other ids, then bring it back: the marked values return
+    with torch.no_grad():
+        m.user.embedding_bags["u"].weight[u[0]].fill_(42.0)
+    for k in range(0, 20, 4):
+        group.transform({"user": kjt("uf", [5_000 + k, 5_001 + k, 5_002 + k, 5_003 + k])})
+    back, _ = group.transform({"user": kjt("uf", [10**12 + 1])})
+    assert m.user.embedding_bags["u"].weight[int(back["user"].values()[0])].tolist() == [42.0] * 4
+    group.save()
+    group.close()
+
+    tl = TensorList([torch.zeros(4, 3), torch.zeros(4, dtype=torch.int64)])
+    assert len(tl) == 2 and tl.row_bytes() == [12, 8] and list(tl.nbytes()) == [48, 32] and list(tl.dtype_codes()) == [0, 3] and tl.pointers()[0] == tl[0].data_ptr()
+    with pytest.raises(ValueError):
+        TensorList([torch.zeros(4, 3).t()])

@@ -4,3 +4,5 @@ from .dataloader import DataLoader, wrap  # noqa: F401
 from .id_transformer import IDTransformer  # noqa: F401
 from .id_transformer_collection import IDTransformerCollection  # noqa: F401
 from .ps import PS, load_io_plugin  # noqa: F401
+from .id_transformer_group import IDTransformerGroup  # noqa: F401,E402
+from .tensor_list import TensorList  # noqa: F401,E402
