@@ -226,3 +226,30 @@ def test_criteo_scripts_and_test_utils(tmp_path):
     assert not (out_s / "day_2_labels.npy").exists()
     with CriteoTest._create_dataset_npys(num_rows=12, filenames=["a", "b"]) as paths:
         assert len(paths) == 6 and np.load(paths[1]).shape == (12, 26)
+
+
+def test_examples_nvt_binary_dataloader_and_data_parallel(tmp_path):
+    import importlib.util
+    import os
+
+    import numpy as np
+
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples")
+
+    def load(name):
+        spec = importlib.util.spec_from_file_location(f"ex_{name}", os.path.join(root, f"{name}.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+
+    nvt = load("nvt_dataloader")
+    nvt.write_binary_dataset(str(tmp_path), 100, [50] * 26, seed=1)
+    raw = np.fromfile(os.path.join(tmp_path, "sparse.bin"), dtype=np.int32).reshape(100, 26)
+    ds0, ds1 = nvt.NvtBinaryDataset(str(tmp_path), 16, rank=0, world_size=2), nvt.NvtBinaryDataset(str(tmp_path), 16, rank=1, world_size=2)
+    assert len(ds0) == len(ds1) == 3                                   # 6 full batches of 16, strided over 2 ranks
+    b = ds1[1]                                                          # global batch 3 -> samples 48..63
+    assert b.sparse_features.keys()[3] == "cat_3" and b.sparse_features.stride() == 16
+    assert b.sparse_features.values().view(26, 16)[3].tolist() == raw[48:64, 3].tolist()
+    assert b.dense_features.shape == (16, 13) and b.dense_features.dtype == torch.float32 and b.labels.shape == (16,)
+    assert nvt.main(steps=60, batch_size=128) < 0.97                    # the planted signal is learnt from the files
+    assert load("golden_training_data_parallel").main(["--cpu", "--steps", "6", "--batch-size", "64"]) < 1.0
