@@ -1,81 +1,84 @@
-"""Guards used while a module is being traced / exported.
+"""Hints for the symbolic-shape engine while a module is exported or traced.
 
-Reference: ``torchrec/pt2/checks.py`` (``set/get_use_torchdynamo_compiling_path`` :18-23, ``is_torchdynamo_compiling`` / ``is_non_strict_exporting`` :26-56,
-``is_pt2_compiling`` :59, ``pt2_checks_tensor_slice`` :63, ``pt2_checks_all_is_size`` :77, ``pt2_check_size_nonzero`` :86, ``pt2_guard_size_oblivious`` :95).
-``torch.compile`` is not this framework's hot path (CUDA graphs are); these checks exist so the export / IR tooling (``ir/``, ``fx/``) can run.
+Counterpart of ``torchrec/pt2/checks.py``. ``torch.compile`` is not a hot path of this framework (CUDA graphs are), so the only consumers are the export /
+IR tooling (``ir/``, ``fx/``): every helper is the identity in eager mode and under TorchScript, and turns into ``torch._check*`` facts when a compile
+or a non-strict export is in flight. The "are we compiling" probe can be forced on for tests with ``set_use_torchdynamo_compiling_path(True)``.
 """
 from __future__ import annotations
 
-from typing import List
+from typing import Callable, Iterable, List, TypeVar
 
 import torch
 
-USE_TORCHDYNAMO_COMPILING_PATH: bool = False
+T = TypeVar("T")
+_forced_compiling = False
 
 
 def set_use_torchdynamo_compiling_path(val: bool) -> None:
-    global USE_TORCHDYNAMO_COMPILING_PATH
-    USE_TORCHDYNAMO_COMPILING_PATH = val
+    global _forced_compiling
+    _forced_compiling = bool(val)
 
 
 def get_use_torchdynamo_compiling_path() -> bool:
-    return USE_TORCHDYNAMO_COMPILING_PATH
+    return _forced_compiling
+
+
+def _probe(name: str) -> bool:
+    fn = getattr(torch.compiler, name, None)
+    try:
+        return bool(fn()) if fn is not None else False
+    except Exception:
+        return False
 
 
 def is_torchdynamo_compiling() -> bool:
-    if USE_TORCHDYNAMO_COMPILING_PATH:
-        return True
-    try:
-        return bool(torch.compiler.is_compiling())
-    except Exception:
-        return False
+    return _forced_compiling or _probe("is_compiling")
 
 
 def is_non_strict_exporting() -> bool:
-    try:
-        return bool(torch.compiler.is_exporting()) and not torch.compiler.is_dynamo_compiling()
-    except Exception:
-        return False
+    return _probe("is_exporting") and not _probe("is_dynamo_compiling")
 
 
 def is_pt2_compiling() -> bool:
     return is_torchdynamo_compiling() or is_non_strict_exporting()
 
 
+def _hints_active() -> bool:
+    return (not torch.jit.is_scripting()) and is_pt2_compiling()
+
+
+def _all_sizes(values: Iterable[int]) -> None:
+    for v in values:
+        torch._check_is_size(v)
+
+
 def pt2_checks_tensor_slice(tensor: torch.Tensor, start_offset: int, end_offset: int, dim: int = 0) -> None:
-    """Tell the symbolic-shape engine that ``[start, end)`` is a valid slice of ``tensor`` along ``dim``."""
-    if torch.jit.is_scripting() or not is_pt2_compiling():
-        return
-    torch._check_is_size(start_offset)
-    torch._check_is_size(end_offset)
-    torch._check_is_size(end_offset - start_offset)
-    torch._check(start_offset <= tensor.size(dim))
-    torch._check(end_offset <= tensor.size(dim))
-    torch._check(end_offset >= start_offset)
+    """``tensor.narrow(dim, start, end - start)`` is in bounds: 0 <= start <= end <= size."""
+    if _hints_active():
+        _all_sizes((start_offset, end_offset, end_offset - start_offset))
+        extent = tensor.size(dim)
+        for fact in (start_offset <= extent, end_offset <= extent, end_offset >= start_offset):
+            torch._check(fact)
 
 
 def pt2_checks_all_is_size(x: List[int]) -> List[int]:
-    if torch.jit.is_scripting() or not is_pt2_compiling():
-        return x
-    for i in x:
-        torch._check_is_size(i)
+    if _hints_active():
+        _all_sizes(x)
     return x
 
 
 def pt2_check_size_nonzero(x: torch.Tensor) -> torch.Tensor:
-    if torch.jit.is_scripting() or not is_pt2_compiling():
-        return x
-    for i in range(x.dim()):
-        torch._check(x.size(i) > 0)
+    if _hints_active():
+        for extent in x.shape:
+            torch._check(extent > 0)
     return x
 
 
 def pt2_guard_size_oblivious(x: bool) -> bool:
-    if torch.jit.is_scripting() or not is_pt2_compiling():
+    if not _hints_active():
         return x
     try:
         from torch.fx.experimental.symbolic_shapes import guard_size_oblivious
-
-        return guard_size_oblivious(x)
-    except Exception:
+    except ImportError:
         return x
+    return guard_size_oblivious(x)
