@@ -5,7 +5,7 @@ import torch
 from torchrec_b200.utils.multiprocess import run_multi_process
 
 
-def _run(ctx, sharding: str, dedup: bool):
+def _run(ctx, sharding: str, dedup: bool, grad_div: bool = False):
     from torchrec_b200.modules.embedding_configs import EmbeddingConfig
     from torchrec_b200.modules.embedding_modules import EmbeddingCollection
     from torchrec_b200.optim.apply_optimizer_in_backward import apply_optimizer_in_backward
@@ -16,7 +16,7 @@ def _run(ctx, sharding: str, dedup: bool):
     from torchrec_b200.parallel.types import ShardingPlan
     from torchrec_b200.sparse import KeyedJaggedTensor
 
-    set_gradient_division(False)
+    set_gradient_division(grad_div)
     torch.manual_seed(0)
     W, B = ctx.world_size, 5
     tables = lambda: [EmbeddingConfig(name="t0", embedding_dim=8, num_embeddings=30, feature_names=["f0", "f1"]),
@@ -41,7 +41,8 @@ def _run(ctx, sharding: str, dedup: bool):
             return self.ec(kjt)
 
     model = DistributedModelParallel(Wrap(local), device=torch.device("cpu"), plan=ShardingPlan({"ec": plan}), sharders=[sharder])
-    gold_opt = torch.optim.SGD(gold.parameters(), lr=0.1)
+    # gradient division: the sequence all-to-all divides by W in backward, i.e. the sharded update uses lr / W
+    gold_opt = torch.optim.SGD(gold.parameters(), lr=0.1 / (ctx.world_size if grad_div else 1))
 
     def batch(seed):
         g = torch.Generator().manual_seed(seed)
@@ -81,3 +82,9 @@ def test_sharded_ec_matches_unsharded(sharding):
 
 def test_sharded_ec_with_index_dedup():
     run_multi_process(_run, world_size=2, backend="gloo", sharding="rw", dedup=True)
+
+
+@pytest.mark.parametrize("sharding", ["tw", "rw"])
+def test_sharded_ec_gradient_division(sharding):
+    """Default setting (gradient division on): sequence embedding gradients are divided by the world size like the pooled path."""
+    run_multi_process(_run, world_size=2, backend="gloo", sharding=sharding, dedup=False, grad_div=True)

@@ -132,3 +132,37 @@ def _staged(ctx):
 
 def test_staged_pipeline_with_sparse_data_dist_util():
     run_multi_process(_staged, world_size=2, backend="gloo")
+
+
+def _bounded_queue(ctx):
+    """execute_all_batches=False: the queue never grows past two batches, every fetched batch but the in-flight tail trains."""
+    from torchrec_b200.datasets.random import RandomRecDataset
+    from torchrec_b200.parallel import train_pipeline as tp
+
+    dmp, opt, keys, hashes = _build(ctx, "tw")
+    ds = RandomRecDataset(keys, 6, hash_sizes=hashes, ids_per_feature=3, min_ids_per_feature=0, num_dense=5, manual_seed=3 + ctx.rank,
+                          num_generated_batches=12, num_batches=12)
+    fetched = [0]
+
+    def counting(it):
+        for b in it:
+            fetched[0] += 1
+            yield b
+
+    pipe = tp.TrainPipelineSparseDist(dmp, opt, torch.device("cpu"), execute_all_batches=False)
+    it = counting(iter(ds))
+    trained, sizes = 0, []
+    while True:
+        try:
+            pipe.progress(it)
+        except StopIteration:
+            break
+        trained += 1
+        sizes.append(len(pipe.batches))
+    assert max(sizes) <= 2, sizes
+    assert fetched[0] == 12
+    assert trained >= 10, (trained, sizes)  # only the batches still in flight when the stream ends are dropped
+
+
+def test_sparse_dist_queue_is_bounded_without_execute_all_batches():
+    run_multi_process(_bounded_queue, world_size=2, backend="gloo")

@@ -108,3 +108,25 @@ def test_stochastic_rounding_is_unbiased_cpu_reference():
 
     assert run(False) == 1.0                                  # round-to-nearest: every update is lost
     assert abs(run(True) - (1.0 + 64 * 2.0**-11)) < 6e-3      # SR: the mean moves by the requested 2^-5 (noise ~ 1e-3)
+
+
+def test_vbe_kjt_permute_split_to_dict():
+    """Variable-batch KJT: permute must move the per-key LENGTH runs (not the stride table) along with the values."""
+    import torch
+
+    from torchrec_b200.sparse.jagged_tensor import KeyedJaggedTensor
+
+    kjt = KeyedJaggedTensor(keys=["a", "b"], values=torch.tensor([10, 20, 21, 30, 31, 32]), lengths=torch.tensor([1, 2, 3]),
+                            stride_per_key_per_rank=[[2], [1]])
+    p = kjt.permute([1, 0])
+    assert p.keys() == ["b", "a"]
+    assert p.lengths().tolist() == [3, 1, 2]
+    assert p.values().tolist() == [30, 31, 32, 10, 20, 21]
+    assert p.stride_per_key() == [1, 2]
+    d = p.to_dict()
+    assert d["a"].lengths().tolist() == [1, 2] and d["a"].values().tolist() == [10, 20, 21]
+    assert d["b"].lengths().tolist() == [3] and d["b"].values().tolist() == [30, 31, 32]
+    first, second = p.split([1, 1])
+    assert first.keys() == ["b"] and first.lengths().tolist() == [3] and second.values().tolist() == [10, 20, 21]
+    rep = kjt.permute([0, 1, 0])  # repeated keys (column-wise sharding replicates features)
+    assert rep.lengths().tolist() == [1, 2, 3, 1, 2] and rep.values().tolist() == [10, 20, 21, 30, 31, 32, 10, 20, 21]

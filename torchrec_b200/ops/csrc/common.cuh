@@ -50,6 +50,36 @@ __device__ __forceinline__ void trb_st_idx(void* p, int64_t i, int is64, int64_t
   else reinterpret_cast<int32_t*>(p)[i] = (int32_t) v;
 }
 
+
+// ---- multi-source id views ----------------------------------------------------------------
+// A table-batched kernel sees B = n_src * src_B samples per feature. With n_src == 1 the ids are one KJT (offsets
+// [F*B + 1] over one indices array). With n_src > 1 (NVLink input dist, csrc/kjt_route.cu) every source rank s wrote
+// ITS samples into a private fixed-capacity region of the receive slot:
+//     offsets_s = offsets + s * off_stride   ([F * src_B + 1], relative to the start of the region)
+//     indices_s = indices + s * idx_stride   (per-sample weights use the same stride)
+// so the lookup / backward kernels consume the received regions in place (no recat / compaction pass).
+struct TrbSrcView {
+  const void* indices;
+  const void* offsets;
+  const float* psw;
+  int64_t idx_stride;
+  int64_t off_stride;
+  int32_t n_src;
+  int32_t src_B;
+  int32_t idx64, off64;
+};
+
+// element index (into offsets) of bag (f, b) and the position base of its source region
+__device__ __forceinline__ int64_t trb_src_off_index(const TrbSrcView& v, int f, int b, int64_t* pos_base) {
+  if (v.n_src <= 1) {
+    *pos_base = 0;
+    return (int64_t) f * v.src_B + b;
+  }
+  const int s = b / v.src_B;
+  *pos_base = (int64_t) s * v.idx_stride;
+  return (int64_t) s * v.off_stride + (int64_t) f * v.src_B + (b - s * v.src_B);
+}
+
 // 4-element vector load/store with conversion to/from float4. Rows are 4-element aligned
 // (embedding dims are multiples of 4, same constraint as the reference TBE).
 template <typename T>

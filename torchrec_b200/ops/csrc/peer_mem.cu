@@ -132,6 +132,57 @@ TRB_API int trb_staging_reduce(const void* staging, int s_dtype, void* out, int 
   return -3;
 }
 
+// Compact-staging variant used by the sparse plane: the staging slabs hold ONLY the columns of row-sharded tables
+// (`n_cols` of them, slab j = partial sums computed by rank j); staged column c lands in output column dst_col[c].
+// Memory is W x B x (row-sharded columns) instead of W full [B, sum D] slabs.
+template <typename S, typename O>
+__global__ void __launch_bounds__(256)
+trb_staging_reduce_cols_kernel(const S* __restrict__ staging, O* __restrict__ out, const uint32_t* __restrict__ col_mask,
+                               const int32_t* __restrict__ dst_col, int B, int n_cols, int64_t stride, int64_t out_stride, int64_t slab, int W) {
+  const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const int vec_cols = n_cols >> 2;
+  if (i >= (int64_t) B * vec_cols) return;
+  const int b = (int) (i / vec_cols);
+  const int c = (int) (i - (int64_t) b * vec_cols) << 2;
+  const uint32_t m = col_mask[c];
+  if (m == 0) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0; j < W; ++j) {
+    if (m & (1u << j)) acc = f4_add(acc, Vec4<S>::ld(staging + j * slab + (int64_t) b * stride + c));
+  }
+  Vec4<O>::st(out + (int64_t) b * out_stride + dst_col[c], acc);
+}
+
+TRB_API int trb_staging_reduce_cols(const void* staging, int s_dtype, void* out, int o_dtype, const uint32_t* col_mask, const int32_t* dst_col, int B,
+                                    int n_cols, int64_t stride, int64_t out_stride, int64_t slab, int W, cudaStream_t stream) {
+  const int64_t n = (int64_t) B * (n_cols / 4);
+  if (n == 0) return 0;
+  const int threads = 256;
+  const unsigned blocks = (unsigned) ((n + threads - 1) / threads);
+#define TRB_SRC(SC, ST, OC, OT)                                                                                            \
+  if (s_dtype == SC && o_dtype == OC) {                                                                                    \
+    trb_staging_reduce_cols_kernel<ST, OT><<<blocks, threads, 0, stream>>>((const ST*) staging, (OT*) out, col_mask,      \
+                                                                             dst_col, B, n_cols, stride, out_stride, slab, W); \
+    TRB_CHECK_LAUNCH();                                                                                                     \
+    return 0;                                                                                                               \
+  }
+  TRB_SRC(TRB_F32, float, TRB_F32, float)
+  TRB_SRC(TRB_BF16, __nv_bfloat16, TRB_BF16, __nv_bfloat16)
+#undef TRB_SRC
+  return -3;
+}
+
+// Single-process multi-GPU harnesses (tools/bench_peer_copy.py, tests): let kernels on `dev` address memory of `peer`.
+TRB_API int trb_enable_peer_access(int dev, int peer) {
+  int cur = 0;
+  TRB_CUDA(cudaGetDevice(&cur));
+  TRB_CUDA(cudaSetDevice(dev));
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+  cudaSetDevice(cur);
+  return (int) e;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Strided cast-copy: dst[b, c] = (D) src[b, c] * scale   (used to stage gradients into the symmetric
 // buffer the peers pull from, with the 1/W gradient division and the wire dtype cast fused in)

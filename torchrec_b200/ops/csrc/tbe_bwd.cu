@@ -56,15 +56,14 @@ struct TbeBwdParams {
   const int64_t* feat_rowbase;  // [F] first global row id of feature f's table
   const int32_t* feat_dim;      // [F]
   const int32_t* feat_col;      // [F]
-  const void* indices;
-  const void* offsets;
-  const float* psw;
+  TrbSrcView src;    // ids (one KJT or per-source regions)
   TrbPeerPtrs grad;  // gradient sources
   int64_t grad_stride;
   int64_t n;  // capacity of indices
   int64_t total_rows;
   int32_t B, B_local, F;
-  int32_t idx64, off64, mean;
+  int32_t mean;
+  float grad_scale;  // multiplies every gradient row (1/W gradient division of the pooled output dist, folded into the kernel)
   int32_t wd_mode;  // 0 none, 1 L2, 2 decoupled
   // workspace
   void* keys;
@@ -89,25 +88,41 @@ __device__ __forceinline__ uint64_t ld_key(const void* p, int64_t i, int key64) 
   return key64 ? reinterpret_cast<const uint64_t*>(p)[i] : (uint64_t) reinterpret_cast<const uint32_t*>(p)[i];
 }
 
+// number of ids in global bag (f * B + b)
+__device__ __forceinline__ int64_t bag_len(const TbeBwdParams& p, int bag) {
+  const int f = bag / p.B;
+  int64_t pos_base;
+  const int64_t oi = trb_src_off_index(p.src, f, bag - f * p.B, &pos_base);
+  return trb_ld_idx(p.src.offsets, oi + 1, p.src.off64) - trb_ld_idx(p.src.offsets, oi, p.src.off64);
+}
+
 __global__ void __launch_bounds__(256) tbe_bwd_build_keys(const TbeBwdParams p) {
   const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) *p.long_count = 0;
   if (i >= p.n) return;
-  const int64_t n_bags = (int64_t) p.F * p.B;
-  const int64_t total = trb_ld_idx(p.offsets, n_bags, p.off64);
+  // position i lives in source region s (one region when n_src == 1); offsets of a region are relative to its start
+  int s = 0;
+  int64_t li = i;
+  if (p.src.n_src > 1) {
+    s = (int) (i / p.src.idx_stride);
+    li = i - (int64_t) s * p.src.idx_stride;
+  }
+  const int64_t n_bags = (int64_t) p.F * p.src.src_B;
+  const int64_t obase = (int64_t) s * p.src.off_stride;
+  const int64_t total = trb_ld_idx(p.src.offsets, obase + n_bags, p.src.off64);
   uint64_t key = (uint64_t) p.total_rows;  // sentinel sorts last
   int32_t bag = 0;
-  const int64_t first = trb_ld_idx(p.offsets, 0, p.off64);  // offsets may be a window into a larger id array
-  if (i >= first && i < total) {
-    // largest bag with offsets[bag] <= i  (bags may be empty -> take the last such bag)
+  const int64_t first = trb_ld_idx(p.src.offsets, obase, p.src.off64);  // offsets may be a window into a larger id array
+  if (s < p.src.n_src && li >= first && li < total) {
+    // largest bag with offsets[bag] <= li  (bags may be empty -> take the last such bag)
     int64_t lo = 0, hi = n_bags - 1;
     while (lo < hi) {
       const int64_t mid = (lo + hi + 1) >> 1;
-      if (trb_ld_idx(p.offsets, mid, p.off64) <= i) lo = mid; else hi = mid - 1;
+      if (trb_ld_idx(p.src.offsets, obase + mid, p.src.off64) <= li) lo = mid; else hi = mid - 1;
     }
-    bag = (int32_t) lo;
-    const int f = (int) (lo / p.B);
-    const int64_t idx = trb_ld_idx(p.indices, i, p.idx64);
+    const int f = (int) (lo / p.src.src_B);
+    bag = (int32_t) ((int64_t) f * p.B + (int64_t) s * p.src.src_B + (lo - (int64_t) f * p.src.src_B));
+    const int64_t idx = trb_ld_idx(p.src.indices, i, p.src.idx64);
     if (idx >= 0 && idx < p.feat_rows[f]) key = (uint64_t) (p.feat_rowbase[f] + idx);
   }
   if (p.key64) reinterpret_cast<uint64_t*>(p.keys)[i] = key;
@@ -381,9 +396,9 @@ __global__ void __launch_bounds__(256) tbe_bwd_unique_kernel(const TbeBwdParams 
   if (lane < cnt) {
     const int val = p.vals_sorted[base + lane];
     bag = p.bag_of[val];
-    scale = p.psw ? p.psw[val] : 1.f;
+    scale = (p.src.psw ? p.src.psw[val] : 1.f) * p.grad_scale;
     if (p.mean) {
-      const int64_t L = trb_ld_idx(p.offsets, (int64_t) bag + 1, p.off64) - trb_ld_idx(p.offsets, bag, p.off64);
+      const int64_t L = bag_len(p, bag);
       scale /= (float) (L > 0 ? L : 1);
     }
   }
@@ -467,9 +482,9 @@ __global__ void __launch_bounds__(256) tbe_bwd_chunk_kernel(const TbeBwdParams p
   float scale = 0.f;
   if (lane < cnt && key != sentinel) {
     bag = p.bag_of[val];
-    scale = p.psw ? p.psw[val] : 1.f;
+    scale = (p.src.psw ? p.src.psw[val] : 1.f) * p.grad_scale;
     if (p.mean) {
-      const int64_t L = trb_ld_idx(p.offsets, (int64_t) bag + 1, p.off64) - trb_ld_idx(p.offsets, bag, p.off64);
+      const int64_t L = bag_len(p, bag);
       scale /= (float) (L > 0 ? L : 1);
     }
   }
@@ -769,36 +784,20 @@ static int dispatch_dim(TbeBwdParams& p, char* ws, cudaStream_t stream) {
 }
 
 // Fused backward + optimizer. `workspace` must hold trb_tbe_bwd_workspace_bytes(n, max_dim, total_rows).
-TRB_API int trb_tbe_bwd_fused_ex(void* weights, int w_dtype, float* state1, float* state2, const float* hyper, int opt,
+// `n` = number of id POSITIONS to scan (capacity of `indices`; with n_src > 1 it must equal n_src * idx_stride).
+TRB_API int trb_tbe_bwd_fused_ms(void* weights, int w_dtype, float* state1, float* state2, const float* hyper, int opt,
                                  int wd_mode, const int64_t* feat_woff, const int64_t* feat_rows,
                                  const int64_t* feat_rowbase, const int32_t* feat_dim, const int32_t* feat_col,
                                  const void* indices, int idx64, const void* offsets, int off64, const float* psw,
-                                 void* const* grad_ptrs, int n_grad, int grad_dtype, int64_t grad_stride, int64_t n,
-                                 int64_t total_rows, int B, int B_local, int F, int max_dim, int mean, void* workspace,
-                                 int stochastic_rounding, unsigned long long sr_seed, cudaStream_t stream);
-
-TRB_API int trb_tbe_bwd_fused(void* weights, int w_dtype, float* state1, float* state2, const float* hyper, int opt,
-                              int wd_mode, const int64_t* feat_woff, const int64_t* feat_rows,
-                              const int64_t* feat_rowbase, const int32_t* feat_dim, const int32_t* feat_col,
-                              const void* indices, int idx64, const void* offsets, int off64, const float* psw,
-                              void* const* grad_ptrs, int n_grad, int grad_dtype, int64_t grad_stride, int64_t n,
-                              int64_t total_rows, int B, int B_local, int F, int max_dim, int mean, void* workspace,
-                              cudaStream_t stream) {
-  return trb_tbe_bwd_fused_ex(weights, w_dtype, state1, state2, hyper, opt, wd_mode, feat_woff, feat_rows, feat_rowbase, feat_dim, feat_col, indices,
-                              idx64, offsets, off64, psw, grad_ptrs, n_grad, grad_dtype, grad_stride, n, total_rows, B, B_local, F, max_dim, mean,
-                              workspace, 0, 0ull, stream);
-}
-
-TRB_API int trb_tbe_bwd_fused_ex(void* weights, int w_dtype, float* state1, float* state2, const float* hyper, int opt,
-                                 int wd_mode, const int64_t* feat_woff, const int64_t* feat_rows,
-                                 const int64_t* feat_rowbase, const int32_t* feat_dim, const int32_t* feat_col,
-                                 const void* indices, int idx64, const void* offsets, int off64, const float* psw,
-                                 void* const* grad_ptrs, int n_grad, int grad_dtype, int64_t grad_stride, int64_t n,
+                                 int n_src, int64_t idx_stride, int64_t off_stride,
+                                 void* const* grad_ptrs, int n_grad, int grad_dtype, int64_t grad_stride, float grad_scale, int64_t n,
                                  int64_t total_rows, int B, int B_local, int F, int max_dim, int mean, void* workspace,
                                  int stochastic_rounding, unsigned long long sr_seed, cudaStream_t stream) {
   if (n <= 0) return 0;
   if (n_grad < 1 || n_grad > TRB_MAX_PEERS) return -1;
   if ((int64_t) B_local * n_grad != B) return -4;
+  if (n_src < 1 || B % n_src != 0) return -4;
+  if (n_src > 1 && n != (int64_t) n_src * idx_stride) return -4;
   TbeBwdParams p;
   p.weights = weights;
   p.state1 = state1;
@@ -809,18 +808,23 @@ TRB_API int trb_tbe_bwd_fused_ex(void* weights, int w_dtype, float* state1, floa
   p.feat_rowbase = feat_rowbase;
   p.feat_dim = feat_dim;
   p.feat_col = feat_col;
-  p.indices = indices;
-  p.offsets = offsets;
-  p.psw = psw;
+  p.src.indices = indices;
+  p.src.offsets = offsets;
+  p.src.psw = psw;
+  p.src.idx_stride = idx_stride;
+  p.src.off_stride = off_stride;
+  p.src.n_src = n_src;
+  p.src.src_B = B / n_src;
+  p.src.idx64 = idx64;
+  p.src.off64 = off64;
   for (int i = 0; i < TRB_MAX_PEERS; ++i) p.grad.p[i] = i < n_grad ? grad_ptrs[i] : nullptr;
   p.grad_stride = grad_stride;
+  p.grad_scale = grad_scale;
   p.n = n;
   p.total_rows = total_rows;
   p.B = B;
   p.B_local = B_local;
   p.F = F;
-  p.idx64 = idx64;
-  p.off64 = off64;
   p.mean = mean;
   p.wd_mode = wd_mode;
   p.max_dim = max_dim;
@@ -843,4 +847,28 @@ TRB_API int trb_tbe_bwd_fused_ex(void* weights, int w_dtype, float* state1, floa
   TRB_BWD_CASE(TRB_F16, __half, TRB_F32, float);
 #undef TRB_BWD_CASE
   return -3;
+}
+
+TRB_API int trb_tbe_bwd_fused_ex(void* weights, int w_dtype, float* state1, float* state2, const float* hyper, int opt,
+                                 int wd_mode, const int64_t* feat_woff, const int64_t* feat_rows,
+                                 const int64_t* feat_rowbase, const int32_t* feat_dim, const int32_t* feat_col,
+                                 const void* indices, int idx64, const void* offsets, int off64, const float* psw,
+                                 void* const* grad_ptrs, int n_grad, int grad_dtype, int64_t grad_stride, int64_t n,
+                                 int64_t total_rows, int B, int B_local, int F, int max_dim, int mean, void* workspace,
+                                 int stochastic_rounding, unsigned long long sr_seed, cudaStream_t stream) {
+  return trb_tbe_bwd_fused_ms(weights, w_dtype, state1, state2, hyper, opt, wd_mode, feat_woff, feat_rows, feat_rowbase, feat_dim, feat_col, indices,
+                              idx64, offsets, off64, psw, 1, 0, 0, grad_ptrs, n_grad, grad_dtype, grad_stride, 1.f, n, total_rows, B, B_local, F,
+                              max_dim, mean, workspace, stochastic_rounding, sr_seed, stream);
+}
+
+TRB_API int trb_tbe_bwd_fused(void* weights, int w_dtype, float* state1, float* state2, const float* hyper, int opt,
+                              int wd_mode, const int64_t* feat_woff, const int64_t* feat_rows,
+                              const int64_t* feat_rowbase, const int32_t* feat_dim, const int32_t* feat_col,
+                              const void* indices, int idx64, const void* offsets, int off64, const float* psw,
+                              void* const* grad_ptrs, int n_grad, int grad_dtype, int64_t grad_stride, int64_t n,
+                              int64_t total_rows, int B, int B_local, int F, int max_dim, int mean, void* workspace,
+                              cudaStream_t stream) {
+  return trb_tbe_bwd_fused_ex(weights, w_dtype, state1, state2, hyper, opt, wd_mode, feat_woff, feat_rows, feat_rowbase, feat_dim, feat_col, indices,
+                              idx64, offsets, off64, psw, grad_ptrs, n_grad, grad_dtype, grad_stride, n, total_rows, B, B_local, F, max_dim, mean,
+                              workspace, 0, 0ull, stream);
 }

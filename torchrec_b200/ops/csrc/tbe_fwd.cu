@@ -29,16 +29,12 @@ struct TbeFwdParams {
   const int64_t* feat_rows;      // [F] rows of feature f's table (bounds check)
   const int32_t* feat_dim;       // [F] embedding dim of feature f
   const int32_t* feat_col;       // [F] output column offset
-  const void* indices;           // [sum L]
-  const void* offsets;           // [F*B + 1]
-  const float* psw;              // per-sample weights or nullptr
+  TrbSrcView src;                // ids: indices [sum L], offsets [F*B + 1], per-sample weights (or per-source regions)
   TrbPeerPtrs out;               // destination buffers (dtype O)
   int64_t out_stride;            // elements between consecutive rows of a destination
   int32_t B;                     // total batch seen by this lookup (W_src * B_local)
   int32_t B_local;               // rows per destination
   int32_t F;
-  int32_t idx64;
-  int32_t off64;
   int32_t mean;                  // 1 = MEAN pooling
 };
 
@@ -58,8 +54,10 @@ __global__ void __launch_bounds__(256) tbe_pooled_fwd_kernel(const TbeFwdParams 
   const int64_t rows = p.feat_rows[f];
   const W* __restrict__ wbase = reinterpret_cast<const W*>(p.weights) + p.feat_woff[f];
 
-  const int64_t start = trb_ld_idx(p.offsets, group, p.off64);
-  const int64_t end = trb_ld_idx(p.offsets, group + 1, p.off64);
+  int64_t pos_base;
+  const int64_t oi = trb_src_off_index(p.src, f, b, &pos_base);
+  const int64_t start = pos_base + trb_ld_idx(p.src.offsets, oi, p.src.off64);
+  const int64_t end = pos_base + trb_ld_idx(p.src.offsets, oi + 1, p.src.off64);
 
   float4 acc[MAXV];
 #pragma unroll
@@ -70,8 +68,8 @@ __global__ void __launch_bounds__(256) tbe_pooled_fwd_kernel(const TbeFwdParams 
     int64_t my_idx = -1;
     float my_w = 0.f;
     if (lig < n) {
-      my_idx = trb_ld_idx(p.indices, l0 + lig, p.idx64);
-      my_w = p.psw ? p.psw[l0 + lig] : 1.f;
+      my_idx = trb_ld_idx(p.src.indices, l0 + lig, p.src.idx64);
+      my_w = p.src.psw ? p.src.psw[l0 + lig] : 1.f;
       if (my_idx < 0 || my_idx >= rows) { my_idx = 0; my_w = 0.f; }  // out-of-range ids contribute zero
     }
     for (int j = 0; j < n; j += UNROLL) {
@@ -121,21 +119,31 @@ template <typename W, typename O, int MAXV, int U>
 __global__ void __launch_bounds__(256) tbe_pooled_fwd_chunk_kernel(const TbeFwdParams p) {
   const int lane = threadIdx.x & 31;
   const int64_t chunk = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int cpf = (p.B + 31) >> 5;  // chunks per feature
+  // chunks never straddle a source region or a destination: they tile the finer of the two partitions of the batch
+  const int part = min(p.src.src_B, p.B_local);
+  const int cpp = (part + 31) >> 5;             // chunks per partition
+  const int cpf = cpp * (p.B / part);           // chunks per feature
   if (chunk >= (int64_t) p.F * cpf) return;
   const int f = (int) (chunk / cpf);
-  const int b0 = (int) (chunk - (int64_t) f * cpf) << 5;
-  const int nb = min(32, p.B - b0);
+  const int rc = (int) (chunk - (int64_t) f * cpf);
+  const int pi = rc / cpp;
+  const int b0l = (rc - pi * cpp) << 5;
+  const int b0 = pi * part + b0l;
+  const int nb = min(32, part - b0l);
   const int D = p.feat_dim[f];
   const int nvec = D >> 2;
   const int64_t rows = p.feat_rows[f];
   const W* __restrict__ wbase = reinterpret_cast<const W*>(p.weights) + p.feat_woff[f];
   const int col = p.feat_col[f];
 
-  const int64_t bag0 = (int64_t) f * p.B + b0;
-  const int64_t my_start = trb_ld_idx(p.offsets, bag0 + min(lane, nb), p.off64);
+  int64_t pos_base;
+  const int64_t bag0 = trb_src_off_index(p.src, f, b0, &pos_base);
+  const void* const ids = p.src.idx64 ? (const void*) (reinterpret_cast<const int64_t*>(p.src.indices) + pos_base)
+                                      : (const void*) (reinterpret_cast<const int32_t*>(p.src.indices) + pos_base);
+  const float* const psw = p.src.psw ? p.src.psw + pos_base : nullptr;
+  const int64_t my_start = trb_ld_idx(p.src.offsets, bag0 + min(lane, nb), p.src.off64);
   int64_t my_end = __shfl_down_sync(0xffffffffu, my_start, 1);
-  const int64_t last_end = trb_ld_idx(p.offsets, bag0 + nb, p.off64);
+  const int64_t last_end = trb_ld_idx(p.src.offsets, bag0 + nb, p.src.off64);
   if (lane >= nb - 1) my_end = last_end;
   const int64_t e_begin = __shfl_sync(0xffffffffu, my_start, 0);
   const int64_t e_end = last_end;
@@ -150,8 +158,8 @@ __global__ void __launch_bounds__(256) tbe_pooled_fwd_chunk_kernel(const TbeFwdP
       int my_idx = 0;
       float my_w = 0.f;
       if (lane < nb) {
-        const int64_t id = trb_ld_idx(p.indices, e_begin + lane, p.idx64);
-        my_w = p.psw ? p.psw[e_begin + lane] : 1.f;
+        const int64_t id = trb_ld_idx(ids, e_begin + lane, p.src.idx64);
+        my_w = psw ? psw[e_begin + lane] : 1.f;
         if (id < 0 || id >= rows) my_w = 0.f; else my_idx = (int) id;
       }
       O* dst0 = reinterpret_cast<O*>(p.out.p[s0]) + (int64_t) (b0 - s0 * p.B_local) * p.out_stride + col;
@@ -214,8 +222,8 @@ __global__ void __launch_bounds__(256) tbe_pooled_fwd_chunk_kernel(const TbeFwdP
     int64_t my_idx = 0;
     float my_w = 0.f;
     if (lane < n) {
-      my_idx = trb_ld_idx(p.indices, e0 + lane, p.idx64);
-      my_w = p.psw ? p.psw[e0 + lane] : 1.f;
+      my_idx = trb_ld_idx(ids, e0 + lane, p.src.idx64);
+      my_w = psw ? psw[e0 + lane] : 1.f;
       if (my_idx < 0 || my_idx >= rows) { my_idx = 0; my_w = 0.f; }
     }
     for (int j = 0; j < n; j += U) {
@@ -260,7 +268,9 @@ __global__ void __launch_bounds__(256) tbe_pooled_fwd_chunk_kernel(const TbeFwdP
 
 template <typename W, typename O, int MAXV, int U>
 static int launch_pooled_chunk(const TbeFwdParams& p, cudaStream_t stream) {
-  const int64_t chunks = (int64_t) p.F * ((p.B + 31) / 32);
+  if (p.B == 0 || p.F == 0) return 0;
+  const int part = p.src.src_B < p.B_local ? p.src.src_B : p.B_local;
+  const int64_t chunks = (int64_t) p.F * ((part + 31) / 32) * (p.B / part);
   if (chunks == 0) return 0;
   const int threads = 256;
   const int64_t blocks = (chunks + 7) / 8;
@@ -303,29 +313,36 @@ static int dispatch_out(const TbeFwdParams& p, int out_dtype, int max_dim, cudaS
 }
 
 // Pooled forward. Returns 0 on success, a cudaError_t (>0) or a negative library error.
-TRB_API int trb_tbe_pooled_fwd(const void* weights, int w_dtype, const int64_t* feat_woff, const int64_t* feat_rows,
-                               const int32_t* feat_dim, const int32_t* feat_col, const void* indices, int idx64,
-                               const void* offsets, int off64, const float* psw, void* const* out_ptrs, int n_out,
-                               int out_dtype, int64_t out_stride, int B, int B_local, int F, int max_dim, int mean,
-                               cudaStream_t stream) {
+// `n_src` > 1: ids arrive in per-source regions (see TrbSrcView); idx_stride / off_stride in elements.
+TRB_API int trb_tbe_pooled_fwd_ms(const void* weights, int w_dtype, const int64_t* feat_woff, const int64_t* feat_rows,
+                                  const int32_t* feat_dim, const int32_t* feat_col, const void* indices, int idx64,
+                                  const void* offsets, int off64, const float* psw, int n_src, int64_t idx_stride, int64_t off_stride,
+                                  void* const* out_ptrs, int n_out, int out_dtype, int64_t out_stride, int B, int B_local, int F,
+                                  int max_dim, int mean, cudaStream_t stream) {
   if (n_out < 1 || n_out > TRB_MAX_PEERS) return -1;
   if ((int64_t) B_local * n_out != B) return -4;
+  if (n_src < 1 || B % n_src != 0) return -4;
+  if (n_src > 1 && n_out > 1 && n_src != n_out) return -4;
   TbeFwdParams p;
   p.weights = weights;
   p.feat_woff = feat_woff;
   p.feat_rows = feat_rows;
   p.feat_dim = feat_dim;
   p.feat_col = feat_col;
-  p.indices = indices;
-  p.offsets = offsets;
-  p.psw = psw;
+  p.src.indices = indices;
+  p.src.offsets = offsets;
+  p.src.psw = psw;
+  p.src.idx_stride = idx_stride;
+  p.src.off_stride = off_stride;
+  p.src.n_src = n_src;
+  p.src.src_B = B / n_src;
+  p.src.idx64 = idx64;
+  p.src.off64 = off64;
   for (int i = 0; i < TRB_MAX_PEERS; ++i) p.out.p[i] = i < n_out ? out_ptrs[i] : nullptr;
   p.out_stride = out_stride;
   p.B = B;
   p.B_local = B_local;
   p.F = F;
-  p.idx64 = idx64;
-  p.off64 = off64;
   p.mean = mean;
   switch (w_dtype) {
     case TRB_F32: return dispatch_out<float>(p, out_dtype, max_dim, stream);
@@ -333,6 +350,15 @@ TRB_API int trb_tbe_pooled_fwd(const void* weights, int w_dtype, const int64_t* 
     case TRB_BF16: return dispatch_out<__nv_bfloat16>(p, out_dtype, max_dim, stream);
   }
   return -3;
+}
+
+TRB_API int trb_tbe_pooled_fwd(const void* weights, int w_dtype, const int64_t* feat_woff, const int64_t* feat_rows,
+                               const int32_t* feat_dim, const int32_t* feat_col, const void* indices, int idx64,
+                               const void* offsets, int off64, const float* psw, void* const* out_ptrs, int n_out,
+                               int out_dtype, int64_t out_stride, int B, int B_local, int F, int max_dim, int mean,
+                               cudaStream_t stream) {
+  return trb_tbe_pooled_fwd_ms(weights, w_dtype, feat_woff, feat_rows, feat_dim, feat_col, indices, idx64, offsets, off64, psw, 1, 0, 0,
+                               out_ptrs, n_out, out_dtype, out_stride, B, B_local, F, max_dim, mean, stream);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -12,12 +12,11 @@ struct PswGradParams {
   const int64_t* feat_rows;
   const int32_t* feat_dim;
   const int32_t* feat_col;
-  const void* indices;
-  const void* offsets;
+  TrbSrcView src;
   TrbPeerPtrs grad;
   int64_t grad_stride;
   float* out;  // [n]
-  int32_t B, B_local, F, idx64, off64, mean;
+  int32_t B, B_local, F, mean;
 };
 
 template <typename W, typename G, int MAXV>
@@ -27,8 +26,10 @@ __global__ void __launch_bounds__(256) tbe_psw_grad_kernel(const PswGradParams p
   if (bag >= (int64_t) p.F * p.B) return;
   const int f = (int) (bag / p.B);
   const int b = (int) (bag - (int64_t) f * p.B);
-  const int64_t start = trb_ld_idx(p.offsets, bag, p.off64);
-  const int64_t end = trb_ld_idx(p.offsets, bag + 1, p.off64);
+  int64_t pos_base;
+  const int64_t oi = trb_src_off_index(p.src, f, b, &pos_base);
+  const int64_t start = pos_base + trb_ld_idx(p.src.offsets, oi, p.src.off64);
+  const int64_t end = pos_base + trb_ld_idx(p.src.offsets, oi + 1, p.src.off64);
   if (end <= start) return;
   const int D = p.feat_dim[f];
   const int nvec = D >> 2;
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(256) tbe_psw_grad_kernel(const PswGradParams p
   }
   const float scale = p.mean ? 1.f / (float) (end - start) : 1.f;
   for (int64_t i = start; i < end; ++i) {
-    const int64_t idx = trb_ld_idx(p.indices, i, p.idx64);
+    const int64_t idx = trb_ld_idx(p.src.indices, i, p.src.idx64);
     float acc = 0.f;
     if (idx >= 0 && idx < rows) {
       const W* row = wbase + idx * D;
@@ -78,16 +79,19 @@ static int launch_psw(const PswGradParams& p, int max_dim, cudaStream_t stream) 
   return 0;
 }
 
-TRB_API int trb_tbe_psw_grad(const void* weights, int w_dtype, const int64_t* feat_woff, const int64_t* feat_rows, const int32_t* feat_dim,
-                             const int32_t* feat_col, const void* indices, int idx64, const void* offsets, int off64, void* const* grad_ptrs,
-                             int n_grad, int grad_dtype, int64_t grad_stride, float* out, int B, int B_local, int F, int max_dim, int mean,
-                             cudaStream_t stream) {
+TRB_API int trb_tbe_psw_grad_ms(const void* weights, int w_dtype, const int64_t* feat_woff, const int64_t* feat_rows, const int32_t* feat_dim,
+                                const int32_t* feat_col, const void* indices, int idx64, const void* offsets, int off64, int n_src, int64_t idx_stride,
+                                int64_t off_stride, void* const* grad_ptrs, int n_grad, int grad_dtype, int64_t grad_stride, float* out, int B,
+                                int B_local, int F, int max_dim, int mean, cudaStream_t stream) {
   if (n_grad < 1 || n_grad > TRB_MAX_PEERS) return -1;
+  if (n_src < 1 || B % n_src != 0) return -4;
   PswGradParams p;
   p.weights = weights; p.feat_woff = feat_woff; p.feat_rows = feat_rows; p.feat_dim = feat_dim; p.feat_col = feat_col;
-  p.indices = indices; p.offsets = offsets; p.grad_stride = grad_stride; p.out = out;
+  p.src.indices = indices; p.src.offsets = offsets; p.src.psw = nullptr; p.src.idx_stride = idx_stride; p.src.off_stride = off_stride;
+  p.src.n_src = n_src; p.src.src_B = B / n_src; p.src.idx64 = idx64; p.src.off64 = off64;
+  p.grad_stride = grad_stride; p.out = out;
   for (int i = 0; i < n_grad; ++i) p.grad.p[i] = grad_ptrs[i];
-  p.B = B; p.B_local = B_local; p.F = F; p.idx64 = idx64; p.off64 = off64; p.mean = mean;
+  p.B = B; p.B_local = B_local; p.F = F; p.mean = mean;
 #define PSW_CASE(WD, WT, GD, GT) if (w_dtype == WD && grad_dtype == GD) return launch_psw<WT, GT>(p, max_dim, stream);
   PSW_CASE(TRB_F32, float, TRB_F32, float)
   PSW_CASE(TRB_F32, float, TRB_BF16, __nv_bfloat16)
@@ -97,4 +101,12 @@ TRB_API int trb_tbe_psw_grad(const void* weights, int w_dtype, const int64_t* fe
   PSW_CASE(TRB_F16, __half, TRB_F32, float)
 #undef PSW_CASE
   return -3;
+}
+
+TRB_API int trb_tbe_psw_grad(const void* weights, int w_dtype, const int64_t* feat_woff, const int64_t* feat_rows, const int32_t* feat_dim,
+                             const int32_t* feat_col, const void* indices, int idx64, const void* offsets, int off64, void* const* grad_ptrs,
+                             int n_grad, int grad_dtype, int64_t grad_stride, float* out, int B, int B_local, int F, int max_dim, int mean,
+                             cudaStream_t stream) {
+  return trb_tbe_psw_grad_ms(weights, w_dtype, feat_woff, feat_rows, feat_dim, feat_col, indices, idx64, offsets, off64, 1, 0, 0, grad_ptrs, n_grad,
+                             grad_dtype, grad_stride, out, B, B_local, F, max_dim, mean, stream);
 }

@@ -509,6 +509,82 @@ def fused_backward(
     _lib.check(code, "trb_tbe_bwd_fused_ex")
 
 
+@dataclass
+class IdRegions:
+    """Ids of a lookup delivered as per-source regions of one receive slot (NVLink input dist, csrc/kjt_route.cu): source
+    rank s wrote offsets ``[F_total * src_B + 1]`` (relative) at ``off_ptr + s * off_stride`` elements and its ids at
+    ``idx_ptr + s * idx_stride`` elements. ``window(u0)`` moves the offsets pointer to the first feature of a kernel group."""
+
+    idx_ptr: int
+    idx64: int
+    off_ptr: int
+    off64: int
+    psw_ptr: int
+    n_src: int
+    idx_stride: int
+    off_stride: int
+    src_B: int
+
+    def window(self, first_feature: int) -> "IdRegions":
+        esz = 8 if self.off64 else 4
+        return IdRegions(self.idx_ptr, self.idx64, self.off_ptr + first_feature * self.src_B * esz, self.off64, self.psw_ptr, self.n_src, self.idx_stride,
+                         self.off_stride, self.src_B)
+
+    @property
+    def positions(self) -> int:
+        return self.n_src * self.idx_stride
+
+
+def pooled_forward_regions(meta: TbeMeta, weights: torch.Tensor, ids: IdRegions, mean: bool, out_dtype: torch.dtype, out_ptrs: Sequence[int],
+                           out_stride: int, B_local: int, device: torch.device) -> None:
+    """Pooled lookup over per-source id regions, pooled rows stored into ``out_ptrs`` (one buffer per destination rank)."""
+    L = _lib.lib()
+    B = ids.n_src * ids.src_B
+    code = L.trb_tbe_pooled_fwd_ms(
+        _lib.ptr(weights), _lib.dtype_code(weights.dtype), _lib.ptr(meta.feat_woff), _lib.ptr(meta.feat_rows), _lib.ptr(meta.feat_dim), _lib.ptr(meta.feat_col),
+        ctypes.c_void_p(ids.idx_ptr), ids.idx64, ctypes.c_void_p(ids.off_ptr), ids.off64, ctypes.c_void_p(ids.psw_ptr), ids.n_src,
+        ctypes.c_int64(ids.idx_stride), ctypes.c_int64(ids.off_stride), _lib.ptr_array(out_ptrs), len(out_ptrs), _lib.dtype_code(out_dtype),
+        ctypes.c_int64(out_stride), B, B_local, meta.num_features, meta.max_dim, int(mean), _lib.stream_ptr(device))
+    _lib.check(code, "trb_tbe_pooled_fwd_ms")
+
+
+def backward_workspace_bytes(n_positions: int, max_dim: int, total_rows: int) -> int:
+    L = _lib.lib()
+    L.trb_tbe_bwd_workspace_bytes.restype = ctypes.c_int64
+    return int(L.trb_tbe_bwd_workspace_bytes(ctypes.c_int64(n_positions), max_dim, ctypes.c_int64(total_rows)))
+
+
+def fused_backward_regions(meta: TbeMeta, weights: torch.Tensor, state1, state2, hyper_dev: torch.Tensor, opt: int, wd_mode: int, ids: IdRegions, mean: bool,
+                           grad_ptrs: Sequence[int], grad_stride: int, grad_dtype: torch.dtype, grad_scale: float, B_local: int, workspace: torch.Tensor,
+                           device: torch.device, stochastic_rounding: bool = False, sr_seed: int = 0) -> None:
+    """Fused backward + optimizer over per-source id regions (gradient rows in ``grad_ptrs`` buffers, scaled by ``grad_scale``)."""
+    L = _lib.lib()
+    B = ids.n_src * ids.src_B
+    code = L.trb_tbe_bwd_fused_ms(
+        _lib.ptr(weights), _lib.dtype_code(weights.dtype), _lib.ptr(state1), _lib.ptr(state2), _lib.ptr(hyper_dev), opt, wd_mode,
+        _lib.ptr(meta.feat_woff), _lib.ptr(meta.feat_rows), _lib.ptr(meta.feat_rowbase), _lib.ptr(meta.feat_dim), _lib.ptr(meta.feat_col),
+        ctypes.c_void_p(ids.idx_ptr), ids.idx64, ctypes.c_void_p(ids.off_ptr), ids.off64, ctypes.c_void_p(ids.psw_ptr), ids.n_src,
+        ctypes.c_int64(ids.idx_stride), ctypes.c_int64(ids.off_stride), _lib.ptr_array(grad_ptrs), len(grad_ptrs), _lib.dtype_code(grad_dtype),
+        ctypes.c_int64(grad_stride), ctypes.c_float(grad_scale), ctypes.c_int64(ids.positions), ctypes.c_int64(meta.total_rows), B, B_local,
+        meta.num_features, meta.max_dim, int(mean), _lib.ptr(workspace), int(bool(stochastic_rounding)), ctypes.c_uint64(int(sr_seed) & 0xFFFFFFFFFFFFFFFF),
+        _lib.stream_ptr(device))
+    _lib.check(code, "trb_tbe_bwd_fused_ms")
+
+
+def psw_grad_regions(meta: TbeMeta, weights: torch.Tensor, ids: IdRegions, mean: bool, grad_ptrs: Sequence[int], grad_stride: int, grad_dtype: torch.dtype,
+                     B_local: int, out: torch.Tensor) -> torch.Tensor:
+    """Per-sample-weight gradient over per-source id regions; ``out`` is fp32 ``[positions]`` (position = s * idx_stride + i)."""
+    L = _lib.lib()
+    B = ids.n_src * ids.src_B
+    code = L.trb_tbe_psw_grad_ms(
+        _lib.ptr(weights), _lib.dtype_code(weights.dtype), _lib.ptr(meta.feat_woff), _lib.ptr(meta.feat_rows), _lib.ptr(meta.feat_dim), _lib.ptr(meta.feat_col),
+        ctypes.c_void_p(ids.idx_ptr), ids.idx64, ctypes.c_void_p(ids.off_ptr), ids.off64, ids.n_src, ctypes.c_int64(ids.idx_stride),
+        ctypes.c_int64(ids.off_stride), _lib.ptr_array(grad_ptrs), len(grad_ptrs), _lib.dtype_code(grad_dtype), ctypes.c_int64(grad_stride), _lib.ptr(out),
+        B, B_local, meta.num_features, meta.max_dim, int(mean), _lib.stream_ptr(out.device))
+    _lib.check(code, "trb_tbe_psw_grad_ms")
+    return out
+
+
 def psw_grad(meta: TbeMeta, weights: torch.Tensor, indices: torch.Tensor, offsets: torch.Tensor, B: int, mean: bool, grad: Optional[torch.Tensor] = None,
              grad_ptrs: Optional[Sequence[int]] = None, grad_stride: Optional[int] = None, grad_dtype: Optional[torch.dtype] = None,
              B_local: Optional[int] = None) -> torch.Tensor:

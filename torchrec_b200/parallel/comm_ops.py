@@ -302,6 +302,8 @@ class _A2ASeqReq(Function):
         if ctx.seg is not None and info.backward_recat_tensor is not None:
             seg_perm = ctx.seg[info.forward_recat_tensor.long()]
             _, g, _ = J.permute_1D_sparse_data(info.backward_recat_tensor, seg_perm, g, None, g.shape[0])
+        if GRADIENT_DIVISION:  # same convention as the pooled all-to-all: every rank's loss is a local mean, the update is the global mean
+            g = g / dist.get_world_size(ctx.pg)
         return None, None, None, g
 
 
@@ -380,9 +382,7 @@ class _A2AV(Function):
         send = torch.cat([g.contiguous().view(-1) for g in grads])
         recv = torch.empty(sum(ctx.in_splits), dtype=send.dtype, device=send.device)
         dist.all_to_all_single(recv, send, ctx.in_splits, ctx.out_splits, group=ctx.pg)
-        g = recv.view(ctx.B_global, -1)
-        if GRADIENT_DIVISION:
-            g = g / ctx.W
+        g = recv.view(ctx.B_global, -1)  # the generic all-to-all-v carries gradients unscaled (only the embedding dists divide by W)
         return (None, None, None) + tuple(g.split(ctx.dims, dim=1))
 
 

@@ -521,6 +521,18 @@ class ShardedEmbeddingBagCollection(
             features = self._pad_vbe(features)
         with torch.no_grad():
             eng = self._engine
+            if (eng is not None and not getattr(ctx, "variable_batch_per_feature", False) and not self._needs_dist_kjt and eng.fused_available(None)
+                    and eng._uniform_batch(features.stride())):
+                # NVLink plane: bucketize + feature permute + peer write in one device-side pass, straight from the batch's KJT
+                # (any mix of sharding types); the only host work is picking the slot
+                order = self._features_order
+                B = features.stride()
+                ctx.B_local = B
+                if self._post_mean:
+                    ctx.mean_divisor = self._mean_divisor(features.permute(order) if self._has_features_permute else features)
+                if self._dp_tables:
+                    ctx.dp_features = features.permute([order[fi] for fi in self._dp_features])
+                return _InputDistAwaitable(NoWait(NoWait(eng.plane_input_dist(features, order, self._total_cols))))
             if not self._post_mean and eng is not None and not eng._row_sharded:
                 # fast path: input order -> unit order in ONE key permutation (feature order, model-parallel subset and unit
                 # replication composed on the host once) instead of three KJT permutes per step
@@ -540,12 +552,7 @@ class ShardedEmbeddingBagCollection(
             B = features.stride()
             ctx.B_local = B
             if self._post_mean:
-                lengths = features.lengths().view(len(self._feature_names), B).t().float()  # [B, F]
-                div = torch.ones(B, len(self._feature_names), device=lengths.device)
-                mask = torch.tensor(self._engine._post_mean_feature, device=lengths.device)
-                div = torch.where(mask.unsqueeze(0), 1.0 / lengths.clamp(min=1.0), div)
-                ctx.mean_divisor = torch.repeat_interleave(div, torch.tensor(self._embedding_dims, device=lengths.device), dim=1,
-                                                           output_size=self._total_cols)
+                ctx.mean_divisor = self._mean_divisor(features)
             if self._dp_tables:
                 ctx.dp_features = features.permute(self._dp_features) if len(self._dp_features) != len(self._feature_names) else features
             if self._engine is None:
@@ -556,10 +563,27 @@ class ShardedEmbeddingBagCollection(
             aw, _ = self._engine.input_dist(mp)
             return _InputDistAwaitable(aw)
 
+    # feature processors compute per-id weights ON the distributed KJT (and need their gradient): those modules ask for a real KJT
+    _needs_dist_kjt: bool = False
+
+    def _mean_divisor(self, features: KeyedJaggedTensor) -> torch.Tensor:
+        """``[B, total_cols]`` factors 1 / bag length for the MEAN-pooled row-sharded features (divided after the reduce), 1 elsewhere;
+        ``features`` in flat feature order."""
+        B = features.stride()
+        lengths = features.lengths().view(len(self._feature_names), B).t().float()  # [B, F]
+        mask = self.__dict__.get("_post_mean_mask")
+        if mask is None or mask.device != lengths.device:
+            mask = self.__dict__["_post_mean_mask"] = torch.tensor(self._engine._post_mean_feature, device=lengths.device)
+            self.__dict__["_embedding_dims_t"] = torch.tensor(self._embedding_dims, device=lengths.device)
+        div = torch.where(mask.unsqueeze(0), 1.0 / lengths.clamp(min=1.0), torch.ones_like(lengths))
+        return torch.repeat_interleave(div, self.__dict__["_embedding_dims_t"], dim=1, output_size=self._total_cols)
+
     def compute(self, ctx: EmbeddingBagCollectionContext, dist_input: KJTList) -> List[torch.Tensor]:
         outs: List[torch.Tensor] = []
         if self._engine is not None:
             kjt = dist_input[0]
+            if not isinstance(kjt, KeyedJaggedTensor):  # handle of the NVLink plane consumed through the 3-phase API: jagged view
+                kjt = kjt.to_kjt()
             spr = kjt._stride_per_rank
             ctx.batch_size_per_rank = spr if spr is not None else None
             outs.append(self._engine.lookup(kjt))

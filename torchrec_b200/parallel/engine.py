@@ -376,16 +376,12 @@ class ShardedLookupEngine(nn.Module):
         """Input dist of a KJT that is already in global unit order (keys = unit features)."""
         if self._kjt_a2a is None:
             return NoWait(NoWait(routed))
-        if self._pooled and not routed.variable_stride_per_key() and self.fused_available(None) and self._uniform_batch(routed.stride()):
-            return NoWait(NoWait(self.p2p_input_dist(routed)))
         return self._kjt_a2a(routed)
 
     def input_dist(self, features: KeyedJaggedTensor) -> Tuple[Awaitable[Awaitable[KeyedJaggedTensor]], Optional[torch.Tensor]]:
         routed, unbucketize = self.route(features)
         if self._kjt_a2a is None:
             return NoWait(NoWait(routed)), unbucketize
-        if self._pooled and not routed.variable_stride_per_key() and self.fused_available(None) and self._uniform_batch(routed.stride()):
-            return NoWait(NoWait(self.p2p_input_dist(routed))), unbucketize
         return self._kjt_a2a(routed), unbucketize
 
     def _uniform_batch(self, B: int) -> bool:
@@ -564,6 +560,8 @@ class ShardedLookupEngine(nn.Module):
             return False  # cached tables translate ids -> cache slots first: portable path
         if batch_size_per_rank is not None and len(set(batch_size_per_rank)) != 1:
             return False
+        if getattr(self._env, "loopback_group", None) is not None:
+            return True
         if not self._p2p_checked:
             from .p2p import PeerGroup
 
@@ -571,262 +569,124 @@ class ShardedLookupEngine(nn.Module):
             self._p2p_checked = True
         return self._p2p_ok
 
-    def p2p_input_dist(self, routed: KeyedJaggedTensor) -> KeyedJaggedTensor:
-        """NVLink input dist without host sync: publish the routed KJT, barrier, pull this rank's unit segments
-        from every peer. Returns the distributed KJT (values buffer sized to capacity, true sizes in ``offsets``)."""
-        import ctypes
+    # ---- NVLink sparse plane (see sparse_plane.py) ------------------------------------------------------------------------
+    def _peer_group(self):
+        lb = getattr(self._env, "loopback_group", None)
+        if lb is not None:
+            return lb.view(self._rank)
+        from .p2p import PeerGroup
 
-        from ..ops import _lib
+        return PeerGroup.get(self._pg, self._device)
 
-        B = routed.stride()
-        values = routed.values()
-        weights = routed.weights_or_none() if self._is_weighted else None
-        st = self._p2p_in
-        if st is None or st.B != B or st.idx_dtype != values.dtype or st.weighted != (weights is not None):
-            # one-time sizing: the largest id count any rank publishes, with head-room for later batches
-            n = torch.tensor([values.numel()], device=self._device, dtype=torch.int64)
+    def _region_capacity(self, features: KeyedJaggedTensor, key_of_feature: List[int]) -> int:
+        """Ids one source may send to one destination per batch: measured on the first batch (max over destinations and ranks),
+        exact when every feature has a fixed bag length, with head-room (TRB_ID_CAPACITY_SLACK, default 1.5) otherwise."""
+        env_cap = int(os.environ.get("TRB_MAX_IDS_PER_RANK", "0"))
+        if env_cap:
+            return env_cap
+        B = features.stride()
+        lengths = features.lengths().view(-1, B)
+        values = features.values()
+        offs = features.offsets()
+        per_dest = torch.zeros(self._W, dtype=torch.int64, device=values.device)
+        lpk = lengths.sum(1)
+        fixed = bool((lengths == lengths[:, :1]).all().item())
+        for u in self._units:
+            k = key_of_feature[u.feature]
+            if self._table_row_sharded[u.shard.table_idx]:
+                seg = values[int(offs[k * B]) : int(offs[(k + 1) * B])]
+                per_dest[u.shard.rank] += ((seg >= u.shard.row_off) & (seg < u.shard.row_off + u.shard.rows)).sum()
+                fixed = False
+            else:
+                per_dest[u.shard.rank] += lpk[k]
+        n = per_dest.max().reshape(1)
+        flag = torch.tensor([0 if fixed else 1], device=n.device, dtype=torch.int64)
+        if self._pg is not None and self._W > 1 and getattr(self._env, "loopback_group", None) is None:
             dist.all_reduce(n, op=dist.ReduceOp.MAX, group=self._pg)
-            import os
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self._pg)
+        if int(flag.item()) == 0:
+            return max(int(n.item()), 32)
+        slack = float(os.environ.get("TRB_ID_CAPACITY_SLACK", "1.5"))
+        return int(int(n.item()) * slack) + 1024
 
-            slack = float(os.environ.get("TRB_ID_CAPACITY_SLACK", "1.5"))
-            cap = int(os.environ.get("TRB_MAX_IDS_PER_RANK", "0")) or int(int(n.item()) * slack) + 1024
-            st = self._p2p_in = _P2PInputState(self, B, cap, values.dtype, weights is not None)
-        if values.numel() > st.local_capacity:
-            raise RuntimeError(f"batch carries {values.numel()} ids but the NVLink input-dist buffers hold {st.local_capacity}; "
-                               "raise TRB_MAX_IDS_PER_RANK / TRB_ID_CAPACITY_SLACK")
-        slot = st.step % st.N_SLOTS
-        st.step += 1
-        base = slot * st.slot_bytes
-        U = len(self._units)
-        off_local = st.buf.local(torch.int64, (U * B + 1,), base)
-        off_local.copy_(routed.offsets())
-        val_local = st.buf.local(st.idx_dtype, (values.numel(),), base + st.off_bytes)
-        val_local.copy_(values)
-        if weights is not None:
-            st.buf.local(torch.float32, (values.numel(),), base + st.off_bytes + st.val_bytes).copy_(weights)
-        st.pg.barrier(st.CHANNEL)
-        W = self._W
-        n_seg = st.U_d * W
-        seg_base = torch.empty(n_seg + 1, dtype=torch.int64, device=self._device)
-        out_off = torch.empty(n_seg * B + 1, dtype=torch.int64, device=self._device)
-        out_val = torch.empty(st.out_capacity, dtype=st.idx_dtype, device=self._device)
-        out_wgt = torch.empty(st.out_capacity, dtype=torch.float32, device=self._device) if weights is not None else None
-        if st.U_d == 0:
-            out_off.zero_()
-        else:
-            L = _lib.lib()
-            code = L.trb_kjt_pull(
-                _lib.ptr_array(st.buf.peer_ptrs(base)), _lib.ptr_array(st.buf.peer_ptrs(base + st.off_bytes)),
-                _lib.ptr_array(st.buf.peer_ptrs(base + st.off_bytes + st.val_bytes)) if weights is not None else ctypes.c_void_p(0),
-                W, _lib.ptr(st.units), st.U_d, B, 8 if st.idx_dtype == torch.int64 else 4, _lib.ptr(seg_base), _lib.ptr(out_off), _lib.ptr(out_val),
-                _lib.ptr(out_wgt), ctypes.c_int64(st.out_capacity), _lib.ptr(st.overflow), ctypes.c_int64(max(1, values.numel() // max(U, 1))),
-                _lib.stream_ptr(self._device))
-            _lib.check(code, "trb_kjt_pull")
-        if st.step % 512 == 0:  # amortised check of the device-side overflow flag
-            if int(st.overflow.item()) != 0:
-                raise RuntimeError("NVLink input dist overflow: a rank received more ids than its buffer holds; raise TRB_ID_CAPACITY_SLACK")
-        return KeyedJaggedTensor(keys=st.keys, values=out_val, weights=out_wgt, offsets=out_off, stride=W * B, stride_per_rank=[B] * W)
+    def plane_for(self, B_local: int, total_cols: int, features: Optional[KeyedJaggedTensor] = None, key_of_feature: Optional[List[int]] = None,
+                  capacity: Optional[int] = None):
+        """The sparse plane serving batches of ``B_local`` samples per rank (built on first use; collective)."""
+        from .sparse_plane import SparsePlane
 
-    def _ensure_p2p(self, B_local: int, total_cols: int) -> "_P2PState":
-        st = self._p2p
-        if st is not None and st.B_local == B_local and st.total_cols == total_cols:
-            return st
-        self._p2p = _P2PState(self, B_local, total_cols)
-        return self._p2p
+        planes = self.__dict__.setdefault("_planes", {})
+        has_input = features is not None
+        key = (B_local, total_cols, has_input)
+        pl = planes.get(key)
+        if pl is None:
+            if has_input:
+                kof = list(key_of_feature) if key_of_feature is not None else None
+                if kof is None:
+                    mp_pos = {f: i for i, f in enumerate(self._mp_features)}
+                    kof = [mp_pos.get(f, 0) for f in range(len(self._feature_names))]
+                cap = int(capacity) if capacity else self._region_capacity(features, kof)
+                pl = SparsePlane(self, self._peer_group(), B_local, total_cols, cap, features.values().dtype, self._is_weighted and features.weights_or_none() is not None, kof)
+            else:
+                pl = SparsePlane(self, self._peer_group(), B_local, total_cols, 0, torch.int64, self._is_weighted, None)
+            planes[key] = pl
+        return pl
 
-    def fused_lookup_dist(self, dist_features: KeyedJaggedTensor, B_local: int, total_cols: int, grad_scale: float, dp: Optional[Tuple] = None) -> torch.Tensor:
+    def plane_input_dist(self, features: KeyedJaggedTensor, key_of_feature: Optional[List[int]], total_cols: int, capacity: Optional[int] = None):
+        """NVLink input dist: ONE device-side pass (bucketize + feature permute + peer write, csrc/kjt_route.cu) straight from the
+        batch's KJT into the owners' receive regions. No host sync, no size exchange. Returns a ``RoutedIds`` handle."""
+        B = features.stride()
+        pl = self.plane_for(B, total_cols, features, key_of_feature, capacity)
+        n_bags = max(1, len(features.keys()) * B)
+        return pl.push_input(features.offsets(), features.values(), features.weights_or_none() if self._is_weighted else None,
+                             avg_len_hint=max(1, features.values().numel() // n_bags))
+
+    def fused_lookup_dist(self, dist_features, B_local: int, total_cols: int, grad_scale: float, dp: Optional[Tuple] = None) -> torch.Tensor:
         """Lookup + pooled output dist in one pass: pooled rows are written straight into the owning
         rank's ``[B_local, total_cols]`` output over NVLink (row-sharded tables via staging slabs
-        reduced at the destination). Returns the local output (final column layout)."""
-        self._run_lookup_hooks(dist_features)
-        st = self._ensure_p2p(B_local, total_cols)
+        reduced at the destination). ``dist_features``: a ``RoutedIds`` handle of the NVLink input dist or a distributed KJT.
+        Returns the local output (final column layout)."""
+        from .sparse_plane import RoutedIds
+
+        routed = isinstance(dist_features, RoutedIds)
+        if self.__dict__.get("_lookup_hooks"):
+            self._run_lookup_hooks(dist_features.to_kjt() if routed else dist_features)
+        pl = dist_features.plane if routed else self.plane_for(B_local, total_cols)
         anchor = None
         for g in self._groups:
             if g.tbe is not None:
                 anchor = g.tbe._dummy
                 break
         if anchor is None:
-            anchor = st.dummy
-        weights = dist_features.weights_or_none() if self._is_weighted else None
+            anchor = pl.dummy
+        weights = None if routed else (dist_features.weights_or_none() if self._is_weighted else None)
         # dp = (dense TBE of the replicated tables, its meta with output columns, local KJT of their features, process group):
         # their rows are looked up locally and written into the same output buffer; the dense gradient is all-reduced in backward
         dp_w = dp[0].weights if dp is not None else None
-        return _FusedLookupDistFn.apply(anchor, self, st, dist_features.values(), dist_features.offsets(), weights, dist_features.stride(), grad_scale, dp_w, dp)
+        return _PlaneLookupFn.apply(anchor, self, pl, dist_features, weights, grad_scale, dp_w, dp)
 
 
-class _P2PInputState:
-    """Symmetric publish buffers + pull outputs of the NVLink input dist (see csrc/kjt_p2p.cu)."""
-
-    N_SLOTS = 2
-    CHANNEL = 1
-
-    def __init__(self, eng: ShardedLookupEngine, B: int, local_capacity: int, idx_dtype: torch.dtype, weighted: bool) -> None:
-        from .p2p import PeerGroup
-
-        self.pg = PeerGroup.get(eng._pg, eng._device)
-        self.B = B
-        self.W = eng._W
-        self.local_capacity = local_capacity  # ids a rank may publish per batch
-        self.idx_dtype = idx_dtype
-        self.weighted = weighted
-        U = len(eng._units)
-        esz = 8 if idx_dtype == torch.int64 else 4
-        self.off_bytes = (U * B + 1) * 8
-        self.off_bytes = (self.off_bytes + 255) // 256 * 256
-        self.val_bytes = (local_capacity * esz + 255) // 256 * 256
-        self.wgt_bytes = (local_capacity * 4 + 255) // 256 * 256 if weighted else 0
-        self.slot_bytes = self.off_bytes + self.val_bytes + self.wgt_bytes
-        self.buf = self.pg.alloc(self.slot_bytes * self.N_SLOTS)
-        self.step = 0
-        self.U_d = eng._units_per_rank[eng._rank]
-        self.units = torch.tensor([u.gidx for u in eng._local_units], dtype=torch.int32, device=eng._device)
-        self.out_capacity = local_capacity * self.W
-        self.overflow = torch.zeros(1, dtype=torch.int32, device=eng._device)
-        self.keys = [eng._feature_names[u.feature] for u in eng._local_units]
-        self.checked_overflow_at = 0
-
-
-class _P2PState:
-    """Symmetric buffers and per-group descriptor tables of the fused path."""
-
-    N_SLOTS = 2
-
-    def __init__(self, eng: ShardedLookupEngine, B_local: int, total_cols: int) -> None:
-        from ..ops.tbe import TbeMeta
-        from .p2p import PeerGroup
-
-        self.B_local = B_local
-        self.total_cols = total_cols
-        self.pg = PeerGroup.get(eng._pg, eng._device)
-        W = eng._W
-        self.wire_dtype = eng._output_dtype
-        esz = torch.empty(0, dtype=self.wire_dtype).element_size()
-        self.slab_bytes = B_local * total_cols * esz
-        self.has_staged = any(eng._table_row_sharded.values())
-        # gradient inbox: [W * B_local, pitch] per slot, pitch = widest per-rank sum of unit columns (same on every rank)
-        dims_f = [eng._tables[ti].embedding_dim for ti in eng._feature_table]
-        base_f = list(itertools.accumulate([0] + dims_f))
-        self.push = os.environ.get("TRB_GRAD_PUSH", "1") != "0"
-        chunks: List[List[int]] = []
-        local_cols_per_rank: List[List[int]] = []
-        # 8-element (16 B for bf16) chunks when every unit width and every source column offset allow it
-        vec = 8 if all(u.shard.cols % 8 == 0 and (base_f[u.feature] + u.shard.col_off) % 8 == 0 for u in eng._units) and total_cols % 8 == 0 else 4
-        self.push_vec = vec
-        for r in range(W):
-            c = 0
-            cols_r = []
-            for u in eng._units[eng._unit_start[r] : eng._unit_start[r + 1]]:
-                src0 = base_f[u.feature] + u.shard.col_off
-                cols_r.append(c)
-                for k in range(0, u.shard.cols, vec):
-                    chunks.append([r, src0 + k, c + k])
-                c += u.shard.cols
-            local_cols_per_rank.append(cols_r)
-        self.inbox_pitch = max(8, (max((sum(u.shard.cols for u in eng._units[eng._unit_start[r] : eng._unit_start[r + 1]]) for r in range(W)), default=8) + 7) // 8 * 8)
-        self.push = self.push and all(u.shard.cols % 4 == 0 for u in eng._units)
-        self.inbox_bytes = (W * B_local * self.inbox_pitch * esz + 255) // 256 * 256 if self.push else 0
-        self.chunks = torch.tensor(chunks, dtype=torch.int32, device=eng._device).contiguous() if self.push else None
-        self.local_cols = local_cols_per_rank[eng._rank]
-        nbytes = self.slab_bytes * (self.N_SLOTS + 1 + (W if self.has_staged else 0)) + 2 * self.inbox_bytes
-        self.buf = self.pg.alloc(nbytes)
-        self.out_off = [i * self.slab_bytes for i in range(self.N_SLOTS)]
-        self.grad_off = self.N_SLOTS * self.slab_bytes
-        self.staging_off = (self.N_SLOTS + 1) * self.slab_bytes
-        self.inbox_off = [self.slab_bytes * (self.N_SLOTS + 1 + (W if self.has_staged else 0)) + i * self.inbox_bytes for i in range(2)]
-        self.bwd_step = 0
-        self.step = 0
-        self.dummy = torch.zeros(1, device=eng._device, requires_grad=True)
-        dims = [eng._tables[ti].embedding_dim for ti in eng._feature_table]
-        out_base = list(itertools.accumulate([0] + dims))
-        # per group: (direct window, staged window) of local units + metas
-        self.group_meta: List[Optional[Dict[str, Any]]] = []
-        col_mask = [0] * total_cols
-        for u in eng._units:
-            if eng._table_row_sharded[u.shard.table_idx]:
-                base = out_base[u.feature] + u.shard.col_off
-                for c in range(base, base + u.shard.cols):
-                    col_mask[c] |= 1 << u.shard.rank
-        self.col_mask = torch.tensor(col_mask, dtype=torch.int64, device=eng._device).to(torch.int32)
-        for g in eng._groups:
-            if g.tbe is None:
-                self.group_meta.append(None)
-                continue
-            u0, u1 = g.unit_range
-            units = eng._local_units[u0:u1]
-            cols = [out_base[u.feature] + u.shard.col_off for u in units]
-            staged = [eng._table_row_sharded[u.shard.table_idx] for u in units]
-            n_direct = staged.index(True) if True in staged else len(units)
-            assert all(staged[n_direct:]), "row-sharded units must follow direct units inside a group"
-            full = g.tbe.meta.with_cols(cols, total_cols)
-            local = g.tbe.meta.with_cols(self.local_cols[u0:u1], self.inbox_pitch) if self.push else None
-            self.group_meta.append({"full": full, "local": local, "n_direct": n_direct, "n": len(units),
-                                    "direct": _slice_meta(full, 0, n_direct), "staged": _slice_meta(full, n_direct, len(units))})
-
-    def out_local(self, slot: int) -> torch.Tensor:
-        return self.buf.local(self.wire_dtype, (self.B_local, self.total_cols), self.out_off[slot])
-
-    def grad_local(self) -> torch.Tensor:
-        return self.buf.local(self.wire_dtype, (self.B_local, self.total_cols), self.grad_off)
-
-    def staging_local(self, W: int) -> torch.Tensor:
-        return self.buf.local(self.wire_dtype, (W, self.B_local, self.total_cols), self.staging_off)
-
-
-def _slice_meta(m, a: int, b: int):
-    from ..ops.tbe import TbeMeta
-
-    if b <= a:
-        return None
-    return TbeMeta(m.feat_woff[a:b].contiguous(), m.feat_rows[a:b].contiguous(), m.feat_rowbase[a:b].contiguous(), m.feat_dim[a:b].contiguous(),
-                   m.feat_col[a:b].contiguous(), m.h_woff[a:b], m.h_rows[a:b], m.h_rowbase[a:b], m.h_dim[a:b], m.h_col[a:b],
-                   max(m.h_dim[a:b]), m.total_rows, m.total_cols, b - a)
-
-
-class _FusedLookupDistFn(torch.autograd.Function):
-    """Forward: table-batched lookup writing pooled rows into the destination ranks' outputs over
-    NVLink + device barrier (+ staging reduce). Backward: stage the local gradient in the symmetric
-    buffer, barrier, fused backward+optimizer kernels pulling gradient rows from the peers."""
+class _PlaneLookupFn(torch.autograd.Function):
+    """Forward: table-batched lookup writing pooled rows into the destination ranks' outputs over NVLink + device barrier
+    (+ staging reduce). Backward: gradient column blocks pushed into the owners' inboxes, barrier, exact fused
+    backward + optimizer over local memory. Both halves replay as CUDA graphs when the ids came through the plane."""
 
     @staticmethod
-    def forward(ctx, anchor, eng: ShardedLookupEngine, st: _P2PState, values, offsets, weights, Bg: int, grad_scale: float, dp_weights=None, dp=None):
+    def forward(ctx, anchor, eng: ShardedLookupEngine, pl, ids, weights, grad_scale: float, dp_weights=None, dp=None):
         from ..ops import tbe as T
-        from . import p2p
 
-        W = eng._W
         for tbe in eng._tbes:  # FULLY_SHARDED 2D strategy: full weights only around the kernels
             if tbe.__dict__.get("_fs") is not None:
                 tbe._fs.before_forward()
-        slot = st.step % st.N_SLOTS
-        st.step += 1
-        out_ptrs = st.buf.peer_ptrs(st.out_off[slot])
-        esz = torch.empty(0, dtype=st.wire_dtype).element_size()
-        stage_ptrs = [p + st.staging_off + eng._rank * st.slab_bytes for p in st.buf.ptrs]
-        for g, gm in zip(eng._groups, st.group_meta):
-            if gm is None:
-                continue
-            u0, _ = g.unit_range
-            mean = g.pooling == T.PoolingMode.MEAN
-            if gm["direct"] is not None:
-                window = offsets[u0 * Bg : (u0 + gm["n_direct"]) * Bg + 1]
-                T.pooled_forward(gm["direct"], g.tbe.weights, values, window, weights, Bg, mean, st.wire_dtype,
-                                 out_ptrs=out_ptrs, out_stride=st.total_cols, B_local=st.B_local)
-            if gm["staged"] is not None:
-                window = offsets[(u0 + gm["n_direct"]) * Bg : (u0 + gm["n"]) * Bg + 1]
-                T.pooled_forward(gm["staged"], g.tbe.weights, values, window, weights, Bg, False, st.wire_dtype,
-                                 out_ptrs=stage_ptrs, out_stride=st.total_cols, B_local=st.B_local)
-        out = st.out_local(slot)
+        training = any(ctx.needs_input_grad)  # grad mode is off inside Function.forward: this is the caller's view
+        out, out_slot = pl.forward(ids, training)
         if dp is not None:  # replicated tables: local lookup straight into their columns (nobody else writes them)
             dp_tbe, dp_meta, dp_kjt, _pg = dp
             dp_psw = dp_kjt.weights_or_none() if eng._is_weighted else None
             T.pooled_forward(dp_meta, dp_weights.detach(), dp_kjt.values(), dp_kjt.offsets(), dp_psw, dp_kjt.stride(), dp_tbe.pooling_mode == T.PoolingMode.MEAN,
-                             st.wire_dtype, out=out)
-        st.pg.barrier()
-        if st.has_staged:
-            p2p.staging_reduce(st.staging_local(W), out, st.col_mask, W)
-        ctx.eng, ctx.st, ctx.Bg, ctx.grad_scale = eng, st, Bg, grad_scale
-        ctx.dp = dp
-        ctx.save_for_backward(values, offsets, weights)
-        if any(t.requires_grad for t in (anchor,)):
+                             pl.wire_dtype, out=out)
+        ctx.eng, ctx.pl, ctx.ids, ctx.grad_scale, ctx.dp = eng, pl, ids, grad_scale, dp
+        ctx.has_weights = weights is not None
+        if training:
             for tbe in eng._tbes:
                 if tbe.__dict__.get("_fs") is not None:
                     tbe._fs.after_forward()
@@ -835,49 +695,24 @@ class _FusedLookupDistFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad):
         from ..ops import tbe as T
-        from . import p2p
 
-        eng, st, Bg = ctx.eng, ctx.st, ctx.Bg
-        values, offsets, weights = ctx.saved_tensors
+        eng, pl, ids = ctx.eng, ctx.pl, ctx.ids
         for tbe in eng._tbes:
             if tbe.__dict__.get("_fs") is not None:
                 tbe._fs.before_backward()
         if grad.stride(1) != 1:
             grad = grad.contiguous()
-        if st.push:
-            # push: scatter my gradient columns into the owners' inboxes (posted NVLink stores), barrier, local backward
-            slot = st.bwd_step % 2
-            st.bwd_step += 1
-            p2p.grad_push(grad, st.chunks, st.buf.peer_ptrs(st.inbox_off[slot]), st.wire_dtype, st.inbox_pitch, eng._rank * st.B_local, ctx.grad_scale, st.push_vec)
-            st.pg.barrier()
-            grad_ptrs = [st.buf.local_ptr + st.inbox_off[slot]]
-            meta_key, g_stride, g_blocal = "local", st.inbox_pitch, Bg
-        else:
-            gbuf = st.grad_local()
-            p2p.cast_copy(grad, gbuf, ctx.grad_scale)
-            st.pg.barrier()
-            grad_ptrs = st.buf.peer_ptrs(st.grad_off)
-            meta_key, g_stride, g_blocal = "full", st.total_cols, st.B_local
+        want_psw = ctx.has_weights and ctx.needs_input_grad[4]
+        if want_psw:
+            n = ids.values().numel()
+            if pl.psw_grad_buf is None or pl.psw_grad_buf.numel() < n:
+                pl.psw_grad_buf = torch.zeros(n, dtype=torch.float32, device=grad.device)
+        pl.backward(ids, grad, ctx.grad_scale, want_psw)
         gpsw = None
-        want_psw = weights is not None and ctx.needs_input_grad[5]
-        for g, gm in zip(eng._groups, st.group_meta):
-            if gm is None:
-                continue
-            u0, u1 = g.unit_range
-            window = offsets[u0 * Bg : u1 * Bg + 1]
-            if want_psw:  # per-sample-weight gradient (feature processors) from the pre-update rows
-                gp = T.psw_grad(gm[meta_key], g.tbe.weights, values, window, Bg, g.pooling == T.PoolingMode.MEAN, grad_ptrs=grad_ptrs,
-                                grad_stride=g_stride, grad_dtype=st.wire_dtype, B_local=g_blocal)
-                gpsw = gp if gpsw is None else gpsw + gp
-            g.tbe._pre_update()
-            T.fused_backward(gm[meta_key], g.tbe.weights, g.tbe.state1, g.tbe.state2, g.tbe.hyper_dev, g.tbe.hyper_host, g.tbe.opt_code,
-                             int(g.tbe.weight_decay_mode), values, window, weights, Bg, g.pooling == T.PoolingMode.MEAN,
-                             grad_ptrs=grad_ptrs, grad_stride=g_stride, grad_dtype=st.wire_dtype, B_local=g_blocal,
-                             stochastic_rounding=g.tbe.stochastic_rounding, sr_seed=g.tbe.next_sr_seed() if g.tbe.stochastic_rounding else 0)
-        if gpsw is not None:
-            gpsw = gpsw.to(weights.dtype)
+        if want_psw:
+            gpsw = pl.psw_grad_buf[: ids.values().numel()].to(ids.weights().dtype)
         g_dp = None
-        if ctx.dp is not None and ctx.needs_input_grad[8]:
+        if ctx.dp is not None and ctx.needs_input_grad[6]:
             dp_tbe, dp_meta, dp_kjt, pg = ctx.dp
             dp_psw = dp_kjt.weights_or_none() if eng._is_weighted else None
             gw = torch.zeros(dp_tbe.weights.numel(), dtype=torch.float32, device=grad.device)
@@ -887,4 +722,4 @@ class _FusedLookupDistFn(torch.autograd.Function):
                 dist.all_reduce(gw, group=pg)
                 gw.div_(eng._W)
             g_dp = gw.to(dp_tbe.weights.dtype)
-        return torch.zeros(1, dtype=torch.float32, device=grad.device), None, None, None, None, gpsw, None, None, g_dp, None
+        return torch.zeros(1, dtype=torch.float32, device=grad.device), None, None, None, gpsw, None, g_dp, None

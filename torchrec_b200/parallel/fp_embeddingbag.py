@@ -88,6 +88,7 @@ class ShardedFeatureProcessedEmbeddingBagCollection(ShardedModule):
         super().__init__()
         self._device, self._env = device, env
         self._embedding_bag_collection: ShardedEmbeddingBagCollection = ebc_sharder.shard(module._embedding_bag_collection, table_name_to_parameter_sharding, env=env, device=device)
+        self._embedding_bag_collection._needs_dist_kjt = True  # processors run on the distributed KJT (jagged view + weight gradients)
         self._row_wise_sharded = any(ps.sharding_type in (ShardingType.ROW_WISE.value, ShardingType.TABLE_ROW_WISE.value, ShardingType.GRID_SHARD.value)
                                      for ps in table_name_to_parameter_sharding.values())
         self._has_dp = any(ps.sharding_type == ShardingType.DATA_PARALLEL.value for ps in table_name_to_parameter_sharding.values())

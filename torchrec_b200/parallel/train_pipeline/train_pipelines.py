@@ -414,15 +414,18 @@ class TrainPipelineSparseDist(TrainPipeline[In, Out]):
                 context.input_dist_splits_requests.clear()
 
     def fill_pipeline(self, dataloader_iter: Iterator[In]) -> None:
-        if self.batches and self._execute_all_batches:
+        """Prime the two-deep queue: batch 0 copied + input dist started and finished, batch 1 copied. A queue that already holds
+        two batches is full (steady state); with ``execute_all_batches`` the tail of the stream drains a shorter queue."""
+        if len(self.batches) >= 2 or (self.batches and self._execute_all_batches):
             return
-        if not self.enqueue_batch(dataloader_iter):
-            return
-        self._init_pipelined_modules(self.batches[0], self.contexts[0])
-        self.start_sparse_data_dist(self.batches[0], self.contexts[0])
-        self.wait_sparse_data_dist(self.contexts[0])
-        if not self.enqueue_batch(dataloader_iter):
-            return
+        primed = bool(self.batches)
+        if not primed:
+            if not self.enqueue_batch(dataloader_iter):
+                return
+            self._init_pipelined_modules(self.batches[0], self.contexts[0])
+            self.start_sparse_data_dist(self.batches[0], self.contexts[0])
+            self.wait_sparse_data_dist(self.contexts[0])
+        self.enqueue_batch(dataloader_iter)
 
     def _late_bind_getters(self, batch: Any) -> None:
         """Resolve modules whose input could only be identified by running a forward."""
@@ -437,39 +440,65 @@ class TrainPipelineSparseDist(TrainPipeline[In, Out]):
                         pf._getter = KJTGetter(path)
         self._recording = None
 
+    # One step = the head of the queue trains while the look-ahead work for the next two batches is slotted around its forward:
+    #
+    #   begin      bind the head's context, clear gradients, make the compute stream wait for the head's input dist
+    #   lookahead  (before forward)  start the input dist of batch 1 on the data-dist stream, copy batch 2 on the memcpy stream
+    #   forward    model(head): every pipelined module picks its already distributed input out of the context
+    #   lookahead  (after forward)   finish batch 1's input dist so that its transfers overlap the backward
+    #   backward   loss.backward (fused sparse optimizers run inside) -> 2D weight sync -> dense optimizer
     def progress(self, dataloader_iter: Iterator[In]) -> Out:
         self.fill_pipeline(dataloader_iter)
         if not self.batches:
             raise StopIteration
-        self._set_module_context(self.contexts[0])
+        head, head_ctx = self.batches[0], self.contexts[0]
+        self._begin_step(head, head_ctx)
+        self._lookahead(dataloader_iter, forward_done=False)
+        losses, output = self._forward_head(head, head_ctx)
+        self._lookahead(dataloader_iter, forward_done=True)
+        if self._model.training:
+            self._backward_head(losses, head_ctx)
+        self.dequeue_batch()
+        return output
+
+    def _begin_step(self, head: In, head_ctx: TrainPipelineContext) -> None:
+        self._set_module_context(head_ctx)
         if self._model.training:
             with record_function("## zero_grad ##"):
                 self._optimizer.zero_grad()
         with record_function("## wait_for_batch ##"):
-            _wait_for_batch(self.batches[0], self._data_dist_stream)
-        if len(self.batches) >= 2:
-            self.start_sparse_data_dist(self.batches[1], self.contexts[1])
-        if not self._enqueue_batch_after_forward:
-            self.enqueue_batch(dataloader_iter)
-        if any(pf.getter is None for pf in self._pipelined_forwards) and self._recording is None and not self._initialized:
-            self._recording = {}
-        with record_function(f"## forward {self.contexts[0].index} ##"):
-            losses, output = self._model_fwd(self.batches[0])
-        if self._recording is not None:
-            self._late_bind_getters(self.batches[0])
-        self._initialized = True
+            _wait_for_batch(head, self._data_dist_stream)
+
+    def _lookahead(self, dataloader_iter: Iterator[In], forward_done: bool) -> None:
+        have_next = len(self.batches) >= 2
+        if not forward_done:
+            if have_next:
+                self.start_sparse_data_dist(self.batches[1], self.contexts[1])
+            if not self._enqueue_batch_after_forward:
+                self.enqueue_batch(dataloader_iter)
+            return
         if self._enqueue_batch_after_forward:
             self.enqueue_batch(dataloader_iter)
-        if len(self.batches) >= 2:
+        if have_next:
             self.wait_sparse_data_dist(self.contexts[1])
-        if self._model.training:
-            with record_function(f"## backward {self.contexts[0].index} ##"):
-                _reduce_losses(losses).backward()
-            self.sync_embeddings()
-            with record_function(f"## optimizer {self.contexts[0].index} ##"):
-                self._optimizer.step()
-        self.dequeue_batch()
-        return output
+
+    def _forward_head(self, head: In, head_ctx: TrainPipelineContext):
+        unresolved = any(pf.getter is None for pf in self._pipelined_forwards)
+        if unresolved and self._recording is None and not self._initialized:
+            self._recording = {}
+        with record_function(f"## forward {head_ctx.index} ##"):
+            losses, output = self._model_fwd(head)
+        if self._recording is not None:
+            self._late_bind_getters(head)
+        self._initialized = True
+        return losses, output
+
+    def _backward_head(self, losses, head_ctx: TrainPipelineContext) -> None:
+        with record_function(f"## backward {head_ctx.index} ##"):
+            _reduce_losses(losses).backward()
+        self.sync_embeddings()
+        with record_function(f"## optimizer {head_ctx.index} ##"):
+            self._optimizer.step()
 
     def sync_embeddings(self) -> None:
         """2D-parallel weight sync across replica groups every N batches (reference :208-239)."""

@@ -372,6 +372,14 @@ class ShardingEnv:
         """Environment without a process group (single-process multi-device inference)."""
         return cls(world_size, rank, None)
 
+    @classmethod
+    def from_loopback(cls, world_size: int, rank: int, group) -> "ShardingEnv":
+        """Virtual rank ``rank`` of ``world_size`` ranks that all live in THIS process on one device (``sparse_plane.LoopbackGroup``):
+        the NVLink plane's kernels run with every "peer" buffer on the local device, the caller drives the ranks in lock step."""
+        env = cls(world_size, rank, None)
+        env.loopback_group = group
+        return env
+
 
 class ShardingStrategy(Enum):
     DEFAULT = "default"

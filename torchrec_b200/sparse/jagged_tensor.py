@@ -538,7 +538,8 @@ class KeyedJaggedTensor(Pipelineable):
             lo = self.lengths_offset_per_key()
             seg_sizes = torch.tensor(self.stride_per_key(), device=self.device(), dtype=torch.int64)
             lengths64 = self.lengths()
-            out_lengths, _, _ = J.permute_1D_sparse_data(indices_tensor, seg_sizes, lengths64, None, sum(self.stride_per_key()[i] for i in indices))
+            # segments = the per-key runs of `lengths` (stride_per_key entries each); the permuted lengths are the op's VALUES output
+            _, out_lengths, _ = J.permute_1D_sparse_data(indices_tensor, seg_sizes, lengths64, None, sum(self.stride_per_key()[i] for i in indices))
             vals_seg = torch.tensor(length_per_key, device=self.device(), dtype=torch.int64)
             _, values, weights = J.permute_1D_sparse_data(indices_tensor, vals_seg, self._values, self._weights, total)
             permuted_lengths = out_lengths
