@@ -44,11 +44,19 @@ def parse_args() -> argparse.Namespace:
     p.add_argument("--row-cap", type=int, default=int(os.environ.get("TRB_BENCH_ROW_CAP", 40_000_000)))
     p.add_argument("--pooling", type=int, default=1, help="ids per sparse feature (Criteo is one-hot)")
     p.add_argument("--lr", type=float, default=0.01)
-    p.add_argument("--sharding", type=str, default="auto", choices=["auto", "table_wise", "row_wise", "column_wise", "planner"],
-                   help="auto: greedy table-wise on 1 GPU, table-wise + data-parallel tiny tables (what EmbeddingShardingPlanner also picks) on N > 1")
+    p.add_argument("--config", type=str, default="dlrm", choices=["dlrm", "rw100m", "dcn_cw", "two_tower"],
+                   help="BASELINE.json configs: dlrm = #2 (table-wise DLRM, the headline); rw100m = #3 (one 100 M-row table row-wise); "
+                        "dcn_cw = #4 (DLRM-DCNv2, column-wise tables, + fp8 quantized inference QPS); two_tower = #5 (retrieval, planner-driven table-row-wise)")
+    p.add_argument("--sharding", type=str, default="auto", choices=["auto", "planner", "table_wise", "row_wise", "column_wise"],
+                   help="auto / planner: EmbeddingShardingPlanner under the config's sharding-type constraint (the SAME rule the reference arm "
+                        "uses: table_wise for the headline); table_wise / row_wise / column_wise: hand-made plans")
+    p.add_argument("--overlap-sparse", type=int, default=int(os.environ.get("TRB_BENCH_OVERLAP", 1)),
+                   help="1: embedding arch on a side stream (forward beside the bottom MLP, gradient push + fused optimizer beside the bottom MLP backward)")
+    p.add_argument("--measure-comm", type=int, default=1, help="N > 1: time the NVLink phases in isolation after the run (exposed all-to-all ms, GB/s)")
     p.add_argument("--dense-backend", type=str, default=os.environ.get("TRB_DENSE_BACKEND", "auto"))
     p.add_argument("--transport", type=str, default=os.environ.get("TRB_TRANSPORT", "auto"), help="auto | p2p | nccl")
-    p.add_argument("--dp-rows", type=int, default=int(os.environ.get("TRB_BENCH_DP_ROWS", 2000)), help="tables with at most this many rows are data-parallel when N > 1 (0 = all table-wise)")
+    p.add_argument("--dp-rows", type=int, default=int(os.environ.get("TRB_BENCH_DP_ROWS", 0)),
+                   help="--sharding table_wise only: tables with at most this many rows are data-parallel when N > 1 (0 = every table model-parallel)")
     p.add_argument("--cuda-graphs", type=int, default=int(os.environ.get("TRB_BENCH_GRAPHS", -1)),
                    help="1 (= -1, the default): replay the dense sub-modules as CUDA graphs (host enqueue 1.6-2.6 ms -> 0.74 ms per step; "
                         "end to end 15.4 M -> 17.7 M samples/s on one GPU); 0: eager")
@@ -149,10 +157,11 @@ def reference_arm(args: argparse.Namespace) -> None:
 
 
 def build_ours(args: argparse.Namespace, device, rank: int, world: int):
+    """Model + plan + optimizer of the selected BASELINE config. Returns (dmp, opt, keys, hashes, ids_per_feature, num_dense, backend, info)."""
     import torch
     import torch.distributed as dist
 
-    from torchrec_b200.models.dlrm import DLRM, DLRMTrain
+    from torchrec_b200.models.dlrm import DLRM, DLRM_DCN, DLRMTrain
     from torchrec_b200.modules.embedding_configs import EmbeddingBagConfig
     from torchrec_b200.modules.embedding_modules import EmbeddingBagCollection
     from torchrec_b200.ops import dense as _dense
@@ -163,63 +172,189 @@ def build_ours(args: argparse.Namespace, device, rank: int, world: int):
     from torchrec_b200.parallel import sharding_plan as sp
     from torchrec_b200.parallel.embeddingbag import EmbeddingBagCollectionSharder
     from torchrec_b200.parallel.model_parallel import DistributedModelParallel
+    from torchrec_b200.parallel.planner import EmbeddingShardingPlanner, Topology
+    from torchrec_b200.parallel.planner.types import ParameterConstraints
     from torchrec_b200.parallel.types import ShardingPlan
 
-    hashes = [min(h, args.row_cap) for h in CRITEO_1TB_40M]
-    keys = [f"cat_{i}" for i in range(26)]
+    cfg = args.config
     D = args.embedding_dim
-    tables = [EmbeddingBagConfig(name=f"t_{keys[i]}", embedding_dim=D, num_embeddings=hashes[i], feature_names=[keys[i]]) for i in range(26)]
+    num_dense = 13
+    if cfg == "two_tower":
+        keys, hashes, num_dense = ["user", "item"], [min(40_000_000, args.row_cap), min(10_000_000, args.row_cap)], 1
+    else:
+        hashes = [min(h, args.row_cap) for h in CRITEO_1TB_40M]
+        keys = [f"cat_{i}" for i in range(26)]
+        if cfg == "rw100m":
+            hashes[0] = 100_000_000
+    tables = [EmbeddingBagConfig(name=f"t_{k}", embedding_dim=D, num_embeddings=h, feature_names=[k]) for k, h in zip(keys, hashes)]
     ebc = EmbeddingBagCollection(tables=tables, device=torch.device("meta"))
     apply_optimizer_in_backward(RowWiseAdagrad, ebc.parameters(), {"lr": args.lr, "eps": 1e-8})
     dense_arch = [int(x) for x in args.dense_arch.split(",")]
     over_arch = [int(x) for x in args.over_arch.split(",")]
-    model = DLRMTrain(DLRM(ebc, 13, dense_arch, over_arch, dense_device=device))
+    if cfg == "two_tower":
+        from examples.two_tower_retrieval import TwoTower, TwoTowerTrainTask
+
+        model = TwoTowerTrainTask(TwoTower(ebc, [256, 128], device=device))
+        module_path = "two_tower.ebc"
+    elif cfg == "dcn_cw":
+        model = DLRMTrain(DLRM_DCN(ebc, 13, dense_arch, over_arch, dcn_num_layers=3, dcn_low_rank_dim=512, dense_device=device))
+        module_path = "model.sparse_arch.embedding_bag_collection"
+    else:
+        model = DLRMTrain(DLRM(ebc, 13, dense_arch, over_arch, dense_device=device))
+        module_path = "model.sparse_arch.embedding_bag_collection"
 
     backend = args.dense_backend
     if backend == "auto":
         backend = os.environ.get("TRB_DENSE_DEFAULT", "tcgen05")  # bf16 tensor-core dense path is the product
     _dense.set_dense_backend(backend)
-
     # bf16 pooled embeddings (half the NVLink / HBM bytes) when the dense arch computes in bf16
     fused_params = {"output_dtype": torch.bfloat16} if backend == "tcgen05" else None
     sharder = EmbeddingBagCollectionSharder(fused_params=fused_params)
-    if args.sharding == "auto":
-        args.sharding = "table_wise"
-    if args.sharding == "planner":
-        plan = None
+
+    # sharding-type constraint of the config (identical rule in the reference arm: baseline/run_reference.py)
+    rule = {"dlrm": "table_wise", "rw100m": "table_wise", "dcn_cw": "column_wise", "two_tower": "table_row_wise"}[cfg]
+    per_table = {t.name: rule for t in tables}
+    if cfg == "rw100m":
+        per_table[tables[0].name] = "row_wise"
+    mode = args.sharding if args.sharding != "auto" else "planner"
+    info = {"plan": mode, "rule": rule if cfg != "rw100m" else "row_wise(t_cat_0: 100 M rows) + table_wise"}
+    if mode == "planner":
+        constraints = {t.name: ParameterConstraints(sharding_types=[per_table[t.name]], compute_kernels=["fused"],
+                                                    **({"min_partition": 32} if per_table[t.name] == "column_wise" else {})) for t in tables}
+        planner = EmbeddingShardingPlanner(topology=Topology(world_size=world, local_world_size=world, compute_device="cuda"), batch_size=args.batch_size,
+                                           constraints=constraints)
+        if world > 1:
+            plan = planner.collective_plan(model, [sharder], dist.GroupMember.WORLD)
+        else:
+            plan = planner.plan(model, [sharder])
+        placed = plan.plan[module_path]
+        info["tables_per_rank"] = [sum(1 for ps in placed.values() if r in (ps.ranks or [])) for r in range(world)]
     else:
-        if args.sharding == "table_wise":
+        if mode == "table_wise":
             # greedy balance: bytes first (big tables spread), then lookups per rank
             load = [[0.0, 0] for _ in range(world)]
             gens = {}
-            order = sorted(range(26), key=lambda i: -hashes[i])
+            order = sorted(range(len(tables)), key=lambda i: -hashes[i])
             tot = float(sum(hashes))
             if world > 1 and args.dp_rows > 0:
-                # tiny tables are replicated (data parallel, dense gradient all-reduced) like the reference planner would place
-                # them: no all-to-all traffic for their features and the model-parallel tables divide evenly over the ranks
                 tiny = [i for i in order if hashes[i] <= args.dp_rows]
-                keep = (26 - len(tiny)) % world  # keep the MP table count a multiple of the world size when possible
-                tiny = tiny[keep:] if keep and len(tiny) > keep else tiny
                 for i in tiny:
                     gens[tables[i].name] = sp.data_parallel()
                 order = [i for i in order if i not in tiny]
             for i in order:
-                r = min(range(world), key=lambda r: (load[r][0] / tot * world + load[r][1] / 26.0 * world, r))
+                r = min(range(world), key=lambda r: (load[r][0] / tot * world + load[r][1] / len(tables) * world, r))
                 load[r][0] += hashes[i]
                 load[r][1] += 1
                 gens[tables[i].name] = sp.table_wise(rank=r)
-        elif args.sharding == "row_wise":
+        elif mode == "row_wise":
             gens = {t.name: sp.row_wise() for t in tables}
         else:
             gens = {t.name: (sp.column_wise(ranks=[(i + j) % world for j in range(min(world, 4))]) if world > 1 else sp.table_wise(rank=0)) for i, t in enumerate(tables)}
         mplan = sp.construct_module_sharding_plan(ebc, gens, sharder=sharder, world_size=world, local_size=world, device_type="cuda")
-        plan = ShardingPlan({"model.sparse_arch.embedding_bag_collection": mplan})
+        plan = ShardingPlan({module_path: mplan})
     # data-parallel wrapping is deferred (main() calls dmp.init_data_parallel()) so that CUDA graphs of the dense sub-modules can
     # be captured first: DDP keeps the parameters' AccumulateGrad nodes alive on the default stream, which a capture may not touch
     dmp = DistributedModelParallel(model, device=device, plan=plan, sharders=[sharder], init_data_parallel=False)
     dense_opt = KeyedOptimizerWrapper(dict(in_backward_optimizer_filter(dmp.named_parameters())), lambda params: torch.optim.SGD(params, lr=args.lr))
     opt = CombinedOptimizer([dmp.fused_optimizer, dense_opt])
-    return dmp, opt, keys, hashes, backend
+    return dmp, opt, keys, hashes, [args.pooling] * len(keys), num_dense, backend, info
+
+
+def find_planes(module) -> list:
+    """NVLink sparse planes created by the sharded modules of ``module`` (one per batch size / id source)."""
+    out = []
+    for m in module.modules():
+        eng = getattr(m, "_engine", None)
+        if eng is not None:
+            out.extend(eng.__dict__.get("_planes", {}).values())
+    return out
+
+
+def measure_comm(dmp, device, world: int, iters: int = 10) -> Optional[Dict[str, Any]]:
+    """Times the NVLink phases of the sparse plane in isolation (CUDA events, every rank in lock step, max over ranks) on the ids of
+    the last batch: the fused lookup + output dist against the SAME lookup writing locally (difference = exposed forward all-to-all),
+    the gradient push (pure communication) and the input dist. Bytes are what this rank stores into peer memory per step."""
+    import torch
+    import torch.distributed as dist
+
+    planes = [p for p in find_planes(dmp) if p.capacity > 0 and p.W > 1]
+    if not planes:
+        return None
+    pl = planes[0]
+    slot = (pl.step - 1) % pl.N_ID_SLOTS
+    reg = pl.regions(slot)
+    esz = torch.empty(0, dtype=pl.wire_dtype).element_size()
+    my_cols = sum(u.shard.cols for u in pl.eng._local_units)
+    sent_fwd = (world - 1) * pl.B_local * my_cols * esz                 # pooled rows of MY units for the other ranks' samples
+    sent_bwd = pl.B_local * (pl.total_cols - my_cols) * esz             # gradient columns of the OTHER ranks' units
+    grad = torch.randn(pl.B_local, pl.total_cols, device=device).to(pl.wire_dtype)
+
+    def timed(fn) -> float:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fn()
+        dist.barrier()
+        torch.cuda.synchronize()
+        pl.group.barrier(0)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / iters], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def fwd_fused():
+        pl._forward_kernels(reg, 1)
+        pl.group.barrier(0)
+
+    def fwd_local():
+        pl._forward_kernels(reg, 1, local_only=True)
+        pl.group.barrier(0)
+
+    def push():
+        pl._push_kernels(grad)
+        pl.group.barrier(0)
+
+    t_fused, t_local, t_push = timed(fwd_fused), timed(fwd_local), timed(push)
+    t_barrier = timed(lambda: pl.group.barrier(0))
+    res = {"fwd_fused_lookup_dist_ms": t_fused, "fwd_same_lookup_local_ms": t_local, "bwd_grad_push_ms": t_push, "device_barrier_ms": t_barrier,
+           "fwd_sent_bytes_per_rank": sent_fwd, "bwd_sent_bytes_per_rank": sent_bwd,
+           "fwd_gbps": sent_fwd / (t_fused * 1e-3) / 1e9, "bwd_gbps": sent_bwd / (max(t_push - t_barrier, 1e-6) * 1e-3) / 1e9,
+           "exposed_fwd_ms": max(0.0, t_fused - t_local), "exposed_bwd_ms": t_push, "nvlink_peak_gbps": 900.0, "nvlink_measured_peer_copy_gbps": 770.0}
+    return res
+
+
+def fp8_inference_qps(args, dmp, device, rank: int, world: int, keys, hashes) -> Dict[str, Any]:
+    """Config #4 tail: quantize the tables to block-scaled FP8 (e4m3 + one fp16 scale per 32 elements) and time the serving
+    lookup (quantized table-batched kernel, bf16 output) on this GPU: fresh tables of the same shapes (the trained shards live on
+    other ranks), one-hot ids, device-timed."""
+    import torch
+
+    from torchrec_b200.ops.quant_tbe import QuantTableBatchedEmbeddingBags
+    from torchrec_b200.types import DataType
+
+    rows = [min(h, 4_000_000) for h in hashes]
+    B = args.batch_size
+    q = QuantTableBatchedEmbeddingBags([(f"t{i}", r, args.embedding_dim, DataType.FP8) for i, r in enumerate(rows)], output_dtype=torch.bfloat16, device=device)
+    q.weights.random_(0, 120)  # arbitrary finite e4m3 payloads / scales: the timing does not depend on the values
+    g = torch.Generator(device="cpu").manual_seed(7)
+    ids = torch.cat([torch.randint(0, r, (B,), generator=g) for r in rows]).to(device)
+    off = torch.arange(0, len(rows) * B + 1, device=device, dtype=torch.int64)
+    for _ in range(3):
+        q(ids, off)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    n = 20
+    for _ in range(n):
+        out = q(ids, off)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    row_bytes = args.embedding_dim + args.embedding_dim // 32 * 2
+    return {"format": "FP8_BLOCK (e4m3, fp16 scale / 32 elems)", "samples_per_s_per_gpu": B / (ms * 1e-3), "ms_per_batch": ms,
+            "table_bytes": int(sum(rows)) * row_bytes, "gathered_gbps": len(rows) * B * row_bytes / (ms * 1e-3) / 1e9, "out_shape": list(out.shape)}
 
 
 def main() -> None:
@@ -249,11 +384,13 @@ def main() -> None:
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group(backend="nccl", device_id=device)
+    if args.transport != "auto":
+        os.environ["TRB_TRANSPORT"] = args.transport  # "nccl": the internal UNFUSED arm (own lookup kernels + NCCL all-to-alls)
     _lib.lib()
 
-    dmp, opt, keys, hashes, dense_backend = build_ours(args, device, rank, world)
+    dmp, opt, keys, hashes, ids_per_feature, num_dense, dense_backend, plan_info = build_ours(args, device, rank, world)
     B = args.batch_size
-    ds = RandomRecDataset(keys, B, hash_sizes=hashes, ids_per_features=[args.pooling] * 26, num_dense=13, manual_seed=1234 + rank,
+    ds = RandomRecDataset(keys, B, hash_sizes=hashes, ids_per_features=ids_per_feature, num_dense=num_dense, manual_seed=1234 + rank,
                           num_generated_batches=args.num_host_batches, pin_memory=True)
     host_batches = ds.batch_generator._generated_batches
     dev_batches = [b.to(device) for b in host_batches]
@@ -263,14 +400,18 @@ def main() -> None:
         args.cuda_graphs = 1
     if not args.cuda_graphs:
         dmp.init_data_parallel()
-    if args.cuda_graphs:
+    inner = getattr(dmp.module, "model", None)
+    if args.cuda_graphs and hasattr(inner, "capture_dense_graphs"):
         # the dense sub-modules (bottom MLP, interaction + top MLP + head) replay as CUDA graphs: their ~50 launches and ~100 ATen
         # calls per step made the step launch-bound once DDP / NVLink dists were added (host enqueue 2.0 ms vs 2.1 ms of GPU time)
-        inner = dmp.module.model
         with torch.no_grad():
             sample_emb = inner.sparse_arch(dev_batches[0].sparse_features)
         inner.capture_dense_graphs(dev_batches[0].dense_features, sample_emb)
+        inner.overlap_sparse_dense = bool(args.overlap_sparse)
         torch.cuda.synchronize()
+        dmp.init_data_parallel()
+    elif args.cuda_graphs:
+        args.cuda_graphs = 0
         dmp.init_data_parallel()
 
     def step(batch) -> "torch.Tensor":
@@ -399,8 +540,15 @@ def main() -> None:
         if not args.no_e2e:
             it2 = host_iter(10 + 4)
             profiled("TrainPipelineSparseDist.progress", lambda i: pipe.progress(it2))
+    comm = None
+    if world > 1 and args.measure_comm and args.transport != "nccl":
+        comm = measure_comm(dmp, device, world)
+    extra: Dict[str, Any] = {}
+    if args.config == "dcn_cw":
+        extra["fp8_inference"] = fp8_inference_qps(args, dmp, device, rank, world, keys, hashes)
+    planes = find_planes(dmp)
     if rank == 0:
-        base = BASELINE_SAMPLES_PER_SEC.get(world)
+        base = BASELINE_SAMPLES_PER_SEC.get(world) if args.config == "dlrm" else None
         out = {
             "metric": "DLRM training throughput (samples/s, whole job, device-timed, max over ranks)",
             "value": value,
@@ -416,12 +564,19 @@ def main() -> None:
             "data": "synthetic (random Criteo-1TB-shaped ids/dense, random-init tables)",
             "impl": "ours",
             "config": {
-                "model": "DLRM (26 sparse x dim %d, dense %s, over %s), fp32 tables + fused row-wise Adagrad, dense SGD" % (args.embedding_dim, args.dense_arch, args.over_arch),
-                "num_embeddings": "Criteo-1TB cardinalities capped at %d rows (%.1f GB fp32 tables)" % (args.row_cap, sum(min(h, args.row_cap) for h in CRITEO_1TB_40M) * args.embedding_dim * 4 / 1e9),
+                "name": args.config,
+                "model": {"dlrm": "DLRM", "rw100m": "DLRM", "dcn_cw": "DLRM-DCNv2 (3 cross layers, rank 512)", "two_tower": "two-tower retrieval (examples/two_tower_retrieval.py)"}[args.config]
+                         + " (%d sparse x dim %d, dense %s, over %s), fp32 tables + fused row-wise Adagrad, dense SGD" % (len(keys), args.embedding_dim, args.dense_arch, args.over_arch),
+                "num_embeddings": "%s (%.1f GB fp32 tables)" % ("Criteo-1TB cardinalities capped at %d rows" % args.row_cap if args.config != "two_tower" else str(hashes),
+                                                                sum(hashes) * args.embedding_dim * 4 / 1e9),
                 "global_batch": B * world,
                 "per_gpu_batch": B,
                 "seq_len": args.pooling,
-                "parallelism": f"{args.sharding} embeddings over {world} GPU(s) + DDP dense" + (f"; tables with <= {args.dp_rows} rows data-parallel (dense SGD)" if world > 1 and args.dp_rows > 0 and args.sharding == "table_wise" else ""),
+                "parallelism": f"{plan_info['rule']} embeddings ({plan_info['plan']} plan) over {world} GPU(s) + DDP dense"
+                               + (f"; tables with <= {args.dp_rows} rows data-parallel" if world > 1 and args.dp_rows > 0 and args.sharding == "table_wise" else ""),
+                "tables_per_rank": plan_info.get("tables_per_rank"),
+                "transport": ("NVLink sparse plane (fused peer-memory kernels%s)" % (", CUDA-graph phases" if any(p._graphs for p in planes) else "")) if planes else "nccl / local",
+                "overlap_sparse_dense": bool(args.overlap_sparse),
                 "pipeline": "TrainPipelineSparseDist (e2e) / plain step (value)",
                 "l2_policy": "inputs > L2: %d distinct batches, random rows of multi-GB tables (L2 126 MB)" % len(dev_batches),
                 "dense_backend": dense_backend,
@@ -435,6 +590,14 @@ def main() -> None:
         }
         if e2e is not None:
             out["e2e"] = e2e
+        if comm is not None:
+            # BASELINE.json: "exposed all-to-all ms/step; pooled-emb all-to-all GB/s vs 900 GB/s". The input dist is hidden by the pipeline
+            # (e2e) and inside the plain step it is part of `comm["input_dist_ms"]`.
+            out["exposed_a2a_ms_per_step"] = comm["exposed_fwd_ms"] + comm["exposed_bwd_ms"]
+            out["pooled_a2a_gbps"] = {"fwd_fused_with_lookup": comm["fwd_gbps"], "bwd_grad_push": comm["bwd_gbps"], "line_rate": 900.0,
+                                      "frac_of_900": max(comm["fwd_gbps"], comm["bwd_gbps"]) / 900.0}
+            out["comm"] = comm
+        out.update(extra)
         print(json.dumps(out))
     if world > 1:
         dist.barrier()

@@ -1,0 +1,139 @@
+"""Keyed optimizers (name-addressed state, in-place load, sharded leaves) and stage-wise learning-rate schedules."""
+import math
+
+import pytest
+import torch
+
+from torchrec_b200.optim.keyed import CombinedOptimizer, KeyedOptimizer, KeyedOptimizerWrapper, OptimizerWrapper, StateMismatch, export_state, import_state
+from torchrec_b200.optim.warmup import WarmupOptimizer, WarmupPolicy, WarmupStage, lr_multiplier
+
+
+def _model():
+    torch.manual_seed(0)
+    return torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2))
+
+
+def _keyed(m, lr=0.1):
+    return KeyedOptimizerWrapper(dict(m.named_parameters()), lambda ps: torch.optim.Adam(ps, lr=lr))
+
+
+def _train(m, opt, n=3):
+    for i in range(n):
+        opt.zero_grad()
+        m(torch.ones(2, 4) * (i + 1)).sum().backward()
+        opt.step()
+
+
+def test_state_is_keyed_by_name_and_loads_in_place():
+    a, b = _model(), _model()
+    oa, ob = _keyed(a), _keyed(b)
+    _train(a, oa)
+    ob.init_state()  # zero-gradient step materialises exp_avg / exp_avg_sq so that there is something to load into
+    sd = oa.state_dict()
+    assert set(sd["state"].keys()) == {"0.weight", "0.bias", "1.weight", "1.bias"} and "param_groups" not in sd
+    exp_avg_before = ob.state[b[0].weight]["exp_avg"]
+    ob.load_state_dict(sd)
+    assert ob.state[b[0].weight]["exp_avg"] is exp_avg_before  # same storage, new values
+    torch.testing.assert_close(exp_avg_before, oa.state[a[0].weight]["exp_avg"])
+    assert float(ob.state[b[1].bias]["step"]) == 3.0
+
+
+def test_param_groups_round_trip_and_mismatch_errors():
+    a, b = _model(), _model()
+    oa, ob = _keyed(a, lr=0.5), _keyed(b, lr=0.1)
+    for o in (oa, ob):
+        o.save_param_groups(True)
+        o.init_state()
+    ob.load_state_dict(oa.state_dict())
+    assert ob.param_groups[0]["lr"] == 0.5
+    sd = oa.state_dict()
+    sd["state"].pop("1.bias")
+    with pytest.raises(StateMismatch, match="parameter count"):
+        ob.load_state_dict(sd)
+    sd = oa.state_dict()
+    sd["state"]["renamed"] = sd["state"].pop("1.bias")
+    with pytest.raises(StateMismatch, match="1.bias not found"):
+        ob.load_state_dict(sd)
+    sd = oa.state_dict()
+    sd["param_groups"][0]["params"] = ["0.weight"]
+    with pytest.raises(StateMismatch, match="Group .* not found"):
+        ob.load_state_dict(sd)
+    with pytest.raises(ValueError, match="must be params"):
+        KeyedOptimizer({"w": a[0].weight}, {a[1].weight: {}}, [{"params": [a[0].weight]}])
+
+
+def test_state_tree_handlers():
+    class Counter:
+        def __init__(self, n):
+            self.n = n
+
+        def state_dict(self):
+            return {"n": self.n}
+
+        def load_state_dict(self, sd):
+            self.n = sd["n"]
+
+    cur = {"t": torch.zeros(3), "nested": {"c": Counter(1), "plain": 5}}
+    new = {"t": torch.arange(3.0), "nested": {"c": {"n": 9}, "plain": [1, 2]}}
+    t = cur["t"]
+    assert export_state(cur)["nested"]["c"] == {"n": 1}
+    import_state(cur, new, [])
+    assert cur["t"] is t and t.tolist() == [0.0, 1.0, 2.0] and cur["nested"]["c"].n == 9 and cur["nested"]["plain"] == [1, 2]
+    with pytest.raises(StateMismatch, match="nested/plain"):
+        import_state(cur, {"t": t, "nested": {"c": {"n": 1}}}, [])
+
+
+def test_combined_optimizer_prefixes_and_uniqueness():
+    a, b = _model(), _model()
+    combo = CombinedOptimizer([("dense", _keyed(a)), ("over", _keyed(b))])
+    assert "dense.0.weight" in combo.params and "over.1.bias" in combo.params
+    _train(a, combo)
+    sd = combo.state_dict()
+    assert "dense.0.weight" in sd["state"] and "over.0.weight" not in sd["state"]  # `b` never stepped: stateless
+    with pytest.raises(ValueError, match="Duplicate param key"):
+        CombinedOptimizer([_keyed(a), _keyed(a)])
+    assert CombinedOptimizer.prepend_opt_key("w", "") == "w" and CombinedOptimizer.prepend_opt_key("", "k") == "k"
+
+
+def test_optimizer_wrapper_aliases_wrapped_state():
+    a = _model()
+    inner = _keyed(a)
+    w = OptimizerWrapper(inner)
+    _train(a, w)
+    assert w.state is inner.state and w.state_dict()["state"].keys() == inner.state_dict()["state"].keys()
+
+
+def test_schedule_shapes():
+    assert lr_multiplier(WarmupStage(WarmupPolicy.LINEAR, max_iters=10, value=0.0), 5) == pytest.approx(0.5)
+    assert lr_multiplier(WarmupStage(WarmupPolicy.CONSTANT, max_iters=10, value=0.3, lr_scale=2.0), 7) == pytest.approx(0.6)
+    assert lr_multiplier(WarmupStage(WarmupPolicy.POLY, max_iters=10, value=2.0, decay_iters=10), 5) == pytest.approx(0.25)
+    assert lr_multiplier(WarmupStage(WarmupPolicy.STEP, max_iters=100, value=0.5, decay_iters=10), 25) == pytest.approx(0.25)
+    assert lr_multiplier(WarmupStage(WarmupPolicy.INVSQRT, max_iters=100), 16) == pytest.approx(0.25)
+    cos = WarmupStage(WarmupPolicy.COSINE_ANNEALING_WARM_RESTARTS, max_iters=100, value=0.1, sgdr_period=10)
+    assert lr_multiplier(cos, 0) == pytest.approx(1.0) and lr_multiplier(cos, 5) == pytest.approx(0.1 + 0.9 * 0.5) and lr_multiplier(cos, 10) == pytest.approx(1.0)
+    itp = WarmupStage(WarmupPolicy.INTERPOLATE, max_iters=30, value=1.0, start_interpolating_iters=10, end_value=0.2)
+    assert lr_multiplier(itp, 10) == pytest.approx(1.0) and lr_multiplier(itp, 20) == pytest.approx(0.6) and lr_multiplier(itp, 30) == pytest.approx(0.2)
+
+
+def test_warmup_optimizer_stages_and_resume():
+    a = _model()
+    stages = [WarmupStage(WarmupPolicy.LINEAR, max_iters=4, value=0.0), WarmupStage(WarmupPolicy.INTERPOLATE, max_iters=8, value=1.0, start_interpolating_iters=4, end_value=0.5)]
+    opt = WarmupOptimizer(_keyed(a), stages, lr=1.0)
+    lrs = []
+    for _ in range(10):
+        lrs.append(opt.param_groups[0]["lr"])
+        _train(a, opt, 1)
+    assert lrs[:5] == pytest.approx([0.0, 0.25, 0.5, 0.75, 1.0])
+    assert lrs[5:9] == pytest.approx([0.875, 0.75, 0.625, 0.5])
+    assert lrs[9] == pytest.approx(1.0)  # past the last stage
+    sd = opt.state_dict()
+    assert sd["state"]["__warmup"]["warmup"].tolist() == [10, 2]
+    b = _model()
+    opt_b = WarmupOptimizer(_keyed(b), [WarmupStage(WarmupPolicy.LINEAR, max_iters=4, value=0.0),
+                                        WarmupStage(WarmupPolicy.INTERPOLATE, max_iters=8, value=1.0, start_interpolating_iters=4, end_value=0.5)], lr=1.0)
+    _train(b, opt_b, 6)
+    assert opt_b.param_groups[0]["lr"] == pytest.approx(0.75)
+    with pytest.raises(AssertionError):
+        WarmupOptimizer(_keyed(_model()), [WarmupStage(max_iters=5), WarmupStage(max_iters=5)])
+    with pytest.raises(AssertionError):
+        WarmupOptimizer(_keyed(_model()), [WarmupStage(WarmupPolicy.INTERPOLATE, max_iters=5)])

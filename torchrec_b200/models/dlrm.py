@@ -236,15 +236,33 @@ class DLRM(nn.Module):
 
         g = self._graphed(dense_features)
         if g is not None:
-            embedded_sparse = self.sparse_arch(sparse_features)
+            overlap = self.overlap_sparse_dense or os.environ.get("TRB_OVERLAP_SPARSE") == "1"
+            if overlap:
+                # embedding arch on a side stream: its forward (lookup + NVLink output dist) runs beside the bottom MLP, and - autograd
+                # replays every op on the stream of its forward - its backward (gradient push over NVLink, fused optimizer) runs beside
+                # the bottom MLP's backward and the dense gradient all-reduce instead of after them
+                main = torch.cuda.current_stream(dense_features.device)
+                side = self._sparse_stream(dense_features.device)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    embedded_sparse = self.sparse_arch(sparse_features)
+                    if isinstance(embedded_sparse, torch.Tensor):
+                        embedded_sparse.record_stream(main)
+                embedded_dense = g["dense"](dense_features)
+                main.wait_stream(side)
+            else:
+                embedded_sparse = self.sparse_arch(sparse_features)
+                embedded_dense = None
             if (tuple(embedded_sparse.shape), embedded_sparse.dtype) == g["sparse_sig"]:
                 from ..ops import _lib
 
-                embedded_dense = g["dense"](dense_features)
+                if embedded_dense is None:
+                    embedded_dense = g["dense"](dense_features)
                 out = g["top"](embedded_dense, embedded_sparse)
                 _lib.add_launches(g["launches_per_step"])
                 return out
-            embedded_dense = self.dense_arch(dense_features)
+            if embedded_dense is None:
+                embedded_dense = self.dense_arch(dense_features)
             return self.over_arch(self.inter_arch(dense_features=embedded_dense, sparse_features=embedded_sparse))
         if dense_features.is_cuda and (self.overlap_sparse_dense or os.environ.get("TRB_OVERLAP_SPARSE") == "1"):
             main = torch.cuda.current_stream(dense_features.device)

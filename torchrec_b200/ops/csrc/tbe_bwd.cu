@@ -82,6 +82,7 @@ struct TbeBwdParams {
   int32_t max_dim;
   int32_t key64;
   int32_t opt;
+  int32_t phase;        // 0: whole backward; 1: prepare only (keys + sort: depends on the ids alone, can run long before the gradient exists); 2: apply only
 };
 
 __device__ __forceinline__ uint64_t ld_key(const void* p, int64_t i, int key64) {
@@ -735,20 +736,23 @@ static int run_bwd(TbeBwdParams& p, char* ws, cudaStream_t stream) {
   p.long_list = (int32_t*) (ws + L.long_list);
   p.long_count = (int32_t*) (ws + L.long_count);
   const int threads = 256;
-  tbe_bwd_build_keys<<<(unsigned) ((p.n + threads - 1) / threads), threads, 0, stream>>>(p);
-  TRB_CHECK_LAUNCH();
-  size_t tmp_bytes = L.total - L.sort_tmp;
-  const int end_bit = bits_needed(p.total_rows);
-  if (key64) {
-    TRB_CUDA(cub::DeviceRadixSort::SortPairs(ws + L.sort_tmp, tmp_bytes, (const uint64_t*) p.keys,
-                                             (uint64_t*) p.keys_sorted, (const int32_t*) p.vals, p.vals_sorted, p.n, 0,
-                                             end_bit, stream));
-  } else {
-    TRB_CUDA(cub::DeviceRadixSort::SortPairs(ws + L.sort_tmp, tmp_bytes, (const uint32_t*) p.keys,
-                                             (uint32_t*) p.keys_sorted, (const int32_t*) p.vals, p.vals_sorted, p.n, 0,
-                                             end_bit, stream));
+  if (p.phase != 2) {
+    tbe_bwd_build_keys<<<(unsigned) ((p.n + threads - 1) / threads), threads, 0, stream>>>(p);
+    TRB_CHECK_LAUNCH();
+    size_t tmp_bytes = L.total - L.sort_tmp;
+    const int end_bit = bits_needed(p.total_rows);
+    if (key64) {
+      TRB_CUDA(cub::DeviceRadixSort::SortPairs(ws + L.sort_tmp, tmp_bytes, (const uint64_t*) p.keys,
+                                               (uint64_t*) p.keys_sorted, (const int32_t*) p.vals, p.vals_sorted, p.n, 0,
+                                               end_bit, stream));
+    } else {
+      TRB_CUDA(cub::DeviceRadixSort::SortPairs(ws + L.sort_tmp, tmp_bytes, (const uint32_t*) p.keys,
+                                               (uint32_t*) p.keys_sorted, (const int32_t*) p.vals, p.vals_sorted, p.n, 0,
+                                               end_bit, stream));
+    }
+    g_trb_launches += 4;  // radix sort passes (library kernels, counted approximately)
   }
-  g_trb_launches += 4;  // radix sort passes (library kernels, counted approximately)
+  if (p.phase == 1) return 0;
   const int64_t chunks = (p.n + 31) / 32;
   const int64_t blocks = (chunks + 7) / 8;
   // pass 1 (optional): chunks of distinct rows with a simple optimizer go through the high-MLP unique kernel
@@ -783,6 +787,15 @@ static int dispatch_dim(TbeBwdParams& p, char* ws, cudaStream_t stream) {
   return -2;
 }
 
+TRB_API int trb_tbe_bwd_fused_phase(void* weights, int w_dtype, float* state1, float* state2, const float* hyper, int opt,
+                                    int wd_mode, const int64_t* feat_woff, const int64_t* feat_rows,
+                                    const int64_t* feat_rowbase, const int32_t* feat_dim, const int32_t* feat_col,
+                                    const void* indices, int idx64, const void* offsets, int off64, const float* psw,
+                                    int n_src, int64_t idx_stride, int64_t off_stride,
+                                    void* const* grad_ptrs, int n_grad, int grad_dtype, int64_t grad_stride, float grad_scale, int64_t n,
+                                    int64_t total_rows, int B, int B_local, int F, int max_dim, int mean, void* workspace,
+                                    int stochastic_rounding, unsigned long long sr_seed, int phase, cudaStream_t stream);
+
 // Fused backward + optimizer. `workspace` must hold trb_tbe_bwd_workspace_bytes(n, max_dim, total_rows).
 // `n` = number of id POSITIONS to scan (capacity of `indices`; with n_src > 1 it must equal n_src * idx_stride).
 TRB_API int trb_tbe_bwd_fused_ms(void* weights, int w_dtype, float* state1, float* state2, const float* hyper, int opt,
@@ -793,12 +806,29 @@ TRB_API int trb_tbe_bwd_fused_ms(void* weights, int w_dtype, float* state1, floa
                                  void* const* grad_ptrs, int n_grad, int grad_dtype, int64_t grad_stride, float grad_scale, int64_t n,
                                  int64_t total_rows, int B, int B_local, int F, int max_dim, int mean, void* workspace,
                                  int stochastic_rounding, unsigned long long sr_seed, cudaStream_t stream) {
+  return trb_tbe_bwd_fused_phase(weights, w_dtype, state1, state2, hyper, opt, wd_mode, feat_woff, feat_rows, feat_rowbase, feat_dim, feat_col, indices, idx64,
+                                 offsets, off64, psw, n_src, idx_stride, off_stride, grad_ptrs, n_grad, grad_dtype, grad_stride, grad_scale, n, total_rows, B,
+                                 B_local, F, max_dim, mean, workspace, stochastic_rounding, sr_seed, 0, stream);
+}
+
+// phase 1 = prepare (keys + radix sort; needs only the ids: run it as soon as the ids exist, off the critical path);
+// phase 2 = apply (run walk + optimizer; needs the gradient and the workspace filled by phase 1); phase 0 = both.
+TRB_API int trb_tbe_bwd_fused_phase(void* weights, int w_dtype, float* state1, float* state2, const float* hyper, int opt,
+                                    int wd_mode, const int64_t* feat_woff, const int64_t* feat_rows,
+                                    const int64_t* feat_rowbase, const int32_t* feat_dim, const int32_t* feat_col,
+                                    const void* indices, int idx64, const void* offsets, int off64, const float* psw,
+                                    int n_src, int64_t idx_stride, int64_t off_stride,
+                                    void* const* grad_ptrs, int n_grad, int grad_dtype, int64_t grad_stride, float grad_scale, int64_t n,
+                                    int64_t total_rows, int B, int B_local, int F, int max_dim, int mean, void* workspace,
+                                    int stochastic_rounding, unsigned long long sr_seed, int phase, cudaStream_t stream) {
   if (n <= 0) return 0;
   if (n_grad < 1 || n_grad > TRB_MAX_PEERS) return -1;
   if ((int64_t) B_local * n_grad != B) return -4;
   if (n_src < 1 || B % n_src != 0) return -4;
   if (n_src > 1 && n != (int64_t) n_src * idx_stride) return -4;
+  if (phase < 0 || phase > 2) return -8;
   TbeBwdParams p;
+  p.phase = phase;
   p.weights = weights;
   p.state1 = state1;
   p.state2 = state2;

@@ -556,19 +556,21 @@ def backward_workspace_bytes(n_positions: int, max_dim: int, total_rows: int) ->
 
 def fused_backward_regions(meta: TbeMeta, weights: torch.Tensor, state1, state2, hyper_dev: torch.Tensor, opt: int, wd_mode: int, ids: IdRegions, mean: bool,
                            grad_ptrs: Sequence[int], grad_stride: int, grad_dtype: torch.dtype, grad_scale: float, B_local: int, workspace: torch.Tensor,
-                           device: torch.device, stochastic_rounding: bool = False, sr_seed: int = 0) -> None:
-    """Fused backward + optimizer over per-source id regions (gradient rows in ``grad_ptrs`` buffers, scaled by ``grad_scale``)."""
+                           device: torch.device, stochastic_rounding: bool = False, sr_seed: int = 0, phase: int = 0) -> None:
+    """Fused backward + optimizer over per-source id regions (gradient rows in ``grad_ptrs`` buffers, scaled by ``grad_scale``).
+    ``phase`` 1 runs only the id-dependent half (key build + radix sort into ``workspace``) - callable as soon as the ids exist, on
+    any stream; ``phase`` 2 runs the gradient-dependent half (run walk + optimizer) over a prepared workspace; 0 = both."""
     L = _lib.lib()
     B = ids.n_src * ids.src_B
-    code = L.trb_tbe_bwd_fused_ms(
+    code = L.trb_tbe_bwd_fused_phase(
         _lib.ptr(weights), _lib.dtype_code(weights.dtype), _lib.ptr(state1), _lib.ptr(state2), _lib.ptr(hyper_dev), opt, wd_mode,
         _lib.ptr(meta.feat_woff), _lib.ptr(meta.feat_rows), _lib.ptr(meta.feat_rowbase), _lib.ptr(meta.feat_dim), _lib.ptr(meta.feat_col),
         ctypes.c_void_p(ids.idx_ptr), ids.idx64, ctypes.c_void_p(ids.off_ptr), ids.off64, ctypes.c_void_p(ids.psw_ptr), ids.n_src,
         ctypes.c_int64(ids.idx_stride), ctypes.c_int64(ids.off_stride), _lib.ptr_array(grad_ptrs), len(grad_ptrs), _lib.dtype_code(grad_dtype),
         ctypes.c_int64(grad_stride), ctypes.c_float(grad_scale), ctypes.c_int64(ids.positions), ctypes.c_int64(meta.total_rows), B, B_local,
         meta.num_features, meta.max_dim, int(mean), _lib.ptr(workspace), int(bool(stochastic_rounding)), ctypes.c_uint64(int(sr_seed) & 0xFFFFFFFFFFFFFFFF),
-        _lib.stream_ptr(device))
-    _lib.check(code, "trb_tbe_bwd_fused_ms")
+        int(phase), _lib.stream_ptr(device))
+    _lib.check(code, "trb_tbe_bwd_fused_phase")
 
 
 def psw_grad_regions(meta: TbeMeta, weights: torch.Tensor, ids: IdRegions, mean: bool, grad_ptrs: Sequence[int], grad_stride: int, grad_dtype: torch.dtype,

@@ -386,6 +386,8 @@ class ShardedLookupEngine(nn.Module):
 
     def _uniform_batch(self, B: int) -> bool:
         """All ranks feed the same local batch size (checked once per size; required by the fixed-slot NVLink buffers)."""
+        if self._W == 1 or self._pg is None:
+            return True
         cache = self.__dict__.setdefault("_uniform_batch_cache", {})
         if B not in cache:
             t = torch.tensor([B, -B], device=self._device, dtype=torch.int64)
@@ -554,13 +556,15 @@ class ShardedLookupEngine(nn.Module):
     # ---- fused NVLink path (single NVLink domain) -----------------------------------------------------------------
     def fused_available(self, batch_size_per_rank: Optional[List[int]]) -> bool:
         """The fused lookup + output-dist kernels can serve this batch (CUDA, one host, even batch)."""
-        if not self._pooled or not self._has_mp or self._device.type != "cuda" or self._W < 2:
+        if not self._pooled or not self._has_mp or self._device.type != "cuda":
+            return False
+        if self._W == 1 and os.environ.get("TRB_PLANE_SINGLE", "1") == "0":
             return False
         if any(getattr(g.tbe, "is_cached", False) for g in self._groups):
             return False  # cached tables translate ids -> cache slots first: portable path
         if batch_size_per_rank is not None and len(set(batch_size_per_rank)) != 1:
             return False
-        if getattr(self._env, "loopback_group", None) is not None:
+        if getattr(self._env, "loopback_group", None) is not None or self._W == 1:
             return True
         if not self._p2p_checked:
             from .p2p import PeerGroup
@@ -574,6 +578,10 @@ class ShardedLookupEngine(nn.Module):
         lb = getattr(self._env, "loopback_group", None)
         if lb is not None:
             return lb.view(self._rank)
+        if self._W == 1:
+            from .sparse_plane import SingleRankGroup
+
+            return SingleRankGroup(self._device)
         from .p2p import PeerGroup
 
         return PeerGroup.get(self._pg, self._device)

@@ -90,6 +90,27 @@ class _LoopbackView:
         return None
 
 
+class SingleRankGroup:
+    """World of one: the "symmetric" buffers are plain device memory, there is nobody to wait for. Lets a single GPU run the same
+    static-shape, graph-replayed sparse phases as a multi-GPU job."""
+
+    is_loopback = False
+    world = 1
+    rank = 0
+
+    def __init__(self, device: torch.device) -> None:
+        self.device = torch.device(device)
+        self._keep: List[torch.Tensor] = []
+
+    def alloc(self, nbytes: int) -> SymmetricBuffer:
+        t = torch.zeros(_align(nbytes), dtype=torch.uint8, device=self.device)
+        self._keep.append(t)
+        return SymmetricBuffer(t.numel(), t.data_ptr(), [t.data_ptr()], self.device)
+
+    def barrier(self, channel: int = 0) -> None:
+        return None
+
+
 # ---------------------------------------------------------------------------------------------------------------
 @dataclass
 class RoutedIds:
@@ -199,7 +220,7 @@ class SparsePlane:
             local_cols_per_rank.append(cols_r)
         assert all(u.shard.cols % 4 == 0 for u in units)
         self.inbox_pitch = max(8, (max((sum(u.shard.cols for u in units[eng._unit_start[r] : eng._unit_start[r + 1]]) for r in range(W)), default=8) + 7) // 8 * 8)
-        self.inbox_bytes = _align(W * B_local * self.inbox_pitch * esz)
+        self.inbox_bytes = _align(W * B_local * self.inbox_pitch * esz) if W > 1 else 256  # one rank: the backward reads the gradient in place
         self.chunks = torch.tensor(chunks, dtype=torch.int32, device=dev).reshape(-1, 3).contiguous()
         self.local_cols = local_cols_per_rank[self.rank]
         # staging for row-sharded tables: slab j of rank d = partial sums computed by rank j, compact staged columns only
@@ -253,13 +274,21 @@ class SparsePlane:
             self.group_meta.append({"n_direct": n_direct, "n": len(gunits), "direct": _slice_meta(full, 0, n_direct),
                                     "staged": _slice_meta(stg, n_direct, len(gunits)) if stg is not None else None, "local": local})
         # backward workspace (one per group, static so that the backward can be captured)
-        self.bwd_ws: List[Optional[torch.Tensor]] = []
-        for g in eng._groups:
-            if g.tbe is None:
-                self.bwd_ws.append(None)
-                continue
-            nb = T.backward_workspace_bytes(self.W * self.capacity, g.tbe.meta.max_dim, g.tbe.meta.total_rows) if dev.type == "cuda" else 0
-            self.bwd_ws.append(torch.empty(nb + 1024, dtype=torch.uint8, device=dev))
+        # one per (id slot, group): the id-dependent half of the backward (keys + sort) runs right after the input dist of a batch,
+        # on an auxiliary stream, while earlier batches are still training
+        self.bwd_ws: List[List[Optional[torch.Tensor]]] = []
+        for _slot in range(self.N_ID_SLOTS):
+            per_group: List[Optional[torch.Tensor]] = []
+            for g in eng._groups:
+                if g.tbe is None or self.capacity == 0:
+                    per_group.append(None)
+                    continue
+                nb = T.backward_workspace_bytes(self.W * self.capacity, g.tbe.meta.max_dim, g.tbe.meta.total_rows) if dev.type == "cuda" else 0
+                per_group.append(torch.empty(nb + 1024, dtype=torch.uint8, device=dev))
+            self.bwd_ws.append(per_group)
+        self.presort = os.environ.get("TRB_BWD_PRESORT", "1") != "0" and self.capacity > 0
+        self._aux_stream: Optional[torch.cuda.Stream] = None
+        self._prepared: List[Optional[torch.cuda.Event]] = [None] * self.N_ID_SLOTS
         self.psw_grad_buf = torch.zeros(self.W * self.capacity, dtype=torch.float32, device=dev) if weighted else None
         self.dummy = torch.zeros(1, device=dev, requires_grad=True)
         self.step = 0
@@ -350,7 +379,28 @@ class SparsePlane:
             self._overflow_event = torch.cuda.Event()
             self._overflow_event.record(stream)
         self.group.barrier(1)
+        if self.presort and torch.is_grad_enabled() and not self.loopback:
+            self.prepare_backward(slot)
         return RoutedIds(self, slot, self.B_local, [self.B_local] * self.W)
+
+    def prepare_backward(self, slot: int, fork: bool = True) -> None:
+        """Id-dependent half of the fused backward (row keys + radix sort) of the batch in ``slot``, on an auxiliary stream forked
+        from the current one: it overlaps the forward / the previous step instead of sitting between the dense backward and the
+        optimizer update."""
+        cur = torch.cuda.current_stream(self.device)
+        if fork:
+            if self._aux_stream is None:
+                self._aux_stream = torch.cuda.Stream(self.device)
+            aux = self._aux_stream
+            aux.wait_stream(cur)
+        else:
+            aux = cur
+        reg = self.regions(slot)
+        with torch.cuda.stream(aux):
+            self._backward_kernels(reg, slot, 1.0, phase=1)
+            ev = torch.cuda.Event()
+            ev.record(aux)
+        self._prepared[slot] = ev
 
     def _check_overflow(self, wait: bool = False) -> None:
         ev = self._overflow_event
@@ -375,10 +425,13 @@ class SparsePlane:
         return T.IdRegions(values.data_ptr(), int(values.dtype == torch.int64), offsets.data_ptr(), int(offsets.dtype == torch.int64),
                            w.data_ptr() if w is not None else 0, 1, values.numel(), 0, ids.stride()), None
 
-    def _forward_kernels(self, reg: T.IdRegions, out_slot: int) -> None:
+    def _forward_kernels(self, reg: T.IdRegions, out_slot: int, local_only: bool = False) -> None:
         eng = self.eng
         out_ptrs = self.buf.peer_ptrs(self.out_off[out_slot])
         stage_ptrs = [p + self.staging_off + self.rank * self.stage_slab_bytes for p in self.buf.ptrs]
+        if local_only:  # measurement aid (bench.py): the same lookup with every destination aliased to local memory = no NVLink traffic
+            out_ptrs = [self.buf.local_ptr + self.out_off[out_slot]] * self.W
+            stage_ptrs = [self.buf.local_ptr + self.staging_off + self.rank * self.stage_slab_bytes] * self.W
         for g, gm in zip(eng._groups, self.group_meta):
             if gm is None:
                 continue
@@ -437,46 +490,70 @@ class SparsePlane:
 
         p2p.grad_push(grad, self.chunks, self.buf.peer_ptrs(self.inbox_off), self.wire_dtype, self.inbox_pitch, self.rank * self.B_local, 1.0, self.push_vec)
 
-    def _apply_kernels(self, reg: T.IdRegions, grad_scale: float, want_psw: bool) -> None:
+    def _backward_kernels(self, reg: T.IdRegions, id_slot: Optional[int], grad_scale: float, phase: int, want_psw: bool = False,
+                          grad: Optional[torch.Tensor] = None) -> None:
         eng = self.eng
-        grad_ptrs = [self.buf.local_ptr + self.inbox_off]
         Bg = self.W * self.B_local
+        if self.W == 1 and grad is not None:  # one rank: gradient rows are read where autograd left them (no inbox, no copy)
+            grad_ptrs, g_stride, g_dtype, mkey = [grad.data_ptr()], grad.stride(0), grad.dtype, "direct"
+        else:
+            grad_ptrs, g_stride, g_dtype, mkey = [self.buf.local_ptr + self.inbox_off], self.inbox_pitch, self.wire_dtype, "local"
         for gi, (g, gm) in enumerate(zip(eng._groups, self.group_meta)):
             if gm is None:
                 continue
             u0, _ = g.unit_range
             mean = g.pooling == T.PoolingMode.MEAN
             w = reg.window(u0)
-            if want_psw:
-                T.psw_grad_regions(gm["local"], g.tbe.weights, w, mean, grad_ptrs, self.inbox_pitch, self.wire_dtype, Bg, self.psw_grad_buf)
-            g.tbe._pre_update()
-            T.fused_backward_regions(gm["local"], g.tbe.weights, g.tbe.state1, g.tbe.state2, g.tbe.hyper_dev, g.tbe.opt_code, int(g.tbe.weight_decay_mode), w, mean,
-                                     grad_ptrs, self.inbox_pitch, self.wire_dtype, grad_scale, Bg, self.bwd_ws[gi], self.device,
-                                     stochastic_rounding=g.tbe.stochastic_rounding, sr_seed=g.tbe.next_sr_seed() if g.tbe.stochastic_rounding else 0)
+            if want_psw and phase != 1:
+                T.psw_grad_regions(gm[mkey], g.tbe.weights, w, mean, grad_ptrs, g_stride, g_dtype, Bg, self.psw_grad_buf)
+            if phase != 1:
+                g.tbe._pre_update()
+            if id_slot is not None:
+                ws = self.bwd_ws[id_slot][gi]
+            else:  # single-source KJT: positions vary per batch
+                ws = T._workspace(T.backward_workspace_bytes(reg.positions, g.tbe.meta.max_dim, g.tbe.meta.total_rows), self.device)
+            sr = g.tbe.stochastic_rounding and phase != 1
+            T.fused_backward_regions(gm[mkey], g.tbe.weights, g.tbe.state1, g.tbe.state2, g.tbe.hyper_dev, g.tbe.opt_code, int(g.tbe.weight_decay_mode), w, mean,
+                                     grad_ptrs, g_stride, g_dtype, grad_scale, Bg, ws, self.device,
+                                     stochastic_rounding=sr, sr_seed=g.tbe.next_sr_seed() if sr else 0, phase=phase)
+
+    def _apply_kernels(self, reg: T.IdRegions, id_slot: Optional[int], grad_scale: float, want_psw: bool, grad: Optional[torch.Tensor] = None) -> None:
+        prepared = id_slot is not None and self._prepared[id_slot] is not None
+        self._backward_kernels(reg, id_slot, grad_scale, phase=2 if prepared else 0, want_psw=want_psw, grad=grad)
 
     def backward(self, ids, grad: torch.Tensor, grad_scale: float, want_psw: bool = False) -> None:
         reg, id_slot = self._ids_of(ids)
         if reg.n_src == 1:
             # single-source ids: positions = the KJT's id count; the static workspace was sized for W * capacity positions
             assert reg.idx_stride <= self.W * self.capacity, "distributed KJT larger than the plane's id capacity"
-        key = ("bwd", id_slot, grad.data_ptr(), tuple(grad.shape), grad.stride(0), float(grad_scale), bool(want_psw))
+        prepared = id_slot is not None and self._prepared[id_slot] is not None
+        if prepared:
+            torch.cuda.current_stream(self.device).wait_event(self._prepared[id_slot])
+        key = ("bwd", id_slot, grad.data_ptr(), tuple(grad.shape), grad.stride(0), float(grad_scale), bool(want_psw), prepared)
         if self.use_graphs and id_slot is not None and self._graphable():
-            self._run_graphed(key, lambda: self._backward_all(reg, grad, grad_scale, want_psw))
+            self._run_graphed(key, lambda: self._backward_all(reg, id_slot, grad, grad_scale, want_psw))
         else:
-            self._backward_all(reg, grad, grad_scale, want_psw)
+            self._backward_all(reg, id_slot, grad, grad_scale, want_psw)
+        if prepared:
+            self._prepared[id_slot] = None
         self._mark_use(id_slot)
 
-    def _backward_all(self, reg: T.IdRegions, grad: torch.Tensor, grad_scale: float, want_psw: bool) -> None:
+    def _backward_all(self, reg: T.IdRegions, id_slot: Optional[int], grad: torch.Tensor, grad_scale: float, want_psw: bool) -> None:
+        if self.W == 1:
+            self._apply_kernels(reg, id_slot, grad_scale, want_psw, grad=grad)
+            return
         self._push_kernels(grad)
         self.group.barrier(0)
-        self._apply_kernels(reg, grad_scale, want_psw)
+        self._apply_kernels(reg, id_slot, grad_scale, want_psw)
 
     def backward_push(self, grad: torch.Tensor) -> None:
         self._push_kernels(grad)
 
     def backward_apply(self, ids, grad_scale: float, want_psw: bool = False) -> None:
-        reg, _ = self._ids_of(ids)
-        self._apply_kernels(reg, grad_scale, want_psw)
+        reg, id_slot = self._ids_of(ids)
+        self._apply_kernels(reg, id_slot, grad_scale, want_psw)
+        if id_slot is not None:
+            self._prepared[id_slot] = None
 
     # ---- CUDA graphs ---------------------------------------------------------------------------------------------------
     def _graphable(self) -> bool:
@@ -500,10 +577,10 @@ class SparsePlane:
             return
         n0 = _lib.launch_count()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        # thread-local capture mode: the NCCL watchdog / other threads keep issuing (harmless) CUDA calls while we capture
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
             fn()
-        self._graph_launches[key] = _lib.launch_count() - n0
-        _lib.launch_count_add(-self._graph_launches[key]) if False else None
+        self._graph_launches[key] = _lib.launch_count() - n0  # counted once by the capture, executed once by this first replay
         self._graphs[key] = graph
         graph.replay()
 
