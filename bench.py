@@ -383,7 +383,12 @@ def main() -> None:
         globals()["_CPU_BINDING"] = f"{len(_bound)} NUMA-local cpus" if _bound else "unchanged"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group(backend="nccl", device_id=device)
+        pg_opts = None
+        try:  # collectives of the dense gradients must not queue behind the long embedding kernels
+            pg_opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        except Exception:
+            pass
+        dist.init_process_group(backend="nccl", device_id=device, pg_options=pg_opts)
     if args.transport != "auto":
         os.environ["TRB_TRANSPORT"] = args.transport  # "nccl": the internal UNFUSED arm (own lookup kernels + NCCL all-to-alls)
     _lib.lib()
@@ -464,7 +469,8 @@ def main() -> None:
     # ---------------- end-to-end through the public pipeline API ------------------------------------
     e2e: Optional[Dict[str, Any]] = None
     if not args.no_e2e:
-        pipe = TrainPipelineSparseDist(dmp, opt, device)
+        late = bool(int(os.environ.get("TRB_BENCH_LATE_DIST", "1")))
+        pipe = TrainPipelineSparseDist(dmp, opt, device, data_dist_after_forward=late, enqueue_batch_after_forward=late)
 
         def host_iter(n: int):
             for i in range(n):
@@ -505,11 +511,23 @@ def main() -> None:
                 loss_host.copy_(out[0].detach().reshape(1), non_blocking=True)
             torch.cuda.synchronize()
         if rank == 0:
+            # compact per-kernel timeline of the LAST profiled step (stream, start us, duration us, name): what overlaps what
+            try:
+                evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.device_time_total > 0]
+                evs.sort(key=lambda e: e.time_range.start)
+                marks = [e.time_range.start for e in evs if "interaction_fwd" in e.name]
+                t_from = marks[-1] - 400 if marks else (evs[0].time_range.start if evs else 0)
+                with open(args.trace_e2e + ".timeline.txt", "w") as f:
+                    for e in evs:
+                        if e.time_range.start >= t_from:
+                            f.write("%10.1f %8.1f  %s\n" % (e.time_range.start - t_from, e.time_range.elapsed_us(), e.name[:100]))
+            except Exception as ex:  # diagnostics only
+                sys.stderr.write(f"timeline dump failed: {ex}\n")
             prof.export_chrome_trace(args.trace_e2e)
             with open(args.trace_e2e + ".txt", "w") as f:
                 f.write(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=45, max_name_column_width=70))
                 f.write("\n\n")
-                f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=30, max_name_column_width=70))
+                f.write(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=70, max_name_column_width=90))
     if args.profile_host:
         # where does the host time of a step go? (diagnostics only; every rank runs the same steps: the NVLink barriers are collective)
         import cProfile

@@ -10,6 +10,8 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional, Tuple
 
+import os
+
 import torch
 from torch import nn
 
@@ -192,6 +194,18 @@ class DLRM(nn.Module):
         ``dmp.init_data_parallel()``): DDP keeps the parameters' AccumulateGrad nodes alive on the default stream and a capture that
         has to synchronise with the legacy stream is rejected by CUDA (cudaErrorStreamCaptureImplicit)."""
         assert sample_dense_features.is_cuda, "CUDA graphs need CUDA tensors"
+        plane = self._sparse_plane()
+
+        from ..ops import gemm as _gemm
+
+        ext_push = plane is not None and plane.W > 1 and os.environ.get("TRB_PUSH_IN_DENSE_GRAPH", "1") != "0"
+
+        def push_embedding_grads(grads) -> None:
+            # backward of the module INPUTS = last node of the captured backward: the NVLink gradient dist of the embedding gradients
+            # becomes part of the dense backward graph, right behind the interaction backward and beside the deferred weight gradients
+            if ext_push:
+                g = grads[1].reshape(grads[1].shape[0], -1)
+                plane._push_kernels(g if g.stride(1) == 1 else g.contiguous())
 
         class _InterOver(nn.Module):
             def __init__(self, inter: nn.Module, over: nn.Module) -> None:
@@ -199,6 +213,8 @@ class DLRM(nn.Module):
                 self.inter, self.over = inter, over
 
             def forward(self, embedded_dense: torch.Tensor, embedded_sparse: torch.Tensor) -> torch.Tensor:
+                if embedded_dense.is_cuda and torch.is_grad_enabled():
+                    embedded_dense, embedded_sparse = _gemm.DeferredGradJoin.apply(push_embedding_grads, embedded_dense, embedded_sparse)
                 return self.over(self.inter(dense_features=embedded_dense, sparse_features=embedded_sparse))
 
         from ..ops import _lib
@@ -217,13 +233,34 @@ class DLRM(nn.Module):
         s_dense = sample_dense_features.detach().clone()
         s_ed = emb_dense.detach().clone().requires_grad_()
         s_es = sample_embedded_sparse.detach().clone().requires_grad_()
+        if plane is not None and sample_embedded_sparse.numel() == plane.B_local * plane.total_cols and sample_embedded_sparse.dtype == plane.wire_dtype:
+            # the embedding arch's TRAINING output always lands in slot 0 of the plane's symmetric buffer: make that memory the graph's
+            # static input, so that the per-step copy of the [B, F * D] embeddings into the graph (73 us on B200) disappears
+            s_es = plane.out_local(0).view(sample_embedded_sparse.shape).requires_grad_()
         inter_over = _InterOver(self.inter_arch, self.over_arch)
-        g_dense, g_top = torch.cuda.make_graphed_callables((_Dense(self.dense_arch), inter_over), ((s_dense,), (s_ed, s_es)), num_warmup_iters=num_warmup_iters)
+        # capture on a HIGH-priority stream: the captured nodes inherit it, the deferred weight-gradient kernels (side stream, default
+        # priority) then yield to the dgrad chain / gradient push whenever both have work
+        prev_cap = torch.cuda.graph.default_capture_stream
+        torch.cuda.graph.default_capture_stream = torch.cuda.Stream(device=sample_dense_features.device, priority=-1)
+        try:
+            with _gemm.defer_wgrad_scope():
+                g_dense, g_top = torch.cuda.make_graphed_callables((_Dense(self.dense_arch), inter_over), ((s_dense,), (s_ed, s_es)), num_warmup_iters=num_warmup_iters)
+        finally:
+            torch.cuda.graph.default_capture_stream = prev_cap
         # native launches replayed per training step by the two graphs (the host counter only sees the capture): forward + backward
         # were each recorded once after `num_warmup_iters` eager warm-up rounds
         per_step = ((_lib.launch_count() - n0) // (num_warmup_iters + 1)) if _lib.available() else 0
         self.__dict__["_trb_graphs"] = {"dense": g_dense, "top": g_top, "dense_sig": (tuple(s_dense.shape), s_dense.dtype),
-                                        "sparse_sig": (tuple(s_es.shape), s_es.dtype), "launches_per_step": int(per_step)}
+                                        "sparse_sig": (tuple(s_es.shape), s_es.dtype), "launches_per_step": int(per_step),
+                                        "ext_push_plane": plane if ext_push else None}
+
+    def _sparse_plane(self):
+        """The NVLink sparse plane behind the embedding arch (None before its first batch / for unsharded collections)."""
+        eng = getattr(self.sparse_arch.embedding_bag_collection, "_engine", None)
+        if eng is None:
+            return None
+        planes = [p for p in eng.__dict__.get("_planes", {}).values() if p.capacity > 0]
+        return planes[0] if len(planes) == 1 else None
 
     def _graphed(self, dense_features: torch.Tensor):
         g = self.__dict__.get("_trb_graphs")
@@ -258,6 +295,8 @@ class DLRM(nn.Module):
 
                 if embedded_dense is None:
                     embedded_dense = g["dense"](dense_features)
+                if g.get("ext_push_plane") is not None:
+                    g["ext_push_plane"].external_push = True  # this step's gradient push is replayed by the top graph's backward
                 out = g["top"](embedded_dense, embedded_sparse)
                 _lib.add_launches(g["launches_per_step"])
                 return out

@@ -6,6 +6,7 @@
 // load/store them directly over NVSwitch (B300_MICROARCH.md "NVLink": peer LDG.128 ~775 GB/s).
 // NCCL stays the control plane (handle exchange, DDP all-reduce, multi-node fallback).
 #include "common.cuh"
+#include <cstdlib>
 #include <cstring>
 #include <cstdio>
 
@@ -228,36 +229,61 @@ TRB_API int trb_cast_copy(const void* src, int s_dtype, void* dst, int d_dtype, 
 // (peer load latency ~1.8k cycles, B300_MICROARCH.md), and the fused backward afterwards only touches local HBM.
 // Parity: the backward all_to_all_single of the pooled output dist (reference comm_ops.py:1581-1646).
 // ---------------------------------------------------------------------------------------------------------------
-// VEC = elements per chunk (4 or 8). 8-element chunks move 16 B per thread for bf16 gradients (the 4-element version issued
-// 8 B accesses and reached only ~0.8 TB/s of combined local + NVLink traffic on 2 GPUs).
-template <typename S, typename D, int VEC>
+// VEC = elements per chunk (4 or 8). 8-element chunks move 16 B per thread for bf16 gradients.
+//
+// PERSISTENT, narrow launch: the kernel is NVLink-bound (posted peer stores), it needs bytes in flight, not thread slots. The
+// first version launched one thread per chunk (53 k blocks for a DLRM batch): those blocks filled every thread slot of every SM for
+// the whole transfer and starved the weight-gradient GEMMs that are meant to run beside it (timeline: profiles/timeline_n2_r2.md).
+// Now ~2 CTAs per SM walk the chunks with a grid stride, UNR independent 16 B loads in flight per thread before the stores.
+template <typename S, typename D, int VEC, int UNR>
 __global__ void __launch_bounds__(256)
 trb_grad_push_kernel(const S* __restrict__ src, int64_t src_stride, const int32_t* __restrict__ chunks, int n_chunks, TrbPeerPtrs dst, int64_t dst_pitch,
                      int64_t row_base, int B_local, float scale) {
-  const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t) B_local * n_chunks) return;
-  const int64_t b = i / n_chunks;
-  const int c = (int) (i - b * n_chunks);
-  const int rank = chunks[3 * c], sc = chunks[3 * c + 1], dc = chunks[3 * c + 2];
-  const S* sp = src + b * src_stride + sc;
-  D* dp = reinterpret_cast<D*>(dst.p[rank]) + (row_base + b) * dst_pitch + dc;
-  if constexpr (VEC == 8 && sizeof(S) == 2 && sizeof(D) == 2) {
-    uint4 v = *reinterpret_cast<const uint4*>(sp);
-    if (scale != 1.f) {
-      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+  const int64_t total = (int64_t) B_local * n_chunks;
+  const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += stride * UNR) {
+    const S* sp[UNR];
+    D* dp[UNR];
+    bool ok[UNR];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float2 f = __bfloat1622float2(h[q]);
-        h[q] = __floats2bfloat162_rn(f.x * scale, f.y * scale);
-      }
+    for (int u = 0; u < UNR; ++u) {
+      const int64_t i = i0 + u * stride;
+      ok[u] = i < total;
+      const int64_t ii = ok[u] ? i : i0;
+      const int64_t b = total < 0x7fffffffLL ? (int64_t) ((uint32_t) ii / (uint32_t) n_chunks) : ii / n_chunks;
+      const int c = (int) (ii - b * n_chunks);
+      const int rank = chunks[3 * c], sc = chunks[3 * c + 1], dc = chunks[3 * c + 2];
+      sp[u] = src + b * src_stride + sc;
+      dp[u] = reinterpret_cast<D*>(dst.p[rank]) + (row_base + b) * dst_pitch + dc;
     }
-    *reinterpret_cast<uint4*>(dp) = v;
-  } else {
+    if constexpr (VEC == 8 && sizeof(S) == 2 && sizeof(D) == 2) {
+      uint4 v[UNR];
 #pragma unroll
-    for (int q = 0; q < VEC / 4; ++q) {
-      float4 v = Vec4<S>::ld(sp + 4 * q);
-      if (scale != 1.f) v = f4_scale(v, scale);
-      Vec4<D>::st(dp + 4 * q, v);
+      for (int u = 0; u < UNR; ++u) v[u] = *reinterpret_cast<const uint4*>(sp[u]);
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        if (scale != 1.f) {
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v[u]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float2 f = __bfloat1622float2(h[q]);
+            h[q] = __floats2bfloat162_rn(f.x * scale, f.y * scale);
+          }
+        }
+        if (ok[u]) *reinterpret_cast<uint4*>(dp[u]) = v[u];
+      }
+    } else {
+      float4 v[UNR][VEC / 4];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u)
+#pragma unroll
+        for (int q = 0; q < VEC / 4; ++q) v[u][q] = Vec4<S>::ld(sp[u] + 4 * q);
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        if (!ok[u]) continue;
+#pragma unroll
+        for (int q = 0; q < VEC / 4; ++q) Vec4<D>::st(dp[u] + 4 * q, scale != 1.f ? f4_scale(v[u][q], scale) : v[u][q]);
+      }
     }
   }
 }
@@ -270,11 +296,17 @@ TRB_API int trb_grad_push(const void* src, int s_dtype, int64_t src_stride, cons
   TrbPeerPtrs d;
   for (int i = 0; i < n_dst; ++i) d.p[i] = dst_ptrs[i];
   const int threads = 256;
-  const unsigned blocks = (unsigned) ((n + threads - 1) / threads);
+  constexpr int UNR = 4;
+  static const int ctas_per_sm = getenv("TRB_PUSH_CTAS_PER_SM") ? atoi(getenv("TRB_PUSH_CTAS_PER_SM")) : 2;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int64_t want = (n + (int64_t) threads * UNR - 1) / ((int64_t) threads * UNR);
+  const unsigned blocks = (unsigned) (want < (int64_t) sms * ctas_per_sm ? want : (int64_t) sms * ctas_per_sm);
 #define TRB_GP(SC, ST, DC, DT)                                                                                                                           \
   if (s_dtype == SC && d_dtype == DC) {                                                                                                                  \
-    if (vec == 8) trb_grad_push_kernel<ST, DT, 8><<<blocks, threads, 0, stream>>>((const ST*) src, src_stride, chunks, n_chunks, d, dst_pitch, row_base, B_local, scale); \
-    else trb_grad_push_kernel<ST, DT, 4><<<blocks, threads, 0, stream>>>((const ST*) src, src_stride, chunks, n_chunks, d, dst_pitch, row_base, B_local, scale);          \
+    if (vec == 8) trb_grad_push_kernel<ST, DT, 8, UNR><<<blocks, threads, 0, stream>>>((const ST*) src, src_stride, chunks, n_chunks, d, dst_pitch, row_base, B_local, scale); \
+    else trb_grad_push_kernel<ST, DT, 4, UNR><<<blocks, threads, 0, stream>>>((const ST*) src, src_stride, chunks, n_chunks, d, dst_pitch, row_base, B_local, scale);          \
     TRB_CHECK_LAUNCH();                                                                                                                                   \
     return 0;                                                                                                                                             \
   }

@@ -149,6 +149,57 @@ def _wgrad_plan(n_out: int, n_in: int, batch: int, sms: int) -> "tuple[int, int]
     return _best_split(m_tiles * ((n_in + 127) // 128), batch, sms), 128
 
 
+COLSUM_OVERLAP = os.environ.get("TRB_COLSUM_OVERLAP", "1") != "0"
+DEFER_WGRAD = os.environ.get("TRB_DEFER_WGRAD", "1") != "0"
+_COLSUM_STREAMS: dict = {}
+
+
+def _colsum_stream(device: torch.device) -> "torch.cuda.Stream":
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    st = _COLSUM_STREAMS.get(key)
+    if st is None:
+        st = _COLSUM_STREAMS[key] = torch.cuda.Stream(device=device)
+    return st
+
+
+_DEFER_SCOPE = {"on": False}
+
+
+class defer_wgrad_scope:
+    """``with defer_wgrad_scope():`` around a CUDA-graph capture whose module inputs pass through ``DeferredGradJoin``: weight / bias
+    gradients of every ``LinearActFn`` inside are left on the side stream until that node joins them."""
+
+    def __enter__(self):
+        self._prev = _DEFER_SCOPE["on"]
+        _DEFER_SCOPE["on"] = True
+        return self
+
+    def __exit__(self, *exc):
+        _DEFER_SCOPE["on"] = self._prev
+        return False
+
+
+class DeferredGradJoin(torch.autograd.Function):
+    """Identity on the inputs of a module whose backward is captured into a CUDA graph. Its backward is the LAST node of that
+    backward: it runs ``on_backward`` (e.g. the NVLink gradient push of the embedding gradients, so that the transfer is part of the
+    graph and overlaps the deferred weight gradients) and then joins the side stream that carries the deferred wgrad / bias-grad
+    kernels of every ``LinearActFn`` above it."""
+
+    @staticmethod
+    def forward(ctx, on_backward, *tensors):
+        ctx.on_backward = on_backward
+        ctx.device = tensors[0].device
+        return tuple(t.view_as(t) for t in tensors)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        if ctx.on_backward is not None:
+            ctx.on_backward(grads)
+        if ctx.device.type == "cuda":
+            torch.cuda.current_stream(ctx.device).wait_stream(_colsum_stream(ctx.device))
+        return (None,) + tuple(grads)
+
+
 def _pad_k(t: torch.Tensor, Kp: int) -> torch.Tensor:
     if t.shape[1] == Kp:
         return t
@@ -204,6 +255,40 @@ class LinearActFn(torch.autograd.Function):
             gy = (gy.float() * yf * (1.0 - yf)).to(torch.bfloat16)
         M = gy.shape[0]
         gx = gw = gb = None
+        # The weight / bias gradients are OFF the critical chain of the backward (the next layer only needs gx). On CUDA they go to a
+        # side stream: the bias gradient (column sums of gy, a pure HBM stream) runs beside the tensor-core-bound GEMMs, and inside
+        # a CUDA-graph capture the wgrad GEMM is DEFERRED too - the side stream is not joined per layer but once, by the node that
+        # ends the captured backward (``DeferredGradJoin``), so the dgrad chain reaches the embedding gradients early and the NVLink
+        # gradient dist overlaps the remaining wgrad work.
+        want_w = ctx.needs_input_grad[1]
+        want_b = ctx.has_bias and ctx.needs_input_grad[2]
+        capturing = gy.is_cuda and DEFER_WGRAD and _DEFER_SCOPE["on"] and torch.cuda.is_current_stream_capturing()
+        side = None
+        if gy.is_cuda and (want_w or want_b) and (capturing or (COLSUM_OVERLAP and want_b and (ctx.needs_input_grad[0] or want_w))):
+            cur = torch.cuda.current_stream(gy.device)
+            side = _colsum_stream(gy.device)
+            side.wait_stream(cur)
+        if want_b:
+            if side is not None:
+                with torch.cuda.stream(side):
+                    gb = colsum_bf16(gy)
+                gb.record_stream(cur)
+            else:
+                gb = colsum_bf16(gy)
+
+        def wgrad():
+            # gw[N, Kp] = gy^T . x with BOTH operands consumed MN-major straight from their row-major storage
+            split, tile_n = _wgrad_plan(gy.shape[1], xb.shape[1], M, _num_sms(gy.device))
+            g = gemm_bf16(gy, xb, a_mn=True, b_mn=True, out_dtype=torch.float32, split_k=split, tile_n=tile_n)[:, : ctx.K]
+            if g.stride(1) != 1 or g.shape[1] != g.stride(0):
+                g = g.contiguous()
+            return g
+
+        if want_w and capturing:
+            gy.record_stream(side)  # read by the deferred kernels after this node returned and dropped its reference
+            with torch.cuda.stream(side):
+                gw = wgrad()
+            gw.record_stream(cur)
         if ctx.needs_input_grad[0]:
             # dgrad: gx[M, Kp] = gy[M, N] . W[N, Kp]; W is consumed as an MN-major B operand (no transpose)
             if ctx.mask_input and xb.shape[1] == ctx.K:
@@ -215,12 +300,10 @@ class LinearActFn(torch.autograd.Function):
                     gx = gx[:, : ctx.K]
             if ctx.x_dtype != torch.bfloat16:
                 gx = gx.to(ctx.x_dtype)
-        if ctx.needs_input_grad[1]:
-            # wgrad: gw[N, Kp] = gy^T . x with BOTH operands consumed MN-major straight from their row-major storage
-            split, tile_n = _wgrad_plan(gy.shape[1], xb.shape[1], M, _num_sms(gy.device))
-            gw = gemm_bf16(gy, xb, a_mn=True, b_mn=True, out_dtype=torch.float32, split_k=split, tile_n=tile_n)[:, : ctx.K]
-            if gw.stride(1) != 1 or gw.shape[1] != gw.stride(0):
-                gw = gw.contiguous()
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = colsum_bf16(gy)
+        if want_w and not capturing:
+            gw = wgrad()
+        if side is not None and (not capturing or not ctx.needs_input_grad[0]):
+            # eager: the results are consumed right after this node (AccumulateGrad) -> join now. Captured: only the LAST node of the
+            # chain (no input gradient wanted) joins; chains that continue are joined by DeferredGradJoin at the module inputs.
+            torch.cuda.current_stream(gy.device).wait_stream(side)
         return gx, gw, gb, None

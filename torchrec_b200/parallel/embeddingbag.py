@@ -532,7 +532,7 @@ class ShardedEmbeddingBagCollection(
                     ctx.mean_divisor = self._mean_divisor(features.permute(order) if self._has_features_permute else features)
                 if self._dp_tables:
                     ctx.dp_features = features.permute([order[fi] for fi in self._dp_features])
-                return _InputDistAwaitable(NoWait(NoWait(eng.plane_input_dist(features, order, self._total_cols))))
+                return _InputDistAwaitable(NoWait(NoWait(eng.plane_input_dist(features, order, self._total_cols, training=self.training))))
             if not self._post_mean and eng is not None and not eng._row_sharded:
                 # fast path: input order -> unit order in ONE key permutation (feature order, model-parallel subset and unit
                 # replication composed on the host once) instead of three KJT permutes per step

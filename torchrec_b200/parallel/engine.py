@@ -639,14 +639,15 @@ class ShardedLookupEngine(nn.Module):
             planes[key] = pl
         return pl
 
-    def plane_input_dist(self, features: KeyedJaggedTensor, key_of_feature: Optional[List[int]], total_cols: int, capacity: Optional[int] = None):
+    def plane_input_dist(self, features: KeyedJaggedTensor, key_of_feature: Optional[List[int]], total_cols: int, capacity: Optional[int] = None,
+                         training: Optional[bool] = None):
         """NVLink input dist: ONE device-side pass (bucketize + feature permute + peer write, csrc/kjt_route.cu) straight from the
         batch's KJT into the owners' receive regions. No host sync, no size exchange. Returns a ``RoutedIds`` handle."""
         B = features.stride()
         pl = self.plane_for(B, total_cols, features, key_of_feature, capacity)
         n_bags = max(1, len(features.keys()) * B)
         return pl.push_input(features.offsets(), features.values(), features.weights_or_none() if self._is_weighted else None,
-                             avg_len_hint=max(1, features.values().numel() // n_bags))
+                             avg_len_hint=max(1, features.values().numel() // n_bags), training=training)
 
     def fused_lookup_dist(self, dist_features, B_local: int, total_cols: int, grad_scale: float, dp: Optional[Tuple] = None) -> torch.Tensor:
         """Lookup + pooled output dist in one pass: pooled rows are written straight into the owning

@@ -293,6 +293,7 @@ class SparsePlane:
         self.dummy = torch.zeros(1, device=dev, requires_grad=True)
         self.step = 0
         self.eval_step = 0
+        self.external_push = False
         self._last_use: List[Optional[torch.cuda.Event]] = [None] * self.N_ID_SLOTS
         # CUDA graphs of the static phases, keyed by (phase, id slot, out slot)
         self.use_graphs = os.environ.get("TRB_SPARSE_GRAPHS", "1") != "0" and not self.loopback
@@ -349,7 +350,8 @@ class SparsePlane:
                                  lengths=lens.to(torch.int64), stride=self.W * B, stride_per_rank=[B] * self.W)
 
     # ---- phase 1: input dist ------------------------------------------------------------------------------------------
-    def push_input(self, in_offsets: torch.Tensor, in_values: torch.Tensor, in_weights: Optional[torch.Tensor], avg_len_hint: int = 1) -> RoutedIds:
+    def push_input(self, in_offsets: torch.Tensor, in_values: torch.Tensor, in_weights: Optional[torch.Tensor], avg_len_hint: int = 1,
+                   training: Optional[bool] = None) -> RoutedIds:
         """Route the local batch to the owners of the lookup units (peer stores). Returns the handle of the batch."""
         assert in_values.dtype == self.idx_dtype, f"ids are {in_values.dtype}, plane was sized for {self.idx_dtype}"
         slot = self.step % self.N_ID_SLOTS
@@ -379,7 +381,9 @@ class SparsePlane:
             self._overflow_event = torch.cuda.Event()
             self._overflow_event.record(stream)
         self.group.barrier(1)
-        if self.presort and torch.is_grad_enabled() and not self.loopback:
+        if training is None:
+            training = torch.is_grad_enabled()
+        if self.presort and training and not self.loopback:
             self.prepare_backward(slot)
         return RoutedIds(self, slot, self.B_local, [self.B_local] * self.W)
 
@@ -529,20 +533,25 @@ class SparsePlane:
         prepared = id_slot is not None and self._prepared[id_slot] is not None
         if prepared:
             torch.cuda.current_stream(self.device).wait_event(self._prepared[id_slot])
-        key = ("bwd", id_slot, grad.data_ptr(), tuple(grad.shape), grad.stride(0), float(grad_scale), bool(want_psw), prepared)
+        # the producer of `grad` may already have pushed it (DLRM: the push is captured inside the dense backward graph, where it
+        # overlaps the deferred weight gradients); the flag is raised per step by that producer's forward
+        ext = bool(self.external_push) and self.W > 1
+        self.external_push = False
+        key = ("bwd", id_slot, grad.data_ptr(), tuple(grad.shape), grad.stride(0), float(grad_scale), bool(want_psw), prepared, ext)
         if self.use_graphs and id_slot is not None and self._graphable():
-            self._run_graphed(key, lambda: self._backward_all(reg, id_slot, grad, grad_scale, want_psw))
+            self._run_graphed(key, lambda: self._backward_all(reg, id_slot, grad, grad_scale, want_psw, ext))
         else:
-            self._backward_all(reg, id_slot, grad, grad_scale, want_psw)
+            self._backward_all(reg, id_slot, grad, grad_scale, want_psw, ext)
         if prepared:
             self._prepared[id_slot] = None
         self._mark_use(id_slot)
 
-    def _backward_all(self, reg: T.IdRegions, id_slot: Optional[int], grad: torch.Tensor, grad_scale: float, want_psw: bool) -> None:
+    def _backward_all(self, reg: T.IdRegions, id_slot: Optional[int], grad: torch.Tensor, grad_scale: float, want_psw: bool, external_push: bool = False) -> None:
         if self.W == 1:
             self._apply_kernels(reg, id_slot, grad_scale, want_psw, grad=grad)
             return
-        self._push_kernels(grad)
+        if not external_push:
+            self._push_kernels(grad)
         self.group.barrier(0)
         self._apply_kernels(reg, id_slot, grad_scale, want_psw)
 

@@ -253,7 +253,12 @@ class TrainPipelineSparseDist(TrainPipeline[In, Out]):
         custom_model_fwd: Optional[Callable[[Optional[In]], Tuple[torch.Tensor, Out]]] = None,
         dmp_collection_sync_interval_batches: Optional[int] = 1,
         enqueue_batch_after_forward: bool = False,
+        data_dist_after_forward: bool = False,
     ) -> None:
+        # data_dist_after_forward: enqueue the head's forward BEFORE the look-ahead input dist. With a device-side input dist (NVLink
+        # plane: no host sync, a handful of launches) the only cost of the look-ahead is host time, and spending it first leaves the
+        # compute stream idle at the start of every step; the dist kernels still run beside the forward on their own stream.
+        self._data_dist_after_forward = data_dist_after_forward
         self._model = model
         self._optimizer = optimizer
         self._device = device
@@ -471,12 +476,15 @@ class TrainPipelineSparseDist(TrainPipeline[In, Out]):
 
     def _lookahead(self, dataloader_iter: Iterator[In], forward_done: bool) -> None:
         have_next = len(self.batches) >= 2
+        late_dist = getattr(self, "_data_dist_after_forward", False)
         if not forward_done:
-            if have_next:
+            if have_next and not late_dist:
                 self.start_sparse_data_dist(self.batches[1], self.contexts[1])
             if not self._enqueue_batch_after_forward:
                 self.enqueue_batch(dataloader_iter)
             return
+        if have_next and late_dist:
+            self.start_sparse_data_dist(self.batches[1], self.contexts[1])
         if self._enqueue_batch_after_forward:
             self.enqueue_batch(dataloader_iter)
         if have_next:
