@@ -57,9 +57,21 @@ class LoopbackGroup:
     virtual rank sees all of them as its peers. The driver (a test, ``__graft_entry__.smoke``) runs the phases of all
     virtual ranks in lock step on one stream, which is what the device barrier guarantees between real ranks."""
 
-    def __init__(self, world: int, device: torch.device) -> None:
+    def __init__(self, world: int, device: torch.device, peer_devices: Optional[Sequence[torch.device]] = None) -> None:
+        """``peer_devices``: optional device of every virtual rank's buffers. ``[cuda:0, cuda:1]`` puts rank 1's memory on a second GPU
+        of THIS process (peer access enabled), so rank 0's kernels really store over NVLink - the single-process harness that ``ncu``
+        can profile (tools/peer_bench.py)."""
         self.world = world
         self.device = torch.device(device)
+        self.peer_devices = [torch.device(d) for d in peer_devices] if peer_devices is not None else [self.device] * world
+        assert len(self.peer_devices) == world
+        if len({str(d) for d in self.peer_devices}) > 1:
+            L = _lib.lib()
+            idx = sorted({d.index for d in self.peer_devices})
+            for a in idx:
+                for b in idx:
+                    if a != b:
+                        _lib.check(L.trb_enable_peer_access(a, b), f"trb_enable_peer_access({a},{b})")
         self._allocs: Dict[int, List[torch.Tensor]] = {}
         self._views = [_LoopbackView(self, r) for r in range(world)]
 
@@ -74,14 +86,14 @@ class _LoopbackView:
         self.group = group
         self.world = group.world
         self.rank = rank
-        self.device = group.device
+        self.device = group.peer_devices[rank]
         self._seq = 0
 
     def alloc(self, nbytes: int) -> SymmetricBuffer:
         nbytes = _align(nbytes)
         bufs = self.group._allocs.get(self._seq)
         if bufs is None:
-            bufs = self.group._allocs[self._seq] = [torch.zeros(nbytes, dtype=torch.uint8, device=self.device) for _ in range(self.world)]
+            bufs = self.group._allocs[self._seq] = [torch.zeros(nbytes, dtype=torch.uint8, device=self.group.peer_devices[r]) for r in range(self.world)]
         assert bufs[0].numel() == nbytes, "virtual ranks must allocate the same sizes in the same order"
         self._seq += 1
         return SymmetricBuffer(nbytes, bufs[self.rank].data_ptr(), [b.data_ptr() for b in bufs], self.device)
