@@ -216,6 +216,8 @@ def build_ours(args: argparse.Namespace, device, rank: int, world: int):
     per_table = {t.name: rule for t in tables}
     if cfg == "rw100m":
         per_table[tables[0].name] = "row_wise"
+    if world == 1:  # one rank: every sharding type degenerates to the whole table on rank 0
+        per_table = {t.name: "table_wise" for t in tables}
     mode = args.sharding if args.sharding != "auto" else "planner"
     info = {"plan": mode, "rule": rule if cfg != "rw100m" else "row_wise(t_cat_0: 100 M rows) + table_wise"}
     if mode == "planner":

@@ -24,7 +24,7 @@ from ..optim.keyed import CombinedOptimizer, KeyedOptimizer
 from ..sparse.jagged_tensor import JaggedTensor, KeyedJaggedTensor
 from ..streamable import Multistreamable
 from .embedding_types import BaseEmbeddingSharder, KJTList
-from .embeddingbag import EmbeddingFusedOptimizer, _sharded_tensor_from_local, _TableParam, optimizer_spec_from
+from .embeddingbag import EmbeddingFusedOptimizer, _local_pieces_with_offsets, _sharded_tensor_from_local, _sharded_view, _TableParam, optimizer_spec_from
 from .engine import OptimizerSpec, ShardedLookupEngine, TableShard
 from .types import Awaitable, CommOp, LazyAwaitable, NoWait, ParameterSharding, QuantizedCommCodecs, ShardedModule, ShardingEnv, ShardingType
 
@@ -219,7 +219,7 @@ class ShardedEmbeddingCollection(ShardedModule[KJTList, List[torch.Tensor], Dict
                 else:
                     local = [(s_st[n], [s.row_off, s.col_off], [s.rows, s.cols]) for s, _, s_st, _ in shards]
                     gl, size = g, [cfg.num_embeddings, cfg.embedding_dim]
-                st[n] = _sharded_tensor_from_local(local, gl, size, torch.float32, self._pg, self._device.type, local_size, self._env.rank)
+                st[n] = _sharded_view(local, gl, size, torch.float32, self._plan[cfg.name].sharding_type, self._env, self._pg, self._device.type, local_size)
             res[cfg.name] = (self._table_params[cfg.name], st)
         return res
 
@@ -369,8 +369,8 @@ class ShardedEmbeddingCollection(ShardedModule[KJTList, List[torch.Tensor], Dict
                     full[o[0] : o[0] + s[0], o[1] : o[1] + s[1]] = t
                 destination[key] = full
             else:
-                destination[key] = _sharded_tensor_from_local(local, self._global_shards(cfg.name), [cfg.num_embeddings, cfg.embedding_dim], dtype,
-                                                              self._pg, self._device.type, local_size, self._env.rank)
+                destination[key] = _sharded_view(local, self._global_shards(cfg.name), [cfg.num_embeddings, cfg.embedding_dim], dtype,
+                                                 self._plan[cfg.name].sharding_type, self._env, self._pg, self._device.type, local_size)
         return destination
 
     @torch.no_grad()
@@ -387,11 +387,12 @@ class ShardedEmbeddingCollection(ShardedModule[KJTList, List[torch.Tensor], Dict
                 missing.append(key)
                 continue
             src = state_dict[key]
+            pieces = _local_pieces_with_offsets(src)
             for s, w, _, _ in by_table.get(cfg.name, []):
-                if isinstance(src, ShardedTensor):
-                    for sh in src.local_shards():
-                        if list(sh.metadata.shard_offsets) == [s.row_off, s.col_off]:
-                            w.copy_(sh.tensor)
+                if pieces is not None:
+                    for t, off in pieces:
+                        if off == [s.row_off, s.col_off]:
+                            w.copy_(t)
                 else:
                     w.copy_(src[s.row_off : s.row_off + s.rows, s.col_off : s.col_off + s.cols])
         unexpected = [k for k in state_dict.keys() if k not in expected]

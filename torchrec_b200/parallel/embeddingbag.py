@@ -143,6 +143,69 @@ def _sharded_tensor_from_local(local: List[Tuple[torch.Tensor, List[int], List[i
     return ShardedTensor._init_from_local_shards_and_global_metadata(local_shards, md, process_group=pg)
 
 
+_MESH_CACHE: Dict[Tuple[int, str], Any] = {}
+
+
+def _mesh_of(env: ShardingEnv, device_type: str):
+    """1-D device mesh over the sharding group (created once per group; collective on first use)."""
+    mesh = getattr(env, "device_mesh", None)
+    if mesh is not None:
+        return mesh
+    key = (id(env.process_group), device_type)
+    if key not in _MESH_CACHE:
+        from torch.distributed.device_mesh import init_device_mesh
+
+        _MESH_CACHE[key] = init_device_mesh(device_type, (env.world_size,))
+    return _MESH_CACHE[key]
+
+
+def _dtensor_from_local(local: List[Tuple[torch.Tensor, List[int], List[int]]], size: List[int], sharding_type: str, env: ShardingEnv, device_type: str):
+    """``env.output_dtensor`` layout of a sharded table / optimizer state: a ``DTensor`` whose local tensor is a ``LocalShardsWrapper``
+    holding this rank's shards with their offsets (several for column-wise tables), placements by sharding type - whole tables
+    ``Replicate()`` (one owner, every other rank holds no shard), row-sharded ``Shard(0)``, column-sharded and table-row-wise
+    ``Shard(1)``; 2D parallelism prepends ``Replicate()`` over the replica dimension. No communication, no copies.
+    Parity: reference embedding_kernel.py:350-520, sharding/{tw,rw,cw,twrw,grid}_sharding.py DTensorMetadata."""
+    from torch.distributed.tensor import DTensor, Replicate
+    from torch.distributed.tensor import Shard as DShard
+
+    from .shards_wrapper import LocalShardsWrapper
+
+    mesh = _mesh_of(env, device_type)
+    if sharding_type in (ShardingType.TABLE_WISE.value, ShardingType.DATA_PARALLEL.value):
+        inner = Replicate()
+    elif sharding_type == ShardingType.ROW_WISE.value:
+        inner = DShard(0)
+    else:  # COLUMN_WISE, TABLE_COLUMN_WISE, TABLE_ROW_WISE, GRID_SHARD
+        inner = DShard(1) if len(size) > 1 else DShard(0)
+    placements = (Replicate(),) * (mesh.ndim - 1) + (inner,)
+    wrapper = LocalShardsWrapper([t for t, _, _ in local], [tuple(o) for _, o, _ in local])
+    stride = (size[1], 1) if len(size) == 2 else (1,)
+    return DTensor.from_local(wrapper, mesh, placements, run_check=False, shape=torch.Size(size), stride=stride)
+
+
+def _sharded_view(local, global_shards, size, dtype, sharding_type: str, env: ShardingEnv, pg, device_type: str, local_size: int):
+    """State-dict value of a sharded tensor in the layout the environment asks for (DTensor or ShardedTensor)."""
+    if getattr(env, "output_dtensor", False) and pg is not None and dist.is_initialized():
+        return _dtensor_from_local(local, size, sharding_type, env, device_type)
+    return _sharded_tensor_from_local(local, global_shards, size, dtype, pg, device_type, local_size, env.rank)
+
+
+def _local_pieces_with_offsets(src) -> Optional[List[Tuple[torch.Tensor, List[int]]]]:
+    """(tensor, offsets) of the rank-local shards of a ShardedTensor / DTensor(LocalShardsWrapper); None for plain tensors."""
+    if isinstance(src, ShardedTensor):
+        return [(sh.tensor, list(sh.metadata.shard_offsets)) for sh in src.local_shards()]
+    try:
+        from torch.distributed.tensor import DTensor
+    except Exception:  # pragma: no cover
+        return None
+    if isinstance(src, DTensor):
+        loc = src.to_local()
+        if hasattr(loc, "shards_with_offsets"):
+            return [(t, list(o)) for t, o in loc.shards_with_offsets()]
+        return None
+    return None
+
+
 class EmbeddingFusedOptimizer(FusedOptimizer):
     """KeyedOptimizer view over the optimizer state living inside the table kernels. ``step`` is a
     no-op apart from pushing the learning rate (reference batched_embedding_kernel.py:1195-1624)."""
@@ -385,8 +448,8 @@ class ShardedEmbeddingBagCollection(
 
     def prefetch(self, ctx, dist_input) -> None:
         """Stage the rows of an already-distributed batch into the HBM caches of UVM_CACHING tables (prefetch pipeline)."""
-        if self._engine is not None and len(dist_input) > 0:
-            self._engine.prefetch(dist_input[0])
+        if self._engine is not None and len(dist_input) > 0 and isinstance(dist_input[0], KeyedJaggedTensor):
+            self._engine.prefetch(dist_input[0])  # (batches routed through the NVLink plane never hit cached tables: nothing to stage)
 
     def reset_rows(self, table: str, global_rows: torch.Tensor) -> int:
         """Re-initialise rows of a sharded table (managed-collision eviction / ITEP); see engine.reset_rows."""
@@ -451,7 +514,7 @@ class ShardedEmbeddingBagCollection(
                     local = [(s_st[n], [s.row_off, s.col_off], [s.rows, s.cols]) for s, _, s_st, _ in shards]
                     g = gshards
                     size = [cfg.num_embeddings, cfg.embedding_dim]
-                st[n] = _sharded_tensor_from_local(local, g, size, torch.float32, self._pg, self._device.type, local_size, self._env.rank)
+                st[n] = _sharded_view(local, g, size, torch.float32, self._plan[cfg.name].sharding_type, self._env, self._pg, self._device.type, local_size)
             res[cfg.name] = (self._table_params[cfg.name], st)
         return res
 
@@ -691,8 +754,8 @@ class ShardedEmbeddingBagCollection(
             if self._pg is None or not dist.is_initialized():
                 destination[key] = self._assemble_local(cfg, local)
             else:
-                destination[key] = _sharded_tensor_from_local(local, self._global_shards(cfg.name), [cfg.num_embeddings, cfg.embedding_dim],
-                                                              dtype, self._pg, self._device.type, local_size, self._env.rank)
+                destination[key] = _sharded_view(local, self._global_shards(cfg.name), [cfg.num_embeddings, cfg.embedding_dim], dtype,
+                                                 self._plan[cfg.name].sharding_type, self._env, self._pg, self._device.type, local_size)
         return destination
 
     def _assemble_local(self, cfg, local) -> torch.Tensor:
@@ -720,17 +783,16 @@ class ShardedEmbeddingBagCollection(
                 dst = self._dp_tbe.split_embedding_weights()[self._dp_tables.index(ti)]
                 dst.copy_(src.local_tensor() if isinstance(src, ShardedTensor) else src)
                 continue
+            pieces = _local_pieces_with_offsets(src)
             for s, w, _, _ in by_table.get(cfg.name, []):
-                if isinstance(src, ShardedTensor):
-                    found = False
-                    for sh in src.local_shards():
-                        if list(sh.metadata.shard_offsets) == [s.row_off, s.col_off]:
-                            w.copy_(sh.tensor)
-                            found = True
-                    if not found:
-                        raise RuntimeError(f"{key}: no local shard at offsets {[s.row_off, s.col_off]} in the loaded ShardedTensor")
-                else:
-                    w.copy_(src[s.row_off : s.row_off + s.rows, s.col_off : s.col_off + s.cols])
+                if pieces is not None:  # ShardedTensor / DTensor over local shards: match shards by their offsets
+                    hit = [t for t, off in pieces if off == [s.row_off, s.col_off]]
+                    if not hit:
+                        raise RuntimeError(f"{key}: no local shard at offsets {[s.row_off, s.col_off]} in the loaded {type(src).__name__}")
+                    w.copy_(hit[0])
+                else:  # full unsharded tensor (or a plain DTensor's local tensor): slice this shard's window
+                    full = src.full_tensor() if hasattr(src, "full_tensor") and not isinstance(src, ShardedTensor) else src
+                    w.copy_(full[s.row_off : s.row_off + s.rows, s.col_off : s.col_off + s.cols])
         for k in state_dict.keys():
             if k not in expected:
                 unexpected.append(k)
