@@ -164,3 +164,41 @@ def test_annotation_estimator_and_shard_estimators():
     stats = EmbeddingOffloadStats(cacheability=0.3, expected_lookups=1000, mrc_hist_counts=torch.tensor([50.0, 30.0, 15.0, 5.0]), height=300)
     assert stats.expected_miss_rate(0.0) == 1.0 and abs(stats.expected_miss_rate(1.0) - 0.05) < 1e-6
     assert stats.expected_miss_rate(0.2) > stats.expected_miss_rate(0.6)
+
+
+def test_perf_model_matches_measured_fused_kernels():
+    """The planner's table-wise costs for the DLRM headline plan against what the kernels measured on 8 x B200 (profiles/scaling_r2.md):
+    fused lookup + output dist 0.490 ms (lookup alone 0.135 ms) on the rank with 4 tables at W = 8, 0.176 ms / 0.110 ms at W = 2."""
+    import torch
+
+    from torchrec_b200.modules.embedding_configs import EmbeddingBagConfig
+    from torchrec_b200.modules.embedding_modules import EmbeddingBagCollection
+    from torchrec_b200.parallel.embeddingbag import EmbeddingBagCollectionSharder
+    from torchrec_b200.parallel.planner import EmbeddingShardingPlanner, Topology, calibration
+    from torchrec_b200.parallel.planner.types import ParameterConstraints
+
+    hashes = [39884406, 39043, 17289, 7420, 20263, 3, 7120, 1543, 63, 38532951, 2953546, 403346, 10, 2208, 11938, 155, 4, 976, 14, 39979771, 25641295, 39664984,
+              585935, 12972, 108, 36]
+    tables = [EmbeddingBagConfig(name=f"t{i}", embedding_dim=128, num_embeddings=h, feature_names=[f"f{i}"]) for i, h in enumerate(hashes)]
+
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.ebc = EmbeddingBagCollection(tables=tables, device=torch.device("meta"))
+
+    measured = {2: (0.110, 0.176), 8: (0.135, 0.490)}
+    for W, (lookup_ms, fused_ms) in measured.items():
+        planner = EmbeddingShardingPlanner(topology=Topology(world_size=W, local_world_size=W, compute_device="cuda"), batch_size=32768,
+                                           constraints={t.name: ParameterConstraints(sharding_types=["table_wise"], compute_kernels=["fused"]) for t in tables})
+        planner.plan(M(), [EmbeddingBagCollectionSharder(fused_params={"output_dtype": torch.bfloat16})])
+        per = {}
+        for so in planner._best_plan:
+            for sh in so.shards:
+                d = per.setdefault(sh.rank, [0.0, 0.0])
+                d[0] += sh.perf.fwd_compute
+                d[1] += sh.perf.fwd_comms
+        fc, fm = max(per.values(), key=lambda d: d[0] + d[1])
+        assert fc == pytest.approx(lookup_ms, rel=0.35), (W, fc, lookup_ms)
+        assert fc + fm == pytest.approx(fused_ms, rel=0.25), (W, fc + fm, fused_ms)
+    assert calibration.all_to_all_gbps(8) < calibration.all_to_all_gbps(2) < calibration.PEER_STORE_GBPS
+    assert calibration.all_to_all_gbps(4) == pytest.approx(670 * 0.85)

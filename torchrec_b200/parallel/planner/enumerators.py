@@ -18,11 +18,12 @@ import torch
 from torch import nn
 
 from ...modules.embedding_configs import DATA_TYPE_NUM_BITS, DataType
+from ...modules.embedding_configs import dtype_to_data_type as _dtype_to_data_type
 from ..embedding_types import EmbeddingComputeKernel
 from ..sharding_plan import calculate_shard_sizes_and_offsets
 from ..types import CacheParams, KeyValueParams, ModuleSharder, ShardingType
+from .calibration import GRAD_PUSH_EXPOSED, PEER_STORE_GBPS, all_to_all_gbps, fused_overlap
 from .constants import (
-    BATCHED_COPY_PERF_FACTOR,
     BIGINT_DTYPE,
     FULL_BLOCK_EMB_DIM,
     HALF_BLOCK_PENALTY,
@@ -186,7 +187,7 @@ class EmbeddingPerfEstimator(ShardEstimator):
                 raise PlannerError(f"No kernel bandwidth for compute device {topo.compute_device}, compute kernel {so.compute_kernel}")
             W, L = topo.world_size, topo.local_world_size
             intra, inter = topo.intra_host_bw, topo.inter_host_bw
-            comm_bw = intra if W <= L else inter
+            comm_bw = intra * all_to_all_gbps(W) / PEER_STORE_GBPS if W <= L else inter  # measured all-to-all efficiency of this world size
             n_row_shards = len({(s.offset[0], s.size[0]) for s in so.shards})
             for shard in so.shards:
                 rows, cols = shard.size
@@ -229,9 +230,8 @@ class EmbeddingPerfEstimator(ShardEstimator):
                             bwd_comms = fwd_comms
                     if W <= L and st in (ShardingType.TABLE_WISE.value, ShardingType.COLUMN_WISE.value, ShardingType.TABLE_COLUMN_WISE.value):
                         # fused lookup + NVLink store: transfer overlaps the gathers tile by tile
-                        overlap = min(fwd_compute, fwd_comms)
-                        fwd_comms -= overlap * 0.8
-                        bwd_comms -= min(bwd_compute, bwd_comms) * 0.8
+                        fwd_comms -= min(fwd_compute, fwd_comms) * fused_overlap(W)
+                        bwd_comms *= GRAD_PUSH_EXPOSED  # pushed from inside the dense backward graph, beside the deferred wgrad GEMMs
                 input_dist = ids * BIGINT_DTYPE * remote_frac / comm_bw if st != ShardingType.DATA_PARALLEL.value else 0.0
                 prefetch_compute = 0.0
                 if prefetch and caching_ratio is not None:
@@ -303,13 +303,19 @@ class EmbeddingEnumerator(Enumerator):
                             continue
                         if sharding_type == ShardingType.COLUMN_WISE.value and len(shard_sizes) > self._world_size:
                             continue
+                        # wire / output dtype of the pooled embeddings: the constraint wins, else the sharder's fused_params["output_dtype"]
+                        sharder_out_dtype = None
+                        fp = getattr(sharder, "fused_params", None) or {}
+                        if fp.get("output_dtype") is not None:
+                            od = fp["output_dtype"]
+                            sharder_out_dtype = od if isinstance(od, DataType) else _dtype_to_data_type(od)
                         sharding_options_per_table.append(ShardingOption(
                             name=name, tensor=param, module=(child_path, child_module), input_lengths=input_lengths, batch_size=self._batch_size,
                             compute_kernel=compute_kernel, sharding_type=sharding_type, partition_by=get_partition_by_type(sharding_type),
                             shards=[Shard(size=list(size), offset=list(offset)) for size, offset in zip(shard_sizes, shard_offsets)],
                             cache_params=c.cache_params if c else None, enforce_hbm=c.enforce_hbm if c else None,
                             stochastic_rounding=c.stochastic_rounding if c else None, bounds_check_mode=c.bounds_check_mode if c else None,
-                            feature_names=feature_by_table.get(name), output_dtype=c.output_dtype if c else None,
+                            feature_names=feature_by_table.get(name), output_dtype=(c.output_dtype if c and c.output_dtype is not None else sharder_out_dtype),
                             key_value_params=c.key_value_params if c else None,
                         ))
                         sharding_options_per_table[-1].is_weighted = is_weighted

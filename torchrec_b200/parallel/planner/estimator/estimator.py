@@ -18,6 +18,7 @@ from torch import nn
 
 from ...embedding_types import EmbeddingComputeKernel
 from ...types import ModuleSharder, ShardingType
+from .. import calibration as CAL
 from .. import constants as K
 from ..types import ParameterConstraints, Perf, PlannerError, ShardEstimator, ShardingOption, Topology
 import importlib
@@ -116,7 +117,6 @@ class EmbeddingShardingPerfEvaluator(ABC):
 
 class TableWiseEvaluator(EmbeddingShardingPerfEvaluator):
     sharding_type = ShardingType.TABLE_WISE.value
-    _FUSED_OVERLAP = 0.8  # share of the NVLink stores hidden behind the gathers by the fused lookup + dist kernel (measured, profiles/)
 
     def fwd_comms(self, ctx: ShardPerfContext) -> float:
         return ctx.num_bags * ctx.shard_cols * ctx.fwd_a2a_comm_data_type_size * self._remote_fraction(ctx) / ctx.comms_bw if ctx.is_pooled else \
@@ -126,9 +126,18 @@ class TableWiseEvaluator(EmbeddingShardingPerfEvaluator):
         rows = ctx.num_bags if ctx.is_pooled else ctx.num_ids
         return rows * ctx.shard_cols * ctx.bwd_a2a_comm_data_type_size * self._remote_fraction(ctx) / ctx.comms_bw
 
+    def bwd_comms(self, ctx: ShardPerfContext) -> float:  # noqa: F811 - fused variant below wraps the plain formula
+        rows = ctx.num_bags if ctx.is_pooled else ctx.num_ids
+        full = rows * ctx.shard_cols * ctx.bwd_a2a_comm_data_type_size * self._remote_fraction(ctx) / ctx.comms_bw
+        if ctx.world_size <= ctx.local_world_size and ctx.compute_device == "cuda" and ctx.is_pooled:
+            # the gradient push is captured inside the dense backward graph and runs beside the deferred weight-gradient GEMMs
+            full *= CAL.GRAD_PUSH_EXPOSED
+        return full
+
     def _overlap(self, ctx: ShardPerfContext, compute: float, comms: float):
+        # fused lookup + output dist: T = lookup + transfer - overlap(W) * min(lookup, transfer)   (measured at W = 2 and W = 8)
         if ctx.world_size <= ctx.local_world_size and ctx.compute_device == "cuda":
-            comms -= min(compute, comms) * self._FUSED_OVERLAP
+            comms -= min(compute, comms) * CAL.fused_overlap(ctx.world_size)
         return compute, comms
 
 

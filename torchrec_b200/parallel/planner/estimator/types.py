@@ -85,7 +85,13 @@ class HardwarePerfConfig:
         return K.kernel_bw_lookup(compute_device, compute_kernel, self.hbm_mem_bw, self.ddr_mem_bw, self.hbm_to_ddr_mem_bw, caching_ratio, prefetch_pipeline)
 
     def get_comms_bw(self, world_size: int, local_world_size: int) -> float:
-        return self.intra_host_bw if world_size <= local_world_size else self.inter_host_bw
+        """Per-direction bytes / ms of one rank inside the job's all-to-all: inside one NVLink domain the measured all-to-all efficiency of
+        that world size applies to the single-peer rate (``planner/calibration.py``); across hosts the NIC is the limit."""
+        if world_size > local_world_size:
+            return self.inter_host_bw
+        from ..calibration import ALL_TO_ALL_EFFICIENCY, PEER_STORE_GBPS, all_to_all_gbps
+
+        return self.intra_host_bw * all_to_all_gbps(world_size) / PEER_STORE_GBPS
 
 
 @dataclass
