@@ -118,6 +118,155 @@ __global__ void __launch_bounds__(256) qtbe_fwd_kernel(const QTbeParams p) {
   }
 }
 
+// ---- 8-bit fast path (INT8 row-wise / FP8 block-scaled, every table of the launch in that one format) --------------------------------
+// Serving batches are dominated by short bags (Criteo: one id per bag). The generic kernel above keeps ONE 4-byte-per-lane row in
+// flight per warp (130-byte rows: ~5 % of the HBM rate). Here 8 lanes own a bag and read a row as 16 B vectors (a 128-element fp8
+// row is exactly one load per lane), every 8-lane group works on U bags at once with the first row of all of them in flight together,
+// and a lane writes 16 consecutive outputs (32 B of bf16).
+template <int FMT>
+__device__ __forceinline__ void dequant16(const uint8_t* row, int D, int e, const uint4 q, float (&v)[16]) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+  if constexpr (FMT == FMT_FP8_BLOCK) {
+    const float s = __half2float(*reinterpret_cast<const __half*>(row + D + (e >> 5) * 2));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __nv_fp8x4_e4m3 x = *reinterpret_cast<const __nv_fp8x4_e4m3*>(&w[k]);
+      const float4 f = static_cast<float4>(x);
+      v[4 * k] = f.x * s; v[4 * k + 1] = f.y * s; v[4 * k + 2] = f.z * s; v[4 * k + 3] = f.w * s;
+    }
+  } else {  // FMT_INT8: value * scale + bias, fp16 (scale, bias) behind the D payload bytes
+    const __half2 sb = *reinterpret_cast<const __half2*>(row + D);
+    const float s = __low2float(sb), b = __high2float(sb);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[4 * k] = (w[k] & 0xff) * s + b; v[4 * k + 1] = ((w[k] >> 8) & 0xff) * s + b;
+      v[4 * k + 2] = ((w[k] >> 16) & 0xff) * s + b; v[4 * k + 3] = (w[k] >> 24) * s + b;
+    }
+  }
+}
+
+template <typename O>
+__device__ __forceinline__ void store16(O* dst, const float (&a)[16]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) Vec4<O>::st(dst + 4 * k, make_float4(a[4 * k], a[4 * k + 1], a[4 * k + 2], a[4 * k + 3]));
+}
+
+template <typename O, int FMT, int MAXV, int U>
+__global__ void __launch_bounds__(256) qtbe_fwd_vec_kernel(const QTbeParams p) {
+  constexpr int LPR = 8;
+  const int lig = threadIdx.x & (LPR - 1);
+  const int64_t group = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+  const int64_t n_bags = (int64_t) p.F * p.B;
+  const int64_t bag0 = group * U;
+  if (bag0 >= n_bags) return;
+  float acc[U][MAXV][16];
+  int64_t st[U], en[U];
+  const uint8_t* wb[U];
+  int64_t rb[U], rows[U];
+  int D[U], col[U], b_of[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int64_t bag = bag0 + u < n_bags ? bag0 + u : n_bags - 1;
+    const int f = (int) (bag / p.B);
+    b_of[u] = (int) (bag - (int64_t) f * p.B);
+    D[u] = p.feat_dim[f];
+    col[u] = p.feat_col[f];
+    rows[u] = p.feat_rows[f];
+    rb[u] = p.feat_row_bytes[f];
+    wb[u] = p.weights + p.feat_woff[f];
+    st[u] = trb_ld_idx(p.offsets, bag, p.off64);
+    en[u] = bag0 + u < n_bags ? trb_ld_idx(p.offsets, bag + 1, p.off64) : st[u];
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k)
+#pragma unroll
+      for (int e = 0; e < 16; ++e) acc[u][k][e] = 0.f;
+  }
+  // first id of every bag: all U x MAXV row vectors in flight before any is consumed
+  uint4 q[U][MAXV];
+  float w0[U];
+  const uint8_t* row0[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    w0[u] = 0.f;
+    row0[u] = wb[u];
+    if (en[u] > st[u]) {
+      const int64_t idx = trb_ld_idx(p.indices, st[u], p.idx64);
+      if (idx >= 0 && idx < rows[u]) {
+        w0[u] = p.psw ? p.psw[st[u]] : 1.f;
+        row0[u] = wb[u] + idx * rb[u];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const int e = (lig + k * LPR) * 16;
+      q[u][k] = (e < D[u]) ? *reinterpret_cast<const uint4*>(row0[u] + e) : make_uint4(0, 0, 0, 0);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const int e = (lig + k * LPR) * 16;
+      if (e < D[u] && w0[u] != 0.f) {
+        float v[16];
+        dequant16<FMT>(row0[u], D[u], e, q[u][k], v);
+#pragma unroll
+        for (int t = 0; t < 16; ++t) acc[u][k][t] = v[t] * w0[u];
+      }
+    }
+    // the rest of the bag (pooling factor > 1)
+    for (int64_t j = st[u] + 1; j < en[u]; ++j) {
+      const int64_t idx = trb_ld_idx(p.indices, j, p.idx64);
+      if (idx < 0 || idx >= rows[u]) continue;
+      const float w = p.psw ? p.psw[j] : 1.f;
+      const uint8_t* row = wb[u] + idx * rb[u];
+#pragma unroll
+      for (int k = 0; k < MAXV; ++k) {
+        const int e = (lig + k * LPR) * 16;
+        if (e < D[u]) {
+          float v[16];
+          dequant16<FMT>(row, D[u], e, *reinterpret_cast<const uint4*>(row + e), v);
+#pragma unroll
+          for (int t = 0; t < 16; ++t) acc[u][k][t] = fmaf(v[t], w, acc[u][k][t]);
+        }
+      }
+    }
+    if (bag0 + u >= n_bags) continue;
+    const float inv = (p.mean && en[u] > st[u]) ? 1.f / (float) (en[u] - st[u]) : 1.f;
+    O* dst = reinterpret_cast<O*>(p.out) + (int64_t) b_of[u] * p.out_stride + col[u];
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const int e = (lig + k * LPR) * 16;
+      if (e < D[u]) {
+        if (inv != 1.f) {
+#pragma unroll
+          for (int t = 0; t < 16; ++t) acc[u][k][t] *= inv;
+        }
+        store16<O>(dst + e, acc[u][k]);
+      }
+    }
+  }
+}
+
+template <typename O, int FMT>
+static int launch_q_vec(const QTbeParams& p, int max_dim, cudaStream_t stream) {
+  const int64_t n_bags = (int64_t) p.F * p.B;
+  if (n_bags == 0) return 0;
+  const int threads = 256;
+#define TRB_QVEC(MAXV, U)                                                                                     \
+  {                                                                                                           \
+    const int64_t groups = (n_bags + U - 1) / U;                                                              \
+    const unsigned blocks = (unsigned) ((groups * 8 + threads - 1) / threads);                                \
+    qtbe_fwd_vec_kernel<O, FMT, MAXV, U><<<blocks, threads, 0, stream>>>(p);                                  \
+  }
+  if (max_dim <= 128) TRB_QVEC(1, 4)
+  else if (max_dim <= 256) TRB_QVEC(2, 2)
+  else TRB_QVEC(4, 1)
+#undef TRB_QVEC
+  TRB_CHECK_LAUNCH();
+  return 0;
+}
+
 // sequence (unpooled): one warp per id position
 template <typename O>
 __global__ void __launch_bounds__(256) qtbe_seq_kernel(const QTbeParams p, int64_t total) {
@@ -143,8 +292,12 @@ __global__ void __launch_bounds__(256) qtbe_seq_kernel(const QTbeParams p, int64
 }
 
 template <typename O>
-static int launch_q(const QTbeParams& p, int max_dim, int64_t total, cudaStream_t stream) {
+static int launch_q(const QTbeParams& p, int max_dim, int64_t total, int uniform_fmt, cudaStream_t stream) {
   const int threads = 256;
+  if (p.pooled && max_dim <= 512 && max_dim % 16 == 0) {
+    if (uniform_fmt == FMT_FP8_BLOCK) return launch_q_vec<O, FMT_FP8_BLOCK>(p, max_dim, stream);
+    if (uniform_fmt == FMT_INT8) return launch_q_vec<O, FMT_INT8>(p, max_dim, stream);
+  }
   if (!p.pooled) {
     if (total == 0) return 0;
     qtbe_seq_kernel<O><<<(unsigned) ((total * 32 + threads - 1) / threads), threads, 0, stream>>>(p, total);
@@ -163,19 +316,33 @@ static int launch_q(const QTbeParams& p, int max_dim, int64_t total, cudaStream_
   return 0;
 }
 
+TRB_API int trb_qtbe_fwd_ex(const void* weights, const int64_t* feat_woff, const int64_t* feat_rows, const int32_t* feat_dim, const int32_t* feat_col,
+                            const int32_t* feat_fmt, const int32_t* feat_row_bytes, const void* indices, int idx64, const void* offsets, int off64,
+                            const float* psw, void* out, int out_dtype, int64_t out_stride, int B, int F, int max_dim, int mean, int pooled,
+                            int64_t total, int uniform_fmt, cudaStream_t stream);
+
 TRB_API int trb_qtbe_fwd(const void* weights, const int64_t* feat_woff, const int64_t* feat_rows, const int32_t* feat_dim, const int32_t* feat_col,
                          const int32_t* feat_fmt, const int32_t* feat_row_bytes, const void* indices, int idx64, const void* offsets, int off64,
                          const float* psw, void* out, int out_dtype, int64_t out_stride, int B, int F, int max_dim, int mean, int pooled,
                          int64_t total, cudaStream_t stream) {
+  return trb_qtbe_fwd_ex(weights, feat_woff, feat_rows, feat_dim, feat_col, feat_fmt, feat_row_bytes, indices, idx64, offsets, off64, psw, out, out_dtype,
+                         out_stride, B, F, max_dim, mean, pooled, total, -1, stream);
+}
+
+// `uniform_fmt`: the row format shared by EVERY table of the launch with all dims % 16 == 0 (enables the vector fast path), or -1
+TRB_API int trb_qtbe_fwd_ex(const void* weights, const int64_t* feat_woff, const int64_t* feat_rows, const int32_t* feat_dim, const int32_t* feat_col,
+                            const int32_t* feat_fmt, const int32_t* feat_row_bytes, const void* indices, int idx64, const void* offsets, int off64,
+                            const float* psw, void* out, int out_dtype, int64_t out_stride, int B, int F, int max_dim, int mean, int pooled,
+                            int64_t total, int uniform_fmt, cudaStream_t stream) {
   QTbeParams p;
   p.weights = reinterpret_cast<const uint8_t*>(weights);
   p.feat_woff = feat_woff; p.feat_rows = feat_rows; p.feat_dim = feat_dim; p.feat_col = feat_col; p.feat_fmt = feat_fmt;
   p.feat_row_bytes = feat_row_bytes; p.indices = indices; p.offsets = offsets; p.psw = psw; p.out = out; p.out_stride = out_stride;
   p.B = B; p.F = F; p.idx64 = idx64; p.off64 = off64; p.mean = mean; p.pooled = pooled;
   switch (out_dtype) {
-    case TRB_F32: return launch_q<float>(p, max_dim, total, stream);
-    case TRB_F16: return launch_q<__half>(p, max_dim, total, stream);
-    case TRB_BF16: return launch_q<__nv_bfloat16>(p, max_dim, total, stream);
+    case TRB_F32: return launch_q<float>(p, max_dim, total, uniform_fmt, stream);
+    case TRB_F16: return launch_q<__half>(p, max_dim, total, uniform_fmt, stream);
+    case TRB_BF16: return launch_q<__nv_bfloat16>(p, max_dim, total, uniform_fmt, stream);
   }
   return -3;
 }

@@ -115,6 +115,9 @@ class QuantTableBatchedEmbeddingBags(nn.Module):
             self.register_buffer("feat_fmt", mk32([FMT[self.embedding_specs[t][3]] for t in fm]), persistent=False)
             self.register_buffer("feat_rb", mk32([self._row_bytes[t] for t in fm]), persistent=False)
         self.max_dim = max(self._h_dim) if self._h_dim else 0
+        fmts = {FMT[dt] for _, _, _, dt in self.embedding_specs}
+        aligned = all(d % 16 == 0 for d in self._h_dim) and all(rb % 16 == 0 for rb in self._row_bytes)
+        self._uniform_fmt = next(iter(fmts)) if len(fmts) == 1 and aligned else -1  # enables the 16-byte vector kernel for INT8 / FP8 tables
 
     def split_embedding_weights(self) -> List[torch.Tensor]:
         """Per table uint8 [rows, row_bytes] views."""
@@ -144,12 +147,12 @@ class QuantTableBatchedEmbeddingBags(nn.Module):
             out = torch.empty(n, D, dtype=self.output_dtype, device=self.weights.device)
             stride = D
         L = _lib.lib()
-        code = L.trb_qtbe_fwd(_lib.ptr(self.weights), _lib.ptr(self.feat_woff), _lib.ptr(self.feat_rows), _lib.ptr(self.feat_dim), _lib.ptr(self.feat_col),
+        code = L.trb_qtbe_fwd_ex(_lib.ptr(self.weights), _lib.ptr(self.feat_woff), _lib.ptr(self.feat_rows), _lib.ptr(self.feat_dim), _lib.ptr(self.feat_col),
                               _lib.ptr(self.feat_fmt), _lib.ptr(self.feat_rb), _lib.ptr(indices), 1 if indices.dtype == torch.int64 else 0,
                               _lib.ptr(offsets), 1 if offsets.dtype == torch.int64 else 0, _lib.ptr(per_sample_weights), _lib.ptr(out),
                               _lib.dtype_code(self.output_dtype), ctypes.c_int64(stride), B, F, self.max_dim, int(self.pooling_mode == 1), int(pooled),
-                              ctypes.c_int64(n), _lib.stream_ptr(self.weights.device))
-        _lib.check(code, "trb_qtbe_fwd")
+                              ctypes.c_int64(n), int(self._uniform_fmt), _lib.stream_ptr(self.weights.device))
+        _lib.check(code, "trb_qtbe_fwd_ex")
         return out
 
     def _ref_forward(self, indices, offsets, psw, B: int, pooled: bool) -> torch.Tensor:

@@ -284,7 +284,8 @@ class EmbeddingEnumerator(Enumerator):
                 if len(input_lengths) == 1 and n_feat > 1:
                     input_lengths = input_lengths * n_feat
                 sharding_options_per_table: List[ShardingOption] = []
-                for sharding_type in self._filter_sharding_types(name, sharder.sharding_types(self._compute_device)):
+                allowed_sharding_types = self._filter_sharding_types(name, sharder.sharding_types(self._compute_device))
+                for sharding_type in allowed_sharding_types:
                     for compute_kernel in self._filter_compute_kernels(name, sharder.compute_kernels(sharding_type, self._compute_device), sharding_type):
                         col_wise_shard_dim = c.min_partition if c else None
                         try:
@@ -297,11 +298,10 @@ class EmbeddingEnumerator(Enumerator):
                             continue  # identical to table-wise
                         if sharding_type == ShardingType.GRID_SHARD.value and (self._world_size <= self._local_world_size or len(shard_sizes) == self._local_world_size):
                             continue  # needs several hosts and several column shards
-                        if sharding_type in (ShardingType.TABLE_ROW_WISE.value,) and self._world_size <= self._local_world_size:
-                            continue  # equals row-wise on one NVLink domain
+                        if sharding_type in (ShardingType.TABLE_ROW_WISE.value,) and self._world_size <= self._local_world_size and \
+                                ShardingType.ROW_WISE.value in allowed_sharding_types:
+                            continue  # equals row-wise on one NVLink domain (kept when it is the only type the user allows)
                         if sharding_type == ShardingType.TABLE_COLUMN_WISE.value and (self._world_size <= self._local_world_size or len(shard_sizes) > self._local_world_size):
-                            continue
-                        if sharding_type == ShardingType.COLUMN_WISE.value and len(shard_sizes) > self._world_size:
                             continue
                         # wire / output dtype of the pooled embeddings: the constraint wins, else the sharder's fused_params["output_dtype"]
                         sharder_out_dtype = None
