@@ -361,7 +361,9 @@ def fp8_inference_qps(args, dmp, device, rank: int, world: int, keys, hashes) ->
     ms = e0.elapsed_time(e1) / n
     row_bytes = args.embedding_dim + args.embedding_dim // 32 * 2
     return {"format": "FP8_BLOCK (e4m3, fp16 scale / 32 elems)", "samples_per_s_per_gpu": B / (ms * 1e-3), "ms_per_batch": ms,
-            "table_bytes": int(sum(rows)) * row_bytes, "gathered_gbps": len(rows) * B * row_bytes / (ms * 1e-3) / 1e9, "out_shape": list(out.shape)}
+            "table_bytes": int(sum(rows)) * row_bytes, "gathered_gbps": len(rows) * B * row_bytes / (ms * 1e-3) / 1e9,
+            "hbm_gbps_rows_plus_bf16_output": len(rows) * B * (row_bytes + args.embedding_dim * 2) / (ms * 1e-3) / 1e9,
+            "l2_policy": "16 distinct one-hot batches (1.9 GB of rows) cycled: no batch is served from the 126 MB L2", "out_shape": list(out.shape)}
 
 
 def main() -> None:

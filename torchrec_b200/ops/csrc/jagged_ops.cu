@@ -94,3 +94,104 @@ TRB_API int trb_row_copy(void* dst, const int64_t* dst_idx, const void* src, con
   TRB_CHECK_LAUNCH();
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// jagged [sum L, D] <-> padded dense [N, max_len, D]   (fbgemm jagged_to_padded_dense / dense_to_jagged, reference
+// sparse/jagged_tensor.py:1001, 1059). One thread per 4-byte word of an output row slot; D_words = row bytes / 4.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) jagged_to_padded_kernel(const uint32_t* __restrict__ values, const int64_t* __restrict__ offsets, uint32_t* __restrict__ out,
+                                                                int64_t N, int max_len, int D_words, uint32_t pad_word) {
+  const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = N * max_len * D_words;
+  if (i >= total) return;
+  const int w = (int) (i % D_words);
+  const int64_t slot = i / D_words;
+  const int pos = (int) (slot % max_len);
+  const int64_t seg = slot / max_len;
+  const int64_t s = offsets[seg], e = offsets[seg + 1];
+  out[i] = (s + pos < e) ? values[(s + pos) * D_words + w] : pad_word;
+}
+
+TRB_API int trb_jagged_to_padded_dense(const void* values, const int64_t* offsets, void* out, int64_t N, int max_len, int row_bytes, uint32_t pad_word,
+                                       cudaStream_t stream) {
+  if (row_bytes % 4) return -2;
+  const int64_t total = N * max_len * (row_bytes / 4);
+  if (total == 0) return 0;
+  jagged_to_padded_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, stream>>>((const uint32_t*) values, offsets, (uint32_t*) out, N, max_len, row_bytes / 4, pad_word);
+  TRB_CHECK_LAUNCH();
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) padded_to_jagged_kernel(const uint32_t* __restrict__ dense, const int64_t* __restrict__ offsets, uint32_t* __restrict__ out,
+                                                                int64_t N, int max_len, int D_words) {
+  const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = N * max_len * D_words;
+  if (i >= total) return;
+  const int w = (int) (i % D_words);
+  const int64_t slot = i / D_words;
+  const int pos = (int) (slot % max_len);
+  const int64_t seg = slot / max_len;
+  const int64_t s = offsets[seg], e = offsets[seg + 1];
+  if (s + pos < e) out[(s + pos) * D_words + w] = dense[i];
+}
+
+TRB_API int trb_dense_to_jagged(const void* dense, const int64_t* offsets, void* out, int64_t N, int max_len, int row_bytes, cudaStream_t stream) {
+  if (row_bytes % 4) return -2;
+  const int64_t total = N * max_len * (row_bytes / 4);
+  if (total == 0) return 0;
+  padded_to_jagged_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, stream>>>((const uint32_t*) dense, offsets, (uint32_t*) out, N, max_len, row_bytes / 4);
+  TRB_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// segment_sum_csr: out[s] = sum(values[csr_seg[s] * batch .. csr_seg[s+1] * batch))   (fbgemm segment_sum_csr; KJT length_per_key
+// on device, mean-pooling divisors: reference sparse/jagged_tensor.py:1342, distributed/embeddingbag.py:2560). One warp per segment.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, typename S>
+__global__ void __launch_bounds__(256) segment_sum_csr_kernel(const T* __restrict__ values, const S* __restrict__ csr, T* __restrict__ out, int64_t n_seg, int batch) {
+  const int lane = threadIdx.x & 31;
+  const int64_t seg = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (seg >= n_seg) return;
+  const int64_t s = (int64_t) csr[seg] * batch, e = (int64_t) csr[seg + 1] * batch;
+  double acc = 0.0;
+  for (int64_t i = s + lane; i < e; i += 32) acc += (double) values[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[seg] = (T) acc;
+}
+
+TRB_API int trb_segment_sum_csr(const void* values, int v_dtype, const void* csr, int csr64, void* out, int64_t n_seg, int batch, cudaStream_t stream) {
+  if (n_seg == 0) return 0;
+  const unsigned blocks = (unsigned) ((n_seg * 32 + 255) / 256);
+#define TRB_SS(VT, ST) segment_sum_csr_kernel<VT, ST><<<blocks, 256, 0, stream>>>((const VT*) values, (const ST*) csr, (VT*) out, n_seg, batch)
+  if (v_dtype == TRB_F32) { if (csr64) TRB_SS(float, int64_t); else TRB_SS(float, int32_t); }
+  else if (v_dtype == TRB_I64) { if (csr64) TRB_SS(int64_t, int64_t); else TRB_SS(int64_t, int32_t); }
+  else if (v_dtype == TRB_I32) { if (csr64) TRB_SS(int32_t, int64_t); else TRB_SS(int32_t, int32_t); }
+  else return -3;
+#undef TRB_SS
+  TRB_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// permute_pooled_embs: column-block permutation of [B, sum D] (restores the feature order after a column-wise output dist; its own
+// backward with the inverse permutation). Block k of the OUTPUT starts at out_off[k], has width dims[k] and comes from in_off[k].
+// Reference: fbgemm permute_pooled_embs_auto_grad, called at distributed/embeddingbag.py:1665, sharding/cw_sharding.py:305.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) permute_pooled_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const int32_t* __restrict__ col_src, int64_t B,
+                                                              int cols_words) {
+  const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * cols_words) return;
+  const int c = (int) (i % cols_words);
+  const int64_t b = i / cols_words;
+  out[i] = in[b * cols_words + col_src[c]];
+}
+
+TRB_API int trb_permute_pooled_embs(const void* in, void* out, const int32_t* col_src_words, int64_t B, int cols_words, cudaStream_t stream) {
+  const int64_t n = B * cols_words;
+  if (n == 0) return 0;
+  permute_pooled_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>((const uint32_t*) in, (uint32_t*) out, col_src_words, B, cols_words);
+  TRB_CHECK_LAUNCH();
+  return 0;
+}

@@ -39,6 +39,10 @@ struct RouteParams {
   TrbPeerPtrs out_val;      // per destination: MY region's ids [capacity]
   TrbPeerPtrs out_wgt;      // per destination: MY region's per-id weights (or nullptr)
   int64_t* unbucketize;     // optional [n_in * fc]: routed position of (input id j, column slice c)
+  int64_t* pos_out;         // optional [capacity]: position of the id inside its ORIGINAL bag (single-destination / compact mode)
+  const int64_t* u_wrap;    // optional [U]: ids >= u_wrap[u] (past the last block of the table) are dealt round-robin: kept by the unit
+  const int32_t* u_wrap_rem;  //             whose remainder id % wrap_mod equals u_wrap_rem[u], with local id = id / wrap_mod
+  int32_t wrap_mod;
   int32_t* overflow;        // set to 1 when a destination region would exceed `capacity`
   int64_t capacity;
   int32_t U, B, n_dest, fc;
@@ -46,6 +50,16 @@ struct RouteParams {
 };
 
 __device__ __forceinline__ bool route_full(const RouteParams& p, int u) { return p.u_row_lo[u] == 0 && p.u_row_hi[u] == INT64_MAX; }
+
+// does unit u take this id, and as which local id? (row range, or the round-robin rule for ids past the table's last block)
+__device__ __forceinline__ bool route_take(const RouteParams& p, int u, int64_t id, int64_t lo, int64_t hi, int64_t* local) {
+  if (p.u_wrap != nullptr && id >= p.u_wrap[u]) {
+    *local = id / p.wrap_mod;
+    return (int32_t) (id % p.wrap_mod) == p.u_wrap_rem[u];
+  }
+  *local = id - lo;
+  return id >= lo && id < hi;
+}
 
 // ---- A: per (unit, sample) lengths ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) kjt_route_len_kernel(const RouteParams p) {
@@ -65,7 +79,8 @@ __global__ void __launch_bounds__(256) kjt_route_len_kernel(const RouteParams p)
     c = 0;
     for (int64_t j = s; j < e; ++j) {
       const int64_t id = trb_ld_idx(p.in_val, j, p.val64);
-      c += (id >= lo && id < hi) ? 1 : 0;
+      int64_t local;
+      c += route_take(p, u, id, lo, hi, &local) ? 1 : 0;
     }
   }
   p.len[t] = c;
@@ -100,10 +115,12 @@ __global__ void __launch_bounds__(256) kjt_route_write_kernel(const RouteParams 
   int64_t k = o;
   for (int64_t j = s; j < e; ++j) {
     const int64_t id = trb_ld_idx(p.in_val, j, p.val64);
-    if (!full && (id < lo || id >= hi)) continue;
+    int64_t local = id - lo;
+    if (!full && !route_take(p, u, id, lo, hi, &local)) continue;
     if (k < C) {
-      trb_st_idx(p.out_val.p[d], k, p.out_val64, id - lo);
+      trb_st_idx(p.out_val.p[d], k, p.out_val64, local);
       if (p.in_wgt != nullptr) wdst[k] = p.in_wgt[j];
+      if (p.pos_out != nullptr) p.pos_out[k] = j - s;
     }
     if (p.unbucketize != nullptr) p.unbucketize[j * p.fc + p.u_cslice[u]] = k + base;
     ++k;
@@ -141,18 +158,20 @@ __global__ void __launch_bounds__(256) kjt_route_write_warp_kernel(const RoutePa
   int64_t k0 = o;
   for (int64_t j0 = s; j0 < e; j0 += 32) {
     const int64_t j = j0 + lane;
-    int64_t id = 0;
+    int64_t id = 0, local = 0;
     bool keep = false;
     if (j < e) {
       id = trb_ld_idx(p.in_val, j, p.val64);
-      keep = full || (id >= lo && id < hi);
+      local = id - lo;
+      keep = full || route_take(p, u, id, lo, hi, &local);
     }
     const unsigned m = __ballot_sync(0xffffffffu, keep);
     if (keep) {
       const int64_t k = k0 + __popc(m & ((1u << lane) - 1u));
       if (k < C) {
-        trb_st_idx(p.out_val.p[d], k, p.out_val64, id - lo);
+        trb_st_idx(p.out_val.p[d], k, p.out_val64, local);
         if (p.in_wgt != nullptr) wdst[k] = p.in_wgt[j];
+        if (p.pos_out != nullptr) p.pos_out[k] = j - s;
       }
       if (p.unbucketize != nullptr) p.unbucketize[j * p.fc + p.u_cslice[u]] = k + base;
     }
@@ -174,11 +193,12 @@ TRB_API int64_t trb_kjt_route_workspace_bytes(int U, int B) {
 }
 
 // Returns 0 on success. `avg_len_hint` (ids per bag, host estimate) picks the thread-per-bag or warp-per-bag writer.
-TRB_API int trb_kjt_route(const void* in_off, int in_off64, const void* in_val, int val64, const float* in_wgt, int B, const int32_t* u_key,
-                          const int64_t* u_row_lo, const int64_t* u_row_hi, const int32_t* u_dest, const int32_t* u_slot,
-                          const int32_t* u_cslice, const int32_t* dest_ustart, int U, int n_dest, void* const* out_off_ptrs, int out_off64,
-                          void* const* out_val_ptrs, int out_val64, void* const* out_wgt_ptrs, int64_t capacity, int64_t* unbucketize, int fc,
-                          int32_t* overflow, void* workspace, int64_t workspace_bytes, int avg_len_hint, cudaStream_t stream) {
+TRB_API int trb_kjt_route_ex(const void* in_off, int in_off64, const void* in_val, int val64, const float* in_wgt, int B, const int32_t* u_key,
+                             const int64_t* u_row_lo, const int64_t* u_row_hi, const int32_t* u_dest, const int32_t* u_slot,
+                             const int32_t* u_cslice, const int32_t* dest_ustart, int U, int n_dest, void* const* out_off_ptrs, int out_off64,
+                             void* const* out_val_ptrs, int out_val64, void* const* out_wgt_ptrs, int64_t capacity, int64_t* unbucketize, int fc,
+                             int64_t* pos_out, const int64_t* u_wrap, const int32_t* u_wrap_rem, int wrap_mod, int32_t* lengths_out,
+                             int32_t* overflow, void* workspace, int64_t workspace_bytes, int avg_len_hint, cudaStream_t stream) {
   if (n_dest < 1 || n_dest > TRB_MAX_PEERS) return -1;
   if (U == 0 || B == 0) return 0;
   const int64_t n = (int64_t) U * B;
@@ -189,7 +209,7 @@ TRB_API int trb_kjt_route(const void* in_off, int in_off64, const void* in_val, 
   p.u_key = u_key; p.u_row_lo = u_row_lo; p.u_row_hi = u_row_hi; p.u_dest = u_dest; p.u_slot = u_slot; p.u_cslice = u_cslice;
   p.dest_ustart = dest_ustart;
   char* ws = reinterpret_cast<char*>(workspace);
-  p.len = reinterpret_cast<int32_t*>(ws);
+  p.len = lengths_out != nullptr ? lengths_out : reinterpret_cast<int32_t*>(ws);  // caller-owned [U * B + 1]: the routed lengths are an output
   p.scan = reinterpret_cast<int32_t*>(ws + route_align((n + 1) * 4));
   void* scan_tmp = ws + 2 * route_align((n + 1) * 4);
   size_t scan_tmp_bytes = route_scan_tmp_bytes(n + 1);
@@ -199,6 +219,7 @@ TRB_API int trb_kjt_route(const void* in_off, int in_off64, const void* in_val, 
     p.out_wgt.p[i] = (i < n_dest && out_wgt_ptrs != nullptr) ? out_wgt_ptrs[i] : nullptr;
   }
   p.unbucketize = unbucketize; p.overflow = overflow; p.capacity = capacity;
+  p.pos_out = pos_out; p.u_wrap = u_wrap; p.u_wrap_rem = u_wrap_rem; p.wrap_mod = wrap_mod > 0 ? wrap_mod : 1;
   p.U = U; p.B = B; p.n_dest = n_dest; p.fc = fc > 0 ? fc : 1;
   p.in_off64 = in_off64; p.val64 = val64; p.out_off64 = out_off64; p.out_val64 = out_val64;
   const int threads = 256;
@@ -213,4 +234,14 @@ TRB_API int trb_kjt_route(const void* in_off, int in_off64, const void* in_val, 
   }
   TRB_CHECK_LAUNCH();
   return 0;
+}
+
+TRB_API int trb_kjt_route(const void* in_off, int in_off64, const void* in_val, int val64, const float* in_wgt, int B, const int32_t* u_key,
+                          const int64_t* u_row_lo, const int64_t* u_row_hi, const int32_t* u_dest, const int32_t* u_slot,
+                          const int32_t* u_cslice, const int32_t* dest_ustart, int U, int n_dest, void* const* out_off_ptrs, int out_off64,
+                          void* const* out_val_ptrs, int out_val64, void* const* out_wgt_ptrs, int64_t capacity, int64_t* unbucketize, int fc,
+                          int32_t* overflow, void* workspace, int64_t workspace_bytes, int avg_len_hint, cudaStream_t stream) {
+  return trb_kjt_route_ex(in_off, in_off64, in_val, val64, in_wgt, B, u_key, u_row_lo, u_row_hi, u_dest, u_slot, u_cslice, dest_ustart, U, n_dest, out_off_ptrs,
+                          out_off64, out_val_ptrs, out_val64, out_wgt_ptrs, capacity, unbucketize, fc, nullptr, nullptr, nullptr, 1, nullptr, overflow, workspace,
+                          workspace_bytes, avg_len_hint, stream);
 }

@@ -51,6 +51,14 @@ def invert_permute(permute: torch.Tensor) -> torch.Tensor:
 
 def segment_sum_csr(batch_size: int, csr_seg: torch.Tensor, values: torch.Tensor) -> torch.Tensor:
     """Sum ``values`` over segments given by offsets ``csr_seg`` counted in units of ``batch_size`` rows."""
+    if values.is_cuda and _lib.available() and values.dtype in (torch.float32, torch.int64, torch.int32) and csr_seg.dtype in (torch.int32, torch.int64) \
+            and values.is_contiguous() and csr_seg.is_contiguous():
+        n_seg = csr_seg.numel() - 1
+        out = torch.empty(n_seg, dtype=values.dtype, device=values.device)
+        code = _lib.lib().trb_segment_sum_csr(_lib.ptr(values), _lib.dtype_code(values.dtype), _lib.ptr(csr_seg), int(csr_seg.dtype == torch.int64), _lib.ptr(out),
+                                              ctypes.c_int64(n_seg), int(batch_size), _lib.stream_ptr(values.device))
+        _lib.check(code, "trb_segment_sum_csr")
+        return out
     seg_off = csr_seg.long() * batch_size
     lengths = seg_off[1:] - seg_off[:-1]
     seg = torch.repeat_interleave(torch.arange(lengths.numel(), device=values.device), lengths, output_size=values.numel())
@@ -164,6 +172,9 @@ def block_bucketize_sparse_features(
     F = block_sizes.numel()
     B = FB // max(F, 1)
     dev = indices.device
+    if (indices.is_cuda and _lib.available() and not keep_orig_idx and batch_size_per_feature is None and keep_orig_idx_per_feature is None
+            and FB > 0 and my_size <= 4096 and indices.dtype in (torch.int32, torch.int64)):
+        return _block_bucketize_cuda(lengths, indices, bucketize_pos, sequence, block_sizes, my_size, weights, block_bucketize_pos, F, B)
     lengths64 = lengths.to(torch.int64)
     bag = torch.repeat_interleave(torch.arange(FB, device=dev), lengths64, output_size=n)
     feat = bag // max(B, 1)
@@ -203,7 +214,77 @@ def block_bucketize_sparse_features(
     return new_lengths, new_indices, new_weights, new_pos, unbucketize
 
 
+_BB_TABLES: dict = {}
+
+
+def _block_bucketize_cuda(lengths, indices, bucketize_pos, sequence, block_sizes, my_size, weights, block_bucketize_pos, F: int, B: int):
+    """Device-side bucketization through the routing kernels of ``csrc/kjt_route.cu`` (3 launches, no host sync): the "units" are the
+    (bucket, feature) pairs in output order; a unit keeps the ids of its row block (or, past the table's last block, the ids whose
+    remainder modulo ``my_size`` is the bucket) and rebases them."""
+    dev = indices.device
+    INT64_MAX = (1 << 63) - 1
+    key = (F, my_size, block_sizes.data_ptr(), None if block_bucketize_pos is None else tuple(t.data_ptr() for t in block_bucketize_pos), str(dev))
+    tab = _BB_TABLES.get(key)
+    if tab is None:
+        bs = block_sizes.to(device=dev, dtype=torch.int64)
+        j = torch.arange(my_size, device=dev, dtype=torch.int64).unsqueeze(1)  # [my_size, 1]
+        if block_bucketize_pos is None:
+            lo = (j * bs.unsqueeze(0)).reshape(-1)
+            hi = ((j + 1) * bs.unsqueeze(0)).reshape(-1)
+            wrap = (bs * my_size).unsqueeze(0).expand(my_size, F).reshape(-1).contiguous()
+        else:
+            pos = torch.stack([p.to(device=dev, dtype=torch.int64) for p in block_bucketize_pos], dim=1)  # [my_size + 1, F]
+            lo, hi = pos[:-1].reshape(-1).contiguous(), pos[1:].reshape(-1).clone()
+            hi.view(my_size, F)[-1] = INT64_MAX  # ids past the last boundary stay in the last bucket
+            wrap = None
+        u_key = torch.arange(F, device=dev, dtype=torch.int32).repeat(my_size)
+        zero = torch.zeros(my_size * F, dtype=torch.int32, device=dev)
+        tab = (lo.contiguous(), hi.contiguous(), wrap, u_key, zero, torch.arange(my_size * F, device=dev, dtype=torch.int32),
+               torch.arange(my_size, device=dev, dtype=torch.int32).repeat_interleave(F),
+               torch.tensor([0, my_size * F], dtype=torch.int32, device=dev), torch.zeros(1, dtype=torch.int32, device=dev))
+        _BB_TABLES[key] = tab
+    lo, hi, wrap, u_key, zero, slot, rem, ustart, overflow = tab
+    U = my_size * F
+    n = indices.numel()
+    in_off = asynchronous_complete_cumsum(lengths.to(torch.int64))
+    L = _lib.lib()
+    L.trb_kjt_route_workspace_bytes.restype = ctypes.c_int64
+    ws = torch.empty(int(L.trb_kjt_route_workspace_bytes(U, B)), dtype=torch.uint8, device=dev)
+    new_len32 = torch.empty(U * B + 1, dtype=torch.int32, device=dev)
+    out_off = torch.empty(U * B + 1, dtype=torch.int32, device=dev)
+    new_indices = torch.empty(n, dtype=indices.dtype, device=dev)
+    new_weights = torch.empty(n, dtype=torch.float32, device=dev) if weights is not None else None
+    new_pos = torch.empty(n, dtype=torch.int64, device=dev) if bucketize_pos else None
+    unbucketize = torch.empty(n, dtype=torch.int64, device=dev) if sequence else None
+    w32 = weights.float().contiguous() if weights is not None else None
+    code = L.trb_kjt_route_ex(
+        _lib.ptr(in_off), 1, _lib.ptr(indices), int(indices.dtype == torch.int64), _lib.ptr(w32), B, _lib.ptr(u_key), _lib.ptr(lo), _lib.ptr(hi), _lib.ptr(zero),
+        _lib.ptr(slot), _lib.ptr(zero), _lib.ptr(ustart), U, 1, _lib.ptr_array([out_off.data_ptr()]), 0, _lib.ptr_array([new_indices.data_ptr()]),
+        int(indices.dtype == torch.int64), _lib.ptr_array([new_weights.data_ptr()]) if new_weights is not None else ctypes.c_void_p(0), ctypes.c_int64(max(n, 1)),
+        _lib.ptr(unbucketize), 1, _lib.ptr(new_pos), _lib.ptr(wrap), _lib.ptr(rem) if wrap is not None else ctypes.c_void_p(0), my_size, _lib.ptr(new_len32),
+        _lib.ptr(overflow), _lib.ptr(ws), ctypes.c_int64(ws.numel()), int(max(1, n // max(F * B, 1))), _lib.stream_ptr(dev))
+    _lib.check(code, "trb_kjt_route_ex")
+    new_lengths = new_len32[: U * B].to(lengths.dtype)
+    if new_weights is not None and weights.dtype != torch.float32:
+        new_weights = new_weights.to(weights.dtype)
+    return (new_lengths, new_indices, new_weights, None if new_pos is None else new_pos.to(indices.dtype),
+            None if unbucketize is None else unbucketize.to(indices.dtype))
+
+
 def jagged_to_padded_dense(values: torch.Tensor, offsets: Sequence[torch.Tensor], max_lengths: Sequence[int], padding_value: float = 0.0) -> torch.Tensor:
+    if values.is_cuda and _lib.available() and values.dim() <= 2 and values.is_contiguous() and (values[0:1].numel() * values.element_size()) % 4 == 0 and values.numel() > 0 \
+            and values.element_size() in (4, 8) :
+        off64 = offsets[0].to(torch.int64).contiguous()
+        N, max_len = off64.numel() - 1, int(max_lengths[0])
+        trail = tuple(values.shape[1:])
+        out = torch.empty((N, max_len) + trail, dtype=values.dtype, device=values.device)
+        row_bytes = values[0:1].numel() * values.element_size()
+        if values.element_size() == 4:
+            pad = torch.tensor([padding_value], dtype=values.dtype).view(torch.int32).item() & 0xFFFFFFFF
+            code = _lib.lib().trb_jagged_to_padded_dense(_lib.ptr(values), _lib.ptr(off64), _lib.ptr(out), ctypes.c_int64(N), max_len, int(row_bytes),
+                                                         ctypes.c_uint32(pad), _lib.stream_ptr(values.device))
+            _lib.check(code, "trb_jagged_to_padded_dense")
+            return out
     off = offsets[0].long()
     N = off.numel() - 1
     max_len = max_lengths[0]
@@ -229,6 +310,15 @@ def jagged_1d_to_dense(values: torch.Tensor, offsets: torch.Tensor, max_sequence
 
 
 def dense_to_jagged(dense: torch.Tensor, offsets: Sequence[torch.Tensor], total_L: Optional[int] = None) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+    if dense.is_cuda and _lib.available() and total_L is not None and dense.is_contiguous() and dense.element_size() == 4 and dense.dim() in (2, 3):
+        off64 = offsets[0].to(torch.int64).contiguous()
+        trail = tuple(dense.shape[2:])
+        out = torch.empty((int(total_L),) + trail, dtype=dense.dtype, device=dense.device)
+        row_bytes = (dense[0, 0:1].numel()) * 4
+        code = _lib.lib().trb_dense_to_jagged(_lib.ptr(dense), _lib.ptr(off64), _lib.ptr(out), ctypes.c_int64(dense.shape[0]), int(dense.shape[1]), int(row_bytes),
+                                              _lib.stream_ptr(dense.device))
+        _lib.check(code, "trb_dense_to_jagged")
+        return out, list(offsets)
     off = offsets[0].long()
     lengths = off[1:] - off[:-1]
     N, max_len = dense.shape[0], dense.shape[1]
@@ -345,8 +435,27 @@ def permute_2D_sparse_data_input1D(permute: torch.Tensor, lengths: torch.Tensor,
     return pl.reshape(-1), pv, pw
 
 
+_PERMUTE_TABLES: dict = {}
+
+
 def permute_pooled_embs(pooled: torch.Tensor, offset_dim_list: Sequence[int], permute_list: Sequence[int]) -> torch.Tensor:
     """Column-block permutation of a [B, sum(D)] tensor (PermutePooledEmbeddings)."""
+    if pooled.is_cuda and _lib.available() and pooled.dim() == 2 and pooled.is_contiguous() and not pooled.requires_grad and len(permute_list) > 0:
+        esz = pooled.element_size()
+        widths = [offset_dim_list[p + 1] - offset_dim_list[p] for p in permute_list]
+        if all((w * esz) % 4 == 0 and (offset_dim_list[p] * esz) % 4 == 0 for w, p in zip(widths, permute_list)) and sum(widths) == pooled.shape[1]:
+            key = (tuple(offset_dim_list), tuple(permute_list), esz, str(pooled.device))
+            src = _PERMUTE_TABLES.get(key)
+            if src is None:
+                words = []
+                for p in permute_list:
+                    words.extend(range(offset_dim_list[p] * esz // 4, offset_dim_list[p + 1] * esz // 4))
+                src = _PERMUTE_TABLES[key] = torch.tensor(words, dtype=torch.int32, device=pooled.device)
+            out = torch.empty_like(pooled)
+            code = _lib.lib().trb_permute_pooled_embs(_lib.ptr(pooled), _lib.ptr(out), _lib.ptr(src), ctypes.c_int64(pooled.shape[0]), int(src.numel()),
+                                                      _lib.stream_ptr(pooled.device))
+            _lib.check(code, "trb_permute_pooled_embs")
+            return out
     cols = []
     for p in permute_list:
         cols.append(torch.arange(offset_dim_list[p], offset_dim_list[p + 1], device=pooled.device))

@@ -85,44 +85,134 @@ class _CastCodec:
         return input_tensor.shape[0], 0
 
 
+_CODEC_ID = {"fp8": 0, "int8": 1, "mx4": 2}
+
+
+def _native(kind: str, encode: bool, x: torch.Tensor, rows: int, row_dim: int) -> torch.Tensor:
+    """CUDA tensors go through the codec kernels of ``ops/csrc/qcomm.cu`` (one warp per row / per 32-element group)."""
+    import ctypes
+
+    from ..ops import _lib
+
+    L = _lib.lib()
+    cid = _CODEC_ID[kind]
+    if encode:
+        L.trb_qcomm_encoded_bytes.restype = ctypes.c_int64
+        nbytes = int(L.trb_qcomm_encoded_bytes(cid, ctypes.c_int64(rows), row_dim))
+        out = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        _lib.check(L.trb_qcomm_encode(cid, _lib.ptr(x), _lib.ptr(out), ctypes.c_int64(rows), row_dim, _lib.stream_ptr(x.device)), "trb_qcomm_encode")
+    else:
+        out = torch.empty(rows * row_dim, dtype=torch.float32, device=x.device)
+        _lib.check(L.trb_qcomm_decode(cid, _lib.ptr(x), _lib.ptr(out), ctypes.c_int64(rows), row_dim, _lib.stream_ptr(x.device)), "trb_qcomm_decode")
+    return out
+
+
 class _RowwiseCodec:
-    """Row-wise scaled 8-bit codec: layout [q bytes for row | fp32 scale] per row of ``row_dim`` elements, uint8 wire."""
+    """Row-wise scaled 8-bit codec, uint8 wire. Per row of ``row_dim`` elements:
+    FP8  ``[row_dim x e4m3][fp32 scale = amax / 448]``;  INT8  ``[row_dim x uint8][fp32 scale][fp32 bias = row min]``.
+    CUDA tensors use the codec kernels, CPU tensors the PyTorch mirror of the same layout (gloo tests, numerics oracle)."""
 
     def __init__(self, row_dim: int, fp8: bool) -> None:
         self._row_dim = row_dim
         self._fp8 = fp8
+        self._tail = 4 if fp8 else 8
 
     def _rows(self, n: int) -> int:
         assert n % self._row_dim == 0, f"tensor size {n} is not a multiple of the quantization row dim {self._row_dim}"
         return n // self._row_dim
 
     def encode(self, x: torch.Tensor, ctx=None) -> torch.Tensor:
-        flat = x.reshape(-1).float()
+        flat = x.reshape(-1).float().contiguous()
         rows = self._rows(flat.numel())
+        if flat.is_cuda:
+            return _native("fp8" if self._fp8 else "int8", True, flat, rows, self._row_dim)
         m = flat.view(rows, self._row_dim)
-        amax = m.abs().amax(dim=1, keepdim=True).clamp(min=1e-12)
         if self._fp8:
-            scale = amax / 448.0
+            amax = m.abs().amax(dim=1, keepdim=True)
+            scale = torch.where(amax > 0, amax / 448.0, torch.ones_like(amax))
             q = (m / scale).to(torch.float8_e4m3fn).view(torch.uint8)
+            tail = scale.view(torch.uint8).view(rows, 4)
         else:
-            scale = amax / 127.0
-            q = torch.clamp(torch.round(m / scale), -127, 127).to(torch.int8).view(torch.uint8)
-        return torch.cat([q, scale.view(torch.uint8).view(rows, 4)], dim=1).reshape(-1)
+            lo, hi = m.amin(dim=1, keepdim=True), m.amax(dim=1, keepdim=True)
+            scale = torch.where(hi > lo, (hi - lo) / 255.0, torch.ones_like(hi))
+            q = torch.clamp(torch.round((m - lo) / scale), 0, 255).to(torch.uint8)
+            tail = torch.cat([scale.view(torch.uint8).view(rows, 4), lo.contiguous().view(torch.uint8).view(rows, 4)], dim=1)
+        return torch.cat([q, tail], dim=1).reshape(-1)
 
     def decode(self, x: torch.Tensor, ctx=None) -> torch.Tensor:
-        rows = x.numel() // (self._row_dim + 4)
-        m = x.view(rows, self._row_dim + 4)
+        rows = x.numel() // (self._row_dim + self._tail)
+        if x.is_cuda:
+            return _native("fp8" if self._fp8 else "int8", False, x.contiguous(), rows, self._row_dim)
+        m = x.view(rows, self._row_dim + self._tail)
         q = m[:, : self._row_dim].contiguous()
-        scale = m[:, self._row_dim :].contiguous().view(torch.float32)
-        vals = q.view(torch.float8_e4m3fn).float() if self._fp8 else q.view(torch.int8).float()
-        return (vals * scale).reshape(-1)
+        scale = m[:, self._row_dim : self._row_dim + 4].contiguous().view(torch.float32)
+        if self._fp8:
+            return (q.view(torch.float8_e4m3fn).float() * scale).reshape(-1)
+        bias = m[:, self._row_dim + 4 :].contiguous().view(torch.float32)
+        return (q.float() * scale + bias).reshape(-1)
 
     @property
     def quantized_dtype(self) -> torch.dtype:
         return torch.uint8
 
     def calc_quantized_size(self, input_len: int, ctx=None) -> int:
-        return self._rows(input_len) * (self._row_dim + 4)
+        return self._rows(input_len) * (self._row_dim + self._tail)
+
+    def create_context(self):
+        return None
+
+    def padded_size(self, input_tensor, dim_per_rank, my_rank, qcomm_ctx):
+        return input_tensor.shape[0], 0
+
+
+_E2M1 = [0.0, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 6.0]
+_E2M1_EDGES = [0.25, 0.75, 1.25, 1.75, 2.5, 3.5, 5.0]
+
+
+class _Mx4Codec:
+    """MX4 (OCP microscaling): groups of 32 elements share one power-of-two scale (e8m0 byte), every element is a 4-bit e2m1 value:
+    17 bytes per 32 elements = 4.25 bits per element on the wire."""
+
+    GROUP = 32
+
+    def __init__(self, row_dim: Optional[int] = None) -> None:
+        self._row_dim = row_dim or 32
+
+    def encode(self, x: torch.Tensor, ctx=None) -> torch.Tensor:
+        flat = x.reshape(-1).float().contiguous()
+        n = flat.numel()
+        if flat.is_cuda:
+            return _native("mx4", True, flat, 1, n)
+        groups = (n + 31) // 32
+        m = torch.zeros(groups * 32, dtype=torch.float32)
+        m[:n] = flat
+        m = m.view(groups, 32)
+        amax = m.abs().amax(dim=1)
+        e = torch.where(amax > 0, torch.floor(torch.log2(amax.clamp(min=1e-38))) - 2, torch.full_like(amax, -127.0)).clamp(-127, 127)
+        scaled = m * torch.exp2(-e).unsqueeze(1)
+        mag = torch.bucketize(scaled.abs(), torch.tensor(_E2M1_EDGES), right=True).to(torch.uint8)
+        q = mag | ((scaled < 0).to(torch.uint8) << 3)
+        packed = q[:, 0::2] | (q[:, 1::2] << 4)
+        return torch.cat([(e + 127).to(torch.uint8).unsqueeze(1), packed], dim=1).reshape(-1)
+
+    def decode(self, x: torch.Tensor, ctx=None, n: Optional[int] = None) -> torch.Tensor:
+        groups = x.numel() // 17
+        n = groups * 32 if n is None else n
+        if x.is_cuda:
+            return _native("mx4", False, x.contiguous(), 1, groups * 32)[:n]
+        m = x.view(groups, 17)
+        scale = torch.exp2(m[:, 0].float() - 127.0).unsqueeze(1)
+        b = m[:, 1:]
+        q = torch.stack([b & 15, b >> 4], dim=2).reshape(groups, 32)
+        vals = torch.tensor(_E2M1)[(q & 7).long()] * torch.where((q & 8) > 0, -1.0, 1.0)
+        return (vals * scale).reshape(-1)[:n]
+
+    @property
+    def quantized_dtype(self) -> torch.dtype:
+        return torch.uint8
+
+    def calc_quantized_size(self, input_len: int, ctx=None) -> int:
+        return (input_len + 31) // 32 * 17
 
     def create_context(self):
         return None
@@ -138,8 +228,10 @@ def get_qcomm_codec(comm_type: CommType, loss_scale: Optional[float], row_dim: O
         return _CastCodec(torch.float16, loss_scale)
     if comm_type == CommType.BF16:
         return _CastCodec(torch.bfloat16, loss_scale)
-    if comm_type in (CommType.FP8, CommType.MX4):
+    if comm_type == CommType.FP8:
         return _RowwiseCodec(row_dim or 32, fp8=True)
+    if comm_type == CommType.MX4:
+        return _Mx4Codec(row_dim)
     if comm_type == CommType.INT8:
         return _RowwiseCodec(row_dim or 32, fp8=False)
     raise ValueError(comm_type)
