@@ -164,12 +164,16 @@ class ShardedLookupEngine(nn.Module):
             opt = opt_specs.get(cfg.name, OptimizerSpec())
             # storage location: compute kernel of the plan (HBM | zero-copy host | host + HBM cache), reference embedding_types.py:75-95
             ck = getattr(ps, "compute_kernel", None) or "fused"
-            loc = {"fused_uvm": 1, "fused_uvm_caching": 2, "key_value": 2}.get(str(ck), 0) if device.type == "cuda" or os.environ.get("TRB_UVM_ON_CPU") else 0
+            # 1 zero-copy host rows, 2 host rows + HBM cache, 3 key-value virtual table in DRAM, 4 key-value virtual table on SSD
+            loc = {"fused_uvm": 1, "fused_uvm_caching": 2, "key_value": 3, "dram_virtual_table": 3, "ssd_virtual_table": 4}.get(str(ck), 0) \
+                if device.type == "cuda" or os.environ.get("TRB_UVM_ON_CPU") else 0
             clf = 0.2
             cp = getattr(ps, "cache_params", None)
             if cp is not None and getattr(cp, "load_factor", None):
                 clf = float(cp.load_factor)
-            key = (str(dtype), int(pooling), opt.key(), loc, clf if loc == 2 else 0)
+            kvp = getattr(ps, "key_value_params", None)
+            kv_dir = getattr(kvp, "ssd_storage_directory", None) if kvp is not None else None
+            key = (str(dtype), int(pooling), opt.key(), loc, clf if loc >= 2 else 0, kv_dir if loc == 4 else None)
             if key not in group_index:
                 group_index[key] = len(self._groups)
                 self._groups.append(_Group(key, pooling, dtype, opt))
@@ -235,6 +239,17 @@ class ShardedLookupEngine(nn.Module):
 
                 cls = UvmCachedEmbeddingBags
                 extra["cache_load_factor"] = clf
+            elif loc in (3, 4):
+                from ..ops.kv_tbe import KeyValueEmbeddingBags
+
+                cls = KeyValueEmbeddingBags
+                extra["cache_load_factor"] = clf
+                extra["backend"] = "ssd" if loc == 4 else "dram"
+                if loc == 4 and g.key[5]:
+                    extra["ssd_storage_directory"] = os.path.join(g.key[5], f"rank{self._rank}_group{gi}")
+                cap = int(os.environ.get("TRB_KV_STORE_ROWS", "0"))
+                if cap:
+                    extra["store_rows"] = [min(s.rows, cap) for s in g.local_shards]
             tbe = cls(
                 embedding_specs=[(s.rows, s.cols) for s in g.local_shards],
                 feature_table_map=[u.shard.local_idx for u in units],
