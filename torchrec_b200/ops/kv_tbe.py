@@ -205,7 +205,7 @@ class KeyValueEmbeddingBags(UvmCachedEmbeddingBags):
         B = batch_size if batch_size is not None else (offsets.numel() - 1) // max(F, 1)
         slots = self._translate_keys(indices, offsets, B)
         self._kv_cached = (indices.data_ptr(), int(indices.numel()), slots)
-        super().prefetch(slots, offsets, B)
+        UvmCachedEmbeddingBags.prefetch(self, slots, offsets, B)
 
     @torch.no_grad()
     def translate(self, indices: torch.Tensor, offsets: torch.Tensor, batch_size: int) -> torch.Tensor:
@@ -215,7 +215,10 @@ class KeyValueEmbeddingBags(UvmCachedEmbeddingBags):
         else:
             slots = self._translate_keys(indices, offsets, batch_size)
         self._kv_cached = None
-        return super().translate(slots, offsets, batch_size)
+        # the parent's cache logic works on store slots; its own `prefetch` must be used here (ours expects keys)
+        if self._prefetched != (slots.data_ptr(), int(slots.numel())):
+            UvmCachedEmbeddingBags.prefetch(self, slots, offsets, batch_size)
+        return UvmCachedEmbeddingBags.translate(self, slots, offsets, batch_size)
 
     # ---- checkpoint view ---------------------------------------------------------------------------------------------------------------
     def key_value_snapshot(self, t: int) -> Tuple[torch.Tensor, torch.Tensor]:
