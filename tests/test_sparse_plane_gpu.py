@@ -215,7 +215,19 @@ def test_routed_ids_jagged_view_matches_eager_route():
                for r in range(W)]
     kjts = [_kjt(tables, B, 9, False, 5 + r, dev, one_hot_first=False) for r in range(W)]
     ids = [engines[r].plane_input_dist(kjts[r], None, total_cols, capacity=6 * B * 9) for r in range(W)]
-    routed = [engines[r].route(kjts[r])[0] for r in range(W)]  # eager reference: global unit order
+    import os
+
+    os.environ["TRB_ROUTE_EAGER"] = "1"  # PyTorch reference of the routing (index arithmetic + stable sort)
+    try:
+        ref = [engines[r].route(kjts[r]) for r in range(W)]
+    finally:
+        os.environ.pop("TRB_ROUTE_EAGER", None)
+    routed = [x[0] for x in ref]
+    # the portable transport's device-side routing (one local destination) produces the very same routed KJT + unbucketize permutation
+    for r in range(W):
+        got, unb = engines[r].route(kjts[r])
+        assert torch.equal(got.lengths().cpu(), routed[r].lengths().cpu()) and torch.equal(got.values().cpu(), routed[r].values().cpu())
+        assert torch.equal(unb.cpu(), ref[r][1].cpu())
     for d in range(W):
         got = ids[d].to_kjt()
         eng = engines[d]

@@ -43,6 +43,8 @@ struct RouteParams {
   const int64_t* u_wrap;    // optional [U]: ids >= u_wrap[u] (past the last block of the table) are dealt round-robin: kept by the unit
   const int32_t* u_wrap_rem;  //             whose remainder id % wrap_mod equals u_wrap_rem[u], with local id = id / wrap_mod
   int32_t wrap_mod;
+  const int32_t* u_edge;    // optional [U]: bit 0 = the unit also keeps ids BELOW its range, bit 1 = ids ABOVE it (first / last row shard of a
+                            // table: invalid ids are forwarded - the lookup kernel zeroes them - so every input id is routed exactly once)
   int32_t* overflow;        // set to 1 when a destination region would exceed `capacity`
   int64_t capacity;
   int32_t U, B, n_dest, fc;
@@ -58,6 +60,10 @@ __device__ __forceinline__ bool route_take(const RouteParams& p, int u, int64_t 
     return (int32_t) (id % p.wrap_mod) == p.u_wrap_rem[u];
   }
   *local = id - lo;
+  if (p.u_edge != nullptr) {
+    const int e = p.u_edge[u];
+    if (((e & 1) && id < lo) || ((e & 2) && id >= hi)) return true;
+  }
   return id >= lo && id < hi;
 }
 
@@ -197,7 +203,7 @@ TRB_API int trb_kjt_route_ex(const void* in_off, int in_off64, const void* in_va
                              const int64_t* u_row_lo, const int64_t* u_row_hi, const int32_t* u_dest, const int32_t* u_slot,
                              const int32_t* u_cslice, const int32_t* dest_ustart, int U, int n_dest, void* const* out_off_ptrs, int out_off64,
                              void* const* out_val_ptrs, int out_val64, void* const* out_wgt_ptrs, int64_t capacity, int64_t* unbucketize, int fc,
-                             int64_t* pos_out, const int64_t* u_wrap, const int32_t* u_wrap_rem, int wrap_mod, int32_t* lengths_out,
+                             int64_t* pos_out, const int64_t* u_wrap, const int32_t* u_wrap_rem, int wrap_mod, const int32_t* u_edge, int32_t* lengths_out,
                              int32_t* overflow, void* workspace, int64_t workspace_bytes, int avg_len_hint, cudaStream_t stream) {
   if (n_dest < 1 || n_dest > TRB_MAX_PEERS) return -1;
   if (U == 0 || B == 0) return 0;
@@ -219,7 +225,7 @@ TRB_API int trb_kjt_route_ex(const void* in_off, int in_off64, const void* in_va
     p.out_wgt.p[i] = (i < n_dest && out_wgt_ptrs != nullptr) ? out_wgt_ptrs[i] : nullptr;
   }
   p.unbucketize = unbucketize; p.overflow = overflow; p.capacity = capacity;
-  p.pos_out = pos_out; p.u_wrap = u_wrap; p.u_wrap_rem = u_wrap_rem; p.wrap_mod = wrap_mod > 0 ? wrap_mod : 1;
+  p.pos_out = pos_out; p.u_wrap = u_wrap; p.u_wrap_rem = u_wrap_rem; p.wrap_mod = wrap_mod > 0 ? wrap_mod : 1; p.u_edge = u_edge;
   p.U = U; p.B = B; p.n_dest = n_dest; p.fc = fc > 0 ? fc : 1;
   p.in_off64 = in_off64; p.val64 = val64; p.out_off64 = out_off64; p.out_val64 = out_val64;
   const int threads = 256;
@@ -242,6 +248,6 @@ TRB_API int trb_kjt_route(const void* in_off, int in_off64, const void* in_val, 
                           void* const* out_val_ptrs, int out_val64, void* const* out_wgt_ptrs, int64_t capacity, int64_t* unbucketize, int fc,
                           int32_t* overflow, void* workspace, int64_t workspace_bytes, int avg_len_hint, cudaStream_t stream) {
   return trb_kjt_route_ex(in_off, in_off64, in_val, val64, in_wgt, B, u_key, u_row_lo, u_row_hi, u_dest, u_slot, u_cslice, dest_ustart, U, n_dest, out_off_ptrs,
-                          out_off64, out_val_ptrs, out_val64, out_wgt_ptrs, capacity, unbucketize, fc, nullptr, nullptr, nullptr, 1, nullptr, overflow, workspace,
+                          out_off64, out_val_ptrs, out_val64, out_wgt_ptrs, capacity, unbucketize, fc, nullptr, nullptr, nullptr, 1, nullptr, nullptr, overflow, workspace,
                           workspace_bytes, avg_len_hint, stream);
 }

@@ -261,7 +261,7 @@ def _block_bucketize_cuda(lengths, indices, bucketize_pos, sequence, block_sizes
         _lib.ptr(in_off), 1, _lib.ptr(indices), int(indices.dtype == torch.int64), _lib.ptr(w32), B, _lib.ptr(u_key), _lib.ptr(lo), _lib.ptr(hi), _lib.ptr(zero),
         _lib.ptr(slot), _lib.ptr(zero), _lib.ptr(ustart), U, 1, _lib.ptr_array([out_off.data_ptr()]), 0, _lib.ptr_array([new_indices.data_ptr()]),
         int(indices.dtype == torch.int64), _lib.ptr_array([new_weights.data_ptr()]) if new_weights is not None else ctypes.c_void_p(0), ctypes.c_int64(max(n, 1)),
-        _lib.ptr(unbucketize), 1, _lib.ptr(new_pos), _lib.ptr(wrap), _lib.ptr(rem) if wrap is not None else ctypes.c_void_p(0), my_size, _lib.ptr(new_len32),
+        _lib.ptr(unbucketize), 1, _lib.ptr(new_pos), _lib.ptr(wrap), _lib.ptr(rem) if wrap is not None else ctypes.c_void_p(0), my_size, ctypes.c_void_p(0), _lib.ptr(new_len32),
         _lib.ptr(overflow), _lib.ptr(ws), ctypes.c_int64(ws.numel()), int(max(1, n // max(F * B, 1))), _lib.stream_ptr(dev))
     _lib.check(code, "trb_kjt_route_ex")
     new_lengths = new_len32[: U * B].to(lengths.dtype)

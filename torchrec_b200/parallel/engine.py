@@ -352,6 +352,8 @@ class ShardedLookupEngine(nn.Module):
             if self._perm_features == list(range(len(features.keys()))):
                 return features, None
             return features.permute(self._perm_features), None
+        if features.values().is_cuda and self._uniform_fc and not features.variable_stride_per_key() and os.environ.get("TRB_ROUTE_EAGER") != "1":
+            return self._route_cuda(features)
         B = features.stride()
         Fm = len(self._mp_features)
         lengths = features.lengths().to(torch.int64)
@@ -386,6 +388,70 @@ class ShardedLookupEngine(nn.Module):
         unbucketize[order] = torch.arange(total, device=dev)
         routed = KeyedJaggedTensor(keys=self._routed_keys, values=new_values, weights=new_weights, lengths=new_lengths, stride=B)
         return routed, unbucketize
+
+    def _route_cuda(self, features: KeyedJaggedTensor) -> Tuple[KeyedJaggedTensor, Optional[torch.Tensor]]:
+        """Row-sharded routing on the GPU for the portable (NCCL) transport: the same device-side pass as the NVLink plane's input dist
+        (``csrc/kjt_route.cu``: bucketize by row range + rebase + permute into unit order + unbucketize permutation) with ONE local
+        destination. No eager index arithmetic, no host sync: every id lands in exactly ``fc`` units (its row shard x the column slices),
+        so the routed KJT holds ``n * fc`` ids."""
+        import ctypes
+
+        from ..ops import _lib
+
+        dev = features.values().device
+        tab = self.__dict__.get("_route_tables")
+        if tab is None or tab["dev"] != dev:
+            mp_pos = {f: i for i, f in enumerate(self._mp_features)}
+            INT64_MAX = (1 << 63) - 1
+            cols_of_feature: Dict[int, List[int]] = {}
+            for u in self._units:
+                cols_of_feature.setdefault(u.feature, [])
+                if u.shard.col_off not in cols_of_feature[u.feature]:
+                    cols_of_feature[u.feature].append(u.shard.col_off)
+            for f in cols_of_feature:
+                cols_of_feature[f].sort()
+            rs = self._table_row_sharded
+            mk32 = lambda x: torch.tensor(x, dtype=torch.int32, device=dev)
+            mk64 = lambda x: torch.tensor(x, dtype=torch.int64, device=dev)
+            U = len(self._units)
+            # first / last row shard of a table also take the ids below / above the table (forwarded as invalid ids), so every id is routed
+            row_los = {ti: min(s.row_off for s in self._table_shards[ti] if s.rows > 0) if any(s.rows > 0 for s in self._table_shards[ti]) else 0 for ti in self._mp_tables}
+            row_his = {ti: max(s.row_off + s.rows for s in self._table_shards[ti]) for ti in self._mp_tables}
+            edge = [((1 if u.shard.row_off == row_los[u.shard.table_idx] and u.shard.rows > 0 else 0) | (2 if u.shard.row_off + u.shard.rows == row_his[u.shard.table_idx] and u.shard.rows > 0 else 0))
+                    if rs[u.shard.table_idx] else 0 for u in self._units]
+            tab = self.__dict__["_route_tables"] = {
+                "dev": dev, "U": U, "fc": int(self._fc_count[0]) if len(self._mp_features) else 1,
+                "key": mk32([mp_pos[u.feature] for u in self._units]),
+                "lo": mk64([u.shard.row_off if rs[u.shard.table_idx] else 0 for u in self._units]),
+                "hi": mk64([u.shard.row_off + u.shard.rows if rs[u.shard.table_idx] else INT64_MAX for u in self._units]),
+                "zero": mk32([0] * U), "slot": mk32(list(range(U))), "cslice": mk32([cols_of_feature[u.feature].index(u.shard.col_off) for u in self._units]),
+                "ustart": mk32([0, U]), "overflow": torch.zeros(1, dtype=torch.int32, device=dev), "edge": mk32(edge)}
+        B = features.stride()
+        values = features.values()
+        n, fc, U = values.numel(), tab["fc"], tab["U"]
+        total = n * fc
+        L = _lib.lib()
+        L.trb_kjt_route_workspace_bytes.restype = ctypes.c_int64
+        ws = torch.empty(int(L.trb_kjt_route_workspace_bytes(U, B)), dtype=torch.uint8, device=dev)
+        len32 = torch.empty(U * B + 1, dtype=torch.int32, device=dev)
+        off32 = torch.empty(U * B + 1, dtype=torch.int32, device=dev)
+        new_values = torch.empty(total, dtype=values.dtype, device=dev)
+        w = features.weights_or_none()
+        w32 = w.float().contiguous() if w is not None else None
+        new_w = torch.empty(total, dtype=torch.float32, device=dev) if w is not None else None
+        unb = torch.empty(total, dtype=torch.int64, device=dev)
+        in_off = features.offsets()
+        code = L.trb_kjt_route_ex(
+            _lib.ptr(in_off), int(in_off.dtype == torch.int64), _lib.ptr(values), int(values.dtype == torch.int64), _lib.ptr(w32), B, _lib.ptr(tab["key"]),
+            _lib.ptr(tab["lo"]), _lib.ptr(tab["hi"]), _lib.ptr(tab["zero"]), _lib.ptr(tab["slot"]), _lib.ptr(tab["cslice"]), _lib.ptr(tab["ustart"]), U, 1,
+            _lib.ptr_array([off32.data_ptr()]), 0, _lib.ptr_array([new_values.data_ptr()]), int(values.dtype == torch.int64),
+            _lib.ptr_array([new_w.data_ptr()]) if new_w is not None else ctypes.c_void_p(0), ctypes.c_int64(max(total, 1)), _lib.ptr(unb), fc, ctypes.c_void_p(0),
+            ctypes.c_void_p(0), ctypes.c_void_p(0), 1, _lib.ptr(tab["edge"]), _lib.ptr(len32), _lib.ptr(tab["overflow"]), _lib.ptr(ws), ctypes.c_int64(ws.numel()),
+            int(max(1, n // max(len(self._mp_features) * B, 1))), _lib.stream_ptr(dev))
+        _lib.check(code, "trb_kjt_route_ex")
+        routed = KeyedJaggedTensor(keys=self._routed_keys, values=new_values, weights=None if new_w is None else new_w.to(w.dtype),
+                                   lengths=len32[: U * B].to(features.lengths().dtype), stride=B)
+        return routed, unb
 
     def input_dist_routed(self, routed: KeyedJaggedTensor) -> Awaitable[Awaitable[KeyedJaggedTensor]]:
         """Input dist of a KJT that is already in global unit order (keys = unit features)."""
