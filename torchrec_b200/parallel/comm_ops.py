@@ -87,6 +87,7 @@ class All2AllPooledInfo:
     dim_sum_per_rank_tensor: Optional[torch.Tensor] = None
     cumsum_dim_sum_per_rank_tensor: Optional[torch.Tensor] = None
     codecs: Optional[QuantizedCommCodecs] = None
+    comm: Optional[Any] = None  # All2AllSingle: allocation + transport of the forward exchange
 
 
 def _enc(codecs: Optional[QuantizedCommCodecs], t: torch.Tensor, fwd: bool) -> torch.Tensor:
@@ -120,9 +121,14 @@ class _A2APooledReq(Function):
         if info.codecs is not None:
             in_splits = [info.codecs.forward.calc_quantized_size(s) for s in in_splits]
             out_splits = [info.codecs.forward.calc_quantized_size(s) for s in out_splits]
-        recv = torch.empty(sum(out_splits), dtype=send.dtype, device=x.device)
+        comm = getattr(info, "comm", None)
         with record_function("## alltoall_pooled fwd ##"):
-            h.work = dist.all_to_all_single(recv, send, out_splits, in_splits, group=pg, async_op=True)
+            if comm is not None:  # caller-provided allocation + transport (All2AllSingle)
+                recv = comm.allocate(sum(out_splits), send.dtype, x.device)
+                h.work = comm.all_to_all_single(recv, send, out_splits, in_splits, async_op=True)
+            else:
+                recv = torch.empty(sum(out_splits), dtype=send.dtype, device=x.device)
+                h.work = dist.all_to_all_single(recv, send, out_splits, in_splits, group=pg, async_op=True)
         h.buf = recv
         h.extra = (out_splits, B_local, x.dtype)
         return x.new_zeros(1)
@@ -178,13 +184,20 @@ def alltoall_pooled(
     cumsum_dim_sum_per_rank_tensor: Optional[torch.Tensor] = None,
     group: Optional[dist.ProcessGroup] = None,
     codecs: Optional[QuantizedCommCodecs] = None,
+    comm: Optional[Any] = None,
 ) -> Awaitable[torch.Tensor]:
     """Pooled embeddings ``[sum_r B_r, D_local]`` (rows grouped by destination rank) ->
-    ``[B_local, sum_r D_r]`` (columns grouped by source rank)."""
+    ``[B_local, sum_r D_r]`` (columns grouped by source rank). ``comm``: an ``All2AllSingle`` (comm_ops_sync.py) that supplies
+    the receive-buffer allocation and the transport of the forward exchange."""
     pg = _pg(group)
     if dist.get_world_size(pg) <= 1:
         return NoWait(a2a_pooled_embs_tensor)
+    if USE_SYNC_COLLECTIVES and codecs is None:
+        from .comm_ops_sync import all2all_pooled_sync
+
+        return NoWait(all2all_pooled_sync(pg, batch_size_per_rank, dim_sum_per_rank, a2a_pooled_embs_tensor, None, GRADIENT_DIVISION))
     info = All2AllPooledInfo(batch_size_per_rank, dim_sum_per_rank, dim_sum_per_rank_tensor, cumsum_dim_sum_per_rank_tensor, codecs)
+    info.comm = comm
     h = _Handle()
     dummy = _A2APooledReq.apply(pg, h, info, a2a_pooled_embs_tensor)
     return Request(lambda: _A2APooledWait.apply(pg, h, info, dummy))
@@ -457,6 +470,10 @@ def reduce_scatter_v_pooled(input: torch.Tensor, input_splits: List[int], group:
     pg = _pg(group)
     if dist.get_world_size(pg) <= 1:
         return NoWait(input)
+    if USE_SYNC_COLLECTIVES and codecs is None:
+        from .comm_ops_sync import reduce_scatter_v_sync
+
+        return NoWait(reduce_scatter_v_sync(pg, input, list(input_splits), GRADIENT_DIVISION))
     return NoWait(_ReduceScatterV.apply(pg, list(input_splits), codecs, input))
 
 
@@ -467,6 +484,10 @@ def reduce_scatter_base_pooled(input: torch.Tensor, group: Optional[dist.Process
     W = dist.get_world_size(pg)
     if W <= 1:
         return NoWait(input)
+    if USE_SYNC_COLLECTIVES and codecs is None:
+        from .comm_ops_sync import reduce_scatter_base_sync
+
+        return NoWait(reduce_scatter_base_sync(pg, input, GRADIENT_DIVISION))
     return NoWait(_ReduceScatterV.apply(pg, [input.shape[0] // W] * W, codecs, input))
 
 
@@ -512,4 +533,8 @@ def all_gather_base_pooled(input: torch.Tensor, group: Optional[dist.ProcessGrou
     pg = _pg(group)
     if dist.get_world_size(pg) <= 1:
         return NoWait(input)
+    if USE_SYNC_COLLECTIVES and codecs is None:
+        from .comm_ops_sync import all_gather_base_sync
+
+        return NoWait(all_gather_base_sync(pg, input, GRADIENT_DIVISION))
     return NoWait(_AllGatherBase.apply(pg, codecs, input))
