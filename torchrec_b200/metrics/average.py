@@ -1,16 +1,35 @@
 """Weighted mean of labels and predictions.
 
-Reference module: ``torchrec/metrics/average.py``. The metric classes live in ``metrics_impl.py`` (one sum-state / sample-buffer base for all 40+ metrics);
-this module gives them their reference import path and holds the stateless ``compute_*`` / ``get_*_states`` helpers."""
+Reference module: ``torchrec/metrics/average.py``. The computation (states, update, reports) and the ``RecMetric`` class of this metric, on the shared bases of ``_bases.py``, plus the stateless
+``compute_*`` / ``get_*_states`` helpers of the reference module."""
 from __future__ import annotations
 
 from typing import Dict, List, Optional
 
 import torch
 
-from .metrics_impl import AverageMetric, AverageMetricComputation  # noqa: F401
+from ._bases import EPS, _SumStatesComputation, _make  # noqa: F401
+from .metrics_namespace import MetricName, MetricNamespace, MetricPrefix  # noqa: F401
+from .rec_metric import MetricComputationReport, RecMetric, RecMetricComputation, RecMetricException  # noqa: F401
 
-EPS = torch.finfo(torch.float64).eps
+
+class AverageMetricComputation(_SumStatesComputation):
+    """Mean of the labels (useful for tracking target statistics)."""
+
+    STATES = ["sum", "num_samples"]
+
+    def _needs(self):
+        return []
+
+    def _batch_states(self, predictions, labels, weights, **kwargs):
+        return {"sum": (labels.double() * weights.double()).sum(-1), "num_samples": weights.double().sum(-1)}
+
+    def _reports(self, get, prefix):
+        return [MetricComputationReport(MetricName.AVERAGE, prefix, get("sum") / (get("num_samples") + EPS))]
+
+
+AverageMetric = _make("AverageMetric", AverageMetricComputation, MetricNamespace.AVERAGE)
+
 
 def compute_average(value_sum: torch.Tensor, weighted_num_samples: torch.Tensor) -> torch.Tensor:
     return torch.where(weighted_num_samples == 0.0, torch.zeros_like(value_sum), value_sum / weighted_num_samples).double()

@@ -1,16 +1,51 @@
 """Precision / recall at the threshold that reaches a target precision in hindsight.
 
-Reference module: ``torchrec/metrics/hindsight_target_pr.py``. The metric classes live in ``metrics_impl.py`` (one sum-state / sample-buffer base for all 40+ metrics);
-this module gives them their reference import path and holds the stateless ``compute_*`` / ``get_*_states`` helpers."""
+Reference module: ``torchrec/metrics/hindsight_target_pr.py``. The computation (states, update, reports) and the ``RecMetric`` class of this metric, on the shared bases of ``_bases.py``, plus the stateless
+``compute_*`` / ``get_*_states`` helpers of the reference module."""
 from __future__ import annotations
 
 from typing import Dict, List, Optional
 
 import torch
 
-from .metrics_impl import HindsightTargetPRMetric, HindsightTargetPRMetricComputation  # noqa: F401
+from ._bases import EPS, _make  # noqa: F401
+from .metrics_namespace import MetricName, MetricNamespace, MetricPrefix  # noqa: F401
+from .rec_metric import MetricComputationReport, RecMetric, RecMetricComputation, RecMetricException  # noqa: F401
+import time
+from typing import Any, Type  # noqa: F401
 
-EPS = torch.finfo(torch.float64).eps
+
+class HindsightTargetPRMetricComputation(RecMetricComputation):
+    """Precision/recall at the threshold that reaches a target precision in hindsight (bucketed thresholds)."""
+
+    def __init__(self, *args: Any, target_precision: float = 0.5, threshold_granularity: int = 1000, **kwargs: Any) -> None:
+        super().__init__(*args, **kwargs)
+        self._target = target_precision
+        self._gran = threshold_granularity
+        for s in ["true_pos_sum", "false_pos_sum", "false_neg_sum"]:
+            self._add_state(s, torch.zeros(self._n_tasks, threshold_granularity, dtype=torch.double), add_window_state=False, dist_reduce_fx="sum")
+
+    def update(self, *, predictions, labels, weights, **kwargs: Any) -> None:
+        th = torch.linspace(0, 1, self._gran, dtype=torch.double).view(1, -1, 1)
+        pred = (predictions.double().unsqueeze(1) >= th).double()
+        l, w = labels.double().unsqueeze(1), weights.double().unsqueeze(1)
+        self.true_pos_sum += (w * pred * l).sum(-1).to(self.true_pos_sum.device)
+        self.false_pos_sum += (w * pred * (1 - l)).sum(-1).to(self.true_pos_sum.device)
+        self.false_neg_sum += (w * (1 - pred) * l).sum(-1).to(self.true_pos_sum.device)
+
+    def _compute(self) -> List[MetricComputationReport]:
+        prec = self.true_pos_sum / (self.true_pos_sum + self.false_pos_sum + EPS)
+        rec = self.true_pos_sum / (self.true_pos_sum + self.false_neg_sum + EPS)
+        ok = prec >= self._target
+        idx = torch.where(ok.any(-1), ok.double().argmax(-1), torch.full((self._n_tasks,), self._gran - 1))
+        ar = torch.arange(self._n_tasks)
+        return [MetricComputationReport(MetricName.HINDSIGHT_TARGET_PR, MetricPrefix.LIFETIME, idx.double() / (self._gran - 1), description="_threshold"),
+                MetricComputationReport(MetricName.HINDSIGHT_TARGET_PR, MetricPrefix.LIFETIME, prec[ar, idx], description="_precision"),
+                MetricComputationReport(MetricName.HINDSIGHT_TARGET_PR, MetricPrefix.LIFETIME, rec[ar, idx], description="_recall")]
+
+
+HindsightTargetPRMetric = _make("HindsightTargetPRMetric", HindsightTargetPRMetricComputation, MetricNamespace.HINDSIGHT_TARGET_PR)
+
 
 def compute_precision(num_true_positives: torch.Tensor, num_false_positives: torch.Tensor) -> torch.Tensor:
     d = num_true_positives + num_false_positives

@@ -182,63 +182,6 @@ class RecMetricModule(nn.Module):
         return total
 
 
-class CPUOffloadedRecMetricModule(RecMetricModule):
-    """Asynchronous variant: ``update`` enqueues non-blocking D2H copies of the model outputs and a background
-    thread updates / computes the metrics on the CPU, keeping the training stream free
-    (reference cpu_offloaded_metric_module.py:136)."""
-
-    def __init__(self, *args: Any, update_queue_size: int = 100, compute_queue_size: int = 100, device: Optional[torch.device] = None, **kwargs: Any) -> None:
-        super().__init__(*args, **kwargs)
-        self._queue: "queue.Queue" = queue.Queue(maxsize=update_queue_size)
-        self._shutdown = threading.Event()
-        self._lock = threading.Lock()
-        self._worker = threading.Thread(target=self._run, daemon=True, name="metric_update")
-        self._executor = concurrent.futures.ThreadPoolExecutor(max_workers=1, thread_name_prefix="metric_compute")
-        self._worker.start()
-
-    def update(self, model_out: Dict[str, torch.Tensor], **kwargs: Any) -> None:
-        cpu_out: Dict[str, torch.Tensor] = {}
-        ev = None
-        for k, v in model_out.items():
-            if isinstance(v, torch.Tensor) and v.is_cuda:
-                buf = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
-                buf.copy_(v.detach(), non_blocking=True)
-                cpu_out[k] = buf
-            else:
-                cpu_out[k] = v
-        if torch.cuda.is_available():
-            ev = torch.cuda.Event()
-            ev.record()
-        self.trained_batches += 1
-        if self.throughput_metric:
-            self.throughput_metric.update()
-        self._queue.put((cpu_out, kwargs, ev))
-
-    def _run(self) -> None:
-        while not self._shutdown.is_set():
-            try:
-                item = self._queue.get(timeout=0.1)
-            except queue.Empty:
-                continue
-            out, kwargs, ev = item
-            if ev is not None:
-                ev.synchronize()
-            with self._lock, torch.no_grad():
-                self._update_rec_metrics(out, **kwargs)
-            self._queue.task_done()
-
-    def compute(self) -> Dict[str, MetricValue]:
-        self._queue.join()
-        with self._lock:
-            return super().compute()
-
-    def async_compute(self) -> "concurrent.futures.Future":
-        return self._executor.submit(self.compute)
-
-    def shutdown(self) -> None:
-        self._shutdown.set()
-        self._worker.join(timeout=5)
-        self._executor.shutdown(wait=False)
 
 
 def _generate_rec_metrics(metrics_config: MetricsConfig, world_size: int, my_rank: int, batch_size: int, process_group: Optional[dist.ProcessGroup] = None) -> RecMetricList:
@@ -291,3 +234,15 @@ def generate_metric_module(metric_class: Type[RecMetricModule], metrics_config: 
                            min_compute_interval=metrics_config.min_compute_interval, max_compute_interval=metrics_config.max_compute_interval)
     metrics.to(device)
     return metrics
+
+
+# ---- moved to ``cpu_offloaded_metric_module.py`` (their reference import path); still importable from here ----
+_MOVED_TO_CPU_OFFLOADED_METRIC_MODULE = ('CPUOffloadedRecMetricModule',)
+
+
+def __getattr__(name: str):
+    if name in _MOVED_TO_CPU_OFFLOADED_METRIC_MODULE:
+        from . import cpu_offloaded_metric_module as _m
+
+        return getattr(_m, name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

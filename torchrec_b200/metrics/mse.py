@@ -1,16 +1,32 @@
 """Mean squared error, RMSE and R^2.
 
-Reference module: ``torchrec/metrics/mse.py``. The metric classes live in ``metrics_impl.py`` (one sum-state / sample-buffer base for all 40+ metrics);
-this module gives them their reference import path and holds the stateless ``compute_*`` / ``get_*_states`` helpers."""
+Reference module: ``torchrec/metrics/mse.py``. The computation (states, update, reports) and the ``RecMetric`` class of this metric, on the shared bases of ``_bases.py``, plus the stateless
+``compute_*`` / ``get_*_states`` helpers of the reference module."""
 from __future__ import annotations
 
 from typing import Dict, List, Optional
 
 import torch
 
-from .metrics_impl import MSEMetric, MSEMetricComputation  # noqa: F401
+from ._bases import EPS, _SumStatesComputation, _make  # noqa: F401
+from .metrics_namespace import MetricName, MetricNamespace, MetricPrefix  # noqa: F401
+from .rec_metric import MetricComputationReport, RecMetric, RecMetricComputation, RecMetricException  # noqa: F401
 
-EPS = torch.finfo(torch.float64).eps
+
+class MSEMetricComputation(_SumStatesComputation):
+    STATES = ["error_sum", "weighted_num_samples"]
+
+    def _batch_states(self, predictions, labels, weights, **kwargs):
+        d = predictions.double() - labels.double()
+        return {"error_sum": (weights.double() * d * d).sum(-1), "weighted_num_samples": weights.double().sum(-1)}
+
+    def _reports(self, get, prefix):
+        mse = get("error_sum") / (get("weighted_num_samples") + EPS)
+        return [MetricComputationReport(MetricName.MSE, prefix, mse), MetricComputationReport(MetricName.RMSE, prefix, torch.sqrt(mse))]
+
+
+MSEMetric = _make("MSEMetric", MSEMetricComputation, MetricNamespace.MSE)
+
 
 def compute_mse(error_sum: torch.Tensor, weighted_num_samples: torch.Tensor) -> torch.Tensor:
     return torch.where(weighted_num_samples == 0.0, torch.zeros_like(error_sum), error_sum / weighted_num_samples).double()

@@ -1,16 +1,27 @@
 """Precision of multi-label predictions at a threshold.
 
-Reference module: ``torchrec/metrics/multi_label_precision.py``. The metric classes live in ``metrics_impl.py`` (one sum-state / sample-buffer base for all 40+ metrics);
-this module gives them their reference import path and holds the stateless ``compute_*`` / ``get_*_states`` helpers."""
+Reference module: ``torchrec/metrics/multi_label_precision.py``. The computation (states, update, reports) and the ``RecMetric`` class of this metric, on the shared bases of ``_bases.py``, plus the stateless
+``compute_*`` / ``get_*_states`` helpers of the reference module."""
 from __future__ import annotations
 
 from typing import Dict, List, Optional
 
 import torch
 
-from .metrics_impl import MultiLabelPrecisionMetric, MultiLabelPrecisionMetricComputation  # noqa: F401
+from ._bases import EPS, _make  # noqa: F401
+from .metrics_namespace import MetricName, MetricNamespace, MetricPrefix  # noqa: F401
+from .rec_metric import MetricComputationReport, RecMetric, RecMetricComputation, RecMetricException  # noqa: F401
+from .precision import PrecisionMetricComputation  # noqa: F401
 
-EPS = torch.finfo(torch.float64).eps
+
+class MultiLabelPrecisionMetricComputation(PrecisionMetricComputation):
+    def _reports(self, get, prefix):
+        r = super()._reports(get, prefix)
+        return [MetricComputationReport(MetricName.MULTI_LABEL_PRECISION, prefix, r[0].value)]
+
+
+MultiLabelPrecisionMetric = _make("MultiLabelPrecisionMetric", MultiLabelPrecisionMetricComputation, MetricNamespace.MULTI_LABEL_PRECISION)
+
 
 def compute_multi_label_precision(true_pos_sum: torch.Tensor, false_pos_sum: torch.Tensor) -> torch.Tensor:
     d = true_pos_sum + false_pos_sum

@@ -1,16 +1,56 @@
 """Normalized entropy.
 
-Reference module: ``torchrec/metrics/ne.py``. The metric classes live in ``metrics_impl.py`` (one sum-state / sample-buffer base for all 40+ metrics);
-this module gives them their reference import path and holds the stateless ``compute_*`` / ``get_*_states`` helpers."""
+Reference module: ``torchrec/metrics/ne.py``. The computation (states, update, reports) and the ``RecMetric`` class of this metric, on the shared bases of ``_bases.py``, plus the stateless
+``compute_*`` / ``get_*_states`` helpers of the reference module."""
 from __future__ import annotations
 
 from typing import Dict, List, Optional
 
 import torch
 
-from .metrics_impl import NEMetric, NEMetricComputation, compute_ne  # noqa: F401
+from ._bases import EPS, _SumStatesComputation, _make  # noqa: F401
+from .metrics_namespace import MetricName, MetricNamespace, MetricPrefix  # noqa: F401
+from .rec_metric import MetricComputationReport, RecMetric, RecMetricComputation, RecMetricException  # noqa: F401
+import time
+from typing import Any, Type  # noqa: F401
 
-EPS = torch.finfo(torch.float64).eps
+
+def _ce(labels, preds, weights, eta=1e-12):
+    p = torch.clamp(preds.double(), eta, 1 - eta)
+    return -weights.double() * (labels.double() * torch.log2(p) + (1 - labels.double()) * torch.log2(1 - p))
+
+
+class NEMetricComputation(_SumStatesComputation):
+    """Normalized entropy = cross entropy / entropy of the base rate. ``include_logloss`` adds logloss."""
+
+    STATES = ["cross_entropy_sum", "weighted_num_samples", "pos_labels", "neg_labels"]
+
+    def __init__(self, *args: Any, include_logloss: bool = False, allow_missing_label_with_zero_weight: bool = False, **kwargs: Any) -> None:
+        self._include_logloss = include_logloss
+        super().__init__(*args, **kwargs)
+        self.eta = 1e-12
+
+    def _batch_states(self, predictions, labels, weights, **kwargs):
+        return {"cross_entropy_sum": _ce(labels, predictions, weights, self.eta).sum(-1), "weighted_num_samples": weights.double().sum(-1),
+                "pos_labels": (weights.double() * labels.double()).sum(-1), "neg_labels": (weights.double() * (1 - labels.double())).sum(-1)}
+
+    def _reports(self, get, prefix):
+        ne = compute_ne(get("cross_entropy_sum"), get("weighted_num_samples"), get("pos_labels"), get("neg_labels"), self.eta)
+        out = [MetricComputationReport(MetricName.NE, prefix, ne)]
+        if self._include_logloss:
+            ll = get("cross_entropy_sum") / (get("weighted_num_samples") + EPS) * torch.log(torch.tensor(2.0, dtype=torch.double))
+            out.append(MetricComputationReport(MetricName.LOG_LOSS, prefix, ll))
+        return out
+
+
+def compute_ne(ce_sum, weighted_num_samples, pos_labels, neg_labels, eta=1e-12) -> torch.Tensor:
+    mean_label = pos_labels / (weighted_num_samples + EPS)
+    ce_norm = -(pos_labels * torch.log2(mean_label + eta) + neg_labels * torch.log2(1 - mean_label + eta))
+    return ce_sum / (ce_norm + EPS)
+
+
+NEMetric = _make("NEMetric", NEMetricComputation, MetricNamespace.NE)
+
 
 def compute_cross_entropy(labels: torch.Tensor, predictions: torch.Tensor, weights: torch.Tensor, eta: float) -> torch.Tensor:
     p = torch.clamp(predictions.double(), eta, 1 - eta)

@@ -1,16 +1,38 @@
 """Weighted precision at a threshold.
 
-Reference module: ``torchrec/metrics/precision.py``. The metric classes live in ``metrics_impl.py`` (one sum-state / sample-buffer base for all 40+ metrics);
-this module gives them their reference import path and holds the stateless ``compute_*`` / ``get_*_states`` helpers."""
+Reference module: ``torchrec/metrics/precision.py``. The computation (states, update, reports) and the ``RecMetric`` class of this metric, on the shared bases of ``_bases.py``, plus the stateless
+``compute_*`` / ``get_*_states`` helpers of the reference module."""
 from __future__ import annotations
 
 from typing import Dict, List, Optional
 
 import torch
 
-from .metrics_impl import PrecisionMetric, PrecisionMetricComputation  # noqa: F401
+from ._bases import EPS, _SumStatesComputation, _make  # noqa: F401
+from .metrics_namespace import MetricName, MetricNamespace, MetricPrefix  # noqa: F401
+from .rec_metric import MetricComputationReport, RecMetric, RecMetricComputation, RecMetricException  # noqa: F401
+import time
+from typing import Any, Type  # noqa: F401
 
-EPS = torch.finfo(torch.float64).eps
+
+class PrecisionMetricComputation(_SumStatesComputation):
+    STATES = ["true_pos_sum", "false_pos_sum"]
+
+    def __init__(self, *args: Any, threshold: float = 0.5, **kwargs: Any) -> None:
+        self._threshold = threshold
+        super().__init__(*args, **kwargs)
+
+    def _batch_states(self, predictions, labels, weights, **kwargs):
+        pred = (predictions.double() >= self._threshold).double()
+        return {"true_pos_sum": (weights.double() * pred * labels.double()).sum(-1), "false_pos_sum": (weights.double() * pred * (1 - labels.double())).sum(-1)}
+
+    def _reports(self, get, prefix):
+        tp, fp = get("true_pos_sum"), get("false_pos_sum")
+        return [MetricComputationReport(MetricName.PRECISION, prefix, torch.where(tp + fp == 0.0, torch.zeros_like(tp), tp / (tp + fp)))]
+
+
+PrecisionMetric = _make("PrecisionMetric", PrecisionMetricComputation, MetricNamespace.PRECISION)
+
 
 def compute_precision(num_true_positives: torch.Tensor, num_false_positives: torch.Tensor) -> torch.Tensor:
     d = num_true_positives + num_false_positives

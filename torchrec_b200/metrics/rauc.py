@@ -1,16 +1,39 @@
 """Regression AUC: fraction of correctly ordered (prediction, label) pairs.
 
-Reference module: ``torchrec/metrics/rauc.py``. The metric classes live in ``metrics_impl.py`` (one sum-state / sample-buffer base for all 40+ metrics);
-this module gives them their reference import path and holds the stateless ``compute_*`` / ``get_*_states`` helpers."""
+Reference module: ``torchrec/metrics/rauc.py``. The computation (states, update, reports) and the ``RecMetric`` class of this metric, on the shared bases of ``_bases.py``, plus the stateless
+``compute_*`` / ``get_*_states`` helpers of the reference module."""
 from __future__ import annotations
 
 from typing import Dict, List, Optional
 
 import torch
 
-from .metrics_impl import RAUCMetric, RAUCMetricComputation  # noqa: F401
+from ._bases import EPS, _SampleBufferComputation, _make  # noqa: F401
+from .metrics_namespace import MetricName, MetricNamespace, MetricPrefix  # noqa: F401
+from .rec_metric import MetricComputationReport, RecMetric, RecMetricComputation, RecMetricException  # noqa: F401
 
-EPS = torch.finfo(torch.float64).eps
+
+class RAUCMetricComputation(_SampleBufferComputation):
+    """Regression AUC: fraction of correctly ordered pairs (concordance) for continuous labels."""
+
+    NAME = MetricName.RAUC
+
+    def _value(self, p, l, w, extra):
+        n = p.numel()
+        if n < 2:
+            return torch.tensor(0.5, dtype=torch.double)
+        if n > 4096:  # subsample for the O(n^2) pair count
+            idx = torch.randperm(n)[:4096]
+            p, l = p[idx], l[idx]
+        dp = p.unsqueeze(0) - p.unsqueeze(1)
+        dl = l.unsqueeze(0) - l.unsqueeze(1)
+        valid = dl != 0
+        conc = ((dp * dl) > 0).double() + 0.5 * (dp == 0).double()
+        return (conc * valid).sum() / (valid.sum() + EPS)
+
+
+RAUCMetric = _make("RAUCMetric", RAUCMetricComputation, MetricNamespace.RAUC)
+
 
 def count_reverse_pairs_divide_and_conquer(input: List[float]) -> float:
     """Number of inversions of ``input`` by merge sort, O(n log n)."""

@@ -1,11 +1,22 @@
 """Calibration of the serving-time prediction.
 
-Reference module: ``torchrec/metrics/serving_calibration.py``. The metric classes live in ``metrics_impl.py`` (one sum-state / sample-buffer base for all 40+ metrics);
-this module gives them their reference import path and holds the stateless ``compute_*`` / ``get_*_states`` helpers."""
+Reference module: ``torchrec/metrics/serving_calibration.py``. The computation (states, update, reports) and the ``RecMetric`` class of this metric, on the shared bases of ``_bases.py``, plus the stateless
+``compute_*`` / ``get_*_states`` helpers of the reference module."""
 from __future__ import annotations
 
 from typing import Dict, List, Optional
 
 import torch
 
-from .metrics_impl import ServingCalibrationMetric, ServingCalibrationMetricComputation  # noqa: F401
+from ._bases import EPS, _make  # noqa: F401
+from .metrics_namespace import MetricName, MetricNamespace, MetricPrefix  # noqa: F401
+from .rec_metric import MetricComputationReport, RecMetric, RecMetricComputation, RecMetricException  # noqa: F401
+from .calibration import CalibrationMetricComputation  # noqa: F401
+
+
+class ServingCalibrationMetricComputation(CalibrationMetricComputation):
+    def _reports(self, get, prefix):
+        return [MetricComputationReport(MetricName.SERVING_CALIBRATION, prefix, get("calibration_num") / (get("calibration_denom") + EPS))]
+
+
+ServingCalibrationMetric = _make("ServingCalibrationMetric", ServingCalibrationMetricComputation, MetricNamespace.SERVING_CALIBRATION)

@@ -1,16 +1,33 @@
 """Weighted sum of the predictions.
 
-Reference module: ``torchrec/metrics/weighted_sum_predictions.py``. The metric classes live in ``metrics_impl.py`` (one sum-state / sample-buffer base for all 40+ metrics);
-this module gives them their reference import path and holds the stateless ``compute_*`` / ``get_*_states`` helpers."""
+Reference module: ``torchrec/metrics/weighted_sum_predictions.py``. The computation (states, update, reports) and the ``RecMetric`` class of this metric, on the shared bases of ``_bases.py``, plus the stateless
+``compute_*`` / ``get_*_states`` helpers of the reference module."""
 from __future__ import annotations
 
 from typing import Dict, List, Optional
 
 import torch
 
-from .metrics_impl import WeightedSumPredictionsMetric, WeightedSumPredictionsMetricComputation  # noqa: F401
+from ._bases import EPS, _SingleSumComputation, _make  # noqa: F401
+from .metrics_namespace import MetricName, MetricNamespace, MetricPrefix  # noqa: F401
+from .rec_metric import MetricComputationReport, RecMetric, RecMetricComputation, RecMetricException  # noqa: F401
 
-EPS = torch.finfo(torch.float64).eps
+
+class WeightedSumPredictionsMetricComputation(_SingleSumComputation):
+    """sum w * prediction (NaN predictions count 0). Parity: weighted_sum_predictions.py:21-99."""
+
+    STATES = ["weighted_predictions_sum"]
+    NAME = MetricName.WEIGHTED_SUM_PREDICTIONS
+
+    def _needs(self):
+        return ["predictions"]
+
+    def _sum(self, predictions, labels, weights):
+        return (weights.double() * torch.nan_to_num(predictions.double(), 0.0)).sum(-1)
+
+
+WeightedSumPredictionsMetric = _make("WeightedSumPredictionsMetric", WeightedSumPredictionsMetricComputation, MetricNamespace.WEIGHTED_SUM_PREDICTIONS)
+
 
 def compute_weighted_predictions_sum(labels: torch.Tensor, predictions: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
     return (weights.double() * torch.nan_to_num(predictions.double(), 0.0)).sum(-1)

@@ -1,16 +1,40 @@
 """Cross AUC for regression: weighted fraction of pairs ordered like their labels.
 
-Reference module: ``torchrec/metrics/xauc.py``. The metric classes live in ``metrics_impl.py`` (one sum-state / sample-buffer base for all 40+ metrics);
-this module gives them their reference import path and holds the stateless ``compute_*`` / ``get_*_states`` helpers."""
+Reference module: ``torchrec/metrics/xauc.py``. The computation (states, update, reports) and the ``RecMetric`` class of this metric, on the shared bases of ``_bases.py``, plus the stateless
+``compute_*`` / ``get_*_states`` helpers of the reference module."""
 from __future__ import annotations
 
 from typing import Dict, List, Optional
 
 import torch
 
-from .metrics_impl import XAUCMetric, XAUCMetricComputation  # noqa: F401
+from ._bases import EPS, _SampleBufferComputation, _make  # noqa: F401
+from .metrics_namespace import MetricName, MetricNamespace, MetricPrefix  # noqa: F401
+from .rec_metric import MetricComputationReport, RecMetric, RecMetricComputation, RecMetricException  # noqa: F401
 
-EPS = torch.finfo(torch.float64).eps
+
+class XAUCMetricComputation(_SampleBufferComputation):
+    """Cross AUC for regression: P(pred_i > pred_j | label_i > label_j), weighted by w_i * w_j."""
+
+    NAME = MetricName.XAUC
+
+    def _value(self, p, l, w, extra):
+        n = p.numel()
+        if n < 2:
+            return torch.tensor(0.0, dtype=torch.double)
+        if n > 4096:
+            idx = torch.randperm(n)[:4096]
+            p, l, w = p[idx], l[idx], w[idx]
+        ww = w.unsqueeze(0) * w.unsqueeze(1)
+        dp = torch.sign(p.unsqueeze(0) - p.unsqueeze(1))
+        dl = torch.sign(l.unsqueeze(0) - l.unsqueeze(1))
+        match = ((dp == dl) & (dl != 0)).double()
+        iu = torch.triu(torch.ones(n, n, dtype=torch.bool), diagonal=1)
+        return (ww * match)[iu].sum() / (ww[iu].sum() + EPS)
+
+
+XAUCMetric = _make("XAUCMetric", XAUCMetricComputation, MetricNamespace.XAUC)
+
 
 def compute_error_sum(labels: torch.Tensor, predictions: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
     """Weighted count of pairs (i < j) whose prediction order agrees with their label order."""

@@ -98,35 +98,13 @@ class RowwiseShardedITEPModule(GenericITEPModule):
         self.table_name_to_sharding_type = table_name_to_sharding_type or {}
 
 
-class ITEPEmbeddingBagCollection(nn.Module):
-    def __init__(self, embedding_bag_collection: EmbeddingBagCollection, itep_module: GenericITEPModule) -> None:
-        super().__init__()
-        self._embedding_bag_collection = embedding_bag_collection
-        self._itep_module = itep_module
-        if not itep_module.feature_to_table:
-            itep_module.feature_to_table = {f: c.name for c in embedding_bag_collection.embedding_bag_configs() for f in c.feature_names}
-        self.register_buffer("_iter", torch.tensor(0, dtype=torch.int64))
-
-    def forward(self, features: KeyedJaggedTensor, force_insert: bool = False) -> KeyedTensor:
-        features = self._itep_module(features, int(self._iter.item()))
-        out = self._embedding_bag_collection(features)
-        if self.training:
-            self._iter += 1
-        return out
+# ---- moved to ``itep_embedding_modules.py`` (their reference import path); still importable from here ----
+_MOVED_TO_ITEP_EMBEDDING_MODULES = ('ITEPEmbeddingBagCollection', 'ITEPEmbeddingCollection')
 
 
-class ITEPEmbeddingCollection(nn.Module):
-    def __init__(self, embedding_collection: EmbeddingCollection, itep_module: GenericITEPModule) -> None:
-        super().__init__()
-        self._embedding_collection = embedding_collection
-        self._itep_module = itep_module
-        if not itep_module.feature_to_table:
-            itep_module.feature_to_table = {f: c.name for c in embedding_collection.embedding_configs() for f in c.feature_names}
-        self.register_buffer("_iter", torch.tensor(0, dtype=torch.int64))
+def __getattr__(name: str):
+    if name in _MOVED_TO_ITEP_EMBEDDING_MODULES:
+        from . import itep_embedding_modules as _m
 
-    def forward(self, features: KeyedJaggedTensor, force_insert: bool = False):
-        features = self._itep_module(features, int(self._iter.item()))
-        out = self._embedding_collection(features)
-        if self.training:
-            self._iter += 1
-        return out
+        return getattr(_m, name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

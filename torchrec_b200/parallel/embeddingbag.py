@@ -143,12 +143,19 @@ def _sharded_tensor_from_local(local: List[Tuple[torch.Tensor, List[int], List[i
     return ShardedTensor._init_from_local_shards_and_global_metadata(local_shards, md, process_group=pg)
 
 
-_MESH_CACHE: Dict[Tuple[int, str], Any] = {}
+_MESH_CACHE: Dict[Any, Any] = {}
 
 
 def _mesh_of(env: ShardingEnv, device_type: str):
     """1-D device mesh over the sharding group (created once per group; collective on first use)."""
     mesh = getattr(env, "device_mesh", None)
+    if isinstance(mesh, (list, tuple)):  # 2D parallel: a [replicas][shards] rank matrix (DMPCollection._create_process_groups)
+        key = (tuple(tuple(r) for r in mesh), device_type)
+        if key not in _MESH_CACHE:
+            from torch.distributed.device_mesh import DeviceMesh
+
+            _MESH_CACHE[key] = DeviceMesh(device_type, torch.tensor(mesh, dtype=torch.int64), mesh_dim_names=("replicate", "shard"))
+        return _MESH_CACHE[key]
     if mesh is not None:
         return mesh
     key = (id(env.process_group), device_type)

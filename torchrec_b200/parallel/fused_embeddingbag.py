@@ -51,25 +51,13 @@ class FusedEmbeddingBagCollectionSharder(BaseEmbeddingSharder[FusedEmbeddingBagC
         return [t for t in super().sharding_types(compute_device_type) if t != ShardingType.DATA_PARALLEL.value]
 
 
-class ShardedFusedEmbeddingCollection(ShardedEmbeddingCollection):
-    def __init__(self, module: FusedEmbeddingCollection, table_name_to_parameter_sharding: Dict[str, ParameterSharding], env: ShardingEnv,
-                 fused_params: Optional[Dict[str, Any]] = None, device: Optional[torch.device] = None, qcomm_codecs_registry=None, **kw: Any) -> None:
-        super().__init__(module, table_name_to_parameter_sharding, env, _fused_params_of(module, fused_params), device, qcomm_codecs_registry, **kw)
+# ---- moved to ``fused_embedding.py`` (their reference import path); still importable from here ----
+_MOVED_TO_FUSED_EMBEDDING = ('ShardedFusedEmbeddingCollection', 'FusedEmbeddingCollectionSharder')
 
 
-class FusedEmbeddingCollectionSharder(BaseEmbeddingSharder[FusedEmbeddingCollection]):
-    def shard(self, module: FusedEmbeddingCollection, params: Dict[str, ParameterSharding], env: ShardingEnv, device: Optional[torch.device] = None,
-              module_fqn: Optional[str] = None) -> ShardedFusedEmbeddingCollection:
-        return ShardedFusedEmbeddingCollection(module, params, env, self.fused_params, device, self.qcomm_codecs_registry)
+def __getattr__(name: str):
+    if name in _MOVED_TO_FUSED_EMBEDDING:
+        from . import fused_embedding as _m
 
-    def shardable_parameters(self, module: FusedEmbeddingCollection) -> Dict[str, nn.Parameter]:
-        return {name: h.weight for name, h in module.embeddings.items()}
-
-    @property
-    def module_type(self) -> Type[FusedEmbeddingCollection]:
-        return FusedEmbeddingCollection
-
-    def sharding_types(self, compute_device_type: str) -> List[str]:
-        from .types import ShardingType
-
-        return [t for t in super().sharding_types(compute_device_type) if t != ShardingType.DATA_PARALLEL.value]
+        return getattr(_m, name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
