@@ -29,6 +29,7 @@ from ...streamable import Multistreamable, Pipelineable
 from ..model_parallel import DistributedModelParallel
 from ..types import Awaitable, ShardedModule
 from .pipeline_context import EmbeddingTrainPipelineContext, PrefetchTrainPipelineContext, TrainPipelineContext
+from .pipeline_stage import PipelineStage  # noqa: F401  (defined there, its reference import path)
 
 logger = logging.getLogger(__name__)
 
@@ -774,15 +775,6 @@ class PrefetchTrainPipelineSparseDist(TrainPipelineSparseDist[In, Out]):
         return output
 
 
-@dataclasses.dataclass
-class PipelineStage:
-    """One user-defined stage of a ``StagedTrainPipeline``."""
-
-    name: str
-    runnable: Callable[[Any], Any]
-    stream: Optional[torch.Stream] = None
-    fill_callback: Optional[Callable[[], None]] = None
-    data_exhausted_callback: Optional[Callable[[], None]] = None
 
 
 class StagedTrainPipeline(TrainPipeline[In, Optional[In]]):
