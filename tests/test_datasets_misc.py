@@ -253,3 +253,29 @@ def test_examples_nvt_binary_dataloader_and_data_parallel(tmp_path):
     assert b.dense_features.shape == (16, 13) and b.dense_features.dtype == torch.float32 and b.labels.shape == (16,)
     assert nvt.main(steps=60, batch_size=128) < 0.97                    # the planted signal is learnt from the files
     assert load("golden_training_data_parallel").main(["--cpu", "--steps", "6", "--batch-size", "64"]) < 1.0
+
+
+def test_kjt_validator_vbe_and_report():
+    import pytest
+    import torch
+
+    from torchrec_b200.modules.embedding_configs import EmbeddingBagConfig
+    from torchrec_b200.sparse.jagged_tensor import KeyedJaggedTensor
+    from torchrec_b200.sparse.jagged_tensor_validator import collect_problems, validate_keyed_jagged_tensor, validate_on_device
+
+    cfgs = [EmbeddingBagConfig(name="t0", embedding_dim=4, num_embeddings=5, feature_names=["a"]),
+            EmbeddingBagConfig(name="t1", embedding_dim=4, num_embeddings=3, feature_names=["b"])]
+    # variable batch: a has 2 samples, b has 1; full batch 3 through the inverse indices
+    vbe = KeyedJaggedTensor(keys=["a", "b"], values=torch.tensor([0, 1, 2, 2]), lengths=torch.tensor([2, 1, 1]), stride_per_key_per_rank=[[2], [1]],
+                            inverse_indices=(["a", "b"], torch.tensor([[0, 1, 0], [0, 0, 0]])))
+    assert validate_keyed_jagged_tensor(vbe, cfgs) is True and collect_problems(vbe, cfgs) == []
+    bad_inv = KeyedJaggedTensor(keys=["a", "b"], values=torch.tensor([0, 1, 2, 2]), lengths=torch.tensor([2, 1, 1]), stride_per_key_per_rank=[[2], [1]],
+                                inverse_indices=(["a", "b"], torch.tensor([[0, 1, 0], [0, 1, 0]])))  # b has one row: index 1 is outside
+    with pytest.raises(ValueError, match="inverse_indices entries"):
+        validate_keyed_jagged_tensor(bad_inv)
+    oob = KeyedJaggedTensor(keys=["a", "b"], values=torch.tensor([0, 7, 2, -1]), lengths=torch.tensor([1, 1, 1, 1]))
+    rep = collect_problems(oob, cfgs)
+    assert len(rep) == 2 and "feature a: 1 of 2" in rep[0] and "feature b: 1 of 2" in rep[1]
+    assert int(validate_on_device(oob, cfgs)) == 8 and int(validate_on_device(vbe, cfgs)) == 0
+    broken = KeyedJaggedTensor(keys=["a", "b"], values=torch.tensor([0, 1]), offsets=torch.tensor([0, 2, 1, 2, 2]))
+    assert int(validate_on_device(broken)) & 2
