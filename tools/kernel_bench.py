@@ -26,7 +26,7 @@ from torchrec_b200.ops.tbe import OptimType  # noqa: E402
 from torchrec_b200.parallel import sharding_plan as sp  # noqa: E402
 from torchrec_b200.parallel.embeddingbag import EmbeddingBagCollectionSharder  # noqa: E402
 from torchrec_b200.parallel.engine import OptimizerSpec, ShardedLookupEngine  # noqa: E402
-from torchrec_b200.parallel.sparse_plane import LoopbackGroup, SingleRankGroup  # noqa: E402
+from torchrec_b200.parallel.sparse_plane import LoopbackGroup  # noqa: E402
 from torchrec_b200.parallel.types import ShardingEnv  # noqa: E402
 from torchrec_b200.sparse.jagged_tensor import KeyedJaggedTensor  # noqa: E402
 
@@ -93,7 +93,7 @@ def sparse_cases(bn: Bench) -> None:
     # ---- one rank (the N=1 bench path: SingleRankGroup) ----
     plan = sp.construct_module_sharding_plan(ebc, {t.name: sp.table_wise(rank=0) for t in tables}, sharder=EmbeddingBagCollectionSharder(),
                                              world_size=1, local_size=1, device_type="cuda")
-    eng = engine(tables, names, plan, ShardingEnv.from_loopback(1, 0, SingleRankGroup(dev)), dev)
+    eng = engine(tables, names, plan, ShardingEnv.from_local(1, 0), dev)
     ids = eng.plane_input_dist(kjt, None, F * D, capacity=N + 64, training=False)
     pl = ids.plane
     reg = pl.regions(ids.slot)
@@ -142,7 +142,7 @@ def quant_cases(bn: Bench) -> None:
     g = torch.Generator().manual_seed(1)
     idx = torch.cat([torch.randint(0, r, (B,), generator=g) for r in rows]).to(dev).to(torch.int32)
     off = torch.arange(F * B + 1, dtype=torch.int32, device=dev)
-    for dt, label in ((DataType.INT8, "int8 rows"), (DataType.FP8_BLOCK, "fp8 128-block rows"), (DataType.INT4, "int4 rows"), (DataType.FP16, "fp16 rows")):
+    for dt, label in ((DataType.INT8, "int8 rows"), (DataType.FP8, "fp8 block-scaled rows"), (DataType.INT4, "int4 rows"), (DataType.FP16, "fp16 rows")):
         q = QuantTableBatchedEmbeddingBags([(f"t{i}", r, D, dt) for i, r in enumerate(rows)], output_dtype=torch.bfloat16, device=dev)
         q.weights.random_(0, 255)
         rb = q._row_bytes[0]

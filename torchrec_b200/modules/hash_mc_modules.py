@@ -3,8 +3,9 @@
 
 Open-addressing table of ``zch_size`` slots: an id hashes to a start slot inside its bucket and probes up to
 ``max_probe`` consecutive slots for itself or for a free / evictable slot. Eviction scoring is pluggable (none, LRU by
-last-seen hour, TTL). Replaces ``fbgemm.zero_collision_hash`` / ``create_zch_buffer``; the probe loop runs vectorised in
-PyTorch on CPU and GPU (all ids probe one step per iteration)."""
+last-seen hour, TTL). Replaces ``fbgemm.zero_collision_hash`` / ``create_zch_buffer``. On CUDA the whole probe is ONE kernel
+(``ops/csrc/zch.cu``: thread per id, atomicCAS slot claims, no host round trip, device-side statistics); on CPU a vectorised
+PyTorch mirror with the same hash, so tables built on either side are interchangeable."""
 from __future__ import annotations
 
 import logging
@@ -14,6 +15,7 @@ from typing import Any, Dict, List, Optional, Tuple
 
 import torch
 
+from ..ops import _lib
 from ..sparse.jagged_tensor import JaggedTensor
 from .mc_modules import ManagedCollisionModule
 
@@ -96,6 +98,9 @@ class HashZchManagedCollisionModule(ManagedCollisionModule):
         self.register_buffer("_hash_zch_metadata", torch.zeros((self._zch_size, 1), dtype=torch.int32, device=device))
         self._scalar_logger = ScalarLogger(name or "zch", self._zch_size, tb_logging_frequency) if tb_logging_frequency > 0 else None
         self._evicted_indices: List[torch.Tensor] = []
+        self._evicted_pending: List[torch.Tensor] = []  # CUDA probe: per-id evicted slot or -1, compacted when evict() is called
+        self._counters: Optional[torch.Tensor] = None
+        self._device_steps = 0
 
     def preprocess(self, features: Dict[str, JaggedTensor]) -> Dict[str, JaggedTensor]:
         return features
@@ -103,11 +108,49 @@ class HashZchManagedCollisionModule(ManagedCollisionModule):
     def _now(self) -> int:
         return int(time.time() // 3600)
 
+    _POLICY_CODE = {HashZchEvictionPolicyName.NONE: 0, HashZchEvictionPolicyName.SINGLE_TTL_EVICTION: 1, HashZchEvictionPolicyName.LRU_EVICTION: 2}
+
+    @torch.no_grad()
+    def _probe_cuda(self, ids: torch.Tensor, readonly: bool) -> torch.Tensor:
+        """One launch of ``trb_zch_probe`` for the whole id list; nothing is read back on the host."""
+        import ctypes
+
+        ids = ids.contiguous()
+        out = torch.empty_like(ids)
+        policy = self._POLICY_CODE[self._eviction_policy_name]
+        evicted = torch.empty_like(ids) if (not readonly and policy != 0) else None
+        if self._counters is None or self._counters.device != ids.device:
+            self._counters = torch.zeros(4, dtype=torch.int32, device=ids.device)
+        ttl = self._eviction_config.single_ttl if (self._eviction_config and self._eviction_config.single_ttl) else -1
+        code = _lib.lib().trb_zch_probe(_lib.ptr(ids), ctypes.c_int64(ids.numel()), _lib.ptr(self._hash_zch_identities), _lib.ptr(self._hash_zch_metadata),
+                                        ctypes.c_int64(max(self._buckets_local, 1)), ctypes.c_int64(max(self._bucket_size, 1)), int(self._max_probe), int(readonly),
+                                        int(self._now()), int(ttl), policy, int(not self._disable_fallback), _lib.ptr(out), _lib.ptr(evicted),
+                                        _lib.ptr(self._counters), _lib.stream_ptr(ids.device))
+        _lib.check(code, "trb_zch_probe")
+        if evicted is not None:
+            self._evicted_pending.append(evicted)
+        if self._scalar_logger is not None:
+            self._device_steps += 1
+            if self._device_steps % max(self._scalar_logger._frequency, 1) == 0:  # the only host read, once per logging period
+                self.flush_statistics()
+        return out
+
+    def flush_statistics(self) -> Dict[str, float]:
+        """Fold the device-side counters of the CUDA probe into the scalar logger (synchronises)."""
+        if self._counters is not None:
+            h, i, c, _ = (int(v) for v in self._counters.tolist())
+            self._counters.zero_()
+            if self._scalar_logger is not None and (h or i or c):
+                self._scalar_logger.update(h, i, c, h + i + c)
+        return self._scalar_logger() if self._scalar_logger is not None else {}
+
     @torch.no_grad()
     def _probe(self, ids: torch.Tensor, readonly: bool) -> torch.Tensor:
         n = ids.numel()
         if n == 0:
             return ids
+        if _lib.use_cuda_kernels(ids):
+            return self._probe_cuda(ids, readonly)
         ident = self._hash_zch_identities.view(-1)
         meta = self._hash_zch_metadata.view(-1)
         h = _mix64(ids)
@@ -194,6 +237,11 @@ class HashZchManagedCollisionModule(ManagedCollisionModule):
         return (self._hash_zch_identities.view(-1) == -1).sum().view(1)
 
     def evict(self) -> Optional[torch.Tensor]:
+        for t in self._evicted_pending:
+            t = t[t >= 0]
+            if t.numel():
+                self._evicted_indices.append(t + self._offset)
+        self._evicted_pending = []
         if not self._evicted_indices:
             return None
         out = torch.cat(self._evicted_indices)
