@@ -110,11 +110,50 @@ class EmbeddingStats(Stats):
             table.append(f"Reserved for dense/KJT: {bytes_to_gb(topology.devices[0].storage.hbm - reserved.devices[0].storage.hbm):.3f} GB HBM per rank")
         crit = max(range(W), key=lambda r: totals[r])
         table.append(f"Critical path rank: {crit}")
+        # the step is bounded by the slowest rank of each PHASE (phases are separated by device barriers), not of the sum
+        phase_max = {k: max(getattr(p, k) for p in perf) for k in ("fwd_compute", "fwd_comms", "bwd_compute", "bwd_comms", "prefetch_compute")}
+        table.append("Per-phase critical path (max over ranks, ms): " + ", ".join(f"{k} {v:.4f}" for k, v in phase_max.items())
+                     + f"  -> sum {sum(phase_max.values()):.4f}")
+        # wire volume per step and rank, from the shard geometry: ids in (input dist), pooled rows out (output dist) and the same back as grads
+        ids_in, emb_out = [0.0] * W, [0.0] * W
+        for so in best_plan:
+            pooling = float(sum(so.input_lengths)) if so.input_lengths else 1.0
+            for shard in so.shards:
+                r = cast(int, shard.rank)
+                frac = shard.size[0] / max(so.tensor.shape[0], 1) if so.sharding_type in ("row_wise", "table_row_wise", "grid_shard") else 1.0
+                ids_in[r] += so.batch_size * W * pooling * frac * 8
+                per_sample = shard.size[1] * (pooling if not so.is_pooled else 1.0)
+                emb_out[r] += so.batch_size * W * per_sample * 2
+        table.append(f"{'Rank':>5} {'ids in (MB)':>13} {'emb out (MB)':>14} {'grads in (MB)':>15}   (per step; bf16 rows on the wire, 8-byte ids)")
+        for r in range(W):
+            table.append(f"{r:>5} {bytes_to_mb(ids_in[r]):>13.2f} {bytes_to_mb(emb_out[r]):>14.2f} {bytes_to_mb(emb_out[r]):>15.2f}")
+        if topology.local_world_size and W > topology.local_world_size:
+            L = topology.local_world_size
+            for h in range(W // L):
+                rs = range(h * L, (h + 1) * L)
+                table.append(f"Host {h}: HBM {bytes_to_gb(sum(used_hbm[r] for r in rs)):.2f} GB, DDR {bytes_to_gb(sum(used_ddr[r] for r in rs)):.2f} GB, "
+                             f"slowest rank {max(rs, key=lambda r: totals[r])} at {max(totals[r] for r in rs):.4f} ms")
+        kernels: Dict[str, int] = defaultdict(int)
+        for so in best_plan:
+            kernels[so.compute_kernel] += 1
+        table.append("Compute kernels: " + ", ".join(f"{k} x{v}" for k, v in sorted(kernels.items())))
+        top_hbm = sorted(best_plan, key=lambda so: -sum(cast(Storage, sh.storage).hbm for sh in so.shards))[:5]
+        table.append("Largest tables (HBM): " + ", ".join(f"{so.name} {bytes_to_gb(sum(cast(Storage, sh.storage).hbm for sh in so.shards)):.2f} GB" for so in top_hbm))
+        top_perf = sorted(best_plan, key=lambda so: -max(cast(Perf, sh.perf).total for sh in so.shards))[:5]
+        table.append("Slowest shards: " + ", ".join(f"{so.name} {max(cast(Perf, sh.perf).total for sh in so.shards):.4f} ms ({_abbr(so.sharding_type)})" for so in top_perf))
+        if constraints:
+            table.append(f"Constraints on {len(constraints)} parameter(s): " + "; ".join(
+                f"{n}: {','.join(_abbr(t) for t in (c.sharding_types or [])) or 'any'}" + (f" / {','.join(c.compute_kernels)}" if c.compute_kernels else "")
+                for n, c in list(constraints.items())[:8]) + (" ..." if len(constraints) > 8 else ""))
         if debug:
-            table.append(f"{'FQN':<48} {'Sharding':>9} {'Kernel':>18} {'Shards':>7} {'Ranks'}")
+            table.append(f"{'FQN':<48} {'Sharding':>9} {'Kernel':>18} {'Shards':>7} {'Rows x Dim':>18} {'Pooling':>8} {'CLF':>5} {'Perf max (ms)':>14}  Ranks")
             for so in best_plan:
                 ranks = [cast(int, s.rank) for s in so.shards]
-                table.append(f"{so.fqn[-48:]:<48} {_abbr(so.sharding_type):>9} {so.compute_kernel:>18} {so.num_shards:>7} {_collapse(ranks)}")
+                shape = f"{so.tensor.shape[0]} x {so.tensor.shape[1]}"
+                pooling = sum(so.input_lengths) if so.input_lengths else 0.0
+                clf = so.cache_load_factor
+                table.append(f"{so.fqn[-48:]:<48} {_abbr(so.sharding_type):>9} {so.compute_kernel:>18} {so.num_shards:>7} {shape:>18} {pooling:>8.1f} "
+                             f"{(f'{clf:.2f}' if clf is not None else '-'):>5} {max(cast(Perf, s.perf).total for s in so.shards):>14.4f}  {_collapse(ranks)}")
         self._stats_table = table
         width = max(len(l) for l in table) + 4
         self._width = max(width, MIN_WIDTH)
