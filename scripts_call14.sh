@@ -1,4 +1,3 @@
-timeout 400 python tools/kernel_bench.py --md gpurun_out/kernel_roofline_r2.md > gpurun_out/kb.log 2>&1
-timeout 700 ncu --set full --clock-control none --import-source on -k regex:'tbe_pooled_fwd|tbe_bwd_chunk|tbe_bwd_span|kjt_route|trb_grad_push|trb_staging|qtbe_fwd|tbe_bwd_build' -c 30 -f -o gpurun_out/ncu_kernels_r2 python tools/kernel_bench.py --iters 1 --warm 0 --no-flush --skip codec,jagged > gpurun_out/ncu_kb.log 2>&1
-timeout 120 python -m pytest tests/test_jagged_qcomm_gpu.py -x -q 2>&1 | tail -3
-tail -40 gpurun_out/kb.log; tail -3 gpurun_out/ncu_kb.log
+timeout 300 python tools/kernel_bench.py --only "tbe_bwd phase 2" --skip quant,codec,jagged 2>&1 | grep "tbe_bwd phase 2" | cut -c1-90
+timeout 600 python -m pytest tests/test_tbe_gpu.py tests/test_sparse_plane_gpu.py tests/test_zch_gpu.py -q 2>&1 | tail -12
+timeout 300 python bench.py --steps 100 --warmup 10 > gpurun_out/r2_b1_c17.json 2> gpurun_out/r2_b1_c17.err; grep '^{' gpurun_out/r2_b1_c17.json | cut -c1-330

@@ -87,6 +87,13 @@ struct Vec4;
 
 template <>
 struct Vec4<float> {
+  // raw = the registers a 4-element load lands in; cvt(raw) -> float4. Kernels that want several rows in flight load raw values for all
+  // of them first and convert later: a load fused with its conversion makes the compiler wait for each load before issuing the next
+  // (measured in tbe_bwd_walk_kernel: the 4 gradient loads of a group shared one destination register and ran back to back).
+  typedef float4 raw;
+  static __device__ __forceinline__ raw ld_raw(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  static __device__ __forceinline__ raw zero_raw() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  static __device__ __forceinline__ float4 cvt(raw r) { return r; }
   static __device__ __forceinline__ float4 ld(const float* p) { return *reinterpret_cast<const float4*>(p); }
   static __device__ __forceinline__ float4 ld_nc(const float* p) {
     float4 r;
@@ -99,6 +106,9 @@ struct Vec4<float> {
 
 template <>
 struct Vec4<__nv_bfloat16> {
+  typedef uint2 raw;
+  static __device__ __forceinline__ raw ld_raw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint2*>(p); }
+  static __device__ __forceinline__ raw zero_raw() { return make_uint2(0u, 0u); }
   static __device__ __forceinline__ float4 cvt(uint2 u) {
     __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&u.x);
     __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&u.y);
@@ -122,6 +132,9 @@ struct Vec4<__nv_bfloat16> {
 
 template <>
 struct Vec4<__half> {
+  typedef uint2 raw;
+  static __device__ __forceinline__ raw ld_raw(const __half* p) { return *reinterpret_cast<const uint2*>(p); }
+  static __device__ __forceinline__ raw zero_raw() { return make_uint2(0u, 0u); }
   static __device__ __forceinline__ float4 cvt(uint2 u) {
     __half2 a = *reinterpret_cast<__half2*>(&u.x);
     __half2 b = *reinterpret_cast<__half2*>(&u.y);

@@ -467,6 +467,174 @@ __global__ void __launch_bounds__(256) tbe_bwd_unique_kernel(const TbeBwdParams 
   }
 }
 
+// ---- multi-row walk ---------------------------------------------------------------------------------------------------
+// The generic walk below handles one run of equal keys at a time: gradient rows -> weight row -> row state -> store is ONE dependent
+// chain per warp, and every lane re-derives the row geometry (two integer divisions) for every gradient row: 182 warp instructions
+// per id at 48 % issue utilisation, 2 TB/s (profiles/ncu_tbe_bwd_chunk_kernel_r1.md). For SGD / row-wise Adagrad without clipping
+// or weight decay this kernel walks the same 32 sorted keys U entries at a time instead:
+//   * geometry (gradient offset, weight offset, scale, source rank) is computed once, one entry per lane, and broadcast by shuffles;
+//   * the U gradient rows AND the weight rows / row states of the runs that end inside the group are all requested before any of
+//     them is consumed (U x (256 B + 512 B) in flight per warp instead of one row);
+//   * runs (duplicates) are handled by carrying the accumulator across entries - run boundaries are a ballot mask, so every branch
+//     is warp-uniform. Accumulation order and fma contraction are those of the generic walk: results are bit-identical.
+// Runs that continue into a neighbouring chunk leave partial rows exactly like the generic walk (span kernels combine them).
+// Chunks it handled are marked in chunk_done; the generic kernel returns immediately for those.
+template <typename W, typename G, int MAXV, int MINB>
+__global__ void __launch_bounds__(256, MINB) tbe_bwd_walk_kernel(const TbeBwdParams p) {
+  typedef uint64_t K;
+  const int lane = threadIdx.x & 31;
+  const int64_t chunk = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t base = chunk << 5;
+  if (base >= p.n) return;
+  if (p.hyper[HP_MAXGRAD] > 0.f) {  // gradient clipping: generic path
+    if (lane == 0) p.chunk_done[chunk] = 0;
+    return;
+  }
+  const int cnt = (int) min((int64_t) 32, p.n - base);
+  const void* keys = p.keys_sorted;
+  const K sentinel = (K) p.total_rows;
+  const K key = lane < cnt ? ld_key(keys, base + lane, p.key64) : sentinel;
+  const bool valid = key != sentinel;  // padding / invalid ids sort last: the valid entries are a prefix of the chunk
+  const int cnt_v = __popc(__ballot_sync(0xffffffffu, valid));
+  const bool has_prev = base > 0, has_next = base + 32 < p.n;
+  const K prev_key = has_prev ? ld_key(keys, base - 1, p.key64) : sentinel;
+  const K next_key = has_next ? ld_key(keys, base + 32, p.key64) : sentinel;
+  if (cnt_v == 0) {
+    if (lane == 0) {
+      p.chunk_done[chunk] = 1;
+      p.span_flags[chunk] = 0;
+    }
+    return;
+  }
+  const K down = __shfl_down_sync(0xffffffffu, key, 1);
+  const unsigned ends = __ballot_sync(0xffffffffu, lane < cnt_v && (lane == cnt_v - 1 || key != down));
+  const K key0 = __shfl_sync(0xffffffffu, key, 0), keyl = __shfl_sync(0xffffffffu, key, cnt_v - 1);
+  const bool head_open = has_prev && prev_key == key0;
+  const bool tail_open = cnt_v == cnt && has_next && next_key == keyl;
+  const int e_first_end = __ffs(ends) - 1;
+
+  float scale = 0.f;
+  int64_t goff = 0, woff = 0;
+  int src_rank = 0, nvec_l = 0;
+  if (lane < cnt_v) {
+    const int val = p.vals_sorted[base + lane];
+    const int bag = p.bag_of[val];
+    scale = (p.src.psw ? p.src.psw[val] : 1.f) * p.grad_scale;
+    if (p.mean) {
+      const int64_t L = bag_len(p, bag);
+      scale /= (float) (L > 0 ? L : 1);
+    }
+    const int f = bag / p.B;
+    const int b = bag - f * p.B;
+    src_rank = b / p.B_local;
+    const int D = p.feat_dim[f];
+    nvec_l = D >> 2;
+    goff = (int64_t) (b - src_rank * p.B_local) * p.grad_stride + p.feat_col[f];
+    woff = p.feat_woff[f] + ((int64_t) key - p.feat_rowbase[f]) * D;
+  }
+  constexpr int U = MAXV == 1 ? 4 : (MAXV == 2 ? 2 : 1);  // entries in flight per warp (register budget: U x MAXV x 2 float4)
+  const int OPT = p.opt;
+  if ((p.prefetch & 4) && lane < cnt_v) {
+    // every lane pulls the lines of ITS entry (weight row, row state, gradient row) towards L2 now: the U-wide groups below then
+    // find them on chip, and the whole chunk (32 rows) is in flight per warp instead of U rows
+    const char* pw = reinterpret_cast<const char*>(reinterpret_cast<const W*>(p.weights) + woff);
+    const int wbytes = nvec_l * 4 * (int) sizeof(W);
+    for (int o = 0; o < wbytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pw + o));
+    if (OPT == OPT_ROWWISE_ADAGRAD) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.state1 + key));
+    if (p.prefetch & 2) {
+      const char* pg = reinterpret_cast<const char*>(reinterpret_cast<const G*>(p.grad.p[src_rank]) + goff);
+      const int gbytes = nvec_l * 4 * (int) sizeof(G);
+      for (int o = 0; o < gbytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pg + o));
+    }
+  }
+  const float lr = p.hyper[HP_LR], eps = p.hyper[HP_EPS];
+  W* const wbase = reinterpret_cast<W*>(p.weights);
+  float4 acc[MAXV];
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  bool wrote_slot1 = false;
+  for (int j = 0; j < cnt_v; j += U) {
+    typename Vec4<G>::raw g[U][MAXV];  // raw registers: converted when consumed, so all loads of the group are issued first
+    typename Vec4<W>::raw wv[U][MAXV];
+    float st[U], sc[U];
+    int64_t wo[U], ky[U];
+    int nv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int e = min(j + u, cnt_v - 1);
+      const int64_t go = __shfl_sync(0xffffffffu, goff, e);
+      const int sr = __shfl_sync(0xffffffffu, src_rank, e);
+      sc[u] = __shfl_sync(0xffffffffu, scale, e);
+      nv[u] = __shfl_sync(0xffffffffu, nvec_l, e);
+      const G* gp = reinterpret_cast<const G*>(p.grad.p[sr]) + go;
+#pragma unroll
+      for (int k = 0; k < MAXV; ++k) {
+        const int vi = lane + k * 32;
+        // unconditional load from a clamped address (a predicated load + select made every load wait for the previous one)
+        g[u][k] = Vec4<G>::ld_raw(gp + ((vi < nv[u]) ? vi * 4 : 0));
+      }
+      const bool fin = j + u < cnt_v && ((ends >> e) & 1u) && !(head_open && e == e_first_end) && !(tail_open && e == cnt_v - 1);
+      wo[u] = 0;
+      ky[u] = 0;
+      st[u] = 0.f;
+      if (fin) {  // this entry closes a run that lives entirely inside the chunk: fetch its row now, consume it below
+        wo[u] = __shfl_sync(0xffffffffu, woff, e);
+        ky[u] = (int64_t) __shfl_sync(0xffffffffu, key, e);
+        const W* wp = wbase + wo[u];
+#pragma unroll
+        for (int k = 0; k < MAXV; ++k) {
+          const int vi = lane + k * 32;
+          wv[u][k] = Vec4<W>::ld_raw(wp + ((vi < nv[u]) ? vi * 4 : 0));
+        }
+        if (OPT == OPT_ROWWISE_ADAGRAD) st[u] = p.state1[ky[u]];  // same address on every lane: one broadcast transaction
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int e = j + u;
+      if (e >= cnt_v) break;
+#pragma unroll
+      for (int k = 0; k < MAXV; ++k)
+        if (lane + k * 32 < nv[u]) acc[k] = f4_fma(Vec4<G>::cvt(g[u][k]), sc[u], acc[k]);
+      if (!((ends >> e) & 1u)) continue;
+      const bool head_p = head_open && e == e_first_end, tail_p = tail_open && e == cnt_v - 1;
+      if (!head_p && !tail_p) {
+        float mult = lr;
+        if (OPT == OPT_ROWWISE_ADAGRAD) {
+          float sq = 0.f;
+#pragma unroll
+          for (int k = 0; k < MAXV; ++k) sq += f4_sq(acc[k]);
+          sq = warp_sum(sq) / (float) (nv[u] << 2);
+          const float ns = st[u] + sq;
+          if (lane == 0) p.state1[ky[u]] = ns;
+          mult = lr / (sqrtf(ns) + eps);
+        }
+        W* wp = wbase + wo[u];
+#pragma unroll
+        for (int k = 0; k < MAXV; ++k) {
+          const int vi = lane + k * 32;
+          if (vi < nv[u]) Vec4<W>::st(wp + vi * 4, f4_fma(acc[k], -mult, Vec4<W>::cvt(wv[u][k])));
+        }
+      } else {
+        const int slot = head_p ? 0 : 1;
+        if (!head_p) wrote_slot1 = true;
+        float* dst = p.partials + ((chunk * 2 + slot) * (int64_t) p.max_dim);
+#pragma unroll
+        for (int k = 0; k < MAXV; ++k) {
+          const int vi = lane + k * 32;
+          if (vi < nv[u]) *reinterpret_cast<float4*>(dst + vi * 4) = acc[k];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < MAXV; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  if (lane == 0) {
+    p.chunk_done[chunk] = 1;
+    p.span_flags[chunk] = wrote_slot1 ? 1 : 0;
+  }
+}
+
 template <typename W, typename G, int MAXV>
 __global__ void __launch_bounds__(256) tbe_bwd_chunk_kernel(const TbeBwdParams p) {
   typedef uint64_t K;
@@ -474,6 +642,7 @@ __global__ void __launch_bounds__(256) tbe_bwd_chunk_kernel(const TbeBwdParams p
   const int64_t chunk = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t base = chunk << 5;
   if (base >= p.n) return;
+  if (p.chunk_done != nullptr && p.chunk_done[chunk]) return;  // already handled by tbe_bwd_walk_kernel / tbe_bwd_unique_kernel
   const int cnt = (int) min((int64_t) 32, p.n - base);
   const void* keys = p.keys_sorted;
   const K sentinel = (K) p.total_rows;
@@ -492,7 +661,6 @@ __global__ void __launch_bounds__(256) tbe_bwd_chunk_kernel(const TbeBwdParams p
   const bool has_prev = base > 0, has_next = base + 32 < p.n;
   const K prev_key = has_prev ? ld_key(keys, base - 1, p.key64) : sentinel;
   const K next_key = has_next ? ld_key(keys, base + 32, p.key64) : sentinel;
-  if (p.chunk_done != nullptr && p.chunk_done[chunk]) return;  // already handled by tbe_bwd_unique_kernel
   const K up = __shfl_up_sync(0xffffffffu, key, 1);
   const bool is_start = (lane == 0) || (key != up);
   unsigned starts = __ballot_sync(0xffffffffu, lane < cnt && is_start);
@@ -587,13 +755,14 @@ __device__ __forceinline__ void span_accumulate(const TbeBwdParams& p, int64_t c
 #pragma unroll
       for (int k = 0; k < MAXV; ++k) {
         const int vi = lane + k * 32;
-        t[q][k] = (vi < nvec) ? *reinterpret_cast<const float4*>(src + vi * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        t[q][k] = *reinterpret_cast<const float4*>(src + ((vi < nvec) ? vi * 4 : 0));  // unconditional: all 4 pieces in flight
       }
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q)
 #pragma unroll
-      for (int k = 0; k < MAXV; ++k) acc[k] = f4_add(acc[k], t[q][k]);
+      for (int k = 0; k < MAXV; ++k)
+        if (lane + k * 32 < nvec) acc[k] = f4_add(acc[k], t[q][k]);
   }
   for (; j < n_pieces; j += stride) {
     const float* src = p.partials + (((c + j) * 2 + (j == 0 ? 1 : 0)) * (int64_t) p.max_dim);
@@ -605,13 +774,28 @@ __device__ __forceinline__ void span_accumulate(const TbeBwdParams& p, int64_t c
   }
 }
 
+// Last chunk of the run of equal keys that leaves chunk c through its last entry. Called by whole warps: a 32-ary search (every lane
+// probes one point per step, 4 steps over 1 M keys) instead of a 20-step binary search of dependent loads - the search was most of
+// the latency of the span kernels (profiles/kernel_roofline_r2.md).
 __device__ __forceinline__ int64_t span_last_chunk(const TbeBwdParams& p, int64_t c, uint64_t* rk_out) {
+  const int lane = threadIdx.x & 31;
   const int64_t last = c * 32 + 31;
   const uint64_t rk = ld_key(p.keys_sorted, last, p.key64);
-  int64_t lo = last + 1, hi = p.n;  // upper bound of rk in keys[last+1 .. n)
-  while (lo < hi) {
-    const int64_t mid = (lo + hi) >> 1;
-    if (ld_key(p.keys_sorted, mid, p.key64) <= rk) lo = mid + 1; else hi = mid;
+  // invariant: keys[i] <= rk for i < lo, keys[i] > rk for i >= hi; result = upper bound of rk
+  int64_t lo = last + 1, hi = p.n;
+  while (hi - lo > 32) {
+    const int64_t step = (hi - lo) >> 5;
+    const int64_t pos = lo + step * (lane + 1) - 1;  // < hi
+    const bool le = ld_key(p.keys_sorted, pos, p.key64) <= rk;
+    const int cnt = __popc(__ballot_sync(0xffffffffu, le));  // keys are sorted: the predicate is a prefix of the lanes
+    const int64_t nlo = cnt > 0 ? lo + step * cnt : lo;
+    if (cnt < 32) hi = lo + step * (cnt + 1) - 1;
+    lo = nlo;
+  }
+  {
+    const int64_t pos = lo + lane;
+    const bool le = pos < hi && ld_key(p.keys_sorted, pos, p.key64) <= rk;
+    lo += __popc(__ballot_sync(0xffffffffu, le));
   }
   *rk_out = rk;
   return (lo - 1) >> 5;
@@ -757,8 +941,16 @@ static int run_bwd(TbeBwdParams& p, char* ws, cudaStream_t stream) {
   const int64_t blocks = (chunks + 7) / 8;
   // pass 1 (optional): chunks of distinct rows with a simple optimizer go through the high-MLP unique kernel
   static const int fast_enabled = getenv("TRB_BWD_UNIQUE") ? atoi(getenv("TRB_BWD_UNIQUE")) : 0;  // measured slower than the generic walk on B200 so far: opt-in
+  static const int walk_enabled = getenv("TRB_BWD_WALK") ? atoi(getenv("TRB_BWD_WALK")) : 1;
+  const bool simple_opt = (p.opt == OPT_SGD || p.opt == OPT_ROWWISE_ADAGRAD) && p.wd_mode == 0 && !(sizeof(W) == 2 && p.sr);
   if constexpr (MAXV <= 4) {
-    if (fast_enabled && (p.opt == OPT_SGD || p.opt == OPT_ROWWISE_ADAGRAD) && p.wd_mode == 0) {
+    if (walk_enabled && simple_opt) {
+      p.chunk_done = (uint8_t*) (ws + L.done);
+      // TRB_BWD_WALK=1: <= 80 registers, 3 CTAs / SM (a few spilled words); =2: 97 registers, 2 CTAs / SM
+      if (walk_enabled == 2) tbe_bwd_walk_kernel<W, G, MAXV, 2><<<(unsigned) blocks, threads, 0, stream>>>(p);
+      else tbe_bwd_walk_kernel<W, G, MAXV, 3><<<(unsigned) blocks, threads, 0, stream>>>(p);
+      TRB_CHECK_LAUNCH();
+    } else if (fast_enabled && simple_opt) {
       p.chunk_done = (uint8_t*) (ws + L.done);
       tbe_bwd_unique_kernel<W, G, MAXV><<<(unsigned) blocks, threads, 0, stream>>>(p);
       TRB_CHECK_LAUNCH();
@@ -864,7 +1056,9 @@ TRB_API int trb_tbe_bwd_fused_phase(void* weights, int w_dtype, float* state1, f
   p.sr_seed = sr_seed;
   {
     static const int pf = getenv("TRB_BWD_PREFETCH") ? atoi(getenv("TRB_BWD_PREFETCH")) : 1;
+    static const int wpf = getenv("TRB_BWD_WALK_PF") ? atoi(getenv("TRB_BWD_WALK_PF")) : 1;
     p.prefetch = pf ? (1 | (n_grad <= 1 ? 2 : 0)) : 0;  // peer-resident gradient rows bypass the local L2: do not prefetch them
+    if (wpf) p.prefetch |= 4 | (wpf >= 2 && n_grad <= 1 ? 2 : 0);
   }
   if (opt < 0 || opt > OPT_LION) return -5;
   char* ws = reinterpret_cast<char*>(workspace);
