@@ -8,7 +8,7 @@
 // Per id:  (1) scan the probe window for the id itself - a free slot ends the scan (slots are never freed, only re-owned), remembering
 //              the first claimable slot: free, expired (TTL policy) or - LRU policy, no free slot in the window - the least recently seen;
 //          (2) hit -> done;  training and a claimable slot -> atomicCAS(expected owner -> id). Losing the race to the SAME id (duplicates
-//              inside the batch) is a hit; losing it to another id restarts the scan from that slot;
+//              inside the batch) is a hit; losing it to another id continues the scan behind that slot;
 //          (3) nothing claimable -> collision: the id falls back to its start slot (or -1 when fallback is disabled).
 // No host round trip per probe step (the PyTorch mirror synchronises every step); hit / insert / collision / evict counters are
 // warp-reduced into 4 device integers; an evicted slot is reported in evicted[i] of the thread that took it.
@@ -60,7 +60,10 @@ __global__ void __launch_bounds__(256) zch_probe_kernel(const ZchParams p) {
     const int window = (int) min((int64_t) p.max_probe, p.bucket_size);
     int64_t res = -1, ev = -1;
     int from = 0;
-    for (int attempt = 0; attempt < 4 && res < 0; ++attempt) {
+    // every failed claim moves `from` past the slot that was lost (its new owner is fresh, so it stays unclaimable), so the loop ends
+    // after at most `window` claims; LRU victims restart the scan and are bounded separately
+    int lru_retries = 0;
+    while (res < 0) {
       int64_t cand = -1;
       unsigned long long cand_owner = 0;
       int64_t lru_slot = -1;
@@ -87,7 +90,8 @@ __global__ void __launch_bounds__(256) zch_probe_kernel(const ZchParams p) {
         if (p.policy == 2 && seen < p.now && seen < lru_seen) { lru_seen = seen; lru_slot = s; lru_owner = cur; }
       }
       if (res >= 0 || p.readonly) break;
-      if (cand < 0 && p.policy == 2 && lru_slot >= 0) { cand = lru_slot; cand_owner = lru_owner; cand_probe = 0; }
+      bool lru_pick = false;
+      if (cand < 0 && p.policy == 2 && lru_slot >= 0 && lru_retries < 8) { cand = lru_slot; cand_owner = lru_owner; lru_pick = true; ++lru_retries; }
       if (cand < 0) break;
       const unsigned long long prev = atomicCAS(p.identities + cand, cand_owner, (unsigned long long) id);
       if (prev == cand_owner) {
@@ -98,7 +102,7 @@ __global__ void __launch_bounds__(256) zch_probe_kernel(const ZchParams p) {
         res = cand;
         hit = 1;
       } else {
-        from = cand_probe;  // somebody else owns it now: look again from here (its new owner is fresh, so not claimable)
+        from = lru_pick ? 0 : cand_probe + 1;  // somebody else owns it now
       }
     }
     if (res >= 0) {
