@@ -123,11 +123,18 @@ __global__ void __launch_bounds__(256) qtbe_fwd_kernel(const QTbeParams p) {
 // flight per warp (130-byte rows: ~5 % of the HBM rate). Here 8 lanes own a bag and read a row as 16 B vectors (a 128-element fp8
 // row is exactly one load per lane), every 8-lane group works on U bags at once with the first row of all of them in flight together,
 // and a lane writes 16 consecutive outputs (32 B of bf16).
+// scale word of the 16 elements starting at e: FP8_BLOCK = the fp16 scale of their 32-element block, INT8 = the row's fp16 (scale, bias)
 template <int FMT>
-__device__ __forceinline__ void dequant16(const uint8_t* row, int D, int e, const uint4 q, float (&v)[16]) {
+__device__ __forceinline__ uint32_t load_scale16(const uint8_t* row, int D, int e) {
+  if constexpr (FMT == FMT_FP8_BLOCK) return *reinterpret_cast<const uint16_t*>(row + D + (e >> 5) * 2);
+  else return *reinterpret_cast<const uint32_t*>(row + D);
+}
+
+template <int FMT>
+__device__ __forceinline__ void dequant16(const uint4 q, const uint32_t sw, float (&v)[16]) {
   const uint32_t w[4] = {q.x, q.y, q.z, q.w};
   if constexpr (FMT == FMT_FP8_BLOCK) {
-    const float s = __half2float(*reinterpret_cast<const __half*>(row + D + (e >> 5) * 2));
+    const float s = __half2float(__ushort_as_half((unsigned short) sw));
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const __nv_fp8x4_e4m3 x = *reinterpret_cast<const __nv_fp8x4_e4m3*>(&w[k]);
@@ -135,7 +142,7 @@ __device__ __forceinline__ void dequant16(const uint8_t* row, int D, int e, cons
       v[4 * k] = f.x * s; v[4 * k + 1] = f.y * s; v[4 * k + 2] = f.z * s; v[4 * k + 3] = f.w * s;
     }
   } else {  // FMT_INT8: value * scale + bias, fp16 (scale, bias) behind the D payload bytes
-    const __half2 sb = *reinterpret_cast<const __half2*>(row + D);
+    const __half2 sb = *reinterpret_cast<const __half2*>(&sw);
     const float s = __low2float(sb), b = __high2float(sb);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -152,14 +159,13 @@ __device__ __forceinline__ void store16(O* dst, const float (&a)[16]) {
 }
 
 template <typename O, int FMT, int MAXV, int U>
-__global__ void __launch_bounds__(256) qtbe_fwd_vec_kernel(const QTbeParams p) {
+__global__ void __launch_bounds__(256, 3) qtbe_fwd_vec_kernel(const QTbeParams p) {
   constexpr int LPR = 8;
   const int lig = threadIdx.x & (LPR - 1);
   const int64_t group = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) / LPR;
   const int64_t n_bags = (int64_t) p.F * p.B;
   const int64_t bag0 = group * U;
   if (bag0 >= n_bags) return;
-  float acc[U][MAXV][16];
   int64_t st[U], en[U];
   const uint8_t* wb[U];
   int64_t rb[U], rows[U];
@@ -176,13 +182,10 @@ __global__ void __launch_bounds__(256) qtbe_fwd_vec_kernel(const QTbeParams p) {
     wb[u] = p.weights + p.feat_woff[f];
     st[u] = trb_ld_idx(p.offsets, bag, p.off64);
     en[u] = bag0 + u < n_bags ? trb_ld_idx(p.offsets, bag + 1, p.off64) : st[u];
-#pragma unroll
-    for (int k = 0; k < MAXV; ++k)
-#pragma unroll
-      for (int e = 0; e < 16; ++e) acc[u][k][e] = 0.f;
   }
   // first id of every bag: all U x MAXV row vectors in flight before any is consumed
   uint4 q[U][MAXV];
+  uint32_t sw[U][MAXV];
   float w0[U];
   const uint8_t* row0[U];
 #pragma unroll
@@ -198,20 +201,29 @@ __global__ void __launch_bounds__(256) qtbe_fwd_vec_kernel(const QTbeParams p) {
     }
 #pragma unroll
     for (int k = 0; k < MAXV; ++k) {
+      // unconditional loads from clamped addresses, payload AND scale word: a predicated load + select (or a scale fetched when the
+      // payload is consumed) made every row wait for the previous one (same finding as tbe_bwd_walk_kernel)
       const int e = (lig + k * LPR) * 16;
-      q[u][k] = (e < D[u]) ? *reinterpret_cast<const uint4*>(row0[u] + e) : make_uint4(0, 0, 0, 0);
+      const int ec = e < D[u] ? e : 0;
+      q[u][k] = *reinterpret_cast<const uint4*>(row0[u] + ec);
+      sw[u][k] = load_scale16<FMT>(row0[u], D[u], ec);
     }
   }
 #pragma unroll
   for (int u = 0; u < U; ++u) {
+    float acc1[MAXV][16];  // one bag's accumulator at a time (the loads of all U bags are already in flight): 64 fewer live registers
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k)
+#pragma unroll
+      for (int t = 0; t < 16; ++t) acc1[k][t] = 0.f;
 #pragma unroll
     for (int k = 0; k < MAXV; ++k) {
       const int e = (lig + k * LPR) * 16;
       if (e < D[u] && w0[u] != 0.f) {
         float v[16];
-        dequant16<FMT>(row0[u], D[u], e, q[u][k], v);
+        dequant16<FMT>(q[u][k], sw[u][k], v);
 #pragma unroll
-        for (int t = 0; t < 16; ++t) acc[u][k][t] = v[t] * w0[u];
+        for (int t = 0; t < 16; ++t) acc1[k][t] = v[t] * w0[u];
       }
     }
     // the rest of the bag (pooling factor > 1)
@@ -225,9 +237,9 @@ __global__ void __launch_bounds__(256) qtbe_fwd_vec_kernel(const QTbeParams p) {
         const int e = (lig + k * LPR) * 16;
         if (e < D[u]) {
           float v[16];
-          dequant16<FMT>(row, D[u], e, *reinterpret_cast<const uint4*>(row + e), v);
+          dequant16<FMT>(*reinterpret_cast<const uint4*>(row + e), load_scale16<FMT>(row, D[u], e), v);
 #pragma unroll
-          for (int t = 0; t < 16; ++t) acc[u][k][t] = fmaf(v[t], w, acc[u][k][t]);
+          for (int t = 0; t < 16; ++t) acc1[k][t] = fmaf(v[t], w, acc1[k][t]);
         }
       }
     }
@@ -240,9 +252,9 @@ __global__ void __launch_bounds__(256) qtbe_fwd_vec_kernel(const QTbeParams p) {
       if (e < D[u]) {
         if (inv != 1.f) {
 #pragma unroll
-          for (int t = 0; t < 16; ++t) acc[u][k][t] *= inv;
+          for (int t = 0; t < 16; ++t) acc1[k][t] *= inv;
         }
-        store16<O>(dst + e, acc[u][k]);
+        store16<O>(dst + e, acc1[k]);
       }
     }
   }
