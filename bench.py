@@ -63,6 +63,7 @@ def parse_args() -> argparse.Namespace:
                         "end to end 15.4 M -> 17.7 M samples/s on one GPU); 0: eager")
     p.add_argument("--profile-host", action="store_true", help="cProfile 10 extra steps on rank 0 (stderr)")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--phase-times", action="store_true", help="diagnostics: forward / backward / optimizer device time of the plain step (stderr)")
     p.add_argument("--trace-e2e", type=str, default="", help="diagnostics: torch.profiler trace (chrome json + op table) of 6 extra pipeline steps")
     p.add_argument("--num-host-batches", type=int, default=8)
     return p.parse_args()
@@ -465,6 +466,23 @@ def main() -> None:
     barrier()
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count() - n0
+    if args.phase_times:  # diagnostics: where the device time of the plain step goes (events on the main stream, no profiler attached)
+        n_ph = 20
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n_ph)]
+        for i in range(n_ph):
+            b = dev_batches[i % len(dev_batches)]
+            evs[i][0].record()
+            opt.zero_grad()
+            loss_p, _ = dmp(b)
+            evs[i][1].record()
+            loss_p.backward()
+            evs[i][2].record()
+            opt.step()
+            evs[i][3].record()
+        torch.cuda.synchronize()
+        ph = [sum(evs[i][k].elapsed_time(evs[i][k + 1]) for i in range(4, n_ph)) / (n_ph - 4) for k in range(3)]
+        gap = sum(evs[i][3].elapsed_time(evs[i + 1][0]) for i in range(4, n_ph - 1)) / (n_ph - 5)
+        sys.stderr.write("phase_ms " + json.dumps({"forward": ph[0], "backward": ph[1], "optimizer": ph[2], "between_steps": gap, "rank": rank}) + "\n")
     clocks = sampler.stop()
     if world > 1:  # worst GPU of the job: lowest median SM clock, union of throttle reasons
         allc: List[Any] = [None] * world

@@ -32,11 +32,11 @@ class Perceptron(nn.Module):
         self._linear: nn.Linear = nn.Linear(self._in_size, self._out_size, bias=bias, device=device, dtype=dtype)
         self._activation_fn = activation
 
-    def forward(self, input: torch.Tensor) -> torch.Tensor:
+    def forward(self, input: torch.Tensor, wb: Optional[torch.Tensor] = None) -> torch.Tensor:
         act = self._activation_fn
         fused = _dense.fused_act_code(act)
         if fused is not None and _dense.can_fuse(input, self._linear):
-            return _dense.linear_act(input, self._linear.weight, self._linear.bias, fused)
+            return _dense.linear_act(input, self._linear.weight, self._linear.bias, fused, wb)
         if input.shape[-1] != self._in_size:  # producer emitted zero-padded columns (see ops.interaction)
             input = input[..., : self._in_size]
         if input.dtype != self._linear.weight.dtype and input.is_floating_point():
@@ -82,4 +82,13 @@ class MLP(nn.Module):
             raise ValueError(f"This MLP only supports str version activation function of relu, sigmoid, and swish_layernorm, got {activation}")
 
     def forward(self, input: torch.Tensor) -> torch.Tensor:
+        layers = list(self._mlp)
+        if input.is_cuda and input.dim() == 2 and len(layers) > 1 and all(isinstance(l, Perceptron) and _dense.fused_act_code(l._activation_fn) is not None for l in layers):
+            # tcgen05 path: the bf16 operands of every layer come from ONE cast kernel in front of the stack
+            wbs = _dense.cast_weights_once([l._linear for l in layers])
+            if wbs is not None:
+                x = input
+                for l, wb in zip(layers, wbs):
+                    x = l(x, wb)
+                return x
         return self._mlp(input)

@@ -1192,3 +1192,52 @@ TRB_API int trb_colsum_bf16(const void* in, float* out, int rows, int cols, int6
   TRB_CHECK_LAUNCH();
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// fp32 master weights -> bf16 GEMM operands (K zero-padded to a multiple of 8) for ALL layers of an MLP in one launch. The per-layer
+// `.to(bf16)` + `pad` pair cost 2-3 tiny kernels per layer in front of every GEMM of the captured forward (13 launch-latency-bound
+// nodes on the critical chain of the DLRM step).
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int kMaxCastTensors = 16;
+struct CastPadTable {
+  const float* src[kMaxCastTensors];
+  __nv_bfloat16* dst[kMaxCastTensors];
+  int32_t rows[kMaxCastTensors], K[kMaxCastTensors], Kp[kMaxCastTensors];
+};
+
+__global__ void __launch_bounds__(256) multi_cast_pad_bf16_kernel(const CastPadTable t) {
+  const int l = blockIdx.y;
+  const int K = t.K[l], Kp = t.Kp[l];
+  const int64_t total = (int64_t) t.rows[l] * (Kp >> 1);  // one bf16x2 per thread-iteration
+  const float* __restrict__ src = t.src[l];
+  __nv_bfloat162* __restrict__ dst = reinterpret_cast<__nv_bfloat162*>(t.dst[l]);
+  const int half = Kp >> 1;
+  for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t) gridDim.x * blockDim.x) {
+    const int r = (int) (i / half), c = (int) (i - (int64_t) r * half) * 2;
+    const float a = c < K ? src[(int64_t) r * K + c] : 0.f;
+    const float b = c + 1 < K ? src[(int64_t) r * K + c + 1] : 0.f;
+    dst[i] = __floats2bfloat162_rn(a, b);
+  }
+}
+
+TRB_API int trb_multi_cast_pad_bf16(const void* const* src, void* const* dst, const int32_t* rows, const int32_t* K, const int32_t* Kp, int n, cudaStream_t stream) {
+  if (n < 1 || n > kMaxCastTensors) return -1;
+  CastPadTable t;
+  int64_t biggest = 0;
+  for (int i = 0; i < n; ++i) {
+    if (Kp[i] % 2 || Kp[i] < K[i]) return -2;
+    t.src[i] = (const float*) src[i];
+    t.dst[i] = (__nv_bfloat16*) dst[i];
+    t.rows[i] = rows[i];
+    t.K[i] = K[i];
+    t.Kp[i] = Kp[i];
+    const int64_t tot = (int64_t) rows[i] * (Kp[i] / 2);
+    biggest = tot > biggest ? tot : biggest;
+  }
+  if (biggest == 0) return 0;
+  int64_t bx = (biggest + 255) / 256;
+  if (bx > 148 * 4) bx = 148 * 4;
+  multi_cast_pad_bf16_kernel<<<dim3((unsigned) bx, (unsigned) n), 256, 0, stream>>>(t);
+  TRB_CHECK_LAUNCH();
+  return 0;
+}

@@ -51,10 +51,23 @@ def can_fuse(x: torch.Tensor, linear: nn.Linear) -> bool:
     return linear.out_features % 8 == 0
 
 
-def linear_act(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], act: int) -> torch.Tensor:
+def linear_act(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], act: int, wb: Optional[torch.Tensor] = None) -> torch.Tensor:
     from .gemm import LinearActFn
 
-    return LinearActFn.apply(x, weight, bias, act)
+    return LinearActFn.apply(x, weight, bias, act, wb)
+
+
+def cast_weights_once(linears) -> Optional[list]:
+    """bf16 operands of a stack of fused Linear layers made by ONE kernel (``gemm.cast_pad_weights``); None when the stack is not on
+    the tcgen05 path (the layers then cast their own weights)."""
+    if _BACKEND != "tcgen05" or not linears or len(linears) > 16:
+        return None
+    ws = [l.weight for l in linears]
+    if not all(w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() and l.out_features % 8 == 0 for w, l in zip(ws, linears)):
+        return None
+    from .gemm import cast_pad_weights
+
+    return cast_pad_weights(ws)
 
 
 def dot_interaction(dense: torch.Tensor, sparse: torch.Tensor) -> torch.Tensor:

@@ -200,6 +200,32 @@ class DeferredGradJoin(torch.autograd.Function):
         return (None,) + tuple(grads)
 
 
+def cast_pad_weights(weights) -> list:
+    """bf16 GEMM operands ``[N, Kp]`` (K zero-padded to a multiple of 8) of several fp32 ``[N, K]`` weights with ONE kernel launch
+    (one flat allocation, per-layer views). ``LinearActFn`` takes them through its ``wb`` argument."""
+    import numpy as np
+
+    ws = [w.detach() for w in weights]
+    assert 0 < len(ws) <= 16 and all(w.is_cuda and w.dtype == torch.float32 and w.dim() == 2 and w.is_contiguous() for w in ws)
+    Kps = [(w.shape[1] + 7) // 8 * 8 for w in ws]
+    sizes = [w.shape[0] * kp for w, kp in zip(ws, Kps)]
+    flat = torch.empty(sum(sizes), dtype=torch.bfloat16, device=ws[0].device)
+    outs, o = [], 0
+    for w, kp, n in zip(ws, Kps, sizes):
+        outs.append(flat[o : o + n].view(w.shape[0], kp))
+        o += n
+    L = _lib.lib()
+    n = len(ws)
+    src = (ctypes.c_void_p * n)(*[w.data_ptr() for w in ws])
+    dst = (ctypes.c_void_p * n)(*[t.data_ptr() for t in outs])
+    i32 = lambda xs: np.ascontiguousarray(np.array(xs, dtype=np.int32)).ctypes.data_as(ctypes.c_void_p)
+    rows, Ks, Kpa = np.array([w.shape[0] for w in ws], dtype=np.int32), np.array([w.shape[1] for w in ws], dtype=np.int32), np.array(Kps, dtype=np.int32)
+    code = L.trb_multi_cast_pad_bf16(src, dst, rows.ctypes.data_as(ctypes.c_void_p), Ks.ctypes.data_as(ctypes.c_void_p), Kpa.ctypes.data_as(ctypes.c_void_p), n,
+                                     _lib.stream_ptr(ws[0].device))
+    _lib.check(code, "trb_multi_cast_pad_bf16")
+    return outs
+
+
 def _pad_k(t: torch.Tensor, Kp: int) -> torch.Tensor:
     if t.shape[1] == Kp:
         return t
@@ -210,7 +236,7 @@ class LinearActFn(torch.autograd.Function):
     """``act(x @ W^T + b)`` on the tcgen05 kernel; bf16 activations, fp32 master weights."""
 
     @staticmethod
-    def forward(ctx, x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], act: int) -> torch.Tensor:
+    def forward(ctx, x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], act: int, wb: Optional[torch.Tensor] = None) -> torch.Tensor:
         N, K = weight.shape
         Kp = (K + 7) // 8 * 8
         xb = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
@@ -218,7 +244,8 @@ class LinearActFn(torch.autograd.Function):
         xb = _pad_k(xb, Kp)
         if xb.stride(1) != 1 or xb.stride(0) % 8 != 0:
             xb = xb.contiguous()
-        wb = _pad_k(weight.detach().to(torch.bfloat16), Kp)
+        if wb is None or tuple(wb.shape) != (N, Kp):  # (``cast_pad_weights`` of the enclosing MLP made the operand already)
+            wb = _pad_k(weight.detach().to(torch.bfloat16), Kp)
         relu_bits = None
         if act == ACT_RELU and RELU_BITS:
             # one bit per output for the next layer's masked dgrad (it would otherwise re-read this whole activation)
@@ -306,4 +333,4 @@ class LinearActFn(torch.autograd.Function):
             # eager: the results are consumed right after this node (AccumulateGrad) -> join now. Captured: only the LAST node of the
             # chain (no input gradient wanted) joins; chains that continue are joined by DeferredGradJoin at the module inputs.
             torch.cuda.current_stream(gy.device).wait_stream(side)
-        return gx, gw, gb, None
+        return gx, gw, gb, None, None
