@@ -200,3 +200,50 @@ def test_relu_bit_mask_roundtrip(M, N, K, tile_n):
     out = gemm_bf16(gy, wt, b_mn=True, act=ACT_RELU_GRAD, mask=y, mask_bits=bits, tile_n=tile_n)
     assert torch.equal(out, ref)
     assert torch.equal(out == 0, (ref == 0)) and bool(((out != 0) <= (y > 0)).all())
+
+
+@pytest.mark.parametrize("M,N,K,masked", [(32768, 1024, 1024, True), (4096, 512, 256, True), (1000, 480, 1024, False), (333, 64, 512, False), (8192, 256, 512, True)])
+def test_epilogue_column_sums_equal_the_column_sums_of_the_output(M, N, K, masked):
+    """The dgrad epilogue's per-32-row column sums (bias gradient of the layer below) reduce to exactly the column sums of the bf16
+    tensor the GEMM wrote (same rounded values, fp32 accumulation)."""
+    from torchrec_b200.ops.gemm import ACT_NONE, ACT_RELU_GRAD, colsum_from_partials, gemm_bf16
+
+    torch.manual_seed(M + N)
+    dev = "cuda"
+    gy = torch.randn(M, K, device=dev).to(torch.bfloat16)
+    w = (torch.randn(K, N, device=dev) / K ** 0.5).to(torch.bfloat16)  # [K, N]: consumed MN-major like a dgrad
+    mask = torch.randn(M, N, device=dev).to(torch.bfloat16) if masked else None
+    ws = torch.full(((M + 31) // 32, N), float("nan"), device=dev)
+    out = gemm_bf16(gy, w, b_mn=True, act=ACT_RELU_GRAD if masked else ACT_NONE, mask=mask, colsum_ws=ws)
+    ref_out = gemm_bf16(gy, w, b_mn=True, act=ACT_RELU_GRAD if masked else ACT_NONE, mask=mask)
+    assert torch.equal(out, ref_out), "asking for the column sums must not change the output"
+    assert not torch.isnan(ws).any()
+    got = colsum_from_partials(ws)
+    want = out.float().sum(0)
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-2)
+    # per-slab partials: rows 32p .. 32p+31
+    p = (M // 32) // 2
+    torch.testing.assert_close(ws[p], out[32 * p : 32 * p + 32].float().sum(0), rtol=1e-5, atol=1e-4)
+
+
+def test_mlp_bias_gradients_from_the_epilogue_match_the_separate_colsum(monkeypatch):
+    import torchrec_b200.ops.dense as Dn
+    import torchrec_b200.ops.gemm as G
+    from torchrec_b200.modules.mlp import MLP
+
+    prev = Dn._BACKEND
+    Dn.set_dense_backend("tcgen05")
+    try:
+        torch.manual_seed(0)
+        mlp = MLP(480, [1024, 512, 256], device=torch.device("cuda"))
+        x = torch.randn(4096, 480, device="cuda").to(torch.bfloat16)
+        grads = {}
+        for flag in (True, False):
+            monkeypatch.setattr(G, "EPI_COLSUM", flag)
+            mlp.zero_grad()
+            mlp(x).float().square().mean().backward()
+            grads[flag] = [p.grad.clone() for p in mlp.parameters()]
+        for a, b in zip(grads[True], grads[False]):
+            torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5)
+    finally:
+        Dn._BACKEND = prev

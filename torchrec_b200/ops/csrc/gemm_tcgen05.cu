@@ -46,6 +46,10 @@ struct GemmParams {
   uint32_t* relu_bits_out;      // ACT_RELU: bit (n % 32) of word [m, n / 32] = (out[m, n] > 0); nullptr: not wanted
   const uint32_t* mask_bits;    // ACT_RELU_GRAD: the same words of the layer whose gradient this is; nullptr: use `mask`
   int64_t ld_bits;              // words per row of either bit matrix
+  // bias gradient of the layer that produced this GEMM's input gradient, folded into the TMA epilogue: every epilogue warp sums the
+  // 32 rows of each [32 x 64] output slab it just wrote to smem and stores the fp32 column sums to colsum_ws[row0 / 32][n]
+  // ([ceil(M / 32), N], deterministic; reduced by trb_colsum_partials). nullptr: not wanted.
+  float* colsum_ws;
 };
 
 // ---- bf16 epilogue through shared memory + TMA stores ---------------------------------------------------------------
@@ -187,6 +191,21 @@ __device__ __forceinline__ void epilogue_bf16_tma_impl(const CUtensorMap* tmap_o
     if (lane == 0 && row0 < p.M) {
       tma_store_2d(tmap_o, slab, n0, row0);
       bulk_commit_group();
+    }
+    if (p.colsum_ws != nullptr && row0 < p.M) {
+      // column sums of the slab (the bf16 values that were just stored, so the result equals a column sum of the output tensor):
+      // lane l owns columns 2l, 2l+1 = one 4-byte word per row; a row's 32 words are its 128 swizzled bytes -> conflict free
+      float s0 = 0.f, s1 = 0.f;
+      const uint32_t piece = (uint32_t) lane >> 2, sub = ((uint32_t) lane & 3u) * 4u;
+      const int rmax = min(32, p.M - row0);
+#pragma unroll 8
+      for (int r = 0; r < rmax; ++r) {
+        const uint32_t u = *reinterpret_cast<const uint32_t*>(slab + r * 128 + ((piece ^ ((uint32_t) r & 7u)) << 4) + sub);
+        s0 += __uint_as_float(u << 16);
+        s1 += __uint_as_float(u & 0xffff0000u);
+      }
+      const int col = n0 + 2 * lane;
+      if (col < p.N) *reinterpret_cast<float2*>(p.colsum_ws + (int64_t) (row0 >> 5) * p.N + col) = make_float2(s0, s1);
     }
     ++store_count;
   }
@@ -840,6 +859,7 @@ static int gemm_dispatch(const void* A, int64_t lda, const void* B, int64_t ldb,
   p.tma_store = (epi_tma && !p.out_f32 && p.split_k <= 1 && (p.ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(p.out) % 16) == 0) ? 1 : 0;
   if (p.tma_store && make_tmap_out(&to, p.out, p.M, p.N, p.ldo) != 0) p.tma_store = 0;  // fall back to the direct epilogue
   if (!p.tma_store) to = ta;                                                                // unused
+  if (p.colsum_ws != nullptr && !p.tma_store) return -14;  // the column sums live in the TMA epilogue (bf16 output, no split-K)
   if (p.N <= 64) {
     rc = B_MN ? make_tmap(&tb, B, p.K, p.N, ldb, 64, 64) : make_tmap(&tb, B, p.N, p.K, ldb, 64);
     if (rc) return rc;
@@ -862,7 +882,7 @@ static int gemm_dispatch(const void* A, int64_t lda, const void* B, int64_t ldb,
   const int64_t tiles256 = (int64_t) ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + 255) / 256) * (p.split_k > 1 ? p.split_k : 1);
   // tile_n == 256: the caller sized its split-K for 128 x 256 tiles (ops/gemm.py: _wgrad_plan); 0: decide here
   const bool use_wide = tile_n == 256 ? true : (tile_n == 0 && p.split_k <= 1 && tiles256 >= 2 * 148);
-  if (wide && use_wide && p.N % 256 == 0) {
+  if (wide && use_wide && p.N % 256 == 0 && p.colsum_ws == nullptr) {  // (the 128 x 256 variant has the direct epilogue)
     rc = B_MN ? make_tmap(&tb, B, p.K, p.N, ldb, 64, 64) : make_tmap(&tb, B, p.N, p.K, ldb, 256);
     if (rc) return rc;
     return launch_gemm<256, 4, A_MN, B_MN>(ta, tb, to, p, stream);
@@ -884,9 +904,21 @@ TRB_API int trb_gemm_bf16_ex(const void* A, int64_t lda, int a_mn, const void* B
 }
 
 // mask_bits / relu_bits_out: int32 [M, ld_bits] bit matrices (bit n % 32 of word n / 32), see GemmParams
+TRB_API int trb_gemm_bf16_ex3(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* out, int64_t ldo, int out_f32, int M,
+                              int N, int K, const float* bias, int act, const void* mask, int64_t ld_mask, float alpha, int split_k, int tile_n,
+                              const void* mask_bits, void* relu_bits_out, int64_t ld_bits, float* colsum_ws, cudaStream_t stream);
+
 TRB_API int trb_gemm_bf16_ex2(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* out, int64_t ldo, int out_f32, int M,
                               int N, int K, const float* bias, int act, const void* mask, int64_t ld_mask, float alpha, int split_k, int tile_n,
                               const void* mask_bits, void* relu_bits_out, int64_t ld_bits, cudaStream_t stream) {
+  return trb_gemm_bf16_ex3(A, lda, a_mn, B, ldb, b_mn, out, ldo, out_f32, M, N, K, bias, act, mask, ld_mask, alpha, split_k, tile_n, mask_bits, relu_bits_out,
+                           ld_bits, nullptr, stream);
+}
+
+// colsum_ws: fp32 [ceil(M / 32), N] or nullptr, see GemmParams (bf16 output without split-K only: -14 otherwise)
+TRB_API int trb_gemm_bf16_ex3(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* out, int64_t ldo, int out_f32, int M,
+                              int N, int K, const float* bias, int act, const void* mask, int64_t ld_mask, float alpha, int split_k, int tile_n,
+                              const void* mask_bits, void* relu_bits_out, int64_t ld_bits, float* colsum_ws, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if ((lda % 8) || (ldb % 8) || (N % 8)) return -12;
   if ((!a_mn && (K % 8)) || (a_mn && (M % 8)) || (b_mn && (N % 8)) || (!b_mn && (K % 8))) return -12;
@@ -904,6 +936,7 @@ TRB_API int trb_gemm_bf16_ex2(const void* A, int64_t lda, int a_mn, const void* 
   p.mask_bits = reinterpret_cast<const uint32_t*>(mask_bits);
   p.relu_bits_out = reinterpret_cast<uint32_t*>(relu_bits_out);
   p.ld_bits = ld_bits;
+  p.colsum_ws = colsum_ws;
   if ((mask_bits != nullptr || relu_bits_out != nullptr) && ld_bits * 32 < N) return -12;
   if (split_k > 1) {
     if (!out_f32 || bias != nullptr || act != ACT_NONE) return -13;  // split-K only for plain fp32 accumulation
@@ -1238,6 +1271,50 @@ TRB_API int trb_multi_cast_pad_bf16(const void* const* src, void* const* dst, co
   int64_t bx = (biggest + 255) / 256;
   if (bx > 148 * 4) bx = 148 * 4;
   multi_cast_pad_bf16_kernel<<<dim3((unsigned) bx, (unsigned) n), 256, 0, stream>>>(t);
+  TRB_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---- final reduction of the epilogue column sums: out[n] = sum_p ws[p][n], fixed order (deterministic) ---------------------------------
+// grid.x = 64-column groups, 8 warps stride over the P partial rows, lanes read float2 (a warp reads 256 contiguous bytes per row).
+__global__ void __launch_bounds__(256) colsum_partials_kernel(const float* __restrict__ ws, int P, int N, float* __restrict__ out) {
+  __shared__ float2 part[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.x * 64 + lane * 2;
+  float2 acc = make_float2(0.f, 0.f);
+  if (col < N) {
+    int r = warp;
+    for (; r + 24 < P; r += 32) {
+      const float2 a = *reinterpret_cast<const float2*>(ws + (int64_t) r * N + col);
+      const float2 b = *reinterpret_cast<const float2*>(ws + (int64_t) (r + 8) * N + col);
+      const float2 c = *reinterpret_cast<const float2*>(ws + (int64_t) (r + 16) * N + col);
+      const float2 d = *reinterpret_cast<const float2*>(ws + (int64_t) (r + 24) * N + col);
+      acc.x += (a.x + b.x) + (c.x + d.x);
+      acc.y += (a.y + b.y) + (c.y + d.y);
+    }
+    for (; r < P; r += 8) {
+      const float2 a = *reinterpret_cast<const float2*>(ws + (int64_t) r * N + col);
+      acc.x += a.x;
+      acc.y += a.y;
+    }
+  }
+  part[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && col < N) {
+    float2 t = part[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      t.x += part[w][lane].x;
+      t.y += part[w][lane].y;
+    }
+    *reinterpret_cast<float2*>(out + col) = t;
+  }
+}
+
+TRB_API int trb_colsum_partials(const float* ws, int P, int N, float* out, cudaStream_t stream) {
+  if (P <= 0 || N <= 0) return 0;
+  if (N % 2) return -1;
+  colsum_partials_kernel<<<(unsigned) ((N + 63) / 64), 256, 0, stream>>>(ws, P, N, out);
   TRB_CHECK_LAUNCH();
   return 0;
 }

@@ -32,7 +32,7 @@ def _check_bf16_2d(t: torch.Tensor, name: str) -> None:
 def gemm_bf16(a: torch.Tensor, b: torch.Tensor, a_mn: bool = False, b_mn: bool = False, bias: Optional[torch.Tensor] = None,
               act: int = ACT_NONE, out_dtype: torch.dtype = torch.bfloat16, mask: Optional[torch.Tensor] = None, alpha: float = 1.0,
               out: Optional[torch.Tensor] = None, split_k: int = 1, tile_n: int = 0, mask_bits: Optional[torch.Tensor] = None,
-              relu_bits_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              relu_bits_out: Optional[torch.Tensor] = None, colsum_ws: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``act(alpha * op(a) @ op(b)^T + bias)`` on the tcgen05 kernel. ``tile_n``: 0 = kernel picks 128 x {64,128,256} tiles,
     128 / 256 = the caller sized ``split_k`` for that tile width. ``relu_bits_out`` (int32 ``[M, ceil(N / 32)]``, with ``ACT_RELU``):
     receives one bit per output (> 0); ``mask_bits`` (same layout, with ``ACT_RELU_GRAD``): used instead of re-reading ``mask``.
@@ -63,14 +63,26 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, a_mn: bool = False, b_mn: bool =
     if bits is not None:
         assert bits.dtype == torch.int32 and bits.dim() == 2 and bits.shape[0] == M and bits.stride(1) == 1 and bits.stride(0) * 32 >= N and bits.device == a.device
         ld_bits = bits.stride(0)
+    if colsum_ws is not None:  # fp32 [ceil(M / 32), N]: per-32-row column sums of the bf16 output, written by the epilogue
+        assert colsum_ws.dtype == torch.float32 and colsum_ws.is_contiguous() and tuple(colsum_ws.shape) == ((M + 31) // 32, N) and out.dtype == torch.bfloat16 and split_k <= 1
     L = _lib.lib()
-    code = L.trb_gemm_bf16_ex2(
+    code = L.trb_gemm_bf16_ex3(
         _lib.ptr(a), ctypes.c_int64(a.stride(0)), int(a_mn), _lib.ptr(b), ctypes.c_int64(b.stride(0)), int(b_mn), _lib.ptr(out),
         ctypes.c_int64(out.stride(0)), 1 if out.dtype == torch.float32 else 0, M, N, K, _lib.ptr(bias), act, _lib.ptr(mask),
         ctypes.c_int64(mask.stride(0) if mask is not None else 0), ctypes.c_float(alpha), int(split_k), int(tile_n),
-        _lib.ptr(mask_bits if act == ACT_RELU_GRAD else None), _lib.ptr(relu_bits_out if act == ACT_RELU else None), ctypes.c_int64(ld_bits), _lib.stream_ptr(a.device),
+        _lib.ptr(mask_bits if act == ACT_RELU_GRAD else None), _lib.ptr(relu_bits_out if act == ACT_RELU else None), ctypes.c_int64(ld_bits),
+        _lib.ptr(colsum_ws), _lib.stream_ptr(a.device),
     )
-    _lib.check(code, "trb_gemm_bf16_ex2")
+    _lib.check(code, "trb_gemm_bf16_ex3")
+    return out
+
+
+def colsum_from_partials(ws: torch.Tensor) -> torch.Tensor:
+    """``ws [P, N]`` (the epilogue column sums of a GEMM, ``colsum_ws``) -> fp32 ``[N]``, fixed summation order."""
+    P, N = ws.shape
+    out = torch.empty(N, dtype=torch.float32, device=ws.device)
+    code = _lib.lib().trb_colsum_partials(_lib.ptr(ws), int(P), int(N), _lib.ptr(out), _lib.stream_ptr(ws.device))
+    _lib.check(code, "trb_colsum_partials")
     return out
 
 
@@ -226,6 +238,12 @@ def cast_pad_weights(weights) -> list:
     return outs
 
 
+# Bias gradients from the dgrad epilogue of the layer above (``colsum_ws``) instead of a separate column-sum kernel. OFF by default:
+# the K <= 1024 dgrads of the DLRM MLPs are epilogue-bound, and the extra 32 LDS + 64 FADD per lane and slab cost more there (1-GPU step
+# 1.395 -> 1.428 ms) than the separate ``trb_colsum`` kernels do on their side stream. Opt in with TRB_EPI_COLSUM=1 for K >> 1024 stacks.
+EPI_COLSUM = os.environ.get("TRB_EPI_COLSUM", "0") == "1"
+
+
 def _pad_k(t: torch.Tensor, Kp: int) -> torch.Tensor:
     if t.shape[1] == Kp:
         return t
@@ -295,13 +313,20 @@ class LinearActFn(torch.autograd.Function):
             cur = torch.cuda.current_stream(gy.device)
             side = _colsum_stream(gy.device)
             side.wait_stream(cur)
+        # gy was written by the dgrad GEMM of the layer above: its epilogue may have left the column sums behind (EPI_COLSUM)
+        parts = getattr(gy, "_trb_colsum_ws", None)
+        if parts is not None and (parts.shape[1] != gy.shape[1] or parts.shape[0] != (M + 31) // 32):
+            parts = None
+        bias_grad = (lambda: colsum_from_partials(parts)) if parts is not None else (lambda: colsum_bf16(gy))
         if want_b:
             if side is not None:
                 with torch.cuda.stream(side):
-                    gb = colsum_bf16(gy)
+                    gb = bias_grad()
                 gb.record_stream(cur)
+                if parts is not None:
+                    parts.record_stream(side)
             else:
-                gb = colsum_bf16(gy)
+                gb = bias_grad()
 
         def wgrad():
             # gw[N, Kp] = gy^T . x with BOTH operands consumed MN-major straight from their row-major storage
@@ -319,8 +344,13 @@ class LinearActFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             # dgrad: gx[M, Kp] = gy[M, N] . W[N, Kp]; W is consumed as an MN-major B operand (no transpose)
             if ctx.mask_input and xb.shape[1] == ctx.K:
-                gx = gemm_bf16(gy, wb, b_mn=True, act=ACT_RELU_GRAD, mask=xb, mask_bits=ctx.mask_bits)
+                # the masked output IS the pre-activation gradient of the layer below: its bias gradient (column sums) comes out of
+                # this GEMM's epilogue instead of a second pass over the [M, K] tensor (trb_colsum was ~9 % of the DLRM step)
+                ws = torch.empty((M + 31) // 32, xb.shape[1], dtype=torch.float32, device=gy.device) if (EPI_COLSUM and gy.is_cuda) else None
+                gx = gemm_bf16(gy, wb, b_mn=True, act=ACT_RELU_GRAD, mask=xb, mask_bits=ctx.mask_bits, colsum_ws=ws)
                 gx._trb_masked = True
+                if ws is not None:
+                    gx._trb_colsum_ws = ws
             else:
                 gx = gemm_bf16(gy, wb, b_mn=True)
                 if not ctx.pre_padded:
