@@ -1,3 +1,2 @@
-timeout 600 python -m pytest tests/test_gemm_gpu.py -q -x 2>&1 | tail -12
-timeout 400 python bench.py --steps 100 --warmup 10 --phase-times 2>&1 | grep "phase_ms\|^{" | cut -c1-330
-TRB_EPI_COLSUM=0 timeout 400 python bench.py --steps 100 --warmup 10 --no-e2e --phase-times 2>&1 | grep "phase_ms\|^{" | cut -c1-230
+timeout 300 python tools/kernel_bench.py --skip sparse,codec,jagged 2>&1 | grep "qtbe" | cut -c1-100
+timeout 600 python -m pytest tests/test_quant_gpu.py tests/test_quant_sharded_gpu.py tests/test_gemm_gpu.py -q 2>&1 | tail -3

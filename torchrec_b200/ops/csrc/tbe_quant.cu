@@ -118,20 +118,30 @@ __global__ void __launch_bounds__(256) qtbe_fwd_kernel(const QTbeParams p) {
   }
 }
 
-// ---- 8-bit fast path (INT8 row-wise / FP8 block-scaled, every table of the launch in that one format) --------------------------------
+// ---- vector fast path (every table of the launch in ONE of INT8 / FP8 block-scaled / FP16 / BF16 / INT4) -----------------------------
 // Serving batches are dominated by short bags (Criteo: one id per bag). The generic kernel above keeps ONE 4-byte-per-lane row in
-// flight per warp (130-byte rows: ~5 % of the HBM rate). Here 8 lanes own a bag and read a row as 16 B vectors (a 128-element fp8
-// row is exactly one load per lane), every 8-lane group works on U bags at once with the first row of all of them in flight together,
-// and a lane writes 16 consecutive outputs (32 B of bf16).
-// scale word of the 16 elements starting at e: FP8_BLOCK = the fp16 scale of their 32-element block, INT8 = the row's fp16 (scale, bias)
+// flight per warp (130-byte rows: ~5 % of the HBM rate). Here 8 lanes own a bag and read a row as 16 B vectors (EPV elements each: 16
+// for the 8-bit formats, 8 for fp16 / bf16, 32 for int4 - a 128-element fp8 row is exactly one load per lane), every 8-lane group works on
+// U bags at once with the first row of all of them in flight together, and a lane writes its EPV consecutive outputs.
+template <int FMT> struct QVec;
+template <> struct QVec<FMT_INT8> { static constexpr int EPV = 16; };
+template <> struct QVec<FMT_FP8_BLOCK> { static constexpr int EPV = 16; };
+template <> struct QVec<FMT_FP16> { static constexpr int EPV = 8; };
+template <> struct QVec<FMT_BF16> { static constexpr int EPV = 8; };
+template <> struct QVec<FMT_INT4> { static constexpr int EPV = 32; };
+
+// scale word that belongs to the vector starting at element e: FP8_BLOCK = the fp16 scale of its 32-element block, INT8 / INT4 = the
+// row's fp16 (scale, bias) behind the payload, fp16 / bf16 rows = none
 template <int FMT>
-__device__ __forceinline__ uint32_t load_scale16(const uint8_t* row, int D, int e) {
+__device__ __forceinline__ uint32_t load_scale_vec(const uint8_t* row, int D, int e) {
   if constexpr (FMT == FMT_FP8_BLOCK) return *reinterpret_cast<const uint16_t*>(row + D + (e >> 5) * 2);
-  else return *reinterpret_cast<const uint32_t*>(row + D);
+  else if constexpr (FMT == FMT_INT8) return *reinterpret_cast<const uint32_t*>(row + D);
+  else if constexpr (FMT == FMT_INT4) return *reinterpret_cast<const uint32_t*>(row + ((D + 1) >> 1));
+  else return 0u;
 }
 
 template <int FMT>
-__device__ __forceinline__ void dequant16(const uint4 q, const uint32_t sw, float (&v)[16]) {
+__device__ __forceinline__ void dequant_vec(const uint4 q, const uint32_t sw, float (&v)[QVec<FMT>::EPV]) {
   const uint32_t w[4] = {q.x, q.y, q.z, q.w};
   if constexpr (FMT == FMT_FP8_BLOCK) {
     const float s = __half2float(__ushort_as_half((unsigned short) sw));
@@ -141,7 +151,7 @@ __device__ __forceinline__ void dequant16(const uint4 q, const uint32_t sw, floa
       const float4 f = static_cast<float4>(x);
       v[4 * k] = f.x * s; v[4 * k + 1] = f.y * s; v[4 * k + 2] = f.z * s; v[4 * k + 3] = f.w * s;
     }
-  } else {  // FMT_INT8: value * scale + bias, fp16 (scale, bias) behind the D payload bytes
+  } else if constexpr (FMT == FMT_INT8) {  // value * scale + bias
     const __half2 sb = *reinterpret_cast<const __half2*>(&sw);
     const float s = __low2float(sb), b = __high2float(sb);
 #pragma unroll
@@ -149,18 +159,37 @@ __device__ __forceinline__ void dequant16(const uint4 q, const uint32_t sw, floa
       v[4 * k] = (w[k] & 0xff) * s + b; v[4 * k + 1] = ((w[k] >> 8) & 0xff) * s + b;
       v[4 * k + 2] = ((w[k] >> 16) & 0xff) * s + b; v[4 * k + 3] = (w[k] >> 24) * s + b;
     }
+  } else if constexpr (FMT == FMT_INT4) {  // low nibble first
+    const __half2 sb = *reinterpret_cast<const __half2*>(&sw);
+    const float s = __low2float(sb), b = __high2float(sb);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int n = 0; n < 8; ++n) v[8 * k + n] = ((w[k] >> (4 * n)) & 0xf) * s + b;
+  } else if constexpr (FMT == FMT_FP16) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+      v[2 * k] = f.x; v[2 * k + 1] = f.y;
+    }
+  } else {  // FMT_BF16
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[2 * k] = __uint_as_float(w[k] << 16); v[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+    }
   }
 }
 
-template <typename O>
-__device__ __forceinline__ void store16(O* dst, const float (&a)[16]) {
+template <typename O, int N>
+__device__ __forceinline__ void store_vec(O* dst, const float (&a)[N]) {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) Vec4<O>::st(dst + 4 * k, make_float4(a[4 * k], a[4 * k + 1], a[4 * k + 2], a[4 * k + 3]));
+  for (int k = 0; k < N / 4; ++k) Vec4<O>::st(dst + 4 * k, make_float4(a[4 * k], a[4 * k + 1], a[4 * k + 2], a[4 * k + 3]));
 }
 
 template <typename O, int FMT, int MAXV, int U>
 __global__ void __launch_bounds__(256, 3) qtbe_fwd_vec_kernel(const QTbeParams p) {
   constexpr int LPR = 8;
+  constexpr int EPV = QVec<FMT>::EPV;
   const int lig = threadIdx.x & (LPR - 1);
   const int64_t group = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) / LPR;
   const int64_t n_bags = (int64_t) p.F * p.B;
@@ -203,27 +232,27 @@ __global__ void __launch_bounds__(256, 3) qtbe_fwd_vec_kernel(const QTbeParams p
     for (int k = 0; k < MAXV; ++k) {
       // unconditional loads from clamped addresses, payload AND scale word: a predicated load + select (or a scale fetched when the
       // payload is consumed) made every row wait for the previous one (same finding as tbe_bwd_walk_kernel)
-      const int e = (lig + k * LPR) * 16;
-      const int ec = e < D[u] ? e : 0;
-      q[u][k] = *reinterpret_cast<const uint4*>(row0[u] + ec);
-      sw[u][k] = load_scale16<FMT>(row0[u], D[u], ec);
+      const int vi = lig + k * LPR;
+      const int vc = vi * EPV < D[u] ? vi : 0;
+      q[u][k] = *reinterpret_cast<const uint4*>(row0[u] + vc * 16);
+      sw[u][k] = load_scale_vec<FMT>(row0[u], D[u], vc * EPV);
     }
   }
 #pragma unroll
   for (int u = 0; u < U; ++u) {
-    float acc1[MAXV][16];  // one bag's accumulator at a time (the loads of all U bags are already in flight): 64 fewer live registers
+    float acc1[MAXV][EPV];  // one bag's accumulator at a time (the loads of all U bags are already in flight)
 #pragma unroll
     for (int k = 0; k < MAXV; ++k)
 #pragma unroll
-      for (int t = 0; t < 16; ++t) acc1[k][t] = 0.f;
+      for (int t = 0; t < EPV; ++t) acc1[k][t] = 0.f;
 #pragma unroll
     for (int k = 0; k < MAXV; ++k) {
-      const int e = (lig + k * LPR) * 16;
+      const int e = (lig + k * LPR) * EPV;
       if (e < D[u] && w0[u] != 0.f) {
-        float v[16];
-        dequant16<FMT>(q[u][k], sw[u][k], v);
+        float v[EPV];
+        dequant_vec<FMT>(q[u][k], sw[u][k], v);
 #pragma unroll
-        for (int t = 0; t < 16; ++t) acc1[k][t] = v[t] * w0[u];
+        for (int t = 0; t < EPV; ++t) acc1[k][t] = v[t] * w0[u];
       }
     }
     // the rest of the bag (pooling factor > 1)
@@ -234,12 +263,13 @@ __global__ void __launch_bounds__(256, 3) qtbe_fwd_vec_kernel(const QTbeParams p
       const uint8_t* row = wb[u] + idx * rb[u];
 #pragma unroll
       for (int k = 0; k < MAXV; ++k) {
-        const int e = (lig + k * LPR) * 16;
+        const int vi = lig + k * LPR;
+        const int e = vi * EPV;
         if (e < D[u]) {
-          float v[16];
-          dequant16<FMT>(*reinterpret_cast<const uint4*>(row + e), load_scale16<FMT>(row, D[u], e), v);
+          float v[EPV];
+          dequant_vec<FMT>(*reinterpret_cast<const uint4*>(row + vi * 16), load_scale_vec<FMT>(row, D[u], e), v);
 #pragma unroll
-          for (int t = 0; t < 16; ++t) acc1[k][t] = fmaf(v[t], w, acc1[k][t]);
+          for (int t = 0; t < EPV; ++t) acc1[k][t] = fmaf(v[t], w, acc1[k][t]);
         }
       }
     }
@@ -248,13 +278,13 @@ __global__ void __launch_bounds__(256, 3) qtbe_fwd_vec_kernel(const QTbeParams p
     O* dst = reinterpret_cast<O*>(p.out) + (int64_t) b_of[u] * p.out_stride + col[u];
 #pragma unroll
     for (int k = 0; k < MAXV; ++k) {
-      const int e = (lig + k * LPR) * 16;
+      const int e = (lig + k * LPR) * EPV;
       if (e < D[u]) {
         if (inv != 1.f) {
 #pragma unroll
-          for (int t = 0; t < 16; ++t) acc1[k][t] *= inv;
+          for (int t = 0; t < EPV; ++t) acc1[k][t] *= inv;
         }
-        store16<O>(dst + e, acc1[k]);
+        store_vec<O, EPV>(dst + e, acc1[k]);
       }
     }
   }
@@ -265,15 +295,17 @@ static int launch_q_vec(const QTbeParams& p, int max_dim, cudaStream_t stream) {
   const int64_t n_bags = (int64_t) p.F * p.B;
   if (n_bags == 0) return 0;
   const int threads = 256;
+  const int vecs = (max_dim + QVec<FMT>::EPV - 1) / QVec<FMT>::EPV;  // 16 B vectors per row; 8 lanes per bag
 #define TRB_QVEC(MAXV, U)                                                                                     \
   {                                                                                                           \
     const int64_t groups = (n_bags + U - 1) / U;                                                              \
     const unsigned blocks = (unsigned) ((groups * 8 + threads - 1) / threads);                                \
     qtbe_fwd_vec_kernel<O, FMT, MAXV, U><<<blocks, threads, 0, stream>>>(p);                                  \
   }
-  if (max_dim <= 128) TRB_QVEC(1, 4)
-  else if (max_dim <= 256) TRB_QVEC(2, 2)
-  else TRB_QVEC(4, 1)
+  if (vecs <= 8) TRB_QVEC(1, 4)
+  else if (vecs <= 16) TRB_QVEC(2, 2)
+  else if (vecs <= 32) TRB_QVEC(4, 1)
+  else return -7;
 #undef TRB_QVEC
   TRB_CHECK_LAUNCH();
   return 0;
@@ -306,9 +338,12 @@ __global__ void __launch_bounds__(256) qtbe_seq_kernel(const QTbeParams p, int64
 template <typename O>
 static int launch_q(const QTbeParams& p, int max_dim, int64_t total, int uniform_fmt, cudaStream_t stream) {
   const int threads = 256;
-  if (p.pooled && max_dim <= 512 && max_dim % 16 == 0) {
-    if (uniform_fmt == FMT_FP8_BLOCK) return launch_q_vec<O, FMT_FP8_BLOCK>(p, max_dim, stream);
-    if (uniform_fmt == FMT_INT8) return launch_q_vec<O, FMT_INT8>(p, max_dim, stream);
+  if (p.pooled && uniform_fmt >= 0) {  // (the caller guarantees rows made of whole 16-byte vectors: quant_tbe.py _uniform_fmt)
+    if (uniform_fmt == FMT_FP8_BLOCK && max_dim <= 512) return launch_q_vec<O, FMT_FP8_BLOCK>(p, max_dim, stream);
+    if (uniform_fmt == FMT_INT8 && max_dim <= 512) return launch_q_vec<O, FMT_INT8>(p, max_dim, stream);
+    if (uniform_fmt == FMT_FP16 && max_dim <= 256) return launch_q_vec<O, FMT_FP16>(p, max_dim, stream);
+    if (uniform_fmt == FMT_BF16 && max_dim <= 256) return launch_q_vec<O, FMT_BF16>(p, max_dim, stream);
+    if (uniform_fmt == FMT_INT4 && max_dim <= 1024) return launch_q_vec<O, FMT_INT4>(p, max_dim, stream);
   }
   if (!p.pooled) {
     if (total == 0) return 0;

@@ -116,8 +116,12 @@ class QuantTableBatchedEmbeddingBags(nn.Module):
             self.register_buffer("feat_rb", mk32([self._row_bytes[t] for t in fm]), persistent=False)
         self.max_dim = max(self._h_dim) if self._h_dim else 0
         fmts = {FMT[dt] for _, _, _, dt in self.embedding_specs}
-        aligned = all(d % 16 == 0 for d in self._h_dim) and all(rb % 16 == 0 for rb in self._row_bytes)
-        self._uniform_fmt = next(iter(fmts)) if len(fmts) == 1 and aligned else -1  # enables the 16-byte vector kernel for INT8 / FP8 tables
+        # one row format for the whole launch + rows made of whole 16-byte vectors -> the vector kernel (tbe_quant.cu: qtbe_fwd_vec_kernel);
+        # elements per vector: 16 for the 8-bit formats, 8 for fp16 / bf16, 32 for int4
+        epv = {FMT[DataType.INT8]: 16, FMT[DataType.FP8]: 16, FMT[DataType.FP16]: 8, FMT[DataType.BF16]: 8, FMT[DataType.INT4]: 32}
+        one = next(iter(fmts)) if len(fmts) == 1 else -1
+        aligned = one in epv and all(d % epv[one] == 0 for d in self._h_dim) and all(rb % 16 == 0 for rb in self._row_bytes)
+        self._uniform_fmt = one if aligned else -1
 
     def split_embedding_weights(self) -> List[torch.Tensor]:
         """Per table uint8 [rows, row_bytes] views."""
