@@ -1,3 +1,4 @@
+import pytest
 import torch
 
 from torchrec_b200.inference import quantize_inference_model, shard_quant_model
@@ -126,3 +127,44 @@ def test_quant_state_specs():
     sd = ShardedQuantEmbeddingModuleState.sharded_state_dict(sharded.ebc, prefix="ebc.")
     assert sd["ebc.embedding_bags.a.weight"].dtype == torch.uint8 and sd["ebc.embedding_bags.a.weight"].shape[0] == 40
     assert isinstance(sd["ebc.embedding_bags.b.weight"], LocalShardsWrapper) and sd["ebc.embedding_bags.b.weight"].local_offsets() == [(0, 0), (32, 0)]
+
+
+@pytest.mark.parametrize("placement", ["table_wise", "row_wise", "column_wise", "table_row_wise", "mixed"])
+def test_sharded_quant_embedding_collection_every_placement(placement):
+    """Sequence quantized lookups sharded TW / RW / CW / TWRW over 4 (virtual) devices == the unsharded quantized module
+    (reference distributed/quant_embedding.py:597, tests test_quant_sequence_model_parallel.py)."""
+    import torch
+
+    from torchrec_b200.modules.embedding_configs import DataType, EmbeddingConfig
+    from torchrec_b200.parallel import sharding_plan as sp
+    from torchrec_b200.parallel.quant_embedding import QuantEmbeddingCollectionSharder
+    from torchrec_b200.parallel.types import ShardingEnv
+    from torchrec_b200.quant.embedding_modules import EmbeddingCollection as QuantEC
+    from torchrec_b200.sparse.jagged_tensor import KeyedJaggedTensor
+
+    torch.manual_seed(3)
+    W = 4
+    tables = [EmbeddingConfig(name="a", embedding_dim=64, num_embeddings=103, feature_names=["fa", "fa2"], data_type=DataType.FP16),
+              EmbeddingConfig(name="b", embedding_dim=64, num_embeddings=57, feature_names=["fb"], data_type=DataType.FP16)]
+    from torchrec_b200.ops.quant_tbe import quantize_rows
+
+    qw = {t.name: (quantize_rows(torch.randn(t.num_embeddings, t.embedding_dim), t.data_type), None) for t in tables}
+    qec = QuantEC(tables, device=torch.device("cpu"), need_indices=True, table_name_to_quantized_weights=qw)
+    gens = {"table_wise": {"a": sp.table_wise(rank=1), "b": sp.table_wise(rank=3)}, "row_wise": {"a": sp.row_wise(), "b": sp.row_wise()},
+            "column_wise": {"a": sp.column_wise(ranks=[0, 2]), "b": sp.column_wise(ranks=[3, 1])},
+            "table_row_wise": {"a": sp.table_row_wise(host_index=0), "b": sp.table_row_wise(host_index=1)},
+            "mixed": {"a": sp.row_wise(), "b": sp.column_wise(ranks=[2, 0])}}[placement]
+    sharder = QuantEmbeddingCollectionSharder()
+    plan = sp.construct_module_sharding_plan(qec, gens, sharder=sharder, world_size=W, local_size=2, device_type="cpu")
+    sharded = sharder.shard(qec, plan, ShardingEnv.from_local(W, 0), device=torch.device("cpu"))
+    lengths = torch.tensor([2, 0, 1, 3, 1, 1, 0, 2, 2, 1, 1, 1])  # 3 features x batch 4
+    n = int(lengths.sum())
+    values = torch.cat([torch.randint(0, 103, (int(lengths[:8].sum()),)), torch.randint(0, 57, (int(lengths[8:].sum()),))])
+    assert values.numel() == n
+    kjt = KeyedJaggedTensor(keys=["fa", "fa2", "fb"], values=values, lengths=lengths)
+    want, got = qec(kjt), sharded(kjt)
+    assert set(got.keys()) == {"fa", "fa2", "fb"}
+    for k in want:
+        torch.testing.assert_close(got[k].values().float(), want[k].values().float(), rtol=2e-3, atol=2e-3)
+        assert torch.equal(got[k].lengths(), want[k].lengths())
+        assert torch.equal(got[k].weights(), want[k].weights())  # need_indices: the ids ride along as weights
