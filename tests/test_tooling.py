@@ -444,3 +444,43 @@ def test_ir_utils_export_with_placeholder_ops_and_rebuild():
     pruned = U.prune_pytree_flatten_unflatten(gm)
     assert not any("tree_flatten_spec" in str(n.target) for n in pruned.graph.nodes)
     assert torch.equal(pruned(torch.ones(2), torch.ones(2)), torch.full((2,), 2.0))
+
+
+def test_fx_markers_constants_and_safe_asserts():
+    import torch
+    from torch import nn
+
+    from torchrec_b200.fx import symbolic_trace
+    from torchrec_b200.fx.utils import assert_fx_safe, fx_marker, is_marker_node, leaf_call_counts, marker_regions
+    from torchrec_b200.modules.embedding_configs import EmbeddingBagConfig
+    from torchrec_b200.modules.embedding_modules import EmbeddingBagCollection
+    from torchrec_b200.sparse.jagged_tensor import KeyedJaggedTensor
+
+    fixed = KeyedJaggedTensor(keys=["f0"], values=torch.tensor([1, 2, 3]), lengths=torch.tensor([2, 1]))
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.ebc = EmbeddingBagCollection(tables=[EmbeddingBagConfig(name="t0", embedding_dim=4, num_embeddings=10, feature_names=["f0"])])
+            self.lin = nn.Linear(4, 2)
+
+        def forward(self, x):
+            assert_fx_safe(x.shape[0] == 2, "batch of two")
+            fx_marker("DENSE_BEGIN", x)
+            y = self.lin(x)
+            fx_marker("DENSE_END", y)
+            return y + self.ebc(fixed).values().sum(dim=1, keepdim=True)  # a KJT constant closed over by forward
+
+    net = Net()
+    gm = symbolic_trace(net)
+    assert leaf_call_counts(gm).get("ebc") == 1
+    assert sum(is_marker_node(n, "DENSE_BEGIN") for n in gm.graph.nodes) == 1
+    regions = marker_regions(gm.graph, "DENSE_BEGIN", "DENSE_END")
+    assert len(regions) == 1 and [n.target for n in regions[0] if n.op == "call_module"] == ["lin"]
+    assert any(n.op == "get_attr" and str(n.target).startswith("_sparse_constant_") for n in gm.graph.nodes)
+    x = torch.randn(2, 4)
+    torch.testing.assert_close(gm(x), net(x))
+    import pytest
+
+    with pytest.raises(AssertionError):
+        assert_fx_safe(False, "eager asserts still fire")

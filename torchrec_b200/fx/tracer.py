@@ -41,6 +41,31 @@ class Tracer(torch.fx.Tracer):
         finally:
             _state.tracing = False
 
+    # KJT-family constants and already-resolved awaitables that reach ``create_arg`` (a model closing over a fixed KJT, a NoWait wrapped
+    # around a proxy) are not fx base types: constants become ``get_attr`` nodes on the root (so the GraphModule carries them),
+    # ``NoWait(x)`` traces as ``x`` (reference fx/tracer.py:95-128)
+    def create_arg(self, a: Any) -> Any:
+        from ..parallel.types import NoWait
+        from ..sparse.jagged_tensor import JaggedTensor, KeyedJaggedTensor, KeyedTensor
+
+        if isinstance(a, NoWait):
+            return self.create_arg(a._obj)
+        if isinstance(a, (KeyedJaggedTensor, JaggedTensor, KeyedTensor)):
+            root = getattr(self, "root", None)
+            if isinstance(root, nn.Module):
+                n = 0
+                while hasattr(root, f"_sparse_constant_{n}"):
+                    if getattr(root, f"_sparse_constant_{n}") is a:
+                        break
+                    n += 1
+                name = f"_sparse_constant_{n}"
+                if not hasattr(root, name):
+                    object.__setattr__(root, name, a)
+                return self.create_node("get_attr", name, (), {})
+        if isinstance(a, torch.device):  # (plain fx accepts devices only through repr-able constants)
+            return a
+        return super().create_arg(a)
+
     def path_of_module(self, mod: nn.Module) -> str:
         try:
             return super().path_of_module(mod)
@@ -55,12 +80,4 @@ def symbolic_trace(root: Union[nn.Module, Callable], concrete_args: Optional[Dic
     return torch.fx.GraphModule(root if isinstance(root, nn.Module) else nn.Module(), graph)
 
 
-def fake_range() -> List[int]:
-    return [0]
-
-
-def dmp_fx_trace_forward(dmp: nn.Module, tracer: Optional[Tracer] = None) -> torch.fx.GraphModule:
-    """Trace the module wrapped by a DistributedModelParallel (DDP stripped)."""
-    from ..parallel.model_parallel import get_unwrapped_module
-
-    return symbolic_trace(get_unwrapped_module(dmp)) if tracer is None else torch.fx.GraphModule(get_unwrapped_module(dmp), tracer.trace(get_unwrapped_module(dmp)))
+from .utils import assert_fx_safe, dmp_fx_trace_forward, fake_range, fx_marker, is_marker_node  # noqa: E402,F401
