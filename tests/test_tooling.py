@@ -484,3 +484,30 @@ def test_fx_markers_constants_and_safe_asserts():
 
     with pytest.raises(AssertionError):
         assert_fx_safe(False, "eager asserts still fire")
+
+
+def test_every_benchmark_yaml_runs_on_cpu_with_tiny_shapes():
+    """All pipeline-benchmark configs under benchmarks/yaml parse and run end to end (CPU, one rank, shapes shrunk): every pipeline
+    name, sharding type, compute kernel and run knob they mention is wired (reference distributed/benchmark/yaml/*.yml)."""
+    import glob
+    import os
+
+    import yaml
+
+    import torchrec_b200.benchmarks.benchmark_train_pipeline as B
+
+    files = sorted(glob.glob(os.path.join(os.path.dirname(B.__file__), "yaml", "*.yml")))
+    assert len(files) >= 14
+    seen_pipes, seen_shard, seen_kernel = set(), set(), set()
+    for f in files:
+        cfg = B._merge(B.DEFAULT, yaml.safe_load(open(f)))
+        seen_pipes.update(cfg["run"]["pipelines"])
+        seen_shard.add(cfg["run"]["sharding"])
+        seen_kernel.add(cfg["run"]["compute_kernel"])
+        assert all(p in B.PIPELINES for p in cfg["run"]["pipelines"]), f
+        small = B._merge(cfg, {"model": {"dense_arch": [16], "over_arch": [16, 1], "embedding_dim": 8}, "tables": {"num": 3, "rows": 50, "pooling": 2},
+                               "run": {"batch_size": 8, "steps": 2, "warmup": 1, "dense_backend": "torch", "local_world_size": 0, "grad_accumulation": min(2, cfg["run"]["grad_accumulation"])}})
+        res = B.run(small)
+        assert len(res) == len(small["run"]["pipelines"]) and all(r["ms_per_step"] > 0 for r in res), f
+    assert {"base", "sparse_dist", "sparse_dist_lite", "fused_sparse_dist", "semi_sync", "prefetch", "emb_stash", "opt_stash", "bwd_opt"} <= seen_pipes
+    assert {"table_wise", "row_wise", "column_wise", "table_row_wise", "planner"} <= seen_shard and {"fused", "fused_uvm_caching", "key_value"} <= seen_kernel

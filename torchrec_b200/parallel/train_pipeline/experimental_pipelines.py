@@ -96,6 +96,11 @@ class TrainPipelineSparseDistOptStash(TrainPipelineSparseDistBwdOpt[In, Out]):
     def __init__(self, *args: Any, site: Optional[InjectionSite] = None, **kwargs: Any) -> None:
         super().__init__(*args, site=site, injected_work=lambda p: MemoryStashingManager.restore_optimizer_state(), **kwargs)
 
+    def _backward_head(self, losses, head_ctx) -> None:
+        if self._site is None:  # no injection site given: the state comes back right before the backward pass starts
+            MemoryStashingManager.restore_optimizer_state()
+        super()._backward_head(losses, head_ctx)
+
     def progress(self, dataloader_iter: Iterator[In]) -> Out:
         try:
             out = super().progress(dataloader_iter)
