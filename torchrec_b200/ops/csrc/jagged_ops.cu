@@ -220,3 +220,32 @@ TRB_API int trb_permute_pooled_embs(const void* in, void* out, const int32_t* co
   TRB_CHECK_LAUNCH();
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// UVM cache: id -> cache slot for a whole batch in one launch (ops/uvm.py: translate). Feature f owns positions
+// [bounds[f], bounds[f+1]) of `indices`; its table's direct map slot_of_row[table][row] holds the HBM cache slot of a resident row.
+// Out-of-range ids and rows that are not resident translate to -1 (the lookup kernels skip negative ids).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cache_translate_kernel(const void* __restrict__ indices, int idx64, const int64_t* __restrict__ bounds, int F,
+                                                              const int64_t* __restrict__ map_ptrs, const int64_t* __restrict__ rows_of_feature,
+                                                              void* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int lo = 0, hi = F - 1;  // last feature whose start <= i
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (bounds[mid] <= i) lo = mid; else hi = mid - 1;
+  }
+  const int64_t id = trb_ld_idx(indices, i, idx64);
+  int64_t slot = -1;
+  if (id >= 0 && id < rows_of_feature[lo]) slot = (int64_t) reinterpret_cast<const int32_t*>(map_ptrs[lo])[id];
+  trb_st_idx(out, i, idx64, slot);
+}
+
+TRB_API int trb_cache_translate(const void* indices, int idx64, const int64_t* bounds, int F, const int64_t* map_ptrs, const int64_t* rows_of_feature, void* out,
+                                int64_t n, cudaStream_t stream) {
+  if (n == 0 || F == 0) return 0;
+  cache_translate_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(indices, idx64, bounds, F, map_ptrs, rows_of_feature, out, n);
+  TRB_CHECK_LAUNCH();
+  return 0;
+}

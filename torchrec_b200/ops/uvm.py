@@ -210,6 +210,22 @@ class UvmCachedEmbeddingBags(nn.Module):
             self.prefetch(indices, offsets, batch_size)
         self._prefetched = None
         F = len(self.feature_table_map)
+        if indices.is_cuda and _lib.use_cuda_kernels(indices) and indices.numel() > 0:
+            # one launch, no host read: per-feature start positions gathered on the device, direct maps addressed through a pointer table
+            tab = self.__dict__.get("_translate_tab")
+            if tab is None or tab[2] != indices.device:
+                ptrs = torch.tensor([self.slot_of_row[t].data_ptr() for t in self.feature_table_map], dtype=torch.int64, device=indices.device)
+                rows = torch.tensor([self.embedding_specs[t][0] for t in self.feature_table_map], dtype=torch.int64, device=indices.device)
+                pick = torch.arange(0, F + 1, device=indices.device) * 1
+                tab = (ptrs, rows, indices.device, pick)
+                self.__dict__["_translate_tab"] = tab
+            bounds_dev = offsets[tab[3] * batch_size].to(torch.int64)
+            idx = indices.contiguous()
+            out = torch.empty_like(idx)
+            code = _lib.lib().trb_cache_translate(_lib.ptr(idx), int(idx.dtype == torch.int64), _lib.ptr(bounds_dev), F, _lib.ptr(tab[0]), _lib.ptr(tab[1]), _lib.ptr(out),
+                                                  ctypes.c_int64(idx.numel()), _lib.stream_ptr(idx.device))
+            _lib.check(code, "trb_cache_translate")
+            return out
         bounds = offsets[torch.arange(0, F + 1, device=offsets.device) * batch_size].tolist()
         out = indices.clone()
         for f, t in enumerate(self.feature_table_map):
