@@ -73,7 +73,7 @@ class Bench:
 
 def engine(tables, names, plan, env, dev, out_dtype=torch.bfloat16):
     return ShardedLookupEngine(tables, names, list(range(len(tables))), plan, env, dev, pooled=True, is_weighted=False,
-                               opt_specs={t.name: OptimizerSpec(optim=OptimType.EXACT_ROWWISE_ADAGRAD) for t in tables}, output_dtype=out_dtype)
+                               opt_specs={t.name: OptimizerSpec(optim=getattr(OptimType, os.environ.get("KB_OPT", "EXACT_ROWWISE_ADAGRAD"))) for t in tables}, output_dtype=out_dtype)
 
 
 def sparse_cases(bn: Bench) -> None:
@@ -131,6 +131,37 @@ def sparse_cases(bn: Bench) -> None:
     bn.run(f"trb_grad_push W={W} (persistent, 2 CTA/SM)", lambda: p0._push_kernels(grad2), 2.0 * B * F * D * 2, "bf16 [B, 3328] read, column slices stored to the owners' inboxes")
     if p0.has_staged:
         bn.run(f"trb_staging_reduce_cols W={W}", lambda: p0._staging_reduce(0), (W + 1) * B * p0.staged_width * 2, "row-wise partial sums of W sources -> output columns")
+
+
+def n8_rank_cases(bn: Bench) -> None:
+    """What the busiest rank of the 8-GPU DLRM job runs locally: 4 of the large tables, the GLOBAL batch (8 x 32768 samples), every id
+    a different row (no duplicates to merge) - the backward is a pure random 512 B read-modify-write stream."""
+    a, dev = bn.a, bn.dev
+    B, D, F = 8 * a.batch, 128, 4
+    rows = [min(r, a.row_cap) for r in (39884406, 38532951, 39979771, 39664984)]
+    tables = [EmbeddingBagConfig(name=f"t{i}", embedding_dim=D, num_embeddings=r, feature_names=[f"f{i}"]) for i, r in enumerate(rows)]
+    names = [f"f{i}" for i in range(F)]
+    ebc = EmbeddingBagCollection(tables=tables, device=torch.device("meta"))
+    g = torch.Generator().manual_seed(0)
+    vals = torch.cat([torch.randint(0, r, (B,), generator=g) for r in rows]).to(dev)
+    kjt = KeyedJaggedTensor(keys=names, values=vals, lengths=torch.ones(F * B, dtype=torch.int64, device=dev), stride=B)
+    N = F * B
+    uniq = sum(int(torch.unique(vals[i * B : (i + 1) * B]).numel()) for i in range(F))
+    plan = sp.construct_module_sharding_plan(ebc, {t.name: sp.table_wise(rank=0) for t in tables}, sharder=EmbeddingBagCollectionSharder(),
+                                             world_size=1, local_size=1, device_type="cuda")
+    eng = engine(tables, names, plan, ShardingEnv.from_local(1, 0), dev)
+    ids = eng.plane_input_dist(kjt, None, F * D, capacity=N + 64, training=False)
+    pl = ids.plane
+    reg = pl.regions(ids.slot)
+    isz = vals.element_size()
+    bn.run("N=8 busiest rank: tbe_pooled_fwd (4 x 40M-row tables, 262144 samples)", lambda: pl._forward_kernels(reg, 0), N * D * (4 + 2) + N * isz,
+           f"{N} rows x 512 B gathered")
+    grad = torch.randn(B, F * D, device=dev).to(torch.bfloat16)
+    pl._backward_kernels(reg, ids.slot, 1.0, phase=1)
+    bn.run("N=8 busiest rank: tbe_bwd phase 2 (all ids distinct)", lambda: pl._backward_kernels(reg, ids.slot, 1.0, phase=2, grad=grad),
+           N * D * 2 + uniq * (2 * D * 4 + 8), f"{uniq} unique rows read-modify-written")
+    del eng, pl
+    torch.cuda.empty_cache()
 
 
 def quant_cases(bn: Bench) -> None:
@@ -201,7 +232,7 @@ def main() -> None:
     a = ap.parse_args()
     torch.cuda.set_device(0)
     bn = Bench(a)
-    for nm, fn in (("sparse", sparse_cases), ("quant", quant_cases), ("codec", codec_cases), ("jagged", jagged_cases)):
+    for nm, fn in (("sparse", sparse_cases), ("n8rank", n8_rank_cases), ("quant", quant_cases), ("codec", codec_cases), ("jagged", jagged_cases)):
         if nm in a.skip.split(","):
             continue
         try:

@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(256) tbe_bwd_unique_kernel(const TbeBwdParams 
 //     is warp-uniform. Accumulation order and fma contraction are those of the generic walk: results are bit-identical.
 // Runs that continue into a neighbouring chunk leave partial rows exactly like the generic walk (span kernels combine them).
 // Chunks it handled are marked in chunk_done; the generic kernel returns immediately for those.
-template <typename W, typename G, int MAXV, int MINB>
+template <typename W, typename G, int MAXV, int MINB, int UU = 0>
 __global__ void __launch_bounds__(256, MINB) tbe_bwd_walk_kernel(const TbeBwdParams p) {
   typedef uint64_t K;
   const int lane = threadIdx.x & 31;
@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(256, MINB) tbe_bwd_walk_kernel(const TbeBwdPar
     goff = (int64_t) (b - src_rank * p.B_local) * p.grad_stride + p.feat_col[f];
     woff = p.feat_woff[f] + ((int64_t) key - p.feat_rowbase[f]) * D;
   }
-  constexpr int U = MAXV == 1 ? 4 : (MAXV == 2 ? 2 : 1);  // entries in flight per warp (register budget: U x MAXV x 2 float4)
+  constexpr int U = UU > 0 ? UU : (MAXV == 1 ? 4 : (MAXV == 2 ? 2 : 1));  // entries in flight per warp (register budget: U x MAXV x 2 float4)
   const int OPT = p.opt;
   if ((p.prefetch & 4) && lane < cnt_v) {
     // every lane pulls the lines of ITS entry (weight row, row state, gradient row) towards L2 now: the U-wide groups below then
@@ -586,7 +586,56 @@ __global__ void __launch_bounds__(256, MINB) tbe_bwd_walk_kernel(const TbeBwdPar
           const int vi = lane + k * 32;
           wv[u][k] = Vec4<W>::ld_raw(wp + ((vi < nv[u]) ? vi * 4 : 0));
         }
-        if (OPT == OPT_ROWWISE_ADAGRAD) st[u] = p.state1[ky[u]];  // same address on every lane: one broadcast transaction
+        if (OPT == OPT_ROWWISE_ADAGRAD && !(p.prefetch & 8)) st[u] = p.state1[ky[u]];  // same address on every lane: one broadcast transaction
+      }
+    }
+    // Group of U DISTINCT rows that all live inside the chunk (the common case for large tables): the U updates are independent, so
+    // their square-sum reductions, square roots and divisions are interleaved instead of running as U dependent chains back to back
+    // (with one warp per scheduler-slot nothing else hides that latency: row-wise Adagrad was 436 us where SGD took 294 us for the
+    // same 1 M rows). Same arithmetic, same order per row as the sequential path below: bit-identical results.
+    if constexpr (U > 1) {
+      constexpr unsigned kAll = (1u << U) - 1u;
+      const bool distinct = j + U <= cnt_v && ((ends >> j) & kAll) == kAll && (j == 0 || ((ends >> (j - 1)) & 1u)) &&
+                            !(head_open && e_first_end >= j && e_first_end < j + U) && !(tail_open && cnt_v - 1 < j + U);
+      if (distinct) {
+        float4 a[U][MAXV];
+        float sq[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          sq[u] = 0.f;
+#pragma unroll
+          for (int k = 0; k < MAXV; ++k) {
+            a[u][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane + k * 32 < nv[u]) a[u][k] = f4_fma(Vec4<G>::cvt(g[u][k]), sc[u], a[u][k]);
+            sq[u] += f4_sq(a[u][k]);
+          }
+        }
+        float mult[U];
+        if (OPT == OPT_ROWWISE_ADAGRAD) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int u = 0; u < U; ++u) sq[u] += __shfl_xor_sync(0xffffffffu, sq[u], o);
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const float ns = st[u] + sq[u] / (float) (nv[u] << 2);
+            if (lane == 0 && !(p.prefetch & 8)) p.state1[ky[u]] = ns;
+            mult[u] = lr / (sqrtf(ns) + eps);
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < U; ++u) mult[u] = lr;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          W* wp = wbase + wo[u];
+#pragma unroll
+          for (int k = 0; k < MAXV; ++k) {
+            const int vi = lane + k * 32;
+            if (vi < nv[u]) Vec4<W>::st(wp + vi * 4, f4_fma(a[u][k], -mult[u], Vec4<W>::cvt(wv[u][k])));
+          }
+        }
+        continue;
       }
     }
 #pragma unroll
@@ -606,7 +655,7 @@ __global__ void __launch_bounds__(256, MINB) tbe_bwd_walk_kernel(const TbeBwdPar
           for (int k = 0; k < MAXV; ++k) sq += f4_sq(acc[k]);
           sq = warp_sum(sq) / (float) (nv[u] << 2);
           const float ns = st[u] + sq;
-          if (lane == 0) p.state1[ky[u]] = ns;
+          if (lane == 0 && !(p.prefetch & 8)) p.state1[ky[u]] = ns;
           mult = lr / (sqrtf(ns) + eps);
         }
         W* wp = wbase + wo[u];
@@ -946,8 +995,11 @@ static int run_bwd(TbeBwdParams& p, char* ws, cudaStream_t stream) {
   if constexpr (MAXV <= 4) {
     if (walk_enabled && simple_opt) {
       p.chunk_done = (uint8_t*) (ws + L.done);
-      // TRB_BWD_WALK=1: <= 80 registers, 3 CTAs / SM (a few spilled words); =2: 97 registers, 2 CTAs / SM
+      // occupancy beats entries in flight per warp (1 M distinct rows: 2 x 4 CTAs 392 us, 4 x 3 CTAs 436 us, 8 x 2 CTAs 488 us).
+      // TRB_BWD_WALK=1 (default): D <= 128 -> 2 entries / 4 CTAs per SM; =3: 4 entries / 3 CTAs; =2: 4 entries / 2 CTAs
       if (walk_enabled == 2) tbe_bwd_walk_kernel<W, G, MAXV, 2><<<(unsigned) blocks, threads, 0, stream>>>(p);
+      else if (walk_enabled == 3 && MAXV == 1) tbe_bwd_walk_kernel<W, G, MAXV, 3, 4><<<(unsigned) blocks, threads, 0, stream>>>(p);   // 4 entries in flight, 3 CTAs / SM
+      else if (MAXV == 1) tbe_bwd_walk_kernel<W, G, MAXV, 4, 2><<<(unsigned) blocks, threads, 0, stream>>>(p);   // default: 2 entries in flight, 4 CTAs / SM
       else tbe_bwd_walk_kernel<W, G, MAXV, 3><<<(unsigned) blocks, threads, 0, stream>>>(p);
       TRB_CHECK_LAUNCH();
     } else if (fast_enabled && simple_opt) {
@@ -1059,6 +1111,8 @@ TRB_API int trb_tbe_bwd_fused_phase(void* weights, int w_dtype, float* state1, f
     static const int wpf = getenv("TRB_BWD_WALK_PF") ? atoi(getenv("TRB_BWD_WALK_PF")) : 1;
     p.prefetch = pf ? (1 | (n_grad <= 1 ? 2 : 0)) : 0;  // peer-resident gradient rows bypass the local L2: do not prefetch them
     if (wpf) p.prefetch |= 4 | (wpf >= 2 && n_grad <= 1 ? 2 : 0);
+    static const int nostate = getenv("TRB_BWD_DEBUG_NOSTATE") ? atoi(getenv("TRB_BWD_DEBUG_NOSTATE")) : 0;  // measurement aid: skip the row-state memory traffic
+    if (nostate) p.prefetch |= 8;
   }
   if (opt < 0 || opt > OPT_LION) return -5;
   char* ws = reinterpret_cast<char*>(workspace);
