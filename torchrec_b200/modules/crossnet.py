@@ -1,4 +1,5 @@
 """Cross networks (DCN family). Reference torchrec/modules/crossnet.py:21-380."""
+import os
 from typing import Callable, Optional, Union
 
 import torch
@@ -23,6 +24,42 @@ class CrossNet(nn.Module):
             xl_w = torch.matmul(self.kernels[layer], x_l)
             x_l = x_0 * (xl_w + self.bias[layer]) + x_l
         return torch.squeeze(x_l, dim=2)
+
+
+_FUSED_COMBINE = os.environ.get("TRB_CROSS_FUSED", "1") != "0"
+
+
+class _CrossCombine(torch.autograd.Function):
+    """``y = x0 * u + xl`` on bf16 CUDA tensors: one element-wise kernel forward; backward ``gu = g * x0`` and ``gx0 = g * u`` in one
+    kernel (x_0 feeds every cross layer: autograd sums the per-layer ``gx0`` terms), ``gxl = g`` without a kernel."""
+
+    @staticmethod
+    def forward(ctx, x0: torch.Tensor, u: torch.Tensor, xl: torch.Tensor) -> torch.Tensor:
+        import ctypes
+
+        from ..ops import _lib
+
+        u = u.contiguous()
+        xl = xl.contiguous()
+        y = torch.empty_like(x0)
+        code = _lib.lib().trb_cross_fwd(_lib.ptr(x0), _lib.ptr(u), _lib.ptr(xl), _lib.ptr(y), ctypes.c_int64(x0.numel()), _lib.stream_ptr(x0.device))
+        _lib.check(code, "trb_cross_fwd")
+        ctx.save_for_backward(x0, u)
+        return y
+
+    @staticmethod
+    def backward(ctx, g: torch.Tensor):
+        import ctypes
+
+        from ..ops import _lib
+
+        x0, u = ctx.saved_tensors
+        g = g.contiguous() if g.dtype == torch.bfloat16 else g.to(torch.bfloat16).contiguous()
+        gu = torch.empty_like(u)
+        gx0 = torch.empty_like(x0)
+        code = _lib.lib().trb_cross_bwd(_lib.ptr(g), _lib.ptr(x0), _lib.ptr(u), _lib.ptr(gu), _lib.ptr(gx0), ctypes.c_int64(x0.numel()), _lib.stream_ptr(x0.device))
+        _lib.check(code, "trb_cross_bwd")
+        return gx0, gu, g
 
 
 class LowRankCrossNet(nn.Module):
@@ -61,12 +98,13 @@ class LowRankCrossNet(nn.Module):
             # epilogue of the second one); the Hadamard + residual stay element-wise in the activation dtype
             from ..ops import dense as _dense
 
-            x_0 = x_0.to(torch.bfloat16)
+            x_0 = x_0.to(torch.bfloat16).contiguous()
             x_l = x_0
+            combine = _CrossCombine.apply if (x_0.numel() % 8 == 0 and _FUSED_COMBINE) else (lambda a, u, b: a * u + b)
             for layer in range(self._num_layers):
                 x_l_v = _dense.linear_act(x_l, self.V_kernels[layer], None, _dense.ACT_NONE)
                 x_l_w = _dense.linear_act(x_l_v, self.W_kernels[layer], self.bias[layer], _dense.ACT_NONE)
-                x_l = x_0 * x_l_w + x_l
+                x_l = combine(x_0, x_l_w, x_l)  # one kernel forward, one backward (ops/csrc/crossnet.cu)
             return x_l.to(input.dtype) if input.dtype != torch.bfloat16 else x_l
         for layer in range(self._num_layers):
             x_l_v = torch.nn.functional.linear(x_l, self.V_kernels[layer])
