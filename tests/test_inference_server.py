@@ -113,3 +113,52 @@ def test_grpc_front_end():
     client.close()
     g.stop(0)
     srv.shutdown()
+
+
+def test_native_network_front_concurrent_clients_and_malformed_input():
+    """C++ TCP front (csrc/serving/net_front.cpp): protobuf requests built by the Python protobuf runtime are parsed by the hand-written
+    wire reader, batched with the requests of other connections, and the hand-encoded responses parse back with the protobuf runtime."""
+    from torchrec_b200.inference.server import InferenceServer, NativePredictorClient, ServerConfig, serve_native
+
+    keys = ["a", "b"]
+    predict = _model(keys)
+    srv = InferenceServer([predict], [torch.device("cpu")], id_list_keys=keys, config=ServerConfig(max_batch_size=64, batching_interval_ms=2.0))
+    front = serve_native(srv, port=0, task_name="ctr")
+    try:
+        assert front.port > 0
+        errors, done = [], []
+
+        def client(seed: int) -> None:
+            try:
+                rng = np.random.default_rng(seed)
+                c = NativePredictorClient("127.0.0.1", front.port)
+                for _ in range(5):
+                    B = int(rng.integers(1, 9))
+                    dense, lengths, values = _request(rng, B, len(keys))
+                    out = c.predict(B, dense=dense, id_list=(lengths, values), num_id_list_features=len(keys))
+                    np.testing.assert_allclose(out["ctr"], _reference(predict, keys, dense, lengths, values, B), rtol=1e-5, atol=1e-6)
+                c.close()
+                done.append(seed)
+            except Exception as e:  # pragma: no cover
+                errors.append(repr(e))
+
+        threads = [threading.Thread(target=client, args=(s,)) for s in range(6)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(timeout=30)
+        assert not errors and len(done) == 6, errors
+        st = srv.stats()
+        assert st["requests"] == 30 and st["batches"] < 30, "requests of different connections share batches"
+        # a malformed frame gets an error response (status field, empty predictions) and the connection stays usable
+        c = NativePredictorClient("127.0.0.1", front.port)
+        raw = c.predict_raw(b"\x08\x02\x12\x05\x08\x03\x12\x01\x00")  # batch 2, 3 float features, but 1 byte of values
+        assert raw == b"\x78\x03"
+        dense, lengths, values = _request(np.random.default_rng(99), 2, len(keys))
+        assert c.predict(2, dense=dense, id_list=(lengths, values), num_id_list_features=len(keys))["ctr"].shape == (2,)
+        c.close()
+        fs = front.stats()
+        assert fs["served"] == 31 and fs["malformed"] == 1
+    finally:
+        front.stop()
+        srv.shutdown()

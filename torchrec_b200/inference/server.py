@@ -298,3 +298,94 @@ class PredictorClient:
 
     def close(self) -> None:
         self._channel.close()
+
+
+# ---- native (C++) network front: csrc/serving/net_front.cpp -------------------------------------------------------------------------
+class NativeFront:
+    """Handle of the C++ TCP front started by ``serve_native``: ``port``, ``stats()``, ``stop()``."""
+
+    def __init__(self, handle: int, port: int) -> None:
+        self._h, self.port = handle, port
+
+    def stats(self) -> Dict[str, int]:
+        a = (ctypes.c_int64 * 3)()
+        _lib().trb_srv_listen_stats(ctypes.c_void_p(self._h), a)
+        return {"served": a[0], "malformed": a[1], "refused": a[2]}
+
+    def stop(self) -> None:
+        if self._h:
+            _lib().trb_srv_listen_stop(ctypes.c_void_p(self._h))
+            self._h = 0
+
+    def __del__(self) -> None:
+        try:
+            self.stop()
+        except Exception:
+            pass
+
+
+def serve_native(server: InferenceServer, port: int = 0, task_name: str = "default", max_connections: int = 64, timeout_s: float = 10.0) -> NativeFront:
+    """Start the C++ network front on 127.0.0.1 (``port=0``: any free port). Sockets, request parsing (the ``predictor.PredictionRequest``
+    protobuf wire format, read by hand), intake into the batching queue and response encoding all run on C++ threads; Python only executes
+    the model on the executor threads. Frames are ``uint32 little-endian length + message bytes`` (grpc++ is not available in this image:
+    the gRPC front ``serve_grpc`` speaks HTTP/2 through the Python grpc runtime instead). Stop the front before shutting the server down."""
+    L = _lib()
+    L.trb_srv_listen.restype = ctypes.c_void_p
+    L.trb_srv_listen.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.POINTER(ctypes.c_int)]
+    L.trb_srv_listen_stop.argtypes = [ctypes.c_void_p]
+    L.trb_srv_listen_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]
+    bound = ctypes.c_int(0)
+    h = L.trb_srv_listen(server._h, int(port), task_name.encode(), int(server.cfg.outputs_per_sample), int(max_connections), int(timeout_s * 1e6), ctypes.byref(bound))
+    if not h:
+        raise RuntimeError(f"cannot listen on 127.0.0.1:{port}")
+    return NativeFront(h, bound.value)
+
+
+class NativePredictorClient:
+    """Client of the native front: the same ``predictor`` protobuf messages as the gRPC client, framed with a 4-byte length."""
+
+    def __init__(self, host: str, port: int, timeout: float = 10.0) -> None:
+        import socket
+
+        self._Req, self._Resp = proto_classes()
+        self._sock = socket.create_connection((host, port), timeout=timeout)
+        self._sock.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
+
+    def _recv(self, n: int) -> bytes:
+        chunks = []
+        while n:
+            c = self._sock.recv(n)
+            if not c:
+                raise ConnectionError("native front closed the connection")
+            chunks.append(c)
+            n -= len(c)
+        return b"".join(chunks)
+
+    def predict_raw(self, payload: bytes) -> bytes:
+        self._sock.sendall(len(payload).to_bytes(4, "little") + payload)
+        n = int.from_bytes(self._recv(4), "little")
+        return self._recv(n)
+
+    def predict(self, batch_size: int, dense: Optional[np.ndarray] = None, id_list: Optional[Tuple[np.ndarray, np.ndarray]] = None, num_id_list_features: int = 0,
+                id_score_list: Optional[Tuple[np.ndarray, np.ndarray, np.ndarray]] = None, num_id_score_list_features: int = 0) -> Dict[str, np.ndarray]:
+        r = self._Req(batch_size=batch_size)
+        if dense is not None:
+            r.float_features.num_features = dense.shape[1]
+            r.float_features.values = np.ascontiguousarray(dense, dtype=np.float32).tobytes()
+        if id_list is not None:
+            r.id_list_features.num_features = num_id_list_features
+            r.id_list_features.lengths = np.ascontiguousarray(id_list[0], dtype=np.int32).tobytes()
+            r.id_list_features.values = np.ascontiguousarray(id_list[1], dtype=np.int64).tobytes()
+        if id_score_list is not None:
+            r.id_score_list_features.num_features = num_id_score_list_features
+            r.id_score_list_features.lengths = np.ascontiguousarray(id_score_list[0], dtype=np.int32).tobytes()
+            r.id_score_list_features.values = np.ascontiguousarray(id_score_list[1], dtype=np.int64).tobytes()
+            r.id_score_list_features.weights = np.ascontiguousarray(id_score_list[2], dtype=np.float32).tobytes()
+        raw = self.predict_raw(r.SerializeToString())
+        resp = self._Resp.FromString(raw)
+        if not resp.predictions:
+            raise RuntimeError(f"native front reported a failed request ({raw.hex()})")
+        return {k: np.asarray(v.data, dtype=np.float32) for k, v in resp.predictions.items()}
+
+    def close(self) -> None:
+        self._sock.close()
