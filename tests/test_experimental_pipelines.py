@@ -39,8 +39,8 @@ def test_stash_and_bwd_injection_pipelines_match_plain():
     from torchrec_b200.parallel.memory_stashing import MemoryStashingManager
     from torchrec_b200.parallel.train_pipeline import TrainPipelineSparseDist
     from torchrec_b200.parallel.train_pipeline.backward_injection import InjectionSite, InjectionTargetType
-    from torchrec_b200.parallel.train_pipeline.experimental_pipelines import (TrainPipelineSparseDistBwdOpt, TrainPipelineSparseDistEmbStash,
-                                                                                TrainPipelineSparseDistOptStash, TrainPipelineSparseDistT)
+    from torchrec_b200.parallel.train_pipeline.experimental_pipelines import (TrainPipelinePrefetchEMS, TrainPipelineSparseDistBwdOpt,
+                                                                                TrainPipelineSparseDistEmbStash, TrainPipelineSparseDistOptStash, TrainPipelineSparseDistT)
 
     ref_dmp, ref_opt, batches = _model()
     ref = TrainPipelineSparseDist(ref_dmp, ref_opt, torch.device("cpu"))
@@ -48,6 +48,7 @@ def test_stash_and_bwd_injection_pipelines_match_plain():
     ref_losses = [float(ref.progress(it)[0]) for _ in range(5)]
     site = InjectionSite(fqn="model.over_arch", target_type=InjectionTargetType.PARAM_GRAD)
     for cls, kw in ((TrainPipelineSparseDistOptStash, {"site": site}), (TrainPipelineSparseDistEmbStash, {}), (TrainPipelineSparseDistT, {}),
+                    (TrainPipelinePrefetchEMS, {}), (TrainPipelineSparseDistOptStash, {}),
                     (TrainPipelineSparseDistBwdOpt, {"site": site, "injected_work": lambda p: None})):
         MemoryStashingManager.reset()
         dmp, opt, _ = _model()

@@ -29,7 +29,7 @@ DEFAULT: Dict[str, Any] = {
 
 PIPELINES = {"base": "TrainPipelineBase", "sparse_dist": "TrainPipelineSparseDist", "sparse_dist_lite": "TrainPipelineSparseDistLite",
              "fused_sparse_dist": "TrainPipelineFusedSparseDist", "semi_sync": "TrainPipelineSemiSync", "prefetch": "PrefetchTrainPipelineSparseDist",
-             "emb_stash": "TrainPipelineSparseDistEmbStash", "opt_stash": "TrainPipelineSparseDistOptStash", "bwd_opt": "TrainPipelineSparseDistBwdOpt"}
+             "emb_stash": "TrainPipelineSparseDistEmbStash", "opt_stash": "TrainPipelineSparseDistOptStash", "bwd_opt": "TrainPipelineSparseDistBwdOpt", "prefetch_ems": "TrainPipelinePrefetchEMS"}
 
 
 def _merge(a: Dict[str, Any], b: Dict[str, Any]) -> Dict[str, Any]:

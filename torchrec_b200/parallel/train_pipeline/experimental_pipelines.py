@@ -7,7 +7,8 @@
 * ``TrainPipelineSparseDistT`` — the H2D batch copy is issued from a helper thread so Python never blocks on it.
 * ``TrainPipelineSparseDistBwdOpt`` — work injected into the backward pass at a chosen module (backward_injection).
 * ``TrainPipelineSparseDistOptStash`` / ``EmbStash`` — optimizer state / embedding weights are stashed to pinned host
-  memory while the dense part runs and restored before they are needed (memory_stashing)."""
+  memory while the dense part runs and restored before they are needed (memory_stashing).
+* ``TrainPipelinePrefetchEMS`` — cache prefetch one batch ahead + embedding-weight stash."""
 from __future__ import annotations
 
 from concurrent.futures import Future, ThreadPoolExecutor
@@ -18,7 +19,7 @@ from torch import nn
 
 from ..memory_stashing import MemoryStashingManager
 from .backward_injection import InjectionSite, register_backward_hook
-from .train_pipelines import In, Out, TrainPipelineSparseDist, _to_device
+from .train_pipelines import In, Out, PrefetchTrainPipelineSparseDist, TrainPipelineSparseDist, _to_device
 
 
 class TrainEvalHybridPipelineBase(TrainPipelineSparseDist[In, Out]):
@@ -114,6 +115,24 @@ class TrainPipelineSparseDistOptStash(TrainPipelineSparseDistBwdOpt[In, Out]):
 class TrainPipelineSparseDistEmbStash(TrainPipelineSparseDist[In, Out]):
     """Embedding weights are stashed after the embedding forward+backward of a step and restored before the next
     lookup; intended for models whose dense phase is the memory high-water mark."""
+
+    def progress(self, dataloader_iter: Iterator[In]) -> Out:
+        MemoryStashingManager.restore_embedding_weights()
+        out = super().progress(dataloader_iter)
+        if self._model.training:
+            MemoryStashingManager.stash_embedding_weights(self._model)
+        return out
+
+    def detach(self) -> nn.Module:
+        MemoryStashingManager.restore_embedding_weights()
+        return super().detach()
+
+
+class TrainPipelinePrefetchEMS(PrefetchTrainPipelineSparseDist[In, Out]):
+    """Cache-prefetch pipeline + embedding-memory stash (reference experimental_pipelines.py:1221): the UVM-cache prefetch of batch
+    i+1 runs one step ahead as in ``PrefetchTrainPipelineSparseDist`` while the embedding weights of HBM-resident tables are parked
+    on the host for the dense phase and come back (async H2D on the stash stream) before the next lookup needs them. Cached tables
+    are not stashed - their HBM footprint is the cache the prefetch is filling."""
 
     def progress(self, dataloader_iter: Iterator[In]) -> Out:
         MemoryStashingManager.restore_embedding_weights()
