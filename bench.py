@@ -62,6 +62,7 @@ def parse_args() -> argparse.Namespace:
                    help="1 (= -1, the default): replay the dense sub-modules as CUDA graphs (host enqueue 1.6-2.6 ms -> 0.74 ms per step; "
                         "end to end 15.4 M -> 17.7 M samples/s on one GPU); 0: eager")
     p.add_argument("--profile-host", action="store_true", help="cProfile 10 extra steps on rank 0 (stderr)")
+    p.add_argument("--ddp-bucket-mb", type=float, default=float(os.environ.get("TRB_BENCH_DDP_BUCKET_MB", 2)), help="DDP gradient bucket size of the dense part")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--phase-times", action="store_true", help="diagnostics: forward / backward / optimizer device time of the plain step (stderr)")
     p.add_argument("--trace-e2e", type=str, default="", help="diagnostics: torch.profiler trace (chrome json + op table) of 6 extra pipeline steps")
@@ -262,7 +263,13 @@ def build_ours(args: argparse.Namespace, device, rank: int, world: int):
         plan = ShardingPlan({module_path: mplan})
     # data-parallel wrapping is deferred (main() calls dmp.init_data_parallel()) so that CUDA graphs of the dense sub-modules can
     # be captured first: DDP keeps the parameters' AccumulateGrad nodes alive on the default stream, which a capture may not touch
-    dmp = DistributedModelParallel(model, device=device, plan=plan, sharders=[sharder], init_data_parallel=False)
+    # small DDP buckets: the dense gradients of the top MLP are reduced while the embedding backward + bottom MLP backward still run; with the
+    # default 25 MB cap everything but the last layer waits in ONE bucket for the very last gradient and the all-reduce (239 us at 8 GPUs in
+    # profiles/step_kernels_n8_r2.md) sits exposed at the end of the step
+    from torchrec_b200.parallel.model_parallel import DefaultDataParallelWrapper
+
+    dmp = DistributedModelParallel(model, device=device, plan=plan, sharders=[sharder], init_data_parallel=False,
+                                   data_parallel_wrapper=DefaultDataParallelWrapper(bucket_cap_mb=args.ddp_bucket_mb))
     dense_opt = KeyedOptimizerWrapper(dict(in_backward_optimizer_filter(dmp.named_parameters())), lambda params: torch.optim.SGD(params, lr=args.lr))
     opt = CombinedOptimizer([dmp.fused_optimizer, dense_opt])
     return dmp, opt, keys, hashes, [args.pooling] * len(keys), num_dense, backend, info

@@ -871,9 +871,13 @@ __global__ void __launch_bounds__(256) tbe_bwd_span_kernel(const TbeBwdParams p)
   apply_row<W, MAXV>(p, (int64_t) rk, f, acc, lane);
 }
 
+// kLongWarps warps per long span: at 8 GPUs the global batch makes the hot rows of the tiny tables 8x longer (a 3-row table: 87 k entries
+// per row = 2730 partial rows); with 8 warps per span this kernel was 81 us at the very end of the step (profiles/step_kernels_n8_r2.md).
+constexpr int kLongWarps = 32;
+
 template <typename W, int MAXV>
-__global__ void __launch_bounds__(256) tbe_bwd_span_long_kernel(const TbeBwdParams p) {
-  extern __shared__ float smem[];  // [8][max_dim]
+__global__ void __launch_bounds__(kLongWarps * 32) tbe_bwd_span_long_kernel(const TbeBwdParams p) {
+  extern __shared__ float smem[];  // [kLongWarps][max_dim]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_long = *p.long_count;
   for (int wi = blockIdx.x; wi < n_long; wi += gridDim.x) {
@@ -885,7 +889,7 @@ __global__ void __launch_bounds__(256) tbe_bwd_span_long_kernel(const TbeBwdPara
     float4 acc[MAXV];
 #pragma unroll
     for (int k = 0; k < MAXV; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    span_accumulate<MAXV>(p, c, warp, c_end - c + 1, 8, nvec, lane, acc);
+    span_accumulate<MAXV>(p, c, warp, c_end - c + 1, kLongWarps, nvec, lane, acc);
 #pragma unroll
     for (int k = 0; k < MAXV; ++k) {
       const int vi = lane + k * 32;
@@ -898,7 +902,7 @@ __global__ void __launch_bounds__(256) tbe_bwd_span_long_kernel(const TbeBwdPara
         const int vi = lane + k * 32;
         float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (vi < nvec)
-          for (int w8 = 0; w8 < 8; ++w8) s4 = f4_add(s4, *reinterpret_cast<const float4*>(smem + w8 * p.max_dim + vi * 4));
+          for (int w8 = 0; w8 < kLongWarps; ++w8) s4 = f4_add(s4, *reinterpret_cast<const float4*>(smem + w8 * p.max_dim + vi * 4));
         acc[k] = s4;
       }
       apply_row<W, MAXV>(p, (int64_t) rk, f, acc, lane);
@@ -1014,10 +1018,10 @@ static int run_bwd(TbeBwdParams& p, char* ws, cudaStream_t stream) {
   // pass 3: combine runs that span chunks (warp per flagged chunk), then the few long spans with whole blocks
   tbe_bwd_span_kernel<W, MAXV><<<(unsigned) blocks, threads, 0, stream>>>(p);
   TRB_CHECK_LAUNCH();
-  const size_t smem = (size_t) 8 * p.max_dim * sizeof(float);
+  const size_t smem = (size_t) kLongWarps * p.max_dim * sizeof(float);
   if (smem > 48 * 1024)
     TRB_CUDA(cudaFuncSetAttribute(tbe_bwd_span_long_kernel<W, MAXV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  tbe_bwd_span_long_kernel<W, MAXV><<<296, threads, smem, stream>>>(p);
+  tbe_bwd_span_long_kernel<W, MAXV><<<148, kLongWarps * 32, smem, stream>>>(p);
   TRB_CHECK_LAUNCH();
   return 0;
 }
