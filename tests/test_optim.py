@@ -137,3 +137,46 @@ def test_warmup_optimizer_stages_and_resume():
         WarmupOptimizer(_keyed(_model()), [WarmupStage(max_iters=5), WarmupStage(max_iters=5)])
     with pytest.raises(AssertionError):
         WarmupOptimizer(_keyed(_model()), [WarmupStage(WarmupPolicy.INTERPOLATE, max_iters=5)])
+
+
+def _clip_rank(ctx):
+    """Global-norm clipping where only rank 0 owns a sharded parameter (and rank 1 has no gradient for its replicated one on the second
+    step): every rank still takes part in the sharded all-reduce, norms agree with a single-process computation."""
+    import torch
+
+    from torchrec_b200.optim.clipping import GradientClipping, GradientClippingOptimizer
+    from torchrec_b200.optim.keyed import KeyedOptimizerWrapper
+
+    me = ctx.rank
+    torch.manual_seed(0)
+    rep = torch.nn.Parameter(torch.ones(4))                      # replicated: same values on every rank, counted once
+    params = {"rep": rep}
+    if me == 0:
+        sh = torch.nn.Parameter(torch.full((3,), 2.0))           # "sharded": only rank 0 holds a shard
+        sh._is_sharded = True
+        params["sh"] = sh
+    opt = GradientClippingOptimizer(KeyedOptimizerWrapper(params, lambda p: torch.optim.SGD(p, lr=1.0)), clipping=GradientClipping.NORM, max_gradient=1.0,
+                                    enable_global_grad_clip=True)
+    assert opt._has_sharded_anywhere  # rank 1 learnt it from rank 0
+    rep.grad = torch.full((4,), 3.0)
+    if me == 0:
+        sh.grad = torch.full((3,), 4.0)
+    total = opt.clip_grad_norm_()
+    want = (4 * 9.0 + 3 * 16.0) ** 0.5                            # ||rep||^2 + ||sh||^2, the replicated part counted once
+    assert abs(float(total) - want) < 1e-4, (me, float(total), want)
+    torch.testing.assert_close(rep.grad, torch.full((4,), 3.0 / want), rtol=1e-4, atol=1e-5)
+    if me == 0:
+        torch.testing.assert_close(sh.grad, torch.full((3,), 4.0 / want), rtol=1e-4, atol=1e-5)
+    # second step: nobody has a sharded gradient, rank 1 has no gradient at all - the collective still lines up (no deadlock)
+    rep.grad = torch.full((4,), 0.1) if me == 0 else None
+    if me == 0:
+        sh.grad = None
+    total2 = opt.clip_grad_norm_()
+    if me == 0:
+        assert abs(float(total2) - (4 * 0.01) ** 0.5) < 1e-5
+
+
+def test_global_grad_norm_clipping_is_collective_safe():
+    from torchrec_b200.utils.multiprocess import run_multi_process
+
+    run_multi_process(_clip_rank, world_size=2, backend="gloo")
