@@ -168,3 +168,27 @@ def test_sharded_quant_embedding_collection_every_placement(placement):
         torch.testing.assert_close(got[k].values().float(), want[k].values().float(), rtol=2e-3, atol=2e-3)
         assert torch.equal(got[k].lengths(), want[k].lengths())
         assert torch.equal(got[k].weights(), want[k].weights())  # need_indices: the ids ride along as weights
+
+
+def test_dlrm_packager_cli_round_trip(tmp_path):
+    """``dlrm_packager`` writes an archive that ``load_predict_factory`` turns back into a working predict module
+    (reference inference/dlrm_packager.py + inference_legacy import paths)."""
+    import torch
+
+    from torchrec_b200.inference import dlrm_packager
+    from torchrec_b200.inference.inference_legacy import model_packager as legacy_packager
+    from torchrec_b200.inference.model_packager import load_predict_factory
+
+    assert legacy_packager.load_predict_factory is load_predict_factory
+    out = tmp_path / "dlrm.zip"
+    dlrm_packager.main(["--output_path", str(out), "--num_embeddings_per_feature", "50,60,70", "--sparse_feature_names", "a,b,c", "--embedding_dim", "8",
+                        "--dense_arch_layer_sizes", "16,8", "--over_arch_layer_sizes", "16,1", "--num_dense_features", "4", "--weight_dtype", "INT8"])
+    factory = load_predict_factory(out)
+    cfg = factory.model_config
+    assert cfg.id_list_features_keys == ["a", "b", "c"] and cfg.num_embeddings_per_feature == [50, 60, 70] and cfg.sample_input.dense_features.shape == (2, 4)
+    module = factory.create_predict_module(world_size=1, device="cpu")
+    b = cfg.sample_input
+    res = module.predict_forward({"float_features": b.dense_features, "id_list_features.lengths": b.sparse_features.lengths(), "id_list_features.values": b.sparse_features.values()})
+    assert res["default"].shape == (2,) and bool(((res["default"] >= 0) & (res["default"] <= 1)).all())
+    with pytest.raises(ValueError):
+        dlrm_packager.main(["--output_path", str(out), "--num_embeddings_per_feature", "50,60", "--sparse_feature_names", "a,b,c"])

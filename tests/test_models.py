@@ -127,3 +127,26 @@ def test_transformer_dlrm_and_experimental_marker():
         warnings.simplefilter("always")
         assert f(1) == 2 and f(2) == 3 and Thing(3).v == 3 and Thing(4).v == 4
     assert len([x for x in w if "experimental" in str(x.message)]) == 2      # once per object
+
+
+def test_inference_mode_does_not_poison_cached_helpers_for_training():
+    """Index / workspace tensors cached by helpers are created outside inference mode: a serving-style forward under
+    ``torch.inference_mode()`` followed by a training step in the same process must work (caches used to hold inference tensors)."""
+    import torch
+
+    from torchrec_b200.models.dlrm import DLRM
+    from torchrec_b200.modules.embedding_configs import EmbeddingBagConfig
+    from torchrec_b200.modules.embedding_modules import EmbeddingBagCollection
+    from torchrec_b200.ops import dense as D
+    from torchrec_b200.sparse.jagged_tensor import KeyedJaggedTensor
+
+    D._TRIU_CACHE.clear()
+    ebc = EmbeddingBagCollection([EmbeddingBagConfig(name=f"t{i}", embedding_dim=8, num_embeddings=20, feature_names=[f"f{i}"]) for i in range(3)])
+    model = DLRM(ebc, 4, [16, 8], [16, 1])
+    kjt = KeyedJaggedTensor(keys=["f2", "f0", "f1"], values=torch.randint(0, 20, (9,)), lengths=torch.tensor([1, 2, 1, 1, 1, 1, 0, 1, 1]))
+    dense = torch.randn(3, 4)
+    with torch.inference_mode():
+        model(dense, kjt.permute([1, 2, 0]))
+    out = model(dense, kjt.permute([1, 2, 0]))  # same permutation, same interaction size: the cached helpers are reused
+    out.sum().backward()
+    assert all(p.grad is not None for p in model.over_arch.parameters())

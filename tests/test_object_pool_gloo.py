@@ -7,7 +7,7 @@ from torchrec_b200.utils.multiprocess import run_multi_process
 
 
 def _run(ctx, replicated: bool):
-    from torchrec_b200.modules.object_pools import KeyedJaggedTensorPool, TensorPool
+    from torchrec_b200.modules.object_pool import KeyedJaggedTensorPool, TensorPool
     from torchrec_b200.parallel.object_pool import KeyedJaggedTensorPoolSharder, ObjectPoolShardingPlan, ObjectPoolShardingType, TensorPoolSharder
     from torchrec_b200.parallel.types import ShardingEnv
     from torchrec_b200.sparse import KeyedJaggedTensor

@@ -37,22 +37,9 @@ def _dict_to_cfg(d: Dict[str, Any]) -> EmbeddingConfig:
                            data_type=DataType(d["data_type"]), weight_init_max=d.get("weight_init_max"), weight_init_min=d.get("weight_init_min"))
 
 
-class SerializerInterface:
-    """``serialize(module) -> (json dict, children names)`` / ``deserialize(dict, device, unflatten children) -> module``."""
 
-    module_cls: Type[nn.Module]
 
-    @classmethod
-    def serialize_to_dict(cls, module: nn.Module) -> Dict[str, Any]:
-        raise NotImplementedError
-
-    @classmethod
-    def deserialize_from_dict(cls, d: Dict[str, Any], device: Optional[torch.device] = None, children: Optional[Dict[str, nn.Module]] = None) -> nn.Module:
-        raise NotImplementedError
-
-    @classmethod
-    def children(cls, module: nn.Module) -> List[str]:
-        return []
+from .types import SerializerInterface  # noqa: E402,F401
 
 
 class EBCJsonSerializer(SerializerInterface):

@@ -6,7 +6,7 @@ from typing import Dict, Generic, List, Optional, Tuple, TypeVar
 import torch
 from torch import nn
 from ..sparse.jagged_tensor import JaggedTensor, KeyedJaggedTensor
-from .object_pools import ObjectPool  # noqa: F401
+from .object_pool import ObjectPool  # noqa: F401
 
 
 class KeyedJaggedTensorPool(ObjectPool[KeyedJaggedTensor]):

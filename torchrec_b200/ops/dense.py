@@ -94,6 +94,9 @@ _TRIU_CACHE: dict = {}
 def _triu_flat_index(n: int, device: torch.device) -> torch.Tensor:
     key = (n, str(device))
     if key not in _TRIU_CACHE:
-        ti = torch.triu_indices(n, n, offset=1, device=device)
-        _TRIU_CACHE[key] = ti[0] * n + ti[1]
+        # a cached tensor must not be an inference tensor: the first caller may be a predict module under torch.inference_mode(), a later
+        # one a training step that saves the index for backward
+        with torch.inference_mode(False):
+            ti = torch.triu_indices(n, n, offset=1, device=device)
+            _TRIU_CACHE[key] = ti[0] * n + ti[1]
     return _TRIU_CACHE[key]

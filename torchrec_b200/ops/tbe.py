@@ -444,7 +444,8 @@ def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
     key = (device.index if device.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(device).cuda_stream)
     ws = _WS_CACHE.get(key)
     if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
+        with torch.inference_mode(False):  # cached across calls: must not become an inference tensor (a training step writes into it later)
+            ws = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
         _WS_CACHE[key] = ws
     return ws
 

@@ -554,9 +554,11 @@ class ShardedLookupEngine(nn.Module):
                     inv = [0] * total_cols
                     for src, dst in enumerate(cols):
                         inv[dst] = src
-                    idx = (True, torch.tensor(inv, dtype=torch.int64, device=x.device))
+                    with torch.inference_mode(False):
+                        idx = (True, torch.tensor(inv, dtype=torch.int64, device=x.device))
                 else:
-                    idx = (False, torch.tensor(cols, dtype=torch.int64, device=x.device))
+                    with torch.inference_mode(False):
+                        idx = (False, torch.tensor(cols, dtype=torch.int64, device=x.device))
                 self._combine_cache[key] = idx
             if idx[0]:
                 out = x.index_select(1, idx[1])

@@ -406,7 +406,7 @@ class DistributedModelParallel(nn.Module, FusedOptimizerModule):
 
     def reshard(self, sharded_module_fqn: str, changed_shard_to_params: Dict[str, Any]) -> None:
         """Move table shards to a new placement at runtime (dynamic re-sharding, reference model_parallel.py:793)."""
-        from .dynamic_sharding import reshard_module
+        from .sharding.dynamic_sharding import reshard_module
 
         steps = sharded_module_fqn.split(".")
         parent = self.module

@@ -13,8 +13,8 @@ import torch
 import torch.distributed as dist
 from torch import nn
 
-from .engine import TableShard, shards_of
-from .types import ParameterSharding, ShardingEnv, ShardingType
+from ..engine import TableShard, shards_of
+from ..types import ParameterSharding, ShardingEnv, ShardingType
 
 
 class _Stub(nn.Module):

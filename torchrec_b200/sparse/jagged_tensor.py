@@ -236,7 +236,8 @@ def _perm_index_tensor(indices: List[int], device: torch.device) -> torch.Tensor
     if t is None:
         if len(_PERM_INDEX_CACHE) > 4096:
             _PERM_INDEX_CACHE.clear()
-        t = _PERM_INDEX_CACHE[key] = torch.tensor(indices, dtype=torch.int32, device=device)
+        with torch.inference_mode(False):  # cached: a serving call under inference_mode must not poison later training calls
+            t = _PERM_INDEX_CACHE[key] = torch.tensor(indices, dtype=torch.int32, device=device)
     return t
 
 
