@@ -150,3 +150,36 @@ def test_inference_mode_does_not_poison_cached_helpers_for_training():
     out = model(dense, kjt.permute([1, 2, 0]))  # same permutation, same interaction size: the cached helpers are reused
     out.sum().backward()
     assert all(p.grad is not None for p in model.over_arch.parameters())
+
+
+def test_itep_prunes_resets_rows_and_reports_stats():
+    """Unsharded ITEP: hot ids take over physical rows at the pruning interval, the re-assigned rows are re-initialised and the
+    eviction statistics add up (reference modules/itep_modules.py:170-452)."""
+    import torch
+
+    from torchrec_b200.modules.embedding_configs import EmbeddingBagConfig
+    from torchrec_b200.modules.embedding_modules import EmbeddingBagCollection
+    from torchrec_b200.modules.itep_embedding_modules import ITEPEmbeddingBagCollection
+    from torchrec_b200.modules.itep_modules import GenericITEPModule
+    from torchrec_b200.sparse.jagged_tensor import KeyedJaggedTensor
+
+    torch.manual_seed(0)
+    ebc = EmbeddingBagCollection([EmbeddingBagConfig(name="t0", embedding_dim=4, num_embeddings=8, feature_names=["f0"])])  # 8 physical rows
+    itep = GenericITEPModule({"t0": 100}, table_name_to_pruned_hash_sizes={"t0": 8}, pruning_interval=3)
+    m = ITEPEmbeddingBagCollection(ebc, itep)
+    m.train()
+    with torch.no_grad():
+        ebc.embedding_bags["t0"].weight.fill_(7.0)  # sentinel: a reset row no longer holds it
+    hot = torch.tensor([50, 60, 70, 50, 60, 70])     # logical rows far outside the initially mapped 0..6
+    for _ in range(4):
+        m(KeyedJaggedTensor(keys=["f0"], values=hot, lengths=torch.tensor([3, 3])))
+    st = itep.eviction_stats()["t0"]
+    assert st["prunes"] == 1 and st["last_evicted"] == 3 and st["evicted_total"] == 3 and st["physical_rows"] == 8 and st["logical_rows"] == 100
+    addr = itep._addr("t0")
+    phys = addr[torch.tensor([50, 60, 70])]
+    assert phys.unique().numel() == 3 and int(phys.max()) < 7, "every hot logical row got its own physical row (the last slot stays the shared one)"
+    w = ebc.embedding_bags["t0"].weight
+    assert bool((w[phys].abs() < 1.0).all()) and bool((w[7] == 7.0).all()), "re-assigned rows were re-initialised, untouched rows kept their values"
+    assert st["access_share_resident"] > 0.99  # all (decayed) accesses now hit rows that own a physical row
+    # cold ids share the last physical row
+    assert int(addr[99]) == 7

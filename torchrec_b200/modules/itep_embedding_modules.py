@@ -19,7 +19,10 @@ class ITEPEmbeddingBagCollection(nn.Module):
         self.register_buffer("_iter", torch.tensor(0, dtype=torch.int64))
 
     def forward(self, features: KeyedJaggedTensor, force_insert: bool = False) -> KeyedTensor:
+        before = self._itep_module.num_prunes
         features = self._itep_module(features, int(self._iter.item()))
+        if self._itep_module.num_prunes != before:  # rows changed owner in this call: they start from a fresh embedding
+            self._itep_module.reset_weight_momentum(self._embedding_bag_collection)
         out = self._embedding_bag_collection(features)
         if self.training:
             self._iter += 1
@@ -36,7 +39,10 @@ class ITEPEmbeddingCollection(nn.Module):
         self.register_buffer("_iter", torch.tensor(0, dtype=torch.int64))
 
     def forward(self, features: KeyedJaggedTensor, force_insert: bool = False):
+        before = self._itep_module.num_prunes
         features = self._itep_module(features, int(self._iter.item()))
+        if self._itep_module.num_prunes != before:
+            self._itep_module.reset_weight_momentum(self._embedding_collection)
         out = self._embedding_collection(features)
         if self.training:
             self._iter += 1

@@ -36,6 +36,9 @@ class GenericITEPModule(nn.Module):
             self.register_buffer(f"row_util_{t}", torch.zeros(unpruned, dtype=torch.float32, device=device))
             self.register_buffer(f"owner_{t}", torch.arange(pruned, dtype=torch.int64, device=device))  # physical row -> logical owner
         self.last_pruned_iter = -1
+        self.last_changed: Dict[str, torch.Tensor] = {}     # physical rows handed to a new logical owner by the latest prune()
+        self.evicted_total: Dict[str, int] = {t: 0 for t in self._tables}
+        self.num_prunes = 0
 
     def _addr(self, t: str) -> torch.Tensor:
         return getattr(self, f"address_lookup_{t}")
@@ -71,23 +74,74 @@ class GenericITEPModule(nn.Module):
         for t in self._tables:
             pruned = self.table_name_to_pruned_hash_sizes[t]
             util, addr, owner = self._util(t), self._addr(t), getattr(self, f"owner_{t}")
-            keep = torch.topk(util, pruned - 1).indices if pruned > 1 else util.new_zeros(0, dtype=torch.long)
-            keep_mask = torch.zeros_like(util, dtype=torch.bool)
-            keep_mask[keep] = True
+            own = owner[: pruned - 1]
+            valid_owner = own >= 0
             owns = torch.zeros_like(util, dtype=torch.bool)
-            valid_owner = owner[: pruned - 1] >= 0
-            owns[owner[: pruned - 1][valid_owner]] = True
-            stay = keep_mask & owns  # hot rows that already own a physical row keep it
-            newcomers = (keep_mask & ~owns).nonzero(as_tuple=True)[0]
-            freed_phys = (~stay[owner[: pruned - 1].clamp(min=0)] | ~valid_owner).nonzero(as_tuple=True)[0]
-            n = min(newcomers.numel(), freed_phys.numel())
-            if n:
-                addr[owner[freed_phys[:n]].clamp(min=0)] = pruned - 1  # old owners fall back to the shared slot
-                owner[freed_phys[:n]] = newcomers[:n]
-                addr[newcomers[:n]] = freed_phys[:n]
-                changed[t] = freed_phys[:n]
+            owns[own[valid_owner]] = True
+            # candidates: accessed logical rows without a physical row, hottest first; victims: physical rows whose owner is coldest
+            # first (an unowned physical row counts as utilisation -1). A candidate only displaces a strictly colder owner, so rows
+            # that were never accessed do not shuffle owners around.
+            cand = ((util > 0) & ~owns).nonzero(as_tuple=True)[0]
+            changed_rows = util.new_zeros(0, dtype=torch.long)
+            if cand.numel() and pruned > 1:
+                cand = cand[torch.argsort(util[cand], descending=True)][: pruned - 1]
+                owner_util = torch.where(valid_owner, util[own.clamp(min=0)], torch.full_like(util[: pruned - 1], -1.0))
+                victims = torch.argsort(owner_util)[: cand.numel()]
+                take = util[cand[: victims.numel()]] > owner_util[victims]
+                n = int(take.sum())  # (both lists are sorted: once a candidate is not hotter than its victim, none of the rest is)
+                if n:
+                    victims, newcomers = victims[:n], cand[:n]
+                    old = own[victims]
+                    addr[old[old >= 0]] = pruned - 1  # old owners fall back to the shared slot
+                    owner[victims] = newcomers
+                    addr[newcomers] = victims
+                    changed_rows = victims
+            if changed_rows.numel():
+                changed[t] = changed_rows
             util.mul_(0.5)  # exponential decay of the access statistics
+        self.last_changed = changed
+        self.num_prunes += 1
+        for t, rows in changed.items():
+            self.evicted_total[t] += int(rows.numel())
         return changed
+
+    def eviction_stats(self) -> Dict[str, Dict[str, float]]:
+        """Per table: physical rows re-assigned by the last pruning step / in total, the share of the id space that currently owns a
+        physical row, and how concentrated the (decayed) access counts are (share of accesses that hit rows with a physical row) - the
+        quantity the pruned table size should be tuned against (reference ``print_itep_eviction_stats`` :170-257)."""
+        out: Dict[str, Dict[str, float]] = {}
+        for t in self._tables:
+            pruned, unpruned = self.table_name_to_pruned_hash_sizes[t], self.table_name_to_unpruned_hash_sizes[t]
+            util, owner = self._util(t), getattr(self, f"owner_{t}")
+            owned = owner[: pruned - 1]
+            owned = owned[owned >= 0]
+            total = float(util.sum())
+            out[t] = {"last_evicted": float(self.last_changed[t].numel()) if t in self.last_changed else 0.0, "evicted_total": float(self.evicted_total[t]),
+                      "physical_rows": float(pruned), "logical_rows": float(unpruned), "resident_fraction": float(owned.numel()) / max(unpruned, 1),
+                      "access_share_resident": (float(util[owned].sum()) / total) if total > 0 else 0.0, "prunes": float(self.num_prunes)}
+        return out
+
+    @torch.no_grad()
+    def reset_weight_momentum(self, collection: nn.Module, changed: Optional[Dict[str, torch.Tensor]] = None) -> int:
+        """Re-initialise the physical rows that just changed owner (the new logical row must not inherit the old one's embedding) and
+        clear their optimizer state when the collection keeps it next to the weights (fused collections: ``reset_rows``). Returns the
+        number of rows reset (reference ``reset_weight_momentum`` :412-452)."""
+        changed = self.last_changed if changed is None else changed
+        n = 0
+        for t, rows in changed.items():
+            if rows.numel() == 0:
+                continue
+            if hasattr(collection, "reset_rows"):
+                collection.reset_rows(t, rows)
+            else:
+                holder = getattr(collection, "embedding_bags", None) or getattr(collection, "embeddings", None)
+                if holder is None or t not in holder:
+                    continue
+                w = holder[t].weight
+                b = (1.0 / max(self.table_name_to_unpruned_hash_sizes[t], 1)) ** 0.5
+                w.data[rows.to(w.device)] = torch.empty(rows.numel(), w.shape[1], dtype=w.dtype, device=w.device).uniform_(-b, b)
+            n += int(rows.numel())
+        return n
 
 
 class RowwiseShardedITEPModule(GenericITEPModule):
