@@ -192,3 +192,52 @@ def test_dlrm_packager_cli_round_trip(tmp_path):
     assert res["default"].shape == (2,) and bool(((res["default"] >= 0) & (res["default"] <= 1)).all())
     with pytest.raises(ValueError):
         dlrm_packager.main(["--output_path", str(out), "--num_embeddings_per_feature", "50,60", "--sparse_feature_names", "a,b,c"])
+
+
+def test_quantized_weight_publish_and_pruning_metadata():
+    import torch
+
+    from torchrec_b200.inference.modules import (MODULE_ATTR_EMB_CONFIG_NAME_TO_NUM_ROWS_POST_PRUNING_DICT, PredictFactory, QualNameMetadata, assign_weights_to_tbe,
+                                                 get_table_to_weights_from_tbe, set_pruning_data)
+    from torchrec_b200.modules.embedding_configs import DataType, EmbeddingConfig
+    from torchrec_b200.ops.quant_tbe import quantize_rows
+    from torchrec_b200.quant.embedding_modules import EmbeddingCollection as QuantEC
+
+    tables = [EmbeddingConfig(name="a", embedding_dim=16, num_embeddings=30, feature_names=["fa"], data_type=DataType.INT8)]
+    qw = {"a": (quantize_rows(torch.randn(30, 16), DataType.INT8), None)}
+    qec = QuantEC(tables, device=torch.device("cpu"), table_name_to_quantized_weights=qw)
+    got = get_table_to_weights_from_tbe(qec)
+    assert set(got) == {"a"} and torch.equal(got["a"], qw["a"][0])
+    fresh = quantize_rows(torch.randn(30, 16), DataType.INT8)
+    assign_weights_to_tbe(qec, {"a": fresh})
+    assert torch.equal(get_table_to_weights_from_tbe(qec)["a"], fresh)
+    with pytest.raises(AssertionError):
+        assign_weights_to_tbe(qec, {"a": fresh[:10]})
+
+    from torchrec_b200.modules.embedding_configs import EmbeddingBagConfig
+    from torchrec_b200.modules.embedding_modules import EmbeddingBagCollection
+
+    ebc = EmbeddingBagCollection([EmbeddingBagConfig(name="t0", embedding_dim=8, num_embeddings=100, feature_names=["f0"])])
+    set_pruning_data(torch.nn.Sequential(ebc), {"t0": 40})
+    assert getattr(ebc, MODULE_ATTR_EMB_CONFIG_NAME_TO_NUM_ROWS_POST_PRUNING_DICT) == {"t0": 40} and ebc.embedding_bag_configs()[0].num_embeddings_post_pruning == 40
+
+    class F(PredictFactory):
+        def create_predict_module(self):
+            return torch.nn.Identity()
+
+        def batching_metadata(self):
+            return {}
+
+        def result_metadata(self):
+            return "dict_of_tensor"
+
+        def run_weights_independent_tranformations(self, m):
+            return m
+
+        def run_weights_dependent_transformations(self, m):
+            return m
+
+        def qualname_metadata(self):
+            return {"model.preproc": QualNameMetadata(need_preproc=True)}
+
+    assert F().qualname_metadata_json() == '{"model.preproc": {"need_preproc": true}}'

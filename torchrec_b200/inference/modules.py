@@ -40,6 +40,13 @@ class BatchingMetadata:
     pinned: List[str]
 
 
+@dataclass
+class QualNameMetadata:
+    """Per-submodule serving metadata keyed by qualified name: does the runtime have to run a pre-processing module in front of it?"""
+
+    need_preproc: bool
+
+
 class PredictFactory(abc.ABC):
     """Creates the (already quantized / sharded) predict module inside the serving process."""
 
@@ -68,8 +75,13 @@ class PredictFactory(abc.ABC):
     def run_weights_dependent_transformations(self, predict_module: torch.nn.Module) -> torch.nn.Module:
         ...
 
-    def qualname_metadata(self) -> Dict[str, Any]:
+    def qualname_metadata(self) -> Dict[str, QualNameMetadata]:
         return {}
+
+    def qualname_metadata_json(self) -> str:
+        import json
+
+        return json.dumps({k: {"need_preproc": bool(v.need_preproc)} for k, v in self.qualname_metadata().items()})
 
     def model_inputs_data(self) -> Dict[str, Any]:
         return {}
@@ -197,3 +209,51 @@ def shard_quant_model(model: torch.nn.Module, world_size: int = 1, compute_devic
     plan = planner.plan(model, sharders)
     sharded = _shard_modules(module=model, device=torch.device(compute_device), sharders=sharders, env=ShardingEnv.from_local(world_size=world_size, rank=0), plan=plan)
     return sharded, plan
+
+
+MODULE_ATTR_EMB_CONFIG_NAME_TO_NUM_ROWS_POST_PRUNING_DICT = "__emb_name_to_num_rows_post_pruning"
+
+
+def set_pruning_data(model: torch.nn.Module, tables_to_rows_post_pruning: Dict[str, int], module_types: Optional[List[Type[nn.Module]]] = None) -> torch.nn.Module:
+    """Record the post-pruning row counts of embedding tables (produced by ITEP / offline pruning) on the collections of ``model``: the
+    quantized modules built from them allocate ``num_embeddings_post_pruning`` rows instead of ``num_embeddings`` and remap ids through the
+    pruning index at lookup time. Both the module attribute of the reference and the per-table config field are set."""
+    from ..modules.embedding_modules import EmbeddingBagCollection, EmbeddingCollection
+
+    types = tuple(module_types) if module_types is not None else (EmbeddingBagCollection, EmbeddingCollection)
+    for m in model.modules():
+        if isinstance(m, types) or type(m).__name__ == "FeatureProcessedEmbeddingBagCollection":
+            setattr(m, MODULE_ATTR_EMB_CONFIG_NAME_TO_NUM_ROWS_POST_PRUNING_DICT, dict(tables_to_rows_post_pruning))
+            cfgs = m.embedding_bag_configs() if hasattr(m, "embedding_bag_configs") else (m.embedding_configs() if hasattr(m, "embedding_configs") else [])
+            for c in cfgs:
+                if c.name in tables_to_rows_post_pruning:
+                    c.num_embeddings_post_pruning = int(tables_to_rows_post_pruning[c.name])
+    return model
+
+
+def _quant_tbes(model: torch.nn.Module):
+    from ..ops.quant_tbe import QuantTableBatchedEmbeddingBags
+
+    return [m for m in model.modules() if isinstance(m, QuantTableBatchedEmbeddingBags)]
+
+
+def get_table_to_weights_from_tbe(model: torch.nn.Module) -> Dict[str, torch.Tensor]:
+    """``{table (shard) name: uint8 [rows, row_bytes]}`` views of every quantized table of ``model`` - sharded modules expose one entry
+    per local shard (``<table>_<row_off>_<col_off>``). The views alias the kernels' storage (weight publishing writes through them)."""
+    out: Dict[str, torch.Tensor] = {}
+    for tbe in _quant_tbes(model):
+        for (name, _, _, _), w in zip(tbe.embedding_specs, tbe.split_embedding_weights()):
+            out[name] = w
+    return out
+
+
+@torch.no_grad()
+def assign_weights_to_tbe(model: torch.nn.Module, table_to_weight: Dict[str, torch.Tensor]) -> None:
+    """Copy quantized rows into the model's tables (e.g. a fresher snapshot published by training): every table of every quantized TBE
+    must be present with its exact ``[rows, row_bytes]`` shape."""
+    for tbe in _quant_tbes(model):
+        for (name, rows, _, _), w in zip(tbe.embedding_specs, tbe.split_embedding_weights()):
+            assert name in table_to_weight, f"{name} not in table_to_weight"
+            src = table_to_weight[name]
+            assert tuple(src.shape) == tuple(w.shape), f"{name}: got {tuple(src.shape)}, table is {tuple(w.shape)}"
+            w.copy_(src.to(w.device))
