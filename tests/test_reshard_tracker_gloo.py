@@ -143,6 +143,17 @@ def _run_tracker(ctx, mode: str):
         for fqn, rows in delta_b.items():
             assert rows.states is not None and rows.states.shape[0] == rows.ids.numel() and bool((rows.states >= 0).all())
     assert tr.get_unique(consumer="b") == {} or all(v.ids.numel() == 0 for v in tr.get_unique(consumer="b").values())
+    # manual recording (modules without an engine hook): ids + states supplied by the caller land in the same store
+    from torchrec_b200.sparse.jagged_tensor import KeyedJaggedTensor
+
+    kjt = KeyedJaggedTensor(keys=["f0"], values=torch.tensor([3, 3, 5]), lengths=torch.tensor([2, 1]))
+    if mode == "embedding":
+        tr.record_embeddings(None, kjt, torch.arange(12, dtype=torch.float32).view(3, 4))
+        got = tr.get_unique(consumer="b")["ebc.embedding_bags.t0"]
+        assert got.ids.tolist() == [3, 5] and torch.equal(got.states[:, :4], torch.tensor([[0.0, 1, 2, 3], [8, 9, 10, 11]]))  # FIRST occurrence wins
+    elif mode == "id_only":
+        tr.record_ids(kjt)
+        assert tr.get_unique_ids(consumer="b")["ebc.embedding_bags.t0"].tolist() == [3, 5]
 
 
 @pytest.mark.parametrize("mode", ["id_only", "embedding", "rowwise_adagrad"])

@@ -158,6 +158,38 @@ class ModelDeltaTrackerTrec(ModelDeltaTracker):
     def record_ids(self, kjt) -> None:
         self.record_lookup(None, kjt, None)
 
+    def record_embeddings(self, emb_module: nn.Module, kjt, states: torch.Tensor) -> None:
+        """EMBEDDING mode by hand: ``states`` = the embedding rows looked up for ``kjt`` (one row per id, in value order)."""
+        assert states is not None and states.shape[0] == kjt.values().numel(), "one state row per id"
+        self.record_lookup(emb_module, kjt, states.detach())
+
+    def _state_rows_of(self, emb_module: nn.Module, kjt, state_name: str) -> torch.Tensor:
+        """Rows of an optimizer state for the (global) ids of ``kjt``, read from the tables' full state tensors of the module's fused
+        optimizer (``<table>.<state_name>`` or ``<table>.weight.<state_name>`` keys)."""
+        opt = getattr(emb_module, "fused_optimizer", None)
+        assert opt is not None, "recording optimizer state needs a module with a fused optimizer"
+        state = opt.state_dict()["state"]
+        cfgs = emb_module.embedding_bag_configs() if hasattr(emb_module, "embedding_bag_configs") else emb_module.embedding_configs()
+        table_of = {f: c.name for c in cfgs for f in c.feature_names}
+        parts = []
+        for k, v in zip(kjt.keys(), torch.split(kjt.values(), kjt.length_per_key())):
+            t = table_of[k]
+            entry = next((val for key, val in state.items() if key.endswith(f"{t}.weight") or key.endswith(t)), None)
+            assert entry is not None and state_name in entry, f"no optimizer state {state_name!r} for table {t}"
+            full = entry[state_name]
+            full = full.full_tensor() if hasattr(full, "full_tensor") else (full.local_tensor() if hasattr(full, "local_tensor") and not isinstance(full, torch.Tensor) else full)
+            rows = full[v.long().to(full.device)]
+            parts.append(rows.unsqueeze(1) if rows.dim() == 1 else rows)
+        return torch.cat(parts) if parts else torch.zeros(0, 1)
+
+    def record_momentum(self, emb_module: nn.Module, kjt) -> None:
+        """MOMENTUM_LAST / MOMENTUM_DIFF by hand: first-moment rows of the ids in ``kjt`` (Adam / LAMB families)."""
+        self.record_lookup(emb_module, kjt, self._state_rows_of(emb_module, kjt, "momentum1"))
+
+    def record_rowwise_optim_state(self, emb_module: nn.Module, kjt) -> None:
+        """ROWWISE_ADAGRAD by hand: the per-row accumulator (one float per row) of the ids in ``kjt``."""
+        self.record_lookup(emb_module, kjt, self._state_rows_of(emb_module, kjt, "momentum1"))
+
     # ---- reading ---------------------------------------------------------------------------------------------
     def step(self) -> None:
         self.curr_batch_idx += 1
