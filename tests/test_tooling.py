@@ -511,3 +511,42 @@ def test_every_benchmark_yaml_runs_on_cpu_with_tiny_shapes():
         assert len(res) == len(small["run"]["pipelines"]) and all(r["ms_per_step"] > 0 for r in res), f
     assert {"base", "sparse_dist", "sparse_dist_lite", "fused_sparse_dist", "semi_sync", "prefetch", "emb_stash", "opt_stash", "bwd_opt"} <= seen_pipes
     assert {"table_wise", "row_wise", "column_wise", "table_row_wise", "planner"} <= seen_shard and {"fused", "fused_uvm_caching", "key_value"} <= seen_kernel
+
+
+def test_pt2_utils_transformer_compile_switch_and_queue():
+    import torch
+
+    from torchrec_b200.pt2.utils import AtomicCounter, TensorQueue, default_pipeline_input_transformer, pt2_compile_callable, register_fake_classes
+    from torchrec_b200.sparse.jagged_tensor import KeyedJaggedTensor
+
+    class B:
+        pass
+
+    b = B()
+    b.id_list_features = KeyedJaggedTensor(keys=["f"], values=torch.tensor([1, 2, 3]), lengths=torch.tensor([2, 1], dtype=torch.int32))
+    b.other = 5
+    out = default_pipeline_input_transformer(b)
+    assert out is b and out.id_list_features.lengths().dtype == torch.int64 and out.other == 5
+
+    calls = []
+
+    class M:
+        enable_pt2_compile = False
+
+        @pt2_compile_callable
+        def update(self, x):
+            calls.append("eager")
+            return x * 2
+
+    m = M()
+    assert torch.equal(m.update(torch.ones(2)), torch.full((2,), 2.0)) and calls == ["eager"] and "_update_pt2_compiled" not in m.__dict__
+    q = TensorQueue(torch.zeros(1))
+    assert q.size() == 0 and torch.equal(q.pop(), torch.zeros(1))
+    q.push(torch.ones(1))
+    q.push(torch.full((1,), 2.0))
+    assert torch.equal(q.top(), torch.ones(1)) and torch.equal(q.pop(), torch.ones(1)) and q.size() == 1
+    c = AtomicCounter()
+    assert c.increment() == 1 and c.increment() == 2 and c.decrement() == 1
+    c.set(7)
+    assert c.get() == 7
+    register_fake_classes()

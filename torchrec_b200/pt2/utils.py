@@ -61,3 +61,88 @@ def kjt_for_pt2_tracing(kjt: KeyedJaggedTensor, convert_to_vb: bool = False, mar
     except Exception:
         pass
     return out
+
+
+def default_pipeline_input_transformer(inp):
+    """Input hook of ``TrainPipelinePT2``: the KJT fields of a batch are re-made for tracing (host caches dropped, value dimension dynamic)."""
+    for attr_name in ("id_list_features", "id_score_list_features", "sparse_features"):
+        attr = getattr(inp, attr_name, None)
+        if isinstance(attr, KeyedJaggedTensor):
+            setattr(inp, attr_name, kjt_for_pt2_tracing(attr))
+    return inp
+
+
+def pt2_compile_callable(f):
+    """Decorator for metric ``update`` / ``compute`` methods: when the owning object sets ``enable_pt2_compile = True`` the method runs
+    through ``torch.compile`` (compiled once per object and cached on it), otherwise it is called as is. Opt-in only: nothing in this
+    framework's hot path depends on a tracing compiler."""
+    import functools
+
+    attr = f"_{f.__name__}_pt2_compiled"
+
+    @functools.wraps(f)
+    def inner(ref, *args, **kwargs):
+        if getattr(ref, "enable_pt2_compile", False):
+            compiled = ref.__dict__.get(attr) if hasattr(ref, "__dict__") else None
+            if compiled is None:
+                compiled = torch.compile(f)
+                object.__setattr__(ref, attr, compiled)
+            return compiled(ref, *args, **kwargs)
+        return f(ref, *args, **kwargs)
+
+    return inner
+
+
+class AtomicCounter:
+    """Python stand-in of the ``fbgemm::AtomicCounter`` script class some reference models hold (per-table step counters): same
+    methods, plain integer. Nothing to register with the fake-class registry - it is an ordinary Python object under tracing too."""
+
+    def __init__(self, counter_: int = 0) -> None:
+        self.counter_ = int(counter_)
+
+    def increment(self) -> int:
+        self.counter_ += 1
+        return self.counter_
+
+    def decrement(self) -> int:
+        self.counter_ -= 1
+        return self.counter_
+
+    def reset(self) -> None:
+        self.counter_ = 0
+
+    def get(self) -> int:
+        return self.counter_
+
+    def set(self, val: int) -> None:
+        self.counter_ = int(val)
+
+
+class TensorQueue:
+    """Python stand-in of ``fbgemm::TensorQueue``: FIFO of tensors, ``pop`` / ``top`` of an empty queue return the initial tensor."""
+
+    def __init__(self, init_tensor: torch.Tensor, queue=None) -> None:
+        self.init_tensor = init_tensor
+        self.queue = list(queue or [])
+
+    def push(self, x: torch.Tensor) -> None:
+        self.queue.append(x)
+
+    def pop(self) -> torch.Tensor:
+        return self.queue.pop(0) if self.queue else self.init_tensor
+
+    def top(self) -> torch.Tensor:
+        return self.queue[0] if self.queue else self.init_tensor
+
+    def size(self) -> int:
+        return len(self.queue)
+
+
+def register_fake_classes() -> None:
+    """The reference registers fake (meta) versions of the two FBGEMM script classes above so they trace under PT2. Here they are Python
+    classes already; kept as a no-op so call sites keep working."""
+    return None
+
+
+def deregister_fake_classes() -> None:
+    return None
