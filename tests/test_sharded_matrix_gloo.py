@@ -1,0 +1,135 @@
+"""Randomised sharding matrix on 4 CPU ranks (gloo): random tables (dims, rows, SUM / MEAN pooling, shared tables with two features,
+weighted or not), a random placement per table out of table-wise / row-wise / column-wise / table-row-wise / table-column-wise / grid /
+data-parallel, random jagged batches with empty bags - the sharded collection must match the unsharded one in the forward output and
+in the weights after two fused-SGD steps. One process group, several seeds per launch (reference: distributed/test_utils/
+test_model_parallel*.py matrices)."""
+import random
+
+import pytest
+import torch
+
+from torchrec_b200.utils.multiprocess import run_multi_process
+
+SEEDS_PER_LAUNCH = 5
+
+
+def _case(seed: int, weighted: bool, W: int, local: int):
+    from torchrec_b200.modules.embedding_configs import EmbeddingBagConfig, PoolingType
+    from torchrec_b200.parallel import sharding_plan as sp
+
+    rng = random.Random(1000 * seed + (7 if weighted else 0))
+    n_tables = rng.randint(3, 5)
+    tables, gens, fid = [], {}, 0
+    for t in range(n_tables):
+        dim = rng.choice([4, 8, 12, 16])
+        rows = rng.randint(9, 40)
+        feats = [f"f{fid + i}" for i in range(rng.choice([1, 1, 2]))]
+        fid += len(feats)
+        pooling = PoolingType.SUM if (weighted or rng.random() < 0.6) else PoolingType.MEAN
+        name = f"t{t}"
+        tables.append(EmbeddingBagConfig(name=name, embedding_dim=dim, num_embeddings=rows, feature_names=feats, pooling=pooling))
+        hosts = W // local
+        kind = rng.choice(["tw", "rw", "cw", "twrw", "twcw", "grid", "dp"])
+        if kind == "cw" and dim % 8 != 0:
+            kind = "tw"
+        if kind in ("twcw", "grid") and dim % 8 != 0:
+            kind = "twrw"
+        if kind == "tw":
+            gens[name] = sp.table_wise(rank=rng.randrange(W))
+        elif kind == "rw":
+            gens[name] = sp.row_wise()
+        elif kind == "cw":
+            gens[name] = sp.column_wise(ranks=rng.sample(range(W), 2))
+        elif kind == "twrw":
+            gens[name] = sp.table_row_wise(host_index=rng.randrange(hosts))
+        elif kind == "twcw":
+            gens[name] = sp.table_column_wise(ranks=rng.sample(range(W), 2)) if hasattr(sp, "table_column_wise") else sp.column_wise(ranks=rng.sample(range(W), 2))
+        elif kind == "grid":
+            gens[name] = sp.grid_shard(host_indexes=list(range(hosts)))
+        else:
+            gens[name] = sp.data_parallel()
+    return tables, gens
+
+
+def _batch(tables, seed: int, rank: int, B: int, weighted: bool):
+    from torchrec_b200.sparse import KeyedJaggedTensor
+
+    g = torch.Generator().manual_seed(7919 * seed + 31 * rank + 1)
+    keys, hashes = [], []
+    for t in tables:
+        for f in t.feature_names:
+            keys.append(f)
+            hashes.append(t.num_embeddings)
+    lengths = torch.randint(0, 4, (len(keys) * B,), generator=g)
+    lengths[torch.rand(lengths.shape, generator=g) < 0.2] = 0  # plenty of empty bags
+    vals = [torch.randint(0, h, (int(lengths[i * B : (i + 1) * B].sum()),), generator=g) for i, h in enumerate(hashes)]
+    values = torch.cat(vals) if vals else torch.zeros(0, dtype=torch.long)
+    w = torch.rand(values.numel(), generator=g) + 0.5 if weighted else None
+    return KeyedJaggedTensor(keys=keys, values=values, lengths=lengths, weights=w)
+
+
+def _run(ctx, weighted: bool, first_seed: int, n_seeds: int = SEEDS_PER_LAUNCH):
+    from torchrec_b200.modules.embedding_modules import EmbeddingBagCollection
+    from torchrec_b200.optim.apply_optimizer_in_backward import apply_optimizer_in_backward
+    from torchrec_b200.parallel import sharding_plan as sp
+    from torchrec_b200.parallel.comm_ops import set_gradient_division
+    from torchrec_b200.parallel.embeddingbag import EmbeddingBagCollectionSharder
+    from torchrec_b200.parallel.model_parallel import DistributedModelParallel
+    from torchrec_b200.parallel.types import ShardingPlan
+
+    set_gradient_division(False)
+    W, local, B, dev = ctx.world_size, 2, 5, ctx.device
+    for seed in range(first_seed, first_seed + n_seeds):
+        tables, gens = _case(seed, weighted, W, local)
+        torch.manual_seed(seed)
+        gold = EmbeddingBagCollection(tables, is_weighted=weighted, device=dev)
+        sharded_src = EmbeddingBagCollection(tables, is_weighted=weighted, device=dev)
+        sharded_src.load_state_dict(gold.state_dict())
+        apply_optimizer_in_backward(torch.optim.SGD, sharded_src.parameters(), {"lr": 0.1})
+        sharder = EmbeddingBagCollectionSharder()
+        plan = sp.construct_module_sharding_plan(sharded_src, gens, sharder=sharder, world_size=W, local_size=local, device_type=dev.type)
+        desc = {n: plan[n].sharding_type for n in plan}
+
+        class Wrap(torch.nn.Module):
+            def __init__(self, ebc):
+                super().__init__()
+                self.ebc = ebc
+
+            def forward(self, kjt):
+                return self.ebc(kjt).values()
+
+        model = DistributedModelParallel(Wrap(sharded_src), device=dev, plan=ShardingPlan({"ebc": plan}), sharders=[sharder])
+        dense_params = [p for _, p in model.named_parameters() if p.requires_grad]  # data-parallel tables
+        dense_opt = torch.optim.SGD(dense_params, lr=0.1) if dense_params else None
+        gold_opt = torch.optim.SGD(gold.parameters(), lr=0.1)
+        for step in range(2):
+            batches = [_batch(tables, 10 * seed + step, r, B, weighted).to(dev) for r in range(W)]
+            out = model(batches[ctx.rank])
+            gouts = [gold(b).values() for b in batches]
+            torch.testing.assert_close(out.float(), gouts[ctx.rank], rtol=1e-5, atol=1e-5, msg=lambda m: f"seed {seed} step {step} plan {desc}: {m}")
+            proj = torch.linspace(0.5, 1.5, out.shape[1], device=dev)
+            (out * proj).sum().backward()
+            if dense_opt is not None:
+                for p in dense_params:  # DDP averages over ranks, the golden sums the per-rank losses
+                    p.grad.mul_(W)
+                dense_opt.step()
+                dense_opt.zero_grad()
+            gold_opt.zero_grad()
+            sum((o * proj).sum() for o in gouts).backward()
+            gold_opt.step()
+        sd = model.state_dict()
+        for t in tables:
+            st = sd[f"ebc.embedding_bags.{t.name}.weight"]
+            ref = gold.embedding_bags[t.name].weight.detach()
+            if hasattr(st, "local_shards"):
+                for sh in st.local_shards():
+                    o, s = sh.metadata.shard_offsets, sh.metadata.shard_sizes
+                    torch.testing.assert_close(sh.tensor, ref[o[0] : o[0] + s[0], o[1] : o[1] + s[1]], rtol=1e-4, atol=1e-5,
+                                               msg=lambda m: f"seed {seed} table {t.name} ({desc[t.name]}): {m}")
+            else:
+                torch.testing.assert_close(st, ref, rtol=1e-4, atol=1e-5, msg=lambda m: f"seed {seed} table {t.name} ({desc[t.name]}): {m}")
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_random_sharding_matrix_4_ranks(weighted):
+    run_multi_process(_run, world_size=4, backend="gloo", weighted=weighted, first_seed=0)

@@ -390,7 +390,12 @@ class ShardedEmbeddingBagCollection(
         self._dp_cols: List[int] = []
         if self._dp_tables:
             pool = {getattr(tables[ti], "pooling", PoolingType.SUM) for ti in self._dp_tables}
-            assert len(pool) == 1, "data-parallel tables of one collection must share a pooling type"
+            # SUM and MEAN tables replicated in one collection: the kernel sums, the MEAN features are divided by their bag lengths
+            # afterwards through the same per-(sample, feature) divisor the row-sharded MEAN tables use (``ctx.mean_divisor``)
+            self._dp_post_mean_features = [fi for fi in self._dp_features if getattr(tables[self._feature_table[fi]], "pooling", PoolingType.SUM) == PoolingType.MEAN] \
+                if len(pool) > 1 else []
+            if len(pool) > 1:
+                pool = {PoolingType.SUM}
             local_idx = {ti: i for i, ti in enumerate(self._dp_tables)}
             dp_tbe = TableBatchedEmbeddingBags(
                 embedding_specs=[(tables[ti].num_embeddings, tables[ti].embedding_dim) for ti in self._dp_tables],
@@ -415,7 +420,10 @@ class ShardedEmbeddingBagCollection(
         self.embedding_bags = nn.ModuleDict()
         self._build_param_views()
         # ---- mean pooling handled after the reduce (row-sharded MEAN tables) -----------------------------------
-        self._post_mean = self._engine is not None and any(self._engine._post_mean_feature)
+        self._post_mean_feature: List[bool] = list(self._engine._post_mean_feature) if self._engine is not None else [False] * len(self._feature_names)
+        for fi in getattr(self, "_dp_post_mean_features", []):
+            self._post_mean_feature[fi] = True
+        self._post_mean = any(self._post_mean_feature)
         self._features_order: Optional[List[int]] = None
         self._has_features_permute = False
         self._optim: Optional[KeyedOptimizer] = None
@@ -643,7 +651,7 @@ class ShardedEmbeddingBagCollection(
         lengths = features.lengths().view(len(self._feature_names), B).t().float()  # [B, F]
         mask = self.__dict__.get("_post_mean_mask")
         if mask is None or mask.device != lengths.device:
-            mask = self.__dict__["_post_mean_mask"] = torch.tensor(self._engine._post_mean_feature, device=lengths.device)
+            mask = self.__dict__["_post_mean_mask"] = torch.tensor(self._post_mean_feature, device=lengths.device)
             self.__dict__["_embedding_dims_t"] = torch.tensor(self._embedding_dims, device=lengths.device)
         div = torch.where(mask.unsqueeze(0), 1.0 / lengths.clamp(min=1.0), torch.ones_like(lengths))
         return torch.repeat_interleave(div, self.__dict__["_embedding_dims_t"], dim=1, output_size=self._total_cols)
