@@ -133,3 +133,86 @@ def _run(ctx, weighted: bool, first_seed: int, n_seeds: int = SEEDS_PER_LAUNCH):
 @pytest.mark.parametrize("weighted", [False, True])
 def test_random_sharding_matrix_4_ranks(weighted):
     run_multi_process(_run, world_size=4, backend="gloo", weighted=weighted, first_seed=0)
+
+
+def _run_ec(ctx, dedup: bool, first_seed: int, n_seeds: int = SEEDS_PER_LAUNCH):
+    """Sequence embeddings: random tables / TW / RW / CW placements / jagged batches, index de-duplication on or off."""
+    from torchrec_b200.modules.embedding_configs import EmbeddingConfig
+    from torchrec_b200.modules.embedding_modules import EmbeddingCollection
+    from torchrec_b200.optim.apply_optimizer_in_backward import apply_optimizer_in_backward
+    from torchrec_b200.parallel import sharding_plan as sp
+    from torchrec_b200.parallel.comm_ops import set_gradient_division
+    from torchrec_b200.parallel.embedding import EmbeddingCollectionSharder
+    from torchrec_b200.parallel.model_parallel import DistributedModelParallel
+    from torchrec_b200.parallel.types import ShardingPlan
+    from torchrec_b200.sparse import KeyedJaggedTensor
+
+    set_gradient_division(False)
+    W, B = ctx.world_size, 4
+    for seed in range(first_seed, first_seed + n_seeds):
+        rng = random.Random(31 * seed + (3 if dedup else 0))
+        dim = rng.choice([8, 16])  # one dim per collection (EmbeddingCollection contract)
+        tables, gens, keys, hashes, fid = [], {}, [], [], 0
+        for t in range(rng.randint(2, 4)):
+            rows = rng.randint(9, 40)
+            feats = [f"f{fid + i}" for i in range(rng.choice([1, 1, 2]))]
+            fid += len(feats)
+            tables.append(EmbeddingConfig(name=f"t{t}", embedding_dim=dim, num_embeddings=rows, feature_names=feats))
+            keys += feats
+            hashes += [rows] * len(feats)
+            kind = rng.choice(["tw", "rw", "cw"])
+            gens[f"t{t}"] = sp.table_wise(rank=rng.randrange(W)) if kind == "tw" else (sp.row_wise() if kind == "rw" else sp.column_wise(ranks=rng.sample(range(W), 2)))
+        torch.manual_seed(seed)
+        gold = EmbeddingCollection(tables)
+        src = EmbeddingCollection(tables)
+        src.load_state_dict(gold.state_dict())
+        apply_optimizer_in_backward(torch.optim.SGD, src.parameters(), {"lr": 0.1})
+        sharder = EmbeddingCollectionSharder(use_index_dedup=dedup)
+        plan = sp.construct_module_sharding_plan(src, gens, sharder=sharder, world_size=W, local_size=W, device_type="cpu")
+        desc = {n: plan[n].sharding_type for n in plan}
+
+        class Wrap(torch.nn.Module):
+            def __init__(self, ec):
+                super().__init__()
+                self.ec = ec
+
+            def forward(self, kjt):
+                return self.ec(kjt)
+
+        model = DistributedModelParallel(Wrap(src), device=torch.device("cpu"), plan=ShardingPlan({"ec": plan}), sharders=[sharder])
+        gold_opt = torch.optim.SGD(gold.parameters(), lr=0.1)
+
+        def batch(s):
+            g = torch.Generator().manual_seed(s)
+            lengths = torch.randint(0, 4, (len(keys) * B,), generator=g)
+            vals = torch.cat([torch.randint(0, hashes[i], (int(lengths[i * B : (i + 1) * B].sum()),), generator=g) for i in range(len(keys))])
+            return KeyedJaggedTensor(keys=keys, values=vals, lengths=lengths)
+
+        for step in range(2):
+            batches = [batch(1000 * seed + 10 * step + r) for r in range(W)]
+            out = model(batches[ctx.rank])
+            gouts = [gold(b) for b in batches]
+            loss = 0
+            for k in keys:
+                v, gv = out[k].values(), gouts[ctx.rank][k].values()
+                torch.testing.assert_close(v.float(), gv, rtol=1e-5, atol=1e-5, msg=lambda m: f"EC seed {seed} step {step} key {k} plan {desc}: {m}")
+                assert torch.equal(out[k].lengths(), gouts[ctx.rank][k].lengths())
+                loss = loss + (v * torch.linspace(0.5, 1.5, v.shape[1])).sum()
+            loss.backward()
+            gold_opt.zero_grad()
+            sum((go[k].values() * torch.linspace(0.5, 1.5, dim)).sum() for go in gouts for k in keys).backward()
+            gold_opt.step()
+        sd = model.state_dict()
+        for t in tables:
+            st = sd[f"ec.embeddings.{t.name}.weight"]
+            ref = gold.embeddings[t.name].weight.detach()
+            shards = st.local_shards() if hasattr(st, "local_shards") else []
+            for sh in shards:
+                o, s = sh.metadata.shard_offsets, sh.metadata.shard_sizes
+                torch.testing.assert_close(sh.tensor, ref[o[0] : o[0] + s[0], o[1] : o[1] + s[1]], rtol=1e-4, atol=1e-5,
+                                           msg=lambda m: f"EC seed {seed} table {t.name} ({desc[t.name]}): {m}")
+
+
+@pytest.mark.parametrize("dedup", [False, True])
+def test_random_sequence_sharding_matrix_4_ranks(dedup):
+    run_multi_process(_run_ec, world_size=4, backend="gloo", dedup=dedup, first_seed=0)

@@ -307,7 +307,8 @@ class ShardedEmbeddingCollection(ShardedModule[KJTList, List[torch.Tensor], Dict
             unit_rows = torch.split(rows, ctx.routed.length_per_key(), dim=0)
             for fi in range(F):
                 us = sorted(self._units_of_feature[fi], key=lambda g: eng.units[g].shard.col_off)
-                parts = [unit_rows[g] for g in us]
+                # (rows are as wide as the widest unit of the rank set: a column slice mixed with whole tables is padded on the right)
+                parts = [unit_rows[g][:, : eng.units[g].shard.cols] for g in us]
                 per_feature.append(parts[0] if len(parts) == 1 else torch.cat(parts, dim=1))
         else:
             # ids were re-sorted by (unit, sample) and replicated once per column slice: undo the sort, then
@@ -315,11 +316,17 @@ class ShardedEmbeddingCollection(ShardedModule[KJTList, List[torch.Tensor], Dict
             restored = rows.index_select(0, ctx.unbucketize)
             off = 0
             for fi in range(F):
-                nc = len({eng.units[g].shard.col_off for g in self._units_of_feature[fi]})
+                slices = sorted({(eng.units[g].shard.col_off, eng.units[g].shard.cols) for g in self._units_of_feature[fi]})
+                nc = len(slices)
                 n = lookup_lpk[fi]
                 block = restored[off : off + n * nc]
                 off += n * nc
-                per_feature.append(block.view(n, nc, -1).reshape(n, -1) if nc > 1 else block)
+                if nc > 1:
+                    b3 = block.view(n, nc, block.shape[1])
+                    block = torch.cat([b3[:, j, :cols] for j, (_, cols) in enumerate(slices)], dim=1)
+                else:
+                    block = block[:, : slices[0][1]]
+                per_feature.append(block)
         lengths2d = feats.lengths().view(F, B)
         values_split = torch.split(feats.values(), feats.length_per_key()) if self._need_indices else None
         out: Dict[str, JaggedTensor] = {}

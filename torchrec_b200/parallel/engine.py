@@ -173,7 +173,9 @@ class ShardedLookupEngine(nn.Module):
                 clf = float(cp.load_factor)
             kvp = getattr(ps, "key_value_params", None)
             kv_dir = getattr(kvp, "ssd_storage_directory", None) if kvp is not None else None
-            key = (str(dtype), int(pooling), opt.key(), loc, clf if loc >= 2 else 0, kv_dir if loc == 4 else None)
+            # sequence (unpooled) kernels emit rows of ONE width per launch: column slices and whole tables of a collection (a column-wise
+            # table next to a row-wise one) go to separate groups; ``lookup`` pads their rows to the widest unit of the job
+            key = (str(dtype), int(pooling), opt.key(), loc, clf if loc >= 2 else 0, kv_dir if loc == 4 else None, None if pooled else shards[0].cols)
             if key not in group_index:
                 group_index[key] = len(self._groups)
                 self._groups.append(_Group(key, pooling, dtype, opt))
@@ -495,8 +497,13 @@ class ShardedLookupEngine(nn.Module):
                 outs.append(g.tbe(values, window, weights, batch_size=Bg))
             else:
                 outs.append(g.tbe(values, window, None, batch_size=Bg))
+        if not self._pooled:
+            Wd = self.__dict__.get("_seq_width")
+            if Wd is None:
+                Wd = self.__dict__["_seq_width"] = max((u.shard.cols for u in self._units), default=self._tables[0].embedding_dim if self._tables else 0)
+            outs = [torch.nn.functional.pad(o, (0, Wd - o.shape[1])) if o.shape[1] < Wd else o for o in outs]
         if not outs:
-            D = 0 if self._pooled else self._tables[0].embedding_dim
+            D = 0 if self._pooled else self.__dict__["_seq_width"]
             # a rank without shards of this module still has to run the BACKWARD collectives of the output dist with its peers:
             # the empty result must be part of the autograd graph (found by the tower test: TW table on one rank only -> hang)
             return torch.zeros(Bg if self._pooled else 0, D, device=values.device, dtype=self._output_dtype, requires_grad=torch.is_grad_enabled())
