@@ -13,7 +13,7 @@ from torchrec_b200.utils.multiprocess import run_multi_process
 SEEDS_PER_LAUNCH = 5
 
 
-def _case(seed: int, weighted: bool, W: int, local: int):
+def _case(seed: int, weighted: bool, W: int, local: int, no_col_split: bool = False):
     from torchrec_b200.modules.embedding_configs import EmbeddingBagConfig, PoolingType
     from torchrec_b200.parallel import sharding_plan as sp
 
@@ -29,7 +29,7 @@ def _case(seed: int, weighted: bool, W: int, local: int):
         name = f"t{t}"
         tables.append(EmbeddingBagConfig(name=name, embedding_dim=dim, num_embeddings=rows, feature_names=feats, pooling=pooling))
         hosts = W // local
-        kind = rng.choice(["tw", "rw", "cw", "twrw", "twcw", "grid", "dp"])
+        kind = rng.choice(["tw", "rw", "twrw", "dp"] if no_col_split else ["tw", "rw", "cw", "twrw", "twcw", "grid", "dp"])
         if kind == "cw" and dim % 8 != 0:
             kind = "tw"
         if kind in ("twcw", "grid") and dim % 8 != 0:
@@ -68,7 +68,7 @@ def _batch(tables, seed: int, rank: int, B: int, weighted: bool):
     return KeyedJaggedTensor(keys=keys, values=values, lengths=lengths, weights=w)
 
 
-def _run(ctx, weighted: bool, first_seed: int, n_seeds: int = SEEDS_PER_LAUNCH):
+def _run(ctx, weighted: bool, first_seed: int, n_seeds: int = SEEDS_PER_LAUNCH, opt: str = "sgd", planner: bool = False):
     from torchrec_b200.modules.embedding_modules import EmbeddingBagCollection
     from torchrec_b200.optim.apply_optimizer_in_backward import apply_optimizer_in_backward
     from torchrec_b200.parallel import sharding_plan as sp
@@ -80,14 +80,39 @@ def _run(ctx, weighted: bool, first_seed: int, n_seeds: int = SEEDS_PER_LAUNCH):
     set_gradient_division(False)
     W, local, B, dev = ctx.world_size, 2, 5, ctx.device
     for seed in range(first_seed, first_seed + n_seeds):
-        tables, gens = _case(seed, weighted, W, local)
+        # row-wise Adagrad normalises per (row, column shard): compared on plans without column splits, as in the reference's matrix
+        tables, gens = _case(seed, weighted, W, local, no_col_split=(opt == "rowwise_adagrad"))
         torch.manual_seed(seed)
         gold = EmbeddingBagCollection(tables, is_weighted=weighted, device=dev)
         sharded_src = EmbeddingBagCollection(tables, is_weighted=weighted, device=dev)
         sharded_src.load_state_dict(gold.state_dict())
-        apply_optimizer_in_backward(torch.optim.SGD, sharded_src.parameters(), {"lr": 0.1})
+        if opt == "rowwise_adagrad":
+            from torchrec_b200.optim.rowwise_adagrad import RowWiseAdagrad
+
+            apply_optimizer_in_backward(RowWiseAdagrad, sharded_src.parameters(), {"lr": 0.1, "eps": 1e-8})
+        else:
+            apply_optimizer_in_backward(torch.optim.SGD, sharded_src.parameters(), {"lr": 0.1})
         sharder = EmbeddingBagCollectionSharder()
-        plan = sp.construct_module_sharding_plan(sharded_src, gens, sharder=sharder, world_size=W, local_size=local, device_type=dev.type)
+        if planner:
+            # the plan comes from EmbeddingShardingPlanner (collective: rank 0 plans, everybody receives it) under random per-table constraints
+            import torch.distributed as dist
+
+            from torchrec_b200.parallel.planner import EmbeddingShardingPlanner, Topology
+            from torchrec_b200.parallel.planner.types import ParameterConstraints
+
+            rng = random.Random(seed)
+            allowed = ["table_wise", "row_wise", "column_wise", "table_row_wise", "data_parallel"] if opt == "sgd" else ["table_wise", "row_wise", "table_row_wise"]
+            cons = {t.name: ParameterConstraints(sharding_types=rng.sample(allowed, rng.randint(1, len(allowed))), min_partition=4) for t in tables}
+
+            class Holder(torch.nn.Module):
+                def __init__(self, ebc):
+                    super().__init__()
+                    self.ebc = ebc
+
+            pl = EmbeddingShardingPlanner(topology=Topology(world_size=W, local_world_size=local, compute_device=dev.type), batch_size=B, constraints=cons)
+            plan = pl.collective_plan(Holder(sharded_src), [sharder], dist.group.WORLD).plan["ebc"]
+        else:
+            plan = sp.construct_module_sharding_plan(sharded_src, gens, sharder=sharder, world_size=W, local_size=local, device_type=dev.type)
         desc = {n: plan[n].sharding_type for n in plan}
 
         class Wrap(torch.nn.Module):
@@ -101,7 +126,14 @@ def _run(ctx, weighted: bool, first_seed: int, n_seeds: int = SEEDS_PER_LAUNCH):
         model = DistributedModelParallel(Wrap(sharded_src), device=dev, plan=ShardingPlan({"ebc": plan}), sharders=[sharder])
         dense_params = [p for _, p in model.named_parameters() if p.requires_grad]  # data-parallel tables
         dense_opt = torch.optim.SGD(dense_params, lr=0.1) if dense_params else None
-        gold_opt = torch.optim.SGD(gold.parameters(), lr=0.1)
+        if opt == "rowwise_adagrad":
+            from torchrec_b200.optim.rowwise_adagrad import RowWiseAdagrad
+
+            dp_names = {n for n in plan if plan[n].sharding_type == "data_parallel"}  # replicated tables train with the dense (SGD) optimizer
+            gold_opt = RowWiseAdagrad([p for n, p in gold.named_parameters() if n.split(".")[1] not in dp_names], lr=0.1, eps=1e-8)
+            gold_dp_opt = torch.optim.SGD([p for n, p in gold.named_parameters() if n.split(".")[1] in dp_names], lr=0.1) if dp_names else None
+        else:
+            gold_opt, gold_dp_opt = torch.optim.SGD(gold.parameters(), lr=0.1), None
         for step in range(2):
             batches = [_batch(tables, 10 * seed + step, r, B, weighted).to(dev) for r in range(W)]
             out = model(batches[ctx.rank])
@@ -115,8 +147,12 @@ def _run(ctx, weighted: bool, first_seed: int, n_seeds: int = SEEDS_PER_LAUNCH):
                 dense_opt.step()
                 dense_opt.zero_grad()
             gold_opt.zero_grad()
+            if gold_dp_opt is not None:
+                gold_dp_opt.zero_grad()
             sum((o * proj).sum() for o in gouts).backward()
             gold_opt.step()
+            if gold_dp_opt is not None:
+                gold_dp_opt.step()
         sd = model.state_dict()
         for t in tables:
             st = sd[f"ebc.embedding_bags.{t.name}.weight"]
@@ -133,6 +169,14 @@ def _run(ctx, weighted: bool, first_seed: int, n_seeds: int = SEEDS_PER_LAUNCH):
 @pytest.mark.parametrize("weighted", [False, True])
 def test_random_sharding_matrix_4_ranks(weighted):
     run_multi_process(_run, world_size=4, backend="gloo", weighted=weighted, first_seed=0)
+
+
+def test_random_sharding_matrix_rowwise_adagrad():
+    run_multi_process(_run, world_size=4, backend="gloo", weighted=False, first_seed=100, n_seeds=4, opt="rowwise_adagrad")
+
+
+def test_random_sharding_matrix_planner_plans():
+    run_multi_process(_run, world_size=4, backend="gloo", weighted=False, first_seed=200, n_seeds=4, planner=True)
 
 
 def _run_ec(ctx, dedup: bool, first_seed: int, n_seeds: int = SEEDS_PER_LAUNCH):

@@ -294,8 +294,9 @@ class EmbeddingEnumerator(Enumerator):
                                 sharding_type=sharding_type, col_wise_shard_dim=col_wise_shard_dim)
                         except ValueError:
                             continue
-                        if sharding_type in (ShardingType.COLUMN_WISE.value, ShardingType.TABLE_COLUMN_WISE.value) and len(shard_sizes) == 1:
-                            continue  # identical to table-wise
+                        if sharding_type in (ShardingType.COLUMN_WISE.value, ShardingType.TABLE_COLUMN_WISE.value) and len(shard_sizes) == 1 and \
+                                any(t not in (ShardingType.COLUMN_WISE.value, ShardingType.TABLE_COLUMN_WISE.value) for t in allowed_sharding_types):
+                            continue  # identical to table-wise (kept when column-wise is all the user allows: a narrow table yields one slice)
                         if sharding_type == ShardingType.GRID_SHARD.value and (self._world_size <= self._local_world_size or len(shard_sizes) == self._local_world_size):
                             continue  # needs several hosts and several column shards
                         if sharding_type in (ShardingType.TABLE_ROW_WISE.value,) and self._world_size <= self._local_world_size and \
