@@ -13,7 +13,7 @@ from torchrec_b200.utils.multiprocess import run_multi_process
 SEEDS_PER_LAUNCH = 5
 
 
-def _case(seed: int, weighted: bool, W: int, local: int, no_col_split: bool = False):
+def _case(seed: int, weighted: bool, W: int, local: int, no_col_split: bool = False, allow_dp: bool = True):
     from torchrec_b200.modules.embedding_configs import EmbeddingBagConfig, PoolingType
     from torchrec_b200.parallel import sharding_plan as sp
 
@@ -30,6 +30,8 @@ def _case(seed: int, weighted: bool, W: int, local: int, no_col_split: bool = Fa
         tables.append(EmbeddingBagConfig(name=name, embedding_dim=dim, num_embeddings=rows, feature_names=feats, pooling=pooling))
         hosts = W // local
         kind = rng.choice(["tw", "rw", "twrw", "dp"] if no_col_split else ["tw", "rw", "cw", "twrw", "twcw", "grid", "dp"])
+        if kind == "dp" and not allow_dp:
+            kind = "rw"
         if kind == "cw" and dim % 8 != 0:
             kind = "tw"
         if kind in ("twcw", "grid") and dim % 8 != 0:
@@ -130,7 +132,8 @@ def _run(ctx, weighted: bool, first_seed: int, n_seeds: int = SEEDS_PER_LAUNCH, 
             from torchrec_b200.optim.rowwise_adagrad import RowWiseAdagrad
 
             dp_names = {n for n in plan if plan[n].sharding_type == "data_parallel"}  # replicated tables train with the dense (SGD) optimizer
-            gold_opt = RowWiseAdagrad([p for n, p in gold.named_parameters() if n.split(".")[1] not in dp_names], lr=0.1, eps=1e-8)
+            mp_params = [p for n, p in gold.named_parameters() if n.split(".")[1] not in dp_names]
+            gold_opt = RowWiseAdagrad(mp_params, lr=0.1, eps=1e-8) if mp_params else torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=0.1)
             gold_dp_opt = torch.optim.SGD([p for n, p in gold.named_parameters() if n.split(".")[1] in dp_names], lr=0.1) if dp_names else None
         else:
             gold_opt, gold_dp_opt = torch.optim.SGD(gold.parameters(), lr=0.1), None
@@ -260,3 +263,63 @@ def _run_ec(ctx, dedup: bool, first_seed: int, n_seeds: int = SEEDS_PER_LAUNCH):
 @pytest.mark.parametrize("dedup", [False, True])
 def test_random_sequence_sharding_matrix_4_ranks(dedup):
     run_multi_process(_run_ec, world_size=4, backend="gloo", dedup=dedup, first_seed=0)
+
+
+def _run_ckpt(ctx, tmp: str, first_seed: int, n_seeds: int = 3):
+    """Checkpoint written under a random plan, loaded under another random plan (weights + fused row-wise Adagrad state), then both
+    models take one more identical step and must stay identical (reference: test_model_parallel checkpoint / resharding tests)."""
+    import os
+
+    from torchrec_b200.modules.embedding_modules import EmbeddingBagCollection
+    from torchrec_b200.optim.apply_optimizer_in_backward import apply_optimizer_in_backward
+    from torchrec_b200.optim.rowwise_adagrad import RowWiseAdagrad
+    from torchrec_b200.parallel import checkpoint as ckpt
+    from torchrec_b200.parallel import sharding_plan as sp
+    from torchrec_b200.parallel.comm_ops import set_gradient_division
+    from torchrec_b200.parallel.embeddingbag import EmbeddingBagCollectionSharder
+    from torchrec_b200.parallel.model_parallel import DistributedModelParallel
+    from torchrec_b200.parallel.types import ShardingPlan
+
+    set_gradient_division(False)
+    W, local, B, dev = ctx.world_size, 2, 5, ctx.device
+    for seed in range(first_seed, first_seed + n_seeds):
+        # (no data-parallel tables: they train with the dense optimizer, so A and B would not hold the same optimizer-state keys)
+        tables, gens_a = _case(seed, False, W, local, no_col_split=True, allow_dp=False)
+        _, gens_b = _case(seed + 5000, False, W, local, no_col_split=True, allow_dp=False)
+        gens_b = {t.name: gens_b.get(t.name, sp.row_wise()) for t in tables}  # B's placements on A's table list
+
+        def build(gens, init_seed):
+            torch.manual_seed(init_seed)
+
+            class M(torch.nn.Module):
+                def __init__(self):
+                    super().__init__()
+                    self.ebc = EmbeddingBagCollection(tables, device=dev)
+
+                def forward(self, k):
+                    return self.ebc(k).values()
+
+            m = M()
+            apply_optimizer_in_backward(RowWiseAdagrad, m.ebc.parameters(), {"lr": 0.1, "eps": 1e-8})
+            sharder = EmbeddingBagCollectionSharder()
+            plan = sp.construct_module_sharding_plan(m.ebc, gens, sharder=sharder, world_size=W, local_size=local, device_type=dev.type)
+            return DistributedModelParallel(m, device=dev, plan=ShardingPlan({"ebc": plan}), sharders=[sharder]), {n: plan[n].sharding_type for n in plan}
+
+        a, da = build(gens_a, seed)
+        kjt = _batch(tables, seed, ctx.rank, B, False).to(dev)
+        for _ in range(2):
+            a(kjt).sum().backward()
+        path = os.path.join(tmp, f"ck{seed}")
+        ckpt.save(a, a.fused_optimizer, path)
+        b, db = build(gens_b, seed + 17)
+        ckpt.load(b, b.fused_optimizer, path)
+        msg = lambda m: f"ckpt seed {seed}: {da} -> {db}: {m}"  # noqa: E731
+        torch.testing.assert_close(b(kjt), a(kjt), msg=msg)
+        if not any(v == "data_parallel" for v in list(da.values()) + list(db.values())):  # (replicated tables train with the dense optimizer)
+            a(kjt).sum().backward()
+            b(kjt).sum().backward()
+            torch.testing.assert_close(b(kjt), a(kjt), rtol=1e-5, atol=1e-6, msg=msg)
+
+
+def test_random_checkpoint_resharding_4_ranks(tmp_path):
+    run_multi_process(_run_ckpt, world_size=4, backend="gloo", tmp=str(tmp_path), first_seed=0)
