@@ -323,3 +323,65 @@ def _run_ckpt(ctx, tmp: str, first_seed: int, n_seeds: int = 3):
 
 def test_random_checkpoint_resharding_4_ranks(tmp_path):
     run_multi_process(_run_ckpt, world_size=4, backend="gloo", tmp=str(tmp_path), first_seed=0)
+
+
+def _run_reshard(ctx, first_seed: int, n_seeds: int = 3):
+    """Live re-sharding: a model training under a random plan is moved to another random plan (weights + fused Adagrad state travel over
+    point-to-point messages), trains on, is moved again - and tracks an unsharded golden model all the way."""
+    from torchrec_b200.modules.embedding_modules import EmbeddingBagCollection
+    from torchrec_b200.optim.apply_optimizer_in_backward import apply_optimizer_in_backward
+    from torchrec_b200.optim.rowwise_adagrad import RowWiseAdagrad
+    from torchrec_b200.parallel import sharding_plan as sp
+    from torchrec_b200.parallel.comm_ops import set_gradient_division
+    from torchrec_b200.parallel.embeddingbag import EmbeddingBagCollectionSharder
+    from torchrec_b200.parallel.model_parallel import DistributedModelParallel
+    from torchrec_b200.parallel.types import ShardingPlan
+
+    set_gradient_division(False)
+    W, local, B, dev = ctx.world_size, 2, 5, ctx.device
+    for seed in range(first_seed, first_seed + n_seeds):
+        tables, gens = _case(seed, False, W, local, no_col_split=True, allow_dp=False)
+        torch.manual_seed(seed)
+        gold = EmbeddingBagCollection(tables, device=dev)
+        src = EmbeddingBagCollection(tables, device=dev)
+        src.load_state_dict(gold.state_dict())
+        apply_optimizer_in_backward(RowWiseAdagrad, src.parameters(), {"lr": 0.1, "eps": 1e-8})
+        sharder = EmbeddingBagCollectionSharder()
+
+        class Wrap(torch.nn.Module):
+            def __init__(self, ebc):
+                super().__init__()
+                self.ebc = ebc
+
+            def forward(self, kjt):
+                return self.ebc(kjt).values()
+
+        plan = sp.construct_module_sharding_plan(src, gens, sharder=sharder, world_size=W, local_size=local, device_type=dev.type)
+        model = DistributedModelParallel(Wrap(src), device=dev, plan=ShardingPlan({"ebc": plan}), sharders=[sharder])
+        gold_opt = RowWiseAdagrad(gold.parameters(), lr=0.1, eps=1e-8)
+        history = [{n: plan[n].sharding_type for n in plan}]
+
+        def step(k):
+            batches = [_batch(tables, 100 * seed + k, r, B, False).to(dev) for r in range(W)]
+            out = model(batches[ctx.rank])
+            gouts = [gold(b).values() for b in batches]
+            torch.testing.assert_close(out.float(), gouts[ctx.rank], rtol=1e-5, atol=1e-5, msg=lambda m: f"reshard seed {seed} step {k} plans {history}: {m}")
+            out.sum().backward()
+            gold_opt.zero_grad()
+            sum(o.sum() for o in gouts).backward()
+            gold_opt.step()
+
+        step(0)
+        meta = EmbeddingBagCollection(tables, device=torch.device("meta"))
+        for hop in (1, 2):
+            _, new_gens = _case(seed + 7000 * hop, False, W, local, no_col_split=True, allow_dp=False)
+            new_gens = {t.name: new_gens.get(t.name, sp.row_wise()) for t in tables}
+            new = sp.construct_module_sharding_plan(meta, new_gens, sharder=sharder, world_size=W, local_size=local, device_type=dev.type)
+            history.append({n: new[n].sharding_type for n in new})
+            model.reshard("ebc", dict(new))
+            step(2 * hop - 1)
+            step(2 * hop)
+
+
+def test_random_live_resharding_4_ranks():
+    run_multi_process(_run_reshard, world_size=4, backend="gloo", first_seed=0)

@@ -145,12 +145,21 @@ def reshard_module(old, changed_shard_to_params: Dict[str, ParameterSharding], e
     new = type(old)(stub, new_plan, **kwargs)
     transfer_state(old, new, env, list(changed_shard_to_params.keys()))
     # carry the scalar optimizer state (step counters, learning rate) over
-    if old.engine is not None and new.engine is not None:
-        steps = [t.hyper_host for t in old.engine._tbes]
-        if steps:
-            for t in new.engine._tbes:
-                t.hyper_host[:] = steps[0]
-                t._push_hyper()
+    # (groups without local shards hold an nn.Identity placeholder; a rank may own no table before and some after the move, so the
+    # scalars are taken from whichever rank has them)
+    real = lambda eng: [t for t in eng._tbes if hasattr(t, "hyper_host")] if eng is not None else []  # noqa: E731
+    mine = real(old.engine)
+    hyper = list(mine[0].hyper_host) if mine else None  # python list of floats (lr, eps, betas, weight decay, step, ...)
+    pg = env.process_group
+    if pg is not None and dist.is_initialized() and dist.get_world_size(pg) > 1:
+        gathered: List[Any] = [None] * dist.get_world_size(pg)
+        dist.all_gather_object(gathered, hyper, group=pg)
+        if hyper is None:
+            hyper = next((h for h in gathered if h is not None), None)
+    if hyper is not None:
+        for t in real(new.engine):
+            t.hyper_host[:] = hyper
+            t._push_hyper()
     new.train(old.training)
     return new
 
