@@ -241,3 +241,61 @@ def test_quantized_weight_publish_and_pruning_metadata():
             return {"model.preproc": QualNameMetadata(need_preproc=True)}
 
     assert F().qualname_metadata_json() == '{"model.preproc": {"need_preproc": true}}'
+
+
+@pytest.mark.parametrize("seed", list(range(8)))
+def test_sharded_quant_ebc_random_placements(seed):
+    """Quantized pooled lookups: random tables (row formats INT8 / INT4 / FP16 / FP8, SUM / MEAN, shared tables), random TW / RW / CW
+    placements over 4 virtual devices - sharded output == unsharded quantized module (re-quantisation of column slices bounds the error)."""
+    import random
+
+    import torch
+
+    from torchrec_b200.modules.embedding_configs import DataType, EmbeddingBagConfig, PoolingType
+    from torchrec_b200.ops.quant_tbe import quantize_rows
+    from torchrec_b200.parallel import sharding_plan as sp
+    from torchrec_b200.parallel.quant_embeddingbag import QuantEmbeddingBagCollectionSharder
+    from torchrec_b200.parallel.types import ShardingEnv
+    from torchrec_b200.quant.embedding_modules import EmbeddingBagCollection as QuantEBC
+    from torchrec_b200.sparse.jagged_tensor import KeyedJaggedTensor
+
+    rng = random.Random(seed)
+    torch.manual_seed(seed)
+    W, B = 4, 5
+    tables, gens, keys, hashes, qw, fid = [], {}, [], [], {}, 0
+    for t in range(rng.randint(2, 5)):
+        dt = rng.choice([DataType.INT8, DataType.FP16, DataType.INT4, DataType.FP8])
+        dim = rng.choice([32, 64])
+        rows = rng.randint(9, 60)
+        feats = [f"f{fid + i}" for i in range(rng.choice([1, 1, 2]))]
+        fid += len(feats)
+        cfg = EmbeddingBagConfig(name=f"t{t}", embedding_dim=dim, num_embeddings=rows, feature_names=feats, data_type=dt, pooling=rng.choice([PoolingType.SUM, PoolingType.MEAN]))
+        tables.append(cfg)
+        keys += feats
+        hashes += [rows] * len(feats)
+        qw[cfg.name] = (quantize_rows(torch.randn(rows, dim) * 0.5, dt), None)
+        kind = rng.choice(["tw", "rw", "cw"])
+        if kind == "cw" and dt == DataType.FP8 and dim < 64:
+            kind = "tw"  # fp8 column shards must be multiples of the 32-element scale block (the sharder says so: checked below)
+        gens[cfg.name] = sp.table_wise(rank=rng.randrange(W)) if kind == "tw" else (sp.row_wise() if kind == "rw" else sp.column_wise(ranks=rng.sample(range(W), 2)))
+    weighted = rng.random() < 0.3
+    q = QuantEBC(tables, is_weighted=weighted, device=torch.device("cpu"), table_name_to_quantized_weights=qw)
+    sharder = QuantEmbeddingBagCollectionSharder()
+    plan = sp.construct_module_sharding_plan(q, gens, sharder=sharder, world_size=W, local_size=W, device_type="cpu")
+    sharded = sharder.shard(q, plan, ShardingEnv.from_local(W, 0), device=torch.device("cpu"))
+    g = torch.Generator().manual_seed(seed)
+    lengths = torch.randint(0, 4, (len(keys) * B,), generator=g)
+    values = torch.cat([torch.randint(0, hashes[i], (int(lengths[i * B : (i + 1) * B].sum()),), generator=g) for i in range(len(keys))])
+    kjt = KeyedJaggedTensor(keys=keys, values=values, lengths=lengths, weights=torch.rand(values.numel(), generator=g) if weighted else None)
+    want, got = q(kjt), sharded(kjt)
+    assert got.keys() == want.keys()
+    desc = {n: (plan[n].sharding_type, str(t.data_type), str(t.pooling)) for n, t in zip(plan, tables)}
+    # column slices are re-quantised with their own row scale: int4 steps are coarse, so the tolerance follows the format
+    tol = 0.2 if any(t.data_type == DataType.INT4 and plan[t.name].sharding_type == "column_wise" for t in tables) else 3e-2
+    torch.testing.assert_close(got.values().float(), want.values().float(), rtol=tol, atol=tol, msg=lambda m: f"seed {seed} {desc}: {m}")
+    if seed == 0:  # a 32-wide fp8 table cannot be split into 16-wide column shards
+        bad = [EmbeddingBagConfig(name="b", embedding_dim=32, num_embeddings=10, feature_names=["fb"], data_type=DataType.FP8)]
+        qb = QuantEBC(bad, is_weighted=False, device=torch.device("cpu"), table_name_to_quantized_weights={"b": (quantize_rows(torch.randn(10, 32), DataType.FP8), None)})
+        pb = sp.construct_module_sharding_plan(qb, {"b": sp.column_wise(ranks=[0, 1])}, sharder=sharder, world_size=W, local_size=W, device_type="cpu")
+        with pytest.raises(ValueError, match="multiples of 32"):
+            sharder.shard(qb, pb, ShardingEnv.from_local(W, 0), device=torch.device("cpu"))

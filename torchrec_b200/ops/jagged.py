@@ -471,6 +471,8 @@ def fused_nbit_rowwise_quantize(weight: torch.Tensor, bit_rate: int) -> torch.Te
     assert bit_rate in (2, 4, 8)
     w = weight.float()
     rows, D = w.shape
+    if rows == 0:  # an empty row shard (row-wise sharding of a table with fewer rows than ranks)
+        return torch.zeros(0, (D * bit_rate + 7) // 8 + 4, dtype=torch.uint8, device=w.device)
     mn = w.min(dim=1, keepdim=True).values
     mx = w.max(dim=1, keepdim=True).values
     qmax = float((1 << bit_rate) - 1)
@@ -492,6 +494,8 @@ def fused_nbit_rowwise_quantize(weight: torch.Tensor, bit_rate: int) -> torch.Te
 
 def fused_nbit_rowwise_dequantize(q: torch.Tensor, bit_rate: int, D: int) -> torch.Tensor:
     rows = q.shape[0]
+    if rows == 0:
+        return torch.zeros(0, D, dtype=torch.float32, device=q.device)
     per_byte = 8 // bit_rate
     nbytes = (D + per_byte - 1) // per_byte
     packed = q[:, :nbytes]

@@ -56,7 +56,7 @@ def quantize_rows(weight: torch.Tensor, data_type: DataType, row_alignment: int 
         scale = (amax / 448.0).half().float().clamp(min=6e-8)
         q = (blocks / scale).to(torch.float8_e4m3fn).view(torch.uint8).view(rows, dim)
         out[:, :dim] = q
-        out[:, dim : dim + (dim // FP8_BLOCK) * 2] = scale.half().contiguous().view(torch.uint8).view(rows, -1)
+        out[:, dim : dim + (dim // FP8_BLOCK) * 2] = scale.half().contiguous().view(torch.uint8).view(rows, (dim // FP8_BLOCK) * 2)
     else:
         raise ValueError(data_type)
     return out

@@ -16,6 +16,7 @@ from ..modules.embedding_modules import get_embedding_names_by_table
 from ..ops.quant_tbe import QuantTableBatchedEmbeddingBags
 from ..quant.embedding_modules import EmbeddingBagCollection as QuantEmbeddingBagCollection
 from ..quant.embedding_modules import EmbeddingCollection as QuantEmbeddingCollection
+from ..types import DataType
 from ..sparse.jagged_tensor import JaggedTensor, KeyedJaggedTensor, KeyedTensor
 from .embedding_types import BaseQuantEmbeddingSharder
 from .engine import shards_of
@@ -54,6 +55,9 @@ class ShardedQuantEmbeddingBagCollection(ShardedModule[List[KeyedJaggedTensor], 
         for ti, t in enumerate(tables):
             ps = table_name_to_parameter_sharding[t.name]
             for s in shards_of(ti, t, ps):
+                if t.data_type == DataType.FP8 and s.cols % 32 != 0:
+                    raise ValueError(f"table {t.name}: block-scaled fp8 rows carry one scale per 32 elements, column shards must be multiples of 32 wide "
+                                     f"(got {s.cols} of {t.embedding_dim}); use fewer column shards or another placement")
                 for fi in [i for i, x in enumerate(feat_table) if x == ti]:
                     per_rank[s.rank].append((ti, s, fi))
         # inside a device, whole-table / column-shard units first, row-sharded units (summed at the destination) after them
