@@ -22,7 +22,7 @@ def _case(seed: int, weighted: bool, W: int, local: int, no_col_split: bool = Fa
     tables, gens, fid = [], {}, 0
     for t in range(n_tables):
         dim = rng.choice([4, 8, 12, 16])
-        rows = rng.randint(9, 40)
+        rows = rng.randint(9, 40) if rng.random() < 0.8 else rng.randint(1, 6)  # tiny tables: row shards of some ranks are empty
         feats = [f"f{fid + i}" for i in range(rng.choice([1, 1, 2]))]
         fid += len(feats)
         pooling = PoolingType.SUM if (weighted or rng.random() < 0.6) else PoolingType.MEAN
