@@ -70,7 +70,7 @@ def _batch(tables, seed: int, rank: int, B: int, weighted: bool):
     return KeyedJaggedTensor(keys=keys, values=values, lengths=lengths, weights=w)
 
 
-def _run(ctx, weighted: bool, first_seed: int, n_seeds: int = SEEDS_PER_LAUNCH, opt: str = "sgd", planner: bool = False):
+def _run(ctx, weighted: bool, first_seed: int, n_seeds: int = SEEDS_PER_LAUNCH, opt: str = "sgd", planner: bool = False, uneven: bool = False):
     from torchrec_b200.modules.embedding_modules import EmbeddingBagCollection
     from torchrec_b200.optim.apply_optimizer_in_backward import apply_optimizer_in_backward
     from torchrec_b200.parallel import sharding_plan as sp
@@ -138,7 +138,8 @@ def _run(ctx, weighted: bool, first_seed: int, n_seeds: int = SEEDS_PER_LAUNCH, 
         else:
             gold_opt, gold_dp_opt = torch.optim.SGD(gold.parameters(), lr=0.1), None
         for step in range(2):
-            batches = [_batch(tables, 10 * seed + step, r, B, weighted).to(dev) for r in range(W)]
+            # uneven: every rank feeds its own batch size (the last partial batch of an epoch)
+            batches = [_batch(tables, 10 * seed + step, r, B + (r + step) % 3 if uneven else B, weighted).to(dev) for r in range(W)]
             out = model(batches[ctx.rank])
             gouts = [gold(b).values() for b in batches]
             torch.testing.assert_close(out.float(), gouts[ctx.rank], rtol=1e-5, atol=1e-5, msg=lambda m: f"seed {seed} step {step} plan {desc}: {m}")
@@ -172,6 +173,10 @@ def _run(ctx, weighted: bool, first_seed: int, n_seeds: int = SEEDS_PER_LAUNCH, 
 @pytest.mark.parametrize("weighted", [False, True])
 def test_random_sharding_matrix_4_ranks(weighted):
     run_multi_process(_run, world_size=4, backend="gloo", weighted=weighted, first_seed=0)
+
+
+def test_random_sharding_matrix_uneven_batch_per_rank():
+    run_multi_process(_run, world_size=4, backend="gloo", weighted=False, first_seed=500, n_seeds=4, uneven=True)
 
 
 def test_random_sharding_matrix_rowwise_adagrad():
@@ -385,3 +390,75 @@ def _run_reshard(ctx, first_seed: int, n_seeds: int = 3):
 
 def test_random_live_resharding_4_ranks():
     run_multi_process(_run_reshard, world_size=4, backend="gloo", first_seed=0)
+
+
+def _vbe_batch(tables, seed: int, rank: int, full_B: int):
+    """Variable batch per feature: feature k carries b_k <= full_B distinct bags and inverse indices that expand them to the full batch."""
+    from torchrec_b200.sparse import KeyedJaggedTensor
+
+    g = torch.Generator().manual_seed(104729 * seed + 13 * rank + 5)
+    keys, hashes = [], []
+    for t in tables:
+        for f in t.feature_names:
+            keys.append(f)
+            hashes.append(t.num_embeddings)
+    bks = [int(torch.randint(1, full_B + 1, (1,), generator=g)) for _ in keys]
+    lens = [torch.randint(0, 4, (b,), generator=g) for b in bks]
+    vals = [torch.randint(0, h, (int(l.sum()),), generator=g) for l, h in zip(lens, hashes)]
+    inv = torch.stack([torch.randint(0, b, (full_B,), generator=g) for b in bks])
+    return KeyedJaggedTensor(keys=keys, values=torch.cat(vals), lengths=torch.cat(lens), stride_per_key_per_rank=[[b] for b in bks], inverse_indices=(keys, inv))
+
+
+def _run_vbe(ctx, first_seed: int, n_seeds: int = 4):
+    from torchrec_b200.modules.embedding_modules import EmbeddingBagCollection
+    from torchrec_b200.optim.apply_optimizer_in_backward import apply_optimizer_in_backward
+    from torchrec_b200.parallel import sharding_plan as sp
+    from torchrec_b200.parallel.comm_ops import set_gradient_division
+    from torchrec_b200.parallel.embeddingbag import EmbeddingBagCollectionSharder
+    from torchrec_b200.parallel.model_parallel import DistributedModelParallel
+    from torchrec_b200.parallel.types import ShardingPlan
+
+    set_gradient_division(False)
+    W, local, dev = ctx.world_size, 2, ctx.device
+    for seed in range(first_seed, first_seed + n_seeds):
+        tables, gens = _case(seed, False, W, local, allow_dp=False)
+        torch.manual_seed(seed)
+        gold = EmbeddingBagCollection(tables, device=dev)
+        src = EmbeddingBagCollection(tables, device=dev)
+        src.load_state_dict(gold.state_dict())
+        apply_optimizer_in_backward(torch.optim.SGD, src.parameters(), {"lr": 0.1})
+        sharder = EmbeddingBagCollectionSharder()
+        plan = sp.construct_module_sharding_plan(src, gens, sharder=sharder, world_size=W, local_size=local, device_type=dev.type)
+        desc = {n: plan[n].sharding_type for n in plan}
+
+        class Wrap(torch.nn.Module):
+            def __init__(self, ebc):
+                super().__init__()
+                self.ebc = ebc
+
+            def forward(self, kjt):
+                return self.ebc(kjt).values()
+
+        model = DistributedModelParallel(Wrap(src), device=dev, plan=ShardingPlan({"ebc": plan}), sharders=[sharder])
+        gold_opt = torch.optim.SGD(gold.parameters(), lr=0.1)
+        for step in range(2):
+            batches = [_vbe_batch(tables, 10 * seed + step, r, 4 + r) for r in range(W)]  # every rank has its own full batch size
+            out = model(batches[ctx.rank])
+            gouts = [gold(b).values() for b in batches]
+            torch.testing.assert_close(out.float(), gouts[ctx.rank], rtol=1e-5, atol=1e-5, msg=lambda m: f"VBE seed {seed} step {step} plan {desc}: {m}")
+            out.sum().backward()
+            gold_opt.zero_grad()
+            sum(o.sum() for o in gouts).backward()
+            gold_opt.step()
+        sd = model.state_dict()
+        for t in tables:
+            st = sd[f"ebc.embedding_bags.{t.name}.weight"]
+            ref = gold.embedding_bags[t.name].weight.detach()
+            for sh in (st.local_shards() if hasattr(st, "local_shards") else []):
+                o, s = sh.metadata.shard_offsets, sh.metadata.shard_sizes
+                torch.testing.assert_close(sh.tensor, ref[o[0] : o[0] + s[0], o[1] : o[1] + s[1]], rtol=1e-4, atol=1e-5,
+                                           msg=lambda m: f"VBE seed {seed} table {t.name} ({desc[t.name]}): {m}")
+
+
+def test_random_variable_batch_matrix_4_ranks():
+    run_multi_process(_run_vbe, world_size=4, backend="gloo", first_seed=0)

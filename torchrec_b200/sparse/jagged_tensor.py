@@ -670,7 +670,7 @@ class KeyedJaggedTensor(Pipelineable):
                 lengths_csum = torch.cat([lengths.new_zeros(1, dtype=torch.int64), torch.cumsum(lengths.to(torch.int64), 0)])
                 seg_off = torch.cat([seg.new_zeros(1), torch.cumsum(seg, 0)])
                 val_seg = lengths_csum[seg_off[1:]] - lengths_csum[seg_off[:-1]]
-                new_lengths, _, _ = J.permute_1D_sparse_data(recat, seg, lengths)
+                _, new_lengths, _ = J.permute_1D_sparse_data(recat, seg, lengths, None, lengths.numel())  # (segment sizes, permuted ENTRIES, weights)
                 _, values, weights = J.permute_1D_sparse_data(recat, val_seg, values, weights, values.numel())
                 lengths = new_lengths
             return KeyedJaggedTensor(keys=keys, values=values, weights=weights, lengths=lengths, stride_per_key_per_rank=spkpr_t)
@@ -688,7 +688,7 @@ class KeyedJaggedTensor(Pipelineable):
                 lengths_csum = torch.cat([lengths.new_zeros(1, dtype=torch.int64), torch.cumsum(lengths.to(torch.int64), 0)])
                 seg_off = torch.cat([seg.new_zeros(1), torch.cumsum(seg, 0)])
                 val_seg = lengths_csum[seg_off[1:]] - lengths_csum[seg_off[:-1]]
-                new_lengths, _, _ = J.permute_1D_sparse_data(recat, seg, lengths)
+                _, new_lengths, _ = J.permute_1D_sparse_data(recat, seg, lengths, None, lengths.numel())  # (segment sizes, permuted ENTRIES, weights)
                 _, values, weights = J.permute_1D_sparse_data(recat, val_seg, values, weights, values.numel())
                 lengths = new_lengths
         return KeyedJaggedTensor(keys=keys, values=values, weights=weights, lengths=lengths,
