@@ -187,7 +187,7 @@ def test_random_sharding_matrix_planner_plans():
     run_multi_process(_run, world_size=4, backend="gloo", weighted=False, first_seed=200, n_seeds=4, planner=True)
 
 
-def _run_ec(ctx, dedup: bool, first_seed: int, n_seeds: int = SEEDS_PER_LAUNCH):
+def _run_ec(ctx, dedup: bool, first_seed: int, n_seeds: int = SEEDS_PER_LAUNCH, uneven: bool = False):
     """Sequence embeddings: random tables / TW / RW / CW placements / jagged batches, index de-duplication on or off."""
     from torchrec_b200.modules.embedding_configs import EmbeddingConfig
     from torchrec_b200.modules.embedding_modules import EmbeddingCollection
@@ -234,14 +234,14 @@ def _run_ec(ctx, dedup: bool, first_seed: int, n_seeds: int = SEEDS_PER_LAUNCH):
         model = DistributedModelParallel(Wrap(src), device=torch.device("cpu"), plan=ShardingPlan({"ec": plan}), sharders=[sharder])
         gold_opt = torch.optim.SGD(gold.parameters(), lr=0.1)
 
-        def batch(s):
+        def batch(s, Bq=B):
             g = torch.Generator().manual_seed(s)
-            lengths = torch.randint(0, 4, (len(keys) * B,), generator=g)
-            vals = torch.cat([torch.randint(0, hashes[i], (int(lengths[i * B : (i + 1) * B].sum()),), generator=g) for i in range(len(keys))])
+            lengths = torch.randint(0, 4, (len(keys) * Bq,), generator=g)
+            vals = torch.cat([torch.randint(0, hashes[i], (int(lengths[i * Bq : (i + 1) * Bq].sum()),), generator=g) for i in range(len(keys))])
             return KeyedJaggedTensor(keys=keys, values=vals, lengths=lengths)
 
         for step in range(2):
-            batches = [batch(1000 * seed + 10 * step + r) for r in range(W)]
+            batches = [batch(1000 * seed + 10 * step + r, B + (r + step) % 3 if uneven else B) for r in range(W)]
             out = model(batches[ctx.rank])
             gouts = [gold(b) for b in batches]
             loss = 0
@@ -268,6 +268,10 @@ def _run_ec(ctx, dedup: bool, first_seed: int, n_seeds: int = SEEDS_PER_LAUNCH):
 @pytest.mark.parametrize("dedup", [False, True])
 def test_random_sequence_sharding_matrix_4_ranks(dedup):
     run_multi_process(_run_ec, world_size=4, backend="gloo", dedup=dedup, first_seed=0)
+
+
+def test_random_sequence_sharding_matrix_uneven_batch_per_rank():
+    run_multi_process(_run_ec, world_size=4, backend="gloo", dedup=False, first_seed=700, n_seeds=4, uneven=True)
 
 
 def _run_ckpt(ctx, tmp: str, first_seed: int, n_seeds: int = 3):

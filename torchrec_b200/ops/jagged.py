@@ -92,7 +92,7 @@ def permute_2D_sparse_data(
     out_len_per_key = len_per_key[perm]
     total = int(out_len_per_key.sum()) if permuted_lengths_sum is None else permuted_lengths_sum
     if total == 0:
-        return out_lengths, values.new_zeros(0), (None if weights is None else weights.new_zeros(0))
+        return out_lengths, values.new_zeros((0,) + tuple(values.shape[1:])), (None if weights is None else weights.new_zeros((0,) + tuple(weights.shape[1:])))
     idx = _segment_gather_index(in_key_off[perm], out_len_per_key, total)
     return out_lengths, values[idx], (None if weights is None else weights[idx])
 
@@ -133,7 +133,7 @@ def permute_1D_sparse_data(
     in_off = torch.cumsum(lengths, 0) - lengths
     total = int(out_lengths.sum()) if permuted_lengths_sum is None else permuted_lengths_sum
     if total == 0:
-        return out_lengths, values.new_zeros(0), (None if weights is None else weights.new_zeros(0))
+        return out_lengths, values.new_zeros((0,) + tuple(values.shape[1:])), (None if weights is None else weights.new_zeros((0,) + tuple(weights.shape[1:])))
     idx = _segment_gather_index(in_off[perm], out_lengths, total)
     return out_lengths, values[idx], (None if weights is None else weights[idx])
 

@@ -271,6 +271,9 @@ class All2AllSequenceInfo:
     variable_batch_size: bool = False
     codecs: Optional[QuantizedCommCodecs] = None
     permuted_lengths_after_sparse_data_all2all: Optional[torch.Tensor] = None
+    # variable batch size per rank: bags per (unit, source rank) segment of ``lengths_after_sparse_data_all2all`` (None: every segment
+    # holds lengths.numel() / n_segments bags)
+    bags_per_segment: Optional[torch.Tensor] = None
 
 
 class _A2ASeqReq(Function):
@@ -286,7 +289,12 @@ class _A2ASeqReq(Function):
             # rows arrive unit-major; regroup them source-rank-major before sending them back (a rank without units has nothing to regroup)
             lengths = info.lengths_after_sparse_data_all2all
             nseg = info.forward_recat_tensor.numel()
-            seg = lengths.view(nseg, -1).sum(1)
+            if info.bags_per_segment is not None:
+                csum = torch.cat([lengths.new_zeros(1, dtype=torch.int64), torch.cumsum(lengths.to(torch.int64), 0)])
+                ends = torch.cumsum(info.bags_per_segment.to(torch.int64), 0)
+                seg = (csum[ends] - csum[ends - info.bags_per_segment.to(torch.int64)]).to(lengths.dtype)
+            else:
+                seg = lengths.view(nseg, -1).sum(1)
             _, x, _ = J.permute_1D_sparse_data(info.forward_recat_tensor, seg, x, None, x.shape[0])
             ctx.seg = seg
         else:
@@ -356,13 +364,20 @@ def alltoall_sequence(
     variable_batch_size: bool = False,
     group: Optional[dist.ProcessGroup] = None,
     codecs: Optional[QuantizedCommCodecs] = None,
+    batch_size_per_rank: Optional[List[int]] = None,
 ) -> Awaitable[torch.Tensor]:
-    """Send unpooled embedding rows ``[sum L, D]`` back to the ranks that own the samples."""
+    """Send unpooled embedding rows ``[sum L, D]`` back to the ranks that own the samples. ``batch_size_per_rank``: the ranks fed
+    different batch sizes (the received lengths are [unit][source rank][that rank's batch])."""
     pg = _pg(group)
     if dist.get_world_size(pg) <= 1:
         return NoWait(a2a_sequence_embs_tensor)
     info = All2AllSequenceInfo(a2a_sequence_embs_tensor.shape[1], lengths_after_sparse_data_all2all, forward_recat_tensor,
                                backward_recat_tensor, input_splits, output_splits, variable_batch_size, codecs)
+    if batch_size_per_rank is not None and len(set(batch_size_per_rank)) > 1 and forward_recat_tensor is not None and forward_recat_tensor.numel() > 0:
+        W = len(batch_size_per_rank)
+        n_units = forward_recat_tensor.numel() // W
+        info.bags_per_segment = torch.tensor(list(batch_size_per_rank) * n_units, dtype=torch.int64, device=a2a_sequence_embs_tensor.device)
+        info.variable_batch_size = True
     h = _Handle()
     dummy = _A2ASeqReq.apply(pg, h, info, a2a_sequence_embs_tensor)
     return Request(lambda: _A2ASeqWait.apply(pg, h, info, dummy))

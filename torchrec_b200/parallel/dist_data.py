@@ -354,7 +354,8 @@ class SequenceEmbeddingsAllToAll(nn.Module):
         variable_batch_size = batch_size_per_rank is not None and len(set(batch_size_per_rank)) > 1
         fwd = self._forward_recat_tensor if sparse_features_recat is None else J.invert_permute(sparse_features_recat)
         bwd = self._backward_recat_tensor if sparse_features_recat is None else sparse_features_recat
-        aw = alltoall_sequence(local_embs, fwd, bwd, lengths, input_splits, output_splits, variable_batch_size, group=self._pg, codecs=self._codecs)
+        aw = alltoall_sequence(local_embs, fwd, bwd, lengths, input_splits, output_splits, variable_batch_size, group=self._pg, codecs=self._codecs,
+                               batch_size_per_rank=batch_size_per_rank)
         return SequenceEmbeddingsAwaitable(aw, unbucketize_permute_tensor, local_embs.shape[1])
 
 

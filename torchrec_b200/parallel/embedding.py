@@ -280,7 +280,7 @@ class ShardedEmbeddingCollection(ShardedModule[KJTList, List[torch.Tensor], Dict
         emb = embs[0]
         eng = self._engine
         if eng._seq_a2a is not None:
-            aw = eng._seq_a2a(emb, dist_kjt.lengths(), ctx.input_splits, ctx.output_splits)
+            aw = eng._seq_a2a(emb, dist_kjt.lengths(), ctx.input_splits, ctx.output_splits, batch_size_per_rank=dist_kjt._stride_per_rank)
         else:
             aw = NoWait(emb)
 
