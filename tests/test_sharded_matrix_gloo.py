@@ -466,3 +466,86 @@ def _run_vbe(ctx, first_seed: int, n_seeds: int = 4):
 
 def test_random_variable_batch_matrix_4_ranks():
     run_multi_process(_run_vbe, world_size=4, backend="gloo", first_seed=0)
+
+
+def _run_pipelines(ctx, first_seed: int, n_seeds: int = 2):
+    """Every pipelined training loop == the plain loop (losses step by step, weights at the end) on random DLRMs / plans at 4 ranks; the
+    last batch of the stream is smaller than the others (end of an epoch)."""
+    from torchrec_b200.datasets.utils import Batch
+    from torchrec_b200.models.dlrm import DLRM, DLRMTrain
+    from torchrec_b200.modules.embedding_modules import EmbeddingBagCollection
+    from torchrec_b200.optim.apply_optimizer_in_backward import apply_optimizer_in_backward
+    from torchrec_b200.optim.keyed import CombinedOptimizer, KeyedOptimizerWrapper
+    from torchrec_b200.optim.optimizers import in_backward_optimizer_filter
+    from torchrec_b200.optim.rowwise_adagrad import RowWiseAdagrad
+    from torchrec_b200.parallel import sharding_plan as sp
+    from torchrec_b200.parallel import train_pipeline as tp
+    from torchrec_b200.parallel.comm_ops import set_gradient_division
+    from torchrec_b200.parallel.embeddingbag import EmbeddingBagCollectionSharder
+    from torchrec_b200.parallel.model_parallel import DistributedModelParallel
+    from torchrec_b200.parallel.types import ShardingPlan
+
+    set_gradient_division(True)
+    W, local = ctx.world_size, 2
+    try:
+        for seed in range(first_seed, first_seed + n_seeds):
+            tables, gens = _case(seed, False, W, local, no_col_split=True, allow_dp=False)
+            tables = [type(t)(name=t.name, embedding_dim=8, num_embeddings=t.num_embeddings, feature_names=t.feature_names, pooling=t.pooling) for t in tables]  # DLRM: one dim
+
+            def build():
+                torch.manual_seed(seed)
+                ebc = EmbeddingBagCollection(tables)
+                apply_optimizer_in_backward(RowWiseAdagrad, ebc.parameters(), {"lr": 0.05})
+                model = DLRMTrain(DLRM(ebc, 5, [16, 8], [16, 1]))
+                sharder = EmbeddingBagCollectionSharder()
+                plan = sp.construct_module_sharding_plan(ebc, gens, sharder=sharder, world_size=W, local_size=local, device_type="cpu")
+                dmp = DistributedModelParallel(model, device=torch.device("cpu"), plan=ShardingPlan({"model.sparse_arch.embedding_bag_collection": plan}), sharders=[sharder])
+                dense_opt = KeyedOptimizerWrapper(dict(in_backward_optimizer_filter(dmp.named_parameters())), lambda p: torch.optim.SGD(p, lr=0.1))
+                return dmp, CombinedOptimizer([dmp.fused_optimizer, dense_opt]), {n: plan[n].sharding_type for n in plan}
+
+            def batches():
+                out = []
+                for i, Bq in enumerate([6, 6, 6, 6, 3]):  # the last batch is a partial one (same size on every rank)
+                    g = torch.Generator().manual_seed(97 * seed + 11 * i + ctx.rank)
+                    kjt = _batch(tables, 50 * seed + i, ctx.rank, Bq, False)
+                    out.append(Batch(dense_features=torch.randn(Bq, 5, generator=g), sparse_features=kjt, labels=torch.randint(0, 2, (Bq,), generator=g).float()))
+                return out
+
+            data = batches()
+            ref, opt_ref, desc = build()
+            ref_losses = []
+            for b in data:
+                opt_ref.zero_grad()
+                loss, _ = ref(b)
+                loss.backward()
+                opt_ref.step()
+                ref_losses.append(loss.detach().clone())
+            sa = ref.state_dict()
+            for name in ("TrainPipelineBase", "TrainPipelineSparseDist", "TrainPipelineSparseDistLite", "TrainPipelineFusedSparseDist", "PrefetchTrainPipelineSparseDist"):
+                dmp, opt, _ = build()
+                pipe = getattr(tp, name)(dmp, opt, torch.device("cpu"))
+                it = iter(data)
+                losses = []
+                while True:
+                    try:
+                        losses.append(pipe.progress(it)[0].clone())
+                    except StopIteration:
+                        break
+                msg = lambda m: f"{name} seed {seed} plan {desc}: {m}"  # noqa: E731
+                assert len(losses) == len(ref_losses), msg(f"{len(losses)} steps instead of {len(ref_losses)}")
+                for a, b in zip(losses, ref_losses):
+                    torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6, msg=msg)
+                sb = dmp.state_dict()
+                for k in sa:
+                    ta, tb = sa[k], sb[k]
+                    if hasattr(ta, "local_shards"):
+                        for x, y in zip(ta.local_shards(), tb.local_shards()):
+                            torch.testing.assert_close(x.tensor, y.tensor, rtol=1e-5, atol=1e-6, msg=msg)
+                    else:
+                        torch.testing.assert_close(ta, tb, rtol=1e-5, atol=1e-6, msg=msg)
+    finally:
+        set_gradient_division(False)
+
+
+def test_random_train_pipelines_match_plain_loop_4_ranks():
+    run_multi_process(_run_pipelines, world_size=4, backend="gloo", first_seed=0)
