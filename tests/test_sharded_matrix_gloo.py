@@ -549,3 +549,81 @@ def _run_pipelines(ctx, first_seed: int, n_seeds: int = 2):
 
 def test_random_train_pipelines_match_plain_loop_4_ranks():
     run_multi_process(_run_pipelines, world_size=4, backend="gloo", first_seed=0)
+
+
+def _run_fp(ctx, first_seed: int, n_seeds: int = 4):
+    """Feature-processed (position-weighted) bags: random tables / placements; the forward output, the embedding rows after two fused
+    SGD steps and the position-weight gradients (data-parallel) match the unsharded module."""
+    from torchrec_b200.modules.embedding_modules import EmbeddingBagCollection
+    from torchrec_b200.modules.feature_processor_ import PositionWeightedModuleCollection
+    from torchrec_b200.modules.fp_embedding_modules import FeatureProcessedEmbeddingBagCollection
+    from torchrec_b200.optim.apply_optimizer_in_backward import apply_optimizer_in_backward
+    from torchrec_b200.parallel import sharding_plan as sp
+    from torchrec_b200.parallel.comm_ops import set_gradient_division
+    from torchrec_b200.parallel.fp_embeddingbag import FeatureProcessedEmbeddingBagCollectionSharder
+    from torchrec_b200.parallel.model_parallel import DistributedModelParallel
+    from torchrec_b200.parallel.types import ShardingPlan
+
+    set_gradient_division(False)
+    W, local, B, dev = ctx.world_size, 2, 5, ctx.device
+    for seed in range(first_seed, first_seed + n_seeds):
+        tables, gens = _case(seed, True, W, local, allow_dp=False)
+        feats = [f for t in tables for f in t.feature_names]
+
+        def make():
+            torch.manual_seed(seed)
+            fp = PositionWeightedModuleCollection({f: 4 for f in feats}, device=dev)
+            with torch.no_grad():
+                for i, p in enumerate(fp.parameters()):
+                    p.copy_(torch.linspace(0.5, 1.5, p.numel()) + 0.1 * i)
+            return FeatureProcessedEmbeddingBagCollection(EmbeddingBagCollection(tables, is_weighted=True, device=dev), fp)
+
+        gold, src = make(), make()
+        src.load_state_dict(gold.state_dict())
+        apply_optimizer_in_backward(torch.optim.SGD, src._embedding_bag_collection.parameters(), {"lr": 0.1})
+        sharder = FeatureProcessedEmbeddingBagCollectionSharder()
+        plan = sp.construct_module_sharding_plan(src, gens, sharder=sharder, world_size=W, local_size=local, device_type=dev.type)
+        desc = {n: plan[n].sharding_type for n in plan}
+        msg = lambda m: f"FP seed {seed} plan {desc}: {m}"  # noqa: E731
+
+        class Wrap(torch.nn.Module):
+            def __init__(self, m):
+                super().__init__()
+                self.m = m
+
+            def forward(self, kjt):
+                out = self.m(kjt)
+                return (out.wait() if hasattr(out, "wait") else out).values()
+
+        model = DistributedModelParallel(Wrap(src), device=dev, plan=ShardingPlan({"m": plan}), sharders=[sharder])
+        gold_emb_opt = torch.optim.SGD(gold._embedding_bag_collection.parameters(), lr=0.1)
+        gp = dict(gold._feature_processors.named_parameters())
+        for step in range(2):
+            batches = [_batch(tables, 10 * seed + step, r, B, False).to(dev) for r in range(W)]
+            out = model(batches[ctx.rank])
+            gouts = [gold(b).values() for b in batches]
+            torch.testing.assert_close(out.float(), gouts[ctx.rank], rtol=1e-5, atol=1e-5, msg=msg)
+            proj = torch.linspace(0.5, 1.5, out.shape[1], device=dev)
+            model.zero_grad()
+            (out * proj).sum().backward()
+            gold.zero_grad()
+            sum((o * proj).sum() for o in gouts).backward()
+            gold_emb_opt.step()
+            n_checked = 0
+            for n, p in model.named_parameters():
+                if p.requires_grad:
+                    key = n.split("_feature_processors.")[-1]
+                    torch.testing.assert_close(p.grad * W, gp[key].grad, rtol=1e-4, atol=1e-5, msg=msg)  # DDP averages, the golden sums
+                    n_checked += 1
+            assert n_checked == len(feats), msg(f"{n_checked} position-weight parameters for {len(feats)} features")
+        sd = model.state_dict()
+        for t in tables:
+            st = sd[f"m._embedding_bag_collection.embedding_bags.{t.name}.weight"]
+            ref = gold._embedding_bag_collection.embedding_bags[t.name].weight.detach()
+            for sh in st.local_shards():
+                o, s = sh.metadata.shard_offsets, sh.metadata.shard_sizes
+                torch.testing.assert_close(sh.tensor, ref[o[0] : o[0] + s[0], o[1] : o[1] + s[1]], rtol=1e-4, atol=1e-5, msg=msg)
+
+
+def test_random_feature_processed_matrix_4_ranks():
+    run_multi_process(_run_fp, world_size=4, backend="gloo", first_seed=0)

@@ -63,6 +63,8 @@ def weights_from_positions(features: KeyedJaggedTensor, table: Dict[str, nn.Para
 def apply_feature_processors_by_position(features: KeyedJaggedTensor, processors: Union[nn.ModuleDict, FeatureProcessorsCollection], is_collection: bool) -> KeyedJaggedTensor:
     """Apply per-feature processors to a KJT whose keys may repeat (one key per lookup unit after the input dist)."""
     keys = features.keys()
+    if len(keys) == 0:  # this rank hosts no table of the group
+        return features
     if len(set(keys)) == len(keys) and is_collection and features._stride_per_rank is None:
         return processors(features)
     lpk = features.length_per_key()
