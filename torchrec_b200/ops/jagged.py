@@ -373,29 +373,35 @@ def batch_index_select_dim0(inputs: torch.Tensor, indices: torch.Tensor, input_n
 
 
 def jagged_unique_indices(hash_size_cumsum: torch.Tensor, hash_size_offsets: torch.Tensor, offsets: torch.Tensor, indices: torch.Tensor):
-    """Per-table unique of a multi-feature id list. Returns (output_lengths, output_offsets,
-    unique_indices, reverse_index) like the fbgemm op (embedding.py:1404)."""
+    """Per-table unique of a multi-feature id list. Returns (output_lengths, output_offsets, unique_indices, reverse_index) like the
+    fbgemm op (reference embedding.py:1404).
+
+    ``hash_size_cumsum`` [F + 1]: linearisation base of every feature (features of one table share the base of the table).
+    ``hash_size_offsets``: feature ranges of the tables - entry i covers features [hso[i], hso[i + 1]); the reference passes one entry
+    per feature (empty ranges for the non-first features of a table), one entry per table works too. All unique ids of a table are put
+    into the first bag of its first feature (any split over the bags of the table is a valid KJT; this one needs no division)."""
     n = indices.numel()
     FB = offsets.numel() - 1
-    num_feat = hash_size_offsets.numel() - 1
-    # feature of each bag: bags are feature-major with equal batch size
-    T = hash_size_cumsum.numel() - 1
-    B = FB // max(T, 1)
+    F = hash_size_cumsum.numel() - 1
+    B = FB // max(F, 1)
+    dev = indices.device
+    cum = hash_size_cumsum.long()
     lengths = offsets[1:] - offsets[:-1]
-    bag = torch.repeat_interleave(torch.arange(FB, device=indices.device), lengths, output_size=n)
+    bag = torch.repeat_interleave(torch.arange(FB, device=dev), lengths, output_size=n)
     feat = bag // max(B, 1)
-    lin = indices.long() + hash_size_cumsum.long()[feat]
-    uniq, inv = torch.unique(lin, return_inverse=True)
-    # table of each unique id
-    table = torch.bucketize(uniq, hash_size_cumsum.long()[1:], right=True)
-    feat_of_table = hash_size_offsets.long()[:-1]
-    out_len_per_table = torch.bincount(table, minlength=num_feat)
-    out_lengths = torch.zeros(FB, dtype=offsets.dtype, device=indices.device)
-    # put all unique ids of a table into the first bag of its first feature (layout used by EC dedup)
-    first_bag = feat_of_table * B
-    out_lengths[first_bag] = out_len_per_table.to(offsets.dtype)[: first_bag.numel()]
+    lin = indices.long() + cum[feat]
+    uniq, inv = torch.unique(lin, return_inverse=True)  # sorted
+    hso = hash_size_offsets.long()
+    first, end = hso[:-1], hso[1:]
+    real = end > first
+    first, end = first[real], end[real]
+    lo, hi = cum[first], cum[end]  # linearised id range of every table
+    counts = torch.searchsorted(uniq, hi) - torch.searchsorted(uniq, lo)
+    out_lengths = torch.zeros(FB, dtype=offsets.dtype, device=dev)
+    out_lengths[first * B] = counts.to(offsets.dtype)
     out_offsets = asynchronous_complete_cumsum(out_lengths)
-    base = hash_size_cumsum.long()[torch.searchsorted(hash_size_cumsum.long()[1:], uniq, right=True)]
+    table = torch.searchsorted(hi, uniq, right=True).clamp(max=max(hi.numel() - 1, 0))
+    base = lo[table] if lo.numel() else torch.zeros_like(uniq)
     return out_lengths, out_offsets, (uniq - base).to(indices.dtype), inv
 
 
