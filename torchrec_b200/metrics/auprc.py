@@ -4,7 +4,7 @@ Reference module: ``torchrec/metrics/auprc.py``. The computation (states, update
 ``compute_*`` / ``get_*_states`` helpers of the reference module."""
 from __future__ import annotations
 
-from typing import Dict, List, Optional
+from typing import Any, Dict, List, Optional
 
 import torch
 
@@ -13,11 +13,31 @@ from .metrics_namespace import MetricName, MetricNamespace, MetricPrefix  # noqa
 from .rec_metric import MetricComputationReport, RecMetric, RecMetricComputation, RecMetricException  # noqa: F401
 
 
+GROUPING_KEYS = "grouping_keys"
+
+
 class AUPRCMetricComputation(_SampleBufferComputation):
+    """Windowed weighted area under the precision-recall curve; ``grouped_auprc`` adds the mean over the groups of
+    ``required_inputs['grouping_keys']`` (``grouped_auprc``)."""
+
     NAME = MetricName.AUPRC
+
+    def __init__(self, *args: Any, grouped_auprc: bool = False, fused_update_limit: int = 0, **kwargs: Any) -> None:
+        if grouped_auprc and fused_update_limit > 0:
+            raise RecMetricException("Grouped AUPRC and Fused Update Limit cannot be enabled together yet.")
+        self._grouped_auprc = grouped_auprc
+        self.EXTRA = [GROUPING_KEYS] if grouped_auprc else []
+        super().__init__(*args, fused_update_limit=fused_update_limit, **kwargs)
 
     def _value(self, p, l, w, extra):
         return _auprc_from_samples(p, l, w)
+
+    def _compute(self) -> List[MetricComputationReport]:
+        reports = super()._compute()
+        if self._grouped_auprc:
+            reports.append(MetricComputationReport(MetricName.GROUPED_AUPRC, MetricPrefix.WINDOW,
+                                                   compute_auprc_per_group(self._n_tasks, self.predictions, self.labels, self.weights, getattr(self, GROUPING_KEYS)[0])))
+        return reports
 
 
 def _auprc_from_samples(preds, labels, weights) -> torch.Tensor:
@@ -38,7 +58,14 @@ def _auprc_from_samples(preds, labels, weights) -> torch.Tensor:
     return ((recall - recall_prev) * precision).sum()
 
 
-AUPRCMetric = _make("AUPRCMetric", AUPRCMetricComputation, MetricNamespace.AUPRC)
+class AUPRCMetric(RecMetric):
+    _namespace: MetricNamespace = MetricNamespace.AUPRC
+    _computation_class = AUPRCMetricComputation
+
+    def __init__(self, *args: Any, **kwargs: Any) -> None:
+        super().__init__(*args, **kwargs)
+        if kwargs.get("grouped_auprc"):
+            self._required_inputs.add(GROUPING_KEYS)
 
 
 def compute_auprc(n_tasks: int, predictions: torch.Tensor, labels: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:

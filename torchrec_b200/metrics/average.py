@@ -14,18 +14,18 @@ from .rec_metric import MetricComputationReport, RecMetric, RecMetricComputation
 
 
 class AverageMetricComputation(_SumStatesComputation):
-    """Mean of the labels (useful for tracking target statistics)."""
+    """Weighted average of the labels (``label_average``) and of the predictions (``prediction_average``)."""
 
-    STATES = ["sum", "num_samples"]
-
-    def _needs(self):
-        return []
+    STATES = ["label_sum", "prediction_sum", "weighted_num_samples"]
 
     def _batch_states(self, predictions, labels, weights, **kwargs):
-        return {"sum": (labels.double() * weights.double()).sum(-1), "num_samples": weights.double().sum(-1)}
+        if predictions is None or weights is None:
+            raise RecMetricException("Inputs 'predictions' and 'weights' should not be None for AverageMetricComputation update")
+        return get_average_states(labels, predictions, weights)
 
     def _reports(self, get, prefix):
-        return [MetricComputationReport(MetricName.AVERAGE, prefix, get("sum") / (get("num_samples") + EPS))]
+        return [MetricComputationReport(MetricName.LABEL_AVERAGE, prefix, compute_average(get("label_sum"), get("weighted_num_samples"))),
+                MetricComputationReport(MetricName.PREDICTION_AVERAGE, prefix, compute_average(get("prediction_sum"), get("weighted_num_samples")))]
 
 
 AverageMetric = _make("AverageMetric", AverageMetricComputation, MetricNamespace.AVERAGE)

@@ -23,25 +23,37 @@ class HindsightTargetPRMetricComputation(RecMetricComputation):
         self._target = target_precision
         self._gran = threshold_granularity
         for s in ["true_pos_sum", "false_pos_sum", "false_neg_sum"]:
-            self._add_state(s, torch.zeros(self._n_tasks, threshold_granularity, dtype=torch.double), add_window_state=False, dist_reduce_fx="sum")
+            self._add_state(s, torch.zeros(self._n_tasks, threshold_granularity, dtype=torch.double), add_window_state=True, dist_reduce_fx="sum", persistent=True)
 
     def update(self, *, predictions, labels, weights, **kwargs: Any) -> None:
-        th = torch.linspace(0, 1, self._gran, dtype=torch.double).view(1, -1, 1)
+        if predictions is None:
+            raise RecMetricException("Inputs 'predictions' should not be None for HindsightTargetPRMetricComputation update")
+        if weights is None:
+            weights = torch.ones_like(predictions)
+        th = torch.linspace(0, 1, self._gran, dtype=torch.double, device=predictions.device).view(1, -1, 1)
         pred = (predictions.double().unsqueeze(1) >= th).double()
         l, w = labels.double().unsqueeze(1), weights.double().unsqueeze(1)
-        self.true_pos_sum += (w * pred * l).sum(-1).to(self.true_pos_sum.device)
-        self.false_pos_sum += (w * pred * (1 - l)).sum(-1).to(self.true_pos_sum.device)
-        self.false_neg_sum += (w * (1 - pred) * l).sum(-1).to(self.true_pos_sum.device)
+        n = predictions.shape[-1]
+        for name, v in (("true_pos_sum", (w * pred * l).sum(-1)), ("false_pos_sum", (w * pred * (1 - l)).sum(-1)), ("false_neg_sum", (w * (1 - pred) * l).sum(-1))):
+            st = getattr(self, name)
+            v = v.to(st.device)
+            st += v
+            self._aggregate_window_state(name, v, n)
+
+    def _one(self, tp: torch.Tensor, fp: torch.Tensor, fn: torch.Tensor, prefix: MetricPrefix) -> List[MetricComputationReport]:
+        prec = compute_precision(tp, fp)
+        ok = prec >= self._target
+        idx = torch.where(ok.any(-1), ok.double().argmax(-1), torch.full((self._n_tasks,), self._gran - 1, device=tp.device))  # first threshold bucket reaching the target
+        ar = torch.arange(self._n_tasks, device=tp.device)
+        return [MetricComputationReport(MetricName.HINDSIGHT_TARGET_PR, prefix, idx.double()),
+                MetricComputationReport(MetricName.HINDSIGHT_TARGET_PRECISION, prefix, prec[ar, idx]),
+                MetricComputationReport(MetricName.HINDSIGHT_TARGET_RECALL, prefix, compute_recall(tp[ar, idx], fn[ar, idx]))]
 
     def _compute(self) -> List[MetricComputationReport]:
-        prec = self.true_pos_sum / (self.true_pos_sum + self.false_pos_sum + EPS)
-        rec = self.true_pos_sum / (self.true_pos_sum + self.false_neg_sum + EPS)
-        ok = prec >= self._target
-        idx = torch.where(ok.any(-1), ok.double().argmax(-1), torch.full((self._n_tasks,), self._gran - 1))
-        ar = torch.arange(self._n_tasks)
-        return [MetricComputationReport(MetricName.HINDSIGHT_TARGET_PR, MetricPrefix.LIFETIME, idx.double() / (self._gran - 1), description="_threshold"),
-                MetricComputationReport(MetricName.HINDSIGHT_TARGET_PR, MetricPrefix.LIFETIME, prec[ar, idx], description="_precision"),
-                MetricComputationReport(MetricName.HINDSIGHT_TARGET_PR, MetricPrefix.LIFETIME, rec[ar, idx], description="_recall")]
+        out = self._one(self.true_pos_sum, self.false_pos_sum, self.false_neg_sum, MetricPrefix.LIFETIME)
+        if self._batch_window_buffers is not None:
+            out += self._one(self.get_window_state("true_pos_sum"), self.get_window_state("false_pos_sum"), self.get_window_state("false_neg_sum"), MetricPrefix.WINDOW)
+        return out
 
 
 HindsightTargetPRMetric = _make("HindsightTargetPRMetric", HindsightTargetPRMetricComputation, MetricNamespace.HINDSIGHT_TARGET_PR)

@@ -10,7 +10,7 @@ from .cali_free_ne import CaliFreeNEMetric, CaliFreeNEMetricComputation  # noqa:
 from .calibration import CalibrationMetric, CalibrationMetricComputation  # noqa: F401
 from .calibration_with_recalibration import RecalibratedCalibrationMetric, RecalibratedCalibrationMetricComputation  # noqa: F401
 from .ctr import CTRMetric, CTRMetricComputation  # noqa: F401
-from .gauc import GAUCMetric, GroupedAUCMetricComputation  # noqa: F401
+from .gauc import GAUCMetric, GAUCMetricComputation  # noqa: F401
 from .hindsight_target_pr import HindsightTargetPRMetric, HindsightTargetPRMetricComputation  # noqa: F401
 from .mae import MAEMetric, MAEMetricComputation  # noqa: F401
 from .mse import MSEMetric, MSEMetricComputation  # noqa: F401

@@ -57,6 +57,19 @@ class MetricName(StrValueMixin, Enum):
     SUM_WEIGHTS = "sum_weights"
     NUM_MISSING_LABELS = "num_missing_labels"
     WEIGHTED_SUM_PREDICTIONS = "weighted_sum_predictions"
+    GAUC = "gauc"
+    GAUC_NUM_SAMPLES = "gauc_num_samples"
+    GROUPED_RAUC = "grouped_rauc"
+    HINDSIGHT_TARGET_PRECISION = "hindsight_target_precision"
+    HINDSIGHT_TARGET_RECALL = "hindsight_target_recall"
+    LABEL_AVERAGE = "label_average"
+    PREDICTION_AVERAGE = "prediction_average"
+    DATA_LABEL_AVERAGE = "data_label_average"
+    R_SQUARED = "r_squared"
+    EFFECTIVE_RATE = "effective_rate"
+    EFFECTIVE_SAMPLE_RATE = "effective_sample_rate"
+    TOTAL_POSITIVE_EXAMPLES = "total_positive_examples"
+    TOTAL_NEGATIVE_EXAMPLES = "total_negative_examples"
 
 
 class MetricNamespaceBase(StrValueMixin, Enum):
@@ -107,6 +120,7 @@ class MetricNamespace(MetricNamespaceBase):
     SUM_WEIGHTS = "sum_weights"
     NUM_MISSING_LABELS = "num_missing_labels"
     WEIGHTED_SUM_PREDICTIONS = "weighted_sum_predictions"
+    GAUC = "gauc"
 
 
 class MetricPrefix(StrValueMixin, Enum):

@@ -1,25 +1,26 @@
 """Session-level precision of the top-ranked items.
 
-Reference module: ``torchrec/metrics/precision_session.py``. The computation (states, update, reports) and the ``RecMetric`` class of this metric, on the shared bases of ``_bases.py``, plus the stateless
-``compute_*`` / ``get_*_states`` helpers of the reference module."""
+Reference module: ``torchrec/metrics/precision_session.py``: the session ranking of ``recall_session.py`` with the states ``num_true_pos`` /
+``num_false_pos``; NaN until a positive prediction has been seen."""
 from __future__ import annotations
 
-from typing import Dict, List, Optional
-
-import torch
-
-from ._bases import EPS, _make  # noqa: F401
 from .metrics_namespace import MetricName, MetricNamespace, MetricPrefix  # noqa: F401
-from .rec_metric import MetricComputationReport, RecMetric, RecMetricComputation, RecMetricException  # noqa: F401
-from .recall_session import RecallSessionMetricComputation  # noqa: F401
+from .rec_metric import MetricComputationReport
+from .recall_session import (NUM_FALSE_POS, NUM_TRUE_POS, _calc_num_false_pos, _calc_num_true_pos, _ratio_or_nan, _SessionRecMetric, _SessionTopKComputation,  # noqa: F401
+                             ranking_within_session)
 
 
-class PrecisionSessionMetricComputation(RecallSessionMetricComputation):
-    NAME = MetricName.PRECISION_SESSION_LEVEL
+class PrecisionSessionMetricComputation(_SessionTopKComputation):
+    STATES = [NUM_TRUE_POS, NUM_FALSE_POS]
 
-    def _value(self, p, l, w, extra):
-        tp, fn, fp = self._counts(p, l, extra["session_ids"])
-        return torch.tensor(tp / (tp + fp) if tp + fp > 0 else 0.0, dtype=torch.double)
+    def _batch_states(self, predictions, labels, weights, **kwargs):
+        labels, pred_pos, weights = self._labelled(predictions, labels, weights, kwargs)
+        return {NUM_TRUE_POS: _calc_num_true_pos(labels, pred_pos, weights), NUM_FALSE_POS: _calc_num_false_pos(labels, pred_pos, weights)}
+
+    def _reports(self, get, prefix):
+        return [MetricComputationReport(MetricName.PRECISION_SESSION_LEVEL, prefix, _ratio_or_nan(get(NUM_TRUE_POS), get(NUM_FALSE_POS)))]
 
 
-PrecisionSessionMetric = _make("PrecisionSessionMetric", PrecisionSessionMetricComputation, MetricNamespace.PRECISION_SESSION_LEVEL)
+class PrecisionSessionMetric(_SessionRecMetric):
+    _namespace: MetricNamespace = MetricNamespace.PRECISION_SESSION_LEVEL
+    _computation_class = PrecisionSessionMetricComputation

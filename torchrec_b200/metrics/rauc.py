@@ -4,7 +4,7 @@ Reference module: ``torchrec/metrics/rauc.py``. The computation (states, update,
 ``compute_*`` / ``get_*_states`` helpers of the reference module."""
 from __future__ import annotations
 
-from typing import Dict, List, Optional
+from typing import Any, Dict, List, Optional
 
 import torch
 
@@ -13,30 +13,46 @@ from .metrics_namespace import MetricName, MetricNamespace, MetricPrefix  # noqa
 from .rec_metric import MetricComputationReport, RecMetric, RecMetricComputation, RecMetricException  # noqa: F401
 
 
+GROUPING_KEYS = "grouping_keys"
+
+
 class RAUCMetricComputation(_SampleBufferComputation):
-    """Regression AUC: fraction of correctly ordered pairs (concordance) for continuous labels."""
+    """Regression AUC over the sample window: 1 - (pairs ordered the wrong way round by the prediction) / (all pairs), counted by
+    merge sort. ``grouped_rauc`` adds the mean over the groups of ``required_inputs['grouping_keys']`` (``grouped_rauc``)."""
 
     NAME = MetricName.RAUC
 
+    def __init__(self, *args: Any, grouped_rauc: bool = False, fused_update_limit: int = 0, **kwargs: Any) -> None:
+        if grouped_rauc and fused_update_limit > 0:
+            raise RecMetricException("Grouped RAUC and Fused Update Limit cannot be enabled together yet.")
+        self._grouped_rauc = grouped_rauc
+        self.EXTRA = [GROUPING_KEYS] if grouped_rauc else []
+        super().__init__(*args, fused_update_limit=fused_update_limit, **kwargs)
+
     def _value(self, p, l, w, extra):
-        n = p.numel()
-        if n < 2:
-            return torch.tensor(0.5, dtype=torch.double)
-        if n > 4096:  # subsample for the O(n^2) pair count
-            idx = torch.randperm(n)[:4096]
-            p, l = p[idx], l[idx]
-        dp = p.unsqueeze(0) - p.unsqueeze(1)
-        dl = l.unsqueeze(0) - l.unsqueeze(1)
-        valid = dl != 0
-        conc = ((dp * dl) > 0).double() + 0.5 * (dp == 0).double()
-        return (conc * valid).sum() / (valid.sum() + EPS)
+        return compute_rauc(1, p.view(1, -1), l.view(1, -1), w.view(1, -1))[0]
+
+    def _compute(self) -> List[MetricComputationReport]:
+        reports = super()._compute()
+        if self._grouped_rauc:
+            reports.append(MetricComputationReport(MetricName.GROUPED_RAUC, MetricPrefix.WINDOW,
+                                                   compute_rauc_per_group(self._n_tasks, self.predictions, self.labels, self.weights, getattr(self, GROUPING_KEYS)[0])))
+        return reports
 
 
-RAUCMetric = _make("RAUCMetric", RAUCMetricComputation, MetricNamespace.RAUC)
+class RAUCMetric(RecMetric):
+    _namespace: MetricNamespace = MetricNamespace.RAUC
+    _computation_class = RAUCMetricComputation
+
+    def __init__(self, *args: Any, **kwargs: Any) -> None:
+        super().__init__(*args, **kwargs)
+        if kwargs.get("grouped_rauc"):
+            self._required_inputs.add(GROUPING_KEYS)
 
 
 def count_reverse_pairs_divide_and_conquer(input: List[float]) -> float:
-    """Number of inversions of ``input`` by merge sort, O(n log n)."""
+    """Fraction of the pairs of ``input`` that are inverted (i < j, input[i] > input[j]), counted by merge sort in O(n log n): 0 for an
+    ascending list, 1 for a strictly descending one (0 for fewer than two elements)."""
     a = list(input)
 
     def rec(lo: int, hi: int) -> int:
@@ -54,17 +70,16 @@ def count_reverse_pairs_divide_and_conquer(input: List[float]) -> float:
         a[lo:hi] = merged
         return n
 
-    return float(rec(0, len(a)))
+    n = len(a)
+    return float(rec(0, n)) / (n * (n - 1) / 2) if n > 1 else 0.0
 
 
 def compute_rauc(n_tasks: int, predictions: torch.Tensor, labels: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
     out = []
     for t in range(n_tasks):
-        order = torch.argsort(predictions[t], stable=True)
-        n = order.numel()
-        total = n * (n - 1) / 2
-        inv = count_reverse_pairs_divide_and_conquer(labels[t][order].tolist())
-        out.append(torch.tensor(1.0 - inv / total if total > 0 else 1.0, dtype=torch.double))
+        by_label = torch.argsort(labels[t], stable=True)  # ties of the prediction are ordered by label: they count as ordered correctly
+        order = by_label[torch.argsort(predictions[t][by_label], stable=True)]
+        out.append(torch.tensor(1.0 - count_reverse_pairs_divide_and_conquer(labels[t][order].tolist()), dtype=torch.double))
     return torch.stack(out)
 
 

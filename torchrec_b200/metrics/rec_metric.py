@@ -236,9 +236,19 @@ class RecMetric(nn.Module, abc.ABC):
             kw = dict(kwargs)
             if task_per_metric == 1 and getattr(task_config, "session_metric_def", None) is not None:
                 kw["session_metric_def"] = task_config.session_metric_def
+            kw.update(self._get_task_kwargs(task_config))
+            self._required_inputs.update(self._get_task_required_inputs(task_config))
             self._metrics_computations.append(self._computation_class(
                 my_rank, batch_size, task_per_metric, self._window_size, compute_on_all_ranks,
                 should_validate_update, process_group=process_group, **kw))
+
+    def _get_task_kwargs(self, task_config: Union[RecTaskInfo, List[RecTaskInfo]]) -> Dict[str, Any]:
+        """Extra constructor arguments of the computation of one task (of all tasks when they are fused)."""
+        return {}
+
+    def _get_task_required_inputs(self, task_config: Union[RecTaskInfo, List[RecTaskInfo]]) -> set:
+        """Names of the extra model outputs the computation of this task reads from ``required_inputs``."""
+        return set()
 
     def _check_fused_update_limit(self) -> None:
         if self._fused_update_limit > 0 and self._compute_mode == RecComputeMode.UNFUSED_TASKS_COMPUTATION:
@@ -277,6 +287,13 @@ class RecMetric(nn.Module, abc.ABC):
                     p, l, w = predictions, labels, weights
                 if w is None and p is not None:
                     w = self._create_default_weights(p)
+                req = kwargs.get("required_inputs")
+                if req is not None:  # per-task tensors (TensorWeightedAvg) travel stacked in task order
+                    targets = [req[t.tensor_name] for t in self._tasks if t.tensor_name and t.tensor_name in req]
+                    if targets:
+                        kwargs = dict(kwargs)
+                        kwargs["required_inputs"] = dict(req)
+                        kwargs["required_inputs"]["target_tensor"] = torch.stack([x.reshape(-1) for x in targets]).view(len(targets), -1)
                 self._metrics_computations[0].update(predictions=p, labels=l, weights=w, **kwargs)
             else:
                 for task, metric_ in zip(self._tasks, self._metrics_computations):

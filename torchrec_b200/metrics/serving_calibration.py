@@ -7,6 +7,7 @@ from __future__ import annotations
 from typing import Dict, List, Optional
 
 import torch
+from typing import Any  # noqa: F401
 
 from ._bases import EPS, _make  # noqa: F401
 from .metrics_namespace import MetricName, MetricNamespace, MetricPrefix  # noqa: F401
@@ -15,8 +16,21 @@ from .calibration import CalibrationMetricComputation  # noqa: F401
 
 
 class ServingCalibrationMetricComputation(CalibrationMetricComputation):
-    def _reports(self, get, prefix):
-        return [MetricComputationReport(MetricName.SERVING_CALIBRATION, prefix, get("calibration_num") / (get("calibration_denom") + EPS))]
+    """Calibration over the serving data + the number of examples with a non-zero weight. Reported as
+    ``serving_calibration-<task>|lifetime_calibration`` / ``window_calibration`` / ``total_examples``."""
+
+    def __init__(self, *args: Any, **kwargs: Any) -> None:
+        super().__init__(*args, **kwargs)
+        self._add_state("num_examples", torch.zeros(self._n_tasks, dtype=torch.long), add_window_state=False, dist_reduce_fx="sum", persistent=True)
+
+    def _batch_states(self, predictions, labels, weights, **kwargs):
+        if predictions is None or weights is None:
+            raise RecMetricException("Inputs 'predictions' and 'weights' should not be None for ServingCalibrationMetricComputation update")
+        self.num_examples += torch.count_nonzero(weights, dim=-1).to(self.num_examples.device)
+        return super()._batch_states(predictions, labels, weights, **kwargs)
+
+    def _extra_reports(self):
+        return [MetricComputationReport(MetricName.TOTAL_EXAMPLES, MetricPrefix.DEFAULT, self.num_examples.detach())]
 
 
 ServingCalibrationMetric = _make("ServingCalibrationMetric", ServingCalibrationMetricComputation, MetricNamespace.SERVING_CALIBRATION)

@@ -16,33 +16,73 @@ from typing import Any, Type  # noqa: F401
 
 
 class TensorWeightedAvgMetricComputation(_SumStatesComputation):
-    """Weighted average of an arbitrary named tensor from ``required_inputs``."""
+    """Weighted average of a tensor handed over in ``required_inputs`` (the sibling of ``WeightedAvg``, which averages the predictions).
+    Every task names its tensor (``RecTaskInfo.tensor_name``) and says whether the example weights apply (``RecTaskInfo.weighted``);
+    with fused tasks the per-task tensors arrive stacked as ``required_inputs['target_tensor']``. Reported as ``weighted_avg``."""
 
     STATES = ["weighted_sum", "weighted_num_samples"]
 
-    def __init__(self, *args: Any, tensor_name: Optional[str] = None, weighted: bool = True, description: Optional[str] = None, **kwargs: Any) -> None:
-        self._tensor_name = tensor_name
-        self._weighted = weighted
-        self._description = description
+    def __init__(self, *args: Any, tasks: Optional[List[Any]] = None, tensor_name: Optional[str] = None, weighted: bool = True, description: Optional[str] = None,
+                 **kwargs: Any) -> None:
         super().__init__(*args, **kwargs)
+        if tasks is None:  # direct construction: one tensor name for all tasks
+            from .rec_metric import RecTaskInfo
+
+            tasks = [RecTaskInfo(name=f"task_{i}", tensor_name=tensor_name, weighted=weighted) for i in range(self._n_tasks)]
+        self.tasks = list(tasks)
+        for task in self.tasks:
+            if task.tensor_name is None:
+                raise RecMetricException("TensorWeightedAvgMetricComputation expects all tasks to have tensor_name, but got None.")
+        self._description = description
+        self.weighted_mask = torch.tensor([bool(t.weighted) for t in self.tasks]).unsqueeze(-1)
 
     def _needs(self):
         return []
 
     def _batch_states(self, predictions, labels, weights, **kwargs):
-        t = kwargs.get("required_inputs", {}).get(self._tensor_name) if self._tensor_name else predictions
-        if t is None:
-            raise RecMetricException(f"TensorWeightedAvg needs required input '{self._tensor_name}'")
-        t = t.reshape(1, -1).double()
-        w = weights.double() if self._weighted else torch.ones_like(t)
-        return {"weighted_sum": (t * w).sum(-1), "weighted_num_samples": w.sum(-1)}
+        req = kwargs.get("required_inputs")
+        if req is None:
+            raise RecMetricException("TensorWeightedAvgMetricComputation expects 'required_inputs' to exist.")
+        if len(self.tasks) > 1 and "target_tensor" in req:
+            target = req["target_tensor"]
+        elif len(self.tasks) > 1:
+            missing = [t.tensor_name for t in self.tasks if t.tensor_name not in req]
+            if missing:
+                raise RecMetricException(f"TensorWeightedAvgMetricComputation expects required_inputs to contain target tensors {missing}")
+            target = torch.stack([req[t.tensor_name].reshape(-1) for t in self.tasks])
+        else:
+            name = self.tasks[0].tensor_name
+            if name not in req:
+                raise RecMetricException(f"TensorWeightedAvgMetricComputation expects required_inputs to contain target tensor {name}")
+            target = req[name]
+        target = target.reshape(len(self.tasks), -1).double()
+        w = weights.double().reshape(len(self.tasks), -1)
+        mask = self.weighted_mask.to(target.device)
+        return {"weighted_sum": torch.where(mask, target * w, target).sum(-1), "weighted_num_samples": torch.where(mask, w, torch.ones_like(w)).sum(-1)}
 
     def _reports(self, get, prefix):
-        return [MetricComputationReport(MetricName.TENSOR_WEIGHTED_AVG, prefix, get("weighted_sum") / (get("weighted_num_samples") + EPS), description=self._description)]
+        return [MetricComputationReport(MetricName.WEIGHTED_AVG, prefix, get_mean(get("weighted_sum"), get("weighted_num_samples")), description=self._description)]
 
 
-TensorWeightedAvgMetric = _make("TensorWeightedAvgMetric", TensorWeightedAvgMetricComputation, MetricNamespace.TENSOR_WEIGHTED_AVG)
+class TensorWeightedAvgMetric(RecMetric):
+    _namespace: MetricNamespace = MetricNamespace.WEIGHTED_AVG
+    _computation_class = TensorWeightedAvgMetricComputation
+
+    def _get_task_kwargs(self, task_config) -> Dict[str, Any]:
+        return {"tasks": [task_config] if not isinstance(task_config, (list, tuple)) else list(task_config)}
+
+    def _get_task_required_inputs(self, task_config) -> set:
+        """The target tensors of the tasks; one tensor must not be registered both weighted and unweighted."""
+        seen: Dict[str, bool] = {}
+        for task in ([task_config] if not isinstance(task_config, (list, tuple)) else task_config):
+            if task.tensor_name is None:
+                continue
+            if task.tensor_name in seen and seen[task.tensor_name] is not task.weighted:
+                raise RecMetricException(f"This target tensor was already registered as weighted={seen[task.tensor_name]}. "
+                                         f"This target tensor cannot be re-registered with weighted={task.weighted}")
+            seen[str(task.tensor_name)] = task.weighted
+        return set(seen)
 
 
 def get_mean(value_sum: torch.Tensor, num_samples: torch.Tensor) -> torch.Tensor:
-    return value_sum / (num_samples + EPS)
+    return value_sum / num_samples

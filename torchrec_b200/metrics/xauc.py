@@ -8,32 +8,24 @@ from typing import Dict, List, Optional
 
 import torch
 
-from ._bases import EPS, _SampleBufferComputation, _make  # noqa: F401
+from ._bases import EPS, _SampleBufferComputation, _SumStatesComputation, _make  # noqa: F401
 from .metrics_namespace import MetricName, MetricNamespace, MetricPrefix  # noqa: F401
 from .rec_metric import MetricComputationReport, RecMetric, RecMetricComputation, RecMetricException  # noqa: F401
 
 
-class XAUCMetricComputation(_SampleBufferComputation):
-    """Cross AUC for regression: P(pred_i > pred_j | label_i > label_j), weighted by w_i * w_j."""
+class XAUCMetricComputation(_SumStatesComputation):
+    """Cross AUC for regression: the weighted share of the pairs (i < j) of a batch whose predictions are ordered like their labels (a
+    pair tied in both counts as ordered), pair weight w_i * w_j; additive states ``error_sum`` / ``weighted_num_pairs``."""
 
-    NAME = MetricName.XAUC
+    STATES = ["error_sum", "weighted_num_pairs"]
 
-    def _value(self, p, l, w, extra):
-        n = p.numel()
-        if n < 2:
-            return torch.tensor(0.0, dtype=torch.double)
-        if n > 4096:
-            idx = torch.randperm(n)[:4096]
-            p, l, w = p[idx], l[idx], w[idx]
-        ww = w.unsqueeze(0) * w.unsqueeze(1)
-        dp = torch.sign(p.unsqueeze(0) - p.unsqueeze(1))
-        dl = torch.sign(l.unsqueeze(0) - l.unsqueeze(1))
-        match = ((dp == dl) & (dl != 0)).double()
-        iu = torch.triu(torch.ones(n, n, dtype=torch.bool), diagonal=1)
-        return (ww * match)[iu].sum() / (ww[iu].sum() + EPS)
+    def _batch_states(self, predictions, labels, weights, **kwargs):
+        if predictions is None or weights is None:
+            raise RecMetricException("Inputs 'predictions' and 'weights' should not be None for XAUCMetricComputation update")
+        return get_xauc_states(labels, predictions, weights)
 
-
-XAUCMetric = _make("XAUCMetric", XAUCMetricComputation, MetricNamespace.XAUC)
+    def _reports(self, get, prefix):
+        return [MetricComputationReport(MetricName.XAUC, prefix, compute_xauc(get("error_sum"), get("weighted_num_pairs")))]
 
 
 def compute_error_sum(labels: torch.Tensor, predictions: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
@@ -57,3 +49,6 @@ def compute_xauc(error_sum: torch.Tensor, weighted_num_pairs: torch.Tensor) -> t
 
 def get_xauc_states(labels: torch.Tensor, predictions: torch.Tensor, weights: torch.Tensor) -> Dict[str, torch.Tensor]:
     return {"error_sum": compute_error_sum(labels, predictions, weights), "weighted_num_pairs": compute_weighted_num_pairs(weights)}
+
+
+XAUCMetric = _make("XAUCMetric", XAUCMetricComputation, MetricNamespace.XAUC)
