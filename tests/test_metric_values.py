@@ -394,3 +394,44 @@ def test_tensor_weighted_avg_and_tower_qps():
     assert int(comp.warmup_examples) == 2 * B and float(comp.time_lapse) >= 0.03
     _close(r["qps-t|lifetime_qps"], 3 * B / float(comp.time_lapse))
     _close(r["qps-t|window_qps"], 3 * B / float(comp.time_lapse))
+
+
+def test_scalar_output_and_multi_label_precision():
+    # scalar: the latest value and the window mean of the per-batch values
+    m = _metric(M.ScalarMetric)
+    vals = [0.5, 2.0, 3.5]
+    for v in vals:
+        m.update(predictions={"t": torch.zeros(4)}, labels={"t": torch.full((4,), v)}, weights={"t": torch.ones(4)})
+    r = m.compute()
+    _close(r["scalar-t|lifetime_scalar"], 3.5)
+    _close(r["scalar-t|window_scalar"], sum(vals) / 3)
+    # output: batch means of two named model outputs, no lifetime / window prefix
+    m = _metric(M.OutputMetric)
+    assert m.get_required_inputs() == {"latest_imp", "total_latest_imp"}
+    with pytest.raises(RecMetricException):
+        m.update(predictions={"t": torch.zeros(4)}, labels={"t": torch.zeros(4)}, weights={"t": torch.ones(4)})
+    m.update(predictions={"t": torch.zeros(4)}, labels={"t": torch.zeros(4)}, weights={"t": torch.ones(4)},
+             required_inputs={"latest_imp": torch.tensor([1.0, 2.0, 3.0, 6.0]), "total_latest_imp": torch.tensor([10.0, 10.0, 20.0, 20.0])})
+    r = m.compute()
+    _close(r["output-t|output_latest_imp"], 3.0)
+    _close(r["output-t|output_total_latest_imp"], 15.0)
+    # multi-label precision: label sets encoded as bits (LSB first)
+    m = _metric(M.MultiLabelPrecisionMetric, num_labels=3, label_names=["cat", "dog", "horse"])
+    rng = random.Random(0)
+    tp, fp = [0.0] * 3, [0.0] * 3
+    for _ in range(3):
+        p = [rng.randrange(8) for _ in range(16)]
+        l = [rng.randrange(8) for _ in range(16)]
+        w = [rng.random() + 0.1 for _ in range(16)]
+        m.update(predictions={"t": torch.tensor(p)}, labels={"t": torch.tensor(l)}, weights={"t": torch.tensor(w)})
+        for pi, li, wi in zip(p, l, w):
+            for bit in range(3):
+                if (pi >> bit) & 1:
+                    if (li >> bit) & 1:
+                        tp[bit] += wi
+                    else:
+                        fp[bit] += wi
+    r = m.compute()
+    for bit, name in enumerate(["cat", "dog", "horse"]):
+        _close(r[f"multi_label_precision-t|lifetime_multi_label_precision{name}"], tp[bit] / (tp[bit] + fp[bit]), 1e-5)
+        _close(r[f"multi_label_precision-t|window_multi_label_precision{name}"], tp[bit] / (tp[bit] + fp[bit]), 1e-5)

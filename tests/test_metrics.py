@@ -120,8 +120,8 @@ def test_ndcg_gauc_recall_session_and_others_run():
         v = list(m.compute().values())[0]
         assert 0.0 <= float(v) <= 1.5, type(m)
     for cls in (M.PrecisionMetric, M.RecallMetric, M.WeightedAvgMetric, M.NMSEMetric, M.XAUCMetric, M.RAUCMetric, M.AUPRCMetric, M.CaliFreeNEMetric,
-                M.UnweightedNEMetric, M.ServingNEMetric, M.ServingCalibrationMetric, M.OutputMetric, M.AverageMetric, M.HindsightTargetPRMetric, M.ScalarMetric,
-                M.TowerQPSMetric, M.MultiLabelPrecisionMetric):
+                M.UnweightedNEMetric, M.ServingNEMetric, M.ServingCalibrationMetric, M.AverageMetric, M.HindsightTargetPRMetric, M.ScalarMetric,
+                M.TowerQPSMetric):
         m = _one(cls)
         for _ in range(3):
             m.update(predictions={"t": p}, labels={"t": l}, weights={"t": w})

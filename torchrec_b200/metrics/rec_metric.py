@@ -159,6 +159,10 @@ class RecMetricComputation(nn.Module, abc.ABC):
                 elif red == "max":
                     t = t.clone()
                     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=pg)
+                elif red == "mean":
+                    t = t.clone()
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=pg)
+                    t /= dist.get_world_size(pg)
                 elif red == "cat":
                     W = dist.get_world_size(pg)
                     sizes = [torch.zeros(1, dtype=torch.long, device=t.device) for _ in range(W)]
