@@ -104,7 +104,14 @@ def test_tensor_dict_interop_and_uintx():
     assert p.shape == (3, 8) and p.elem.shape == (3, 4) and torch.equal(p.unpack().long(), v)
     v2 = torch.randint(0, 4, (2, 16))
     p2 = UInt2Tensor.pack(v2)
-    assert p2.elem.shape == (2, 4) and torch.equal(p2.unpack().long(), v2) and p2[0].shape == (1, 16)
+    assert p2.elem.shape == (2, 4) and torch.equal(p2.unpack().long(), v2) and p2[0].shape == (16,) and isinstance(p2, torch.Tensor)
+    # a real tensor subclass: row / whole-byte column slices, clone / detach / copy_ / byte view keep working on the packed storage
+    assert torch.equal(p[1:3, 2:6].unpack().long(), v[1:3, 2:6]) and type(p[1:3]) is UInt4Tensor
+    q = p.clone().detach()
+    q.copy_(UInt4Tensor.pack((v + 1) % 16))
+    assert torch.equal(q.unpack().long(), (v + 1) % 16) and torch.equal(p.unpack().long(), v) and p.view(torch.uint8).shape == (3, 4)
+    with pytest.raises(NotImplementedError):
+        p[:, 1:3]  # not whole bytes
 
 
 def test_group_index_select_and_inference_gathers():

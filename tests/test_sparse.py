@@ -395,3 +395,50 @@ def test_keyed_tensor_regroup_backward_and_from_tensor_list():
     assert kt0.key_dim() == 0 and kt0["p"].shape == (3, 2) and kt0["q"].shape == (1, 2)
     assert "KeyedTensor" in str(kt)
     assert kt.to(torch.device("cpu")).keys() == ["p", "q"]
+
+
+def test_construct_jagged_tensors_column_blocks_dedup_and_inference_form():
+    """Sequence lookups come back as one [sum L, D] tensor: per-feature JaggedTensors, column-wise sharded tables as several blocks that
+    are concatenated (in permuted order), de-duplicated ids expanded by the reverse index, ids in the weights slot on request."""
+    from torchrec_b200.modules.utils import (construct_jagged_tensors, construct_jagged_tensors_inference, construct_modulelist_from_single_module,
+                                             init_mlp_weights_xavier_uniform, reset_module_states_post_sharding)
+
+    # features as the lookup saw them: f0 once, f1 twice (two column blocks of one table)
+    lengths = torch.tensor([2, 0, 1, 1, 2, 0, 1, 2, 0])
+    values = torch.tensor([10, 11, 12, 20, 21, 21, 20, 21, 21])
+    feats = KeyedJaggedTensor(keys=["f0", "f1", "f1"], values=values, lengths=lengths)
+    emb = torch.arange(9 * 2, dtype=torch.float32).view(9, 2)
+    out = construct_jagged_tensors(emb, feats, ["f0", "f1", "f1"], need_indices=True, features_to_permute_indices={"f1": [1, 0]})
+    assert set(out) == {"f0", "f1"}
+    assert out["f0"].lengths().tolist() == [2, 0, 1] and torch.equal(out["f0"].values(), emb[:3]) and out["f0"].weights().tolist() == [10, 11, 12]
+    assert out["f1"].values().shape == (3, 4) and torch.equal(out["f1"].values(), torch.cat([emb[6:9], emb[3:6]], dim=1))  # block order swapped
+    assert out["f1"].lengths().tolist() == [1, 2, 0]
+    plain = construct_jagged_tensors(emb, feats, ["f0", "f1", "f1"])
+    assert plain["f0"].weights_or_none() is None and torch.equal(plain["f1"].values(), torch.cat([emb[3:6], emb[6:9]], dim=1))
+    # de-duplicated lookup: 3 unique rows, reverse index per original id
+    uniq = torch.tensor([[1.0, 1.0], [2.0, 2.0], [3.0, 3.0]])
+    rev = torch.tensor([2, 0, 0, 1])
+    orig = KeyedJaggedTensor(keys=["a", "b"], values=torch.tensor([7, 5, 5, 6]), lengths=torch.tensor([1, 1, 2, 0]))
+    for gather in (False, True):
+        got = construct_jagged_tensors(uniq, orig, ["a", "b"], original_features=orig, reverse_indices=rev, use_gather_select=gather)
+        assert got["a"].values().tolist() == [[3.0, 3.0], [1.0, 1.0]] and got["b"].values().tolist() == [[1.0, 1.0], [2.0, 2.0]] and got["b"].lengths().tolist() == [2, 0]
+    # inference form: plain tensors, padding rows cut
+    padded = torch.cat([emb, torch.zeros(3, 2)])
+    inf = construct_jagged_tensors_inference(padded, lengths.view(3, 3), values, ["f0", "f1", "f1"], need_indices=True, remove_padding=True)
+    assert torch.equal(inf["f0"].values(), emb[:3]) and torch.equal(inf["f1"].values(), torch.cat([emb[3:6], emb[6:9]], dim=1)) and inf["f1"].weights().tolist() == [20, 21, 21]
+    # module helpers
+    mlp = torch.nn.Sequential(torch.nn.Linear(4, 4), torch.nn.ReLU())
+    grid = construct_modulelist_from_single_module(mlp, (2, 3))
+    assert len(grid) == 2 and len(grid[0]) == 3 and grid[0][0][0].weight.data_ptr() != grid[1][2][0].weight.data_ptr()
+    assert float(grid[1][1][0].bias.abs().sum()) == 0.0 and not torch.equal(grid[0][0][0].weight, grid[0][1][0].weight)
+    init_mlp_weights_xavier_uniform(torch.nn.ReLU())  # no-op on other layers
+
+    from torchrec_b200.modules.regroup import KTRegroupAsDict
+
+    re = KTRegroupAsDict([["x"], ["y"]], ["g0", "g1"])
+    kt = KeyedTensor(keys=["x", "y"], length_per_key=[2, 1], values=torch.randn(2, 3))
+    re([kt])
+    assert re._is_inited
+    reset_module_states_post_sharding(torch.nn.Sequential(re))
+    assert not re._is_inited
+    assert torch.equal(re([kt])["g1"], kt["y"])

@@ -156,6 +156,9 @@ class DistributedModelParallel(nn.Module, FusedOptimizerModule):
             self._init_parameters(self.module)
         if init_data_parallel:
             self.init_data_parallel()
+        from ..modules.utils import reset_module_states_post_sharding
+
+        reset_module_states_post_sharding(self._dmp_wrapped_module)  # caches taken on the unsharded model (KTRegroupAsDict, ...) are stale now
         self._model_tracker = None
         if model_tracker_config is not None:
             from .model_tracker import ModelDeltaTracker

@@ -9,6 +9,7 @@ all-to-all uses. The implementation is new: all jagged math goes through
 """
 from __future__ import annotations
 
+import abc
 import operator
 from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
 
@@ -90,7 +91,12 @@ def _pin_and_move(t: torch.Tensor, device: torch.device) -> torch.Tensor:
 
 
 # ---------------------------------------------------------------------------------------------
-class JaggedTensor(Pipelineable):
+class JaggedTensorMeta(abc.ABCMeta, torch.fx._symbolic_trace.ProxyableClassMeta):
+    """Constructing a JaggedTensor / KeyedJaggedTensor / KeyedTensor from fx proxies inside a symbolic trace records a node instead of
+    failing (reference jagged_tensor.py:630)."""
+
+
+class JaggedTensor(Pipelineable, metaclass=JaggedTensorMeta):
     """A tensor with one jagged dimension: ``values`` [sum L (, D)] + ``lengths`` / ``offsets`` [B]."""
 
     _fields = ["_values", "_weights", "_lengths", "_offsets"]
@@ -241,7 +247,7 @@ def _perm_index_tensor(indices: List[int], device: torch.device) -> torch.Tensor
     return t
 
 
-class KeyedJaggedTensor(Pipelineable):
+class KeyedJaggedTensor(Pipelineable, metaclass=JaggedTensorMeta):
     """Multi-feature jagged batch (see module docstring). Layout: values are key-major; lengths are
     ``[F * B]`` (or a per-key variable batch when ``stride_per_key_per_rank`` is given)."""
 
@@ -734,7 +740,7 @@ def unflatten_kjt_list(values, contexts) -> List[KeyedJaggedTensor]:
 
 
 # ---------------------------------------------------------------------------------------------
-class KeyedTensor(Pipelineable):
+class KeyedTensor(Pipelineable, metaclass=JaggedTensorMeta):
     """Dense tensor whose ``key_dim`` is a concatenation of per-key blocks ([B, sum(D)] for pooled
     embeddings). Parity: jagged_tensor.py:3503-3770."""
 
@@ -851,6 +857,18 @@ def _kt_unflatten(values, context) -> KeyedTensor:
 
 
 register_pytree_node(KeyedTensor, _kt_flatten, _kt_unflatten, serialized_type_name="torchrec_b200.sparse.KeyedTensor")
+
+
+def jt_is_equal(jt_1: "JaggedTensor", jt_2: "JaggedTensor") -> bool:
+    """Same values, weights, lengths and offsets (an optional field must be present on both sides or on neither)."""
+    if not isinstance(jt_1, JaggedTensor) or not isinstance(jt_2, JaggedTensor):
+        return False
+    if jt_1.values().shape != jt_2.values().shape or not torch.allclose(jt_1.values(), jt_2.values()):
+        return False
+    wa, wb = jt_1.weights_or_none(), jt_2.weights_or_none()
+    if (wa is None) != (wb is None) or (wa is not None and (wa.shape != wb.shape or not torch.allclose(wa, wb))):
+        return False
+    return torch.equal(jt_1.lengths(), jt_2.lengths()) and torch.equal(jt_1.offsets(), jt_2.offsets())
 
 
 def kjt_is_equal(a: "KeyedJaggedTensor", b: "KeyedJaggedTensor") -> bool:
