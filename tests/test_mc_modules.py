@@ -111,3 +111,43 @@ def test_raw_id_tracker_streams_latest_raw_id_per_row():
     mcc.eval()
     mcc(KeyedJaggedTensor.from_lengths_sync(["f"], raw2, torch.tensor([1, 1])))
     assert tracker.get_raw_id_map("a") == {}                       # eval lookups are not tracked
+
+
+def test_train_input_mapper_and_merged_serving_module():
+    """MPZCH trained row-wise sharded, served from one merged identity table: every id is probed inside the range of the rank that
+    owned it in training and gets the slot training gave it; ids never seen fall back inside that range."""
+    from torchrec_b200.modules.hash_mc_modules import HashZchManagedCollisionModule, TrainInputMapper
+    from torchrec_b200.modules.mc_modules import apply_mc_method_to_jt_dict
+    from torchrec_b200.parallel.mc_modules import _owner_of
+    from torchrec_b200.sparse.jagged_tensor import JaggedTensor
+
+    W = 4
+    full = HashZchManagedCollisionModule(zch_size=256, device=torch.device("cpu"), total_num_buckets=W)
+    segs = [64 * i for i in range(W + 1)]
+    shards = [full.rebuild_with_output_id_range((segs[r], segs[r + 1]), segs) for r in range(W)]
+    g = torch.Generator().manual_seed(0)
+    ids = torch.randint(0, 10**9, (150,), generator=g)
+    owner = _owner_of(ids, W)
+    train_slots = torch.empty_like(ids)
+    for r in range(W):
+        m = owner == r
+        shards[r].train()
+        train_slots[m] = shards[r]({"f": JaggedTensor(values=ids[m], lengths=torch.ones(int(m.sum()), dtype=torch.long))})["f"].values()
+    merged = HashZchManagedCollisionModule.merge_trained_shards(shards)
+    feats = {"f": JaggedTensor(values=ids, lengths=torch.ones(150, dtype=torch.long))}
+    got = apply_mc_method_to_jt_dict(merged, "remap", feats)["f"].values()
+    assert torch.equal(got, train_slots)
+    before = merged._hash_zch_identities.clone()
+    unseen = torch.randint(10**9, 2 * 10**9, (40,), generator=g)
+    out = merged({"f": JaggedTensor(values=unseen, lengths=torch.ones(40, dtype=torch.long))})["f"].values()
+    assert torch.equal(merged._hash_zch_identities, before), "serving never inserts"
+    lo = torch.tensor(segs)[_owner_of(unseen, W)]
+    assert bool(((out >= lo) & (out < lo + 64)).all())
+    # the reference's dispatch rules
+    sizes, offs = torch.tensor([10, 20, 30]), torch.tensor([0, 10, 30])
+    mod = TrainInputMapper(input_hash_size=0, total_num_buckets=3, size_per_rank=sizes, train_rank_offsets=offs, inference_dispatch_div_train_world_size=True)
+    v, s, o = mod(torch.tensor([0, 1, 2, 7]))
+    assert v.tolist() == [0, 0, 0, 2] and s.tolist() == [10, 20, 30, 20] and o.tolist() == [0, 10, 30, 10]
+    blk = TrainInputMapper(input_hash_size=100, total_num_buckets=3, size_per_rank=sizes, train_rank_offsets=offs)
+    v, s, o = blk(torch.tensor([0, 33, 34, 99]), output_offset=torch.tensor(10))
+    assert v.tolist() == [0, 33, 34, 99] and s.tolist() == [10, 10, 20, 30] and o.tolist() == [-10, -10, 0, 20]

@@ -119,6 +119,14 @@ class FeatureScoreBasedEvictionPolicy(VirtualTableEvictionPolicy):
 
 
 @dataclass
+class FeatureScoreMapping:
+    """Per-feature score weights of a virtual table (feature-score based eviction) and whether eviction is on."""
+
+    feature_score_mapping: Dict[str, float] = field(default_factory=dict)
+    eviction_enabled: bool = False
+
+
+@dataclass
 class TimestampBasedEvictionPolicy(VirtualTableEvictionPolicy):
     training_id_eviction_trigger_count: int = 0
     eviction_ttl_mins: int = 24 * 60
@@ -232,3 +240,13 @@ class QuantConfig(NamedTuple):
     activation: object
     weight: object
     per_table_weight_dtype: Optional[Dict[str, torch.dtype]] = None
+
+
+def data_type_to_sparse_type(data_type: DataType) -> str:
+    """Row format name of a table data type. The reference returns FBGEMM's ``SparseType`` enum; this framework has no FBGEMM and its
+    kernels key on the lower-case format name (``"fp32"``, ``"fp16"``, ``"bf16"``, ``"int8"``, ``"int4"``, ``"int2"``, ``"fp8"``)."""
+    names = {"FP32": "fp32", "FP16": "fp16", "BF16": "bf16", "INT8": "int8", "UINT8": "int8", "INT4": "int4", "INT2": "int2", "FP8": "fp8", "NFP8": "fp8"}
+    key = data_type.name if hasattr(data_type, "name") else str(data_type)
+    if key not in names:
+        raise ValueError(f"Invalid DataType {data_type}")
+    return names[key]

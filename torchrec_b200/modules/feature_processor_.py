@@ -58,6 +58,11 @@ def get_weights_list(cat_seq: torch.Tensor, features: KeyedJaggedTensor, positio
     return torch.cat(weights_list) if weights_list else features.weights_or_none()
 
 
+def get_stride_per_key_per_rank(kjt: KeyedJaggedTensor) -> Optional[List[List[int]]]:
+    """The per-key per-rank batch sizes of a variable-batch KJT, None for a fixed batch."""
+    return kjt.stride_per_key_per_rank() if kjt.variable_stride_per_key() else None
+
+
 class PositionWeightedModuleCollection(FeatureProcessorsCollection, CopyMixIn):
     """One position-weight vector per feature (``max_feature_lengths``: feature -> max length)."""
 

@@ -67,6 +67,55 @@ def _mix64(x: torch.Tensor) -> torch.Tensor:
     return x ^ (x >> 31)
 
 
+class TrainInputMapper(torch.nn.Module):
+    """Maps inference ids to the chunk of the identity table they lived in during training. Row-wise sharded training gives every
+    dispatch unit (a training rank, or one of its buckets) its own range of the identity table; for serving the ranges are merged
+    into one table and every id must be probed inside the range its training unit owned (reference hash_mc_modules.py:82).
+
+    ``forward(values, output_offset)`` -> (values, local_sizes, offsets): per id the size and the start of its unit's range
+    (minus ``output_offset``). The unit of an id follows the input dist of training: ``"modulo"`` (``id % units`` - the reference's rule
+    for ``input_hash_size == 0``), ``"block"`` (``id // ceil(input_hash_size / units)`` - the reference's rule otherwise) or ``"hash"``
+    (the multiplicative hash this framework's sharded managed-collision collection dispatches with); ``"auto"`` picks modulo / block
+    from ``input_hash_size`` like the reference. With ``inference_dispatch_div_train_world_size`` the ids are reduced the way the
+    training input dist reduced them (``id // units`` / ``id % block``)."""
+
+    def __init__(self, input_hash_size: int, total_num_buckets: int, size_per_rank: torch.Tensor, train_rank_offsets: torch.Tensor,
+                 inference_dispatch_div_train_world_size: bool = False, name: Optional[str] = None, dispatch: str = "auto") -> None:
+        super().__init__()
+        assert total_num_buckets > 0, f"{total_num_buckets=} must be positive"
+        assert dispatch in ("auto", "modulo", "block", "hash")
+        self._input_hash_size = input_hash_size
+        self._buckets = total_num_buckets
+        self._inference_dispatch_div_train_world_size = inference_dispatch_div_train_world_size
+        self._name = name
+        self._dispatch = dispatch if dispatch != "auto" else ("modulo" if input_hash_size == 0 else "block")
+        self.register_buffer("_zch_size_per_training_rank", size_per_rank.to(torch.int64), persistent=False)
+        self.register_buffer("_train_rank_offsets", train_rank_offsets.to(torch.int64), persistent=False)
+
+    def _get_values_sizes_offsets(self, x: torch.Tensor, output_offset: Optional[torch.Tensor]):
+        sizes, offs = self._zch_size_per_training_rank.to(x.device), self._train_rank_offsets.to(x.device)
+        if self._dispatch == "hash":
+            h = (x ^ (x >> 31)) * -7046029254386353131
+            unit = torch.remainder(h ^ (h >> 29), self._buckets)
+        elif self._dispatch == "modulo":
+            unit = x % self._buckets
+            if self._inference_dispatch_div_train_world_size:
+                x = x // self._buckets
+        else:
+            blk = self._input_hash_size // self._buckets + (0 if self._input_hash_size % self._buckets == 0 else 1)
+            unit = (x // blk).clamp(max=self._buckets - 1)
+            if self._inference_dispatch_div_train_world_size:
+                x = x % blk
+        local_sizes = sizes.index_select(0, unit)
+        offsets = offs.index_select(0, unit)
+        if output_offset is not None:
+            offsets = offsets - output_offset
+        return x, local_sizes, offsets
+
+    def forward(self, values: torch.Tensor, output_offset: Optional[torch.Tensor] = None):
+        return self._get_values_sizes_offsets(values.to(torch.int64), output_offset)
+
+
 class HashZchManagedCollisionModule(ManagedCollisionModule):
     def __init__(self, zch_size: int, device: torch.device, total_num_buckets: int, max_probe: int = 128, input_hash_size: int = (2**63) - 1,
                  output_segments: Optional[List[int]] = None, is_inference: bool = False, name: Optional[str] = None, tb_logging_frequency: int = 0,
@@ -101,6 +150,8 @@ class HashZchManagedCollisionModule(ManagedCollisionModule):
         self._evicted_pending: List[torch.Tensor] = []  # CUDA probe: per-id evicted slot or -1, compacted when evict() is called
         self._counters: Optional[torch.Tensor] = None
         self._device_steps = 0
+        self._train_input_mapper: Optional[TrainInputMapper] = None
+        self._train_unit_buckets = 1
 
     def preprocess(self, features: Dict[str, JaggedTensor]) -> Dict[str, JaggedTensor]:
         return features
@@ -145,27 +196,65 @@ class HashZchManagedCollisionModule(ManagedCollisionModule):
         return self._scalar_logger() if self._scalar_logger is not None else {}
 
     @torch.no_grad()
+    def set_train_input_mapper(self, mapper: Optional[TrainInputMapper], buckets_per_unit: int = 1) -> None:
+        """Serving a table whose identities were trained row-wise sharded and merged afterwards: every id is probed inside the range of
+        its training unit (``buckets_per_unit`` buckets each, as the unit's module had them). Lookups only."""
+        self._train_input_mapper = mapper
+        self._train_unit_buckets = buckets_per_unit
+
+    @classmethod
+    def merge_trained_shards(cls, shards: List["HashZchManagedCollisionModule"], device: Optional[torch.device] = None, **kwargs) -> "HashZchManagedCollisionModule":
+        """One serving module from the per-rank modules of a row-wise sharded training run (rank order): identities / metadata are
+        concatenated, a ``TrainInputMapper`` with this framework's dispatch hash sends every id to its training rank's range."""
+        first = shards[0]
+        dev = device or first._hash_zch_identities.device
+        sizes = [m._zch_size for m in shards]
+        total = sum(sizes)
+        merged = cls(zch_size=total, device=dev, total_num_buckets=len(shards), max_probe=first._max_probe, input_hash_size=first._input_hash_size,
+                     output_segments=[sum(sizes[:i]) for i in range(len(shards) + 1)], is_inference=True, name=first._name, disable_fallback=first._disable_fallback, **kwargs)
+        merged._hash_zch_identities.copy_(torch.cat([m._hash_zch_identities.to(dev) for m in shards]))
+        merged._hash_zch_metadata.copy_(torch.cat([m._hash_zch_metadata.to(dev) for m in shards]))
+        offs = torch.tensor([sum(sizes[:i]) for i in range(len(shards))], dtype=torch.int64)
+        merged.set_train_input_mapper(TrainInputMapper(first._input_hash_size, len(shards), torch.tensor(sizes, dtype=torch.int64), offs, dispatch="hash", name=first._name),
+                                      buckets_per_unit=first._buckets_local)
+        return merged
+
+    def _probe_mapped(self, ids: torch.Tensor) -> torch.Tensor:
+        vals, sizes, offsets = self._train_input_mapper(ids)
+        out = torch.empty_like(ids)
+        ident, meta = self._hash_zch_identities.view(-1), self._hash_zch_metadata.view(-1)
+        for off in torch.unique(offsets).tolist():
+            m = offsets == off
+            size = int(sizes[m][0])
+            nb = max(self._train_unit_buckets, 1)
+            out[m] = self._probe_torch(vals[m], True, ident[off : off + size], meta[off : off + size], nb, size // nb) + off
+        return out
+
     def _probe(self, ids: torch.Tensor, readonly: bool) -> torch.Tensor:
         n = ids.numel()
         if n == 0:
             return ids
+        if self._train_input_mapper is not None:
+            return self._probe_mapped(ids)
         if _lib.use_cuda_kernels(ids):
             return self._probe_cuda(ids, readonly)
-        ident = self._hash_zch_identities.view(-1)
-        meta = self._hash_zch_metadata.view(-1)
+        return self._probe_torch(ids, readonly, self._hash_zch_identities.view(-1), self._hash_zch_metadata.view(-1), self._buckets_local, self._bucket_size)
+
+    def _probe_torch(self, ids: torch.Tensor, readonly: bool, ident: torch.Tensor, meta: torch.Tensor, buckets_local: int, bucket_size: int) -> torch.Tensor:
+        n = ids.numel()
         h = _mix64(ids)
-        bucket = torch.remainder(h, max(self._buckets_local, 1))
-        start = torch.remainder(h >> 16, max(self._bucket_size, 1))
+        bucket = torch.remainder(h, max(buckets_local, 1))
+        start = torch.remainder(h >> 16, max(bucket_size, 1))
         out = torch.full_like(ids, -1)
         pending = torch.ones(n, dtype=torch.bool, device=ids.device)
         now = self._now()
         ttl = self._eviction_config.single_ttl if (self._eviction_config and self._eviction_config.single_ttl) else None
         hits = inserts = 0
-        for p in range(min(self._max_probe, max(self._bucket_size, 1))):
+        for p in range(min(self._max_probe, max(bucket_size, 1))):
             if not bool(pending.any()):
                 break
             idx = pending.nonzero(as_tuple=True)[0]
-            slot = bucket[idx] * self._bucket_size + torch.remainder(start[idx] + p, max(self._bucket_size, 1))
+            slot = bucket[idx] * bucket_size + torch.remainder(start[idx] + p, max(bucket_size, 1))
             cur = ident[slot]
             hit = cur == ids[idx]
             out[idx[hit]] = slot[hit]
@@ -206,7 +295,7 @@ class HashZchManagedCollisionModule(ManagedCollisionModule):
         if self._scalar_logger is not None:
             self._scalar_logger.update(hits, inserts, int(pending.sum()), n)
         # ids that found no slot fall back to their start slot (collision) unless disabled
-        fb = bucket * self._bucket_size + start
+        fb = bucket * bucket_size + start
         out = torch.where(out >= 0, out, fb if not self._disable_fallback else torch.full_like(out, -1))
         return out
 

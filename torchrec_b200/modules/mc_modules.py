@@ -18,6 +18,12 @@ from torch import nn
 from ..sparse.jagged_tensor import JaggedTensor, KeyedJaggedTensor
 
 
+def apply_mc_method_to_jt_dict(mc_module: nn.Module, method: str, features_dict: Dict[str, JaggedTensor]) -> Dict[str, JaggedTensor]:
+    """``getattr(mc_module, method)(features_dict)`` - the named step (``preprocess`` / ``profile`` / ``remap``) of a managed-collision
+    module on a dict of jagged tensors, same key order out (reference mc_modules.py:24)."""
+    return getattr(mc_module, method)(features_dict)
+
+
 class ManagedCollisionModule(nn.Module):
     """Abstract remapper of the ids of one table."""
 

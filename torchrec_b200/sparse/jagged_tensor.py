@@ -93,7 +93,12 @@ def _pin_and_move(t: torch.Tensor, device: torch.device) -> torch.Tensor:
 # ---------------------------------------------------------------------------------------------
 class JaggedTensorMeta(abc.ABCMeta, torch.fx._symbolic_trace.ProxyableClassMeta):
     """Constructing a JaggedTensor / KeyedJaggedTensor / KeyedTensor from fx proxies inside a symbolic trace records a node instead of
-    failing (reference jagged_tensor.py:630)."""
+    failing (reference jagged_tensor.py:630). Outside a trace construction is the plain one (one module-flag read per call)."""
+
+    def __call__(cls, *args, **kwargs):
+        if not torch.fx._symbolic_trace._is_fx_tracing_flag:
+            return type.__call__(cls, *args, **kwargs)
+        return torch.fx._symbolic_trace.ProxyableClassMeta.__call__(cls, *args, **kwargs)
 
 
 class JaggedTensor(Pipelineable, metaclass=JaggedTensorMeta):
