@@ -1,4 +1,5 @@
 """The shipped testing toolkit (``torchrec_b200.distributed.test_utils``): synthetic inputs, reference models, pinned sharders, configs, harness."""
+import pytest
 import torch
 
 from torchrec_b200.utils.multiprocess import run_multi_process
@@ -69,3 +70,50 @@ def test_configs_drive_a_sharded_training_run():
     from torchrec_b200.distributed.test_utils import run_multi_process_func
 
     run_multi_process_func(_train_with_configs, world_size=2, backend="gloo", steps=3)
+
+
+def test_infer_utils_quantize_shard_compare():
+    """The inference test kit: TestSparseNN behind a plain-tensor signature, its quantized copy, the quantized copy sharded over two local
+    devices with a forced sharding type - all three agree; expected shards are checked against the plan; mock kernels keep shapes."""
+    import torch
+
+    from torchrec_b200.parallel.test_utils.infer_utils import (KJTInputExportWrapper, MockTBE, assert_close, create_cw_min_partition_constraints, create_test_model,
+                                                               create_test_model_ebc_only, model_input_to_forward_args, model_input_to_forward_args_kjt, prep_inputs,
+                                                               prep_inputs_multiprocess, quantize, replace_registered_tbes_with_mock_tbes, shard_qebc)
+    from torchrec_b200.parallel.types import ShardingType
+
+    dev = torch.device("cpu")
+    mi = create_test_model(num_embeddings=64, emb_dim=16, world_size=2, batch_size=4, dense_device=dev, sparse_device=dev, num_features=2, num_weighted_features=1)
+    inputs = prep_inputs(mi, 2, batch_size=4, count=2)
+    assert len(prep_inputs_multiprocess(mi, 2, 4, count=3)) == 3
+    for st in (ShardingType.TABLE_WISE, ShardingType.ROW_WISE, ShardingType.COLUMN_WISE):
+        sharded = shard_qebc(mi, st, dev, shard_score_ebc=True)
+        assert type(sharded._module.sparse.ebc).__name__ == "ShardedQuantEmbeddingBagCollection"
+        for b in inputs:
+            args = model_input_to_forward_args(b)
+            assert_close(mi.quant_model(*args), sharded(*args))
+            # int8 rows: close to the float model, not equal
+            assert float((mi.model(*args) - mi.quant_model(*args)).abs().max()) < 0.05
+    rw = [[((0, 0, 32, 16), "rank:0/cpu"), ((32, 0, 32, 16), "rank:1/cpu")]] * 2
+    shard_qebc(mi, ShardingType.ROW_WISE, dev, expected_shards=rw)
+    with pytest.raises(AssertionError):
+        shard_qebc(mi, ShardingType.ROW_WISE, dev, expected_shards=[[((0, 0, 64, 16), "rank:0/cpu")]] * 2)
+    cons = create_cw_min_partition_constraints([("table_0", 8)])
+    assert cons["table_0"].min_partition == 8 and cons["table_0"].sharding_types == ["column_wise"]
+    # bags only, KJT arguments, kernels registered as sub-modules
+    mi2 = create_test_model_ebc_only(64, 16, 2, 4, dev, dev, num_features=2, compute_device="cpu")
+    b = prep_inputs(mi2, 2, 4, 1)[0]
+    a = model_input_to_forward_args_kjt(b)
+    out_q = mi2.quant_model(*a)
+    sh = shard_qebc(mi2, ShardingType.TABLE_WISE, dev, ebc_fqn="_module_kjt_input.sparse.ebc")
+    assert_close(out_q, sh(*a))
+    export = KJTInputExportWrapper(mi2.quant_model._module_kjt_input, a[0])
+    assert_close([out_q.values()], export(a[1], a[3]))
+    with pytest.raises(AssertionError):
+        assert_close(out_q, mi2.model(*a))  # float vs int8 rows differ beyond the default tolerance
+    int4 = quantize(mi2.model, inplace=False, weight_dtype=torch.quint4x2)
+    assert float((int4(*a).values() - mi2.model(*a).values()).abs().max()) < 0.5
+    replace_registered_tbes_with_mock_tbes(mi2.quant_model)
+    mocks = [m for m in mi2.quant_model.modules() if isinstance(m, MockTBE)]
+    assert mocks and sum(len(m.embedding_specs) for m in mocks) == 2
+    assert mi2.quant_model(*a).values().shape == out_q.values().shape and float(mi2.quant_model(*a).values().abs().sum()) == 0.0

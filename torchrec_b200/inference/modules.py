@@ -184,8 +184,8 @@ def quantize_inference_model(model: torch.nn.Module, quantization_mapping: Optio
 
 def shard_quant_model(model: torch.nn.Module, world_size: int = 1, compute_device: str = "cuda", sharding_device: str = "meta",
                       sharders: Optional[List[Any]] = None, device_memory_size: Optional[int] = None, constraints: Optional[Dict[str, Any]] = None,
-                      ddr_cap: Optional[int] = None) -> Tuple[torch.nn.Module, Any]:
-    """Plan (inference cost model, no reservation) and shard a quantized model over ``world_size`` local devices."""
+                      ddr_cap: Optional[int] = None, sharding_plan: Optional[Any] = None) -> Tuple[torch.nn.Module, Any]:
+    """Plan (inference cost model, no reservation; or take ``sharding_plan``) and shard a quantized model over ``world_size`` local devices."""
     from ..parallel.planner import EmbeddingShardingPlanner, Topology
     from ..parallel.planner.enumerators import EmbeddingEnumerator, EmbeddingPerfEstimator, EmbeddingStorageEstimator
     from ..parallel.planner.storage_reservations import FixedPercentageStorageReservation
@@ -206,7 +206,7 @@ def shard_quant_model(model: torch.nn.Module, world_size: int = 1, compute_devic
                                                 EmbeddingStorageEstimator(topology=topology, constraints=constraints, is_inference=True)])
     planner = EmbeddingShardingPlanner(topology=topology, batch_size=1, enumerator=enumerator, storage_reservation=FixedPercentageStorageReservation(percentage=0.0),
                                        constraints=constraints)
-    plan = planner.plan(model, sharders)
+    plan = sharding_plan if sharding_plan is not None else planner.plan(model, sharders)
     sharded = _shard_modules(module=model, device=torch.device(compute_device), sharders=sharders, env=ShardingEnv.from_local(world_size=world_size, rank=0), plan=plan)
     return sharded, plan
 
