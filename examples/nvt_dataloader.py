@@ -81,6 +81,35 @@ class NvtBinaryDataset(torch.utils.data.Dataset):
             yield self[i]
 
 
+class NvtSplitBinaryDataset(NvtBinaryDataset):
+    """The per-column layout ``torchrec_b200.datasets.scripts.nvt.split_binary_dataset`` writes (the reference's NVT dataloader layout):
+    ``numerical.bin`` float32 [N, 13], ``label.bin`` float32 [N], ``cat_<i>.bin`` int32 [N] for i in 0..25. One contiguous read per
+    column file per batch; the ids arrive feature-major, which is the KJT value order."""
+
+    def __init__(self, directory: str, batch_size: int, rank: int = 0, world_size: int = 1, drop_last: bool = True, pin_memory: bool = False) -> None:
+        self.n = os.path.getsize(os.path.join(directory, "label.bin")) // 4
+        self.B, self.rank, self.world = batch_size, rank, world_size
+        self.labels = np.memmap(os.path.join(directory, "label.bin"), dtype=np.float32, mode="r", shape=(self.n,))
+        self.dense = np.memmap(os.path.join(directory, "numerical.bin"), dtype=np.float32, mode="r", shape=(self.n, NUM_DENSE))
+        self.cats = [np.memmap(os.path.join(directory, f"cat_{i}.bin"), dtype=np.int32, mode="r", shape=(self.n,)) for i in range(NUM_SPARSE)]
+        total = self.n // batch_size if drop_last else -(-self.n // batch_size)
+        self.num_batches = total // world_size
+        self.pin = pin_memory and torch.cuda.is_available()
+        self._lengths = torch.ones(NUM_SPARSE * batch_size, dtype=torch.int32)
+
+    def __getitem__(self, i: int) -> Batch:
+        if not 0 <= i < self.num_batches:
+            raise IndexError(i)
+        lo = (i * self.world + self.rank) * self.B
+        hi = min(lo + self.B, self.n)
+        dense = torch.from_numpy(np.array(self.dense[lo:hi], dtype=np.float32))
+        labels = torch.from_numpy(np.array(self.labels[lo:hi], dtype=np.float32))
+        ids = torch.from_numpy(np.concatenate([c[lo:hi] for c in self.cats]).astype(np.int64))  # feature-major: [26 * B]
+        lengths = self._lengths if hi - lo == self.B else torch.ones(NUM_SPARSE * (hi - lo), dtype=torch.int32)
+        b = Batch(dense_features=dense, sparse_features=KeyedJaggedTensor(keys=KEYS, values=ids, lengths=lengths, stride=hi - lo), labels=labels)
+        return b.pin_memory() if self.pin else b
+
+
 def main(steps: int = 60, batch_size: int = 256, directory: Optional[str] = None) -> float:
     from torchrec_b200.models.dlrm import DLRM, DLRMTrain
     from torchrec_b200.modules.embedding_configs import EmbeddingBagConfig
