@@ -550,3 +550,61 @@ def test_pt2_utils_transformer_compile_switch_and_queue():
     c.set(7)
     assert c.get() == 7
     register_fake_classes()
+
+
+def test_distributed_benchmark_package(tmp_path):
+    """``torchrec_b200.distributed.benchmark``: the harness modules under the reference's names, the micro-benchmarks run on CPU, trace /
+    snapshot post-processing on synthetic files."""
+    import importlib
+    import json
+    import pickle
+
+    import torch
+
+    base = importlib.import_module("torchrec_b200.distributed.benchmark.base")
+    import torchrec_b200.benchmarks.base as real_base
+
+    assert base is real_base and importlib.import_module("torchrec_b200.distributed.benchmark.benchmark_train_pipeline").__name__ == "torchrec_b200.benchmarks.benchmark_train_pipeline"
+    from torchrec_b200.distributed.benchmark import utils as bu
+    from torchrec_b200.distributed.benchmark.benchmark_set_sharding_context_post_a2a import _set_sharding_context_post_a2a_previous, op_bench as ctx_bench
+    from torchrec_b200.distributed.benchmark.benchmark_split_table_batched_embeddings import op_bench as tbe_bench
+    from torchrec_b200.distributed.benchmark.benchmark_train import benchmark_ec_write
+    from torchrec_b200.distributed.benchmark.embedding_collection_wrappers import benchmark_ebc_module, get_tables
+    from torchrec_b200.parallel.embedding_sharding import _set_sharding_context_post_a2a
+
+    r = tbe_bench(1000, 16, 2, 32, 4, num_benchmarks=2, device="cpu")
+    assert r.gpu_elapsed_time.numel() == 2 and r.qps is not None and r.cpu_mem_stats and "fwdbwd" in r.short_name
+    assert ctx_bench(20, 5, _set_sharding_context_post_a2a_previous)["ms"] > 0 and ctx_bench(20, 5, _set_sharding_context_post_a2a)["ms"] > 0
+    w = benchmark_ec_write(num_embeddings=500, embedding_dim=8, num_tables=2, batch_size=16, iters=2, device=torch.device("cpu"))
+    assert "ec_write_read" in w.short_name
+    # a sharded EBC under two sharding types, 2 gloo ranks
+    from torchrec_b200.modules.embedding_configs import DataType
+    from torchrec_b200.modules.embedding_modules import EmbeddingBagCollection
+    from torchrec_b200.optim.apply_optimizer_in_backward import apply_optimizer_in_backward
+    from torchrec_b200.parallel.embeddingbag import EmbeddingBagCollectionSharder
+    from torchrec_b200.parallel.types import ShardingType
+
+    tables = get_tables([(200, 8), (100, 8)], data_type=DataType.FP32)
+    ebc = EmbeddingBagCollection(tables)
+    apply_optimizer_in_backward(torch.optim.SGD, ebc.parameters(), {"lr": 0.1})
+    res = benchmark_ebc_module(ebc, EmbeddingBagCollectionSharder(), [ShardingType.TABLE_WISE, ShardingType.ROW_WISE], [base.CompileMode.EAGER], tables, warmup_iters=1,
+                               bench_iters=2, prof_iters=1, batch_size=8, world_size=2, num_benchmarks=2, device_type="cpu")
+    assert [x.short_name for x in res] == ["table_wise-eager", "row_wise-eager"] and all(x.gpu_elapsed_time.numel() == 2 for x in res)
+    report = tmp_path / "report.txt"
+    base.write_report(res, str(report), "header\n", num_requests=16)
+    assert "table_wise-eager" in report.read_text() and "Avg QPS" in report.read_text()
+    out = bu.dump_benchmark_result(res[0], str(tmp_path / "json"), extra={"note": "x"})
+    assert json.load(open(out))["name"] == "table_wise-eager"
+    # chrome trace: two streams, [0, 10) + [5, 20) on stream 7, [30, 40) on stream 9 over a span of 40 us
+    trace = {"traceEvents": [{"ph": "X", "cat": "kernel", "ts": 0, "dur": 10, "args": {"stream": 7}}, {"ph": "X", "cat": "kernel", "ts": 5, "dur": 15, "args": {"stream": 7}},
+                             {"ph": "X", "cat": "gpu_memcpy", "ts": 30, "dur": 10, "args": {"stream": 9}}, {"ph": "X", "cat": "cpu_op", "ts": 0, "dur": 100}]}
+    tp = tmp_path / bu.create_trace_file_name("p", 0)
+    tp.write_text(json.dumps(trace))
+    u = bu.parse_chrome_trace_gpu_utilization(str(tp))
+    assert u["gpu_utilization"] == 30 / 40 and u["stream_7_utilization"] == 20 / 40 and u["stream_9_utilization"] == 10 / 40
+    snap = {"device_traces": [[{"action": "alloc", "size": 4 << 20, "stream": 0}, {"action": "alloc", "size": 2 << 20, "stream": 3}, {"action": "free_completed", "size": 4 << 20, "stream": 0},
+                               {"action": "alloc", "size": 1 << 20, "stream": 0}]]}
+    sp_ = tmp_path / bu.create_snapshot_file_name("p", 0)
+    sp_.write_bytes(pickle.dumps(snap))
+    assert bu.parse_memory_snapshot_peak_per_stream(str(sp_)) == {"stream_0_peak_mb": 4.0, "stream_3_peak_mb": 2.0, "total_peak_mb": 6.0}
+    assert bu.get_cpu_type() and bu.get_gpu_type()
