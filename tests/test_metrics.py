@@ -254,3 +254,34 @@ def test_per_metric_modules_and_functional_helpers():
     torch.testing.assert_close(compute_rauc(1, torch.tensor([[0.1, 0.2, 0.3]]), torch.tensor([[1.0, 2.0, 3.0]]), torch.ones(1, 3)), torch.ones(1, dtype=torch.double))
     xs = get_xauc_states(torch.tensor([[1.0, 2.0, 3.0]]), torch.tensor([[0.1, 0.3, 0.2]]), torch.ones(1, 3))
     torch.testing.assert_close(compute_xauc(xs["error_sum"], xs["weighted_num_pairs"]), torch.tensor([2.0 / 3.0], dtype=torch.double))
+
+
+def test_mock_rec_metric_records_calls_and_exposes_states():
+    from torchrec_b200.metrics.rec_metric import RecComputeMode
+    from torchrec_b200.metrics.test_utils import (MockRecMetric, assert_tensor_dict_equals, create_metric_states_dict, create_tensor_list_states, create_tensor_states)
+
+    tasks = [RecTaskInfo(name="a"), RecTaskInfo(name="b")]
+    init = create_tensor_states(["s1", "s2"])
+    m = MockRecMetric(world_size=1, my_rank=0, batch_size=4, tasks=tasks, initial_states={k: v.clone() for k, v in init.items()})
+    assert not m.update_called() and not m.compute_called() and m.verify_sync_disabled()
+    p = {"a": torch.rand(4), "b": torch.rand(4)}
+    m.update(predictions=p, labels=p, weights=None)
+    m.update(predictions=p, labels=p, weights=p)
+    assert m.update_called_count == 2 and m.predictions_update_calls[0] is p and m.weights_update_calls == [None, p] and m.compute() == {} and m.compute_called()
+    assert_tensor_dict_equals(m.get_computation_states(), init)
+    m.add_to_computation_states({"s1": torch.ones(1)})
+    assert_tensor_dict_equals(m.get_computation_states(), {"s1": init["s1"] + 1, "s2": init["s2"]})
+    m.set_computation_states({"s2": torch.zeros(1)})
+    assert float(m.get_computation_states()["s2"]) == 0.0 and len(m._metrics_computations) == 2
+    m.reset()
+    assert not m.update_called() and not m.compute_called()
+    with pytest.raises(AssertionError):
+        assert_tensor_dict_equals(m.get_computation_states(), init)
+    lists = create_tensor_list_states(["preds", "labels"])
+    fused = MockRecMetric(world_size=1, my_rank=0, batch_size=4, tasks=tasks, compute_mode=RecComputeMode.FUSED_TASKS_COMPUTATION, initial_states=lists, is_tensor_list=True,
+                          reduction_fn="cat")
+    assert len(fused._metrics_computations) == 1
+    extra = torch.rand(1, 3)
+    fused.append_to_computation_states({"preds": extra})
+    assert_tensor_dict_equals(fused.get_computation_states(), {"preds": lists["preds"] + [extra], "labels": lists["labels"]})
+    assert create_metric_states_dict("a", "MockRecMetricComputation", {"s1": 1}) == {"a_MockRecMetricComputation_s1": 1}
