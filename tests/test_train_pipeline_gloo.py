@@ -166,3 +166,78 @@ def _bounded_queue(ctx):
 
 def test_sparse_dist_queue_is_bounded_without_execute_all_batches():
     run_multi_process(_bounded_queue, world_size=2, backend="gloo")
+
+
+def _run_eval_fused(ctx):
+    """EvalPipelineFusedSparseDist: outputs equal the plain eval forward batch by batch, weights untouched, a detached model is
+    re-attached by progress."""
+    from torchrec_b200.datasets.random import RandomRecDataset
+    from torchrec_b200.parallel import train_pipeline as tp
+
+    dmp, opt, keys, hashes = _build(ctx, "tw")
+    ds = RandomRecDataset(keys, 6, hash_sizes=hashes, ids_per_feature=3, min_ids_per_feature=0, num_dense=5, manual_seed=3 + ctx.rank, num_generated_batches=4, num_batches=4)
+    batches = list(iter(ds))
+    dmp.eval()
+    with torch.no_grad():
+        want = [dmp(b) for b in batches]
+    def local(v):
+        if hasattr(v, "local_shards"):
+            return v.local_shards()[0].tensor if v.local_shards() else None
+        return v if isinstance(v, torch.Tensor) else None
+
+    before = {k: (local(v).clone() if local(v) is not None else None) for k, v in dmp.state_dict().items()}
+    pipe = tp.EvalPipelineFusedSparseDist(dmp, opt, torch.device("cpu"))
+    it = iter(batches)
+    got = [pipe.progress(it), pipe.progress(it)]
+    pipe.detach()
+    assert not pipe._model_attached
+    while True:
+        try:
+            got.append(pipe.progress(it))  # re-attaches
+        except StopIteration:
+            break
+    assert pipe._model_attached and len(got) == len(want)
+    for g, w in zip(got, want):
+        g_pred, w_pred = g[1], w[1][1]  # the model returns (loss, (loss, logits, labels)); the pipeline hands out the inner tuple
+        torch.testing.assert_close(g_pred, w_pred, rtol=1e-5, atol=1e-6)
+        assert not g_pred.requires_grad
+    for k, v in dmp.state_dict().items():
+        cur = local(v)
+        if cur is not None and before[k] is not None:
+            assert torch.equal(cur, before[k]), k
+
+
+def test_eval_pipeline_fused_sparse_dist():
+    run_multi_process(_run_eval_fused, world_size=2, backend="gloo")
+
+
+def test_future_deque_and_postproc_context_switch():
+    from concurrent.futures import ThreadPoolExecutor
+
+    from torchrec_b200.parallel.train_pipeline.pipeline_context import CPUEmbeddingTrainPipelineContext, TrainPipelineContext
+    from torchrec_b200.parallel.train_pipeline.train_pipelines import TorchCompileConfig
+    from torchrec_b200.parallel.train_pipeline.utils import FutureDeque, get_h2d_func, use_context_for_postprocs
+
+    with ThreadPoolExecutor(1) as ex:
+        q = FutureDeque([ex.submit(lambda: 1), 2, ex.submit(lambda: 3), ex.submit(lambda: 4)])
+        assert q[0] == 1 and q[0] == 1 and q.pop() == 4 and q.popleft() == 1 and list(q)[0] == 2 and q[1] == 3
+
+    class P:
+        def __init__(self):
+            self.ctx = "cur"
+
+        def get_context(self):
+            return self.ctx
+
+        def set_context(self, c):
+            self.ctx = c
+
+    ps = [P(), P()]
+    nxt = TrainPipelineContext()
+    with use_context_for_postprocs(ps, nxt):
+        assert all(p.ctx is nxt for p in ps)
+    assert all(p.ctx == "cur" for p in ps)
+    c = CPUEmbeddingTrainPipelineContext(dense_gpu_device="cuda:0")
+    c.gpu_embedding_outputs["ebc"] = torch.zeros(1)
+    assert c.dense_gpu_device == "cuda:0" and TorchCompileConfig().compile_on_iter == 3
+    assert get_h2d_func(torch.ones(2), torch.device("cpu")).tolist() == [1.0, 1.0]

@@ -1,6 +1,9 @@
 from .pipeline_context import EmbeddingTrainPipelineContext, PrefetchTrainPipelineContext, TrainPipelineContext  # noqa: F401
 from .train_pipelines import (  # noqa: F401
+    EvalPipelineFusedSparseDist,
     EvalPipelineSparseDist,
+    ModelDetachedException,
+    TorchCompileConfig,
     PipelinedForward,
     PipelineStage,
     PrefetchTrainPipelineSparseDist,

@@ -39,3 +39,16 @@ class EmbeddingTrainPipelineContext(TrainPipelineContext):
     embedding_tensors: List[List[torch.Tensor]] = field(default_factory=list)
     embedding_features: List[List[Any]] = field(default_factory=list)
     detached_embedding_tensors: List[List[torch.Tensor]] = field(default_factory=list)
+
+
+@dataclass
+class CPUEmbeddingTrainPipelineContext(EmbeddingTrainPipelineContext):
+    """Embedding lookup on the host (tables in host memory / a parameter server), dense part on a GPU: the stage that copies the looked-up
+    embeddings to the device stores them here, keyed by the fqn of the embedding module (reference pipeline_context.py:101)."""
+
+    dense_gpu_device: str = field(default_factory=str)
+    gpu_embedding_outputs: Dict[str, Any] = field(default_factory=dict)
+
+
+In = Any
+Out = Any

@@ -14,6 +14,7 @@ pre-distributed input.
 from __future__ import annotations
 
 import abc
+from dataclasses import dataclass
 import contextlib
 import dataclasses
 import logging
@@ -66,6 +67,23 @@ def _wait_for_events(batch: In, context: TrainPipelineContext, stream: Optional[
     context.events.clear()
     if stream is not None:
         batch.record_stream(stream)
+
+
+class ModelDetachedException(Exception):
+    """A pipeline step was asked for while the model is detached (its sharded modules run their plain forward)."""
+
+
+@dataclass
+class TorchCompileConfig:
+    """``torch.compile`` options of ``TrainPipelinePT2`` when the caller asks for a tracing compiler (this framework's hot path is
+    hand-written kernels + CUDA graphs; nothing compiles unless ``compile_fn`` / this config is given): ``fullgraph`` - one graph or
+    error; ``dynamic`` - dynamic shapes (None: automatic); ``backend``; ``compile_on_iter`` - compile at this step, so the first steps
+    can be profiled uncompiled."""
+
+    fullgraph: bool = False
+    dynamic: Optional[bool] = None
+    backend: str = "inductor"
+    compile_on_iter: int = 3
 
 
 class TrainPipeline(abc.ABC, Generic[In, Out]):
@@ -727,6 +745,49 @@ class TrainPipelineFusedSparseDist(TrainPipelineSparseDist[In, Out]):
         return output
 
 
+class EvalPipelineFusedSparseDist(TrainPipelineFusedSparseDist[In, Out]):
+    """Evaluation through the fused pipeline: the embedding lookup of batch i+1 runs on the lookup stream while batch i is in the dense
+    forward; no backward, no optimizer step (in training mode the gradients are only cleared). A detached model is re-attached by
+    ``progress``. Reference train_pipelines.py:2396-2461."""
+
+    def progress(self, dataloader_iter: Iterator[In]) -> Out:
+        if not self._model_attached:
+            self.attach(self._model)
+        self.fill_pipeline(dataloader_iter)
+        if not self.batches:
+            raise StopIteration
+        ctx0 = self.contexts[0]
+        self._set_module_context(ctx0)
+        if self._model.training:
+            self._optimizer.zero_grad()
+        _wait_for_batch(self.batches[0], self._data_dist_stream)
+        if len(self.batches) >= 2:
+            self.start_sparse_data_dist(self.batches[1], self.contexts[1])
+        self.enqueue_batch(dataloader_iter)
+        pre = self._precomputed.pop(id(ctx0), None)
+        saved = []
+        if pre:
+            if self._emb_stream is not None:
+                torch.cuda.current_stream().wait_stream(self._emb_stream)
+            for pf, m in zip(self._pipelined_forwards, self._pipelined_modules):
+                if pf.name in pre:
+                    saved.append((m, m.forward))
+                    m.forward = (lambda r: (lambda *a, **k: r))(pre[pf.name])  # type: ignore[method-assign]
+        try:
+            with torch.no_grad():
+                losses, output = self._model_fwd(self.batches[0])
+        finally:
+            for m, f in saved:
+                m.forward = f  # type: ignore[method-assign]
+        if len(self.batches) >= 2:
+            self.wait_sparse_data_dist(self.contexts[1])
+            if self._emb_stream is not None:
+                self._emb_stream.wait_stream(torch.cuda.current_stream())
+            self._embedding_lookup(self.contexts[1])
+        self.dequeue_batch()
+        return output
+
+
 class PrefetchTrainPipelineSparseDist(TrainPipelineSparseDist[In, Out]):
     """Four-stage pipeline adding a cache-prefetch stage for host-offloaded (UVM-caching style)
     tables: the rows a batch will touch are staged into the HBM cache on a prefetch stream one
@@ -884,8 +945,13 @@ class TrainPipelinePT2(TrainPipelineBase[In, Out]):
 
     def __init__(self, model: nn.Module, optimizer: torch.optim.Optimizer, device: torch.device, compile_fn: Optional[Callable[[nn.Module], nn.Module]] = None,
                  pre_compile_fn: Optional[Callable[[nn.Module], None]] = None, post_compile_fn: Optional[Callable[[nn.Module], None]] = None,
-                 input_transformer: Optional[Callable[[In], In]] = None, num_pre_compile_steps: int = 1) -> None:
+                 input_transformer: Optional[Callable[[In], In]] = None, num_pre_compile_steps: int = 1,
+                 torch_compile_config: Optional[TorchCompileConfig] = None) -> None:
         super().__init__(model, optimizer, device)
+        if torch_compile_config is not None and compile_fn is None:
+            cfg = torch_compile_config
+            compile_fn = lambda m: torch.compile(m, fullgraph=cfg.fullgraph, dynamic=cfg.dynamic, backend=cfg.backend)  # noqa: E731
+            num_pre_compile_steps = cfg.compile_on_iter
         self._compile_fn = compile_fn
         self._pre_compile_fn = pre_compile_fn
         self._post_compile_fn = post_compile_fn

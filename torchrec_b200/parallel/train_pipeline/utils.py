@@ -6,8 +6,11 @@ Parity: reference ``train_pipeline/utils.py`` (``DataLoadingThread`` :780-900), 
 from __future__ import annotations
 
 import queue
+import contextlib
 import threading
-from typing import Any, Callable, Dict, Generic, Iterator, List, Optional, TypeVar
+from collections import deque
+from concurrent.futures import Future
+from typing import Any, Callable, Dict, Generator, Generic, Iterator, List, Optional, TypeVar
 
 import torch
 from torch import nn
@@ -96,6 +99,70 @@ class DataLoadingThread(threading.Thread, Generic[In]):
 
 
 
+
+
+def get_h2d_func(batch: Any, device: torch.device) -> Any:
+    """The default host-to-device move of a pipeline stage: ``batch.to(device, non_blocking=True)``."""
+    return batch.to(device, non_blocking=True)
+
+
+class FutureDeque(deque):
+    """A deque whose entries may be ``concurrent.futures.Future``s (batches still being produced by a worker): reading an entry
+    (index, ``pop``, ``popleft``) waits for it and, for an index read, replaces the future by its result."""
+
+    def __getitem__(self, index: Any) -> Any:
+        item = super().__getitem__(index)
+        if isinstance(item, Future):
+            item = item.result()
+            super().__setitem__(index, item)
+        return item
+
+    def pop(self) -> Any:  # type: ignore[override]
+        item = super().pop()
+        return item.result() if isinstance(item, Future) else item
+
+    def popleft(self) -> Any:
+        item = super().popleft()
+        return item.result() if isinstance(item, Future) else item
+
+
+@contextlib.contextmanager
+def use_context_for_postprocs(pipelined_postprocs: List[Any], next_batch_context: Any) -> Generator[None, None, None]:
+    """While the block runs the pipelined post-processing modules write into the context of the NEXT batch (their outputs are cached
+    there for its forward); the contexts of the current batch are restored afterwards."""
+    original = [p.get_context() for p in pipelined_postprocs]
+    for p in pipelined_postprocs:
+        p.set_context(next_batch_context)
+    try:
+        yield
+    finally:
+        for p, ctx in zip(pipelined_postprocs, original):
+            p.set_context(ctx)
+
+
+def prefetch_embeddings(context: Any, pipelined_modules: List[Any], device: torch.device, stream_context: Callable[[Optional[torch.Stream]], Any],
+                        data_dist_stream: Optional[torch.Stream], forward_stream: Optional[torch.Stream]) -> None:
+    """For every pipelined sharded module: finish the input dist of the batch (on the data-dist stream), let the prefetch stream wait
+    for it, start the cache prefetch of the ids and park input + module context in ``context.module_input_post_prefetch`` /
+    ``module_contexts_post_prefetch`` for the forward (reference train_pipeline/utils.py:728)."""
+    if data_dist_stream is None:
+        return
+    cur = torch.get_device_module(device).current_stream() if device.type == "cuda" else None
+    for m in pipelined_modules:
+        name = getattr(m.forward, "_name", None) or getattr(m.forward, "name", None)
+        assert name in context.input_dist_tensors_requests, f"no input dist request for {name}"
+        request = context.input_dist_tensors_requests.pop(name)
+        with stream_context(data_dist_stream):
+            dist_input = request.wait()
+        if cur is not None:
+            cur.wait_stream(data_dist_stream)
+            if hasattr(dist_input, "record_stream"):
+                dist_input.record_stream(cur)
+        mctx = context.module_contexts_next_batch.pop(name, None) or context.module_contexts.get(name)
+        if hasattr(m, "prefetch"):
+            m.prefetch(ctx=mctx, dist_input=dist_input, forward_stream=forward_stream)
+        context.module_input_post_prefetch[name] = dist_input
+        context.module_contexts_post_prefetch[name] = mctx
 
 
 # ---- moved to ``postproc.py`` (their reference import path); still importable from here ----
