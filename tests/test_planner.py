@@ -202,3 +202,115 @@ def test_perf_model_matches_measured_fused_kernels():
         assert fc + fm == pytest.approx(fused_ms, rel=0.25), (W, fc + fm, fused_ms)
     assert calibration.all_to_all_gbps(8) < calibration.all_to_all_gbps(2) < calibration.PEER_STORE_GBPS
     assert calibration.all_to_all_gbps(4) == pytest.approx(670 * 0.85)
+
+
+def test_plan_loader_topology_factory_and_planner_helpers():
+    """A stored plan is re-used (no search) when the planner inputs hash to the stored context, refused otherwise; topology from the
+    trainer / hardware / kernel layers; validators; small search / formatting helpers."""
+    from typing import Dict, Optional
+
+    from torchrec_b200.modules.embedding_configs import EmbeddingBagConfig
+    from torchrec_b200.modules.embedding_modules import EmbeddingBagCollection
+    from torchrec_b200.parallel.embeddingbag import EmbeddingBagCollectionSharder
+    from torchrec_b200.parallel.planner import EmbeddingShardingPlanner, Topology
+    from torchrec_b200.parallel.planner.partitioners import OrderedDeviceHardware
+    from torchrec_b200.parallel.planner.perf_models import NoopStorageModel
+    from torchrec_b200.parallel.planner.planners import extract_plan, validate_compute_kernels, validate_modules_inclusion_in_sharding_plan, validate_rank_assignment
+    from torchrec_b200.parallel.planner.stats import round_to_one_sigfig
+    from torchrec_b200.parallel.planner.types import (CriticalPathEstimate, HardwareConfig, KernelConfig, PlanLoader, PlannerError, PlannerErrorType, ShardingOption,
+                                                      TopologyFactory, TrainerConfig, hash_sha256_str, hash_sha256_to_int, round_to_nearest)
+    from torchrec_b200.parallel.planner.utils import LuusJaakolaSearch, build_sharder_data, extract_comm_data_type_size, get_num_poolings, is_prefetch_pipelined, mb_to_bytes
+    from torchrec_b200.parallel.types import ShardingPlan
+
+    class Model(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.ebc = EmbeddingBagCollection([EmbeddingBagConfig(name=f"t{i}", embedding_dim=16, num_embeddings=1000 * (i + 1), feature_names=[f"f{i}"]) for i in range(4)],
+                                              device=torch.device("meta"))
+
+    def planner(loader=None, batch_size=64):
+        return EmbeddingShardingPlanner(topology=Topology(world_size=4, local_world_size=4, compute_device="cuda"), batch_size=batch_size, plan_loader=loader)
+
+    sharders = [EmbeddingBagCollectionSharder()]
+    first = planner()
+    plan_a = first.plan(Model(), sharders)
+    stored = {so.storage_hash(): so for so in first.best_plan}
+    ctx_hash = first.hash_planner_context_inputs_str()
+    assert len(stored) == 4 and isinstance(first.hash_planner_context_inputs(), int) and len(ctx_hash) == 64
+
+    class Loader(PlanLoader):
+        def __init__(self, options: Optional[Dict[int, ShardingOption]], ctx: Optional[str]):
+            self.options, self.ctx, self.loads = options, ctx, 0
+
+        def load(self):
+            self.loads += 1
+            return self.options
+
+        def plan_context_hash(self):
+            return self.ctx
+
+        def get_plan_id(self):
+            return "stored-1"
+
+    loader = Loader(stored, ctx_hash)
+    second = planner(loader)
+    plan_b = second.plan(Model(), sharders)
+    assert loader.loads == 1 and second._num_proposals == 0, "the stored plan is used as is"
+    for name, ps in plan_a.plan["ebc"].items():
+        other = plan_b.plan["ebc"][name]
+        assert (ps.sharding_type, ps.compute_kernel, ps.ranks) == (other.sharding_type, other.compute_kernel, other.ranks)
+    with pytest.raises(PlannerError) as e:
+        planner(Loader(stored, ctx_hash), batch_size=128).plan(Model(), sharders)  # other inputs: the stored plan is not trusted
+    assert e.value.error_type == PlannerErrorType.PLANNER_INPUT_CONTEXT_MISMATCH
+    with pytest.raises(PlannerError) as e:
+        planner(Loader({**stored, 12345: next(iter(stored.values()))}, None)).plan(Model(), sharders)  # an option the search space does not have
+    assert e.value.error_type == PlannerErrorType.PLAN_LOADING_FAILED
+    assert planner(Loader(None, None)).plan(Model(), sharders).plan["ebc"].keys() == plan_a.plan["ebc"].keys()  # nothing stored: normal search
+    assert len(extract_plan(list(first._enumerator.last_stored_search_space), stored)) == 4
+    # validators
+    validate_rank_assignment(plan_a, Topology(world_size=4, compute_device="cuda"))
+    with pytest.raises(PlannerError):
+        validate_rank_assignment(plan_a, Topology(world_size=1, compute_device="cuda"))
+    validate_compute_kernels(first.best_plan)
+    bad = first.best_plan[0]
+    bad.compute_kernel = "warp_drive"
+    with pytest.raises(PlannerError) as e:
+        validate_compute_kernels([bad])
+    assert e.value.error_type == PlannerErrorType.INVALID_COMPUTE_KERNEL
+    validate_modules_inclusion_in_sharding_plan(plan_a, Model(), sharders)
+    with pytest.raises(PlannerError) as e:
+        validate_modules_inclusion_in_sharding_plan(ShardingPlan({}), Model(), sharders)
+    assert e.value.error_type == PlannerErrorType.MISSING_MODULE_IN_PLAN
+    # topology from layers: trainer > hardware > defaults; dry run; bandwidths only from hardware when asked
+    hw = HardwareConfig(hbm_cap_bytes=180 * 2**30, ddr_cap_bytes=2**40, intra_host_bw=7.0, hbm_mem_bw=9.0, additional_params={"gen": "b200"})
+    t = TopologyFactory.create_topology(TrainerConfig(world_size=16, local_world_size=8, hbm_cap_bytes=100 * 2**30), hw, KernelConfig(use_hardware_based_bandwidth=True))
+    assert (t.world_size, t.local_world_size, t.devices[3].storage.hbm, t.devices[3].storage.ddr) == (16, 8, 100 * 2**30, 2**40)
+    assert t.comms_bandwidths.intra_host_bw == 7.0 and t.hbm_mem_bw == 9.0 and hw.get_param("gen") == "b200" and not hw.has_param("x")
+    t2 = TopologyFactory.create_topology(TrainerConfig(world_size=2, is_dry_run=True, dry_run_hbm_bytes=5 * 2**30), hw)
+    assert t2.devices[0].storage.hbm == 5 * 2**30 and t2.comms_bandwidths.intra_host_bw != 7.0
+    with pytest.raises(ValueError):
+        TopologyFactory.create_topology(TrainerConfig())
+    with pytest.raises(ValueError):
+        TopologyFactory.create_topology(TrainerConfig(world_size=2, pod_size=4))
+    with pytest.raises(ValueError):
+        TopologyFactory.create_topology(TrainerConfig(world_size=2), kernel_config=KernelConfig(compute_device="tpu"))
+    # helpers
+    assert CriticalPathEstimate(1.5, 2.0).total() == 3.5 and round_to_nearest(149 * 2**30, 100 * 2**30) == 100 * 2**30
+    assert hash_sha256_to_int([1, "a"]) == int(hash_sha256_str([1, "a"]), 16)
+    assert round_to_one_sigfig(0.0342) == "0.03" and round_to_one_sigfig(1234) == "1000" and mb_to_bytes(1.5) == 1572864
+    s = LuusJaakolaSearch(0, 10, 80, left_cost=(0 - 3.3) ** 2)
+    y = s.next(0.0)
+    while y is not None:
+        assert 0 <= y <= 10
+        y = s.next((y - 3.3) ** 2)
+    assert abs(s.best()[0] - 3.3) < 0.5
+    s.shrink_right(2.0)
+    assert s.right == 2.0 and s.best()[0] <= 2.0
+    so = second.best_plan[0]
+    data = build_sharder_data(sharders[0])
+    assert data.storage_usage_type.value == "base" and extract_comm_data_type_size(so, data) == (4, 4, 4, 4) and not is_prefetch_pipelined(so, data)
+    assert get_num_poolings(None, so) == [1.0] * len(so.input_lengths)
+    assert NoopStorageModel(Topology(world_size=4, compute_device="cuda")).rate(second.best_plan) > 0
+    devs = Topology(world_size=4, local_world_size=2, compute_device="cuda").devices
+    order = sorted(OrderedDeviceHardware(d, 2) for d in devs)
+    assert [o.device.rank for o in order] == [0, 2, 1, 3]  # equal load: local rank 0 of every host first

@@ -65,3 +65,5 @@ def kernel_bw_lookup(compute_device: str, compute_kernel: str, hbm_mem_bw: float
     if prefetch_pipeline and compute_device == "cuda" and compute_kernel == EmbeddingComputeKernel.FUSED_UVM_CACHING.value:
         return lookup.get(("cuda", EmbeddingComputeKernel.FUSED.value))
     return lookup.get((compute_device, compute_kernel))
+
+NUM_POOLINGS: float = 1.0  # poolings per feature and example unless a constraint says otherwise

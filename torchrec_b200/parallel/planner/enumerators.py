@@ -369,7 +369,7 @@ class EmbeddingEnumerator(Enumerator):
         if EmbeddingComputeKernel.DENSE.value in filtered and EmbeddingComputeKernel.FUSED.value in filtered:
             filtered.remove(EmbeddingComputeKernel.DENSE.value)  # fused is a strict improvement
         if not filtered:
-            logger.warn(f"No available compute kernels after applying user provided constraints for {name}; allowed: {allowed_compute_kernels}")
+            logger.warning(f"No available compute kernels after applying user provided constraints for {name}; allowed: {allowed_compute_kernels}")
         return filtered
 
 

@@ -63,6 +63,21 @@ def _group_and_sort_non_uniform_sharding_options(sharding_options: List[Sharding
     return lst
 
 
+@dataclass
+class OrderedDeviceHardware:
+    """Heap entry of a device: least loaded first; ties go to the lower LOCAL rank (spreads tables over hosts before filling one
+    host's DDR), then to the lower rank."""
+
+    device: DeviceHardware
+    local_world_size: int
+
+    def _key(self) -> Tuple[float, int, int]:
+        return (self.device.perf.total, self.device.rank % self.local_world_size, self.device.rank)
+
+    def __lt__(self, other: "OrderedDeviceHardware") -> bool:
+        return self._key() < other._key()
+
+
 class GreedyPerfPartitioner(Partitioner):
     """Greedy: biggest groups first, each shard onto the currently least-loaded device (by accumulated perf)
     that still has room. HOST-partitioned options (TWRW/TWCW) choose the least-loaded host; UNIFORM options

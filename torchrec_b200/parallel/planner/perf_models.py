@@ -36,3 +36,17 @@ class NoopCriticalPathPerfModel(PerfModel):
                 bc[r] += p.bwd_compute
                 bcm[r] += p.bwd_comms
         return max(fc) + max(fcm) + max(bc) + max(bcm)
+
+
+class NoopStorageModel(PerfModel):
+    """Rates a plan by the largest HBM use of any rank (lower = more evenly spread memory) without running anything."""
+
+    def __init__(self, topology: Topology) -> None:
+        self._topology = topology
+
+    def rate(self, plan: List[ShardingOption]) -> float:
+        hbm = [0] * self._topology.world_size
+        for so in plan:
+            for shard in so.shards:
+                hbm[shard.rank] += shard.storage.hbm
+        return max(hbm)

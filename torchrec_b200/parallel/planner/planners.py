@@ -79,6 +79,100 @@ def _merge_plans(best_plans: List[ShardingPlan]) -> ShardingPlan:
     return merged
 
 
+def validate_rank_assignment(sharding_plan: ShardingPlan, topology: Topology) -> None:
+    """Every shard of the plan sits on a rank in [0, world size)."""
+    for module_plan in sharding_plan.plan.values():
+        for param_plan in module_plan.values():
+            if param_plan.sharding_spec is None:
+                continue
+            for shard in param_plan.sharding_spec.shards:
+                rank = shard.placement.rank()
+                if rank is None or rank < 0:
+                    raise PlannerError(error_type=PlannerErrorType.INVALID_RANK_ASSIGNMENT, message=f"Rank is not assigned for shard {shard}")
+                if rank >= topology.world_size:
+                    raise PlannerError(error_type=PlannerErrorType.INVALID_RANK_ASSIGNMENT,
+                                       message=f"Shard {shard} has rank {rank} which is not below the world size {topology.world_size}.")
+
+
+def validate_compute_kernels(best_plan: List[ShardingOption]) -> None:
+    """The kernels of the chosen options exist and fit the rest of the option: the dense kernel only for data-parallel tables, a cache
+    load factor strictly between 0 and 1 for the caching kernels, no negative storage."""
+    from ..embedding_types import EmbeddingComputeKernel
+    from ..types import ShardingType
+
+    valid = {k.value for k in EmbeddingComputeKernel}
+    caching = {k.value for k in EmbeddingComputeKernel if "caching" in k.value}
+    violations: List[str] = []
+    for so in best_plan:
+        fqn, kernel = so.fqn, so.compute_kernel
+        if kernel not in valid:
+            violations.append(f"{fqn}: unknown compute kernel '{kernel}'")
+            continue
+        if kernel == EmbeddingComputeKernel.DENSE.value and so.sharding_type != ShardingType.DATA_PARALLEL.value:
+            violations.append(f"{fqn}: DENSE kernel requires DATA_PARALLEL sharding, got '{so.sharding_type}'")
+        if kernel in caching:
+            clf = so.cache_load_factor
+            if clf is not None and (clf <= 0 or clf >= 1):
+                violations.append(f"{fqn}: {kernel} requires cache_load_factor strictly between 0 and 1, got {clf}")
+        storage = so.total_storage
+        if storage.hbm < 0:
+            violations.append(f"{fqn}: {kernel} has negative HBM storage ({storage.hbm})")
+        if storage.ddr < 0:
+            violations.append(f"{fqn}: {kernel} has negative DDR storage ({storage.ddr})")
+    if violations:
+        raise PlannerError(error_type=PlannerErrorType.INVALID_COMPUTE_KERNEL,
+                           message=f"Compute kernel validation failed with {len(violations)} violation(s):\n" + "\n".join(f"  - {v}" for v in violations))
+
+
+def validate_modules_inclusion_in_sharding_plan(sharding_plan: ShardingPlan, module: nn.Module, sharders: List[ModuleSharder[nn.Module]],
+                                                constraints: Optional[Dict[str, ParameterConstraints]] = None, device_group: Optional[str] = None) -> None:
+    """Every module that has a sharder AND parameters that sharder would shard appears in the plan (with ``device_group``: only the
+    modules whose tables are constrained to that group)."""
+    from .utils import sharder_name
+
+    sharder_map = {sharder_name(s.module_type): s for s in sharders}
+    expected = set()
+    queue: List[Tuple[str, nn.Module]] = [("", module)]
+    while queue:
+        path, child = queue.pop(0)
+        sharder = sharder_map.get(sharder_name(type(child)))
+        params = sharder.shardable_parameters(child) if sharder else None
+        if params:
+            in_group = device_group is None or constraints is None or any(
+                getattr(constraints.get(n), "device_group", None) in (None, device_group) for n in params)
+            if in_group:
+                expected.add(path)
+            continue
+        for n, m in child.named_children():
+            queue.append((f"{path}.{n}" if path else n, m))
+    missing = sorted(expected - set(sharding_plan.plan.keys()))
+    if missing:
+        group = f" for device group '{device_group}'" if device_group else ""
+        raise PlannerError(error_type=PlannerErrorType.MISSING_MODULE_IN_PLAN, message=f"The following shardable modules are not present in the sharding plan{group}: {missing}.")
+
+
+def extract_plan(search_space: List[ShardingOption], loaded_sharding_options: Dict[int, ShardingOption]) -> List[ShardingOption]:
+    """The options of the enumerated search space a stored plan chose, carrying the stored shards (placement included); every stored
+    option must be found, and no two enumerated options may share a storage hash."""
+    chosen: List[ShardingOption] = []
+    seen = set()
+    for so in search_space:
+        h = so.storage_hash()
+        if h in seen:
+            raise PlannerError(error_type=PlannerErrorType.PLAN_LOADING_FAILED, message=f"Found a duplicate storage hash {h} for FQNs {[x.fqn for x in search_space]}\n")
+        seen.add(h)
+        loaded = loaded_sharding_options.get(h)
+        if loaded is not None:
+            picked = copy.copy(so)
+            picked.shards = loaded.shards
+            chosen.append(picked)
+    if len(chosen) != len(loaded_sharding_options):
+        raise PlannerError(error_type=PlannerErrorType.PLAN_LOADING_FAILED,
+                           message=f"Loaded sharding options from Storage, but not all search space is covered. Merged search space len {len(chosen)} != "
+                                   f"loaded Sharding options len {len(loaded_sharding_options)}\n")
+    return chosen
+
+
 class EmbeddingPlannerBase(ShardingPlanner):
     def __init__(self, topology: Optional[Topology] = None, batch_size: Optional[int] = None, enumerator: Optional[Enumerator] = None,
                  storage_reservation: Optional[StorageReservation] = None, stats: Optional[Union[Stats, List[Stats]]] = None,
@@ -138,8 +232,28 @@ class EmbeddingShardingPlanner(EmbeddingPlannerBase):
         self._plan_loader = plan_loader
 
     def hash_planner_context_inputs(self) -> int:
+        """Hash of the planner inputs (topology, batch size, search space, reservation, constraints); needs ``plan`` (or the enumerator
+        and the reservation) to have run - before that: topology, batch size and constraint names only."""
+        from .types import hash_planner_context_inputs
+
+        if getattr(self._enumerator, "last_stored_search_space", None) is not None and self._storage_reservation.last_reserved_topology is not None:
+            return hash_planner_context_inputs(self._topology, self._batch_size, self._enumerator, self._storage_reservation, self._constraints)
         parts = [self._topology._hash(), self._batch_size, repr(sorted((self._constraints or {}).keys()))]
         return int(hashlib.sha256(repr(parts).encode()).hexdigest()[:15], 16)
+
+    def hash_planner_context_inputs_str(self) -> str:
+        from .types import hash_planner_context_inputs_str
+
+        return hash_planner_context_inputs_str(self._topology, self._batch_size, self._enumerator, self._storage_reservation, self._constraints)
+
+    @property
+    def plan_loader(self):
+        return self._plan_loader
+
+    @property
+    def best_plan(self) -> Optional[List[ShardingOption]]:
+        """The chosen sharding options of the last ``plan`` call (what a ``PlanLoader`` stores, keyed by ``storage_hash()``)."""
+        return self._best_plan
 
     def plan(self, module: nn.Module, sharders: Optional[List[ModuleSharder[nn.Module]]] = None) -> ShardingPlan:
         if sharders is None:
@@ -159,9 +273,24 @@ class EmbeddingShardingPlanner(EmbeddingPlannerBase):
         if not search_space:
             return ShardingPlan({})
         proposal_cache: Dict[Tuple[int, ...], Tuple[bool, Optional[List[ShardingOption]], Optional[float]]] = {}
-        for proposer in self._proposers:
+        proposers = self._proposers
+        if self._plan_loader is not None:
+            # a stored plan is only valid for the planner inputs it was computed for
+            stored_hash = self._plan_loader.plan_context_hash()
+            if stored_hash is not None and stored_hash != self.hash_planner_context_inputs_str():
+                raise PlannerError(error_type=PlannerErrorType.PLANNER_INPUT_CONTEXT_MISMATCH,
+                                   message="Unable to load, because of planner input mismatch - cannot validate this plan is the best plan for current context.. \n"
+                                           f"Planner input context mismatch detected for {self._plan_loader.get_plan_id()} and current planner set up:"
+                                           f"\nCurrent planner hash: {self.hash_planner_context_inputs_str()}, Loaded plan hash: {stored_hash}")
+            loaded = self._plan_loader.load()
+            if loaded is not None:
+                best_plan = copy.deepcopy(extract_plan(search_space, loaded))
+                best_perf_rating = self._perf_model.rate(plan=best_plan)
+                logger.info("Loaded sharding options from storage (plan id %s): skipping the search", self._plan_loader.get_plan_id())
+                proposers = []
+        for proposer in proposers:
             proposer.load(search_space=search_space, enumerator=self._enumerator)
-        for proposer in self._proposers:
+        for proposer in proposers:
             proposal = proposer.propose()
             while proposal:
                 end_time = time.perf_counter()

@@ -179,3 +179,8 @@ def _collapse(ranks: List[int]) -> str:
     if len(ranks) > 2 and ranks == list(range(ranks[0], ranks[-1] + 1)):
         return f"{ranks[0]}-{ranks[-1]}"
     return ",".join(str(r) for r in ranks)
+
+
+def round_to_one_sigfig(x: float) -> str:
+    """``0.0342 -> '0.03'``, ``1234 -> '1000'``: one significant figure, no exponent for ordinary magnitudes."""
+    return f'{float(f"{x:.1g}"):g}'

@@ -39,6 +39,10 @@ class PlannerErrorType(Enum):
     STRICT_CONSTRAINTS = "strict_constraints"
     PARTITION = "partition"
     PLANNER_INPUT_CONTEXT_MISMATCH = "planner_input_context_mismatch"
+    PLAN_LOADING_FAILED = "plan_loading_failed"
+    INVALID_RANK_ASSIGNMENT = "invalid_rank_assignment"
+    INVALID_COMPUTE_KERNEL = "invalid_compute_kernel"
+    MISSING_MODULE_IN_PLAN = "missing_module_in_plan"
     OTHER = "other"
 
 
@@ -416,6 +420,12 @@ class ShardingOption:
                         return False
         return True
 
+    def storage_hash(self) -> int:
+        """Identity of this option BEFORE planning (fqn, sharding type, kernel, cache load factor, shard count): the key under which
+        a stored plan keeps the shards it chose for it (BLAKE2b, 56 bits - stable across processes and machines)."""
+        key = f"{self.fqn}|{self.sharding_type}|{self.compute_kernel}|{self.cache_load_factor}|{self.num_shards}"
+        return int.from_bytes(hashlib.blake2b(key.encode("utf-8"), digest_size=7).digest(), byteorder="big")
+
     def __hash__(self) -> int:
         return hash((self.fqn, self.sharding_type, self.compute_kernel, tuple(self.shards), self.cache_params))
 
@@ -542,3 +552,240 @@ class Stats(abc.ABC):
             num_plans: int, run_time: float, best_plan: List[ShardingOption], constraints: Optional[Dict[str, ParameterConstraints]] = None,
             sharders: Optional[List[ModuleSharder[nn.Module]]] = None, debug: bool = False) -> None:
         ...
+
+
+# ---- stored plans ------------------------------------------------------------------------------------------------------------------------------------
+@dataclass
+class PlanDebugStats:
+    """What is logged about how a plan came about."""
+
+    planner_type: str
+    timeout_seconds: Optional[int]
+
+
+class PlanLoader(abc.ABC):
+    """Source of a previously computed plan: re-use it instead of searching again (restarts), or start the next search from it.
+    ``load`` returns {``ShardingOption.storage_hash()``: the option with the shards the stored plan chose}; ``plan_context_hash`` the
+    hash of the planner inputs the plan was computed for (checked against the current planner before the plan is used)."""
+
+    @abc.abstractmethod
+    def load(self) -> Optional[Dict[int, "ShardingOption"]]:
+        ...
+
+    @abc.abstractmethod
+    def plan_context_hash(self) -> Optional[str]:
+        ...
+
+    def get_plan_id(self) -> Optional[str]:
+        return None
+
+
+@dataclass
+class CriticalPathEstimate:
+    comms_estimate: float
+    comp_estimate: float
+
+    def total(self) -> float:
+        return self.comms_estimate + self.comp_estimate
+
+
+# ---- topology from configuration layers -----------------------------------------------------------------------------------------------------------------
+class TopologyConfigBase(abc.ABC):
+    """A layer of topology configuration with an open key-value side channel (``additional_params``) for data the schema does not
+    know (per-device capacities of a heterogeneous job, hardware generation, experiments)."""
+
+    additional_params: Dict[str, Any]
+
+    def get_param(self, key: str, default: Any = None) -> Any:
+        return self.additional_params.get(key, default)
+
+    def has_param(self, key: str) -> bool:
+        return key in self.additional_params
+
+    @abc.abstractmethod
+    def validate(self) -> None:
+        ...
+
+
+@dataclass(frozen=True)
+class HardwareConfig(TopologyConfigBase):
+    """What the hardware offers (detected or looked up per machine type): capacities in bytes, bandwidths in bytes / ms. Subclass with
+    defaults for a machine type (e.g. a B200 HGX host: 180 GB HBM, NVLink 5 intra-host bandwidth)."""
+
+    hbm_cap_bytes: Optional[int] = None
+    ddr_cap_bytes: Optional[int] = None
+    ssd_cap_bytes: Optional[int] = None
+    intra_host_bw: Optional[float] = None
+    inter_host_bw: Optional[float] = None
+    hbm_mem_bw: Optional[float] = None
+    ddr_mem_bw: Optional[float] = None
+    hbm_to_ddr_mem_bw: Optional[float] = None
+    ssd_mem_bw: Optional[float] = None
+    additional_params: Dict[str, Any] = field(default_factory=dict)
+
+    def validate(self) -> None:
+        for name in ("hbm_cap_bytes", "ddr_cap_bytes", "ssd_cap_bytes", "intra_host_bw", "inter_host_bw", "hbm_mem_bw", "ddr_mem_bw", "hbm_to_ddr_mem_bw", "ssd_mem_bw"):
+            v = getattr(self, name)
+            if v is not None and v < 0:
+                raise ValueError(f"{name} must not be negative, got {v}")
+
+
+@dataclass(frozen=True)
+class TrainerConfig(TopologyConfigBase):
+    """What the job asks for - wins over the hardware layer: world size (required), ranks per host, capacity overrides, dry-run
+    capacities (plan for hardware that is not there), hosts per NVLink domain (``pod_size``)."""
+
+    world_size: Optional[int] = None
+    local_world_size: Optional[int] = None
+    hbm_cap_bytes: Optional[int] = None
+    ddr_cap_bytes: Optional[int] = None
+    ssd_cap_bytes: Optional[int] = None
+    is_dry_run: bool = False
+    dry_run_hbm_bytes: Optional[int] = None
+    dry_run_ddr_bytes: Optional[int] = None
+    pod_size: Optional[int] = None
+    additional_params: Dict[str, Any] = field(default_factory=dict)
+
+    def validate(self) -> None:
+        if self.world_size is None:
+            raise ValueError("world_size must be provided in TrainerConfig")
+        if self.pod_size is not None and self.pod_size > self.world_size:
+            raise ValueError(f"pod_size ({self.pod_size}) cannot be greater than world_size ({self.world_size})")
+
+
+@dataclass(frozen=True)
+class KernelConfig(TopologyConfigBase):
+    """What the compute kernels need the cost model to know: device type, backward / weighted-feature / uneven-shard multipliers,
+    whether bandwidths come from the hardware layer, an explicit collective bandwidth model."""
+
+    compute_device: str = "cuda"
+    bwd_compute_multiplier: float = BWD_COMPUTE_MULTIPLIER
+    weighted_feature_bwd_compute_multiplier: float = WEIGHTED_KERNEL_MULTIPLIER
+    uneven_sharding_perf_multiplier: float = 1.0
+    use_hardware_based_bandwidth: bool = False
+    generalized_comms_bandwidths: Optional[GeneralizedCommsBandwidth] = None
+    additional_params: Dict[str, Any] = field(default_factory=dict)
+
+    def validate(self) -> None:
+        if self.compute_device not in ("cpu", "cuda", "mtia"):
+            raise ValueError(f"compute_device must be one of ('cpu', 'cuda', 'mtia'), got {self.compute_device}")
+
+
+class TopologyFactory:
+    """``Topology`` from the three layers: trainer (explicit) > hardware (detected) > built-in defaults."""
+
+    @staticmethod
+    def create_topology(trainer_config: TrainerConfig, hardware_config: Optional[HardwareConfig] = None, kernel_config: Optional[KernelConfig] = None) -> "Topology":
+        hardware, kernel = hardware_config or HardwareConfig(), kernel_config or KernelConfig()
+        trainer_config.validate()
+        hardware.validate()
+        kernel.validate()
+        first = lambda *xs: next((x for x in xs if x is not None), None)  # noqa: E731
+        kw: Dict[str, Any] = {"world_size": trainer_config.world_size, "compute_device": kernel.compute_device, "bwd_compute_multiplier": kernel.bwd_compute_multiplier,
+                              "weighted_feature_bwd_compute_multiplier": kernel.weighted_feature_bwd_compute_multiplier,
+                              "uneven_sharding_perf_multiplier": kernel.uneven_sharding_perf_multiplier}
+        if trainer_config.local_world_size is not None:
+            kw["local_world_size"] = trainer_config.local_world_size
+        if trainer_config.pod_size is not None:
+            kw["pod_size"] = trainer_config.pod_size
+        hbm, ddr, ssd = first(trainer_config.hbm_cap_bytes, hardware.hbm_cap_bytes), first(trainer_config.ddr_cap_bytes, hardware.ddr_cap_bytes), \
+            first(trainer_config.ssd_cap_bytes, hardware.ssd_cap_bytes)
+        if trainer_config.is_dry_run:
+            hbm, ddr = first(trainer_config.dry_run_hbm_bytes, hbm), first(trainer_config.dry_run_ddr_bytes, ddr)
+        for key, v in (("hbm_cap", hbm), ("ddr_cap", ddr), ("ssd_cap", ssd)):
+            if v is not None:
+                kw[key] = v
+        custom = trainer_config.get_param("custom_topology_data")
+        if custom is not None:
+            kw["custom_topology_data"] = custom
+        hw = kernel.use_hardware_based_bandwidth
+        kw["hbm_mem_bw"] = first(hardware.hbm_mem_bw if hw else None, HBM_MEM_BW)
+        kw["ddr_mem_bw"] = first(hardware.ddr_mem_bw if hw else None, DDR_MEM_BW)
+        kw["ssd_mem_bw"] = first(hardware.ssd_mem_bw if hw else None, SSD_MEM_BW)
+        kw["hbm_to_ddr_mem_bw"] = first(hardware.hbm_to_ddr_mem_bw if hw else None, HBM_TO_DDR_MEM_BW)
+        if kernel.generalized_comms_bandwidths is not None:
+            kw["generalized_comms_bandwidths"] = kernel.generalized_comms_bandwidths
+        else:
+            kw["intra_host_bw"] = first(hardware.intra_host_bw if hw else None, INTRA_NODE_BANDWIDTH)
+            kw["inter_host_bw"] = first(hardware.inter_host_bw if hw else None, CROSS_NODE_BANDWIDTH)
+        topology = Topology(**kw)
+        topology.created_by_factory = True
+        return topology
+
+
+# ---- planner context hashing ---------------------------------------------------------------------------------------------------------------------------------
+HUNDRED_GB = 100 * 1024 * 1024 * 1024
+
+
+def hash_sha256_to_int(hashable_list: List[Any]) -> int:
+    return int(hashlib.sha256(str(hashable_list).encode("utf-8")).hexdigest(), 16)
+
+
+def hash_sha256_str(hashable_list: List[Any]) -> str:
+    return hashlib.sha256(str(hashable_list).encode("utf-8")).hexdigest()
+
+
+def round_to_nearest(x: int, unit: int) -> int:
+    """Round to the nearest unit (e.g. 100 GB)."""
+    return round(x / unit) * unit
+
+
+def _topology_hash_components(topology: "Topology", round_unit: int = HUNDRED_GB) -> List[Any]:
+    """The fields of a topology that decide a plan; device memory rounded to ``round_unit`` so that small driver / OS differences
+    between otherwise identical machines do not invalidate a stored plan."""
+    devices = [(d.rank, round_to_nearest(d.storage.hbm, round_unit), round_to_nearest(d.storage.ddr, round_unit), round_to_nearest(getattr(d.storage, "ssd", 0), round_unit))
+               for d in topology.devices]
+    return [topology.world_size, topology.compute_device, devices, topology.local_world_size, getattr(topology, "intra_group_size", topology.local_world_size),
+            topology.hbm_mem_bw, topology.ddr_mem_bw, topology.ssd_mem_bw, topology.hbm_to_ddr_mem_bw, topology.comms_bandwidths.intra_host_bw,
+            topology.comms_bandwidths.inter_host_bw, topology.bwd_compute_multiplier, topology.weighted_feature_bwd_compute_multiplier,
+            topology.uneven_sharding_perf_multiplier]
+
+
+def _shard_hash_components(shard: "Shard") -> tuple:
+    st = shard.storage
+    return (tuple(shard.size), tuple(shard.offset), shard.rank, (st.hbm, st.ddr, getattr(st, "ssd", 0)) if st else None)
+
+
+def _build_hashable_list(topology: "Topology", batch_size: int, enumerator: "Enumerator", storage_reservation: "StorageReservation",
+                         constraints: Optional[Dict[str, "ParameterConstraints"]]) -> List[Any]:
+    assert hasattr(enumerator, "last_stored_search_space"), "This enumerator is not compatible with hashing"
+    search_space = enumerator.last_stored_search_space
+    assert search_space is not None, "Unable to hash planner context without an enumerator that has a precomputed search space"
+    reserved = storage_reservation.last_reserved_topology
+    assert reserved is not None, "Unable to hash planner context without a storage reservation that has a precomputed topology"
+    return [hash_sha256_to_int(_topology_hash_components(topology)), batch_size,
+            [[so.fqn, so.sharding_type, so.compute_kernel, tuple(_shard_hash_components(sh) for sh in so.shards), so.cache_params] for so in search_space],
+            type(storage_reservation).__name__, hash_sha256_to_int(_topology_hash_components(reserved)),
+            tuple((k, hash_sha256_str([repr(v)])) for k, v in sorted(constraints.items())) if constraints else None]
+
+
+def hash_planner_context_inputs(topology: "Topology", batch_size: int, enumerator: "Enumerator", storage_reservation: "StorageReservation",
+                                constraints: Optional[Dict[str, "ParameterConstraints"]], hash_function: Callable[[List[Any]], int] = hash_sha256_to_int) -> int:
+    """Hash of everything a plan depends on (topology, batch size, enumerated search space, reservation policy and reserved
+    topology, constraints): equal hashes <=> a stored plan is valid for this planner."""
+    return hash_function(_build_hashable_list(topology, batch_size, enumerator, storage_reservation, constraints))
+
+
+def hash_planner_context_inputs_str(topology: "Topology", batch_size: int, enumerator: "Enumerator", storage_reservation: "StorageReservation",
+                                    constraints: Optional[Dict[str, "ParameterConstraints"]], hash_function: Callable[[List[Any]], str] = hash_sha256_str) -> str:
+    return hash_function(_build_hashable_list(topology, batch_size, enumerator, storage_reservation, constraints))
+
+
+# ---- picklable sharder snapshot (the estimators work from this, not from live sharder objects) ---------------------------------------------------------------
+class StorageUsageType(Enum):
+    """Which storage formula a sharder uses: its own ``storage_usage`` (DEFAULT), the training embedding sharders' (BASE), the
+    quantized inference sharders' (BASE_QUANT)."""
+
+    DEFAULT = "default"
+    BASE = "base"
+    BASE_QUANT = "base_quant"
+
+
+@dataclass
+class SharderData:
+    fused_params: Dict[str, Any]
+    qcomm_dtype_sizes: Dict[str, Tuple[float, float]]
+    storage_usage_type: StorageUsageType
+
+
+SharderDataMap = Dict[str, SharderData]
