@@ -103,3 +103,38 @@ def _qcomm_sharded(ctx):
 
 def test_qcomms_shard_api_and_collective_utils():
     run_multi_process(_qcomm_sharded, world_size=2, backend="gloo")
+
+
+def test_topology_group_sizes_and_storage_accounting(monkeypatch):
+    import torch
+
+    from torchrec_b200.parallel import comm
+    from torchrec_b200.parallel.types import (ComputeDevice, ComputeKernel, DeviceToHostTensorAwaitable, LazyAwaitable, LazyGetItemMixin, ParameterStorage, StorageUsageType,
+                                              compute_storage_usage)
+
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "4")
+    monkeypatch.delenv("TOPOLOGY_DOMAIN_MULTIPLE", raising=False)
+    assert comm.get_topology_domain_multiple() is None and comm.get_topology_group_world_size(16) == 4 and comm.get_node_group_size(16) == 4
+    monkeypatch.setenv("TOPOLOGY_DOMAIN_MULTIPLE", "2")
+    assert comm.get_topology_domain_multiple() == 2 and comm.get_topology_group_world_size(16) == 8
+    with pytest.raises(ValueError):
+        comm.get_topology_group_world_size(12)
+    t = torch.empty(10, 4)
+    assert compute_storage_usage(t, "cuda", "fused", StorageUsageType.BASE) == {"hbm": 160}
+    assert compute_storage_usage(t, "cuda", "fused_uvm_caching", StorageUsageType.BASE) == {"ddr": 160}
+    assert compute_storage_usage(t, "cuda", "quant", StorageUsageType.BASE_QUANT) == {"hbm": 200} and compute_storage_usage(t, "cpu", "dense", StorageUsageType.DEFAULT) == {"ddr": 160}
+    assert ParameterStorage.HBM.value == "hbm" and ComputeDevice.CUDA.value == "cuda" and ComputeKernel.DEFAULT.value == "default"
+
+    class Out(LazyGetItemMixin, LazyAwaitable):
+        def __init__(self):
+            super().__init__()
+            self.waits = 0
+
+        def _wait_impl(self):
+            self.waits += 1
+            return {"a": torch.ones(2)}
+
+    out = Out()
+    item = out["a"]
+    assert out.waits == 0 and (item + 1).tolist() == [2.0, 2.0] and out.waits == 1
+    assert DeviceToHostTensorAwaitable(torch.arange(3)).wait().tolist() == [0, 1, 2]

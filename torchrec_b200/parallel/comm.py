@@ -62,6 +62,34 @@ def get_num_groups(world_size: Optional[int] = None) -> int:
     return world_size // get_local_size(world_size)
 
 
+_NODE_GROUP_SIZE_2D: Optional[int] = None  # set while the process groups of a 2D-parallel job are built
+
+
+def get_node_group_size(world_size: Optional[int] = None) -> int:
+    """Ranks per node as the current sharding group sees it: the 2D node group size when one is active, else the local world size."""
+    return get_local_size(world_size) if _NODE_GROUP_SIZE_2D is None else _NODE_GROUP_SIZE_2D
+
+
+def get_topology_domain_multiple() -> Optional[int]:
+    """Hosts per high-bandwidth domain (an NVLink / NVSwitch pod spanning several hosts, e.g. NVL72): ``TOPOLOGY_DOMAIN_MULTIPLE``."""
+    v = _env2int(["TOPOLOGY_DOMAIN_MULTIPLE"], -1)
+    return None if v == -1 else v
+
+
+def get_topology_group_world_size(world_size: Optional[int] = None) -> int:
+    """Processes linked by the high-bandwidth fabric: hosts per domain x ranks per host (the local world size when no domain multiple is
+    set); the world size must be a multiple of it."""
+    multiple = get_topology_domain_multiple()
+    if multiple is None:
+        return get_local_size(world_size)
+    per_host = _env2int(["LOCAL_WORLD_SIZE", "MPI_LOCALNRANKS", "OMPI_COMM_WORLD_LOCAL_SIZE", "MV2_COMM_WORLD_LOCAL_SIZE"], 8)  # ``get_local_size`` already spans the domain
+    per_domain = multiple * per_host
+    world_size = dist.get_world_size() if world_size is None else world_size
+    if world_size % per_domain != 0:
+        raise ValueError(f"World size {world_size} is not a multiple of the topology group: {per_domain}")
+    return per_domain
+
+
 def intra_and_cross_node_pg(device: Optional[torch.device] = None, backend: Optional[str] = None) -> Tuple[Optional[dist.ProcessGroup], Optional[dist.ProcessGroup]]:
     """(intra-node group, cross-node group of same-local-rank peers); cached."""
     global _INTRA_PG, _CROSS_PG, _PG_KEY
@@ -101,6 +129,8 @@ def intra_and_cross_node_pg_2D(env, device: Optional[torch.device] = None) -> Tu
     ranks = dist.get_process_group_ranks(env.sharding_pg)
     local_size = env.node_group_size if env.node_group_size else get_local_size(len(ranks))
     local_size = min(local_size, len(ranks))
+    global _NODE_GROUP_SIZE_2D
+    _NODE_GROUP_SIZE_2D = local_size
     intra = cross = None
     world = dist.get_world_size()
     step = env.num_sharding_groups

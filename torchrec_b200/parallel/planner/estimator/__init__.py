@@ -6,6 +6,7 @@ from .estimator import (  # noqa: F401
     DataParallelEvaluator,
     EmbeddingPerfEstimator,
     EmbeddingPerfEstimatorFactory,
+    EmbeddingPerfEstimatorV2,
     EmbeddingShardingPerfEvaluator,
     GridShardEvaluator,
     RowWiseEvaluator,

@@ -320,6 +320,9 @@ class EmbeddingPerfEstimator(ShardEstimator):
             comms_bw=self._config.get_comms_bw(topo.world_size, topo.local_world_size))
 
 
+EmbeddingPerfEstimatorV2 = EmbeddingPerfEstimator  # the annotation-driven estimator under its versioned name
+
+
 class EmbeddingPerfEstimatorFactory:
     """Registry of hardware configs by name: ``EmbeddingPerfEstimatorFactory.create("b200", topology)`` (reference :1779-1936)."""
 

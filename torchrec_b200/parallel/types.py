@@ -629,3 +629,88 @@ def delegating_load_state_dict(module: nn.Module, state_dict: Dict[str, Any], st
     if strict and (missing or unexpected):
         raise RuntimeError(f"Error(s) in loading state_dict for {type(module).__name__}: missing {missing}, unexpected {unexpected}")
     return _IncompatibleKeys(missing, unexpected)
+
+
+# ---- well-known resources / devices, storage accounting ------------------------------------------------------------------------------------------------
+class ParameterStorage(Enum):
+    """Physical memories a planner constraint can name."""
+
+    HBM = "hbm"  # GPU-attached
+    DDR = "ddr"  # CPU-attached
+
+
+class StorageUsageType(Enum):
+    BASE_QUANT = "BaseQuantEmbeddingSharder"
+    BASE = "BaseEmbeddingSharder"
+    DEFAULT = "ModuleSharder"
+
+
+class ComputeDevice(Enum):
+    CUDA = "cuda"
+    CPU = "cpu"
+    MTIA = "mtia"
+
+
+@unique
+class ComputeKernel(Enum):
+    DEFAULT = "default"
+
+
+def compute_storage_usage(tensor: torch.Tensor, compute_device_type: str, compute_kernel: str, storage_usage_type: StorageUsageType) -> Dict[str, int]:
+    """{memory: bytes} a parameter needs under a kernel: the tensor's bytes (+ 4 bytes per row of scale / bias for quantized tables); the
+    UVM kernels keep the rows in host memory, everything else in the memory of the compute device."""
+    size = tensor.element_size() * tensor.nelement()
+    if storage_usage_type == StorageUsageType.BASE_QUANT:
+        size += tensor.shape[0] * 4
+        if compute_kernel in {"quant_uvm", "quant_uvm_caching"}:
+            return {ParameterStorage.DDR.value: size}
+        where = {"cuda": ParameterStorage.HBM, "cpu": ParameterStorage.DDR, "mtia": ParameterStorage.DDR}
+    elif storage_usage_type == StorageUsageType.BASE:
+        if compute_kernel in {"fused_uvm", "fused_uvm_caching"}:
+            return {ParameterStorage.DDR.value: size}
+        where = {"cuda": ParameterStorage.HBM, "cpu": ParameterStorage.DDR, "mtia": ParameterStorage.HBM}
+    else:
+        where = {"cuda": ParameterStorage.HBM, "cpu": ParameterStorage.DDR, "mtia": ParameterStorage.HBM}
+    return {where.get(compute_device_type, ParameterStorage.HBM).value: size}
+
+
+class DeviceToHostTensorAwaitable(LazyAwaitable[torch.Tensor]):
+    """A device tensor on its way to the host: the copy is enqueued at construction (non-blocking), ``wait()`` blocks on the event
+    recorded behind it."""
+
+    def __init__(self, tensor_on_device: torch.Tensor) -> None:
+        super().__init__()
+        self._tensor = tensor_on_device.to("cpu", non_blocking=True)
+        self._event = None
+        if tensor_on_device.is_cuda:
+            self._event = torch.cuda.Event()
+            self._event.record()
+
+    def _wait_impl(self) -> torch.Tensor:
+        if self._event is not None:
+            self._event.synchronize()
+        return self._tensor
+
+
+KT = TypeVar("KT")
+VT_co = TypeVar("VT_co")
+ParentW = TypeVar("ParentW")
+
+
+class GetItemLazyAwaitable(LazyAwaitable[W], Generic[W, ParentW, KT]):
+    """``parent[key]`` without waiting for the parent yet: waits for it and indexes the result when its own value is asked for."""
+
+    def __init__(self, parent: LazyAwaitable, key: Any) -> None:
+        super().__init__()
+        self._parent = parent
+        self._key = key
+
+    def _wait_impl(self) -> W:
+        return LazyAwaitable._wait_async(self._parent)[self._key]
+
+
+class LazyGetItemMixin(Generic[KT, VT_co]):
+    """For LazyAwaitables of mappings: ``awaitable[key]`` returns a ``GetItemLazyAwaitable`` instead of waiting."""
+
+    def __getitem__(self, key: Any) -> "GetItemLazyAwaitable":
+        return GetItemLazyAwaitable(self, key)  # type: ignore[arg-type]
