@@ -12,6 +12,7 @@ kernels in ``torchrec_b200.parallel.p2p`` instead, which need none of the pack/u
 """
 from __future__ import annotations
 
+import contextlib
 from dataclasses import dataclass, field
 from typing import Any, List, Optional, Tuple
 
@@ -553,3 +554,80 @@ def all_gather_base_pooled(input: torch.Tensor, group: Optional[dist.ProcessGrou
 
         return NoWait(all_gather_base_sync(pg, input, GRADIENT_DIVISION))
     return NoWait(_AllGatherBase.apply(pg, codecs, input))
+
+
+# ---- reference surface: argument records of the collectives, sync-mode switch, names of the sync transports ---------------------------------------------
+@contextlib.contextmanager
+def torchrec_use_sync_collectives():
+    """Inside the block the functional (traceable, blocking) collectives of ``comm_ops_sync`` are used instead of the request / wait pair."""
+    original = get_use_sync_collectives()
+    set_use_sync_collectives(True)
+    try:
+        yield
+    finally:
+        set_use_sync_collectives(original)
+
+
+def pg_name(pg: dist.ProcessGroup) -> str:
+    """The registered name of a process group (what the functional collectives take)."""
+    return dist._functional_collectives._resolve_group_name(pg, "")
+
+
+@dataclass
+class All2AllVInfo:
+    """Arguments of ``alltoallv``: column counts per rank, global / local batch sizes, per-table batch sizes and dims, split sizes."""
+
+    dims_sum_per_rank: List[int]
+    B_global: int
+    B_local: int
+    B_local_list: List[int]
+    D_local_list: List[int]
+    input_split_sizes: List[int] = field(default_factory=list)
+    output_split_sizes: List[int] = field(default_factory=list)
+    codecs: Optional[QuantizedCommCodecs] = None
+
+
+@dataclass
+class ReduceScatterInfo:
+    input_sizes: List[torch.Size]
+    codecs: Optional[QuantizedCommCodecs] = None
+
+
+@dataclass
+class ReduceScatterBaseInfo:
+    input_sizes: torch.Size
+    codecs: Optional[QuantizedCommCodecs] = None
+
+
+@dataclass
+class AllGatherBaseInfo:
+    input_size: torch.Size
+    codecs: Optional[QuantizedCommCodecs] = None
+
+
+@dataclass
+class ReduceScatterVInfo:
+    input_sizes: List[List[int]]
+    input_splits: List[int]
+    equal_splits: bool
+    total_input_size: List[int]
+    codecs: Optional[QuantizedCommCodecs] = None
+
+
+@dataclass
+class All2AllDenseInfo:
+    output_splits: List[int]
+    batch_size: int
+    input_shape: List[int]
+    input_splits: List[int]
+
+
+def __getattr__(name: str):
+    """The blocking functional collectives and their transports live in ``comm_ops_sync``; they are importable from here under the
+    reference's names."""
+    if name in ("all2all_pooled_sync", "all2all_sequence_sync", "reduce_scatter_base_sync", "all_gather_base_sync", "reduce_scatter_v_sync",
+                "variable_batch_all2all_pooled_sync", "reduce_scatter_tensor", "all_gather_into_tensor", "Comm", "All2AllSingle", "DefaultAll2AllSingle"):
+        from . import comm_ops_sync as _m
+
+        return getattr(_m, name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
