@@ -179,3 +179,52 @@ def _rank_without_shards(ctx):
 
 def test_rank_without_shards_joins_backward_collectives():
     run_multi_process(_rank_without_shards, world_size=2, backend="gloo")
+
+
+def _run_embedding_module_interface(ctx):
+    """ShardedEmbeddingModule surface of the sharded bags: sharding scheme by type, post-lookup tracker callback with the ids this rank
+    looks up, output-dist tracker registration."""
+    from torchrec_b200.modules.embedding_configs import EmbeddingBagConfig
+    from torchrec_b200.modules.embedding_modules import EmbeddingBagCollection
+    from torchrec_b200.parallel import sharding_plan as sp
+    from torchrec_b200.parallel.embedding_types import ShardedEmbeddingModule
+    from torchrec_b200.parallel.embeddingbag import EmbeddingBagCollectionSharder
+    from torchrec_b200.parallel.model_parallel import DistributedModelParallel
+    from torchrec_b200.parallel.types import ShardingPlan
+    from torchrec_b200.sparse import KeyedJaggedTensor
+
+    tables = [EmbeddingBagConfig(name="t0", embedding_dim=8, num_embeddings=20, feature_names=["f0", "f0b"]), EmbeddingBagConfig(name="t1", embedding_dim=8, num_embeddings=30, feature_names=["f1"])]
+    ebc = EmbeddingBagCollection(tables)
+    sharder = EmbeddingBagCollectionSharder()
+    plan = sp.construct_module_sharding_plan(ebc, {"t0": sp.table_wise(rank=1), "t1": sp.row_wise()}, sharder=sharder, world_size=2, local_size=2, device_type="cpu")
+
+    class W(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.ebc = ebc
+
+        def forward(self, k):
+            return self.ebc(k).values()
+
+    dmp = DistributedModelParallel(W(), device=torch.device("cpu"), plan=ShardingPlan({"ebc": plan}), sharders=[sharder])
+    sebc = dmp.module.ebc
+    assert isinstance(sebc, ShardedEmbeddingModule) and sebc.unsharded_module_type is EmbeddingBagCollection
+    sh = sebc.shardings
+    assert set(sh) == {"table_wise", "row_wise"}
+    assert sh["table_wise"].feature_names() == ["f0", "f0b"] and sh["table_wise"].feature_names_per_rank() == [[], ["f0", "f0b"]] and sh["table_wise"].features_per_rank() == [0, 2]
+    assert sh["row_wise"].feature_names_per_rank() == [["f1"], ["f1"]]
+    seen = []
+    sebc.register_post_lookup_tracker_fn(lambda feats, emb, module, extra: seen.append((feats.keys(), int(feats.values().numel()), emb, module)))
+    sebc.register_post_odist_tracker_fn(lambda *a: None)
+    kjt = KeyedJaggedTensor(keys=["f0", "f0b", "f1"], values=torch.tensor([1, 2, 3, 4, 5, 6]) + ctx.rank, lengths=torch.tensor([1, 1, 1, 1, 1, 1]))
+    dmp(kjt)
+    assert len(seen) == 1 and seen[0][2] is None and seen[0][3] is sebc
+    if ctx.rank == 1:
+        assert "f0" in seen[0][0] and seen[0][1] >= 8  # both ranks' f0 / f0b ids arrive at the owner of t0
+    sebc.register_post_lookup_tracker_fn(lambda *a: seen.append("second"))  # replaces the first callback
+    dmp(kjt)
+    assert seen[-1] == "second" and len(seen) == 2
+
+
+def test_sharded_embedding_module_interface():
+    run_multi_process(_run_embedding_module_interface, world_size=2, backend="gloo")

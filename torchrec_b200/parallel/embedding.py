@@ -23,7 +23,7 @@ from ..optim.fused import FusedOptimizerModule
 from ..optim.keyed import CombinedOptimizer, KeyedOptimizer
 from ..sparse.jagged_tensor import JaggedTensor, KeyedJaggedTensor
 from ..streamable import Multistreamable
-from .embedding_types import BaseEmbeddingSharder, KJTList
+from .embedding_types import BaseEmbeddingSharder, KJTList, ShardedEmbeddingModule
 from .embeddingbag import EmbeddingFusedOptimizer, _local_pieces_with_offsets, _sharded_tensor_from_local, _sharded_view, _TableParam, optimizer_spec_from
 from .engine import OptimizerSpec, ShardedLookupEngine, TableShard
 from .types import Awaitable, CommOp, LazyAwaitable, NoWait, ParameterSharding, QuantizedCommCodecs, ShardedModule, ShardingEnv, ShardingType
@@ -97,7 +97,7 @@ class _SeqInputDistTensors(Awaitable[KJTList]):
         return KJTList([self._inner.wait()])
 
 
-class ShardedEmbeddingCollection(ShardedModule[KJTList, List[torch.Tensor], Dict[str, JaggedTensor], EmbeddingCollectionContext], FusedOptimizerModule):
+class ShardedEmbeddingCollection(ShardedEmbeddingModule[KJTList, List[torch.Tensor], Dict[str, JaggedTensor], EmbeddingCollectionContext], FusedOptimizerModule):
     """Sharded ``EmbeddingCollection``: KJT -> Dict[embedding name, JaggedTensor]."""
 
     def __init__(self, module: EmbeddingCollectionInterface, table_name_to_parameter_sharding: Dict[str, ParameterSharding], env: ShardingEnv,

@@ -5,10 +5,13 @@ import abc
 import copy
 from dataclasses import dataclass, field
 from enum import Enum, unique
-from typing import Any, Dict, Generic, Iterator, List, Optional, Tuple, TypeVar, Union
+import logging
+from typing import Any, Callable, Dict, Generic, Iterator, List, Optional, Tuple, Type, TypeVar, Union
 
 import torch
 from torch import nn
+
+logger = logging.getLogger(__name__)
 
 from ..modules.embedding_configs import DataType, EmbeddingTableConfig, PoolingType
 from ..ops.tbe import OptimType  # noqa: F401  (re-export: reference exposes OptimType here)
@@ -164,6 +167,132 @@ class FeatureShardingMixIn:
 
     def features_per_rank(self) -> List[int]:
         raise NotImplementedError
+
+
+class ListOfKJTList(Multistreamable):
+    """Per device one ``KJTList`` (inference: one process drives several devices)."""
+
+    def __init__(self, features: List[KJTList]) -> None:
+        self.features_list = features
+
+    def __len__(self) -> int:
+        return len(self.features_list)
+
+    def __setitem__(self, key: int, item: KJTList) -> None:
+        self.features_list[key] = item
+
+    def __getitem__(self, key: int) -> KJTList:
+        return self.features_list[key]
+
+    def __iter__(self) -> Iterator[KJTList]:
+        return iter(self.features_list)
+
+    def record_stream(self, stream: torch.Stream) -> None:
+        for f in self.features_list:
+            f.record_stream(stream)
+
+
+@dataclass
+class DTensorMetadata:
+    """How a table shard appears as a DTensor: mesh, placements, global size and stride."""
+
+    mesh: Optional[Any] = None
+    placements: Optional[Tuple[Any, ...]] = None
+    size: Optional[Tuple[int, ...]] = None
+    stride: Optional[Tuple[int, ...]] = None
+
+
+class BaseEmbeddingUpdate(abc.ABC, nn.Module, Generic[F]):
+    """Interface of embedding implementations that take row updates (``forward(embeddings)`` writes them into the tables)."""
+
+    @abc.abstractmethod
+    def forward(self, embeddings: F) -> None:
+        ...
+
+
+class BaseGroupedFeatureProcessor(nn.Module):
+    """Interface of feature processors applied to the features of one table group: KJT in, KJT out."""
+
+    @abc.abstractmethod
+    def forward(self, features: KeyedJaggedTensor) -> KeyedJaggedTensor:
+        ...
+
+
+class _TableFeatureSharding(FeatureShardingMixIn):
+    """The features of the tables placed with one sharding type, and which rank looks them up."""
+
+    def __init__(self, names: List[str], per_rank: List[List[str]]) -> None:
+        self._names, self._per_rank = names, per_rank
+
+    def feature_names(self) -> List[str]:
+        return list(self._names)
+
+    def feature_names_per_rank(self) -> List[List[str]]:
+        return [list(x) for x in self._per_rank]
+
+    def features_per_rank(self) -> List[int]:
+        return [len(x) for x in self._per_rank]
+
+
+class ModuleShardingMixIn:
+    """Access to a sharded module's sharding scheme: sharding type -> the features sharded that way (per rank)."""
+
+    @property
+    def shardings(self) -> Dict[str, FeatureShardingMixIn]:
+        plan = getattr(self, "_plan", None)
+        cfgs = self.embedding_bag_configs() if hasattr(self, "embedding_bag_configs") else self.embedding_configs() if hasattr(self, "embedding_configs") else None
+        if plan is None or cfgs is None:
+            raise NotImplementedError
+        world = getattr(getattr(self, "_env", None), "world_size", 1)
+        out: Dict[str, FeatureShardingMixIn] = {}
+        by_type: Dict[str, Tuple[List[str], List[List[str]]]] = {}
+        for c in cfgs:
+            ps = plan[c.name]
+            names, per_rank = by_type.setdefault(ps.sharding_type, ([], [[] for _ in range(world)]))
+            names.extend(c.feature_names)
+            for r in (ps.ranks if ps.ranks else range(world)):
+                if r < world:
+                    per_rank[r].extend(c.feature_names)
+        for st, (names, per_rank) in by_type.items():
+            out[st] = _TableFeatureSharding(names, per_rank)
+        return out
+
+
+Out = TypeVar("Out")
+CompIn = TypeVar("CompIn", KJTList, ListOfKJTList, KeyedJaggedTensor)
+DistOut = TypeVar("DistOut")
+ShrdCtx = TypeVar("ShrdCtx", bound=Multistreamable)
+
+
+class ShardedEmbeddingModule(ShardedModule[CompIn, DistOut, Out, ShrdCtx], ModuleShardingMixIn):
+    """What every model-parallel embedding module offers besides the ``ShardedModule`` stages: its sharding scheme (``shardings``),
+    cache prefetch over its lookups, and tracker callbacks - ``register_post_lookup_tracker_fn(fn)``: ``fn(features, embeddings,
+    module, extra)`` for every lookup of this rank (the distributed features, i.e. the ids this rank looks up; this framework's fused
+    kernels do not materialise per-id embeddings at that point, ``embeddings`` is None - the delta tracker reads rows by id instead),
+    ``register_post_odist_tracker_fn(fn)``: ``fn()`` after every output dist has been issued."""
+
+    post_lookup_tracker_fn: Optional[Callable[..., None]] = None
+    post_odist_tracker_fn: Optional[Callable[..., None]] = None
+    _remove_lookup_tracker: Optional[Callable[[], None]] = None
+
+    def register_post_lookup_tracker_fn(self, record_fn: Callable[..., None]) -> None:
+        if self.post_lookup_tracker_fn is not None:
+            logger.warning("[ModelDeltaTracker] Custom record function already defined, overriding with new callable")
+            if self._remove_lookup_tracker is not None:
+                self._remove_lookup_tracker()
+        self.post_lookup_tracker_fn = record_fn
+        engine = getattr(self, "engine", None)
+        if engine is not None:
+            self._remove_lookup_tracker = engine.register_lookup_hook(lambda eng, feats: record_fn(feats, None, self, None))
+
+    def register_post_odist_tracker_fn(self, record_fn: Callable[..., None]) -> None:
+        if self.post_odist_tracker_fn is not None:
+            logger.warning("[ModelDeltaTracker] Compaction function already defined, overriding with new callable")
+        self.post_odist_tracker_fn = record_fn
+
+    @property
+    def unsharded_module_type(self) -> Type[nn.Module]:
+        return nn.Module
 
 
 class BaseEmbeddingSharder(ModuleSharder[M]):

@@ -26,7 +26,7 @@ from ..optim.fused import EmptyFusedOptimizer, FusedOptimizer, FusedOptimizerMod
 from ..optim.keyed import CombinedOptimizer, KeyedOptimizer
 from ..sparse.jagged_tensor import KeyedJaggedTensor, KeyedTensor
 from ..streamable import Multistreamable
-from .embedding_types import BaseEmbeddingSharder, EmbeddingComputeKernel, KJTList
+from .embedding_types import BaseEmbeddingSharder, EmbeddingComputeKernel, KJTList, ShardedEmbeddingModule
 from .engine import OptimizerSpec, ShardedLookupEngine, TableShard
 from .sharding_plan import placement
 from .types import (
@@ -321,7 +321,7 @@ class _DenseLookup(nn.Module):
 
 
 class ShardedEmbeddingBagCollection(
-    ShardedModule[KJTList, List[torch.Tensor], KeyedTensor, EmbeddingBagCollectionContext],
+    ShardedEmbeddingModule[KJTList, List[torch.Tensor], KeyedTensor, EmbeddingBagCollectionContext],
     FusedOptimizerModule,
 ):
     """Sharded ``EmbeddingBagCollection``."""
