@@ -138,3 +138,45 @@ def test_topology_group_sizes_and_storage_accounting(monkeypatch):
     item = out["a"]
     assert out.waits == 0 and (item + 1).tolist() == [2.0, 2.0] and out.waits == 1
     assert DeviceToHostTensorAwaitable(torch.arange(3)).wait().tolist() == [0, 1, 2]
+
+
+def test_plan_shape_bucket_and_precision_helpers():
+    import torch
+
+    from torchrec_b200.modules.embedding_configs import DataType
+    from torchrec_b200.ops.tbe import TableBatchedEmbeddingBags
+    from torchrec_b200.parallel import sharding_plan as sp
+    from torchrec_b200.parallel.types import EmbeddingEvent, ParameterSharding, ShardingType, ShardMetadata
+    from torchrec_b200.parallel.types import EnumerableShardingSpec
+    from torchrec_b200.parallel.utils import (EmbeddingQuantizationUtils, convert_to_fbgemm_types, create_global_tensor_shape_stride_from_metadata,
+                                              get_bucket_metadata_from_shard_metadata, maybe_annotate_embedding_event)
+
+    rw = [ShardMetadata([0, 0], [40, 8], "rank:0/cpu"), ShardMetadata([40, 0], [60, 8], "rank:1/cpu")]
+    m = get_bucket_metadata_from_shard_metadata(rw, 10)
+    assert (m.num_buckets_per_shard, m.bucket_offsets_per_shard, m.bucket_size) == ([4, 6], [0, 4], 10)
+    with pytest.raises(AssertionError):
+        get_bucket_metadata_from_shard_metadata(rw, 8)  # buckets would straddle the shard boundary
+
+    def ps(st, shards):
+        return ParameterSharding(sharding_type=st, compute_kernel="fused", ranks=list(range(len(shards))), sharding_spec=EnumerableShardingSpec(shards))
+
+    assert create_global_tensor_shape_stride_from_metadata(ps("row_wise", rw)) == (torch.Size([100, 8]), (8, 1))
+    cw = [ShardMetadata([0, 0], [100, 16], "rank:0/cpu"), ShardMetadata([0, 16], [100, 16], "rank:1/cpu")]
+    assert create_global_tensor_shape_stride_from_metadata(ps("column_wise", cw)) == (torch.Size([100, 32]), (32, 1))
+    grid = [ShardMetadata([r * 50, c * 16], [50, 16], f"rank:{c * 2 + r}/cpu") for c in range(2) for r in range(2)]
+    assert create_global_tensor_shape_stride_from_metadata(ps("grid_shard", grid), devices_per_node=2)[0] == torch.Size([100, 32])
+    assert create_global_tensor_shape_stride_from_metadata(ps("table_wise", [ShardMetadata([0, 0], [7, 4], "rank:0/cpu")]))[0] == torch.Size([7, 4])
+    assert convert_to_fbgemm_types({"cache_precision": DataType.FP16, "lr": 0.1}) == {"cache_precision": "fp16", "lr": 0.1}
+    with maybe_annotate_embedding_event(EmbeddingEvent.LOOKUP, "sparse.ebc", "row_wise"):
+        pass
+    with maybe_annotate_embedding_event(EmbeddingEvent.LOOKUP, None, None):
+        pass
+    assert sp.get_sharding_constructor_from_type(ShardingType.TABLE_ROW_WISE) is sp.table_row_wise and sp.placement_helper("cuda", 1, 3) == "rank:3/cuda:1"
+    # narrow the kernels of a model and restore them
+    t = TableBatchedEmbeddingBags([(10, 4), (5, 4)])
+    w0 = t.weights.detach().clone()
+    u = EmbeddingQuantizationUtils()
+    u.quantize_embedding_modules(t, DataType.FP16)
+    assert t.weights.dtype == torch.float16
+    u.recreate_embedding_modules(t)
+    assert t.weights.dtype == torch.float32 and float((t.weights - w0).abs().max()) < 1e-3

@@ -324,3 +324,14 @@ def construct_module_sharding_plan(
     for name, gen in per_param_sharding.items():
         plan[name] = gen(shardable[name], local_size, world_size, device_type, sharder)
     return plan
+
+
+def placement_helper(device_type: str, index: int = 0, rank: int = 0) -> str:
+    """Placement string of a shard: ``rank:<rank>/<device>:<index>``; cpu shards all live on rank 0's host."""
+    return f"rank:0/{device_type}" if device_type == "cpu" else f"rank:{rank}/{device_type}:{index}"
+
+
+def get_sharding_constructor_from_type(sharding_type: ShardingType) -> Callable[..., ParameterShardingGenerator]:
+    """The ``construct_module_sharding_plan`` helper (``table_wise``, ``row_wise``, ...) that makes a placement of this type."""
+    return {ShardingType.TABLE_WISE: table_wise, ShardingType.ROW_WISE: row_wise, ShardingType.COLUMN_WISE: column_wise, ShardingType.TABLE_ROW_WISE: table_row_wise,
+            ShardingType.GRID_SHARD: grid_shard, ShardingType.DATA_PARALLEL: data_parallel}[sharding_type]

@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import copy
 from collections import OrderedDict
-from typing import Any, Dict, List, Optional, Set, Type, TypeVar, Union
+from typing import Any, Dict, List, Optional, Set, Tuple, Type, TypeVar, Union
 
 import torch
 from torch import nn
@@ -219,3 +219,126 @@ def weights_bytes_in_emb_kernel(emb: nn.Module) -> int:
         if isinstance(w, torch.Tensor) and hasattr(m, "embedding_specs"):
             total += w.numel() * w.element_size()
     return total
+
+
+def convert_to_fbgemm_types(fused_params: Dict[str, Any]) -> Dict[str, Any]:
+    """``cache_precision`` / ``weights_precision`` / ``output_dtype`` given as ``DataType`` become the row-format names this framework's
+    kernels key on (the reference converts to FBGEMM's ``SparseType``)."""
+    from ..modules.embedding_configs import DataType, data_type_to_sparse_type
+
+    for key in ("cache_precision", "weights_precision", "output_dtype"):
+        if isinstance(fused_params.get(key), DataType):
+            fused_params[key] = data_type_to_sparse_type(fused_params[key])
+    return fused_params
+
+
+def maybe_annotate_embedding_event(event: Any, module_fqn: Optional[str], sharding_type: Optional[str]):
+    """A profiler range ``[<event>]_[<module>]_[<sharding type>]`` around a stage of a sharded embedding module (no-op without both names)."""
+    import contextlib
+
+    from torch.autograd.profiler import record_function
+
+    if module_fqn and sharding_type:
+        return record_function(f"[{event.value}]_[{module_fqn}]_[{sharding_type}]")
+    return contextlib.nullcontext()
+
+
+def create_global_tensor_shape_stride_from_metadata(parameter_sharding: ParameterSharding, devices_per_node: Optional[int] = None) -> Tuple[torch.Size, Tuple[int, int]]:
+    """Global shape and (row-major) stride of a table from the shards of its plan entry; grid shards need the ranks per node."""
+    from .types import ShardingType
+
+    shards = parameter_sharding.sharding_spec.shards if parameter_sharding.sharding_spec is not None else []
+    st = parameter_sharding.sharding_type
+    size = None
+    if st in (ShardingType.COLUMN_WISE.value, ShardingType.TABLE_COLUMN_WISE.value):
+        size = torch.Size([shards[0].shard_sizes[0], sum(s.shard_sizes[1] for s in shards)])
+    elif st in (ShardingType.ROW_WISE.value, ShardingType.TABLE_ROW_WISE.value):
+        size = torch.Size([sum(s.shard_sizes[0] for s in shards), shards[0].shard_sizes[1]])
+    elif st == ShardingType.TABLE_WISE.value:
+        size = torch.Size(shards[0].shard_sizes)
+    elif st == ShardingType.GRID_SHARD.value:
+        assert devices_per_node is not None, "grid shards: the global shape needs the number of ranks per node"
+        size = torch.Size([shards[0].shard_sizes[0] * devices_per_node, shards[0].shard_sizes[1] * (len(shards) // devices_per_node)])
+    if size is None:
+        return torch.Size([0, 0]), (0, 1)
+    return size, (size[1], 1)
+
+
+def get_bucket_metadata_from_shard_metadata(shards: List[Any], num_buckets: int):
+    """A row-wise sharded table cut into ``num_buckets`` equal buckets (ZCH: buckets never straddle shards): buckets per shard, index of
+    every shard's first bucket, rows per bucket."""
+    from .types import ShardingBucketMetadata
+
+    assert len(shards) > 0, "Shards cannot be empty"
+    table_size = shards[-1].shard_offsets[0] + shards[-1].shard_sizes[0]
+    assert table_size % num_buckets == 0, f"Table size '{table_size}' must be divisible by num_buckets '{num_buckets}'"
+    bucket_size = table_size // num_buckets
+    meta = ShardingBucketMetadata(num_buckets_per_shard=[], bucket_offsets_per_shard=[], bucket_size=bucket_size)
+    offset = 0
+    for shard in shards:
+        assert len(shard.shard_offsets) == 1 or shard.shard_offsets[1] == 0, \
+            f"Shard shard_offsets[1] '{shard.shard_offsets[1]}' is not 0. Table should be only row-wise sharded for bucketization"
+        assert shard.shard_sizes[0] % bucket_size == 0, f"Shard size[0] '{shard.shard_sizes[0]}' is not divisible by bucket size '{bucket_size}'"
+        n = shard.shard_sizes[0] // bucket_size
+        meta.num_buckets_per_shard.append(n)
+        meta.bucket_offsets_per_shard.append(offset)
+        offset += n
+    return meta
+
+
+def modify_input_for_feature_processor(features: Any, feature_processors: Any, is_collection: bool) -> None:
+    """Run the input-side part of the feature processors BEFORE the input dist, in place on the KJT (row-wise sharding splits bags
+    across ranks, so what depends on the position inside a bag must be computed while the bag is whole): the KJT gets a weights tensor
+    if it has none, then ``pre_process_input(kjt)`` of the collection, or of every per-feature processor on its feature's slice."""
+    with torch.no_grad():
+        if features.weights_or_none() is None:
+            features._weights = torch.zeros_like(features.values(), dtype=torch.float32)
+        if is_collection:
+            if hasattr(feature_processors, "pre_process_input"):
+                feature_processors.pre_process_input(features)
+            return
+        for feature in features.keys():
+            if feature in feature_processors and hasattr(feature_processors[feature], "pre_process_input"):
+                feature_processors[feature].pre_process_input(features[feature])
+
+
+class EmbeddingQuantizationUtils:
+    """Temporarily hold the table-batched kernels of a sharded model in a narrower float type (e.g. fp16 while a memory-hungry
+    evaluation runs) and restore them: ``quantize_embedding_modules(model, DataType.FP16)`` converts the weights buffers of every kernel
+    (smallest first, so the peak is one extra copy of the largest table group), ``recreate_embedding_modules(model)`` converts them
+    back to the precision they had. Optimizer states are not touched."""
+
+    _DTYPES = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}
+
+    def __init__(self) -> None:
+        self._original: Dict[nn.Module, torch.dtype] = {}
+
+    @staticmethod
+    def _kernels(module: nn.Module) -> List[nn.Module]:
+        ks = [m for m in module.modules() if hasattr(m, "embedding_specs") and isinstance(getattr(m, "weights", None), torch.Tensor)]
+        return sorted(ks, key=weights_bytes_in_emb_kernel)
+
+    @staticmethod
+    def _convert(k: nn.Module, dtype: torch.dtype, use_cpu_turnaround_optimization: bool) -> None:
+        w = k.weights
+        if w.dtype == dtype:
+            return
+        with torch.no_grad():
+            new = w.detach().cpu().to(dtype).to(w.device) if use_cpu_turnaround_optimization else w.detach().to(dtype)
+        if isinstance(w, nn.Parameter):
+            k.weights = nn.Parameter(new, requires_grad=w.requires_grad)
+        else:
+            k._buffers["weights"] = new
+
+    def quantize_embedding_modules(self, module: nn.Module, converted_dtype: Any, use_cpu_turnaround_optimization: bool = False) -> None:
+        from ..modules.embedding_configs import data_type_to_sparse_type
+
+        dtype = self._DTYPES[data_type_to_sparse_type(converted_dtype)]
+        for k in self._kernels(module):
+            self._original.setdefault(k, k.weights.dtype)
+            self._convert(k, dtype, use_cpu_turnaround_optimization)
+
+    def recreate_embedding_modules(self, module: nn.Module, use_cpu_turnaround_optimization: bool = False) -> None:
+        for k in self._kernels(module):
+            if k in self._original:
+                self._convert(k, self._original[k], use_cpu_turnaround_optimization)
