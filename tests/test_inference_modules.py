@@ -299,3 +299,64 @@ def test_sharded_quant_ebc_random_placements(seed):
         pb = sp.construct_module_sharding_plan(qb, {"b": sp.column_wise(ranks=[0, 1])}, sharder=sharder, world_size=W, local_size=W, device_type="cpu")
         with pytest.raises(ValueError, match="multiples of 32"):
             sharder.shard(qb, pb, ShardingEnv.from_local(W, 0), device=torch.device("cpu"))
+
+
+def test_shard_quantized_fp_and_mc_collections():
+    """The quantized FP-EBC / MC-EC / MC-EBC shard over two local devices with the default inference sharders and give the unsharded
+    quantized module's results."""
+    import copy
+
+    import torch
+
+    from torchrec_b200.inference.modules import quantize_embeddings, shard_quant_model
+    from torchrec_b200.modules.embedding_configs import DataType, EmbeddingBagConfig, EmbeddingConfig
+    from torchrec_b200.modules.embedding_modules import EmbeddingBagCollection, EmbeddingCollection
+    from torchrec_b200.modules.feature_processor_ import PositionWeightedModuleCollection
+    from torchrec_b200.modules.fp_embedding_modules import FeatureProcessedEmbeddingBagCollection
+    from torchrec_b200.modules.mc_embedding_modules import ManagedCollisionEmbeddingBagCollection, ManagedCollisionEmbeddingCollection
+    from torchrec_b200.modules.mc_modules import DistanceLFU_EvictionPolicy, ManagedCollisionCollection, MCHManagedCollisionModule
+    from torchrec_b200.sparse import KeyedJaggedTensor
+
+    torch.manual_seed(0)
+    bag_cfgs = [EmbeddingBagConfig(name=f"t{i}", embedding_dim=16, num_embeddings=64, feature_names=[f"f{i}"]) for i in range(2)]
+    seq_cfgs = [EmbeddingConfig(name=f"t{i}", embedding_dim=16, num_embeddings=64, feature_names=[f"f{i}"]) for i in range(2)]
+    fp = PositionWeightedModuleCollection({"f0": 4, "f1": 4})
+    with torch.no_grad():
+        for p in fp.parameters():
+            p.copy_(torch.linspace(0.5, 1.5, p.numel()))
+
+    def mcc(cfgs):
+        return ManagedCollisionCollection({c.name: MCHManagedCollisionModule(zch_size=64, device=torch.device("cpu"), eviction_policy=DistanceLFU_EvictionPolicy(),
+                                                                            eviction_interval=2, input_hash_size=10**9) for c in cfgs}, cfgs)
+
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fp = FeatureProcessedEmbeddingBagCollection(EmbeddingBagCollection(bag_cfgs, is_weighted=True), fp)
+            self.mc_ec = ManagedCollisionEmbeddingCollection(EmbeddingCollection(seq_cfgs), mcc(seq_cfgs), return_remapped_features=True)
+            self.mc_ebc = ManagedCollisionEmbeddingBagCollection(EmbeddingBagCollection(bag_cfgs), mcc(bag_cfgs), return_remapped_features=True)
+
+        def forward(self, small, raw):
+            a = self.fp(small).values()
+            b, rb = self.mc_ec(raw)
+            c, rc = self.mc_ebc(raw)
+            return a, {k: v.values() for k, v in b.items()}, c.values(), rb.values(), rc.values()
+
+    small = KeyedJaggedTensor(keys=["f0", "f1"], values=torch.randint(0, 64, (12,)), lengths=torch.tensor([3, 1, 2, 2, 0, 4]))
+    raw = KeyedJaggedTensor(keys=["f0", "f1"], values=torch.randint(0, 10**6, (12,)), lengths=torch.tensor([3, 1, 2, 2, 0, 4]))
+    m = M()
+    m.train()
+    for _ in range(6):
+        m(small, raw)
+    m.eval()
+    q = quantize_embeddings(m, DataType.INT8, inplace=False)
+    want = q(small, raw)
+    sharded, plan = shard_quant_model(copy.deepcopy(q), world_size=2, compute_device="cpu", sharding_device="cpu")
+    assert set(plan.plan.keys()) == {"fp", "mc_ec", "mc_ebc"}
+    assert type(sharded.fp).__name__ == "ShardedQuantFeatureProcessedEmbeddingBagCollection" and type(sharded.mc_ec).__name__ == "ShardedQuantManagedCollisionEmbeddingCollection"
+    got = sharded(small, raw)
+    torch.testing.assert_close(got[0], want[0])
+    for k in want[1]:
+        torch.testing.assert_close(got[1][k], want[1][k])
+    torch.testing.assert_close(got[2], want[2])
+    assert torch.equal(got[3], want[3]) and torch.equal(got[4], want[4])

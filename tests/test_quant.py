@@ -73,3 +73,83 @@ def test_quant_utils_fx_names_and_meta_to_cpu():
     assert meta.q.device.type == "meta"
     meta_to_cpu_placement(meta)
     assert meta.q.device.type == "cpu" and [c.name for c in meta.q.embedding_bag_configs()] == ["a", "b"]
+
+
+def test_quantized_feature_processed_and_managed_collision_collections():
+    """``quantize_embeddings`` swaps FP-EBC / MC-EC / MC-EBC for their quantized versions: position weights still apply, raw ids are
+    remapped exactly like in the trained float module, serving unseen ids never changes the collision state."""
+    import copy
+
+    from torchrec_b200.inference.modules import quantize_embeddings
+    from torchrec_b200.modules.embedding_configs import DataType, EmbeddingBagConfig, EmbeddingConfig
+    from torchrec_b200.modules.embedding_modules import EmbeddingBagCollection, EmbeddingCollection
+    from torchrec_b200.modules.feature_processor_ import PositionWeightedModuleCollection
+    from torchrec_b200.modules.fp_embedding_modules import FeatureProcessedEmbeddingBagCollection
+    from torchrec_b200.modules.mc_embedding_modules import ManagedCollisionEmbeddingBagCollection, ManagedCollisionEmbeddingCollection
+    from torchrec_b200.modules.mc_modules import DistanceLFU_EvictionPolicy, ManagedCollisionCollection, MCHManagedCollisionModule
+    from torchrec_b200.quant.embedding_modules import (FeatureProcessedEmbeddingBagCollection as QFP, QuantManagedCollisionEmbeddingBagCollection,
+                                                       QuantManagedCollisionEmbeddingCollection, for_each_module_of_type_do, quant_prep_enable_cache_features_order,
+                                                       quant_prep_enable_quant_state_dict_split_scale_bias_for_types)
+    from torchrec_b200.sparse import KeyedJaggedTensor
+
+    torch.manual_seed(0)
+    # feature processed bags
+    tables = [EmbeddingBagConfig(name="t0", embedding_dim=16, num_embeddings=50, feature_names=["f0"]), EmbeddingBagConfig(name="t1", embedding_dim=16, num_embeddings=40, feature_names=["f1"])]
+    fp = PositionWeightedModuleCollection({"f0": 5, "f1": 5})
+    with torch.no_grad():
+        for p in fp.parameters():
+            p.copy_(torch.linspace(0.5, 2.0, p.numel()))
+    model = torch.nn.Sequential(FeatureProcessedEmbeddingBagCollection(EmbeddingBagCollection(tables, is_weighted=True), fp))
+    kjt = KeyedJaggedTensor(keys=["f0", "f1"], values=torch.tensor([1, 2, 3, 4, 5, 6, 7]), lengths=torch.tensor([3, 1, 0, 3]))
+    want = model(kjt).values()
+    seen = []
+    for_each_module_of_type_do(model, [FeatureProcessedEmbeddingBagCollection], lambda m: seen.append(type(m).__name__))
+    assert seen == ["FeatureProcessedEmbeddingBagCollection"]
+    quant_prep_enable_cache_features_order(model, [FeatureProcessedEmbeddingBagCollection])
+    quant_prep_enable_quant_state_dict_split_scale_bias_for_types(model, [EmbeddingBagCollection])
+    q = quantize_embeddings(model, DataType.INT8, inplace=False)
+    assert isinstance(q[0], QFP) and q[0]._get_name() == "QuantFeatureProcessedEmbeddingBagCollection"
+    got = q(kjt).values()
+    assert got.shape == want.shape and float((got - want).abs().max()) < 0.05
+    unweighted = FeatureProcessedEmbeddingBagCollection(EmbeddingBagCollection(tables, is_weighted=True), PositionWeightedModuleCollection({"f0": 5, "f1": 5}))
+    unweighted._embedding_bag_collection.load_state_dict(model[0]._embedding_bag_collection.state_dict())
+    assert float((unweighted(kjt).values() - want).abs().max()) > 0.01, "the position weights matter in this test"
+
+    # managed collision: sequence and bags
+    def mc_model(kind):
+        if kind == "ec":
+            cfgs = [EmbeddingConfig(name="t0", embedding_dim=8, num_embeddings=64, feature_names=["f0"]), EmbeddingConfig(name="t1", embedding_dim=8, num_embeddings=64, feature_names=["f1"])]
+            emb, wrap = EmbeddingCollection(cfgs), ManagedCollisionEmbeddingCollection
+        else:
+            cfgs = [EmbeddingBagConfig(name="t0", embedding_dim=8, num_embeddings=64, feature_names=["f0"]), EmbeddingBagConfig(name="t1", embedding_dim=8, num_embeddings=64, feature_names=["f1"])]
+            emb, wrap = EmbeddingBagCollection(cfgs), ManagedCollisionEmbeddingBagCollection
+        mcc = ManagedCollisionCollection({c.name: MCHManagedCollisionModule(zch_size=64, device=torch.device("cpu"), eviction_policy=DistanceLFU_EvictionPolicy(), eviction_interval=2,
+                                                                            input_hash_size=10**9) for c in cfgs}, cfgs)
+        return wrap(emb, mcc, return_remapped_features=True)
+
+    g = torch.Generator().manual_seed(1)
+    raw = torch.randint(0, 10**6, (20,), generator=g)
+    batch = KeyedJaggedTensor(keys=["f0", "f1"], values=torch.cat([raw[:10], raw[10:]]), lengths=torch.full((10,), 2))
+    for kind, qcls in (("ec", QuantManagedCollisionEmbeddingCollection), ("ebc", QuantManagedCollisionEmbeddingBagCollection)):
+        m = mc_model(kind)
+        m.train()
+        for _ in range(6):
+            m(batch)  # the ids get admitted
+        m.eval()
+        out_f, remap_f = m(batch)
+        qm = quantize_embeddings(torch.nn.Sequential(copy.deepcopy(m)), DataType.INT8, inplace=True)[0]
+        assert isinstance(qm, qcls)
+        out_q, remap_q = qm(batch)
+        assert torch.equal(remap_q.values(), remap_f.values()), kind
+        if kind == "ec":
+            for k in out_f:
+                assert float((out_q[k].values() - out_f[k].values()).abs().max()) < 0.05
+        else:
+            assert float((out_q.values() - out_f.values()).abs().max()) < 0.05
+        state = {k: v.clone() for k, v in qm._managed_collision_collection.state_dict().items()}
+        qm.train()  # a parent switched to train mode must not unfreeze the collision modules
+        unseen = KeyedJaggedTensor(keys=["f0", "f1"], values=torch.randint(10**7, 10**8, (20,), generator=g), lengths=torch.full((10,), 2))
+        for _ in range(4):
+            qm(unseen)
+        for k, v in qm._managed_collision_collection.state_dict().items():
+            assert torch.equal(v, state[k]), (kind, k)

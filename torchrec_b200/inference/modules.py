@@ -124,7 +124,15 @@ def quantize_embeddings(module: nn.Module, dtype: Union[torch.dtype, DataType], 
                         per_table_weight_dtype: Optional[Dict[str, Union[torch.dtype, DataType]]] = None) -> nn.Module:
     """Swap float EmbeddingBagCollection / EmbeddingCollection modules for their quantized versions."""
     qconfig = QuantConfig(activation=output_dtype, weight=dtype, per_table_weight_dtype=per_table_weight_dtype)
-    mapping: Dict[Type[nn.Module], Type[nn.Module]] = {EmbeddingBagCollection: QuantEmbeddingBagCollection, EmbeddingCollection: QuantEmbeddingCollection}
+    from ..modules.fp_embedding_modules import FeatureProcessedEmbeddingBagCollection
+    from ..modules.mc_embedding_modules import ManagedCollisionEmbeddingBagCollection, ManagedCollisionEmbeddingCollection
+    from ..quant.embedding_modules import FeatureProcessedEmbeddingBagCollection as QuantFeatureProcessedEmbeddingBagCollection
+    from ..quant.embedding_modules import QuantManagedCollisionEmbeddingBagCollection, QuantManagedCollisionEmbeddingCollection
+
+    mapping: Dict[Type[nn.Module], Type[nn.Module]] = {EmbeddingBagCollection: QuantEmbeddingBagCollection, EmbeddingCollection: QuantEmbeddingCollection,
+                                                       FeatureProcessedEmbeddingBagCollection: QuantFeatureProcessedEmbeddingBagCollection,
+                                                       ManagedCollisionEmbeddingCollection: QuantManagedCollisionEmbeddingCollection,
+                                                       ManagedCollisionEmbeddingBagCollection: QuantManagedCollisionEmbeddingBagCollection}
     if additional_mapping is not None:
         mapping.update(additional_mapping)
     if not inplace:
@@ -197,7 +205,11 @@ def shard_quant_model(model: torch.nn.Module, world_size: int = 1, compute_devic
     if constraints is None:
         constraints = {}
     if sharders is None:
-        sharders = [QuantEmbeddingBagCollectionSharder(), QuantEmbeddingCollectionSharder()]
+        from ..parallel.quant_embedding import QuantManagedCollisionEmbeddingCollectionSharder
+        from ..parallel.quant_embeddingbag import QuantFeatureProcessedEmbeddingBagCollectionSharder, QuantManagedCollisionEmbeddingBagCollectionSharder
+
+        sharders = [QuantEmbeddingBagCollectionSharder(), QuantEmbeddingCollectionSharder(), QuantFeatureProcessedEmbeddingBagCollectionSharder(),
+                    QuantManagedCollisionEmbeddingCollectionSharder(), QuantManagedCollisionEmbeddingBagCollectionSharder()]
     if compute_device == "cuda" and not torch.cuda.is_available():
         compute_device = "cpu"
     topology = Topology(world_size=world_size, compute_device=compute_device, local_world_size=world_size, hbm_cap=device_memory_size, ddr_cap=ddr_cap)

@@ -46,6 +46,12 @@ class ManagedCollisionModule(nn.Module):
         """Slots whose ids were replaced since the last call (their embedding rows should be reset)."""
 
     @abc.abstractmethod
+    def reset_inference_mode(self) -> None:
+        """Switch to serving: lookups only (no admission, no eviction, no statistics)."""
+        self.train(False)
+        if hasattr(self, "_is_inference"):
+            self._is_inference = True
+
     def remap(self, features: Dict[str, JaggedTensor]) -> Dict[str, JaggedTensor]:
         ...
 

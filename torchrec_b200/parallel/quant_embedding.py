@@ -137,3 +137,32 @@ class QuantEmbeddingCollectionSharder(BaseQuantEmbeddingSharder[QuantEmbeddingCo
     @property
     def module_type(self) -> Type[QuantEmbeddingCollection]:
         return QuantEmbeddingCollection
+
+
+class ShardedQuantManagedCollisionEmbeddingCollection(nn.Module):
+    """Quantized sequence tables sharded like a plain quantized collection; the managed-collision collection is replicated (read-only
+    when serving) and remaps the raw ids of the full batch before the lookup. Returns ``(embeddings, remapped features)``."""
+
+    def __init__(self, module, params, env, fused_params=None, device=None) -> None:
+        super().__init__()
+        self._sharded = ShardedQuantEmbeddingCollection(module, params, env, fused_params, device)
+        self._managed_collision_collection = module._managed_collision_collection
+        self._configs = list(module.embedding_configs())
+
+    def embedding_configs(self):
+        return self._configs
+
+    def forward(self, features: KeyedJaggedTensor):
+        features = self._managed_collision_collection(features)
+        return self._sharded(features), features
+
+
+class QuantManagedCollisionEmbeddingCollectionSharder(QuantEmbeddingCollectionSharder):
+    def shard(self, module, params, env, device=None, module_fqn=None):
+        return ShardedQuantManagedCollisionEmbeddingCollection(module, params, env, self.fused_params, device)
+
+    @property
+    def module_type(self):
+        from ..quant.embedding_modules import QuantManagedCollisionEmbeddingCollection
+
+        return QuantManagedCollisionEmbeddingCollection

@@ -378,3 +378,66 @@ class QuantEmbeddingBagCollectionSharder(BaseQuantEmbeddingSharder[QuantEmbeddin
     @property
     def module_type(self) -> Type[QuantEmbeddingBagCollection]:
         return QuantEmbeddingBagCollection
+
+
+# ---- feature-processed / managed-collision quantized bags: the processors and the collision modules are replicated (they are small and
+# read-only when serving), the tables are sharded like plain quantized bags ------------------------------------------------------------------------
+class _PreprocessedShardedQuantModule(nn.Module):
+    """``pre(features)`` on the full batch, then the sharded quantized lookup; with ``return_features`` the pre-processed (remapped)
+    features are returned next to the embeddings like the unsharded module does."""
+
+    def __init__(self, sharded: nn.Module, pre: nn.Module, return_features: bool, configs: List[Any]) -> None:
+        super().__init__()
+        self._sharded = sharded
+        self._pre = pre
+        self._return_features = return_features
+        self._configs = list(configs)
+
+    def embedding_bag_configs(self) -> List[Any]:
+        return self._configs
+
+    def forward(self, features: KeyedJaggedTensor):
+        features = self._pre(features)
+        out = self._sharded(features)
+        return (out, features) if self._return_features else out
+
+    def sharded_module_weights_spec(self):  # plan / weight-spec tooling looks through the wrapper
+        return getattr(self._sharded, "sharded_module_weights_spec", lambda: {})()
+
+
+class ShardedQuantFeatureProcessedEmbeddingBagCollection(_PreprocessedShardedQuantModule):
+    def __init__(self, module, params, env, fused_params=None, device=None) -> None:
+        super().__init__(ShardedQuantEmbeddingBagCollection(module, params, env, fused_params, device=device), module.feature_processor, False, module.embedding_bag_configs())
+
+    @property
+    def feature_processor(self) -> nn.Module:
+        return self._pre
+
+
+class ShardedQuantManagedCollisionEmbeddingBagCollection(_PreprocessedShardedQuantModule):
+    def __init__(self, module, params, env, fused_params=None, device=None) -> None:
+        super().__init__(ShardedQuantEmbeddingBagCollection(module, params, env, fused_params, device=device), module._managed_collision_collection, True, module.embedding_bag_configs())
+
+
+def _quant_cls(name: str):
+    from ..quant import embedding_modules as q
+
+    return getattr(q, name)
+
+
+class QuantFeatureProcessedEmbeddingBagCollectionSharder(QuantEmbeddingBagCollectionSharder):
+    def shard(self, module, params, env, device=None, module_fqn=None):
+        return ShardedQuantFeatureProcessedEmbeddingBagCollection(module, params, env, self.fused_params, device=device)
+
+    @property
+    def module_type(self):
+        return _quant_cls("FeatureProcessedEmbeddingBagCollection")
+
+
+class QuantManagedCollisionEmbeddingBagCollectionSharder(QuantEmbeddingBagCollectionSharder):
+    def shard(self, module, params, env, device=None, module_fqn=None):
+        return ShardedQuantManagedCollisionEmbeddingBagCollection(module, params, env, self.fused_params, device=device)
+
+    @property
+    def module_type(self):
+        return _quant_cls("QuantManagedCollisionEmbeddingBagCollection")

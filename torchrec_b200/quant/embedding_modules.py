@@ -6,7 +6,7 @@ follows the reference: ``embedding_bags.<table>.weight`` (uint8 rows incl. the f
 from __future__ import annotations
 
 import copy
-from typing import Any, Dict, List, Optional, Tuple
+from typing import Any, Callable, Dict, List, Optional, Tuple
 
 import torch
 import torch.nn as nn
@@ -262,3 +262,174 @@ class EmbeddingCollection(EmbeddingCollectionInterface):
     @property
     def device(self) -> torch.device:
         return self._device
+
+
+# ---- feature-processed and managed-collision variants ----------------------------------------------------------------------------------------------------
+MODULE_ATTR_CACHE_FEATURES_ORDER = "__cache_features_order"
+
+
+def for_each_module_of_type_do(module: nn.Module, module_types: List[type], op: Callable[[nn.Module], None]) -> None:
+    """``op(m)`` for every sub-module (the root included) whose type is one of ``module_types``."""
+    for m in module.modules():
+        if any(type(m) is t for t in module_types):
+            op(m)
+
+
+def quant_prep_enable_quant_state_dict_split_scale_bias_for_types(module: nn.Module, module_types: List[type]) -> None:
+    """Mark the float modules of these types: their quantized versions keep scale / bias as separate state-dict tensors."""
+    for_each_module_of_type_do(module, module_types, lambda m: setattr(m, MODULE_ATTR_QUANT_STATE_DICT_SPLIT_SCALE_BIAS, True))
+
+
+def quant_prep_enable_cache_features_order(module: nn.Module, module_types: List[type]) -> None:
+    """Mark the float modules of these types: their quantized versions remember the feature permutation of the first batch (inputs
+    always arrive in the same key order when serving)."""
+    for_each_module_of_type_do(module, module_types, lambda m: setattr(m, MODULE_ATTR_CACHE_FEATURES_ORDER, True))
+
+
+def _quantized_tables(configs, qconfig, pruning: Optional[Dict[str, int]] = None):
+    per_table = getattr(qconfig, "per_table_weight_dtype", None)
+    w = qconfig.weight
+    wdtype = w().dtype if callable(w) else w
+    tables, name_to_dt = [], {}
+    for cfg in configs:
+        c = copy.deepcopy(cfg)
+        c.data_type = _data_type_of(wdtype, per_table, cfg.name)
+        if pruning and cfg.name in pruning:
+            c.num_embeddings_post_pruning = pruning[cfg.name]
+        tables.append(c)
+        name_to_dt[cfg.name] = c.data_type
+    act = qconfig.activation
+    out_dtype = act().dtype if callable(act) else (act if isinstance(act, torch.dtype) else torch.float)
+    return tables, name_to_dt, out_dtype
+
+
+class FeatureProcessedEmbeddingBagCollection(EmbeddingBagCollection):
+    """Quantized bags behind (float) feature processors: ``forward`` applies the processors to the KJT, then looks up
+    (reference quant/embedding_modules.py:636)."""
+
+    def __init__(self, tables: List[EmbeddingBagConfig], is_weighted: bool, device: torch.device, output_dtype: torch.dtype = torch.float,
+                 table_name_to_quantized_weights: Optional[Dict[str, Tuple[torch.Tensor, Optional[torch.Tensor]]]] = None, register_tbes: bool = False,
+                 quant_state_dict_split_scale_bias: bool = False, row_alignment: int = DEFAULT_ROW_ALIGNMENT, feature_processor: Optional[nn.Module] = None,
+                 cache_features_order: bool = False) -> None:
+        super().__init__(tables, is_weighted, device, output_dtype, table_name_to_quantized_weights, register_tbes, quant_state_dict_split_scale_bias, row_alignment,
+                         cache_features_order)
+        assert feature_processor is not None, "Use EmbeddingBagCollection for no feature_processor"
+        self.feature_processor = feature_processor
+
+    def forward(self, features: KeyedJaggedTensor) -> KeyedTensor:
+        return super().forward(self.feature_processor(features))
+
+    def _get_name(self) -> str:
+        return "QuantFeatureProcessedEmbeddingBagCollection"
+
+    @classmethod
+    def from_float(cls, module: nn.Module, use_precomputed_fake_quant: bool = False) -> "FeatureProcessedEmbeddingBagCollection":
+        assert hasattr(module, "qconfig"), "FeatureProcessedEmbeddingBagCollection input float module must have qconfig defined"
+        ebc = module._embedding_bag_collection
+        pruning = getattr(module, MODULE_ATTR_EMB_CONFIG_NAME_TO_NUM_ROWS_POST_PRUNING_DICT, None)
+        tables, name_to_dt, out_dtype = _quantized_tables(ebc.embedding_bag_configs(), module.qconfig, pruning)
+        qw: Dict[str, Tuple[torch.Tensor, Optional[torch.Tensor]]] = {}
+        device = quantize_state_dict(ebc, qw, name_to_dt, pruning)
+        fp = module._feature_processors
+        return cls(tables, ebc.is_weighted(), device=device, output_dtype=out_dtype, table_name_to_quantized_weights=qw,
+                   register_tbes=getattr(module, MODULE_ATTR_REGISTER_TBES_BOOL, False),
+                   quant_state_dict_split_scale_bias=getattr(ebc, MODULE_ATTR_QUANT_STATE_DICT_SPLIT_SCALE_BIAS, False),
+                   row_alignment=getattr(ebc, MODULE_ATTR_ROW_ALIGNMENT_INT, DEFAULT_ROW_ALIGNMENT), feature_processor=fp.to(device) if device.type != "meta" else fp,
+                   cache_features_order=getattr(module, MODULE_ATTR_CACHE_FEATURES_ORDER, False))
+
+
+def _freeze_mcc(mcc: nn.Module) -> None:
+    """Serving: the managed-collision modules only look ids up (no insertion, no eviction)."""
+    for m in getattr(mcc, "_managed_collision_modules", {}).values():
+        if hasattr(m, "reset_inference_mode"):
+            m.reset_inference_mode()
+        elif hasattr(m, "_is_inference"):
+            m._is_inference = True
+        m.train(False)
+
+
+class QuantManagedCollisionEmbeddingCollection(EmbeddingCollection):
+    """Quantized sequence embeddings behind a managed-collision collection: raw ids are remapped to table slots (read-only), then
+    looked up; ``forward`` returns ``(embeddings, remapped features)`` (reference quant/embedding_modules.py:1050)."""
+
+    def __init__(self, tables: List[EmbeddingConfig], device: torch.device, need_indices: bool = False, output_dtype: torch.dtype = torch.float,
+                 table_name_to_quantized_weights: Optional[Dict[str, Tuple[torch.Tensor, Optional[torch.Tensor]]]] = None, register_tbes: bool = False,
+                 quant_state_dict_split_scale_bias: bool = False, row_alignment: int = DEFAULT_ROW_ALIGNMENT, managed_collision_collection: Optional[nn.Module] = None,
+                 return_remapped_features: bool = False, cache_features_order: bool = False) -> None:
+        super().__init__(tables, device, need_indices, output_dtype, table_name_to_quantized_weights, register_tbes, quant_state_dict_split_scale_bias, row_alignment,
+                         cache_features_order)
+        assert managed_collision_collection, "Managed collision collection cannot be None"
+        self._managed_collision_collection = managed_collision_collection
+        self._return_remapped_features = return_remapped_features
+        assert [c.name for c in self.embedding_configs()] == [c.name for c in managed_collision_collection.embedding_configs()], \
+            "Embedding Collection and Managed Collision Collection must contain the same Embedding Configs"
+        _freeze_mcc(managed_collision_collection)
+
+    def forward(self, features: KeyedJaggedTensor):
+        features = self._managed_collision_collection(features)
+        return super().forward(features), features
+
+    def train(self, mode: bool = True):
+        super().train(mode)
+        _freeze_mcc(self._managed_collision_collection)  # serving never inserts or evicts, whatever mode the parent model is put in
+        return self
+
+    def _get_name(self) -> str:
+        return "QuantManagedCollisionEmbeddingCollection"
+
+    @classmethod
+    def from_float(cls, module: nn.Module, return_remapped_features: bool = False) -> "QuantManagedCollisionEmbeddingCollection":
+        assert hasattr(module, "qconfig"), "QuantManagedCollisionEmbeddingCollection input float module must have qconfig defined"
+        ec = module._embedding_module
+        tables, name_to_dt, out_dtype = _quantized_tables(ec.embedding_configs(), module.qconfig)
+        qw: Dict[str, Tuple[torch.Tensor, Optional[torch.Tensor]]] = {}
+        device = quantize_state_dict(ec, qw, name_to_dt)
+        return cls(tables, device=device, need_indices=ec.need_indices(), output_dtype=out_dtype, table_name_to_quantized_weights=qw,
+                   register_tbes=getattr(module, MODULE_ATTR_REGISTER_TBES_BOOL, False),
+                   quant_state_dict_split_scale_bias=getattr(ec, MODULE_ATTR_QUANT_STATE_DICT_SPLIT_SCALE_BIAS, False),
+                   row_alignment=getattr(ec, MODULE_ATTR_ROW_ALIGNMENT_INT, DEFAULT_ROW_ALIGNMENT), managed_collision_collection=module._managed_collision_collection,
+                   return_remapped_features=return_remapped_features or module._return_remapped_features,
+                   cache_features_order=getattr(ec, MODULE_ATTR_CACHE_FEATURES_ORDER, False))
+
+
+class QuantManagedCollisionEmbeddingBagCollection(EmbeddingBagCollection):
+    """Quantized bags behind a managed-collision collection; ``forward`` returns ``(KeyedTensor, remapped features)``."""
+
+    def __init__(self, tables: List[EmbeddingBagConfig], is_weighted: bool, device: torch.device, output_dtype: torch.dtype = torch.float,
+                 table_name_to_quantized_weights: Optional[Dict[str, Tuple[torch.Tensor, Optional[torch.Tensor]]]] = None, register_tbes: bool = False,
+                 quant_state_dict_split_scale_bias: bool = False, row_alignment: int = DEFAULT_ROW_ALIGNMENT, managed_collision_collection: Optional[nn.Module] = None,
+                 return_remapped_features: bool = False, cache_features_order: bool = False) -> None:
+        super().__init__(tables, is_weighted, device, output_dtype, table_name_to_quantized_weights, register_tbes, quant_state_dict_split_scale_bias, row_alignment,
+                         cache_features_order)
+        assert managed_collision_collection, "Managed collision collection cannot be None"
+        self._managed_collision_collection = managed_collision_collection
+        self._return_remapped_features = return_remapped_features
+        assert [c.name for c in self.embedding_bag_configs()] == [c.name for c in managed_collision_collection.embedding_configs()], \
+            "Embedding Bag Collection and Managed Collision Collection must contain the same Embedding Configs"
+        _freeze_mcc(managed_collision_collection)
+
+    def forward(self, features: KeyedJaggedTensor):
+        features = self._managed_collision_collection(features)
+        return super().forward(features), features
+
+    def train(self, mode: bool = True):
+        super().train(mode)
+        _freeze_mcc(self._managed_collision_collection)  # serving never inserts or evicts, whatever mode the parent model is put in
+        return self
+
+    def _get_name(self) -> str:
+        return "QuantManagedCollisionEmbeddingBagCollection"
+
+    @classmethod
+    def from_float(cls, module: nn.Module, return_remapped_features: bool = False) -> "QuantManagedCollisionEmbeddingBagCollection":
+        assert hasattr(module, "qconfig"), "QuantManagedCollisionEmbeddingBagCollection input float module must have qconfig defined"
+        ebc = module._embedding_module
+        tables, name_to_dt, out_dtype = _quantized_tables(ebc.embedding_bag_configs(), module.qconfig)
+        qw: Dict[str, Tuple[torch.Tensor, Optional[torch.Tensor]]] = {}
+        device = quantize_state_dict(ebc, qw, name_to_dt)
+        return cls(tables, ebc.is_weighted(), device=device, output_dtype=out_dtype, table_name_to_quantized_weights=qw,
+                   register_tbes=getattr(module, MODULE_ATTR_REGISTER_TBES_BOOL, False),
+                   quant_state_dict_split_scale_bias=getattr(ebc, MODULE_ATTR_QUANT_STATE_DICT_SPLIT_SCALE_BIAS, False),
+                   row_alignment=getattr(ebc, MODULE_ATTR_ROW_ALIGNMENT_INT, DEFAULT_ROW_ALIGNMENT), managed_collision_collection=module._managed_collision_collection,
+                   return_remapped_features=return_remapped_features or module._return_remapped_features,
+                   cache_features_order=getattr(ebc, MODULE_ATTR_CACHE_FEATURES_ORDER, False))
