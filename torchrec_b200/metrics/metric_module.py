@@ -44,6 +44,12 @@ MEMORY_AVG_WARNING_PERCENTAGE = 20
 MEMORY_AVG_WARNING_WARMUP = 100
 
 MetricValue = Union[torch.Tensor, float]
+MetricsResult = Dict[str, MetricValue]  # what ``compute`` returns
+MetricsFuture = concurrent.futures.Future  # of a MetricsResult (asynchronous compute)
+MetricsOutput = Union[MetricsResult, MetricsFuture, "DeferrableMetrics"]
+PublishableMetrics = Dict[str, Any]  # after the values were made plain (floats / lists) for a metrics sink
+PublishableMetricsFuture = concurrent.futures.Future
+PublishableMetricsOutput = Union[PublishableMetrics, PublishableMetricsFuture, "DeferrableMetrics"]
 
 
 class StateMetric(abc.ABC):

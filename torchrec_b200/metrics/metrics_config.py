@@ -111,3 +111,13 @@ DefaultMetricsConfig = MetricsConfig(
 )
 
 EmptyMetricsConfig = MetricsConfig(rec_tasks=[], rec_metrics={}, throughput_metric=None, state_metrics=[])
+
+
+def validate_batch_size_stages(batch_size_stages: Optional[List[BatchSizeStage]]) -> None:
+    """A batch-size schedule is a list of stages; only the last one may (and must) be open ended (``max_iters=None``)."""
+    if not batch_size_stages:
+        return
+    if batch_size_stages[-1].max_iters is not None:
+        raise ValueError(f"Batch size stages last stage should have max_iters = None, but get {batch_size_stages[-1].max_iters}")
+    if any(stage.max_iters is None for stage in batch_size_stages[:-1]):
+        raise ValueError("Batch size stages should have max_iters set for every stage but the last")

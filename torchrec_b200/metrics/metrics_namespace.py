@@ -8,7 +8,11 @@ class StrValueMixin:
         return self.value  # type: ignore[attr-defined]
 
 
-class MetricName(StrValueMixin, Enum):
+class MetricNameBase(StrValueMixin, Enum):
+    """Base of metric-name enums (projects add their own names by subclassing)."""
+
+
+class MetricName(MetricNameBase):
     DEFAULT = ""
     NE = "ne"
     NE_POSITIVE = "ne_positive"

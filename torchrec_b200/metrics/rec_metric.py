@@ -26,6 +26,9 @@ class RecComputeMode(Enum):
     FUSED_TASKS_AND_STATES_COMPUTATION = 3
 
 
+RecModelOutput = Union[torch.Tensor, Dict[str, torch.Tensor]]
+
+
 @dataclass
 class RecTaskInfo:
     name: str = "DefaultTask"
