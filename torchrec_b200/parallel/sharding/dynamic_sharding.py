@@ -175,3 +175,68 @@ def output_sharding_plan_delta(old_plan: Dict[str, ParameterSharding], new_plan:
         if v.sharding_spec is not None:
             vol += sum(s.shard_sizes[0] * s.shard_sizes[1] * 4 for s in v.sharding_spec.shards)
     return delta, vol
+
+
+# ---- plan deltas in the reference's shapes ----------------------------------------------------------------------------------------------------------------
+def output_sharding_plan_delta_single(old_plan: Dict[str, ParameterSharding], new_plan: Dict[str, ParameterSharding], return_data_volume: bool = False):
+    """``(megabytes that would move, {table: new ParameterSharding})`` for the tables whose placement differs between two plans of one
+    module (same tables in both). What ``DistributedModelParallel.reshard`` takes as ``changed_shard_to_params``."""
+    import copy
+
+    from ..types import EmbeddingModuleShardingPlan
+
+    assert len(old_plan) == len(new_plan), "both plans must cover the same tables"
+    delta = output_sharding_plan_delta(old_plan, new_plan)
+    diff = EmbeddingModuleShardingPlan({k: copy.deepcopy(v) for k, v in delta.items()})
+    volume = 0.0
+    if return_data_volume:
+        for v in diff.values():
+            if v.sharding_spec is not None:
+                volume += sum(s.shard_sizes[0] * s.shard_sizes[1] * 4 / (1024 * 1024) for s in v.sharding_spec.shards)  # float rows
+    return volume, diff
+
+
+def output_sharding_plans_delta(old_plan: Dict[str, Dict[str, ParameterSharding]], new_plan: Dict[str, Dict[str, ParameterSharding]], return_data_volume: bool = False):
+    """Per module fqn (the layout of ``ShardingPlan.plan``): ``output_sharding_plan_delta_single`` of its old and new plan."""
+    out = {}
+    for key, plan in old_plan.items():
+        assert key in new_plan, f"module {key} is missing from the new plan"
+        out[key] = output_sharding_plan_delta_single(plan, new_plan[key], return_data_volume)
+    return out
+
+
+def update_module_sharding_plan(module, changed_sharding_params: Dict[str, ParameterSharding], sharding_type_to_sharding_infos: Optional[Dict[str, List[Any]]] = None) -> None:
+    """Record new placements in a sharded module's plan (``module_sharding_plan`` / ``_plan``) and in the matching sharding infos."""
+    plan = getattr(module, "module_sharding_plan", None)
+    if plan is None:
+        plan = getattr(module, "_plan", None)
+    if plan is None:
+        raise RuntimeError("Module does not have a module_sharding_plan attribute")
+    for name, param in changed_sharding_params.items():
+        plan[name] = param
+        for info in (sharding_type_to_sharding_infos or {}).get(param.sharding_type, []):
+            if info.embedding_config.name == name:
+                info.param_sharding = param
+
+
+def move_sharded_tensors_to_cpu(state_dict: Dict[str, Any]) -> Dict[str, Any]:
+    """Move the local shards of every ShardedTensor in a (nested) state dict to host memory - frees HBM while a re-shard or a checkpoint
+    holds a second copy of the state."""
+    def walk(item: Any) -> Any:
+        if hasattr(item, "local_shards") and callable(item.local_shards):
+            for shard in item.local_shards():
+                if shard.tensor.device.type == "cuda":
+                    shard.tensor = shard.tensor.cpu()
+            return item
+        if isinstance(item, dict):
+            return {k: walk(v) for k, v in item.items()}
+        if isinstance(item, list):
+            return [walk(v) for v in item]
+        if isinstance(item, tuple):
+            return tuple(walk(v) for v in item)
+        return item
+
+    out = walk(state_dict)
+    if torch.cuda.is_available():
+        torch.cuda.empty_cache()
+    return out

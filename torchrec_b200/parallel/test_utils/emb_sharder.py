@@ -39,3 +39,56 @@ TestEBCSharder = _pinned(EmbeddingBagCollectionSharder)
 TestECSharder = _pinned(EmbeddingCollectionSharder)
 TestFusedEBCSharder = _pinned(FusedEmbeddingBagCollectionSharder)
 TestFusedECSharder = _pinned(FusedEmbeddingCollectionSharder)
+
+
+# ---- the other sharders of the reference's test kit ----------------------------------------------------------------------------------------------------------
+from ..embedding_tower_sharding import EmbeddingTowerCollectionSharder, EmbeddingTowerSharder  # noqa: E402
+from ..embeddingbag import EmbeddingBagSharder  # noqa: E402
+from ..mc_embedding import ManagedCollisionEmbeddingCollectionSharder  # noqa: E402
+from ..mc_embeddingbag import ManagedCollisionEmbeddingBagCollectionSharder  # noqa: E402
+from ..mc_modules import ManagedCollisionCollectionSharder  # noqa: E402
+
+TestEBSharder = _pinned(EmbeddingBagSharder)  # nn.EmbeddingBag
+TestETSharder = _pinned(EmbeddingTowerSharder)
+TestETCSharder = _pinned(EmbeddingTowerCollectionSharder)
+
+
+class TestMCSharder(ManagedCollisionCollectionSharder):
+    """Managed-collision collection pinned to one sharding type."""
+
+    __test__ = False
+
+    def __init__(self, sharding_type: str, qcomm_codecs_registry: Optional[Dict[str, QuantizedCommCodecs]] = None) -> None:
+        super().__init__()
+        self._sharding_type = sharding_type
+
+    def sharding_types(self, compute_device_type: str) -> List[str]:
+        return [self._sharding_type]
+
+
+class TestEBCSharderMCH(ManagedCollisionEmbeddingBagCollectionSharder):
+    """MC-EBC whose bags and collision modules are pinned to one sharding type / kernel."""
+
+    __test__ = False
+
+    def __init__(self, sharding_type: str, kernel_type: str, fused_params: Optional[Dict[str, Any]] = None,
+                 qcomm_codecs_registry: Optional[Dict[str, QuantizedCommCodecs]] = None) -> None:
+        super().__init__(TestEBCSharder(sharding_type, kernel_type, fused_params, qcomm_codecs_registry), TestMCSharder(sharding_type, qcomm_codecs_registry),
+                         fused_params=fused_params, qcomm_codecs_registry=qcomm_codecs_registry)
+        self._sharding_type = sharding_type
+
+    def sharding_types(self, compute_device_type: str) -> List[str]:
+        return [self._sharding_type]
+
+
+class TestECSharderMCH(ManagedCollisionEmbeddingCollectionSharder):
+    __test__ = False
+
+    def __init__(self, sharding_type: str, kernel_type: str, fused_params: Optional[Dict[str, Any]] = None,
+                 qcomm_codecs_registry: Optional[Dict[str, QuantizedCommCodecs]] = None) -> None:
+        super().__init__(TestECSharder(sharding_type, kernel_type, fused_params, qcomm_codecs_registry), TestMCSharder(sharding_type, qcomm_codecs_registry),
+                         fused_params=fused_params, qcomm_codecs_registry=qcomm_codecs_registry)
+        self._sharding_type = sharding_type
+
+    def sharding_types(self, compute_device_type: str) -> List[str]:
+        return [self._sharding_type]

@@ -10,6 +10,9 @@ import torch
 from torch import nn
 
 
+BackwardHookWork = Callable[[Any], None]  # work injected into the backward pass; receives the train pipeline
+
+
 @unique
 class InjectionTargetType(Enum):
     PARAM_GRAD = "param_grad"   # post-accumulate-grad hook on one parameter of the target module
@@ -46,6 +49,44 @@ class FirstGradTensorFinder:
 
     def __call__(self, module: nn.Module, inputs: Any, output: Any) -> Optional[torch.Tensor]:
         return self._search(output)
+
+
+@dataclass
+class OutputDistTensorFinder:
+    """Hook point at the output dist of ONE sharding type of a pipelined sharded embedding module: the tensor whose gradient arrives when
+    the backward of that sharding type's output collective starts. The module output is an awaitable made of per-sharding awaitables
+    (``_awaitables`` / ``_awaitables_per_sharding`` + ``_sharding_types``); the one of ``sharding_type`` is picked (replicated tables
+    have no collective and are skipped) and the first gradient-carrying tensor of its result returned - None when that sharding type
+    produces no differentiable output on this rank."""
+
+    sharding_type: Any = None
+
+    def __post_init__(self) -> None:
+        from ..types import ShardingType
+
+        if self.sharding_type is None:
+            self.sharding_type = ShardingType.TABLE_WISE
+
+    def __call__(self, module: nn.Module, inputs: Any, output: Any) -> Optional[torch.Tensor]:
+        from ..types import NoWait, ShardingType
+
+        if isinstance(output, tuple):  # managed-collision modules return (embeddings, remapped features)
+            output = output[0]
+        awaitables = getattr(output, "_awaitables", None)
+        if awaitables is None:
+            awaitables = getattr(output, "_awaitables_per_sharding", None)
+        types = getattr(output, "_sharding_types", None)
+        if awaitables is None or types is None:
+            # this framework's fused engine issues ONE output collective for all sharding types: the first gradient tensor of the
+            # module output is the hook point of every type
+            return FirstGradTensorFinder()(module, inputs, output)
+        for w, st in zip(awaitables, types):
+            if isinstance(w, NoWait):
+                continue
+            if ShardingType(st) == self.sharding_type:
+                dummy = getattr(getattr(w, "_tensor_awaitable", None), "dummy_tensor", None)
+                return dummy if dummy is not None else FirstGradTensorFinder()._search(w)
+        raise RuntimeError(f"Could not find awaitable for sharding type: {self.sharding_type}")
 
 
 @dataclass
