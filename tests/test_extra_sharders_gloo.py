@@ -339,3 +339,46 @@ def _pec(ctx):
 
 def test_pec_embedding_collection():
     run_multi_process(_pec, world_size=2, backend="gloo")
+
+
+def _run_tower_models(ctx):
+    """The tower test models sharded by the planner (towers are placed as units) give the unsharded model's predictions."""
+    import copy
+
+    from torchrec_b200.modules.embedding_configs import EmbeddingBagConfig
+    from torchrec_b200.parallel.model_parallel import DistributedModelParallel
+    from torchrec_b200.parallel.test_utils.model_config import create_model_config
+    from torchrec_b200.parallel.test_utils.model_input import ModelInput
+
+    tables = [EmbeddingBagConfig(name=f"table_{i}", embedding_dim=8, num_embeddings=20 + i, feature_names=[f"feature_{i}"]) for i in range(4)]
+    weighted = [EmbeddingBagConfig(name="weighted_table_0", embedding_dim=8, num_embeddings=15, feature_names=["weighted_feature_0"])]
+    for name in ("test_tower_sparse_nn", "test_tower_collection_sparse_nn"):
+        torch.manual_seed(0)
+        model = create_model_config(name, num_float_features=6).generate_model(tables, weighted, torch.device("cpu"))
+        gold = copy.deepcopy(model).to_empty(device="cpu") if any(p.is_meta for p in model.parameters()) else copy.deepcopy(model)
+        torch.manual_seed(1)
+        for p in gold.parameters():
+            torch.nn.init.uniform_(p, -0.1, 0.1)
+        dmp = DistributedModelParallel(model, device=torch.device("cpu"))
+        # same weights on both sides: unsharded state dict -> sharded module
+        sd = dmp.state_dict()
+        gsd = gold.state_dict()
+        for k, v in sd.items():
+            if hasattr(v, "local_shards"):
+                for sh in v.local_shards():
+                    o, s = sh.metadata.shard_offsets, sh.metadata.shard_sizes
+                    sh.tensor.copy_(gsd[k][o[0] : o[0] + s[0], o[1] : o[1] + s[1]])
+            else:
+                v.copy_(gsd[k])
+        dmp.eval()
+        gold.eval()
+        g = torch.Generator().manual_seed(5)
+        _, locals_ = ModelInput.generate_global_and_local_batches(ctx.world_size, batch_size=4, tables=tables, weighted_tables=weighted, num_float_features=6, generator=g)
+        with torch.no_grad():
+            torch.testing.assert_close(dmp(locals_[ctx.rank]), gold(locals_[ctx.rank]), rtol=1e-5, atol=1e-6, msg=lambda m: f"{name}: {m}")
+        kinds = {type(m).__name__ for m in dmp.modules()}
+        assert ("ShardedEmbeddingTower" in kinds) or ("ShardedEmbeddingTowerCollection" in kinds), (name, kinds)
+
+
+def test_tower_test_models_sharded():
+    run_multi_process(_run_tower_models, world_size=2, backend="gloo")

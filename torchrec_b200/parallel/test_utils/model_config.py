@@ -55,6 +55,36 @@ class DLRMConfig(BaseModelConfig):
 
 
 @dataclass
+class TestTowerSparseNNConfig(BaseModelConfig):
+    """Two embedding towers + a plain sparse arch (``TestTowerSparseNN``: four tables, one weighted table)."""
+
+    __test__ = False
+    embedding_groups: Optional[Dict[str, List[str]]] = None
+    feature_processor_modules: Optional[Dict[str, nn.Module]] = None
+
+    def generate_model(self, tables, weighted_tables, dense_device, **kwargs: Any) -> nn.Module:
+        from .test_model import TestTowerSparseNN
+
+        return TestTowerSparseNN(tables=tables, num_float_features=self.num_float_features, weighted_tables=weighted_tables, dense_device=dense_device,
+                                 sparse_device=torch.device("meta"), embedding_groups=self.embedding_groups, feature_processor_modules=self.feature_processor_modules)
+
+
+@dataclass
+class TestTowerCollectionSparseNNConfig(BaseModelConfig):
+    """One tower collection of three towers (``TestTowerCollectionSparseNN``: three tables, one weighted table)."""
+
+    __test__ = False
+    embedding_groups: Optional[Dict[str, List[str]]] = None
+    feature_processor_modules: Optional[Dict[str, nn.Module]] = None
+
+    def generate_model(self, tables, weighted_tables, dense_device, **kwargs: Any) -> nn.Module:
+        from .test_model import TestTowerCollectionSparseNN
+
+        return TestTowerCollectionSparseNN(tables=tables, num_float_features=self.num_float_features, weighted_tables=weighted_tables, dense_device=dense_device,
+                                           sparse_device=torch.device("meta"), embedding_groups=self.embedding_groups, feature_processor_modules=self.feature_processor_modules)
+
+
+@dataclass
 class DeepFMConfig(BaseModelConfig):
     hidden_layer_size: int = 20
     deep_fm_dimension: int = 5
@@ -89,7 +119,8 @@ class _BatchAdapter(nn.Module):
         return self.model(Batch(dense_features=input.float_features, sparse_features=input.idlist_features, labels=input.label))
 
 
-_REGISTRY = {"test_sparse_nn": TestSparseNNConfig, "test_model_with_preproc": TestModelWithPreprocConfig, "dlrm": DLRMConfig, "deepfm": DeepFMConfig}
+_REGISTRY = {"test_sparse_nn": TestSparseNNConfig, "test_model_with_preproc": TestModelWithPreprocConfig, "dlrm": DLRMConfig, "deepfm": DeepFMConfig,
+             "test_tower_sparse_nn": TestTowerSparseNNConfig, "test_tower_collection_sparse_nn": TestTowerCollectionSparseNNConfig}
 
 
 def create_model_config(model_name: str, **kwargs: Any) -> BaseModelConfig:

@@ -130,3 +130,86 @@ class TestModelWithPreproc(nn.Module):
         weighted = self.weighted_ebc(self.postproc_weighted(input.idscore_features)) if self.weighted_ebc is not None and input.idscore_features is not None else None
         pred = torch.sigmoid(torch.mean(self.over(self.dense(input.float_features), sparse, weighted), dim=1))
         return torch.nn.functional.binary_cross_entropy(pred, input.label), pred
+
+
+# ---- tower models (reference test_model.py:1888-2120) --------------------------------------------------------------------------------------------------------
+class TestTowerInteraction(nn.Module):
+    """The interaction of a test tower: a Linear over the concatenated embeddings of the tower's features (unweighted first)."""
+
+    __test__ = False
+
+    def __init__(self, tables: List[EmbeddingBagConfig], weighted_tables: Optional[List[EmbeddingBagConfig]] = None, device: Optional[torch.device] = None) -> None:
+        super().__init__()
+        self._features = [f for t in tables for f in t.feature_names]
+        self._weighted_features = [f for t in (weighted_tables or []) for f in t.feature_names]
+        n = sum(t.embedding_dim * len(t.feature_names) for t in list(tables) + list(weighted_tables or []))
+        self.linear = nn.Linear(n, n, device=device or torch.device("cpu"))
+
+    def forward(self, sparse: KeyedTensor, weighted_sparse: Optional[KeyedTensor] = None) -> torch.Tensor:
+        cols = [sparse[f] for f in self._features]
+        if weighted_sparse is not None:
+            cols += [weighted_sparse[f] for f in self._weighted_features]
+        return self.linear(torch.cat(cols, dim=1))
+
+
+def _bce_or_pred(model: nn.Module, over_r: torch.Tensor, label: torch.Tensor):
+    pred = torch.sigmoid(torch.mean(over_r, dim=1))
+    if model.training:
+        return torch.nn.functional.binary_cross_entropy_with_logits(pred, label), pred
+    return pred
+
+
+class TestTowerSparseNN(TestSparseNNBase):
+    """Dense arch + two ``EmbeddingTower``s (tables 2, 3 and table 0) + a plain sparse arch (table 1 and the first weighted table); needs
+    four tables and one weighted table. Towers are sharded as units: all tables of a tower live on one host."""
+
+    def __init__(self, tables: List[EmbeddingBagConfig], num_float_features: int = 10, weighted_tables: Optional[List[EmbeddingBagConfig]] = None,
+                 embedding_groups: Optional[Dict[str, List[str]]] = None, dense_device: Optional[torch.device] = None, sparse_device: Optional[torch.device] = None,
+                 feature_processor_modules: Optional[Dict[str, nn.Module]] = None) -> None:
+        super().__init__(tables, weighted_tables, num_float_features, dense_device, sparse_device)
+        from ...modules.embedding_tower import EmbeddingTower
+
+        weighted_tables = weighted_tables or []
+        assert len(tables) >= 4 and len(weighted_tables) >= 1, "TestTowerSparseNN needs four tables and one weighted table"
+        self.dense = TestDenseArch(num_float_features, dense_device)
+        self.tower_0 = EmbeddingTower(EmbeddingBagCollection(tables=[tables[2], tables[3]], device=sparse_device), TestTowerInteraction([tables[2], tables[3]], device=dense_device))
+        self.tower_1 = EmbeddingTower(EmbeddingBagCollection(tables=[tables[0]], device=sparse_device), TestTowerInteraction([tables[0]], device=dense_device))
+        self.sparse_arch = TestEBCSparseArch([tables[1]], [weighted_tables[0]], sparse_device)
+        self._arch_features = list(tables[1].feature_names)
+        self._arch_weighted_features = list(weighted_tables[0].feature_names)
+        width = 8 + self.tower_0.interaction.linear.out_features + self.tower_1.interaction.linear.out_features \
+            + tables[1].embedding_dim * len(tables[1].feature_names) + weighted_tables[0].embedding_dim * len(weighted_tables[0].feature_names)
+        self.over = nn.Linear(width, 16, device=dense_device)
+
+    def forward(self, input: ModelInput):
+        dense_r = self.dense(input.float_features)
+        sparse, weighted = self.sparse_arch(input.idlist_features, input.idscore_features)
+        arch = torch.cat([sparse[f] for f in self._arch_features] + [weighted[f] for f in self._arch_weighted_features], dim=1)
+        sparse_r = torch.cat([self.tower_0(input.idlist_features), self.tower_1(input.idlist_features), arch], dim=1)
+        return _bce_or_pred(self, self.over(torch.cat([dense_r, sparse_r], dim=1)), input.label)
+
+
+class TestTowerCollectionSparseNN(TestSparseNNBase):
+    """Dense arch + one ``EmbeddingTowerCollection`` of three towers: tables 0, 2 / table 1 / the first weighted table (a weighted tower)."""
+
+    def __init__(self, tables: List[EmbeddingBagConfig], num_float_features: int = 10, weighted_tables: Optional[List[EmbeddingBagConfig]] = None,
+                 embedding_groups: Optional[Dict[str, List[str]]] = None, dense_device: Optional[torch.device] = None, sparse_device: Optional[torch.device] = None,
+                 feature_processor_modules: Optional[Dict[str, nn.Module]] = None) -> None:
+        super().__init__(tables, weighted_tables, num_float_features, dense_device, sparse_device)
+        from ...modules.embedding_tower import EmbeddingTower, EmbeddingTowerCollection
+
+        weighted_tables = weighted_tables or []
+        assert len(tables) >= 3 and len(weighted_tables) >= 1, "TestTowerCollectionSparseNN needs three tables and one weighted table"
+        self.dense = TestDenseArch(num_float_features, dense_device)
+        t0 = EmbeddingTower(EmbeddingBagCollection(tables=[tables[0], tables[2]], device=sparse_device), TestTowerInteraction([tables[0], tables[2]], device=dense_device))
+        t1 = EmbeddingTower(EmbeddingBagCollection(tables=[tables[1]], device=sparse_device), TestTowerInteraction([tables[1]], device=dense_device))
+        t2 = EmbeddingTower(EmbeddingBagCollection(tables=[weighted_tables[0]], is_weighted=True, device=sparse_device),
+                            TestTowerInteraction([weighted_tables[0]], device=dense_device))
+        self.tower_arch = EmbeddingTowerCollection(towers=[t0, t1, t2])
+        width = 8 + sum(t.interaction.linear.out_features for t in (t0, t1, t2))
+        self.over = nn.Linear(width, 16, device=dense_device)
+
+    def forward(self, input: ModelInput):
+        dense_r = self.dense(input.float_features)
+        sparse_r = self.tower_arch(input.idlist_features, input.idscore_features)
+        return _bce_or_pred(self, self.over(torch.cat([dense_r, sparse_r], dim=1)), input.label)
