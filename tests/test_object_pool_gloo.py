@@ -89,3 +89,37 @@ def _composable_pool_shardings(ctx):
 
 def test_composable_pool_shardings():
     run_multi_process(_composable_pool_shardings, world_size=2)
+
+
+def test_inference_pools_over_local_devices():
+    """Serving form of the pools: one process, the rows block-partitioned over W local devices (cpu stand-ins here); lookups return the
+    unsharded pool's answer in the caller's order; updates are refused."""
+    from torchrec_b200.modules.object_pool import KeyedJaggedTensorPool, TensorPool
+    from torchrec_b200.parallel.keyed_jagged_tensor_pool import ShardedInferenceKeyedJaggedTensorPool
+    from torchrec_b200.parallel.object_pool import KeyedJaggedTensorPoolSharder, ObjectPoolShardingPlan, ObjectPoolShardingType, TensorPoolSharder
+    from torchrec_b200.parallel.tensor_pool import LocalShardPool, ShardedInferenceTensorPool
+    from torchrec_b200.parallel.types import ShardingEnv
+    from torchrec_b200.sparse import KeyedJaggedTensor
+
+    env = ShardingEnv.from_local(world_size=3, rank=0)
+    plan = ObjectPoolShardingPlan(ObjectPoolShardingType.ROW_WISE, inference=True)
+    tp = TensorPool(11, 4, torch.float32)
+    tp.update(torch.arange(11), torch.arange(44, dtype=torch.float32).view(11, 4))
+    stp = TensorPoolSharder().shard(tp, plan, env, torch.device("cpu"))
+    assert isinstance(stp, ShardedInferenceTensorPool) and [p._shard.shape[0] for p in stp._local_shard_pools] == [4, 4, 3] and isinstance(stp._local_shard_pools[0], LocalShardPool)
+    q = torch.tensor([10, 0, 7, 3, 4, 10, 8])
+    torch.testing.assert_close(stp(q), tp.lookup(q))
+    assert stp.lookup(torch.zeros(0, dtype=torch.long)).shape == (0, 4) and (stp.pool_size, stp.dim) == (11, 4)
+    with pytest.raises(NotImplementedError):
+        stp.update(q, torch.zeros(7, 4))
+    kp = KeyedJaggedTensorPool(8, {"a": 3, "b": 2})
+    kp.update(torch.tensor([1, 6, 4]), KeyedJaggedTensor(keys=["a", "b"], values=torch.tensor([11, 12, 61, 41, 42, 43, 13, 44]), lengths=torch.tensor([2, 1, 3, 1, 0, 1])))
+    skp = KeyedJaggedTensorPoolSharder().shard(kp, plan, env, torch.device("cpu"))
+    assert isinstance(skp, ShardedInferenceKeyedJaggedTensorPool)
+    ids = torch.tensor([6, 4, 1, 0, 7])
+    got, want = skp(ids), kp.lookup(ids)
+    assert got.keys() == want.keys() and torch.equal(got.values(), want.values()) and torch.equal(got.lengths(), want.lengths())
+    with pytest.raises(NotImplementedError):
+        skp.update(ids, got)
+    # the training form is still what a plan without the inference flag gives
+    assert type(TensorPoolSharder().shard(tp, ObjectPoolShardingPlan(ObjectPoolShardingType.ROW_WISE), ShardingEnv.from_local(1, 0), torch.device("cpu"))).__name__ == "ShardedTensorPool"

@@ -79,3 +79,53 @@ class KeyedJaggedTensorPoolSharder:
 
     def shard(self, module: KeyedJaggedTensorPool, plan: ObjectPoolShardingPlan, env: ShardingEnv, device: Optional[torch.device] = None) -> ShardedKeyedJaggedTensorPool:
         return ShardedKeyedJaggedTensorPool(module, plan, env, device)
+
+
+class ShardedInferenceKeyedJaggedTensorPool(nn.Module):
+    """A ``KeyedJaggedTensorPool`` served by one process over the devices of its host: the per-id jagged rows are block partitioned
+    over ``env.world_size`` local devices, ``lookup(ids)`` returns the KJT of the ids in the caller's order on the device of ``ids``.
+    Read-only (reference keyed_jagged_tensor_pool.py ``ShardedInferenceKeyedJaggedTensorPool``)."""
+
+    def __init__(self, pool: KeyedJaggedTensorPool, plan: ObjectPoolShardingPlan, env: ShardingEnv, device: Optional[torch.device] = None) -> None:
+        super().__init__()
+        from .tensor_pool import LocalShardPool, _device_of, _LocalDeviceRouter
+
+        self._keys, self._offsets, self._pool_size = list(pool._keys), list(pool._offsets), pool.pool_size
+        dev_type = (device or pool._device).type
+        if dev_type == "cuda" and (not torch.cuda.is_available() or torch.cuda.device_count() < env.world_size):
+            dev_type = "cpu"
+        self._router = _LocalDeviceRouter(self._pool_size, env.world_size)
+        b = self._router.block
+        rows = lambda t, r: t[r * b : min((r + 1) * b, self._pool_size)].detach().clone().to(_device_of(dev_type, r))  # noqa: E731
+        self._value_shards = nn.ModuleList([LocalShardPool(rows(pool._values, r)) for r in range(env.world_size)])
+        self._length_shards = nn.ModuleList([LocalShardPool(rows(pool._lengths, r)) for r in range(env.world_size)])
+
+    @property
+    def pool_size(self) -> int:
+        return self._pool_size
+
+    @torch.no_grad()
+    def lookup(self, ids: torch.Tensor) -> KeyedJaggedTensor:
+        from .tensor_pool import _LocalDeviceRouter
+
+        parts, order = self._router.split(ids)
+        dense = _LocalDeviceRouter.merge([p(i) for p, i in zip(self._value_shards, parts)], order, ids.device)
+        lengths = _LocalDeviceRouter.merge([p(i) for p, i in zip(self._length_shards, parts)], order, ids.device)
+        vals = []
+        for fi in range(len(self._keys)):
+            block = dense[:, self._offsets[fi] : self._offsets[fi + 1]]
+            vals.append(block[torch.arange(block.shape[1], device=block.device).unsqueeze(0) < lengths[:, fi : fi + 1]])
+        return KeyedJaggedTensor(keys=self._keys, values=torch.cat(vals), lengths=lengths.t().reshape(-1), stride=dense.shape[0])
+
+    def forward(self, ids: torch.Tensor) -> KeyedJaggedTensor:
+        return self.lookup(ids)
+
+    def update(self, ids: torch.Tensor, values: KeyedJaggedTensor) -> None:
+        raise NotImplementedError("Inference does not support update")
+
+
+def _infer_shard(self, module: KeyedJaggedTensorPool, plan: ObjectPoolShardingPlan, env: ShardingEnv, device: Optional[torch.device] = None):
+    return ShardedInferenceKeyedJaggedTensorPool(module, plan, env, device) if getattr(plan, "inference", False) else ShardedKeyedJaggedTensorPool(module, plan, env, device)
+
+
+KeyedJaggedTensorPoolSharder.shard = _infer_shard  # type: ignore[method-assign]
