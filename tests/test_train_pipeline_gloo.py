@@ -241,3 +241,60 @@ def test_future_deque_and_postproc_context_switch():
     c.gpu_embedding_outputs["ebc"] = torch.zeros(1)
     assert c.dense_gpu_device == "cuda:0" and TorchCompileConfig().compile_on_iter == 3
     assert get_h2d_func(torch.ones(2), torch.device("cpu")).tolist() == [1.0, 1.0]
+
+
+def _run_mixed_model_pipeline(ctx):
+    """Pooled + sequence collections in one model: the sparse-dist pipeline pipelines both sharded modules and matches the plain loop."""
+    from torchrec_b200.modules.embedding_configs import EmbeddingBagConfig, EmbeddingConfig
+    from torchrec_b200.optim.apply_optimizer_in_backward import apply_optimizer_in_backward
+    from torchrec_b200.optim.keyed import CombinedOptimizer, KeyedOptimizerWrapper
+    from torchrec_b200.optim.optimizers import in_backward_optimizer_filter
+    from torchrec_b200.parallel import train_pipeline as tp
+    from torchrec_b200.parallel.model_parallel import DistributedModelParallel
+    from torchrec_b200.parallel.test_utils.model_input import ModelInput
+    from torchrec_b200.parallel.test_utils.test_model import TestMixedEmbeddingSparseArch
+
+    tables = [EmbeddingBagConfig(name="b0", embedding_dim=8, num_embeddings=30, feature_names=["fb0"]), EmbeddingBagConfig(name="b1", embedding_dim=8, num_embeddings=20, feature_names=["fb1"]),
+              EmbeddingConfig(name="s0", embedding_dim=4, num_embeddings=25, feature_names=["fs0"])]
+
+    def build():
+        torch.manual_seed(0)
+        m = TestMixedEmbeddingSparseArch(tables, num_float_features=5)
+        apply_optimizer_in_backward(torch.optim.SGD, list(m.ebc.parameters()) + list(m.ec.parameters()), {"lr": 0.1})
+        dmp = DistributedModelParallel(m, device=torch.device("cpu"))
+        dense = KeyedOptimizerWrapper(dict(in_backward_optimizer_filter(dmp.named_parameters())), lambda p: torch.optim.SGD(p, lr=0.05))
+        return dmp, CombinedOptimizer([dmp.fused_optimizer, dense])
+
+    a, opt_a = build()
+    b, opt_b = build()
+    b.load_state_dict(a.state_dict())
+    g = torch.Generator().manual_seed(10 + ctx.rank)
+    batches = [ModelInput.generate(batch_size=4, tables=tables, num_float_features=5, pooling_avg=3, generator=g) for _ in range(4)]
+    ref = []
+    for x in batches:
+        opt_a.zero_grad()
+        loss, _ = a(x)
+        loss.backward()
+        opt_a.step()
+        ref.append(loss.detach().clone())
+    pipe = tp.TrainPipelineSparseDist(b, opt_b, torch.device("cpu"))
+    it, got = iter(batches), []
+    while True:
+        try:
+            got.append(pipe.progress(it))
+        except StopIteration:
+            break
+    assert len(pipe._pipelined_modules) == 2, [type(m).__name__ for m in pipe._pipelined_modules]
+    # the pipeline returns the model output (loss, prediction): compare predictions of the last step and the weights
+    sa, sb = a.state_dict(), b.state_dict()
+    for k in sa:
+        if hasattr(sa[k], "local_shards"):
+            for x, y in zip(sa[k].local_shards(), sb[k].local_shards()):
+                torch.testing.assert_close(x.tensor, y.tensor, rtol=1e-5, atol=1e-6)
+        else:
+            torch.testing.assert_close(sa[k], sb[k], rtol=1e-5, atol=1e-6)
+    assert len(got) == 4
+
+
+def test_mixed_pooled_and_sequence_model_pipeline():
+    run_multi_process(_run_mixed_model_pipeline, world_size=2, backend="gloo")

@@ -96,6 +96,34 @@ class DeepFMConfig(BaseModelConfig):
         return _BatchAdapter(_WithLoss(SimpleDeepFMNN(self.num_float_features, ebc, self.hidden_layer_size, self.deep_fm_dimension)))
 
 
+@dataclass
+class MixedEmbeddingConfig(BaseModelConfig):
+    """Pooled + sequence tables in one model (``TestMixedEmbeddingSparseArch``); ``over_arch_clazz``: a class or ``"default"`` /
+    ``"large_activation"``."""
+
+    embedding_groups: Optional[Dict[str, List[str]]] = None
+    over_arch_clazz: Any = "default"
+    enable_activation_stashing: bool = False
+    dense_arch_hidden_sizes: Optional[List[int]] = None
+    over_arch_kwargs: Optional[Dict[str, Any]] = None
+
+    def __post_init__(self) -> None:
+        from .test_model import MIXED_OVER_ARCH_CLASSES
+
+        if isinstance(self.over_arch_clazz, str):
+            if self.over_arch_clazz not in MIXED_OVER_ARCH_CLASSES:
+                raise ValueError(f"Unknown mixed over_arch_clazz: {self.over_arch_clazz}. Available: {list(MIXED_OVER_ARCH_CLASSES.keys())}")
+            self.over_arch_clazz = MIXED_OVER_ARCH_CLASSES[self.over_arch_clazz]
+
+    def generate_model(self, tables, weighted_tables=None, dense_device=None, **kwargs: Any) -> nn.Module:
+        from .test_model import TestMixedEmbeddingSparseArch
+
+        return TestMixedEmbeddingSparseArch(tables=tables, num_float_features=self.num_float_features, weighted_tables=weighted_tables, embedding_groups=self.embedding_groups,
+                                            dense_device=dense_device, sparse_device=torch.device("meta"), over_arch_clazz=self.over_arch_clazz, device=torch.device("meta"),
+                                            enable_activation_stashing=self.enable_activation_stashing, dense_arch_hidden_sizes=self.dense_arch_hidden_sizes,
+                                            over_arch_kwargs=self.over_arch_kwargs)
+
+
 class _WithLoss(nn.Module):
     def __init__(self, model: nn.Module) -> None:
         super().__init__()
@@ -120,7 +148,7 @@ class _BatchAdapter(nn.Module):
 
 
 _REGISTRY = {"test_sparse_nn": TestSparseNNConfig, "test_model_with_preproc": TestModelWithPreprocConfig, "dlrm": DLRMConfig, "deepfm": DeepFMConfig,
-             "test_tower_sparse_nn": TestTowerSparseNNConfig, "test_tower_collection_sparse_nn": TestTowerCollectionSparseNNConfig}
+             "test_tower_sparse_nn": TestTowerSparseNNConfig, "test_tower_collection_sparse_nn": TestTowerCollectionSparseNNConfig, "mixed_embedding": MixedEmbeddingConfig}
 
 
 def create_model_config(model_name: str, **kwargs: Any) -> BaseModelConfig:

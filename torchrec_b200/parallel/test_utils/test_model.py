@@ -213,3 +213,111 @@ class TestTowerCollectionSparseNN(TestSparseNNBase):
         dense_r = self.dense(input.float_features)
         sparse_r = self.tower_arch(input.idlist_features, input.idscore_features)
         return _bce_or_pred(self, self.over(torch.cat([dense_r, sparse_r], dim=1)), input.label)
+
+
+# ---- pooled + sequence tables in one model (reference test_model.py:2632-2960) -------------------------------------------------------------------------------------
+MAX_SEQUENCE_LENGTH = 20
+DENSE_LAYER_OUT_SIZE = 8
+OVER_ARCH_OUT_SIZE = 16
+
+
+def _tables_dim_sum(tables: List[Any], per_feature_multiplier: int = 1) -> int:
+    return sum(t.embedding_dim * len(t.feature_names) * per_feature_multiplier for t in tables)
+
+
+class TestMixedSequenceOverArch(nn.Module):
+    """One Linear over [dense | pooled embeddings | sequence embeddings padded to ``max_sequence_length``]."""
+
+    __test__ = False
+
+    def __init__(self, ebc_tables: List[EmbeddingBagConfig], ec_tables: List[EmbeddingConfig], weighted_tables: List[EmbeddingBagConfig], device: Optional[torch.device] = None,
+                 max_sequence_length: Optional[int] = None, dense_arch_out_size: Optional[int] = None, over_arch_out_size: Optional[int] = None) -> None:
+        super().__init__()
+        width = (dense_arch_out_size or DENSE_LAYER_OUT_SIZE) + _tables_dim_sum(ebc_tables) + _tables_dim_sum(ec_tables, max_sequence_length or MAX_SEQUENCE_LENGTH) \
+            + _tables_dim_sum(weighted_tables)
+        self.linear = nn.Linear(width, over_arch_out_size or OVER_ARCH_OUT_SIZE, device=device or torch.device("cpu"))
+
+    def forward(self, dense: torch.Tensor, sparse: torch.Tensor) -> torch.Tensor:
+        return self.linear(torch.cat([dense, sparse], dim=1))
+
+
+class TestMixedSequenceOverArchLargeActivation(nn.Module):
+    """The same inputs through a stack of wide hidden layers: a large activation footprint in backward (memory-stashing tests)."""
+
+    __test__ = False
+
+    def __init__(self, ebc_tables: List[EmbeddingBagConfig], ec_tables: List[EmbeddingConfig], weighted_tables: List[EmbeddingBagConfig], device: Optional[torch.device] = None,
+                 max_sequence_length: Optional[int] = None, dense_arch_out_size: Optional[int] = None, over_arch_out_size: Optional[int] = None,
+                 large_activation_dim: int = 1024, num_hidden_layers: int = 3) -> None:
+        super().__init__()
+        dev = device or torch.device("cpu")
+        width = (dense_arch_out_size or DENSE_LAYER_OUT_SIZE) + _tables_dim_sum(ebc_tables) + _tables_dim_sum(ec_tables, max_sequence_length or MAX_SEQUENCE_LENGTH) \
+            + _tables_dim_sum(weighted_tables)
+        layers: List[nn.Module] = []
+        for i in range(num_hidden_layers):
+            layers += [nn.Linear(width if i == 0 else large_activation_dim, large_activation_dim, device=dev), nn.ReLU()]
+        layers.append(nn.Linear(large_activation_dim if num_hidden_layers else width, over_arch_out_size or OVER_ARCH_OUT_SIZE, device=dev))
+        self.mlp = nn.Sequential(*layers)
+
+    def forward(self, dense: torch.Tensor, sparse: torch.Tensor) -> torch.Tensor:
+        return self.mlp(torch.cat([dense, sparse], dim=1))
+
+
+MIXED_OVER_ARCH_CLASSES: Dict[str, Any] = {"default": TestMixedSequenceOverArch, "large_activation": TestMixedSequenceOverArchLargeActivation}
+
+
+class TestMixedEmbeddingSparseArch(TestSparseNNBase):
+    """Pooled tables (EmbeddingBagConfig -> one EmbeddingBagCollection) and sequence tables (EmbeddingConfig -> one EmbeddingCollection,
+    outputs padded to 20 positions) in one model: both collections are sharded and pipelined side by side. ``sparse_forward`` /
+    ``dense_forward`` are separate so pipelines can run them in different stages."""
+
+    def __init__(self, tables: List[Any], num_float_features: int = 10, weighted_tables: Optional[List[EmbeddingBagConfig]] = None,
+                 embedding_groups: Optional[Dict[str, List[str]]] = None, dense_device: Optional[torch.device] = None, sparse_device: Optional[torch.device] = None,
+                 feature_processor_modules: Optional[Dict[str, nn.Module]] = None, over_arch_clazz: Any = TestMixedSequenceOverArch, device: Optional[torch.device] = None,
+                 enable_activation_stashing: bool = False, dense_arch_hidden_sizes: Optional[List[int]] = None, over_arch_kwargs: Optional[Dict[str, Any]] = None) -> None:
+        super().__init__([], weighted_tables, num_float_features, dense_device, sparse_device)
+        dev = device or sparse_device or torch.device("cpu")
+        ebc_tables = [t for t in tables if isinstance(t, EmbeddingBagConfig)]
+        ec_tables = [t for t in tables if isinstance(t, EmbeddingConfig) and not isinstance(t, EmbeddingBagConfig)]
+        if len(ebc_tables) + len(ec_tables) != len(tables):
+            raise ValueError(f"Unsupported table type among {[type(t).__name__ for t in tables]}")
+        self.ebc = EmbeddingBagCollection(tables=ebc_tables, device=dev) if ebc_tables else None
+        self.ec = EmbeddingCollection(tables=ec_tables, device=dev) if ec_tables else None
+        self.ec_embedding_dim = ec_tables[0].embedding_dim if ec_tables else 0
+        self._ebc_features = [f for t in ebc_tables for f in t.feature_names]
+        self._ec_features = [f for t in ec_tables for f in t.feature_names]
+        self._enable_activation_stashing = enable_activation_stashing
+        hidden = list(dense_arch_hidden_sizes or [])
+        if hidden:
+            layers: List[nn.Module] = []
+            for i, h in enumerate(hidden):
+                layers += [nn.Linear(num_float_features if i == 0 else hidden[i - 1], h, device=dense_device), nn.ReLU()]
+            self.dense: nn.Module = nn.Sequential(*layers)
+            dense_out = hidden[-1]
+        else:
+            self.dense = TestDenseArch(num_float_features, dense_device)
+            dense_out = DENSE_LAYER_OUT_SIZE
+        if isinstance(over_arch_clazz, str):
+            over_arch_clazz = MIXED_OVER_ARCH_CLASSES[over_arch_clazz]
+        self.over = over_arch_clazz(ebc_tables, ec_tables, weighted_tables or [], dense_device, dense_arch_out_size=dense_out, **(over_arch_kwargs or {}))
+
+    def sparse_forward(self, input: ModelInput) -> torch.Tensor:
+        from ...ops import jagged as J
+
+        features = input.idlist_features
+        parts: List[torch.Tensor] = []
+        if self.ebc is not None:
+            kt = self.ebc(features if features.keys() == self._ebc_features else features.permute([features.keys().index(f) for f in self._ebc_features]))
+            parts.append(kt.values())
+        if self.ec is not None:
+            out = self.ec(features if features.keys() == self._ec_features else features.permute([features.keys().index(f) for f in self._ec_features]))
+            for f in self._ec_features:
+                jt = out[f]
+                parts.append(J.jagged_2d_to_dense(jt.values(), jt.offsets(), MAX_SEQUENCE_LENGTH).reshape(-1, MAX_SEQUENCE_LENGTH * self.ec_embedding_dim))
+        return torch.cat(parts, dim=1)
+
+    def dense_forward(self, input: ModelInput, sparse_output: torch.Tensor):
+        return _bce_or_pred(self, self.over(self.dense(input.float_features), sparse_output), input.label)
+
+    def forward(self, input: ModelInput):
+        return self.dense_forward(input, self.sparse_forward(input))
