@@ -84,6 +84,13 @@ def apply_feature_processors_by_position(features: KeyedJaggedTensor, processors
                              stride_per_rank=features._stride_per_rank, length_per_key=lpk)
 
 
+def param_dp_sync(kt: KeyedTensor, no_op_tensor: torch.Tensor) -> KeyedTensor:
+    """Tie a (zero) tensor computed from every data-parallel processor parameter into the output, so that all of them take part in the
+    backward on every rank (DDP expects a gradient for each of its parameters even when a rank saw none of a feature's ids)."""
+    kt._values.add_(no_op_tensor)
+    return kt
+
+
 class ShardedFeatureProcessedEmbeddingBagCollection(ShardedModule):
     def __init__(self, module: FeatureProcessedEmbeddingBagCollection, table_name_to_parameter_sharding: Dict[str, ParameterSharding],
                  ebc_sharder: EmbeddingBagCollectionSharder, env: ShardingEnv, device: torch.device, module_fqn: Optional[str] = None) -> None:

@@ -97,3 +97,49 @@ def sharded_tbes_weights_spec(sharded_model: nn.Module) -> Dict[str, WeightSpec]
                 ret[key] = WeightSpec(fqn=f"{fqn + '.' if fqn else ''}{kind}.{table}.weight", shard_offsets=[r0, c0], shard_sizes=[rows, cols],
                                       sharding_type=_sharding_type(per_table[table]), device=dev, data_type=str(getattr(dt, "name", dt)))
     return ret
+
+
+def get_param_id_from_type(is_sqebc: bool, is_sqmcec: bool, is_sfpebc: bool) -> str:
+    """Attribute path of the per-table weights inside a sharded quantized module's state dict: bags, managed-collision sequence
+    collection, feature-processed bags, or (default) plain sequence collection."""
+    if is_sqebc:
+        return "embedding_bags"
+    if is_sqmcec:
+        return "_embedding_module.embeddings"
+    if is_sfpebc:
+        return "_embedding_bag_collection.embedding_bags"
+    return "embeddings"
+
+
+def get_bucket_offsets_per_virtual_table(grouped_embedding_config: List[Any], virtual_table_name_to_bucket_lengths: Dict[str, List[int]]) -> Dict[str, List[int]]:
+    """For every virtual (key-value) table: the index of the first bucket of each of its row shards, from the shard metadata of the
+    grouped configs (all groups must agree on a table's shards) and the number of buckets the table was trained with."""
+    from collections import defaultdict
+
+    from .utils import get_bucket_metadata_from_shard_metadata
+
+    shards_of: Dict[str, List[Any]] = defaultdict(list)
+    for config in grouped_embedding_config:
+        for table in config.embedding_tables:
+            meta = getattr(table, "global_metadata", None)
+            assert meta is not None and meta.shards_metadata is not None, f"Table: {table.name} doesn't have global metadata in grouped embedding config"
+            if table.name in virtual_table_name_to_bucket_lengths:
+                if table.name in shards_of:
+                    assert shards_of[table.name] == meta.shards_metadata, f"Virtual table: {table.name} should have same global metadata across all grouped embedding configs"
+                else:
+                    shards_of[table.name] = meta.shards_metadata
+    return {name: get_bucket_metadata_from_shard_metadata(shards, len(virtual_table_name_to_bucket_lengths[name])).bucket_offsets_per_shard for name, shards in shards_of.items()}
+
+
+def post_state_dict_hook(module: nn.Module, destination: Dict[str, torch.Tensor], prefix: str, _local_metadata: Dict[str, Any], tables_weights_prefix: str) -> None:
+    """State-dict hook of a sharded quantized module: per table ``<prefix><tables_weights_prefix>.<table>.weight`` (+ ``weight_qscale`` /
+    ``weight_qbias`` when scale and bias are split) from the module's per-table sharded views."""
+    for name, t in getattr(module, "_table_name_to_sharded_tensor", {}).items():
+        destination[f"{prefix}{tables_weights_prefix}.{name}.weight"] = t
+    for sfx, sharded, lists in (("weight_qscale", "_table_name_to_sharded_tensor_qscale", "_table_name_to_tensors_list_qscale"),
+                                ("weight_qbias", "_table_name_to_sharded_tensor_qbias", "_table_name_to_tensors_list_qbias")):
+        for name, t in getattr(module, sharded, {}).items():
+            destination[f"{prefix}{tables_weights_prefix}.{name}.{sfx}"] = t
+        for name, ts in getattr(module, lists, {}).items():
+            for i, t in enumerate(ts):
+                destination[f"{prefix}{tables_weights_prefix}.{name}.{sfx}.{i}"] = t
