@@ -435,3 +435,35 @@ def test_scalar_output_and_multi_label_precision():
     for bit, name in enumerate(["cat", "dog", "horse"]):
         _close(r[f"multi_label_precision-t|lifetime_multi_label_precision{name}"], tp[bit] / (tp[bit] + fp[bit]), 1e-5)
         _close(r[f"multi_label_precision-t|window_multi_label_precision{name}"], tp[bit] / (tp[bit] + fp[bit]), 1e-5)
+
+
+def test_fused_tasks_equal_unfused_tasks():
+    """Stacking the tasks into one computation (FUSED_TASKS_COMPUTATION) gives the same report as one computation per task."""
+    tasks = [RecTaskInfo(name=f"t{i}") for i in range(3)]
+    g = torch.Generator().manual_seed(21)
+    batches = []
+    for _ in range(3):
+        p = {t.name: torch.rand(B, generator=g) for t in tasks}
+        l = {t.name: (torch.rand(B, generator=g) < 0.4).float() for t in tasks}
+        w = {t.name: torch.rand(B, generator=g) + 0.1 for t in tasks}
+        batches.append((p, l, w))
+    sess = [torch.randint(0, 6, (B,), generator=g) for _ in range(3)]
+    lens = [torch.tensor([10, 7, 13, 10]) for _ in range(3)]
+    keys = [torch.randint(0, 3, (B,), generator=g) for _ in range(3)]
+    cases = [(M.NEMetric, {}, None), (M.CalibrationMetric, {}, None), (M.CTRMetric, {}, None), (M.MSEMetric, {"include_r_squared": True}, None), (M.MAEMetric, {}, None),
+             (M.AccuracyMetric, {}, None), (M.PrecisionMetric, {}, None), (M.RecallMetric, {}, None), (M.NMSEMetric, {}, None), (M.XAUCMetric, {}, None),
+             (M.AverageMetric, {}, None), (M.WeightedAvgMetric, {}, None), (M.CaliFreeNEMetric, {}, None), (M.UnweightedNEMetric, {}, None),
+             (M.HindsightTargetPRMetric, {}, None), (M.AUCMetric, {}, None), (M.AUPRCMetric, {}, None), (M.RAUCMetric, {}, None),
+             (M.NDCGMetric, {}, lambda i: {"required_inputs": {"session_id": sess[i]}}), (M.GAUCMetric, {}, lambda i: {"num_candidates": lens[i]}),
+             (M.SegmentedNEMetric, {"num_groups": 3}, lambda i: {"required_inputs": {"grouping_keys": keys[i]}}), (M.ServingNEMetric, {}, None)]
+    for cls, kw, extra in cases:
+        out = {}
+        for mode in (RecComputeMode.UNFUSED_TASKS_COMPUTATION, RecComputeMode.FUSED_TASKS_COMPUTATION):
+            m = cls(world_size=1, my_rank=0, batch_size=B, tasks=tasks, window_size=10_000, compute_mode=mode, **kw)
+            for i, (p, l, w) in enumerate(batches):
+                m.update(predictions=p, labels=l, weights=w, **(extra(i) if extra else {}))
+            out[mode] = m.compute()
+        a, b = out[RecComputeMode.UNFUSED_TASKS_COMPUTATION], out[RecComputeMode.FUSED_TASKS_COMPUTATION]
+        assert set(a) == set(b) and len(a) >= 3, (cls.__name__, sorted(a), sorted(b))
+        for k in a:
+            torch.testing.assert_close(torch.as_tensor(a[k]).double().reshape(-1), torch.as_tensor(b[k]).double().reshape(-1), rtol=1e-9, atol=1e-12, msg=lambda m_: f"{cls.__name__} {k}: {m_}")

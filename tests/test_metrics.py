@@ -101,6 +101,30 @@ def _dist_metric(ctx):
     auc = M.AUCMetric(world_size=ctx.world_size, my_rank=ctx.rank, batch_size=100, tasks=[RecTaskInfo(name="t")], window_size=1000, compute_on_all_ranks=True)
     auc.update(predictions={"t": ps[ctx.rank]}, labels={"t": ls[ctx.rank]}, weights={"t": ws[ctx.rank]})
     assert auc.compute()["auc-t|window_auc"].item() == pytest.approx(M._auc_from_samples(p.double(), l.double(), w.double()).item(), rel=1e-6)
+    # states of the other shapes: mean over ranks (scalar), session sums (NDCG), per-threshold sums (hindsight PR), grouped window keys (grouped AUC)
+    kw = dict(world_size=ctx.world_size, my_rank=ctx.rank, batch_size=100, tasks=[RecTaskInfo(name="t")], window_size=1000, compute_on_all_ranks=True)
+    sc = M.ScalarMetric(**kw)
+    sc.update(predictions={"t": ps[ctx.rank]}, labels={"t": torch.full((100,), float(ctx.rank + 1))}, weights={"t": ws[ctx.rank]})
+    assert sc.compute()["scalar-t|lifetime_scalar"].item() == pytest.approx(sum(range(1, ctx.world_size + 1)) / ctx.world_size)
+    sess = torch.arange(100) // 5
+    nd, single = M.NDCGMetric(**kw), []
+    nd.update(predictions={"t": ps[ctx.rank]}, labels={"t": ls[ctx.rank]}, weights={"t": ws[ctx.rank]}, required_inputs={"session_id": sess})
+    for r in range(ctx.world_size):
+        one = M.NDCGMetric(world_size=1, my_rank=0, batch_size=100, tasks=[RecTaskInfo(name="t")], window_size=1000)
+        one.update(predictions={"t": ps[r]}, labels={"t": ls[r]}, weights={"t": ws[r]}, required_inputs={"session_id": sess})
+        single.append(one.compute()["ndcg-t|lifetime_ndcg"].item())
+    assert nd.compute()["ndcg-t|lifetime_ndcg"].item() == pytest.approx(sum(single) / len(single), rel=1e-9)  # equal session counts per rank
+    hp, whole = M.HindsightTargetPRMetric(**kw), M.HindsightTargetPRMetric(world_size=1, my_rank=0, batch_size=200, tasks=[RecTaskInfo(name="t")], window_size=1000)
+    hp.update(predictions={"t": ps[ctx.rank]}, labels={"t": ls[ctx.rank]}, weights={"t": ws[ctx.rank]})
+    whole.update(predictions={"t": p}, labels={"t": l}, weights={"t": w})
+    for k, v in whole.compute().items():
+        assert hp.compute()[k].item() == pytest.approx(v.item(), rel=1e-9), k
+    ga = M.AUCMetric(grouped_auc=True, **kw)
+    keys = [torch.arange(100) % 3 + 10 * r for r in range(ctx.world_size)]  # disjoint groups per rank
+    ga.update(predictions={"t": ps[ctx.rank]}, labels={"t": ls[ctx.rank]}, weights={"t": ws[ctx.rank]}, required_inputs={"grouping_keys": keys[ctx.rank]})
+    want = sum(M._auc_from_samples(ps[r][keys[r] == g].double(), ls[r][keys[r] == g].double(), ws[r][keys[r] == g].double()).item()
+               for r in range(ctx.world_size) for g in keys[r].unique()) / (3 * ctx.world_size)
+    assert ga.compute()["auc-t|window_grouped_auc"].item() == pytest.approx(want, rel=1e-6)
 
 
 def test_metrics_sync_across_ranks():
