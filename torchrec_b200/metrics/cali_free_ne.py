@@ -50,3 +50,8 @@ def get_cali_free_ne_states(labels: torch.Tensor, predictions: torch.Tensor, wei
 
 
 CaliFreeNEMetric = _make("CaliFreeNEMetric", CaliFreeNEMetricComputation, MetricNamespace.CALI_FREE_NE)
+
+
+def compute_cross_entropy(labels: torch.Tensor, predictions: torch.Tensor, weights: torch.Tensor, eta: float) -> torch.Tensor:
+    p = predictions.double().clamp(min=eta, max=1 - eta)
+    return -weights.double() * labels.double() * torch.log2(p) - weights.double() * (1.0 - labels.double()) * torch.log2(1.0 - p)

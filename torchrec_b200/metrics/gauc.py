@@ -72,3 +72,24 @@ class GAUCMetricComputation(_SumStatesComputation):
 class GAUCMetric(RecMetric):
     _namespace: MetricNamespace = MetricNamespace.GAUC
     _computation_class = GAUCMetricComputation
+
+
+def to_3d(tensor_2d: torch.Tensor, seq_lengths: torch.Tensor, max_length: int) -> torch.Tensor:
+    """[n, n_task] rows laid out session by session -> [n_sessions, max_length, n_task], zero padded."""
+    from ..ops import jagged as J
+
+    return J.jagged_2d_to_dense(tensor_2d, J.asynchronous_complete_cumsum(seq_lengths.long()), max_length)
+
+
+def compute_gauc_3d(predictions: torch.Tensor, labels: torch.Tensor, weights: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """The padded form: [n_task, n_session, max_len] tensors (padding = zeros) -> {auc_sum, num_samples}; sessions with one label class
+    or with identical (non-zero) predictions do not count."""
+    order = torch.argsort(predictions, dim=-1)
+    ys, ws = torch.gather(labels, -1, order), torch.gather(weights, -1, order)
+    neg = ws * (1 - ys)
+    num = (ys * ws * torch.cumsum(neg, dim=-1)).sum(-1)
+    w_pos, w_neg = (ys * ws).sum(-1), neg.sum(-1)
+    auc = num / (w_pos * w_neg + 1e-10)
+    varied = ~torch.all((predictions == predictions[:, :, 0:1]) | (predictions == 0), dim=-1)
+    keep = (w_pos > 0) & (w_neg > 0) & varied
+    return {"auc_sum": (auc * keep).sum(-1), "num_samples": keep.sum(-1)}

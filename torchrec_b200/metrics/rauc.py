@@ -89,3 +89,29 @@ def compute_rauc_per_group(n_tasks: int, predictions: torch.Tensor, labels: torc
         vals = [compute_rauc(1, predictions[t : t + 1, grouping_keys == g], labels[t : t + 1, grouping_keys == g], weights[t : t + 1, grouping_keys == g])[0] for g in torch.unique(grouping_keys)]
         out.append(torch.stack(vals).mean() if vals else torch.tensor(0.5, dtype=torch.double))
     return torch.stack(out)
+
+
+def conquer_and_count(input: List[float], left_index: int, mid_index: int, right_index: int) -> int:
+    """Merge the sorted halves ``input[left:mid+1]`` and ``input[mid+1:right+1]`` in place; returns the inversions between them."""
+    left, right = input[left_index : mid_index + 1], input[mid_index + 1 : right_index + 1]
+    i = j = inversions = 0
+    k = left_index
+    while i < len(left) and j < len(right):
+        if left[i] <= right[j]:
+            input[k] = left[i]
+            i += 1
+        else:
+            input[k] = right[j]
+            j += 1
+            inversions += len(left) - i
+        k += 1
+    input[k : right_index + 1] = left[i:] + right[j:]
+    return inversions
+
+
+def divide(input: List[float], low: int, high: int) -> int:
+    """Merge sort of ``input[low:high+1]`` in place; returns its number of inversions."""
+    if low >= high:
+        return 0
+    mid = low + (high - low) // 2
+    return divide(input, low, mid) + divide(input, mid + 1, high) + conquer_and_count(input, low, mid, high)

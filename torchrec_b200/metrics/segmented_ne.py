@@ -134,3 +134,36 @@ class SegmentedNEMetric(RecMetric):
         super().__init__(*args, **kwargs)
         for cfg in _normalize_grouping_keys_config(kwargs.get("grouping_keys", "grouping_keys"), kwargs.get("num_groups", 1), kwargs.get("cast_keys_to_int", False)):
             self._required_inputs.add(cfg.name)
+
+
+# ---- stateless helpers of the reference module -----------------------------------------------------------------------------------------------------------------
+from .ne import compute_cross_entropy, compute_logloss  # noqa: E402,F401
+
+
+def get_segemented_ne_states_fused(labels: torch.Tensor, predictions: torch.Tensor, weights: torch.Tensor, grouping_keys: torch.Tensor, eta: float, num_groups: int,
+                                   n_tasks: int) -> Dict[str, torch.Tensor]:
+    """[n_tasks, n] inputs + one group id per example -> the four NE states as [n_tasks, num_groups] scatter sums."""
+    idx = grouping_keys.long().reshape(1, -1).expand(n_tasks, -1)
+    w, y = weights.double(), labels.double()
+
+    def scatter(v: torch.Tensor) -> torch.Tensor:
+        return torch.zeros(n_tasks, num_groups, dtype=torch.double, device=v.device).scatter_add_(1, idx, v.double())
+
+    return {"cross_entropy_sum": scatter(compute_cross_entropy(labels, predictions, weights, eta)), "weighted_num_samples": scatter(w), "pos_labels": scatter(w * y),
+            "neg_labels": scatter(w * (1.0 - y))}
+
+
+def get_segemented_ne_states(labels: torch.Tensor, predictions: torch.Tensor, weights: torch.Tensor, grouping_keys: torch.Tensor, eta: float, num_groups: int) -> Dict[str, torch.Tensor]:
+    """Single task form: states as [1, num_groups]."""
+    return get_segemented_ne_states_fused(labels.reshape(1, -1), predictions.reshape(1, -1), weights.reshape(1, -1), grouping_keys, eta, num_groups, 1)
+
+
+def compute_ne_helper(ce_sum: torch.Tensor, weighted_num_samples: torch.Tensor, pos_labels: torch.Tensor, neg_labels: torch.Tensor, eta: float) -> torch.Tensor:
+    return compute_ne(ce_sum, weighted_num_samples, pos_labels, neg_labels, eta)
+
+
+def compute_ne_fused(ce_sum: torch.Tensor, weighted_num_samples: torch.Tensor, pos_labels: torch.Tensor, neg_labels: torch.Tensor, num_groups: int, n_tasks: int,
+                     eta: float) -> torch.Tensor:
+    """NE of every (task, group) cell at once: [n_tasks, num_groups]."""
+    return compute_ne(ce_sum.reshape(n_tasks, num_groups), weighted_num_samples.reshape(n_tasks, num_groups), pos_labels.reshape(n_tasks, num_groups),
+                      neg_labels.reshape(n_tasks, num_groups), eta)

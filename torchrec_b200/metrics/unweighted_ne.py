@@ -25,3 +25,23 @@ class UnweightedNEMetricComputation(NEMetricComputation):
 
 
 UnweightedNEMetric = _make("UnweightedNEMetric", UnweightedNEMetricComputation, MetricNamespace.UNWEIGHTED_NE)
+
+
+def compute_cross_entropy(labels: torch.Tensor, predictions: torch.Tensor, weights: torch.Tensor, eta: float) -> torch.Tensor:
+    """Base-2 cross entropy per example with every weight taken as 1."""
+    p = torch.clamp(predictions.double(), eta, 1 - eta)
+    y = labels.double()
+    return -(y * torch.log2(p) + (1.0 - y) * torch.log2(1.0 - p))
+
+
+def compute_ne(ce_sum: torch.Tensor, weighted_num_samples: torch.Tensor, pos_labels: torch.Tensor, neg_labels: torch.Tensor, eta: float) -> torch.Tensor:
+    from .ne import compute_ne as _compute_ne
+
+    return _compute_ne(ce_sum, weighted_num_samples, pos_labels, neg_labels, eta)
+
+
+def get_unweighted_ne_states(labels: torch.Tensor, predictions: torch.Tensor, weights: torch.Tensor, eta: float) -> Dict[str, torch.Tensor]:
+    y = labels.double()
+    ones = torch.ones_like(y)
+    return {"cross_entropy_sum": compute_cross_entropy(labels, predictions, weights, eta).sum(-1), "weighted_num_samples": ones.sum(-1), "pos_labels": y.sum(-1),
+            "neg_labels": (1.0 - y).sum(-1)}
