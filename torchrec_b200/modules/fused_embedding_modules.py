@@ -29,6 +29,20 @@ def _optim_type(optimizer_type: Type[torch.optim.Optimizer]) -> OptimType:
     return m[optimizer_type]
 
 
+def convert_optimizer_type_and_kwargs(optimizer_type: Type[torch.optim.Optimizer], optimizer_kwargs: Dict[str, Any]) -> Optional[Tuple[OptimType, Dict[str, Any]]]:
+    """A torch (or shell) optimizer class + its kwargs -> (fused kernel optimizer, kernel kwargs: ``lr`` becomes ``learning_rate``); None
+    when the class has no fused counterpart."""
+    import copy
+
+    kwargs = copy.deepcopy(optimizer_kwargs)
+    if "lr" in kwargs:
+        kwargs["learning_rate"] = kwargs.pop("lr")
+    try:
+        return _optim_type(optimizer_type), kwargs
+    except ValueError:
+        return None
+
+
 class _TbeFusedOptimizer(FusedOptimizer):
     def __init__(self, tbes: List[TableBatchedEmbeddingBags], params: Dict[str, torch.Tensor], state: Dict[Any, Any]) -> None:
         self._tbes = tbes
@@ -227,3 +241,6 @@ def fuse_embedding_optimizer(model: nn.Module, optimizer_type: Type[torch.optim.
         return m
 
     return swap(model)
+
+
+EmbeddingFusedOptimizer = _TbeFusedOptimizer  # the fused optimizer handle of the fused collections under its reference name
