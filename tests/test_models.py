@@ -183,3 +183,18 @@ def test_itep_prunes_resets_rows_and_reports_stats():
     assert st["access_share_resident"] > 0.99  # all (decayed) accesses now hit rows that own a physical row
     # cold ids share the last physical row
     assert int(addr[99]) == 7
+
+
+def test_legacy_position_weighted_module_over_jt_dict():
+    from torchrec_b200.modules.feature_processor import PositionWeightedModule, offsets_to_range_traceble
+    from torchrec_b200.sparse import JaggedTensor
+
+    m = PositionWeightedModule({"a": 3})
+    with torch.no_grad():
+        m.position_weights["a"].copy_(torch.tensor([1.0, 2.0, 3.0]))
+    feats = {"a": JaggedTensor(values=torch.arange(6), lengths=torch.tensor([2, 0, 4])), "b": JaggedTensor(values=torch.arange(2), lengths=torch.tensor([1, 1, 0]))}
+    out = m(feats)
+    assert out["a"].weights().tolist() == [1.0, 2.0, 1.0, 2.0, 3.0, 3.0] and out["b"].weights_or_none() is None and list(out) == ["a", "b"]
+    out["a"].weights().sum().backward()
+    assert m.position_weights["a"].grad.tolist() == [2.0, 2.0, 2.0]
+    assert offsets_to_range_traceble(torch.tensor([0, 2, 2, 5]), torch.arange(5)).tolist() == [0, 1, 0, 1, 2]
