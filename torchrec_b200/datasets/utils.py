@@ -89,10 +89,10 @@ def rand_split_train_val(datapipe: Iterable, train_perc: float, random_seed: int
     return _Split(True), _Split(False)
 
 
-def idx_split_train_val(datapipe: Iterable, train_perc: float, decimal_places_compared: int = 3, key_fn: Callable = lambda x: x):
+def idx_split_train_val(datapipe: Iterable, train_perc: float, decimal_places: int = 3, key_fn: Callable = lambda x: x):
     if not 0.0 < train_perc < 1.0:
         raise ValueError("train_perc must be in (0, 1)")
-    shift = 10**decimal_places_compared
+    shift = 10**decimal_places
     thr = int(train_perc * shift)
 
     class _Split:
@@ -159,10 +159,10 @@ def _default_dp_selector(datapipes):
     return datapipes[info.id :: info.num_workers]
 
 
-def train_filter(key_fn: Callable[[int], int], train_perc: float, decimal_places_compared: int, idx: int) -> bool:
-    shift = 10**decimal_places_compared
+def train_filter(key_fn: Callable[[int], int], train_perc: float, decimal_places: int, idx: int) -> bool:
+    shift = 10**decimal_places
     return (key_fn(idx) % shift) < round(train_perc * shift)
 
 
-def val_filter(key_fn: Callable[[int], int], train_perc: float, decimal_places_compared: int, idx: int) -> bool:
-    return not train_filter(key_fn, train_perc, decimal_places_compared, idx)
+def val_filter(key_fn: Callable[[int], int], train_perc: float, decimal_places: int, idx: int) -> bool:
+    return not train_filter(key_fn, train_perc, decimal_places, idx)

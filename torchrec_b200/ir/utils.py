@@ -125,13 +125,14 @@ def _dim(name: str, min: Optional[int] = None, max: Optional[int] = None):
 _DIM_COUNTER = {"n": 0}
 
 
-def mark_dynamic_kjt(kjt: KeyedJaggedTensor, shapes_collection=None, variable_length: bool = False, vlen=None, llen=None):
+def mark_dynamic_kjt(kjt: KeyedJaggedTensor, shapes_collection=None, variable_length: bool = False, vlen=None, llen=None, variable_batch: bool = False):
     """Register the data-dependent dimensions of a KJT input with a ``torch.export.ShapesCollection``: the number of values (shared by
     ``values`` and ``weights``) always, the number of bags (``lengths`` / ``offsets``) when ``variable_length`` (variable batch). The
     collection is what ``torch.export.export(..., dynamic_shapes=collection)`` takes. ``vlen`` / ``llen``: reuse Dims across KJTs that
     must agree."""
     from torch.export import ShapesCollection
 
+    variable_length = variable_length or variable_batch  # the reference's name of the flag
     if shapes_collection is None:
         shapes_collection = ShapesCollection()
     _DIM_COUNTER["n"] += 1

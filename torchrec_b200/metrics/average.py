@@ -31,8 +31,8 @@ class AverageMetricComputation(_SumStatesComputation):
 AverageMetric = _make("AverageMetric", AverageMetricComputation, MetricNamespace.AVERAGE)
 
 
-def compute_average(value_sum: torch.Tensor, weighted_num_samples: torch.Tensor) -> torch.Tensor:
-    return torch.where(weighted_num_samples == 0.0, torch.zeros_like(value_sum), value_sum / weighted_num_samples).double()
+def compute_average(weighted_sum: torch.Tensor, weighted_num_samples: torch.Tensor) -> torch.Tensor:
+    return torch.where(weighted_num_samples == 0.0, torch.zeros_like(weighted_sum), weighted_sum / weighted_num_samples).double()
 
 
 def get_average_states(labels: torch.Tensor, predictions: torch.Tensor, weights: torch.Tensor) -> Dict[str, torch.Tensor]:

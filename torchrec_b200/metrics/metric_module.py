@@ -230,14 +230,17 @@ def _generate_state_metrics(metrics_config: MetricsConfig, state_metrics_mapping
 
 def generate_metric_module(metric_class: Type[RecMetricModule], metrics_config: MetricsConfig, batch_size: int, world_size: int, my_rank: int,
                            state_metrics_mapping: Dict[StateMetricEnum, StateMetric], device: torch.device, process_group: Optional[dist.ProcessGroup] = None,
-                           batching_metadata: Optional[Any] = None) -> RecMetricModule:
+                           batching_metadata: Optional[Any] = None, batch_size_stages: Optional[List[Any]] = None, module_kwargs: Optional[Dict[str, Any]] = None) -> RecMetricModule:
+    from .metrics_config import validate_batch_size_stages
+
+    validate_batch_size_stages(batch_size_stages)
     rec_metrics = _generate_rec_metrics(metrics_config, world_size, my_rank, batch_size, process_group)
     throughput_metric = ThroughputMetric(batch_size=batch_size, world_size=world_size, window_seconds=metrics_config.throughput_metric.window_size) \
         if metrics_config.throughput_metric else None
     state_metrics = _generate_state_metrics(metrics_config, state_metrics_mapping)
     metrics = metric_class(batch_size=batch_size, world_size=world_size, rec_tasks=metrics_config.rec_tasks, rec_metrics=rec_metrics,
                            throughput_metric=throughput_metric, state_metrics=state_metrics, compute_interval_steps=metrics_config.compute_interval_steps,
-                           min_compute_interval=metrics_config.min_compute_interval, max_compute_interval=metrics_config.max_compute_interval)
+                           min_compute_interval=metrics_config.min_compute_interval, max_compute_interval=metrics_config.max_compute_interval, **(module_kwargs or {}))
     metrics.to(device)
     return metrics
 

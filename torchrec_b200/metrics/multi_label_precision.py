@@ -14,9 +14,9 @@ from .rec_metric import MetricComputationReport, RecMetric, RecMetricComputation
 from typing import Any  # noqa: F401
 
 
-def compute_multi_label_precision(true_pos_sum: torch.Tensor, false_pos_sum: torch.Tensor) -> torch.Tensor:
-    d = true_pos_sum + false_pos_sum
-    return torch.where(d == 0.0, torch.zeros_like(d), true_pos_sum / torch.where(d == 0.0, torch.ones_like(d), d)).double()
+def compute_multi_label_precision(num_true_positives: torch.Tensor, num_false_positives: torch.Tensor) -> torch.Tensor:
+    d = num_true_positives + num_false_positives
+    return torch.where(d == 0.0, torch.zeros_like(d), num_true_positives / torch.where(d == 0.0, torch.ones_like(d), d)).double()
 
 
 def decode_integer_to_labels(tensor: torch.Tensor, num_labels: int) -> torch.Tensor:

@@ -27,6 +27,7 @@ class NEMetricComputation(_SumStatesComputation):
 
     def __init__(self, *args: Any, include_logloss: bool = False, allow_missing_label_with_zero_weight: bool = False, **kwargs: Any) -> None:
         self._include_logloss = include_logloss
+        self._allow_missing_label = allow_missing_label_with_zero_weight
         super().__init__(*args, **kwargs)
         self.eta = 1e-12
 
@@ -35,7 +36,7 @@ class NEMetricComputation(_SumStatesComputation):
                 "pos_labels": (weights.double() * labels.double()).sum(-1), "neg_labels": (weights.double() * (1 - labels.double())).sum(-1)}
 
     def _reports(self, get, prefix):
-        ne = compute_ne(get("cross_entropy_sum"), get("weighted_num_samples"), get("pos_labels"), get("neg_labels"), self.eta)
+        ne = compute_ne(get("cross_entropy_sum"), get("weighted_num_samples"), get("pos_labels"), get("neg_labels"), self.eta, getattr(self, "_allow_missing_label", False))
         out = [MetricComputationReport(MetricName.NE, prefix, ne)]
         if self._include_logloss:
             ll = get("cross_entropy_sum") / (get("weighted_num_samples") + EPS) * torch.log(torch.tensor(2.0, dtype=torch.double))
@@ -43,10 +44,15 @@ class NEMetricComputation(_SumStatesComputation):
         return out
 
 
-def compute_ne(ce_sum, weighted_num_samples, pos_labels, neg_labels, eta=1e-12) -> torch.Tensor:
+def compute_ne(ce_sum, weighted_num_samples, pos_labels, neg_labels, eta=1e-12, allow_missing_label_with_zero_weight: bool = False) -> torch.Tensor:
+    """cross entropy / cross entropy of the base rate. ``allow_missing_label_with_zero_weight``: tasks that saw no weight yet report ``eta``
+    instead of 0 / 0."""
     mean_label = pos_labels / (weighted_num_samples + EPS)
     ce_norm = -(pos_labels * torch.log2(mean_label + eta) + neg_labels * torch.log2(1 - mean_label + eta))
-    return ce_sum / (ce_norm + EPS)
+    ne = ce_sum / (ce_norm + EPS)
+    if allow_missing_label_with_zero_weight and not bool(torch.as_tensor(weighted_num_samples).all()):
+        return torch.where(weighted_num_samples > 0, ne, torch.full_like(ne, eta))
+    return ne
 
 
 NEMetric = _make("NEMetric", NEMetricComputation, MetricNamespace.NE)

@@ -44,9 +44,13 @@ def compute_cross_entropy_positive(labels: torch.Tensor, predictions: torch.Tens
     return -weights.double() * labels.double() * torch.log2(torch.clamp(predictions.double(), eta, 1 - eta))
 
 
-def compute_ne_positive(ce_positive_sum: torch.Tensor, weighted_num_samples: torch.Tensor, pos_labels: torch.Tensor, neg_labels: torch.Tensor, eta: float) -> torch.Tensor:
+def compute_ne_positive(ce_positive_sum: torch.Tensor, weighted_num_samples: torch.Tensor, pos_labels: torch.Tensor, neg_labels: torch.Tensor, eta: float,
+                        allow_missing_label_with_zero_weight: bool = False) -> torch.Tensor:
     mean_label = pos_labels / (weighted_num_samples + EPS)
-    return ce_positive_sum / (-pos_labels * torch.log2(mean_label + eta) + EPS)
+    ne = ce_positive_sum / (-pos_labels * torch.log2(mean_label + eta) + EPS)
+    if allow_missing_label_with_zero_weight and not bool(torch.as_tensor(weighted_num_samples).all()):
+        return torch.where(weighted_num_samples > 0, ne, torch.full_like(ne, eta))
+    return ne
 
 
 def get_ne_positive_states(labels: torch.Tensor, predictions: torch.Tensor, weights: torch.Tensor, eta: float) -> Dict[str, torch.Tensor]:

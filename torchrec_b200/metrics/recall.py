@@ -34,8 +34,8 @@ class RecallMetricComputation(_SumStatesComputation):
 RecallMetric = _make("RecallMetric", RecallMetricComputation, MetricNamespace.RECALL)
 
 
-def compute_recall(num_true_positives: torch.Tensor, num_false_negatives: torch.Tensor) -> torch.Tensor:
-    d = num_true_positives + num_false_negatives
+def compute_recall(num_true_positives: torch.Tensor, num_false_negitives: torch.Tensor) -> torch.Tensor:  # (sic: the reference's spelling of the keyword)
+    d = num_true_positives + num_false_negitives
     return torch.where(d == 0.0, torch.zeros_like(d), num_true_positives / d).double()
 
 

@@ -34,10 +34,11 @@ def compute_cross_entropy(labels: torch.Tensor, predictions: torch.Tensor, weigh
     return -(y * torch.log2(p) + (1.0 - y) * torch.log2(1.0 - p))
 
 
-def compute_ne(ce_sum: torch.Tensor, weighted_num_samples: torch.Tensor, pos_labels: torch.Tensor, neg_labels: torch.Tensor, eta: float) -> torch.Tensor:
+def compute_ne(ce_sum: torch.Tensor, weighted_num_samples: torch.Tensor, pos_labels: torch.Tensor, neg_labels: torch.Tensor, eta: float,
+               allow_missing_label_with_zero_weight: bool = False) -> torch.Tensor:
     from .ne import compute_ne as _compute_ne
 
-    return _compute_ne(ce_sum, weighted_num_samples, pos_labels, neg_labels, eta)
+    return _compute_ne(ce_sum, weighted_num_samples, pos_labels, neg_labels, eta, allow_missing_label_with_zero_weight)
 
 
 def get_unweighted_ne_states(labels: torch.Tensor, predictions: torch.Tensor, weights: torch.Tensor, eta: float) -> Dict[str, torch.Tensor]:

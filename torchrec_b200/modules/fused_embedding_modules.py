@@ -217,13 +217,15 @@ class FusedEmbeddingCollection(EmbeddingCollectionInterface, FusedOptimizerModul
         return self._device
 
 
-def fuse_embedding_optimizer(model: nn.Module, optimizer_type: Type[torch.optim.Optimizer], optimizer_kwargs: Dict[str, Any], device: torch.device) -> nn.Module:
-    """Swap every EmbeddingBagCollection / EmbeddingCollection of ``model`` for its fused version (weights copied)."""
+def fuse_embedding_optimizer(model: nn.Module, optimizer_type: Type[torch.optim.Optimizer], optimizer_kwargs: Dict[str, Any], device: torch.device,
+                             location: Optional[Any] = None) -> nn.Module:
+    """Swap every EmbeddingBagCollection / EmbeddingCollection of ``model`` for its fused version (weights copied). ``location``: where the
+    fused bag tables live (``EmbeddingLocation``: HBM / host-mapped / cached)."""
     from .embedding_modules import EmbeddingBagCollection, EmbeddingCollection
 
     def swap(m: nn.Module) -> nn.Module:
         if isinstance(m, EmbeddingBagCollection):
-            f = FusedEmbeddingBagCollection(m.embedding_bag_configs(), optimizer_type, optimizer_kwargs, m.is_weighted(), device)
+            f = FusedEmbeddingBagCollection(m.embedding_bag_configs(), optimizer_type, optimizer_kwargs, m.is_weighted(), device, location)
             with torch.no_grad():
                 for n, bag in m.embedding_bags.items():
                     if bag.weight.device.type != "meta":

@@ -56,8 +56,10 @@ class MLP(nn.Module):
         activation: Union[str, Callable[[], nn.Module], nn.Module, Callable[[torch.Tensor], torch.Tensor]] = torch.relu,
         device: Optional[torch.device] = None,
         dtype: torch.dtype = torch.float32,
+        activation_on_last: bool = True,
     ) -> None:
         super().__init__()
+        last = len(layer_sizes) - 1
         if activation == "relu":
             activation = torch.relu
         elif activation == "sigmoid":
@@ -66,7 +68,7 @@ class MLP(nn.Module):
             self._mlp: nn.Module = nn.Sequential(*[
                 Perceptron(
                     layer_sizes[i - 1] if i > 0 else in_size, layer_sizes[i], bias=bias,
-                    activation=extract_module_or_tensor_callable(activation), device=device, dtype=dtype,
+                    activation=nn.Identity() if (not activation_on_last and i == last) else extract_module_or_tensor_callable(activation), device=device, dtype=dtype,
                 )
                 for i in range(len(layer_sizes))
             ])
@@ -74,7 +76,7 @@ class MLP(nn.Module):
             self._mlp = nn.Sequential(*[
                 Perceptron(
                     layer_sizes[i - 1] if i > 0 else in_size, layer_sizes[i], bias=bias,
-                    activation=SwishLayerNorm(layer_sizes[i], device=device), device=device,
+                    activation=nn.Identity() if (not activation_on_last and i == last) else SwishLayerNorm(layer_sizes[i], device=device), device=device,
                 )
                 for i in range(len(layer_sizes))
             ])

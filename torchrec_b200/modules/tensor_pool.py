@@ -13,13 +13,16 @@ class TensorPool(ObjectPool[torch.Tensor]):
     """``pool_size`` rows of ``dim`` values addressed by id (e.g. cached user embeddings)."""
 
     def __init__(self, pool_size: int, dim: int, dtype: torch.dtype, sharding_env=None, sharding_plan=None, device: Optional[torch.device] = None,
-                 loading_required: bool = False, enable_uvm: bool = False) -> None:
+                 loading_required: bool = False, enable_uvm: bool = False, loaded_values: Optional[torch.Tensor] = None) -> None:
         super().__init__()
         self._pool_size, self._dim, self._dtype = pool_size, dim, dtype
         self._device = device if device is not None else torch.device("cpu")
         self._enable_uvm = enable_uvm
         store_device = torch.device("cpu") if enable_uvm else self._device
         self.register_buffer("_pool", torch.zeros(pool_size, dim, dtype=dtype, device=store_device, pin_memory=enable_uvm and torch.cuda.is_available()))
+        if loaded_values is not None:  # pre-computed rows instead of zeros
+            assert tuple(loaded_values.shape) == (pool_size, dim), f"loaded_values must be [{pool_size}, {dim}], got {tuple(loaded_values.shape)}"
+            self._pool.copy_(loaded_values.to(dtype))
 
     @property
     def pool_size(self) -> int:

@@ -275,8 +275,9 @@ class CombinedOptimizer(KeyedOptimizer):
 class KeyedOptimizerWrapper(KeyedOptimizer):
     """``optim_factory(list of parameters) -> torch optimizer`` turned into a keyed optimizer (state and groups are shared with it)."""
 
-    def __init__(self, params: Mapping[str, ParamLike], optim_factory: OptimizerFactory) -> None:
-        self._optimizer: optim.Optimizer = optim_factory(list(params.values()))
+    def __init__(self, params: Mapping[str, ParamLike], optim_factory: OptimizerFactory, pass_params_dict: bool = False) -> None:
+        # ``pass_params_dict``: the factory wants the name -> parameter mapping (e.g. to build per-name groups) instead of the list
+        self._optimizer: optim.Optimizer = optim_factory(params if pass_params_dict else list(params.values()))
         super().__init__(params, self._optimizer.state, self._optimizer.param_groups)
 
     def zero_grad(self, set_to_none: bool = True) -> None:

@@ -186,6 +186,7 @@ def alltoall_pooled(
     group: Optional[dist.ProcessGroup] = None,
     codecs: Optional[QuantizedCommCodecs] = None,
     comm: Optional[Any] = None,
+    all_to_all_single_comm: Optional[Any] = None,
 ) -> Awaitable[torch.Tensor]:
     """Pooled embeddings ``[sum_r B_r, D_local]`` (rows grouped by destination rank) ->
     ``[B_local, sum_r D_r]`` (columns grouped by source rank). ``comm``: an ``All2AllSingle`` (comm_ops_sync.py) that supplies
@@ -198,7 +199,7 @@ def alltoall_pooled(
 
         return NoWait(all2all_pooled_sync(pg, batch_size_per_rank, dim_sum_per_rank, a2a_pooled_embs_tensor, None, GRADIENT_DIVISION))
     info = All2AllPooledInfo(batch_size_per_rank, dim_sum_per_rank, dim_sum_per_rank_tensor, cumsum_dim_sum_per_rank_tensor, codecs)
-    info.comm = comm
+    info.comm = comm if comm is not None else all_to_all_single_comm  # ``all_to_all_single_comm``: the reference's name of the argument
     h = _Handle()
     dummy = _A2APooledReq.apply(pg, h, info, a2a_pooled_embs_tensor)
     return Request(lambda: _A2APooledWait.apply(pg, h, info, dummy))
@@ -251,6 +252,7 @@ def variable_batch_alltoall_pooled(
     emb_dim_per_rank_per_feature: List[List[int]],
     group: Optional[dist.ProcessGroup] = None,
     codecs: Optional[QuantizedCommCodecs] = None,
+    all_to_all_single_comm: Optional[Any] = None,
 ) -> Awaitable[torch.Tensor]:
     """1-D flattened variable-batch (VBE) pooled all-to-all (reference comm_ops.py:668-745)."""
     pg = _pg(group)

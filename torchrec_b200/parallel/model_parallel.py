@@ -124,6 +124,7 @@ class DistributedModelParallel(nn.Module, FusedOptimizerModule):
         init_parameters: bool = True,
         data_parallel_wrapper: Optional[DataParallelWrapper] = None,
         model_tracker_config: Optional[Any] = None,
+        model_tracker_configs: Optional[Any] = None,
     ) -> None:
         super().__init__()
         torch._C._log_api_usage_once(f"torchrec_b200.parallel.{self.__class__.__name__}")
@@ -170,6 +171,22 @@ class DistributedModelParallel(nn.Module, FusedOptimizerModule):
                 kw = dict(consumers=getattr(cfg, "consumers", None), delete_on_read=getattr(cfg, "delete_on_read", True), auto_compact=getattr(cfg, "auto_compact", False),
                           mode=getattr(cfg, "tracking_mode", None) or getattr(cfg, "mode"), fqns_to_skip=getattr(cfg, "fqns_to_skip", ()))
             self._model_tracker = ModelDeltaTracker(self._dmp_wrapped_module, **kw)
+        # ``ModelTrackerConfigs`` (the reference's newer argument): trackers by kind, kept in ``model_trackers``
+        self.model_trackers: Dict[str, Any] = {}
+        if model_tracker_configs is not None:
+            from .model_tracker import ModelDeltaTracker
+            from .model_tracker.trackers.raw_id_tracker import RawIdTracker
+            from .model_tracker.types import Trackers
+
+            raw = getattr(model_tracker_configs, "raw_id_tracker_config", None)
+            if raw is not None:
+                self.model_trackers[Trackers.RAW_ID_TRACKER.name] = RawIdTracker(self._dmp_wrapped_module, delete_on_read=raw.delete_on_read, fqns_to_skip=raw.fqns_to_skip)
+            delta = getattr(model_tracker_configs, "delta_tracker_config", None)
+            if delta is not None and self._model_tracker is None:
+                self._model_tracker = ModelDeltaTracker(self._dmp_wrapped_module, consumers=delta.consumers, delete_on_read=delta.delete_on_read,
+                                                        auto_compact=delta.auto_compact, mode=delta.tracking_mode, fqns_to_skip=getattr(delta, "fqns_to_skip", ()))
+            if self._model_tracker is not None:
+                self.model_trackers[Trackers.DELTA_TRACKER.name] = self._model_tracker
 
     # ---- public surface -------------------------------------------------------------------------------------
     @property

@@ -227,8 +227,10 @@ def row_wise(sizes_placement: Optional[Tuple[List[int], Union[str, List[str]]]] 
     return gen
 
 
-def column_wise(ranks: Optional[List[int]] = None, size_per_rank: Optional[List[int]] = None, compute_kernel: Optional[str] = None) -> ParameterShardingGenerator:
-    """Split the embedding dim over ``ranks`` (evenly) or by explicit ``size_per_rank``."""
+def column_wise(ranks: Optional[List[int]] = None, size_per_rank: Optional[List[int]] = None, compute_kernel: Optional[str] = None,
+                device_types: Optional[List[str]] = None) -> ParameterShardingGenerator:
+    """Split the embedding dim over ``ranks`` (evenly) or by explicit ``size_per_rank``. ``device_types``: one device type per column shard
+    (heterogeneous inference: some shards in host memory) instead of the module's device type for all."""
 
     def gen(param, local_size, world_size, device_type, sharder) -> ParameterSharding:
         rows, cols = param.shape
@@ -246,8 +248,16 @@ def column_wise(ranks: Optional[List[int]] = None, size_per_rank: Optional[List[
         for s in sizes:
             offs.append([0, o])
             o += s[1]
+        placements = None
+        if device_types is not None:
+            assert len(device_types) == len(rk), "device_types must have one entry per column shard"
+            index: Dict[str, int] = {}
+            placements = []
+            for dt, r in zip(device_types, rk):
+                placements.append(placement_helper(dt, index.get(dt, 0), r))
+                index[dt] = index.get(dt, 0) + 1
         return _get_parameter_sharding(param, ShardingType.COLUMN_WISE.value, list(zip(sizes, offs, rk)), local_size, device_type, sharder,
-                                       compute_kernel=compute_kernel)
+                                       placements=placements, compute_kernel=compute_kernel)
 
     return gen
 

@@ -268,7 +268,9 @@ class KeyedJaggedTensor(Pipelineable, metaclass=JaggedTensorMeta):
         stride: Optional[int] = None,
         stride_per_key_per_rank: Optional[Union[torch.Tensor, List[List[int]]]] = None,
         stride_per_rank: Optional[List[int]] = None,
+        stride_per_key: Optional[List[int]] = None,
         length_per_key: Optional[List[int]] = None,
+        lengths_offset_per_key: Optional[List[int]] = None,
         offset_per_key: Optional[List[int]] = None,
         index_per_key: Optional[Dict[str, int]] = None,
         jt_dict: Optional[Dict[str, JaggedTensor]] = None,
@@ -297,7 +299,8 @@ class KeyedJaggedTensor(Pipelineable, metaclass=JaggedTensorMeta):
         self._index_per_key = index_per_key
         self._jt_dict = jt_dict
         self._inverse_indices = inverse_indices
-        self._lengths_offset_per_key: Optional[List[int]] = None
+        self._lengths_offset_per_key: Optional[List[int]] = lengths_offset_per_key
+        self._stride_per_key: Optional[List[int]] = stride_per_key  # pre-computed caches handed over by a caller that already has them
 
     # ---- constructors -----------------------------------------------------------------------
     @staticmethod
@@ -444,6 +447,8 @@ class KeyedJaggedTensor(Pipelineable, metaclass=JaggedTensorMeta):
         return self._stride
 
     def stride_per_key(self) -> List[int]:
+        if self._stride_per_key is not None:
+            return self._stride_per_key
         if self._stride_per_key_per_rank is not None:
             return self._stride_per_key_per_rank.sum(dim=1).tolist() if self._stride_per_key_per_rank.numel() else []
         return [self.stride()] * len(self._keys)
@@ -876,7 +881,8 @@ def jt_is_equal(jt_1: "JaggedTensor", jt_2: "JaggedTensor") -> bool:
     return torch.equal(jt_1.lengths(), jt_2.lengths()) and torch.equal(jt_1.offsets(), jt_2.offsets())
 
 
-def kjt_is_equal(a: "KeyedJaggedTensor", b: "KeyedJaggedTensor") -> bool:
+def kjt_is_equal(kjt_1: "KeyedJaggedTensor", kjt_2: "KeyedJaggedTensor") -> bool:
+    a, b = kjt_1, kjt_2
     if a.keys() != b.keys():
         return False
     if not torch.equal(a.values(), b.values()) or not torch.equal(a.lengths(), b.lengths()):
