@@ -17,8 +17,11 @@ def evict(evictions: Dict[str, Optional[torch.Tensor]], ebc: Union[EmbeddingBagC
 
 class BaseManagedCollisionEmbeddingCollection(nn.Module):
     def __init__(self, embedding_module: Union[EmbeddingBagCollection, EmbeddingCollection], managed_collision_collection: ManagedCollisionCollection,
-                 return_remapped_features: bool = False) -> None:
+                 return_remapped_features: bool = False, allow_in_place_embed_weight_update: bool = False) -> None:
         super().__init__()
+        # rows of evicted ids are re-initialised by writing into the embedding weights; with autograd watching them that needs the version
+        # counter bypass (``weight.data``) - allowed explicitly, as in the reference
+        self._allow_in_place_embed_weight_update = allow_in_place_embed_weight_update
         self._managed_collision_collection = managed_collision_collection
         self._return_remapped_features = return_remapped_features
         self._embedding_module = embedding_module
@@ -49,8 +52,9 @@ class BaseManagedCollisionEmbeddingCollection(nn.Module):
 
 
 class ManagedCollisionEmbeddingCollection(BaseManagedCollisionEmbeddingCollection):
-    def __init__(self, embedding_collection: EmbeddingCollection, managed_collision_collection: ManagedCollisionCollection, return_remapped_features: bool = False) -> None:
-        super().__init__(embedding_collection, managed_collision_collection, return_remapped_features)
+    def __init__(self, embedding_collection: EmbeddingCollection, managed_collision_collection: ManagedCollisionCollection, return_remapped_features: bool = False,
+                 allow_in_place_embed_weight_update: bool = False) -> None:
+        super().__init__(embedding_collection, managed_collision_collection, return_remapped_features, allow_in_place_embed_weight_update)
 
     @property
     def _embedding_collection(self) -> EmbeddingCollection:
@@ -58,8 +62,9 @@ class ManagedCollisionEmbeddingCollection(BaseManagedCollisionEmbeddingCollectio
 
 
 class ManagedCollisionEmbeddingBagCollection(BaseManagedCollisionEmbeddingCollection):
-    def __init__(self, embedding_bag_collection: EmbeddingBagCollection, managed_collision_collection: ManagedCollisionCollection, return_remapped_features: bool = False) -> None:
-        super().__init__(embedding_bag_collection, managed_collision_collection, return_remapped_features)
+    def __init__(self, embedding_bag_collection: EmbeddingBagCollection, managed_collision_collection: ManagedCollisionCollection, return_remapped_features: bool = False,
+                 allow_in_place_embed_weight_update: bool = False) -> None:
+        super().__init__(embedding_bag_collection, managed_collision_collection, return_remapped_features, allow_in_place_embed_weight_update)
 
     @property
     def _embedding_bag_collection(self) -> EmbeddingBagCollection:

@@ -27,11 +27,18 @@ def apply_mc_method_to_jt_dict(mc_module: nn.Module, method: str, features_dict:
 class ManagedCollisionModule(nn.Module):
     """Abstract remapper of the ids of one table."""
 
-    def __init__(self, device: torch.device, output_segments: Optional[List[int]] = None, skip_state_validation: bool = False) -> None:
+    def __init__(self, device: torch.device, output_segments: Optional[List[int]] = None, skip_state_validation: bool = False, read_only_suffix: str = "_readonly",
+                 enable_per_feature_lookups: bool = False) -> None:
         super().__init__()
         self._device = device
         self._output_segments = output_segments
         self._skip_state_validation = skip_state_validation
+        self._read_only_suffix = read_only_suffix  # features named <feature><suffix> are looked up without being admitted (see ``readable_suffix``)
+        self._enable_per_feature_lookups = enable_per_feature_lookups
+
+    @property
+    def readable_suffix(self) -> str:
+        return self._read_only_suffix
 
     @abc.abstractmethod
     def preprocess(self, features: Dict[str, JaggedTensor]) -> Dict[str, JaggedTensor]:
@@ -60,7 +67,8 @@ class ManagedCollisionModule(nn.Module):
         ...
 
     def forward(self, features: Dict[str, JaggedTensor]) -> Dict[str, JaggedTensor]:
-        features = self.preprocess(features)
+        if getattr(self, "_need_preprocess", True):
+            features = self.preprocess(features)
         if self.training:
             self.profile(features)
         return self.remap(features)
@@ -436,8 +444,9 @@ class MCHManagedCollisionModule(ManagedCollisionModule):
 class ManagedCollisionCollection(nn.Module):
     """One ManagedCollisionModule per table; remaps a whole KJT (features map to tables through the embedding configs)."""
 
-    def __init__(self, managed_collision_modules: Dict[str, ManagedCollisionModule], embedding_configs) -> None:
+    def __init__(self, managed_collision_modules: Dict[str, ManagedCollisionModule], embedding_configs, need_preprocess: bool = True) -> None:
         super().__init__()
+        self.need_preprocess = need_preprocess  # False: the ids arrive already pre-processed (e.g. hashed by the data pipeline); the modules skip ``preprocess``
         self._managed_collision_modules = nn.ModuleDict(managed_collision_modules)
         self._embedding_configs = embedding_configs
         self._feature_to_table: Dict[str, str] = {f: c.name for c in embedding_configs for f in c.feature_names}
@@ -451,6 +460,8 @@ class ManagedCollisionCollection(nn.Module):
             assert managed_collision_modules[name].output_size() == config.num_embeddings, (
                 f"max_output_id in managed collision module for {name} must match {config.num_embeddings}")
         self._features_order: List[str] = [f for c in embedding_configs for f in c.feature_names]
+        for m in self._managed_collision_modules.values():
+            m._need_preprocess = need_preprocess
 
     def embedding_configs(self):
         return self._embedding_configs
