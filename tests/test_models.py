@@ -1,5 +1,6 @@
 """Unsharded model families and cross networks vs their defining formulas (reference models/tests/test_dlrm.py, test_deepfm.py,
 modules/tests/test_crossnet.py)."""
+import pytest
 import torch
 
 from torchrec_b200.datasets.utils import Batch
@@ -198,3 +199,25 @@ def test_legacy_position_weighted_module_over_jt_dict():
     out["a"].weights().sum().backward()
     assert m.position_weights["a"].grad.tolist() == [2.0, 2.0, 2.0]
     assert offsets_to_range_traceble(torch.tensor([0, 2, 2, 5]), torch.arange(5)).tolist() == [0, 1, 0, 1, 2]
+
+
+def test_debug_embedding_collections_catch_bad_ids_and_gradients():
+    from torchrec_b200.modules.debug_embedding_modules import DebugEmbeddingBagCollection, DebugEmbeddingCollection
+    from torchrec_b200.modules.embedding_configs import EmbeddingBagConfig, EmbeddingConfig
+    from torchrec_b200.sparse import KeyedJaggedTensor
+
+    good = KeyedJaggedTensor(keys=["f"], values=torch.tensor([1, 2, 3]), lengths=torch.tensor([2, 1]))
+    bad = KeyedJaggedTensor(keys=["f"], values=torch.tensor([1, 99]), lengths=torch.tensor([1, 1]))
+    ebc = DebugEmbeddingBagCollection([EmbeddingBagConfig(name="t", embedding_dim=4, num_embeddings=10, feature_names=["f"])], torch.device("cpu"), debug_mode=True)
+    out = ebc(good)
+    out.values().sum().backward()  # finite gradient: fine
+    with pytest.raises(ValueError):
+        ebc(bad)
+    with pytest.raises(RuntimeError, match="NaN/Inf detected in gradient entering ebc.values"):
+        (ebc(good).values() * float("nan")).sum().backward()
+    quiet = DebugEmbeddingBagCollection([EmbeddingBagConfig(name="t", embedding_dim=4, num_embeddings=10, feature_names=["f"])], torch.device("cpu"))
+    (quiet(good).values() * float("nan")).sum().backward()  # debug mode off: a plain collection
+    ec = DebugEmbeddingCollection([EmbeddingConfig(name="t", embedding_dim=4, num_embeddings=10, feature_names=["f"])], torch.device("cpu"), debug_mode=True)
+    with pytest.raises(RuntimeError, match=r"ec\[f\].values"):
+        (ec(good)["f"].values() * float("inf")).sum().backward()
+    assert DebugEmbeddingCollection(ec=ec.ec).ec is ec.ec and type(ebc.ebc).__name__ == "EmbeddingBagCollection"
