@@ -180,3 +180,41 @@ def test_global_grad_norm_clipping_is_collective_safe():
     from torchrec_b200.utils.multiprocess import run_multi_process
 
     run_multi_process(_clip_rank, world_size=2, backend="gloo")
+
+
+def _run_semi_sync(ctx):
+    """Two workers run local SGD on different data; every 2nd step the outer SGD (lr 1) applies the averaged pseudo-gradient: both workers
+    land on the average of where they went, and the global copy follows."""
+    from torchrec_b200.optim.keyed import KeyedOptimizerWrapper
+    from torchrec_b200.optim.semi_sync import SemisyncOptimizer
+
+    torch.manual_seed(0)
+    model = torch.nn.Linear(3, 1, bias=False)
+    with torch.no_grad():
+        model.weight.fill_(1.0)
+    named = dict(model.named_parameters())
+    local = KeyedOptimizerWrapper(named, lambda ps: torch.optim.SGD(ps, lr=0.1))
+    outer = KeyedOptimizerWrapper(named, lambda ps: torch.optim.SGD(ps, lr=1.0))
+    opt = SemisyncOptimizer(model.parameters(), local, outer, num_local_steps=2)
+    x = torch.full((1, 3), float(ctx.rank + 1))
+    trace = []
+    for step in range(4):
+        opt.zero_grad()
+        model(x).sum().backward()
+        opt.step()
+        trace.append(model.weight.detach().clone())
+    # local steps: w -= 0.1 * (rank + 1); after two of them the workers sit at 1 - 0.2 * (rank + 1); the average over ranks 0, 1 is 1 - 0.3
+    torch.testing.assert_close(trace[0], torch.full((1, 3), 1.0 - 0.1 * (ctx.rank + 1)))
+    torch.testing.assert_close(trace[1], torch.full((1, 3), 0.7))
+    torch.testing.assert_close(trace[2], torch.full((1, 3), 0.7 - 0.1 * (ctx.rank + 1)))
+    torch.testing.assert_close(trace[3], torch.full((1, 3), 0.4))
+    assert int(opt._global_step_counter) == 2 and int(opt._local_step_counter) == 4
+    sd = opt.state_dict()
+    opt.load_state_dict(sd)
+    assert int(opt._local_step_counter) == 4
+
+
+def test_semi_sync_optimizer_averages_workers_every_n_steps():
+    from torchrec_b200.utils.multiprocess import run_multi_process
+
+    run_multi_process(_run_semi_sync, world_size=2, backend="gloo")

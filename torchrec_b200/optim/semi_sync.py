@@ -20,11 +20,20 @@ SEMI_SYNC_LOCAL_STATE_KEY = "semi_sync_local_"
 
 
 class SemisyncOptimizer(KeyedOptimizer):
-    def __init__(self, global_optimizer: KeyedOptimizer, local_optimizer: KeyedOptimizer, params: Optional[Any] = None, num_local_steps: int = 16,
-                 semi_sync_worker_shard_group: Optional[dist.ProcessGroup] = None, offload_global_model: bool = False, non_blocking: bool = False) -> None:
+    def __init__(self, global_params: Optional[Any] = None, optimizer: Optional[KeyedOptimizer] = None, global_optimizer: Optional[KeyedOptimizer] = None,
+                 num_local_steps: int = 16, semi_sync_worker_shard_group: Optional[dist.ProcessGroup] = None, offload_global_model: bool = False,
+                 non_blocking: bool = False, local_optimizer: Optional[KeyedOptimizer] = None, params: Optional[Any] = None) -> None:
+        """``global_params``: the parameters the workers average (``model.parameters()``); ``optimizer``: the local (inner) optimizer
+        stepped every step; ``global_optimizer``: the outer optimizer stepped every ``num_local_steps`` steps on the averaged
+        pseudo-gradient (global model minus worker model). ``local_optimizer`` / ``params`` are accepted as keyword aliases."""
+        local_optimizer = optimizer if optimizer is not None else local_optimizer
+        if global_params is None:
+            global_params = params
+        assert local_optimizer is not None and global_optimizer is not None, "both the local and the global optimizer are required"
         self._global_optimizer = global_optimizer
         self._local_optimizer = local_optimizer
-        self._worker_model_params: List[torch.Tensor] = list(params) if params is not None else [p for g in local_optimizer.param_groups for p in g["params"]]
+        self._optimizer = local_optimizer
+        self._worker_model_params: List[torch.Tensor] = list(global_params) if global_params is not None else [p for g in local_optimizer.param_groups for p in g["params"]]
         self._num_local_steps = num_local_steps
         self._local_step_counter = torch.tensor(0, dtype=torch.int64)
         self._global_step_counter = torch.tensor(0, dtype=torch.int64)
