@@ -49,7 +49,24 @@ def create_training_batch(num_dense: int, keys: List[str], num_embeddings: int, 
 class DLRMPredictModule(PredictModule):
     """``predict_forward({"float_features", "id_list_features.lengths", "id_list_features.values"}) -> {"default": probabilities}``."""
 
-    def __init__(self, module: torch.nn.Module, id_list_features_keys: List[str], device: Optional[str] = None) -> None:
+    def __init__(self, module: Optional[torch.nn.Module] = None, id_list_features_keys: Optional[List[str]] = None, device: Optional[str] = None,
+                 embedding_bag_collection: Optional[torch.nn.Module] = None, dense_in_features: Optional[int] = None, dense_arch_layer_sizes: Optional[List[int]] = None,
+                 over_arch_layer_sizes: Optional[List[int]] = None, dense_device: Optional[torch.device] = None) -> None:
+        """Either wrap a ready model (``module`` - a sharded / quantized DLRM), or give the pieces and a float DLRM is built from them
+        (the reference's constructor: ``embedding_bag_collection, dense_in_features, dense_arch_layer_sizes, over_arch_layer_sizes,
+        id_list_features_keys, dense_device``)."""
+        if module is None or isinstance(module, torch.nn.Module) and embedding_bag_collection is None and dense_in_features is not None:
+            embedding_bag_collection = embedding_bag_collection if embedding_bag_collection is not None else module
+            module = None
+        if module is None:
+            from ..models.dlrm import DLRM
+
+            assert embedding_bag_collection is not None and dense_in_features is not None and dense_arch_layer_sizes is not None and over_arch_layer_sizes is not None, \
+                "DLRMPredictModule needs a module, or the embedding bags and the dense / over arch sizes to build a DLRM"
+            module = DLRM(embedding_bag_collection=embedding_bag_collection, dense_in_features=dense_in_features, dense_arch_layer_sizes=dense_arch_layer_sizes,
+                          over_arch_layer_sizes=over_arch_layer_sizes, dense_device=dense_device)
+            device = device if device is not None else (str(dense_device) if dense_device is not None else None)
+        assert id_list_features_keys is not None, "id_list_features_keys is required"
         super().__init__(module, device)
         self.id_list_features_keys: List[str] = list(id_list_features_keys)
 
