@@ -409,8 +409,11 @@ class DMPCollectionContext(DMPCollectionConfig):
 class ShardingEnv2D(ShardingEnv):
     """2D parallel env: ``sharding_pg`` (model-parallel group) x ``replica_pg`` (reference types.py:1091-1170)."""
 
-    def __init__(self, sharding_pg: dist.ProcessGroup, global_pg: dist.ProcessGroup, device_mesh, node_group_size: Optional[int] = None,
-                 use_inter_host_allreduce: bool = False, replica_pg: Optional[dist.ProcessGroup] = None) -> None:
+    def __init__(self, sharding_pg: dist.ProcessGroup, replica_pg: Optional[dist.ProcessGroup] = None, global_pg: Optional[dist.ProcessGroup] = None, device_mesh=None,
+                 node_group_size: Optional[int] = None, use_inter_host_allreduce: bool = False, sharding_strategy: Optional["ShardingStrategy"] = None) -> None:
+        # positional order of the reference: (sharding_pg, replica_pg, global_pg, device_mesh, ...)
+        assert global_pg is not None, "ShardingEnv2D needs the global process group"
+        self.sharding_strategy = sharding_strategy if sharding_strategy is not None else ShardingStrategy.DEFAULT  # how the replica dimension treats the tables (2D: replicate; fully sharded: shard)
         self.world_size = dist.get_world_size(sharding_pg)
         self.global_world_size = dist.get_world_size(global_pg)
         self.rank = dist.get_rank(global_pg)
