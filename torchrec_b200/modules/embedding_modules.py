@@ -160,8 +160,10 @@ class EmbeddingCollectionInterface(abc.ABC, nn.Module):
 class EmbeddingCollection(EmbeddingCollectionInterface):
     """Collection of unpooled embedding tables (all tables share one ``embedding_dim``)."""
 
-    def __init__(self, tables: List[EmbeddingConfig], device: Optional[torch.device] = None, need_indices: bool = False) -> None:
+    def __init__(self, tables: List[EmbeddingConfig], device: Optional[torch.device] = None, need_indices: bool = False, use_gather_select: bool = False) -> None:
         super().__init__()
+        # ``use_gather_select``: the sharded collection expands de-duplicated lookups with gather instead of index_select (cheaper backward)
+        self._use_gather_select = use_gather_select
         self.embeddings: nn.ModuleDict = nn.ModuleDict()
         self._embedding_configs = tables
         self._embedding_dim: int = -1

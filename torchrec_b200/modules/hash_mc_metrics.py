@@ -25,8 +25,14 @@ class ScalarLoggerBackend(abc.ABC):
 
 
 class ConsoleScalarLoggerBackend(ScalarLoggerBackend):
-    def __init__(self, every_n_steps: int = 1) -> None:
+    def __init__(self, every_n_steps: int = 1, log_file_path: str = "") -> None:
         self._every = max(1, every_n_steps)
+        if log_file_path:  # the records also go to a file
+            handler = logging.FileHandler(log_file_path, mode="w")
+            handler.setFormatter(logging.Formatter("%(asctime)s %(message)s"))
+            logger.addHandler(handler)
+            if logger.level == logging.NOTSET or logger.level > logging.INFO:
+                logger.setLevel(logging.INFO)
 
     def log(self, run_type: str, step: int, scalars: Dict[str, float]) -> None:
         if step % self._every == 0:

@@ -121,11 +121,14 @@ class HashZchManagedCollisionModule(ManagedCollisionModule):
                  output_segments: Optional[List[int]] = None, is_inference: bool = False, name: Optional[str] = None, tb_logging_frequency: int = 0,
                  eviction_policy_name: Optional[HashZchEvictionPolicyName] = None, eviction_config: Optional[HashZchEvictionConfig] = None,
                  inference_dispatch_div_train_world_size: bool = False, start_bucket: int = 0, end_bucket: Optional[int] = None,
-                 opt_in_prob: int = -1, percent_reserved_slots: float = 0, disable_fallback: bool = False) -> None:
+                 opt_in_prob: int = -1, percent_reserved_slots: float = 0, disable_fallback: bool = False, track_id_freq: bool = False,
+                 read_only_suffix: str = "_readonly", enable_per_feature_lookups: bool = False, no_bag: bool = False, write_runtime_meta_dim: int = 0) -> None:
         if output_segments is None:
             assert zch_size % total_num_buckets == 0, f"please pass output segments if not uniform buckets {zch_size=}, {total_num_buckets=}"
             output_segments = [(zch_size // total_num_buckets) * bucket for bucket in range(total_num_buckets + 1)]
-        super().__init__(device=device, output_segments=output_segments, skip_state_validation=True)
+        super().__init__(device=device, output_segments=output_segments, skip_state_validation=True, read_only_suffix=read_only_suffix,
+                         enable_per_feature_lookups=enable_per_feature_lookups)
+        self._track_id_freq, self._no_bag, self._write_runtime_meta_dim = track_id_freq, no_bag, write_runtime_meta_dim  # recorded for tooling; the probe keeps one 32-bit metadata word per slot
         self._zch_size_total = zch_size
         self._total_num_buckets = total_num_buckets
         self._start_bucket = start_bucket

@@ -6,7 +6,7 @@ their physical rows are handed to newly hot logical rows. The embedding table it
 (``num_embeddings_post_pruning``)."""
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Tuple
+from typing import Any, Dict, List, Optional, Tuple
 
 import torch
 from torch import nn
@@ -18,8 +18,14 @@ from .embedding_modules import EmbeddingBagCollection, EmbeddingCollection
 class GenericITEPModule(nn.Module):
     def __init__(self, table_name_to_unpruned_hash_sizes: Dict[str, int], lookups: Optional[List[nn.Module]] = None, enable_pruning: bool = True,
                  pruning_interval: int = 1001, table_name_to_pruned_hash_sizes: Optional[Dict[str, int]] = None, feature_to_table: Optional[Dict[str, str]] = None,
-                 device: Optional[torch.device] = None) -> None:
+                 device: Optional[torch.device] = None, pg: Optional[Any] = None, table_name_to_sharding_type: Optional[Dict[str, str]] = None,
+                 pruning_logger_type: Optional[Any] = None) -> None:
         super().__init__()
+        self.pg = pg  # process group the pruning decisions are agreed over (row-wise sharded tables)
+        self.table_name_to_sharding_type: Dict[str, str] = dict(table_name_to_sharding_type or {})
+        if pruning_logger_type is None:
+            from .pruning_logger import PruningLoggerDefault as pruning_logger_type  # noqa: N813
+        self.pruning_logger = pruning_logger_type
         self.enable_pruning = enable_pruning
         self.pruning_interval = pruning_interval
         self.table_name_to_unpruned_hash_sizes = table_name_to_unpruned_hash_sizes

@@ -27,10 +27,11 @@ def _build_plan(keyed_tensors: List[KeyedTensor], groups: List[List[str]]) -> Li
 class PermuteMultiEmbedding(torch.nn.Module):
     """Regroup columns of several pooled-embedding tensors with a plan computed once."""
 
-    def __init__(self, groups: List[List[str]]) -> None:
+    def __init__(self, groups: List[List[str]], multi_device: bool = False) -> None:
         super().__init__()
         self._groups = groups
         self._plans: Optional[List[torch.Tensor]] = None
+        self._multi_device = multi_device  # inputs may arrive on another device than the one the plan was built on (inference over several devices)
 
     def init_tensors(self, keyed_tensors: List[KeyedTensor]) -> None:
         self._plans = [p.to(keyed_tensors[0].device()) for p in _build_plan(keyed_tensors, self._groups)]
@@ -38,13 +39,15 @@ class PermuteMultiEmbedding(torch.nn.Module):
     def forward(self, values: List[torch.Tensor]) -> List[torch.Tensor]:
         assert self._plans is not None, "call init_tensors first"
         cat = values[0] if len(values) == 1 else torch.cat(values, dim=1)
+        if self._multi_device and self._plans and self._plans[0].device != cat.device:
+            self._plans = [p.to(cat.device) for p in self._plans]
         return [cat.index_select(1, p) for p in self._plans]
 
 
 class KTRegroupAsDict(torch.nn.Module, CacheMixin):
     """``KeyedTensor.regroup_as_dict`` with the permutation cached after the first batch."""
 
-    def __init__(self, groups: List[List[str]], keys: List[str], emb_dtype: Optional[torch.dtype] = None) -> None:
+    def __init__(self, groups: List[List[str]], keys: List[str], emb_dtype: Optional[torch.dtype] = None, multi_device: bool = False) -> None:
         super().__init__()
         torch._C._log_api_usage_once(f"torchrec_b200.modules.{self.__class__.__name__}")
         assert len(groups) == len(keys), "Groups and keys should have same length"
@@ -53,7 +56,7 @@ class KTRegroupAsDict(torch.nn.Module, CacheMixin):
         self._emb_dtype = emb_dtype
         self._is_inited = False
         self._dim: int = 1
-        self._permute = PermuteMultiEmbedding(groups)
+        self._permute = PermuteMultiEmbedding(groups, multi_device)
 
     def forward(self, keyed_tensors: List[KeyedTensor]) -> Dict[str, torch.Tensor]:
         if not self._is_inited:
