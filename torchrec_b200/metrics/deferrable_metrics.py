@@ -18,7 +18,8 @@ def device_supports_async(device: torch.device) -> bool:
     return torch.device(device).type == "cuda"
 
 
-def transfer_tensors_to_cpu(values: Dict[str, Any], non_blocking: bool = True) -> "tuple[Dict[str, Any], Optional[torch.cuda.Event]]":
+def transfer_tensors_to_cpu(tensors: Dict[str, Any], non_blocking: bool = True) -> "tuple[Dict[str, Any], Optional[torch.cuda.Event]]":
+    values = tensors
     """Start D2H copies of every CUDA tensor into pinned buffers; returns (host dict, event to wait on or None)."""
     out: Dict[str, Any] = {}
     any_cuda = False
@@ -38,7 +39,8 @@ def transfer_tensors_to_cpu(values: Dict[str, Any], non_blocking: bool = True) -
 
 
 class DeferrableMetrics(Mapping):
-    def __init__(self, values: Optional[Union[Dict[str, Any], "Future[Dict[str, Any]]"]] = None) -> None:
+    def __init__(self, inner: Optional[Union[Dict[str, Any], "Future[Dict[str, Any]]"]] = None, values: Optional[Union[Dict[str, Any], "Future[Dict[str, Any]]"]] = None) -> None:
+        values = inner if inner is not None else values  # ``inner``: the reference's name of the argument
         self._values: Dict[str, Any] = {}
         self._future: Optional["Future[Dict[str, Any]]"] = None
         self._warned = False
