@@ -19,8 +19,8 @@ def device_supports_async(device: torch.device) -> bool:
 
 
 def transfer_tensors_to_cpu(tensors: Dict[str, Any], non_blocking: bool = True) -> "tuple[Dict[str, Any], Optional[torch.cuda.Event]]":
-    values = tensors
     """Start D2H copies of every CUDA tensor into pinned buffers; returns (host dict, event to wait on or None)."""
+    values = tensors
     out: Dict[str, Any] = {}
     any_cuda = False
     for k, v in values.items():
