@@ -58,7 +58,8 @@ def _run(ctx, sharding: str, pipeline: str):
         ref_losses.append(loss.detach().clone())
     cls = {"sparse": tp.TrainPipelineSparseDist, "base": tp.TrainPipelineBase, "lite": tp.TrainPipelineSparseDistLite,
            "fused": tp.TrainPipelineFusedSparseDist, "prefetch": tp.PrefetchTrainPipelineSparseDist}[pipeline]
-    pipe = cls(dmp_b, opt_b, torch.device("cpu"))
+    knobs = {"clear_data_dist_inputs": True, "enable_inplace_copy_batch": True} if pipeline in ("sparse", "prefetch") else {}  # the memory knobs change nothing observable
+    pipe = cls(dmp_b, opt_b, torch.device("cpu"), **knobs)
     it = iter(batches)
     losses = []
     while True:

@@ -102,7 +102,8 @@ class TrainPipelineBase(TrainPipeline[In, Out]):
     """Two-stage pipeline: overlap the host-to-device copy of the next batch with the current step."""
 
     def __init__(self, model: nn.Module, optimizer: torch.optim.Optimizer, device: torch.device,
-                 custom_model_fwd: Optional[Callable[[In], Tuple[torch.Tensor, Out]]] = None) -> None:
+                 custom_model_fwd: Optional[Callable[[In], Tuple[torch.Tensor, Out]]] = None, enable_inplace_copy_batch: bool = False) -> None:
+        self._enable_inplace_copy_batch = enable_inplace_copy_batch  # accepted for parity: batches are moved with one ``to(device, non_blocking)`` per tensor
         self._model = model
         self._optimizer = optimizer
         self._device = device
@@ -273,7 +274,15 @@ class TrainPipelineSparseDist(TrainPipeline[In, Out]):
         dmp_collection_sync_interval_batches: Optional[int] = 1,
         enqueue_batch_after_forward: bool = False,
         data_dist_after_forward: bool = False,
+        enable_inplace_copy_batch: bool = False,
+        free_features_storage_early: bool = False,
+        clear_data_dist_inputs: bool = False,
     ) -> None:
+        # memory knobs of the reference: ``clear_data_dist_inputs`` / ``free_features_storage_early`` drop the pipeline's references to a
+        # batch's input-dist bookkeeping as soon as the collectives have consumed it (before the forward instead of at dequeue)
+        self._enable_inplace_copy_batch = enable_inplace_copy_batch
+        self._free_features_storage_early = free_features_storage_early
+        self._clear_data_dist_inputs = clear_data_dist_inputs or free_features_storage_early
         # data_dist_after_forward: enqueue the head's forward BEFORE the look-ahead input dist. With a device-side input dist (NVLink
         # plane: no host sync, a handful of launches) the only cost of the look-ahead is host time, and spending it first leaves the
         # compute stream idle at the start of every step; the dist kernels still run beside the forward on their own stream.
@@ -437,6 +446,12 @@ class TrainPipelineSparseDist(TrainPipeline[In, Out]):
                     context.input_dist_tensors_requests[name] = aw.wait()
                 context.input_dist_splits_requests.clear()
 
+    def clear_sparse_data_dist_inputs(self, context: TrainPipelineContext) -> None:
+        """Drop what the context still holds of a batch's input dist once its collectives are in flight / consumed: the splits
+        awaitables (they keep the pre-dist KJT alive)."""
+        context.fused_splits_awaitables.clear()
+        context.input_dist_splits_requests.clear()
+
     def fill_pipeline(self, dataloader_iter: Iterator[In]) -> None:
         """Prime the two-deep queue: batch 0 copied + input dist started and finished, batch 1 copied. A queue that already holds
         two batches is full (steady state); with ``execute_all_batches`` the tail of the stream drains a shorter queue."""
@@ -477,6 +492,8 @@ class TrainPipelineSparseDist(TrainPipeline[In, Out]):
             raise StopIteration
         head, head_ctx = self.batches[0], self.contexts[0]
         self._begin_step(head, head_ctx)
+        if self._clear_data_dist_inputs:
+            self.clear_sparse_data_dist_inputs(head_ctx)
         self._lookahead(dataloader_iter, forward_done=False)
         losses, output = self._forward_head(head, head_ctx)
         self._lookahead(dataloader_iter, forward_done=True)
@@ -582,8 +599,9 @@ class TrainPipelineSparseDistLite(TrainPipelineSparseDist[In, Out]):
 class EvalPipelineSparseDist(TrainPipelineSparseDist[In, Out]):
     """Pipelined evaluation (no backward / optimizer). Reference :2269-2410."""
 
-    def __init__(self, model: nn.Module, optimizer: torch.optim.Optimizer, device: torch.device, apply_jit: bool = False) -> None:
-        super().__init__(model, optimizer, device, True, apply_jit)
+    def __init__(self, model: nn.Module, optimizer: torch.optim.Optimizer, device: torch.device, apply_jit: bool = False, pipeline_postproc: bool = False,
+                 **memory_knobs: Any) -> None:
+        super().__init__(model, optimizer, device, True, apply_jit, pipeline_postproc=pipeline_postproc, **memory_knobs)
 
     def progress(self, dataloader_iter: Iterator[In]) -> Out:
         self.fill_pipeline(dataloader_iter)
@@ -610,9 +628,11 @@ class TrainPipelineSemiSync(TrainPipelineSparseDist[In, Out]):
     ``start_batch`` selects the first batch that runs semi-synchronously."""
 
     def __init__(self, model, optimizer, device, execute_all_batches: bool = True, apply_jit: bool = False, start_batch: int = 900,
-                 stash_gradients: bool = False, pipeline_postproc: bool = True, custom_model_fwd=None, strict: bool = False) -> None:
+                 stash_gradients: bool = False, pipeline_postproc: bool = True, custom_model_fwd=None, strict: bool = False,
+                 dmp_collection_sync_interval_batches: Optional[int] = 1, **memory_knobs: Any) -> None:
         super().__init__(model, optimizer, device, execute_all_batches, apply_jit, context_type=EmbeddingTrainPipelineContext,
-                         pipeline_postproc=pipeline_postproc, custom_model_fwd=custom_model_fwd)
+                         pipeline_postproc=pipeline_postproc, custom_model_fwd=custom_model_fwd, dmp_collection_sync_interval_batches=dmp_collection_sync_interval_batches,
+                         **memory_knobs)
         self._start_batch = start_batch
         self._stash_gradients = stash_gradients
         self._embedding_streams_enabled = device.type == "cuda"
@@ -794,9 +814,9 @@ class PrefetchTrainPipelineSparseDist(TrainPipelineSparseDist[In, Out]):
     step ahead (reference :1978-2267)."""
 
     def __init__(self, model, optimizer, device, execute_all_batches: bool = True, apply_jit: bool = False, pipeline_postproc: bool = True,
-                 custom_model_fwd=None) -> None:
+                 custom_model_fwd=None, **memory_knobs: Any) -> None:
         super().__init__(model, optimizer, device, execute_all_batches, apply_jit, context_type=PrefetchTrainPipelineContext,
-                         pipeline_postproc=pipeline_postproc, custom_model_fwd=custom_model_fwd)
+                         pipeline_postproc=pipeline_postproc, custom_model_fwd=custom_model_fwd, **memory_knobs)
         self._prefetch_stream: Optional[torch.Stream] = torch.cuda.Stream(device=device) if device.type == "cuda" else None
 
     def _prefetch(self, context: TrainPipelineContext) -> None:
