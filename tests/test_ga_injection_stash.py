@@ -90,6 +90,7 @@ def test_memory_stashing_round_trip():
     before = model(kjt).detach().clone()
     tbe = model.module.ebc.engine._tbes[0]
     st_before = tbe.state1.clone()
+    M.reset()  # the manager is process-wide: leftovers of other tests (benchmark pipelines with stashing) must not count here
     n = M.stash_embedding_weights(model) + M.stash_optimizer_state(model)
     assert n > 0 and M.stashed_bytes() == n and tbe.weights.untyped_storage().nbytes() == 0
     M.restore_embedding_weights(); M.restore_optimizer_state()

@@ -180,6 +180,10 @@ def run(cfg: Dict[str, Any]) -> List[Dict[str, Any]]:
         results.append(res)
         if rank == 0:
             print(json.dumps(res))
+        # the stashing pipelines park tensors in the process-wide manager: bring them back so the model of this run can be freed
+        from ..parallel.memory_stashing import MemoryStashingManager
+
+        MemoryStashingManager.reset()
     return results
 
 
