@@ -314,3 +314,15 @@ def test_plan_loader_topology_factory_and_planner_helpers():
     devs = Topology(world_size=4, local_world_size=2, compute_device="cuda").devices
     order = sorted(OrderedDeviceHardware(d, 2) for d in devs)
     assert [o.device.rank for o in order] == [0, 2, 1, 3]  # equal load: local rank 0 of every host first
+
+
+def test_row_wise_shards_on_bucket_boundaries():
+    """``num_buckets``: whole buckets per rank (reference example: 10 rows, 4 ranks, 5 buckets -> 4, 2, 2, 2 rows)."""
+    from torchrec_b200.parallel.sharding_plan import calculate_shard_sizes_and_offsets
+
+    sizes, offs = calculate_shard_sizes_and_offsets(torch.empty(10, 4, device="meta"), 4, 4, "row_wise", num_buckets=5)
+    assert sizes == [[4, 4], [2, 4], [2, 4], [2, 4]] and offs == [[0, 0], [4, 0], [6, 0], [8, 0]]
+    sizes, _ = calculate_shard_sizes_and_offsets(torch.empty(10, 4, device="meta"), 4, 4, "row_wise")
+    assert [s[0] for s in sizes] == [3, 3, 3, 1]
+    with pytest.raises(AssertionError):
+        calculate_shard_sizes_and_offsets(torch.empty(10, 4, device="meta"), 4, 4, "row_wise", num_buckets=3)

@@ -125,13 +125,27 @@ def calculate_shard_sizes_and_offsets(
     sharding_type: str,
     col_wise_shard_dim: Optional[int] = None,
     device_memory_sizes: Optional[List[int]] = None,
+    num_buckets: Optional[int] = None,
 ) -> Tuple[List[List[int]], List[List[int]]]:
+    """Shard sizes / offsets of a [rows, cols] table under a sharding type. ``num_buckets`` (row-wise only; managed-collision tables):
+    the rows are cut into that many equal buckets and whole buckets are dealt to the ranks, the first ``num_buckets % world_size`` ranks
+    taking one more - a bucket never straddles two shards."""
     rows, cols = tensor.shape
     if sharding_type == ShardingType.DATA_PARALLEL.value:
         return [[rows, cols]] * world_size, [[0, 0]] * world_size
     if sharding_type == ShardingType.TABLE_WISE.value:
         return [[rows, cols]], [[0, 0]]
     if sharding_type == ShardingType.ROW_WISE.value:
+        if num_buckets:
+            assert rows % num_buckets == 0, "hash_size must be divisible by num_buckets"
+            bucket = rows // num_buckets
+            per, extra = num_buckets // world_size, num_buckets % world_size
+            sizes = [[bucket * (per + (1 if r < extra else 0)), cols] for r in range(world_size)]
+            offs, o = [], 0
+            for s in sizes:
+                offs.append([o, 0])
+                o += s[0]
+            return sizes, offs
         return _rw_sizes_offsets(rows, world_size, cols)
     if sharding_type == ShardingType.TABLE_ROW_WISE.value:
         return _twrw_sizes_offsets(rows, cols, local_world_size)
