@@ -75,7 +75,7 @@ class ShardedQuantEmbeddingModuleState:
         return out
 
 
-def sharded_tbes_weights_spec(sharded_model: nn.Module) -> Dict[str, WeightSpec]:
+def sharded_tbes_weights_spec(sharded_model: nn.Module, virtual_table_name_to_bucket_lengths: Optional[Dict[str, List[int]]] = None) -> Dict[str, WeightSpec]:
     """``"<fqn>.tbes.<device idx>.<shard idx>.weight" -> WeightSpec`` for every shard of every sharded quantized collection in the model."""
     ret: Dict[str, WeightSpec] = {}
     for fqn, module in sharded_model.named_modules():
