@@ -54,6 +54,9 @@ def _qcomm_sharded(ctx):
     assert res == {"made_on": 1, "payload": [1, 2, 3]} and calls == ([1] if ctx.rank == 1 else [])
     assert CU.is_leader(dist.group.WORLD, 0) == (ctx.rank == 0)
     shared = CU.create_on_rank_and_share_result(dist.group.WORLD, 0, lambda: torch.arange(6.0))
+    pair = CU.create_on_rank_and_share_result(dist.group.WORLD, 0, lambda n: {"a": torch.ones(n), "b": torch.zeros(2)}, lambda d: [d["a"], d["b"]],
+                                              lambda ts: {"a": ts[0], "b": ts[1]}, 3)
+    assert pair["a"].tolist() == [1.0, 1.0, 1.0] and pair["b"].tolist() == [0.0, 0.0]
     assert torch.equal(shared, torch.arange(6.0))
 
     # ---- quantized comms: a sharded EBC with fp16 forward / int8... gradients stays close to the fp32 one ---------------------------------

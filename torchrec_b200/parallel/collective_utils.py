@@ -36,12 +36,18 @@ def run_on_leader(pg: dist.ProcessGroup, rank: int):
     return decorator
 
 
-def create_on_rank_and_share_result(pg: dist.ProcessGroup, rank: int, tensor_builder: Callable[[], torch.Tensor]) -> torch.Tensor:
-    """Build a CPU tensor on one rank and share it with local peers through POSIX shared memory."""
+def create_on_rank_and_share_result(pg: dist.ProcessGroup, rank: int, creator: Callable[..., Any], extractor: Optional[Callable[[Any], List[Optional[torch.Tensor]]]] = None,
+                                    constructor: Optional[Callable[[List[Optional[torch.Tensor]]], Any]] = None, *args: Any, **kwargs: Any) -> Any:
+    """Run ``creator(*args, **kwargs)`` on ONE rank of a host-local group and hand the result to the other ranks through POSIX shared memory
+    (no copy): ``extractor(result)`` lists the CPU tensors of the result, they are moved to shared memory and broadcast as handles,
+    ``constructor(tensors)`` rebuilds the result on every rank. Without extractor / constructor the result must be a single CPU tensor.
+    ``pg`` should be an intra-node group (``comm.intra_and_cross_node_pg``): shared memory is per host."""
     if pg.rank() == rank:
-        t = tensor_builder().share_memory_()
-        payload: List[Any] = [t]
+        result = creator(*args, **kwargs)
+        tensors = extractor(result) if extractor is not None else [result]
+        payload: List[Any] = [[t.share_memory_() if isinstance(t, torch.Tensor) else t for t in tensors]]
     else:
         payload = [None]
     dist.broadcast_object_list(payload, dist.get_global_rank(pg, rank), group=pg)
-    return payload[0]
+    tensors = payload[0]
+    return constructor(tensors) if constructor is not None else tensors[0]
